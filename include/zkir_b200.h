@@ -1,0 +1,148 @@
+/* zkir_b200.h -- C ABI of the B200-native STARK proving backend for the ZKIR v3.4 VM.
+ *
+ * The reference (seceq/zkir, /root/reference) has NO plugin / FFI seam and NO prover: its public runtime API
+ * ends at `zkir_runtime::run()` / `VM::run` returning `ExecutionResult` (zkir-runtime/src/lib.rs:29-62,
+ * zkir-runtime/src/vm.rs:54-78,208-358).  This header therefore DEFINES the seam a Rust `prove()` placed next to
+ * `run()` would bind (see INTEGRATION.md for the `extern "C"` block and the safe wrapper).  Each entry point
+ * below names the reference item it sits behind or replaces.
+ *
+ * Conventions: all integers little-endian; field elements are canonical BabyBear values (uint32_t < p,
+ * p = 2^31 - 2^27 + 1) on this boundary; matrices are column-major `[width][1 << log_n]`.
+ * Return 0 = OK, negative = error (ZKIR_ERR_*); nothing throws or exits across the ABI.  A `zkir_ctx` is
+ * single-owner (one host thread at a time); independent contexts may live on different threads/devices.
+ * There is NO CPU fallback: every proving entry point fails with ZKIR_ERR_CUDA if no sm_100 device is usable.
+ */
+#ifndef ZKIR_B200_H
+#define ZKIR_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ZKIR_OK 0
+#define ZKIR_ERR_ARG (-1)   /* bad argument / unsupported shape        -> RuntimeError::Other (zkir-runtime/src/error.rs:35-36) */
+#define ZKIR_ERR_CUDA (-2)  /* CUDA runtime failure or no device */
+#define ZKIR_ERR_NCCL (-3)
+#define ZKIR_ERR_OOM (-4)
+#define ZKIR_ERR_VM (-5)    /* guest fault: DivisionByZero / MisalignedAccess / InvalidSyscall ... (error.rs:6-39) */
+#define ZKIR_ERR_AIR (-6)   /* trace uses an opcode / value the core AIR v1 does not constrain */
+#define ZKIR_ERR_VERIFY (-7)
+
+#define ZKIR_BABYBEAR_P 2013265921u
+#define ZKIR_AIR_V1_WIDTH 112u
+#define ZKIR_AIR_V1_NUM_PUBLIC 4u
+
+/* ---- proving parameters (the reference has none; Plonky3's FriConfig fields) */
+typedef struct {
+  uint32_t log_blowup;  /* >= 1 */
+  uint32_t num_queries;
+  uint32_t pow_bits;
+  uint32_t width;       /* must equal ZKIR_AIR_V1_WIDTH */
+  uint32_t num_public;  /* must equal ZKIR_AIR_V1_NUM_PUBLIC */
+} zkir_params;
+
+typedef struct zkir_ctx zkir_ctx;
+
+/* ---- context: one per GPU.  (No reference counterpart.) */
+int zkir_b200_create(zkir_ctx** out, int device_id);
+void zkir_b200_destroy(zkir_ctx*);
+const char* zkir_b200_last_error(const zkir_ctx*); /* ctx may be NULL: last create/VM error of this thread */
+/* pinned host buffers the interpreter records into (north_star: "records the execution trace into pinned memory") */
+void* zkir_b200_alloc_pinned(size_t bytes);
+void zkir_b200_free_pinned(void*);
+
+/* ---- the hot path: trace columns -> proof.  Sits where `zkir_runtime::prove()` would call into Plonky3
+ * (the call does not exist in the reference: zkir-runtime/src/lib.rs:29-62).  `trace_cols` is HOST memory
+ * (pinned recommended), `[width][1 << log_n]`; `public_values[num_public]`.  The proof buffer is owned by the
+ * library until zkir_b200_free_proof.  H2D of the trace and D2H of the proof happen inside this call. */
+int zkir_b200_prove(zkir_ctx*, const zkir_params*, const uint32_t* trace_cols, uint32_t log_n,
+                    const uint32_t* public_values, uint8_t** proof, size_t* proof_len);
+/* same, trace already resident in device memory (canonical values); used by bench `value` timing */
+int zkir_b200_prove_device(zkir_ctx*, const zkir_params*, const uint32_t* d_trace_cols, uint32_t log_n,
+                           const uint32_t* public_values, uint8_t** proof, size_t* proof_len);
+/* many independent small proofs (BASELINE config 4); traces[i] is host memory [width][1<<log_ns[i]] */
+int zkir_b200_prove_batch(zkir_ctx*, const zkir_params*, const uint32_t* const* traces, const uint32_t* log_ns,
+                          const uint32_t* const* public_values, uint32_t n_proofs, uint8_t** proofs, size_t* proof_lens);
+void zkir_b200_free_proof(uint8_t*);
+size_t zkir_b200_proof_size(const zkir_params*, uint32_t log_n); /* bytes; depends only on the shape */
+/* CPU verifier (host code, no GPU needed).  0 = accept, ZKIR_ERR_VERIFY = reject (reason via last_error(NULL)). */
+int zkir_b200_verify(const zkir_params*, const uint8_t* proof, size_t len, const uint32_t* public_values);
+
+/* ---- per-kernel entry points (parity tests, ncu captures, roofline harness).  Device pointers, canonical values. */
+/* batched NTT over `n_cols` contiguous columns of length 1<<log_n, in place, natural order in and out.
+ * coset_shift != 0 (forward only): evaluates on shift*H instead of H. */
+int zkir_b200_ntt(zkir_ctx*, uint32_t* d_cols, uint32_t n_cols, uint32_t log_n, int inverse, uint32_t coset_shift);
+/* low-degree extension: d_in [n_cols][1<<log_n] evaluations on H -> d_out [n_cols][1<<(log_n+log_blowup)] on 31*H */
+int zkir_b200_lde(zkir_ctx*, const uint32_t* d_in, uint32_t* d_out, uint32_t n_cols, uint32_t log_n, uint32_t log_blowup);
+int zkir_b200_poseidon2_permute(zkir_ctx*, uint32_t* d_states /* [n][16] */, uint64_t n);
+/* leaf = sponge over a row of the column-major matrix; d_tree receives (2*rows-1)*8 words (leaves first) */
+int zkir_b200_merkle_commit(zkir_ctx*, const uint32_t* d_matrix, uint32_t n_cols, uint32_t log_rows, uint32_t* d_tree,
+                            uint32_t root[8]);
+/* quotient values of the core AIR on the LDE coset: d_lde [width][M], out d_q [4][M], M = 1<<(log_n+log_blowup) */
+int zkir_b200_quotient(zkir_ctx*, const zkir_params*, const uint32_t* d_lde, uint32_t log_n, const uint32_t* public_values,
+                       const uint32_t alpha[4], uint32_t* d_q);
+/* one FRI fold: d_in [1<<log_n][4] (ext4, AoS) on shift*H -> d_out [1<<(log_n-1)][4] */
+int zkir_b200_fri_fold(zkir_ctx*, const uint32_t* d_in, uint32_t* d_out, uint32_t log_n, uint32_t shift, const uint32_t beta[4]);
+/* device memory helpers so ctypes callers need no CUDA binding of their own */
+int zkir_b200_dev_alloc(zkir_ctx*, void** d_ptr, size_t bytes);
+int zkir_b200_dev_free(zkir_ctx*, void* d_ptr);
+int zkir_b200_h2d(zkir_ctx*, void* d_dst, const void* h_src, size_t bytes);
+int zkir_b200_d2h(zkir_ctx*, void* h_dst, const void* d_src, size_t bytes);
+int zkir_b200_sync(zkir_ctx*);
+/* stage timings (ms, CUDA events on the ctx stream) of the last zkir_b200_prove*: see ZKIR_STAGE_* */
+#define ZKIR_STAGE_H2D 0
+#define ZKIR_STAGE_LDE 1
+#define ZKIR_STAGE_TRACE_COMMIT 2
+#define ZKIR_STAGE_QUOTIENT 3
+#define ZKIR_STAGE_QUOTIENT_COMMIT 4
+#define ZKIR_STAGE_OPENINGS 5
+#define ZKIR_STAGE_FRI 6
+#define ZKIR_STAGE_QUERIES_D2H 7
+#define ZKIR_STAGE_COUNT 8
+int zkir_b200_last_stage_ms(zkir_ctx*, float out[ZKIR_STAGE_COUNT]);
+uint64_t zkir_b200_kernel_launches(const zkir_ctx*); /* kernels launched by this ctx so far */
+
+/* ---- host side above the ABI: the interpreter that produces the trace.  Restates, in C++ (no Rust toolchain in
+ * this image), zkir-runtime's VM: VM::new/VM::run (vm.rs:138-358), execute (execute.rs:35-673), Memory
+ * (memory.rs:243-489), syscalls (syscall.rs:94-177), encode/decode (encoder.rs:18-151, decoder.rs:20-192). */
+#define ZKIR_HALT_EXIT 0        /* HaltReason::Exit(code) */
+#define ZKIR_HALT_EBREAK 1      /* HaltReason::Ebreak */
+#define ZKIR_HALT_CYCLE_LIMIT 2 /* HaltReason::CycleLimit */
+typedef struct { /* zkir-spec/src/trace.rs:149-167 (MemoryOp; the bound field is host bookkeeping and omitted) */
+  uint64_t address, value, timestamp;
+  uint8_t is_write, width;
+} zkir_mem_op;
+typedef struct zkir_vm_result zkir_vm_result;
+
+uint32_t zkir_encode(uint32_t opcode, uint32_t r_a, uint32_t r_b, uint32_t r_c, int32_t imm);
+int zkir_decode(uint32_t word, uint32_t out5[5]);
+int zkir_vm_run(const uint32_t* code, size_t n_code, const uint8_t* data, size_t n_data, uint32_t entry_point,
+                const uint64_t* inputs, size_t n_inputs, uint64_t max_cycles, int record_trace, zkir_vm_result** out);
+void zkir_vm_free(zkir_vm_result*);
+const char* zkir_vm_last_error(void);
+uint64_t zkir_vm_cycles(const zkir_vm_result*);
+int zkir_vm_halt_kind(const zkir_vm_result*);
+uint64_t zkir_vm_exit_code(const zkir_vm_result*);
+size_t zkir_vm_num_outputs(const zkir_vm_result*);
+const uint64_t* zkir_vm_outputs(const zkir_vm_result*);
+size_t zkir_vm_trace_len(const zkir_vm_result*);
+const uint64_t* zkir_vm_trace_pc(const zkir_vm_result*);
+const uint32_t* zkir_vm_trace_instr(const zkir_vm_result*);
+const uint64_t* zkir_vm_trace_regs(const zkir_vm_result*); /* [cycle][16], PRE-state (vm.rs:245-253) */
+const uint64_t* zkir_vm_trace_aux(const zkir_vm_result*);
+const uint64_t* zkir_vm_trace_memop_begin(const zkir_vm_result*);
+const zkir_mem_op* zkir_vm_trace_memops(const zkir_vm_result*);
+uint64_t zkir_vm_final_pc(const zkir_vm_result*);
+const uint64_t* zkir_vm_final_regs(const zkir_vm_result*);
+
+/* "converter" TraceRow -> field columns (named but absent in the reference: zkir-spec/src/trace.rs:41,
+ * zkir-runtime/src/vm.rs:243-244).  Writes cols[width][1<<log_n] (host, pinned recommended) and
+ * public_values[4] = {entry_pc, num_cycles, exit_lo, exit_hi}.  min log_n via zkir_pack_min_log_n. */
+uint32_t zkir_pack_min_log_n(const zkir_vm_result*);
+int zkir_pack_trace(const zkir_vm_result*, uint32_t entry_point, uint32_t log_n, uint32_t* cols, uint32_t* public_values);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,529 @@
+// zkir-b200 ORACLE -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+//
+// CPU restatement of the trace->proof path that docs/PROVER_SPEC.md freezes.  Only tests/,
+// __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load this library.
+//
+// PARITY UNPINNED: /root/reference (seceq/zkir @ 82da87e9) contains no prover -- no NTT, no Poseidon2
+// (zkir-runtime/src/crypto.rs:299-315 is a stub that returns Err), no Merkle/FRI, and Plonky3 is a
+// commented-out, unpinned dependency (Cargo.toml:67-69).  There is therefore no reference output to pin
+// this file against; what it follows is this repo's written spec.  The upstream (VM/trace) half *is*
+// pinned by the reference's tests; that lives in zkir_b200/csrc/host/vm.cc and tests/test_vm_*.py.
+//
+// Deliberately dumb and structurally different from the CUDA path: canonical u32 values with 64-bit `%`
+// reduction (the kernels use Montgomery form), textbook bit-reversal radix-2 NTT (the kernels use a
+// multi-pass four-step), row-at-a-time hashing.  OpenMP only parallelises outer loops.
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdio.h>
+#include <vector>
+#include <algorithm>
+#include "constants_generated.h"
+#include "air_generated.h"
+
+typedef uint32_t u32;
+typedef uint64_t u64;
+static const u32 P = ZKIR_BB_P;
+
+// ------------------------------------------------------------------ base field (canonical)
+static inline u32 fadd(u32 a, u32 b) { u32 s = a + b; return s >= P ? s - P : s; }
+static inline u32 fsub(u32 a, u32 b) { return a >= b ? a - b : a + P - b; }
+static inline u32 fmul(u32 a, u32 b) { return (u32)(((u64)a * b) % P); }
+static u32 fpow(u32 a, u64 e) { u32 r = 1; while (e) { if (e & 1) r = fmul(r, a); a = fmul(a, a); e >>= 1; } return r; }
+static inline u32 finv(u32 a) { return fpow(a, P - 2); }
+
+struct Fp {  // thin wrapper so air_generated.h can be instantiated with operators
+  u32 v;
+  Fp() : v(0) {}
+  explicit Fp(u32 x) : v(x) {}
+};
+static inline Fp operator+(Fp a, Fp b) { return Fp(fadd(a.v, b.v)); }
+static inline Fp operator-(Fp a, Fp b) { return Fp(fsub(a.v, b.v)); }
+static inline Fp operator*(Fp a, Fp b) { return Fp(fmul(a.v, b.v)); }
+
+// ------------------------------------------------------------------ extension F_p[X]/(X^4 - 11)
+struct E4 { u32 c[4]; };
+static inline E4 e4_zero() { E4 r = {{0, 0, 0, 0}}; return r; }
+static inline E4 e4_from(u32 a) { E4 r = {{a, 0, 0, 0}}; return r; }
+static inline E4 e4_add(E4 a, E4 b) { E4 r; for (int i = 0; i < 4; i++) r.c[i] = fadd(a.c[i], b.c[i]); return r; }
+static inline E4 e4_sub(E4 a, E4 b) { E4 r; for (int i = 0; i < 4; i++) r.c[i] = fsub(a.c[i], b.c[i]); return r; }
+static inline E4 e4_mulb(E4 a, u32 b) { E4 r; for (int i = 0; i < 4; i++) r.c[i] = fmul(a.c[i], b); return r; }
+static E4 e4_mul(E4 a, E4 b) {
+  // schoolbook product, then X^4 -> 11
+  u32 t[7] = {0, 0, 0, 0, 0, 0, 0};
+  for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) t[i + j] = fadd(t[i + j], fmul(a.c[i], b.c[j]));
+  E4 r;
+  for (int i = 0; i < 4; i++) r.c[i] = t[i];
+  for (int i = 4; i < 7; i++) r.c[i - 4] = fadd(r.c[i - 4], fmul(ZKIR_EXT_W, t[i]));
+  return r;
+}
+static E4 e4_pow(E4 a, u64 e) { E4 r = e4_from(1); while (e) { if (e & 1) r = e4_mul(r, a); a = e4_mul(a, a); e >>= 1; } return r; }
+static E4 e4_inv(E4 a) {
+  // dumbest correct way: a^(p^4 - 2) by square-and-multiply over a 124-bit exponent
+  unsigned __int128 e = (unsigned __int128)P * P; e = e * P * P - 2;
+  E4 r = e4_from(1);
+  while (e) { if (e & 1) r = e4_mul(r, a); a = e4_mul(a, a); e >>= 1; }
+  return r;
+}
+// Montgomery's trick: invert a whole vector with one field inversion (entries must be non-zero)
+static void e4_batch_inv(E4* v, size_t n) {
+  if (!n) return;
+  std::vector<E4> pre(n);
+  E4 acc = e4_from(1);
+  for (size_t i = 0; i < n; i++) { pre[i] = acc; acc = e4_mul(acc, v[i]); }
+  E4 inv = e4_inv(acc);
+  for (size_t i = n; i-- > 0;) { E4 t = e4_mul(inv, pre[i]); inv = e4_mul(inv, v[i]); v[i] = t; }
+}
+static inline bool e4_eq(E4 a, E4 b) { return !memcmp(a.c, b.c, 16); }
+
+// ------------------------------------------------------------------ NTT (natural in, natural out)
+static u32 root_of_unity(int logn) { return ZKIR_BB_ROOTS[logn]; }
+static void ntt_inplace(u32* a, int logn, bool inverse) {
+  size_t n = (size_t)1 << logn;
+  for (size_t i = 0; i < n; i++) {  // bit reversal
+    size_t j = 0;
+    for (int b = 0; b < logn; b++) if (i >> b & 1) j |= (size_t)1 << (logn - 1 - b);
+    if (j > i) std::swap(a[i], a[j]);
+  }
+  for (int s = 1; s <= logn; s++) {
+    size_t m = (size_t)1 << s, h = m >> 1;
+    u32 wm = root_of_unity(s);
+    if (inverse) wm = finv(wm);
+    for (size_t k = 0; k < n; k += m) {
+      u32 w = 1;
+      for (size_t j = 0; j < h; j++) {
+        u32 t = fmul(w, a[k + j + h]), u = a[k + j];
+        a[k + j] = fadd(u, t);
+        a[k + j + h] = fsub(u, t);
+        w = fmul(w, wm);
+      }
+    }
+  }
+  if (inverse) { u32 ninv = finv((u32)(n % P)); for (size_t i = 0; i < n; i++) a[i] = fmul(a[i], ninv); }
+}
+// evaluations of the degree<N polynomial with coefficient vector c on the coset shift*H_{M}, M = N<<logb
+static void coset_eval(const u32* coef, size_t ncoef, u32* out, int logm, u32 shift) {
+  size_t m = (size_t)1 << logm;
+  u32 s = 1;
+  for (size_t j = 0; j < m; j++) { out[j] = j < ncoef ? fmul(coef[j], s) : 0; if (j < ncoef) s = fmul(s, shift); }
+  ntt_inplace(out, logm, false);
+}
+
+// ------------------------------------------------------------------ Poseidon2 (width 16, x^7, 8+13)
+static inline u32 sbox(u32 x) { u32 x2 = fmul(x, x), x3 = fmul(x2, x), x4 = fmul(x2, x2); return fmul(x4, x3); }
+static void m4(u32* x) {  // circ(2,3,1,1)
+  u32 y[4];
+  for (int j = 0; j < 4; j++) {
+    u32 a = x[j], b = x[(j + 1) & 3], c = x[(j + 2) & 3], d = x[(j + 3) & 3];
+    y[j] = fadd(fadd(fadd(a, a), fadd(fadd(b, b), b)), fadd(c, d));
+  }
+  memcpy(x, y, 16);
+}
+static void external_linear(u32* s) {
+  for (int c = 0; c < 4; c++) m4(s + 4 * c);
+  u32 sums[4];
+  for (int k = 0; k < 4; k++) sums[k] = fadd(fadd(s[k], s[4 + k]), fadd(s[8 + k], s[12 + k]));
+  for (int i = 0; i < 16; i++) s[i] = fadd(s[i], sums[i & 3]);
+}
+static void internal_linear(u32* s) {
+  u32 sum = 0;
+  for (int i = 0; i < 16; i++) sum = fadd(sum, s[i]);
+  for (int i = 0; i < 16; i++) s[i] = fadd(fmul(s[i], ZKIR_P2_DIAG[i]), sum);
+}
+static void poseidon2(u32* s) {
+  external_linear(s);
+  for (int r = 0; r < 4; r++) {
+    for (int i = 0; i < 16; i++) s[i] = sbox(fadd(s[i], ZKIR_P2_RC_EXT[r * 16 + i]));
+    external_linear(s);
+  }
+  for (int r = 0; r < ZKIR_P2_RP; r++) {
+    s[0] = sbox(fadd(s[0], ZKIR_P2_RC_INT[r]));
+    internal_linear(s);
+  }
+  for (int r = 4; r < 8; r++) {
+    for (int i = 0; i < 16; i++) s[i] = sbox(fadd(s[i], ZKIR_P2_RC_EXT[r * 16 + i]));
+    external_linear(s);
+  }
+}
+// overwrite-mode sponge, rate 8, digest 8 (no padding)
+static void hash_elems(const u32* in, size_t n, u32* digest) {
+  u32 st[16] = {0};
+  for (size_t i = 0; i < n; i += 8) {
+    size_t len = std::min<size_t>(8, n - i);
+    for (size_t k = 0; k < len; k++) st[k] = in[i + k];
+    poseidon2(st);
+  }
+  memcpy(digest, st, 32);
+}
+static void compress(const u32* l, const u32* r, u32* out) {
+  u32 st[16];
+  memcpy(st, l, 32); memcpy(st + 8, r, 32);
+  poseidon2(st);
+  memcpy(out, st, 32);
+}
+// tree layout: level 0 = leaves [n][8], then n/2 nodes, ... , root; total (2n-1)*8 words
+static void merkle_build(u32* tree, size_t nleaves) {
+  u32* lvl = tree;
+  for (size_t n = nleaves; n > 1; n >>= 1) {
+    u32* nxt = lvl + n * 8;
+#pragma omp parallel for if (n > 256)
+    for (size_t i = 0; i < n / 2; i++) compress(lvl + 16 * i, lvl + 16 * i + 8, nxt + 8 * i);
+    lvl = nxt;
+  }
+}
+static const u32* merkle_root(const u32* tree, size_t nleaves) { return tree + (2 * nleaves - 2) * 8; }
+static void merkle_path(const u32* tree, size_t nleaves, size_t idx, u32* out) {
+  const u32* lvl = tree;
+  for (size_t n = nleaves; n > 1; n >>= 1) { memcpy(out, lvl + ((idx ^ 1) * 8), 32); out += 8; lvl += n * 8; idx >>= 1; }
+}
+
+// ------------------------------------------------------------------ duplex challenger (width 16, rate 8)
+struct Chal {
+  u32 st[16]; u32 in[8]; int nin; u32 out[8]; int nout;
+  Chal() { memset(this, 0, sizeof(*this)); }
+  void duplex() { for (int i = 0; i < nin; i++) st[i] = in[i]; nin = 0; poseidon2(st); memcpy(out, st, 32); nout = 8; }
+  void observe(u32 x) { nout = 0; in[nin++] = x; if (nin == 8) duplex(); }
+  void observe_n(const u32* x, size_t n) { for (size_t i = 0; i < n; i++) observe(x[i]); }
+  u32 sample() { if (nin > 0 || nout == 0) duplex(); return out[--nout]; }
+  E4 sample_ext() { E4 r; for (int i = 0; i < 4; i++) r.c[i] = sample(); return r; }
+  u32 sample_bits(int b) { u32 v = sample(); return b >= 32 ? v : (v & ((1u << b) - 1)); }
+};
+
+// ------------------------------------------------------------------ AIR evaluation contexts
+struct AirRowCtx {  // base-field row check / quotient numerator at one point
+  typedef Fp F;
+  const u32* data; size_t stride, row, nxt; const u32* pv;
+  Fp is_first, is_last, is_trans;
+  u32 vals[ZKIR_AIR_NUM_CONSTRAINTS];
+  Fp L(int i) const { return Fp(data[i * stride + row]); }
+  Fp N(int i) const { return Fp(data[i * stride + nxt]); }
+  Fp PV(int i) const { return Fp(pv[i]); }
+  Fp K(u32 k) const { return Fp(k); }
+  void emit(int idx, Fp v) { vals[idx] = v.v; }
+};
+
+struct Params { u32 log_blowup, num_queries, pow_bits, width, num_public; };
+static const u32 PROOF_MAGIC = 0x5A4B5052u, PROOF_VERSION = 1u;
+
+static size_t proof_words(const Params& p, u32 log_n) {
+  size_t lg = log_n + p.log_blowup, W = p.width, R = log_n;
+  size_t n = 8 + p.num_public + 16 + (2 * W + 8) * 4 + R * 8 + 4 + 1;
+  size_t perq = W + lg * 8 + 8 + lg * 8;
+  for (size_t r = 0; r < R; r++) perq += 8 + (lg - 1 - r) * 8;
+  return n + perq * p.num_queries;
+}
+
+// Quotient values on the LDE coset, natural order: out[4][M] (ext4 coefficient planes)
+static void quotient_evals(const Params& p, u32 log_n, const u32* lde, const u32* pv, E4 alpha, u32* out) {
+  const int K = ZKIR_AIR_NUM_CONSTRAINTS;
+  size_t N = (size_t)1 << log_n, B = (size_t)1 << p.log_blowup, M = N * B;
+  u32 w = root_of_unity(log_n + p.log_blowup), g_inv = finv(root_of_unity(log_n));
+  std::vector<E4> apow(K);  // apow[i] = alpha^(K-1-i)
+  E4 a = e4_from(1);
+  for (int i = K - 1; i >= 0; i--) { apow[i] = a; a = e4_mul(a, alpha); }
+  std::vector<u32> xs(M);
+  u32 x = ZKIR_BB_GEN;
+  for (size_t i = 0; i < M; i++) { xs[i] = x; x = fmul(x, w); }
+#pragma omp parallel for schedule(static)
+  for (size_t i = 0; i < M; i++) {
+    u32 xi = xs[i];
+    u32 zh = fsub(fpow(xi, N), 1);                 // Z_H(x) = x^N - 1
+    u32 zh_inv = finv(zh);
+    AirRowCtx c;
+    c.data = lde; c.stride = M; c.row = i; c.nxt = (i + B) % M; c.pv = pv;
+    c.is_first = Fp(fmul(zh, finv(fsub(xi, 1))));  // Z_H(x)/(x-1)
+    c.is_last = Fp(fmul(zh, finv(fsub(xi, g_inv))));
+    c.is_trans = Fp(fsub(xi, g_inv));
+    zkir_air_eval(c);
+    E4 acc = e4_zero();
+    for (int k = 0; k < K; k++) acc = e4_add(acc, e4_mulb(apow[k], c.vals[k]));
+    acc = e4_mulb(acc, zh_inv);
+    for (int k = 0; k < 4; k++) out[k * M + i] = acc.c[k];
+  }
+  (void)p;
+}
+
+struct Dump {  // optional intermediates for stage-by-stage parity tests
+  u32 alpha[4], zeta[4], alpha_fri[4];
+  u32* quotient;     // [4][M] or null
+  u32* fri_input;    // [M][4] or null
+  u32* lde;          // [W][M] or null
+  u32* betas;        // [R][4] or null
+};
+
+static int prove(const Params& p, const u32* trace, u32 log_n, const u32* pv, u32* proof, Dump* dump) {
+  const size_t W = p.width, N = (size_t)1 << log_n, B = (size_t)1 << p.log_blowup, M = N * B;
+  const int lg = log_n + p.log_blowup;
+  const u32 shift = ZKIR_BB_GEN;
+  if (W != ZKIR_AIR_WIDTH || p.num_public != ZKIR_AIR_NUM_PUBLIC) return -1;
+  u32* out = proof;
+  *out++ = PROOF_MAGIC; *out++ = PROOF_VERSION; *out++ = log_n; *out++ = p.width; *out++ = p.log_blowup;
+  *out++ = p.num_queries; *out++ = p.pow_bits; *out++ = p.num_public;
+  for (u32 i = 0; i < p.num_public; i++) *out++ = pv[i];
+
+  // ---- 1. trace LDE + commit
+  std::vector<u32> coef(W * N), lde(W * M);
+#pragma omp parallel for
+  for (size_t k = 0; k < W; k++) {
+    memcpy(&coef[k * N], trace + k * N, N * 4);
+    ntt_inplace(&coef[k * N], log_n, true);
+    coset_eval(&coef[k * N], N, &lde[k * M], lg, shift);
+  }
+  if (dump && dump->lde) memcpy(dump->lde, lde.data(), W * M * 4);
+  std::vector<u32> ttree((2 * M - 1) * 8);
+#pragma omp parallel for
+  for (size_t i = 0; i < M; i++) {
+    u32 row[ZKIR_AIR_WIDTH];
+    for (size_t k = 0; k < W; k++) row[k] = lde[k * M + i];
+    hash_elems(row, W, &ttree[i * 8]);
+  }
+  merkle_build(ttree.data(), M);
+  Chal ch;
+  ch.observe(log_n); ch.observe(p.width); ch.observe(p.log_blowup); ch.observe(p.num_queries); ch.observe(p.pow_bits);
+  ch.observe(p.num_public);
+  ch.observe_n(pv, p.num_public);
+  ch.observe_n(merkle_root(ttree.data(), M), 8);
+  memcpy(out, merkle_root(ttree.data(), M), 32); out += 8;
+  u32* quot_root_slot = out; out += 8;
+
+  // ---- 2. quotient
+  E4 alpha = ch.sample_ext();
+  std::vector<u32> q(4 * M);
+  quotient_evals(p, log_n, lde.data(), pv, alpha, q.data());
+  if (dump) { memcpy(dump->alpha, alpha.c, 16); if (dump->quotient) memcpy(dump->quotient, q.data(), 4 * M * 4); }
+  // coefficients of Q: inverse NTT on the coset, then undo the shift
+  std::vector<u32> qcoef(8 * N), qlde(8 * M);
+  u32 sinv = finv(shift);
+  for (int k = 0; k < 4; k++) {
+    ntt_inplace(&q[k * M], lg, true);
+    u32 s = 1;
+    for (size_t j = 0; j < M; j++) { q[k * M + j] = fmul(q[k * M + j], s); s = fmul(s, sinv); }
+    for (size_t j = 2 * N; j < M; j++) if (q[k * M + j] != 0) return -2;  // quotient degree must be < 2N
+    // chunk c, plane k  ->  committed column 2*k + c
+    for (int c = 0; c < 2; c++) memcpy(&qcoef[(2 * k + c) * N], &q[k * M + c * N], N * 4);
+  }
+#pragma omp parallel for
+  for (int k = 0; k < 8; k++) coset_eval(&qcoef[k * N], N, &qlde[k * M], lg, shift);
+  std::vector<u32> qtree((2 * M - 1) * 8);
+#pragma omp parallel for
+  for (size_t i = 0; i < M; i++) {
+    u32 row[8];
+    for (int k = 0; k < 8; k++) row[k] = qlde[k * M + i];
+    hash_elems(row, 8, &qtree[i * 8]);
+  }
+  merkle_build(qtree.data(), M);
+  ch.observe_n(merkle_root(qtree.data(), M), 8);
+  memcpy(quot_root_slot, merkle_root(qtree.data(), M), 32);
+
+  // ---- 3. out-of-domain openings (Horner on coefficients)
+  E4 zeta = ch.sample_ext();
+  E4 gzeta = e4_mulb(zeta, root_of_unity(log_n));
+  if (dump) memcpy(dump->zeta, zeta.c, 16);
+  std::vector<E4> ot(W), otg(W), oq(8);
+  {
+    std::vector<E4> zp(N), gzp(N);  // powers of zeta and g*zeta
+    zp[0] = gzp[0] = e4_from(1);
+    for (size_t j = 1; j < N; j++) { zp[j] = e4_mul(zp[j - 1], zeta); gzp[j] = e4_mul(gzp[j - 1], gzeta); }
+    auto eval = [&](const u32* c, const std::vector<E4>& pw) { E4 acc = e4_zero(); for (size_t j = 0; j < N; j++) acc = e4_add(acc, e4_mulb(pw[j], c[j])); return acc; };
+#pragma omp parallel for
+    for (size_t k = 0; k < W; k++) { ot[k] = eval(&coef[k * N], zp); otg[k] = eval(&coef[k * N], gzp); }
+    for (int k = 0; k < 8; k++) oq[k] = eval(&qcoef[k * N], zp);
+  }
+  for (size_t k = 0; k < W; k++) { memcpy(out, ot[k].c, 16); out += 4; }
+  for (size_t k = 0; k < W; k++) { memcpy(out, otg[k].c, 16); out += 4; }
+  for (int k = 0; k < 8; k++) { memcpy(out, oq[k].c, 16); out += 4; }
+  ch.observe_n(out - (2 * W + 8) * 4, (2 * W + 8) * 4);
+
+  // ---- 4. FRI input: batched DEEP quotients on the coset
+  E4 af = ch.sample_ext();
+  if (dump) memcpy(dump->alpha_fri, af.c, 16);
+  std::vector<E4> afp(2 * W + 8);
+  afp[0] = e4_from(1);
+  for (size_t k = 1; k < 2 * W + 8; k++) afp[k] = e4_mul(afp[k - 1], af);
+  std::vector<E4> f(M);
+  {
+    u32 w = root_of_unity(lg);
+    std::vector<u32> xs(M);
+    u32 x = shift;
+    for (size_t i = 0; i < M; i++) { xs[i] = x; x = fmul(x, w); }
+    // F(x) = (Rt(x)-A1)/(x-zeta) + alpha^W (Rt(x)-A2)/(x-g zeta) + alpha^2W (Rq(x)-A3)/(x-zeta),
+    // Rt(x) = sum_k alpha^k t_k(x), A1 = sum_k alpha^k t_k(zeta), ... (same sum as the per-column DEEP quotients)
+    E4 A1 = e4_zero(), A2 = e4_zero(), A3 = e4_zero();
+    for (size_t k = 0; k < W; k++) { A1 = e4_add(A1, e4_mul(afp[k], ot[k])); A2 = e4_add(A2, e4_mul(afp[k], otg[k])); }
+    for (int k = 0; k < 8; k++) A3 = e4_add(A3, e4_mul(afp[k], oq[k]));
+    std::vector<E4> iz(M), igz(M);
+    for (size_t i = 0; i < M; i++) { iz[i] = e4_sub(e4_from(xs[i]), zeta); igz[i] = e4_sub(e4_from(xs[i]), gzeta); }
+    const size_t CH = 4096;
+#pragma omp parallel for
+    for (size_t c0 = 0; c0 < M; c0 += CH) { size_t len = std::min(CH, M - c0); e4_batch_inv(&iz[c0], len); e4_batch_inv(&igz[c0], len); }
+#pragma omp parallel for
+    for (size_t i = 0; i < M; i++) {
+      E4 rt = e4_zero(), rq = e4_zero();
+      for (size_t k = 0; k < W; k++) rt = e4_add(rt, e4_mulb(afp[k], lde[k * M + i]));
+      for (int k = 0; k < 8; k++) rq = e4_add(rq, e4_mulb(afp[k], qlde[k * M + i]));
+      E4 acc = e4_mul(e4_sub(rt, A1), iz[i]);
+      acc = e4_add(acc, e4_mul(afp[W], e4_mul(e4_sub(rt, A2), igz[i])));
+      acc = e4_add(acc, e4_mul(afp[2 * W], e4_mul(e4_sub(rq, A3), iz[i])));
+      f[i] = acc;
+    }
+  }
+  if (dump && dump->fri_input) memcpy(dump->fri_input, f.data(), M * 16);
+
+  // ---- 5. FRI commit phase
+  const size_t R = log_n;
+  std::vector<std::vector<E4>> layers;
+  std::vector<std::vector<u32>> trees;
+  u32 half_inv = finv(2);
+  u32 lshift = shift;  // coset shift of the current layer
+  for (size_t r = 0; r < R; r++) {
+    size_t n = M >> r, h = n / 2;
+    std::vector<u32> tree((2 * h - 1) * 8);
+#pragma omp parallel for if (h > 256)
+    for (size_t i = 0; i < h; i++) {
+      u32 leaf[8];
+      memcpy(leaf, f[i].c, 16); memcpy(leaf + 4, f[i + h].c, 16);
+      hash_elems(leaf, 8, &tree[i * 8]);
+    }
+    merkle_build(tree.data(), h);
+    const u32* root = merkle_root(tree.data(), h);
+    memcpy(out, root, 32); out += 8;
+    ch.observe_n(root, 8);
+    E4 beta = ch.sample_ext();
+    if (dump && dump->betas) memcpy(dump->betas + 4 * r, beta.c, 16);
+    std::vector<E4> g(h);
+    u32 w = root_of_unity(lg - (int)r), x = lshift;
+    std::vector<u32> xs(h);
+    for (size_t i = 0; i < h; i++) { xs[i] = x; x = fmul(x, w); }
+#pragma omp parallel for if (h > 256)
+    for (size_t i = 0; i < h; i++) {
+      E4 s = e4_mulb(e4_add(f[i], f[i + h]), half_inv);
+      E4 d = e4_mulb(e4_sub(f[i], f[i + h]), finv(fmul(2, xs[i])));
+      g[i] = e4_add(s, e4_mul(beta, d));
+    }
+    layers.push_back(f); trees.push_back(tree);
+    f.swap(g);
+    lshift = fmul(lshift, lshift);
+  }
+  for (size_t i = 1; i < f.size(); i++) if (!e4_eq(f[i], f[0])) return -3;  // final layer must be constant
+  memcpy(out, f[0].c, 16); out += 4;
+  ch.observe_n(f[0].c, 4);
+
+  // ---- 6. proof of work
+  u32 witness = 0;
+  for (;; witness++) {
+    Chal c2 = ch;
+    c2.observe(witness);
+    if (c2.sample_bits(p.pow_bits) == 0) break;
+    if (witness == P - 1) return -4;
+  }
+  ch.observe(witness);
+  ch.sample_bits(p.pow_bits);
+  *out++ = witness;
+
+  // ---- 7. queries
+  for (u32 qi = 0; qi < p.num_queries; qi++) {
+    size_t idx = ch.sample_bits(lg);
+    for (size_t k = 0; k < W; k++) *out++ = lde[k * M + idx];
+    merkle_path(ttree.data(), M, idx, out); out += lg * 8;
+    for (int k = 0; k < 8; k++) *out++ = qlde[k * M + idx];
+    merkle_path(qtree.data(), M, idx, out); out += lg * 8;
+    size_t i = idx;
+    for (size_t r = 0; r < R; r++) {
+      size_t h = (M >> r) / 2;
+      i = i % h;
+      memcpy(out, layers[r][i].c, 16); memcpy(out + 4, layers[r][i + h].c, 16); out += 8;
+      merkle_path(trees[r].data(), h, i, out); out += (lg - 1 - r) * 8;
+    }
+  }
+  if ((size_t)(out - proof) != proof_words(p, log_n)) return -5;
+  return 0;
+}
+
+// ------------------------------------------------------------------ C entry points (ctypes)
+extern "C" {
+void oracle_ntt(u32* a, int logn, int inverse) { ntt_inplace(a, logn, inverse != 0); }
+void oracle_ntt_batch(u32* a, int ncols, int logn, int inverse) {
+#pragma omp parallel for
+  for (int k = 0; k < ncols; k++) ntt_inplace(a + ((size_t)k << logn), logn, inverse != 0);
+}
+// out[ncols][N<<logb] = LDE of in[ncols][N] onto the coset 31*H
+void oracle_lde_batch(const u32* in, u32* out, int ncols, int logn, int logb) {
+  size_t N = (size_t)1 << logn, M = N << logb;
+#pragma omp parallel for
+  for (int k = 0; k < ncols; k++) {
+    std::vector<u32> c(in + k * N, in + (k + 1) * N);
+    ntt_inplace(c.data(), logn, true);
+    coset_eval(c.data(), N, out + k * M, logn + logb, ZKIR_BB_GEN);
+  }
+}
+void oracle_poseidon2(u32* states, u64 n) {
+#pragma omp parallel for
+  for (u64 i = 0; i < n; i++) poseidon2(states + 16 * i);
+}
+// column-major matrix [ncols][nrows] -> tree ((2*nrows-1)*8 words), returns root
+void oracle_merkle_commit(const u32* mat, int ncols, int log_rows, u32* tree, u32* root) {
+  size_t n = (size_t)1 << log_rows;
+#pragma omp parallel for
+  for (size_t i = 0; i < n; i++) {
+    std::vector<u32> row(ncols);
+    for (int k = 0; k < ncols; k++) row[k] = mat[(size_t)k * n + i];
+    hash_elems(row.data(), ncols, tree + 8 * i);
+  }
+  merkle_build(tree, n);
+  memcpy(root, merkle_root(tree, n), 32);
+}
+void oracle_quotient(const u32* params5, u32 log_n, const u32* lde, const u32* pv, const u32* alpha, u32* out) {
+  Params p = {params5[0], params5[1], params5[2], params5[3], params5[4]};
+  E4 a; memcpy(a.c, alpha, 16);
+  quotient_evals(p, log_n, lde, pv, a, out);
+}
+// one FRI fold: in[n][4] on coset shift*H_n -> out[n/2][4]
+void oracle_fri_fold(const u32* in, u32* out, int logn, u32 shift, const u32* beta4) {
+  size_t n = (size_t)1 << logn, h = n / 2;
+  E4 beta; memcpy(beta.c, beta4, 16);
+  u32 w = root_of_unity(logn), x = shift, half_inv = finv(2);
+  for (size_t i = 0; i < h; i++) {
+    E4 a, b; memcpy(a.c, in + 4 * i, 16); memcpy(b.c, in + 4 * (i + h), 16);
+    E4 s = e4_mulb(e4_add(a, b), half_inv);
+    E4 d = e4_mulb(e4_sub(a, b), finv(fmul(2, x)));
+    E4 g = e4_add(s, e4_mul(beta, d));
+    memcpy(out + 4 * i, g.c, 16);
+    x = fmul(x, w);
+  }
+}
+// checks every AIR constraint on the (unextended) trace rows; returns -1 if all hold, else the index of the
+// first failing constraint (row in *bad_row)
+int oracle_check_trace(const u32* trace, u32 log_n, const u32* pv, u64* bad_row) {
+  size_t N = (size_t)1 << log_n;
+  for (size_t i = 0; i < N; i++) {
+    AirRowCtx c;
+    c.data = trace; c.stride = N; c.row = i; c.nxt = (i + 1) % N; c.pv = pv;
+    c.is_first = Fp(i == 0); c.is_last = Fp(i == N - 1); c.is_trans = Fp(i != N - 1);
+    zkir_air_eval(c);
+    for (int k = 0; k < ZKIR_AIR_NUM_CONSTRAINTS; k++) if (c.vals[k]) { if (bad_row) *bad_row = i; return k; }
+  }
+  return -1;
+}
+u64 oracle_proof_words(const u32* params5, u32 log_n) {
+  Params p = {params5[0], params5[1], params5[2], params5[3], params5[4]};
+  return proof_words(p, log_n);
+}
+// params5 = {log_blowup, num_queries, pow_bits, width, num_public}; trace column-major [width][1<<log_n]
+int oracle_prove(const u32* params5, const u32* trace, u32 log_n, const u32* pv, u32* proof) {
+  Params p = {params5[0], params5[1], params5[2], params5[3], params5[4]};
+  return prove(p, trace, log_n, pv, proof, nullptr);
+}
+int oracle_prove_dump(const u32* params5, const u32* trace, u32 log_n, const u32* pv, u32* proof, u32* challenges12,
+                      u32* lde, u32* quotient, u32* fri_input, u32* betas) {
+  Params p = {params5[0], params5[1], params5[2], params5[3], params5[4]};
+  Dump d; memset(&d, 0, sizeof(d));
+  d.lde = lde; d.quotient = quotient; d.fri_input = fri_input; d.betas = betas;
+  int rc = prove(p, trace, log_n, pv, proof, &d);
+  if (challenges12) { memcpy(challenges12, d.alpha, 16); memcpy(challenges12 + 4, d.zeta, 16); memcpy(challenges12 + 8, d.alpha_fri, 16); }
+  return rc;
+}
+void oracle_ext_mul(const u32* a, const u32* b, u32* out) { E4 x, y; memcpy(x.c, a, 16); memcpy(y.c, b, 16); E4 r = e4_mul(x, y); memcpy(out, r.c, 16); }
+void oracle_ext_inv(const u32* a, u32* out) { E4 x; memcpy(x.c, a, 16); E4 r = e4_inv(x); memcpy(out, r.c, 16); }
+void oracle_hash(const u32* in, u64 n, u32* digest) { hash_elems(in, n, digest); }
+void oracle_compress(const u32* l, const u32* r, u32* out) { compress(l, r, out); }
+}

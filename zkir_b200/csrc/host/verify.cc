@@ -1,0 +1,258 @@
+// CPU verifier for zkir-b200 proofs (product host code; shares no source with oracle/).
+//
+// The reference has no proof type and no verifier (zkir-runtime/src/lib.rs:29-62); this implements the verifier
+// side of docs/PROVER_SPEC.md: replay the Fiat-Shamir transcript, check the AIR identity at zeta
+// (air_generated.h instantiated over ext4), recompute the DEEP/FRI input at every query from the opened rows,
+// check all Merkle paths and the FRI folding chain down to the constant.
+#include <stdint.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include "zkir_b200.h"
+#include "../constants_generated.h"
+#include "../air_generated.h"
+
+std::string& zkir_host_error();
+#define g_verify_error zkir_host_error()
+namespace {
+typedef uint32_t u32;
+typedef uint64_t u64;
+const u32 P = ZKIR_BB_P;
+
+inline u32 add(u32 a, u32 b) { u64 s = (u64)a + b; return (u32)(s >= P ? s - P : s); }
+inline u32 sub(u32 a, u32 b) { return a >= b ? a - b : (u32)((u64)a + P - b); }
+inline u32 mul(u32 a, u32 b) { return (u32)((u64)a * b % P); }
+u32 pw(u32 a, u64 e) { u32 r = 1; for (; e; e >>= 1, a = mul(a, a)) if (e & 1) r = mul(r, a); return r; }
+inline u32 inv(u32 a) { return pw(a, P - 2); }
+
+struct X4 {  // F_p[X]/(X^4-11)
+  u32 c[4];
+  X4() { c[0] = c[1] = c[2] = c[3] = 0; }
+  explicit X4(u32 b) { c[0] = b; c[1] = c[2] = c[3] = 0; }
+};
+inline X4 operator+(const X4& a, const X4& b) { X4 r; for (int i = 0; i < 4; i++) r.c[i] = add(a.c[i], b.c[i]); return r; }
+inline X4 operator-(const X4& a, const X4& b) { X4 r; for (int i = 0; i < 4; i++) r.c[i] = sub(a.c[i], b.c[i]); return r; }
+inline X4 operator*(const X4& a, const X4& b) {
+  u64 t[7] = {0, 0, 0, 0, 0, 0, 0};
+  for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) t[i + j] = (t[i + j] + (u64)a.c[i] * b.c[j]) % P;
+  X4 r;
+  for (int i = 0; i < 4; i++) r.c[i] = (u32)t[i];
+  for (int i = 4; i < 7; i++) r.c[i - 4] = (u32)((r.c[i - 4] + (u64)ZKIR_EXT_W * t[i]) % P);
+  return r;
+}
+inline X4 scale(const X4& a, u32 b) { X4 r; for (int i = 0; i < 4; i++) r.c[i] = mul(a.c[i], b); return r; }
+inline bool eq(const X4& a, const X4& b) { return !memcmp(a.c, b.c, 16); }
+X4 xpow(X4 a, u64 e) { X4 r(1); for (; e; e >>= 1, a = a * a) if (e & 1) r = r * a; return r; }
+// inverse by solving the 4x4 linear system  M_a * y = e_0  (Gaussian elimination over F_p)
+bool xinv(const X4& a, X4* out) {
+  u32 m[4][5];
+  for (int col = 0; col < 4; col++) {  // column `col` of M_a is a * X^col
+    X4 b; b.c[col] = 1;
+    X4 pr = a * b;
+    for (int row = 0; row < 4; row++) m[row][col] = pr.c[row];
+  }
+  for (int row = 0; row < 4; row++) m[row][4] = row == 0;
+  for (int col = 0; col < 4; col++) {
+    int piv = -1;
+    for (int r = col; r < 4; r++) if (m[r][col]) { piv = r; break; }
+    if (piv < 0) return false;
+    if (piv != col) for (int k = 0; k < 5; k++) std::swap(m[piv][k], m[col][k]);
+    u32 iv = inv(m[col][col]);
+    for (int k = 0; k < 5; k++) m[col][k] = mul(m[col][k], iv);
+    for (int r = 0; r < 4; r++) if (r != col && m[r][col]) {
+      u32 f = m[r][col];
+      for (int k = 0; k < 5; k++) m[r][k] = sub(m[r][k], mul(f, m[col][k]));
+    }
+  }
+  for (int i = 0; i < 4; i++) out->c[i] = m[i][4];
+  return true;
+}
+
+// ---- Poseidon2 width 16
+inline u32 sbox(u32 x) { u32 x2 = mul(x, x), x4 = mul(x2, x2); return mul(mul(x4, x2), x); }
+void ext_layer(u32* s) {
+  u32 t[16];
+  for (int g = 0; g < 4; g++) for (int j = 0; j < 4; j++) {
+    const u32* x = s + 4 * g;
+    u64 v = 2ull * x[j] + 3ull * x[(j + 1) & 3] + x[(j + 2) & 3] + x[(j + 3) & 3];
+    t[4 * g + j] = (u32)(v % P);
+  }
+  for (int i = 0; i < 16; i++) {
+    u64 v = (u64)t[i] + t[i & 3] + t[4 + (i & 3)] + t[8 + (i & 3)] + t[12 + (i & 3)];
+    s[i] = (u32)(v % P);
+  }
+}
+void permute(u32* s) {
+  ext_layer(s);
+  for (int r = 0; r < 8; r++) {
+    if (r == 4) {
+      for (int k = 0; k < ZKIR_P2_RP; k++) {
+        s[0] = sbox(add(s[0], ZKIR_P2_RC_INT[k]));
+        u64 sum = 0;
+        for (int i = 0; i < 16; i++) sum += s[i];
+        u32 sm = (u32)(sum % P);
+        for (int i = 0; i < 16; i++) s[i] = add(mul(s[i], ZKIR_P2_DIAG[i]), sm);
+      }
+    }
+    for (int i = 0; i < 16; i++) s[i] = sbox(add(s[i], ZKIR_P2_RC_EXT[16 * r + i]));
+    ext_layer(s);
+  }
+}
+void hash_n(const u32* in, size_t n, u32* d) {
+  u32 s[16] = {0};
+  for (size_t i = 0; i < n; i += 8) { for (size_t k = 0; k < 8 && i + k < n; k++) s[k] = in[i + k]; permute(s); }
+  memcpy(d, s, 32);
+}
+void compress2(const u32* l, const u32* r, u32* d) { u32 s[16]; memcpy(s, l, 32); memcpy(s + 8, r, 32); permute(s); memcpy(d, s, 32); }
+bool check_path(const u32* leaf_digest, u64 idx, const u32* path, u32 depth, const u32* root) {
+  u32 cur[8]; memcpy(cur, leaf_digest, 32);
+  for (u32 l = 0; l < depth; l++, idx >>= 1) {
+    u32 nxt[8];
+    if (idx & 1) compress2(path + 8 * l, cur, nxt); else compress2(cur, path + 8 * l, nxt);
+    memcpy(cur, nxt, 32);
+  }
+  return !memcmp(cur, root, 32);
+}
+
+struct Challenger {
+  u32 st[16], in[8], out[8]; int nin, nout;
+  Challenger() { memset(this, 0, sizeof(*this)); }
+  void duplex() { for (int i = 0; i < nin; i++) st[i] = in[i]; nin = 0; permute(st); memcpy(out, st, 32); nout = 8; }
+  void observe(u32 x) { nout = 0; in[nin++] = x; if (nin == 8) duplex(); }
+  void observe(const u32* x, size_t n) { for (size_t i = 0; i < n; i++) observe(x[i]); }
+  u32 sample() { if (nin || !nout) duplex(); return out[--nout]; }
+  X4 sample_ext() { X4 r; for (int i = 0; i < 4; i++) r.c[i] = sample(); return r; }
+  u32 bits(u32 b) { u32 v = sample(); return b >= 32 ? v : v & ((1u << b) - 1); }
+};
+
+struct AirAtZeta {  // air_generated.h context over ext4
+  typedef X4 F;
+  const X4 *loc, *nxt; const u32* pv;
+  X4 is_first, is_last, is_trans, alpha, acc;
+  X4 L(int i) const { return loc[i]; }
+  X4 N(int i) const { return nxt[i]; }
+  X4 PV(int i) const { return X4(pv[i]); }
+  X4 K(u32 k) const { return X4(k); }
+  void emit(int, const X4& v) { acc = acc * alpha + v; }  // Horner: sum_i alpha^(K-1-i) c_i
+};
+
+bool fail(const char* m) { g_verify_error = m; return false; }
+
+bool verify(const zkir_params* p, const u32* w, size_t nwords, const u32* pv_in) {
+  if (!p || !w) return fail("null argument");
+  if (p->width != ZKIR_AIR_WIDTH || p->num_public != ZKIR_AIR_NUM_PUBLIC || p->log_blowup < 1) return fail("unsupported params");
+  if (nwords < 8) return fail("proof too short");
+  if (w[0] != 0x5A4B5052u || w[1] != 1) return fail("bad magic/version");
+  const u32 log_n = w[2];
+  if (w[3] != p->width || w[4] != p->log_blowup || w[5] != p->num_queries || w[6] != p->pow_bits || w[7] != p->num_public)
+    return fail("proof header does not match params");
+  if (log_n < 2 || log_n + p->log_blowup > 27) return fail("bad log_n");
+  if (nwords * 4 != zkir_b200_proof_size(p, log_n)) return fail("proof length mismatch");
+  const u32 W = p->width, np = p->num_public, lg = log_n + p->log_blowup, R = log_n, QW = 8;
+  const u64 N = 1ull << log_n, M = 1ull << lg;
+  for (size_t i = 8; i < nwords; i++) if (w[i] >= P) return fail("non-canonical field element");
+  const u32* q = w + 8;
+  const u32* pv = q; q += np;
+  if (pv_in) for (u32 i = 0; i < np; i++) if (pv[i] != pv_in[i]) return fail("public values differ");
+  const u32* troot = q; q += 8;
+  const u32* qroot = q; q += 8;
+  const u32* open = q;
+  std::vector<X4> ot(W), otg(W), oq(QW);
+  for (u32 k = 0; k < W; k++) { memcpy(ot[k].c, q, 16); q += 4; }
+  for (u32 k = 0; k < W; k++) { memcpy(otg[k].c, q, 16); q += 4; }
+  for (u32 k = 0; k < QW; k++) { memcpy(oq[k].c, q, 16); q += 4; }
+  const u32* fri_roots = q; q += 8 * R;
+  X4 final_v; memcpy(final_v.c, q, 16); const u32* final_w = q; q += 4;
+  const u32 witness = *q++;
+
+  // ---- transcript
+  Challenger ch;
+  const u32 hdr[6] = {log_n, W, p->log_blowup, p->num_queries, p->pow_bits, np};
+  ch.observe(hdr, 6); ch.observe(pv, np); ch.observe(troot, 8);
+  const X4 alpha = ch.sample_ext();
+  ch.observe(qroot, 8);
+  const X4 zeta = ch.sample_ext();
+  ch.observe(open, (2 * W + QW) * 4);
+  const X4 afri = ch.sample_ext();
+  std::vector<X4> betas(R);
+  for (u32 r = 0; r < R; r++) { ch.observe(fri_roots + 8 * r, 8); betas[r] = ch.sample_ext(); }
+  ch.observe(final_w, 4);
+  ch.observe(witness);
+  if (ch.bits(p->pow_bits) != 0) return fail("proof-of-work check failed");
+
+  // ---- AIR identity at zeta:  C(zeta) = Z_H(zeta) * (q0(zeta) + zeta^N q1(zeta))
+  const u32 g = ZKIR_BB_ROOTS[log_n], g_inv = inv(g);
+  const X4 zN = xpow(zeta, N), zh = zN - X4(1);
+  X4 i1, i2;
+  if (!xinv(zeta - X4(1), &i1) || !xinv(zeta - X4(g_inv), &i2)) return fail("zeta hits the trace domain");
+  AirAtZeta c;
+  c.loc = ot.data(); c.nxt = otg.data(); c.pv = pv; c.alpha = alpha;
+  c.is_first = zh * i1; c.is_last = zh * i2; c.is_trans = zeta - X4(g_inv);
+  zkir_air_eval(c);
+  X4 xp[4]; for (int k = 0; k < 4; k++) { xp[k] = X4(); xp[k].c[k] = 1; }  // basis 1, X, X^2, X^3
+  X4 qz;
+  for (int chunk = 0; chunk < 2; chunk++) {
+    X4 v;
+    for (int k = 0; k < 4; k++) v = v + xp[k] * oq[2 * k + chunk];
+    qz = qz + (chunk ? zN * v : v);
+  }
+  if (!eq(c.acc, zh * qz)) return fail("constraint identity fails at zeta");
+
+  // ---- queries
+  std::vector<X4> afp(2 * W + 1);
+  afp[0] = X4(1);
+  for (u32 k = 1; k <= 2 * W; k++) afp[k] = afp[k - 1] * afri;
+  X4 A1, A2, A3;
+  for (u32 k = 0; k < W; k++) { A1 = A1 + afp[k] * ot[k]; A2 = A2 + afp[k] * otg[k]; }
+  for (u32 k = 0; k < QW; k++) A3 = A3 + afp[k] * oq[k];
+  const X4 gzeta = scale(zeta, g);
+  const u32 wM = ZKIR_BB_ROOTS[lg], half = inv(2);
+  for (u32 qi = 0; qi < p->num_queries; qi++) {
+    const u64 idx = ch.bits(lg);
+    const u32* trow = q; q += W;
+    const u32* tpath = q; q += 8 * lg;
+    const u32* qrow = q; q += QW;
+    const u32* qpath = q; q += 8 * lg;
+    u32 d[8];
+    hash_n(trow, W, d);
+    if (!check_path(d, idx, tpath, lg, troot)) return fail("trace Merkle path");
+    hash_n(qrow, QW, d);
+    if (!check_path(d, idx, qpath, lg, qroot)) return fail("quotient Merkle path");
+    const u32 x = mul(ZKIR_BB_GEN, pw(wM, idx));
+    X4 rt, rq, iz, igz;
+    for (u32 k = 0; k < W; k++) rt = rt + scale(afp[k], trow[k]);
+    for (u32 k = 0; k < QW; k++) rq = rq + scale(afp[k], qrow[k]);
+    if (!xinv(X4(x) - zeta, &iz) || !xinv(X4(x) - gzeta, &igz)) return fail("zeta on the LDE coset");
+    X4 v = (rt - A1) * iz + afp[W] * ((rt - A2) * igz) + afp[2 * W] * ((rq - A3) * iz);
+    u64 i = idx;
+    u32 lshift = ZKIR_BB_GEN;
+    for (u32 r = 0; r < R; r++) {
+      const u64 h = (M >> r) / 2;
+      const u32 hi = (u32)(i / h);
+      i %= h;
+      X4 a, b; memcpy(a.c, q, 16); memcpy(b.c, q + 4, 16);
+      const u32* pair = q; q += 8;
+      const u32* path = q; q += 8 * (lg - 1 - r);
+      if (!eq(hi ? b : a, v)) return fail("FRI layer value does not match the folded value");
+      hash_n(pair, 8, d);
+      if (!check_path(d, i, path, lg - 1 - r, fri_roots + 8 * r)) return fail("FRI Merkle path");
+      const u32 xi = mul(lshift, pw(ZKIR_BB_ROOTS[lg - r], i));
+      v = scale(a + b, half) + betas[r] * scale(a - b, inv(mul(2, xi)));
+      lshift = mul(lshift, lshift);
+    }
+    if (!eq(v, final_v)) return fail("FRI final value mismatch");
+  }
+  if ((size_t)(q - w) != nwords) return fail("trailing data");
+  return true;
+}
+}  // namespace
+
+extern "C" {
+int zkir_b200_verify(const zkir_params* p, const uint8_t* proof, size_t len, const uint32_t* public_values) {
+  g_verify_error.clear();
+  if (!proof || len % 4) { g_verify_error = "bad proof buffer"; return ZKIR_ERR_VERIFY; }
+  std::vector<u32> w(len / 4);
+  memcpy(w.data(), proof, len);
+  return verify(p, w.data(), w.size(), public_values) ? 0 : ZKIR_ERR_VERIFY;
+}
+}

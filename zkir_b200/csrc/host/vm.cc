@@ -1,0 +1,312 @@
+// Host side above the C ABI: C++ restatement of the ZKIR v3.4 interpreter, with a linear-time SoA trace
+// recorder.  The reference's host code is Rust and no Rust toolchain exists in this image, so this file plays
+// the role of zkir-runtime's VM for the drop-in `prove()` path; it mirrors the reference's observable behaviour
+// (cycle counts, outputs, halt reasons, trace rows, memory-op placement) and is pinned by the reference's own
+// test expectations in tests/test_vm_reference.py.
+//
+// Follows (file:line in /root/reference):
+//   encode               zkir-assembler/src/encoder.rs:18-151
+//   decode               zkir-disassembler/src/decoder.rs:20-192
+//   VM::new / VM::run    zkir-runtime/src/vm.rs:138-205, 208-358, 362-379
+//   execute              zkir-runtime/src/execute.rs:35-673   (40-bit semantics: zkir-spec/src/value.rs:592-697)
+//   VMState              zkir-runtime/src/state.rs:55-133
+//   Memory               zkir-runtime/src/memory.rs:243-489
+//   syscalls             zkir-runtime/src/syscall.rs:18-24, 30-78, 94-177
+//   Program bytes        zkir-spec/src/program.rs:170-213, 300-346
+// Deliberate difference: the reference collects a row's memory ops by scanning the whole memory trace every
+// cycle (vm.rs:287-298, O(n^2)); here the recorder remembers where the cycle's ops start.  The filter it applies
+// (timestamp == cycle && address != fetch pc) is reproduced exactly.
+#include <stdint.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include <unordered_map>
+#include <memory>
+#include "../../../include/zkir_b200.h"
+
+namespace {
+
+typedef uint64_t u64;
+typedef uint32_t u32;
+typedef int64_t i64;
+
+const u64 MASK40 = (1ull << 40) - 1;
+const u64 CODE_BASE = 0x1000;
+
+enum Op : u32 {
+  ADD = 0x00, SUB, MUL, MULH, DIVU, REMU, DIV, REM, ADDI,
+  AND = 0x10, OR, XOR, ANDI, ORI, XORI,
+  SLL = 0x18, SRL, SRA, SLLI, SRLI, SRAI,
+  SLTU = 0x20, SGEU, SLT, SGE, SEQ, SNE, CMOV, CMOVZ, CMOVNZ,
+  LB = 0x30, LBU, LH, LHU, LW, LD,
+  SB = 0x38, SH, SW, SD,
+  BEQ = 0x40, BNE, BLT, BGE, BLTU, BGEU,
+  JAL = 0x48, JALR,
+  ECALL = 0x50, EBREAK,
+};
+
+bool valid_opcode(u32 op) {
+  return op <= 0x08 || (op >= 0x10 && op <= 0x15) || (op >= 0x18 && op <= 0x1D) || (op >= 0x20 && op <= 0x28) ||
+         (op >= 0x30 && op <= 0x35) || (op >= 0x38 && op <= 0x3B) || (op >= 0x40 && op <= 0x45) || op == 0x48 ||
+         op == 0x49 || op == 0x50 || op == 0x51;
+}
+// format classes (encoder.rs:98-151)
+enum Fmt { FR, FI, FSHIFT, FS, FB, FJ, FSYS };
+Fmt format_of(u32 op) {
+  if (op == ADDI || (op >= ANDI && op <= XORI) || (op >= LB && op <= LD) || op == JALR) return FI;
+  if (op >= SLLI && op <= SRAI) return FSHIFT;
+  if (op >= SB && op <= SD) return FS;
+  if (op >= BEQ && op <= BGEU) return FB;
+  if (op == JAL) return FJ;
+  if (op == ECALL || op == EBREAK) return FSYS;
+  return FR;
+}
+inline int32_t sext(u32 v, int bits) { int sh = 32 - bits; return ((int32_t)(v << sh)) >> sh; }
+
+struct Memory {  // sparse 4 KiB pages, little endian, uninitialised reads 0 (memory.rs:297-309)
+  std::unordered_map<u64, std::unique_ptr<uint8_t[]>> pages;
+  u64 last_page = ~0ull; uint8_t* last_ptr = nullptr;
+  bool trace_enabled = false;
+  u64 timestamp = 0;
+  std::vector<zkir_mem_op> trace;
+  uint8_t* page(u64 pn, bool create) {
+    if (pn == last_page && last_ptr) return last_ptr;
+    auto it = pages.find(pn);
+    if (it == pages.end()) {
+      if (!create) return nullptr;
+      std::unique_ptr<uint8_t[]> p(new uint8_t[4096]());
+      it = pages.emplace(pn, std::move(p)).first;
+    }
+    last_page = pn; last_ptr = it->second.get();
+    return last_ptr;
+  }
+  uint8_t rd8(u64 a) { uint8_t* p = page(a >> 12, false); return p ? p[a & 4095] : 0; }
+  void wr8(u64 a, uint8_t v) { page(a >> 12, true)[a & 4095] = v; }
+  void rec(u64 addr, u64 value, bool w, uint8_t width) {
+    if (!trace_enabled) return;
+    zkir_mem_op op; op.address = addr; op.value = value; op.timestamp = timestamp; op.is_write = w; op.width = width;
+    trace.push_back(op);
+  }
+  u64 read(u64 a, int width) {
+    u64 v = 0;
+    for (int i = 0; i < width; i++) v |= (u64)rd8(a + i) << (8 * i);
+    rec(a, v, false, (uint8_t)width);
+    return v;
+  }
+  void write(u64 a, u64 v, int width) {
+    for (int i = 0; i < width; i++) wr8(a + i, (uint8_t)(v >> (8 * i)));
+    rec(a, v, true, (uint8_t)width);
+  }
+};
+
+}  // namespace
+
+struct zkir_vm_result {
+  u64 cycles = 0;
+  int halt_kind = ZKIR_HALT_EBREAK;
+  u64 exit_code = 0;
+  std::vector<u64> outputs;
+  u64 final_pc = 0;
+  u64 final_regs[16] = {0};
+  // SoA trace (one entry per cycle), PRE-state registers (vm.rs:245-253,302-312)
+  std::vector<u64> pc;
+  std::vector<u32> instr;
+  std::vector<u64> regs;       // [cycle][16]
+  std::vector<u64> aux;        // READ: value read; WRITE: value written; else 0
+  std::vector<u64> memop_begin;  // CSR offsets into memops, size cycles+1
+  std::vector<zkir_mem_op> memops;  // data memory ops per row (fetch excluded)
+  std::string error;
+};
+
+std::string& zkir_host_error() { static thread_local std::string e; return e; }
+#define g_vm_error zkir_host_error()
+
+extern "C" {
+
+uint32_t zkir_encode(uint32_t opcode, uint32_t r_a, uint32_t r_b, uint32_t r_c, int32_t imm) {
+  // R: rd=r_a rs1=r_b rs2=r_c | I/shift: rd=r_a rs1=r_b imm | S,B: rs1=r_a rs2=r_b imm | J: rd=r_a imm
+  u32 w = opcode & 0x7F;
+  switch (format_of(opcode & 0x7F)) {
+    case FR: w |= (r_a & 0xF) << 7 | (r_b & 0xF) << 11 | (r_c & 0xF) << 15; break;
+    case FI: case FSHIFT: w |= (r_a & 0xF) << 7 | (r_b & 0xF) << 11 | ((u32)imm & 0x1FFFF) << 15; break;
+    case FS: case FB: w |= (r_a & 0xF) << 7 | (r_b & 0xF) << 11 | ((u32)imm & 0x1FFFF) << 15; break;
+    case FJ: w |= (r_a & 0xF) << 7 | ((u32)imm & 0x1FFFFF) << 11; break;
+    case FSYS: break;
+  }
+  return w;
+}
+
+// out = {opcode, r_a, r_b, r_c, imm(as u32 two's complement)} with the same field meaning as zkir_encode
+int zkir_decode(uint32_t word, uint32_t* out5) {
+  u32 op = word & 0x7F;
+  if (!valid_opcode(op)) return -1;
+  out5[0] = op; out5[1] = (word >> 7) & 0xF; out5[2] = (word >> 11) & 0xF; out5[3] = 0; out5[4] = 0;
+  switch (format_of(op)) {
+    case FR: out5[3] = (word >> 15) & 0xF; break;
+    case FI: case FS: case FB: out5[4] = (u32)sext((word >> 15) & 0x1FFFF, 17); break;
+    case FSHIFT: out5[4] = (word >> 15) & 0xFF; break;
+    case FJ: out5[2] = 0; out5[4] = (u32)sext((word >> 11) & 0x1FFFFF, 21); break;
+    case FSYS: out5[1] = out5[2] = 0; break;
+  }
+  return 0;
+}
+
+const char* zkir_vm_last_error(void) { return g_vm_error.c_str(); }
+
+void zkir_vm_free(zkir_vm_result* r) { delete r; }
+
+int zkir_vm_run(const uint32_t* code, size_t n_code, const uint8_t* data, size_t n_data, uint32_t entry_point,
+                const uint64_t* inputs, size_t n_inputs, uint64_t max_cycles, int record_trace, zkir_vm_result** out) {
+  *out = nullptr;
+  if (entry_point < 0x1000) {  // vm.rs:141-147 (the reference panics)
+    g_vm_error = "Program appears to be in debug format (entry_point < 0x1000)";
+    return ZKIR_ERR_ARG;
+  }
+  std::unique_ptr<zkir_vm_result> res(new zkir_vm_result());
+  Memory mem;
+  for (size_t i = 0; i < n_code; i++) mem.write(CODE_BASE + 4 * i, code[i], 4);
+  for (size_t i = 0; i < n_data; i++) mem.wr8(CODE_BASE + 4 * n_code + i, data[i]);
+  mem.trace.clear();
+  mem.trace_enabled = record_trace != 0;
+  u64 regs[16] = {0};
+  u64 pc = entry_point, cycles = 0;
+  size_t input_pos = 0;
+  bool halted = false;
+  auto R = [&](u32 i) -> u64 { return i == 0 ? 0 : regs[i]; };
+  auto W = [&](u32 i, u64 v) { if (i) regs[i] = v; };
+  auto fail = [&](const std::string& m) { g_vm_error = m; return ZKIR_ERR_VM; };
+  auto slt40 = [](u64 a, u64 b) { u64 s = 1ull << 39; return ((a & MASK40) ^ s) < ((b & MASK40) ^ s); };
+  auto sra40 = [](u64 v, u32 sh) -> u64 {
+    bool neg = v & (1ull << 39);
+    if (sh >= 40) return neg ? MASK40 : 0;
+    u64 r = v >> sh;
+    if (neg) r |= ((1ull << sh) - 1) << (40 - sh);
+    return r & MASK40;
+  };
+  if (record_trace) res->memop_begin.push_back(0);
+
+  while (!halted) {
+    if (cycles >= max_cycles) { res->halt_kind = ZKIR_HALT_CYCLE_LIMIT; break; }
+    mem.timestamp = cycles;
+    const u64 fetch_pc = pc;
+    if (pc % 4 != 0) { char b[64]; snprintf(b, sizeof b, "Misaligned PC: %#llx", (unsigned long long)pc); return fail(b); }
+    const size_t ops_before = mem.trace.size();
+    u32 word = (u32)mem.read(pc, 4);
+    u32 op = word & 0x7F;
+    if (!valid_opcode(op)) { char b[64]; snprintf(b, sizeof b, "Decode error: unknown opcode %#x", op); return fail(b); }
+    if (record_trace) {
+      res->pc.push_back(fetch_pc); res->instr.push_back(word);
+      res->regs.insert(res->regs.end(), regs, regs + 16);
+      res->aux.push_back(0);
+    }
+    const u32 fa = (word >> 7) & 0xF, fb = (word >> 11) & 0xF, fc = (word >> 15) & 0xF;
+    const i64 imm17 = sext((word >> 15) & 0x1FFFF, 17);
+    const u32 shamt = (word >> 15) & 0xFF;
+    u64 next_pc = pc + 4;
+    bool is_ecall = false;
+    auto misaligned = [&](u64 a, int al) { char b[96]; snprintf(b, sizeof b, "Misaligned access at %#llx (alignment %d)", (unsigned long long)a, al); return fail(b); };
+    switch (op) {
+      case ADD: W(fa, ((R(fb) & MASK40) + (R(fc) & MASK40)) & MASK40); break;
+      case SUB: W(fa, ((R(fb) & MASK40) - (R(fc) & MASK40)) & MASK40); break;
+      case MUL: W(fa, ((R(fb) & MASK40) * (R(fc) & MASK40)) & MASK40); break;
+      case MULH: { unsigned __int128 p = (unsigned __int128)R(fb) * R(fc); W(fa, (u64)(p >> 40) & MASK40); break; }
+      case DIVU: case REMU: case DIV: case REM: {
+        u64 a = R(fb), b = R(fc);
+        if (b == 0) { char m[64]; snprintf(m, sizeof m, "Division by zero at PC %#llx", (unsigned long long)pc); return fail(m); }
+        u64 r;
+        if (op == DIVU) r = a / b;
+        else if (op == REMU) r = a % b;
+        else if (op == DIV) r = ((i64)a == INT64_MIN && (i64)b == -1) ? a : (u64)((i64)a / (i64)b);
+        else r = ((i64)a == INT64_MIN && (i64)b == -1) ? 0 : (u64)((i64)a % (i64)b);
+        W(fa, r);
+        break;
+      }
+      case ADDI: W(fa, ((R(fb) & MASK40) + ((u64)imm17 & MASK40)) & MASK40); break;
+      case AND: W(fa, R(fb) & R(fc) & MASK40); break;
+      case OR: W(fa, (R(fb) | R(fc)) & MASK40); break;
+      case XOR: W(fa, (R(fb) ^ R(fc)) & MASK40); break;
+      case ANDI: W(fa, R(fb) & (u64)imm17 & MASK40); break;
+      case ORI: W(fa, (R(fb) | (u64)imm17) & MASK40); break;
+      case XORI: W(fa, (R(fb) ^ (u64)imm17) & MASK40); break;
+      case SLL: case SLLI: { u32 sh = op == SLL ? (u32)(R(fc) & 0x3F) : shamt; W(fa, sh >= 40 ? 0 : ((R(fb) & MASK40) << sh) & MASK40); break; }
+      case SRL: case SRLI: { u32 sh = op == SRL ? (u32)(R(fc) & 0x3F) : shamt; W(fa, sh >= 40 ? 0 : (R(fb) & MASK40) >> sh); break; }
+      case SRA: case SRAI: { u32 sh = op == SRA ? (u32)(R(fc) & 0x3F) : shamt; W(fa, sra40(R(fb) & MASK40, sh)); break; }
+      case SLTU: W(fa, (R(fb) & MASK40) < (R(fc) & MASK40)); break;
+      case SGEU: W(fa, !((R(fb) & MASK40) < (R(fc) & MASK40))); break;
+      case SLT: W(fa, slt40(R(fb), R(fc))); break;
+      case SGE: W(fa, !slt40(R(fb), R(fc))); break;
+      case SEQ: W(fa, R(fb) == R(fc)); break;
+      case SNE: W(fa, R(fb) != R(fc)); break;
+      case CMOV: case CMOVNZ: if (R(fc) != 0) W(fa, R(fb)); break;
+      case CMOVZ: if (R(fc) == 0) W(fa, R(fb)); break;
+      case LB: W(fa, (u64)(i64)(int8_t)mem.read(R(fb) + (u64)imm17, 1)); break;
+      case LBU: W(fa, mem.read(R(fb) + (u64)imm17, 1)); break;
+      case LH: case LHU: {
+        u64 a = R(fb) + (u64)imm17;
+        if (a % 2) return misaligned(a, 2);
+        u64 v = mem.read(a, 2);
+        W(fa, op == LH ? (u64)(i64)(int16_t)v : v);
+        break;
+      }
+      case LW: { u64 a = R(fb) + (u64)imm17; if (a % 4) return misaligned(a, 4); W(fa, mem.read(a, 4)); break; }
+      case LD: { u64 a = R(fb) + (u64)imm17; if (a % 8) return misaligned(a, 8); W(fa, mem.read(a, 8)); break; }
+      // stores: S-type has rs1 (base) in bits 10:7 and rs2 (value) in bits 14:11 (encoder.rs:122-130)
+      case SB: mem.write(R(fa) + (u64)imm17, R(fb) & 0xFF, 1); break;
+      case SH: { u64 a = R(fa) + (u64)imm17; if (a % 2) return misaligned(a, 2); mem.write(a, R(fb) & 0xFFFF, 2); break; }
+      case SW: { u64 a = R(fa) + (u64)imm17; if (a % 4) return misaligned(a, 4); mem.write(a, R(fb) & 0xFFFFFFFFull, 4); break; }
+      case SD: { u64 a = R(fa) + (u64)imm17; if (a % 8) return misaligned(a, 8); mem.write(a, R(fb), 8); break; }
+      case BEQ: if (R(fa) == R(fb)) next_pc = pc + (u64)imm17; break;
+      case BNE: if (R(fa) != R(fb)) next_pc = pc + (u64)imm17; break;
+      case BLT: if (slt40(R(fa), R(fb))) next_pc = pc + (u64)imm17; break;
+      case BGE: if (!slt40(R(fa), R(fb))) next_pc = pc + (u64)imm17; break;
+      case BLTU: if ((R(fa) & MASK40) < (R(fb) & MASK40)) next_pc = pc + (u64)imm17; break;
+      case BGEU: if (!((R(fa) & MASK40) < (R(fb) & MASK40))) next_pc = pc + (u64)imm17; break;
+      case JAL: { i64 off = sext((word >> 11) & 0x1FFFFF, 21); W(fa, pc + 4); next_pc = pc + (u64)off; break; }
+      case JALR: { u64 t = R(fb) + (u64)imm17; W(fa, pc + 4); next_pc = t & ~1ull; break; }
+      case ECALL: is_ecall = true; break;
+      case EBREAK: halted = true; res->halt_kind = ZKIR_HALT_EBREAK; next_pc = pc; break;
+    }
+    pc = next_pc;
+    if (is_ecall) {  // syscall.rs:94-177: number in R10
+      u64 num = regs[10];
+      switch (num) {
+        case 0: halted = true; res->halt_kind = ZKIR_HALT_EXIT; res->exit_code = regs[11]; break;
+        case 1: { u64 v = input_pos < n_inputs ? inputs[input_pos++] : 0; regs[10] = v; if (record_trace) res->aux.back() = v; break; }
+        case 2: res->outputs.push_back(regs[11]); if (record_trace) res->aux.back() = regs[11]; break;
+        case 4: return fail("Poseidon2 not yet implemented");  // crypto.rs:306-315 (the reference errors too)
+        case 3: case 5: case 6: return fail("hash syscalls (SHA-256/Keccak-256/Blake3) are outside the proving path and not restated here");
+        default: { char m[64]; snprintf(m, sizeof m, "Invalid syscall: %llu", (unsigned long long)num); return fail(m); }
+      }
+    }
+    if (record_trace) {
+      // data memory ops of this cycle: timestamp == cycle && address != fetch pc (vm.rs:291-298)
+      for (size_t i = ops_before; i < mem.trace.size(); i++)
+        if (mem.trace[i].address != fetch_pc) res->memops.push_back(mem.trace[i]);
+      res->memop_begin.push_back(res->memops.size());
+      mem.trace.resize(ops_before);  // keep the scratch list bounded
+    }
+    cycles++;
+  }
+  res->cycles = cycles;
+  res->final_pc = pc;
+  memcpy(res->final_regs, regs, sizeof regs);
+  *out = res.release();
+  return 0;
+}
+
+uint64_t zkir_vm_cycles(const zkir_vm_result* r) { return r->cycles; }
+int zkir_vm_halt_kind(const zkir_vm_result* r) { return r->halt_kind; }
+uint64_t zkir_vm_exit_code(const zkir_vm_result* r) { return r->exit_code; }
+size_t zkir_vm_num_outputs(const zkir_vm_result* r) { return r->outputs.size(); }
+const uint64_t* zkir_vm_outputs(const zkir_vm_result* r) { return r->outputs.data(); }
+size_t zkir_vm_trace_len(const zkir_vm_result* r) { return r->pc.size(); }
+const uint64_t* zkir_vm_trace_pc(const zkir_vm_result* r) { return r->pc.data(); }
+const uint32_t* zkir_vm_trace_instr(const zkir_vm_result* r) { return r->instr.data(); }
+const uint64_t* zkir_vm_trace_regs(const zkir_vm_result* r) { return r->regs.data(); }
+const uint64_t* zkir_vm_trace_memop_begin(const zkir_vm_result* r) { return r->memop_begin.data(); }
+const zkir_mem_op* zkir_vm_trace_memops(const zkir_vm_result* r) { return r->memops.data(); }
+uint64_t zkir_vm_final_pc(const zkir_vm_result* r) { return r->final_pc; }
+const uint64_t* zkir_vm_final_regs(const zkir_vm_result* r) { return r->final_regs; }
+const uint64_t* zkir_vm_trace_aux(const zkir_vm_result* r) { return r->aux.data(); }
+
+}  // extern "C"

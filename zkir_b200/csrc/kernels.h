@@ -1,0 +1,79 @@
+// Internal launcher interface between the .cu translation units of libzkir_b200.so (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "bb.cuh"
+
+namespace zkir {
+
+struct ChalState {  // duplex challenger, Poseidon2 width 16 / rate 8 (docs/PROVER_SPEC.md "Transcript")
+  u32 sponge[16];
+  u32 inbuf[8];
+  u32 outbuf[8];
+  u32 n_in, n_out;
+};
+
+// ---- ntt.cu
+struct NttTables;
+NttTables* ntt_tables_create(cudaStream_t st, u64* launch_counter);
+void ntt_tables_destroy(NttTables*);
+u32* ntt_powers_table(NttTables*, u32 base_canon, u32 c0_canon, u64 n);  // cached c0*base^i, Montgomery
+int ntt_run(NttTables* tb, const u32* d_in, u64 in_col_stride, u32* d_out, u64 out_col_stride, u32* tmp, u64 tmp_words,
+            u32 n_cols, int log_n, bool inverse, int log_pad, const u32* in_scale, const u32* out_scale,
+            u32 out_const_mont, bool use_out_const, cudaStream_t st);
+
+// ---- poseidon2.cu
+int poseidon2_init_constants();
+int launch_permute(u32* d_states, u64 n, bool canonical_io, cudaStream_t st, u64* launches);
+int launch_leaf_hash(const u32* mat, u64 col_stride, u32 n_cols, u64 n_rows, u32* digests, cudaStream_t st, u64* launches);
+int launch_leaf_hash_pairs(const u32* layer, u64 h, u32* digests, cudaStream_t st, u64* launches);
+int launch_merkle_levels(u32* tree, u64 n_leaves, cudaStream_t st, u64* launches);
+int launch_challenger(ChalState* st_dev, const u32* in, u32 n_in, u32* out, u32 n_out, u32 bits, cudaStream_t st, u64* launches);
+int launch_pow_grind(const ChalState* st_dev, u32 bits, u32* result, cudaStream_t st, u64* launches);
+
+// ---- quotient.cu
+struct QuotientArgs {
+  const u32* lde;      // [width][M] Montgomery
+  u32* q;              // [4][M]
+  u32 log_n, log_blowup;
+  const u32* pv;       // device, num_public Montgomery values
+  const u32* alpha;    // device, ext4 Montgomery
+  const u32* xs;       // [M] x_i = shift*w^i
+  const u32* dinv;     // [M] 1/(x_i - 1)
+  u32* apow_scratch;   // [K][4] device scratch for alpha powers
+};
+int launch_quotient(const QuotientArgs& a, cudaStream_t st, u64* launches);
+int launch_domain_tables(u32* xs, u32* dinv, u32 log_m, u32 shift_canon, cudaStream_t st, u64* launches);
+
+// ---- stark.cu (openings, DEEP combination, FRI fold, queries, misc)
+int launch_map(u32* dst, const u32* src, u64 n, int to_mont, cudaStream_t st, u64* launches);
+int launch_ext_powers(const u32* base_ext, const u32* mul_base_dev, u32 mul_const, E4* out, u64 n, cudaStream_t st, u64* launches);
+// out1[k] = sum_j coef[k][j]*U1[j], out2[k] = sum_j coef[k][j]*U2[j]
+int launch_open(const u32* coef, u64 col_stride, u32 n_cols, u64 n, const E4* U1, const E4* U2, E4* out1, E4* out2,
+                E4* partial_scratch, cudaStream_t st, u64* launches);
+struct DeepArgs {
+  const u32* lde; u64 M; u32 width;       // trace LDE [width][M]
+  const u32* qlde; u32 qwidth;            // quotient LDE [8][M]
+  const u32* xs;                          // [M]
+  const u32* zeta; u32 g_mont;            // device ext4; generator of H_N (Montgomery)
+  const u32* alpha_fri;                   // device ext4
+  const E4* open_t; const E4* open_tg; const E4* open_q;  // device openings
+  E4* afp_scratch;                        // [2*width+qwidth+3] scratch
+  E4* out;                                // [M]
+};
+int launch_deep(const DeepArgs& a, cudaStream_t st, u64* launches);
+int launch_fri_fold(const E4* in, E4* out, u64 h, const u32* beta_dev, const u32* inv_w_table, u32 tw_stride, u32 c_mont,
+                    cudaStream_t st, u64* launches);
+struct QueryArgs {
+  const u32* indices;   // device [num_queries], canonical
+  u32 num_queries, log_m, width, log_n;
+  const u32* lde; const u32* ttree;
+  const u32* qlde; const u32* qtree;
+  const E4* const* layers;        // device array [R] of layer pointers
+  const u32* const* ltrees;       // device array [R] of layer trees
+  u32* out;                       // proof words at the start of the query section
+  u32 words_per_query;
+};
+int launch_queries(const QueryArgs& a, cudaStream_t st, u64* launches);
+
+}  // namespace zkir

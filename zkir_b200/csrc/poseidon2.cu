@@ -1,0 +1,293 @@
+// Poseidon2-BabyBear (width 16, x^7, 8 external + 13 internal rounds) kernels: permutation, row sponge (Merkle
+// leaves), 2-to-1 compression (Merkle levels), the duplex challenger and the proof-of-work grinder.
+//
+// The reference's Poseidon2 is a stub that returns Err (zkir-runtime/src/crypto.rs:299-315, pinned by
+// zkir-runtime/tests/syscall_integration.rs:400-422), so there is nothing upstream to match; parameters and
+// round constants are frozen by docs/PROVER_SPEC.md / tools/gen_constants.py.  All values are Montgomery form.
+// Bound: integer ALU (about 770 modular multiplies per permutation), not HBM.
+#include <cuda_runtime.h>
+#include "bb.cuh"
+#include "kernels.h"
+#include "constants_generated.h"
+
+namespace zkir {
+
+__constant__ u32 c_rc_ext[128];
+__constant__ u32 c_rc_int[ZKIR_P2_RP];
+__constant__ u32 c_diag[16];
+
+int poseidon2_init_constants() {
+  u32 h[128];
+  for (int i = 0; i < 128; i++) h[i] = bb_to_mont_c(ZKIR_P2_RC_EXT[i]);
+  if (cudaMemcpyToSymbol(c_rc_ext, h, sizeof(u32) * 128) != cudaSuccess) return -2;
+  for (int i = 0; i < ZKIR_P2_RP; i++) h[i] = bb_to_mont_c(ZKIR_P2_RC_INT[i]);
+  if (cudaMemcpyToSymbol(c_rc_int, h, sizeof(u32) * ZKIR_P2_RP) != cudaSuccess) return -2;
+  for (int i = 0; i < 16; i++) h[i] = bb_to_mont_c(ZKIR_P2_DIAG[i]);
+  if (cudaMemcpyToSymbol(c_diag, h, sizeof(u32) * 16) != cudaSuccess) return -2;
+  return 0;
+}
+
+__device__ __forceinline__ u32 sbox7(u32 x) {
+  u32 x2 = bb_sqr(x), x3 = bb_mul(x2, x), x4 = bb_sqr(x2);
+  return bb_mul(x4, x3);
+}
+// circ(2,3,1,1) on 4 values
+__device__ __forceinline__ void m4(u32& a, u32& b, u32& c, u32& d) {
+  u32 t01 = bb_add(a, b), t23 = bb_add(c, d);
+  u32 t0123 = bb_add(t01, t23);
+  u32 t01123 = bb_add(t0123, b), t01233 = bb_add(t0123, d);
+  u32 nd = bb_add(t01233, bb_dbl(a));  // 3a + b + c + 2d
+  u32 nb = bb_add(t01123, bb_dbl(c));  // a + 2b + 3c + d
+  u32 na = bb_add(t01123, t01);        // 2a + 3b + c + d
+  u32 nc = bb_add(t01233, t23);        // a + b + 2c + 3d
+  a = na; b = nb; c = nc; d = nd;
+}
+__device__ __forceinline__ void external_linear(u32* s) {
+#pragma unroll
+  for (int c = 0; c < 4; c++) m4(s[4 * c], s[4 * c + 1], s[4 * c + 2], s[4 * c + 3]);
+  u32 sums[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) sums[k] = bb_add(bb_add(s[k], s[4 + k]), bb_add(s[8 + k], s[12 + k]));
+#pragma unroll
+  for (int i = 0; i < 16; i++) s[i] = bb_add(s[i], sums[i & 3]);
+}
+__device__ __forceinline__ void poseidon2_permute(u32* s) {
+  external_linear(s);
+#pragma unroll 1
+  for (int r = 0; r < 4; r++) {
+#pragma unroll
+    for (int i = 0; i < 16; i++) s[i] = sbox7(bb_add(s[i], c_rc_ext[r * 16 + i]));
+    external_linear(s);
+  }
+#pragma unroll 1
+  for (int r = 0; r < ZKIR_P2_RP; r++) {
+    s[0] = sbox7(bb_add(s[0], c_rc_int[r]));
+    u32 sum = s[0];
+#pragma unroll
+    for (int i = 1; i < 16; i++) sum = bb_add(sum, s[i]);
+#pragma unroll
+    for (int i = 0; i < 16; i++) s[i] = bb_add(bb_mul(s[i], c_diag[i]), sum);
+  }
+#pragma unroll 1
+  for (int r = 4; r < 8; r++) {
+#pragma unroll
+    for (int i = 0; i < 16; i++) s[i] = sbox7(bb_add(s[i], c_rc_ext[r * 16 + i]));
+    external_linear(s);
+  }
+}
+
+__global__ void permute_kernel(u32* states, u64 n, int canonical_io) {
+  u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  u32 s[16];
+  uint4* p = reinterpret_cast<uint4*>(states + 16 * i);
+#pragma unroll
+  for (int k = 0; k < 4; k++) { uint4 v = p[k]; s[4 * k] = v.x; s[4 * k + 1] = v.y; s[4 * k + 2] = v.z; s[4 * k + 3] = v.w; }
+  if (canonical_io) for (int k = 0; k < 16; k++) s[k] = bb_to_mont(s[k]);
+  poseidon2_permute(s);
+  if (canonical_io) for (int k = 0; k < 16; k++) s[k] = bb_from_mont(s[k]);
+#pragma unroll
+  for (int k = 0; k < 4; k++) p[k] = make_uint4(s[4 * k], s[4 * k + 1], s[4 * k + 2], s[4 * k + 3]);
+}
+
+// leaf i = overwrite-mode sponge (rate 8) over row i of a column-major matrix [n_cols][col_stride]
+__global__ void __launch_bounds__(128) leaf_hash_kernel(const u32* __restrict__ mat, u64 col_stride, u32 n_cols, u64 n_rows, u32* __restrict__ digests) {
+  u64 row = blockIdx.x * (u64)blockDim.x + threadIdx.x;
+  if (row >= n_rows) return;
+  u32 s[16];
+#pragma unroll
+  for (int k = 0; k < 16; k++) s[k] = 0;
+  const u32* p = mat + row;
+  u32 c = 0;
+  for (; c + 8 <= n_cols; c += 8) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) s[k] = __ldg(p + (u64)(c + k) * col_stride);
+    poseidon2_permute(s);
+  }
+  if (c < n_cols) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) if (c + k < n_cols) s[k] = __ldg(p + (u64)(c + k) * col_stride);
+    poseidon2_permute(s);
+  }
+  uint4* d = reinterpret_cast<uint4*>(digests + 8 * row);
+  d[0] = make_uint4(s[0], s[1], s[2], s[3]);
+  d[1] = make_uint4(s[4], s[5], s[6], s[7]);
+}
+
+// FRI layer leaves: leaf i = hash(F[i] || F[i+h]) (8 elements = one permutation)
+__global__ void __launch_bounds__(128) leaf_hash_pairs_kernel(const uint4* __restrict__ layer, u64 h, u32* __restrict__ digests) {
+  u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x;
+  if (i >= h) return;
+  uint4 a = layer[i], b = layer[i + h];
+  u32 s[16] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, 0, 0, 0, 0, 0, 0, 0, 0};
+  poseidon2_permute(s);
+  uint4* d = reinterpret_cast<uint4*>(digests + 8 * i);
+  d[0] = make_uint4(s[0], s[1], s[2], s[3]);
+  d[1] = make_uint4(s[4], s[5], s[6], s[7]);
+}
+
+// one Merkle level: out[i] = compress(in[2i], in[2i+1])
+__global__ void __launch_bounds__(128) compress_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, u64 n_out) {
+  u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x;
+  if (i >= n_out) return;
+  u32 s[16];
+#pragma unroll
+  for (int k = 0; k < 4; k++) { uint4 v = in[4 * i + k]; s[4 * k] = v.x; s[4 * k + 1] = v.y; s[4 * k + 2] = v.z; s[4 * k + 3] = v.w; }
+  poseidon2_permute(s);
+  out[2 * i] = make_uint4(s[0], s[1], s[2], s[3]);
+  out[2 * i + 1] = make_uint4(s[4], s[5], s[6], s[7]);
+}
+// the top of a tree in one block: levels from n_in (<= 2048 nodes) down to the root, synchronising in-block
+__global__ void __launch_bounds__(1024) compress_tail_kernel(uint4* tree_level, u64 n_in) {
+  uint4* in = tree_level;
+  for (u64 n = n_in; n > 1; n >>= 1) {
+    uint4* out = in + 2 * n;
+    for (u64 i = threadIdx.x; i < n / 2; i += blockDim.x) {
+      u32 s[16];
+#pragma unroll
+      for (int k = 0; k < 4; k++) { uint4 v = in[4 * i + k]; s[4 * k] = v.x; s[4 * k + 1] = v.y; s[4 * k + 2] = v.z; s[4 * k + 3] = v.w; }
+      poseidon2_permute(s);
+      out[2 * i] = make_uint4(s[0], s[1], s[2], s[3]);
+      out[2 * i + 1] = make_uint4(s[4], s[5], s[6], s[7]);
+    }
+    __syncthreads();
+    in = out;
+  }
+}
+
+static inline unsigned nblk(u64 n, unsigned t) { return (unsigned)((n + t - 1) / t); }
+
+int launch_permute(u32* d_states, u64 n, bool canonical_io, cudaStream_t st, u64* launches) {
+  if (!n) return 0;
+  permute_kernel<<<nblk(n, 128), 128, 0, st>>>(d_states, n, canonical_io);
+  (*launches)++;
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+int launch_leaf_hash(const u32* mat, u64 col_stride, u32 n_cols, u64 n_rows, u32* digests, cudaStream_t st, u64* launches) {
+  leaf_hash_kernel<<<nblk(n_rows, 128), 128, 0, st>>>(mat, col_stride, n_cols, n_rows, digests);
+  (*launches)++;
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+int launch_leaf_hash_pairs(const u32* layer, u64 h, u32* digests, cudaStream_t st, u64* launches) {
+  leaf_hash_pairs_kernel<<<nblk(h, 128), 128, 0, st>>>(reinterpret_cast<const uint4*>(layer), h, digests);
+  (*launches)++;
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+// tree: level 0 = n_leaves digests already in place; builds the upper levels behind it
+int launch_merkle_levels(u32* tree, u64 n_leaves, cudaStream_t st, u64* launches) {
+  u32* lvl = tree;
+  u64 n = n_leaves;
+  while (n > 2048) {
+    u32* nxt = lvl + n * 8;
+    compress_kernel<<<nblk(n / 2, 128), 128, 0, st>>>(reinterpret_cast<const uint4*>(lvl), reinterpret_cast<uint4*>(nxt), n / 2);
+    (*launches)++;
+    lvl = nxt; n >>= 1;
+  }
+  if (n > 1) {
+    compress_tail_kernel<<<1, 1024, 0, st>>>(reinterpret_cast<uint4*>(lvl), n);
+    (*launches)++;
+  }
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+// ---------------------------------------------------------------- duplex challenger, one warp, lane i < 16 owns state[i]
+__device__ __forceinline__ u32 permute_warp(u32 x, int lane) {
+  const unsigned FULL = 0xffffffffu;
+  const int l16 = lane & 15, grp = lane & ~3, j = lane & 3;
+  auto ext_lin = [&](u32 v) {
+    u32 b = __shfl_sync(FULL, v, grp | ((j + 1) & 3));
+    u32 c = __shfl_sync(FULL, v, grp | ((j + 2) & 3));
+    u32 d = __shfl_sync(FULL, v, grp | ((j + 3) & 3));
+    u32 y = bb_add(bb_add(bb_dbl(v), bb_add(bb_dbl(b), b)), bb_add(c, d));  // 2v + 3b + c + d
+    u32 s1 = bb_add(y, __shfl_xor_sync(FULL, y, 4));
+    u32 s2 = bb_add(s1, __shfl_xor_sync(FULL, s1, 8));
+    return bb_add(y, s2);
+  };
+  x = ext_lin(x);
+  for (int r = 0; r < 4; r++) { x = sbox7(bb_add(x, c_rc_ext[r * 16 + l16])); x = ext_lin(x); }
+  for (int r = 0; r < ZKIR_P2_RP; r++) {
+    if (l16 == 0) x = sbox7(bb_add(x, c_rc_int[r]));
+    u32 s = x;
+    s = bb_add(s, __shfl_xor_sync(FULL, s, 1));
+    s = bb_add(s, __shfl_xor_sync(FULL, s, 2));
+    s = bb_add(s, __shfl_xor_sync(FULL, s, 4));
+    s = bb_add(s, __shfl_xor_sync(FULL, s, 8));
+    x = bb_add(bb_mul(x, c_diag[l16]), s);
+  }
+  for (int r = 4; r < 8; r++) { x = sbox7(bb_add(x, c_rc_ext[r * 16 + l16])); x = ext_lin(x); }
+  return x;
+}
+
+// observe n_in field elements (Montgomery) then sample n_out; bits > 0: outputs are canonical integers masked to
+// `bits` bits (query indices / PoW check), else Montgomery field elements.  One warp.
+__global__ void __launch_bounds__(32) challenger_kernel(ChalState* st, const u32* in, u32 n_in, u32* out, u32 n_out, u32 bits) {
+  const int lane = threadIdx.x;
+  u32 x = lane < 16 ? st->sponge[lane] : 0;
+  u32 nin = st->n_in, nout = st->n_out;
+  u32 inb = lane < 8 ? st->inbuf[lane] : 0;    // lane k < 8 holds input buffer slot k
+  u32 outb = lane < 8 ? st->outbuf[lane] : 0;  // lane k < 8 holds output buffer slot k
+  auto duplex = [&]() {
+    if (lane < (int)nin) x = inb;
+    nin = 0;
+    x = permute_warp(x, lane);
+    outb = x;  // lanes 0..7 matter
+    nout = 8;
+  };
+  for (u32 i = 0; i < n_in; i++) {
+    u32 v = in[i];
+    nout = 0;
+    if (lane == (int)nin) inb = v;
+    nin++;
+    if (nin == 8) duplex();
+  }
+  for (u32 i = 0; i < n_out; i++) {
+    if (nin > 0 || nout == 0) duplex();
+    nout--;
+    u32 v = __shfl_sync(0xffffffffu, outb, nout);
+    if (bits) { v = bb_from_mont(v); if (bits < 32) v &= (1u << bits) - 1; }
+    if (lane == 0) out[i] = v;
+  }
+  if (lane < 16) st->sponge[lane] = x;
+  if (lane < 8) { st->inbuf[lane] = inb; st->outbuf[lane] = outb; }
+  if (lane == 0) { st->n_in = nin; st->n_out = nout; }
+}
+
+// proof of work: smallest canonical w such that, after observe(w), sample_bits(bits) == 0.
+__global__ void pow_grind_kernel(const ChalState* st, u32 bits, u32* result /* init 0xffffffff */) {
+  __shared__ u32 base[16];
+  __shared__ u32 s_nin;
+  if (threadIdx.x < 16) base[threadIdx.x] = st->sponge[threadIdx.x];
+  if (threadIdx.x == 0) s_nin = st->n_in;
+  __syncthreads();
+  const u32 nin = s_nin;  // < 8 pending inputs
+  if (threadIdx.x < nin) base[threadIdx.x] = st->inbuf[threadIdx.x];
+  __syncthreads();
+  const u64 G = (u64)gridDim.x * blockDim.x;
+  const u32 mask = bits >= 32 ? 0xffffffffu : ((1u << bits) - 1);
+  for (u64 w = blockIdx.x * (u64)blockDim.x + threadIdx.x; w < BB_P; w += G) {
+    const u64 sweep_end = (w / G + 1) * G;
+    u32 s[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) s[k] = base[k];
+    s[nin] = bb_to_mont((u32)w);
+    poseidon2_permute(s);
+    // observe(w) fills slot nin; if that makes 8 the duplex already ran and sample pops out[7]; otherwise sample
+    // triggers the duplex.  Either way exactly one permutation and the popped element is state[7].
+    if ((bb_from_mont(s[7]) & mask) == 0) atomicMin(result, (u32)w);
+    if (*(volatile u32*)result < sweep_end) break;  // every smaller candidate lives in a sweep that is complete
+  }
+}
+
+int launch_challenger(ChalState* st_dev, const u32* in, u32 n_in, u32* out, u32 n_out, u32 bits, cudaStream_t st, u64* launches) {
+  challenger_kernel<<<1, 32, 0, st>>>(st_dev, in, n_in, out, n_out, bits);
+  (*launches)++;
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+int launch_pow_grind(const ChalState* st_dev, u32 bits, u32* result, cudaStream_t st, u64* launches) {
+  cudaMemsetAsync(result, 0xff, 4, st);
+  pow_grind_kernel<<<148 * 4, 256, 0, st>>>(st_dev, bits, result);
+  (*launches)++;
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+}  // namespace zkir

@@ -1,0 +1,556 @@
+// C ABI + orchestration of the trace->proof path on one B200 (include/zkir_b200.h).
+//
+// Sits where a Rust `zkir_runtime::prove()` would call into a prover; the reference has neither (its runtime API
+// ends at run()/VM::run, zkir-runtime/src/lib.rs:29-62, vm.rs:54-78).  Protocol: docs/PROVER_SPEC.md.
+// Everything between the H2D copy of the trace and the D2H copy of the proof is a fixed sequence of kernel
+// launches on one stream: the Fiat-Shamir challenger, the PoW grinder and the query sampler run on the device, so
+// the host never synchronises inside a proof.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include <map>
+#include "zkir_b200.h"
+#include "bb.cuh"
+#include "kernels.h"
+#include "constants_generated.h"
+#include "air_generated.h"
+
+using namespace zkir;
+namespace zkir { u64 open_scratch_elems(u32 n_cols, u64 n); }
+
+std::string& zkir_host_error();
+#define g_last_error zkir_host_error()
+
+#define CU(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e__ = (call);                                                                      \
+    if (e__ != cudaSuccess) {                                                                      \
+      ctx->err = std::string(#call) + ": " + cudaGetErrorString(e__);                              \
+      return e__ == cudaErrorMemoryAllocation ? ZKIR_ERR_OOM : ZKIR_ERR_CUDA;                      \
+    }                                                                                              \
+  } while (0)
+#define RC(call)                                                                                   \
+  do {                                                                                             \
+    int r__ = (call);                                                                              \
+    if (r__ != 0) {                                                                                \
+      if (ctx->err.empty()) ctx->err = std::string(#call) + " failed";                             \
+      cudaError_t le = cudaGetLastError();                                                         \
+      if (le != cudaSuccess) ctx->err += std::string(": ") + cudaGetErrorString(le);               \
+      return r__ == -4 ? ZKIR_ERR_OOM : (r__ == -1 ? ZKIR_ERR_ARG : ZKIR_ERR_CUDA);                \
+    }                                                                                              \
+  } while (0)
+
+static u32 hpow(u32 a, u64 e) { u64 r = 1, b = a; while (e) { if (e & 1) r = r * b % BB_P; b = b * b % BB_P; e >>= 1; } return (u32)r; }
+static u32 hinv(u32 a) { return hpow(a, BB_P - 2); }
+static u32 hmul(u32 a, u32 b) { return (u32)((u64)a * b % BB_P); }
+
+static const u32 PROOF_MAGIC = 0x5A4B5052u, PROOF_VERSION = 1u;
+static const u32 QW = 8;  // quotient columns: 4 ext planes x 2 chunks, column = 2*plane + chunk
+
+struct Layout {  // proof word offsets
+  u32 log_n, log_m, width, np, nq, R;
+  size_t pv, troot, qroot, open_t, open_tg, open_q, fri_roots, final_, pow_, queries, per_query, total;
+};
+static Layout make_layout(const zkir_params* p, u32 log_n) {
+  Layout L;
+  L.log_n = log_n; L.log_m = log_n + p->log_blowup; L.width = p->width; L.np = p->num_public; L.nq = p->num_queries; L.R = log_n;
+  size_t o = 8;
+  L.pv = o; o += L.np;
+  L.troot = o; o += 8;
+  L.qroot = o; o += 8;
+  L.open_t = o; o += 4 * (size_t)L.width;
+  L.open_tg = o; o += 4 * (size_t)L.width;
+  L.open_q = o; o += 4 * QW;
+  L.fri_roots = o; o += 8 * (size_t)L.R;
+  L.final_ = o; o += 4;
+  L.pow_ = o; o += 1;
+  L.queries = o;
+  size_t pq = L.width + 8 * (size_t)L.log_m + QW + 8 * (size_t)L.log_m;
+  for (u32 r = 0; r < L.R; r++) pq += 8 + 8 * (size_t)(L.log_m - 1 - r);
+  L.per_query = pq;
+  L.total = o + pq * L.nq;
+  return L;
+}
+
+struct Workspace {
+  u32 log_n = 0, log_blowup = 0, width = 0, nq = 0;
+  bool valid = false;
+  std::vector<void*> allocs;
+  u32 *trace = nullptr, *coef = nullptr, *lde = nullptr, *ttree = nullptr;
+  u32 *q = nullptr, *qcoef = nullptr, *qlde = nullptr, *qtree = nullptr;
+  u32 *xs = nullptr, *dinv = nullptr, *qscale = nullptr;
+  E4 *U1 = nullptr, *U2 = nullptr, *open_scratch = nullptr, *dummy_open = nullptr;
+  E4* layers = nullptr;      // all FRI layers back to back: M + M/2 + ... + B
+  u32* ltrees = nullptr;     // all layer trees back to back
+  std::vector<E4*> h_layers; std::vector<u32*> h_ltrees;
+  E4** d_layers = nullptr; u32** d_ltrees = nullptr;
+  ChalState* chal = nullptr;
+  u32* chal_buf = nullptr;   // alpha[4] zeta[4] alpha_fri[4] betas[R][4] pow_raw[1] pow_sample[1] hdr_mont[6+np]
+  u32* indices = nullptr;
+  u32* apow = nullptr; E4* afp = nullptr;
+  u32* proof = nullptr;      // device proof words
+  u32* h_proof = nullptr;    // pinned
+  u32* h_stage = nullptr;    // pinned staging for header words
+};
+
+struct zkir_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  NttTables* tables = nullptr;
+  u64 launches = 0;
+  std::string err;
+  u32* ntt_tmp = nullptr; u64 ntt_tmp_words = 0;
+  Workspace ws;
+  cudaEvent_t ev[ZKIR_STAGE_COUNT + 1];
+  float stage_ms[ZKIR_STAGE_COUNT] = {0};
+  bool have_stage = false;
+};
+
+static void ws_free(zkir_ctx* ctx) {
+  Workspace& w = ctx->ws;
+  for (void* p : w.allocs) cudaFree(p);
+  if (w.h_proof) cudaFreeHost(w.h_proof);
+  if (w.h_stage) cudaFreeHost(w.h_stage);
+  w = Workspace();
+}
+template <class T>
+static int ws_alloc(zkir_ctx* ctx, T** p, size_t count) {
+  void* d = nullptr;
+  cudaError_t e = cudaMalloc(&d, count * sizeof(T) > 0 ? count * sizeof(T) : 16);
+  if (e != cudaSuccess) { ctx->err = std::string("cudaMalloc: ") + cudaGetErrorString(e); return ZKIR_ERR_OOM; }
+  ctx->ws.allocs.push_back(d);
+  *p = reinterpret_cast<T*>(d);
+  return 0;
+}
+static int ensure_ntt_tmp(zkir_ctx* ctx, u64 n) {
+  // batch scratch for multi-pass NTTs: default 32 MiB so that a batch stays L2-resident between passes
+  u64 want = 8ull << 20;  // words
+  const char* env = getenv("ZKIR_NTT_BATCH_MB");
+  if (env) want = (u64)atoi(env) * (1ull << 18);
+  if (want < n) want = n;
+  if (ctx->ntt_tmp_words >= want) return 0;
+  if (ctx->ntt_tmp) cudaFree(ctx->ntt_tmp);
+  ctx->ntt_tmp = nullptr; ctx->ntt_tmp_words = 0;
+  CU(cudaMalloc(&ctx->ntt_tmp, want * 4));
+  ctx->ntt_tmp_words = want;
+  return 0;
+}
+
+static int ws_prepare(zkir_ctx* ctx, const zkir_params* p, u32 log_n) {
+  Workspace& w = ctx->ws;
+  if (w.valid && w.log_n == log_n && w.log_blowup == p->log_blowup && w.width == p->width && w.nq == p->num_queries) return 0;
+  ws_free(ctx);
+  const u64 N = 1ull << log_n, M = N << p->log_blowup, W = p->width;
+  const u32 R = log_n;
+  const Layout L = make_layout(p, log_n);
+  int rc;
+#define A(ptr, cnt) if ((rc = ws_alloc(ctx, &w.ptr, (cnt))) != 0) return rc;
+  A(trace, W * N) A(coef, W * N) A(lde, W * M) A(ttree, (2 * M - 1) * 8)
+  A(q, 4 * M) A(qlde, QW * M) A(qtree, (2 * M - 1) * 8)
+  if (p->log_blowup > 1) { A(qcoef, QW * N) }
+  A(xs, M) A(dinv, M) A(qscale, M)
+  A(U1, N) A(U2, N) A(open_scratch, open_scratch_elems((u32)W, N)) A(dummy_open, W)
+  A(layers, 2 * M) A(ltrees, 2 * M * 8)
+  A(d_layers, R + 1) A(d_ltrees, R + 1)
+  A(chal, 1) A(chal_buf, 12 + 4 * R + 2 + 6 + p->num_public) A(indices, p->num_queries + 1)
+  A(apow, 4 * ZKIR_AIR_NUM_CONSTRAINTS) A(afp, W + 5)
+  A(proof, L.total)
+#undef A
+  CU(cudaMallocHost(&w.h_proof, L.total * 4));
+  CU(cudaMallocHost(&w.h_stage, (8 + 6 + 2 * p->num_public) * 4));
+  // layer pointers
+  w.h_layers.resize(R + 1); w.h_ltrees.resize(R + 1);
+  E4* lp = w.layers; u32* tp = w.ltrees;
+  for (u32 r = 0; r <= R; r++) {
+    w.h_layers[r] = lp; w.h_ltrees[r] = tp;
+    const u64 n = M >> r;
+    lp += n; tp += n * 8;  // tree of n/2 leaves needs (n-1)*8 words
+  }
+  CU(cudaMemcpyAsync(w.d_layers, w.h_layers.data(), (R + 1) * sizeof(E4*), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(w.d_ltrees, w.h_ltrees.data(), (R + 1) * sizeof(u32*), cudaMemcpyHostToDevice, ctx->stream));
+  RC(launch_domain_tables(w.xs, w.dinv, log_n + p->log_blowup, ZKIR_BB_GEN, ctx->stream, &ctx->launches));
+  {  // quotient inverse-NTT output scale: qscale[j] = (1/M) * shift^(-N * floor(j/N))   (Montgomery)
+    std::vector<u32> h(M);
+    const u32 minv = hinv((u32)(M % BB_P)), step = hinv(hpow(ZKIR_BB_GEN, N));
+    u32 c = minv;
+    for (u64 b = 0; b < (M >> log_n); b++) { u32 cm = bb_to_mont_c(c); for (u64 j = 0; j < N; j++) h[b * N + j] = cm; c = hmul(c, step); }
+    CU(cudaMemcpy(w.qscale, h.data(), M * 4, cudaMemcpyHostToDevice));
+  }
+  CU(cudaStreamSynchronize(ctx->stream));
+  w.log_n = log_n; w.log_blowup = p->log_blowup; w.width = p->width; w.nq = p->num_queries; w.valid = true;
+  return 0;
+}
+
+static int check_params(zkir_ctx* ctx, const zkir_params* p, u32 log_n) {
+  if (!p || p->width != ZKIR_AIR_WIDTH || p->num_public != ZKIR_AIR_NUM_PUBLIC || p->log_blowup < 1 || p->log_blowup > 4 ||
+      log_n < 2 || log_n + p->log_blowup > 27 || p->pow_bits > 30 || p->num_queries > 4096) {
+    ctx->err = "bad params: need width=112, num_public=4, 1<=log_blowup<=4, 2<=log_n, log_n+log_blowup<=27, pow_bits<=30";
+    return ZKIR_ERR_ARG;
+  }
+  return 0;
+}
+
+// the device part of a proof; trace already in ws.trace (canonical values)
+static int prove_resident(zkir_ctx* ctx, const zkir_params* p, u32 log_n, const u32* pv) {
+  Workspace& w = ctx->ws;
+  cudaStream_t st = ctx->stream;
+  u64* LC = &ctx->launches;
+  const u64 N = 1ull << log_n, M = N << p->log_blowup, W = p->width;
+  const u32 log_m = log_n + p->log_blowup, R = log_n, np = p->num_public;
+  const Layout L = make_layout(p, log_n);
+  const u32 shift = ZKIR_BB_GEN;
+  RC(ensure_ntt_tmp(ctx, M));
+  u32* c_alpha = w.chal_buf, *c_zeta = w.chal_buf + 4, *c_afri = w.chal_buf + 8, *c_betas = w.chal_buf + 12;
+  u32* c_pow_raw = w.chal_buf + 12 + 4 * R, *c_pow_sample = c_pow_raw + 1, *c_hdr = c_pow_raw + 2;
+
+  // ---- header + public values
+  u32* hs = w.h_stage;
+  hs[0] = PROOF_MAGIC; hs[1] = PROOF_VERSION; hs[2] = log_n; hs[3] = p->width; hs[4] = p->log_blowup; hs[5] = p->num_queries;
+  hs[6] = p->pow_bits; hs[7] = np;
+  for (u32 i = 0; i < np; i++) { if (pv[i] >= BB_P) { ctx->err = "public value not canonical"; return ZKIR_ERR_ARG; } hs[8 + i] = pv[i]; }
+  u32* hm = hs + 8 + np;  // Montgomery copy for the transcript
+  for (u32 i = 0; i < 6; i++) hm[i] = bb_to_mont_c(hs[2 + i]);
+  for (u32 i = 0; i < np; i++) hm[6 + i] = bb_to_mont_c(pv[i]);
+  CU(cudaMemcpyAsync(w.proof, hs, (8 + np) * 4, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(c_hdr, hm, (6 + np) * 4, cudaMemcpyHostToDevice, st));
+  CU(cudaMemsetAsync(w.chal, 0, sizeof(ChalState), st));
+
+  // ---- 1. LDE: iNTT (scale by shift^j/N and lift to Montgomery), zero-pad, forward NTT on the coset
+  CU(cudaEventRecord(ctx->ev[ZKIR_STAGE_LDE], st));
+  {
+    const u32 c0 = hmul(hinv((u32)(N % BB_P)), (u32)((1ull << 32) % BB_P));  // R/N: the table carries one extra factor R
+    const u32* sc = ntt_powers_table(ctx->tables, shift, c0, N);
+    if (!sc) { ctx->err = "table alloc"; return ZKIR_ERR_OOM; }
+    RC(ntt_run(ctx->tables, w.trace, N, w.coef, N, ctx->ntt_tmp, ctx->ntt_tmp_words, (u32)W, log_n, true, 0, nullptr, sc, BB_ONE, false, st));
+    RC(ntt_run(ctx->tables, w.coef, N, w.lde, M, ctx->ntt_tmp, ctx->ntt_tmp_words, (u32)W, log_m, false, p->log_blowup, nullptr, nullptr, BB_ONE, false, st));
+  }
+  // ---- 2. trace commitment
+  CU(cudaEventRecord(ctx->ev[ZKIR_STAGE_TRACE_COMMIT], st));
+  RC(launch_leaf_hash(w.lde, M, (u32)W, M, w.ttree, st, LC));
+  RC(launch_merkle_levels(w.ttree, M, st, LC));
+  const u32* troot = w.ttree + (2 * M - 2) * 8;
+  CU(cudaMemcpyAsync(w.proof + L.troot, troot, 32, cudaMemcpyDeviceToDevice, st));
+  RC(launch_challenger(w.chal, c_hdr, 6 + np, nullptr, 0, 0, st, LC));
+  RC(launch_challenger(w.chal, troot, 8, c_alpha, 4, 0, st, LC));
+  // ---- 3. quotient
+  CU(cudaEventRecord(ctx->ev[ZKIR_STAGE_QUOTIENT], st));
+  {
+    QuotientArgs qa;
+    qa.lde = w.lde; qa.q = w.q; qa.log_n = log_n; qa.log_blowup = p->log_blowup; qa.pv = c_hdr + 6; qa.alpha = c_alpha;
+    qa.xs = w.xs; qa.dinv = w.dinv; qa.apow_scratch = w.apow;
+    RC(launch_quotient(qa, st, LC));
+  }
+  CU(cudaEventRecord(ctx->ev[ZKIR_STAGE_QUOTIENT_COMMIT], st));
+  // coefficients on the coset (in place), chunk c of plane k = words [k*M + c*N, +N)
+  RC(ntt_run(ctx->tables, w.q, M, w.q, M, ctx->ntt_tmp, ctx->ntt_tmp_words, 4, log_m, true, 0, nullptr, w.qscale, BB_ONE, false, st));
+  const u32* qcoef = w.q;
+  if (p->log_blowup > 1) {  // compact the two chunks of every plane: column 2k+c <- q[k*M + c*N ..]
+    CU(cudaMemcpy2DAsync(w.qcoef, 2 * N * 4, w.q, M * 4, 2 * N * 4, 4, cudaMemcpyDeviceToDevice, st));
+    qcoef = w.qcoef;
+  }
+  RC(ntt_run(ctx->tables, qcoef, N, w.qlde, M, ctx->ntt_tmp, ctx->ntt_tmp_words, QW, log_m, false, p->log_blowup, nullptr, nullptr, BB_ONE, false, st));
+  RC(launch_leaf_hash(w.qlde, M, QW, M, w.qtree, st, LC));
+  RC(launch_merkle_levels(w.qtree, M, st, LC));
+  const u32* qroot = w.qtree + (2 * M - 2) * 8;
+  CU(cudaMemcpyAsync(w.proof + L.qroot, qroot, 32, cudaMemcpyDeviceToDevice, st));
+  RC(launch_challenger(w.chal, qroot, 8, c_zeta, 4, 0, st, LC));
+  // ---- 4. openings at zeta and g*zeta, evaluated on the shifted coefficients at zeta/shift
+  CU(cudaEventRecord(ctx->ev[ZKIR_STAGE_OPENINGS], st));
+  {
+    const u32 sinv = hinv(shift), g = ZKIR_BB_ROOTS[log_n];
+    RC(launch_ext_powers(c_zeta, nullptr, bb_to_mont_c(sinv), w.U1, N, st, LC));
+    RC(launch_ext_powers(c_zeta, nullptr, bb_to_mont_c(hmul(sinv, g)), w.U2, N, st, LC));
+    E4* ot = reinterpret_cast<E4*>(w.proof + L.open_t);
+    E4* otg = reinterpret_cast<E4*>(w.proof + L.open_tg);
+    E4* oq = reinterpret_cast<E4*>(w.proof + L.open_q);
+    RC(launch_open(w.coef, N, (u32)W, N, w.U1, w.U2, ot, otg, w.open_scratch, st, LC));
+    RC(launch_open(qcoef, N, QW, N, w.U1, w.U1, oq, w.dummy_open, w.open_scratch, st, LC));
+    RC(launch_challenger(w.chal, w.proof + L.open_t, (u32)(2 * W + QW) * 4, c_afri, 4, 0, st, LC));
+    DeepArgs da;
+    da.lde = w.lde; da.M = M; da.width = (u32)W; da.qlde = w.qlde; da.qwidth = QW; da.xs = w.xs; da.zeta = c_zeta;
+    da.g_mont = bb_to_mont_c(g); da.alpha_fri = c_afri; da.open_t = ot; da.open_tg = otg; da.open_q = oq; da.afp_scratch = w.afp;
+    da.out = w.h_layers[0];
+    RC(launch_deep(da, st, LC));
+  }
+  // ---- 5. FRI commit phase
+  CU(cudaEventRecord(ctx->ev[ZKIR_STAGE_FRI], st));
+  {
+    const u32* inv_w = ntt_powers_table(ctx->tables, hinv(ZKIR_BB_ROOTS[log_m]), 1, M / 2);
+    if (!inv_w) { ctx->err = "table alloc"; return ZKIR_ERR_OOM; }
+    u32 lshift = shift;
+    for (u32 r = 0; r < R; r++) {
+      const u64 h = (M >> r) / 2;
+      RC(launch_leaf_hash_pairs(reinterpret_cast<const u32*>(w.h_layers[r]), h, w.h_ltrees[r], st, LC));
+      RC(launch_merkle_levels(w.h_ltrees[r], h, st, LC));
+      const u32* root = w.h_ltrees[r] + (2 * h - 2) * 8;
+      CU(cudaMemcpyAsync(w.proof + L.fri_roots + 8 * r, root, 32, cudaMemcpyDeviceToDevice, st));
+      RC(launch_challenger(w.chal, root, 8, c_betas + 4 * r, 4, 0, st, LC));
+      const u32 c = hinv(hmul(2, lshift));
+      RC(launch_fri_fold(w.h_layers[r], w.h_layers[r + 1], h, c_betas + 4 * r, inv_w, 1u << r, bb_to_mont_c(c), st, LC));
+      lshift = hmul(lshift, lshift);
+    }
+    CU(cudaMemcpyAsync(w.proof + L.final_, w.h_layers[R], 16, cudaMemcpyDeviceToDevice, st));
+    RC(launch_challenger(w.chal, w.proof + L.final_, 4, nullptr, 0, 0, st, LC));
+    RC(launch_pow_grind(w.chal, p->pow_bits, c_pow_raw, st, LC));
+    RC(launch_map(w.proof + L.pow_, c_pow_raw, 1, 1, st, LC));
+    RC(launch_challenger(w.chal, w.proof + L.pow_, 1, c_pow_sample, 1, p->pow_bits, st, LC));
+    RC(launch_challenger(w.chal, nullptr, 0, w.indices, p->num_queries, log_m, st, LC));
+  }
+  // ---- 6. queries, canonicalise, D2H
+  CU(cudaEventRecord(ctx->ev[ZKIR_STAGE_QUERIES_D2H], st));
+  {
+    QueryArgs qa;
+    qa.indices = w.indices; qa.num_queries = p->num_queries; qa.log_m = log_m; qa.width = (u32)W; qa.log_n = log_n;
+    qa.lde = w.lde; qa.ttree = w.ttree; qa.qlde = w.qlde; qa.qtree = w.qtree;
+    qa.layers = w.d_layers; qa.ltrees = w.d_ltrees; qa.out = w.proof + L.queries; qa.words_per_query = (u32)L.per_query;
+    RC(launch_queries(qa, st, LC));
+    RC(launch_map(w.proof + 8 + np, w.proof + 8 + np, L.total - 8 - np, 0, st, LC));
+    CU(cudaMemcpyAsync(w.h_proof, w.proof, L.total * 4, cudaMemcpyDeviceToHost, st));
+  }
+  CU(cudaEventRecord(ctx->ev[ZKIR_STAGE_COUNT], st));
+  return 0;
+}
+
+static int finish_proof(zkir_ctx* ctx, const zkir_params* p, u32 log_n, uint8_t** proof, size_t* proof_len) {
+  CU(cudaStreamSynchronize(ctx->stream));
+  const Layout L = make_layout(p, log_n);
+  uint8_t* out = (uint8_t*)malloc(L.total * 4);
+  if (!out) { ctx->err = "malloc"; return ZKIR_ERR_OOM; }
+  memcpy(out, ctx->ws.h_proof, L.total * 4);
+  *proof = out; *proof_len = L.total * 4;
+  for (int s = 0; s < ZKIR_STAGE_COUNT; s++) cudaEventElapsedTime(&ctx->stage_ms[s], ctx->ev[s], ctx->ev[s + 1]);
+  ctx->have_stage = true;
+  return 0;
+}
+
+extern "C" {
+
+int zkir_b200_create(zkir_ctx** out, int device_id) {
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) { g_last_error = std::string("no CUDA device: ") + cudaGetErrorString(e); return ZKIR_ERR_CUDA; }
+  if (device_id < 0 || device_id >= n) { g_last_error = "device id out of range"; return ZKIR_ERR_ARG; }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device_id) != cudaSuccess || prop.major != 10) {
+    g_last_error = "zkir_b200 kernels are built for sm_100a only; device is not compute capability 10.x";
+    return ZKIR_ERR_CUDA;
+  }
+  if (cudaSetDevice(device_id) != cudaSuccess) { g_last_error = "cudaSetDevice failed"; return ZKIR_ERR_CUDA; }
+  zkir_ctx* ctx = new zkir_ctx();
+  ctx->device = device_id;
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; g_last_error = "stream"; return ZKIR_ERR_CUDA; }
+  for (int i = 0; i <= ZKIR_STAGE_COUNT; i++) cudaEventCreate(&ctx->ev[i]);
+  if (poseidon2_init_constants() != 0) { g_last_error = "constant upload failed"; delete ctx; return ZKIR_ERR_CUDA; }
+  ctx->tables = ntt_tables_create(ctx->stream, &ctx->launches);
+  *out = ctx;
+  return 0;
+}
+
+void zkir_b200_destroy(zkir_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  ws_free(ctx);
+  if (ctx->ntt_tmp) cudaFree(ctx->ntt_tmp);
+  ntt_tables_destroy(ctx->tables);
+  for (int i = 0; i <= ZKIR_STAGE_COUNT; i++) cudaEventDestroy(ctx->ev[i]);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char* zkir_b200_last_error(const zkir_ctx* ctx) {
+  return ctx ? ctx->err.c_str() : g_last_error.c_str();
+}
+
+void* zkir_b200_alloc_pinned(size_t bytes) { void* p = nullptr; return cudaMallocHost(&p, bytes) == cudaSuccess ? p : nullptr; }
+void zkir_b200_free_pinned(void* p) { if (p) cudaFreeHost(p); }
+void zkir_b200_free_proof(uint8_t* p) { free(p); }
+size_t zkir_b200_proof_size(const zkir_params* p, uint32_t log_n) { return make_layout(p, log_n).total * 4; }
+
+int zkir_b200_prove(zkir_ctx* ctx, const zkir_params* p, const uint32_t* trace_cols, uint32_t log_n, const uint32_t* pv,
+                    uint8_t** proof, size_t* proof_len) {
+  if (!ctx) return ZKIR_ERR_ARG;
+  ctx->err.clear();
+  cudaSetDevice(ctx->device);
+  int rc = check_params(ctx, p, log_n);
+  if (rc) return rc;
+  if (!trace_cols || !pv || !proof || !proof_len) { ctx->err = "null argument"; return ZKIR_ERR_ARG; }
+  if ((rc = ws_prepare(ctx, p, log_n)) != 0) return rc;
+  CU(cudaEventRecord(ctx->ev[ZKIR_STAGE_H2D], ctx->stream));
+  CU(cudaMemcpyAsync(ctx->ws.trace, trace_cols, ((size_t)p->width << log_n) * 4, cudaMemcpyHostToDevice, ctx->stream));
+  if ((rc = prove_resident(ctx, p, log_n, pv)) != 0) return rc;
+  return finish_proof(ctx, p, log_n, proof, proof_len);
+}
+
+int zkir_b200_prove_device(zkir_ctx* ctx, const zkir_params* p, const uint32_t* d_trace, uint32_t log_n, const uint32_t* pv,
+                           uint8_t** proof, size_t* proof_len) {
+  if (!ctx) return ZKIR_ERR_ARG;
+  ctx->err.clear();
+  cudaSetDevice(ctx->device);
+  int rc = check_params(ctx, p, log_n);
+  if (rc) return rc;
+  if (!d_trace || !pv || !proof || !proof_len) { ctx->err = "null argument"; return ZKIR_ERR_ARG; }
+  if ((rc = ws_prepare(ctx, p, log_n)) != 0) return rc;
+  CU(cudaEventRecord(ctx->ev[ZKIR_STAGE_H2D], ctx->stream));
+  CU(cudaMemcpyAsync(ctx->ws.trace, d_trace, ((size_t)p->width << log_n) * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+  if ((rc = prove_resident(ctx, p, log_n, pv)) != 0) return rc;
+  return finish_proof(ctx, p, log_n, proof, proof_len);
+}
+
+int zkir_b200_prove_batch(zkir_ctx* ctx, const zkir_params* p, const uint32_t* const* traces, const uint32_t* log_ns,
+                          const uint32_t* const* pvs, uint32_t n_proofs, uint8_t** proofs, size_t* proof_lens) {
+  if (!ctx || !traces || !log_ns || !pvs || !proofs || !proof_lens) return ZKIR_ERR_ARG;
+  for (uint32_t i = 0; i < n_proofs; i++) {
+    int rc = zkir_b200_prove(ctx, p, traces[i], log_ns[i], pvs[i], &proofs[i], &proof_lens[i]);
+    if (rc) { for (uint32_t j = 0; j < i; j++) { free(proofs[j]); proofs[j] = nullptr; } return rc; }
+  }
+  return 0;
+}
+
+int zkir_b200_last_stage_ms(zkir_ctx* ctx, float* out) {
+  if (!ctx || !ctx->have_stage) return ZKIR_ERR_ARG;
+  memcpy(out, ctx->stage_ms, sizeof(ctx->stage_ms));
+  return 0;
+}
+uint64_t zkir_b200_kernel_launches(const zkir_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ---------------------------------------------------------------- per-kernel entry points (canonical device data)
+int zkir_b200_ntt(zkir_ctx* ctx, uint32_t* d_cols, uint32_t n_cols, uint32_t log_n, int inverse, uint32_t coset_shift) {
+  if (!ctx || !d_cols || log_n < 1 || log_n > 27 || (inverse && coset_shift)) return ZKIR_ERR_ARG;
+  ctx->err.clear();
+  cudaSetDevice(ctx->device);
+  const u64 n = 1ull << log_n;
+  RC(ensure_ntt_tmp(ctx, n));
+  const u32* in_scale = nullptr;
+  if (coset_shift) { in_scale = ntt_powers_table(ctx->tables, coset_shift % BB_P, 1, n); if (!in_scale) return ZKIR_ERR_OOM; }
+  const u32 ninv = bb_to_mont_c(hinv((u32)(n % BB_P)));
+  RC(ntt_run(ctx->tables, d_cols, n, d_cols, n, ctx->ntt_tmp, ctx->ntt_tmp_words, n_cols, log_n, inverse != 0, 0, in_scale, nullptr,
+             ninv, inverse != 0, ctx->stream));
+  return 0;
+}
+
+int zkir_b200_lde(zkir_ctx* ctx, const uint32_t* d_in, uint32_t* d_out, uint32_t n_cols, uint32_t log_n, uint32_t log_blowup) {
+  if (!ctx || !d_in || !d_out || log_n < 1 || log_blowup < 1 || log_n + log_blowup > 27) return ZKIR_ERR_ARG;
+  ctx->err.clear();
+  cudaSetDevice(ctx->device);
+  const u64 N = 1ull << log_n, M = N << log_blowup;
+  RC(ensure_ntt_tmp(ctx, M));
+  const u32* sc = ntt_powers_table(ctx->tables, ZKIR_BB_GEN, hinv((u32)(N % BB_P)), N);
+  if (!sc) return ZKIR_ERR_OOM;
+  u32* coef = nullptr;
+  CU(cudaMallocAsync(&coef, (size_t)n_cols * N * 4, ctx->stream));
+  int rc = ntt_run(ctx->tables, d_in, N, coef, N, ctx->ntt_tmp, ctx->ntt_tmp_words, n_cols, log_n, true, 0, nullptr, sc, BB_ONE, false, ctx->stream);
+  if (!rc) rc = ntt_run(ctx->tables, coef, N, d_out, M, ctx->ntt_tmp, ctx->ntt_tmp_words, n_cols, log_n + log_blowup, false, log_blowup, nullptr, nullptr,
+                        BB_ONE, false, ctx->stream);
+  cudaFreeAsync(coef, ctx->stream);
+  RC(rc);
+  return 0;
+}
+
+int zkir_b200_poseidon2_permute(zkir_ctx* ctx, uint32_t* d_states, uint64_t n) {
+  if (!ctx || !d_states) return ZKIR_ERR_ARG;
+  ctx->err.clear();
+  cudaSetDevice(ctx->device);
+  RC(launch_permute(d_states, n, true, ctx->stream, &ctx->launches));
+  return 0;
+}
+
+int zkir_b200_merkle_commit(zkir_ctx* ctx, const uint32_t* d_matrix, uint32_t n_cols, uint32_t log_rows, uint32_t* d_tree, uint32_t root[8]) {
+  if (!ctx || !d_matrix || !d_tree || !root || n_cols == 0 || log_rows > 27) return ZKIR_ERR_ARG;
+  ctx->err.clear();
+  cudaSetDevice(ctx->device);
+  const u64 rows = 1ull << log_rows;
+  u32* mont = nullptr;
+  CU(cudaMallocAsync(&mont, (size_t)n_cols * rows * 4, ctx->stream));
+  int rc = launch_map(mont, d_matrix, (u64)n_cols * rows, 1, ctx->stream, &ctx->launches);
+  if (!rc) rc = launch_leaf_hash(mont, rows, n_cols, rows, d_tree, ctx->stream, &ctx->launches);
+  if (!rc) rc = launch_merkle_levels(d_tree, rows, ctx->stream, &ctx->launches);
+  if (!rc) rc = launch_map(d_tree, d_tree, (2 * rows - 1) * 8, 0, ctx->stream, &ctx->launches);
+  cudaFreeAsync(mont, ctx->stream);
+  RC(rc);
+  CU(cudaMemcpyAsync(root, d_tree + (2 * rows - 2) * 8, 32, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int zkir_b200_quotient(zkir_ctx* ctx, const zkir_params* p, const uint32_t* d_lde, uint32_t log_n, const uint32_t* pv,
+                       const uint32_t alpha[4], uint32_t* d_q) {
+  if (!ctx) return ZKIR_ERR_ARG;
+  ctx->err.clear();
+  cudaSetDevice(ctx->device);
+  int rc = check_params(ctx, p, log_n);
+  if (rc) return rc;
+  const u32 log_m = log_n + p->log_blowup;
+  const u64 M = 1ull << log_m;
+  u32 *lde_m = nullptr, *xs = nullptr, *dinv = nullptr, *small = nullptr;
+  CU(cudaMallocAsync(&lde_m, (size_t)p->width * M * 4, ctx->stream));
+  CU(cudaMallocAsync(&xs, M * 4, ctx->stream));
+  CU(cudaMallocAsync(&dinv, M * 4, ctx->stream));
+  CU(cudaMallocAsync(&small, (8 + 4 * ZKIR_AIR_NUM_CONSTRAINTS) * 4, ctx->stream));
+  u32 h[8];
+  for (int i = 0; i < 4; i++) h[i] = bb_to_mont_c(pv[i] % BB_P);
+  for (int i = 0; i < 4; i++) h[4 + i] = bb_to_mont_c(alpha[i] % BB_P);
+  CU(cudaMemcpyAsync(small, h, 32, cudaMemcpyHostToDevice, ctx->stream));
+  rc = launch_map(lde_m, d_lde, (u64)p->width * M, 1, ctx->stream, &ctx->launches);
+  if (!rc) rc = launch_domain_tables(xs, dinv, log_m, ZKIR_BB_GEN, ctx->stream, &ctx->launches);
+  QuotientArgs qa;
+  qa.lde = lde_m; qa.q = d_q; qa.log_n = log_n; qa.log_blowup = p->log_blowup; qa.pv = small; qa.alpha = small + 4;
+  qa.xs = xs; qa.dinv = dinv; qa.apow_scratch = small + 8;
+  if (!rc) rc = launch_quotient(qa, ctx->stream, &ctx->launches);
+  if (!rc) rc = launch_map(d_q, d_q, 4 * M, 0, ctx->stream, &ctx->launches);
+  CU(cudaStreamSynchronize(ctx->stream));
+  cudaFreeAsync(lde_m, ctx->stream); cudaFreeAsync(xs, ctx->stream); cudaFreeAsync(dinv, ctx->stream); cudaFreeAsync(small, ctx->stream);
+  RC(rc);
+  return 0;
+}
+
+int zkir_b200_fri_fold(zkir_ctx* ctx, const uint32_t* d_in, uint32_t* d_out, uint32_t log_n, uint32_t shift, const uint32_t beta[4]) {
+  if (!ctx || !d_in || !d_out || log_n < 1 || log_n > 27 || shift == 0) return ZKIR_ERR_ARG;
+  ctx->err.clear();
+  cudaSetDevice(ctx->device);
+  const u64 n = 1ull << log_n, h = n / 2;
+  const u32* inv_w = ntt_powers_table(ctx->tables, hinv(ZKIR_BB_ROOTS[log_n]), 1, h);
+  if (!inv_w) return ZKIR_ERR_OOM;
+  u32 *in_m = nullptr, *b = nullptr;
+  CU(cudaMallocAsync(&in_m, n * 16, ctx->stream));
+  CU(cudaMallocAsync(&b, 16, ctx->stream));
+  u32 hb[4];
+  for (int i = 0; i < 4; i++) hb[i] = bb_to_mont_c(beta[i] % BB_P);
+  CU(cudaMemcpyAsync(b, hb, 16, cudaMemcpyHostToDevice, ctx->stream));
+  int rc = launch_map(in_m, d_in, n * 4, 1, ctx->stream, &ctx->launches);
+  if (!rc) rc = launch_fri_fold(reinterpret_cast<const E4*>(in_m), reinterpret_cast<E4*>(d_out), h, b, inv_w, 1,
+                                bb_to_mont_c(hinv(hmul(2, shift % BB_P))), ctx->stream, &ctx->launches);
+  if (!rc) rc = launch_map(d_out, d_out, h * 4, 0, ctx->stream, &ctx->launches);
+  CU(cudaStreamSynchronize(ctx->stream));
+  cudaFreeAsync(in_m, ctx->stream); cudaFreeAsync(b, ctx->stream);
+  RC(rc);
+  return 0;
+}
+
+int zkir_b200_dev_alloc(zkir_ctx* ctx, void** d_ptr, size_t bytes) {
+  if (!ctx || !d_ptr) return ZKIR_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  CU(cudaMalloc(d_ptr, bytes ? bytes : 16));
+  return 0;
+}
+int zkir_b200_dev_free(zkir_ctx* ctx, void* d_ptr) { if (!ctx) return ZKIR_ERR_ARG; cudaSetDevice(ctx->device); CU(cudaFree(d_ptr)); return 0; }
+int zkir_b200_h2d(zkir_ctx* ctx, void* d, const void* h, size_t bytes) {
+  if (!ctx) return ZKIR_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  CU(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+int zkir_b200_d2h(zkir_ctx* ctx, void* h, const void* d, size_t bytes) {
+  if (!ctx) return ZKIR_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  CU(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+int zkir_b200_sync(zkir_ctx* ctx) { if (!ctx) return ZKIR_ERR_ARG; cudaSetDevice(ctx->device); CU(cudaStreamSynchronize(ctx->stream)); return 0; }
+
+}  // extern "C"

@@ -1,0 +1,95 @@
+// AIR quotient sweep: one thread per row of the LDE coset evaluates every constraint of the core AIR v1
+// (air_generated.h, emitted by tools/gen_air.py -- the same list the CPU oracle and the verifier instantiate),
+// folds them with powers of alpha in ext4 and divides by the vanishing polynomial.  Column-major LDE so adjacent
+// threads read adjacent addresses; "next row" is row + blowup in natural order.
+//
+// The reference has no constraint system; the transition semantics encoded are those of
+// zkir-runtime/src/execute.rs and syscall.rs as cited in tools/gen_air.py.
+// Bound: HBM (reads 2 x 4*M*W bytes unless the +blowup row hits L2, writes 16*M).
+#include <cuda_runtime.h>
+#include "bb.cuh"
+#include "kernels.h"
+#include "air_generated.h"
+#include "constants_generated.h"
+
+namespace zkir {
+
+struct QCtx {
+  typedef Fm F;
+  const u32* lde; u64 M, row, nxt;
+  const u32* pv;       // shared
+  const E4* apow;      // shared, apow[i] = alpha^(K-1-i)
+  Fm is_first, is_last, is_trans;
+  E4 acc;
+  __device__ __forceinline__ Fm L(int i) const { return Fm(__ldg(lde + (u64)i * M + row)); }
+  __device__ __forceinline__ Fm N(int i) const { return Fm(__ldg(lde + (u64)i * M + nxt)); }
+  __device__ __forceinline__ Fm PV(int i) const { return Fm(pv[i]); }
+  __device__ __forceinline__ Fm K(u32 k) const { return Fm(bb_to_mont_c(k)); }
+  __device__ __forceinline__ void emit(int idx, Fm v) {
+    const E4 a = apow[idx];
+#pragma unroll
+    for (int k = 0; k < 4; k++) acc.c[k] = bb_add(acc.c[k], bb_mul(a.c[k], v.v));
+  }
+};
+
+__global__ void alpha_powers_kernel(const u32* alpha, E4* apow) {  // apow[i] = alpha^(K-1-i); one thread
+  E4 a; for (int k = 0; k < 4; k++) a.c[k] = alpha[k];
+  E4 cur = e4_one();
+  for (int i = ZKIR_AIR_NUM_CONSTRAINTS - 1; i >= 0; i--) { apow[i] = cur; cur = e4_mul(cur, a); }
+}
+
+__global__ void __launch_bounds__(128) quotient_kernel(QuotientArgs a, const E4* apow_g, u32 g_inv, u32 g, u32 snn /* shift^N */, u32 wb /* w_B */) {
+  __shared__ E4 apow[ZKIR_AIR_NUM_CONSTRAINTS];
+  __shared__ u32 pv[ZKIR_AIR_NUM_PUBLIC];
+  for (int i = threadIdx.x; i < ZKIR_AIR_NUM_CONSTRAINTS; i += blockDim.x) apow[i] = apow_g[i];
+  if (threadIdx.x < ZKIR_AIR_NUM_PUBLIC) pv[threadIdx.x] = a.pv[threadIdx.x];
+  __syncthreads();
+  const u64 M = 1ull << (a.log_n + a.log_blowup), B = 1ull << a.log_blowup;
+  const u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  QCtx c;
+  c.lde = a.lde; c.M = M; c.row = i; c.nxt = (i + B) & (M - 1); c.pv = pv; c.apow = apow;
+  const u32 x = a.xs[i];
+  // Z_H(x) = x^N - 1 = shift^N * w_B^(i mod B) - 1
+  const u32 zh = bb_sub(bb_mul(snn, bb_pow(wb, i & (B - 1))), BB_ONE);
+  c.is_first = Fm(bb_mul(zh, a.dinv[i]));                         // Z_H/(x-1)
+  c.is_last = Fm(bb_mul(zh, bb_mul(g, a.dinv[c.nxt])));  // Z_H/(x-g^-1) = Z_H*g/(g x-1), g*x_i = x_{i+B}
+  c.is_trans = Fm(bb_sub(x, g_inv));
+  c.acc = e4_zero();
+  zkir_air_eval(c);
+  const u32 zi = bb_inv(zh);
+#pragma unroll
+  for (int k = 0; k < 4; k++) a.q[(u64)k * M + i] = bb_mul(c.acc.c[k], zi);
+}
+
+__global__ void domain_tables_kernel(u32* xs, u32* dinv, u64 M, u32 shift, u32 w) {
+  u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  u32 x = bb_mul(shift, bb_pow(w, i));
+  xs[i] = x;
+  dinv[i] = bb_inv(bb_sub(x, BB_ONE));
+}
+
+static u32 hpow(u32 a, u64 e) { u64 r = 1, b = a; while (e) { if (e & 1) r = r * b % BB_P; b = b * b % BB_P; e >>= 1; } return (u32)r; }
+
+int launch_domain_tables(u32* xs, u32* dinv, u32 log_m, u32 shift_canon, cudaStream_t st, u64* launches) {
+  u64 M = 1ull << log_m;
+  domain_tables_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(xs, dinv, M, bb_to_mont_c(shift_canon), bb_to_mont_c(ZKIR_BB_ROOTS[log_m]));
+  (*launches)++;
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+int launch_quotient(const QuotientArgs& a, cudaStream_t st, u64* launches) {
+  const u64 M = 1ull << (a.log_n + a.log_blowup);
+  alpha_powers_kernel<<<1, 1, 0, st>>>(a.alpha, reinterpret_cast<E4*>(a.apow_scratch));
+  const u32 g = ZKIR_BB_ROOTS[a.log_n];
+  const u32 g_inv = hpow(g, BB_P - 2);
+  const u32 snn = hpow(ZKIR_BB_GEN, 1ull << a.log_n);
+  const u32 wb = ZKIR_BB_ROOTS[a.log_blowup];
+  quotient_kernel<<<(unsigned)((M + 127) / 128), 128, 0, st>>>(a, reinterpret_cast<const E4*>(a.apow_scratch), bb_to_mont_c(g_inv), bb_to_mont_c(g),
+                                                              bb_to_mont_c(snn), bb_to_mont_c(wb));
+  (*launches) += 2;
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+}  // namespace zkir

@@ -1,0 +1,213 @@
+// The remaining trace->proof kernels: out-of-domain openings, DEEP combination (the FRI input codeword), FRI
+// folding, query gathering and representation changes.  All field data is Montgomery form on the device; ext4
+// elements are stored AoS (16 B, uint4 loads).  No reference counterpart; the maths is
+// docs/PROVER_SPEC.md sections "Openings", "FRI" and "Queries".
+#include <cuda_runtime.h>
+#include "bb.cuh"
+#include "kernels.h"
+
+namespace zkir {
+
+static inline unsigned nblk(u64 n, unsigned t) { return (unsigned)((n + t - 1) / t); }
+#define CHECK_LAUNCH() (cudaGetLastError() == cudaSuccess ? 0 : -2)
+
+__global__ void map_kernel(u32* dst, const u32* src, u64 n, int to_mont) {
+  u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = to_mont ? bb_to_mont(src[i]) : bb_from_mont(src[i]);
+}
+int launch_map(u32* dst, const u32* src, u64 n, int to_mont, cudaStream_t st, u64* launches) {
+  if (!n) return 0;
+  map_kernel<<<nblk(n, 256), 256, 0, st>>>(dst, src, n, to_mont);
+  (*launches)++;
+  return CHECK_LAUNCH();
+}
+
+__device__ __forceinline__ E4 ld_e4(const E4* p) { uint4 v = *reinterpret_cast<const uint4*>(p); E4 r; r.c[0] = v.x; r.c[1] = v.y; r.c[2] = v.z; r.c[3] = v.w; return r; }
+__device__ __forceinline__ void st_e4(E4* p, E4 v) { *reinterpret_cast<uint4*>(p) = make_uint4(v.c[0], v.c[1], v.c[2], v.c[3]); }
+__device__ E4 e4_pow_dev(E4 a, u64 e) { E4 r = e4_one(); while (e) { if (e & 1) r = e4_mul(r, a); a = e4_mul(a, a); e >>= 1; } return r; }
+
+// out[j] = (base * mul)^j, j < n;  each thread owns 64 consecutive exponents
+#define EP_CHUNK 64
+__global__ void ext_powers_kernel(const u32* base_ext, u32 mul_const, E4* out, u64 n) {
+  u64 t = blockIdx.x * (u64)blockDim.x + threadIdx.x;
+  u64 j0 = t * EP_CHUNK;
+  if (j0 >= n) return;
+  E4 u; for (int k = 0; k < 4; k++) u.c[k] = bb_mul(base_ext[k], mul_const);
+  E4 cur = e4_pow_dev(u, j0);
+  for (u64 j = j0; j < n && j < j0 + EP_CHUNK; j++) { st_e4(out + j, cur); cur = e4_mul(cur, u); }
+}
+int launch_ext_powers(const u32* base_ext, const u32*, u32 mul_const, E4* out, u64 n, cudaStream_t st, u64* launches) {
+  ext_powers_kernel<<<nblk((n + EP_CHUNK - 1) / EP_CHUNK, 128), 128, 0, st>>>(base_ext, mul_const, out, n);
+  (*launches)++;
+  return CHECK_LAUNCH();
+}
+
+// ---- openings: out1[k] = sum_j coef[k][j]*U1[j], out2[k] = sum_j coef[k][j]*U2[j]
+#define OPEN_COLS 4
+#define OPEN_THREADS 256
+#define OPEN_RPT 16
+#define OPEN_CHUNK (OPEN_THREADS * OPEN_RPT)
+__global__ void __launch_bounds__(OPEN_THREADS) open_partial_kernel(const u32* __restrict__ coef, u64 col_stride, u32 n_cols, u64 n,
+                                                                   const E4* __restrict__ U1, const E4* __restrict__ U2,
+                                                                   E4* partial, u32 n_chunks) {
+  const u32 k0 = blockIdx.y * OPEN_COLS, chunk = blockIdx.x;
+  E4 a1[OPEN_COLS], a2[OPEN_COLS];
+#pragma unroll
+  for (int c = 0; c < OPEN_COLS; c++) { a1[c] = e4_zero(); a2[c] = e4_zero(); }
+  for (int r = 0; r < OPEN_RPT; r++) {
+    const u64 j = (u64)chunk * OPEN_CHUNK + (u64)r * OPEN_THREADS + threadIdx.x;
+    if (j >= n) break;
+    const E4 u1 = ld_e4(U1 + j), u2 = ld_e4(U2 + j);
+#pragma unroll
+    for (int c = 0; c < OPEN_COLS; c++) {
+      if (k0 + c < n_cols) {
+        const u32 v = __ldg(coef + (u64)(k0 + c) * col_stride + j);
+        a1[c] = e4_add(a1[c], e4_mulb(u1, v));
+        a2[c] = e4_add(a2[c], e4_mulb(u2, v));
+      }
+    }
+  }
+  __shared__ u32 red[OPEN_THREADS / 32][OPEN_COLS * 8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int c = 0; c < OPEN_COLS; c++) {
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      u32 x = a1[c].c[k], y = a2[c].c[k];
+      for (int o = 16; o > 0; o >>= 1) { x = bb_add(x, __shfl_xor_sync(0xffffffffu, x, o)); y = bb_add(y, __shfl_xor_sync(0xffffffffu, y, o)); }
+      if (lane == 0) { red[warp][c * 8 + k] = x; red[warp][c * 8 + 4 + k] = y; }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < OPEN_COLS * 8) {
+    u32 s = 0;
+    for (int w = 0; w < OPEN_THREADS / 32; w++) s = bb_add(s, red[w][threadIdx.x]);
+    const u32 c = threadIdx.x / 8, which = (threadIdx.x / 4) & 1, k = threadIdx.x & 3;
+    if (k0 + c < n_cols) partial[(((u64)which * n_cols + k0 + c) * n_chunks + chunk)].c[k] = s;
+  }
+}
+__global__ void open_final_kernel(const E4* partial, u32 n_cols, u32 n_chunks, E4* out1, E4* out2) {
+  // one warp per (which, column)
+  const u32 id = blockIdx.x;  // which * n_cols + k
+  E4 acc = e4_zero();
+  for (u32 c = threadIdx.x; c < n_chunks; c += 32) acc = e4_add(acc, ld_e4(partial + (u64)id * n_chunks + c));
+  for (int k = 0; k < 4; k++) {
+    u32 x = acc.c[k];
+    for (int o = 16; o > 0; o >>= 1) x = bb_add(x, __shfl_xor_sync(0xffffffffu, x, o));
+    acc.c[k] = x;
+  }
+  if (threadIdx.x == 0) { if (id < n_cols) st_e4(out1 + id, acc); else st_e4(out2 + (id - n_cols), acc); }
+}
+int launch_open(const u32* coef, u64 col_stride, u32 n_cols, u64 n, const E4* U1, const E4* U2, E4* out1, E4* out2,
+                E4* partial_scratch, cudaStream_t st, u64* launches) {
+  const u32 n_chunks = (u32)((n + OPEN_CHUNK - 1) / OPEN_CHUNK);
+  dim3 grid(n_chunks, (n_cols + OPEN_COLS - 1) / OPEN_COLS);
+  open_partial_kernel<<<grid, OPEN_THREADS, 0, st>>>(coef, col_stride, n_cols, n, U1, U2, partial_scratch, n_chunks);
+  open_final_kernel<<<2 * n_cols, 32, 0, st>>>(partial_scratch, n_cols, n_chunks, out1, out2);
+  (*launches) += 2;
+  return CHECK_LAUNCH();
+}
+u64 open_scratch_elems(u32 n_cols, u64 n) { return 2ull * n_cols * ((n + OPEN_CHUNK - 1) / OPEN_CHUNK); }
+
+// ---- DEEP combination
+// scratch layout: afp[0..width) = alpha^k, then [width+0]=A1, +1=A2, +2=A3, +3=alpha^W, +4=alpha^2W
+__global__ void deep_prep_kernel(DeepArgs a) {
+  const u32 W = a.width;
+  E4 al; for (int k = 0; k < 4; k++) al.c[k] = a.alpha_fri[k];
+  E4 cur = e4_one();
+  E4 A1 = e4_zero(), A2 = e4_zero(), A3 = e4_zero(), aW = e4_one(), a2W = e4_one();
+  for (u32 k = 0; k < 2 * W + 1; k++) {
+    if (k < W) {
+      a.afp_scratch[k] = cur;
+      A1 = e4_add(A1, e4_mul(cur, a.open_t[k]));
+      A2 = e4_add(A2, e4_mul(cur, a.open_tg[k]));
+      if (k < a.qwidth) A3 = e4_add(A3, e4_mul(cur, a.open_q[k]));
+    }
+    if (k == W) aW = cur;
+    if (k == 2 * W) a2W = cur;
+    cur = e4_mul(cur, al);
+  }
+  a.afp_scratch[W] = A1; a.afp_scratch[W + 1] = A2; a.afp_scratch[W + 2] = A3; a.afp_scratch[W + 3] = aW; a.afp_scratch[W + 4] = a2W;
+}
+__global__ void __launch_bounds__(128) deep_kernel(DeepArgs a) {
+  extern __shared__ E4 afp[];  // width + 5
+  for (u32 i = threadIdx.x; i < a.width + 5; i += blockDim.x) afp[i] = a.afp_scratch[i];
+  __syncthreads();
+  const u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x;
+  if (i >= a.M) return;
+  E4 rt = e4_zero(), rq = e4_zero();
+  for (u32 k = 0; k < a.width; k++) rt = e4_add(rt, e4_mulb(afp[k], __ldg(a.lde + (u64)k * a.M + i)));
+  for (u32 k = 0; k < a.qwidth; k++) rq = e4_add(rq, e4_mulb(afp[k], __ldg(a.qlde + (u64)k * a.M + i)));
+  const u32 W = a.width;
+  const u32 x = a.xs[i];
+  E4 z; for (int k = 0; k < 4; k++) z.c[k] = a.zeta[k];
+  E4 gz = e4_mulb(z, a.g_mont);
+  E4 dz = e4_sub(e4_from_base(x), z), dgz = e4_sub(e4_from_base(x), gz);
+  E4 iz = e4_inv(dz), igz = e4_inv(dgz);
+  E4 f = e4_mul(e4_sub(rt, afp[W]), iz);
+  f = e4_add(f, e4_mul(afp[W + 3], e4_mul(e4_sub(rt, afp[W + 1]), igz)));
+  f = e4_add(f, e4_mul(afp[W + 4], e4_mul(e4_sub(rq, afp[W + 2]), iz)));
+  st_e4(a.out + i, f);
+}
+int launch_deep(const DeepArgs& a, cudaStream_t st, u64* launches) {
+  deep_prep_kernel<<<1, 1, 0, st>>>(a);
+  deep_kernel<<<nblk(a.M, 128), 128, (a.width + 5) * sizeof(E4), st>>>(a);
+  (*launches) += 2;
+  return CHECK_LAUNCH();
+}
+
+// ---- FRI fold: out[i] = (f[i]+f[i+h])/2 + beta * (f[i]-f[i+h]) * c * w^-i,  c = 1/(2*shift_r)
+__global__ void __launch_bounds__(256) fri_fold_kernel(const E4* __restrict__ in, E4* __restrict__ out, u64 h, const u32* beta_dev,
+                                                      const u32* __restrict__ inv_w, u32 tw_stride, u32 c_mont) {
+  const u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x;
+  if (i >= h) return;
+  E4 beta; for (int k = 0; k < 4; k++) beta.c[k] = beta_dev[k];
+  const E4 a = ld_e4(in + i), b = ld_e4(in + i + h);
+  const u32 half = bb_to_mont_c((BB_P + 1) / 2);
+  E4 s = e4_mulb(e4_add(a, b), half);
+  E4 d = e4_mulb(e4_sub(a, b), bb_mul(c_mont, inv_w[i * tw_stride]));
+  st_e4(out + i, e4_add(s, e4_mul(beta, d)));
+}
+int launch_fri_fold(const E4* in, E4* out, u64 h, const u32* beta_dev, const u32* inv_w_table, u32 tw_stride, u32 c_mont,
+                    cudaStream_t st, u64* launches) {
+  fri_fold_kernel<<<nblk(h, 256), 256, 0, st>>>(in, out, h, beta_dev, inv_w_table, tw_stride, c_mont);
+  (*launches)++;
+  return CHECK_LAUNCH();
+}
+
+// ---- query gather: one block per query, everything copied into the proof at fixed offsets
+__device__ __forceinline__ void copy_path(const u32* tree, u64 n_leaves, u32 log_leaves, u64 idx, u32* out) {
+  for (u32 t = threadIdx.x; t < log_leaves * 8; t += blockDim.x) {
+    const u32 lvl = t >> 3, w = t & 7;
+    const u64 off = 2 * n_leaves - 2 * (n_leaves >> lvl);  // node offset of level lvl
+    out[t] = tree[(off + ((idx >> lvl) ^ 1)) * 8 + w];
+  }
+}
+__global__ void __launch_bounds__(128) query_kernel(QueryArgs a) {
+  const u32 qi = blockIdx.x;
+  const u64 M = 1ull << a.log_m;
+  const u64 q = a.indices[qi];
+  u32* out = a.out + (u64)qi * a.words_per_query;
+  for (u32 k = threadIdx.x; k < a.width; k += blockDim.x) out[k] = a.lde[(u64)k * M + q];
+  out += a.width;
+  copy_path(a.ttree, M, a.log_m, q, out); out += a.log_m * 8;
+  for (u32 k = threadIdx.x; k < 8; k += blockDim.x) out[k] = a.qlde[(u64)k * M + q];
+  out += 8;
+  copy_path(a.qtree, M, a.log_m, q, out); out += a.log_m * 8;
+  for (u32 r = 0; r < a.log_n; r++) {
+    const u64 h = (M >> r) / 2, i = q & (h - 1);
+    const u32* lay = reinterpret_cast<const u32*>(a.layers[r]);
+    if (threadIdx.x < 4) out[threadIdx.x] = lay[4 * i + threadIdx.x];
+    else if (threadIdx.x < 8) out[threadIdx.x] = lay[4 * (i + h) + threadIdx.x - 4];
+    out += 8;
+    copy_path(a.ltrees[r], h, a.log_m - 1 - r, i, out); out += (a.log_m - 1 - r) * 8;
+  }
+}
+int launch_queries(const QueryArgs& a, cudaStream_t st, u64* launches) {
+  if (!a.num_queries) return 0;
+  query_kernel<<<a.num_queries, 128, 0, st>>>(a);
+  (*launches)++;
+  return CHECK_LAUNCH();
+}
+
+}  // namespace zkir

@@ -1,0 +1,327 @@
+"""Host-side mirror of the reference's runtime interface for the Program -> Proof path.
+
+Same names and argument meaning as zkir-runtime's public API (zkir-runtime/src/lib.rs:29-62): `VMConfig`
+(vm.rs:15-50), `VM(program, inputs, config).run()` / `run(program, inputs)` returning an `ExecutionResult`
+(vm.rs:54-78), `HaltReason` (state.rs), plus the `prove()` the north star places next to `run()`.
+The interpreter is the C++ restatement behind the C ABI (zkir_b200/csrc/host/vm.cc); proving always goes to the
+CUDA library -- there is no CPU fallback here.
+"""
+import ctypes as C
+from dataclasses import dataclass, field
+import numpy as np
+from . import _ffi
+from .air_layout import WIDTH, NUM_PUBLIC
+
+P = 2013265921
+
+
+class RuntimeError_(Exception):
+    """zkir-runtime/src/error.rs:6-39 (`RuntimeError`); `.code` is the C ABI return value."""
+
+    def __init__(self, code, message):
+        super().__init__(message)
+        self.code = code
+
+
+@dataclass
+class VMConfig:  # vm.rs:15-50
+    max_cycles: int = 1_000_000
+    trace: bool = False
+    enable_range_checking: bool = False
+    enable_execution_trace: bool = False
+    enable_deferred_model: bool = False
+
+
+@dataclass
+class HaltReason:  # Exit(code) | Ebreak | CycleLimit
+    kind: str
+    code: int = 0
+
+    def __eq__(self, other):
+        return isinstance(other, HaltReason) and self.kind == other.kind and (self.kind != "Exit" or self.code == other.code)
+
+    @staticmethod
+    def Exit(code):
+        return HaltReason("Exit", code)
+
+
+HaltReason.Ebreak = HaltReason("Ebreak")
+HaltReason.CycleLimit = HaltReason("CycleLimit")
+_HALT = {0: "Exit", 1: "Ebreak", 2: "CycleLimit"}
+
+
+@dataclass
+class MemoryOp:  # zkir-spec/src/trace.rs:149-167
+    address: int
+    value: int
+    timestamp: int
+    is_write: bool
+    width: int
+
+
+@dataclass
+class TraceRow:  # zkir-spec/src/trace.rs:24-50 (bounds / register_states are host bookkeeping, not recorded)
+    cycle: int
+    pc: int
+    instruction: int
+    registers: list
+    memory_ops: list
+
+
+class ExecutionResult:  # vm.rs:54-78
+    def __init__(self, handle, entry_point):
+        self._h = handle
+        self._entry = entry_point
+        l = _ffi.lib()
+        self.cycles = l.zkir_vm_cycles(handle)
+        n = l.zkir_vm_num_outputs(handle)
+        self.outputs = [l.zkir_vm_outputs(handle)[i] for i in range(n)]
+        self.halt_reason = HaltReason(_HALT[l.zkir_vm_halt_kind(handle)], l.zkir_vm_exit_code(handle))
+        self.range_check_witnesses = []
+        self.normalization_witnesses = []
+        self._trace = None
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            _ffi.lib().zkir_vm_free(self._h)
+            self._h = None
+
+    @property
+    def trace_len(self):
+        return _ffi.lib().zkir_vm_trace_len(self._h)
+
+    @property
+    def execution_trace(self):
+        if self._trace is None:
+            l = _ffi.lib()
+            n = l.zkir_vm_trace_len(self._h)
+            pcs, ins, regs = l.zkir_vm_trace_pc(self._h), l.zkir_vm_trace_instr(self._h), l.zkir_vm_trace_regs(self._h)
+            beg, ops = l.zkir_vm_trace_memop_begin(self._h), l.zkir_vm_trace_memops(self._h)
+            rows = []
+            for i in range(n):
+                mops = [MemoryOp(ops[j].address, ops[j].value, ops[j].timestamp, bool(ops[j].is_write), ops[j].width)
+                        for j in range(beg[i], beg[i + 1])]
+                rows.append(TraceRow(i, pcs[i], ins[i], [regs[16 * i + k] for k in range(16)], mops))
+            self._trace = rows
+        return self._trace
+
+    def get_memory_trace(self):  # vm.rs:85-94, order trace.rs:210-223
+        ops = [op for row in self.execution_trace for op in row.memory_ops]
+        return sorted(ops, key=lambda o: (o.timestamp, o.address, o.is_write))
+
+    def memory_op_count(self):
+        return sum(len(r.memory_ops) for r in self.execution_trace)
+
+    # ---- trace -> columns ("converter", trace.rs:41)
+    def min_log_n(self):
+        return _ffi.lib().zkir_pack_min_log_n(self._h)
+
+    def pack(self, log_n=None, out=None):
+        """-> (cols[WIDTH][1<<log_n] uint32, public_values[4] uint32).  `out` may be a pinned buffer view."""
+        l = _ffi.lib()
+        if log_n is None:
+            log_n = self.min_log_n()
+        cols = out if out is not None else np.empty((WIDTH, 1 << log_n), dtype=np.uint32)
+        assert cols.dtype == np.uint32 and cols.shape == (WIDTH, 1 << log_n) and cols.flags["C_CONTIGUOUS"]
+        pv = np.zeros(NUM_PUBLIC, dtype=np.uint32)
+        rc = l.zkir_pack_trace(self._h, self._entry, log_n, cols.ctypes.data, pv.ctypes.data_as(_ffi.u32p))
+        if rc != 0:
+            raise RuntimeError_(rc, l.zkir_b200_last_error(None).decode())
+        return cols, pv
+
+
+class VM:  # vm.rs:104-205
+    def __init__(self, program, inputs=(), config=None):
+        if program.entry_point < 0x1000:  # vm.rs:141-147 panics
+            raise RuntimeError_(_ffi.ERR_ARG, f"Program appears to be in debug format (entry_point={program.entry_point:#x})")
+        self.program, self.inputs, self.config = program, list(inputs), config or VMConfig()
+
+    def run(self):
+        l = _ffi.lib()
+        code = (C.c_uint32 * max(1, len(self.program.code)))(*self.program.code)
+        data = (C.c_uint8 * max(1, len(self.program.data)))(*self.program.data)
+        inp = (C.c_uint64 * max(1, len(self.inputs)))(*[v & (2**64 - 1) for v in self.inputs])
+        h = C.c_void_p()
+        rc = l.zkir_vm_run(code, len(self.program.code), data, len(self.program.data), self.program.entry_point,
+                           inp, len(self.inputs), self.config.max_cycles, int(self.config.enable_execution_trace), C.byref(h))
+        if rc != 0:
+            raise RuntimeError_(rc, l.zkir_vm_last_error().decode())
+        return ExecutionResult(h, self.program.entry_point)
+
+
+def run(program, inputs=()):  # zkir-runtime/src/lib.rs:59-62
+    return VM(program, inputs, VMConfig()).run()
+
+
+# ------------------------------------------------------------------------------------------------ proving
+@dataclass
+class ProverConfig:
+    log_blowup: int = 1
+    num_queries: int = 100
+    pow_bits: int = 16
+    max_cycles: int = (1 << 24) + 16
+    device: int = 0
+
+    def params(self):
+        return _ffi.Params(self.log_blowup, self.num_queries, self.pow_bits, WIDTH, NUM_PUBLIC)
+
+
+@dataclass
+class Proof:
+    bytes_: bytes
+    public_values: np.ndarray
+    log_n: int
+    cycles: int
+    outputs: list = field(default_factory=list)
+    stage_ms: dict = field(default_factory=dict)
+
+
+class Context:
+    """One zkir_ctx (one GPU).  Raises if the CUDA library or a B200 is missing."""
+
+    def __init__(self, device=0):
+        self._l = _ffi.lib()
+        self._h = C.c_void_p()
+        rc = self._l.zkir_b200_create(C.byref(self._h), device)
+        if rc != 0:
+            raise RuntimeError_(rc, "zkir_b200_create: " + self._l.zkir_b200_last_error(None).decode())
+
+    def close(self):
+        if self._h:
+            self._l.zkir_b200_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    def _check(self, rc):
+        if rc != 0:
+            raise RuntimeError_(rc, self._l.zkir_b200_last_error(self._h).decode())
+
+    # -- device memory helpers
+    def alloc(self, nbytes):
+        p = C.c_void_p()
+        self._check(self._l.zkir_b200_dev_alloc(self._h, C.byref(p), nbytes))
+        return p
+
+    def free(self, p):
+        self._check(self._l.zkir_b200_dev_free(self._h, p))
+
+    def to_device(self, arr):
+        arr = np.ascontiguousarray(arr)
+        p = self.alloc(arr.nbytes)
+        self._check(self._l.zkir_b200_h2d(self._h, p, arr.ctypes.data, arr.nbytes))
+        return p
+
+    def to_host(self, p, shape, dtype=np.uint32):
+        out = np.empty(shape, dtype=dtype)
+        self._check(self._l.zkir_b200_d2h(self._h, out.ctypes.data, p, out.nbytes))
+        return out
+
+    def sync(self):
+        self._check(self._l.zkir_b200_sync(self._h))
+
+    @property
+    def kernel_launches(self):
+        return self._l.zkir_b200_kernel_launches(self._h)
+
+    def stage_ms(self):
+        out = (C.c_float * len(_ffi.STAGES))()
+        self._check(self._l.zkir_b200_last_stage_ms(self._h, out))
+        return dict(zip(_ffi.STAGES, list(out)))
+
+    # -- hot path
+    def prove_columns(self, cols, public_values, cfg, device_resident=None):
+        """cols: host uint32 [WIDTH][2^log_n] (or `device_resident`: a device pointer with the same layout)."""
+        params = cfg.params()
+        pv = np.ascontiguousarray(public_values, dtype=np.uint32)
+        proof, plen = C.c_void_p(), C.c_size_t()
+        if device_resident is not None:
+            ptr, log_n = device_resident
+            rc = self._l.zkir_b200_prove_device(self._h, C.byref(params), ptr, log_n, pv.ctypes.data_as(_ffi.u32p), C.byref(proof), C.byref(plen))
+        else:
+            assert cols.dtype == np.uint32 and cols.flags["C_CONTIGUOUS"] and cols.shape[0] == WIDTH
+            log_n = int(cols.shape[1]).bit_length() - 1
+            assert cols.shape[1] == 1 << log_n
+            rc = self._l.zkir_b200_prove(self._h, C.byref(params), cols.ctypes.data, log_n, pv.ctypes.data_as(_ffi.u32p), C.byref(proof), C.byref(plen))
+        self._check(rc)
+        out = C.string_at(proof, plen.value)
+        self._l.zkir_b200_free_proof(proof)
+        return out
+
+    # -- per-kernel entry points (device pointers)
+    def ntt(self, d_cols, n_cols, log_n, inverse=False, coset_shift=0):
+        self._check(self._l.zkir_b200_ntt(self._h, d_cols, n_cols, log_n, int(inverse), coset_shift))
+
+    def lde(self, d_in, d_out, n_cols, log_n, log_blowup):
+        self._check(self._l.zkir_b200_lde(self._h, d_in, d_out, n_cols, log_n, log_blowup))
+
+    def poseidon2_permute(self, d_states, n):
+        self._check(self._l.zkir_b200_poseidon2_permute(self._h, d_states, n))
+
+    def merkle_commit(self, d_matrix, n_cols, log_rows, d_tree):
+        root = np.zeros(8, dtype=np.uint32)
+        self._check(self._l.zkir_b200_merkle_commit(self._h, d_matrix, n_cols, log_rows, d_tree, root.ctypes.data_as(_ffi.u32p)))
+        return root
+
+    def quotient(self, cfg, d_lde, log_n, public_values, alpha, d_q):
+        params = cfg.params()
+        pv = np.ascontiguousarray(public_values, dtype=np.uint32)
+        al = np.ascontiguousarray(alpha, dtype=np.uint32)
+        self._check(self._l.zkir_b200_quotient(self._h, C.byref(params), d_lde, log_n, pv.ctypes.data_as(_ffi.u32p), al.ctypes.data_as(_ffi.u32p), d_q))
+
+    def fri_fold(self, d_in, d_out, log_n, shift, beta):
+        b = np.ascontiguousarray(beta, dtype=np.uint32)
+        self._check(self._l.zkir_b200_fri_fold(self._h, d_in, d_out, log_n, shift, b.ctypes.data_as(_ffi.u32p)))
+
+
+class PinnedBuffer:
+    """uint32 matrix in page-locked host memory (zkir_b200_alloc_pinned) the interpreter's packer writes into."""
+
+    def __init__(self, shape):
+        self._l = _ffi.lib()
+        n = int(np.prod(shape)) * 4
+        self._p = self._l.zkir_b200_alloc_pinned(n)
+        if not self._p:
+            raise RuntimeError_(_ffi.ERR_OOM, "zkir_b200_alloc_pinned failed (needs a CUDA device)")
+        self.array = np.ctypeslib.as_array(C.cast(self._p, _ffi.u32p), shape=(int(np.prod(shape)),)).reshape(shape)
+
+    def close(self):
+        if self._p:
+            self.array = None
+            self._l.zkir_b200_free_pinned(self._p)
+            self._p = None
+
+    __del__ = close
+
+
+_default_ctx = {}
+
+
+def _ctx(device):
+    if device not in _default_ctx:
+        _default_ctx[device] = Context(device)
+    return _default_ctx[device]
+
+
+def prove(program, inputs=(), cfg=None):
+    """Program -> Proof: run the interpreter with trace recording, pack the rows into columns, prove on the GPU.
+    The drop-in the north star describes for `zkir_runtime::prove()` (absent upstream: lib.rs:29-62)."""
+    cfg = cfg or ProverConfig()
+    res = VM(program, inputs, VMConfig(max_cycles=cfg.max_cycles, enable_execution_trace=True)).run()
+    cols, pv = res.pack()
+    ctx = _ctx(cfg.device)
+    pb = ctx.prove_columns(cols, pv, cfg)
+    return Proof(pb, pv, int(cols.shape[1]).bit_length() - 1, res.cycles, res.outputs, ctx.stage_ms())
+
+
+def verify(proof, cfg=None, public_values=None):
+    """CPU verification through the C ABI; returns (ok, reason)."""
+    cfg = cfg or ProverConfig()
+    l = _ffi.lib()
+    pb = proof.bytes_ if isinstance(proof, Proof) else bytes(proof)
+    pv = public_values if public_values is not None else (proof.public_values if isinstance(proof, Proof) else None)
+    params = cfg.params()
+    buf = C.create_string_buffer(pb, len(pb))
+    pvp = np.ascontiguousarray(pv, dtype=np.uint32).ctypes.data_as(_ffi.u32p) if pv is not None else None
+    rc = l.zkir_b200_verify(C.byref(params), C.cast(buf, C.c_void_p), len(pb), pvp)
+    return rc == 0, ("" if rc == 0 else l.zkir_b200_last_error(None).decode())
