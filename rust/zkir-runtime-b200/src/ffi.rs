@@ -1,0 +1,41 @@
+//! Raw `extern "C"` view of include/zkir_b200.h (hot-path subset).  One line per C declaration.
+#![allow(non_camel_case_types)]
+use std::os::raw::{c_char, c_int, c_void};
+
+#[repr(C)]
+pub struct zkir_ctx {
+    _private: [u8; 0],
+}
+
+#[repr(C)]
+#[derive(Clone, Copy, Debug)]
+pub struct zkir_params {
+    pub log_blowup: u32,
+    pub num_queries: u32,
+    pub pow_bits: u32,
+    pub width: u32,
+    pub num_public: u32,
+}
+
+pub const ZKIR_OK: c_int = 0;
+pub const ZKIR_AIR_V1_WIDTH: u32 = 112;
+pub const ZKIR_AIR_V1_NUM_PUBLIC: u32 = 4;
+
+extern "C" {
+    pub fn zkir_b200_create(out: *mut *mut zkir_ctx, device_id: c_int) -> c_int;
+    pub fn zkir_b200_destroy(ctx: *mut zkir_ctx);
+    pub fn zkir_b200_last_error(ctx: *const zkir_ctx) -> *const c_char;
+    pub fn zkir_b200_alloc_pinned(bytes: usize) -> *mut c_void;
+    pub fn zkir_b200_free_pinned(p: *mut c_void);
+    pub fn zkir_b200_prove(
+        ctx: *mut zkir_ctx,
+        params: *const zkir_params,
+        trace_cols: *const u32, // [width][1 << log_n], column-major, canonical BabyBear values, host memory
+        log_n: u32,
+        public_values: *const u32,
+        proof: *mut *mut u8,
+        proof_len: *mut usize,
+    ) -> c_int;
+    pub fn zkir_b200_free_proof(p: *mut u8);
+    pub fn zkir_b200_verify(params: *const zkir_params, proof: *const u8, len: usize, public_values: *const u32) -> c_int;
+}
