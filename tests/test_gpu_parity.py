@@ -38,10 +38,26 @@ def test_ntt_roundtrip(gpu_ctx, log_n):
     assert np.array_equal(got, a)
 
 
-@pytest.mark.parametrize("log_n,log_b", [(2, 1), (6, 1), (10, 1), (10, 2), (12, 1), (15, 2), (18, 1)])
+@pytest.mark.parametrize("log_n", [8, 9, 14, 19])
+def test_coset_ntt_matches_oracle(gpu_ctx, oracle, log_n):
+    """forward NTT on the coset 31*H: scale by 31^j then transform (docs/PROVER_SPEC.md section 4 step 1)."""
+    rng = np.random.default_rng(300 + log_n)
+    a = rand_field(rng, (3, 1 << log_n))
+    d = gpu_ctx.to_device(a)
+    gpu_ctx.ntt(d, 3, log_n, inverse=False, coset_shift=31)
+    got = gpu_ctx.to_host(d, a.shape)
+    gpu_ctx.free(d)
+    pw = np.ones(1 << log_n, dtype=object)
+    for j in range(1, 1 << log_n):
+        pw[j] = pw[j - 1] * 31 % P
+    scaled = ((a.astype(object) * pw) % P).astype(np.uint32)
+    assert np.array_equal(got, oracle.ntt(scaled, False))
+
+
+@pytest.mark.parametrize("log_n,log_b", [(2, 1), (6, 1), (8, 1), (9, 3), (10, 1), (10, 2), (11, 4), (12, 1), (15, 2), (18, 1), (21, 1)])
 def test_lde_matches_oracle(gpu_ctx, oracle, log_n, log_b):
     rng = np.random.default_rng(50 + log_n)
-    n_cols = 5
+    n_cols = 5 if log_n < 20 else 2
     a = rand_field(rng, (n_cols, 1 << log_n))
     d_in = gpu_ctx.to_device(a)
     d_out = gpu_ctx.alloc(n_cols * (4 << (log_n + log_b)))

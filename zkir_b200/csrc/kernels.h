@@ -22,10 +22,27 @@ int ntt_run(NttTables* tb, const u32* d_in, u64 in_col_stride, u32* d_out, u64 o
             u32 n_cols, int log_n, bool inverse, int log_pad, const u32* in_scale, const u32* out_scale,
             u32 out_const_mont, bool use_out_const, cudaStream_t st);
 
+// ---- ntt_fast.cu (register radix-32 tiles, digit-reversed coefficients, coset-major LDE)
+struct FastNtt;
+struct FastPlan { int log_n, nd, d[4]; };   // digit bits, top to bottom in the memory position
+FastNtt* fast_ntt_create(cudaStream_t st, u64* launch_counter);
+void fast_ntt_destroy(FastNtt*);
+bool fast_plan(int log_n, FastPlan* out);   // false when log_n < 8 (callers use the generic path)
+u64 fast_plan_coef_index(const FastPlan& pl, u64 pos);
+int fast_intt(FastNtt* f, const FastPlan& pl, const u32* in, u64 in_col, u32* coef, u64 coef_col, u32 n_cols, u32 c0_canon,
+              const uint2* coef_tab, u32 split_log, u32 split_max, u32 split_extra, u32* split_out, u64 split_out_col, cudaStream_t st);
+int fast_coset_ntt(FastNtt* f, const FastPlan& pl, const u32* coef, u64 coef_col, u32* out, u64 out_col, u32 n_cols, u32 nz,
+                   u32 base_canon, u32 zroot_canon, u32 c0_canon, cudaStream_t st);
+int fast_ntt_natural(FastNtt* f, int log_n, bool inverse, u32 coset_shift, const u32* in, u64 in_col, u32* tmp, u32* out, u64 out_col,
+                     u32 n_cols, cudaStream_t st);
+int launch_coset_reorder(const u32* in, u32* out, u32 n_cols, u32 log_n, u32 log_b, int to_natural, cudaStream_t st, u64* launches);
+const uint2* fast_scale_table(FastNtt* f, const FastPlan& pl, u32 base_canon, u32 c0_canon);  // [N] pairs c0*base^k(pos)
+
 // ---- poseidon2.cu
 int poseidon2_init_constants();
 int launch_permute(u32* d_states, u64 n, bool canonical_io, cudaStream_t st, u64* launches);
-int launch_leaf_hash(const u32* mat, u64 col_stride, u32 n_cols, u64 n_rows, u32* digests, cudaStream_t st, u64* launches);
+// matrix rows are coset-major (kernels.h: see ntt_fast.cu), leaves natural; log_b = 0 for a natural-order matrix
+int launch_leaf_hash(const u32* mat, u64 col_stride, u32 n_cols, u64 n_rows, u32 log_b, u32* digests, cudaStream_t st, u64* launches);
 int launch_leaf_hash_pairs(const u32* layer, u64 h, u32* digests, cudaStream_t st, u64* launches);
 int launch_merkle_levels(u32* tree, u64 n_leaves, cudaStream_t st, u64* launches);
 int launch_challenger(ChalState* st_dev, const u32* in, u32 n_in, u32* out, u32 n_out, u32 bits, cudaStream_t st, u64* launches);
@@ -33,40 +50,42 @@ int launch_pow_grind(const ChalState* st_dev, u32 bits, u32* result, cudaStream_
 
 // ---- quotient.cu
 struct QuotientArgs {
-  const u32* lde;      // [width][M] Montgomery
-  u32* q;              // [4][M]
+  const u32* lde;      // [width][B][N] Montgomery, coset-major: row z*N+i is the point of natural index i*B+z
+  u32* q;              // [4][M], natural order
   u32 log_n, log_blowup;
   const u32* pv;       // device, num_public Montgomery values
   const u32* alpha;    // device, ext4 Montgomery
-  const u32* xs;       // [M] x_i = shift*w^i
-  const u32* dinv;     // [M] 1/(x_i - 1)
+  const u32* xs;       // [M] coset-major: x = shift*w^(i*B+z) at z*N+i
+  const u32* dinv;     // [M] 1/(x - 1), same order
   u32* apow_scratch;   // [K][4] device scratch for alpha powers
 };
 int launch_quotient(const QuotientArgs& a, cudaStream_t st, u64* launches);
-int launch_domain_tables(u32* xs, u32* dinv, u32 log_m, u32 shift_canon, cudaStream_t st, u64* launches);
+int launch_domain_tables(u32* xs, u32* dinv, u32 log_n, u32 log_b, u32 shift_canon, cudaStream_t st, u64* launches);
 
 // ---- stark.cu (openings, DEEP combination, FRI fold, queries, misc)
 int launch_map(u32* dst, const u32* src, u64 n, int to_mont, cudaStream_t st, u64* launches);
-int launch_ext_powers(const u32* base_ext, const u32* mul_base_dev, u32 mul_const, E4* out, u64 n, cudaStream_t st, u64* launches);
+// out[pos] = (base_ext * mul_const)^(k(pos)), k = coefficient index of memory position pos under `plan` (nd = 1: natural)
+int launch_ext_powers(const u32* base_ext, u32 mul_const, const FastPlan& plan, E4* out, cudaStream_t st, u64* launches);
 // out1[k] = sum_j coef[k][j]*U1[j], out2[k] = sum_j coef[k][j]*U2[j]
 int launch_open(const u32* coef, u64 col_stride, u32 n_cols, u64 n, const E4* U1, const E4* U2, E4* out1, E4* out2,
                 E4* partial_scratch, cudaStream_t st, u64* launches);
 struct DeepArgs {
-  const u32* lde; u64 M; u32 width;       // trace LDE [width][M]
-  const u32* qlde; u32 qwidth;            // quotient LDE [8][M]
-  const u32* xs;                          // [M]
+  const u32* lde; u64 M; u32 width;       // trace LDE [width][M], coset-major rows
+  const u32* qlde; u32 qwidth;            // quotient LDE [8][M], coset-major rows
+  u32 log_n, log_b;
+  const u32* xs;                          // [M] coset-major
   const u32* zeta; u32 g_mont;            // device ext4; generator of H_N (Montgomery)
   const u32* alpha_fri;                   // device ext4
   const E4* open_t; const E4* open_tg; const E4* open_q;  // device openings
   E4* afp_scratch;                        // [2*width+qwidth+3] scratch
-  E4* out;                                // [M]
+  E4* out;                                // [M], natural order
 };
 int launch_deep(const DeepArgs& a, cudaStream_t st, u64* launches);
 int launch_fri_fold(const E4* in, E4* out, u64 h, const u32* beta_dev, const u32* inv_w_table, u32 tw_stride, u32 c_mont,
                     cudaStream_t st, u64* launches);
 struct QueryArgs {
   const u32* indices;   // device [num_queries], canonical
-  u32 num_queries, log_m, width, log_n;
+  u32 num_queries, log_m, width, log_n;   // lde / qlde rows are coset-major, trees and layers natural
   const u32* lde; const u32* ttree;
   const u32* qlde; const u32* qtree;
   const E4* const* layers;        // device array [R] of layer pointers

@@ -90,8 +90,11 @@ __global__ void permute_kernel(u32* states, u64 n, int canonical_io) {
   for (int k = 0; k < 4; k++) p[k] = make_uint4(s[4 * k], s[4 * k + 1], s[4 * k + 2], s[4 * k + 3]);
 }
 
-// leaf i = overwrite-mode sponge (rate 8) over row i of a column-major matrix [n_cols][col_stride]
-__global__ void __launch_bounds__(128) leaf_hash_kernel(const u32* __restrict__ mat, u64 col_stride, u32 n_cols, u64 n_rows, u32* __restrict__ digests) {
+// leaf = overwrite-mode sponge (rate 8) over one memory row of a column-major matrix [n_cols][col_stride].
+// The matrix is coset-major (row r = z * 2^log_nc + i holds the LDE point of natural index i * 2^log_b + z), the tree is
+// in natural order: the digest of memory row r goes to leaf ((r mod 2^log_nc) << log_b) | (r >> log_nc).  log_b = 0: identity.
+__global__ void __launch_bounds__(128) leaf_hash_kernel(const u32* __restrict__ mat, u64 col_stride, u32 n_cols, u64 n_rows, u32 log_nc, u32 log_b,
+                                                        u32* __restrict__ digests) {
   u64 row = blockIdx.x * (u64)blockDim.x + threadIdx.x;
   if (row >= n_rows) return;
   u32 s[16];
@@ -109,7 +112,8 @@ __global__ void __launch_bounds__(128) leaf_hash_kernel(const u32* __restrict__ 
     for (int k = 0; k < 8; k++) if (c + k < n_cols) s[k] = __ldg(p + (u64)(c + k) * col_stride);
     poseidon2_permute(s);
   }
-  uint4* d = reinterpret_cast<uint4*>(digests + 8 * row);
+  const u64 leaf = ((row & ((1ull << log_nc) - 1)) << log_b) | (row >> log_nc);
+  uint4* d = reinterpret_cast<uint4*>(digests + 8 * leaf);
   d[0] = make_uint4(s[0], s[1], s[2], s[3]);
   d[1] = make_uint4(s[4], s[5], s[6], s[7]);
 }
@@ -163,8 +167,10 @@ int launch_permute(u32* d_states, u64 n, bool canonical_io, cudaStream_t st, u64
   (*launches)++;
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
-int launch_leaf_hash(const u32* mat, u64 col_stride, u32 n_cols, u64 n_rows, u32* digests, cudaStream_t st, u64* launches) {
-  leaf_hash_kernel<<<nblk(n_rows, 128), 128, 0, st>>>(mat, col_stride, n_cols, n_rows, digests);
+int launch_leaf_hash(const u32* mat, u64 col_stride, u32 n_cols, u64 n_rows, u32 log_b, u32* digests, cudaStream_t st, u64* launches) {
+  u32 log_rows = 0;
+  while ((1ull << log_rows) < n_rows) log_rows++;
+  leaf_hash_kernel<<<nblk(n_rows, 128), 128, 0, st>>>(mat, col_stride, n_cols, n_rows, log_rows - log_b, log_b, digests);
   (*launches)++;
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }

@@ -80,8 +80,10 @@ struct Workspace {
   std::vector<void*> allocs;
   u32 *trace = nullptr, *coef = nullptr, *lde = nullptr, *ttree = nullptr;
   u32 *q = nullptr, *qcoef = nullptr, *qlde = nullptr, *qtree = nullptr;
-  u32 *xs = nullptr, *dinv = nullptr, *qscale = nullptr;
-  E4 *U1 = nullptr, *U2 = nullptr, *open_scratch = nullptr, *dummy_open = nullptr;
+  u32 *xs = nullptr, *dinv = nullptr, *qscale = nullptr, *lde_nat = nullptr;
+  E4 *U1 = nullptr, *U2 = nullptr, *U1q = nullptr, *open_scratch = nullptr, *dummy_open = nullptr;
+  bool fast = false;            // register-tile NTT path (log_n >= 8): digit-reversed coefficients
+  FastPlan plan_n, plan_m, plan_chunk;
   E4* layers = nullptr;      // all FRI layers back to back: M + M/2 + ... + B
   u32* ltrees = nullptr;     // all layer trees back to back
   std::vector<E4*> h_layers; std::vector<u32*> h_ltrees;
@@ -99,9 +101,11 @@ struct zkir_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   NttTables* tables = nullptr;
+  FastNtt* fast = nullptr;
   u64 launches = 0;
   std::string err;
   u32* ntt_tmp = nullptr; u64 ntt_tmp_words = 0;
+  u32* scratch[2] = {nullptr, nullptr}; size_t scratch_bytes[2] = {0, 0};
   Workspace ws;
   cudaEvent_t ev[ZKIR_STAGE_COUNT + 1];
   float stage_ms[ZKIR_STAGE_COUNT] = {0};
@@ -138,6 +142,18 @@ static int ensure_ntt_tmp(zkir_ctx* ctx, u64 n) {
   return 0;
 }
 
+// persistent scratch for the per-kernel entry points (cudaMallocAsync would return the pool to the OS at every sync)
+static int ensure_scratch(zkir_ctx* ctx, int which, size_t bytes, u32** out) {
+  if (ctx->scratch_bytes[which] < bytes) {
+    if (ctx->scratch[which]) cudaFree(ctx->scratch[which]);
+    ctx->scratch[which] = nullptr; ctx->scratch_bytes[which] = 0;
+    CU(cudaMalloc(&ctx->scratch[which], bytes));
+    ctx->scratch_bytes[which] = bytes;
+  }
+  *out = ctx->scratch[which];
+  return 0;
+}
+
 static int ws_prepare(zkir_ctx* ctx, const zkir_params* p, u32 log_n) {
   Workspace& w = ctx->ws;
   if (w.valid && w.log_n == log_n && w.log_blowup == p->log_blowup && w.width == p->width && w.nq == p->num_queries) return 0;
@@ -147,11 +163,23 @@ static int ws_prepare(zkir_ctx* ctx, const zkir_params* p, u32 log_n) {
   const Layout L = make_layout(p, log_n);
   int rc;
 #define A(ptr, cnt) if ((rc = ws_alloc(ctx, &w.ptr, (cnt))) != 0) return rc;
+  // NTT path: the fast kernels need every digit of the three plans to span >= 16 lanes
+  w.fast = !getenv("ZKIR_FORCE_GENERIC_NTT") && fast_plan((int)log_n, &w.plan_n) && fast_plan((int)(log_n + p->log_blowup), &w.plan_m) &&
+           w.plan_m.d[w.plan_m.nd - 1] - (int)p->log_blowup >= 4;
+  if (w.fast) {
+    w.plan_chunk = w.plan_m;
+    w.plan_chunk.log_n = (int)log_n;
+    w.plan_chunk.d[w.plan_m.nd - 1] -= (int)p->log_blowup;
+  } else {
+    w.plan_n.log_n = (int)log_n; w.plan_n.nd = 1; w.plan_n.d[0] = (int)log_n; w.plan_n.d[1] = w.plan_n.d[2] = w.plan_n.d[3] = 0;
+    w.plan_chunk = w.plan_n;
+  }
   A(trace, W * N) A(coef, W * N) A(lde, W * M) A(ttree, (2 * M - 1) * 8)
   A(q, 4 * M) A(qlde, QW * M) A(qtree, (2 * M - 1) * 8)
-  if (p->log_blowup > 1) { A(qcoef, QW * N) }
-  A(xs, M) A(dinv, M) A(qscale, M)
-  A(U1, N) A(U2, N) A(open_scratch, open_scratch_elems((u32)W, N)) A(dummy_open, W)
+  A(qcoef, QW * N)
+  A(xs, M) A(dinv, M)
+  if (!w.fast) { A(qscale, M) A(lde_nat, W * M) }
+  A(U1, N) A(U2, N) A(U1q, N) A(open_scratch, open_scratch_elems((u32)W, N)) A(dummy_open, W)
   A(layers, 2 * M) A(ltrees, 2 * M * 8)
   A(d_layers, R + 1) A(d_ltrees, R + 1)
   A(chal, 1) A(chal_buf, 12 + 4 * R + 2 + 6 + p->num_public) A(indices, p->num_queries + 1)
@@ -170,8 +198,8 @@ static int ws_prepare(zkir_ctx* ctx, const zkir_params* p, u32 log_n) {
   }
   CU(cudaMemcpyAsync(w.d_layers, w.h_layers.data(), (R + 1) * sizeof(E4*), cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemcpyAsync(w.d_ltrees, w.h_ltrees.data(), (R + 1) * sizeof(u32*), cudaMemcpyHostToDevice, ctx->stream));
-  RC(launch_domain_tables(w.xs, w.dinv, log_n + p->log_blowup, ZKIR_BB_GEN, ctx->stream, &ctx->launches));
-  {  // quotient inverse-NTT output scale: qscale[j] = (1/M) * shift^(-N * floor(j/N))   (Montgomery)
+  RC(launch_domain_tables(w.xs, w.dinv, log_n, p->log_blowup, ZKIR_BB_GEN, ctx->stream, &ctx->launches));
+  if (!w.fast) {  // quotient inverse-NTT output scale: qscale[j] = (1/M) * shift^(-N * floor(j/N))   (Montgomery)
     std::vector<u32> h(M);
     const u32 minv = hinv((u32)(M % BB_P)), step = hinv(hpow(ZKIR_BB_GEN, N));
     u32 c = minv;
@@ -192,8 +220,8 @@ static int check_params(zkir_ctx* ctx, const zkir_params* p, u32 log_n) {
   return 0;
 }
 
-// the device part of a proof; trace already in ws.trace (canonical values)
-static int prove_resident(zkir_ctx* ctx, const zkir_params* p, u32 log_n, const u32* pv) {
+// the device part of a proof; `trace` = canonical column-major values already on the device
+static int prove_resident(zkir_ctx* ctx, const zkir_params* p, u32 log_n, const u32* pv, const u32* trace) {
   Workspace& w = ctx->ws;
   cudaStream_t st = ctx->stream;
   u64* LC = &ctx->launches;
@@ -201,7 +229,8 @@ static int prove_resident(zkir_ctx* ctx, const zkir_params* p, u32 log_n, const 
   const u32 log_m = log_n + p->log_blowup, R = log_n, np = p->num_public;
   const Layout L = make_layout(p, log_n);
   const u32 shift = ZKIR_BB_GEN;
-  RC(ensure_ntt_tmp(ctx, M));
+  const u32 B = 1u << p->log_blowup;
+  if (!w.fast) RC(ensure_ntt_tmp(ctx, M));
   u32* c_alpha = w.chal_buf, *c_zeta = w.chal_buf + 4, *c_afri = w.chal_buf + 8, *c_betas = w.chal_buf + 12;
   u32* c_pow_raw = w.chal_buf + 12 + 4 * R, *c_pow_sample = c_pow_raw + 1, *c_hdr = c_pow_raw + 2;
 
@@ -219,16 +248,27 @@ static int prove_resident(zkir_ctx* ctx, const zkir_params* p, u32 log_n, const 
 
   // ---- 1. LDE: iNTT (scale by shift^j/N and lift to Montgomery), zero-pad, forward NTT on the coset
   CU(cudaEventRecord(ctx->ev[ZKIR_STAGE_LDE], st));
-  {
-    const u32 c0 = hmul(hinv((u32)(N % BB_P)), (u32)((1ull << 32) % BB_P));  // R/N: the table carries one extra factor R
+  const u32 c0 = hmul(hinv((u32)(N % BB_P)), (u32)((1ull << 32) % BB_P));  // R/N: scales by 1/N and lifts to Montgomery form
+  if (w.fast) {
+    // column batches: the coefficients of a batch are still L2-resident when the coset transforms read them
+    u32 cb = 16;
+    const char* env = getenv("ZKIR_LDE_BATCH");
+    if (env && atoi(env) > 0) cb = (u32)atoi(env);
+    for (u32 k0 = 0; k0 < W; k0 += cb) {
+      const u32 nc = W - k0 < cb ? (u32)(W - k0) : cb;
+      RC(fast_intt(ctx->fast, w.plan_n, trace + (u64)k0 * N, N, w.coef + (u64)k0 * N, N, nc, c0, nullptr, 32, 0, 0, nullptr, 0, st));
+      RC(fast_coset_ntt(ctx->fast, w.plan_n, w.coef + (u64)k0 * N, N, w.lde + (u64)k0 * M, M, nc, B, shift, ZKIR_BB_ROOTS[log_m], 1u, st));
+    }
+  } else {
     const u32* sc = ntt_powers_table(ctx->tables, shift, c0, N);
     if (!sc) { ctx->err = "table alloc"; return ZKIR_ERR_OOM; }
-    RC(ntt_run(ctx->tables, w.trace, N, w.coef, N, ctx->ntt_tmp, ctx->ntt_tmp_words, (u32)W, log_n, true, 0, nullptr, sc, BB_ONE, false, st));
-    RC(ntt_run(ctx->tables, w.coef, N, w.lde, M, ctx->ntt_tmp, ctx->ntt_tmp_words, (u32)W, log_m, false, p->log_blowup, nullptr, nullptr, BB_ONE, false, st));
+    RC(ntt_run(ctx->tables, trace, N, w.coef, N, ctx->ntt_tmp, ctx->ntt_tmp_words, (u32)W, log_n, true, 0, nullptr, sc, BB_ONE, false, st));
+    RC(ntt_run(ctx->tables, w.coef, N, w.lde_nat, M, ctx->ntt_tmp, ctx->ntt_tmp_words, (u32)W, log_m, false, p->log_blowup, nullptr, nullptr, BB_ONE, false, st));
+    RC(launch_coset_reorder(w.lde_nat, w.lde, (u32)W, log_n, p->log_blowup, 0, st, LC));
   }
   // ---- 2. trace commitment
   CU(cudaEventRecord(ctx->ev[ZKIR_STAGE_TRACE_COMMIT], st));
-  RC(launch_leaf_hash(w.lde, M, (u32)W, M, w.ttree, st, LC));
+  RC(launch_leaf_hash(w.lde, M, (u32)W, M, p->log_blowup, w.ttree, st, LC));
   RC(launch_merkle_levels(w.ttree, M, st, LC));
   const u32* troot = w.ttree + (2 * M - 2) * 8;
   CU(cudaMemcpyAsync(w.proof + L.troot, troot, 32, cudaMemcpyDeviceToDevice, st));
@@ -243,15 +283,27 @@ static int prove_resident(zkir_ctx* ctx, const zkir_params* p, u32 log_n, const 
     RC(launch_quotient(qa, st, LC));
   }
   CU(cudaEventRecord(ctx->ev[ZKIR_STAGE_QUOTIENT_COMMIT], st));
-  // coefficients on the coset (in place), chunk c of plane k = words [k*M + c*N, +N)
-  RC(ntt_run(ctx->tables, w.q, M, w.q, M, ctx->ntt_tmp, ctx->ntt_tmp_words, 4, log_m, true, 0, nullptr, w.qscale, BB_ONE, false, st));
-  const u32* qcoef = w.q;
-  if (p->log_blowup > 1) {  // compact the two chunks of every plane: column 2k+c <- q[k*M + c*N ..]
-    CU(cudaMemcpy2DAsync(w.qcoef, 2 * N * 4, w.q, M * 4, 2 * N * 4, 4, cudaMemcpyDeviceToDevice, st));
-    qcoef = w.qcoef;
+  const u32* qcoef = w.qcoef;
+  if (w.fast) {
+    // inverse transform over the whole coset (digits of plan_m, in place on q), unshift by shift^-k, and let the last pass
+    // split the lowest digit into the two degree-<N chunks: column 2*plane + chunk of qcoef, digit-reversed under plan_chunk
+    const uint2* unshift = fast_scale_table(ctx->fast, w.plan_m, hinv(shift), 1u);
+    if (!unshift) { ctx->err = "table alloc"; return ZKIR_ERR_OOM; }
+    const u32 split_log = (u32)w.plan_chunk.d[w.plan_chunk.nd - 1];
+    RC(fast_intt(ctx->fast, w.plan_m, w.q, M, w.q, M, 4, hinv((u32)(M % BB_P)), unshift, split_log, 2, (u32)N, w.qcoef, 2 * N, st));
+    RC(fast_coset_ntt(ctx->fast, w.plan_chunk, w.qcoef, N, w.qlde, M, QW, B, shift, ZKIR_BB_ROOTS[log_m], 1u, st));
+  } else {
+    // coefficients on the coset (in place), chunk c of plane k = words [k*M + c*N, +N)
+    RC(ntt_run(ctx->tables, w.q, M, w.q, M, ctx->ntt_tmp, ctx->ntt_tmp_words, 4, log_m, true, 0, nullptr, w.qscale, BB_ONE, false, st));
+    if (p->log_blowup > 1) {  // compact the two chunks of every plane: column 2k+c <- q[k*M + c*N ..]
+      CU(cudaMemcpy2DAsync(w.qcoef, 2 * N * 4, w.q, M * 4, 2 * N * 4, 4, cudaMemcpyDeviceToDevice, st));
+    } else {
+      qcoef = w.q;
+    }
+    RC(ntt_run(ctx->tables, qcoef, N, w.lde_nat, M, ctx->ntt_tmp, ctx->ntt_tmp_words, QW, log_m, false, p->log_blowup, nullptr, nullptr, BB_ONE, false, st));
+    RC(launch_coset_reorder(w.lde_nat, w.qlde, QW, log_n, p->log_blowup, 0, st, LC));
   }
-  RC(ntt_run(ctx->tables, qcoef, N, w.qlde, M, ctx->ntt_tmp, ctx->ntt_tmp_words, QW, log_m, false, p->log_blowup, nullptr, nullptr, BB_ONE, false, st));
-  RC(launch_leaf_hash(w.qlde, M, QW, M, w.qtree, st, LC));
+  RC(launch_leaf_hash(w.qlde, M, QW, M, p->log_blowup, w.qtree, st, LC));
   RC(launch_merkle_levels(w.qtree, M, st, LC));
   const u32* qroot = w.qtree + (2 * M - 2) * 8;
   CU(cudaMemcpyAsync(w.proof + L.qroot, qroot, 32, cudaMemcpyDeviceToDevice, st));
@@ -259,17 +311,19 @@ static int prove_resident(zkir_ctx* ctx, const zkir_params* p, u32 log_n, const 
   // ---- 4. openings at zeta and g*zeta, evaluated on the shifted coefficients at zeta/shift
   CU(cudaEventRecord(ctx->ev[ZKIR_STAGE_OPENINGS], st));
   {
-    const u32 sinv = hinv(shift), g = ZKIR_BB_ROOTS[log_n];
-    RC(launch_ext_powers(c_zeta, nullptr, bb_to_mont_c(sinv), w.U1, N, st, LC));
-    RC(launch_ext_powers(c_zeta, nullptr, bb_to_mont_c(hmul(sinv, g)), w.U2, N, st, LC));
+    // fast path: plain coefficients, digit-reversed; generic path: coefficients pre-multiplied by shift^k, natural order
+    const u32 g = ZKIR_BB_ROOTS[log_n], um = w.fast ? 1u : hinv(shift);
+    RC(launch_ext_powers(c_zeta, bb_to_mont_c(um), w.plan_n, w.U1, st, LC));
+    RC(launch_ext_powers(c_zeta, bb_to_mont_c(hmul(um, g)), w.plan_n, w.U2, st, LC));
+    RC(launch_ext_powers(c_zeta, bb_to_mont_c(um), w.plan_chunk, w.U1q, st, LC));
     E4* ot = reinterpret_cast<E4*>(w.proof + L.open_t);
     E4* otg = reinterpret_cast<E4*>(w.proof + L.open_tg);
     E4* oq = reinterpret_cast<E4*>(w.proof + L.open_q);
     RC(launch_open(w.coef, N, (u32)W, N, w.U1, w.U2, ot, otg, w.open_scratch, st, LC));
-    RC(launch_open(qcoef, N, QW, N, w.U1, w.U1, oq, w.dummy_open, w.open_scratch, st, LC));
+    RC(launch_open(qcoef, N, QW, N, w.U1q, w.U1q, oq, w.dummy_open, w.open_scratch, st, LC));
     RC(launch_challenger(w.chal, w.proof + L.open_t, (u32)(2 * W + QW) * 4, c_afri, 4, 0, st, LC));
     DeepArgs da;
-    da.lde = w.lde; da.M = M; da.width = (u32)W; da.qlde = w.qlde; da.qwidth = QW; da.xs = w.xs; da.zeta = c_zeta;
+    da.lde = w.lde; da.M = M; da.width = (u32)W; da.qlde = w.qlde; da.qwidth = QW; da.log_n = log_n; da.log_b = p->log_blowup; da.xs = w.xs; da.zeta = c_zeta;
     da.g_mont = bb_to_mont_c(g); da.alpha_fri = c_afri; da.open_t = ot; da.open_tg = otg; da.open_q = oq; da.afp_scratch = w.afp;
     da.out = w.h_layers[0];
     RC(launch_deep(da, st, LC));
@@ -345,6 +399,7 @@ int zkir_b200_create(zkir_ctx** out, int device_id) {
   for (int i = 0; i <= ZKIR_STAGE_COUNT; i++) cudaEventCreate(&ctx->ev[i]);
   if (poseidon2_init_constants() != 0) { g_last_error = "constant upload failed"; delete ctx; return ZKIR_ERR_CUDA; }
   ctx->tables = ntt_tables_create(ctx->stream, &ctx->launches);
+  ctx->fast = fast_ntt_create(ctx->stream, &ctx->launches);
   *out = ctx;
   return 0;
 }
@@ -355,7 +410,9 @@ void zkir_b200_destroy(zkir_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   ws_free(ctx);
   if (ctx->ntt_tmp) cudaFree(ctx->ntt_tmp);
+  for (int i = 0; i < 2; i++) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
   ntt_tables_destroy(ctx->tables);
+  fast_ntt_destroy(ctx->fast);
   for (int i = 0; i <= ZKIR_STAGE_COUNT; i++) cudaEventDestroy(ctx->ev[i]);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -381,7 +438,7 @@ int zkir_b200_prove(zkir_ctx* ctx, const zkir_params* p, const uint32_t* trace_c
   if ((rc = ws_prepare(ctx, p, log_n)) != 0) return rc;
   CU(cudaEventRecord(ctx->ev[ZKIR_STAGE_H2D], ctx->stream));
   CU(cudaMemcpyAsync(ctx->ws.trace, trace_cols, ((size_t)p->width << log_n) * 4, cudaMemcpyHostToDevice, ctx->stream));
-  if ((rc = prove_resident(ctx, p, log_n, pv)) != 0) return rc;
+  if ((rc = prove_resident(ctx, p, log_n, pv, ctx->ws.trace)) != 0) return rc;
   return finish_proof(ctx, p, log_n, proof, proof_len);
 }
 
@@ -395,8 +452,7 @@ int zkir_b200_prove_device(zkir_ctx* ctx, const zkir_params* p, const uint32_t* 
   if (!d_trace || !pv || !proof || !proof_len) { ctx->err = "null argument"; return ZKIR_ERR_ARG; }
   if ((rc = ws_prepare(ctx, p, log_n)) != 0) return rc;
   CU(cudaEventRecord(ctx->ev[ZKIR_STAGE_H2D], ctx->stream));
-  CU(cudaMemcpyAsync(ctx->ws.trace, d_trace, ((size_t)p->width << log_n) * 4, cudaMemcpyDeviceToDevice, ctx->stream));
-  if ((rc = prove_resident(ctx, p, log_n, pv)) != 0) return rc;
+  if ((rc = prove_resident(ctx, p, log_n, pv, d_trace)) != 0) return rc;  // read in place: no pass writes the caller's matrix
   return finish_proof(ctx, p, log_n, proof, proof_len);
 }
 
@@ -423,6 +479,14 @@ int zkir_b200_ntt(zkir_ctx* ctx, uint32_t* d_cols, uint32_t n_cols, uint32_t log
   ctx->err.clear();
   cudaSetDevice(ctx->device);
   const u64 n = 1ull << log_n;
+  FastPlan fp;
+  if (!getenv("ZKIR_FORCE_GENERIC_NTT") && fast_plan((int)log_n, &fp) && fp.nd == 2) {
+    // register-tile kernels: pass A (strided, top digit) into a scratch matrix, pass B (rows, transposing store) back
+    u32* tmp = nullptr;
+    RC(ensure_scratch(ctx, 0, (size_t)n_cols * n * 4, &tmp));
+    RC(fast_ntt_natural(ctx->fast, (int)log_n, inverse != 0, coset_shift % BB_P, d_cols, n, tmp, d_cols, n, n_cols, ctx->stream));
+    return 0;
+  }
   RC(ensure_ntt_tmp(ctx, n));
   const u32* in_scale = nullptr;
   if (coset_shift) { in_scale = ntt_powers_table(ctx->tables, coset_shift % BB_P, 1, n); if (!in_scale) return ZKIR_ERR_OOM; }
@@ -437,6 +501,18 @@ int zkir_b200_lde(zkir_ctx* ctx, const uint32_t* d_in, uint32_t* d_out, uint32_t
   ctx->err.clear();
   cudaSetDevice(ctx->device);
   const u64 N = 1ull << log_n, M = N << log_blowup;
+  FastPlan fp;
+  if (!getenv("ZKIR_FORCE_GENERIC_NTT") && fast_plan((int)log_n, &fp)) {
+    // same kernels as the prover: digit-reversed coefficients, coset-major LDE, then reorder to the natural order this entry point documents
+    u32 *coef = nullptr, *cm = nullptr;
+    RC(ensure_scratch(ctx, 0, (size_t)n_cols * N * 4, &coef));
+    RC(ensure_scratch(ctx, 1, (size_t)n_cols * M * 4, &cm));
+    int frc = fast_intt(ctx->fast, fp, d_in, N, coef, N, n_cols, hinv((u32)(N % BB_P)), nullptr, 32, 0, 0, nullptr, 0, ctx->stream);
+    if (!frc) frc = fast_coset_ntt(ctx->fast, fp, coef, N, cm, M, n_cols, 1u << log_blowup, ZKIR_BB_GEN, ZKIR_BB_ROOTS[log_n + log_blowup], 1u, ctx->stream);
+    if (!frc) frc = launch_coset_reorder(cm, d_out, n_cols, log_n, log_blowup, 1, ctx->stream, &ctx->launches);
+    RC(frc);
+    return 0;
+  }
   RC(ensure_ntt_tmp(ctx, M));
   const u32* sc = ntt_powers_table(ctx->tables, ZKIR_BB_GEN, hinv((u32)(N % BB_P)), N);
   if (!sc) return ZKIR_ERR_OOM;
@@ -466,7 +542,7 @@ int zkir_b200_merkle_commit(zkir_ctx* ctx, const uint32_t* d_matrix, uint32_t n_
   u32* mont = nullptr;
   CU(cudaMallocAsync(&mont, (size_t)n_cols * rows * 4, ctx->stream));
   int rc = launch_map(mont, d_matrix, (u64)n_cols * rows, 1, ctx->stream, &ctx->launches);
-  if (!rc) rc = launch_leaf_hash(mont, rows, n_cols, rows, d_tree, ctx->stream, &ctx->launches);
+  if (!rc) rc = launch_leaf_hash(mont, rows, n_cols, rows, 0, d_tree, ctx->stream, &ctx->launches);
   if (!rc) rc = launch_merkle_levels(d_tree, rows, ctx->stream, &ctx->launches);
   if (!rc) rc = launch_map(d_tree, d_tree, (2 * rows - 1) * 8, 0, ctx->stream, &ctx->launches);
   cudaFreeAsync(mont, ctx->stream);
@@ -485,8 +561,9 @@ int zkir_b200_quotient(zkir_ctx* ctx, const zkir_params* p, const uint32_t* d_ld
   if (rc) return rc;
   const u32 log_m = log_n + p->log_blowup;
   const u64 M = 1ull << log_m;
-  u32 *lde_m = nullptr, *xs = nullptr, *dinv = nullptr, *small = nullptr;
+  u32 *lde_m = nullptr, *lde_cm = nullptr, *xs = nullptr, *dinv = nullptr, *small = nullptr;
   CU(cudaMallocAsync(&lde_m, (size_t)p->width * M * 4, ctx->stream));
+  CU(cudaMallocAsync(&lde_cm, (size_t)p->width * M * 4, ctx->stream));
   CU(cudaMallocAsync(&xs, M * 4, ctx->stream));
   CU(cudaMallocAsync(&dinv, M * 4, ctx->stream));
   CU(cudaMallocAsync(&small, (8 + 4 * ZKIR_AIR_NUM_CONSTRAINTS) * 4, ctx->stream));
@@ -495,14 +572,15 @@ int zkir_b200_quotient(zkir_ctx* ctx, const zkir_params* p, const uint32_t* d_ld
   for (int i = 0; i < 4; i++) h[4 + i] = bb_to_mont_c(alpha[i] % BB_P);
   CU(cudaMemcpyAsync(small, h, 32, cudaMemcpyHostToDevice, ctx->stream));
   rc = launch_map(lde_m, d_lde, (u64)p->width * M, 1, ctx->stream, &ctx->launches);
-  if (!rc) rc = launch_domain_tables(xs, dinv, log_m, ZKIR_BB_GEN, ctx->stream, &ctx->launches);
+  if (!rc) rc = launch_coset_reorder(lde_m, lde_cm, p->width, log_n, p->log_blowup, 0, ctx->stream, &ctx->launches);  // the kernel sweeps coset-major rows
+  if (!rc) rc = launch_domain_tables(xs, dinv, log_n, p->log_blowup, ZKIR_BB_GEN, ctx->stream, &ctx->launches);
   QuotientArgs qa;
-  qa.lde = lde_m; qa.q = d_q; qa.log_n = log_n; qa.log_blowup = p->log_blowup; qa.pv = small; qa.alpha = small + 4;
+  qa.lde = lde_cm; qa.q = d_q; qa.log_n = log_n; qa.log_blowup = p->log_blowup; qa.pv = small; qa.alpha = small + 4;
   qa.xs = xs; qa.dinv = dinv; qa.apow_scratch = small + 8;
   if (!rc) rc = launch_quotient(qa, ctx->stream, &ctx->launches);
   if (!rc) rc = launch_map(d_q, d_q, 4 * M, 0, ctx->stream, &ctx->launches);
   CU(cudaStreamSynchronize(ctx->stream));
-  cudaFreeAsync(lde_m, ctx->stream); cudaFreeAsync(xs, ctx->stream); cudaFreeAsync(dinv, ctx->stream); cudaFreeAsync(small, ctx->stream);
+  cudaFreeAsync(lde_m, ctx->stream); cudaFreeAsync(lde_cm, ctx->stream); cudaFreeAsync(xs, ctx->stream); cudaFreeAsync(dinv, ctx->stream); cudaFreeAsync(small, ctx->stream);
   RC(rc);
   return 0;
 }

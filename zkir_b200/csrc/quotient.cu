@@ -1,7 +1,7 @@
 // AIR quotient sweep: one thread per row of the LDE coset evaluates every constraint of the core AIR v1
 // (air_generated.h, emitted by tools/gen_air.py -- the same list the CPU oracle and the verifier instantiate),
 // folds them with powers of alpha in ext4 and divides by the vanishing polynomial.  Column-major LDE so adjacent
-// threads read adjacent addresses; "next row" is row + blowup in natural order.
+// threads read adjacent addresses; the LDE is coset-major, so "next row" (g*x) is simply the next memory row of the same coset.
 //
 // The reference has no constraint system; the transition semantics encoded are those of
 // zkir-runtime/src/execute.rs and syscall.rs as cited in tools/gen_air.py.
@@ -44,37 +44,41 @@ __global__ void __launch_bounds__(128) quotient_kernel(QuotientArgs a, const E4*
   for (int i = threadIdx.x; i < ZKIR_AIR_NUM_CONSTRAINTS; i += blockDim.x) apow[i] = apow_g[i];
   if (threadIdx.x < ZKIR_AIR_NUM_PUBLIC) pv[threadIdx.x] = a.pv[threadIdx.x];
   __syncthreads();
-  const u64 M = 1ull << (a.log_n + a.log_blowup), B = 1ull << a.log_blowup;
-  const u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x;
+  const u64 M = 1ull << (a.log_n + a.log_blowup), N = 1ull << a.log_n;
+  const u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x;  // memory row: coset z = i / N, point j = i % N, natural index j*B + z
   if (i >= M) return;
+  const u64 z = i >> a.log_n, j = i & (N - 1);
   QCtx c;
-  c.lde = a.lde; c.M = M; c.row = i; c.nxt = (i + B) & (M - 1); c.pv = pv; c.apow = apow;
+  c.lde = a.lde; c.M = M; c.row = i; c.nxt = (z << a.log_n) | ((j + 1) & (N - 1)); c.pv = pv; c.apow = apow;
   const u32 x = a.xs[i];
-  // Z_H(x) = x^N - 1 = shift^N * w_B^(i mod B) - 1
-  const u32 zh = bb_sub(bb_mul(snn, bb_pow(wb, i & (B - 1))), BB_ONE);
+  // Z_H(x) = x^N - 1 = shift^N * w_B^z - 1
+  const u32 zh = bb_sub(bb_mul(snn, bb_pow(wb, z)), BB_ONE);
   c.is_first = Fm(bb_mul(zh, a.dinv[i]));                         // Z_H/(x-1)
   c.is_last = Fm(bb_mul(zh, bb_mul(g, a.dinv[c.nxt])));  // Z_H/(x-g^-1) = Z_H*g/(g x-1), g*x_i = x_{i+B}
   c.is_trans = Fm(bb_sub(x, g_inv));
   c.acc = e4_zero();
   zkir_air_eval(c);
   const u32 zi = bb_inv(zh);
+  const u64 nat = (j << a.log_blowup) | z;
 #pragma unroll
-  for (int k = 0; k < 4; k++) a.q[(u64)k * M + i] = bb_mul(c.acc.c[k], zi);
+  for (int k = 0; k < 4; k++) a.q[(u64)k * M + nat] = bb_mul(c.acc.c[k], zi);
 }
 
-__global__ void domain_tables_kernel(u32* xs, u32* dinv, u64 M, u32 shift, u32 w) {
+__global__ void domain_tables_kernel(u32* xs, u32* dinv, u64 M, u32 log_n, u32 log_b, u32 shift, u32 w) {
   u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x;
   if (i >= M) return;
-  u32 x = bb_mul(shift, bb_pow(w, i));
+  const u64 nat = ((i & ((1ull << log_n) - 1)) << log_b) | (i >> log_n);
+  u32 x = bb_mul(shift, bb_pow(w, nat));
   xs[i] = x;
   dinv[i] = bb_inv(bb_sub(x, BB_ONE));
 }
 
 static u32 hpow(u32 a, u64 e) { u64 r = 1, b = a; while (e) { if (e & 1) r = r * b % BB_P; b = b * b % BB_P; e >>= 1; } return (u32)r; }
 
-int launch_domain_tables(u32* xs, u32* dinv, u32 log_m, u32 shift_canon, cudaStream_t st, u64* launches) {
+int launch_domain_tables(u32* xs, u32* dinv, u32 log_n, u32 log_b, u32 shift_canon, cudaStream_t st, u64* launches) {
+  const u32 log_m = log_n + log_b;
   u64 M = 1ull << log_m;
-  domain_tables_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(xs, dinv, M, bb_to_mont_c(shift_canon), bb_to_mont_c(ZKIR_BB_ROOTS[log_m]));
+  domain_tables_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(xs, dinv, M, log_n, log_b, bb_to_mont_c(shift_canon), bb_to_mont_c(ZKIR_BB_ROOTS[log_m]));
   (*launches)++;
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }

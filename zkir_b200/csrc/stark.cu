@@ -26,18 +26,34 @@ __device__ __forceinline__ E4 ld_e4(const E4* p) { uint4 v = *reinterpret_cast<c
 __device__ __forceinline__ void st_e4(E4* p, E4 v) { *reinterpret_cast<uint4*>(p) = make_uint4(v.c[0], v.c[1], v.c[2], v.c[3]); }
 __device__ E4 e4_pow_dev(E4 a, u64 e) { E4 r = e4_one(); while (e) { if (e & 1) r = e4_mul(r, a); a = e4_mul(a, a); e >>= 1; } return r; }
 
-// out[j] = (base * mul)^j, j < n;  each thread owns 64 consecutive exponents
+// out[pos] = (base * mul)^(k(pos)): k = coefficient index stored at memory position pos under the digit plan (the
+// coefficient vectors of ntt_fast.cu are digit-reversed; nd = 1 means natural order).  Each thread owns a run of
+// consecutive positions inside one row of the lowest digit, where k advances by 2^(sum of the upper digits).
 #define EP_CHUNK 64
-__global__ void ext_powers_kernel(const u32* base_ext, u32 mul_const, E4* out, u64 n) {
-  u64 t = blockIdx.x * (u64)blockDim.x + threadIdx.x;
-  u64 j0 = t * EP_CHUNK;
-  if (j0 >= n) return;
+__global__ void ext_powers_kernel(const u32* base_ext, u32 mul_const, FastPlan plan, u32 chunk, E4* out, u64 n) {
+  const u64 t = blockIdx.x * (u64)blockDim.x + threadIdx.x;
+  const u64 p0 = t * chunk;
+  if (p0 >= n) return;
   E4 u; for (int k = 0; k < 4; k++) u.c[k] = bb_mul(base_ext[k], mul_const);
-  E4 cur = e4_pow_dev(u, j0);
-  for (u64 j = j0; j < n && j < j0 + EP_CHUNK; j++) { st_e4(out + j, cur); cur = e4_mul(cur, u); }
+  // k(pos): digits top->bottom x_1..x_D, k = x_1 + 2^d1 x_2 + ...
+  int below = 0, upper = 0;
+  for (int j = 0; j < plan.nd; j++) below += plan.d[j];
+  for (int j = 0; j + 1 < plan.nd; j++) upper += plan.d[j];
+  u64 k0 = 0; int wshift = 0;
+  for (int j = 0; j < plan.nd; j++) {
+    below -= plan.d[j];
+    k0 |= ((p0 >> below) & ((1ull << plan.d[j]) - 1)) << wshift;
+    wshift += plan.d[j];
+  }
+  E4 cur = e4_pow_dev(u, k0);
+  const E4 step = e4_pow_dev(u, 1ull << upper);
+  for (u32 j = 0; j < chunk; j++) { st_e4(out + p0 + j, cur); cur = e4_mul(cur, step); }
 }
-int launch_ext_powers(const u32* base_ext, const u32*, u32 mul_const, E4* out, u64 n, cudaStream_t st, u64* launches) {
-  ext_powers_kernel<<<nblk((n + EP_CHUNK - 1) / EP_CHUNK, 128), 128, 0, st>>>(base_ext, mul_const, out, n);
+int launch_ext_powers(const u32* base_ext, u32 mul_const, const FastPlan& plan, E4* out, cudaStream_t st, u64* launches) {
+  const u64 n = 1ull << plan.log_n;
+  const u64 m = 1ull << plan.d[plan.nd - 1];
+  const u32 chunk = (u32)(m < EP_CHUNK ? m : EP_CHUNK);
+  ext_powers_kernel<<<nblk(n / chunk, 128), 128, 0, st>>>(base_ext, mul_const, plan, chunk, out, n);
   (*launches)++;
   return CHECK_LAUNCH();
 }
@@ -133,8 +149,9 @@ __global__ void __launch_bounds__(128) deep_kernel(DeepArgs a) {
   extern __shared__ E4 afp[];  // width + 5
   for (u32 i = threadIdx.x; i < a.width + 5; i += blockDim.x) afp[i] = a.afp_scratch[i];
   __syncthreads();
-  const u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x;
+  const u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x;  // memory row (coset-major)
   if (i >= a.M) return;
+  const u64 nat = ((i & ((1ull << a.log_n) - 1)) << a.log_b) | (i >> a.log_n);
   E4 rt = e4_zero(), rq = e4_zero();
   for (u32 k = 0; k < a.width; k++) rt = e4_add(rt, e4_mulb(afp[k], __ldg(a.lde + (u64)k * a.M + i)));
   for (u32 k = 0; k < a.qwidth; k++) rq = e4_add(rq, e4_mulb(afp[k], __ldg(a.qlde + (u64)k * a.M + i)));
@@ -147,7 +164,7 @@ __global__ void __launch_bounds__(128) deep_kernel(DeepArgs a) {
   E4 f = e4_mul(e4_sub(rt, afp[W]), iz);
   f = e4_add(f, e4_mul(afp[W + 3], e4_mul(e4_sub(rt, afp[W + 1]), igz)));
   f = e4_add(f, e4_mul(afp[W + 4], e4_mul(e4_sub(rq, afp[W + 2]), iz)));
-  st_e4(a.out + i, f);
+  st_e4(a.out + nat, f);
 }
 int launch_deep(const DeepArgs& a, cudaStream_t st, u64* launches) {
   deep_prep_kernel<<<1, 1, 0, st>>>(a);
@@ -187,11 +204,13 @@ __global__ void __launch_bounds__(128) query_kernel(QueryArgs a) {
   const u32 qi = blockIdx.x;
   const u64 M = 1ull << a.log_m;
   const u64 q = a.indices[qi];
+  const u32 log_b = a.log_m - a.log_n;
+  const u64 qrow = ((q & ((1ull << log_b) - 1)) << a.log_n) | (q >> log_b);  // memory row of natural index q
   u32* out = a.out + (u64)qi * a.words_per_query;
-  for (u32 k = threadIdx.x; k < a.width; k += blockDim.x) out[k] = a.lde[(u64)k * M + q];
+  for (u32 k = threadIdx.x; k < a.width; k += blockDim.x) out[k] = a.lde[(u64)k * M + qrow];
   out += a.width;
   copy_path(a.ttree, M, a.log_m, q, out); out += a.log_m * 8;
-  for (u32 k = threadIdx.x; k < 8; k += blockDim.x) out[k] = a.qlde[(u64)k * M + q];
+  for (u32 k = threadIdx.x; k < 8; k += blockDim.x) out[k] = a.qlde[(u64)k * M + qrow];
   out += 8;
   copy_path(a.qtree, M, a.log_m, q, out); out += a.log_m * 8;
   for (u32 r = 0; r < a.log_n; r++) {
