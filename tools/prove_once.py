@@ -1,0 +1,22 @@
+#!/usr/bin/env python3
+"""Profiling driver: build the 2^20-row fibonacci trace once, prove it `reps` times from device memory."""
+import sys, os, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+import zkir_b200
+from conftest import fib_trace
+
+reps = int(sys.argv[1]) if len(sys.argv) > 1 else 3
+n = int(sys.argv[2]) if len(sys.argv) > 2 else 209715
+res, cols, pv = fib_trace(n_input=n)
+log_n = int(cols.shape[1]).bit_length() - 1
+ctx = zkir_b200.Context(0)
+cfg = zkir_b200.ProverConfig()
+d = ctx.to_device(cols)
+for i in range(reps):
+    t0 = time.perf_counter()
+    pb = ctx.prove_columns(None, pv, cfg, device_resident=(d, log_n))
+    dt = (time.perf_counter() - t0) * 1e3
+    print(f"proof {i}: {dt:.2f} ms wall, stages {ctx.stage_ms()}")
+ok, why = zkir_b200.verify(pb, cfg, pv)
+print("verify", ok, why)

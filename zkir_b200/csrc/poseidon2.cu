@@ -141,24 +141,6 @@ __global__ void __launch_bounds__(128) compress_kernel(const uint4* __restrict__
   out[2 * i] = make_uint4(s[0], s[1], s[2], s[3]);
   out[2 * i + 1] = make_uint4(s[4], s[5], s[6], s[7]);
 }
-// the top of a tree in one block: levels from n_in (<= 2048 nodes) down to the root, synchronising in-block
-__global__ void __launch_bounds__(1024) compress_tail_kernel(uint4* tree_level, u64 n_in) {
-  uint4* in = tree_level;
-  for (u64 n = n_in; n > 1; n >>= 1) {
-    uint4* out = in + 2 * n;
-    for (u64 i = threadIdx.x; i < n / 2; i += blockDim.x) {
-      u32 s[16];
-#pragma unroll
-      for (int k = 0; k < 4; k++) { uint4 v = in[4 * i + k]; s[4 * k] = v.x; s[4 * k + 1] = v.y; s[4 * k + 2] = v.z; s[4 * k + 3] = v.w; }
-      poseidon2_permute(s);
-      out[2 * i] = make_uint4(s[0], s[1], s[2], s[3]);
-      out[2 * i + 1] = make_uint4(s[4], s[5], s[6], s[7]);
-    }
-    __syncthreads();
-    in = out;
-  }
-}
-
 static inline unsigned nblk(u64 n, unsigned t) { return (unsigned)((n + t - 1) / t); }
 
 int launch_permute(u32* d_states, u64 n, bool canonical_io, cudaStream_t st, u64* launches) {
@@ -179,18 +161,35 @@ int launch_leaf_hash_pairs(const u32* layer, u64 h, u32* digests, cudaStream_t s
   (*launches)++;
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
-// tree: level 0 = n_leaves digests already in place; builds the upper levels behind it
-int launch_merkle_levels(u32* tree, u64 n_leaves, cudaStream_t st, u64* launches) {
+#define COOP_THREADS 1024
+#define COOP_CHUNK 256
+__global__ void merkle_coop_kernel(const u32* __restrict__ level, u64 n_in, u32 chunk, ChalState* chal, u32* root_dst, u32* sample_out, u32 n_sample);
+__global__ void challenger_kernel(ChalState* st, const u32* in, u32 n_in, u32* out, u32 n_out, u32 bits);
+// tree: level 0 = n_leaves digests already in place; builds the upper levels behind it.  Wide levels: one thread per
+// compression (throughput); from 32768 nodes down: the cooperative kernel (latency).  If `chal` is given, the launch that
+// produces the root also copies it to root_dst, observes it and samples n_sample elements into sample_out.
+int launch_merkle_levels(u32* tree, u64 n_leaves, cudaStream_t st, u64* launches, ChalState* chal, u32* root_dst, u32* sample_out, u32 n_sample) {
   u32* lvl = tree;
   u64 n = n_leaves;
-  while (n > 2048) {
+  while (n > 32768) {
     u32* nxt = lvl + n * 8;
     compress_kernel<<<nblk(n / 2, 128), 128, 0, st>>>(reinterpret_cast<const uint4*>(lvl), reinterpret_cast<uint4*>(nxt), n / 2);
     (*launches)++;
     lvl = nxt; n >>= 1;
   }
-  if (n > 1) {
-    compress_tail_kernel<<<1, 1024, 0, st>>>(reinterpret_cast<uint4*>(lvl), n);
+  bool chal_done = false;
+  while (n > 1) {
+    const u32 chunk = n < COOP_CHUNK ? (u32)n : COOP_CHUNK;
+    const u32 blocks = (u32)(n / chunk);
+    const bool last = blocks == 1;
+    merkle_coop_kernel<<<blocks, COOP_THREADS, 0, st>>>(lvl, n, chunk, last ? chal : nullptr, root_dst, sample_out, n_sample);
+    (*launches)++;
+    if (last && chal) chal_done = true;
+    for (u32 c = chunk; c > 1; c >>= 1) { lvl += n * 8; n >>= 1; }
+  }
+  if (chal && !chal_done) {  // single-leaf tree: the leaf is the root
+    if (root_dst) cudaMemcpyAsync(root_dst, lvl, 32, cudaMemcpyDeviceToDevice, st);
+    challenger_kernel<<<1, 32, 0, st>>>(chal, lvl, 8, sample_out, n_sample, 0);
     (*launches)++;
   }
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
@@ -224,10 +223,9 @@ __device__ __forceinline__ u32 permute_warp(u32 x, int lane) {
   return x;
 }
 
-// observe n_in field elements (Montgomery) then sample n_out; bits > 0: outputs are canonical integers masked to
-// `bits` bits (query indices / PoW check), else Montgomery field elements.  One warp.
-__global__ void __launch_bounds__(32) challenger_kernel(ChalState* st, const u32* in, u32 n_in, u32* out, u32 n_out, u32 bits) {
-  const int lane = threadIdx.x;
+// observe n_in field elements (Montgomery) then sample n_out;  bits > 0: outputs are canonical integers masked to
+// `bits` bits (query indices / PoW check), else Montgomery field elements.  One full warp must call this.
+__device__ __forceinline__ void challenger_step(ChalState* st, const u32* in, u32 n_in, u32* out, u32 n_out, u32 bits, int lane) {
   u32 x = lane < 16 ? st->sponge[lane] : 0;
   u32 nin = st->n_in, nout = st->n_out;
   u32 inb = lane < 8 ? st->inbuf[lane] : 0;    // lane k < 8 holds input buffer slot k
@@ -253,9 +251,52 @@ __global__ void __launch_bounds__(32) challenger_kernel(ChalState* st, const u32
     if (bits) { v = bb_from_mont(v); if (bits < 32) v &= (1u << bits) - 1; }
     if (lane == 0) out[i] = v;
   }
+  __syncwarp();
   if (lane < 16) st->sponge[lane] = x;
   if (lane < 8) { st->inbuf[lane] = inb; st->outbuf[lane] = outb; }
   if (lane == 0) { st->n_in = nin; st->n_out = nout; }
+}
+__global__ void __launch_bounds__(32) challenger_kernel(ChalState* st, const u32* in, u32 n_in, u32* out, u32 n_out, u32 bits) {
+  challenger_step(st, in, n_in, out, n_out, bits, threadIdx.x);
+}
+
+// Upper part of a Merkle tree, latency-oriented: 16 lanes cooperate on one compression (permute_warp), a block of 1024
+// threads owns `chunk` <= 256 consecutive nodes of the input level and climbs log2(chunk) levels through shared memory,
+// writing every level to the global tree (authentication paths need them).  A thread-per-permutation level costs one
+// full permutation latency (~9 us) however small it is; this kernel costs ~3 us per level.
+// When the block reaches the root (single block), warp 0 can also run the Fiat-Shamir step that always follows:
+// copy the root into the proof, observe it, sample `n_sample` field elements.
+__global__ void __launch_bounds__(COOP_THREADS) merkle_coop_kernel(const u32* __restrict__ level, u64 n_in, u32 chunk, ChalState* chal,
+                                                                   u32* root_dst, u32* sample_out, u32 n_sample) {
+  __shared__ u32 buf[2][COOP_CHUNK * 8];
+  const u32 tid = threadIdx.x, lane = tid & 31, l16 = tid & 15, slot = tid >> 4;
+  const u32* src = level + (u64)blockIdx.x * chunk * 8;
+  for (u32 i = tid; i < chunk * 8; i += COOP_THREADS) buf[0][i] = src[i];
+  __syncthreads();
+  u32 cur = 0, n = chunk;
+  u64 level_n = n_in;
+  u32* out_base = const_cast<u32*>(level) + n_in * 8;
+  while (n > 1) {
+    const u32 n_out = n >> 1;
+    for (u32 s0 = 0; s0 < n_out; s0 += COOP_THREADS / 16) {   // warp-uniform trip count
+      const u32 sidx = s0 + slot;
+      const bool active = sidx < n_out;
+      u32 x = active ? buf[cur][16 * sidx + l16] : 0u;
+      x = permute_warp(x, lane);
+      if (active && l16 < 8) {
+        buf[cur ^ 1][8 * sidx + l16] = x;
+        out_base[((u64)blockIdx.x * n_out + sidx) * 8 + l16] = x;
+      }
+    }
+    __syncthreads();
+    cur ^= 1; n = n_out;
+    level_n >>= 1;
+    out_base += level_n * 8;
+  }
+  if (chal != nullptr && gridDim.x == 1 && tid < 32) {
+    if (root_dst && lane < 8) root_dst[lane] = buf[cur][lane];
+    challenger_step(chal, buf[cur], 8, sample_out, n_sample, 0, lane);
+  }
 }
 
 // proof of work: smallest canonical w such that, after observe(w), sample_bits(bits) == 0.

@@ -269,11 +269,8 @@ static int prove_resident(zkir_ctx* ctx, const zkir_params* p, u32 log_n, const 
   // ---- 2. trace commitment
   CU(cudaEventRecord(ctx->ev[ZKIR_STAGE_TRACE_COMMIT], st));
   RC(launch_leaf_hash(w.lde, M, (u32)W, M, p->log_blowup, w.ttree, st, LC));
-  RC(launch_merkle_levels(w.ttree, M, st, LC));
-  const u32* troot = w.ttree + (2 * M - 2) * 8;
-  CU(cudaMemcpyAsync(w.proof + L.troot, troot, 32, cudaMemcpyDeviceToDevice, st));
   RC(launch_challenger(w.chal, c_hdr, 6 + np, nullptr, 0, 0, st, LC));
-  RC(launch_challenger(w.chal, troot, 8, c_alpha, 4, 0, st, LC));
+  RC(launch_merkle_levels(w.ttree, M, st, LC, w.chal, w.proof + L.troot, c_alpha, 4));  // root -> proof, observe, sample alpha
   // ---- 3. quotient
   CU(cudaEventRecord(ctx->ev[ZKIR_STAGE_QUOTIENT], st));
   {
@@ -304,10 +301,7 @@ static int prove_resident(zkir_ctx* ctx, const zkir_params* p, u32 log_n, const 
     RC(launch_coset_reorder(w.lde_nat, w.qlde, QW, log_n, p->log_blowup, 0, st, LC));
   }
   RC(launch_leaf_hash(w.qlde, M, QW, M, p->log_blowup, w.qtree, st, LC));
-  RC(launch_merkle_levels(w.qtree, M, st, LC));
-  const u32* qroot = w.qtree + (2 * M - 2) * 8;
-  CU(cudaMemcpyAsync(w.proof + L.qroot, qroot, 32, cudaMemcpyDeviceToDevice, st));
-  RC(launch_challenger(w.chal, qroot, 8, c_zeta, 4, 0, st, LC));
+  RC(launch_merkle_levels(w.qtree, M, st, LC, w.chal, w.proof + L.qroot, c_zeta, 4));  // root -> proof, observe, sample zeta
   // ---- 4. openings at zeta and g*zeta, evaluated on the shifted coefficients at zeta/shift
   CU(cudaEventRecord(ctx->ev[ZKIR_STAGE_OPENINGS], st));
   {
@@ -337,10 +331,7 @@ static int prove_resident(zkir_ctx* ctx, const zkir_params* p, u32 log_n, const 
     for (u32 r = 0; r < R; r++) {
       const u64 h = (M >> r) / 2;
       RC(launch_leaf_hash_pairs(reinterpret_cast<const u32*>(w.h_layers[r]), h, w.h_ltrees[r], st, LC));
-      RC(launch_merkle_levels(w.h_ltrees[r], h, st, LC));
-      const u32* root = w.h_ltrees[r] + (2 * h - 2) * 8;
-      CU(cudaMemcpyAsync(w.proof + L.fri_roots + 8 * r, root, 32, cudaMemcpyDeviceToDevice, st));
-      RC(launch_challenger(w.chal, root, 8, c_betas + 4 * r, 4, 0, st, LC));
+      RC(launch_merkle_levels(w.h_ltrees[r], h, st, LC, w.chal, w.proof + L.fri_roots + 8 * r, c_betas + 4 * r, 4));  // + observe root, sample beta_r
       const u32 c = hinv(hmul(2, lshift));
       RC(launch_fri_fold(w.h_layers[r], w.h_layers[r + 1], h, c_betas + 4 * r, inv_w, 1u << r, bb_to_mont_c(c), st, LC));
       lshift = hmul(lshift, lshift);
