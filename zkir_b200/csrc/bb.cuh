@@ -55,6 +55,28 @@ BB_HD u32 bb_pow(u32 a, u64 e) {
 }
 BB_HD u32 bb_inv(u32 a) { return bb_pow(a, BB_P - 2); }
 
+// a/2
+BB_HD u32 bb_halve(u32 a) { return (a >> 1) + ((a & 1u) ? (BB_P + 1) / 2 : 0u); }
+
+// ---- compile-time helpers on canonical values, and Shoup multiplication by a constant
+constexpr u32 c_mul(u32 a, u32 b) { return (u32)(((u64)a * b) % BB_P); }
+constexpr u32 c_pow(u32 a, u64 e) {
+  u32 r = 1;
+  while (e) { if (e & 1) r = c_mul(r, a); a = c_mul(a, a); e >>= 1; }
+  return r;
+}
+constexpr u32 c_shoup(u32 w) { return (u32)((((u64)w) << 32) / BB_P); }  // floor(w * 2^32 / p)
+#ifdef __CUDACC__
+// x * w mod p for a constant w (canonical) with wq = c_shoup(w); x may be ANY u32 (canonical or Montgomery
+// representative, reduced or not); result in [0, p).  mul.hi + 2 mul.lo: 4 issue slots of the integer-multiply pipe
+// against 5 for a Montgomery product (profiles/r01_microbench_b200.txt).
+__device__ __forceinline__ u32 shoup_mul(u32 x, u32 w, u32 wq) {
+  const u32 q = __umulhi(x, wq);
+  const u32 r = x * w - q * BB_P;  // in [0, 2p)
+  return min(r, r - BB_P);
+}
+#endif
+
 // wrapper with operators, used to instantiate the generated AIR
 struct Fm {
   u32 v;

@@ -30,23 +30,9 @@
 namespace zkir {
 
 // ---------------------------------------------------------------- compile-time field helpers (canonical values)
-constexpr u32 c_mul(u32 a, u32 b) { return (u32)(((u64)a * b) % BB_P); }
-constexpr u32 c_pow(u32 a, u64 e) {
-  u32 r = 1;
-  while (e) { if (e & 1) r = c_mul(r, a); a = c_mul(a, a); e >>= 1; }
-  return r;
-}
 constexpr u32 C_G27 = 0x1a427a41u;  // generator of the 2^27 subgroup, 31^15
 constexpr u32 c_root(int k) { return c_pow(C_G27, 1ull << (27 - k)); }  // == ZKIR_BB_ROOTS[k]
-constexpr u32 c_shoup(u32 w) { return (u32)((((u64)w) << 32) / BB_P); }
 static_assert(c_root(1) == BB_P - 1 && c_root(2) == 1728404513u, "root chain must match ZKIR_BB_ROOTS");
-
-// x * w mod p for a constant w with precomputed wq = floor(w * 2^32 / p); x may be any u32; result in [0, p)
-__device__ __forceinline__ u32 shoup_mul(u32 x, u32 w, u32 wq) {
-  const u32 q = __umulhi(x, wq);
-  const u32 r = x * w - q * BB_P;  // in [0, 2p)
-  return min(r, r - BB_P);
-}
 
 // ---------------------------------------------------------------- register DIF, compile-time twiddles
 template <int A, bool INV, int S, int I>

@@ -24,6 +24,12 @@ int poseidon2_init_constants() {
   if (cudaMemcpyToSymbol(c_rc_int, h, sizeof(u32) * ZKIR_P2_RP) != cudaSuccess) return -2;
   for (int i = 0; i < 16; i++) h[i] = bb_to_mont_c(ZKIR_P2_DIAG[i]);
   if (cudaMemcpyToSymbol(c_diag, h, sizeof(u32) * 16) != cudaSuccess) return -2;
+  // internal_linear() hard-codes the structure of the diagonal: refuse to run if the generated constants ever change
+  const u32 half = (BB_P + 1) / 2;
+  auto hp = [](u32 a, u32 e) { u64 r = 1, b = a; while (e) { if (e & 1) r = r * b % BB_P; b = b * b % BB_P; e >>= 1; } return (u32)r; };
+  const u32 want[16] = {BB_P - 2, 1, 2, half, 3, 4, BB_P - half, BB_P - 3, BB_P - 4, hp(half, 8), hp(half, 2), hp(half, 3), hp(half, 27),
+                        BB_P - hp(half, 8), BB_P - hp(half, 4), BB_P - hp(half, 27)};
+  for (int i = 0; i < 16; i++) if (ZKIR_P2_DIAG[i] != want[i]) return -2;
   return 0;
 }
 
@@ -51,6 +57,39 @@ __device__ __forceinline__ void external_linear(u32* s) {
 #pragma unroll
   for (int i = 0; i < 16; i++) s[i] = bb_add(s[i], sums[i & 3]);
 }
+// s[i] <- V[i]*s[i] + sum(s) with the frozen diagonal V = [-2, 1, 2, 1/2, 3, 4, -1/2, -3, -4, 2^-8, 1/4, 1/8, 2^-27,
+// -2^-8, -1/16, -2^-27] (docs/PROVER_SPEC.md section 2; poseidon2_init_constants() checks the generated header against it).
+// The nine small entries are additions / halvings (no integer-multiply pipe work), the other seven are Shoup products
+// by compile-time constants; the values stay Montgomery representatives throughout (the map is linear).
+constexpr u32 C_HALF = (BB_P + 1) / 2;
+constexpr u32 C_DIAG_TAIL[7] = {c_pow(C_HALF, 8), c_pow(C_HALF, 2), c_pow(C_HALF, 3), c_pow(C_HALF, 27),
+                                BB_P - c_pow(C_HALF, 8), BB_P - c_pow(C_HALF, 4), BB_P - c_pow(C_HALF, 27)};
+template <int I>
+__device__ __forceinline__ u32 diag_tail_mul(u32 x) {
+  constexpr u32 w = C_DIAG_TAIL[I], wq = c_shoup(w);
+  return shoup_mul(x, w, wq);
+}
+__device__ __forceinline__ void internal_linear(u32* s) {
+  u32 sum = s[0];
+#pragma unroll
+  for (int i = 1; i < 16; i++) sum = bb_add(sum, s[i]);
+  s[0] = bb_sub(sum, bb_dbl(s[0]));
+  s[1] = bb_add(s[1], sum);
+  s[2] = bb_add(bb_dbl(s[2]), sum);
+  s[3] = bb_add(bb_halve(s[3]), sum);
+  s[4] = bb_add(bb_add(bb_dbl(s[4]), s[4]), sum);
+  s[5] = bb_add(bb_dbl(bb_dbl(s[5])), sum);
+  s[6] = bb_sub(sum, bb_halve(s[6]));
+  s[7] = bb_sub(sum, bb_add(bb_dbl(s[7]), s[7]));
+  s[8] = bb_sub(sum, bb_dbl(bb_dbl(s[8])));
+  s[9] = bb_add(diag_tail_mul<0>(s[9]), sum);
+  s[10] = bb_add(diag_tail_mul<1>(s[10]), sum);
+  s[11] = bb_add(diag_tail_mul<2>(s[11]), sum);
+  s[12] = bb_add(diag_tail_mul<3>(s[12]), sum);
+  s[13] = bb_add(diag_tail_mul<4>(s[13]), sum);
+  s[14] = bb_add(diag_tail_mul<5>(s[14]), sum);
+  s[15] = bb_add(diag_tail_mul<6>(s[15]), sum);
+}
 __device__ __forceinline__ void poseidon2_permute(u32* s) {
   external_linear(s);
 #pragma unroll 1
@@ -62,11 +101,7 @@ __device__ __forceinline__ void poseidon2_permute(u32* s) {
 #pragma unroll 1
   for (int r = 0; r < ZKIR_P2_RP; r++) {
     s[0] = sbox7(bb_add(s[0], c_rc_int[r]));
-    u32 sum = s[0];
-#pragma unroll
-    for (int i = 1; i < 16; i++) sum = bb_add(sum, s[i]);
-#pragma unroll
-    for (int i = 0; i < 16; i++) s[i] = bb_add(bb_mul(s[i], c_diag[i]), sum);
+    internal_linear(s);
   }
 #pragma unroll 1
   for (int r = 4; r < 8; r++) {
@@ -280,6 +315,7 @@ __global__ void __launch_bounds__(COOP_THREADS) merkle_coop_kernel(const u32* __
     const u32 n_out = n >> 1;
     for (u32 s0 = 0; s0 < n_out; s0 += COOP_THREADS / 16) {   // warp-uniform trip count
       const u32 sidx = s0 + slot;
+      if (s0 + (tid >> 5) * 2 >= n_out) break;  // neither half of this warp has a node: warp-uniform exit
       const bool active = sidx < n_out;
       u32 x = active ? buf[cur][16 * sidx + l16] : 0u;
       x = permute_warp(x, lane);

@@ -32,10 +32,13 @@ struct QCtx {
   }
 };
 
-__global__ void alpha_powers_kernel(const u32* alpha, E4* apow) {  // apow[i] = alpha^(K-1-i); one thread
+__global__ void alpha_powers_kernel(const u32* alpha, E4* apow) {  // apow[i] = alpha^(K-1-i); thread per power
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ZKIR_AIR_NUM_CONSTRAINTS) return;
   E4 a; for (int k = 0; k < 4; k++) a.c[k] = alpha[k];
-  E4 cur = e4_one();
-  for (int i = ZKIR_AIR_NUM_CONSTRAINTS - 1; i >= 0; i--) { apow[i] = cur; cur = e4_mul(cur, a); }
+  E4 r = e4_one();
+  for (u32 e = ZKIR_AIR_NUM_CONSTRAINTS - 1 - i; e; e >>= 1) { if (e & 1) r = e4_mul(r, a); a = e4_mul(a, a); }
+  apow[i] = r;
 }
 
 __global__ void __launch_bounds__(128) quotient_kernel(QuotientArgs a, const E4* apow_g, u32 g_inv, u32 g, u32 snn /* shift^N */, u32 wb /* w_B */) {
@@ -85,7 +88,7 @@ int launch_domain_tables(u32* xs, u32* dinv, u32 log_n, u32 log_b, u32 shift_can
 
 int launch_quotient(const QuotientArgs& a, cudaStream_t st, u64* launches) {
   const u64 M = 1ull << (a.log_n + a.log_blowup);
-  alpha_powers_kernel<<<1, 1, 0, st>>>(a.alpha, reinterpret_cast<E4*>(a.apow_scratch));
+  alpha_powers_kernel<<<(ZKIR_AIR_NUM_CONSTRAINTS + 63) / 64, 64, 0, st>>>(a.alpha, reinterpret_cast<E4*>(a.apow_scratch));
   const u32 g = ZKIR_BB_ROOTS[a.log_n];
   const u32 g_inv = hpow(g, BB_P - 2);
   const u32 snn = hpow(ZKIR_BB_GEN, 1ull << a.log_n);

@@ -127,23 +127,28 @@ u64 open_scratch_elems(u32 n_cols, u64 n) { return 2ull * n_cols * ((n + OPEN_CH
 
 // ---- DEEP combination
 // scratch layout: afp[0..width) = alpha^k, then [width+0]=A1, +1=A2, +2=A3, +3=alpha^W, +4=alpha^2W
-__global__ void deep_prep_kernel(DeepArgs a) {
-  const u32 W = a.width;
+__global__ void __launch_bounds__(128) deep_prep_kernel(DeepArgs a) {
+  // one block: thread k owns alpha^k (square-and-multiply) and its three products; exact field sums, any order
+  __shared__ E4 r1[128], r2[128], r3[128];
+  const u32 W = a.width, t = threadIdx.x;
   E4 al; for (int k = 0; k < 4; k++) al.c[k] = a.alpha_fri[k];
-  E4 cur = e4_one();
-  E4 A1 = e4_zero(), A2 = e4_zero(), A3 = e4_zero(), aW = e4_one(), a2W = e4_one();
-  for (u32 k = 0; k < 2 * W + 1; k++) {
-    if (k < W) {
-      a.afp_scratch[k] = cur;
-      A1 = e4_add(A1, e4_mul(cur, a.open_t[k]));
-      A2 = e4_add(A2, e4_mul(cur, a.open_tg[k]));
-      if (k < a.qwidth) A3 = e4_add(A3, e4_mul(cur, a.open_q[k]));
-    }
-    if (k == W) aW = cur;
-    if (k == 2 * W) a2W = cur;
-    cur = e4_mul(cur, al);
+  E4 s1 = e4_zero(), s2 = e4_zero(), s3 = e4_zero();
+  for (u32 k = t; k < W; k += blockDim.x) {
+    const E4 pw = e4_pow_dev(al, k);
+    a.afp_scratch[k] = pw;
+    s1 = e4_add(s1, e4_mul(pw, a.open_t[k]));
+    s2 = e4_add(s2, e4_mul(pw, a.open_tg[k]));
+    if (k < a.qwidth) s3 = e4_add(s3, e4_mul(pw, a.open_q[k]));
   }
-  a.afp_scratch[W] = A1; a.afp_scratch[W + 1] = A2; a.afp_scratch[W + 2] = A3; a.afp_scratch[W + 3] = aW; a.afp_scratch[W + 4] = a2W;
+  r1[t] = s1; r2[t] = s2; r3[t] = s3;
+  __syncthreads();
+  for (u32 h = blockDim.x / 2; h > 0; h >>= 1) {
+    if (t < h) { r1[t] = e4_add(r1[t], r1[t + h]); r2[t] = e4_add(r2[t], r2[t + h]); r3[t] = e4_add(r3[t], r3[t + h]); }
+    __syncthreads();
+  }
+  if (t == 0) { a.afp_scratch[W] = r1[0]; a.afp_scratch[W + 1] = r2[0]; a.afp_scratch[W + 2] = r3[0]; }
+  if (t == 1) a.afp_scratch[W + 3] = e4_pow_dev(al, W);
+  if (t == 2) a.afp_scratch[W + 4] = e4_pow_dev(al, 2ull * W);
 }
 __global__ void __launch_bounds__(128) deep_kernel(DeepArgs a) {
   extern __shared__ E4 afp[];  // width + 5
@@ -167,7 +172,7 @@ __global__ void __launch_bounds__(128) deep_kernel(DeepArgs a) {
   st_e4(a.out + nat, f);
 }
 int launch_deep(const DeepArgs& a, cudaStream_t st, u64* launches) {
-  deep_prep_kernel<<<1, 1, 0, st>>>(a);
+  deep_prep_kernel<<<1, 128, 0, st>>>(a);
   deep_kernel<<<nblk(a.M, 128), 128, (a.width + 5) * sizeof(E4), st>>>(a);
   (*launches) += 2;
   return CHECK_LAUNCH();
