@@ -250,8 +250,8 @@ static int prove_resident(zkir_ctx* ctx, const zkir_params* p, u32 log_n, const 
   CU(cudaEventRecord(ctx->ev[ZKIR_STAGE_LDE], st));
   const u32 c0 = hmul(hinv((u32)(N % BB_P)), (u32)((1ull << 32) % BB_P));  // R/N: scales by 1/N and lifts to Montgomery form
   if (w.fast) {
-    // column batches: the coefficients of a batch are still L2-resident when the coset transforms read them
-    u32 cb = 16;
+    // column batches (ZKIR_LDE_BATCH) are possible, one batch = all columns by default
+    u32 cb = (u32)W;  // measured: the passes are integer-pipe bound, larger launches win over L2 residency
     const char* env = getenv("ZKIR_LDE_BATCH");
     if (env && atoi(env) > 0) cb = (u32)atoi(env);
     for (u32 k0 = 0; k0 < W; k0 += cb) {

@@ -7,6 +7,7 @@
 // zkir-runtime/src/execute.rs and syscall.rs as cited in tools/gen_air.py.
 // Bound: HBM (reads 2 x 4*M*W bytes unless the +blowup row hits L2, writes 16*M).
 #include <cuda_runtime.h>
+#include <stdlib.h>
 #include "bb.cuh"
 #include "kernels.h"
 #include "air_generated.h"
@@ -20,15 +21,14 @@ struct QCtx {
   const u32* pv;       // shared
   const E4* apow;      // shared, apow[i] = alpha^(K-1-i)
   Fm is_first, is_last, is_trans;
-  E4 acc;
+  Acc4 acc;  // lazy 64-bit accumulator of sum_i alpha^(K-1-i) * C_i (bb.cuh)
   __device__ __forceinline__ Fm L(int i) const { return Fm(__ldg(lde + (u64)i * M + row)); }
   __device__ __forceinline__ Fm N(int i) const { return Fm(__ldg(lde + (u64)i * M + nxt)); }
   __device__ __forceinline__ Fm PV(int i) const { return Fm(pv[i]); }
   __device__ __forceinline__ Fm K(u32 k) const { return Fm(bb_to_mont_c(k)); }
   __device__ __forceinline__ void emit(int idx, Fm v) {
-    const E4 a = apow[idx];
-#pragma unroll
-    for (int k = 0; k < 4; k++) acc.c[k] = bb_add(acc.c[k], bb_mul(a.c[k], v.v));
+    acc4_mac(acc, apow[idx], v.v);
+    if (idx & 1) acc4_fix(acc);  // idx is a literal in the generated code: every second emit
   }
 };
 
@@ -41,7 +41,8 @@ __global__ void alpha_powers_kernel(const u32* alpha, E4* apow) {  // apow[i] = 
   apow[i] = r;
 }
 
-__global__ void __launch_bounds__(128) quotient_kernel(QuotientArgs a, const E4* apow_g, u32 g_inv, u32 g, u32 snn /* shift^N */, u32 wb /* w_B */) {
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) quotient_kernel(QuotientArgs a, const E4* apow_g, u32 g_inv, u32 g, u32 snn /* shift^N */, u32 wb /* w_B */) {
   __shared__ E4 apow[ZKIR_AIR_NUM_CONSTRAINTS];
   __shared__ u32 pv[ZKIR_AIR_NUM_PUBLIC];
   for (int i = threadIdx.x; i < ZKIR_AIR_NUM_CONSTRAINTS; i += blockDim.x) apow[i] = apow_g[i];
@@ -59,12 +60,13 @@ __global__ void __launch_bounds__(128) quotient_kernel(QuotientArgs a, const E4*
   c.is_first = Fm(bb_mul(zh, a.dinv[i]));                         // Z_H/(x-1)
   c.is_last = Fm(bb_mul(zh, bb_mul(g, a.dinv[c.nxt])));  // Z_H/(x-g^-1) = Z_H*g/(g x-1), g*x_i = x_{i+B}
   c.is_trans = Fm(bb_sub(x, g_inv));
-  c.acc = e4_zero();
+  c.acc = acc4_zero();
   zkir_air_eval(c);
   const u32 zi = bb_inv(zh);
   const u64 nat = (j << a.log_blowup) | z;
+  const E4 accv = acc4_finish(c.acc);
 #pragma unroll
-  for (int k = 0; k < 4; k++) a.q[(u64)k * M + nat] = bb_mul(c.acc.c[k], zi);
+  for (int k = 0; k < 4; k++) a.q[(u64)k * M + nat] = bb_mul(accv.c[k], zi);
 }
 
 __global__ void domain_tables_kernel(u32* xs, u32* dinv, u64 M, u32 log_n, u32 log_b, u32 shift, u32 w) {
@@ -93,8 +95,14 @@ int launch_quotient(const QuotientArgs& a, cudaStream_t st, u64* launches) {
   const u32 g_inv = hpow(g, BB_P - 2);
   const u32 snn = hpow(ZKIR_BB_GEN, 1ull << a.log_n);
   const u32 wb = ZKIR_BB_ROOTS[a.log_blowup];
-  quotient_kernel<<<(unsigned)((M + 127) / 128), 128, 0, st>>>(a, reinterpret_cast<const E4*>(a.apow_scratch), bb_to_mont_c(g_inv), bb_to_mont_c(g),
-                                                              bb_to_mont_c(snn), bb_to_mont_c(wb));
+  static int variant = -1;
+  if (variant < 0) { const char* e = getenv("ZKIR_QUOTIENT_VARIANT"); variant = e ? atoi(e) : 2; }  // 64 registers measured fastest
+  const unsigned grid = (unsigned)((M + 127) / 128);
+  const E4* ap = reinterpret_cast<const E4*>(a.apow_scratch);
+  const u32 m_ginv = bb_to_mont_c(g_inv), m_g = bb_to_mont_c(g), m_snn = bb_to_mont_c(snn), m_wb = bb_to_mont_c(wb);
+  if (variant == 1) quotient_kernel<6><<<grid, 128, 0, st>>>(a, ap, m_ginv, m_g, m_snn, m_wb);
+  else if (variant == 2) quotient_kernel<8><<<grid, 128, 0, st>>>(a, ap, m_ginv, m_g, m_snn, m_wb);
+  else quotient_kernel<4><<<grid, 128, 0, st>>>(a, ap, m_ginv, m_g, m_snn, m_wb);
   (*launches) += 2;
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }

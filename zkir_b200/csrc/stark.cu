@@ -67,9 +67,10 @@ __global__ void __launch_bounds__(OPEN_THREADS) open_partial_kernel(const u32* _
                                                                    const E4* __restrict__ U1, const E4* __restrict__ U2,
                                                                    E4* partial, u32 n_chunks) {
   const u32 k0 = blockIdx.y * OPEN_COLS, chunk = blockIdx.x;
-  E4 a1[OPEN_COLS], a2[OPEN_COLS];
+  Acc4 l1[OPEN_COLS], l2[OPEN_COLS];  // lazy 64-bit accumulators (bb.cuh): mad.wide per term, fixed every second row
 #pragma unroll
-  for (int c = 0; c < OPEN_COLS; c++) { a1[c] = e4_zero(); a2[c] = e4_zero(); }
+  for (int c = 0; c < OPEN_COLS; c++) { l1[c] = acc4_zero(); l2[c] = acc4_zero(); }
+#pragma unroll 2
   for (int r = 0; r < OPEN_RPT; r++) {
     const u64 j = (u64)chunk * OPEN_CHUNK + (u64)r * OPEN_THREADS + threadIdx.x;
     if (j >= n) break;
@@ -78,11 +79,15 @@ __global__ void __launch_bounds__(OPEN_THREADS) open_partial_kernel(const u32* _
     for (int c = 0; c < OPEN_COLS; c++) {
       if (k0 + c < n_cols) {
         const u32 v = __ldg(coef + (u64)(k0 + c) * col_stride + j);
-        a1[c] = e4_add(a1[c], e4_mulb(u1, v));
-        a2[c] = e4_add(a2[c], e4_mulb(u2, v));
+        acc4_mac(l1[c], u1, v);
+        acc4_mac(l2[c], u2, v);
+        if (r & 1) { acc4_fix(l1[c]); acc4_fix(l2[c]); }
       }
     }
   }
+  E4 a1[OPEN_COLS], a2[OPEN_COLS];
+#pragma unroll
+  for (int c = 0; c < OPEN_COLS; c++) { a1[c] = acc4_finish(l1[c]); a2[c] = acc4_finish(l2[c]); }
   __shared__ u32 red[OPEN_THREADS / 32][OPEN_COLS * 8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -157,9 +162,18 @@ __global__ void __launch_bounds__(128) deep_kernel(DeepArgs a) {
   const u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x;  // memory row (coset-major)
   if (i >= a.M) return;
   const u64 nat = ((i & ((1ull << a.log_n) - 1)) << a.log_b) | (i >> a.log_n);
-  E4 rt = e4_zero(), rq = e4_zero();
-  for (u32 k = 0; k < a.width; k++) rt = e4_add(rt, e4_mulb(afp[k], __ldg(a.lde + (u64)k * a.M + i)));
-  for (u32 k = 0; k < a.qwidth; k++) rq = e4_add(rq, e4_mulb(afp[k], __ldg(a.qlde + (u64)k * a.M + i)));
+  Acc4 lt = acc4_zero(), lq = acc4_zero();  // lazy accumulators, fixed every second term
+#pragma unroll 4
+  for (u32 k = 0; k < a.width; k++) {
+    acc4_mac(lt, afp[k], __ldg(a.lde + (u64)k * a.M + i));
+    if (k & 1) acc4_fix(lt);
+  }
+#pragma unroll 4
+  for (u32 k = 0; k < a.qwidth; k++) {
+    acc4_mac(lq, afp[k], __ldg(a.qlde + (u64)k * a.M + i));
+    if (k & 1) acc4_fix(lq);
+  }
+  const E4 rt = acc4_finish(lt), rq = acc4_finish(lq);
   const u32 W = a.width;
   const u32 x = a.xs[i];
   E4 z; for (int k = 0; k < 4; k++) z.c[k] = a.zeta[k];
