@@ -72,10 +72,12 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.rows)}
 
 
-def make_trace(fib_n):
+def make_trace(fib_n, want_rows=False):
     from conftest import fib_trace
     t0 = time.time()
     res, cols, pv = fib_trace(n_input=fib_n)
+    if want_rows:
+        return res.cycles, cols, pv, time.time() - t0, res
     return res.cycles, cols, pv, time.time() - t0
 
 
@@ -141,12 +143,17 @@ def main():
         if dist is not None:
             dist.barrier()
 
-    cycles, cols, pv, vm_s = make_trace(args.fib_n)
+    cycles, cols, pv, vm_s, res = make_trace(args.fib_n, want_rows=True)
     log_n = int(cols.shape[1]).bit_length() - 1
     ctx = zkir_b200.Context(local_rank)
     cfg = zkir_b200.ProverConfig()
-    pinned = zkir_b200.PinnedBuffer(cols.shape)
-    pinned.array[:] = cols
+    # the interpreter's raw rows (TraceRow: pc, word, 16 registers) in pinned host memory: what crosses PCIe per step
+    rows = res.rows()
+    pin = {k: zkir_b200.PinnedBuffer(rows[k].shape, rows[k].dtype) for k in ("pcs", "instrs", "regs")}
+    for k in pin:
+        pin[k].array[...] = rows[k]
+    prows = dict(rows, **{k: pin[k].array for k in pin})
+    rows_bytes = int(sum(pin[k].array.nbytes for k in pin))
     d_trace = ctx.to_device(cols)
     proof_bytes = 0
 
@@ -174,11 +181,13 @@ def main():
     launches = ctx.kernel_launches - l0
     # ---------------- end-to-end arm (host buffers through the C ABI)
     for _ in range(2):
-        ctx.prove_columns(pinned.array, pv, cfg)
+        pb_rows, pv_rows = ctx.prove_rows(prows, cfg, log_n)
+    if pb_rows != pb or list(pv_rows) != list(pv):
+        raise SystemExit("prove_rows (device converter) and prove_columns (host converter) disagree")
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        ctx.prove_columns(pinned.array, pv, cfg)
+        ctx.prove_rows(prows, cfg, log_n)
     barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3
     e2e_stage = ctx.stage_ms()
@@ -226,7 +235,8 @@ def main():
                    "vm_trace_seconds": round(vm_s, 3), "proof_bytes": proof_bytes},
         "clocks": clocks,
         "e2e": {"value": world * cycles / (e2e_ms / K * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms / K,
-                "h2d_bytes_per_step": int(cols.nbytes), "d2h_bytes_per_step": proof_bytes, "h2d_ms": e2e_stage["h2d"]},
+                "h2d_bytes_per_step": rows_bytes, "d2h_bytes_per_step": proof_bytes, "h2d_and_convert_ms": e2e_stage["h2d"],
+                "api": "zkir_b200_prove_rows: raw interpreter rows (pc, word, regs[16]) in pinned host memory -> proof bytes in host memory"},
         "gpu_launches": int(launches),
         "stage_ms": {k: v / K for k, v in stage_acc.items()},
         "roofline": {"kernel": "LDE stage (ntt_pass_kernel launches: iNTT 2^20 + coset NTT 2^21, 112 columns)", "bound": "hbm",

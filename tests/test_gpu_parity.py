@@ -138,6 +138,75 @@ def test_proof_bytes_match_oracle_and_verify(gpu_ctx, oracle, n, log_b, nq, pow_
     assert ok, why
 
 
+ROW_PROGRAMS = {
+    "fib30": ("fib", 30, []),
+    "fib_input": ("fib_input", None, [77]),
+    "mixed": ("src", """
+addi r10, r0, 1
+ecall
+add r1, r10, r0
+addi r10, r0, 1
+ecall
+sub r2, r1, r10
+sub r3, r10, r1
+beq r2, r3, 8
+addi r4, r0, -5
+jal r5, 8
+addi r6, r0, 9
+bne r1, r10, 8
+addi r7, r0, 1
+add r11, r2, r0
+addi r10, r0, 2
+ecall
+addi r11, r0, 3
+addi r10, r0, 0
+ecall
+""", [123456789012, 7]),
+}
+
+
+def _rows_case(name):
+    from conftest import fib_program, fib_program_input
+    kind, arg, inputs = ROW_PROGRAMS[name]
+    prog = fib_program(arg) if kind == "fib" else (fib_program_input() if kind == "fib_input" else zkir_b200.assemble(arg))
+    return zkir_b200.VM(prog, inputs, zkir_b200.VMConfig(max_cycles=1 << 20, enable_execution_trace=True)).run()
+
+
+@pytest.mark.parametrize("name", sorted(ROW_PROGRAMS))
+def test_expand_rows_matches_host_packer(gpu_ctx, name):
+    """device converter (trace_expand.cu) == host converter (pack.cc), bit for bit, including padding rows"""
+    res = _rows_case(name)
+    for log_n in (res.min_log_n(), res.min_log_n() + 2):
+        cols, pv = res.pack(log_n)
+        d = gpu_ctx.alloc(cols.nbytes)
+        gpu_ctx.expand_rows(res.rows(), log_n, d)
+        got = gpu_ctx.to_host(d, cols.shape)
+        gpu_ctx.free(d)
+        bad = np.argwhere(got != cols)
+        assert bad.size == 0, f"first mismatch column {zkir_b200.air_layout.COLUMNS[bad[0][0]]} row {bad[0][1]}: gpu={got[tuple(bad[0])]} host={cols[tuple(bad[0])]}"
+
+
+def test_expand_rows_rejects_unconstrained_opcode(gpu_ctx):
+    prog = zkir_b200.assemble("addi r1, r0, 3\nmul r2, r1, r1\nadd r10, r0, r0\necall\n")
+    res = zkir_b200.VM(prog, [], zkir_b200.VMConfig(enable_execution_trace=True)).run()
+    d = gpu_ctx.alloc(112 * 4 * 4)
+    with pytest.raises(zkir_b200.RuntimeError) as ei:
+        gpu_ctx.expand_rows(res.rows(), 2, d)
+    gpu_ctx.free(d)
+    assert ei.value.code == -6 and "row 1" in str(ei.value)
+
+
+@pytest.mark.parametrize("name", sorted(ROW_PROGRAMS))
+def test_prove_rows_equals_prove_columns(gpu_ctx, oracle, name):
+    res = _rows_case(name)
+    cfg = zkir_b200.ProverConfig(num_queries=12, pow_bits=6)
+    cols, pv = res.pack()
+    from_cols = gpu_ctx.prove_columns(cols, pv, cfg)
+    from_rows, pv2 = gpu_ctx.prove_rows(res.rows(), cfg)
+    assert np.array_equal(pv, pv2)
+    assert from_rows == from_cols == oracle.prove(cfg, cols, pv)
+
+
 def test_prove_api_end_to_end(gpu_ctx):
     from conftest import fib_program
     cfg = zkir_b200.ProverConfig(num_queries=20, pow_bits=8)

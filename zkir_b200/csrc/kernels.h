@@ -64,6 +64,19 @@ struct QuotientArgs {
 int launch_quotient(const QuotientArgs& a, cudaStream_t st, u64* launches);
 int launch_domain_tables(u32* xs, u32* dinv, u32 log_n, u32 log_b, u32 shift_canon, cudaStream_t st, u64* launches);
 
+// ---- trace_expand.cu: raw interpreter rows -> AIR columns on the device
+struct ExpandArgs {
+  const u64* pcs;        // [T]
+  const u32* ins;        // [T]
+  const u64* regs;       // [T][16] pre-state
+  u64 T, N;              // live rows, padded rows (power of two)
+  u64 final_regs[16];    // state after the last instruction (padding rows, last READ value)
+  u64 final_pc;
+  u32* cols;             // out [112][N], canonical
+  u64* err;              // out: min over offending rows of (row << 8 | reason); ~0 = none
+};
+int launch_trace_expand(const ExpandArgs& a, cudaStream_t st, u64* launches);
+
 // ---- stark.cu (openings, DEEP combination, FRI fold, queries, misc)
 int launch_map(u32* dst, const u32* src, u64 n, int to_mont, cudaStream_t st, u64* launches);
 // out[pos] = (base_ext * mul_const)^(k(pos)), k = coefficient index of memory position pos under `plan` (nd = 1: natural)

@@ -106,6 +106,8 @@ struct zkir_ctx {
   std::string err;
   u32* ntt_tmp = nullptr; u64 ntt_tmp_words = 0;
   u32* scratch[2] = {nullptr, nullptr}; size_t scratch_bytes[2] = {0, 0};
+  void* rows_dev = nullptr; size_t rows_bytes = 0;   // staging for raw interpreter rows (prove_rows)
+  u64* d_err = nullptr; u64* h_err = nullptr;
   Workspace ws;
   cudaEvent_t ev[ZKIR_STAGE_COUNT + 1];
   float stage_ms[ZKIR_STAGE_COUNT] = {0};
@@ -402,6 +404,9 @@ void zkir_b200_destroy(zkir_ctx* ctx) {
   ws_free(ctx);
   if (ctx->ntt_tmp) cudaFree(ctx->ntt_tmp);
   for (int i = 0; i < 2; i++) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
+  if (ctx->rows_dev) cudaFree(ctx->rows_dev);
+  if (ctx->d_err) cudaFree(ctx->d_err);
+  if (ctx->h_err) cudaFreeHost(ctx->h_err);
   ntt_tables_destroy(ctx->tables);
   fast_ntt_destroy(ctx->fast);
   for (int i = 0; i <= ZKIR_STAGE_COUNT; i++) cudaEventDestroy(ctx->ev[i]);
@@ -445,6 +450,77 @@ int zkir_b200_prove_device(zkir_ctx* ctx, const zkir_params* p, const uint32_t* 
   CU(cudaEventRecord(ctx->ev[ZKIR_STAGE_H2D], ctx->stream));
   if ((rc = prove_resident(ctx, p, log_n, pv, d_trace)) != 0) return rc;  // read in place: no pass writes the caller's matrix
   return finish_proof(ctx, p, log_n, proof, proof_len);
+}
+
+// H2D of the raw rows + the device converter; columns land in d_cols
+static int expand_rows(zkir_ctx* ctx, const uint64_t* pcs, const uint32_t* instrs, const uint64_t* regs, uint64_t T, const uint64_t* final_regs,
+                       uint64_t final_pc, uint32_t log_n, u32* d_cols) {
+  const u64 N = 1ull << log_n;
+  if (T > N || !pcs || !instrs || !regs || !final_regs) { ctx->err = "bad rows: need n_rows <= 2^log_n and non-null arrays"; return ZKIR_ERR_ARG; }
+  const size_t need = T * (8 + 4 + 128) + 64;
+  if (ctx->rows_bytes < need) {
+    if (ctx->rows_dev) cudaFree(ctx->rows_dev);
+    ctx->rows_dev = nullptr; ctx->rows_bytes = 0;
+    CU(cudaMalloc(&ctx->rows_dev, need));
+    ctx->rows_bytes = need;
+  }
+  if (!ctx->d_err) { CU(cudaMalloc(&ctx->d_err, 8)); CU(cudaMallocHost(&ctx->h_err, 8)); }
+  char* base = (char*)ctx->rows_dev;
+  u64* d_regs = (u64*)base;
+  u64* d_pcs = (u64*)(base + T * 128);
+  u32* d_ins = (u32*)(base + T * 136);
+  cudaStream_t st = ctx->stream;
+  CU(cudaMemcpyAsync(d_regs, regs, T * 128, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d_pcs, pcs, T * 8, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d_ins, instrs, T * 4, cudaMemcpyHostToDevice, st));
+  CU(cudaMemsetAsync(ctx->d_err, 0xff, 8, st));
+  ExpandArgs ea;
+  ea.pcs = d_pcs; ea.ins = d_ins; ea.regs = d_regs; ea.T = T; ea.N = N;
+  for (int k = 0; k < 16; k++) ea.final_regs[k] = final_regs[k];
+  ea.final_pc = final_pc; ea.cols = d_cols; ea.err = ctx->d_err;
+  RC(launch_trace_expand(ea, st, &ctx->launches));
+  CU(cudaMemcpyAsync(ctx->h_err, ctx->d_err, 8, cudaMemcpyDeviceToHost, st));
+  return 0;
+}
+static int expand_error(zkir_ctx* ctx) {  // after the stream is drained
+  const u64 e = *ctx->h_err;
+  if (e == ~0ull) return 0;
+  static const char* why[] = {"", "pc does not fit 30 bits", "register value exceeds 40 bits", "input tape value exceeds 40 bits",
+                              "syscall other than EXIT/READ/WRITE", "opcode is not constrained"};
+  const u32 code = (u32)(e & 0xff);
+  ctx->err = "core AIR v1 cannot constrain row " + std::to_string((unsigned long long)(e >> 8)) + ": " + (code < 6 ? why[code] : "?");
+  return ZKIR_ERR_AIR;
+}
+
+int zkir_b200_prove_rows(zkir_ctx* ctx, const zkir_params* p, const uint64_t* pcs, const uint32_t* instrs, const uint64_t* regs,
+                         uint64_t n_rows, const uint64_t* final_regs, uint64_t final_pc, uint32_t entry_point, uint64_t exit_code,
+                         uint32_t log_n, uint32_t* pv_out, uint8_t** proof, size_t* proof_len) {
+  if (!ctx) return ZKIR_ERR_ARG;
+  ctx->err.clear();
+  cudaSetDevice(ctx->device);
+  int rc = check_params(ctx, p, log_n);
+  if (rc) return rc;
+  if (!pv_out || !proof || !proof_len) { ctx->err = "null argument"; return ZKIR_ERR_ARG; }
+  if ((rc = ws_prepare(ctx, p, log_n)) != 0) return rc;
+  CU(cudaEventRecord(ctx->ev[ZKIR_STAGE_H2D], ctx->stream));
+  if ((rc = expand_rows(ctx, pcs, instrs, regs, n_rows, final_regs, final_pc, log_n, ctx->ws.trace)) != 0) return rc;
+  const u64 LIMB = (1u << 20) - 1;
+  pv_out[0] = entry_point; pv_out[1] = (u32)(n_rows % BB_P); pv_out[2] = (u32)(exit_code & LIMB); pv_out[3] = (u32)((exit_code >> 20) & LIMB);
+  if ((rc = prove_resident(ctx, p, log_n, pv_out, ctx->ws.trace)) != 0) return rc;
+  if ((rc = finish_proof(ctx, p, log_n, proof, proof_len)) != 0) return rc;
+  if ((rc = expand_error(ctx)) != 0) { free(*proof); *proof = nullptr; *proof_len = 0; return rc; }
+  return 0;
+}
+
+int zkir_b200_expand_rows(zkir_ctx* ctx, const uint64_t* pcs, const uint32_t* instrs, const uint64_t* regs, uint64_t n_rows,
+                          const uint64_t* final_regs, uint64_t final_pc, uint32_t log_n, uint32_t* d_cols) {
+  if (!ctx || !d_cols || log_n < 2 || log_n > 26) return ZKIR_ERR_ARG;
+  ctx->err.clear();
+  cudaSetDevice(ctx->device);
+  int rc = expand_rows(ctx, pcs, instrs, regs, n_rows, final_regs, final_pc, log_n, d_cols);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(ctx->stream));
+  return expand_error(ctx);
 }
 
 int zkir_b200_prove_batch(zkir_ctx* ctx, const zkir_params* p, const uint32_t* const* traces, const uint32_t* log_ns,

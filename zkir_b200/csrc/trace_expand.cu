@@ -1,0 +1,144 @@
+// Device-side trace converter: raw interpreter rows -> the 112 BabyBear columns of the core AIR v1.
+//
+// The reference's hand-off type is `Vec<TraceRow>` -- cycle, pc, instruction word and the PRE-state registers
+// (zkir-spec/src/trace.rs:24-50, recorded at zkir-runtime/src/vm.rs:245-253,302-312); the "converter" that turns rows
+// into field columns is named there (trace.rs:41, vm.rs:243-244) but absent.  zkir_b200/csrc/host/pack.cc is the host
+// restatement; this kernel is the same function with one thread per row, so that only the raw rows (140 B/row instead
+// of 448 B/row of columns) cross PCIe.  The two must agree bit for bit (tests/test_gpu_parity.py::test_expand_*).
+//
+// Bound: HBM writes (448 B/row) -- every store of a warp is one 128 B segment of one column.
+#include <cuda_runtime.h>
+#include "bb.cuh"
+#include "kernels.h"
+#include "air_columns.h"
+
+namespace zkir {
+
+__device__ __forceinline__ int sext_dev(u32 v, int bits) { const int sh = 32 - bits; return ((int)(v << sh)) >> sh; }
+
+__global__ void __launch_bounds__(128) trace_expand_kernel(ExpandArgs a) {
+  const u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x;
+  const u64 N = a.N, T = a.T;
+  if (i >= N) return;
+  const u64 LIMB = (1u << 20) - 1, M40 = (1ull << 40) - 1;
+  const bool live = i < T;
+  u64 rg[16];
+#pragma unroll
+  for (int k = 0; k < 16; k++) rg[k] = live ? a.regs[16 * i + k] : a.final_regs[k];
+  const u64 pc = live ? a.pcs[i] : a.final_pc;
+  u32 err = 0;
+  if (pc + 4 >= (1u << 30)) err = 1;
+#pragma unroll
+  for (int k = 1; k < 16; k++) if (rg[k] >> 40) err = 2;
+  u32* col = a.cols + i;
+  auto W = [&](int c, u32 v) { col[(u64)c * N] = v; };
+
+  W(ZKIR_COL_CLK, (u32)((live ? i : T) % BB_P));
+  W(ZKIR_COL_PC, (u32)pc);
+  W(ZKIR_COL_R0_LO, 0); W(ZKIR_COL_R0_HI, 0);
+#pragma unroll
+  for (int k = 1; k < 16; k++) { W(ZKIR_COL_R0_LO + 2 * k, (u32)(rg[k] & LIMB)); W(ZKIR_COL_R0_LO + 2 * k + 1, (u32)(rg[k] >> 20)); }
+
+  u32 rd = 0, rs1 = 0, rs2 = 0;
+  u32 s_add = 0, s_sub = 0, s_addi = 0, s_beq = 0, s_bne = 0, s_jal = 0, s_ecall = 0, s_pad = 0;
+  u32 is_exit = 0, is_read = 0, is_write = 0;
+  u64 av = 0, bv = 0, cv = 0, io = 0;
+  long long imm = 0;
+  bool has_imm = false;
+  u32 carry0 = 0, carry1 = 0, inv_lo = 0, inv_hi = 0, ne_lo = 0, ne_hi = 0, taken = 0;
+  if (!live) {
+    s_pad = 1;
+  } else {
+    const u32 w = a.ins[i], op = w & 0x7F;
+    const u32 fa = (w >> 7) & 0xF, fb = (w >> 11) & 0xF, fc = (w >> 15) & 0xF;
+    auto R = [&](u32 k) -> u64 {  // register read without dynamic indexing of the local array
+      u64 v = 0;
+#pragma unroll
+      for (int j = 1; j < 16; j++) if (k == (u32)j) v = rg[j];
+      return v;
+    };
+    if (op == 0x00 || op == 0x01) {          // ADD / SUB (execute.rs:43-78)
+      rd = fa; rs1 = fb; rs2 = fc;
+      av = R(rs1); bv = R(rs2);
+      if (op == 0) s_add = 1; else s_sub = 1;
+    } else if (op == 0x08) {                 // ADDI (execute.rs:185-197)
+      rd = fa; rs1 = fb; imm = sext_dev((w >> 15) & 0x1FFFF, 17); has_imm = true;
+      av = R(rs1); bv = (u64)imm & M40;
+      s_addi = 1;
+    } else if (op == 0x40 || op == 0x41) {   // BEQ / BNE, B-type: rs1 bits 10:7, rs2 bits 14:11 (encoder.rs:132-140)
+      rs1 = fa; rs2 = fb; imm = sext_dev((w >> 15) & 0x1FFFF, 17); has_imm = true;
+      av = R(rs1); bv = R(rs2);
+      if (op == 0x40) s_beq = 1; else s_bne = 1;
+    } else if (op == 0x48) {                 // JAL (execute.rs:639-647)
+      rd = fa; imm = sext_dev((w >> 11) & 0x1FFFFF, 21); has_imm = true;
+      cv = pc + 4;
+      s_jal = 1;
+    } else if (op == 0x50) {                 // ECALL (syscall.rs:94-119)
+      s_ecall = 1;
+      const u64 num = rg[10];
+      if (num == 0) is_exit = 1;
+      else if (num == 1) {                   // READ: the value is the post-state r10 = next row's pre-state r10
+        is_read = 1; rd = 10;
+        io = (i + 1 < T) ? a.regs[16 * (i + 1) + 10] : a.final_regs[10];
+        cv = io;
+        if (io >> 40) err = 3;
+      } else if (num == 2) { is_write = 1; io = rg[11]; }
+      else err = 4;
+    } else {
+      err = 5;
+    }
+    const u64 a_lo = av & LIMB, a_hi = av >> 20, b_lo = bv & LIMB, b_hi = bv >> 20;
+    if (op == 0x00 || op == 0x08) {
+      cv = (av + bv) & M40;
+      const u64 k0 = (a_lo + b_lo) >> 20;
+      carry0 = (u32)k0; carry1 = (u32)((a_hi + b_hi + k0) >> 20);
+    } else if (op == 0x01) {
+      cv = (av - bv) & M40;
+      const u64 k0 = a_lo < b_lo;
+      carry0 = (u32)k0; carry1 = (u32)(a_hi < b_hi + k0);
+    }
+    if (op == 0x40 || op == 0x41) {
+      const u32 d_lo = bb_sub((u32)a_lo, (u32)b_lo), d_hi = bb_sub((u32)a_hi, (u32)b_hi);
+      ne_lo = d_lo != 0; ne_hi = d_hi != 0;
+      inv_lo = d_lo ? bb_from_mont(bb_inv(bb_to_mont(d_lo))) : 0;
+      inv_hi = d_hi ? bb_from_mont(bb_inv(bb_to_mont(d_hi))) : 0;
+      const u32 ne = ne_lo | ne_hi;
+      taken = op == 0x41 ? ne : !ne;
+    }
+  }
+  u32 imm_lo = 0, imm_hi = 0, imm_sign = 0, imm_f = 0;
+  if (has_imm) {
+    const u64 m = (u64)imm & M40;
+    imm_lo = (u32)(m & LIMB); imm_hi = (u32)(m >> 20);
+    imm_sign = imm < 0;
+    imm_f = imm < 0 ? BB_P - (u32)(-imm) : (u32)imm;
+  }
+  W(ZKIR_COL_IMM_LO, imm_lo); W(ZKIR_COL_IMM_HI, imm_hi); W(ZKIR_COL_IMM_F, imm_f); W(ZKIR_COL_IMM_SIGN, imm_sign);
+  W(ZKIR_COL_S_ADD, s_add); W(ZKIR_COL_S_SUB, s_sub); W(ZKIR_COL_S_ADDI, s_addi); W(ZKIR_COL_S_BEQ, s_beq);
+  W(ZKIR_COL_S_BNE, s_bne); W(ZKIR_COL_S_JAL, s_jal); W(ZKIR_COL_S_ECALL, s_ecall); W(ZKIR_COL_S_PAD, s_pad);
+#pragma unroll
+  for (int k = 0; k < 16; k++) {
+    W(ZKIR_COL_SEL_RD0 + k, rd == (u32)k);
+    W(ZKIR_COL_SEL_RS1_0 + k, rs1 == (u32)k);
+    W(ZKIR_COL_SEL_RS2_0 + k, rs2 == (u32)k);
+  }
+  W(ZKIR_COL_A_LO, (u32)(av & LIMB)); W(ZKIR_COL_A_HI, (u32)(av >> 20));
+  W(ZKIR_COL_B_LO, (u32)(bv & LIMB)); W(ZKIR_COL_B_HI, (u32)(bv >> 20));
+  W(ZKIR_COL_C_LO, (u32)(cv & LIMB)); W(ZKIR_COL_C_HI, (u32)(cv >> 20));
+  W(ZKIR_COL_CARRY0, carry0); W(ZKIR_COL_CARRY1, carry1);
+  W(ZKIR_COL_INV_LO, inv_lo); W(ZKIR_COL_INV_HI, inv_hi); W(ZKIR_COL_NE_LO, ne_lo); W(ZKIR_COL_NE_HI, ne_hi); W(ZKIR_COL_TAKEN, taken);
+  W(ZKIR_COL_IS_EXIT, is_exit); W(ZKIR_COL_IS_READ, is_read); W(ZKIR_COL_IS_WRITE, is_write);
+  W(ZKIR_COL_IO_LO, (u32)(io & LIMB)); W(ZKIR_COL_IO_HI, (u32)(io >> 20));
+  if (err) {  // first offending row wins; the host reports it after the stream is drained
+    const unsigned long long packed = (i << 8) | err;
+    atomicMin(reinterpret_cast<unsigned long long*>(a.err), packed);
+  }
+}
+
+int launch_trace_expand(const ExpandArgs& a, cudaStream_t st, u64* launches) {
+  trace_expand_kernel<<<(unsigned)((a.N + 127) / 128), 128, 0, st>>>(a);
+  (*launches)++;
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+}  // namespace zkir

@@ -112,6 +112,22 @@ class ExecutionResult:  # vm.rs:54-78
     def memory_op_count(self):
         return sum(len(r.memory_ops) for r in self.execution_trace)
 
+    # ---- raw rows, as `Vec<TraceRow>` holds them (trace.rs:24-50): zero-copy numpy views of the recorder's arrays
+    def rows(self):
+        """-> dict(pcs u64[T], instrs u32[T], regs u64[T,16], final_regs u64[16], final_pc, exit_code)."""
+        l = _ffi.lib()
+        n = l.zkir_vm_trace_len(self._h)
+        as_np = lambda ptr, shape, dt: np.ctypeslib.as_array(ptr, shape=shape).view(dt) if n else np.zeros(shape, dtype=dt)
+        return {
+            "pcs": as_np(l.zkir_vm_trace_pc(self._h), (n,), np.uint64),
+            "instrs": as_np(l.zkir_vm_trace_instr(self._h), (n,), np.uint32),
+            "regs": as_np(l.zkir_vm_trace_regs(self._h), (n * 16,), np.uint64).reshape(n, 16),
+            "final_regs": np.ctypeslib.as_array(l.zkir_vm_final_regs(self._h), shape=(16,)).copy(),
+            "final_pc": l.zkir_vm_final_pc(self._h),
+            "exit_code": self.halt_reason.code if self.halt_reason.kind == "Exit" else 0,
+            "entry_point": self._entry,
+        }
+
     # ---- trace -> columns ("converter", trace.rs:41)
     def min_log_n(self):
         return _ffi.lib().zkir_pack_min_log_n(self._h)
@@ -248,6 +264,33 @@ class Context:
         self._l.zkir_b200_free_proof(proof)
         return out
 
+    def prove_rows(self, rows, cfg, log_n=None):
+        """rows: dict as returned by ExecutionResult.rows() (arrays may live in PinnedBuffers).  The device runs the
+        converter; returns (proof bytes, public values)."""
+        params = cfg.params()
+        n = int(rows["pcs"].shape[0])
+        if log_n is None:
+            log_n = max(2, (n - 1).bit_length())
+        pcs, ins, regs = (np.ascontiguousarray(rows[k]) for k in ("pcs", "instrs", "regs"))
+        assert pcs.dtype == np.uint64 and ins.dtype == np.uint32 and regs.dtype == np.uint64 and regs.shape == (n, 16)
+        fr = np.ascontiguousarray(rows["final_regs"], dtype=np.uint64)
+        pv = np.zeros(NUM_PUBLIC, dtype=np.uint32)
+        proof, plen = C.c_void_p(), C.c_size_t()
+        rc = self._l.zkir_b200_prove_rows(self._h, C.byref(params), pcs.ctypes.data, ins.ctypes.data, regs.ctypes.data, n,
+                                          fr.ctypes.data_as(_ffi.u64p), int(rows["final_pc"]), int(rows["entry_point"]), int(rows["exit_code"]),
+                                          log_n, pv.ctypes.data_as(_ffi.u32p), C.byref(proof), C.byref(plen))
+        self._check(rc)
+        out = C.string_at(proof, plen.value)
+        self._l.zkir_b200_free_proof(proof)
+        return out, pv
+
+    def expand_rows(self, rows, log_n, d_cols):
+        n = int(rows["pcs"].shape[0])
+        pcs, ins, regs = (np.ascontiguousarray(rows[k]) for k in ("pcs", "instrs", "regs"))
+        fr = np.ascontiguousarray(rows["final_regs"], dtype=np.uint64)
+        self._check(self._l.zkir_b200_expand_rows(self._h, pcs.ctypes.data, ins.ctypes.data, regs.ctypes.data, n, fr.ctypes.data_as(_ffi.u64p),
+                                                  int(rows["final_pc"]), log_n, d_cols))
+
     # -- per-kernel entry points (device pointers)
     def ntt(self, d_cols, n_cols, log_n, inverse=False, coset_shift=0):
         self._check(self._l.zkir_b200_ntt(self._h, d_cols, n_cols, log_n, int(inverse), coset_shift))
@@ -275,15 +318,17 @@ class Context:
 
 
 class PinnedBuffer:
-    """uint32 matrix in page-locked host memory (zkir_b200_alloc_pinned) the interpreter's packer writes into."""
+    """array in page-locked host memory (zkir_b200_alloc_pinned) the interpreter's recorder / packer writes into."""
 
-    def __init__(self, shape):
+    def __init__(self, shape, dtype=np.uint32):
         self._l = _ffi.lib()
-        n = int(np.prod(shape)) * 4
-        self._p = self._l.zkir_b200_alloc_pinned(n)
+        dt = np.dtype(dtype)
+        count = int(np.prod(shape))
+        self._p = self._l.zkir_b200_alloc_pinned(max(count * dt.itemsize, 16))
         if not self._p:
             raise RuntimeError_(_ffi.ERR_OOM, "zkir_b200_alloc_pinned failed (needs a CUDA device)")
-        self.array = np.ctypeslib.as_array(C.cast(self._p, _ffi.u32p), shape=(int(np.prod(shape)),)).reshape(shape)
+        raw = np.ctypeslib.as_array(C.cast(self._p, C.POINTER(C.c_uint8)), shape=(max(count * dt.itemsize, 16),))
+        self.array = raw[:count * dt.itemsize].view(dt).reshape(shape)
 
     def close(self):
         if self._p:
@@ -308,10 +353,10 @@ def prove(program, inputs=(), cfg=None):
     The drop-in the north star describes for `zkir_runtime::prove()` (absent upstream: lib.rs:29-62)."""
     cfg = cfg or ProverConfig()
     res = VM(program, inputs, VMConfig(max_cycles=cfg.max_cycles, enable_execution_trace=True)).run()
-    cols, pv = res.pack()
     ctx = _ctx(cfg.device)
-    pb = ctx.prove_columns(cols, pv, cfg)
-    return Proof(pb, pv, int(cols.shape[1]).bit_length() - 1, res.cycles, res.outputs, ctx.stage_ms())
+    log_n = res.min_log_n()
+    pb, pv = ctx.prove_rows(res.rows(), cfg, log_n)   # raw rows over PCIe, converter on the device
+    return Proof(pb, pv, log_n, res.cycles, res.outputs, ctx.stage_ms())
 
 
 def verify(proof, cfg=None, public_values=None):
