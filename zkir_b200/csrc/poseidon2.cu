@@ -245,14 +245,19 @@ __device__ __forceinline__ u32 permute_warp(u32 x, int lane) {
   };
   x = ext_lin(x);
   for (int r = 0; r < 4; r++) { x = sbox7(bb_add(x, c_rc_ext[r * 16 + l16])); x = ext_lin(x); }
+  const u32 dg = c_diag[l16];
   for (int r = 0; r < ZKIR_P2_RP; r++) {
-    if (l16 == 0) x = sbox7(bb_add(x, c_rc_int[r]));
+    // latency matters here, not throughput: the sum of the OLD state and the diagonal products of lanes 1..15 do not
+    // depend on the S-box, so they overlap it; afterwards only (new s0 - old s0) has to be broadcast.
     u32 s = x;
     s = bb_add(s, __shfl_xor_sync(FULL, s, 1));
     s = bb_add(s, __shfl_xor_sync(FULL, s, 2));
     s = bb_add(s, __shfl_xor_sync(FULL, s, 4));
     s = bb_add(s, __shfl_xor_sync(FULL, s, 8));
-    x = bb_add(bb_mul(x, c_diag[l16]), s);
+    const u32 x0 = sbox7(bb_add(x, c_rc_int[r]));                       // meaningful in lane 0 of each state
+    const u32 delta = __shfl_sync(FULL, bb_sub(x0, x), lane & ~15);
+    const u32 xi = l16 == 0 ? x0 : x;
+    x = bb_add(bb_mul(xi, dg), bb_add(s, delta));
   }
   for (int r = 4; r < 8; r++) { x = sbox7(bb_add(x, c_rc_ext[r * 16 + l16])); x = ext_lin(x); }
   return x;

@@ -59,52 +59,53 @@ int launch_ext_powers(const u32* base_ext, u32 mul_const, const FastPlan& plan, 
 }
 
 // ---- openings: out1[k] = sum_j coef[k][j]*U1[j], out2[k] = sum_j coef[k][j]*U2[j]
+// Block = 8 warps x 4 columns = 32 columns over OPEN_ROWS rows: lane = row (128 B coalesced column reads), warp = column
+// group, so the eight warps read the SAME 32 B/row of U1/U2 and seven of them hit L1.  Lazy 64-bit accumulators (bb.cuh).
 #define OPEN_COLS 4
-#define OPEN_THREADS 256
-#define OPEN_RPT 16
-#define OPEN_CHUNK (OPEN_THREADS * OPEN_RPT)
+#define OPEN_WARPS 8
+#define OPEN_THREADS (32 * OPEN_WARPS)
+#define OPEN_ROWS 2048
 __global__ void __launch_bounds__(OPEN_THREADS) open_partial_kernel(const u32* __restrict__ coef, u64 col_stride, u32 n_cols, u64 n,
                                                                    const E4* __restrict__ U1, const E4* __restrict__ U2,
                                                                    E4* partial, u32 n_chunks) {
-  const u32 k0 = blockIdx.y * OPEN_COLS, chunk = blockIdx.x;
-  Acc4 l1[OPEN_COLS], l2[OPEN_COLS];  // lazy 64-bit accumulators (bb.cuh): mad.wide per term, fixed every second row
+  const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5, chunk = blockIdx.x;
+  const u32 k0 = (blockIdx.y * OPEN_WARPS + warp) * OPEN_COLS;
+  if (k0 >= n_cols) return;
+  Acc4 l1[OPEN_COLS], l2[OPEN_COLS];
 #pragma unroll
   for (int c = 0; c < OPEN_COLS; c++) { l1[c] = acc4_zero(); l2[c] = acc4_zero(); }
+  const u64 j0 = (u64)chunk * OPEN_ROWS + lane;
 #pragma unroll 2
-  for (int r = 0; r < OPEN_RPT; r++) {
-    const u64 j = (u64)chunk * OPEN_CHUNK + (u64)r * OPEN_THREADS + threadIdx.x;
-    if (j >= n) break;
-    const E4 u1 = ld_e4(U1 + j), u2 = ld_e4(U2 + j);
+  for (int r = 0; r < OPEN_ROWS / 32; r++) {
+    const u64 j = j0 + (u64)r * 32;
+    if (j < n) {
+      const E4 u1 = ld_e4(U1 + j), u2 = ld_e4(U2 + j);
 #pragma unroll
-    for (int c = 0; c < OPEN_COLS; c++) {
-      if (k0 + c < n_cols) {
-        const u32 v = __ldg(coef + (u64)(k0 + c) * col_stride + j);
-        acc4_mac(l1[c], u1, v);
-        acc4_mac(l2[c], u2, v);
-        if (r & 1) { acc4_fix(l1[c]); acc4_fix(l2[c]); }
+      for (int c = 0; c < OPEN_COLS; c++) {
+        if (k0 + c < n_cols) {
+          const u32 v = __ldg(coef + (u64)(k0 + c) * col_stride + j);
+          acc4_mac(l1[c], u1, v);
+          acc4_mac(l2[c], u2, v);
+        }
       }
     }
-  }
-  E4 a1[OPEN_COLS], a2[OPEN_COLS];
+    if (r & 1) {
 #pragma unroll
-  for (int c = 0; c < OPEN_COLS; c++) { a1[c] = acc4_finish(l1[c]); a2[c] = acc4_finish(l2[c]); }
-  __shared__ u32 red[OPEN_THREADS / 32][OPEN_COLS * 8];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-  for (int c = 0; c < OPEN_COLS; c++) {
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-      u32 x = a1[c].c[k], y = a2[c].c[k];
-      for (int o = 16; o > 0; o >>= 1) { x = bb_add(x, __shfl_xor_sync(0xffffffffu, x, o)); y = bb_add(y, __shfl_xor_sync(0xffffffffu, y, o)); }
-      if (lane == 0) { red[warp][c * 8 + k] = x; red[warp][c * 8 + 4 + k] = y; }
+      for (int c = 0; c < OPEN_COLS; c++) { acc4_fix(l1[c]); acc4_fix(l2[c]); }
     }
   }
-  __syncthreads();
-  if (threadIdx.x < OPEN_COLS * 8) {
-    u32 s = 0;
-    for (int w = 0; w < OPEN_THREADS / 32; w++) s = bb_add(s, red[w][threadIdx.x]);
-    const u32 c = threadIdx.x / 8, which = (threadIdx.x / 4) & 1, k = threadIdx.x & 3;
-    if (k0 + c < n_cols) partial[(((u64)which * n_cols + k0 + c) * n_chunks + chunk)].c[k] = s;
+#pragma unroll
+  for (int c = 0; c < OPEN_COLS; c++) {
+    const E4 a1 = acc4_finish(l1[c]), a2 = acc4_finish(l2[c]);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      u32 x = a1.c[k], y = a2.c[k];
+      for (int o = 16; o > 0; o >>= 1) { x = bb_add(x, __shfl_xor_sync(0xffffffffu, x, o)); y = bb_add(y, __shfl_xor_sync(0xffffffffu, y, o)); }
+      if (lane == 0 && k0 + c < n_cols) {
+        partial[((u64)(k0 + c)) * n_chunks + chunk].c[k] = x;
+        partial[((u64)n_cols + k0 + c) * n_chunks + chunk].c[k] = y;
+      }
+    }
   }
 }
 __global__ void open_final_kernel(const E4* partial, u32 n_cols, u32 n_chunks, E4* out1, E4* out2) {
@@ -121,14 +122,14 @@ __global__ void open_final_kernel(const E4* partial, u32 n_cols, u32 n_chunks, E
 }
 int launch_open(const u32* coef, u64 col_stride, u32 n_cols, u64 n, const E4* U1, const E4* U2, E4* out1, E4* out2,
                 E4* partial_scratch, cudaStream_t st, u64* launches) {
-  const u32 n_chunks = (u32)((n + OPEN_CHUNK - 1) / OPEN_CHUNK);
-  dim3 grid(n_chunks, (n_cols + OPEN_COLS - 1) / OPEN_COLS);
+  const u32 n_chunks = (u32)((n + OPEN_ROWS - 1) / OPEN_ROWS);
+  dim3 grid(n_chunks, (n_cols + OPEN_COLS * OPEN_WARPS - 1) / (OPEN_COLS * OPEN_WARPS));
   open_partial_kernel<<<grid, OPEN_THREADS, 0, st>>>(coef, col_stride, n_cols, n, U1, U2, partial_scratch, n_chunks);
   open_final_kernel<<<2 * n_cols, 32, 0, st>>>(partial_scratch, n_cols, n_chunks, out1, out2);
   (*launches) += 2;
   return CHECK_LAUNCH();
 }
-u64 open_scratch_elems(u32 n_cols, u64 n) { return 2ull * n_cols * ((n + OPEN_CHUNK - 1) / OPEN_CHUNK); }
+u64 open_scratch_elems(u32 n_cols, u64 n) { return 2ull * n_cols * ((n + OPEN_ROWS - 1) / OPEN_ROWS); }
 
 // ---- DEEP combination
 // scratch layout: afp[0..width) = alpha^k, then [width+0]=A1, +1=A2, +2=A3, +3=alpha^W, +4=alpha^2W
