@@ -59,13 +59,13 @@ int launch_ext_powers(const u32* base_ext, u32 mul_const, const FastPlan& plan, 
 }
 
 // ---- openings: out1[k] = sum_j coef[k][j]*U1[j], out2[k] = sum_j coef[k][j]*U2[j]
-// Block = 8 warps x 4 columns = 32 columns over OPEN_ROWS rows: lane = row (128 B coalesced column reads), warp = column
+// Block = 8 warps x 2 columns = 16 columns over OPEN_ROWS rows: lane = row (128 B coalesced column reads), warp = column
 // group, so the eight warps read the SAME 32 B/row of U1/U2 and seven of them hit L1.  Lazy 64-bit accumulators (bb.cuh).
-#define OPEN_COLS 4
+#define OPEN_COLS 2
 #define OPEN_WARPS 8
 #define OPEN_THREADS (32 * OPEN_WARPS)
 #define OPEN_ROWS 2048
-__global__ void __launch_bounds__(OPEN_THREADS) open_partial_kernel(const u32* __restrict__ coef, u64 col_stride, u32 n_cols, u64 n,
+__global__ void __launch_bounds__(OPEN_THREADS, 3) open_partial_kernel(const u32* __restrict__ coef, u64 col_stride, u32 n_cols, u64 n,
                                                                    const E4* __restrict__ U1, const E4* __restrict__ U2,
                                                                    E4* partial, u32 n_chunks) {
   const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5, chunk = blockIdx.x;
@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(128) deep_kernel(DeepArgs a) {
   if (i >= a.M) return;
   const u64 nat = ((i & ((1ull << a.log_n) - 1)) << a.log_b) | (i >> a.log_n);
   Acc4 lt = acc4_zero(), lq = acc4_zero();  // lazy accumulators, fixed every second term
-#pragma unroll 4
+#pragma unroll 8
   for (u32 k = 0; k < a.width; k++) {
     acc4_mac(lt, afp[k], __ldg(a.lde + (u64)k * a.M + i));
     if (k & 1) acc4_fix(lt);
