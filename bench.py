@@ -4,8 +4,9 @@
 Step = one full proof of the 2^20-row fibonacci trace (BASELINE configs[1]): LDE, Merkle commitments, quotient,
 openings, FRI, queries.  `value` = real VM cycles proved per second with the packed trace already in HBM
 (device time of the step from CUDA events on the library's launch stream); `e2e` = the same through
-zkir_b200_prove with the trace in pinned HOST memory (H2D of the trace and D2H of the proof inside the timed
-region, wall clock bracketed by device syncs).  N>1: every rank proves its own trace (independent proofs, no
+zkir_b200_prove_rows with the interpreter's raw rows (pc, word, regs[16]: what the reference's TraceRow holds) in pinned
+HOST memory: H2D of the rows, the device-side converter and the D2H of the proof are inside the timed region (wall
+clock bracketed by device syncs).  N>1: every rank proves its own trace (independent proofs, no
 data-path collective; weak scaling), value = cycles of all ranks / max-over-ranks time.
 
 `--impl reference`: the reference contains no prover, so the reference arm times this
@@ -45,31 +46,41 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
+    """One long-lived `nvidia-smi -lms 100` child (the recipe's clocks line); rows are read as they stream in."""
+
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], False
+        self.index, self.rows, self.proc = index, [], None
 
     def run(self):
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
-        while not self.stop_flag:
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                parts = [x.strip() for x in line.strip().split(",")]
+                if len(parts) >= 6:
+                    self.rows.append(parts)
+        except Exception:
+            pass
+
+    def mark(self):
+        return len(self.rows)
+
+    def summary(self, first=0):
+        if self.proc is not None:
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
+                self.proc.terminate()
             except Exception:
                 pass
-            time.sleep(0.2)
-
-    def summary(self):
-        self.stop_flag = True
-        if not self.rows:
+        rows = self.rows[first:] or self.rows
+        if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        sm = sorted(int(r[0]) for r in rows if r[0].isdigit())
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(self.rows[0][1]) if self.rows[0][1].isdigit() else None,
-                "reasons": reasons, "samples": len(self.rows)}
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(rows[0][1]) if rows[0][1].isdigit() else None,
+                "reasons": reasons, "samples": len(rows), "window": "device-resident + end-to-end timed loops"}
 
 
 def make_trace(fib_n, want_rows=False):
@@ -158,15 +169,16 @@ def main():
     proof_bytes = 0
 
     # ---------------- device-resident arm (value)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         pb = ctx.prove_columns(None, pv, cfg, device_resident=(d_trace, log_n))
     proof_bytes = len(pb)
     ok, why = zkir_b200.verify(pb, cfg, pv)
     if not ok:
         raise SystemExit(f"proof rejected by the verifier: {why}")
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     barrier()
+    clk_mark = sampler.mark()
     l0 = ctx.kernel_launches
     dev_ms, stage_acc = 0.0, {}
     t0 = time.perf_counter()
@@ -191,22 +203,21 @@ def main():
     barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3
     e2e_stage = ctx.stage_ms()
-    clocks = sampler.summary()
+    clocks = sampler.summary(clk_mark)
 
-    # ---------------- NTT roofline microbench: forward NTT of the LDE size, 8*n*C algorithmic bytes per launch set
-    ntt_log, ntt_cols = log_n + cfg.log_blowup, 32
+    # ---------------- NTT roofline microbench: one forward transform of the trace size on all W columns (8*n*C algorithmic
+    # bytes), natural order in and out, timed with CUDA events on the library's stream
+    ntt_log, ntt_cols = log_n, int(cols.shape[0])
     rng = np.random.default_rng(0x5EED)
     d_ntt = ctx.to_device(rng.integers(0, 2013265921, size=(ntt_cols, 1 << ntt_log), dtype=np.uint64).astype(np.uint32))
     for _ in range(3):
         ctx.ntt(d_ntt, ntt_cols, ntt_log)
     ctx.sync()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     reps = 10
-    tt0 = time.perf_counter()
+    ctx.timer_start()
     for _ in range(reps):
         ctx.ntt(d_ntt, ntt_cols, ntt_log)
-    ctx.sync()
-    ntt_ms = (time.perf_counter() - tt0) * 1e3 / reps
+    ntt_ms = ctx.timer_stop() / reps
     ctx.free(d_ntt)
 
     # max over ranks
@@ -226,6 +237,16 @@ def main():
     lde_ms = stage_acc["lde"] / K
     lde_gbs = lde_bytes / (lde_ms * 1e-3) / 1e9
     ntt_gbs = 8 * (1 << ntt_log) * ntt_cols / (ntt_ms * 1e-3) / 1e9
+    commit_ms = stage_acc["trace_commit"] / K
+    hash_gps = (B * N * ((W + 7) // 8) + B * N - 1) / (commit_ms * 1e-3) / 1e9
+    lde_traffic, lde_traffic_src = None, None
+    tp = os.path.join(ROOT, "profiles", "r01_lde_traffic.json")
+    if os.path.exists(tp) and N == 1 << 20:
+        try:
+            tj = json.load(open(tp))
+            lde_traffic, lde_traffic_src = int(tj["lde_dram_bytes_total_estimate"]), tj["source"]
+        except Exception:
+            pass
     out = {
         "metric": METRIC, "value": world * cycles / (dev_ms / K * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
         "ms_per_step": dev_ms / K, "wall_ms_per_step": wall_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -239,11 +260,16 @@ def main():
                 "api": "zkir_b200_prove_rows: raw interpreter rows (pc, word, regs[16]) in pinned host memory -> proof bytes in host memory"},
         "gpu_launches": int(launches),
         "stage_ms": {k: v / K for k, v in stage_acc.items()},
-        "roofline": {"kernel": "LDE stage (ntt_pass_kernel launches: iNTT 2^20 + coset NTT 2^21, 112 columns)", "bound": "hbm",
-                     "achieved": lde_gbs, "peak": peak, "unit": "GB/s", "frac": lde_gbs / peak, "traffic": None,
-                     "algorithmic_bytes": lde_bytes, "ms": lde_ms, "peak_source": peak_src},
-        "ntt_roofline": {"kernel": f"forward NTT 2^{ntt_log} x {ntt_cols} columns via zkir_b200_ntt (8*n*C bytes)", "bound": "hbm",
-                         "achieved": ntt_gbs, "peak": peak, "unit": "GB/s", "frac": ntt_gbs / peak, "ms": ntt_ms, "timing": "wall clock around synced launches"},
+        "roofline": {"kernel": "dft_tile_kernel: LDE stage = 2 inverse + 2x2 forward digit passes (radix-32 register tiles) over 112 columns, 2^20 -> 2^21 points",
+                     "bound": "hbm", "achieved": lde_gbs, "peak": peak, "unit": "GB/s", "frac": lde_gbs / peak, "traffic": lde_traffic,
+                     "traffic_source": lde_traffic_src, "algorithmic_bytes": lde_bytes, "ms": lde_ms, "peak_source": peak_src,
+                     "note": "ncu: integer-multiply pipe (fmaheavy) 57-66 % active, DRAM 37-45 %: the passes are bound by BabyBear multiplies, not HBM (DESIGN.md 3.1)"},
+        "ntt_roofline": {"kernel": f"dft_tile_kernel x2: forward NTT 2^{ntt_log} x {ntt_cols} columns via zkir_b200_ntt, natural order in/out (8*n*C bytes)", "bound": "hbm",
+                         "achieved": ntt_gbs, "peak": peak, "unit": "GB/s", "frac": ntt_gbs / peak, "ms": ntt_ms, "timing": "CUDA events on the library stream, 10 launches"},
+        "hash_roofline": {"kernel": "leaf_hash_kernel (Poseidon2 sponge over the 2^21 LDE rows, 14 permutations each) + Merkle levels", "bound": "integer-multiply pipe",
+                          "achieved": hash_gps, "unit": "G permutations/s", "ms": commit_ms,
+                          "ncu_fmaheavy_active_frac": 0.854, "ncu_source": "profiles/r01_ncu_v5.md",
+                          "share_of_step": commit_ms / (dev_ms / K)},
     }
     if not args.no_cpu_baseline:
         v, dt, cores, ccycles, clog = cpu_oracle_run(CPU_SAMPLE_N, 1, 0)

@@ -114,6 +114,10 @@ int zkir_b200_sync(zkir_ctx*);
 #define ZKIR_STAGE_COUNT 8
 int zkir_b200_last_stage_ms(zkir_ctx*, float out[ZKIR_STAGE_COUNT]);
 uint64_t zkir_b200_kernel_launches(const zkir_ctx*); /* kernels launched by this ctx so far */
+/* CUDA-event stopwatch on the context's own stream (the per-kernel entry points launch there, so an outside event on
+ * another stream would not see them): start records an event, stop records a second one, waits for it and returns ms. */
+int zkir_b200_timer_start(zkir_ctx*);
+int zkir_b200_timer_stop(zkir_ctx*, float* ms);
 
 /* ---- host side above the ABI: the interpreter that produces the trace.  Restates, in C++ (no Rust toolchain in
  * this image), zkir-runtime's VM: VM::new/VM::run (vm.rs:138-358), execute (execute.rs:35-673), Memory

@@ -50,6 +50,8 @@ SYMBOLS = {
     "zkir_b200_sync": (C.c_int, [vp]),
     "zkir_b200_last_stage_ms": (C.c_int, [vp, C.POINTER(C.c_float)]),
     "zkir_b200_kernel_launches": (C.c_uint64, [vp]),
+    "zkir_b200_timer_start": (C.c_int, [vp]),
+    "zkir_b200_timer_stop": (C.c_int, [vp, C.POINTER(C.c_float)]),
     "zkir_encode": (C.c_uint32, [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int32]),
     "zkir_decode": (C.c_int, [C.c_uint32, u32p]),
     "zkir_vm_run": (C.c_int, [u32p, C.c_size_t, u8p, C.c_size_t, C.c_uint32, u64p, C.c_size_t, C.c_uint64, C.c_int, C.POINTER(vp)]),

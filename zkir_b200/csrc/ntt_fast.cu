@@ -77,6 +77,7 @@ struct TileParams {
   const u32* in;
   u32* out;
   u32 tiles_per_col, tiles_b;  // tile id -> (a = id / tiles_b, b = id % tiles_b)
+  u32 nz;                      // cosets: blockIdx.x = (col * tiles_per_col + tile) * nz + z, so the nz readers of a tile are co-scheduled (L2)
   u64 in_col, out_col;         // column strides (elements)
   u64 in_z, out_z;             // blockIdx.y (coset) strides
   u32 in_a, in_b, in_r, in_t;  // offsets inside a column (elements)
@@ -105,7 +106,8 @@ dft_tile_kernel(const TileParams p) {
   constexpr int A = SH::A, B_ = SH::B_, EA = SH::EA, XB = SH::XB;
   extern __shared__ u32 sm[];
   const u32 tid = threadIdx.x;
-  const u32 tile = blockIdx.x % p.tiles_per_col, col = blockIdx.x / p.tiles_per_col, z = blockIdx.y;
+  const u32 z = blockIdx.x % p.nz, bid = blockIdx.x / p.nz;
+  const u32 tile = bid % p.tiles_per_col, col = bid / p.tiles_per_col;
   const u32 ta = tile / p.tiles_b, tb = tile - ta * p.tiles_b;
   const u32 in_off0 = ta * p.in_a + tb * p.in_b, out_off0 = ta * p.out_a + tb * p.out_b;
   // no __restrict__ / ld.global.nc on the data: most passes run in place (a tile reads all of its points before the
@@ -240,7 +242,9 @@ static cudaError_t launch_tile_t(const TileParams& p, u32 blocks, u32 z, cudaStr
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  kern<<<dim3(blocks, z), SH::NT, smem, st>>>(p);
+  TileParams q = p;
+  q.nz = z;
+  kern<<<blocks * z, SH::NT, smem, st>>>(q);
   return cudaGetLastError();
 }
 template <int MODE, bool INV>

@@ -110,6 +110,7 @@ struct zkir_ctx {
   u64* d_err = nullptr; u64* h_err = nullptr;
   Workspace ws;
   cudaEvent_t ev[ZKIR_STAGE_COUNT + 1];
+  cudaEvent_t tev[2];
   float stage_ms[ZKIR_STAGE_COUNT] = {0};
   bool have_stage = false;
 };
@@ -390,6 +391,7 @@ int zkir_b200_create(zkir_ctx** out, int device_id) {
   ctx->device = device_id;
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; g_last_error = "stream"; return ZKIR_ERR_CUDA; }
   for (int i = 0; i <= ZKIR_STAGE_COUNT; i++) cudaEventCreate(&ctx->ev[i]);
+  cudaEventCreate(&ctx->tev[0]); cudaEventCreate(&ctx->tev[1]);
   if (poseidon2_init_constants() != 0) { g_last_error = "constant upload failed"; delete ctx; return ZKIR_ERR_CUDA; }
   ctx->tables = ntt_tables_create(ctx->stream, &ctx->launches);
   ctx->fast = fast_ntt_create(ctx->stream, &ctx->launches);
@@ -410,6 +412,7 @@ void zkir_b200_destroy(zkir_ctx* ctx) {
   ntt_tables_destroy(ctx->tables);
   fast_ntt_destroy(ctx->fast);
   for (int i = 0; i <= ZKIR_STAGE_COUNT; i++) cudaEventDestroy(ctx->ev[i]);
+  cudaEventDestroy(ctx->tev[0]); cudaEventDestroy(ctx->tev[1]);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -539,6 +542,20 @@ int zkir_b200_last_stage_ms(zkir_ctx* ctx, float* out) {
   return 0;
 }
 uint64_t zkir_b200_kernel_launches(const zkir_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int zkir_b200_timer_start(zkir_ctx* ctx) {
+  if (!ctx) return ZKIR_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  CU(cudaEventRecord(ctx->tev[0], ctx->stream));
+  return 0;
+}
+int zkir_b200_timer_stop(zkir_ctx* ctx, float* ms) {
+  if (!ctx || !ms) return ZKIR_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  CU(cudaEventRecord(ctx->tev[1], ctx->stream));
+  CU(cudaEventSynchronize(ctx->tev[1]));
+  CU(cudaEventElapsedTime(ms, ctx->tev[0], ctx->tev[1]));
+  return 0;
+}
 
 // ---------------------------------------------------------------- per-kernel entry points (canonical device data)
 int zkir_b200_ntt(zkir_ctx* ctx, uint32_t* d_cols, uint32_t n_cols, uint32_t log_n, int inverse, uint32_t coset_shift) {

@@ -240,6 +240,15 @@ class Context:
     def kernel_launches(self):
         return self._l.zkir_b200_kernel_launches(self._h)
 
+    def timer_start(self):
+        self._check(self._l.zkir_b200_timer_start(self._h))
+
+    def timer_stop(self):
+        """ms between timer_start() and now, CUDA events on the library's launch stream."""
+        ms = C.c_float()
+        self._check(self._l.zkir_b200_timer_stop(self._h, C.byref(ms)))
+        return float(ms.value)
+
     def stage_ms(self):
         out = (C.c_float * len(_ffi.STAGES))()
         self._check(self._l.zkir_b200_last_stage_ms(self._h, out))
