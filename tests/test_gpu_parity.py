@@ -228,3 +228,44 @@ def test_large_trace_proves_and_verifies(gpu_ctx):
     pb = gpu_ctx.prove_columns(cols, pv, cfg)
     ok, why = zkir_b200.verify(pb, cfg, pv)
     assert ok, why
+
+
+def test_2p22_row_trace_proves_and_verifies(gpu_ctx):
+    """BASELINE config 3 size (2^22 rows; three NTT digits 8+7+7): raw rows in, device converter, proof accepted by the
+    independent CPU verifier, and a flipped proof bit rejected.  (Byte comparison with the scalar oracle would take minutes.)"""
+    from conftest import fib_program_input
+    n = 838860                                   # 5n - 2 = 4_194_298 cycles <= 2^22
+    res = zkir_b200.VM(fib_program_input(), [n], zkir_b200.VMConfig(max_cycles=1 << 23, enable_execution_trace=True)).run()
+    assert res.cycles == 5 * n - 2 and res.min_log_n() == 22
+    cfg = zkir_b200.ProverConfig(num_queries=40, pow_bits=12)
+    pb, pv = gpu_ctx.prove_rows(res.rows(), cfg, 22)
+    assert list(pv[:2]) == [0x1000, (5 * n - 2) % P]
+    ok, why = zkir_b200.verify(pb, cfg, pv)
+    assert ok, why
+    bad = bytearray(pb)
+    bad[len(bad) // 2] ^= 4
+    ok, _ = zkir_b200.verify(bytes(bad), cfg, pv)
+    assert not ok
+
+
+ADD_SRC = "addi r10, r0, 1\necall\nadd r1, r10, r0\naddi r10, r0, 1\necall\nadd r11, r1, r10\naddi r10, r0, 2\necall\naddi r10, r0, 0\naddi r11, r0, 0\necall\n"
+
+
+def test_prove_batch_matches_single_proofs(gpu_ctx, oracle):
+    """BASELINE config 4 (a+b, 11 cycles -> 2^4 rows, many independent proofs): the concurrent batch path returns, for
+    every i, exactly the bytes a single zkir_b200_prove gives, which equal the oracle's."""
+    prog = zkir_b200.assemble(ADD_SRC)
+    cfg = zkir_b200.ProverConfig(num_queries=16, pow_bits=4)
+    traces = []
+    for i in range(24):
+        res = zkir_b200.VM(prog, [i, 2 * i + 1], zkir_b200.VMConfig(enable_execution_trace=True)).run()
+        assert res.outputs == [3 * i + 1] and res.cycles == 11
+        traces.append(res.pack())
+    batch = gpu_ctx.prove_batch([c for c, _ in traces], [p for _, p in traces], cfg)
+    assert len(batch) == 24
+    for i, (cols, pv) in enumerate(traces):
+        assert batch[i] == gpu_ctx.prove_columns(cols, pv, cfg)
+        ok, why = zkir_b200.verify(batch[i], cfg, pv)
+        assert ok, why
+    for i in (0, 7, 23):
+        assert batch[i] == oracle.prove(cfg, *traces[i])

@@ -11,6 +11,7 @@
 #include <string>
 #include <vector>
 #include <map>
+#include <thread>
 #include "zkir_b200.h"
 #include "bb.cuh"
 #include "kernels.h"
@@ -108,6 +109,7 @@ struct zkir_ctx {
   u32* scratch[2] = {nullptr, nullptr}; size_t scratch_bytes[2] = {0, 0};
   void* rows_dev = nullptr; size_t rows_bytes = 0;   // staging for raw interpreter rows (prove_rows)
   u64* d_err = nullptr; u64* h_err = nullptr;
+  std::vector<zkir_ctx*> workers;                    // extra contexts of the same device for prove_batch
   Workspace ws;
   cudaEvent_t ev[ZKIR_STAGE_COUNT + 1];
   cudaEvent_t tev[2];
@@ -401,6 +403,8 @@ int zkir_b200_create(zkir_ctx** out, int device_id) {
 
 void zkir_b200_destroy(zkir_ctx* ctx) {
   if (!ctx) return;
+  for (zkir_ctx* w : ctx->workers) zkir_b200_destroy(w);
+  ctx->workers.clear();
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   ws_free(ctx);
@@ -526,12 +530,48 @@ int zkir_b200_expand_rows(zkir_ctx* ctx, const uint64_t* pcs, const uint32_t* in
   return expand_error(ctx);
 }
 
+// Many independent small proofs (BASELINE config 4).  A tiny proof is launch-latency bound (about 150 dependent launches),
+// so the batch is spread over up to 8 worker contexts of the same device, each with its own stream and host thread:
+// the GPU overlaps their kernels.  Proof i is bit-identical to zkir_b200_prove(traces[i]) on a single context.
 int zkir_b200_prove_batch(zkir_ctx* ctx, const zkir_params* p, const uint32_t* const* traces, const uint32_t* log_ns,
                           const uint32_t* const* pvs, uint32_t n_proofs, uint8_t** proofs, size_t* proof_lens) {
   if (!ctx || !traces || !log_ns || !pvs || !proofs || !proof_lens) return ZKIR_ERR_ARG;
-  for (uint32_t i = 0; i < n_proofs; i++) {
-    int rc = zkir_b200_prove(ctx, p, traces[i], log_ns[i], pvs[i], &proofs[i], &proof_lens[i]);
-    if (rc) { for (uint32_t j = 0; j < i; j++) { free(proofs[j]); proofs[j] = nullptr; } return rc; }
+  ctx->err.clear();
+  for (uint32_t i = 0; i < n_proofs; i++) { proofs[i] = nullptr; proof_lens[i] = 0; }
+  uint32_t nw = n_proofs < 8 ? n_proofs : 8;
+  const char* env = getenv("ZKIR_BATCH_WORKERS");
+  if (env && atoi(env) > 0) nw = (uint32_t)atoi(env) < n_proofs ? (uint32_t)atoi(env) : n_proofs;
+  if (nw <= 1) {
+    for (uint32_t i = 0; i < n_proofs; i++) {
+      int rc = zkir_b200_prove(ctx, p, traces[i], log_ns[i], pvs[i], &proofs[i], &proof_lens[i]);
+      if (rc) { for (uint32_t j = 0; j < i; j++) { free(proofs[j]); proofs[j] = nullptr; } return rc; }
+    }
+    return 0;
+  }
+  while (ctx->workers.size() < nw) {
+    zkir_ctx* w = nullptr;
+    int rc = zkir_b200_create(&w, ctx->device);
+    if (rc) { ctx->err = "worker context: " + g_last_error; return rc; }
+    ctx->workers.push_back(w);
+  }
+  std::vector<int> rcs(nw, 0);
+  std::vector<std::thread> th;
+  for (uint32_t w = 0; w < nw; w++) {
+    th.emplace_back([&, w]() {
+      zkir_ctx* wc = ctx->workers[w];
+      for (uint32_t i = w; i < n_proofs; i += nw) {
+        int rc = zkir_b200_prove(wc, p, traces[i], log_ns[i], pvs[i], &proofs[i], &proof_lens[i]);
+        if (rc) { rcs[w] = rc; return; }
+      }
+    });
+  }
+  for (auto& t : th) t.join();
+  for (uint32_t w = 0; w < nw; w++) {
+    if (rcs[w]) {
+      ctx->err = ctx->workers[w]->err;
+      for (uint32_t j = 0; j < n_proofs; j++) { free(proofs[j]); proofs[j] = nullptr; proof_lens[j] = 0; }
+      return rcs[w];
+    }
   }
   return 0;
 }

@@ -273,6 +273,24 @@ class Context:
         self._l.zkir_b200_free_proof(proof)
         return out
 
+    def prove_batch(self, cols_list, pv_list, cfg):
+        """Independent proofs of many (small) traces: zkir_b200_prove_batch.  Returns the list of proof bytes."""
+        n = len(cols_list)
+        params = cfg.params()
+        keep = [np.ascontiguousarray(c, dtype=np.uint32) for c in cols_list]
+        pvs = [np.ascontiguousarray(p, dtype=np.uint32) for p in pv_list]
+        tr = (C.c_void_p * n)(*[c.ctypes.data for c in keep])
+        pp = (C.c_void_p * n)(*[p.ctypes.data for p in pvs])
+        lg = (C.c_uint32 * n)(*[int(c.shape[1]).bit_length() - 1 for c in keep])
+        out = (C.c_void_p * n)()
+        lens = (C.c_size_t * n)()
+        self._check(self._l.zkir_b200_prove_batch(self._h, C.byref(params), tr, lg, pp, n, out, lens))
+        res = []
+        for i in range(n):
+            res.append(C.string_at(out[i], lens[i]))
+            self._l.zkir_b200_free_proof(out[i])
+        return res
+
     def prove_rows(self, rows, cfg, log_n=None):
         """rows: dict as returned by ExecutionResult.rows() (arrays may live in PinnedBuffers).  The device runs the
         converter; returns (proof bytes, public values)."""
