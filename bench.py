@@ -4,9 +4,9 @@
 Step = one full proof of the 2^20-row fibonacci trace (BASELINE configs[1]): LDE, Merkle commitments, quotient,
 openings, FRI, queries.  `value` = real VM cycles proved per second with the packed trace already in HBM
 (device time of the step from CUDA events on the library's launch stream); `e2e` = the same through
-zkir_b200_prove_rows with the interpreter's raw rows (pc, word, regs[16]: what the reference's TraceRow holds) in pinned
-HOST memory: H2D of the rows, the device-side converter and the D2H of the proof are inside the timed region (wall
-clock bracketed by device syncs).  N>1: every rank proves its own trace (independent proofs, no
+zkir_b200_prove_writelog with the interpreter's register write log (pc, word, written register and value per cycle) in
+pinned HOST memory: the H2D copy, the device-side register reconstruction + converter and the D2H of the proof are inside
+the timed region (wall clock bracketed by device syncs); `e2e.full_rows` is the same with the reference's full TraceRow data.  N>1: every rank proves its own trace (independent proofs, no
 data-path collective; weak scaling), value = cycles of all ranks / max-over-ranks time.
 
 `--impl reference`: the reference contains no prover, so the reference arm times this
@@ -165,6 +165,12 @@ def main():
         pin[k].array[...] = rows[k]
     prows = dict(rows, **{k: pin[k].array for k in pin})
     rows_bytes = int(sum(pin[k].array.nbytes for k in pin))
+    # the same execution as a register write log (pc32, word, (reg << 56 | value)): 16 B/row, also pinned
+    T = int(rows["pcs"].shape[0])
+    pin_wl = {"pcs": zkir_b200.PinnedBuffer((T,), np.uint32), "wlog": zkir_b200.PinnedBuffer((T,), np.uint64), "instrs": pin["instrs"]}
+    wl = res.writelog(out={"pcs": pin_wl["pcs"].array, "wlog": pin_wl["wlog"].array})
+    wl["instrs"] = pin["instrs"].array
+    wl_bytes = int(wl["pcs"].nbytes + wl["wlog"].nbytes + wl["instrs"].nbytes)
     d_trace = ctx.to_device(cols)
     proof_bytes = 0
 
@@ -194,15 +200,21 @@ def main():
     # ---------------- end-to-end arm (host buffers through the C ABI)
     for _ in range(2):
         pb_rows, pv_rows = ctx.prove_rows(prows, cfg, log_n)
-    if pb_rows != pb or list(pv_rows) != list(pv):
-        raise SystemExit("prove_rows (device converter) and prove_columns (host converter) disagree")
+        pb_wl, pv_wl = ctx.prove_writelog(wl, cfg, log_n)
+    if pb_rows != pb or list(pv_rows) != list(pv) or pb_wl != pb or list(pv_wl) != list(pv):
+        raise SystemExit("device converters (rows / write log) and the host converter disagree")
     barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ctx.prove_writelog(wl, cfg, log_n)
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    e2e_stage = ctx.stage_ms()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         ctx.prove_rows(prows, cfg, log_n)
     barrier()
-    e2e_ms = (time.perf_counter() - t0) * 1e3
-    e2e_stage = ctx.stage_ms()
+    e2e_rows_ms = (time.perf_counter() - t0) * 1e3
     clocks = sampler.summary(clk_mark)
 
     # ---------------- NTT roofline microbench: one forward transform of the trace size on all W columns (8*n*C algorithmic
@@ -221,10 +233,10 @@ def main():
     ctx.free(d_ntt)
 
     # max over ranks
-    vals = torch.tensor([dev_ms, wall_ms, e2e_ms], dtype=torch.float64, device="cuda")
+    vals = torch.tensor([dev_ms, wall_ms, e2e_ms, e2e_rows_ms], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(vals, op=dist.ReduceOp.MAX)
-    dev_ms, wall_ms, e2e_ms = [float(x) for x in vals.tolist()]
+    dev_ms, wall_ms, e2e_ms, e2e_rows_ms = [float(x) for x in vals.tolist()]
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -256,8 +268,10 @@ def main():
                    "vm_trace_seconds": round(vm_s, 3), "proof_bytes": proof_bytes},
         "clocks": clocks,
         "e2e": {"value": world * cycles / (e2e_ms / K * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms / K,
-                "h2d_bytes_per_step": rows_bytes, "d2h_bytes_per_step": proof_bytes, "h2d_and_convert_ms": e2e_stage["h2d"],
-                "api": "zkir_b200_prove_rows: raw interpreter rows (pc, word, regs[16]) in pinned host memory -> proof bytes in host memory"},
+                "h2d_bytes_per_step": wl_bytes, "d2h_bytes_per_step": proof_bytes, "h2d_and_convert_ms": e2e_stage["h2d"],
+                "api": "zkir_b200_prove_writelog: the interpreter's register write log (pc, word, reg<<56|value) in pinned host memory -> proof bytes in host memory",
+                "full_rows": {"value": world * cycles / (e2e_rows_ms / K * 1e-3), "ms_per_step": e2e_rows_ms / K, "h2d_bytes_per_step": rows_bytes,
+                              "api": "zkir_b200_prove_rows: TraceRow data as recorded upstream (pc, word, regs[16])"}},
         "gpu_launches": int(launches),
         "stage_ms": {k: v / K for k, v in stage_acc.items()},
         "roofline": {"kernel": "dft_tile_kernel: LDE stage = 2 inverse + 2x2 forward digit passes (radix-32 register tiles) over 112 columns, 2^20 -> 2^21 points",

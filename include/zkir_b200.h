@@ -70,6 +70,16 @@ int zkir_b200_prove_device(zkir_ctx*, const zkir_params*, const uint32_t* d_trac
 int zkir_b200_prove_rows(zkir_ctx*, const zkir_params*, const uint64_t* pcs, const uint32_t* instrs, const uint64_t* regs,
                          uint64_t n_rows, const uint64_t* final_regs, uint64_t final_pc, uint32_t entry_point, uint64_t exit_code,
                          uint32_t log_n, uint32_t* public_values_out, uint8_t** proof, size_t* proof_len);
+/* same from the interpreter's REGISTER WRITE LOG, the most compact hand-off: per row pc (u32), instruction word and
+ * wlog = (k << 56) | value if the row changed register k, else 0 (zkir_vm_trace_writelog builds it from recorded rows; a
+ * Rust recorder logs it where VMState writes a register, zkir-runtime/src/state.rs:76-91).  The device rebuilds the
+ * pre-state registers of every row with a last-writer scan (registers start at 0: vm.rs:177-181), then runs the same
+ * converter.  16 B/row cross PCIe. */
+int zkir_b200_prove_writelog(zkir_ctx*, const zkir_params*, const uint32_t* pcs, const uint32_t* instrs, const uint64_t* wlog,
+                             uint64_t n_rows, uint64_t final_pc, uint32_t entry_point, uint64_t exit_code, uint32_t log_n,
+                             uint32_t* public_values_out, uint8_t** proof, size_t* proof_len);
+int zkir_b200_expand_writelog(zkir_ctx*, const uint32_t* pcs, const uint32_t* instrs, const uint64_t* wlog, uint64_t n_rows,
+                              uint64_t final_pc, uint32_t log_n, uint32_t* d_cols);
 /* the device converter alone (parity tests): rows -> d_cols [112][1 << log_n] canonical, device memory */
 int zkir_b200_expand_rows(zkir_ctx*, const uint64_t* pcs, const uint32_t* instrs, const uint64_t* regs, uint64_t n_rows,
                           const uint64_t* final_regs, uint64_t final_pc, uint32_t log_n, uint32_t* d_cols);
@@ -149,6 +159,7 @@ const uint64_t* zkir_vm_trace_regs(const zkir_vm_result*); /* [cycle][16], PRE-s
 const uint64_t* zkir_vm_trace_aux(const zkir_vm_result*);
 const uint64_t* zkir_vm_trace_memop_begin(const zkir_vm_result*);
 const zkir_mem_op* zkir_vm_trace_memops(const zkir_vm_result*);
+int zkir_vm_trace_writelog(const zkir_vm_result*, uint32_t* pcs32 /*[trace_len]*/, uint64_t* wlog /*[trace_len]*/);
 uint64_t zkir_vm_final_pc(const zkir_vm_result*);
 const uint64_t* zkir_vm_final_regs(const zkir_vm_result*);
 

@@ -165,6 +165,9 @@ ecall
 }
 
 
+ROW_PROGRAMS["read_one"] = ("src", "addi r10, r0, 1\necall\nadd r3, r10, r10\naddi r10, r0, 1\necall\nadd r10, r0, r0\necall\n", [1, 1])
+
+
 def _rows_case(name):
     from conftest import fib_program, fib_program_input
     kind, arg, inputs = ROW_PROGRAMS[name]
@@ -186,6 +189,32 @@ def test_expand_rows_matches_host_packer(gpu_ctx, name):
         assert bad.size == 0, f"first mismatch column {zkir_b200.air_layout.COLUMNS[bad[0][0]]} row {bad[0][1]}: gpu={got[tuple(bad[0])]} host={cols[tuple(bad[0])]}"
 
 
+@pytest.mark.parametrize("name", sorted(ROW_PROGRAMS))
+def test_expand_writelog_matches_host_packer(gpu_ctx, name):
+    """register write log (16 B/row) -> last-writer scan -> converter == host converter on the full rows"""
+    res = _rows_case(name)
+    for log_n in (res.min_log_n(), res.min_log_n() + 1, 11):
+        cols, pv = res.pack(log_n)
+        d = gpu_ctx.alloc(cols.nbytes)
+        gpu_ctx.expand_writelog(res.writelog(), log_n, d)
+        got = gpu_ctx.to_host(d, cols.shape)
+        gpu_ctx.free(d)
+        bad = np.argwhere(got != cols)
+        assert bad.size == 0, f"first mismatch column {zkir_b200.air_layout.COLUMNS[bad[0][0]]} row {bad[0][1]}: gpu={got[tuple(bad[0])]} host={cols[tuple(bad[0])]}"
+
+
+def test_expand_writelog_long_trace(gpu_ctx):
+    """many chunks: exercises the cross-chunk scan (2^16 rows = 256 chunks of 256 rows)"""
+    _, cols, pv = fib_trace(n_input=13000, log_n=16)
+    from conftest import fib_program_input
+    res = zkir_b200.VM(fib_program_input(), [13000], zkir_b200.VMConfig(max_cycles=1 << 20, enable_execution_trace=True)).run()
+    d = gpu_ctx.alloc(cols.nbytes)
+    gpu_ctx.expand_writelog(res.writelog(), 16, d)
+    got = gpu_ctx.to_host(d, cols.shape)
+    gpu_ctx.free(d)
+    assert np.array_equal(got, cols)
+
+
 def test_expand_rows_rejects_unconstrained_opcode(gpu_ctx):
     prog = zkir_b200.assemble("addi r1, r0, 3\nmul r2, r1, r1\nadd r10, r0, r0\necall\n")
     res = zkir_b200.VM(prog, [], zkir_b200.VMConfig(enable_execution_trace=True)).run()
@@ -203,8 +232,9 @@ def test_prove_rows_equals_prove_columns(gpu_ctx, oracle, name):
     cols, pv = res.pack()
     from_cols = gpu_ctx.prove_columns(cols, pv, cfg)
     from_rows, pv2 = gpu_ctx.prove_rows(res.rows(), cfg)
-    assert np.array_equal(pv, pv2)
-    assert from_rows == from_cols == oracle.prove(cfg, cols, pv)
+    from_wl, pv3 = gpu_ctx.prove_writelog(res.writelog(), cfg)
+    assert np.array_equal(pv, pv2) and np.array_equal(pv, pv3)
+    assert from_rows == from_cols == from_wl == oracle.prove(cfg, cols, pv)
 
 
 def test_prove_api_end_to_end(gpu_ctx):

@@ -208,3 +208,22 @@ def test_runtime_errors():
         VM(Program([encode("ebreak")], entry_point=0x10))                       # vm.rs:141-147
     with pytest.raises(z.RuntimeError, match="Decode error"):
         VM(prog([0x7F])).run()
+
+
+def test_writelog_matches_register_diff():
+    """zkir_vm_trace_writelog == the diff of consecutive PRE-state register files (what a Rust recorder would log in
+    VMState::write_reg, zkir-runtime/src/state.rs:76-91)."""
+    import numpy as np
+    from conftest import fib_program_input
+    res = VM(fib_program_input(), [40], VMConfig(enable_execution_trace=True)).run()
+    rows, wl = res.rows(), res.writelog()
+    regs = np.vstack([rows["regs"], rows["final_regs"][None, :]])
+    assert np.array_equal(wl["pcs"].astype(np.uint64), rows["pcs"])
+    for i in range(res.cycles):
+        changed = np.nonzero(regs[i + 1] != regs[i])[0]
+        if len(changed) == 0:
+            assert wl["wlog"][i] == 0
+        else:
+            assert len(changed) == 1
+            k = int(changed[0])
+            assert int(wl["wlog"][i]) == (k << 56) | int(regs[i + 1][k])

@@ -33,6 +33,9 @@ SYMBOLS = {
     "zkir_b200_prove_rows": (C.c_int, [vp, C.POINTER(Params), vp, vp, vp, C.c_uint64, u64p, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint32, u32p,
                                       C.POINTER(vp), C.POINTER(C.c_size_t)]),
     "zkir_b200_expand_rows": (C.c_int, [vp, vp, vp, vp, C.c_uint64, u64p, C.c_uint64, C.c_uint32, vp]),
+    "zkir_b200_prove_writelog": (C.c_int, [vp, C.POINTER(Params), vp, vp, vp, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint32, u32p,
+                                          C.POINTER(vp), C.POINTER(C.c_size_t)]),
+    "zkir_b200_expand_writelog": (C.c_int, [vp, vp, vp, vp, C.c_uint64, C.c_uint64, C.c_uint32, vp]),
     "zkir_b200_prove_batch": (C.c_int, [vp, C.POINTER(Params), C.POINTER(vp), u32p, C.POINTER(vp), C.c_uint32, C.POINTER(vp), C.POINTER(C.c_size_t)]),
     "zkir_b200_free_proof": (None, [vp]),
     "zkir_b200_proof_size": (C.c_size_t, [C.POINTER(Params), C.c_uint32]),
@@ -69,6 +72,7 @@ SYMBOLS = {
     "zkir_vm_trace_aux": (u64p, [vp]),
     "zkir_vm_trace_memop_begin": (u64p, [vp]),
     "zkir_vm_trace_memops": (C.POINTER(MemOp), [vp]),
+    "zkir_vm_trace_writelog": (C.c_int, [vp, vp, vp]),
     "zkir_vm_final_pc": (C.c_uint64, [vp]),
     "zkir_vm_final_regs": (u64p, [vp]),
     "zkir_pack_min_log_n": (C.c_uint32, [vp]),

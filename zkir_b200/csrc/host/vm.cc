@@ -309,4 +309,30 @@ uint64_t zkir_vm_final_pc(const zkir_vm_result* r) { return r->final_pc; }
 const uint64_t* zkir_vm_final_regs(const zkir_vm_result* r) { return r->final_regs; }
 const uint64_t* zkir_vm_trace_aux(const zkir_vm_result* r) { return r->aux.data(); }
 
+// Register write log of the recorded rows: pcs32[i] = pc of row i, wlog[i] = (k << 56) | value when row i changed
+// register k (pre-state of row i+1 differs from row i; r0 never changes), 0 when it changed nothing.  Returns
+// ZKIR_ERR_AIR if a row changed more than one register or wrote a value above 40 bits (the compact format cannot
+// express it; use the full-row entry point).  16 B/row instead of 140 B/row cross PCIe.
+int zkir_vm_trace_writelog(const zkir_vm_result* r, uint32_t* pcs32, uint64_t* wlog) {
+  const size_t T = r->pc.size();
+  for (size_t i = 0; i < T; i++) {
+    const u64* cur = r->regs.data() + 16 * i;
+    const u64* nxt = i + 1 < T ? cur + 16 : r->final_regs;
+    u64 w = 0;
+    int changed = 0;
+    for (int k = 1; k < 16; k++) {
+      if (nxt[k] != cur[k]) {
+        changed++;
+        if (nxt[k] >> 40) { g_vm_error = "write log: value above 40 bits at row " + std::to_string(i); return ZKIR_ERR_AIR; }
+        w = ((u64)k << 56) | nxt[k];
+      }
+    }
+    if (changed > 1) { g_vm_error = "write log: more than one register changed at row " + std::to_string(i); return ZKIR_ERR_AIR; }
+    if (r->pc[i] >> 32) { g_vm_error = "write log: pc above 32 bits at row " + std::to_string(i); return ZKIR_ERR_AIR; }
+    pcs32[i] = (u32)r->pc[i];
+    wlog[i] = w;
+  }
+  return 0;
+}
+
 }  // extern "C"

@@ -76,6 +76,18 @@ struct ExpandArgs {
   u64* err;              // out: min over offending rows of (row << 8 | reason); ~0 = none
 };
 int launch_trace_expand(const ExpandArgs& a, cudaStream_t st, u64* launches);
+struct WlArgs {          // register write log instead of full rows (trace_expand.cu)
+  const u32* pcs;        // [T]
+  const u32* ins;        // [T]
+  const u64* wlog;       // [T]: (k << 56) | value when the row changed register k, else 0
+  u64 T, N;
+  u64 final_pc;
+  int* chunk_prev;       // scratch, trace_expand_wl_scratch_ints(N) ints
+  u32* cols;
+  u64* err;
+};
+u64 trace_expand_wl_scratch_ints(u64 N);
+int launch_trace_expand_wl(const WlArgs& a, cudaStream_t st, u64* launches);
 
 // ---- stark.cu (openings, DEEP combination, FRI fold, queries, misc)
 int launch_map(u32* dst, const u32* src, u64 n, int to_mont, cudaStream_t st, u64* launches);

@@ -519,6 +519,68 @@ int zkir_b200_prove_rows(zkir_ctx* ctx, const zkir_params* p, const uint64_t* pc
   return 0;
 }
 
+// write-log flavour: H2D of (pc32, word, wlog) + last-writer scan + converter
+static int expand_writelog(zkir_ctx* ctx, const uint32_t* pcs, const uint32_t* instrs, const uint64_t* wlog, uint64_t T, uint64_t final_pc,
+                           uint32_t log_n, u32* d_cols) {
+  const u64 N = 1ull << log_n;
+  if (T > N || !pcs || !instrs || !wlog) { ctx->err = "bad write log: need n_rows <= 2^log_n and non-null arrays"; return ZKIR_ERR_ARG; }
+  const size_t scratch = trace_expand_wl_scratch_ints(N) * 4;
+  const size_t need = T * 16 + scratch + 64;
+  if (ctx->rows_bytes < need) {
+    if (ctx->rows_dev) cudaFree(ctx->rows_dev);
+    ctx->rows_dev = nullptr; ctx->rows_bytes = 0;
+    CU(cudaMalloc(&ctx->rows_dev, need));
+    ctx->rows_bytes = need;
+  }
+  if (!ctx->d_err) { CU(cudaMalloc(&ctx->d_err, 8)); CU(cudaMallocHost(&ctx->h_err, 8)); }
+  char* base = (char*)ctx->rows_dev;
+  u64* d_wlog = (u64*)base;
+  u32* d_pcs = (u32*)(base + T * 8);
+  u32* d_ins = (u32*)(base + T * 12);
+  int* d_scr = (int*)(base + ((T * 16 + 15) & ~(size_t)15));
+  cudaStream_t st = ctx->stream;
+  CU(cudaMemcpyAsync(d_wlog, wlog, T * 8, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d_pcs, pcs, T * 4, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d_ins, instrs, T * 4, cudaMemcpyHostToDevice, st));
+  CU(cudaMemsetAsync(ctx->d_err, 0xff, 8, st));
+  WlArgs wa;
+  wa.pcs = d_pcs; wa.ins = d_ins; wa.wlog = d_wlog; wa.T = T; wa.N = N; wa.final_pc = final_pc; wa.chunk_prev = d_scr; wa.cols = d_cols; wa.err = ctx->d_err;
+  RC(launch_trace_expand_wl(wa, st, &ctx->launches));
+  CU(cudaMemcpyAsync(ctx->h_err, ctx->d_err, 8, cudaMemcpyDeviceToHost, st));
+  return 0;
+}
+
+int zkir_b200_prove_writelog(zkir_ctx* ctx, const zkir_params* p, const uint32_t* pcs, const uint32_t* instrs, const uint64_t* wlog,
+                             uint64_t n_rows, uint64_t final_pc, uint32_t entry_point, uint64_t exit_code, uint32_t log_n,
+                             uint32_t* pv_out, uint8_t** proof, size_t* proof_len) {
+  if (!ctx) return ZKIR_ERR_ARG;
+  ctx->err.clear();
+  cudaSetDevice(ctx->device);
+  int rc = check_params(ctx, p, log_n);
+  if (rc) return rc;
+  if (!pv_out || !proof || !proof_len) { ctx->err = "null argument"; return ZKIR_ERR_ARG; }
+  if ((rc = ws_prepare(ctx, p, log_n)) != 0) return rc;
+  CU(cudaEventRecord(ctx->ev[ZKIR_STAGE_H2D], ctx->stream));
+  if ((rc = expand_writelog(ctx, pcs, instrs, wlog, n_rows, final_pc, log_n, ctx->ws.trace)) != 0) return rc;
+  const u64 LIMB = (1u << 20) - 1;
+  pv_out[0] = entry_point; pv_out[1] = (u32)(n_rows % BB_P); pv_out[2] = (u32)(exit_code & LIMB); pv_out[3] = (u32)((exit_code >> 20) & LIMB);
+  if ((rc = prove_resident(ctx, p, log_n, pv_out, ctx->ws.trace)) != 0) return rc;
+  if ((rc = finish_proof(ctx, p, log_n, proof, proof_len)) != 0) return rc;
+  if ((rc = expand_error(ctx)) != 0) { free(*proof); *proof = nullptr; *proof_len = 0; return rc; }
+  return 0;
+}
+
+int zkir_b200_expand_writelog(zkir_ctx* ctx, const uint32_t* pcs, const uint32_t* instrs, const uint64_t* wlog, uint64_t n_rows,
+                              uint64_t final_pc, uint32_t log_n, uint32_t* d_cols) {
+  if (!ctx || !d_cols || log_n < 2 || log_n > 26) return ZKIR_ERR_ARG;
+  ctx->err.clear();
+  cudaSetDevice(ctx->device);
+  int rc = expand_writelog(ctx, pcs, instrs, wlog, n_rows, final_pc, log_n, d_cols);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(ctx->stream));
+  return expand_error(ctx);
+}
+
 int zkir_b200_expand_rows(zkir_ctx* ctx, const uint64_t* pcs, const uint32_t* instrs, const uint64_t* regs, uint64_t n_rows,
                           const uint64_t* final_regs, uint64_t final_pc, uint32_t log_n, uint32_t* d_cols) {
   if (!ctx || !d_cols || log_n < 2 || log_n > 26) return ZKIR_ERR_ARG;

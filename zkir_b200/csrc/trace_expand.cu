@@ -16,21 +16,15 @@ namespace zkir {
 
 __device__ __forceinline__ int sext_dev(u32 v, int bits) { const int sh = 32 - bits; return ((int)(v << sh)) >> sh; }
 
-__global__ void __launch_bounds__(128) trace_expand_kernel(ExpandArgs a) {
-  const u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x;
-  const u64 N = a.N, T = a.T;
-  if (i >= N) return;
+// One row: rg = PRE-state registers, w = instruction word, read_val = post-state r10 (only used by READ rows).
+__device__ __forceinline__ void expand_row(u64 i, u64 N, u64 T, const u64 (&rg)[16], u64 pc, u32 w, u64 read_val, u32* cols, u64* errp) {
   const u64 LIMB = (1u << 20) - 1, M40 = (1ull << 40) - 1;
   const bool live = i < T;
-  u64 rg[16];
-#pragma unroll
-  for (int k = 0; k < 16; k++) rg[k] = live ? a.regs[16 * i + k] : a.final_regs[k];
-  const u64 pc = live ? a.pcs[i] : a.final_pc;
   u32 err = 0;
   if (pc + 4 >= (1u << 30)) err = 1;
 #pragma unroll
   for (int k = 1; k < 16; k++) if (rg[k] >> 40) err = 2;
-  u32* col = a.cols + i;
+  u32* col = cols + i;
   auto W = [&](int c, u32 v) { col[(u64)c * N] = v; };
 
   W(ZKIR_COL_CLK, (u32)((live ? i : T) % BB_P));
@@ -49,7 +43,7 @@ __global__ void __launch_bounds__(128) trace_expand_kernel(ExpandArgs a) {
   if (!live) {
     s_pad = 1;
   } else {
-    const u32 w = a.ins[i], op = w & 0x7F;
+    const u32 op = w & 0x7F;
     const u32 fa = (w >> 7) & 0xF, fb = (w >> 11) & 0xF, fc = (w >> 15) & 0xF;
     auto R = [&](u32 k) -> u64 {  // register read without dynamic indexing of the local array
       u64 v = 0;
@@ -77,9 +71,9 @@ __global__ void __launch_bounds__(128) trace_expand_kernel(ExpandArgs a) {
       s_ecall = 1;
       const u64 num = rg[10];
       if (num == 0) is_exit = 1;
-      else if (num == 1) {                   // READ: the value is the post-state r10 = next row's pre-state r10
+      else if (num == 1) {                   // READ: the value is the post-state r10
         is_read = 1; rd = 10;
-        io = (i + 1 < T) ? a.regs[16 * (i + 1) + 10] : a.final_regs[10];
+        io = read_val;
         cv = io;
         if (io >> 40) err = 3;
       } else if (num == 2) { is_write = 1; io = rg[11]; }
@@ -131,13 +125,117 @@ __global__ void __launch_bounds__(128) trace_expand_kernel(ExpandArgs a) {
   W(ZKIR_COL_IO_LO, (u32)(io & LIMB)); W(ZKIR_COL_IO_HI, (u32)(io >> 20));
   if (err) {  // first offending row wins; the host reports it after the stream is drained
     const unsigned long long packed = (i << 8) | err;
-    atomicMin(reinterpret_cast<unsigned long long*>(a.err), packed);
+    atomicMin(reinterpret_cast<unsigned long long*>(errp), packed);
   }
+}
+
+
+__global__ void __launch_bounds__(128) trace_expand_kernel(ExpandArgs a) {
+  const u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x;
+  if (i >= a.N) return;
+  const bool live = i < a.T;
+  u64 rg[16];
+#pragma unroll
+  for (int k = 0; k < 16; k++) rg[k] = live ? a.regs[16 * i + k] : a.final_regs[k];
+  const u64 read_val = (i + 1 < a.T) ? a.regs[16 * (i + 1) + 10] : a.final_regs[10];
+  expand_row(i, a.N, a.T, rg, live ? a.pcs[i] : a.final_pc, live ? a.ins[i] : 0u, read_val, a.cols, a.err);
+}
+
+// ---- write-log input: rebuild the pre-state registers with a last-writer scan.
+// wlog[i] = (k << 56) | value if row i changed register k.  Chunk = WL_CHUNK rows = one block, one row per thread (so
+// every column store of a warp is still one 128 B segment).
+//   pass 1: per chunk and register, the last row of the chunk that wrote it (shared-memory atomicMax)
+//   pass 2: one block turns that into "last writer before the chunk starts" (running maximum over chunks)
+//   pass 3: per chunk, an exclusive prefix maximum over the rows (warp shuffles + one cross-warp step) gives every row
+//           its last writer of each register; the register value is gathered from wlog (recent rows: L2 hits).
+#define WL_CHUNK 256
+#define WL_SCAN_THREADS 512
+__global__ void __launch_bounds__(WL_CHUNK) wl_chunk_last_kernel(const u64* __restrict__ wlog, u64 T, int* __restrict__ chunk_last) {
+  __shared__ int last[16];
+  if (threadIdx.x < 16) last[threadIdx.x] = -1;
+  __syncthreads();
+  const u64 i = (u64)blockIdx.x * WL_CHUNK + threadIdx.x;
+  if (i < T) {
+    const u32 k = (u32)(wlog[i] >> 56) & 15u;
+    if (k) atomicMax(&last[k], (int)i);
+  }
+  __syncthreads();
+  if (threadIdx.x < 16) chunk_last[blockIdx.x * 16 + threadIdx.x] = last[threadIdx.x];
+}
+// in place: chunk_last[c][k] becomes the last writer of k BEFORE chunk c.  One block; each thread owns a contiguous range.
+__global__ void __launch_bounds__(WL_SCAN_THREADS) wl_chunk_scan_kernel(int* cl, u32 n_chunks) {
+  __shared__ int tot[WL_SCAN_THREADS][16];
+  const u32 t = threadIdx.x, per = (n_chunks + WL_SCAN_THREADS - 1) / WL_SCAN_THREADS;
+  const u32 c0 = t * per, c1 = c0 + per < n_chunks ? c0 + per : n_chunks;
+  int run[16];
+#pragma unroll
+  for (int k = 0; k < 16; k++) run[k] = -1;
+  for (u32 c = c0; c < c1; c++) {
+#pragma unroll
+    for (int k = 0; k < 16; k++) { const int v = cl[c * 16 + k]; run[k] = v > run[k] ? v : run[k]; }
+  }
+#pragma unroll
+  for (int k = 0; k < 16; k++) tot[t][k] = run[k];
+  __syncthreads();
+  if (t < 16) {
+    int r = -1;
+    for (u32 u = 0; u < WL_SCAN_THREADS; u++) { const int v = tot[u][t]; tot[u][t] = r; r = v > r ? v : r; }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 16; k++) run[k] = tot[t][k];
+  for (u32 c = c0; c < c1; c++) {
+#pragma unroll
+    for (int k = 0; k < 16; k++) { const int v = cl[c * 16 + k]; cl[c * 16 + k] = run[k]; run[k] = v > run[k] ? v : run[k]; }
+  }
+}
+__global__ void __launch_bounds__(WL_CHUNK) trace_expand_wl_kernel(WlArgs a) {
+  __shared__ int warp_tot[WL_CHUNK / 32][16];
+  const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const u64 i = (u64)blockIdx.x * WL_CHUNK + tid;
+  const u64 M40 = (1ull << 40) - 1;
+  const u64 wl = i < a.T ? a.wlog[i] : 0;
+  const u32 kw = (u32)(wl >> 56) & 15u;
+  int before[16];
+#pragma unroll
+  for (int k = 1; k < 16; k++) {
+    int v = kw == (u32)k ? (int)i : -1;  // inclusive prefix maximum inside the warp
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, v, o); if (lane >= (u32)o) v = t > v ? t : v; }
+    if (lane == 31) warp_tot[warp][k] = v;
+    const int ex = __shfl_up_sync(0xffffffffu, v, 1);
+    before[k] = lane ? ex : -1;
+  }
+  __syncthreads();
+  const int* prev = a.chunk_prev + (u64)blockIdx.x * 16;
+  u64 rg[16];
+  rg[0] = 0;
+#pragma unroll
+  for (int k = 1; k < 16; k++) {
+    int v = prev[k];
+    for (u32 w = 0; w < warp; w++) { const int t = warp_tot[w][k]; v = t > v ? t : v; }
+    v = before[k] > v ? before[k] : v;
+    rg[k] = v >= 0 ? (a.wlog[v] & M40) : 0;
+  }
+  if (i >= a.N) return;
+  const bool live = i < a.T;
+  // READ rows need the post-state r10: the logged value if the row changed r10, else the unchanged pre-state
+  const u64 read_val = kw == 10u ? (wl & M40) : rg[10];
+  expand_row(i, a.N, a.T, rg, live ? (u64)a.pcs[i] : a.final_pc, live ? a.ins[i] : 0u, read_val, a.cols, a.err);
 }
 
 int launch_trace_expand(const ExpandArgs& a, cudaStream_t st, u64* launches) {
   trace_expand_kernel<<<(unsigned)((a.N + 127) / 128), 128, 0, st>>>(a);
   (*launches)++;
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+u64 trace_expand_wl_scratch_ints(u64 N) { return ((N + WL_CHUNK - 1) / WL_CHUNK) * 16; }
+int launch_trace_expand_wl(const WlArgs& a, cudaStream_t st, u64* launches) {
+  const u32 n_chunks = (u32)((a.N + WL_CHUNK - 1) / WL_CHUNK);
+  wl_chunk_last_kernel<<<n_chunks, WL_CHUNK, 0, st>>>(a.wlog, a.T, a.chunk_prev);
+  wl_chunk_scan_kernel<<<1, WL_SCAN_THREADS, 0, st>>>(a.chunk_prev, n_chunks);
+  trace_expand_wl_kernel<<<n_chunks, WL_CHUNK, 0, st>>>(a);
+  (*launches) += 3;
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 

@@ -128,6 +128,20 @@ class ExecutionResult:  # vm.rs:54-78
             "entry_point": self._entry,
         }
 
+    def writelog(self, out=None):
+        """Register write log of the recorded rows (zkir_vm_trace_writelog): dict(pcs u32[T], instrs u32[T], wlog u64[T], ...).
+        `out` = optional dict of preallocated (pinned) arrays 'pcs', 'wlog'."""
+        l = _ffi.lib()
+        n = l.zkir_vm_trace_len(self._h)
+        pcs = out["pcs"] if out else np.empty(n, dtype=np.uint32)
+        wlog = out["wlog"] if out else np.empty(n, dtype=np.uint64)
+        assert pcs.dtype == np.uint32 and wlog.dtype == np.uint64 and pcs.shape == (n,) and wlog.shape == (n,)
+        rc = l.zkir_vm_trace_writelog(self._h, pcs.ctypes.data, wlog.ctypes.data)
+        if rc != 0:
+            raise RuntimeError_(rc, l.zkir_vm_last_error().decode())
+        r = self.rows()
+        return {"pcs": pcs, "instrs": r["instrs"], "wlog": wlog, "final_pc": r["final_pc"], "exit_code": r["exit_code"], "entry_point": r["entry_point"]}
+
     # ---- trace -> columns ("converter", trace.rs:41)
     def min_log_n(self):
         return _ffi.lib().zkir_pack_min_log_n(self._h)
@@ -311,6 +325,28 @@ class Context:
         self._l.zkir_b200_free_proof(proof)
         return out, pv
 
+    def prove_writelog(self, wl, cfg, log_n=None):
+        """wl: dict as returned by ExecutionResult.writelog().  Returns (proof bytes, public values)."""
+        params = cfg.params()
+        n = int(wl["pcs"].shape[0])
+        if log_n is None:
+            log_n = max(2, (n - 1).bit_length())
+        pcs, ins, wlog = (np.ascontiguousarray(wl[k]) for k in ("pcs", "instrs", "wlog"))
+        assert pcs.dtype == np.uint32 and ins.dtype == np.uint32 and wlog.dtype == np.uint64
+        pv = np.zeros(NUM_PUBLIC, dtype=np.uint32)
+        proof, plen = C.c_void_p(), C.c_size_t()
+        rc = self._l.zkir_b200_prove_writelog(self._h, C.byref(params), pcs.ctypes.data, ins.ctypes.data, wlog.ctypes.data, n, int(wl["final_pc"]),
+                                              int(wl["entry_point"]), int(wl["exit_code"]), log_n, pv.ctypes.data_as(_ffi.u32p), C.byref(proof), C.byref(plen))
+        self._check(rc)
+        out = C.string_at(proof, plen.value)
+        self._l.zkir_b200_free_proof(proof)
+        return out, pv
+
+    def expand_writelog(self, wl, log_n, d_cols):
+        n = int(wl["pcs"].shape[0])
+        pcs, ins, wlog = (np.ascontiguousarray(wl[k]) for k in ("pcs", "instrs", "wlog"))
+        self._check(self._l.zkir_b200_expand_writelog(self._h, pcs.ctypes.data, ins.ctypes.data, wlog.ctypes.data, n, int(wl["final_pc"]), log_n, d_cols))
+
     def expand_rows(self, rows, log_n, d_cols):
         n = int(rows["pcs"].shape[0])
         pcs, ins, regs = (np.ascontiguousarray(rows[k]) for k in ("pcs", "instrs", "regs"))
@@ -382,7 +418,7 @@ def prove(program, inputs=(), cfg=None):
     res = VM(program, inputs, VMConfig(max_cycles=cfg.max_cycles, enable_execution_trace=True)).run()
     ctx = _ctx(cfg.device)
     log_n = res.min_log_n()
-    pb, pv = ctx.prove_rows(res.rows(), cfg, log_n)   # raw rows over PCIe, converter on the device
+    pb, pv = ctx.prove_writelog(res.writelog(), cfg, log_n)   # 16 B/row over PCIe, registers rebuilt + converter on the device
     return Proof(pb, pv, log_n, res.cycles, res.outputs, ctx.stage_ms())
 
 
