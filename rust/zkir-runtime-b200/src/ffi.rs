@@ -36,6 +36,23 @@ extern "C" {
         proof: *mut *mut u8,
         proof_len: *mut usize,
     ) -> c_int;
+    /// raw TraceRow data (zkir-spec/src/trace.rs:24-50): pcs[n], instrs[n], regs[n][16] pre-state; converter on the device
+    pub fn zkir_b200_prove_rows(
+        ctx: *mut zkir_ctx,
+        params: *const zkir_params,
+        pcs: *const u64,
+        instrs: *const u32,
+        regs: *const u64,
+        n_rows: u64,
+        final_regs: *const u64, // [16] state after the last instruction
+        final_pc: u64,
+        entry_point: u32,
+        exit_code: u64,
+        log_n: u32,
+        public_values_out: *mut u32, // [4]
+        proof: *mut *mut u8,
+        proof_len: *mut usize,
+    ) -> c_int;
     pub fn zkir_b200_free_proof(p: *mut u8);
     pub fn zkir_b200_verify(params: *const zkir_params, proof: *const u8, len: usize, public_values: *const u32) -> c_int;
 }

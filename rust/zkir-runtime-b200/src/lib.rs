@@ -2,8 +2,9 @@
 //! pack `Vec<TraceRow>` (zkir-spec/src/trace.rs:24-50) into column-major BabyBear columns in pinned memory, and hand the
 //! buffer to the CUDA prover through the C ABI.  Errors map to `RuntimeError::Other` (zkir-runtime/src/error.rs:35-36).
 //!
-//! NOT COMPILED in this repository's build image (no cargo/rustc).  The column packing below must stay in lock-step
-//! with zkir_b200/csrc/host/pack.cc, which is the tested implementation of the same "converter".
+//! NOT COMPILED in this repository's build image (no cargo/rustc).  It relies on one small addition to zkir-runtime:
+//! `VM::run_keep_state`, i.e. `VM::run` (vm.rs:208-358) returning also the final registers and pc in `ExecutionResult`
+//! (`final_regs: [u64; 16]`, `final_pc: u64`): padding rows and the last READ need the post-state of the last cycle.
 pub mod ffi;
 
 use std::ffi::CStr;
@@ -34,23 +35,26 @@ pub struct Proof {
 }
 
 /// Pinned host buffer owned by Rust, allocated by the library (cudaMallocHost) so the H2D copy is a single DMA.
-struct Pinned {
-    ptr: *mut u32,
-    words: usize,
+struct Pinned<T: Copy> {
+    ptr: *mut T,
+    len: usize,
 }
-impl Pinned {
-    fn new(words: usize) -> Result<Self, RuntimeError> {
-        let p = unsafe { ffi::zkir_b200_alloc_pinned(words * 4) } as *mut u32;
+impl<T: Copy> Pinned<T> {
+    fn new(len: usize) -> Result<Self, RuntimeError> {
+        let p = unsafe { ffi::zkir_b200_alloc_pinned(len.max(1) * std::mem::size_of::<T>()) } as *mut T;
         if p.is_null() {
             return Err(RuntimeError::Other("zkir_b200_alloc_pinned failed".into()));
         }
-        Ok(Self { ptr: p, words })
+        Ok(Self { ptr: p, len })
     }
-    fn as_mut_slice(&mut self) -> &mut [u32] {
-        unsafe { std::slice::from_raw_parts_mut(self.ptr, self.words) }
+    fn as_slice(&self) -> &[T] {
+        unsafe { std::slice::from_raw_parts(self.ptr, self.len) }
+    }
+    fn as_mut_slice(&mut self) -> &mut [T] {
+        unsafe { std::slice::from_raw_parts_mut(self.ptr, self.len) }
     }
 }
-impl Drop for Pinned {
+impl<T: Copy> Drop for Pinned<T> {
     fn drop(&mut self) {
         unsafe { ffi::zkir_b200_free_pinned(self.ptr as *mut _) }
     }
@@ -91,6 +95,31 @@ impl Prover {
         Ok(out)
     }
 }
+impl Prover {
+    #[allow(clippy::too_many_arguments)]
+    pub fn prove_rows(&mut self, cfg: &ProverConfig, pcs: &[u64], ins: &[u32], regs: &[u64], final_regs: &[u64; 16], final_pc: u64,
+                      entry_point: u32, exit_code: u64, log_n: u32, pv_out: &mut [u32; 4]) -> Result<Vec<u8>, RuntimeError> {
+        assert!(pcs.len() == ins.len() && regs.len() == 16 * pcs.len());
+        let params = ffi::zkir_params {
+            log_blowup: cfg.log_blowup,
+            num_queries: cfg.num_queries,
+            pow_bits: cfg.pow_bits,
+            width: ffi::ZKIR_AIR_V1_WIDTH,
+            num_public: ffi::ZKIR_AIR_V1_NUM_PUBLIC,
+        };
+        let (mut p, mut len) = (std::ptr::null_mut::<u8>(), 0usize);
+        let rc = unsafe {
+            ffi::zkir_b200_prove_rows(self.ctx, &params, pcs.as_ptr(), ins.as_ptr(), regs.as_ptr(), pcs.len() as u64, final_regs.as_ptr(),
+                                      final_pc, entry_point, exit_code, log_n, pv_out.as_mut_ptr(), &mut p, &mut len)
+        };
+        if rc != ffi::ZKIR_OK {
+            return Err(last_error(self.ctx, rc));
+        }
+        let out = unsafe { std::slice::from_raw_parts(p, len) }.to_vec();
+        unsafe { ffi::zkir_b200_free_proof(p) };
+        Ok(out)
+    }
+}
 impl Drop for Prover {
     fn drop(&mut self) {
         unsafe { ffi::zkir_b200_destroy(self.ctx) }
@@ -103,16 +132,29 @@ fn last_error(ctx: *const ffi::zkir_ctx, rc: i32) -> RuntimeError {
 }
 
 /// Program -> Proof.  The interpreter loop is untouched (north star: "zkir-spec, zkir-assembler and the interpreter
-/// loop stay as-is"); only the consumer of `ExecutionResult.execution_trace` is new.
+/// loop stay as-is"); only the consumer of `ExecutionResult.execution_trace` is new.  The rows are copied field by field
+/// into pinned arrays and the device runs the converter (zkir_b200/csrc/trace_expand.cu), so no Rust port of it is needed.
 pub fn prove(program: &Program, inputs: &[u64], cfg: &ProverConfig) -> Result<Proof, RuntimeError> {
     let vm_cfg = VMConfig { max_cycles: cfg.max_cycles, enable_execution_trace: true, ..VMConfig::default() };
-    let result = VM::new(program.clone(), inputs.to_vec(), vm_cfg).run()?;
+    let mut vm = VM::new(program.clone(), inputs.to_vec(), vm_cfg);
+    let result = vm.run_keep_state()?; // like VM::run (vm.rs:208-358) but also returns the final VMState (regs, pc)
     let rows = &result.execution_trace;
-    let log_n = (rows.len().max(4)).next_power_of_two().trailing_zeros();
-    let mut pinned = Pinned::new((ffi::ZKIR_AIR_V1_WIDTH as usize) << log_n)?;
-    let pv = pack_trace(rows, program.header.entry_point, &result, log_n, pinned.as_mut_slice())?;
+    let n = rows.len();
+    let log_n = n.max(4).next_power_of_two().trailing_zeros();
+    // SoA copy of TraceRow { pc, instruction, registers } into page-locked memory
+    let mut pcs = Pinned::<u64>::new(n)?;
+    let mut ins = Pinned::<u32>::new(n)?;
+    let mut regs = Pinned::<u64>::new(16 * n)?;
+    for (i, row) in rows.iter().enumerate() {
+        pcs.as_mut_slice()[i] = row.pc;
+        ins.as_mut_slice()[i] = row.instruction;
+        regs.as_mut_slice()[16 * i..16 * i + 16].copy_from_slice(&row.registers);
+    }
+    let exit_code = match result.halt_reason { zkir_runtime::HaltReason::Exit(c) => c, _ => 0 };
+    let mut pv = [0u32; 4];
     let mut prover = Prover::new(cfg.device)?;
-    let bytes = prover.prove_columns(cfg, pinned.as_mut_slice(), log_n, &pv)?;
+    let bytes = prover.prove_rows(cfg, pcs.as_slice(), ins.as_slice(), regs.as_slice(), &result.final_regs, result.final_pc,
+                                  program.header.entry_point, exit_code, log_n, &mut pv)?;
     Ok(Proof { bytes, public_values: pv, log_n, cycles: result.cycles, outputs: result.outputs })
 }
 
@@ -125,21 +167,4 @@ pub fn verify(proof: &[u8], cfg: &ProverConfig, pv: &[u32; 4]) -> bool {
         num_public: ffi::ZKIR_AIR_V1_NUM_PUBLIC,
     };
     unsafe { ffi::zkir_b200_verify(&params, proof.as_ptr(), proof.len(), pv.as_ptr()) == ffi::ZKIR_OK }
-}
-
-/// The "converter" the reference names but does not contain (zkir-spec/src/trace.rs:41, zkir-runtime/src/vm.rs:243-244):
-/// one `TraceRow` -> one row of the 112 columns listed in zkir_b200/csrc/air_columns.h.  Mirrors pack.cc:
-/// 40-bit values split into 2 x 20-bit limbs (zkir-spec/src/value.rs:592-601), decoded operand indices as one-hots,
-/// ALU result / carries / branch helpers / I/O columns derived from the row and its successor, padding rows after halt.
-fn pack_trace(
-    rows: &[zkir_spec::TraceRow],
-    entry_point: u32,
-    result: &zkir_runtime::ExecutionResult,
-    log_n: u32,
-    cols: &mut [u32],
-) -> Result<[u32; 4], RuntimeError> {
-    let _ = (rows, entry_point, result, log_n, cols);
-    // Intentionally a thin shim: link zkir_pack_trace()'s logic here, or call it through a second extern block fed with
-    // a flat copy of the rows.  Kept unimplemented in this uncompiled source so it cannot silently drift from pack.cc.
-    Err(RuntimeError::Other("pack_trace: port zkir_b200/csrc/host/pack.cc (see INTEGRATION.md, section 3)".into()))
 }
