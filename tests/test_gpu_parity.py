@@ -122,7 +122,8 @@ def test_quotient_matches_oracle(gpu_ctx, oracle, n, log_b):
     assert np.array_equal(got, oracle.quotient(cfg, lde, log_n, pv, alpha))
 
 
-@pytest.mark.parametrize("n,log_b,nq,pow_bits", [(3, 1, 3, 0), (10, 1, 10, 8), (30, 1, 100, 16), (30, 2, 20, 4), (205, 1, 100, 16), (1000, 1, 30, 10)])
+@pytest.mark.parametrize("n,log_b,nq,pow_bits", [(3, 1, 3, 0), (10, 1, 10, 8), (30, 1, 100, 16), (30, 2, 20, 4), (205, 1, 100, 16), (1000, 1, 30, 10),
+                                                    (205, 2, 12, 5), (205, 3, 8, 3), (1000, 2, 10, 6), (3000, 4, 6, 2)])
 def test_proof_bytes_match_oracle_and_verify(gpu_ctx, oracle, n, log_b, nq, pow_bits):
     """BASELINE config 1 (fib n=30 / n=205): whole proof bytes GPU == oracle, and the verifier accepts."""
     _, cols, pv = fib_trace(n)
@@ -299,3 +300,29 @@ def test_prove_batch_matches_single_proofs(gpu_ctx, oracle):
         assert ok, why
     for i in (0, 7, 23):
         assert batch[i] == oracle.prove(cfg, *traces[i])
+
+
+def test_error_paths_return_codes(gpu_ctx):
+    """error behaviour of the boundary: bad shapes / values are ZKIR_ERR_ARG (-1), unconstrained rows ZKIR_ERR_AIR (-6);
+    the context stays usable afterwards"""
+    import ctypes as C
+    from zkir_b200 import _ffi
+    _, cols, pv = fib_trace(30)
+    cfg = zkir_b200.ProverConfig(num_queries=4, pow_bits=2)
+    bad_pv = pv.copy(); bad_pv[1] = P                     # not canonical
+    with pytest.raises(zkir_b200.RuntimeError) as ei:
+        gpu_ctx.prove_columns(cols, bad_pv, cfg)
+    assert ei.value.code == -1
+    l = _ffi.lib()
+    params = _ffi.Params(1, 4, 2, 111, 4)                 # wrong width
+    proof, plen = C.c_void_p(), C.c_size_t()
+    rc = l.zkir_b200_prove(gpu_ctx._h, C.byref(params), cols.ctypes.data, 8, pv.ctypes.data_as(_ffi.u32p), C.byref(proof), C.byref(plen))
+    assert rc == -1 and b"width" in l.zkir_b200_last_error(gpu_ctx._h)
+    prog = zkir_b200.assemble("addi r1, r0, 3\nmul r2, r1, r1\nadd r10, r0, r0\necall\n")
+    res = zkir_b200.VM(prog, [], zkir_b200.VMConfig(enable_execution_trace=True)).run()
+    for call in (lambda: gpu_ctx.prove_rows(res.rows(), cfg), lambda: gpu_ctx.prove_writelog(res.writelog(), cfg)):
+        with pytest.raises(zkir_b200.RuntimeError) as ei:
+            call()
+        assert ei.value.code == -6 and "row 1" in str(ei.value)
+    ok, why = zkir_b200.verify(gpu_ctx.prove_columns(cols, pv, cfg), cfg, pv)   # still healthy
+    assert ok, why

@@ -161,11 +161,9 @@ static cudaError_t launch_pass_r(const PassParams& p, u32 blocks, cudaStream_t s
   constexpr int NT = ITEMS >= 512 ? 512 : (ITEMS >= 256 ? 256 : (ITEMS >= 128 ? 128 : 64));
   const size_t smem = (size_t)(R * (T + 1) + (R / 2 > 0 ? R / 2 : 1)) * sizeof(u32);
   auto kern = ntt_pass_kernel<LOG_R, LOG_T, NT>;
-  static bool attr_set = false;
-  if (!attr_set && smem > 48 * 1024) {
+  if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    attr_set = true;
   }
   kern<<<blocks, NT, smem, st>>>(p);
   return cudaGetLastError();

@@ -236,11 +236,9 @@ static cudaError_t launch_tile_t(const TileParams& p, u32 blocks, u32 z, cudaStr
   typedef TileShape<LOG_R, MODE> SH;
   const size_t smem = (size_t)SH::SMEM_WORDS * sizeof(u32);
   auto kern = dft_tile_kernel<LOG_R, MODE, INV, LOG_S>;
-  static bool attr_set = false;
-  if (!attr_set && smem > 48 * 1024) {
+  if (smem > 48 * 1024) {  // per device and cheap: set it on every launch rather than caching a process-wide flag
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    attr_set = true;
   }
   TileParams q = p;
   q.nz = z;
