@@ -45,8 +45,9 @@ int launch_permute(u32* d_states, u64 n, bool canonical_io, cudaStream_t st, u64
 int launch_leaf_hash(const u32* mat, u64 col_stride, u32 n_cols, u64 n_rows, u32 log_b, u32* digests, cudaStream_t st, u64* launches);
 int launch_leaf_hash_pairs(const u32* layer, u64 h, u32* digests, cudaStream_t st, u64* launches);
 // optional fused Fiat-Shamir step on the root: copy to root_dst, observe, sample n_sample elements into sample_out
+// pair_layer != nullptr: the leaves are FRI leaves hash(f[i] || f[i + n_leaves]) of that ext4 layer and are computed here too
 int launch_merkle_levels(u32* tree, u64 n_leaves, cudaStream_t st, u64* launches, ChalState* chal = nullptr, u32* root_dst = nullptr,
-                         u32* sample_out = nullptr, u32 n_sample = 0);
+                         u32* sample_out = nullptr, u32 n_sample = 0, const u32* pair_layer = nullptr);
 int launch_challenger(ChalState* st_dev, const u32* in, u32 n_in, u32* out, u32 n_out, u32 bits, cudaStream_t st, u64* launches);
 int launch_pow_grind(const ChalState* st_dev, u32 bits, u32* result, cudaStream_t st, u64* launches);
 

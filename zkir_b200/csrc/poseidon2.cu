@@ -196,16 +196,24 @@ int launch_leaf_hash_pairs(const u32* layer, u64 h, u32* digests, cudaStream_t s
   (*launches)++;
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
-#define COOP_THREADS 1024
-#define COOP_CHUNK 256
-__global__ void merkle_coop_kernel(const u32* __restrict__ level, u64 n_in, u32 chunk, ChalState* chal, u32* root_dst, u32* sample_out, u32 n_sample);
+__global__ void merkle_coop_kernel(u32* level, u64 n_in, u32 chunk, const u32* __restrict__ pair_layer, ChalState* chal, u32* root_dst,
+                                   u32* sample_out, u32 n_sample);
 __global__ void challenger_kernel(ChalState* st, const u32* in, u32 n_in, u32* out, u32 n_out, u32 bits);
-// tree: level 0 = n_leaves digests already in place; builds the upper levels behind it.  Wide levels: one thread per
-// compression (throughput); from 32768 nodes down: the cooperative kernel (latency).  If `chal` is given, the launch that
-// produces the root also copies it to root_dst, observes it and samples n_sample elements into sample_out.
-int launch_merkle_levels(u32* tree, u64 n_leaves, cudaStream_t st, u64* launches, ChalState* chal, u32* root_dst, u32* sample_out, u32 n_sample) {
+__global__ void leaf_hash_pairs_kernel(const uint4* __restrict__ layer, u64 h, u32* __restrict__ digests);
+// tree: level 0 = n_leaves digests (already in place, or computed here from the FRI layer `pair_layer` of 2*n_leaves ext4
+// values); builds the upper levels behind it.  Wide levels: one thread per compression (throughput); from 32768 nodes down
+// the cooperative kernel (latency): 32-node blocks climbing 5 levels while the level is wide, one block at the end.
+// If `chal` is given, the launch that produces the root also copies it to root_dst, observes it and samples n_sample
+// elements into sample_out.
+int launch_merkle_levels(u32* tree, u64 n_leaves, cudaStream_t st, u64* launches, ChalState* chal, u32* root_dst, u32* sample_out, u32 n_sample,
+                         const u32* pair_layer) {
   u32* lvl = tree;
   u64 n = n_leaves;
+  if (pair_layer && n > 32768) {
+    leaf_hash_pairs_kernel<<<nblk(n, 128), 128, 0, st>>>(reinterpret_cast<const uint4*>(pair_layer), n, tree);
+    (*launches)++;
+    pair_layer = nullptr;
+  }
   while (n > 32768) {
     u32* nxt = lvl + n * 8;
     compress_kernel<<<nblk(n / 2, 128), 128, 0, st>>>(reinterpret_cast<const uint4*>(lvl), reinterpret_cast<uint4*>(nxt), n / 2);
@@ -213,16 +221,20 @@ int launch_merkle_levels(u32* tree, u64 n_leaves, cudaStream_t st, u64* launches
     lvl = nxt; n >>= 1;
   }
   bool chal_done = false;
-  while (n > 1) {
-    const u32 chunk = n < COOP_CHUNK ? (u32)n : COOP_CHUNK;
+  while (n > 1 || pair_layer) {
+    const u32 chunk = n > 128 ? 32u : (u32)n;
     const u32 blocks = (u32)(n / chunk);
     const bool last = blocks == 1;
-    merkle_coop_kernel<<<blocks, COOP_THREADS, 0, st>>>(lvl, n, chunk, last ? chal : nullptr, root_dst, sample_out, n_sample);
+    u32 threads = 16 * (chunk / 2);
+    if (threads < 32) threads = 32;
+    merkle_coop_kernel<<<blocks, threads, 0, st>>>(lvl, n, chunk, pair_layer, last ? chal : nullptr, root_dst, sample_out, n_sample);
     (*launches)++;
+    pair_layer = nullptr;
     if (last && chal) chal_done = true;
     for (u32 c = chunk; c > 1; c >>= 1) { lvl += n * 8; n >>= 1; }
+    if (last) break;
   }
-  if (chal && !chal_done) {  // single-leaf tree: the leaf is the root
+  if (chal && !chal_done) {  // not reached: every path above ends in a single-block launch
     if (root_dst) cudaMemcpyAsync(root_dst, lvl, 32, cudaMemcpyDeviceToDevice, st);
     challenger_kernel<<<1, 32, 0, st>>>(chal, lvl, 8, sample_out, n_sample, 0);
     (*launches)++;
@@ -300,25 +312,43 @@ __global__ void __launch_bounds__(32) challenger_kernel(ChalState* st, const u32
   challenger_step(st, in, n_in, out, n_out, bits, threadIdx.x);
 }
 
-// Upper part of a Merkle tree, latency-oriented: 16 lanes cooperate on one compression (permute_warp), a block of 1024
-// threads owns `chunk` <= 256 consecutive nodes of the input level and climbs log2(chunk) levels through shared memory,
-// writing every level to the global tree (authentication paths need them).  A thread-per-permutation level costs one
-// full permutation latency (~9 us) however small it is; this kernel costs ~3 us per level.
-// When the block reaches the root (single block), warp 0 can also run the Fiat-Shamir step that always follows:
+// Upper part of a Merkle tree, latency-oriented: 16 lanes cooperate on one compression (permute_warp); a block of
+// 16 * chunk / 2 threads owns `chunk` consecutive nodes of the input level and climbs log2(chunk) levels through shared
+// memory, writing every level to the global tree (authentication paths need them).  A thread-per-permutation level costs
+// one full permutation latency (~9 us) however small it is; this kernel costs ~3 us per level, and wide levels are cut
+// into many 32-node blocks so that all SMs share them.
+// Leaf mode (pair_layer != nullptr): the input level does not exist yet; node i is first computed as the FRI leaf
+// hash(f[i] || f[i + h]) of the ext4 layer and stored as level 0.
+// When the block reaches the root (single block), warp 0 also runs the Fiat-Shamir step that always follows:
 // copy the root into the proof, observe it, sample `n_sample` field elements.
-__global__ void __launch_bounds__(COOP_THREADS) merkle_coop_kernel(const u32* __restrict__ level, u64 n_in, u32 chunk, ChalState* chal,
-                                                                   u32* root_dst, u32* sample_out, u32 n_sample) {
-  __shared__ u32 buf[2][COOP_CHUNK * 8];
-  const u32 tid = threadIdx.x, lane = tid & 31, l16 = tid & 15, slot = tid >> 4;
-  const u32* src = level + (u64)blockIdx.x * chunk * 8;
-  for (u32 i = tid; i < chunk * 8; i += COOP_THREADS) buf[0][i] = src[i];
+#define COOP_MAX_CHUNK 128
+__global__ void __launch_bounds__(16 * COOP_MAX_CHUNK / 2) merkle_coop_kernel(u32* level, u64 n_in, u32 chunk, const u32* __restrict__ pair_layer,
+                                                                             ChalState* chal, u32* root_dst, u32* sample_out, u32 n_sample) {
+  __shared__ u32 buf[2][COOP_MAX_CHUNK * 8];
+  const u32 tid = threadIdx.x, lane = tid & 31, l16 = tid & 15, slot = tid >> 4, slots = blockDim.x >> 4;
+  const u64 node0 = (u64)blockIdx.x * chunk;
+  if (pair_layer) {
+    const u64 h = n_in;  // leaves of this layer = half its length
+    for (u32 s0 = 0; s0 < chunk; s0 += slots) {
+      if (s0 + (tid >> 5) * 2 >= chunk) break;
+      const u32 sidx = s0 + slot;
+      const bool active = sidx < chunk;
+      u32 x = 0;
+      if (active && l16 < 8) x = pair_layer[4 * (node0 + sidx + (l16 >= 4 ? h : 0)) + (l16 & 3)];
+      x = permute_warp(x, lane);
+      if (active && l16 < 8) { buf[0][8 * sidx + l16] = x; level[(node0 + sidx) * 8 + l16] = x; }
+    }
+  } else {
+    const u32* src = level + node0 * 8;
+    for (u32 i = tid; i < chunk * 8; i += blockDim.x) buf[0][i] = src[i];
+  }
   __syncthreads();
   u32 cur = 0, n = chunk;
   u64 level_n = n_in;
-  u32* out_base = const_cast<u32*>(level) + n_in * 8;
+  u32* out_base = level + n_in * 8;
   while (n > 1) {
     const u32 n_out = n >> 1;
-    for (u32 s0 = 0; s0 < n_out; s0 += COOP_THREADS / 16) {   // warp-uniform trip count
+    for (u32 s0 = 0; s0 < n_out; s0 += slots) {   // warp-uniform trip count
       const u32 sidx = s0 + slot;
       if (s0 + (tid >> 5) * 2 >= n_out) break;  // neither half of this warp has a node: warp-uniform exit
       const bool active = sidx < n_out;

@@ -335,8 +335,9 @@ static int prove_resident(zkir_ctx* ctx, const zkir_params* p, u32 log_n, const 
     u32 lshift = shift;
     for (u32 r = 0; r < R; r++) {
       const u64 h = (M >> r) / 2;
-      RC(launch_leaf_hash_pairs(reinterpret_cast<const u32*>(w.h_layers[r]), h, w.h_ltrees[r], st, LC));
-      RC(launch_merkle_levels(w.h_ltrees[r], h, st, LC, w.chal, w.proof + L.fri_roots + 8 * r, c_betas + 4 * r, 4));  // + observe root, sample beta_r
+      // leaves hash(f[i] || f[i+h]) + tree + root -> proof, observe, sample beta_r
+      RC(launch_merkle_levels(w.h_ltrees[r], h, st, LC, w.chal, w.proof + L.fri_roots + 8 * r, c_betas + 4 * r, 4,
+                              reinterpret_cast<const u32*>(w.h_layers[r])));
       const u32 c = hinv(hmul(2, lshift));
       RC(launch_fri_fold(w.h_layers[r], w.h_layers[r + 1], h, c_betas + 4 * r, inv_w, 1u << r, bb_to_mont_c(c), st, LC));
       lshift = hmul(lshift, lshift);
