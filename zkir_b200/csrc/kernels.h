@@ -43,7 +43,6 @@ int poseidon2_init_constants();
 int launch_permute(u32* d_states, u64 n, bool canonical_io, cudaStream_t st, u64* launches);
 // matrix rows are coset-major (kernels.h: see ntt_fast.cu), leaves natural; log_b = 0 for a natural-order matrix
 int launch_leaf_hash(const u32* mat, u64 col_stride, u32 n_cols, u64 n_rows, u32 log_b, u32* digests, cudaStream_t st, u64* launches);
-int launch_leaf_hash_pairs(const u32* layer, u64 h, u32* digests, cudaStream_t st, u64* launches);
 // optional fused Fiat-Shamir step on the root: copy to root_dst, observe, sample n_sample elements into sample_out
 // pair_layer != nullptr: the leaves are FRI leaves hash(f[i] || f[i + n_leaves]) of that ext4 layer and are computed here too
 int launch_merkle_levels(u32* tree, u64 n_leaves, cudaStream_t st, u64* launches, ChalState* chal = nullptr, u32* root_dst = nullptr,

@@ -191,11 +191,6 @@ int launch_leaf_hash(const u32* mat, u64 col_stride, u32 n_cols, u64 n_rows, u32
   (*launches)++;
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
-int launch_leaf_hash_pairs(const u32* layer, u64 h, u32* digests, cudaStream_t st, u64* launches) {
-  leaf_hash_pairs_kernel<<<nblk(h, 128), 128, 0, st>>>(reinterpret_cast<const uint4*>(layer), h, digests);
-  (*launches)++;
-  return cudaGetLastError() == cudaSuccess ? 0 : -2;
-}
 __global__ void merkle_coop_kernel(u32* level, u64 n_in, u32 chunk, const u32* __restrict__ pair_layer, ChalState* chal, u32* root_dst,
                                    u32* sample_out, u32 n_sample);
 __global__ void challenger_kernel(ChalState* st, const u32* in, u32 n_in, u32* out, u32 n_out, u32 bits);
