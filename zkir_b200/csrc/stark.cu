@@ -65,7 +65,7 @@ int launch_ext_powers(const u32* base_ext, u32 mul_const, const FastPlan& plan, 
 #define OPEN_WARPS 8
 #define OPEN_THREADS (32 * OPEN_WARPS)
 #define OPEN_ROWS 2048
-__global__ void __launch_bounds__(OPEN_THREADS, 3) open_partial_kernel(const u32* __restrict__ coef, u64 col_stride, u32 n_cols, u64 n,
+__global__ void __launch_bounds__(OPEN_THREADS, 2) open_partial_kernel(const u32* __restrict__ coef, u64 col_stride, u32 n_cols, u64 n,
                                                                    const E4* __restrict__ U1, const E4* __restrict__ U2,
                                                                    E4* partial, u32 n_chunks) {
   const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5, chunk = blockIdx.x;
@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(OPEN_THREADS, 3) open_partial_kernel(const u32
 #pragma unroll
   for (int c = 0; c < OPEN_COLS; c++) { l1[c] = acc4_zero(); l2[c] = acc4_zero(); }
   const u64 j0 = (u64)chunk * OPEN_ROWS + lane;
-#pragma unroll 2
+#pragma unroll 4
   for (int r = 0; r < OPEN_ROWS / 32; r++) {
     const u64 j = j0 + (u64)r * 32;
     if (j < n) {
