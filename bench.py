@@ -122,7 +122,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    workload = f"fibonacci via input tape n={args.fib_n} ({5 * args.fib_n - 2} cycles -> 2^20-row trace, W=112, log_blowup=1, 100 queries, 16 PoW bits)"
+    workload = f"fibonacci via input tape n={args.fib_n} ({5 * args.fib_n - 2} cycles -> 2^20-row trace, W=90, log_blowup=1, 100 queries, 16 PoW bits)"
 
     if args.impl == "reference":
         if rank != 0:
@@ -256,7 +256,8 @@ def main():
     if os.path.exists(tp) and N == 1 << 20:
         try:
             tj = json.load(open(tp))
-            lde_traffic, lde_traffic_src = int(tj["lde_dram_bytes_total_estimate"]), tj["source"]
+            if int(tj.get("width", 0)) == int(W):   # the capture must be of this column count
+                lde_traffic, lde_traffic_src = int(tj["lde_dram_bytes_total_estimate"]), tj["source"]
         except Exception:
             pass
     out = {
@@ -264,7 +265,7 @@ def main():
         "ms_per_step": dev_ms / K, "wall_ms_per_step": wall_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u32 (BabyBear mod p, Montgomery)", "data": "synthetic",
         "config": {"workload": workload, "rows": N, "width": int(W), "log_blowup": cfg.log_blowup, "num_queries": cfg.num_queries,
-                   "pow_bits": cfg.pow_bits, "l2": "inputs exceed L2 (trace 470 MB, LDE 940 MB per step)", "parallelism": f"{world} independent proofs (one per GPU)",
+                   "pow_bits": cfg.pow_bits, "l2": f"inputs exceed L2 (trace {4 * N * W >> 20} MiB, LDE {4 * N * W * B >> 20} MiB per step)", "parallelism": f"{world} independent proofs (one per GPU)",
                    "vm_trace_seconds": round(vm_s, 3), "proof_bytes": proof_bytes},
         "clocks": clocks,
         "e2e": {"value": world * cycles / (e2e_ms / K * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms / K,
@@ -274,13 +275,13 @@ def main():
                               "api": "zkir_b200_prove_rows: TraceRow data as recorded upstream (pc, word, regs[16])"}},
         "gpu_launches": int(launches),
         "stage_ms": {k: v / K for k, v in stage_acc.items()},
-        "roofline": {"kernel": "dft_tile_kernel: LDE stage = 2 inverse + 2x2 forward digit passes (radix-32 register tiles) over 112 columns, 2^20 -> 2^21 points",
+        "roofline": {"kernel": "dft_tile_kernel: LDE stage = 2 inverse + 2x2 forward digit passes (radix-32 register tiles) over 90 columns, 2^20 -> 2^21 points",
                      "bound": "hbm", "achieved": lde_gbs, "peak": peak, "unit": "GB/s", "frac": lde_gbs / peak, "traffic": lde_traffic,
                      "traffic_source": lde_traffic_src, "algorithmic_bytes": lde_bytes, "ms": lde_ms, "peak_source": peak_src,
                      "note": "ncu: integer-multiply pipe (fmaheavy) 59-66 % active, DRAM 29-45 %: the passes are bound by BabyBear multiplies, not HBM (DESIGN.md 3.1)"},
         "ntt_roofline": {"kernel": f"dft_tile_kernel x2: forward NTT 2^{ntt_log} x {ntt_cols} columns via zkir_b200_ntt, natural order in/out (8*n*C bytes)", "bound": "hbm",
                          "achieved": ntt_gbs, "peak": peak, "unit": "GB/s", "frac": ntt_gbs / peak, "ms": ntt_ms, "timing": "CUDA events on the library stream, 10 launches"},
-        "hash_roofline": {"kernel": "leaf_hash_kernel (Poseidon2 sponge over the 2^21 LDE rows, 14 permutations each) + Merkle levels", "bound": "integer-multiply pipe",
+        "hash_roofline": {"kernel": "leaf_hash_kernel (Poseidon2 sponge over the 2^21 LDE rows, 12 permutations each) + Merkle levels", "bound": "integer-multiply pipe",
                           "achieved": hash_gps, "unit": "G permutations/s", "ms": commit_ms,
                           "ncu_fmaheavy_active_frac": 0.854, "ncu_source": "profiles/r01_ncu_v8.md",
                           "share_of_step": commit_ms / (dev_ms / K)},

@@ -34,25 +34,28 @@ CLK = col("clk")
 PC = col("pc")
 IMM_LO = col("imm_lo")
 IMM_HI = col("imm_hi")
-IMM_F = col("imm_f")
 IMM_SIGN = col("imm_sign")
-REG_LO = []
-REG_HI = []
-for i in range(16):
+# register file, PRE-state; r0 is hard-wired to zero (state.rs:76-91) and has no columns
+REG_LO = [None]
+REG_HI = [None]
+for i in range(1, 16):
     REG_LO.append(col(f"r{i}_lo"))
     REG_HI.append(col(f"r{i}_hi"))
-SEL_NAMES = ["s_add", "s_sub", "s_addi", "s_beq", "s_bne", "s_jal", "s_ecall", "s_pad"]
+# opcode selectors; an ECALL row is is_exit + is_read + is_write (no separate column)
+SEL_NAMES = ["s_add", "s_sub", "s_addi", "s_beq", "s_bne", "s_jal", "s_pad"]
 S = {n: col(n) for n in SEL_NAMES}
-SEL_RD = [col(f"sel_rd{i}") for i in range(16)]
-SEL_RS1 = [col(f"sel_rs1_{i}") for i in range(16)]
-SEL_RS2 = [col(f"sel_rs2_{i}") for i in range(16)]
+SEL_RD = [col(f"sel_rd{i}") for i in range(16)]          # one-hot: the write-back constraint needs degree 1 here
+# source operands: index = 4*h + l as a product of two 4-way one-hots (16 columns for both operands instead of 32)
+RS1_H = [col(f"rs1_h{i}") for i in range(4)]
+RS1_L = [col(f"rs1_l{i}") for i in range(4)]
+RS2_H = [col(f"rs2_h{i}") for i in range(4)]
+RS2_L = [col(f"rs2_l{i}") for i in range(4)]
 A_LO, A_HI, B_LO, B_HI, C_LO, C_HI = (col(n) for n in ["a_lo", "a_hi", "b_lo", "b_hi", "c_lo", "c_hi"])
 CARRY0, CARRY1 = col("carry0"), col("carry1")
 INV_LO, INV_HI, NE_LO, NE_HI, TAKEN = (col(n) for n in ["inv_lo", "inv_hi", "ne_lo", "ne_hi", "taken"])
 IS_EXIT, IS_READ, IS_WRITE = col("is_exit"), col("is_read"), col("is_write")
-IO_LO, IO_HI = col("io_lo"), col("io_hi")
 WIDTH = len(COLS)
-assert WIDTH == 112
+assert WIDTH == 90   # 12 sponge absorptions per Merkle leaf (rate 8)
 
 PV_NAMES = ["entry_pc", "num_cycles", "exit_lo", "exit_hi"]
 NUM_PUBLIC = len(PV_NAMES)
@@ -140,33 +143,40 @@ def build():
     first, last, trans = E("c.is_first", True), E("c.is_last", True), E("c.is_trans", True)
     TWO20 = 1 << 20
     s = {n: L(S[n]) for n in SEL_NAMES}
+    s_ecall = g.tmp(L(IS_EXIT) + L(IS_READ) + L(IS_WRITE), "ecall row (syscall.rs:94-119)")
 
     # --- booleans
-    bools = [S[n] for n in SEL_NAMES] + SEL_RD + SEL_RS1 + SEL_RS2 + [CARRY0, CARRY1, IMM_SIGN, IS_EXIT, IS_READ, IS_WRITE]
+    bools = ([S[n] for n in SEL_NAMES] + SEL_RD + RS1_H + RS1_L + RS2_H + RS2_L +
+             [CARRY0, CARRY1, IMM_SIGN, IS_EXIT, IS_READ, IS_WRITE])
     for b in bools:
         x = L(b)
         g.emit(x * (x - 1), f"bool {COLS[b]}")
     # --- one-hot sums
-    g.emit(sum_e(s.values()) - 1, "exactly one opcode selector")
+    g.emit(sum_e(s.values()) + s_ecall - 1, "exactly one opcode selector")
     g.emit(sum_e(L(i) for i in SEL_RD) - 1, "one-hot rd")
-    g.emit(sum_e(L(i) for i in SEL_RS1) - 1, "one-hot rs1")
-    g.emit(sum_e(L(i) for i in SEL_RS2) - 1, "one-hot rs2")
-    # --- r0 == 0 (state.rs:76-91)
-    g.emit(L(REG_LO[0]), "r0.lo = 0")
-    g.emit(L(REG_HI[0]), "r0.hi = 0")
-    # --- operand fetch
-    rs1_lo = g.tmp(sum_e(L(SEL_RS1[i]) * L(REG_LO[i]) for i in range(16)), "rs1.lo")
-    rs1_hi = g.tmp(sum_e(L(SEL_RS1[i]) * L(REG_HI[i]) for i in range(16)), "rs1.hi")
-    rs2_lo = g.tmp(sum_e(L(SEL_RS2[i]) * L(REG_LO[i]) for i in range(16)), "rs2.lo")
-    rs2_hi = g.tmp(sum_e(L(SEL_RS2[i]) * L(REG_HI[i]) for i in range(16)), "rs2.hi")
+    for name, grp in (("rs1.h", RS1_H), ("rs1.l", RS1_L), ("rs2.h", RS2_H), ("rs2.l", RS2_L)):
+        g.emit(sum_e(L(i) for i in grp) - 1, f"one-hot {name}")
+
+    # --- operand fetch: reg[4h+l] selected by H[h]*L[l]; r0 contributes nothing (state.rs:76-91)
+    def fetch(H, Lo, limb, note):
+        terms = []
+        for h in range(4):
+            inner = [L(Lo[l]) * L(limb[4 * h + l]) for l in range(4) if 4 * h + l != 0]
+            terms.append(L(H[h]) * sum_e(inner))
+        return g.tmp(sum_e(terms), note)
+    rs1_lo = fetch(RS1_H, RS1_L, REG_LO, "rs1.lo")
+    rs1_hi = fetch(RS1_H, RS1_L, REG_HI, "rs1.hi")
+    rs2_lo = fetch(RS2_H, RS2_L, REG_LO, "rs2.lo")
+    rs2_hi = fetch(RS2_H, RS2_L, REG_HI, "rs2.hi")
     a_lo, a_hi, b_lo, b_hi, c_lo, c_hi = (L(x) for x in (A_LO, A_HI, B_LO, B_HI, C_LO, C_HI))
     g.emit(a_lo - rs1_lo, "a.lo = reg[rs1].lo")
     g.emit(a_hi - rs1_hi, "a.hi = reg[rs1].hi")
-    not_addi = g.tmp(1 - s["s_addi"])
-    g.emit(b_lo - not_addi * rs2_lo - s["s_addi"] * L(IMM_LO), "b.lo = addi ? imm.lo : reg[rs2].lo")
-    g.emit(b_hi - not_addi * rs2_hi - s["s_addi"] * L(IMM_HI), "b.hi = addi ? imm.hi : reg[rs2].hi")
-    # --- immediate: imm_f = imm_lo + 2^20 imm_hi - sign * 2^40  (execute.rs:187 `imm as u64` masked to 40 bits)
-    g.emit(L(IMM_F) - L(IMM_LO) - TWO20 * L(IMM_HI) + ((1 << 40) % P) * L(IMM_SIGN), "signed immediate vs 40-bit limbs")
+    # ADDI has no rs2: the converter selects r0 there, which is enforced, so b = reg[rs2] + addi * imm stays degree 3
+    g.emit(s["s_addi"] * (1 - L(RS2_H[0]) * L(RS2_L[0])), "addi: rs2 selector points at r0")
+    g.emit(b_lo - rs2_lo - s["s_addi"] * L(IMM_LO), "b.lo = reg[rs2].lo + addi * imm.lo")
+    g.emit(b_hi - rs2_hi - s["s_addi"] * L(IMM_HI), "b.hi = reg[rs2].hi + addi * imm.hi")
+    # --- immediate as a field element: imm_lo + 2^20 imm_hi - sign * 2^40  (execute.rs:187 `imm as u64` masked to 40 bits)
+    imm_f = g.tmp(L(IMM_LO) + TWO20 * L(IMM_HI) - ((1 << 40) % P) * L(IMM_SIGN), "signed immediate")
     # --- ALU (value.rs:620-631 wrap mod 2^40: carry1 is discarded)
     addlike = g.tmp(s["s_add"] + s["s_addi"], "add-like")
     k0, k1 = L(CARRY0), L(CARRY1)
@@ -175,9 +185,7 @@ def build():
     g.emit(s["s_sub"] * (a_lo - b_lo - c_lo + TWO20 * k0), "sub lo limb (carry0 = borrow)")
     g.emit(s["s_sub"] * (a_hi - b_hi - k0 - c_hi + TWO20 * k1), "sub hi limb")
     g.emit(s["s_jal"] * (c_lo + TWO20 * c_hi - L(PC) - 4), "jal link = pc + 4 (execute.rs:639-647)")
-    g.emit(L(IS_READ) * (c_lo - L(IO_LO)), "read: result = tape value (syscall.rs:104-109)")
-    g.emit(L(IS_READ) * (c_hi - L(IO_HI)), "read: result hi")
-    g.emit(L(IS_READ) * (L(SEL_RD[10]) - 1), "read writes r10")
+    g.emit(L(IS_READ) * (L(SEL_RD[10]) - 1), "read writes r10 (syscall.rs:104-109); c = the tape value")
     # --- register write-back, pre-state rows: next.r[i] = sel_rd[i]*w ? c : r[i]
     w = g.tmp(s["s_add"] + s["s_sub"] + s["s_addi"] + s["s_jal"] + L(IS_READ), "write enable")
     for i in range(1, 16):
@@ -197,17 +205,16 @@ def build():
     g.emit(L(TAKEN) - s["s_bne"] * ne - s["s_beq"] * (1 - ne), "branch taken")
     # --- pc / clk / padding
     live = g.tmp(1 - s["s_pad"])
-    g.emit(trans * (N(PC) - L(PC) - 4 * live - (L(TAKEN) + s["s_jal"]) * (L(IMM_F) - 4)), "next pc")
+    g.emit(trans * (N(PC) - L(PC) - 4 * live - (L(TAKEN) + s["s_jal"]) * (imm_f - 4)), "next pc")
     g.emit(trans * (N(CLK) - L(CLK) - live), "clk counts live rows")
     g.emit(last * (L(CLK) + live - g.PV(1)), "last row: clk (+1 if live) = num_cycles")
     g.emit(trans * (s["s_pad"] * (1 - N(S["s_pad"]))), "padding is sticky")
     g.emit(trans * (L(IS_EXIT) * (1 - N(S["s_pad"]))), "exit is followed by padding")
     # --- ecall decode (syscall.rs:18-24,94-119): number in r10
-    g.emit(s["s_ecall"] - L(IS_EXIT) - L(IS_READ) - L(IS_WRITE), "ecall kind")
     g.emit(L(IS_EXIT) * L(REG_LO[10]), "exit: r10 = 0")
     g.emit(L(IS_READ) * (L(REG_LO[10]) - 1), "read: r10 = 1")
     g.emit(L(IS_WRITE) * (L(REG_LO[10]) - 2), "write: r10 = 2")
-    g.emit(s["s_ecall"] * L(REG_HI[10]), "ecall: r10.hi = 0")
+    g.emit(s_ecall * L(REG_HI[10]), "ecall: r10.hi = 0")
     g.emit(L(IS_EXIT) * (L(REG_LO[11]) - g.PV(2)), "exit code lo (public)")
     g.emit(L(IS_EXIT) * (L(REG_HI[11]) - g.PV(3)), "exit code hi (public)")
     # --- first row (vm.rs:149,177-181; state.rs:55-71)
@@ -222,7 +229,7 @@ def build():
 def main():
     g = build()
     hdr = []
-    hdr.append("// GENERATED by tools/gen_air.py -- do not edit.  zkir-b200 core AIR v1.")
+    hdr.append("// GENERATED by tools/gen_air.py -- do not edit.  zkir-b200 core AIR v1 (90 columns).")
     hdr.append("#pragma once")
     hdr.append(f"#define ZKIR_AIR_WIDTH {WIDTH}")
     hdr.append(f"#define ZKIR_AIR_NUM_CONSTRAINTS {g.idx}")

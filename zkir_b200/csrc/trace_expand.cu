@@ -1,12 +1,12 @@
-// Device-side trace converter: raw interpreter rows -> the 112 BabyBear columns of the core AIR v1.
+// Device-side trace converter: raw interpreter rows -> the 90 BabyBear columns of the core AIR v1.
 //
 // The reference's hand-off type is `Vec<TraceRow>` -- cycle, pc, instruction word and the PRE-state registers
 // (zkir-spec/src/trace.rs:24-50, recorded at zkir-runtime/src/vm.rs:245-253,302-312); the "converter" that turns rows
 // into field columns is named there (trace.rs:41, vm.rs:243-244) but absent.  zkir_b200/csrc/host/pack.cc is the host
 // restatement; this kernel is the same function with one thread per row, so that only the raw rows (140 B/row instead
-// of 448 B/row of columns) cross PCIe.  The two must agree bit for bit (tests/test_gpu_parity.py::test_expand_*).
+// of 360 B/row of columns) cross PCIe.  The two must agree bit for bit (tests/test_gpu_parity.py::test_expand_*).
 //
-// Bound: HBM writes (448 B/row) -- every store of a warp is one 128 B segment of one column.
+// Bound: HBM writes (360 B/row) -- every store of a warp is one 128 B segment of one column.
 #include <cuda_runtime.h>
 #include "bb.cuh"
 #include "kernels.h"
@@ -29,14 +29,13 @@ __device__ __forceinline__ void expand_row(u64 i, u64 N, u64 T, const u64 (&rg)[
 
   W(ZKIR_COL_CLK, (u32)((live ? i : T) % BB_P));
   W(ZKIR_COL_PC, (u32)pc);
-  W(ZKIR_COL_R0_LO, 0); W(ZKIR_COL_R0_HI, 0);
 #pragma unroll
-  for (int k = 1; k < 16; k++) { W(ZKIR_COL_R0_LO + 2 * k, (u32)(rg[k] & LIMB)); W(ZKIR_COL_R0_LO + 2 * k + 1, (u32)(rg[k] >> 20)); }
+  for (int k = 1; k < 16; k++) { W(ZKIR_COL_R1_LO + 2 * (k - 1), (u32)(rg[k] & LIMB)); W(ZKIR_COL_R1_LO + 2 * (k - 1) + 1, (u32)(rg[k] >> 20)); }
 
   u32 rd = 0, rs1 = 0, rs2 = 0;
-  u32 s_add = 0, s_sub = 0, s_addi = 0, s_beq = 0, s_bne = 0, s_jal = 0, s_ecall = 0, s_pad = 0;
+  u32 s_add = 0, s_sub = 0, s_addi = 0, s_beq = 0, s_bne = 0, s_jal = 0, s_pad = 0;
   u32 is_exit = 0, is_read = 0, is_write = 0;
-  u64 av = 0, bv = 0, cv = 0, io = 0;
+  u64 av = 0, bv = 0, cv = 0;
   long long imm = 0;
   bool has_imm = false;
   u32 carry0 = 0, carry1 = 0, inv_lo = 0, inv_hi = 0, ne_lo = 0, ne_hi = 0, taken = 0;
@@ -68,15 +67,13 @@ __device__ __forceinline__ void expand_row(u64 i, u64 N, u64 T, const u64 (&rg)[
       cv = pc + 4;
       s_jal = 1;
     } else if (op == 0x50) {                 // ECALL (syscall.rs:94-119)
-      s_ecall = 1;
-      const u64 num = rg[10];
+      const u64 num = rg[10];            // an ECALL row is is_exit + is_read + is_write
       if (num == 0) is_exit = 1;
       else if (num == 1) {                   // READ: the value is the post-state r10
         is_read = 1; rd = 10;
-        io = read_val;
-        cv = io;
-        if (io >> 40) err = 3;
-      } else if (num == 2) { is_write = 1; io = rg[11]; }
+        cv = read_val;
+        if (cv >> 40) err = 3;
+      } else if (num == 2) is_write = 1;
       else err = 4;
     } else {
       err = 5;
@@ -100,21 +97,21 @@ __device__ __forceinline__ void expand_row(u64 i, u64 N, u64 T, const u64 (&rg)[
       taken = op == 0x41 ? ne : !ne;
     }
   }
-  u32 imm_lo = 0, imm_hi = 0, imm_sign = 0, imm_f = 0;
+  u32 imm_lo = 0, imm_hi = 0, imm_sign = 0;
   if (has_imm) {
     const u64 m = (u64)imm & M40;
     imm_lo = (u32)(m & LIMB); imm_hi = (u32)(m >> 20);
     imm_sign = imm < 0;
-    imm_f = imm < 0 ? BB_P - (u32)(-imm) : (u32)imm;
   }
-  W(ZKIR_COL_IMM_LO, imm_lo); W(ZKIR_COL_IMM_HI, imm_hi); W(ZKIR_COL_IMM_F, imm_f); W(ZKIR_COL_IMM_SIGN, imm_sign);
+  W(ZKIR_COL_IMM_LO, imm_lo); W(ZKIR_COL_IMM_HI, imm_hi); W(ZKIR_COL_IMM_SIGN, imm_sign);
   W(ZKIR_COL_S_ADD, s_add); W(ZKIR_COL_S_SUB, s_sub); W(ZKIR_COL_S_ADDI, s_addi); W(ZKIR_COL_S_BEQ, s_beq);
-  W(ZKIR_COL_S_BNE, s_bne); W(ZKIR_COL_S_JAL, s_jal); W(ZKIR_COL_S_ECALL, s_ecall); W(ZKIR_COL_S_PAD, s_pad);
+  W(ZKIR_COL_S_BNE, s_bne); W(ZKIR_COL_S_JAL, s_jal); W(ZKIR_COL_S_PAD, s_pad);
 #pragma unroll
-  for (int k = 0; k < 16; k++) {
-    W(ZKIR_COL_SEL_RD0 + k, rd == (u32)k);
-    W(ZKIR_COL_SEL_RS1_0 + k, rs1 == (u32)k);
-    W(ZKIR_COL_SEL_RS2_0 + k, rs2 == (u32)k);
+  for (int k = 0; k < 16; k++) W(ZKIR_COL_SEL_RD0 + k, rd == (u32)k);
+#pragma unroll
+  for (int k = 0; k < 4; k++) {  // source operand index = 4*h + l, two 4-way one-hots each
+    W(ZKIR_COL_RS1_H0 + k, (rs1 >> 2) == (u32)k); W(ZKIR_COL_RS1_L0 + k, (rs1 & 3u) == (u32)k);
+    W(ZKIR_COL_RS2_H0 + k, (rs2 >> 2) == (u32)k); W(ZKIR_COL_RS2_L0 + k, (rs2 & 3u) == (u32)k);
   }
   W(ZKIR_COL_A_LO, (u32)(av & LIMB)); W(ZKIR_COL_A_HI, (u32)(av >> 20));
   W(ZKIR_COL_B_LO, (u32)(bv & LIMB)); W(ZKIR_COL_B_HI, (u32)(bv >> 20));
@@ -122,7 +119,6 @@ __device__ __forceinline__ void expand_row(u64 i, u64 N, u64 T, const u64 (&rg)[
   W(ZKIR_COL_CARRY0, carry0); W(ZKIR_COL_CARRY1, carry1);
   W(ZKIR_COL_INV_LO, inv_lo); W(ZKIR_COL_INV_HI, inv_hi); W(ZKIR_COL_NE_LO, ne_lo); W(ZKIR_COL_NE_HI, ne_hi); W(ZKIR_COL_TAKEN, taken);
   W(ZKIR_COL_IS_EXIT, is_exit); W(ZKIR_COL_IS_READ, is_read); W(ZKIR_COL_IS_WRITE, is_write);
-  W(ZKIR_COL_IO_LO, (u32)(io & LIMB)); W(ZKIR_COL_IO_HI, (u32)(io >> 20));
   if (err) {  // first offending row wins; the host reports it after the stream is drained
     const unsigned long long packed = (i << 8) | err;
     atomicMin(reinterpret_cast<unsigned long long*>(errp), packed);
