@@ -75,7 +75,7 @@ impl Prover {
         Ok(Self { ctx })
     }
 
-    /// `cols`: `[90][1 << log_n]` column-major canonical values (see `pack_trace`).
+    /// `cols`: `[85][1 << log_n]` column-major canonical values (see `pack_trace`).
     pub fn prove_columns(&mut self, cfg: &ProverConfig, cols: &[u32], log_n: u32, pv: &[u32; 4]) -> Result<Vec<u8>, RuntimeError> {
         assert_eq!(cols.len(), (ffi::ZKIR_AIR_V1_WIDTH as usize) << log_n);
         let params = ffi::zkir_params {

@@ -219,7 +219,7 @@ def test_expand_writelog_long_trace(gpu_ctx):
 def test_expand_rows_rejects_unconstrained_opcode(gpu_ctx):
     prog = zkir_b200.assemble("addi r1, r0, 3\nmul r2, r1, r1\nadd r10, r0, r0\necall\n")
     res = zkir_b200.VM(prog, [], zkir_b200.VMConfig(enable_execution_trace=True)).run()
-    d = gpu_ctx.alloc(90 * 4 * 4)
+    d = gpu_ctx.alloc(85 * 4 * 4)
     with pytest.raises(zkir_b200.RuntimeError) as ei:
         gpu_ctx.expand_rows(res.rows(), 2, d)
     gpu_ctx.free(d)
@@ -314,7 +314,7 @@ def test_error_paths_return_codes(gpu_ctx):
         gpu_ctx.prove_columns(cols, bad_pv, cfg)
     assert ei.value.code == -1
     l = _ffi.lib()
-    params = _ffi.Params(1, 4, 2, 89, 4)                 # wrong width
+    params = _ffi.Params(1, 4, 2, 84, 4)                 # wrong width
     proof, plen = C.c_void_p(), C.c_size_t()
     rc = l.zkir_b200_prove(gpu_ctx._h, C.byref(params), cols.ctypes.data, 8, pv.ctypes.data_as(_ffi.u32p), C.byref(proof), C.byref(plen))
     assert rc == -1 and b"width" in l.zkir_b200_last_error(gpu_ctx._h)

@@ -32,9 +32,8 @@ def col(name):
 
 CLK = col("clk")
 PC = col("pc")
-IMM_LO = col("imm_lo")
-IMM_HI = col("imm_hi")
-IMM_SIGN = col("imm_sign")
+IMM_LO = col("imm_lo")      # low 20 bits of the sign-extended 40-bit immediate
+IMM_SIGN = col("imm_sign")  # its high limb is sign * (2^20 - 1): immediates are 17 / 21 bits (encoder.rs:98-151)
 # register file, PRE-state; r0 is hard-wired to zero (state.rs:76-91) and has no columns
 REG_LO = [None]
 REG_HI = [None]
@@ -44,8 +43,11 @@ for i in range(1, 16):
 # opcode selectors; an ECALL row is is_exit + is_read + is_write (no separate column)
 SEL_NAMES = ["s_add", "s_sub", "s_addi", "s_beq", "s_bne", "s_jal", "s_pad"]
 S = {n: col(n) for n in SEL_NAMES}
-SEL_RD = [col(f"sel_rd{i}") for i in range(16)]          # one-hot: the write-back constraint needs degree 1 here
-# source operands: index = 4*h + l as a product of two 4-way one-hots (16 columns for both operands instead of 32)
+# register indices: index = 4*h + l as a product of two 4-way one-hots (8 columns per operand instead of 16).
+# rd additionally carries rdw[h] = rd_h[h] * (write enable), so that the write-back selector rdw[h]*rd_l[l] is degree 2.
+RD_H = [col(f"rd_h{i}") for i in range(4)]
+RD_L = [col(f"rd_l{i}") for i in range(4)]
+RDW = [col(f"rdw{i}") for i in range(4)]
 RS1_H = [col(f"rs1_h{i}") for i in range(4)]
 RS1_L = [col(f"rs1_l{i}") for i in range(4)]
 RS2_H = [col(f"rs2_h{i}") for i in range(4)]
@@ -55,7 +57,7 @@ CARRY0, CARRY1 = col("carry0"), col("carry1")
 INV_LO, INV_HI, NE_LO, NE_HI, TAKEN = (col(n) for n in ["inv_lo", "inv_hi", "ne_lo", "ne_hi", "taken"])
 IS_EXIT, IS_READ, IS_WRITE = col("is_exit"), col("is_read"), col("is_write")
 WIDTH = len(COLS)
-assert WIDTH == 90   # 12 sponge absorptions per Merkle leaf (rate 8)
+assert WIDTH == 85   # 11 sponge absorptions per Merkle leaf (rate 8)
 
 PV_NAMES = ["entry_pc", "num_cycles", "exit_lo", "exit_hi"]
 NUM_PUBLIC = len(PV_NAMES)
@@ -146,15 +148,14 @@ def build():
     s_ecall = g.tmp(L(IS_EXIT) + L(IS_READ) + L(IS_WRITE), "ecall row (syscall.rs:94-119)")
 
     # --- booleans
-    bools = ([S[n] for n in SEL_NAMES] + SEL_RD + RS1_H + RS1_L + RS2_H + RS2_L +
+    bools = ([S[n] for n in SEL_NAMES] + RD_H + RD_L + RS1_H + RS1_L + RS2_H + RS2_L +
              [CARRY0, CARRY1, IMM_SIGN, IS_EXIT, IS_READ, IS_WRITE])
     for b in bools:
         x = L(b)
         g.emit(x * (x - 1), f"bool {COLS[b]}")
     # --- one-hot sums
     g.emit(sum_e(s.values()) + s_ecall - 1, "exactly one opcode selector")
-    g.emit(sum_e(L(i) for i in SEL_RD) - 1, "one-hot rd")
-    for name, grp in (("rs1.h", RS1_H), ("rs1.l", RS1_L), ("rs2.h", RS2_H), ("rs2.l", RS2_L)):
+    for name, grp in (("rd.h", RD_H), ("rd.l", RD_L), ("rs1.h", RS1_H), ("rs1.l", RS1_L), ("rs2.h", RS2_H), ("rs2.l", RS2_L)):
         g.emit(sum_e(L(i) for i in grp) - 1, f"one-hot {name}")
 
     # --- operand fetch: reg[4h+l] selected by H[h]*L[l]; r0 contributes nothing (state.rs:76-91)
@@ -174,9 +175,10 @@ def build():
     # ADDI has no rs2: the converter selects r0 there, which is enforced, so b = reg[rs2] + addi * imm stays degree 3
     g.emit(s["s_addi"] * (1 - L(RS2_H[0]) * L(RS2_L[0])), "addi: rs2 selector points at r0")
     g.emit(b_lo - rs2_lo - s["s_addi"] * L(IMM_LO), "b.lo = reg[rs2].lo + addi * imm.lo")
-    g.emit(b_hi - rs2_hi - s["s_addi"] * L(IMM_HI), "b.hi = reg[rs2].hi + addi * imm.hi")
-    # --- immediate as a field element: imm_lo + 2^20 imm_hi - sign * 2^40  (execute.rs:187 `imm as u64` masked to 40 bits)
-    imm_f = g.tmp(L(IMM_LO) + TWO20 * L(IMM_HI) - ((1 << 40) % P) * L(IMM_SIGN), "signed immediate")
+    imm_hi = g.tmp((TWO20 - 1) * L(IMM_SIGN), "imm.hi = sign-extension limb")
+    g.emit(b_hi - rs2_hi - s["s_addi"] * imm_hi, "b.hi = reg[rs2].hi + addi * imm.hi")
+    # --- immediate as a field element: imm_lo + 2^20 imm_hi - sign * 2^40 = imm_lo - 2^20 sign  (execute.rs:187)
+    imm_f = g.tmp(L(IMM_LO) - TWO20 * L(IMM_SIGN), "signed immediate")
     # --- ALU (value.rs:620-631 wrap mod 2^40: carry1 is discarded)
     addlike = g.tmp(s["s_add"] + s["s_addi"], "add-like")
     k0, k1 = L(CARRY0), L(CARRY1)
@@ -185,11 +187,13 @@ def build():
     g.emit(s["s_sub"] * (a_lo - b_lo - c_lo + TWO20 * k0), "sub lo limb (carry0 = borrow)")
     g.emit(s["s_sub"] * (a_hi - b_hi - k0 - c_hi + TWO20 * k1), "sub hi limb")
     g.emit(s["s_jal"] * (c_lo + TWO20 * c_hi - L(PC) - 4), "jal link = pc + 4 (execute.rs:639-647)")
-    g.emit(L(IS_READ) * (L(SEL_RD[10]) - 1), "read writes r10 (syscall.rs:104-109); c = the tape value")
-    # --- register write-back, pre-state rows: next.r[i] = sel_rd[i]*w ? c : r[i]
+    g.emit(L(IS_READ) * (L(RD_H[2]) * L(RD_L[2]) - 1), "read writes r10 (syscall.rs:104-109); c = the tape value")
+    # --- register write-back, pre-state rows: next.r[i] = (rd == i && w) ? c : r[i]
     w = g.tmp(s["s_add"] + s["s_sub"] + s["s_addi"] + s["s_jal"] + L(IS_READ), "write enable")
+    for h in range(4):
+        g.emit(L(RDW[h]) - L(RD_H[h]) * w, f"rdw{h} = rd.h{h} * write enable")
     for i in range(1, 16):
-        wi = g.tmp(L(SEL_RD[i]) * w)
+        wi = g.tmp(L(RDW[i >> 2]) * L(RD_L[i & 3]))
         g.emit(trans * (N(REG_LO[i]) - L(REG_LO[i]) - wi * (c_lo - L(REG_LO[i]))), f"write-back r{i}.lo")
         g.emit(trans * (N(REG_HI[i]) - L(REG_HI[i]) - wi * (c_hi - L(REG_HI[i]))), f"write-back r{i}.hi")
     # --- branches: raw equality of both limbs (execute.rs:578-596)
@@ -229,7 +233,7 @@ def build():
 def main():
     g = build()
     hdr = []
-    hdr.append("// GENERATED by tools/gen_air.py -- do not edit.  zkir-b200 core AIR v1 (90 columns).")
+    hdr.append("// GENERATED by tools/gen_air.py -- do not edit.  zkir-b200 core AIR v1 (85 columns).")
     hdr.append("#pragma once")
     hdr.append(f"#define ZKIR_AIR_WIDTH {WIDTH}")
     hdr.append(f"#define ZKIR_AIR_NUM_CONSTRAINTS {g.idx}")

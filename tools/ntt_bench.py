@@ -8,7 +8,7 @@ import zkir_b200
 
 ctx = zkir_b200.Context(0)
 rng = np.random.default_rng(1)
-for log_n, cols in [(20, 32), (20, 90), (16, 90)]:
+for log_n, cols in [(20, 32), (20, 85), (16, 85)]:
     a = rng.integers(0, 2013265921, size=(cols, 1 << log_n), dtype=np.uint64).astype(np.uint32)
     d = ctx.to_device(a)
     for _ in range(3):

@@ -1,12 +1,12 @@
-// Device-side trace converter: raw interpreter rows -> the 90 BabyBear columns of the core AIR v1.
+// Device-side trace converter: raw interpreter rows -> the 85 BabyBear columns of the core AIR v1.
 //
 // The reference's hand-off type is `Vec<TraceRow>` -- cycle, pc, instruction word and the PRE-state registers
 // (zkir-spec/src/trace.rs:24-50, recorded at zkir-runtime/src/vm.rs:245-253,302-312); the "converter" that turns rows
 // into field columns is named there (trace.rs:41, vm.rs:243-244) but absent.  zkir_b200/csrc/host/pack.cc is the host
 // restatement; this kernel is the same function with one thread per row, so that only the raw rows (140 B/row instead
-// of 360 B/row of columns) cross PCIe.  The two must agree bit for bit (tests/test_gpu_parity.py::test_expand_*).
+// of 340 B/row of columns) cross PCIe.  The two must agree bit for bit (tests/test_gpu_parity.py::test_expand_*).
 //
-// Bound: HBM writes (360 B/row) -- every store of a warp is one 128 B segment of one column.
+// Bound: HBM writes (340 B/row) -- every store of a warp is one 128 B segment of one column.
 #include <cuda_runtime.h>
 #include "bb.cuh"
 #include "kernels.h"
@@ -32,7 +32,7 @@ __device__ __forceinline__ void expand_row(u64 i, u64 N, u64 T, const u64 (&rg)[
 #pragma unroll
   for (int k = 1; k < 16; k++) { W(ZKIR_COL_R1_LO + 2 * (k - 1), (u32)(rg[k] & LIMB)); W(ZKIR_COL_R1_LO + 2 * (k - 1) + 1, (u32)(rg[k] >> 20)); }
 
-  u32 rd = 0, rs1 = 0, rs2 = 0;
+  u32 rd = 0, rs1 = 0, rs2 = 0, writes = 0;  // writes: ADD, SUB, ADDI, JAL, READ
   u32 s_add = 0, s_sub = 0, s_addi = 0, s_beq = 0, s_bne = 0, s_jal = 0, s_pad = 0;
   u32 is_exit = 0, is_read = 0, is_write = 0;
   u64 av = 0, bv = 0, cv = 0;
@@ -51,11 +51,11 @@ __device__ __forceinline__ void expand_row(u64 i, u64 N, u64 T, const u64 (&rg)[
       return v;
     };
     if (op == 0x00 || op == 0x01) {          // ADD / SUB (execute.rs:43-78)
-      rd = fa; rs1 = fb; rs2 = fc;
+      rd = fa; rs1 = fb; rs2 = fc; writes = 1;
       av = R(rs1); bv = R(rs2);
       if (op == 0) s_add = 1; else s_sub = 1;
     } else if (op == 0x08) {                 // ADDI (execute.rs:185-197)
-      rd = fa; rs1 = fb; imm = sext_dev((w >> 15) & 0x1FFFF, 17); has_imm = true;
+      rd = fa; rs1 = fb; imm = sext_dev((w >> 15) & 0x1FFFF, 17); has_imm = true; writes = 1;
       av = R(rs1); bv = (u64)imm & M40;
       s_addi = 1;
     } else if (op == 0x40 || op == 0x41) {   // BEQ / BNE, B-type: rs1 bits 10:7, rs2 bits 14:11 (encoder.rs:132-140)
@@ -63,14 +63,14 @@ __device__ __forceinline__ void expand_row(u64 i, u64 N, u64 T, const u64 (&rg)[
       av = R(rs1); bv = R(rs2);
       if (op == 0x40) s_beq = 1; else s_bne = 1;
     } else if (op == 0x48) {                 // JAL (execute.rs:639-647)
-      rd = fa; imm = sext_dev((w >> 11) & 0x1FFFFF, 21); has_imm = true;
+      rd = fa; imm = sext_dev((w >> 11) & 0x1FFFFF, 21); has_imm = true; writes = 1;
       cv = pc + 4;
       s_jal = 1;
     } else if (op == 0x50) {                 // ECALL (syscall.rs:94-119)
       const u64 num = rg[10];            // an ECALL row is is_exit + is_read + is_write
       if (num == 0) is_exit = 1;
       else if (num == 1) {                   // READ: the value is the post-state r10
-        is_read = 1; rd = 10;
+        is_read = 1; rd = 10; writes = 1;
         cv = read_val;
         if (cv >> 40) err = 3;
       } else if (num == 2) is_write = 1;
@@ -97,19 +97,18 @@ __device__ __forceinline__ void expand_row(u64 i, u64 N, u64 T, const u64 (&rg)[
       taken = op == 0x41 ? ne : !ne;
     }
   }
-  u32 imm_lo = 0, imm_hi = 0, imm_sign = 0;
+  u32 imm_lo = 0, imm_sign = 0;  // the high limb is the sign extension (0 or 2^20-1): not a column
   if (has_imm) {
-    const u64 m = (u64)imm & M40;
-    imm_lo = (u32)(m & LIMB); imm_hi = (u32)(m >> 20);
+    imm_lo = (u32)(((u64)imm & M40) & LIMB);
     imm_sign = imm < 0;
   }
-  W(ZKIR_COL_IMM_LO, imm_lo); W(ZKIR_COL_IMM_HI, imm_hi); W(ZKIR_COL_IMM_SIGN, imm_sign);
+  W(ZKIR_COL_IMM_LO, imm_lo); W(ZKIR_COL_IMM_SIGN, imm_sign);
   W(ZKIR_COL_S_ADD, s_add); W(ZKIR_COL_S_SUB, s_sub); W(ZKIR_COL_S_ADDI, s_addi); W(ZKIR_COL_S_BEQ, s_beq);
   W(ZKIR_COL_S_BNE, s_bne); W(ZKIR_COL_S_JAL, s_jal); W(ZKIR_COL_S_PAD, s_pad);
 #pragma unroll
-  for (int k = 0; k < 16; k++) W(ZKIR_COL_SEL_RD0 + k, rd == (u32)k);
-#pragma unroll
-  for (int k = 0; k < 4; k++) {  // source operand index = 4*h + l, two 4-way one-hots each
+  for (int k = 0; k < 4; k++) {  // register index = 4*h + l, two 4-way one-hots each; rdw[h] = rd_h[h] * writes
+    W(ZKIR_COL_RD_H0 + k, (rd >> 2) == (u32)k); W(ZKIR_COL_RD_L0 + k, (rd & 3u) == (u32)k);
+    W(ZKIR_COL_RDW0 + k, ((rd >> 2) == (u32)k) ? writes : 0u);
     W(ZKIR_COL_RS1_H0 + k, (rs1 >> 2) == (u32)k); W(ZKIR_COL_RS1_L0 + k, (rs1 & 3u) == (u32)k);
     W(ZKIR_COL_RS2_H0 + k, (rs2 >> 2) == (u32)k); W(ZKIR_COL_RS2_L0 + k, (rs2 & 3u) == (u32)k);
   }
