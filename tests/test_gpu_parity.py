@@ -351,3 +351,19 @@ def test_full_size_lde_linearity_and_interpolation(gpu_ctx):
     gpu_ctx.ntt(d, n_cols, log_n, inverse=True)
     assert np.array_equal(gpu_ctx.to_host(d, a.shape), a)
     gpu_ctx.free(d)
+
+
+def test_minimal_programs(gpu_ctx, oracle):
+    """smallest traces: a lone ECALL (r10 = 0 -> EXIT 0 at cycle 0: one live row padded to 4) and a 2-cycle exit with a code"""
+    cfg = zkir_b200.ProverConfig(num_queries=5, pow_bits=3)
+    for src, code, cycles in (("ecall\n", 0, 1), ("addi r11, r0, 9\necall\n", 9, 2)):
+        res = zkir_b200.VM(zkir_b200.assemble(src), [], zkir_b200.VMConfig(enable_execution_trace=True)).run()
+        assert res.cycles == cycles and res.halt_reason == zkir_b200.HaltReason.Exit(code)
+        cols, pv = res.pack()
+        assert cols.shape[1] == 4 and oracle.check_trace(cols, pv)[0] == -1
+        want = oracle.prove(cfg, cols, pv)
+        assert gpu_ctx.prove_columns(cols, pv, cfg) == want
+        assert gpu_ctx.prove_rows(res.rows(), cfg)[0] == want
+        assert gpu_ctx.prove_writelog(res.writelog(), cfg)[0] == want
+        ok, why = zkir_b200.verify(want, cfg, pv)
+        assert ok, why
