@@ -88,6 +88,22 @@ int zkir_b200_prove_batch(zkir_ctx*, const zkir_params*, const uint32_t* const* 
                           const uint32_t* const* public_values, uint32_t n_proofs, uint8_t** proofs, size_t* proof_lens);
 void zkir_b200_free_proof(uint8_t*);
 size_t zkir_b200_proof_size(const zkir_params*, uint32_t log_n); /* bytes; depends only on the shape */
+/* ---- ONE proof sharded over several GPUs of a box (BASELINE config 5), one context per GPU, normally one
+ * process per GPU.  (No reference counterpart.)  Rank 0 draws an id, the host distributes it (torch.distributed / MPI / a
+ * pipe), every rank calls comm_init: NCCL (bound with dlopen at this point, ZKIR_NCCL_LIB overrides the library) links the
+ * contexts.  From then on every zkir_b200_prove* call on these contexts is COLLECTIVE: all ranks call it with the same trace
+ * and parameters.  The LDE matrix is replicated; the Merkle leaf ranges of the trace, quotient and large FRI-layer trees are
+ * cut into `world` contiguous segments (rank g hashes leaves [g*M/world, (g+1)*M/world) and builds that subtree), the
+ * segment roots are exchanged with one all-gather of world*8 words per tree, and the authentication-path pieces each rank owns
+ * are merged with one all-reduce at the end.  Every rank returns the same proof, bit-identical to the single-GPU proof. */
+#define ZKIR_COMM_ID_LEN 128
+int zkir_b200_comm_unique_id(uint8_t id[ZKIR_COMM_ID_LEN]);
+int zkir_b200_comm_init(zkir_ctx*, const uint8_t id[ZKIR_COMM_ID_LEN], int rank, int world); /* world: power of two <= 64 */
+int zkir_b200_comm_shutdown(zkir_ctx*);
+/* test hook: run the sharded code path for `shards` segments on ONE GPU without NCCL (the context computes every segment in
+ * turn); min_segment_leaves != 0 lowers the size below which a tree is not sharded (default 4096 leaves per segment). */
+int zkir_b200_emulate_shards(zkir_ctx*, uint32_t shards, uint64_t min_segment_leaves);
+
 /* CPU verifier (host code, no GPU needed).  0 = accept, ZKIR_ERR_VERIFY = reject (reason via last_error(NULL)). */
 int zkir_b200_verify(const zkir_params*, const uint8_t* proof, size_t len, const uint32_t* public_values);
 

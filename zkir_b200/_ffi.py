@@ -37,6 +37,10 @@ SYMBOLS = {
                                           C.POINTER(vp), C.POINTER(C.c_size_t)]),
     "zkir_b200_expand_writelog": (C.c_int, [vp, vp, vp, vp, C.c_uint64, C.c_uint64, C.c_uint32, vp]),
     "zkir_b200_prove_batch": (C.c_int, [vp, C.POINTER(Params), C.POINTER(vp), u32p, C.POINTER(vp), C.c_uint32, C.POINTER(vp), C.POINTER(C.c_size_t)]),
+    "zkir_b200_comm_unique_id": (C.c_int, [vp]),
+    "zkir_b200_comm_init": (C.c_int, [vp, vp, C.c_int, C.c_int]),
+    "zkir_b200_comm_shutdown": (C.c_int, [vp]),
+    "zkir_b200_emulate_shards": (C.c_int, [vp, C.c_uint32, C.c_uint64]),
     "zkir_b200_free_proof": (None, [vp]),
     "zkir_b200_proof_size": (C.c_size_t, [C.POINTER(Params), C.c_uint32]),
     "zkir_b200_verify": (C.c_int, [C.POINTER(Params), vp, C.c_size_t, u32p]),

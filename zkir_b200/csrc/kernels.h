@@ -42,11 +42,13 @@ const uint2* fast_scale_table(FastNtt* f, const FastPlan& pl, u32 base_canon, u3
 int poseidon2_init_constants();
 int launch_permute(u32* d_states, u64 n, bool canonical_io, cudaStream_t st, u64* launches);
 // matrix rows are coset-major (kernels.h: see ntt_fast.cu), leaves natural; log_b = 0 for a natural-order matrix
-int launch_leaf_hash(const u32* mat, u64 col_stride, u32 n_cols, u64 n_rows, u32 log_b, u32* digests, cudaStream_t st, u64* launches);
+// first_leaf / seg_leaves != 0: only that range of (natural-order) leaves, for a proof sharded over several GPUs
+int launch_leaf_hash(const u32* mat, u64 col_stride, u32 n_cols, u64 n_rows, u32 log_b, u32* digests, cudaStream_t st, u64* launches,
+                     u64 first_leaf = 0, u64 seg_leaves = 0);
 // optional fused Fiat-Shamir step on the root: copy to root_dst, observe, sample n_sample elements into sample_out
 // pair_layer != nullptr: the leaves are FRI leaves hash(f[i] || f[i + n_leaves]) of that ext4 layer and are computed here too
 int launch_merkle_levels(u32* tree, u64 n_leaves, cudaStream_t st, u64* launches, ChalState* chal = nullptr, u32* root_dst = nullptr,
-                         u32* sample_out = nullptr, u32 n_sample = 0, const u32* pair_layer = nullptr);
+                         u32* sample_out = nullptr, u32 n_sample = 0, const u32* pair_layer = nullptr, u64 first = 0, u64 seg = 0);
 int launch_challenger(ChalState* st_dev, const u32* in, u32 n_in, u32* out, u32 n_out, u32 bits, cudaStream_t st, u64* launches);
 int launch_pow_grind(const ChalState* st_dev, u32 bits, u32* result, cudaStream_t st, u64* launches);
 
@@ -119,6 +121,10 @@ struct QueryArgs {
   const u32* const* ltrees;       // device array [R] of layer trees
   u32* out;                       // proof words at the start of the query section
   u32 words_per_query;
+  // one proof sharded over several GPUs: this context owns the leaf segments [shard_lo, shard_hi); the lowest *_sl levels of a
+  // tree exist only on the owner of the leaf (segment = 2^sl leaves).  Pieces this context does not own are written as 0.
+  u32 shard_lo = 0, shard_hi = 1, ttree_sl = 0, qtree_sl = 0;
+  u32 layer_sl[32] = {0};
 };
 int launch_queries(const QueryArgs& a, cudaStream_t st, u64* launches);
 

@@ -128,10 +128,13 @@ __global__ void permute_kernel(u32* states, u64 n, int canonical_io) {
 // leaf = overwrite-mode sponge (rate 8) over one memory row of a column-major matrix [n_cols][col_stride].
 // The matrix is coset-major (row r = z * 2^log_nc + i holds the LDE point of natural index i * 2^log_b + z), the tree is
 // in natural order: the digest of memory row r goes to leaf ((r mod 2^log_nc) << log_b) | (r >> log_nc).  log_b = 0: identity.
-__global__ void __launch_bounds__(128) leaf_hash_kernel(const u32* __restrict__ mat, u64 col_stride, u32 n_cols, u64 n_rows, u32 log_nc, u32 log_b,
-                                                        u32* __restrict__ digests) {
-  u64 row = blockIdx.x * (u64)blockDim.x + threadIdx.x;
-  if (row >= n_rows) return;
+// Segment form (one proof sharded over several GPUs): only the leaves [i0 << log_b, (i0 + 2^log_ni) << log_b) are hashed, i.e. the
+// memory rows z * 2^log_nc + i with i in [i0, i0 + 2^log_ni) of every coset z; thread t -> z = t >> log_ni, i = i0 + (t mod 2^log_ni).
+__global__ void __launch_bounds__(128) leaf_hash_kernel(const u32* __restrict__ mat, u64 col_stride, u32 n_cols, u64 n_threads, u32 log_nc, u32 log_b,
+                                                        u32 log_ni, u64 i0, u32* __restrict__ digests) {
+  const u64 t = blockIdx.x * (u64)blockDim.x + threadIdx.x;
+  if (t >= n_threads) return;
+  const u64 row = ((t >> log_ni) << log_nc) + i0 + (t & ((1ull << log_ni) - 1));
   u32 s[16];
 #pragma unroll
   for (int k = 0; k < 16; k++) s[k] = 0;
@@ -154,9 +157,10 @@ __global__ void __launch_bounds__(128) leaf_hash_kernel(const u32* __restrict__ 
 }
 
 // FRI layer leaves: leaf i = hash(F[i] || F[i+h]) (8 elements = one permutation)
-__global__ void __launch_bounds__(128) leaf_hash_pairs_kernel(const uint4* __restrict__ layer, u64 h, u32* __restrict__ digests) {
+__global__ void __launch_bounds__(128) leaf_hash_pairs_kernel(const uint4* __restrict__ layer, u64 h, u64 first, u64 count, u32* __restrict__ digests) {
   u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x;
-  if (i >= h) return;
+  if (i >= count) return;
+  i += first;
   uint4 a = layer[i], b = layer[i + h];
   u32 s[16] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, 0, 0, 0, 0, 0, 0, 0, 0};
   poseidon2_permute(s);
@@ -184,36 +188,53 @@ int launch_permute(u32* d_states, u64 n, bool canonical_io, cudaStream_t st, u64
   (*launches)++;
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
-int launch_leaf_hash(const u32* mat, u64 col_stride, u32 n_cols, u64 n_rows, u32 log_b, u32* digests, cudaStream_t st, u64* launches) {
+int launch_leaf_hash(const u32* mat, u64 col_stride, u32 n_cols, u64 n_rows, u32 log_b, u32* digests, cudaStream_t st, u64* launches,
+                     u64 first_leaf, u64 seg_leaves) {
   u32 log_rows = 0;
   while ((1ull << log_rows) < n_rows) log_rows++;
-  leaf_hash_kernel<<<nblk(n_rows, 128), 128, 0, st>>>(mat, col_stride, n_cols, n_rows, log_rows - log_b, log_b, digests);
+  const u32 log_nc = log_rows - log_b;
+  u64 n_threads = n_rows, i0 = 0;
+  u32 log_ni = log_nc;
+  if (seg_leaves && seg_leaves < n_rows) {  // leaf range of one shard: a multiple of 2^log_b leaves, power-of-two long
+    if ((seg_leaves & (seg_leaves - 1)) || (seg_leaves >> log_b) == 0 || first_leaf % seg_leaves) return -1;
+    n_threads = seg_leaves; i0 = first_leaf >> log_b;
+    log_ni = 0;
+    while ((1ull << log_ni) < (seg_leaves >> log_b)) log_ni++;
+  }
+  leaf_hash_kernel<<<nblk(n_threads, 128), 128, 0, st>>>(mat, col_stride, n_cols, n_threads, log_nc, log_b, log_ni, i0, digests);
   (*launches)++;
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
-__global__ void merkle_coop_kernel(u32* level, u64 n_in, u32 chunk, const u32* __restrict__ pair_layer, ChalState* chal, u32* root_dst,
+__global__ void merkle_coop_kernel(u32* level, u64 n_in, u64 first, u32 chunk, const u32* __restrict__ pair_layer, ChalState* chal, u32* root_dst,
                                    u32* sample_out, u32 n_sample);
 __global__ void challenger_kernel(ChalState* st, const u32* in, u32 n_in, u32* out, u32 n_out, u32 bits);
-__global__ void leaf_hash_pairs_kernel(const uint4* __restrict__ layer, u64 h, u32* __restrict__ digests);
 // tree: level 0 = n_leaves digests (already in place, or computed here from the FRI layer `pair_layer` of 2*n_leaves ext4
 // values); builds the upper levels behind it.  Wide levels: one thread per compression (throughput); from 32768 nodes down
 // the cooperative kernel (latency): 32-node blocks climbing 5 levels while the level is wide, one block at the end.
 // If `chal` is given, the launch that produces the root also copies it to root_dst, observes it and samples n_sample
 // elements into sample_out.
+// Segment form (first, seg != 0): only the subtree above the leaves [first, first + seg) is built (seg a power of two dividing
+// first); every level keeps its place in the global tree layout, so after an all-gather of the level that holds the segment
+// roots the rest is an ordinary tree over n_leaves / seg nodes.  No Fiat-Shamir step in that case.
 int launch_merkle_levels(u32* tree, u64 n_leaves, cudaStream_t st, u64* launches, ChalState* chal, u32* root_dst, u32* sample_out, u32 n_sample,
-                         const u32* pair_layer) {
+                         const u32* pair_layer, u64 first, u64 seg) {
   u32* lvl = tree;
-  u64 n = n_leaves;
+  u64 n_tot = n_leaves, f = 0, n = n_leaves;
+  if (seg && seg < n_leaves) {
+    if ((seg & (seg - 1)) || first % seg || first + seg > n_leaves) return -1;
+    f = first; n = seg; chal = nullptr;
+  }
+  const bool whole = n == n_tot;
   if (pair_layer && n > 32768) {
-    leaf_hash_pairs_kernel<<<nblk(n, 128), 128, 0, st>>>(reinterpret_cast<const uint4*>(pair_layer), n, tree);
+    leaf_hash_pairs_kernel<<<nblk(n, 128), 128, 0, st>>>(reinterpret_cast<const uint4*>(pair_layer), n_tot, f, n, tree);
     (*launches)++;
     pair_layer = nullptr;
   }
   while (n > 32768) {
-    u32* nxt = lvl + n * 8;
-    compress_kernel<<<nblk(n / 2, 128), 128, 0, st>>>(reinterpret_cast<const uint4*>(lvl), reinterpret_cast<uint4*>(nxt), n / 2);
+    u32* nxt = lvl + n_tot * 8;
+    compress_kernel<<<nblk(n / 2, 128), 128, 0, st>>>(reinterpret_cast<const uint4*>(lvl + f * 8), reinterpret_cast<uint4*>(nxt + (f / 2) * 8), n / 2);
     (*launches)++;
-    lvl = nxt; n >>= 1;
+    lvl = nxt; n >>= 1; n_tot >>= 1; f >>= 1;
   }
   bool chal_done = false;
   while (n > 1 || pair_layer) {
@@ -222,11 +243,11 @@ int launch_merkle_levels(u32* tree, u64 n_leaves, cudaStream_t st, u64* launches
     const bool last = blocks == 1;
     u32 threads = 16 * (chunk / 2);
     if (threads < 32) threads = 32;
-    merkle_coop_kernel<<<blocks, threads, 0, st>>>(lvl, n, chunk, pair_layer, last ? chal : nullptr, root_dst, sample_out, n_sample);
+    merkle_coop_kernel<<<blocks, threads, 0, st>>>(lvl, n_tot, f, chunk, pair_layer, last && whole ? chal : nullptr, root_dst, sample_out, n_sample);
     (*launches)++;
     pair_layer = nullptr;
     if (last && chal) chal_done = true;
-    for (u32 c = chunk; c > 1; c >>= 1) { lvl += n * 8; n >>= 1; }
+    for (u32 c = chunk; c > 1; c >>= 1) { lvl += n_tot * 8; n >>= 1; n_tot >>= 1; f >>= 1; }
     if (last) break;
   }
   if (chal && !chal_done) {  // not reached: every path above ends in a single-block launch
@@ -317,11 +338,13 @@ __global__ void __launch_bounds__(32) challenger_kernel(ChalState* st, const u32
 // When the block reaches the root (single block), warp 0 also runs the Fiat-Shamir step that always follows:
 // copy the root into the proof, observe it, sample `n_sample` field elements.
 #define COOP_MAX_CHUNK 128
-__global__ void __launch_bounds__(16 * COOP_MAX_CHUNK / 2) merkle_coop_kernel(u32* level, u64 n_in, u32 chunk, const u32* __restrict__ pair_layer,
-                                                                             ChalState* chal, u32* root_dst, u32* sample_out, u32 n_sample) {
+__global__ void __launch_bounds__(16 * COOP_MAX_CHUNK / 2) merkle_coop_kernel(u32* level, u64 n_in, u64 first, u32 chunk,
+                                                                             const u32* __restrict__ pair_layer, ChalState* chal, u32* root_dst,
+                                                                             u32* sample_out, u32 n_sample) {
   __shared__ u32 buf[2][COOP_MAX_CHUNK * 8];
   const u32 tid = threadIdx.x, lane = tid & 31, l16 = tid & 15, slot = tid >> 4, slots = blockDim.x >> 4;
-  const u64 node0 = (u64)blockIdx.x * chunk;
+  // `level` is the start of a whole tree level of n_in nodes; the grid covers the nodes [first, first + gridDim.x * chunk)
+  const u64 node0 = first + (u64)blockIdx.x * chunk;
   if (pair_layer) {
     const u64 h = n_in;  // leaves of this layer = half its length
     for (u32 s0 = 0; s0 < chunk; s0 += slots) {
@@ -339,10 +362,11 @@ __global__ void __launch_bounds__(16 * COOP_MAX_CHUNK / 2) merkle_coop_kernel(u3
   }
   __syncthreads();
   u32 cur = 0, n = chunk;
-  u64 level_n = n_in;
+  u64 level_n = n_in, out0 = node0;
   u32* out_base = level + n_in * 8;
   while (n > 1) {
     const u32 n_out = n >> 1;
+    out0 >>= 1;                                   // first node of this block in the level being written
     for (u32 s0 = 0; s0 < n_out; s0 += slots) {   // warp-uniform trip count
       const u32 sidx = s0 + slot;
       if (s0 + (tid >> 5) * 2 >= n_out) break;  // neither half of this warp has a node: warp-uniform exit
@@ -351,7 +375,7 @@ __global__ void __launch_bounds__(16 * COOP_MAX_CHUNK / 2) merkle_coop_kernel(u3
       x = permute_warp(x, lane);
       if (active && l16 < 8) {
         buf[cur ^ 1][8 * sidx + l16] = x;
-        out_base[((u64)blockIdx.x * n_out + sidx) * 8 + l16] = x;
+        out_base[(out0 + sidx) * 8 + l16] = x;
       }
     }
     __syncthreads();

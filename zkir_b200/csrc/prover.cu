@@ -15,6 +15,7 @@
 #include "zkir_b200.h"
 #include "bb.cuh"
 #include "kernels.h"
+#include "comm.h"
 #include "constants_generated.h"
 #include "air_generated.h"
 
@@ -110,6 +111,11 @@ struct zkir_ctx {
   void* rows_dev = nullptr; size_t rows_bytes = 0;   // staging for raw interpreter rows (prove_rows)
   u64* d_err = nullptr; u64* h_err = nullptr;
   std::vector<zkir_ctx*> workers;                    // extra contexts of the same device for prove_batch
+  // one proof sharded over `shards` GPUs (zkir_b200_comm_init): this context computes the Merkle leaf segments
+  // [shard_lo, shard_hi) -- its own rank with a communicator, all of them when the shards are emulated on one GPU (tests)
+  Comm* comm = nullptr;
+  u32 shards = 1, shard_lo = 0, shard_hi = 1;
+  u64 shard_min_seg = 4096;                          // trees with fewer leaves per shard are built whole on every rank
   Workspace ws;
   cudaEvent_t ev[ZKIR_STAGE_COUNT + 1];
   cudaEvent_t tev[2];
@@ -225,6 +231,42 @@ static int check_params(zkir_ctx* ctx, const zkir_params* p, u32 log_n) {
   return 0;
 }
 
+// Merkle commitment of one matrix (leaf i = sponge over LDE row i) or one FRI layer (leaf i = hash(f[i] || f[i+h])), followed
+// by the Fiat-Shamir step on its root.  With shards > 1 the leaf range is cut into `shards` contiguous segments: this context
+// hashes its segments and builds their subtrees in place in the global tree layout, the segment roots are exchanged with ONE
+// all-gather of shards * 8 words ("Merkle-root reduction"), and the top log2(shards) levels + the transcript step run
+// redundantly on every rank, so every rank continues with the same challenges.  *shard_levels = number of bottom path levels
+// that only the owner of a leaf holds (0 = the whole tree is local).
+static int commit_tree(zkir_ctx* ctx, const u32* mat, u32 n_cols, u32 log_b, const u32* pair_layer, u32* tree, u64 n_leaves, u32* root_dst,
+                       u32* sample_out, u32 n_sample, u32* shard_levels) {
+  cudaStream_t st = ctx->stream;
+  u64* LC = &ctx->launches;
+  Workspace& w = ctx->ws;
+  const u64 G = ctx->shards, seg = n_leaves / (G ? G : 1);
+  u64 min_seg = ctx->shard_min_seg;
+  if (mat && min_seg < (1ull << log_b)) min_seg = 1ull << log_b;
+  if (min_seg < 2) min_seg = 2;
+  *shard_levels = 0;
+  if (G <= 1 || seg < min_seg) {
+    if (mat) RC(launch_leaf_hash(mat, n_leaves, n_cols, n_leaves, log_b, tree, st, LC));
+    RC(launch_merkle_levels(tree, n_leaves, st, LC, w.chal, root_dst, sample_out, n_sample, pair_layer));
+    return 0;
+  }
+  for (u32 g = ctx->shard_lo; g < ctx->shard_hi; g++) {
+    if (mat) RC(launch_leaf_hash(mat, n_leaves, n_cols, n_leaves, log_b, tree, st, LC, g * seg, seg));
+    RC(launch_merkle_levels(tree, n_leaves, st, LC, nullptr, nullptr, nullptr, 0, pair_layer, g * seg, seg));
+  }
+  u32 ls = 0;
+  while ((1ull << ls) < seg) ls++;
+  u32* roots = tree + 8 * (2 * n_leaves - 2 * (n_leaves >> ls));  // the level that holds the G segment roots
+  if (ctx->comm) {
+    if (comm_all_gather_u32(ctx->comm, roots, 8, st, &ctx->err) != 0) return ZKIR_ERR_NCCL;
+  }
+  RC(launch_merkle_levels(roots, G, st, LC, w.chal, root_dst, sample_out, n_sample));
+  *shard_levels = ls;
+  return 0;
+}
+
 // the device part of a proof; `trace` = canonical column-major values already on the device
 static int prove_resident(zkir_ctx* ctx, const zkir_params* p, u32 log_n, const u32* pv, const u32* trace) {
   Workspace& w = ctx->ws;
@@ -273,9 +315,10 @@ static int prove_resident(zkir_ctx* ctx, const zkir_params* p, u32 log_n, const 
   }
   // ---- 2. trace commitment
   CU(cudaEventRecord(ctx->ev[ZKIR_STAGE_TRACE_COMMIT], st));
-  RC(launch_leaf_hash(w.lde, M, (u32)W, M, p->log_blowup, w.ttree, st, LC));
+  u32 t_sl = 0, q_sl = 0;
+  int crc;
   RC(launch_challenger(w.chal, c_hdr, 6 + np, nullptr, 0, 0, st, LC));
-  RC(launch_merkle_levels(w.ttree, M, st, LC, w.chal, w.proof + L.troot, c_alpha, 4));  // root -> proof, observe, sample alpha
+  if ((crc = commit_tree(ctx, w.lde, (u32)W, p->log_blowup, nullptr, w.ttree, M, w.proof + L.troot, c_alpha, 4, &t_sl)) != 0) return crc;  // root -> proof, observe, sample alpha
   // ---- 3. quotient
   CU(cudaEventRecord(ctx->ev[ZKIR_STAGE_QUOTIENT], st));
   {
@@ -305,8 +348,7 @@ static int prove_resident(zkir_ctx* ctx, const zkir_params* p, u32 log_n, const 
     RC(ntt_run(ctx->tables, qcoef, N, w.lde_nat, M, ctx->ntt_tmp, ctx->ntt_tmp_words, QW, log_m, false, p->log_blowup, nullptr, nullptr, BB_ONE, false, st));
     RC(launch_coset_reorder(w.lde_nat, w.qlde, QW, log_n, p->log_blowup, 0, st, LC));
   }
-  RC(launch_leaf_hash(w.qlde, M, QW, M, p->log_blowup, w.qtree, st, LC));
-  RC(launch_merkle_levels(w.qtree, M, st, LC, w.chal, w.proof + L.qroot, c_zeta, 4));  // root -> proof, observe, sample zeta
+  if ((crc = commit_tree(ctx, w.qlde, QW, p->log_blowup, nullptr, w.qtree, M, w.proof + L.qroot, c_zeta, 4, &q_sl)) != 0) return crc;  // root -> proof, observe, sample zeta
   // ---- 4. openings at zeta and g*zeta, evaluated on the shifted coefficients at zeta/shift
   CU(cudaEventRecord(ctx->ev[ZKIR_STAGE_OPENINGS], st));
   {
@@ -329,6 +371,7 @@ static int prove_resident(zkir_ctx* ctx, const zkir_params* p, u32 log_n, const 
   }
   // ---- 5. FRI commit phase
   CU(cudaEventRecord(ctx->ev[ZKIR_STAGE_FRI], st));
+  u32 l_sl[32] = {0};
   {
     const u32* inv_w = ntt_powers_table(ctx->tables, hinv(ZKIR_BB_ROOTS[log_m]), 1, M / 2);
     if (!inv_w) { ctx->err = "table alloc"; return ZKIR_ERR_OOM; }
@@ -336,8 +379,8 @@ static int prove_resident(zkir_ctx* ctx, const zkir_params* p, u32 log_n, const 
     for (u32 r = 0; r < R; r++) {
       const u64 h = (M >> r) / 2;
       // leaves hash(f[i] || f[i+h]) + tree + root -> proof, observe, sample beta_r
-      RC(launch_merkle_levels(w.h_ltrees[r], h, st, LC, w.chal, w.proof + L.fri_roots + 8 * r, c_betas + 4 * r, 4,
-                              reinterpret_cast<const u32*>(w.h_layers[r])));
+      if ((crc = commit_tree(ctx, nullptr, 0, 0, reinterpret_cast<const u32*>(w.h_layers[r]), w.h_ltrees[r], h, w.proof + L.fri_roots + 8 * r,
+                             c_betas + 4 * r, 4, &l_sl[r])) != 0) return crc;
       const u32 c = hinv(hmul(2, lshift));
       RC(launch_fri_fold(w.h_layers[r], w.h_layers[r + 1], h, c_betas + 4 * r, inv_w, 1u << r, bb_to_mont_c(c), st, LC));
       lshift = hmul(lshift, lshift);
@@ -356,7 +399,12 @@ static int prove_resident(zkir_ctx* ctx, const zkir_params* p, u32 log_n, const 
     qa.indices = w.indices; qa.num_queries = p->num_queries; qa.log_m = log_m; qa.width = (u32)W; qa.log_n = log_n;
     qa.lde = w.lde; qa.ttree = w.ttree; qa.qlde = w.qlde; qa.qtree = w.qtree;
     qa.layers = w.d_layers; qa.ltrees = w.d_ltrees; qa.out = w.proof + L.queries; qa.words_per_query = (u32)L.per_query;
+    // sharded trees: the bottom path levels of a leaf exist only on its owner; every rank writes the pieces it owns (zeros
+    // elsewhere, rank 0 also everything that is replicated) and one all-reduce assembles the query section ("query gather")
+    qa.shard_lo = ctx->shard_lo; qa.shard_hi = ctx->shard_hi; qa.ttree_sl = t_sl; qa.qtree_sl = q_sl;
+    for (u32 r = 0; r < 32; r++) qa.layer_sl[r] = l_sl[r];
     RC(launch_queries(qa, st, LC));
+    if (ctx->comm && comm_all_reduce_sum_u32(ctx->comm, w.proof + L.queries, L.per_query * L.nq, st, &ctx->err) != 0) return ZKIR_ERR_NCCL;
     RC(launch_map(w.proof + 8 + np, w.proof + 8 + np, L.total - 8 - np, 0, st, LC));
     CU(cudaMemcpyAsync(w.h_proof, w.proof, L.total * 4, cudaMemcpyDeviceToHost, st));
   }
@@ -408,6 +456,8 @@ void zkir_b200_destroy(zkir_ctx* ctx) {
   ctx->workers.clear();
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  comm_destroy(ctx->comm);
+  ctx->comm = nullptr;
   ws_free(ctx);
   if (ctx->ntt_tmp) cudaFree(ctx->ntt_tmp);
   for (int i = 0; i < 2; i++) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
@@ -636,6 +686,44 @@ int zkir_b200_prove_batch(zkir_ctx* ctx, const zkir_params* p, const uint32_t* c
       return rcs[w];
     }
   }
+  return 0;
+}
+
+// ---------------------------------------------------------------- one proof sharded over several GPUs (BASELINE config 5)
+int zkir_b200_comm_unique_id(uint8_t id[ZKIR_COMM_ID_LEN]) {
+  if (!id) return ZKIR_ERR_ARG;
+  return comm_unique_id(id, &g_last_error) == 0 ? 0 : ZKIR_ERR_NCCL;
+}
+
+int zkir_b200_comm_init(zkir_ctx* ctx, const uint8_t id[ZKIR_COMM_ID_LEN], int rank, int world) {
+  if (!ctx || !id) return ZKIR_ERR_ARG;
+  ctx->err.clear();
+  if (world < 1 || world > 64 || (world & (world - 1)) || rank < 0 || rank >= world) { ctx->err = "comm_init: world must be a power of two <= 64, 0 <= rank < world"; return ZKIR_ERR_ARG; }
+  cudaSetDevice(ctx->device);
+  CU(cudaStreamSynchronize(ctx->stream));
+  comm_destroy(ctx->comm);
+  ctx->comm = nullptr; ctx->shards = 1; ctx->shard_lo = 0; ctx->shard_hi = 1;
+  if (world == 1) return 0;
+  if (comm_create(&ctx->comm, id, rank, world, &ctx->err) != 0) return ZKIR_ERR_NCCL;
+  ctx->shards = (u32)world; ctx->shard_lo = (u32)rank; ctx->shard_hi = (u32)rank + 1;
+  const char* env = getenv("ZKIR_SHARD_MIN_SEG");
+  if (env && atoll(env) > 0) ctx->shard_min_seg = (u64)atoll(env);
+  return 0;
+}
+
+int zkir_b200_comm_shutdown(zkir_ctx* ctx) {
+  if (!ctx) return ZKIR_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  CU(cudaStreamSynchronize(ctx->stream));
+  comm_destroy(ctx->comm);
+  ctx->comm = nullptr; ctx->shards = 1; ctx->shard_lo = 0; ctx->shard_hi = 1;
+  return 0;
+}
+
+int zkir_b200_emulate_shards(zkir_ctx* ctx, uint32_t shards, uint64_t min_segment_leaves) {
+  if (!ctx || ctx->comm || shards < 1 || shards > 64 || (shards & (shards - 1))) return ZKIR_ERR_ARG;
+  ctx->shards = shards; ctx->shard_lo = 0; ctx->shard_hi = shards;
+  if (min_segment_leaves) ctx->shard_min_seg = min_segment_leaves;
   return 0;
 }
 

@@ -213,11 +213,12 @@ int launch_fri_fold(const E4* in, E4* out, u64 h, const u32* beta_dev, const u32
 }
 
 // ---- query gather: one block per query, everything copied into the proof at fixed offsets
-__device__ __forceinline__ void copy_path(const u32* tree, u64 n_leaves, u32 log_leaves, u64 idx, u32* out) {
+__device__ __forceinline__ void copy_path(const u32* tree, u64 n_leaves, u32 log_leaves, u64 idx, u32* out, u32 sl, bool own_leaf, bool own_top) {
   for (u32 t = threadIdx.x; t < log_leaves * 8; t += blockDim.x) {
     const u32 lvl = t >> 3, w = t & 7;
     const u64 off = 2 * n_leaves - 2 * (n_leaves >> lvl);  // node offset of level lvl
-    out[t] = tree[(off + ((idx >> lvl) ^ 1)) * 8 + w];
+    const bool mine = lvl < sl ? own_leaf : own_top;
+    out[t] = mine ? tree[(off + ((idx >> lvl) ^ 1)) * 8 + w] : 0u;
   }
 }
 __global__ void __launch_bounds__(128) query_kernel(QueryArgs a) {
@@ -226,20 +227,22 @@ __global__ void __launch_bounds__(128) query_kernel(QueryArgs a) {
   const u64 q = a.indices[qi];
   const u32 log_b = a.log_m - a.log_n;
   const u64 qrow = ((q & ((1ull << log_b) - 1)) << a.log_n) | (q >> log_b);  // memory row of natural index q
+  const bool top = a.shard_lo == 0;  // replicated data is contributed by the context that owns segment 0
+  auto owns = [&](u64 leaf, u32 sl) { const u64 o = leaf >> sl; return sl == 0 ? top : (o >= a.shard_lo && o < a.shard_hi); };
   u32* out = a.out + (u64)qi * a.words_per_query;
-  for (u32 k = threadIdx.x; k < a.width; k += blockDim.x) out[k] = a.lde[(u64)k * M + qrow];
+  for (u32 k = threadIdx.x; k < a.width; k += blockDim.x) out[k] = top ? a.lde[(u64)k * M + qrow] : 0u;
   out += a.width;
-  copy_path(a.ttree, M, a.log_m, q, out); out += a.log_m * 8;
-  for (u32 k = threadIdx.x; k < 8; k += blockDim.x) out[k] = a.qlde[(u64)k * M + qrow];
+  copy_path(a.ttree, M, a.log_m, q, out, a.ttree_sl, owns(q, a.ttree_sl), top); out += a.log_m * 8;
+  for (u32 k = threadIdx.x; k < 8; k += blockDim.x) out[k] = top ? a.qlde[(u64)k * M + qrow] : 0u;
   out += 8;
-  copy_path(a.qtree, M, a.log_m, q, out); out += a.log_m * 8;
+  copy_path(a.qtree, M, a.log_m, q, out, a.qtree_sl, owns(q, a.qtree_sl), top); out += a.log_m * 8;
   for (u32 r = 0; r < a.log_n; r++) {
     const u64 h = (M >> r) / 2, i = q & (h - 1);
     const u32* lay = reinterpret_cast<const u32*>(a.layers[r]);
-    if (threadIdx.x < 4) out[threadIdx.x] = lay[4 * i + threadIdx.x];
-    else if (threadIdx.x < 8) out[threadIdx.x] = lay[4 * (i + h) + threadIdx.x - 4];
+    if (threadIdx.x < 4) out[threadIdx.x] = top ? lay[4 * i + threadIdx.x] : 0u;
+    else if (threadIdx.x < 8) out[threadIdx.x] = top ? lay[4 * (i + h) + threadIdx.x - 4] : 0u;
     out += 8;
-    copy_path(a.ltrees[r], h, a.log_m - 1 - r, i, out); out += (a.log_m - 1 - r) * 8;
+    copy_path(a.ltrees[r], h, a.log_m - 1 - r, i, out, a.layer_sl[r], owns(i, a.layer_sl[r]), top); out += (a.log_m - 1 - r) * 8;
   }
 }
 int launch_queries(const QueryArgs& a, cudaStream_t st, u64* launches) {

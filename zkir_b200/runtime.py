@@ -268,6 +268,24 @@ class Context:
         self._check(self._l.zkir_b200_last_stage_ms(self._h, out))
         return dict(zip(_ffi.STAGES, list(out)))
 
+    # -- one proof sharded over several GPUs (include/zkir_b200.h: zkir_b200_comm_*)
+    def comm_init(self, rank=None, world=None, group=None):
+        """Link this context with the contexts of the other ranks (one process per GPU, torch.distributed already
+        initialised: NCCL on the GPU box, gloo works too -- it only carries the 128-byte id).  Afterwards every prove_*
+        call on this context is collective (same trace on every rank) and returns the single-GPU proof bytes."""
+        from . import multi
+        rank, world, ident = multi.exchange_comm_id(self._l, rank, world, group)
+        if world > 1:
+            self._check(self._l.zkir_b200_comm_init(self._h, ident, rank, world))
+        return rank, world
+
+    def comm_shutdown(self):
+        self._check(self._l.zkir_b200_comm_shutdown(self._h))
+
+    def emulate_shards(self, shards, min_segment_leaves=0):
+        """Test hook: run the sharded code path (segment kernels, no NCCL) for `shards` segments on this one GPU."""
+        self._check(self._l.zkir_b200_emulate_shards(self._h, shards, min_segment_leaves))
+
     # -- hot path
     def prove_columns(self, cols, public_values, cfg, device_resident=None):
         """cols: host uint32 [WIDTH][2^log_n] (or `device_resident`: a device pointer with the same layout)."""
