@@ -20,6 +20,8 @@ struct NcclApi {
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
   ncclResult_t (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
@@ -46,6 +48,8 @@ static NcclApi* api() {
     BIND(CommDestroy, "ncclCommDestroy")
     BIND(AllGather, "ncclAllGather")
     BIND(AllReduce, "ncclAllReduce")
+    BIND(Send, "ncclSend")
+    BIND(Recv, "ncclRecv")
     BIND(GroupStart, "ncclGroupStart")
     BIND(GroupEnd, "ncclGroupEnd")
     BIND(GetErrorString, "ncclGetErrorString")
@@ -118,5 +122,20 @@ int comm_all_gather_group_u32(Comm* c, unsigned* const* bufs, const size_t* word
   NC(a->GroupEnd(), "ncclGroupEnd");
   return 0;
 }
+
+int comm_exchange_u32(Comm* c, const P2POp* ops, size_t n, cudaStream_t st, std::string* err) {
+  NcclApi* a = api();
+  if (!n) return 0;
+  NC(a->GroupStart(), "ncclGroupStart");
+  for (size_t j = 0; j < n; j++) {
+    const P2POp& o = ops[j];
+    ncclResult_t r = o.is_send ? a->Send(o.ptr, o.words, kNcclUint32, o.peer, c->comm, st) : a->Recv(o.ptr, o.words, kNcclUint32, o.peer, c->comm, st);
+    if (r != 0) { a->GroupEnd(); return fail(err, o.is_send ? "ncclSend" : "ncclRecv", r); }
+  }
+  NC(a->GroupEnd(), "ncclGroupEnd");
+  return 0;
+}
+int comm_rank(const Comm* c) { return c->rank; }
+int comm_world(const Comm* c) { return c->world; }
 
 }  // namespace zkir

@@ -22,4 +22,11 @@ int comm_all_reduce_sum_u32(Comm*, unsigned* buf, size_t words, cudaStream_t st,
 // several all-gathers fused into one NCCL group (one launch): piece j is bufs[j] with words_per_rank[j]
 int comm_all_gather_group_u32(Comm*, unsigned* const* bufs, const size_t* words_per_rank, int n, cudaStream_t st, std::string* err);
 
+// point-to-point exchange, all operations in ONE NCCL group; for every ordered pair of ranks the sends of the source must be listed
+// in the same order as the matching receives of the destination
+struct P2POp { int peer; int is_send; unsigned* ptr; size_t words; };
+int comm_exchange_u32(Comm*, const P2POp* ops, size_t n, cudaStream_t st, std::string* err);
+int comm_rank(const Comm*);
+int comm_world(const Comm*);
+
 }  // namespace zkir

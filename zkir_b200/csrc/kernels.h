@@ -62,6 +62,9 @@ struct QuotientArgs {
   const u32* xs;       // [M] coset-major: x = shift*w^(i*B+z) at z*N+i
   const u32* dinv;     // [M] 1/(x - 1), same order
   u32* apow_scratch;   // [K][4] device scratch for alpha powers
+  // row segment (one proof sharded over several GPUs): only the points j in [seg_j0, seg_j0 + 2^seg_log_nj) of every coset, i.e.
+  // the natural indices [seg_j0 << log_blowup, ...); seg_log_nj = 0xffffffff: all rows.  Reads one halo row (j + 1 mod N).
+  u32 seg_log_nj = 0xffffffffu; u64 seg_j0 = 0;
 };
 int launch_quotient(const QuotientArgs& a, cudaStream_t st, u64* launches);
 int launch_domain_tables(u32* xs, u32* dinv, u32 log_n, u32 log_b, u32 shift_canon, cudaStream_t st, u64* launches);
@@ -91,6 +94,12 @@ struct WlArgs {          // register write log instead of full rows (trace_expan
 u64 trace_expand_wl_scratch_ints(u64 N);
 int launch_trace_expand_wl(const WlArgs& a, cudaStream_t st, u64* launches);
 
+// ---- peer.cu: rows of the column-sharded LDE stored straight into the peers' matrices (NVLink peer memory)
+#define ZKIR_MAX_SHARDS 64
+struct PeerPtrs { u32* p[ZKIR_MAX_SHARDS]; };   // base of every rank's LDE matrix as seen from this device (own entry included)
+int launch_lde_scatter(const u32* lde, const PeerPtrs& peers, u32 me, u32 G, u32 c_lo, u32 n_cols, u64 N, u32 B, u64 nj, cudaStream_t st,
+                       u64* launches);
+
 // ---- stark.cu (openings, DEEP combination, FRI fold, queries, misc)
 int launch_map(u32* dst, const u32* src, u64 n, int to_mont, cudaStream_t st, u64* launches);
 // out[pos] = (base_ext * mul_const)^(k(pos)), k = coefficient index of memory position pos under `plan` (nd = 1: natural)
@@ -108,6 +117,7 @@ struct DeepArgs {
   const E4* open_t; const E4* open_tg; const E4* open_q;  // device openings
   E4* afp_scratch;                        // [2*width+qwidth+3] scratch
   E4* out;                                // [M], natural order
+  u32 seg_log_nj = 0xffffffffu; u64 seg_j0 = 0;   // row segment as in QuotientArgs
 };
 int launch_deep(const DeepArgs& a, cudaStream_t st, u64* launches);
 int launch_fri_fold(const E4* in, E4* out, u64 h, const u32* beta_dev, const u32* inv_w_table, u32 tw_stride, u32 c_mont,
@@ -124,6 +134,7 @@ struct QueryArgs {
   // one proof sharded over several GPUs: this context owns the leaf segments [shard_lo, shard_hi); the lowest *_sl levels of a
   // tree exist only on the owner of the leaf (segment = 2^sl leaves).  Pieces this context does not own are written as 0.
   u32 shard_lo = 0, shard_hi = 1, ttree_sl = 0, qtree_sl = 0;
+  u32 lde_sl = 0;       // != 0: the trace LDE rows themselves are row-sharded with segments of 2^lde_sl leaves
   u32 layer_sl[32] = {0};
 };
 int launch_queries(const QueryArgs& a, cudaStream_t st, u64* launches);

@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <string.h>
+#include <unistd.h>
 #include <string>
 #include <vector>
 #include <map>
@@ -97,6 +98,10 @@ struct Workspace {
   u32* proof = nullptr;      // device proof words
   u32* h_proof = nullptr;    // pinned
   u32* h_stage = nullptr;    // pinned staging for header words
+  // sharded proofs: every rank's LDE matrix as mapped into this process (CUDA IPC / peer access), see peer.cu
+  PeerPtrs peers; bool peers_valid = false;
+  std::vector<void*> ipc_opened;
+  u32* xchg = nullptr;       // [ZKIR_MAX_SHARDS][24] words: handle exchange; word 0 doubles as the barrier token
 };
 
 struct zkir_ctx {
@@ -123,8 +128,15 @@ struct zkir_ctx {
   bool have_stage = false;
 };
 
+static void peers_close(zkir_ctx* ctx) {
+  Workspace& w = ctx->ws;
+  for (void* p : w.ipc_opened) cudaIpcCloseMemHandle(p);
+  w.ipc_opened.clear();
+  w.peers_valid = false;
+}
 static void ws_free(zkir_ctx* ctx) {
   Workspace& w = ctx->ws;
+  peers_close(ctx);
   for (void* p : w.allocs) cudaFree(p);
   if (w.h_proof) cudaFreeHost(w.h_proof);
   if (w.h_stage) cudaFreeHost(w.h_stage);
@@ -195,7 +207,7 @@ static int ws_prepare(zkir_ctx* ctx, const zkir_params* p, u32 log_n) {
   A(d_layers, R + 1) A(d_ltrees, R + 1)
   A(chal, 1) A(chal_buf, 12 + 4 * R + 2 + 6 + p->num_public) A(indices, p->num_queries + 1)
   A(apow, 4 * ZKIR_AIR_NUM_CONSTRAINTS) A(afp, W + 5)
-  A(proof, L.total)
+  A(proof, L.total) A(xchg, ZKIR_MAX_SHARDS * 24)
 #undef A
   CU(cudaMallocHost(&w.h_proof, L.total * 4));
   CU(cudaMallocHost(&w.h_stage, (8 + 6 + 2 * p->num_public) * 4));
@@ -231,6 +243,80 @@ static int check_params(zkir_ctx* ctx, const zkir_params* p, u32 log_n) {
   return 0;
 }
 
+// One proof over `shards` GPUs: the columns are cut into `shards` contiguous ranges for the per-column work
+// (LDE, openings), the rows into `shards` contiguous ranges of the trace domain (points j in [g*N/G, (g+1)*N/G) of every
+// coset = the natural-order leaves [g*M/G, (g+1)*M/G)) for the per-row work (leaf hashing, quotient, DEEP, queries).
+struct ShardPlan {
+  bool on = false;
+  u32 G = 1, lo = 0, hi = 1, log_nj = 0;
+  u64 nj = 0;          // points per coset and shard
+  u32 cols_per = 0, W = 0;
+  u32 c_lo(u32 g) const { const u32 c = g * cols_per; return c < W ? c : W; }
+  u32 c_hi(u32 g) const { const u32 c = (g + 1) * cols_per; return c < W ? c : W; }
+};
+
+// After the column-sharded LDE every rank holds whole columns [c_lo, c_hi) of the coset-major matrix [W][B][N]; this moves, for
+// every column, the rows each OTHER rank needs (its points j0..j0+nj of every coset plus the one halo row the quotient reads
+// as "next row") into the same place of that rank's matrix: (G-1)/G of a rank's W/G columns leave it, i.e. about 1/G of the matrix
+// per rank crosses NVLink, instead of the whole matrix for an all-gather.
+static int exchange_lde_rows(zkir_ctx* ctx, const ShardPlan& sp, u32* lde, u64 N, u32 B) {
+  const u64 M = N * B;
+  const int me = comm_rank(ctx->comm);
+  std::vector<P2POp> ops;
+  auto pieces = [&](u32 c, int owner_of_rows, int peer, int is_send) {
+    const u64 j0 = (u64)owner_of_rows * sp.nj;
+    const bool wrap = j0 + sp.nj == N;      // the last shard's halo row is point 0
+    for (u32 z = 0; z < B; z++) {
+      u32* base = lde + (u64)c * M + (u64)z * N;
+      ops.push_back({peer, is_send, base + j0, (size_t)(wrap ? sp.nj : sp.nj + 1)});
+      if (wrap) ops.push_back({peer, is_send, base, 1});
+    }
+  };
+  for (int peer = 0; peer < (int)sp.G; peer++) {
+    if (peer == me) continue;
+    for (u32 c = sp.c_lo(me); c < sp.c_hi(me); c++) pieces(c, peer, peer, 1);   // my columns, the peer's rows
+    for (u32 c = sp.c_lo(peer); c < sp.c_hi(peer); c++) pieces(c, me, peer, 0); // the peer's columns, my rows
+  }
+  if (comm_exchange_u32(ctx->comm, ops.data(), ops.size(), ctx->stream, &ctx->err) != 0) return ZKIR_ERR_NCCL;
+  return 0;
+}
+
+// Map every rank's LDE matrix into this process.  Collective (one all-gather of 96-byte records); runs once per workspace shape.
+struct PeerRec { u64 pid, ptr; u32 dev, pad[3]; cudaIpcMemHandle_t handle; };
+static_assert(sizeof(PeerRec) == 96, "PeerRec layout");
+static int peers_open(zkir_ctx* ctx) {
+  Workspace& w = ctx->ws;
+  peers_close(ctx);
+  const int G = comm_world(ctx->comm), me = comm_rank(ctx->comm);
+  PeerRec mine;
+  memset(&mine, 0, sizeof(mine));
+  mine.pid = (u64)getpid(); mine.ptr = (u64)(uintptr_t)w.lde; mine.dev = (u32)ctx->device;
+  CU(cudaIpcGetMemHandle(&mine.handle, w.lde));
+  std::vector<PeerRec> all(G);
+  CU(cudaMemcpyAsync(w.xchg + (size_t)me * 24, &mine, sizeof(mine), cudaMemcpyHostToDevice, ctx->stream));
+  if (comm_all_gather_u32(ctx->comm, w.xchg, 24, ctx->stream, &ctx->err) != 0) return ZKIR_ERR_NCCL;
+  CU(cudaMemcpyAsync(all.data(), w.xchg, sizeof(PeerRec) * G, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  for (int t = 0; t < G; t++) {
+    if (t == me) { w.peers.p[t] = w.lde; continue; }
+    if (all[t].pid == mine.pid) {   // another context of this process (threads as ranks): plain peer access
+      if ((int)all[t].dev != ctx->device) {
+        cudaError_t e = cudaDeviceEnablePeerAccess((int)all[t].dev, 0);
+        if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+        else if (e != cudaSuccess) { ctx->err = std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e); return ZKIR_ERR_CUDA; }
+      }
+      w.peers.p[t] = reinterpret_cast<u32*>((uintptr_t)all[t].ptr);
+    } else {
+      void* ptr = nullptr;
+      CU(cudaIpcOpenMemHandle(&ptr, all[t].handle, cudaIpcMemLazyEnablePeerAccess));
+      w.ipc_opened.push_back(ptr);
+      w.peers.p[t] = reinterpret_cast<u32*>(ptr);
+    }
+  }
+  w.peers_valid = true;
+  return 0;
+}
+
 // Merkle commitment of one matrix (leaf i = sponge over LDE row i) or one FRI layer (leaf i = hash(f[i] || f[i+h])), followed
 // by the Fiat-Shamir step on its root.  With shards > 1 the leaf range is cut into `shards` contiguous segments: this context
 // hashes its segments and builds their subtrees in place in the global tree layout, the segment roots are exchanged with ONE
@@ -238,7 +324,7 @@ static int check_params(zkir_ctx* ctx, const zkir_params* p, u32 log_n) {
 // redundantly on every rank, so every rank continues with the same challenges.  *shard_levels = number of bottom path levels
 // that only the owner of a leaf holds (0 = the whole tree is local).
 static int commit_tree(zkir_ctx* ctx, const u32* mat, u32 n_cols, u32 log_b, const u32* pair_layer, u32* tree, u64 n_leaves, u32* root_dst,
-                       u32* sample_out, u32 n_sample, u32* shard_levels) {
+                       u32* sample_out, u32 n_sample, u32* shard_levels, int mode = -1 /* -1: by size, 0: whole, 1: sharded */) {
   cudaStream_t st = ctx->stream;
   u64* LC = &ctx->launches;
   Workspace& w = ctx->ws;
@@ -247,7 +333,7 @@ static int commit_tree(zkir_ctx* ctx, const u32* mat, u32 n_cols, u32 log_b, con
   if (mat && min_seg < (1ull << log_b)) min_seg = 1ull << log_b;
   if (min_seg < 2) min_seg = 2;
   *shard_levels = 0;
-  if (G <= 1 || seg < min_seg) {
+  if (G <= 1 || mode == 0 || (mode < 0 && seg < min_seg)) {
     if (mat) RC(launch_leaf_hash(mat, n_leaves, n_cols, n_leaves, log_b, tree, st, LC));
     RC(launch_merkle_levels(tree, n_leaves, st, LC, w.chal, root_dst, sample_out, n_sample, pair_layer));
     return 0;
@@ -278,6 +364,14 @@ static int prove_resident(zkir_ctx* ctx, const zkir_params* p, u32 log_n, const 
   const u32 shift = ZKIR_BB_GEN;
   const u32 B = 1u << p->log_blowup;
   if (!w.fast) RC(ensure_ntt_tmp(ctx, M));
+  ShardPlan sp;
+  sp.G = ctx->shards; sp.lo = ctx->shard_lo; sp.hi = ctx->shard_hi; sp.W = (u32)W;
+  if (sp.G > 1 && w.fast && N >= sp.G && M / sp.G >= ctx->shard_min_seg && M / sp.G >= 2) {
+    sp.on = true;
+    sp.nj = N / sp.G;
+    while ((1ull << sp.log_nj) < sp.nj) sp.log_nj++;
+    sp.cols_per = (u32)((W + sp.G - 1) / sp.G);
+  }
   u32* c_alpha = w.chal_buf, *c_zeta = w.chal_buf + 4, *c_afri = w.chal_buf + 8, *c_betas = w.chal_buf + 12;
   u32* c_pow_raw = w.chal_buf + 12 + 4 * R, *c_pow_sample = c_pow_raw + 1, *c_hdr = c_pow_raw + 2;
 
@@ -296,7 +390,29 @@ static int prove_resident(zkir_ctx* ctx, const zkir_params* p, u32 log_n, const 
   // ---- 1. LDE: iNTT (scale by shift^j/N and lift to Montgomery), zero-pad, forward NTT on the coset
   CU(cudaEventRecord(ctx->ev[ZKIR_STAGE_LDE], st));
   const u32 c0 = hmul(hinv((u32)(N % BB_P)), (u32)((1ull << 32) % BB_P));  // R/N: scales by 1/N and lifts to Montgomery form
-  if (w.fast) {
+  if (sp.on) {
+    // column-sharded: this rank transforms only its W/G columns, then the rows are redistributed
+    for (u32 g = sp.lo; g < sp.hi; g++) {
+      const u32 k0 = sp.c_lo(g), nc = sp.c_hi(g) - k0;
+      if (!nc) continue;
+      RC(fast_intt(ctx->fast, w.plan_n, trace + (u64)k0 * N, N, w.coef + (u64)k0 * N, N, nc, c0, nullptr, 32, 0, 0, nullptr, 0, st));
+      RC(fast_coset_ntt(ctx->fast, w.plan_n, w.coef + (u64)k0 * N, N, w.lde + (u64)k0 * M, M, nc, B, shift, ZKIR_BB_ROOTS[log_m], 1u, st));
+    }
+    if (ctx->comm) {
+      // rows -> owners.  Default: one kernel storing into the peers' matrices over NVLink, then a one-word all-reduce as the
+      // barrier that orders every rank's stores before every rank's reads.  ZKIR_LDE_EXCHANGE=nccl: grouped ncclSend/ncclRecv.
+      static const bool use_nccl = getenv("ZKIR_LDE_EXCHANGE") && !strcmp(getenv("ZKIR_LDE_EXCHANGE"), "nccl");
+      if (use_nccl) {
+        int xrc = exchange_lde_rows(ctx, sp, w.lde, N, B);
+        if (xrc) return xrc;
+      } else {
+        if (!w.peers_valid) { int xrc = peers_open(ctx); if (xrc) return xrc; }
+        const u32 me = (u32)comm_rank(ctx->comm);
+        RC(launch_lde_scatter(w.lde, w.peers, me, sp.G, sp.c_lo(me), sp.c_hi(me) - sp.c_lo(me), N, B, sp.nj, st, LC));
+        if (comm_all_reduce_sum_u32(ctx->comm, w.xchg, 1, st, &ctx->err) != 0) return ZKIR_ERR_NCCL;
+      }
+    }
+  } else if (w.fast) {
     // column batches (ZKIR_LDE_BATCH) are possible, one batch = all columns by default
     u32 cb = (u32)W;  // measured: the passes are integer-pipe bound, larger launches win over L2 residency
     const char* env = getenv("ZKIR_LDE_BATCH");
@@ -318,14 +434,27 @@ static int prove_resident(zkir_ctx* ctx, const zkir_params* p, u32 log_n, const 
   u32 t_sl = 0, q_sl = 0;
   int crc;
   RC(launch_challenger(w.chal, c_hdr, 6 + np, nullptr, 0, 0, st, LC));
-  if ((crc = commit_tree(ctx, w.lde, (u32)W, p->log_blowup, nullptr, w.ttree, M, w.proof + L.troot, c_alpha, 4, &t_sl)) != 0) return crc;  // root -> proof, observe, sample alpha
+  if ((crc = commit_tree(ctx, w.lde, (u32)W, p->log_blowup, nullptr, w.ttree, M, w.proof + L.troot, c_alpha, 4, &t_sl, sp.on ? 1 : 0)) != 0) return crc;  // root -> proof, observe, sample alpha
   // ---- 3. quotient
   CU(cudaEventRecord(ctx->ev[ZKIR_STAGE_QUOTIENT], st));
   {
     QuotientArgs qa;
     qa.lde = w.lde; qa.q = w.q; qa.log_n = log_n; qa.log_blowup = p->log_blowup; qa.pv = c_hdr + 6; qa.alpha = c_alpha;
     qa.xs = w.xs; qa.dinv = w.dinv; qa.apow_scratch = w.apow;
-    RC(launch_quotient(qa, st, LC));
+    if (sp.on) {
+      // row-sharded: every rank evaluates its natural-order range of Q, the four planes are completed with one grouped all-gather
+      for (u32 g = sp.lo; g < sp.hi; g++) {
+        qa.seg_log_nj = sp.log_nj; qa.seg_j0 = (u64)g * sp.nj;
+        RC(launch_quotient(qa, st, LC));
+      }
+      if (ctx->comm) {
+        unsigned* planes[4] = {w.q, w.q + M, w.q + 2 * M, w.q + 3 * M};
+        const size_t per[4] = {(size_t)(M / sp.G), (size_t)(M / sp.G), (size_t)(M / sp.G), (size_t)(M / sp.G)};
+        if (comm_all_gather_group_u32(ctx->comm, planes, per, 4, st, &ctx->err) != 0) return ZKIR_ERR_NCCL;
+      }
+    } else {
+      RC(launch_quotient(qa, st, LC));
+    }
   }
   CU(cudaEventRecord(ctx->ev[ZKIR_STAGE_QUOTIENT_COMMIT], st));
   const u32* qcoef = w.qcoef;
@@ -360,14 +489,33 @@ static int prove_resident(zkir_ctx* ctx, const zkir_params* p, u32 log_n, const 
     E4* ot = reinterpret_cast<E4*>(w.proof + L.open_t);
     E4* otg = reinterpret_cast<E4*>(w.proof + L.open_tg);
     E4* oq = reinterpret_cast<E4*>(w.proof + L.open_q);
-    RC(launch_open(w.coef, N, (u32)W, N, w.U1, w.U2, ot, otg, w.open_scratch, st, LC));
+    if (sp.on) {
+      // column-sharded like the LDE (a rank holds the coefficients of its own columns only); disjoint pieces merged by all-reduce
+      if (ctx->comm) CU(cudaMemsetAsync(w.proof + L.open_t, 0, 2 * W * 16, st));
+      for (u32 g = sp.lo; g < sp.hi; g++) {
+        const u32 k0 = sp.c_lo(g), nc = sp.c_hi(g) - k0;
+        if (nc) RC(launch_open(w.coef + (u64)k0 * N, N, nc, N, w.U1, w.U2, ot + k0, otg + k0, w.open_scratch, st, LC));
+      }
+      if (ctx->comm && comm_all_reduce_sum_u32(ctx->comm, w.proof + L.open_t, 2 * W * 4, st, &ctx->err) != 0) return ZKIR_ERR_NCCL;
+    } else {
+      RC(launch_open(w.coef, N, (u32)W, N, w.U1, w.U2, ot, otg, w.open_scratch, st, LC));
+    }
     RC(launch_open(qcoef, N, QW, N, w.U1q, w.U1q, oq, w.dummy_open, w.open_scratch, st, LC));
     RC(launch_challenger(w.chal, w.proof + L.open_t, (u32)(2 * W + QW) * 4, c_afri, 4, 0, st, LC));
     DeepArgs da;
     da.lde = w.lde; da.M = M; da.width = (u32)W; da.qlde = w.qlde; da.qwidth = QW; da.log_n = log_n; da.log_b = p->log_blowup; da.xs = w.xs; da.zeta = c_zeta;
     da.g_mont = bb_to_mont_c(g); da.alpha_fri = c_afri; da.open_t = ot; da.open_tg = otg; da.open_q = oq; da.afp_scratch = w.afp;
     da.out = w.h_layers[0];
-    RC(launch_deep(da, st, LC));
+    if (sp.on) {
+      // row-sharded; FRI layer 0 (natural order, ext4) is completed with one all-gather
+      for (u32 g = sp.lo; g < sp.hi; g++) {
+        da.seg_log_nj = sp.log_nj; da.seg_j0 = (u64)g * sp.nj;
+        RC(launch_deep(da, st, LC));
+      }
+      if (ctx->comm && comm_all_gather_u32(ctx->comm, reinterpret_cast<u32*>(w.h_layers[0]), 4 * (M / sp.G), st, &ctx->err) != 0) return ZKIR_ERR_NCCL;
+    } else {
+      RC(launch_deep(da, st, LC));
+    }
   }
   // ---- 5. FRI commit phase
   CU(cudaEventRecord(ctx->ev[ZKIR_STAGE_FRI], st));
@@ -401,7 +549,7 @@ static int prove_resident(zkir_ctx* ctx, const zkir_params* p, u32 log_n, const 
     qa.layers = w.d_layers; qa.ltrees = w.d_ltrees; qa.out = w.proof + L.queries; qa.words_per_query = (u32)L.per_query;
     // sharded trees: the bottom path levels of a leaf exist only on its owner; every rank writes the pieces it owns (zeros
     // elsewhere, rank 0 also everything that is replicated) and one all-reduce assembles the query section ("query gather")
-    qa.shard_lo = ctx->shard_lo; qa.shard_hi = ctx->shard_hi; qa.ttree_sl = t_sl; qa.qtree_sl = q_sl;
+    qa.shard_lo = ctx->shard_lo; qa.shard_hi = ctx->shard_hi; qa.ttree_sl = t_sl; qa.qtree_sl = q_sl; qa.lde_sl = sp.on ? t_sl : 0;
     for (u32 r = 0; r < 32; r++) qa.layer_sl[r] = l_sl[r];
     RC(launch_queries(qa, st, LC));
     if (ctx->comm && comm_all_reduce_sum_u32(ctx->comm, w.proof + L.queries, L.per_query * L.nq, st, &ctx->err) != 0) return ZKIR_ERR_NCCL;
@@ -701,6 +849,7 @@ int zkir_b200_comm_init(zkir_ctx* ctx, const uint8_t id[ZKIR_COMM_ID_LEN], int r
   if (world < 1 || world > 64 || (world & (world - 1)) || rank < 0 || rank >= world) { ctx->err = "comm_init: world must be a power of two <= 64, 0 <= rank < world"; return ZKIR_ERR_ARG; }
   cudaSetDevice(ctx->device);
   CU(cudaStreamSynchronize(ctx->stream));
+  peers_close(ctx);
   comm_destroy(ctx->comm);
   ctx->comm = nullptr; ctx->shards = 1; ctx->shard_lo = 0; ctx->shard_hi = 1;
   if (world == 1) return 0;
@@ -715,6 +864,7 @@ int zkir_b200_comm_shutdown(zkir_ctx* ctx) {
   if (!ctx) return ZKIR_ERR_ARG;
   cudaSetDevice(ctx->device);
   CU(cudaStreamSynchronize(ctx->stream));
+  peers_close(ctx);
   comm_destroy(ctx->comm);
   ctx->comm = nullptr; ctx->shards = 1; ctx->shard_lo = 0; ctx->shard_hi = 1;
   return 0;

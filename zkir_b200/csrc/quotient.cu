@@ -49,9 +49,11 @@ __global__ void __launch_bounds__(128, MINB) quotient_kernel(QuotientArgs a, con
   if (threadIdx.x < ZKIR_AIR_NUM_PUBLIC) pv[threadIdx.x] = a.pv[threadIdx.x];
   __syncthreads();
   const u64 M = 1ull << (a.log_n + a.log_blowup), N = 1ull << a.log_n;
-  const u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x;  // memory row: coset z = i / N, point j = i % N, natural index j*B + z
-  if (i >= M) return;
-  const u64 z = i >> a.log_n, j = i & (N - 1);
+  const u64 t = blockIdx.x * (u64)blockDim.x + threadIdx.x;  // memory row: coset z = i / N, point j = i % N, natural index j*B + z
+  const u32 log_nj = a.seg_log_nj == 0xffffffffu ? a.log_n : a.seg_log_nj;
+  if (t >= (1ull << (log_nj + a.log_blowup))) return;
+  const u64 z = t >> log_nj, j = a.seg_j0 + (t & ((1ull << log_nj) - 1));
+  const u64 i = (z << a.log_n) | j;
   QCtx c;
   c.lde = a.lde; c.M = M; c.row = i; c.nxt = (z << a.log_n) | ((j + 1) & (N - 1)); c.pv = pv; c.apow = apow;
   const u32 x = a.xs[i];
@@ -97,7 +99,8 @@ int launch_quotient(const QuotientArgs& a, cudaStream_t st, u64* launches) {
   const u32 wb = ZKIR_BB_ROOTS[a.log_blowup];
   static int variant = -1;
   if (variant < 0) { const char* e = getenv("ZKIR_QUOTIENT_VARIANT"); variant = e ? atoi(e) : 2; }  // 64 registers measured fastest
-  const unsigned grid = (unsigned)((M + 127) / 128);
+  const u64 n_threads = a.seg_log_nj == 0xffffffffu ? M : (1ull << (a.seg_log_nj + a.log_blowup));
+  const unsigned grid = (unsigned)((n_threads + 127) / 128);
   const E4* ap = reinterpret_cast<const E4*>(a.apow_scratch);
   const u32 m_ginv = bb_to_mont_c(g_inv), m_g = bb_to_mont_c(g), m_snn = bb_to_mont_c(snn), m_wb = bb_to_mont_c(wb);
   if (variant == 1) quotient_kernel<6><<<grid, 128, 0, st>>>(a, ap, m_ginv, m_g, m_snn, m_wb);

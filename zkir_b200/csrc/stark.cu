@@ -160,8 +160,10 @@ __global__ void __launch_bounds__(128) deep_kernel(DeepArgs a) {
   extern __shared__ E4 afp[];  // width + 5
   for (u32 i = threadIdx.x; i < a.width + 5; i += blockDim.x) afp[i] = a.afp_scratch[i];
   __syncthreads();
-  const u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x;  // memory row (coset-major)
-  if (i >= a.M) return;
+  const u64 t = blockIdx.x * (u64)blockDim.x + threadIdx.x;
+  const u32 log_nj = a.seg_log_nj == 0xffffffffu ? a.log_n : a.seg_log_nj;
+  if (t >= (1ull << (log_nj + a.log_b))) return;
+  const u64 i = ((t >> log_nj) << a.log_n) | (a.seg_j0 + (t & ((1ull << log_nj) - 1)));  // memory row (coset-major)
   const u64 nat = ((i & ((1ull << a.log_n) - 1)) << a.log_b) | (i >> a.log_n);
   Acc4 lt = acc4_zero(), lq = acc4_zero();  // lazy accumulators, fixed every second term
 #pragma unroll 8
@@ -188,7 +190,8 @@ __global__ void __launch_bounds__(128) deep_kernel(DeepArgs a) {
 }
 int launch_deep(const DeepArgs& a, cudaStream_t st, u64* launches) {
   deep_prep_kernel<<<1, 128, 0, st>>>(a);
-  deep_kernel<<<nblk(a.M, 128), 128, (a.width + 5) * sizeof(E4), st>>>(a);
+  const u64 n_threads = a.seg_log_nj == 0xffffffffu ? a.M : (1ull << (a.seg_log_nj + a.log_b));
+  deep_kernel<<<nblk(n_threads, 128), 128, (a.width + 5) * sizeof(E4), st>>>(a);
   (*launches) += 2;
   return CHECK_LAUNCH();
 }
@@ -230,7 +233,8 @@ __global__ void __launch_bounds__(128) query_kernel(QueryArgs a) {
   const bool top = a.shard_lo == 0;  // replicated data is contributed by the context that owns segment 0
   auto owns = [&](u64 leaf, u32 sl) { const u64 o = leaf >> sl; return sl == 0 ? top : (o >= a.shard_lo && o < a.shard_hi); };
   u32* out = a.out + (u64)qi * a.words_per_query;
-  for (u32 k = threadIdx.x; k < a.width; k += blockDim.x) out[k] = top ? a.lde[(u64)k * M + qrow] : 0u;
+  const bool row_mine = a.lde_sl ? owns(q, a.lde_sl) : top;
+  for (u32 k = threadIdx.x; k < a.width; k += blockDim.x) out[k] = row_mine ? a.lde[(u64)k * M + qrow] : 0u;
   out += a.width;
   copy_path(a.ttree, M, a.log_m, q, out, a.ttree_sl, owns(q, a.ttree_sl), top); out += a.log_m * 8;
   for (u32 k = threadIdx.x; k < 8; k += blockDim.x) out[k] = top ? a.qlde[(u64)k * M + qrow] : 0u;
