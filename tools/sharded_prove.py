@@ -11,7 +11,7 @@ sharded proof bytes equal the single-GPU bytes on every rank and pass the CPU ve
 import json
 import os
 import sys
-import time
+import numpy as np  # noqa: F401
 
 import torch
 import torch.distributed as dist
@@ -35,8 +35,13 @@ def main():
     for log_n in sizes:
         n = ((1 << log_n) + 2) // 5                      # 5n - 2 cycles <= 2^log_n
         res = zkir_b200.VM(fib_program_input(), [n], zkir_b200.VMConfig(max_cycles=1 << 26, enable_execution_trace=True)).run()
-        wl = res.writelog()
+        wl0 = res.writelog()
         assert res.min_log_n() == log_n, (res.cycles, log_n)
+        pins = {k: zkir_b200.PinnedBuffer(wl0[k].shape, wl0[k].dtype) for k in ("pcs", "instrs", "wlog")}   # the hand-off buffers are pinned
+        wl = dict(wl0)
+        for k, pb in pins.items():
+            pb.array[...] = wl0[k]
+            wl[k] = pb.array
         ctx.comm_shutdown()
         single = []
         for _ in range(3):
@@ -64,7 +69,9 @@ def main():
                               "cycles_per_s_sharded": round(res.cycles / t[1] * 1e3), "bytes_identical_on_all_ranks": t[2] == 0.0,
                               "verifier_accepts": bool(ok), "stage_ms_single": {k: round(v, 3) for k, v in single_stage.items()},
                               "stage_ms_sharded_rank0": {k: round(v, 3) for k, v in stage.items()}}), flush=True)
-        del res, wl
+        del res, wl, wl0
+        for pb in pins.values():
+            pb.close()
     ctx.close()
     if world > 1:
         dist.destroy_process_group()

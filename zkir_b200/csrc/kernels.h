@@ -65,6 +65,9 @@ struct QuotientArgs {
   // row segment (one proof sharded over several GPUs): only the points j in [seg_j0, seg_j0 + 2^seg_log_nj) of every coset, i.e.
   // the natural indices [seg_j0 << log_blowup, ...); seg_log_nj = 0xffffffff: all rows.  Reads one halo row (j + 1 mod N).
   u32 seg_log_nj = 0xffffffffu; u64 seg_j0 = 0;
+  // plane-sharded quotient commit: plane k is stored into q_plane[k] (the matrix of the rank that will transform that plane,
+  // possibly peer memory over NVLink) instead of q; nullptr = q
+  u32* q_plane[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 int launch_quotient(const QuotientArgs& a, cudaStream_t st, u64* launches);
 int launch_domain_tables(u32* xs, u32* dinv, u32 log_n, u32 log_b, u32 shift_canon, cudaStream_t st, u64* launches);
@@ -135,6 +138,7 @@ struct QueryArgs {
   // tree exist only on the owner of the leaf (segment = 2^sl leaves).  Pieces this context does not own are written as 0.
   u32 shard_lo = 0, shard_hi = 1, ttree_sl = 0, qtree_sl = 0;
   u32 lde_sl = 0;       // != 0: the trace LDE rows themselves are row-sharded with segments of 2^lde_sl leaves
+  u32 qlde_sl = 0;      // same for the quotient LDE rows
   u32 layer_sl[32] = {0};
 };
 int launch_queries(const QueryArgs& a, cudaStream_t st, u64* launches);

@@ -77,6 +77,8 @@ static Layout make_layout(const zkir_params* p, u32 log_n) {
   return L;
 }
 
+enum { PEER_LDE = 0, PEER_Q = 1, PEER_QLDE = 2, PEER_BUFS = 3 };
+#define PEER_REC_WORDS 60
 struct Workspace {
   u32 log_n = 0, log_blowup = 0, width = 0, nq = 0;
   bool valid = false;
@@ -99,9 +101,9 @@ struct Workspace {
   u32* h_proof = nullptr;    // pinned
   u32* h_stage = nullptr;    // pinned staging for header words
   // sharded proofs: every rank's LDE matrix as mapped into this process (CUDA IPC / peer access), see peer.cu
-  PeerPtrs peers; bool peers_valid = false;
+  PeerPtrs peers[3]; bool peers_valid = false;   // PEER_LDE, PEER_Q, PEER_QLDE
   std::vector<void*> ipc_opened;
-  u32* xchg = nullptr;       // [ZKIR_MAX_SHARDS][24] words: handle exchange; word 0 doubles as the barrier token
+  u32* xchg = nullptr;       // [ZKIR_MAX_SHARDS][PEER_REC_WORDS] words: handle exchange; word 0 doubles as the barrier token
 };
 
 struct zkir_ctx {
@@ -207,7 +209,7 @@ static int ws_prepare(zkir_ctx* ctx, const zkir_params* p, u32 log_n) {
   A(d_layers, R + 1) A(d_ltrees, R + 1)
   A(chal, 1) A(chal_buf, 12 + 4 * R + 2 + 6 + p->num_public) A(indices, p->num_queries + 1)
   A(apow, 4 * ZKIR_AIR_NUM_CONSTRAINTS) A(afp, W + 5)
-  A(proof, L.total) A(xchg, ZKIR_MAX_SHARDS * 24)
+  A(proof, L.total) A(xchg, ZKIR_MAX_SHARDS * PEER_REC_WORDS)
 #undef A
   CU(cudaMallocHost(&w.h_proof, L.total * 4));
   CU(cudaMallocHost(&w.h_stage, (8 + 6 + 2 * p->num_public) * 4));
@@ -251,6 +253,9 @@ struct ShardPlan {
   u32 G = 1, lo = 0, hi = 1, log_nj = 0;
   u64 nj = 0;          // points per coset and shard
   u32 cols_per = 0, W = 0;
+  u32 planes_per = 1;  // quotient planes (of 4) per rank; ranks beyond 4 / planes_per own none
+  u32 p_lo(u32 g) const { const u32 c = g * planes_per; return c < 4 ? c : 4; }
+  u32 p_hi(u32 g) const { const u32 c = (g + 1) * planes_per; return c < 4 ? c : 4; }
   u32 c_lo(u32 g) const { const u32 c = g * cols_per; return c < W ? c : W; }
   u32 c_hi(u32 g) const { const u32 c = (g + 1) * cols_per; return c < W ? c : W; }
 };
@@ -282,39 +287,49 @@ static int exchange_lde_rows(zkir_ctx* ctx, const ShardPlan& sp, u32* lde, u64 N
 }
 
 // Map every rank's LDE matrix into this process.  Collective (one all-gather of 96-byte records); runs once per workspace shape.
-struct PeerRec { u64 pid, ptr; u32 dev, pad[3]; cudaIpcMemHandle_t handle; };
-static_assert(sizeof(PeerRec) == 96, "PeerRec layout");
+struct PeerRec { u64 pid; u32 dev, pad; u64 ptr[PEER_BUFS]; cudaIpcMemHandle_t handle[PEER_BUFS]; u64 pad2; };
+static_assert(sizeof(PeerRec) == 4 * PEER_REC_WORDS, "PeerRec layout");
 static int peers_open(zkir_ctx* ctx) {
   Workspace& w = ctx->ws;
   peers_close(ctx);
   const int G = comm_world(ctx->comm), me = comm_rank(ctx->comm);
+  u32* bufs[PEER_BUFS] = {w.lde, w.q, w.qlde};
   PeerRec mine;
   memset(&mine, 0, sizeof(mine));
-  mine.pid = (u64)getpid(); mine.ptr = (u64)(uintptr_t)w.lde; mine.dev = (u32)ctx->device;
-  CU(cudaIpcGetMemHandle(&mine.handle, w.lde));
+  mine.pid = (u64)getpid(); mine.dev = (u32)ctx->device;
+  for (int b = 0; b < PEER_BUFS; b++) {
+    mine.ptr[b] = (u64)(uintptr_t)bufs[b];
+    CU(cudaIpcGetMemHandle(&mine.handle[b], bufs[b]));
+  }
   std::vector<PeerRec> all(G);
-  CU(cudaMemcpyAsync(w.xchg + (size_t)me * 24, &mine, sizeof(mine), cudaMemcpyHostToDevice, ctx->stream));
-  if (comm_all_gather_u32(ctx->comm, w.xchg, 24, ctx->stream, &ctx->err) != 0) return ZKIR_ERR_NCCL;
+  CU(cudaMemcpyAsync(w.xchg + (size_t)me * PEER_REC_WORDS, &mine, sizeof(mine), cudaMemcpyHostToDevice, ctx->stream));
+  if (comm_all_gather_u32(ctx->comm, w.xchg, PEER_REC_WORDS, ctx->stream, &ctx->err) != 0) return ZKIR_ERR_NCCL;
   CU(cudaMemcpyAsync(all.data(), w.xchg, sizeof(PeerRec) * G, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   for (int t = 0; t < G; t++) {
-    if (t == me) { w.peers.p[t] = w.lde; continue; }
+    if (t == me) { for (int b = 0; b < PEER_BUFS; b++) w.peers[b].p[t] = bufs[b]; continue; }
     if (all[t].pid == mine.pid) {   // another context of this process (threads as ranks): plain peer access
       if ((int)all[t].dev != ctx->device) {
         cudaError_t e = cudaDeviceEnablePeerAccess((int)all[t].dev, 0);
         if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
         else if (e != cudaSuccess) { ctx->err = std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e); return ZKIR_ERR_CUDA; }
       }
-      w.peers.p[t] = reinterpret_cast<u32*>((uintptr_t)all[t].ptr);
+      for (int b = 0; b < PEER_BUFS; b++) w.peers[b].p[t] = reinterpret_cast<u32*>((uintptr_t)all[t].ptr[b]);
     } else {
-      void* ptr = nullptr;
-      CU(cudaIpcOpenMemHandle(&ptr, all[t].handle, cudaIpcMemLazyEnablePeerAccess));
-      w.ipc_opened.push_back(ptr);
-      w.peers.p[t] = reinterpret_cast<u32*>(ptr);
+      for (int b = 0; b < PEER_BUFS; b++) {
+        void* ptr = nullptr;
+        CU(cudaIpcOpenMemHandle(&ptr, all[t].handle[b], cudaIpcMemLazyEnablePeerAccess));
+        w.ipc_opened.push_back(ptr);
+        w.peers[b].p[t] = reinterpret_cast<u32*>(ptr);
+      }
     }
   }
   w.peers_valid = true;
   return 0;
+}
+// one-word all-reduce: orders every rank's peer-memory stores (kernels before it) before every rank's reads (kernels after it)
+static int peers_barrier(zkir_ctx* ctx) {
+  return comm_all_reduce_sum_u32(ctx->comm, ctx->ws.xchg, 1, ctx->stream, &ctx->err) != 0 ? ZKIR_ERR_NCCL : 0;
 }
 
 // Merkle commitment of one matrix (leaf i = sponge over LDE row i) or one FRI layer (leaf i = hash(f[i] || f[i+h])), followed
@@ -371,7 +386,12 @@ static int prove_resident(zkir_ctx* ctx, const zkir_params* p, u32 log_n, const 
     sp.nj = N / sp.G;
     while ((1ull << sp.log_nj) < sp.nj) sp.log_nj++;
     sp.cols_per = (u32)((W + sp.G - 1) / sp.G);
+    sp.planes_per = (4 + sp.G - 1) / sp.G;
   }
+  const bool p2p = sp.on && ctx->comm != nullptr;
+  static const bool lde_via_nccl = getenv("ZKIR_LDE_EXCHANGE") && !strcmp(getenv("ZKIR_LDE_EXCHANGE"), "nccl");
+  if (p2p && !w.peers_valid) { int xrc = peers_open(ctx); if (xrc) return xrc; }
+  const u32 me = p2p ? (u32)comm_rank(ctx->comm) : 0;
   u32* c_alpha = w.chal_buf, *c_zeta = w.chal_buf + 4, *c_afri = w.chal_buf + 8, *c_betas = w.chal_buf + 12;
   u32* c_pow_raw = w.chal_buf + 12 + 4 * R, *c_pow_sample = c_pow_raw + 1, *c_hdr = c_pow_raw + 2;
 
@@ -401,15 +421,12 @@ static int prove_resident(zkir_ctx* ctx, const zkir_params* p, u32 log_n, const 
     if (ctx->comm) {
       // rows -> owners.  Default: one kernel storing into the peers' matrices over NVLink, then a one-word all-reduce as the
       // barrier that orders every rank's stores before every rank's reads.  ZKIR_LDE_EXCHANGE=nccl: grouped ncclSend/ncclRecv.
-      static const bool use_nccl = getenv("ZKIR_LDE_EXCHANGE") && !strcmp(getenv("ZKIR_LDE_EXCHANGE"), "nccl");
-      if (use_nccl) {
+      if (lde_via_nccl) {
         int xrc = exchange_lde_rows(ctx, sp, w.lde, N, B);
         if (xrc) return xrc;
       } else {
-        if (!w.peers_valid) { int xrc = peers_open(ctx); if (xrc) return xrc; }
-        const u32 me = (u32)comm_rank(ctx->comm);
-        RC(launch_lde_scatter(w.lde, w.peers, me, sp.G, sp.c_lo(me), sp.c_hi(me) - sp.c_lo(me), N, B, sp.nj, st, LC));
-        if (comm_all_reduce_sum_u32(ctx->comm, w.xchg, 1, st, &ctx->err) != 0) return ZKIR_ERR_NCCL;
+        RC(launch_lde_scatter(w.lde, w.peers[PEER_LDE], me, sp.G, sp.c_lo(me), sp.c_hi(me) - sp.c_lo(me), N, B, sp.nj, st, LC));
+        int brc = peers_barrier(ctx); if (brc) return brc;
       }
     }
   } else if (w.fast) {
@@ -442,16 +459,14 @@ static int prove_resident(zkir_ctx* ctx, const zkir_params* p, u32 log_n, const 
     qa.lde = w.lde; qa.q = w.q; qa.log_n = log_n; qa.log_blowup = p->log_blowup; qa.pv = c_hdr + 6; qa.alpha = c_alpha;
     qa.xs = w.xs; qa.dinv = w.dinv; qa.apow_scratch = w.apow;
     if (sp.on) {
-      // row-sharded: every rank evaluates its natural-order range of Q, the four planes are completed with one grouped all-gather
+      // row-sharded: every rank evaluates its natural-order range of Q and stores plane k straight into the matrix of the rank
+      // that transforms that plane (NVLink peer stores from the quotient kernel itself); a barrier completes the planes
+      if (p2p) for (u32 k = 0; k < 4; k++) qa.q_plane[k] = w.peers[PEER_Q].p[k / sp.planes_per];
       for (u32 g = sp.lo; g < sp.hi; g++) {
         qa.seg_log_nj = sp.log_nj; qa.seg_j0 = (u64)g * sp.nj;
         RC(launch_quotient(qa, st, LC));
       }
-      if (ctx->comm) {
-        unsigned* planes[4] = {w.q, w.q + M, w.q + 2 * M, w.q + 3 * M};
-        const size_t per[4] = {(size_t)(M / sp.G), (size_t)(M / sp.G), (size_t)(M / sp.G), (size_t)(M / sp.G)};
-        if (comm_all_gather_group_u32(ctx->comm, planes, per, 4, st, &ctx->err) != 0) return ZKIR_ERR_NCCL;
-      }
+      if (p2p) { int brc = peers_barrier(ctx); if (brc) return brc; }
     } else {
       RC(launch_quotient(qa, st, LC));
     }
@@ -464,8 +479,23 @@ static int prove_resident(zkir_ctx* ctx, const zkir_params* p, u32 log_n, const 
     const uint2* unshift = fast_scale_table(ctx->fast, w.plan_m, hinv(shift), 1u);
     if (!unshift) { ctx->err = "table alloc"; return ZKIR_ERR_OOM; }
     const u32 split_log = (u32)w.plan_chunk.d[w.plan_chunk.nd - 1];
-    RC(fast_intt(ctx->fast, w.plan_m, w.q, M, w.q, M, 4, hinv((u32)(M % BB_P)), unshift, split_log, 2, (u32)N, w.qcoef, 2 * N, st));
-    RC(fast_coset_ntt(ctx->fast, w.plan_chunk, w.qcoef, N, w.qlde, M, QW, B, shift, ZKIR_BB_ROOTS[log_m], 1u, st));
+    if (sp.on) {
+      // plane-sharded: a rank transforms its planes (2 quotient columns each), then the rows go to their owners like the trace LDE
+      for (u32 g = sp.lo; g < sp.hi; g++) {
+        const u32 p0 = sp.p_lo(g), npl = sp.p_hi(g) - p0;
+        if (!npl) continue;
+        RC(fast_intt(ctx->fast, w.plan_m, w.q + (u64)p0 * M, M, w.q + (u64)p0 * M, M, npl, hinv((u32)(M % BB_P)), unshift, split_log, 2, (u32)N,
+                     w.qcoef + (u64)p0 * 2 * N, 2 * N, st));
+        RC(fast_coset_ntt(ctx->fast, w.plan_chunk, w.qcoef + (u64)p0 * 2 * N, N, w.qlde + (u64)p0 * 2 * M, M, 2 * npl, B, shift, ZKIR_BB_ROOTS[log_m], 1u, st));
+      }
+      if (p2p) {
+        RC(launch_lde_scatter(w.qlde, w.peers[PEER_QLDE], me, sp.G, 2 * sp.p_lo(me), 2 * (sp.p_hi(me) - sp.p_lo(me)), N, B, sp.nj, st, LC));
+        int brc = peers_barrier(ctx); if (brc) return brc;
+      }
+    } else {
+      RC(fast_intt(ctx->fast, w.plan_m, w.q, M, w.q, M, 4, hinv((u32)(M % BB_P)), unshift, split_log, 2, (u32)N, w.qcoef, 2 * N, st));
+      RC(fast_coset_ntt(ctx->fast, w.plan_chunk, w.qcoef, N, w.qlde, M, QW, B, shift, ZKIR_BB_ROOTS[log_m], 1u, st));
+    }
   } else {
     // coefficients on the coset (in place), chunk c of plane k = words [k*M + c*N, +N)
     RC(ntt_run(ctx->tables, w.q, M, w.q, M, ctx->ntt_tmp, ctx->ntt_tmp_words, 4, log_m, true, 0, nullptr, w.qscale, BB_ONE, false, st));
@@ -477,7 +507,7 @@ static int prove_resident(zkir_ctx* ctx, const zkir_params* p, u32 log_n, const 
     RC(ntt_run(ctx->tables, qcoef, N, w.lde_nat, M, ctx->ntt_tmp, ctx->ntt_tmp_words, QW, log_m, false, p->log_blowup, nullptr, nullptr, BB_ONE, false, st));
     RC(launch_coset_reorder(w.lde_nat, w.qlde, QW, log_n, p->log_blowup, 0, st, LC));
   }
-  if ((crc = commit_tree(ctx, w.qlde, QW, p->log_blowup, nullptr, w.qtree, M, w.proof + L.qroot, c_zeta, 4, &q_sl)) != 0) return crc;  // root -> proof, observe, sample zeta
+  if ((crc = commit_tree(ctx, w.qlde, QW, p->log_blowup, nullptr, w.qtree, M, w.proof + L.qroot, c_zeta, 4, &q_sl, sp.on ? 1 : -1)) != 0) return crc;  // root -> proof, observe, sample zeta
   // ---- 4. openings at zeta and g*zeta, evaluated on the shifted coefficients at zeta/shift
   CU(cudaEventRecord(ctx->ev[ZKIR_STAGE_OPENINGS], st));
   {
@@ -491,16 +521,18 @@ static int prove_resident(zkir_ctx* ctx, const zkir_params* p, u32 log_n, const 
     E4* oq = reinterpret_cast<E4*>(w.proof + L.open_q);
     if (sp.on) {
       // column-sharded like the LDE (a rank holds the coefficients of its own columns only); disjoint pieces merged by all-reduce
-      if (ctx->comm) CU(cudaMemsetAsync(w.proof + L.open_t, 0, 2 * W * 16, st));
+      if (ctx->comm) CU(cudaMemsetAsync(w.proof + L.open_t, 0, (2 * W + QW) * 16, st));
       for (u32 g = sp.lo; g < sp.hi; g++) {
         const u32 k0 = sp.c_lo(g), nc = sp.c_hi(g) - k0;
         if (nc) RC(launch_open(w.coef + (u64)k0 * N, N, nc, N, w.U1, w.U2, ot + k0, otg + k0, w.open_scratch, st, LC));
+        const u32 q0 = 2 * sp.p_lo(g), nqc = 2 * sp.p_hi(g) - q0;
+        if (nqc) RC(launch_open(qcoef + (u64)q0 * N, N, nqc, N, w.U1q, w.U1q, oq + q0, w.dummy_open, w.open_scratch, st, LC));
       }
-      if (ctx->comm && comm_all_reduce_sum_u32(ctx->comm, w.proof + L.open_t, 2 * W * 4, st, &ctx->err) != 0) return ZKIR_ERR_NCCL;
+      if (ctx->comm && comm_all_reduce_sum_u32(ctx->comm, w.proof + L.open_t, (2 * W + QW) * 4, st, &ctx->err) != 0) return ZKIR_ERR_NCCL;
     } else {
       RC(launch_open(w.coef, N, (u32)W, N, w.U1, w.U2, ot, otg, w.open_scratch, st, LC));
+      RC(launch_open(qcoef, N, QW, N, w.U1q, w.U1q, oq, w.dummy_open, w.open_scratch, st, LC));
     }
-    RC(launch_open(qcoef, N, QW, N, w.U1q, w.U1q, oq, w.dummy_open, w.open_scratch, st, LC));
     RC(launch_challenger(w.chal, w.proof + L.open_t, (u32)(2 * W + QW) * 4, c_afri, 4, 0, st, LC));
     DeepArgs da;
     da.lde = w.lde; da.M = M; da.width = (u32)W; da.qlde = w.qlde; da.qwidth = QW; da.log_n = log_n; da.log_b = p->log_blowup; da.xs = w.xs; da.zeta = c_zeta;
@@ -549,7 +581,7 @@ static int prove_resident(zkir_ctx* ctx, const zkir_params* p, u32 log_n, const 
     qa.layers = w.d_layers; qa.ltrees = w.d_ltrees; qa.out = w.proof + L.queries; qa.words_per_query = (u32)L.per_query;
     // sharded trees: the bottom path levels of a leaf exist only on its owner; every rank writes the pieces it owns (zeros
     // elsewhere, rank 0 also everything that is replicated) and one all-reduce assembles the query section ("query gather")
-    qa.shard_lo = ctx->shard_lo; qa.shard_hi = ctx->shard_hi; qa.ttree_sl = t_sl; qa.qtree_sl = q_sl; qa.lde_sl = sp.on ? t_sl : 0;
+    qa.shard_lo = ctx->shard_lo; qa.shard_hi = ctx->shard_hi; qa.ttree_sl = t_sl; qa.qtree_sl = q_sl; qa.lde_sl = sp.on ? t_sl : 0; qa.qlde_sl = sp.on ? q_sl : 0;
     for (u32 r = 0; r < 32; r++) qa.layer_sl[r] = l_sl[r];
     RC(launch_queries(qa, st, LC));
     if (ctx->comm && comm_all_reduce_sum_u32(ctx->comm, w.proof + L.queries, L.per_query * L.nq, st, &ctx->err) != 0) return ZKIR_ERR_NCCL;

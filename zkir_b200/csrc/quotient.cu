@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(128, MINB) quotient_kernel(QuotientArgs a, con
   const u64 nat = (j << a.log_blowup) | z;
   const E4 accv = acc4_finish(c.acc);
 #pragma unroll
-  for (int k = 0; k < 4; k++) a.q[(u64)k * M + nat] = bb_mul(accv.c[k], zi);
+  for (int k = 0; k < 4; k++) (a.q_plane[k] ? a.q_plane[k] : a.q)[(u64)k * M + nat] = bb_mul(accv.c[k], zi);
 }
 
 __global__ void domain_tables_kernel(u32* xs, u32* dinv, u64 M, u32 log_n, u32 log_b, u32 shift, u32 w) {

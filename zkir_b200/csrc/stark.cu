@@ -237,7 +237,8 @@ __global__ void __launch_bounds__(128) query_kernel(QueryArgs a) {
   for (u32 k = threadIdx.x; k < a.width; k += blockDim.x) out[k] = row_mine ? a.lde[(u64)k * M + qrow] : 0u;
   out += a.width;
   copy_path(a.ttree, M, a.log_m, q, out, a.ttree_sl, owns(q, a.ttree_sl), top); out += a.log_m * 8;
-  for (u32 k = threadIdx.x; k < 8; k += blockDim.x) out[k] = top ? a.qlde[(u64)k * M + qrow] : 0u;
+  const bool qrow_mine = a.qlde_sl ? owns(q, a.qlde_sl) : top;
+  for (u32 k = threadIdx.x; k < 8; k += blockDim.x) out[k] = qrow_mine ? a.qlde[(u64)k * M + qrow] : 0u;
   out += 8;
   copy_path(a.qtree, M, a.log_m, q, out, a.qtree_sl, owns(q, a.qtree_sl), top); out += a.log_m * 8;
   for (u32 r = 0; r < a.log_n; r++) {
