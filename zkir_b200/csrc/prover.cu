@@ -755,8 +755,14 @@ static int expand_writelog(zkir_ctx* ctx, const uint32_t* pcs, const uint32_t* i
                            uint32_t log_n, u32* d_cols) {
   const u64 N = 1ull << log_n;
   if (T > N || !pcs || !instrs || !wlog) { ctx->err = "bad write log: need n_rows <= 2^log_n and non-null arrays"; return ZKIR_ERR_ARG; }
+  // Sharded proof (collective call, every rank holds the same log in host memory): each rank uploads only ITS row segment over
+  // PCIe and the segments are exchanged over NVLink with one grouped all-gather, so the host link carries T/G rows per GPU.
+  const u32 G = ctx->comm ? ctx->shards : 1;
+  const bool split = G > 1 && T >= 65536;
+  const u64 chunk = split ? (((T + G - 1) / G + 3) & ~3ull) : T;   // rows per rank
+  const u64 Tc = split ? chunk * G : T;                             // capacity of the device arrays
   const size_t scratch = trace_expand_wl_scratch_ints(N) * 4;
-  const size_t need = T * 16 + scratch + 64;
+  const size_t need = Tc * 16 + scratch + 64;
   if (ctx->rows_bytes < need) {
     if (ctx->rows_dev) cudaFree(ctx->rows_dev);
     ctx->rows_dev = nullptr; ctx->rows_bytes = 0;
@@ -766,13 +772,25 @@ static int expand_writelog(zkir_ctx* ctx, const uint32_t* pcs, const uint32_t* i
   if (!ctx->d_err) { CU(cudaMalloc(&ctx->d_err, 8)); CU(cudaMallocHost(&ctx->h_err, 8)); }
   char* base = (char*)ctx->rows_dev;
   u64* d_wlog = (u64*)base;
-  u32* d_pcs = (u32*)(base + T * 8);
-  u32* d_ins = (u32*)(base + T * 12);
-  int* d_scr = (int*)(base + ((T * 16 + 15) & ~(size_t)15));
+  u32* d_pcs = (u32*)(base + Tc * 8);
+  u32* d_ins = (u32*)(base + Tc * 12);
+  int* d_scr = (int*)(base + ((Tc * 16 + 15) & ~(size_t)15));
   cudaStream_t st = ctx->stream;
-  CU(cudaMemcpyAsync(d_wlog, wlog, T * 8, cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(d_pcs, pcs, T * 4, cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(d_ins, instrs, T * 4, cudaMemcpyHostToDevice, st));
+  if (split) {
+    const u64 r0 = (u64)comm_rank(ctx->comm) * chunk, r1 = r0 + chunk < T ? r0 + chunk : T;
+    if (r1 > r0) {
+      CU(cudaMemcpyAsync(d_wlog + r0, wlog + r0, (r1 - r0) * 8, cudaMemcpyHostToDevice, st));
+      CU(cudaMemcpyAsync(d_pcs + r0, pcs + r0, (r1 - r0) * 4, cudaMemcpyHostToDevice, st));
+      CU(cudaMemcpyAsync(d_ins + r0, instrs + r0, (r1 - r0) * 4, cudaMemcpyHostToDevice, st));
+    }
+    unsigned* bufs[3] = {reinterpret_cast<unsigned*>(d_wlog), d_pcs, d_ins};
+    const size_t per[3] = {(size_t)chunk * 2, (size_t)chunk, (size_t)chunk};
+    if (comm_all_gather_group_u32(ctx->comm, bufs, per, 3, st, &ctx->err) != 0) return ZKIR_ERR_NCCL;
+  } else {
+    CU(cudaMemcpyAsync(d_wlog, wlog, T * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_pcs, pcs, T * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_ins, instrs, T * 4, cudaMemcpyHostToDevice, st));
+  }
   CU(cudaMemsetAsync(ctx->d_err, 0xff, 8, st));
   WlArgs wa;
   wa.pcs = d_pcs; wa.ins = d_ins; wa.wlog = d_wlog; wa.T = T; wa.N = N; wa.final_pc = final_pc; wa.chunk_prev = d_scr; wa.cols = d_cols; wa.err = ctx->d_err;
