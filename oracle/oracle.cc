@@ -203,13 +203,17 @@ struct AirRowCtx {  // base-field row check / quotient numerator at one point
 };
 
 struct Params { u32 log_blowup, num_queries, pow_bits, width, num_public; };
-static const u32 PROOF_MAGIC = 0x5A4B5052u, PROOF_VERSION = 1u;
+static const u32 PROOF_MAGIC = 0x5A4B5052u, PROOF_VERSION = 2u;
 
+// FRI rounds (docs/PROVER_SPEC.md section 4.6): log_n / 2 rounds that fold by 4, then one that folds by 2 if log_n is odd
+static size_t fri_rounds(u32 log_n) { return log_n / 2 + (log_n & 1); }
+static u32 fri_log_arity(u32 log_n, size_t t) { return t < log_n / 2 ? 2 : 1; }
 static size_t proof_words(const Params& p, u32 log_n) {
-  size_t lg = log_n + p.log_blowup, W = p.width, R = log_n;
+  size_t lg = log_n + p.log_blowup, W = p.width, R = fri_rounds(log_n);
   size_t n = 8 + p.num_public + 16 + (2 * W + 8) * 4 + R * 8 + 4 + 1;
   size_t perq = W + lg * 8 + 8 + lg * 8;
-  for (size_t r = 0; r < R; r++) perq += 8 + (lg - 1 - r) * 8;
+  size_t ll = lg;  // log2 of the layer length
+  for (size_t t = 0; t < R; t++) { const u32 la = fri_log_arity(log_n, t); perq += (4u << la) + (ll - la) * 8; ll -= la; }
   return n + perq * p.num_queries;
 }
 
@@ -369,40 +373,48 @@ static int prove(const Params& p, const u32* trace, u32 log_n, const u32* pv, u3
   }
   if (dump && dump->fri_input) memcpy(dump->fri_input, f.data(), M * 16);
 
-  // ---- 5. FRI commit phase
-  const size_t R = log_n;
+  // ---- 5. FRI commit phase: a round commits the layer with leaves of `arity` values (the fibre of one point of the layer
+  // after the round), samples beta and folds by 2 with beta, then -- arity 4 -- once more with beta^2
+  const size_t R = fri_rounds(log_n);
   std::vector<std::vector<E4>> layers;
   std::vector<std::vector<u32>> trees;
   u32 half_inv = finv(2);
   u32 lshift = shift;  // coset shift of the current layer
-  for (size_t r = 0; r < R; r++) {
-    size_t n = M >> r, h = n / 2;
-    std::vector<u32> tree((2 * h - 1) * 8);
-#pragma omp parallel for if (h > 256)
-    for (size_t i = 0; i < h; i++) {
-      u32 leaf[8];
-      memcpy(leaf, f[i].c, 16); memcpy(leaf + 4, f[i + h].c, 16);
-      hash_elems(leaf, 8, &tree[i * 8]);
+  int ll = lg;         // log2 of the current layer length
+  for (size_t t = 0; t < R; t++) {
+    const u32 la = fri_log_arity(log_n, t), arity = 1u << la;
+    size_t n = (size_t)1 << ll, q = n >> la;
+    std::vector<u32> tree((2 * q - 1) * 8);
+#pragma omp parallel for if (q > 256)
+    for (size_t i = 0; i < q; i++) {
+      u32 leaf[16];
+      for (u32 k = 0; k < arity; k++) memcpy(leaf + 4 * k, f[i + k * q].c, 16);
+      hash_elems(leaf, 4 * arity, &tree[i * 8]);
     }
-    merkle_build(tree.data(), h);
-    const u32* root = merkle_root(tree.data(), h);
+    merkle_build(tree.data(), q);
+    const u32* root = merkle_root(tree.data(), q);
     memcpy(out, root, 32); out += 8;
     ch.observe_n(root, 8);
     E4 beta = ch.sample_ext();
-    if (dump && dump->betas) memcpy(dump->betas + 4 * r, beta.c, 16);
-    std::vector<E4> g(h);
-    u32 w = root_of_unity(lg - (int)r), x = lshift;
-    std::vector<u32> xs(h);
-    for (size_t i = 0; i < h; i++) { xs[i] = x; x = fmul(x, w); }
-#pragma omp parallel for if (h > 256)
-    for (size_t i = 0; i < h; i++) {
-      E4 s = e4_mulb(e4_add(f[i], f[i + h]), half_inv);
-      E4 d = e4_mulb(e4_sub(f[i], f[i + h]), finv(fmul(2, xs[i])));
-      g[i] = e4_add(s, e4_mul(beta, d));
-    }
+    if (dump && dump->betas) memcpy(dump->betas + 4 * t, beta.c, 16);
     layers.push_back(f); trees.push_back(tree);
-    f.swap(g);
-    lshift = fmul(lshift, lshift);
+    for (u32 step = 0; step < la; step++) {
+      const size_t h = ((size_t)1 << ll) / 2;
+      std::vector<E4> g(h);
+      u32 w = root_of_unity(ll), x = lshift;
+      std::vector<u32> xs(h);
+      for (size_t i = 0; i < h; i++) { xs[i] = x; x = fmul(x, w); }
+#pragma omp parallel for if (h > 256)
+      for (size_t i = 0; i < h; i++) {
+        E4 s = e4_mulb(e4_add(f[i], f[i + h]), half_inv);
+        E4 d = e4_mulb(e4_sub(f[i], f[i + h]), finv(fmul(2, xs[i])));
+        g[i] = e4_add(s, e4_mul(beta, d));
+      }
+      f.swap(g);
+      lshift = fmul(lshift, lshift);
+      beta = e4_mul(beta, beta);
+      ll--;
+    }
   }
   for (size_t i = 1; i < f.size(); i++) if (!e4_eq(f[i], f[0])) return -3;  // final layer must be constant
   memcpy(out, f[0].c, 16); out += 4;
@@ -428,11 +440,14 @@ static int prove(const Params& p, const u32* trace, u32 log_n, const u32* pv, u3
     for (int k = 0; k < 8; k++) *out++ = qlde[k * M + idx];
     merkle_path(qtree.data(), M, idx, out); out += lg * 8;
     size_t i = idx;
-    for (size_t r = 0; r < R; r++) {
-      size_t h = (M >> r) / 2;
-      i = i % h;
-      memcpy(out, layers[r][i].c, 16); memcpy(out + 4, layers[r][i + h].c, 16); out += 8;
-      merkle_path(trees[r].data(), h, i, out); out += (lg - 1 - r) * 8;
+    int ql = lg;
+    for (size_t t = 0; t < R; t++) {
+      const u32 la = fri_log_arity(log_n, t), arity = 1u << la;
+      size_t q = ((size_t)1 << ql) >> la;
+      i = i % q;
+      for (u32 k = 0; k < arity; k++) { memcpy(out, layers[t][i + k * q].c, 16); out += 4; }
+      merkle_path(trees[t].data(), q, i, out); out += (ql - la) * 8;
+      ql -= la;
     }
   }
   if ((size_t)(out - proof) != proof_words(p, log_n)) return -5;

@@ -142,13 +142,13 @@ bool verify(const zkir_params* p, const u32* w, size_t nwords, const u32* pv_in)
   if (!p || !w) return fail("null argument");
   if (p->width != ZKIR_AIR_WIDTH || p->num_public != ZKIR_AIR_NUM_PUBLIC || p->log_blowup < 1) return fail("unsupported params");
   if (nwords < 8) return fail("proof too short");
-  if (w[0] != 0x5A4B5052u || w[1] != 1) return fail("bad magic/version");
+  if (w[0] != 0x5A4B5052u || w[1] != 2) return fail("bad magic/version");
   const u32 log_n = w[2];
   if (w[3] != p->width || w[4] != p->log_blowup || w[5] != p->num_queries || w[6] != p->pow_bits || w[7] != p->num_public)
     return fail("proof header does not match params");
   if (log_n < 2 || log_n + p->log_blowup > 27) return fail("bad log_n");
   if (nwords * 4 != zkir_b200_proof_size(p, log_n)) return fail("proof length mismatch");
-  const u32 W = p->width, np = p->num_public, lg = log_n + p->log_blowup, R = log_n, QW = 8;
+  const u32 W = p->width, np = p->num_public, lg = log_n + p->log_blowup, R = log_n / 2 + (log_n & 1), QW = 8;  // R FRI rounds: fold by 4, last by 2 if log_n is odd
   const u64 N = 1ull << log_n, M = 1ull << lg;
   for (size_t i = 8; i < nwords; i++) if (w[i] >= P) return fail("non-canonical field element");
   const u32* q = w + 8;
@@ -226,19 +226,32 @@ bool verify(const zkir_params* p, const u32* w, size_t nwords, const u32* pv_in)
     X4 v = (rt - A1) * iz + afp[W] * ((rt - A2) * igz) + afp[2 * W] * ((rq - A3) * iz);
     u64 i = idx;
     u32 lshift = ZKIR_BB_GEN;
-    for (u32 r = 0; r < R; r++) {
-      const u64 h = (M >> r) / 2;
-      const u32 hi = (u32)(i / h);
-      i %= h;
-      X4 a, b; memcpy(a.c, q, 16); memcpy(b.c, q + 4, 16);
-      const u32* pair = q; q += 8;
-      const u32* path = q; q += 8 * (lg - 1 - r);
-      if (!eq(hi ? b : a, v)) return fail("FRI layer value does not match the folded value");
-      hash_n(pair, 8, d);
-      if (!check_path(d, i, path, lg - 1 - r, fri_roots + 8 * r)) return fail("FRI Merkle path");
-      const u32 xi = mul(lshift, pw(ZKIR_BB_ROOTS[lg - r], i));
-      v = scale(a + b, half) + betas[r] * scale(a - b, inv(mul(2, xi)));
-      lshift = mul(lshift, lshift);
+    u32 ll = lg;  // log2 of the layer length
+    for (u32 t = 0; t < R; t++) {
+      const u32 la = t < log_n / 2 ? 2 : 1, arity = 1u << la;
+      const u64 qn = (1ull << ll) >> la;            // leaves of this layer; the opened values sit at i + k*qn
+      const u32 pos = (u32)(i / qn);
+      i %= qn;
+      X4 a[4];
+      for (u32 k = 0; k < arity; k++) memcpy(a[k].c, q + 4 * k, 16);
+      const u32* vals = q; q += 4 * arity;
+      const u32* path = q; q += 8 * (ll - la);
+      if (!eq(a[pos], v)) return fail("FRI layer value does not match the folded value");
+      hash_n(vals, 4 * arity, d);
+      if (!check_path(d, i, path, ll - la, fri_roots + 8 * t)) return fail("FRI Merkle path");
+      const u32 xi = mul(lshift, pw(ZKIR_BB_ROOTS[ll], i));
+      if (la == 1) {
+        v = scale(a[0] + a[1], half) + betas[t] * scale(a[0] - a[1], inv(mul(2, xi)));
+      } else {
+        // fold by 2 with beta: pairs (i, i + n/2) and (i + n/4, i + 3n/4), the second at the point xi * w_4; then the two results
+        // are the pair (i, i + n/4) of the half-length layer on the squared coset, folded with beta^2
+        const u32 xj = mul(xi, ZKIR_BB_ROOTS[2]);
+        const X4 g0 = scale(a[0] + a[2], half) + betas[t] * scale(a[0] - a[2], inv(mul(2, xi)));
+        const X4 g1 = scale(a[1] + a[3], half) + betas[t] * scale(a[1] - a[3], inv(mul(2, xj)));
+        v = scale(g0 + g1, half) + (betas[t] * betas[t]) * scale(g0 - g1, inv(mul(2, mul(xi, xi))));
+      }
+      for (u32 k = 0; k < la; k++) lshift = mul(lshift, lshift);
+      ll -= la;
     }
     if (!eq(v, final_v)) return fail("FRI final value mismatch");
   }

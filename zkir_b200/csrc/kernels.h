@@ -48,7 +48,8 @@ int launch_leaf_hash(const u32* mat, u64 col_stride, u32 n_cols, u64 n_rows, u32
 // optional fused Fiat-Shamir step on the root: copy to root_dst, observe, sample n_sample elements into sample_out
 // pair_layer != nullptr: the leaves are FRI leaves hash(f[i] || f[i + n_leaves]) of that ext4 layer and are computed here too
 int launch_merkle_levels(u32* tree, u64 n_leaves, cudaStream_t st, u64* launches, ChalState* chal = nullptr, u32* root_dst = nullptr,
-                         u32* sample_out = nullptr, u32 n_sample = 0, const u32* pair_layer = nullptr, u64 first = 0, u64 seg = 0);
+                         u32* sample_out = nullptr, u32 n_sample = 0, const u32* pair_layer = nullptr, u64 first = 0, u64 seg = 0,
+                         u32 leaf_arity = 2);
 int launch_challenger(ChalState* st_dev, const u32* in, u32 n_in, u32* out, u32 n_out, u32 bits, cudaStream_t st, u64* launches);
 int launch_pow_grind(const ChalState* st_dev, u32 bits, u32* result, cudaStream_t st, u64* launches);
 
@@ -123,15 +124,17 @@ struct DeepArgs {
   u32 seg_log_nj = 0xffffffffu; u64 seg_j0 = 0;   // row segment as in QuotientArgs
 };
 int launch_deep(const DeepArgs& a, cudaStream_t st, u64* launches);
+// square_beta: fold with beta^2 (the second half-fold of a fold-by-4 round)
 int launch_fri_fold(const E4* in, E4* out, u64 h, const u32* beta_dev, const u32* inv_w_table, u32 tw_stride, u32 c_mont,
-                    cudaStream_t st, u64* launches);
+                    cudaStream_t st, u64* launches, int square_beta = 0);
 struct QueryArgs {
   const u32* indices;   // device [num_queries], canonical
   u32 num_queries, log_m, width, log_n;   // lde / qlde rows are coset-major, trees and layers natural
   const u32* lde; const u32* ttree;
   const u32* qlde; const u32* qtree;
-  const E4* const* layers;        // device array [R] of layer pointers
-  const u32* const* ltrees;       // device array [R] of layer trees
+  const E4* const* layers;        // device array of layer pointers, indexed by fold LEVEL (layer length M >> level)
+  const u32* const* ltrees;       // device array of layer trees, same index (only committed levels are used)
+  u32 fold4_rounds = 0, fri_rounds = 0;   // rounds that fold by 4 come first, the rest fold by 2 (docs/PROVER_SPEC.md section 4.6)
   u32* out;                       // proof words at the start of the query section
   u32 words_per_query;
   // one proof sharded over several GPUs: this context owns the leaf segments [shard_lo, shard_hi); the lowest *_sl levels of a

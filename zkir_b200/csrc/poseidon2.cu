@@ -156,14 +156,21 @@ __global__ void __launch_bounds__(128) leaf_hash_kernel(const u32* __restrict__ 
   d[1] = make_uint4(s[4], s[5], s[6], s[7]);
 }
 
-// FRI layer leaves: leaf i = hash(F[i] || F[i+h]) (8 elements = one permutation)
-__global__ void __launch_bounds__(128) leaf_hash_pairs_kernel(const uint4* __restrict__ layer, u64 h, u64 first, u64 count, u32* __restrict__ digests) {
+// FRI layer leaves: leaf i = hash(F[i] || F[i+q] [|| F[i+2q] || F[i+3q]]) over the q leaves of a layer of arity*q ext4 values
+// (arity 2: 8 elements = one permutation; arity 4: 16 elements = two absorptions of the overwrite-mode sponge)
+__global__ void __launch_bounds__(128) leaf_hash_pairs_kernel(const uint4* __restrict__ layer, u64 q, u64 first, u64 count, u32 arity,
+                                                              u32* __restrict__ digests) {
   u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x;
   if (i >= count) return;
   i += first;
-  uint4 a = layer[i], b = layer[i + h];
+  uint4 a = layer[i], b = layer[i + q];
   u32 s[16] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, 0, 0, 0, 0, 0, 0, 0, 0};
   poseidon2_permute(s);
+  if (arity == 4) {
+    a = layer[i + 2 * q]; b = layer[i + 3 * q];
+    s[0] = a.x; s[1] = a.y; s[2] = a.z; s[3] = a.w; s[4] = b.x; s[5] = b.y; s[6] = b.z; s[7] = b.w;
+    poseidon2_permute(s);
+  }
   uint4* d = reinterpret_cast<uint4*>(digests + 8 * i);
   d[0] = make_uint4(s[0], s[1], s[2], s[3]);
   d[1] = make_uint4(s[4], s[5], s[6], s[7]);
@@ -205,8 +212,8 @@ int launch_leaf_hash(const u32* mat, u64 col_stride, u32 n_cols, u64 n_rows, u32
   (*launches)++;
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
-__global__ void merkle_coop_kernel(u32* level, u64 n_in, u64 first, u32 chunk, const u32* __restrict__ pair_layer, ChalState* chal, u32* root_dst,
-                                   u32* sample_out, u32 n_sample);
+__global__ void merkle_coop_kernel(u32* level, u64 n_in, u64 first, u32 chunk, const u32* __restrict__ pair_layer, u32 leaf_arity, ChalState* chal,
+                                   u32* root_dst, u32* sample_out, u32 n_sample);
 __global__ void challenger_kernel(ChalState* st, const u32* in, u32 n_in, u32* out, u32 n_out, u32 bits);
 // tree: level 0 = n_leaves digests (already in place, or computed here from the FRI layer `pair_layer` of 2*n_leaves ext4
 // values); builds the upper levels behind it.  Wide levels: one thread per compression (throughput); from 32768 nodes down
@@ -217,7 +224,7 @@ __global__ void challenger_kernel(ChalState* st, const u32* in, u32 n_in, u32* o
 // first); every level keeps its place in the global tree layout, so after an all-gather of the level that holds the segment
 // roots the rest is an ordinary tree over n_leaves / seg nodes.  No Fiat-Shamir step in that case.
 int launch_merkle_levels(u32* tree, u64 n_leaves, cudaStream_t st, u64* launches, ChalState* chal, u32* root_dst, u32* sample_out, u32 n_sample,
-                         const u32* pair_layer, u64 first, u64 seg) {
+                         const u32* pair_layer, u64 first, u64 seg, u32 leaf_arity) {
   u32* lvl = tree;
   u64 n_tot = n_leaves, f = 0, n = n_leaves;
   if (seg && seg < n_leaves) {
@@ -226,7 +233,7 @@ int launch_merkle_levels(u32* tree, u64 n_leaves, cudaStream_t st, u64* launches
   }
   const bool whole = n == n_tot;
   if (pair_layer && n > 32768) {
-    leaf_hash_pairs_kernel<<<nblk(n, 128), 128, 0, st>>>(reinterpret_cast<const uint4*>(pair_layer), n_tot, f, n, tree);
+    leaf_hash_pairs_kernel<<<nblk(n, 128), 128, 0, st>>>(reinterpret_cast<const uint4*>(pair_layer), n_tot, f, n, leaf_arity, tree);
     (*launches)++;
     pair_layer = nullptr;
   }
@@ -243,7 +250,8 @@ int launch_merkle_levels(u32* tree, u64 n_leaves, cudaStream_t st, u64* launches
     const bool last = blocks == 1;
     u32 threads = 16 * (chunk / 2);
     if (threads < 32) threads = 32;
-    merkle_coop_kernel<<<blocks, threads, 0, st>>>(lvl, n_tot, f, chunk, pair_layer, last && whole ? chal : nullptr, root_dst, sample_out, n_sample);
+    merkle_coop_kernel<<<blocks, threads, 0, st>>>(lvl, n_tot, f, chunk, pair_layer, leaf_arity, last && whole ? chal : nullptr, root_dst, sample_out,
+                                                   n_sample);
     (*launches)++;
     pair_layer = nullptr;
     if (last && chal) chal_done = true;
@@ -334,19 +342,19 @@ __global__ void __launch_bounds__(32) challenger_kernel(ChalState* st, const u32
 // one full permutation latency (~9 us) however small it is; this kernel costs ~3 us per level, and wide levels are cut
 // into many 32-node blocks so that all SMs share them.
 // Leaf mode (pair_layer != nullptr): the input level does not exist yet; node i is first computed as the FRI leaf
-// hash(f[i] || f[i + h]) of the ext4 layer and stored as level 0.
+// hash(f[i] || f[i + h] [|| f[i + 2h] || f[i + 3h]]) of the ext4 layer and stored as level 0.
 // When the block reaches the root (single block), warp 0 also runs the Fiat-Shamir step that always follows:
 // copy the root into the proof, observe it, sample `n_sample` field elements.
 #define COOP_MAX_CHUNK 128
 __global__ void __launch_bounds__(16 * COOP_MAX_CHUNK / 2) merkle_coop_kernel(u32* level, u64 n_in, u64 first, u32 chunk,
-                                                                             const u32* __restrict__ pair_layer, ChalState* chal, u32* root_dst,
-                                                                             u32* sample_out, u32 n_sample) {
+                                                                             const u32* __restrict__ pair_layer, u32 leaf_arity, ChalState* chal,
+                                                                             u32* root_dst, u32* sample_out, u32 n_sample) {
   __shared__ u32 buf[2][COOP_MAX_CHUNK * 8];
   const u32 tid = threadIdx.x, lane = tid & 31, l16 = tid & 15, slot = tid >> 4, slots = blockDim.x >> 4;
   // `level` is the start of a whole tree level of n_in nodes; the grid covers the nodes [first, first + gridDim.x * chunk)
   const u64 node0 = first + (u64)blockIdx.x * chunk;
   if (pair_layer) {
-    const u64 h = n_in;  // leaves of this layer = half its length
+    const u64 h = n_in;  // leaves of this layer = its length / arity; the values of leaf i sit at i, i + h, (i + 2h, i + 3h)
     for (u32 s0 = 0; s0 < chunk; s0 += slots) {
       if (s0 + (tid >> 5) * 2 >= chunk) break;
       const u32 sidx = s0 + slot;
@@ -354,6 +362,10 @@ __global__ void __launch_bounds__(16 * COOP_MAX_CHUNK / 2) merkle_coop_kernel(u3
       u32 x = 0;
       if (active && l16 < 8) x = pair_layer[4 * (node0 + sidx + (l16 >= 4 ? h : 0)) + (l16 & 3)];
       x = permute_warp(x, lane);
+      if (leaf_arity == 4) {   // second absorption of the overwrite-mode sponge
+        if (active && l16 < 8) x = pair_layer[4 * (node0 + sidx + (l16 >= 4 ? 3 * h : 2 * h)) + (l16 & 3)];
+        x = permute_warp(x, lane);
+      }
       if (active && l16 < 8) { buf[0][8 * sidx + l16] = x; level[(node0 + sidx) * 8 + l16] = x; }
     }
   } else {

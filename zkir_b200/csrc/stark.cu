@@ -198,10 +198,11 @@ int launch_deep(const DeepArgs& a, cudaStream_t st, u64* launches) {
 
 // ---- FRI fold: out[i] = (f[i]+f[i+h])/2 + beta * (f[i]-f[i+h]) * c * w^-i,  c = 1/(2*shift_r)
 __global__ void __launch_bounds__(256) fri_fold_kernel(const E4* __restrict__ in, E4* __restrict__ out, u64 h, const u32* beta_dev,
-                                                      const u32* __restrict__ inv_w, u32 tw_stride, u32 c_mont) {
+                                                      const u32* __restrict__ inv_w, u32 tw_stride, u32 c_mont, int square_beta) {
   const u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x;
   if (i >= h) return;
   E4 beta; for (int k = 0; k < 4; k++) beta.c[k] = beta_dev[k];
+  if (square_beta) beta = e4_mul(beta, beta);
   const E4 a = ld_e4(in + i), b = ld_e4(in + i + h);
   const u32 half = bb_to_mont_c((BB_P + 1) / 2);
   E4 s = e4_mulb(e4_add(a, b), half);
@@ -209,8 +210,8 @@ __global__ void __launch_bounds__(256) fri_fold_kernel(const E4* __restrict__ in
   st_e4(out + i, e4_add(s, e4_mul(beta, d)));
 }
 int launch_fri_fold(const E4* in, E4* out, u64 h, const u32* beta_dev, const u32* inv_w_table, u32 tw_stride, u32 c_mont,
-                    cudaStream_t st, u64* launches) {
-  fri_fold_kernel<<<nblk(h, 256), 256, 0, st>>>(in, out, h, beta_dev, inv_w_table, tw_stride, c_mont);
+                    cudaStream_t st, u64* launches, int square_beta) {
+  fri_fold_kernel<<<nblk(h, 256), 256, 0, st>>>(in, out, h, beta_dev, inv_w_table, tw_stride, c_mont, square_beta);
   (*launches)++;
   return CHECK_LAUNCH();
 }
@@ -241,13 +242,16 @@ __global__ void __launch_bounds__(128) query_kernel(QueryArgs a) {
   for (u32 k = threadIdx.x; k < 8; k += blockDim.x) out[k] = qrow_mine ? a.qlde[(u64)k * M + qrow] : 0u;
   out += 8;
   copy_path(a.qtree, M, a.log_m, q, out, a.qtree_sl, owns(q, a.qtree_sl), top); out += a.log_m * 8;
-  for (u32 r = 0; r < a.log_n; r++) {
-    const u64 h = (M >> r) / 2, i = q & (h - 1);
-    const u32* lay = reinterpret_cast<const u32*>(a.layers[r]);
-    if (threadIdx.x < 4) out[threadIdx.x] = top ? lay[4 * i + threadIdx.x] : 0u;
-    else if (threadIdx.x < 8) out[threadIdx.x] = top ? lay[4 * (i + h) + threadIdx.x - 4] : 0u;
-    out += 8;
-    copy_path(a.ltrees[r], h, a.log_m - 1 - r, i, out, a.layer_sl[r], owns(i, a.layer_sl[r]), top); out += (a.log_m - 1 - r) * 8;
+  u32 level = 0;
+  for (u32 t = 0; t < a.fri_rounds; t++) {
+    const u32 la = t < a.fold4_rounds ? 2 : 1;                 // log2 of the fold arity of this round
+    const u64 qn = (M >> level) >> la, i = q & (qn - 1);       // leaves of the layer; opened values at i + k*qn
+    const u32* lay = reinterpret_cast<const u32*>(a.layers[level]);
+    if (threadIdx.x < (4u << la)) out[threadIdx.x] = top ? lay[4 * (i + (threadIdx.x >> 2) * qn) + (threadIdx.x & 3)] : 0u;
+    out += 4u << la;
+    const u32 depth = a.log_m - level - la;
+    copy_path(a.ltrees[level], qn, depth, i, out, a.layer_sl[t], owns(i, a.layer_sl[t]), top); out += depth * 8;
+    level += la;
   }
 }
 int launch_queries(const QueryArgs& a, cudaStream_t st, u64* launches) {
