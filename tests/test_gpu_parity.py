@@ -219,7 +219,7 @@ def test_expand_writelog_long_trace(gpu_ctx):
 def test_expand_rows_rejects_unconstrained_opcode(gpu_ctx):
     prog = zkir_b200.assemble("addi r1, r0, 3\nmul r2, r1, r1\nadd r10, r0, r0\necall\n")
     res = zkir_b200.VM(prog, [], zkir_b200.VMConfig(enable_execution_trace=True)).run()
-    d = gpu_ctx.alloc(85 * 4 * 4)
+    d = gpu_ctx.alloc(zkir_b200.air_layout.WIDTH * 4 * 4)
     with pytest.raises(zkir_b200.RuntimeError) as ei:
         gpu_ctx.expand_rows(res.rows(), 2, d)
     gpu_ctx.free(d)

@@ -40,24 +40,26 @@ REG_HI = [None]
 for i in range(1, 16):
     REG_LO.append(col(f"r{i}_lo"))
     REG_HI.append(col(f"r{i}_hi"))
-# opcode selectors; an ECALL row is is_exit + is_read + is_write (no separate column)
-SEL_NAMES = ["s_add", "s_sub", "s_addi", "s_beq", "s_bne", "s_jal", "s_pad"]
+# opcode selectors; an ECALL row is is_exit + is_read + is_write (no separate column), and a padding row is
+# s_pad = 1 - (all other selectors): the last member of every "exactly one" group is a linear expression, not a column
+SEL_NAMES = ["s_add", "s_sub", "s_addi", "s_beq", "s_bne", "s_jal"]
 S = {n: col(n) for n in SEL_NAMES}
-# register indices: index = 4*h + l as a product of two 4-way one-hots (8 columns per operand instead of 16).
-# rd additionally carries rdw[h] = rd_h[h] * (write enable), so that the write-back selector rdw[h]*rd_l[l] is degree 2.
-RD_H = [col(f"rd_h{i}") for i in range(4)]
-RD_L = [col(f"rd_l{i}") for i in range(4)]
-RDW = [col(f"rdw{i}") for i in range(4)]
-RS1_H = [col(f"rs1_h{i}") for i in range(4)]
-RS1_L = [col(f"rs1_l{i}") for i in range(4)]
-RS2_H = [col(f"rs2_h{i}") for i in range(4)]
-RS2_L = [col(f"rs2_l{i}") for i in range(4)]
+# register indices: index = 4*h + l as a product of two 4-way one-hots; entry 3 of each is 1 - (entries 0..2), so an operand
+# costs 6 columns.  rd additionally carries rdw[h] = rd_h[h] * (write enable) for h < 3 (rdw[3] = w - rdw[0] - rdw[1] - rdw[2]),
+# so that the write-back selector rdw[h]*rd_l[l] is degree 2.
+RD_H = [col(f"rd_h{i}") for i in range(3)]
+RD_L = [col(f"rd_l{i}") for i in range(3)]
+RDW = [col(f"rdw{i}") for i in range(3)]
+RS1_H = [col(f"rs1_h{i}") for i in range(3)]
+RS1_L = [col(f"rs1_l{i}") for i in range(3)]
+RS2_H = [col(f"rs2_h{i}") for i in range(3)]
+RS2_L = [col(f"rs2_l{i}") for i in range(3)]
 A_LO, A_HI, B_LO, B_HI, C_LO, C_HI = (col(n) for n in ["a_lo", "a_hi", "b_lo", "b_hi", "c_lo", "c_hi"])
 CARRY0, CARRY1 = col("carry0"), col("carry1")
 INV_LO, INV_HI, NE_LO, NE_HI, TAKEN = (col(n) for n in ["inv_lo", "inv_hi", "ne_lo", "ne_hi", "taken"])
 IS_EXIT, IS_READ, IS_WRITE = col("is_exit"), col("is_read"), col("is_write")
 WIDTH = len(COLS)
-assert WIDTH == 85   # 11 sponge absorptions per Merkle leaf (rate 8)
+assert WIDTH == 77   # 10 sponge absorptions per Merkle leaf (rate 8)
 
 PV_NAMES = ["entry_pc", "num_cycles", "exit_lo", "exit_hi"]
 NUM_PUBLIC = len(PV_NAMES)
@@ -146,34 +148,41 @@ def build():
     TWO20 = 1 << 20
     s = {n: L(S[n]) for n in SEL_NAMES}
     s_ecall = g.tmp(L(IS_EXIT) + L(IS_READ) + L(IS_WRITE), "ecall row (syscall.rs:94-119)")
+    s["s_pad"] = g.tmp(1 - sum_e(s.values()) - s_ecall, "padding row: no other selector set")
 
-    # --- booleans
-    bools = ([S[n] for n in SEL_NAMES] + RD_H + RD_L + RS1_H + RS1_L + RS2_H + RS2_L +
-             [CARRY0, CARRY1, IMM_SIGN, IS_EXIT, IS_READ, IS_WRITE])
-    for b in bools:
+    def onehot(grp, note):
+        """4-way one-hot from 3 columns; the derived entry makes the sum 1 by construction."""
+        xs = [L(i) for i in grp]
+        return xs + [g.tmp(1 - sum_e(xs), note + "[3]")]
+    rd_h, rd_l = onehot(RD_H, "rd.h"), onehot(RD_L, "rd.l")
+    rs1_h, rs1_l = onehot(RS1_H, "rs1.h"), onehot(RS1_L, "rs1.l")
+    rs2_h, rs2_l = onehot(RS2_H, "rs2.h"), onehot(RS2_L, "rs2.l")
+
+    # --- booleans (derived entries included: with the sums fixed to 1 this makes every group exactly-one-hot)
+    for b in [S[n] for n in SEL_NAMES] + [CARRY0, CARRY1, IMM_SIGN, IS_EXIT, IS_READ, IS_WRITE]:
         x = L(b)
         g.emit(x * (x - 1), f"bool {COLS[b]}")
-    # --- one-hot sums
-    g.emit(sum_e(s.values()) + s_ecall - 1, "exactly one opcode selector")
-    for name, grp in (("rd.h", RD_H), ("rd.l", RD_L), ("rs1.h", RS1_H), ("rs1.l", RS1_L), ("rs2.h", RS2_H), ("rs2.l", RS2_L)):
-        g.emit(sum_e(L(i) for i in grp) - 1, f"one-hot {name}")
+    g.emit(s["s_pad"] * (s["s_pad"] - 1), "bool s_pad (derived): exactly one opcode selector")
+    for name, grp in (("rd.h", rd_h), ("rd.l", rd_l), ("rs1.h", rs1_h), ("rs1.l", rs1_l), ("rs2.h", rs2_h), ("rs2.l", rs2_l)):
+        for k, x in enumerate(grp):
+            g.emit(x * (x - 1), f"bool {name}[{k}]")
 
     # --- operand fetch: reg[4h+l] selected by H[h]*L[l]; r0 contributes nothing (state.rs:76-91)
     def fetch(H, Lo, limb, note):
         terms = []
         for h in range(4):
-            inner = [L(Lo[l]) * L(limb[4 * h + l]) for l in range(4) if 4 * h + l != 0]
-            terms.append(L(H[h]) * sum_e(inner))
+            inner = [Lo[l] * L(limb[4 * h + l]) for l in range(4) if 4 * h + l != 0]
+            terms.append(H[h] * sum_e(inner))
         return g.tmp(sum_e(terms), note)
-    rs1_lo = fetch(RS1_H, RS1_L, REG_LO, "rs1.lo")
-    rs1_hi = fetch(RS1_H, RS1_L, REG_HI, "rs1.hi")
-    rs2_lo = fetch(RS2_H, RS2_L, REG_LO, "rs2.lo")
-    rs2_hi = fetch(RS2_H, RS2_L, REG_HI, "rs2.hi")
+    rs1_lo = fetch(rs1_h, rs1_l, REG_LO, "rs1.lo")
+    rs1_hi = fetch(rs1_h, rs1_l, REG_HI, "rs1.hi")
+    rs2_lo = fetch(rs2_h, rs2_l, REG_LO, "rs2.lo")
+    rs2_hi = fetch(rs2_h, rs2_l, REG_HI, "rs2.hi")
     a_lo, a_hi, b_lo, b_hi, c_lo, c_hi = (L(x) for x in (A_LO, A_HI, B_LO, B_HI, C_LO, C_HI))
     g.emit(a_lo - rs1_lo, "a.lo = reg[rs1].lo")
     g.emit(a_hi - rs1_hi, "a.hi = reg[rs1].hi")
     # ADDI has no rs2: the converter selects r0 there, which is enforced, so b = reg[rs2] + addi * imm stays degree 3
-    g.emit(s["s_addi"] * (1 - L(RS2_H[0]) * L(RS2_L[0])), "addi: rs2 selector points at r0")
+    g.emit(s["s_addi"] * (1 - rs2_h[0] * rs2_l[0]), "addi: rs2 selector points at r0")
     g.emit(b_lo - rs2_lo - s["s_addi"] * L(IMM_LO), "b.lo = reg[rs2].lo + addi * imm.lo")
     imm_hi = g.tmp((TWO20 - 1) * L(IMM_SIGN), "imm.hi = sign-extension limb")
     g.emit(b_hi - rs2_hi - s["s_addi"] * imm_hi, "b.hi = reg[rs2].hi + addi * imm.hi")
@@ -187,13 +196,15 @@ def build():
     g.emit(s["s_sub"] * (a_lo - b_lo - c_lo + TWO20 * k0), "sub lo limb (carry0 = borrow)")
     g.emit(s["s_sub"] * (a_hi - b_hi - k0 - c_hi + TWO20 * k1), "sub hi limb")
     g.emit(s["s_jal"] * (c_lo + TWO20 * c_hi - L(PC) - 4), "jal link = pc + 4 (execute.rs:639-647)")
-    g.emit(L(IS_READ) * (L(RD_H[2]) * L(RD_L[2]) - 1), "read writes r10 (syscall.rs:104-109); c = the tape value")
+    g.emit(L(IS_READ) * (rd_h[2] * rd_l[2] - 1), "read writes r10 (syscall.rs:104-109); c = the tape value")
     # --- register write-back, pre-state rows: next.r[i] = (rd == i && w) ? c : r[i]
     w = g.tmp(s["s_add"] + s["s_sub"] + s["s_addi"] + s["s_jal"] + L(IS_READ), "write enable")
-    for h in range(4):
-        g.emit(L(RDW[h]) - L(RD_H[h]) * w, f"rdw{h} = rd.h{h} * write enable")
+    rdw = [L(RDW[h]) for h in range(3)]
+    for h in range(3):
+        g.emit(rdw[h] - rd_h[h] * w, f"rdw{h} = rd.h{h} * write enable")
+    rdw.append(g.tmp(w - sum_e(rdw), "rdw3 = rd.h3 * write enable, implied by the three above"))
     for i in range(1, 16):
-        wi = g.tmp(L(RDW[i >> 2]) * L(RD_L[i & 3]))
+        wi = g.tmp(rdw[i >> 2] * rd_l[i & 3])
         g.emit(trans * (N(REG_LO[i]) - L(REG_LO[i]) - wi * (c_lo - L(REG_LO[i]))), f"write-back r{i}.lo")
         g.emit(trans * (N(REG_HI[i]) - L(REG_HI[i]) - wi * (c_hi - L(REG_HI[i]))), f"write-back r{i}.hi")
     # --- branches: raw equality of both limbs (execute.rs:578-596)
@@ -212,8 +223,9 @@ def build():
     g.emit(trans * (N(PC) - L(PC) - 4 * live - (L(TAKEN) + s["s_jal"]) * (imm_f - 4)), "next pc")
     g.emit(trans * (N(CLK) - L(CLK) - live), "clk counts live rows")
     g.emit(last * (L(CLK) + live - g.PV(1)), "last row: clk (+1 if live) = num_cycles")
-    g.emit(trans * (s["s_pad"] * (1 - N(S["s_pad"]))), "padding is sticky")
-    g.emit(trans * (L(IS_EXIT) * (1 - N(S["s_pad"]))), "exit is followed by padding")
+    n_live = g.tmp(sum_e(N(S[n]) for n in SEL_NAMES) + N(IS_EXIT) + N(IS_READ) + N(IS_WRITE), "1 - next.s_pad")
+    g.emit(trans * (s["s_pad"] * n_live), "padding is sticky")
+    g.emit(trans * (L(IS_EXIT) * n_live), "exit is followed by padding")
     # --- ecall decode (syscall.rs:18-24,94-119): number in r10
     g.emit(L(IS_EXIT) * L(REG_LO[10]), "exit: r10 = 0")
     g.emit(L(IS_READ) * (L(REG_LO[10]) - 1), "read: r10 = 1")
@@ -233,7 +245,7 @@ def build():
 def main():
     g = build()
     hdr = []
-    hdr.append("// GENERATED by tools/gen_air.py -- do not edit.  zkir-b200 core AIR v1 (85 columns).")
+    hdr.append(f"// GENERATED by tools/gen_air.py -- do not edit.  zkir-b200 core AIR v1 ({WIDTH} columns).")
     hdr.append("#pragma once")
     hdr.append(f"#define ZKIR_AIR_WIDTH {WIDTH}")
     hdr.append(f"#define ZKIR_AIR_NUM_CONSTRAINTS {g.idx}")

@@ -81,7 +81,7 @@ struct ExpandArgs {
   u64 T, N;              // live rows, padded rows (power of two)
   u64 final_regs[16];    // state after the last instruction (padding rows, last READ value)
   u64 final_pc;
-  u32* cols;             // out [85][N], canonical
+  u32* cols;             // out [77][N], canonical
   u64* err;              // out: min over offending rows of (row << 8 | reason); ~0 = none
 };
 int launch_trace_expand(const ExpandArgs& a, cudaStream_t st, u64* launches);

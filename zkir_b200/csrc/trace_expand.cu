@@ -1,12 +1,12 @@
-// Device-side trace converter: raw interpreter rows -> the 85 BabyBear columns of the core AIR v1.
+// Device-side trace converter: raw interpreter rows -> the 77 BabyBear columns of the core AIR v1.
 //
 // The reference's hand-off type is `Vec<TraceRow>` -- cycle, pc, instruction word and the PRE-state registers
 // (zkir-spec/src/trace.rs:24-50, recorded at zkir-runtime/src/vm.rs:245-253,302-312); the "converter" that turns rows
 // into field columns is named there (trace.rs:41, vm.rs:243-244) but absent.  zkir_b200/csrc/host/pack.cc is the host
 // restatement; this kernel is the same function with one thread per row, so that only the raw rows (140 B/row instead
-// of 340 B/row of columns) cross PCIe.  The two must agree bit for bit (tests/test_gpu_parity.py::test_expand_*).
+// of 308 B/row of columns) cross PCIe.  The two must agree bit for bit (tests/test_gpu_parity.py::test_expand_*).
 //
-// Bound: HBM writes (340 B/row) -- every store of a warp is one 128 B segment of one column.
+// Bound: HBM writes (308 B/row) -- every store of a warp is one 128 B segment of one column.
 #include <cuda_runtime.h>
 #include "bb.cuh"
 #include "kernels.h"
@@ -104,9 +104,9 @@ __device__ __forceinline__ void expand_row(u64 i, u64 N, u64 T, const u64 (&rg)[
   }
   W(ZKIR_COL_IMM_LO, imm_lo); W(ZKIR_COL_IMM_SIGN, imm_sign);
   W(ZKIR_COL_S_ADD, s_add); W(ZKIR_COL_S_SUB, s_sub); W(ZKIR_COL_S_ADDI, s_addi); W(ZKIR_COL_S_BEQ, s_beq);
-  W(ZKIR_COL_S_BNE, s_bne); W(ZKIR_COL_S_JAL, s_jal); W(ZKIR_COL_S_PAD, s_pad);
+  W(ZKIR_COL_S_BNE, s_bne); W(ZKIR_COL_S_JAL, s_jal);   // s_pad = 1 - (the others) is not a column
 #pragma unroll
-  for (int k = 0; k < 4; k++) {  // register index = 4*h + l, two 4-way one-hots each; rdw[h] = rd_h[h] * writes
+  for (int k = 0; k < 3; k++) {  // register index = 4*h + l, two 4-way one-hots each (entry 3 implied); rdw[h] = rd_h[h] * writes
     W(ZKIR_COL_RD_H0 + k, (rd >> 2) == (u32)k); W(ZKIR_COL_RD_L0 + k, (rd & 3u) == (u32)k);
     W(ZKIR_COL_RDW0 + k, ((rd >> 2) == (u32)k) ? writes : 0u);
     W(ZKIR_COL_RS1_H0 + k, (rs1 >> 2) == (u32)k); W(ZKIR_COL_RS1_L0 + k, (rs1 & 3u) == (u32)k);
