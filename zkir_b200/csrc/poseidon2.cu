@@ -6,6 +6,7 @@
 // round constants are frozen by docs/PROVER_SPEC.md / tools/gen_constants.py.  All values are Montgomery form.
 // Bound: integer ALU (about 770 modular multiplies per permutation), not HBM.
 #include <cuda_runtime.h>
+#include <stdlib.h>
 #include "bb.cuh"
 #include "kernels.h"
 #include "constants_generated.h"
@@ -216,7 +217,7 @@ __global__ void merkle_coop_kernel(u32* level, u64 n_in, u64 first, u32 chunk, c
                                    u32* root_dst, u32* sample_out, u32 n_sample);
 __global__ void challenger_kernel(ChalState* st, const u32* in, u32 n_in, u32* out, u32 n_out, u32 bits);
 // tree: level 0 = n_leaves digests (already in place, or computed here from the FRI layer `pair_layer` of 2*n_leaves ext4
-// values); builds the upper levels behind it.  Wide levels: one thread per compression (throughput); from 32768 nodes down
+// values); builds the upper levels behind it.  Wide levels: one thread per compression (throughput); from 16384 nodes (ZKIR_COOP_MAX) down
 // the cooperative kernel (latency): 32-node blocks climbing 5 levels while the level is wide, one block at the end.
 // If `chal` is given, the launch that produces the root also copies it to root_dst, observes it and samples n_sample
 // elements into sample_out.
@@ -227,17 +228,19 @@ int launch_merkle_levels(u32* tree, u64 n_leaves, cudaStream_t st, u64* launches
                          const u32* pair_layer, u64 first, u64 seg, u32 leaf_arity) {
   u32* lvl = tree;
   u64 n_tot = n_leaves, f = 0, n = n_leaves;
+  static u64 coop_max = 0;   // levels wider than this use one thread per compression (ZKIR_COOP_MAX, power of two >= 256)
+  if (!coop_max) { const char* e = getenv("ZKIR_COOP_MAX"); coop_max = e && atoll(e) >= 256 ? (u64)atoll(e) : 16384; }   // measured best of 1024..65536
   if (seg && seg < n_leaves) {
     if ((seg & (seg - 1)) || first % seg || first + seg > n_leaves) return -1;
     f = first; n = seg; chal = nullptr;
   }
   const bool whole = n == n_tot;
-  if (pair_layer && n > 32768) {
+  if (pair_layer && n > coop_max) {
     leaf_hash_pairs_kernel<<<nblk(n, 128), 128, 0, st>>>(reinterpret_cast<const uint4*>(pair_layer), n_tot, f, n, leaf_arity, tree);
     (*launches)++;
     pair_layer = nullptr;
   }
-  while (n > 32768) {
+  while (n > coop_max) {
     u32* nxt = lvl + n_tot * 8;
     compress_kernel<<<nblk(n / 2, 128), 128, 0, st>>>(reinterpret_cast<const uint4*>(lvl + f * 8), reinterpret_cast<uint4*>(nxt + (f / 2) * 8), n / 2);
     (*launches)++;

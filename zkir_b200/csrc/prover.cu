@@ -591,7 +591,7 @@ static int prove_resident(zkir_ctx* ctx, const zkir_params* p, u32 log_n, const 
     qa.shard_lo = ctx->shard_lo; qa.shard_hi = ctx->shard_hi; qa.ttree_sl = t_sl; qa.qtree_sl = q_sl; qa.lde_sl = sp.on ? t_sl : 0; qa.qlde_sl = sp.on ? q_sl : 0;
     for (u32 r = 0; r < 32; r++) qa.layer_sl[r] = l_sl[r];
     RC(launch_queries(qa, st, LC));
-    if (ctx->comm && comm_all_reduce_sum_u32(ctx->comm, w.proof + L.queries, L.per_query * L.nq, st, &ctx->err) != 0) return ZKIR_ERR_NCCL;
+    if (ctx->comm && L.nq && comm_all_reduce_sum_u32(ctx->comm, w.proof + L.queries, L.per_query * L.nq, st, &ctx->err) != 0) return ZKIR_ERR_NCCL;
     RC(launch_map(w.proof + 8 + np, w.proof + 8 + np, L.total - 8 - np, 0, st, LC));
     CU(cudaMemcpyAsync(w.h_proof, w.proof, L.total * 4, cudaMemcpyDeviceToHost, st));
   }
