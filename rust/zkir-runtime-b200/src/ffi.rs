@@ -53,6 +53,28 @@ extern "C" {
         proof: *mut *mut u8,
         proof_len: *mut usize,
     ) -> c_int;
+    /// register write log: pcs[n] (u32), instrs[n], wlog[n] = (k << 56) | value when the row changed register k, else 0
+    /// (logged where VMState::write_reg runs, zkir-runtime/src/state.rs:76-91); 16 B/row over PCIe, the fastest hand-off
+    pub fn zkir_b200_prove_writelog(
+        ctx: *mut zkir_ctx,
+        params: *const zkir_params,
+        pcs: *const u32,
+        instrs: *const u32,
+        wlog: *const u64,
+        n_rows: u64,
+        final_pc: u64,
+        entry_point: u32,
+        exit_code: u64,
+        log_n: u32,
+        public_values_out: *mut u32, // [4]
+        proof: *mut *mut u8,
+        proof_len: *mut usize,
+    ) -> c_int;
+    /// one proof sharded over several GPUs (one context per GPU): rank 0 draws the id, the host hands it to the other ranks,
+    /// every rank calls comm_init; afterwards the prove_* calls are collective and return the single-GPU proof bytes everywhere
+    pub fn zkir_b200_comm_unique_id(id: *mut u8 /* [128] */) -> c_int;
+    pub fn zkir_b200_comm_init(ctx: *mut zkir_ctx, id: *const u8 /* [128] */, rank: c_int, world: c_int) -> c_int;
+    pub fn zkir_b200_comm_shutdown(ctx: *mut zkir_ctx) -> c_int;
     pub fn zkir_b200_free_proof(p: *mut u8);
     pub fn zkir_b200_verify(params: *const zkir_params, proof: *const u8, len: usize, public_values: *const u32) -> c_int;
 }
