@@ -367,3 +367,27 @@ def test_minimal_programs(gpu_ctx, oracle):
         assert gpu_ctx.prove_writelog(res.writelog(), cfg)[0] == want
         ok, why = zkir_b200.verify(want, cfg, pv)
         assert ok, why
+
+
+def test_small_proofs_replay_a_captured_graph(gpu_ctx, oracle):
+    """Proofs of up to 2^12 rows run as ONE captured CUDA graph from the third proof of a shape on (first: ordinary launches
+    that fill the table caches, second: capture + replay).  Every replay must pick up the new trace / public values / PoW
+    parameter and give the oracle's bytes."""
+    cfg = zkir_b200.ProverConfig(num_queries=12, pow_bits=5)
+    prog = zkir_b200.assemble(ADD_SRC)
+    ctx = zkir_b200.Context(0)
+    try:
+        for i in range(6):
+            res = zkir_b200.VM(prog, [7 * i + 1, i * i], zkir_b200.VMConfig(enable_execution_trace=True)).run()
+            cols, pv = res.pack()
+            if i == 4:
+                cfg = zkir_b200.ProverConfig(num_queries=12, pow_bits=9)   # same workspace shape, different PoW: re-capture
+            got = ctx.prove_columns(cols, pv, cfg)
+            assert got == oracle.prove(cfg, cols, pv), f"proof {i} differs from the oracle"
+        _, cols, pv = fib_trace(205)                                       # 2^10 rows, fast NTT path
+        cfg = zkir_b200.ProverConfig(num_queries=20, pow_bits=6)
+        want = oracle.prove(cfg, cols, pv)
+        for i in range(4):
+            assert ctx.prove_columns(cols, pv, cfg) == want
+    finally:
+        ctx.close()

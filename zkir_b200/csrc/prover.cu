@@ -104,6 +104,13 @@ struct Workspace {
   // sharded proofs: every rank's LDE matrix as mapped into this process (CUDA IPC / peer access), see peer.cu
   PeerPtrs peers[3]; bool peers_valid = false;   // PEER_LDE, PEER_Q, PEER_QLDE
   std::vector<void*> ipc_opened;
+  // small proofs are launch-latency bound (about 100 dependent launches): after one ordinary proof of a shape (which fills every
+  // table cache) the whole H2D -> kernels -> D2H sequence is captured once into a CUDA graph and replayed for later proofs
+  cudaGraphExec_t gexec = nullptr;
+  u32 proofs_done = 0; bool graph_failed = false, graph_run = false;
+  u32 graph_pow_bits = 0;         // the one proving parameter that is not part of the workspace shape
+  u64 graph_launches = 0;         // kernels in one proof of this shape (the launch counter advances by this per replay)
+  u32* h_trace_stage = nullptr;   // pinned, [W][N]: the fixed source address of the graph's H2D node
   u32* xchg = nullptr;       // [ZKIR_MAX_SHARDS][PEER_REC_WORDS] words: handle exchange; word 0 doubles as the barrier token
 };
 
@@ -141,6 +148,8 @@ static void ws_free(zkir_ctx* ctx) {
   Workspace& w = ctx->ws;
   peers_close(ctx);
   for (void* p : w.allocs) cudaFree(p);
+  if (w.gexec) cudaGraphExecDestroy(w.gexec);
+  if (w.h_trace_stage) cudaFreeHost(w.h_trace_stage);
   if (w.h_proof) cudaFreeHost(w.h_proof);
   if (w.h_stage) cudaFreeHost(w.h_stage);
   w = Workspace();
@@ -369,6 +378,21 @@ static int commit_tree(zkir_ctx* ctx, const u32* mat, u32 n_cols, u32 log_b, con
   return 0;
 }
 
+// Host staging of one proof: header words + public values (canonical, copied into the proof) and their Montgomery copies (absorbed
+// by the transcript).  The only per-proof host data of the device part, so a captured graph of prove_resident is replayed
+// after refilling this buffer (and the pinned trace staging).
+static int fill_header_stage(zkir_ctx* ctx, const zkir_params* p, u32 log_n, const u32* pv) {
+  const u32 np = p->num_public;
+  u32* hs = ctx->ws.h_stage;
+  hs[0] = PROOF_MAGIC; hs[1] = PROOF_VERSION; hs[2] = log_n; hs[3] = p->width; hs[4] = p->log_blowup; hs[5] = p->num_queries;
+  hs[6] = p->pow_bits; hs[7] = np;
+  for (u32 i = 0; i < np; i++) { if (pv[i] >= BB_P) { ctx->err = "public value not canonical"; return ZKIR_ERR_ARG; } hs[8 + i] = pv[i]; }
+  u32* hm = hs + 8 + np;  // Montgomery copy for the transcript
+  for (u32 i = 0; i < 6; i++) hm[i] = bb_to_mont_c(hs[2 + i]);
+  for (u32 i = 0; i < np; i++) hm[6 + i] = bb_to_mont_c(pv[i]);
+  return 0;
+}
+
 // the device part of a proof; `trace` = canonical column-major values already on the device
 static int prove_resident(zkir_ctx* ctx, const zkir_params* p, u32 log_n, const u32* pv, const u32* trace) {
   Workspace& w = ctx->ws;
@@ -396,14 +420,10 @@ static int prove_resident(zkir_ctx* ctx, const zkir_params* p, u32 log_n, const 
   u32* c_alpha = w.chal_buf, *c_zeta = w.chal_buf + 4, *c_afri = w.chal_buf + 8, *c_betas = w.chal_buf + 12;
   u32* c_pow_raw = w.chal_buf + 12 + 4 * R, *c_pow_sample = c_pow_raw + 1, *c_hdr = c_pow_raw + 2;
 
-  // ---- header + public values
+  // ---- header + public values (host staging filled by fill_header_stage: also the per-proof step of a graph replay)
+  { int frc = fill_header_stage(ctx, p, log_n, pv); if (frc) return frc; }
   u32* hs = w.h_stage;
-  hs[0] = PROOF_MAGIC; hs[1] = PROOF_VERSION; hs[2] = log_n; hs[3] = p->width; hs[4] = p->log_blowup; hs[5] = p->num_queries;
-  hs[6] = p->pow_bits; hs[7] = np;
-  for (u32 i = 0; i < np; i++) { if (pv[i] >= BB_P) { ctx->err = "public value not canonical"; return ZKIR_ERR_ARG; } hs[8 + i] = pv[i]; }
   u32* hm = hs + 8 + np;  // Montgomery copy for the transcript
-  for (u32 i = 0; i < 6; i++) hm[i] = bb_to_mont_c(hs[2 + i]);
-  for (u32 i = 0; i < np; i++) hm[6 + i] = bb_to_mont_c(pv[i]);
   CU(cudaMemcpyAsync(w.proof, hs, (8 + np) * 4, cudaMemcpyHostToDevice, st));
   CU(cudaMemcpyAsync(c_hdr, hm, (6 + np) * 4, cudaMemcpyHostToDevice, st));
   CU(cudaMemsetAsync(w.chal, 0, sizeof(ChalState), st));
@@ -606,8 +626,12 @@ static int finish_proof(zkir_ctx* ctx, const zkir_params* p, u32 log_n, uint8_t*
   if (!out) { ctx->err = "malloc"; return ZKIR_ERR_OOM; }
   memcpy(out, ctx->ws.h_proof, L.total * 4);
   *proof = out; *proof_len = L.total * 4;
-  for (int s = 0; s < ZKIR_STAGE_COUNT; s++) cudaEventElapsedTime(&ctx->stage_ms[s], ctx->ev[s], ctx->ev[s + 1]);
-  ctx->have_stage = true;
+  if (ctx->ws.graph_run) {   // the stage events of a replayed graph are not re-recorded
+    ctx->have_stage = false;
+  } else {
+    for (int s = 0; s < ZKIR_STAGE_COUNT; s++) cudaEventElapsedTime(&ctx->stage_ms[s], ctx->ev[s], ctx->ev[s + 1]);
+    ctx->have_stage = true;
+  }
   return 0;
 }
 
@@ -677,9 +701,49 @@ int zkir_b200_prove(zkir_ctx* ctx, const zkir_params* p, const uint32_t* trace_c
   if (rc) return rc;
   if (!trace_cols || !pv || !proof || !proof_len) { ctx->err = "null argument"; return ZKIR_ERR_ARG; }
   if ((rc = ws_prepare(ctx, p, log_n)) != 0) return rc;
+  Workspace& w = ctx->ws;
+  const size_t trace_bytes = ((size_t)p->width << log_n) * 4;
+  w.graph_run = false;
+  static const int graph_max_log_n = getenv("ZKIR_GRAPH_MAX_LOG_N") ? atoi(getenv("ZKIR_GRAPH_MAX_LOG_N")) : 12;   // 0 disables
+  if ((int)log_n <= graph_max_log_n && !ctx->comm && ctx->shards == 1 && !w.graph_failed && w.proofs_done >= 1) {
+    if (!w.h_trace_stage) CU(cudaMallocHost(&w.h_trace_stage, trace_bytes));
+    memcpy(w.h_trace_stage, trace_cols, trace_bytes);
+    if (w.gexec && w.graph_pow_bits != p->pow_bits) { cudaGraphExecDestroy(w.gexec); w.gexec = nullptr; }
+    if (!w.gexec) {
+      // capture once; thread-local mode: other contexts (prove_batch workers) keep allocating and launching meanwhile
+      cudaGraph_t graph = nullptr;
+      const u64 launches_before = ctx->launches;
+      CU(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+      cudaError_t ce = cudaMemcpyAsync(w.trace, w.h_trace_stage, trace_bytes, cudaMemcpyHostToDevice, ctx->stream);
+      rc = ce == cudaSuccess ? prove_resident(ctx, p, log_n, pv, w.trace) : ZKIR_ERR_CUDA;
+      cudaError_t ee = cudaStreamEndCapture(ctx->stream, &graph);
+      w.graph_launches = ctx->launches - launches_before;
+      ctx->launches = launches_before;   // nothing ran yet: the replay below counts
+      w.graph_pow_bits = p->pow_bits;
+      if (rc == 0 && ee == cudaSuccess && graph && cudaGraphInstantiate(&w.gexec, graph, 0) == cudaSuccess) {
+        cudaGraphDestroy(graph);
+      } else {                     // fall back to ordinary launches for this shape (still the CUDA path, never a CPU path)
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        w.gexec = nullptr; w.graph_failed = true;
+        if (rc == ZKIR_ERR_ARG) return rc;
+      }
+    }
+    if (w.gexec) {
+      if ((rc = fill_header_stage(ctx, p, log_n, pv)) != 0) return rc;
+      CU(cudaGraphLaunch(w.gexec, ctx->stream));
+      ctx->launches += w.graph_launches;
+      w.graph_run = true;
+      w.proofs_done++;
+      return finish_proof(ctx, p, log_n, proof, proof_len);
+    }
+  }
+  const u64 l0 = ctx->launches;
   CU(cudaEventRecord(ctx->ev[ZKIR_STAGE_H2D], ctx->stream));
-  CU(cudaMemcpyAsync(ctx->ws.trace, trace_cols, ((size_t)p->width << log_n) * 4, cudaMemcpyHostToDevice, ctx->stream));
-  if ((rc = prove_resident(ctx, p, log_n, pv, ctx->ws.trace)) != 0) return rc;
+  CU(cudaMemcpyAsync(w.trace, trace_cols, trace_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  if ((rc = prove_resident(ctx, p, log_n, pv, w.trace)) != 0) return rc;
+  w.graph_launches = ctx->launches - l0;
+  w.proofs_done++;
   return finish_proof(ctx, p, log_n, proof, proof_len);
 }
 
