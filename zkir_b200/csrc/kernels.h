@@ -22,6 +22,9 @@ int ntt_run(NttTables* tb, const u32* d_in, u64 in_col_stride, u32* d_out, u64 o
             u32 n_cols, int log_n, bool inverse, int log_pad, const u32* in_scale, const u32* out_scale,
             u32 out_const_mont, bool use_out_const, cudaStream_t st);
 
+#define ZKIR_MAX_SHARDS 64
+struct PeerPtrs { u32* p[ZKIR_MAX_SHARDS]; };   // base of every rank's matrix as seen from this device (own entry included)
+
 // ---- ntt_fast.cu (register radix-32 tiles, digit-reversed coefficients, coset-major LDE)
 struct FastNtt;
 struct FastPlan { int log_n, nd, d[4]; };   // digit bits, top to bottom in the memory position
@@ -31,8 +34,12 @@ bool fast_plan(int log_n, FastPlan* out);   // false when log_n < 8 (callers use
 u64 fast_plan_coef_index(const FastPlan& pl, u64 pos);
 int fast_intt(FastNtt* f, const FastPlan& pl, const u32* in, u64 in_col, u32* coef, u64 coef_col, u32 n_cols, u32 c0_canon,
               const uint2* coef_tab, u32 split_log, u32 split_max, u32 split_extra, u32* split_out, u64 split_out_col, cudaStream_t st);
+// Sharded proofs (peers != nullptr): the LAST pass stores every output row straight into the matrix of the rank that owns the row
+// (rows [g*nj, (g+1)*nj) of every coset, plus the halo row (g+1)*nj mod N) through the peer pointers instead of into `out`; `out`
+// must lie inside the matrix whose base is peers->p[me].  Requires G <= 2^(top digit), see fast_coset_ntt_can_fuse.
 int fast_coset_ntt(FastNtt* f, const FastPlan& pl, const u32* coef, u64 coef_col, u32* out, u64 out_col, u32 n_cols, u32 nz,
-                   u32 base_canon, u32 zroot_canon, u32 c0_canon, cudaStream_t st);
+                   u32 base_canon, u32 zroot_canon, u32 c0_canon, cudaStream_t st, const PeerPtrs* peers = nullptr, u32 me = 0, u32 G = 1);
+bool fast_coset_ntt_can_fuse(const FastPlan& pl, u32 G);
 int fast_ntt_natural(FastNtt* f, int log_n, bool inverse, u32 coset_shift, const u32* in, u64 in_col, u32* tmp, u32* out, u64 out_col,
                      u32 n_cols, cudaStream_t st);
 int launch_coset_reorder(const u32* in, u32* out, u32 n_cols, u32 log_n, u32 log_b, int to_natural, cudaStream_t st, u64* launches);
@@ -99,8 +106,6 @@ u64 trace_expand_wl_scratch_ints(u64 N);
 int launch_trace_expand_wl(const WlArgs& a, cudaStream_t st, u64* launches);
 
 // ---- peer.cu: rows of the column-sharded LDE stored straight into the peers' matrices (NVLink peer memory)
-#define ZKIR_MAX_SHARDS 64
-struct PeerPtrs { u32* p[ZKIR_MAX_SHARDS]; };   // base of every rank's LDE matrix as seen from this device (own entry included)
 int launch_lde_scatter(const u32* lde, const PeerPtrs& peers, u32 me, u32 G, u32 c_lo, u32 n_cols, u64 N, u32 B, u64 nj, cudaStream_t st,
                        u64* launches);
 

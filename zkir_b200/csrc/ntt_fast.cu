@@ -86,6 +86,11 @@ struct TileParams {
   const uint2* in_tab;  u32 in_tab_z, in_tab_mask;    // (w, wq) at ((input offset inside the column) & mask) + z * in_tab_z
   const uint2* out_tab; u32 out_tab_z, out_tab_mask;  // same for the (pre-split) output offset
   const uint2* tw_mid;         // [2^a][2^b]: w_R^(+-ks*q)
+  // MODE 0, last pass of a sharded LDE: output row r of a coset goes to peer.p[r >> peer_log_nj] (and, if r is the first row of a
+  // segment, also to the previous rank as its halo row) at the same matrix offset; peer_shift = log2(rows per segment / digit
+  // stride), 0xffffffff = plain store into `out`
+  u32 peer_shift, peer_mask;   // peer_mask = G - 1
+  PeerPtrs peer;               // already offset like `out` relative to the own matrix
 };
 
 // MODE 0: lanes contiguous on both sides (in_t = out_t = 1, in_r = out_k = digit stride): a strided digit.
@@ -161,6 +166,23 @@ dft_tile_kernel(const TileParams p) {
     }
     u32* po = out + (out_off0 + thr);
     const size_t kstep = (size_t)KSTEP * out_k;
+    if (MODE == 0 && p.peer_shift != 0xffffffffu) {
+      // fused redistribution: digit index k = ks + KSTEP*brev(j) decides the owner of the row; (out_off0 + thr) < stride never carries
+      const size_t moff = (size_t)(po - p.out);
+      const bool low0 = (out_off0 + lane) == 0;   // this thread's rows are multiples of the digit stride
+      const u32 seg_mask = (1u << p.peer_shift) - 1;
+#pragma unroll
+      for (int j = 0; j < CNT; j++) {
+        const u32 k = ks_thr + KSTEP * brev<LC>(j);
+        const u32 dest = k >> p.peer_shift;
+        p.peer.p[dest][moff + brev<LC>(j) * kstep] = y[j];
+        if (low0 && (k & seg_mask) == 0) {
+          const u32 prev = (dest - 1) & p.peer_mask;
+          if (prev != dest) p.peer.p[prev][moff + brev<LC>(j) * kstep] = y[j];
+        }
+      }
+      return;
+    }
     if (p.out_tab) {
       // row mode: the table follows the input layout of the row, otherwise the output layout
       const u32 toff = MODE == 1 ? (in_off0 + lane * p.in_t + ks_thr) : (out_off0 + thr);
@@ -406,11 +428,12 @@ u64 fast_plan_coef_index(const FastPlan& pl, u64 pos) { return plan_coef_index(t
 
 #define FCHECK(e) do { if ((e) != cudaSuccess) return -2; } while (0)
 
-static void no_split(TileParams& p) { p.split_log = 32; p.split_max = 0; p.split_extra = 0; }
+static void no_split(TileParams& p) { p.split_log = 32; p.split_max = 0; p.split_extra = 0; p.peer_shift = 0xffffffffu; p.peer_mask = 0; }
 
 // strided pass over digit j (0-based) of `pl`, in place or in -> out with identical layouts
 static int strided_pass(FastNtt* f, const FastPlan& pl, int j, bool inv, const u32* in, u64 in_col, u64 in_z, u32* out, u64 out_col, u64 out_z,
-                        u32 n_cols, u32 nz, const uint2* out_tab, u32 out_tab_mask, const uint2* in_tab, u32 in_tab_mask, cudaStream_t st) {
+                        u32 n_cols, u32 nz, const uint2* out_tab, u32 out_tab_mask, const uint2* in_tab, u32 in_tab_mask, cudaStream_t st,
+                        const PeerPtrs* peers = nullptr, u32 me = 0, u32 G = 1) {
   int log_stride = 0;
   for (int i = j + 1; i < pl.nd; i++) log_stride += pl.d[i];
   const int log_block = log_stride + pl.d[j];
@@ -428,6 +451,16 @@ static int strided_pass(FastNtt* f, const FastPlan& pl, int j, bool inv, const u
   p.out_tab = out_tab; p.out_tab_mask = out_tab_mask;
   p.tw_mid = f->tw_mid(pl.d[j], inv);
   if (!p.tw_mid) return -4;
+  if (peers) {   // only the top digit spans all row segments: rows per segment = 2^(log_n) / G = 2^peer_shift digit strides
+    if (j != 0 || out_tab) return -1;
+    int log_g = 0;
+    while ((1u << log_g) < G) log_g++;
+    if (log_g > pl.d[0]) return -1;
+    p.peer_shift = (u32)(pl.d[0] - log_g);
+    p.peer_mask = G - 1;
+    const ptrdiff_t rel = out - peers->p[me];
+    for (u32 g = 0; g < G; g++) p.peer.p[g] = peers->p[g] + rel;
+  }
   FCHECK(launch_tile(pl.d[j], 0, inv, p, n_cols * p.tiles_per_col, nz, st));
   (*f->launches)++;
   return 0;
@@ -447,7 +480,7 @@ static int row_pass(FastNtt* f, const FastPlan& pl, bool inv, const u32* in, u64
   p.out_k = 1;
   if (split_log < 32) { p.out_b = 16u << split_log; p.out_t = 1u << split_log; }
   else { p.out_b = 16 * m; p.out_t = m; }
-  p.split_log = split_log; p.split_max = split_max; p.split_extra = split_extra;
+  p.split_log = split_log; p.split_max = split_max; p.split_extra = split_extra; p.peer_shift = 0xffffffffu; p.peer_mask = 0;
   p.in_tab = in_tab; p.in_tab_z = in_tab_z; p.in_tab_mask = 0xffffffffu;
   p.out_tab = out_tab; p.out_tab_mask = out_tab_mask;
   p.tw_mid = f->tw_mid(dl, inv);
@@ -482,8 +515,10 @@ int fast_intt(FastNtt* f, const FastPlan& pl, const u32* in, u64 in_col, u32* co
 
 // Forward transforms on nz cosets from digit-reversed coefficients: out[col][z][i] = sum_k coef[k] (base*zroot^z)^k w_N^(ik) * c0
 // coef layout [n_cols][N] (column stride coef_col), out column stride out_col, coset stride N.
+bool fast_coset_ntt_can_fuse(const FastPlan& pl, u32 G) { return G >= 2 && (G & (G - 1)) == 0 && G <= (1u << pl.d[0]) && G <= ZKIR_MAX_SHARDS; }
+
 int fast_coset_ntt(FastNtt* f, const FastPlan& pl, const u32* coef, u64 coef_col, u32* out, u64 out_col, u32 n_cols, u32 nz,
-                   u32 base, u32 zroot, u32 c0, cudaStream_t st) {
+                   u32 base, u32 zroot, u32 c0, cudaStream_t st, const PeerPtrs* peers, u32 me, u32 G) {
   const u64 N = 1ull << pl.log_n;
   const uint2* sc = f->scale(to_digit_plan(pl), base, zroot, nz, c0);
   if (!sc) return -4;
@@ -507,7 +542,7 @@ int fast_coset_ntt(FastNtt* f, const FastPlan& pl, const u32* coef, u64 coef_col
       if (!tw) return -4;
       mask = (u32)((1ull << log_up) - 1);
     }
-    int rc = strided_pass(f, pl, j, false, out, out_col, N, out, out_col, N, n_cols, nz, tw, mask, nullptr, 0, st);
+    int rc = strided_pass(f, pl, j, false, out, out_col, N, out, out_col, N, n_cols, nz, tw, mask, nullptr, 0, st, j == 0 ? peers : nullptr, me, G);
     if (rc) return rc;
     log_rest = log_block;
   }

@@ -414,7 +414,7 @@ static int prove_resident(zkir_ctx* ctx, const zkir_params* p, u32 log_n, const 
     sp.planes_per = (4 + sp.G - 1) / sp.G;
   }
   const bool p2p = sp.on && ctx->comm != nullptr;
-  static const bool lde_via_nccl = getenv("ZKIR_LDE_EXCHANGE") && !strcmp(getenv("ZKIR_LDE_EXCHANGE"), "nccl");
+  static const int lde_mode = !getenv("ZKIR_LDE_EXCHANGE") ? 0 : (!strcmp(getenv("ZKIR_LDE_EXCHANGE"), "nccl") ? 2 : (!strcmp(getenv("ZKIR_LDE_EXCHANGE"), "scatter") ? 1 : 0));
   if (p2p && !w.peers_valid) { int xrc = peers_open(ctx); if (xrc) return xrc; }
   const u32 me = p2p ? (u32)comm_rank(ctx->comm) : 0;
   u32* c_alpha = w.chal_buf, *c_zeta = w.chal_buf + 4, *c_afri = w.chal_buf + 8, *c_betas = w.chal_buf + 12;
@@ -432,21 +432,24 @@ static int prove_resident(zkir_ctx* ctx, const zkir_params* p, u32 log_n, const 
   CU(cudaEventRecord(ctx->ev[ZKIR_STAGE_LDE], st));
   const u32 c0 = hmul(hinv((u32)(N % BB_P)), (u32)((1ull << 32) % BB_P));  // R/N: scales by 1/N and lifts to Montgomery form
   if (sp.on) {
-    // column-sharded: this rank transforms only its W/G columns, then the rows are redistributed
+    // column-sharded: this rank transforms only its W/G columns, and the rows go to their owners.  Default: FUSED -- the last pass
+    // of the coset NTT stores every output row straight into the owner's matrix over NVLink (ntt_fast.cu, TileParams::peer), no
+    // separate copy; ZKIR_LDE_EXCHANGE=scatter: plain LDE + one scatter kernel (peer.cu); =nccl: plain LDE + grouped ncclSend/Recv.
+    // A one-word all-reduce is the barrier that orders every rank's peer stores before every rank's reads.
+    const bool fuse_t = p2p && lde_mode == 0 && fast_coset_ntt_can_fuse(w.plan_n, sp.G);
     for (u32 g = sp.lo; g < sp.hi; g++) {
       const u32 k0 = sp.c_lo(g), nc = sp.c_hi(g) - k0;
       if (!nc) continue;
       RC(fast_intt(ctx->fast, w.plan_n, trace + (u64)k0 * N, N, w.coef + (u64)k0 * N, N, nc, c0, nullptr, 32, 0, 0, nullptr, 0, st));
-      RC(fast_coset_ntt(ctx->fast, w.plan_n, w.coef + (u64)k0 * N, N, w.lde + (u64)k0 * M, M, nc, B, shift, ZKIR_BB_ROOTS[log_m], 1u, st));
+      RC(fast_coset_ntt(ctx->fast, w.plan_n, w.coef + (u64)k0 * N, N, w.lde + (u64)k0 * M, M, nc, B, shift, ZKIR_BB_ROOTS[log_m], 1u, st,
+                        fuse_t ? &w.peers[PEER_LDE] : nullptr, me, sp.G));
     }
     if (ctx->comm) {
-      // rows -> owners.  Default: one kernel storing into the peers' matrices over NVLink, then a one-word all-reduce as the
-      // barrier that orders every rank's stores before every rank's reads.  ZKIR_LDE_EXCHANGE=nccl: grouped ncclSend/ncclRecv.
-      if (lde_via_nccl) {
+      if (lde_mode == 2) {
         int xrc = exchange_lde_rows(ctx, sp, w.lde, N, B);
         if (xrc) return xrc;
       } else {
-        RC(launch_lde_scatter(w.lde, w.peers[PEER_LDE], me, sp.G, sp.c_lo(me), sp.c_hi(me) - sp.c_lo(me), N, B, sp.nj, st, LC));
+        if (!fuse_t) RC(launch_lde_scatter(w.lde, w.peers[PEER_LDE], me, sp.G, sp.c_lo(me), sp.c_hi(me) - sp.c_lo(me), N, B, sp.nj, st, LC));
         int brc = peers_barrier(ctx); if (brc) return brc;
       }
     }
@@ -502,15 +505,17 @@ static int prove_resident(zkir_ctx* ctx, const zkir_params* p, u32 log_n, const 
     const u32 split_log = (u32)w.plan_chunk.d[w.plan_chunk.nd - 1];
     if (sp.on) {
       // plane-sharded: a rank transforms its planes (2 quotient columns each), then the rows go to their owners like the trace LDE
+      const bool fuse_q = p2p && lde_mode == 0 && fast_coset_ntt_can_fuse(w.plan_chunk, sp.G);
       for (u32 g = sp.lo; g < sp.hi; g++) {
         const u32 p0 = sp.p_lo(g), npl = sp.p_hi(g) - p0;
         if (!npl) continue;
         RC(fast_intt(ctx->fast, w.plan_m, w.q + (u64)p0 * M, M, w.q + (u64)p0 * M, M, npl, hinv((u32)(M % BB_P)), unshift, split_log, 2, (u32)N,
                      w.qcoef + (u64)p0 * 2 * N, 2 * N, st));
-        RC(fast_coset_ntt(ctx->fast, w.plan_chunk, w.qcoef + (u64)p0 * 2 * N, N, w.qlde + (u64)p0 * 2 * M, M, 2 * npl, B, shift, ZKIR_BB_ROOTS[log_m], 1u, st));
+        RC(fast_coset_ntt(ctx->fast, w.plan_chunk, w.qcoef + (u64)p0 * 2 * N, N, w.qlde + (u64)p0 * 2 * M, M, 2 * npl, B, shift, ZKIR_BB_ROOTS[log_m], 1u, st,
+                          fuse_q ? &w.peers[PEER_QLDE] : nullptr, me, sp.G));
       }
       if (p2p) {
-        RC(launch_lde_scatter(w.qlde, w.peers[PEER_QLDE], me, sp.G, 2 * sp.p_lo(me), 2 * (sp.p_hi(me) - sp.p_lo(me)), N, B, sp.nj, st, LC));
+        if (!fuse_q) RC(launch_lde_scatter(w.qlde, w.peers[PEER_QLDE], me, sp.G, 2 * sp.p_lo(me), 2 * (sp.p_hi(me) - sp.p_lo(me)), N, B, sp.nj, st, LC));
         int brc = peers_barrier(ctx); if (brc) return brc;
       }
     } else {
