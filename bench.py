@@ -99,6 +99,8 @@ def cpu_oracle_run(fib_n, steps, warmup):
     import zkir_b200
     cycles, cols, pv, _ = make_trace(fib_n)
     o = Oracle()
+    # all host cores, whatever OMP_NUM_THREADS the launcher exported (torchrun sets it to 1); `cores` = the team size in effect
+    cores = int(o.l.oracle_set_threads(len(os.sched_getaffinity(0))))
     cfg = zkir_b200.ProverConfig()
     for _ in range(warmup):
         o.prove(cfg, cols, pv)
@@ -106,7 +108,6 @@ def cpu_oracle_run(fib_n, steps, warmup):
     for _ in range(steps):
         o.prove(cfg, cols, pv)
     dt = (time.time() - t0) / steps
-    cores = len(os.sched_getaffinity(0))
     return cycles / dt, dt, cores, cycles, int(cols.shape[1]).bit_length() - 1
 
 

@@ -17,6 +17,9 @@
 #include <string.h>
 #include <stdio.h>
 #include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 #include <algorithm>
 #include "constants_generated.h"
 #include "air_generated.h"
@@ -456,6 +459,16 @@ static int prove(const Params& p, const u32* trace, u32 log_n, const u32* pv, u3
 
 // ------------------------------------------------------------------ C entry points (ctypes)
 extern "C" {
+// OpenMP team size of the oracle (launchers such as torchrun export OMP_NUM_THREADS=1); returns the value in effect
+int oracle_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+  return omp_get_max_threads();
+#else
+  (void)n;
+  return 1;
+#endif
+}
 void oracle_ntt(u32* a, int logn, int inverse) { ntt_inplace(a, logn, inverse != 0); }
 void oracle_ntt_batch(u32* a, int ncols, int logn, int inverse) {
 #pragma omp parallel for
