@@ -90,6 +90,7 @@ struct ExpandArgs {
   u64 final_pc;
   u32* cols;             // out [77][N], canonical
   u64* err;              // out: min over offending rows of (row << 8 | reason); ~0 = none
+  u32 col_lo = 0, col_hi = 0xffffffffu;   // only columns [col_lo, col_hi) are written (sharded proofs: the rank's own share)
 };
 int launch_trace_expand(const ExpandArgs& a, cudaStream_t st, u64* launches);
 struct WlArgs {          // register write log instead of full rows (trace_expand.cu)
@@ -101,6 +102,7 @@ struct WlArgs {          // register write log instead of full rows (trace_expan
   int* chunk_prev;       // scratch, trace_expand_wl_scratch_ints(N) ints
   u32* cols;
   u64* err;
+  u32 col_lo = 0, col_hi = 0xffffffffu;
 };
 u64 trace_expand_wl_scratch_ints(u64 N);
 int launch_trace_expand_wl(const WlArgs& a, cudaStream_t st, u64* launches);

@@ -270,6 +270,27 @@ struct ShardPlan {
   u32 c_hi(u32 g) const { const u32 c = (g + 1) * cols_per; return c < W ? c : W; }
 };
 
+// the plan of one proof; needs the workspace of that shape (ws_prepare) for `fast`
+static ShardPlan make_shard_plan(const zkir_ctx* ctx, const zkir_params* p, u32 log_n) {
+  const u64 N = 1ull << log_n, M = N << p->log_blowup, W = p->width;
+  ShardPlan sp;
+  sp.G = ctx->shards; sp.lo = ctx->shard_lo; sp.hi = ctx->shard_hi; sp.W = (u32)W;
+  if (sp.G > 1 && ctx->ws.fast && N >= sp.G && M / sp.G >= ctx->shard_min_seg && M / sp.G >= 2) {
+    sp.on = true;
+    sp.nj = N / sp.G;
+    while ((1ull << sp.log_nj) < sp.nj) sp.log_nj++;
+    sp.cols_per = (u32)((W + sp.G - 1) / sp.G);
+    sp.planes_per = (4 + sp.G - 1) / sp.G;
+  }
+  return sp;
+}
+// columns of the trace this context has to materialise: all of them, or -- sharded proof with a communicator -- its own share
+static void trace_col_range(const zkir_ctx* ctx, const zkir_params* p, u32 log_n, u32* lo, u32* hi) {
+  *lo = 0; *hi = p->width;
+  const ShardPlan sp = make_shard_plan(ctx, p, log_n);
+  if (sp.on && ctx->comm) { const u32 me = (u32)comm_rank(ctx->comm); *lo = sp.c_lo(me); *hi = sp.c_hi(me); }
+}
+
 // After the column-sharded LDE every rank holds whole columns [c_lo, c_hi) of the coset-major matrix [W][B][N]; this moves, for
 // every column, the rows each OTHER rank needs (its points j0..j0+nj of every coset plus the one halo row the quotient reads
 // as "next row") into the same place of that rank's matrix: (G-1)/G of a rank's W/G columns leave it, i.e. about 1/G of the matrix
@@ -404,15 +425,7 @@ static int prove_resident(zkir_ctx* ctx, const zkir_params* p, u32 log_n, const 
   const u32 shift = ZKIR_BB_GEN;
   const u32 B = 1u << p->log_blowup;
   if (!w.fast) RC(ensure_ntt_tmp(ctx, M));
-  ShardPlan sp;
-  sp.G = ctx->shards; sp.lo = ctx->shard_lo; sp.hi = ctx->shard_hi; sp.W = (u32)W;
-  if (sp.G > 1 && w.fast && N >= sp.G && M / sp.G >= ctx->shard_min_seg && M / sp.G >= 2) {
-    sp.on = true;
-    sp.nj = N / sp.G;
-    while ((1ull << sp.log_nj) < sp.nj) sp.log_nj++;
-    sp.cols_per = (u32)((W + sp.G - 1) / sp.G);
-    sp.planes_per = (4 + sp.G - 1) / sp.G;
-  }
+  const ShardPlan sp = make_shard_plan(ctx, p, log_n);
   const bool p2p = sp.on && ctx->comm != nullptr;
   static const int lde_mode = !getenv("ZKIR_LDE_EXCHANGE") ? 0 : (!strcmp(getenv("ZKIR_LDE_EXCHANGE"), "nccl") ? 2 : (!strcmp(getenv("ZKIR_LDE_EXCHANGE"), "scatter") ? 1 : 0));
   if (p2p && !w.peers_valid) { int xrc = peers_open(ctx); if (xrc) return xrc; }
@@ -768,7 +781,7 @@ int zkir_b200_prove_device(zkir_ctx* ctx, const zkir_params* p, const uint32_t* 
 
 // H2D of the raw rows + the device converter; columns land in d_cols
 static int expand_rows(zkir_ctx* ctx, const uint64_t* pcs, const uint32_t* instrs, const uint64_t* regs, uint64_t T, const uint64_t* final_regs,
-                       uint64_t final_pc, uint32_t log_n, u32* d_cols) {
+                       uint64_t final_pc, uint32_t log_n, u32* d_cols, u32 col_lo = 0, u32 col_hi = 0xffffffffu) {
   const u64 N = 1ull << log_n;
   if (T > N || !pcs || !instrs || !regs || !final_regs) { ctx->err = "bad rows: need n_rows <= 2^log_n and non-null arrays"; return ZKIR_ERR_ARG; }
   const size_t need = T * (8 + 4 + 128) + 64;
@@ -791,7 +804,7 @@ static int expand_rows(zkir_ctx* ctx, const uint64_t* pcs, const uint32_t* instr
   ExpandArgs ea;
   ea.pcs = d_pcs; ea.ins = d_ins; ea.regs = d_regs; ea.T = T; ea.N = N;
   for (int k = 0; k < 16; k++) ea.final_regs[k] = final_regs[k];
-  ea.final_pc = final_pc; ea.cols = d_cols; ea.err = ctx->d_err;
+  ea.final_pc = final_pc; ea.cols = d_cols; ea.err = ctx->d_err; ea.col_lo = col_lo; ea.col_hi = col_hi;
   RC(launch_trace_expand(ea, st, &ctx->launches));
   CU(cudaMemcpyAsync(ctx->h_err, ctx->d_err, 8, cudaMemcpyDeviceToHost, st));
   return 0;
@@ -817,7 +830,9 @@ int zkir_b200_prove_rows(zkir_ctx* ctx, const zkir_params* p, const uint64_t* pc
   if (!pv_out || !proof || !proof_len) { ctx->err = "null argument"; return ZKIR_ERR_ARG; }
   if ((rc = ws_prepare(ctx, p, log_n)) != 0) return rc;
   CU(cudaEventRecord(ctx->ev[ZKIR_STAGE_H2D], ctx->stream));
-  if ((rc = expand_rows(ctx, pcs, instrs, regs, n_rows, final_regs, final_pc, log_n, ctx->ws.trace)) != 0) return rc;
+  u32 c_lo, c_hi;
+  trace_col_range(ctx, p, log_n, &c_lo, &c_hi);   // a sharded proof only materialises the columns this rank transforms
+  if ((rc = expand_rows(ctx, pcs, instrs, regs, n_rows, final_regs, final_pc, log_n, ctx->ws.trace, c_lo, c_hi)) != 0) return rc;
   const u64 LIMB = (1u << 20) - 1;
   pv_out[0] = entry_point; pv_out[1] = (u32)(n_rows % BB_P); pv_out[2] = (u32)(exit_code & LIMB); pv_out[3] = (u32)((exit_code >> 20) & LIMB);
   if ((rc = prove_resident(ctx, p, log_n, pv_out, ctx->ws.trace)) != 0) return rc;
@@ -828,7 +843,7 @@ int zkir_b200_prove_rows(zkir_ctx* ctx, const zkir_params* p, const uint64_t* pc
 
 // write-log flavour: H2D of (pc32, word, wlog) + last-writer scan + converter
 static int expand_writelog(zkir_ctx* ctx, const uint32_t* pcs, const uint32_t* instrs, const uint64_t* wlog, uint64_t T, uint64_t final_pc,
-                           uint32_t log_n, u32* d_cols) {
+                           uint32_t log_n, u32* d_cols, u32 col_lo = 0, u32 col_hi = 0xffffffffu) {
   const u64 N = 1ull << log_n;
   if (T > N || !pcs || !instrs || !wlog) { ctx->err = "bad write log: need n_rows <= 2^log_n and non-null arrays"; return ZKIR_ERR_ARG; }
   // Sharded proof (collective call, every rank holds the same log in host memory): each rank uploads only ITS row segment over
@@ -869,7 +884,7 @@ static int expand_writelog(zkir_ctx* ctx, const uint32_t* pcs, const uint32_t* i
   }
   CU(cudaMemsetAsync(ctx->d_err, 0xff, 8, st));
   WlArgs wa;
-  wa.pcs = d_pcs; wa.ins = d_ins; wa.wlog = d_wlog; wa.T = T; wa.N = N; wa.final_pc = final_pc; wa.chunk_prev = d_scr; wa.cols = d_cols; wa.err = ctx->d_err;
+  wa.pcs = d_pcs; wa.ins = d_ins; wa.wlog = d_wlog; wa.T = T; wa.N = N; wa.final_pc = final_pc; wa.chunk_prev = d_scr; wa.cols = d_cols; wa.err = ctx->d_err; wa.col_lo = col_lo; wa.col_hi = col_hi;
   RC(launch_trace_expand_wl(wa, st, &ctx->launches));
   CU(cudaMemcpyAsync(ctx->h_err, ctx->d_err, 8, cudaMemcpyDeviceToHost, st));
   return 0;
@@ -886,7 +901,9 @@ int zkir_b200_prove_writelog(zkir_ctx* ctx, const zkir_params* p, const uint32_t
   if (!pv_out || !proof || !proof_len) { ctx->err = "null argument"; return ZKIR_ERR_ARG; }
   if ((rc = ws_prepare(ctx, p, log_n)) != 0) return rc;
   CU(cudaEventRecord(ctx->ev[ZKIR_STAGE_H2D], ctx->stream));
-  if ((rc = expand_writelog(ctx, pcs, instrs, wlog, n_rows, final_pc, log_n, ctx->ws.trace)) != 0) return rc;
+  u32 c_lo, c_hi;
+  trace_col_range(ctx, p, log_n, &c_lo, &c_hi);   // a sharded proof only materialises the columns this rank transforms
+  if ((rc = expand_writelog(ctx, pcs, instrs, wlog, n_rows, final_pc, log_n, ctx->ws.trace, c_lo, c_hi)) != 0) return rc;
   const u64 LIMB = (1u << 20) - 1;
   pv_out[0] = entry_point; pv_out[1] = (u32)(n_rows % BB_P); pv_out[2] = (u32)(exit_code & LIMB); pv_out[3] = (u32)((exit_code >> 20) & LIMB);
   if ((rc = prove_resident(ctx, p, log_n, pv_out, ctx->ws.trace)) != 0) return rc;

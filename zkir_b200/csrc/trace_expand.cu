@@ -17,7 +17,8 @@ namespace zkir {
 __device__ __forceinline__ int sext_dev(u32 v, int bits) { const int sh = 32 - bits; return ((int)(v << sh)) >> sh; }
 
 // One row: rg = PRE-state registers, w = instruction word, read_val = post-state r10 (only used by READ rows).
-__device__ __forceinline__ void expand_row(u64 i, u64 N, u64 T, const u64 (&rg)[16], u64 pc, u32 w, u64 read_val, u32* cols, u64* errp) {
+__device__ __forceinline__ void expand_row(u64 i, u64 N, u64 T, const u64 (&rg)[16], u64 pc, u32 w, u64 read_val, u32* cols, u64* errp,
+                                           u32 col_lo, u32 col_hi) {
   const u64 LIMB = (1u << 20) - 1, M40 = (1ull << 40) - 1;
   const bool live = i < T;
   u32 err = 0;
@@ -25,7 +26,7 @@ __device__ __forceinline__ void expand_row(u64 i, u64 N, u64 T, const u64 (&rg)[
 #pragma unroll
   for (int k = 1; k < 16; k++) if (rg[k] >> 40) err = 2;
   u32* col = cols + i;
-  auto W = [&](int c, u32 v) { col[(u64)c * N] = v; };
+  auto W = [&](int c, u32 v) { if ((u32)c >= col_lo && (u32)c < col_hi) col[(u64)c * N] = v; };
 
   W(ZKIR_COL_CLK, (u32)((live ? i : T) % BB_P));
   W(ZKIR_COL_PC, (u32)pc);
@@ -133,7 +134,7 @@ __global__ void __launch_bounds__(128) trace_expand_kernel(ExpandArgs a) {
 #pragma unroll
   for (int k = 0; k < 16; k++) rg[k] = live ? a.regs[16 * i + k] : a.final_regs[k];
   const u64 read_val = (i + 1 < a.T) ? a.regs[16 * (i + 1) + 10] : a.final_regs[10];
-  expand_row(i, a.N, a.T, rg, live ? a.pcs[i] : a.final_pc, live ? a.ins[i] : 0u, read_val, a.cols, a.err);
+  expand_row(i, a.N, a.T, rg, live ? a.pcs[i] : a.final_pc, live ? a.ins[i] : 0u, read_val, a.cols, a.err, a.col_lo, a.col_hi);
 }
 
 // ---- write-log input: rebuild the pre-state registers with a last-writer scan.
@@ -216,7 +217,7 @@ __global__ void __launch_bounds__(WL_CHUNK) trace_expand_wl_kernel(WlArgs a) {
   const bool live = i < a.T;
   // READ rows need the post-state r10: the logged value if the row changed r10, else the unchanged pre-state
   const u64 read_val = kw == 10u ? (wl & M40) : rg[10];
-  expand_row(i, a.N, a.T, rg, live ? (u64)a.pcs[i] : a.final_pc, live ? a.ins[i] : 0u, read_val, a.cols, a.err);
+  expand_row(i, a.N, a.T, rg, live ? (u64)a.pcs[i] : a.final_pc, live ? a.ins[i] : 0u, read_val, a.cols, a.err, a.col_lo, a.col_hi);
 }
 
 int launch_trace_expand(const ExpandArgs& a, cudaStream_t st, u64* launches) {
