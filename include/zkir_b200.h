@@ -30,7 +30,7 @@ extern "C" {
 #define ZKIR_ERR_VERIFY (-7)
 
 #define ZKIR_BABYBEAR_P 2013265921u
-#define ZKIR_AIR_V1_WIDTH 77u
+#define ZKIR_AIR_V1_WIDTH 72u
 #define ZKIR_AIR_V1_NUM_PUBLIC 4u
 
 /* ---- proving parameters (the reference has none; Plonky3's FriConfig fields) */
@@ -80,7 +80,7 @@ int zkir_b200_prove_writelog(zkir_ctx*, const zkir_params*, const uint32_t* pcs,
                              uint32_t* public_values_out, uint8_t** proof, size_t* proof_len);
 int zkir_b200_expand_writelog(zkir_ctx*, const uint32_t* pcs, const uint32_t* instrs, const uint64_t* wlog, uint64_t n_rows,
                               uint64_t final_pc, uint32_t log_n, uint32_t* d_cols);
-/* the device converter alone (parity tests): rows -> d_cols [77][1 << log_n] canonical, device memory */
+/* the device converter alone (parity tests): rows -> d_cols [72][1 << log_n] canonical, device memory */
 int zkir_b200_expand_rows(zkir_ctx*, const uint64_t* pcs, const uint32_t* instrs, const uint64_t* regs, uint64_t n_rows,
                           const uint64_t* final_regs, uint64_t final_pc, uint32_t log_n, uint32_t* d_cols);
 /* many independent small proofs (BASELINE config 4); traces[i] is host memory [width][1<<log_ns[i]] */

@@ -37,7 +37,7 @@ class Oracle:
         return a.ctypes.data_as(C.c_void_p)
 
     def params(self, cfg):
-        return np.array([cfg.log_blowup, cfg.num_queries, cfg.pow_bits, 77, 4], dtype=np.uint32)
+        return np.array([cfg.log_blowup, cfg.num_queries, cfg.pow_bits, 72, 4], dtype=np.uint32)
 
     def ntt(self, cols, inverse=False):
         a = np.ascontiguousarray(cols, dtype=np.uint32).copy()

@@ -56,10 +56,14 @@ RS2_H = [col(f"rs2_h{i}") for i in range(3)]
 RS2_L = [col(f"rs2_l{i}") for i in range(3)]
 A_LO, A_HI, B_LO, B_HI, C_LO, C_HI = (col(n) for n in ["a_lo", "a_hi", "b_lo", "b_hi", "c_lo", "c_hi"])
 CARRY0, CARRY1 = col("carry0"), col("carry1")
-INV_LO, INV_HI, NE_LO, NE_HI, TAKEN = (col(n) for n in ["inv_lo", "inv_hi", "ne_lo", "ne_hi", "taken"])
+# Branch rows have no result, no carries and no destination register, so their helper values live in the cells the other row
+# kinds use for those (every constraint on these cells is gated by the row kind):
+#   c_lo / c_hi      = inverses of the limb differences a - b            (ALU / JAL / READ rows: the result limbs)
+#   carry0 / carry1  = flags "limb differs"                               (ADD / SUB / ADDI rows: carry / borrow)
+#   rd_l[1]          = branch taken (B-type words have no rd field)       (writing rows: a bit of the rd index)
 IS_EXIT, IS_READ, IS_WRITE = col("is_exit"), col("is_read"), col("is_write")
 WIDTH = len(COLS)
-assert WIDTH == 77   # 10 sponge absorptions per Merkle leaf (rate 8)
+assert WIDTH == 72   # 9 sponge absorptions per Merkle leaf (rate 8)
 
 PV_NAMES = ["entry_pc", "num_cycles", "exit_lo", "exit_hi"]
 NUM_PUBLIC = len(PV_NAMES)
@@ -210,17 +214,17 @@ def build():
     # --- branches: raw equality of both limbs (execute.rs:578-596)
     d_lo = g.tmp(a_lo - b_lo)
     d_hi = g.tmp(a_hi - b_hi)
-    ne_lo, ne_hi = L(NE_LO), L(NE_HI)
+    ne_lo, ne_hi, inv_lo, inv_hi, taken = k0, k1, c_lo, c_hi, rd_l[1]   # shared cells, see the column layout
     br = g.tmp(s["s_beq"] + s["s_bne"], "branch row")
-    g.emit(br * (ne_lo - d_lo * L(INV_LO)), "branch: ne.lo = d.lo * inv.lo")
+    g.emit(br * (ne_lo - d_lo * inv_lo), "branch: ne.lo = d.lo * inv.lo")
     g.emit(br * (d_lo * (1 - ne_lo)), "branch: d.lo != 0 -> ne.lo = 1")
-    g.emit(br * (ne_hi - d_hi * L(INV_HI)), "branch: ne.hi = d.hi * inv.hi")
+    g.emit(br * (ne_hi - d_hi * inv_hi), "branch: ne.hi = d.hi * inv.hi")
     g.emit(br * (d_hi * (1 - ne_hi)), "branch: d.hi != 0 -> ne.hi = 1")
     ne = g.tmp(ne_lo + ne_hi - ne_lo * ne_hi, "a != b")
-    g.emit(L(TAKEN) - s["s_bne"] * ne - s["s_beq"] * (1 - ne), "branch taken")
+    g.emit(s["s_bne"] * (taken - ne) + s["s_beq"] * (taken - 1 + ne), "branch taken (exactly one selector is set on a row)")
     # --- pc / clk / padding
     live = g.tmp(1 - s["s_pad"])
-    g.emit(trans * (N(PC) - L(PC) - 4 * live - (L(TAKEN) + s["s_jal"]) * (imm_f - 4)), "next pc")
+    g.emit(trans * (N(PC) - L(PC) - 4 * live - (br * taken + s["s_jal"]) * (imm_f - 4)), "next pc")
     g.emit(trans * (N(CLK) - L(CLK) - live), "clk counts live rows")
     g.emit(last * (L(CLK) + live - g.PV(1)), "last row: clk (+1 if live) = num_cycles")
     n_live = g.tmp(sum_e(N(S[n]) for n in SEL_NAMES) + N(IS_EXIT) + N(IS_READ) + N(IS_WRITE), "1 - next.s_pad")

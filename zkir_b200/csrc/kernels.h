@@ -88,7 +88,7 @@ struct ExpandArgs {
   u64 T, N;              // live rows, padded rows (power of two)
   u64 final_regs[16];    // state after the last instruction (padding rows, last READ value)
   u64 final_pc;
-  u32* cols;             // out [77][N], canonical
+  u32* cols;             // out [72][N], canonical
   u64* err;              // out: min over offending rows of (row << 8 | reason); ~0 = none
   u32 col_lo = 0, col_hi = 0xffffffffu;   // only columns [col_lo, col_hi) are written (sharded proofs: the rank's own share)
 };

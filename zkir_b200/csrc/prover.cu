@@ -249,7 +249,7 @@ static int ws_prepare(zkir_ctx* ctx, const zkir_params* p, u32 log_n) {
 static int check_params(zkir_ctx* ctx, const zkir_params* p, u32 log_n) {
   if (!p || p->width != ZKIR_AIR_WIDTH || p->num_public != ZKIR_AIR_NUM_PUBLIC || p->log_blowup < 1 || p->log_blowup > 4 ||
       log_n < 2 || log_n + p->log_blowup > 27 || p->pow_bits > 30 || p->num_queries > 4096) {
-    ctx->err = "bad params: need width=77, num_public=4, 1<=log_blowup<=4, 2<=log_n, log_n+log_blowup<=27, pow_bits<=30";
+    ctx->err = "bad params: need width=72, num_public=4, 1<=log_blowup<=4, 2<=log_n, log_n+log_blowup<=27, pow_bits<=30";
     return ZKIR_ERR_ARG;
   }
   return 0;

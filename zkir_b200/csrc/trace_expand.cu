@@ -1,12 +1,12 @@
-// Device-side trace converter: raw interpreter rows -> the 77 BabyBear columns of the core AIR v1.
+// Device-side trace converter: raw interpreter rows -> the 72 BabyBear columns of the core AIR v1.
 //
 // The reference's hand-off type is `Vec<TraceRow>` -- cycle, pc, instruction word and the PRE-state registers
 // (zkir-spec/src/trace.rs:24-50, recorded at zkir-runtime/src/vm.rs:245-253,302-312); the "converter" that turns rows
 // into field columns is named there (trace.rs:41, vm.rs:243-244) but absent.  zkir_b200/csrc/host/pack.cc is the host
 // restatement; this kernel is the same function with one thread per row, so that only the raw rows (140 B/row instead
-// of 308 B/row of columns) cross PCIe.  The two must agree bit for bit (tests/test_gpu_parity.py::test_expand_*).
+// of 288 B/row of columns) cross PCIe.  The two must agree bit for bit (tests/test_gpu_parity.py::test_expand_*).
 //
-// Bound: HBM writes (308 B/row) -- every store of a warp is one 128 B segment of one column.
+// Bound: HBM writes (288 B/row) -- every store of a warp is one 128 B segment of one column.
 #include <cuda_runtime.h>
 #include "bb.cuh"
 #include "kernels.h"
@@ -39,7 +39,8 @@ __device__ __forceinline__ void expand_row(u64 i, u64 N, u64 T, const u64 (&rg)[
   u64 av = 0, bv = 0, cv = 0;
   long long imm = 0;
   bool has_imm = false;
-  u32 carry0 = 0, carry1 = 0, inv_lo = 0, inv_hi = 0, ne_lo = 0, ne_hi = 0, taken = 0;
+  u32 carry0 = 0, carry1 = 0, inv_lo = 0, inv_hi = 0, taken = 0;
+  bool is_branch = false;
   if (!live) {
     s_pad = 1;
   } else {
@@ -90,10 +91,13 @@ __device__ __forceinline__ void expand_row(u64 i, u64 N, u64 T, const u64 (&rg)[
       carry0 = (u32)k0; carry1 = (u32)(a_hi < b_hi + k0);
     }
     if (op == 0x40 || op == 0x41) {
+      // a branch row has no result, no carries and no destination register: the inverses live in the c cells, the "limb differs"
+      // flags in the carry cells and `taken` in rd_l[1] (tools/gen_air.py, column layout)
       const u32 d_lo = bb_sub((u32)a_lo, (u32)b_lo), d_hi = bb_sub((u32)a_hi, (u32)b_hi);
-      ne_lo = d_lo != 0; ne_hi = d_hi != 0;
+      const u32 ne_lo = d_lo != 0, ne_hi = d_hi != 0;
       inv_lo = d_lo ? bb_from_mont(bb_inv(bb_to_mont(d_lo))) : 0;
       inv_hi = d_hi ? bb_from_mont(bb_inv(bb_to_mont(d_hi))) : 0;
+      is_branch = true; carry0 = ne_lo; carry1 = ne_hi;
       const u32 ne = ne_lo | ne_hi;
       taken = op == 0x41 ? ne : !ne;
     }
@@ -108,16 +112,15 @@ __device__ __forceinline__ void expand_row(u64 i, u64 N, u64 T, const u64 (&rg)[
   W(ZKIR_COL_S_BNE, s_bne); W(ZKIR_COL_S_JAL, s_jal);   // s_pad = 1 - (the others) is not a column
 #pragma unroll
   for (int k = 0; k < 3; k++) {  // register index = 4*h + l, two 4-way one-hots each (entry 3 implied); rdw[h] = rd_h[h] * writes
-    W(ZKIR_COL_RD_H0 + k, (rd >> 2) == (u32)k); W(ZKIR_COL_RD_L0 + k, (rd & 3u) == (u32)k);
+    W(ZKIR_COL_RD_H0 + k, (rd >> 2) == (u32)k); W(ZKIR_COL_RD_L0 + k, ((taken ? 1u : (rd & 3u))) == (u32)k);
     W(ZKIR_COL_RDW0 + k, ((rd >> 2) == (u32)k) ? writes : 0u);
     W(ZKIR_COL_RS1_H0 + k, (rs1 >> 2) == (u32)k); W(ZKIR_COL_RS1_L0 + k, (rs1 & 3u) == (u32)k);
     W(ZKIR_COL_RS2_H0 + k, (rs2 >> 2) == (u32)k); W(ZKIR_COL_RS2_L0 + k, (rs2 & 3u) == (u32)k);
   }
   W(ZKIR_COL_A_LO, (u32)(av & LIMB)); W(ZKIR_COL_A_HI, (u32)(av >> 20));
   W(ZKIR_COL_B_LO, (u32)(bv & LIMB)); W(ZKIR_COL_B_HI, (u32)(bv >> 20));
-  W(ZKIR_COL_C_LO, (u32)(cv & LIMB)); W(ZKIR_COL_C_HI, (u32)(cv >> 20));
+  W(ZKIR_COL_C_LO, is_branch ? inv_lo : (u32)(cv & LIMB)); W(ZKIR_COL_C_HI, is_branch ? inv_hi : (u32)(cv >> 20));
   W(ZKIR_COL_CARRY0, carry0); W(ZKIR_COL_CARRY1, carry1);
-  W(ZKIR_COL_INV_LO, inv_lo); W(ZKIR_COL_INV_HI, inv_hi); W(ZKIR_COL_NE_LO, ne_lo); W(ZKIR_COL_NE_HI, ne_hi); W(ZKIR_COL_TAKEN, taken);
   W(ZKIR_COL_IS_EXIT, is_exit); W(ZKIR_COL_IS_READ, is_read); W(ZKIR_COL_IS_WRITE, is_write);
   if (err) {  // first offending row wins; the host reports it after the stream is drained
     const unsigned long long packed = (i << 8) | err;
