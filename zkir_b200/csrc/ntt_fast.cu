@@ -104,7 +104,9 @@ struct TileShape {
   static constexpr int SMEM_WORDS = B_ == 0 ? 0 : (MODE == 2 ? 16 * (R + 1) : (MODE == 1 ? 16 * ROW_PITCH : 16 * R));
 };
 
-template <int LOG_R, int MODE, bool INV, int LOG_S>
+// PEER: the fused row redistribution of a sharded LDE (TileParams::peer); a separate instantiation so that the ordinary kernels
+// keep their code and register allocation.
+template <int LOG_R, int MODE, bool INV, int LOG_S, bool PEER = false>
 __global__ void __launch_bounds__(TileShape<LOG_R, MODE>::NT, (LOG_R >= 10 ? 2 : (LOG_R >= 8 ? 4 : 8)))
 dft_tile_kernel(const TileParams p) {
   typedef TileShape<LOG_R, MODE> SH;
@@ -166,7 +168,7 @@ dft_tile_kernel(const TileParams p) {
     }
     u32* po = out + (out_off0 + thr);
     const size_t kstep = (size_t)KSTEP * out_k;
-    if (MODE == 0 && p.peer_shift != 0xffffffffu) {
+    if constexpr (PEER) {
       // fused redistribution: digit index k = ks + KSTEP*brev(j) decides the owner of the row; (out_off0 + thr) < stride never carries
       const size_t moff = (size_t)(po - p.out);
       const bool low0 = (out_off0 + lane) == 0;   // this thread's rows are multiples of the digit stride
@@ -253,11 +255,11 @@ dft_tile_kernel(const TileParams p) {
   }
 }
 
-template <int LOG_R, int MODE, bool INV, int LOG_S = -1>
+template <int LOG_R, int MODE, bool INV, int LOG_S = -1, bool PEER = false>
 static cudaError_t launch_tile_t(const TileParams& p, u32 blocks, u32 z, cudaStream_t st) {
   typedef TileShape<LOG_R, MODE> SH;
   const size_t smem = (size_t)SH::SMEM_WORDS * sizeof(u32);
-  auto kern = dft_tile_kernel<LOG_R, MODE, INV, LOG_S>;
+  auto kern = dft_tile_kernel<LOG_R, MODE, INV, LOG_S, PEER>;
   if (smem > 48 * 1024) {  // per device and cheap: set it on every launch rather than caching a process-wide flag
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -269,6 +271,21 @@ static cudaError_t launch_tile_t(const TileParams& p, u32 blocks, u32 z, cudaStr
 }
 template <int MODE, bool INV>
 static cudaError_t launch_tile_m(int log_r, const TileParams& p, u32 blocks, u32 z, cudaStream_t st) {
+  if constexpr (MODE == 0 && !INV) {
+    if (p.peer_shift != 0xffffffffu) {   // last pass of a sharded LDE: top digits are 4..10 bits wide
+      if (log_r == 10 && p.in_r == 1024u) return launch_tile_t<10, 0, false, 10, true>(p, blocks, z, st);
+      switch (log_r) {
+        case 4: return launch_tile_t<4, 0, false, -1, true>(p, blocks, z, st);
+        case 5: return launch_tile_t<5, 0, false, -1, true>(p, blocks, z, st);
+        case 6: return launch_tile_t<6, 0, false, -1, true>(p, blocks, z, st);
+        case 7: return launch_tile_t<7, 0, false, -1, true>(p, blocks, z, st);
+        case 8: return launch_tile_t<8, 0, false, -1, true>(p, blocks, z, st);
+        case 9: return launch_tile_t<9, 0, false, -1, true>(p, blocks, z, st);
+        case 10: return launch_tile_t<10, 0, false, -1, true>(p, blocks, z, st);
+      }
+      return cudaErrorInvalidValue;
+    }
+  }
   // hot shape of a 2^20-row trace (digits 10+10): strided digit with a compile-time stride of 2^10
   if (MODE == 0 && log_r == 10 && p.in_r == 1024u) return launch_tile_t<10, MODE, INV, (MODE == 0 ? 10 : -1)>(p, blocks, z, st);
   switch (log_r) {
