@@ -3,6 +3,7 @@
 // elements are stored AoS (16 B, uint4 loads).  No reference counterpart; the maths is
 // docs/PROVER_SPEC.md sections "Openings", "FRI" and "Queries".
 #include <cuda_runtime.h>
+#include <stdlib.h>
 #include "bb.cuh"
 #include "kernels.h"
 
@@ -59,15 +60,17 @@ int launch_ext_powers(const u32* base_ext, u32 mul_const, const FastPlan& plan, 
 }
 
 // ---- openings: out1[k] = sum_j coef[k][j]*U1[j], out2[k] = sum_j coef[k][j]*U2[j]
-// Block = 8 warps x 2 columns = 16 columns over OPEN_ROWS rows: lane = row (128 B coalesced column reads), warp = column
+// Block = 8 warps x OPEN_COLS columns over OPEN_ROWS rows: lane = row (128 B coalesced column reads), warp = column
 // group, so the eight warps read the SAME 32 B/row of U1/U2 and seven of them hit L1.  Lazy 64-bit accumulators (bb.cuh).
-#define OPEN_COLS 2
+// The kernel is latency-bound (few warps, long dependent accumulation chains): one column per warp at 64 registers and
+// 4 CTAs/SM measured faster than two columns per warp at 80 registers and 2 CTAs/SM (ZKIR_OPEN_VARIANT=1).
 #define OPEN_WARPS 8
 #define OPEN_THREADS (32 * OPEN_WARPS)
-#define OPEN_ROWS 2048
-__global__ void __launch_bounds__(OPEN_THREADS, 2) open_partial_kernel(const u32* __restrict__ coef, u64 col_stride, u32 n_cols, u64 n,
-                                                                   const E4* __restrict__ U1, const E4* __restrict__ U2,
-                                                                   E4* partial, u32 n_chunks) {
+#define OPEN_ROWS_MIN 512   // smallest row chunk of any variant: sizes the partial-sum scratch
+template <int OPEN_COLS, int OPEN_ROWS, int UNROLL, int MINB>
+__global__ void __launch_bounds__(OPEN_THREADS, MINB) open_partial_kernel(const u32* __restrict__ coef, u64 col_stride, u32 n_cols, u64 n,
+                                                                      const E4* __restrict__ U1, const E4* __restrict__ U2,
+                                                                      E4* partial, u32 n_chunks) {
   const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5, chunk = blockIdx.x;
   const u32 k0 = (blockIdx.y * OPEN_WARPS + warp) * OPEN_COLS;
   if (k0 >= n_cols) return;
@@ -75,7 +78,7 @@ __global__ void __launch_bounds__(OPEN_THREADS, 2) open_partial_kernel(const u32
 #pragma unroll
   for (int c = 0; c < OPEN_COLS; c++) { l1[c] = acc4_zero(); l2[c] = acc4_zero(); }
   const u64 j0 = (u64)chunk * OPEN_ROWS + lane;
-#pragma unroll 4
+#pragma unroll UNROLL
   for (int r = 0; r < OPEN_ROWS / 32; r++) {
     const u64 j = j0 + (u64)r * 32;
     if (j < n) {
@@ -120,16 +123,28 @@ __global__ void open_final_kernel(const E4* partial, u32 n_cols, u32 n_chunks, E
   }
   if (threadIdx.x == 0) { if (id < n_cols) st_e4(out1 + id, acc); else st_e4(out2 + (id - n_cols), acc); }
 }
+template <int COLS, int ROWS, int UNROLL, int MINB>
+static void launch_open_t(const u32* coef, u64 col_stride, u32 n_cols, u64 n, const E4* U1, const E4* U2, E4* partial, u32* n_chunks_out, cudaStream_t st) {
+  const u32 n_chunks = (u32)((n + ROWS - 1) / ROWS);
+  dim3 grid(n_chunks, (n_cols + COLS * OPEN_WARPS - 1) / (COLS * OPEN_WARPS));
+  open_partial_kernel<COLS, ROWS, UNROLL, MINB><<<grid, OPEN_THREADS, 0, st>>>(coef, col_stride, n_cols, n, U1, U2, partial, n_chunks);
+  *n_chunks_out = n_chunks;
+}
 int launch_open(const u32* coef, u64 col_stride, u32 n_cols, u64 n, const E4* U1, const E4* U2, E4* out1, E4* out2,
                 E4* partial_scratch, cudaStream_t st, u64* launches) {
-  const u32 n_chunks = (u32)((n + OPEN_ROWS - 1) / OPEN_ROWS);
-  dim3 grid(n_chunks, (n_cols + OPEN_COLS * OPEN_WARPS - 1) / (OPEN_COLS * OPEN_WARPS));
-  open_partial_kernel<<<grid, OPEN_THREADS, 0, st>>>(coef, col_stride, n_cols, n, U1, U2, partial_scratch, n_chunks);
+  static int variant = -1;   // ZKIR_OPEN_VARIANT: experiments, 0 = default
+  if (variant < 0) { const char* e = getenv("ZKIR_OPEN_VARIANT"); variant = e ? atoi(e) : 0; }
+  u32 n_chunks = 0;
+  switch (variant) {   // measured on the 2^20-row proof (openings stage): 0.80 / 0.98 / 0.81 ms
+    case 1: launch_open_t<2, 2048, 4, 2>(coef, col_stride, n_cols, n, U1, U2, partial_scratch, &n_chunks, st); break;   // two columns per warp, 80 registers
+    case 2: launch_open_t<1, 1024, 4, 4>(coef, col_stride, n_cols, n, U1, U2, partial_scratch, &n_chunks, st); break;
+    default: launch_open_t<1, 2048, 4, 4>(coef, col_stride, n_cols, n, U1, U2, partial_scratch, &n_chunks, st); break;  // one column per warp, 64 registers, 4 CTAs/SM
+  }
   open_final_kernel<<<2 * n_cols, 32, 0, st>>>(partial_scratch, n_cols, n_chunks, out1, out2);
   (*launches) += 2;
   return CHECK_LAUNCH();
 }
-u64 open_scratch_elems(u32 n_cols, u64 n) { return 2ull * n_cols * ((n + OPEN_ROWS - 1) / OPEN_ROWS); }
+u64 open_scratch_elems(u32 n_cols, u64 n) { return 2ull * n_cols * ((n + OPEN_ROWS_MIN - 1) / OPEN_ROWS_MIN); }
 
 // ---- DEEP combination
 // scratch layout: afp[0..width) = alpha^k, then [width+0]=A1, +1=A2, +2=A3, +3=alpha^W, +4=alpha^2W
