@@ -175,6 +175,16 @@ static void merkle_build(u32* tree, size_t nleaves) {
   }
 }
 static const u32* merkle_root(const u32* tree, size_t nleaves) { return tree + (2 * nleaves - 2) * 8; }
+// digest of a long message for the transcript (docs/PROVER_SPEC.md section 2, `hash_tree`): chunks of 8 words are leaves
+// (last one may be short), padded with all-zero digests to a power of two, Merkle root.  Log-depth instead of a serial sponge.
+static void hash_tree(const u32* words, size_t n, u32* digest) {
+  size_t chunks = (n + 7) / 8, leaves = 1;
+  while (leaves < chunks) leaves <<= 1;
+  std::vector<u32> tree((2 * leaves - 1) * 8, 0);
+  for (size_t c = 0; c < chunks; c++) hash_elems(words + 8 * c, n - 8 * c < 8 ? n - 8 * c : 8, &tree[c * 8]);
+  merkle_build(tree.data(), leaves);
+  memcpy(digest, merkle_root(tree.data(), leaves), 32);
+}
 static void merkle_path(const u32* tree, size_t nleaves, size_t idx, u32* out) {
   const u32* lvl = tree;
   for (size_t n = nleaves; n > 1; n >>= 1) { memcpy(out, lvl + ((idx ^ 1) * 8), 32); out += 8; lvl += n * 8; idx >>= 1; }
@@ -339,7 +349,11 @@ static int prove(const Params& p, const u32* trace, u32 log_n, const u32* pv, u3
   for (size_t k = 0; k < W; k++) { memcpy(out, ot[k].c, 16); out += 4; }
   for (size_t k = 0; k < W; k++) { memcpy(out, otg[k].c, 16); out += 4; }
   for (int k = 0; k < 8; k++) { memcpy(out, oq[k].c, 16); out += 4; }
-  ch.observe_n(out - (2 * W + 8) * 4, (2 * W + 8) * 4);
+  {
+    u32 od[8];
+    hash_tree(out - (2 * W + 8) * 4, (2 * W + 8) * 4, od);   // the transcript absorbs the tree hash of the opened values
+    ch.observe_n(od, 8);
+  }
 
   // ---- 4. FRI input: batched DEEP quotients on the coset
   E4 af = ch.sample_ext();

@@ -104,6 +104,17 @@ void hash_n(const u32* in, size_t n, u32* d) {
   memcpy(d, s, 32);
 }
 void compress2(const u32* l, const u32* r, u32* d) { u32 s[16]; memcpy(s, l, 32); memcpy(s + 8, r, 32); permute(s); memcpy(d, s, 32); }
+// transcript digest of a long message (docs/PROVER_SPEC.md section 2, `hash_tree`): 8-word chunks are leaves, zero digests pad
+// the leaf level to a power of two, the Merkle root is the digest
+void hash_tree(const u32* words, size_t n, u32* digest) {
+  size_t chunks = (n + 7) / 8, leaves = 1;
+  while (leaves < chunks) leaves <<= 1;
+  std::vector<u32> lvl(leaves * 8, 0);
+  for (size_t c = 0; c < chunks; c++) hash_n(words + 8 * c, n - 8 * c < 8 ? n - 8 * c : 8, &lvl[8 * c]);
+  for (size_t m = leaves; m > 1; m >>= 1)
+    for (size_t i = 0; i < m / 2; i++) { u32 d[8]; compress2(&lvl[16 * i], &lvl[16 * i + 8], d); memcpy(&lvl[8 * i], d, 32); }
+  memcpy(digest, lvl.data(), 32);
+}
 bool check_path(const u32* leaf_digest, u64 idx, const u32* path, u32 depth, const u32* root) {
   u32 cur[8]; memcpy(cur, leaf_digest, 32);
   for (u32 l = 0; l < depth; l++, idx >>= 1) {
@@ -172,7 +183,9 @@ bool verify(const zkir_params* p, const u32* w, size_t nwords, const u32* pv_in)
   const X4 alpha = ch.sample_ext();
   ch.observe(qroot, 8);
   const X4 zeta = ch.sample_ext();
-  ch.observe(open, (2 * W + QW) * 4);
+  u32 open_digest[8];
+  hash_tree(open, (2 * W + QW) * 4, open_digest);
+  ch.observe(open_digest, 8);
   const X4 afri = ch.sample_ext();
   std::vector<X4> betas(R);
   for (u32 r = 0; r < R; r++) { ch.observe(fri_roots + 8 * r, 8); betas[r] = ch.sample_ext(); }

@@ -58,6 +58,9 @@ int launch_merkle_levels(u32* tree, u64 n_leaves, cudaStream_t st, u64* launches
                          u32* sample_out = nullptr, u32 n_sample = 0, const u32* pair_layer = nullptr, u64 first = 0, u64 seg = 0,
                          u32 leaf_arity = 2);
 int launch_challenger(ChalState* st_dev, const u32* in, u32 n_in, u32* out, u32 n_out, u32 bits, cudaStream_t st, u64* launches);
+// observe hash_tree(words) (docs/PROVER_SPEC.md section 2) and sample n_sample elements; tree_scratch: hash_tree_scratch_words(n_words) words
+u64 hash_tree_scratch_words(u32 n_words);
+int launch_observe_hash_tree(const u32* words, u32 n_words, u32* tree_scratch, ChalState* chal, u32* sample_out, u32 n_sample, cudaStream_t st, u64* launches);
 int launch_pow_grind(const ChalState* st_dev, u32 bits, u32* result, cudaStream_t st, u64* launches);
 
 // ---- quotient.cu

@@ -177,6 +177,24 @@ __global__ void __launch_bounds__(128) leaf_hash_pairs_kernel(const uint4* __res
   d[1] = make_uint4(s[4], s[5], s[6], s[7]);
 }
 
+// leaves of hash_tree (docs/PROVER_SPEC.md section 2): leaf c = hash(words[8c .. 8c+8)) (the last chunk may be short), leaves beyond the
+// message are all-zero digests
+__global__ void __launch_bounds__(128) words_leaf_hash_kernel(const u32* __restrict__ words, u32 n_words, u32 n_leaves, u32* __restrict__ digests) {
+  const u32 c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_leaves) return;
+  u32 s[16];
+#pragma unroll
+  for (int k = 0; k < 16; k++) s[k] = 0;
+  if (8 * c < n_words) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) if (8 * c + k < n_words) s[k] = words[8 * c + k];
+    poseidon2_permute(s);
+  }
+  uint4* d = reinterpret_cast<uint4*>(digests + 8 * c);
+  d[0] = make_uint4(s[0], s[1], s[2], s[3]);
+  d[1] = make_uint4(s[4], s[5], s[6], s[7]);
+}
+
 // one Merkle level: out[i] = compress(in[2i], in[2i+1])
 __global__ void __launch_bounds__(128) compress_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, u64 n_out) {
   u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x;
@@ -269,6 +287,13 @@ int launch_merkle_levels(u32* tree, u64 n_leaves, cudaStream_t st, u64* launches
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
+u64 hash_tree_scratch_words(u32 n_words) {
+  u64 chunks = (n_words + 7) / 8, leaves = 1;
+  while (leaves < chunks) leaves <<= 1;
+  return (2 * leaves - 1) * 8 + 8;
+}
+// transcript step on a long message: observe hash_tree(words) and sample; log-depth instead of n_words / 8 serial permutations
+int launch_observe_hash_tree(const u32* words, u32 n_words, u32* tree_scratch, ChalState* chal, u32* sample_out, u32 n_sample, cudaStream_t st, u64* launches);
 // ---------------------------------------------------------------- duplex challenger, one warp, lane i < 16 owns state[i]
 __device__ __forceinline__ u32 permute_warp(u32 x, int lane) {
   const unsigned FULL = 0xffffffffu;
@@ -430,6 +455,18 @@ __global__ void pow_grind_kernel(const ChalState* st, u32 bits, u32* result /* i
   }
 }
 
+int launch_observe_hash_tree(const u32* words, u32 n_words, u32* tree_scratch, ChalState* chal, u32* sample_out, u32 n_sample, cudaStream_t st, u64* launches) {
+  u32 chunks = (n_words + 7) / 8, leaves = 1;
+  while (leaves < chunks) leaves <<= 1;
+  words_leaf_hash_kernel<<<nblk(leaves, 128), 128, 0, st>>>(words, n_words, leaves, tree_scratch);
+  (*launches)++;
+  if (leaves == 1) {   // the single leaf digest is the root
+    challenger_kernel<<<1, 32, 0, st>>>(chal, tree_scratch, 8, sample_out, n_sample, 0);
+    (*launches)++;
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+  }
+  return launch_merkle_levels(tree_scratch, leaves, st, launches, chal, nullptr, sample_out, n_sample);
+}
 int launch_challenger(ChalState* st_dev, const u32* in, u32 n_in, u32* out, u32 n_out, u32 bits, cudaStream_t st, u64* launches) {
   challenger_kernel<<<1, 32, 0, st>>>(st_dev, in, n_in, out, n_out, bits);
   (*launches)++;

@@ -98,6 +98,7 @@ struct Workspace {
   u32* chal_buf = nullptr;   // alpha[4] zeta[4] alpha_fri[4] betas[R][4] pow_raw[1] pow_sample[1] hdr_mont[6+np]
   u32* indices = nullptr;
   u32* apow = nullptr; E4* afp = nullptr;
+  u32* otree = nullptr;      // scratch of the tree hash of the opened values
   u32* proof = nullptr;      // device proof words
   u32* h_proof = nullptr;    // pinned
   u32* h_stage = nullptr;    // pinned staging for header words
@@ -219,7 +220,7 @@ static int ws_prepare(zkir_ctx* ctx, const zkir_params* p, u32 log_n) {
   A(d_layers, R + 1) A(d_ltrees, R + 1)
   A(chal, 1) A(chal_buf, 12 + 4 * R + 2 + 6 + p->num_public) A(indices, p->num_queries + 1)
   A(apow, 4 * ZKIR_AIR_NUM_CONSTRAINTS) A(afp, W + 5)
-  A(proof, L.total) A(xchg, ZKIR_MAX_SHARDS * PEER_REC_WORDS)
+  A(proof, L.total) A(xchg, ZKIR_MAX_SHARDS * PEER_REC_WORDS) A(otree, hash_tree_scratch_words((u32)(2 * W + QW) * 4))
 #undef A
   CU(cudaMallocHost(&w.h_proof, L.total * 4));
   CU(cudaMallocHost(&w.h_stage, (8 + 6 + 2 * p->num_public) * 4));
@@ -572,7 +573,7 @@ static int prove_resident(zkir_ctx* ctx, const zkir_params* p, u32 log_n, const 
       RC(launch_open(w.coef, N, (u32)W, N, w.U1, w.U2, ot, otg, w.open_scratch, st, LC));
       RC(launch_open(qcoef, N, QW, N, w.U1q, w.U1q, oq, w.dummy_open, w.open_scratch, st, LC));
     }
-    RC(launch_challenger(w.chal, w.proof + L.open_t, (u32)(2 * W + QW) * 4, c_afri, 4, 0, st, LC));
+    RC(launch_observe_hash_tree(w.proof + L.open_t, (u32)(2 * W + QW) * 4, w.otree, w.chal, c_afri, 4, st, LC));   // observe the tree hash, sample gamma
     DeepArgs da;
     da.lde = w.lde; da.M = M; da.width = (u32)W; da.qlde = w.qlde; da.qwidth = QW; da.log_n = log_n; da.log_b = p->log_blowup; da.xs = w.xs; da.zeta = c_zeta;
     da.g_mont = bb_to_mont_c(g); da.alpha_fri = c_afri; da.open_t = ot; da.open_tg = otg; da.open_q = oq; da.afp_scratch = w.afp;
