@@ -343,12 +343,12 @@ def main():
         "roofline": {"kernel": "dft_tile_kernel: LDE stage = 2 inverse + 2x2 forward digit passes (radix-32 register tiles) over 72 columns, 2^20 -> 2^21 points",
                      "bound": "hbm", "achieved": lde_gbs, "peak": peak, "unit": "GB/s", "frac": lde_gbs / peak, "traffic": lde_traffic,
                      "traffic_source": lde_traffic_src, "algorithmic_bytes": lde_bytes, "ms": lde_ms, "peak_source": peak_src,
-                     "note": "ncu (profiles/r01_ncu_v13.md): integer-multiply pipe (fmaheavy) 58-66 % active, DRAM 29-44 %: the passes are bound by BabyBear multiplies, not HBM (DESIGN.md 3.1)"},
+                     "note": "ncu (profiles/r01_ncu_v17.md): integer-multiply pipe (fmaheavy) 58-65 % active, DRAM 29-44 %: the passes are bound by BabyBear multiplies, not HBM (DESIGN.md 3.1)"},
         "ntt_roofline": {"kernel": f"dft_tile_kernel x2: forward NTT 2^{ntt_log} x {ntt_cols} columns via zkir_b200_ntt, natural order in/out (8*n*C bytes)", "bound": "hbm",
                          "achieved": ntt_gbs, "peak": peak, "unit": "GB/s", "frac": ntt_gbs / peak, "ms": ntt_ms, "timing": "CUDA events on the library stream, 10 launches"},
         "hash_roofline": {"kernel": "leaf_hash_kernel (Poseidon2 sponge over the 2^21 LDE rows, 9 permutations each) + Merkle levels", "bound": "integer-multiply pipe",
                           "achieved": hash_gps, "unit": "G permutations/s", "ms": commit_ms,
-                          "ncu_fmaheavy_active_frac": 0.859, "ncu_source": "profiles/r01_ncu_v13.md",
+                          "ncu_fmaheavy_active_frac": 0.864, "ncu_source": "profiles/r01_ncu_v17.md",
                           "share_of_step": commit_ms / (dev_ms / K)},
     }
     if world > 1:
