@@ -546,6 +546,7 @@ int oracle_check_trace(const u32* trace, u32 log_n, const u32* pv, u64* bad_row)
   }
   return -1;
 }
+void oracle_hash_tree(const u32* words, u64 n, u32* digest8) { hash_tree(words, (size_t)n, digest8); }
 u64 oracle_proof_words(const u32* params5, u32 log_n) {
   Params p = {params5[0], params5[1], params5[2], params5[3], params5[4]};
   return proof_words(p, log_n);

@@ -57,6 +57,12 @@ class Oracle:
         self.l.oracle_poseidon2(self._p(a), C.c_uint64(a.shape[0]))
         return a
 
+    def hash_tree(self, words):
+        a = np.ascontiguousarray(words, dtype=np.uint32)
+        d = np.empty(8, dtype=np.uint32)
+        self.l.oracle_hash_tree(self._p(a), C.c_uint64(a.shape[0]), self._p(d))
+        return d
+
     def merkle_commit(self, mat):
         a = np.ascontiguousarray(mat, dtype=np.uint32)
         n_cols, rows = a.shape
