@@ -216,11 +216,11 @@ struct AirRowCtx {  // base-field row check / quotient numerator at one point
 };
 
 struct Params { u32 log_blowup, num_queries, pow_bits, width, num_public; };
-static const u32 PROOF_MAGIC = 0x5A4B5052u, PROOF_VERSION = 2u;
+static const u32 PROOF_MAGIC = 0x5A4B5052u, PROOF_VERSION = 3u;
 
-// FRI rounds (docs/PROVER_SPEC.md section 4.6): log_n / 2 rounds that fold by 4, then one that folds by 2 if log_n is odd
-static size_t fri_rounds(u32 log_n) { return log_n / 2 + (log_n & 1); }
-static u32 fri_log_arity(u32 log_n, size_t t) { return t < log_n / 2 ? 2 : 1; }
+// FRI rounds (docs/PROVER_SPEC.md section 4.6): log_n / 3 rounds that fold by 8, then one that folds by 2^(log_n mod 3) if that is > 1
+static size_t fri_rounds(u32 log_n) { return log_n / 3 + (log_n % 3 ? 1 : 0); }
+static u32 fri_log_arity(u32 log_n, size_t t) { return t < log_n / 3 ? 3 : log_n % 3; }
 static size_t proof_words(const Params& p, u32 log_n) {
   size_t lg = log_n + p.log_blowup, W = p.width, R = fri_rounds(log_n);
   size_t n = 8 + p.num_public + 16 + (2 * W + 8) * 4 + R * 8 + 4 + 1;
@@ -391,7 +391,7 @@ static int prove(const Params& p, const u32* trace, u32 log_n, const u32* pv, u3
   if (dump && dump->fri_input) memcpy(dump->fri_input, f.data(), M * 16);
 
   // ---- 5. FRI commit phase: a round commits the layer with leaves of `arity` values (the fibre of one point of the layer
-  // after the round), samples beta and folds by 2 with beta, then -- arity 4 -- once more with beta^2
+  // after the round), samples beta and folds by 2 with beta, beta^2, beta^4 ... (log2(arity) half-folds)
   const size_t R = fri_rounds(log_n);
   std::vector<std::vector<E4>> layers;
   std::vector<std::vector<u32>> trees;
@@ -404,7 +404,7 @@ static int prove(const Params& p, const u32* trace, u32 log_n, const u32* pv, u3
     std::vector<u32> tree((2 * q - 1) * 8);
 #pragma omp parallel for if (q > 256)
     for (size_t i = 0; i < q; i++) {
-      u32 leaf[16];
+      u32 leaf[32];
       for (u32 k = 0; k < arity; k++) memcpy(leaf + 4 * k, f[i + k * q].c, 16);
       hash_elems(leaf, 4 * arity, &tree[i * 8]);
     }

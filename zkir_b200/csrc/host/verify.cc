@@ -153,13 +153,13 @@ bool verify(const zkir_params* p, const u32* w, size_t nwords, const u32* pv_in)
   if (!p || !w) return fail("null argument");
   if (p->width != ZKIR_AIR_WIDTH || p->num_public != ZKIR_AIR_NUM_PUBLIC || p->log_blowup < 1) return fail("unsupported params");
   if (nwords < 8) return fail("proof too short");
-  if (w[0] != 0x5A4B5052u || w[1] != 2) return fail("bad magic/version");
+  if (w[0] != 0x5A4B5052u || w[1] != 3) return fail("bad magic/version");
   const u32 log_n = w[2];
   if (w[3] != p->width || w[4] != p->log_blowup || w[5] != p->num_queries || w[6] != p->pow_bits || w[7] != p->num_public)
     return fail("proof header does not match params");
   if (log_n < 2 || log_n + p->log_blowup > 27) return fail("bad log_n");
   if (nwords * 4 != zkir_b200_proof_size(p, log_n)) return fail("proof length mismatch");
-  const u32 W = p->width, np = p->num_public, lg = log_n + p->log_blowup, R = log_n / 2 + (log_n & 1), QW = 8;  // R FRI rounds: fold by 4, last by 2 if log_n is odd
+  const u32 W = p->width, np = p->num_public, lg = log_n + p->log_blowup, R = log_n / 3 + (log_n % 3 ? 1 : 0), QW = 8;  // R FRI rounds: fold by 8, the last by 2^(log_n mod 3)
   const u64 N = 1ull << log_n, M = 1ull << lg;
   for (size_t i = 8; i < nwords; i++) if (w[i] >= P) return fail("non-canonical field element");
   const u32* q = w + 8;
@@ -241,28 +241,31 @@ bool verify(const zkir_params* p, const u32* w, size_t nwords, const u32* pv_in)
     u32 lshift = ZKIR_BB_GEN;
     u32 ll = lg;  // log2 of the layer length
     for (u32 t = 0; t < R; t++) {
-      const u32 la = t < log_n / 2 ? 2 : 1, arity = 1u << la;
+      const u32 la = t < log_n / 3 ? 3 : log_n % 3, arity = 1u << la;
       const u64 qn = (1ull << ll) >> la;            // leaves of this layer; the opened values sit at i + k*qn
       const u32 pos = (u32)(i / qn);
       i %= qn;
-      X4 a[4];
+      X4 a[8];
       for (u32 k = 0; k < arity; k++) memcpy(a[k].c, q + 4 * k, 16);
       const u32* vals = q; q += 4 * arity;
       const u32* path = q; q += 8 * (ll - la);
       if (!eq(a[pos], v)) return fail("FRI layer value does not match the folded value");
       hash_n(vals, 4 * arity, d);
       if (!check_path(d, i, path, ll - la, fri_roots + 8 * t)) return fail("FRI Merkle path");
+      // log2(arity) half-folds: step s pairs value k with k + arity/2^(s+1) at the point (x_i * w_arity^k)^(2^s), challenge beta^(2^s)
+      u32 pts[4];
       const u32 xi = mul(lshift, pw(ZKIR_BB_ROOTS[ll], i));
-      if (la == 1) {
-        v = scale(a[0] + a[1], half) + betas[t] * scale(a[0] - a[1], inv(mul(2, xi)));
-      } else {
-        // fold by 2 with beta: pairs (i, i + n/2) and (i + n/4, i + 3n/4), the second at the point xi * w_4; then the two results
-        // are the pair (i, i + n/4) of the half-length layer on the squared coset, folded with beta^2
-        const u32 xj = mul(xi, ZKIR_BB_ROOTS[2]);
-        const X4 g0 = scale(a[0] + a[2], half) + betas[t] * scale(a[0] - a[2], inv(mul(2, xi)));
-        const X4 g1 = scale(a[1] + a[3], half) + betas[t] * scale(a[1] - a[3], inv(mul(2, xj)));
-        v = scale(g0 + g1, half) + (betas[t] * betas[t]) * scale(g0 - g1, inv(mul(2, mul(xi, xi))));
+      for (u32 k = 0; k < arity / 2; k++) pts[k] = mul(xi, pw(ZKIR_BB_ROOTS[la], k));
+      X4 bp = betas[t];
+      for (u32 s = 0; s < la; s++) {
+        const u32 half_n = arity >> (s + 1);
+        for (u32 k = 0; k < half_n; k++) {
+          a[k] = scale(a[k] + a[k + half_n], half) + bp * scale(a[k] - a[k + half_n], inv(mul(2, pts[k])));
+          pts[k] = mul(pts[k], pts[k]);
+        }
+        bp = bp * bp;
       }
+      v = a[0];
       for (u32 k = 0; k < la; k++) lshift = mul(lshift, lshift);
       ll -= la;
     }

@@ -134,7 +134,7 @@ struct DeepArgs {
   u32 seg_log_nj = 0xffffffffu; u64 seg_j0 = 0;   // row segment as in QuotientArgs
 };
 int launch_deep(const DeepArgs& a, cudaStream_t st, u64* launches);
-// square_beta: fold with beta^2 (the second half-fold of a fold-by-4 round)
+// square_beta = s: fold with beta^(2^s) (the later half-folds of a fold-by-4/8 round)
 int launch_fri_fold(const E4* in, E4* out, u64 h, const u32* beta_dev, const u32* inv_w_table, u32 tw_stride, u32 c_mont,
                     cudaStream_t st, u64* launches, int square_beta = 0);
 struct QueryArgs {
@@ -144,7 +144,7 @@ struct QueryArgs {
   const u32* qlde; const u32* qtree;
   const E4* const* layers;        // device array of layer pointers, indexed by fold LEVEL (layer length M >> level)
   const u32* const* ltrees;       // device array of layer trees, same index (only committed levels are used)
-  u32 fold4_rounds = 0, fri_rounds = 0;   // rounds that fold by 4 come first, the rest fold by 2 (docs/PROVER_SPEC.md section 4.6)
+  u32 fold8_rounds = 0, last_log_arity = 0, fri_rounds = 0;   // log_n / 3 rounds fold by 8, one more by 2^(log_n mod 3) (docs/PROVER_SPEC.md 4.6)
   u32* out;                       // proof words at the start of the query section
   u32 words_per_query;
   // one proof sharded over several GPUs: this context owns the leaf segments [shard_lo, shard_hi); the lowest *_sl levels of a

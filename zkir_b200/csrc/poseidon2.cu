@@ -157,18 +157,18 @@ __global__ void __launch_bounds__(128) leaf_hash_kernel(const u32* __restrict__ 
   d[1] = make_uint4(s[4], s[5], s[6], s[7]);
 }
 
-// FRI layer leaves: leaf i = hash(F[i] || F[i+q] [|| F[i+2q] || F[i+3q]]) over the q leaves of a layer of arity*q ext4 values
-// (arity 2: 8 elements = one permutation; arity 4: 16 elements = two absorptions of the overwrite-mode sponge)
+// FRI layer leaves: leaf i = hash(F[i] || F[i+q] || ... || F[i+(arity-1)q]) over the q leaves of a layer of arity*q ext4 values:
+// arity/2 absorptions of the overwrite-mode sponge (8 words each)
 __global__ void __launch_bounds__(128) leaf_hash_pairs_kernel(const uint4* __restrict__ layer, u64 q, u64 first, u64 count, u32 arity,
                                                               u32* __restrict__ digests) {
   u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x;
   if (i >= count) return;
   i += first;
-  uint4 a = layer[i], b = layer[i + q];
-  u32 s[16] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, 0, 0, 0, 0, 0, 0, 0, 0};
-  poseidon2_permute(s);
-  if (arity == 4) {
-    a = layer[i + 2 * q]; b = layer[i + 3 * q];
+  u32 s[16];
+#pragma unroll
+  for (int k = 0; k < 16; k++) s[k] = 0;
+  for (u32 m = 0; m < arity; m += 2) {
+    const uint4 a = layer[i + (u64)m * q], b = layer[i + (u64)(m + 1) * q];
     s[0] = a.x; s[1] = a.y; s[2] = a.z; s[3] = a.w; s[4] = b.x; s[5] = b.y; s[6] = b.z; s[7] = b.w;
     poseidon2_permute(s);
   }
@@ -370,7 +370,7 @@ __global__ void __launch_bounds__(32) challenger_kernel(ChalState* st, const u32
 // one full permutation latency (~9 us) however small it is; this kernel costs ~3 us per level, and wide levels are cut
 // into many 32-node blocks so that all SMs share them.
 // Leaf mode (pair_layer != nullptr): the input level does not exist yet; node i is first computed as the FRI leaf
-// hash(f[i] || f[i + h] [|| f[i + 2h] || f[i + 3h]]) of the ext4 layer and stored as level 0.
+// hash(f[i] || f[i + h] || ... || f[i + (arity-1)h]) of the ext4 layer and stored as level 0.
 // When the block reaches the root (single block), warp 0 also runs the Fiat-Shamir step that always follows:
 // copy the root into the proof, observe it, sample `n_sample` field elements.
 #define COOP_MAX_CHUNK 128
@@ -382,16 +382,14 @@ __global__ void __launch_bounds__(16 * COOP_MAX_CHUNK / 2) merkle_coop_kernel(u3
   // `level` is the start of a whole tree level of n_in nodes; the grid covers the nodes [first, first + gridDim.x * chunk)
   const u64 node0 = first + (u64)blockIdx.x * chunk;
   if (pair_layer) {
-    const u64 h = n_in;  // leaves of this layer = its length / arity; the values of leaf i sit at i, i + h, (i + 2h, i + 3h)
+    const u64 h = n_in;  // leaves of this layer = its length / arity; the values of leaf i sit at i, i + h, ..., i + (arity-1)h
     for (u32 s0 = 0; s0 < chunk; s0 += slots) {
       if (s0 + (tid >> 5) * 2 >= chunk) break;
       const u32 sidx = s0 + slot;
       const bool active = sidx < chunk;
       u32 x = 0;
-      if (active && l16 < 8) x = pair_layer[4 * (node0 + sidx + (l16 >= 4 ? h : 0)) + (l16 & 3)];
-      x = permute_warp(x, lane);
-      if (leaf_arity == 4) {   // second absorption of the overwrite-mode sponge
-        if (active && l16 < 8) x = pair_layer[4 * (node0 + sidx + (l16 >= 4 ? 3 * h : 2 * h)) + (l16 & 3)];
+      for (u32 m = 0; m < leaf_arity; m += 2) {   // one absorption of the overwrite-mode sponge per pair of values
+        if (active && l16 < 8) x = pair_layer[4 * (node0 + sidx + (u64)(m + (l16 >= 4 ? 1u : 0u)) * h) + (l16 & 3)];
         x = permute_warp(x, lane);
       }
       if (active && l16 < 8) { buf[0][8 * sidx + l16] = x; level[(node0 + sidx) * 8 + l16] = x; }

@@ -49,7 +49,7 @@ static u32 hpow(u32 a, u64 e) { u64 r = 1, b = a; while (e) { if (e & 1) r = r *
 static u32 hinv(u32 a) { return hpow(a, BB_P - 2); }
 static u32 hmul(u32 a, u32 b) { return (u32)((u64)a * b % BB_P); }
 
-static const u32 PROOF_MAGIC = 0x5A4B5052u, PROOF_VERSION = 2u;
+static const u32 PROOF_MAGIC = 0x5A4B5052u, PROOF_VERSION = 3u;
 static const u32 QW = 8;  // quotient columns: 4 ext planes x 2 chunks, column = 2*plane + chunk
 
 struct Layout {  // proof word offsets
@@ -59,7 +59,7 @@ struct Layout {  // proof word offsets
 static Layout make_layout(const zkir_params* p, u32 log_n) {
   Layout L;
   L.log_n = log_n; L.log_m = log_n + p->log_blowup; L.width = p->width; L.np = p->num_public; L.nq = p->num_queries;
-  L.R = log_n / 2 + (log_n & 1);   // FRI rounds: log_n / 2 that fold by 4, one more by 2 if log_n is odd (docs/PROVER_SPEC.md 4.6)
+  L.R = log_n / 3 + (log_n % 3 ? 1 : 0);   // FRI rounds: log_n / 3 that fold by 8, one more by 2^(log_n mod 3) (docs/PROVER_SPEC.md 4.6)
   size_t o = 8;
   L.pv = o; o += L.np;
   L.troot = o; o += 8;
@@ -72,7 +72,7 @@ static Layout make_layout(const zkir_params* p, u32 log_n) {
   L.pow_ = o; o += 1;
   L.queries = o;
   size_t pq = L.width + 8 * (size_t)L.log_m + QW + 8 * (size_t)L.log_m;
-  for (u32 t = 0, ll = L.log_m; t < L.R; t++) { const u32 la = t < log_n / 2 ? 2 : 1; pq += (4u << la) + 8 * (size_t)(ll - la); ll -= la; }
+  for (u32 t = 0, ll = L.log_m; t < L.R; t++) { const u32 la = t < log_n / 3 ? 3 : log_n % 3; pq += (4u << la) + 8 * (size_t)(ll - la); ll -= la; }
   L.per_query = pq;
   L.total = o + pq * L.nq;
   return L;
@@ -598,12 +598,12 @@ static int prove_resident(zkir_ctx* ctx, const zkir_params* p, u32 log_n, const 
     u32 lshift = shift;
     u32 level = 0;   // fold level: layer `level` has M >> level values
     for (u32 t = 0; t < L.R; t++) {
-      const u32 la = t < log_n / 2 ? 2 : 1;
+      const u32 la = t < log_n / 3 ? 3 : log_n % 3;
       const u64 qn = (M >> level) >> la;
-      // leaves hash(f[i] || f[i+qn] [|| f[i+2qn] || f[i+3qn]]) + tree + root -> proof, observe, sample beta_t
+      // leaves hash(f[i] || f[i+qn] || ... || f[i+(2^la-1)qn]) + tree + root -> proof, observe, sample beta_t
       if ((crc = commit_tree(ctx, nullptr, 0, 0, reinterpret_cast<const u32*>(w.h_layers[level]), w.h_ltrees[level], qn, w.proof + L.fri_roots + 8 * t,
                              c_betas + 4 * t, 4, &l_sl[t], -1, 1u << la)) != 0) return crc;
-      for (u32 s = 0; s < la; s++) {   // fold by 2 with beta, then (fold-by-4 round) with beta^2 on the squared coset
+      for (u32 s = 0; s < la; s++) {   // half-folds with beta, beta^2, beta^4 on the coset, its square, its fourth power
         const u64 h = (M >> level) / 2;
         const u32 c = hinv(hmul(2, lshift));
         RC(launch_fri_fold(w.h_layers[level], w.h_layers[level + 1], h, c_betas + 4 * t, inv_w, 1u << level, bb_to_mont_c(c), st, LC, (int)s));
@@ -624,7 +624,7 @@ static int prove_resident(zkir_ctx* ctx, const zkir_params* p, u32 log_n, const 
     QueryArgs qa;
     qa.indices = w.indices; qa.num_queries = p->num_queries; qa.log_m = log_m; qa.width = (u32)W; qa.log_n = log_n;
     qa.lde = w.lde; qa.ttree = w.ttree; qa.qlde = w.qlde; qa.qtree = w.qtree;
-    qa.layers = w.d_layers; qa.ltrees = w.d_ltrees; qa.fold4_rounds = log_n / 2; qa.fri_rounds = (u32)L.R; qa.out = w.proof + L.queries; qa.words_per_query = (u32)L.per_query;
+    qa.layers = w.d_layers; qa.ltrees = w.d_ltrees; qa.fold8_rounds = log_n / 3; qa.last_log_arity = log_n % 3; qa.fri_rounds = (u32)L.R; qa.out = w.proof + L.queries; qa.words_per_query = (u32)L.per_query;
     // sharded trees: the bottom path levels of a leaf exist only on its owner; every rank writes the pieces it owns (zeros
     // elsewhere, rank 0 also everything that is replicated) and one all-reduce assembles the query section ("query gather")
     qa.shard_lo = ctx->shard_lo; qa.shard_hi = ctx->shard_hi; qa.ttree_sl = t_sl; qa.qtree_sl = q_sl; qa.lde_sl = sp.on ? t_sl : 0; qa.qlde_sl = sp.on ? q_sl : 0;

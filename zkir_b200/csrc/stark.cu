@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(256) fri_fold_kernel(const E4* __restrict__ in
   const u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x;
   if (i >= h) return;
   E4 beta; for (int k = 0; k < 4; k++) beta.c[k] = beta_dev[k];
-  if (square_beta) beta = e4_mul(beta, beta);
+  for (int k = 0; k < square_beta; k++) beta = e4_mul(beta, beta);   // beta^(2^square_beta): later half-folds of a fold-by-4/8 round
   const E4 a = ld_e4(in + i), b = ld_e4(in + i + h);
   const u32 half = bb_to_mont_c((BB_P + 1) / 2);
   E4 s = e4_mulb(e4_add(a, b), half);
@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(128) query_kernel(QueryArgs a) {
   copy_path(a.qtree, M, a.log_m, q, out, a.qtree_sl, owns(q, a.qtree_sl), top); out += a.log_m * 8;
   u32 level = 0;
   for (u32 t = 0; t < a.fri_rounds; t++) {
-    const u32 la = t < a.fold4_rounds ? 2 : 1;                 // log2 of the fold arity of this round
+    const u32 la = t < a.fold8_rounds ? 3 : a.last_log_arity;  // log2 of the fold arity of this round
     const u64 qn = (M >> level) >> la, i = q & (qn - 1);       // leaves of the layer; opened values at i + k*qn
     const u32* lay = reinterpret_cast<const u32*>(a.layers[level]);
     if (threadIdx.x < (4u << la)) out[threadIdx.x] = top ? lay[4 * (i + (threadIdx.x >> 2) * qn) + (threadIdx.x & 3)] : 0u;
