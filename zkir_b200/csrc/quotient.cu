@@ -98,7 +98,7 @@ int launch_quotient(const QuotientArgs& a, cudaStream_t st, u64* launches) {
   const u32 snn = hpow(ZKIR_BB_GEN, 1ull << a.log_n);
   const u32 wb = ZKIR_BB_ROOTS[a.log_blowup];
   static int variant = -1;
-  if (variant < 0) { const char* e = getenv("ZKIR_QUOTIENT_VARIANT"); variant = e ? atoi(e) : 2; }  // 64 registers measured fastest
+  if (variant < 0) { const char* e = getenv("ZKIR_QUOTIENT_VARIANT"); variant = e ? atoi(e) : 0; }  // 72-column AIR: 128 registers (4 CTAs/SM) measured fastest: 0.49 / 0.50 / 0.53 ms for variants 0 / 1 / 2
   const u64 n_threads = a.seg_log_nj == 0xffffffffu ? M : (1ull << (a.seg_log_nj + a.log_blowup));
   const unsigned grid = (unsigned)((n_threads + 127) / 128);
   const E4* ap = reinterpret_cast<const E4*>(a.apow_scratch);
