@@ -18,7 +18,7 @@ pub struct zkir_params {
 }
 
 pub const ZKIR_OK: c_int = 0;
-pub const ZKIR_AIR_V1_WIDTH: u32 = 85;
+pub const ZKIR_AIR_V1_WIDTH: u32 = 72;
 pub const ZKIR_AIR_V1_NUM_PUBLIC: u32 = 4;
 
 extern "C" {

@@ -1,21 +1,25 @@
-//! `prove()` next to `zkir_runtime::run()` (zkir-runtime/src/lib.rs:59-62): run the interpreter with trace recording,
-//! pack `Vec<TraceRow>` (zkir-spec/src/trace.rs:24-50) into column-major BabyBear columns in pinned memory, and hand the
-//! buffer to the CUDA prover through the C ABI.  Errors map to `RuntimeError::Other` (zkir-runtime/src/error.rs:35-36).
+//! `prove()` / `verify()` next to `zkir_runtime::run()` (zkir-runtime/src/lib.rs:59-62), backed by libzkir_b200.so.
 //!
-//! NOT COMPILED in this repository's build image (no cargo/rustc).  It relies on one small addition to zkir-runtime:
-//! `VM::run_keep_state`, i.e. `VM::run` (vm.rs:208-358) returning also the final registers and pc in `ExecutionResult`
-//! (`final_regs: [u64; 16]`, `final_pc: u64`): padding rows and the last READ need the post-state of the last cycle.
+//! SOURCE ONLY: the build image has no Rust toolchain, so this file has never been compiled; it is the
+//! binding a zkir-runtime maintainer would add.  The interpreter stays the upstream Rust one: the
+//! only thing this crate does with an execution is copy `TraceRow.pc / instruction / registers` (zkir-spec/src/trace.rs:24-50)
+//! into page-locked arrays and hand them to the C ABI of include/zkir_b200.h.  Nothing here computes a proof on the CPU.
 pub mod ffi;
 
 use std::ffi::CStr;
-use zkir_runtime::{RuntimeError, VMConfig, VM};
+use std::os::raw::c_int;
+use std::ptr;
+
+use zkir_runtime::{HaltReason, RuntimeError, VMConfig, VM};
 use zkir_spec::Program;
 
+/// Proving parameters (Plonky3's FriConfig fields; docs/PROVER_SPEC.md section 4).
 #[derive(Clone, Copy, Debug)]
 pub struct ProverConfig {
     pub log_blowup: u32,
     pub num_queries: u32,
     pub pow_bits: u32,
+    /// `VMConfig.max_cycles` defaults to 1_000_000 (zkir-runtime/src/vm.rs:43): too small for a 2^20-cycle trace.
     pub max_cycles: u64,
     pub device: i32,
 }
@@ -26,6 +30,20 @@ impl Default for ProverConfig {
     }
 }
 
+impl ProverConfig {
+    fn params(&self) -> ffi::zkir_params {
+        ffi::zkir_params {
+            log_blowup: self.log_blowup,
+            num_queries: self.num_queries,
+            pow_bits: self.pow_bits,
+            width: ffi::ZKIR_AIR_V1_WIDTH,
+            num_public: ffi::ZKIR_AIR_V1_NUM_PUBLIC,
+        }
+    }
+}
+
+/// Proof bytes (docs/PROVER_SPEC.md section 5) with the public values they bind: `[entry_pc, num_cycles, exit_lo, exit_hi]`.
+#[derive(Clone, Debug)]
 pub struct Proof {
     pub bytes: Vec<u8>,
     pub public_values: [u32; 4],
@@ -34,137 +52,164 @@ pub struct Proof {
     pub outputs: Vec<u64>,
 }
 
-/// Pinned host buffer owned by Rust, allocated by the library (cudaMallocHost) so the H2D copy is a single DMA.
-struct Pinned<T: Copy> {
+fn error_of(ctx: *const ffi::zkir_ctx, code: c_int) -> RuntimeError {
+    // ZKIR_ERR_* -> RuntimeError::Other(String) (zkir-runtime/src/error.rs:35-36); the message comes from the library
+    let msg = unsafe {
+        let p = ffi::zkir_b200_last_error(ctx);
+        if p.is_null() { String::new() } else { CStr::from_ptr(p).to_string_lossy().into_owned() }
+    };
+    RuntimeError::Other(format!("zkir_b200 error {code}: {msg}"))
+}
+
+/// Page-locked host array the recorder writes into (`zkir_b200_alloc_pinned`): the H2D copy is then one DMA.
+pub struct Pinned<T: Copy> {
     ptr: *mut T,
     len: usize,
 }
+
 impl<T: Copy> Pinned<T> {
-    fn new(len: usize) -> Result<Self, RuntimeError> {
-        let p = unsafe { ffi::zkir_b200_alloc_pinned(len.max(1) * std::mem::size_of::<T>()) } as *mut T;
+    pub fn new(len: usize) -> Result<Self, RuntimeError> {
+        let bytes = len.max(1) * std::mem::size_of::<T>();
+        let p = unsafe { ffi::zkir_b200_alloc_pinned(bytes) } as *mut T;
         if p.is_null() {
-            return Err(RuntimeError::Other("zkir_b200_alloc_pinned failed".into()));
+            return Err(RuntimeError::Other("zkir_b200_alloc_pinned failed (no CUDA device?)".to_string()));
         }
         Ok(Self { ptr: p, len })
     }
-    fn as_slice(&self) -> &[T] {
-        unsafe { std::slice::from_raw_parts(self.ptr, self.len) }
-    }
-    fn as_mut_slice(&mut self) -> &mut [T] {
+    pub fn as_mut_slice(&mut self) -> &mut [T] {
         unsafe { std::slice::from_raw_parts_mut(self.ptr, self.len) }
     }
+    pub fn as_ptr(&self) -> *const T {
+        self.ptr
+    }
 }
+
 impl<T: Copy> Drop for Pinned<T> {
     fn drop(&mut self) {
         unsafe { ffi::zkir_b200_free_pinned(self.ptr as *mut _) }
     }
 }
 
+/// One `zkir_ctx` = one GPU.  Single-owner: `&mut self` on every proving call.
 pub struct Prover {
     ctx: *mut ffi::zkir_ctx,
 }
-unsafe impl Send for Prover {} // a zkir_ctx is single-owner; moving it between threads is fine
+
+// the context may move between threads, but is used by one thread at a time (include/zkir_b200.h, threading note)
+unsafe impl Send for Prover {}
 
 impl Prover {
     pub fn new(device: i32) -> Result<Self, RuntimeError> {
-        let mut ctx = std::ptr::null_mut();
-        let rc = unsafe { ffi::zkir_b200_create(&mut ctx, device) };
+        let mut ctx = ptr::null_mut();
+        let rc = unsafe { ffi::zkir_b200_create(&mut ctx, device as c_int) };
         if rc != ffi::ZKIR_OK {
-            return Err(last_error(std::ptr::null(), rc));
+            return Err(error_of(ptr::null(), rc)); // no CPU fallback: without an sm_100 device this is the end
         }
         Ok(Self { ctx })
     }
 
-    /// `cols`: `[85][1 << log_n]` column-major canonical values (see `pack_trace`).
+    /// Link this context with the contexts of the other ranks for ONE proof over several GPUs (BASELINE config 5).
+    /// `id` comes from `Prover::comm_unique_id()` on rank 0 and is handed to the other ranks by the host (pipe, MPI, file ...).
+    /// Afterwards every `prove_*` call on the linked contexts is collective and returns the single-GPU proof bytes everywhere.
+    pub fn comm_init(&mut self, id: &[u8; 128], rank: i32, world: i32) -> Result<(), RuntimeError> {
+        let rc = unsafe { ffi::zkir_b200_comm_init(self.ctx, id.as_ptr(), rank as c_int, world as c_int) };
+        if rc != ffi::ZKIR_OK { Err(error_of(self.ctx, rc)) } else { Ok(()) }
+    }
+
+    pub fn comm_unique_id() -> Result<[u8; 128], RuntimeError> {
+        let mut id = [0u8; 128];
+        let rc = unsafe { ffi::zkir_b200_comm_unique_id(id.as_mut_ptr()) };
+        if rc != ffi::ZKIR_OK { Err(error_of(ptr::null(), rc)) } else { Ok(id) }
+    }
+
+    /// Packed columns in (`[72][1 << log_n]`, column-major canonical values, host memory): `zkir_b200_prove`.
     pub fn prove_columns(&mut self, cfg: &ProverConfig, cols: &[u32], log_n: u32, pv: &[u32; 4]) -> Result<Vec<u8>, RuntimeError> {
         assert_eq!(cols.len(), (ffi::ZKIR_AIR_V1_WIDTH as usize) << log_n);
-        let params = ffi::zkir_params {
-            log_blowup: cfg.log_blowup,
-            num_queries: cfg.num_queries,
-            pow_bits: cfg.pow_bits,
-            width: ffi::ZKIR_AIR_V1_WIDTH,
-            num_public: ffi::ZKIR_AIR_V1_NUM_PUBLIC,
-        };
-        let (mut p, mut len) = (std::ptr::null_mut::<u8>(), 0usize);
-        let rc = unsafe { ffi::zkir_b200_prove(self.ctx, &params, cols.as_ptr(), log_n, pv.as_ptr(), &mut p, &mut len) };
+        let params = cfg.params();
+        let (mut proof, mut len) = (ptr::null_mut::<u8>(), 0usize);
+        let rc = unsafe { ffi::zkir_b200_prove(self.ctx, &params, cols.as_ptr(), log_n, pv.as_ptr(), &mut proof, &mut len) };
         if rc != ffi::ZKIR_OK {
-            return Err(last_error(self.ctx, rc));
+            return Err(error_of(self.ctx, rc));
         }
-        let out = unsafe { std::slice::from_raw_parts(p, len) }.to_vec();
-        unsafe { ffi::zkir_b200_free_proof(p) };
-        Ok(out)
+        let bytes = unsafe { std::slice::from_raw_parts(proof, len) }.to_vec();
+        unsafe { ffi::zkir_b200_free_proof(proof) };
+        Ok(bytes)
     }
-}
-impl Prover {
+
+    /// Raw rows in, proof bytes out: the converter (zkir-spec/src/trace.rs:41, absent upstream) runs on the device.
     #[allow(clippy::too_many_arguments)]
-    pub fn prove_rows(&mut self, cfg: &ProverConfig, pcs: &[u64], ins: &[u32], regs: &[u64], final_regs: &[u64; 16], final_pc: u64,
-                      entry_point: u32, exit_code: u64, log_n: u32, pv_out: &mut [u32; 4]) -> Result<Vec<u8>, RuntimeError> {
-        assert!(pcs.len() == ins.len() && regs.len() == 16 * pcs.len());
-        let params = ffi::zkir_params {
-            log_blowup: cfg.log_blowup,
-            num_queries: cfg.num_queries,
-            pow_bits: cfg.pow_bits,
-            width: ffi::ZKIR_AIR_V1_WIDTH,
-            num_public: ffi::ZKIR_AIR_V1_NUM_PUBLIC,
-        };
-        let (mut p, mut len) = (std::ptr::null_mut::<u8>(), 0usize);
+    pub fn prove_rows(
+        &mut self,
+        cfg: &ProverConfig,
+        pcs: &Pinned<u64>,
+        instrs: &Pinned<u32>,
+        regs: &Pinned<u64>, // [n_rows][16], PRE-state (zkir-runtime/src/vm.rs:245-253)
+        n_rows: u64,
+        final_regs: &[u64; 16],
+        final_pc: u64,
+        entry_point: u32,
+        exit_code: u64,
+        log_n: u32,
+    ) -> Result<(Vec<u8>, [u32; 4]), RuntimeError> {
+        let params = cfg.params();
+        let mut pv = [0u32; 4];
+        let (mut proof, mut len) = (ptr::null_mut::<u8>(), 0usize);
         let rc = unsafe {
-            ffi::zkir_b200_prove_rows(self.ctx, &params, pcs.as_ptr(), ins.as_ptr(), regs.as_ptr(), pcs.len() as u64, final_regs.as_ptr(),
-                                      final_pc, entry_point, exit_code, log_n, pv_out.as_mut_ptr(), &mut p, &mut len)
+            ffi::zkir_b200_prove_rows(
+                self.ctx, &params, pcs.as_ptr(), instrs.as_ptr(), regs.as_ptr(), n_rows, final_regs.as_ptr(), final_pc,
+                entry_point, exit_code, log_n, pv.as_mut_ptr(), &mut proof, &mut len,
+            )
         };
         if rc != ffi::ZKIR_OK {
-            return Err(last_error(self.ctx, rc));
+            return Err(error_of(self.ctx, rc));
         }
-        let out = unsafe { std::slice::from_raw_parts(p, len) }.to_vec();
-        unsafe { ffi::zkir_b200_free_proof(p) };
-        Ok(out)
+        let bytes = unsafe { std::slice::from_raw_parts(proof, len) }.to_vec();
+        unsafe { ffi::zkir_b200_free_proof(proof) }; // the library owns the buffer until here
+        Ok((bytes, pv))
     }
 }
+
 impl Drop for Prover {
     fn drop(&mut self) {
         unsafe { ffi::zkir_b200_destroy(self.ctx) }
     }
 }
 
-fn last_error(ctx: *const ffi::zkir_ctx, rc: i32) -> RuntimeError {
-    let msg = unsafe { CStr::from_ptr(ffi::zkir_b200_last_error(ctx)) }.to_string_lossy().into_owned();
-    RuntimeError::Other(format!("zkir_b200 error {rc}: {msg}"))
-}
-
-/// Program -> Proof.  The interpreter loop is untouched (north star: "zkir-spec, zkir-assembler and the interpreter
-/// loop stay as-is"); only the consumer of `ExecutionResult.execution_trace` is new.  The rows are copied field by field
-/// into pinned arrays and the device runs the converter (zkir_b200/csrc/trace_expand.cu), so no Rust port of it is needed.
+/// The new public function, next to `run()`: interpret with the upstream VM (execution trace on), prove on the GPU.
+///
+/// Needs one upstream addition: `ExecutionResult` must carry the machine state after the last instruction
+/// (`final_regs`, `final_pc`); padding rows and the value of a trailing READ are taken from it.
 pub fn prove(program: &Program, inputs: &[u64], cfg: &ProverConfig) -> Result<Proof, RuntimeError> {
     let vm_cfg = VMConfig { max_cycles: cfg.max_cycles, enable_execution_trace: true, ..VMConfig::default() };
-    let mut vm = VM::new(program.clone(), inputs.to_vec(), vm_cfg);
-    let result = vm.run_keep_state()?; // like VM::run (vm.rs:208-358) but also returns the final VMState (regs, pc)
-    let rows = &result.execution_trace;
+    let entry_point = program.header.entry_point;
+    let result = VM::new(program.clone(), inputs.to_vec(), vm_cfg).run()?; // interpreter untouched
+    let rows = &result.execution_trace; // Vec<TraceRow>, one per cycle, PRE-state registers
     let n = rows.len();
-    let log_n = n.max(4).next_power_of_two().trailing_zeros();
-    // SoA copy of TraceRow { pc, instruction, registers } into page-locked memory
-    let mut pcs = Pinned::<u64>::new(n)?;
-    let mut ins = Pinned::<u32>::new(n)?;
-    let mut regs = Pinned::<u64>::new(16 * n)?;
-    for (i, row) in rows.iter().enumerate() {
-        pcs.as_mut_slice()[i] = row.pc;
-        ins.as_mut_slice()[i] = row.instruction;
-        regs.as_mut_slice()[16 * i..16 * i + 16].copy_from_slice(&row.registers);
+    let log_n = (n.max(4).next_power_of_two().trailing_zeros()).max(2);
+
+    let (mut pcs, mut ins, mut regs) = (Pinned::<u64>::new(n)?, Pinned::<u32>::new(n)?, Pinned::<u64>::new(16 * n)?);
+    {
+        let (p, i, r) = (pcs.as_mut_slice(), ins.as_mut_slice(), regs.as_mut_slice());
+        for (k, row) in rows.iter().enumerate() {
+            p[k] = row.pc;
+            i[k] = row.instruction;
+            r[16 * k..16 * k + 16].copy_from_slice(&row.registers);
+        }
     }
-    let exit_code = match result.halt_reason { zkir_runtime::HaltReason::Exit(c) => c, _ => 0 };
-    let mut pv = [0u32; 4];
+    let exit_code = match result.halt_reason {
+        HaltReason::Exit(code) => code,
+        _ => 0,
+    };
     let mut prover = Prover::new(cfg.device)?;
-    let bytes = prover.prove_rows(cfg, pcs.as_slice(), ins.as_slice(), regs.as_slice(), &result.final_regs, result.final_pc,
-                                  program.header.entry_point, exit_code, log_n, &mut pv)?;
-    Ok(Proof { bytes, public_values: pv, log_n, cycles: result.cycles, outputs: result.outputs })
+    let (bytes, public_values) = prover.prove_rows(
+        cfg, &pcs, &ins, &regs, n as u64, &result.final_regs, result.final_pc, entry_point, exit_code, log_n,
+    )?;
+    Ok(Proof { bytes, public_values, log_n, cycles: result.cycles, outputs: result.outputs.clone() })
 }
 
-pub fn verify(proof: &[u8], cfg: &ProverConfig, pv: &[u32; 4]) -> bool {
-    let params = ffi::zkir_params {
-        log_blowup: cfg.log_blowup,
-        num_queries: cfg.num_queries,
-        pow_bits: cfg.pow_bits,
-        width: ffi::ZKIR_AIR_V1_WIDTH,
-        num_public: ffi::ZKIR_AIR_V1_NUM_PUBLIC,
-    };
-    unsafe { ffi::zkir_b200_verify(&params, proof.as_ptr(), proof.len(), pv.as_ptr()) == ffi::ZKIR_OK }
+/// CPU verifier (no GPU needed): accepts or rejects `proof` for these parameters and public values.
+pub fn verify(proof: &Proof, cfg: &ProverConfig) -> bool {
+    let params = cfg.params();
+    let rc = unsafe { ffi::zkir_b200_verify(&params, proof.bytes.as_ptr(), proof.bytes.len(), proof.public_values.as_ptr()) };
+    rc == ffi::ZKIR_OK
 }
