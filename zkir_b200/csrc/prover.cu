@@ -1,10 +1,17 @@
-// C ABI + orchestration of the trace->proof path on one B200 (include/zkir_b200.h).
+// C ABI + orchestration of the trace->proof path on B200s (include/zkir_b200.h).
 //
 // Sits where a Rust `zkir_runtime::prove()` would call into a prover; the reference has neither (its runtime API
 // ends at run()/VM::run, zkir-runtime/src/lib.rs:29-62, vm.rs:54-78).  Protocol: docs/PROVER_SPEC.md.
 // Everything between the H2D copy of the trace and the D2H copy of the proof is a fixed sequence of kernel
 // launches on one stream: the Fiat-Shamir challenger, the PoW grinder and the query sampler run on the device, so
-// the host never synchronises inside a proof.
+// the host never synchronises inside a proof.  Three execution shapes share prove_resident():
+//   * one context, ordinary launches (any size);
+//   * one context, the whole sequence captured once into a CUDA graph and replayed (proofs of up to 2^12 rows, which are
+//     bound by launch and permutation latency: zkir_b200_prove, zkir_b200_prove_batch);
+//   * several contexts linked by zkir_b200_comm_init, ONE proof sharded over their GPUs: columns for the
+//     per-column transforms, row segments for the per-row sweeps, NVLink peer stores fused into the producing kernels for the
+//     bulk exchanges (ntt_fast.cu TileParams::peer, quotient.cu q_plane), NCCL (comm.cu, bound with dlopen) for segment roots,
+//     openings, FRI layer 0, query pieces and the barriers.  zkir_b200_emulate_shards runs that control flow on one GPU.
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <string.h>
