@@ -103,6 +103,10 @@ int zkir_b200_comm_shutdown(zkir_ctx*);
 /* test hook: run the sharded code path for `shards` segments on ONE GPU without NCCL (the context computes every segment in
  * turn); min_segment_leaves != 0 lowers the size below which a tree is not sharded (default 4096 leaves per segment). */
 int zkir_b200_emulate_shards(zkir_ctx*, uint32_t shards, uint64_t min_segment_leaves);
+/* the partition a sharded proof uses (host arithmetic only, no GPU needed): out = {sharded?, col_lo, col_hi, row_j0, row_count,
+ * plane_lo, plane_hi, leaves_per_segment}: rank transforms trace columns [col_lo, col_hi) and quotient planes [plane_lo, plane_hi),
+ * and owns the points [row_j0, row_j0 + row_count) of every coset.  min_segment_leaves = 0: the default threshold (4096). */
+int zkir_b200_shard_plan(uint32_t world, uint32_t rank, const zkir_params*, uint32_t log_n, uint64_t min_segment_leaves, uint64_t out[8]);
 
 /* CPU verifier (host code, no GPU needed).  0 = accept, ZKIR_ERR_VERIFY = reject (reason via last_error(NULL)). */
 int zkir_b200_verify(const zkir_params*, const uint8_t* proof, size_t len, const uint32_t* public_values);

@@ -63,3 +63,47 @@ def test_single_process_is_identity():
     assert multi.shard_indices(5, 0, 1) == [0, 1, 2, 3, 4]
     assert multi.max_over_ranks([1.5, 2.5]) == [1.5, 2.5]
     assert multi.exchange_comm_id(None) == (0, 1, None)                   # no peers: no id is drawn, comm_init is a no-op
+
+
+def test_shard_plan_partitions_columns_rows_and_planes():
+    """The partition of ONE proof over `world` GPUs (zkir_b200_shard_plan, host arithmetic of csrc/prover.cu): over all ranks the
+    column ranges, the row segments and the quotient-plane ranges are disjoint and complete, a rank's Merkle leaf segment is its
+    row segment times the blowup, and sizes too small to shard fall back to the unsharded plan on every rank alike."""
+    import ctypes as C
+    import numpy as np
+    import zkir_b200
+    from zkir_b200 import _ffi
+    lib = _ffi.lib()
+
+    def plan(world, rank, cfg, log_n, min_seg=0):
+        out = (C.c_uint64 * 8)()
+        p = cfg.params()
+        assert lib.zkir_b200_shard_plan(world, rank, C.byref(p), log_n, min_seg, out) == 0
+        return list(out)
+
+    W = zkir_b200.air_layout.WIDTH
+    for world in (2, 4, 8, 64):
+        for log_n, log_b in ((20, 1), (24, 1), (16, 2), (12, 1)):
+            cfg = zkir_b200.ProverConfig(log_blowup=log_b)
+            N, M = 1 << log_n, 1 << (log_n + log_b)
+            plans = [plan(world, r, cfg, log_n) for r in range(world)]
+            on = plans[0][0]
+            assert all(p[0] == on for p in plans)                       # every rank takes the same branch
+            if M // world < 4096:
+                assert not on                                           # below the segment threshold: whole proof everywhere
+            if not on:
+                assert all(p[1:] == [0, W, 0, N, 0, 4, M] for p in plans)
+                continue
+            cols = np.zeros(W, dtype=int); rows = np.zeros(N, dtype=int); planes = np.zeros(4, dtype=int)
+            for r, (_, c0, c1, j0, nj, p0, p1, seg) in enumerate(plans):
+                cols[c0:c1] += 1; rows[j0:j0 + nj] += 1; planes[p0:p1] += 1
+                assert nj * world == N and j0 == r * nj and seg == nj << log_b
+                assert c1 - c0 <= -(-W // world) and p1 - p0 <= -(-4 // world)
+            assert (cols == 1).all() and (rows == 1).all() and (planes == 1).all()
+    # a lower threshold shards small proofs too (what the GPU tests use), and bad arguments are rejected
+    cfg = zkir_b200.ProverConfig()
+    assert plan(8, 3, cfg, 8, min_seg=2)[0] == 1 and plan(8, 3, cfg, 8)[0] == 0
+    out = (C.c_uint64 * 8)()
+    p = cfg.params()
+    assert lib.zkir_b200_shard_plan(3, 0, C.byref(p), 20, 0, out) == _ffi.ERR_ARG      # world must be a power of two
+    assert lib.zkir_b200_shard_plan(4, 4, C.byref(p), 20, 0, out) == _ffi.ERR_ARG      # rank < world

@@ -41,6 +41,7 @@ SYMBOLS = {
     "zkir_b200_comm_init": (C.c_int, [vp, vp, C.c_int, C.c_int]),
     "zkir_b200_comm_shutdown": (C.c_int, [vp]),
     "zkir_b200_emulate_shards": (C.c_int, [vp, C.c_uint32, C.c_uint64]),
+    "zkir_b200_shard_plan": (C.c_int, [C.c_uint32, C.c_uint32, C.POINTER(Params), C.c_uint32, C.c_uint64, u64p]),
     "zkir_b200_free_proof": (None, [vp]),
     "zkir_b200_proof_size": (C.c_size_t, [C.POINTER(Params), C.c_uint32]),
     "zkir_b200_verify": (C.c_int, [C.POINTER(Params), vp, C.c_size_t, u32p]),

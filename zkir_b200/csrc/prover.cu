@@ -197,6 +197,12 @@ static int ensure_scratch(zkir_ctx* ctx, int which, size_t bytes, u32** out) {
   return 0;
 }
 
+// NTT path: the fast kernels need every digit of the plans (trace, LDE domain, quotient chunks) to span >= 16 lanes
+static bool fast_path_ok(u32 log_n, u32 log_blowup, FastPlan* plan_n, FastPlan* plan_m) {
+  return !getenv("ZKIR_FORCE_GENERIC_NTT") && fast_plan((int)log_n, plan_n) && fast_plan((int)(log_n + log_blowup), plan_m) &&
+         plan_m->d[plan_m->nd - 1] - (int)log_blowup >= 4;
+}
+
 static int ws_prepare(zkir_ctx* ctx, const zkir_params* p, u32 log_n) {
   Workspace& w = ctx->ws;
   if (w.valid && w.log_n == log_n && w.log_blowup == p->log_blowup && w.width == p->width && w.nq == p->num_queries) return 0;
@@ -207,8 +213,7 @@ static int ws_prepare(zkir_ctx* ctx, const zkir_params* p, u32 log_n) {
   int rc;
 #define A(ptr, cnt) if ((rc = ws_alloc(ctx, &w.ptr, (cnt))) != 0) return rc;
   // NTT path: the fast kernels need every digit of the three plans to span >= 16 lanes
-  w.fast = !getenv("ZKIR_FORCE_GENERIC_NTT") && fast_plan((int)log_n, &w.plan_n) && fast_plan((int)(log_n + p->log_blowup), &w.plan_m) &&
-           w.plan_m.d[w.plan_m.nd - 1] - (int)p->log_blowup >= 4;
+  w.fast = fast_path_ok(log_n, p->log_blowup, &w.plan_n, &w.plan_m);
   if (w.fast) {
     w.plan_chunk = w.plan_m;
     w.plan_chunk.log_n = (int)log_n;
@@ -278,18 +283,24 @@ struct ShardPlan {
   u32 c_hi(u32 g) const { const u32 c = (g + 1) * cols_per; return c < W ? c : W; }
 };
 
+// the partition itself: pure arithmetic, also exported as zkir_b200_shard_plan for host-side tests
+static ShardPlan shard_plan_for(u32 G, u32 W, u32 log_n, u32 log_blowup, bool fast, u64 min_seg) {
+  const u64 N = 1ull << log_n, M = N << log_blowup;
+  ShardPlan sp;
+  sp.G = G; sp.W = W;
+  if (G > 1 && fast && N >= G && M / G >= min_seg && M / G >= 2) {
+    sp.on = true;
+    sp.nj = N / G;
+    while ((1ull << sp.log_nj) < sp.nj) sp.log_nj++;
+    sp.cols_per = (W + G - 1) / G;
+    sp.planes_per = (4 + G - 1) / G;
+  }
+  return sp;
+}
 // the plan of one proof; needs the workspace of that shape (ws_prepare) for `fast`
 static ShardPlan make_shard_plan(const zkir_ctx* ctx, const zkir_params* p, u32 log_n) {
-  const u64 N = 1ull << log_n, M = N << p->log_blowup, W = p->width;
-  ShardPlan sp;
-  sp.G = ctx->shards; sp.lo = ctx->shard_lo; sp.hi = ctx->shard_hi; sp.W = (u32)W;
-  if (sp.G > 1 && ctx->ws.fast && N >= sp.G && M / sp.G >= ctx->shard_min_seg && M / sp.G >= 2) {
-    sp.on = true;
-    sp.nj = N / sp.G;
-    while ((1ull << sp.log_nj) < sp.nj) sp.log_nj++;
-    sp.cols_per = (u32)((W + sp.G - 1) / sp.G);
-    sp.planes_per = (4 + sp.G - 1) / sp.G;
-  }
+  ShardPlan sp = shard_plan_for(ctx->shards, p->width, log_n, p->log_blowup, ctx->ws.fast, ctx->shard_min_seg);
+  sp.lo = ctx->shard_lo; sp.hi = ctx->shard_hi;
   return sp;
 }
 // columns of the trace this context has to materialise: all of them, or -- sharded proof with a communicator -- its own share
@@ -1018,6 +1029,20 @@ int zkir_b200_comm_shutdown(zkir_ctx* ctx) {
   peers_close(ctx);
   comm_destroy(ctx->comm);
   ctx->comm = nullptr; ctx->shards = 1; ctx->shard_lo = 0; ctx->shard_hi = 1;
+  return 0;
+}
+
+int zkir_b200_shard_plan(uint32_t world, uint32_t rank, const zkir_params* p, uint32_t log_n, uint64_t min_segment_leaves, uint64_t out[8]) {
+  if (!p || !out || world < 1 || world > ZKIR_MAX_SHARDS || (world & (world - 1)) || rank >= world || log_n < 2 || log_n + p->log_blowup > 27) return ZKIR_ERR_ARG;
+  FastPlan a, b;
+  const ShardPlan sp = shard_plan_for(world, p->width, log_n, p->log_blowup, fast_path_ok(log_n, p->log_blowup, &a, &b),
+                                      min_segment_leaves ? min_segment_leaves : 4096);
+  const u64 N = 1ull << log_n, M = N << p->log_blowup;
+  out[0] = sp.on ? 1 : 0;
+  out[1] = sp.on ? sp.c_lo(rank) : 0;          out[2] = sp.on ? sp.c_hi(rank) : p->width;   // trace columns transformed by this rank
+  out[3] = sp.on ? (u64)rank * sp.nj : 0;      out[4] = sp.on ? sp.nj : N;                  // points j of every coset = its row segment
+  out[5] = sp.on ? sp.p_lo(rank) : 0;          out[6] = sp.on ? sp.p_hi(rank) : 4;          // quotient planes transformed by this rank
+  out[7] = sp.on ? M / world : M;                                                           // Merkle leaves per segment
   return 0;
 }
 
