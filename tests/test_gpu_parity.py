@@ -251,6 +251,50 @@ def test_prove_api_end_to_end(gpu_ctx):
     assert not ok
 
 
+@pytest.mark.parametrize("n_input,log_n", [(13000, 16), (209715, 20)])
+def test_full_size_proof_bytes_match_oracle(gpu_ctx, oracle, n_input, log_n):
+    """BASELINE config 2 itself (fibonacci n=209715: 1_048_573 cycles, 2^20 rows, default parameters) and its 2^16-row
+    sibling: the WHOLE proof, byte for byte, GPU == CPU oracle (OpenMP; about 10 s at 2^20), through every entry point the
+    benchmark times (resident columns, raw rows, register write log)."""
+    res, cols, pv = fib_trace(n_input=n_input)
+    assert cols.shape[1] == 1 << log_n and res.cycles == 5 * n_input - 2
+    cfg = zkir_b200.ProverConfig()
+    want = oracle.prove(cfg, cols, pv)
+    got = gpu_ctx.prove_columns(cols, pv, cfg)
+    assert len(got) == len(want)
+    if got != want:
+        g, w = np.frombuffer(got, dtype=np.uint32), np.frombuffer(want, dtype=np.uint32)
+        first = int(np.nonzero(g != w)[0][0])
+        pytest.fail(f"2^{log_n}-row proof differs from the oracle first at word {first}: gpu={g[first]} oracle={w[first]}")
+    from_wl, pv_wl = gpu_ctx.prove_writelog(res.writelog(), cfg, log_n)
+    assert from_wl == want and list(pv_wl) == list(pv)
+    ok, why = zkir_b200.verify(got, cfg, pv)
+    assert ok, why
+
+
+def test_writelog_rejects_values_above_40_bits(gpu_ctx):
+    """A caller that logs the reference's unmasked u64 register writes must get ZKIR_ERR_AIR from the write-log path exactly as
+    from the full-row path -- never a proof of a truncated execution (bits 40..55 of a log word, bits 60..63, or a payload
+    without a register index)."""
+    res = _rows_case("mixed")
+    cfg = zkir_b200.ProverConfig(num_queries=4, pow_bits=2)
+    good = res.writelog()
+    row = int(np.nonzero(good["wlog"] >> np.uint64(56))[0][3])       # some row that writes a register
+    for bad_word in (good["wlog"][row] | np.uint64(1 << 41), good["wlog"][row] | np.uint64(1 << 61), np.uint64(5)):
+        wl = dict(good, wlog=good["wlog"].copy())
+        wl["wlog"][row] = bad_word
+        with pytest.raises(zkir_b200.RuntimeError) as ei:
+            gpu_ctx.prove_writelog(wl, cfg)
+        assert ei.value.code == -6 and f"row {row}" in str(ei.value)
+    rows = res.rows()
+    regs = rows["regs"].copy()
+    regs[row + 1, int(good["wlog"][row] >> np.uint64(56))] |= np.uint64(1 << 41)
+    with pytest.raises(zkir_b200.RuntimeError) as ei:
+        gpu_ctx.prove_rows(dict(rows, regs=regs), cfg)
+    assert ei.value.code == -6
+    assert gpu_ctx.prove_writelog(good, cfg)[0] == gpu_ctx.prove_rows(rows, cfg)[0]    # the context is still healthy
+
+
 def test_large_trace_proves_and_verifies(gpu_ctx):
     """2^16-row trace: too slow for a byte comparison with the scalar oracle in CI time, so use the size-independent
     property: the independent CPU verifier accepts and rejects a flipped bit."""

@@ -1,0 +1,24 @@
+#!/usr/bin/env python3
+"""Identity of the CUDA build: sha256 over the library's sources (zkir_b200/csrc/**, include/*.h), first 12 hex digits.
+bench.py prints it, the profile tools store it, so a number read from profiles/ can be matched to the build that produced it."""
+import hashlib
+import os
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def build_id():
+    h = hashlib.sha256()
+    files = []
+    for d in ("zkir_b200/csrc", "zkir_b200/csrc/host", "include"):
+        for f in sorted(os.listdir(os.path.join(ROOT, d))):
+            if f.endswith((".cu", ".cc", ".h", ".cuh")):
+                files.append(os.path.join(d, f))
+    for rel in files:
+        h.update(rel.encode())
+        h.update(open(os.path.join(ROOT, rel), "rb").read())
+    return h.hexdigest()[:12]
+
+
+if __name__ == "__main__":
+    print(build_id())

@@ -146,6 +146,7 @@ struct zkir_ctx {
   bool have_stage = false;
 };
 
+static int peers_barrier(zkir_ctx* ctx);
 static void peers_close(zkir_ctx* ctx) {
   Workspace& w = ctx->ws;
   for (void* p : w.ipc_opened) cudaIpcCloseMemHandle(p);
@@ -206,6 +207,13 @@ static bool fast_path_ok(u32 log_n, u32 log_blowup, FastPlan* plan_n, FastPlan* 
 static int ws_prepare(zkir_ctx* ctx, const zkir_params* p, u32 log_n) {
   Workspace& w = ctx->ws;
   if (w.valid && w.log_n == log_n && w.log_blowup == p->log_blowup && w.width == p->width && w.nq == p->num_queries) return 0;
+  if (ctx->comm && w.valid) {
+    // Sharded mode: other ranks may still have this workspace mapped (cudaIpcOpenMemHandle); freeing exported memory before the
+    // importers closed it is undefined.  A shape change is collective, so: everyone closes its mappings, one barrier, then free.
+    peers_close(ctx);
+    int brc = peers_barrier(ctx); if (brc) return brc;
+    CU(cudaStreamSynchronize(ctx->stream));
+  }
   ws_free(ctx);
   const u64 N = 1ull << log_n, M = N << p->log_blowup, W = p->width;
   const u32 R = log_n;
@@ -793,6 +801,7 @@ int zkir_b200_prove_device(zkir_ctx* ctx, const zkir_params* p, const uint32_t* 
   if (rc) return rc;
   if (!d_trace || !pv || !proof || !proof_len) { ctx->err = "null argument"; return ZKIR_ERR_ARG; }
   if ((rc = ws_prepare(ctx, p, log_n)) != 0) return rc;
+  ctx->ws.graph_run = false;   // only zkir_b200_prove replays graphs; a stale flag would hide this proof's stage timings
   CU(cudaEventRecord(ctx->ev[ZKIR_STAGE_H2D], ctx->stream));
   if ((rc = prove_resident(ctx, p, log_n, pv, d_trace)) != 0) return rc;  // read in place: no pass writes the caller's matrix
   return finish_proof(ctx, p, log_n, proof, proof_len);
@@ -848,6 +857,7 @@ int zkir_b200_prove_rows(zkir_ctx* ctx, const zkir_params* p, const uint64_t* pc
   if (rc) return rc;
   if (!pv_out || !proof || !proof_len) { ctx->err = "null argument"; return ZKIR_ERR_ARG; }
   if ((rc = ws_prepare(ctx, p, log_n)) != 0) return rc;
+  ctx->ws.graph_run = false;   // only zkir_b200_prove replays graphs; a stale flag would hide this proof's stage timings
   CU(cudaEventRecord(ctx->ev[ZKIR_STAGE_H2D], ctx->stream));
   u32 c_lo, c_hi;
   trace_col_range(ctx, p, log_n, &c_lo, &c_hi);   // a sharded proof only materialises the columns this rank transforms
@@ -919,6 +929,7 @@ int zkir_b200_prove_writelog(zkir_ctx* ctx, const zkir_params* p, const uint32_t
   if (rc) return rc;
   if (!pv_out || !proof || !proof_len) { ctx->err = "null argument"; return ZKIR_ERR_ARG; }
   if ((rc = ws_prepare(ctx, p, log_n)) != 0) return rc;
+  ctx->ws.graph_run = false;   // only zkir_b200_prove replays graphs; a stale flag would hide this proof's stage timings
   CU(cudaEventRecord(ctx->ev[ZKIR_STAGE_H2D], ctx->stream));
   u32 c_lo, c_hi;
   trace_col_range(ctx, p, log_n, &c_lo, &c_hi);   // a sharded proof only materialises the columns this rank transforms
@@ -1026,6 +1037,11 @@ int zkir_b200_comm_shutdown(zkir_ctx* ctx) {
   if (!ctx) return ZKIR_ERR_ARG;
   cudaSetDevice(ctx->device);
   CU(cudaStreamSynchronize(ctx->stream));
+  if (ctx->comm && ctx->ws.valid) {   // collective: every rank closes its peer mappings before any rank may free its workspace
+    peers_close(ctx);
+    int brc = peers_barrier(ctx); if (brc) return brc;
+    CU(cudaStreamSynchronize(ctx->stream));
+  }
   peers_close(ctx);
   comm_destroy(ctx->comm);
   ctx->comm = nullptr; ctx->shards = 1; ctx->shard_lo = 0; ctx->shard_hi = 1;

@@ -218,6 +218,13 @@ __global__ void __launch_bounds__(WL_CHUNK) trace_expand_wl_kernel(WlArgs a) {
   }
   if (i >= a.N) return;
   const bool live = i < a.T;
+  // The log word is (k << 56) | value with value < 2^40 and bits 40..55 zero: a caller that logged an unmasked u64 (the reference's
+  // write_reg takes any u64, state.rs:76-91) must get ZKIR_ERR_AIR like zkir_pack_trace / prove_rows give, not a proof of a truncated
+  // execution.  Checked BEFORE the masks below; a payload without a register index (k = 0 is "nothing written") is rejected too.
+  if (live && (((wl >> 40) & 0xFFFFull) || (wl >> 60) || (kw == 0 && wl != 0))) {
+    const bool read_row = (a.ins[i] & 0x7F) == 0x50 && rg[10] == 1;
+    atomicMin(reinterpret_cast<unsigned long long*>(a.err), (unsigned long long)((i << 8) | (read_row ? 3u : 2u)));
+  }
   // READ rows need the post-state r10: the logged value if the row changed r10, else the unchanged pre-state
   const u64 read_val = kw == 10u ? (wl & M40) : rg[10];
   expand_row(i, a.N, a.T, rg, live ? (u64)a.pcs[i] : a.final_pc, live ? a.ins[i] : 0u, read_val, a.cols, a.err, a.col_lo, a.col_hi);

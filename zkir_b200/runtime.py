@@ -264,8 +264,10 @@ class Context:
         return float(ms.value)
 
     def stage_ms(self):
+        """per-stage device times of the last proof; {} when it was a CUDA-graph replay (no per-stage events)"""
         out = (C.c_float * len(_ffi.STAGES))()
-        self._check(self._l.zkir_b200_last_stage_ms(self._h, out))
+        if self._l.zkir_b200_last_stage_ms(self._h, out) != 0:
+            return {}
         return dict(zip(_ffi.STAGES, list(out)))
 
     # -- one proof sharded over several GPUs (include/zkir_b200.h: zkir_b200_comm_*)

@@ -1,0 +1,69 @@
+"""Synthetic workloads of the BASELINE configs, shared by bench.py, the smoke check and the tests.
+
+Programs are written in the v3.4 assembly the reference's own tests use (tests/end_to_end.rs:310-332 for the fibonacci loop,
+syscall numbers in R10 per zkir-runtime/src/syscall.rs:82-87)."""
+import time
+
+FIB_SRC = """
+addi r1, r0, 0
+addi r2, r0, 1
+addi r3, r0, {n}
+addi r4, r0, 2
+add r5, r1, r2
+add r1, r0, r2
+add r2, r0, r5
+addi r4, r4, 1
+bne r4, r3, -16
+add r10, r0, r0
+ecall
+"""
+
+# BASELINE config 4: a + b from the input tape, 11 cycles
+ADD_SRC = ("addi r10, r0, 1\necall\nadd r1, r10, r0\naddi r10, r0, 1\necall\nadd r11, r1, r10\naddi r10, r0, 2\necall\n"
+           "addi r10, r0, 0\naddi r11, r0, 0\necall\n")
+
+FIB_N_FULL = 209715          # 5n - 2 = 1_048_573 cycles -> 2^20 rows (BASELINE config 2)
+
+
+def fib_program(n):
+    """BASELINE config 1: the reference's runnable fibonacci with `addi r3,r0,n` (n fits the 17-bit immediate)."""
+    from . import assemble
+    return assemble(FIB_SRC.format(n=n))
+
+
+def fib_program_input():
+    """BASELINE config 2: n comes from the input tape (17-bit immediates cannot hold 209715; encoder.rs:117)."""
+    from . import assemble
+    body = FIB_SRC.format(n=0).strip().splitlines()
+    return assemble("addi r10, r0, 1\necall\nadd r3, r10, r0\n" + "\n".join(body[:2] + body[3:]))
+
+
+def add_program():
+    from . import assemble
+    return assemble(ADD_SRC)
+
+
+def run_traced(prog, inputs=(), max_cycles=1 << 26):
+    from . import VM, VMConfig
+    return VM(prog, list(inputs), VMConfig(max_cycles=max_cycles, enable_execution_trace=True)).run()
+
+
+def fib_trace(n=None, n_input=None, log_n=None):
+    """-> (ExecutionResult, columns, public values) of the fibonacci workload (host packer)."""
+    if n_input is not None:
+        prog, inputs = fib_program_input(), [n_input]
+    else:
+        prog, inputs = fib_program(n), []
+    res = run_traced(prog, inputs)
+    cols, pv = res.pack(log_n)
+    return res, cols, pv
+
+
+def timed_fib_trace(n_input):
+    """-> (ExecutionResult, cols, pv, interpreter seconds, packer seconds)"""
+    prog = fib_program_input()
+    t0 = time.perf_counter()
+    res = run_traced(prog, [n_input])
+    t1 = time.perf_counter()
+    cols, pv = res.pack(None)
+    return res, cols, pv, t1 - t0, time.perf_counter() - t1
