@@ -107,19 +107,19 @@ def cpu_oracle_run(fib_n, steps, warmup, budget_s=CPU_BUDGET_S):
     cores = int(o.l.oracle_set_threads(len(os.sched_getaffinity(0))))
     cfg = zkir_b200.ProverConfig()
     t0 = time.time()
-    pb = o.prove(cfg, cols, pv)           # probe (and the one warm-up proof when warmup >= 1)
+    pb = o.prove(cfg, cols, pv, res.program)           # probe (and the one warm-up proof when warmup >= 1)
     probe = time.time() - t0
-    ok, why = zkir_b200.verify(pb, cfg, pv)
+    ok, why = zkir_b200.verify(pb, cfg, pv, res.program)
     if not ok:
         raise SystemExit(f"CPU oracle proof rejected by the verifier: {why}")
     warm_done = 1
     for _ in range(max(0, min(warmup, 1) - warm_done)):
-        o.prove(cfg, cols, pv)
+        o.prove(cfg, cols, pv, res.program)
     if warmup >= 1:
         steps = max(1, min(steps, int(budget_s / max(probe, 1e-3))))
         t0 = time.time()
         for _ in range(steps):
-            o.prove(cfg, cols, pv)
+            o.prove(cfg, cols, pv, res.program)
         dt = (time.time() - t0) / steps
     else:                                  # no warm-up asked: the probe IS the single timed proof
         steps, dt = 1, probe
@@ -195,6 +195,7 @@ def main():
     cycles = res.cycles
     log_n = int(cols.shape[1]).bit_length() - 1
     ctx = zkir_b200.Context(local_rank)
+    ctx.set_program(res.program)
     cfg = zkir_b200.ProverConfig()
     workload = workload_name(args.fib_n, log_n, int(cols.shape[0]), cfg)
     # the interpreter's raw rows (TraceRow: pc, word, 16 registers) in pinned host memory: what crosses PCIe per step
@@ -219,7 +220,7 @@ def main():
     for _ in range(args.warmup):
         pb = ctx.prove_columns(None, pv, cfg, device_resident=(d_trace, log_n))
     proof_bytes = len(pb)
-    ok, why = zkir_b200.verify(pb, cfg, pv)
+    ok, why = zkir_b200.verify(pb, cfg, pv, res.program)
     if not ok:
         raise SystemExit(f"proof rejected by the verifier: {why}")
     barrier()
@@ -259,6 +260,7 @@ def main():
     # ---------------- throughput mode: two proofs in flight on this GPU (second context = own stream + host thread); the
     # latency-bound phases of one proof (FRI, Merkle tops, Fiat-Shamir steps) overlap the hashing of the other
     ctx2 = zkir_b200.Context(local_rank)
+    ctx2.set_program(res.program)
     d_trace2 = ctx2.to_device(cols)
     for _ in range(2):
         ctx2.prove_columns(None, pv, cfg, device_resident=(d_trace2, log_n))
@@ -322,7 +324,7 @@ def main():
         # ENFORCED on every rank: the sharded proof must be the single-GPU proof, byte for byte, and the verifier must accept it.
         # A mismatch ends the benchmark with a non-zero exit code (no JSON line), it is not a reported flag.
         shard_sha = hashlib.sha256(pb_sh).hexdigest()
-        ok_sh, why_sh = zkir_b200.verify(pb_sh, cfg, pv)
+        ok_sh, why_sh = zkir_b200.verify(pb_sh, cfg, pv, res.program)
         same = torch.tensor([1 if (pb_sh == pb and ok_sh) else 0], dtype=torch.int32, device="cuda")
         dist.all_reduce(same, op=dist.ReduceOp.MIN)
         print(f"[rank {rank}] one_proof_sharded sha256={shard_sha} single_gpu sha256={hashlib.sha256(pb).hexdigest()} verifier={'ok' if ok_sh else why_sh}",

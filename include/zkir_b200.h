@@ -26,20 +26,21 @@ extern "C" {
 #define ZKIR_ERR_NCCL (-3)
 #define ZKIR_ERR_OOM (-4)
 #define ZKIR_ERR_VM (-5)    /* guest fault: DivisionByZero / MisalignedAccess / InvalidSyscall ... (error.rs:6-39) */
-#define ZKIR_ERR_AIR (-6)   /* trace uses an opcode / value the core AIR v1 does not constrain */
+#define ZKIR_ERR_AIR (-6)   /* trace uses an opcode / value the AIR v2 does not constrain */
 #define ZKIR_ERR_VERIFY (-7)
 
 #define ZKIR_BABYBEAR_P 2013265921u
-#define ZKIR_AIR_V1_WIDTH 72u
-#define ZKIR_AIR_V1_NUM_PUBLIC 4u
+#define ZKIR_AIR_V2_WIDTH 88u      /* main trace columns (docs/PROVER_SPEC.md section 3); 16 aux + 4 public columns are internal */
+#define ZKIR_AIR_V2_NUM_PUBLIC 5u  /* entry_pc, num_cycles, exit_lo, exit_hi, halted */
+#define ZKIR_MIN_LOG_N 10u         /* the 1024-entry range table (zkir-spec/src/config.rs:76-80) occupies trace rows */
 
 /* ---- proving parameters (the reference has none; Plonky3's FriConfig fields) */
 typedef struct {
   uint32_t log_blowup;  /* >= 1 */
   uint32_t num_queries;
   uint32_t pow_bits;
-  uint32_t width;       /* must equal ZKIR_AIR_V1_WIDTH */
-  uint32_t num_public;  /* must equal ZKIR_AIR_V1_NUM_PUBLIC */
+  uint32_t width;       /* must equal ZKIR_AIR_V2_WIDTH */
+  uint32_t num_public;  /* must equal ZKIR_AIR_V2_NUM_PUBLIC */
 } zkir_params;
 
 typedef struct zkir_ctx zkir_ctx;
@@ -51,6 +52,12 @@ const char* zkir_b200_last_error(const zkir_ctx*); /* ctx may be NULL: last crea
 /* pinned host buffers the interpreter records into (north_star: "records the execution trace into pinned memory") */
 void* zkir_b200_alloc_pinned(size_t bytes);
 void zkir_b200_free_pinned(void*);
+
+/* ---- the program whose executions this context proves: `Program.code` (zkir-spec/src/program.rs:241-250), loaded at 0x1000 by
+ * VM::new (vm.rs:138-205).  The AIR binds every executed (pc, instruction) to this ROM through a lookup argument, and the
+ * transcript absorbs its digest, so a proof is a statement about THIS program.  Must be called before the first prove call and
+ * whenever the program changes (the decoded ROM columns and their LDE are cached per trace size).  Copies the words. */
+int zkir_b200_set_program(zkir_ctx*, const uint32_t* code, size_t n_code);
 
 /* ---- the hot path: trace columns -> proof.  Sits where `zkir_runtime::prove()` would call into Plonky3
  * (the call does not exist in the reference: zkir-runtime/src/lib.rs:29-62).  `trace_cols` is HOST memory
@@ -65,22 +72,28 @@ int zkir_b200_prove_device(zkir_ctx*, const zkir_params*, const uint32_t* d_trac
  * (zkir-spec/src/trace.rs:24-50: pc, instruction word, PRE-state registers[16]; cycle = row index), host memory (pinned
  * recommended).  The converter (trace.rs:41) runs on the device, so 140 B/row cross PCIe instead of 340 B/row.
  * final_regs / final_pc: machine state after the last instruction; exit_code: HaltReason::Exit code (0 otherwise).
- * Writes the 4 public values {entry_pc, num_cycles, exit_lo, exit_hi} it proves to public_values_out.
- * Rows the core AIR v1 cannot constrain give ZKIR_ERR_AIR (same rules as zkir_pack_trace). */
+ * halt_kind: ZKIR_HALT_* of the run.  Writes the 5 public values {entry_pc, num_cycles, exit_lo, exit_hi, halted} it proves to
+ * public_values_out.  Rows the AIR v2 cannot constrain give ZKIR_ERR_AIR (same rules as zkir_pack_trace). */
 int zkir_b200_prove_rows(zkir_ctx*, const zkir_params*, const uint64_t* pcs, const uint32_t* instrs, const uint64_t* regs,
                          uint64_t n_rows, const uint64_t* final_regs, uint64_t final_pc, uint32_t entry_point, uint64_t exit_code,
-                         uint32_t log_n, uint32_t* public_values_out, uint8_t** proof, size_t* proof_len);
+                         int halt_kind, uint32_t log_n, uint32_t* public_values_out, uint8_t** proof, size_t* proof_len);
 /* same from the interpreter's REGISTER WRITE LOG, the most compact hand-off: per row pc (u32), instruction word and
  * wlog = (k << 56) | value if the row changed register k, else 0 (zkir_vm_trace_writelog builds it from recorded rows; a
  * Rust recorder logs it where VMState writes a register, zkir-runtime/src/state.rs:76-91).  The device rebuilds the
  * pre-state registers of every row with a last-writer scan (registers start at 0: vm.rs:177-181), then runs the same
  * converter.  16 B/row cross PCIe. */
 int zkir_b200_prove_writelog(zkir_ctx*, const zkir_params*, const uint32_t* pcs, const uint32_t* instrs, const uint64_t* wlog,
-                             uint64_t n_rows, uint64_t final_pc, uint32_t entry_point, uint64_t exit_code, uint32_t log_n,
+                             uint64_t n_rows, uint64_t final_pc, uint32_t entry_point, uint64_t exit_code, int halt_kind, uint32_t log_n,
                              uint32_t* public_values_out, uint8_t** proof, size_t* proof_len);
+/* Program -> Proof in one call, the drop-in for `zkir_runtime::prove(program, inputs)` (absent upstream: lib.rs:29-62): runs the
+ * interpreter (vm.cc) with the register write log recorded straight into pinned memory, uploads the log in chunks WHILE the
+ * interpreter is still running, then proves.  Sets the context's program itself.  out_cycles / out_log_n may be NULL. */
+int zkir_b200_prove_program(zkir_ctx*, const zkir_params*, const uint32_t* code, size_t n_code, const uint8_t* data, size_t n_data,
+                            uint32_t entry_point, const uint64_t* inputs, size_t n_inputs, uint64_t max_cycles,
+                            uint32_t* public_values_out, uint64_t* out_cycles, uint32_t* out_log_n, uint8_t** proof, size_t* proof_len);
 int zkir_b200_expand_writelog(zkir_ctx*, const uint32_t* pcs, const uint32_t* instrs, const uint64_t* wlog, uint64_t n_rows,
                               uint64_t final_pc, uint32_t log_n, uint32_t* d_cols);
-/* the device converter alone (parity tests): rows -> d_cols [72][1 << log_n] canonical, device memory */
+/* the device converter alone (parity tests): rows -> d_cols [width][1 << log_n] canonical, device memory */
 int zkir_b200_expand_rows(zkir_ctx*, const uint64_t* pcs, const uint32_t* instrs, const uint64_t* regs, uint64_t n_rows,
                           const uint64_t* final_regs, uint64_t final_pc, uint32_t log_n, uint32_t* d_cols);
 /* many independent small proofs (BASELINE config 4); traces[i] is host memory [width][1<<log_ns[i]] */
@@ -108,8 +121,14 @@ int zkir_b200_emulate_shards(zkir_ctx*, uint32_t shards, uint64_t min_segment_le
  * and owns the points [row_j0, row_j0 + row_count) of every coset.  min_segment_leaves = 0: the default threshold (4096). */
 int zkir_b200_shard_plan(uint32_t world, uint32_t rank, const zkir_params*, uint32_t log_n, uint64_t min_segment_leaves, uint64_t out[8]);
 
-/* CPU verifier (host code, no GPU needed).  0 = accept, ZKIR_ERR_VERIFY = reject (reason via last_error(NULL)). */
-int zkir_b200_verify(const zkir_params*, const uint8_t* proof, size_t len, const uint32_t* public_values);
+/* CPU verifier (host code, no GPU needed).  0 = accept, ZKIR_ERR_VERIFY = reject (reason via last_error(NULL)).  `code` = the
+ * program the proof is about (the verifier evaluates the ROM polynomials itself and absorbs the program digest). */
+int zkir_b200_verify(const zkir_params*, const uint8_t* proof, size_t len, const uint32_t* public_values, const uint32_t* code,
+                     size_t n_code);
+/* host helpers shared by the interpreter, the prover's ROM builder and guest-side tooling */
+void zkir_host_poseidon2_permute(uint32_t state16[16]);          /* width-16 Poseidon2 of docs/PROVER_SPEC.md section 2, canonical */
+void zkir_rom_entry(uint32_t word, uint32_t* dec, uint32_t* imm); /* decoded ROM row of one instruction word (spec section 3.3) */
+void zkir_program_digest(const uint32_t* code, size_t n_code, uint32_t digest8[8]); /* what the transcript absorbs for the program */
 
 /* ---- per-kernel entry points (parity tests, ncu captures, roofline harness).  Device pointers, canonical values. */
 /* batched NTT over `n_cols` contiguous columns of length 1<<log_n, in place, natural order in and out.
@@ -121,9 +140,13 @@ int zkir_b200_poseidon2_permute(zkir_ctx*, uint32_t* d_states /* [n][16] */, uin
 /* leaf = sponge over a row of the column-major matrix; d_tree receives (2*rows-1)*8 words (leaves first) */
 int zkir_b200_merkle_commit(zkir_ctx*, const uint32_t* d_matrix, uint32_t n_cols, uint32_t log_rows, uint32_t* d_tree,
                             uint32_t root[8]);
-/* quotient values of the core AIR on the LDE coset: d_lde [width][M], out d_q [4][M], M = 1<<(log_n+log_blowup) */
-int zkir_b200_quotient(zkir_ctx*, const zkir_params*, const uint32_t* d_lde, uint32_t log_n, const uint32_t* public_values,
-                       const uint32_t alpha[4], uint32_t* d_q);
+/* quotient values of the AIR on the LDE coset: d_lde [width + 16][M] (main then aux columns), d_publde [4][M] (public columns),
+ * lookup = {z[4], theta[4]}, out d_q [4][M], M = 1<<(log_n+log_blowup); all natural order */
+int zkir_b200_quotient(zkir_ctx*, const zkir_params*, const uint32_t* d_lde, const uint32_t* d_publde, uint32_t log_n,
+                       const uint32_t* public_values, const uint32_t lookup[8], const uint32_t alpha[4], uint32_t* d_q);
+/* the LogUp aux columns of a trace for given lookup challenges: d_trace [width][N] canonical -> d_aux [16][N] canonical; uses the
+ * context's program for the ROM columns.  (The prover draws the challenges from the transcript; this entry point is for parity tests.) */
+int zkir_b200_aux_columns(zkir_ctx*, const uint32_t* d_trace, uint32_t log_n, const uint32_t lookup[8], uint32_t* d_aux);
 /* one FRI fold: d_in [1<<log_n][4] (ext4, AoS) on shift*H -> d_out [1<<(log_n-1)][4] */
 int zkir_b200_fri_fold(zkir_ctx*, const uint32_t* d_in, uint32_t* d_out, uint32_t log_n, uint32_t shift, const uint32_t beta[4]);
 /* device memory helpers so ctypes callers need no CUDA binding of their own */
@@ -136,12 +159,13 @@ int zkir_b200_sync(zkir_ctx*);
 #define ZKIR_STAGE_H2D 0
 #define ZKIR_STAGE_LDE 1
 #define ZKIR_STAGE_TRACE_COMMIT 2
-#define ZKIR_STAGE_QUOTIENT 3
-#define ZKIR_STAGE_QUOTIENT_COMMIT 4
-#define ZKIR_STAGE_OPENINGS 5
-#define ZKIR_STAGE_FRI 6
-#define ZKIR_STAGE_QUERIES_D2H 7
-#define ZKIR_STAGE_COUNT 8
+#define ZKIR_STAGE_AUX 3 /* LogUp aux columns: generation, LDE, commitment */
+#define ZKIR_STAGE_QUOTIENT 4
+#define ZKIR_STAGE_QUOTIENT_COMMIT 5
+#define ZKIR_STAGE_OPENINGS 6
+#define ZKIR_STAGE_FRI 7
+#define ZKIR_STAGE_QUERIES_D2H 8
+#define ZKIR_STAGE_COUNT 9
 int zkir_b200_last_stage_ms(zkir_ctx*, float out[ZKIR_STAGE_COUNT]);
 uint64_t zkir_b200_kernel_launches(const zkir_ctx*); /* kernels launched by this ctx so far */
 /* CUDA-event stopwatch on the context's own stream (the per-kernel entry points launch there, so an outside event on
@@ -165,6 +189,9 @@ uint32_t zkir_encode(uint32_t opcode, uint32_t r_a, uint32_t r_b, uint32_t r_c, 
 int zkir_decode(uint32_t word, uint32_t out5[5]);
 int zkir_vm_run(const uint32_t* code, size_t n_code, const uint8_t* data, size_t n_data, uint32_t entry_point,
                 const uint64_t* inputs, size_t n_inputs, uint64_t max_cycles, int record_trace, zkir_vm_result** out);
+/* SYS_POSEIDON2 (syscall 4) errors by default like the reference's stub (crypto.rs:299-315); on != 0 enables this build's
+ * semantics for the calling thread: 16 LE u32 words at R11 (mod p) -> width-16 Poseidon2 -> 16 words at R13, R10 <- 0 */
+void zkir_vm_enable_poseidon2(int on);
 void zkir_vm_free(zkir_vm_result*);
 const char* zkir_vm_last_error(void);
 uint64_t zkir_vm_cycles(const zkir_vm_result*);
@@ -180,12 +207,28 @@ const uint64_t* zkir_vm_trace_aux(const zkir_vm_result*);
 const uint64_t* zkir_vm_trace_memop_begin(const zkir_vm_result*);
 const zkir_mem_op* zkir_vm_trace_memops(const zkir_vm_result*);
 int zkir_vm_trace_writelog(const zkir_vm_result*, uint32_t* pcs32 /*[trace_len]*/, uint64_t* wlog /*[trace_len]*/);
+/* the recorder the north star describes: the interpreter appends (pc, word, (reg << 56) | value) for every cycle STRAIGHT into the
+ * caller's arrays (pinned memory, zkir_b200_alloc_pinned) while it executes -- where VMState::write_reg is called upstream
+ * (zkir-runtime/src/state.rs:76-91).  No per-cycle register snapshot is taken.  zkir_vm_logged_rows = cycles. */
+int zkir_vm_run_writelog(const uint32_t* code, size_t n_code, const uint8_t* data, size_t n_data, uint32_t entry_point,
+                         const uint64_t* inputs, size_t n_inputs, uint64_t max_cycles, uint32_t* pcs32, uint32_t* instrs,
+                         uint64_t* wlog, uint64_t capacity, zkir_vm_result** out);
+/* same with a progress callback every chunk_rows cycles (rows before rows_done are final); zkir_b200_prove_program uses it to overlap
+ * the host->device copy of the log with the execution */
+int zkir_vm_run_writelog_cb(const uint32_t* code, size_t n_code, const uint8_t* data, size_t n_data, uint32_t entry_point,
+                            const uint64_t* inputs, size_t n_inputs, uint64_t max_cycles, uint32_t* pcs32, uint32_t* instrs,
+                            uint64_t* wlog, uint64_t capacity, void (*on_chunk)(void* user, uint64_t rows_done), void* user,
+                            uint64_t chunk_rows, zkir_vm_result** out);
+uint64_t zkir_vm_logged_rows(const zkir_vm_result*);
+size_t zkir_vm_code_len(const zkir_vm_result*);
+const uint32_t* zkir_vm_code(const zkir_vm_result*);
 uint64_t zkir_vm_final_pc(const zkir_vm_result*);
 const uint64_t* zkir_vm_final_regs(const zkir_vm_result*);
 
 /* "converter" TraceRow -> field columns (named but absent in the reference: zkir-spec/src/trace.rs:41,
  * zkir-runtime/src/vm.rs:243-244).  Writes cols[width][1<<log_n] (host, pinned recommended) and
- * public_values[4] = {entry_pc, num_cycles, exit_lo, exit_hi}.  min log_n via zkir_pack_min_log_n. */
+ * public_values[5] = {entry_pc, num_cycles, exit_lo, exit_hi, halted}.  min log_n via zkir_pack_min_log_n (>= 10: the range
+ * table and the program ROM occupy trace rows). */
 uint32_t zkir_pack_min_log_n(const zkir_vm_result*);
 int zkir_pack_trace(const zkir_vm_result*, uint32_t entry_point, uint32_t log_n, uint32_t* cols, uint32_t* public_values);
 

@@ -30,8 +30,15 @@ class Oracle:
     def _p(a):
         return a.ctypes.data_as(C.c_void_p)
 
+    WIDTH, AUX_WIDTH, PUB_WIDTH, NUM_PUBLIC = 88, 16, 4, 5   # AIR v2 (oracle/air_generated.h)
+    LOOKUP_TEST = np.array([3, 1, 4, 1, 5, 9, 2, 6], dtype=np.uint32)   # fixed lookup challenges z, theta for row-domain checks
+
     def params(self, cfg):
-        return np.array([cfg.log_blowup, cfg.num_queries, cfg.pow_bits, 72, 4], dtype=np.uint32)
+        return np.array([cfg.log_blowup, cfg.num_queries, cfg.pow_bits, self.WIDTH, self.NUM_PUBLIC], dtype=np.uint32)
+
+    @staticmethod
+    def _code(program):
+        return np.ascontiguousarray(getattr(program, "code", program), dtype=np.uint32)
 
     def ntt(self, cols, inverse=False):
         a = np.ascontiguousarray(cols, dtype=np.uint32).copy()
@@ -65,14 +72,37 @@ class Oracle:
         self.l.oracle_merkle_commit(self._p(a), n_cols, int(rows).bit_length() - 1, self._p(tree), self._p(root))
         return tree, root
 
-    def quotient(self, cfg, lde, log_n, pv, alpha):
+    def quotient(self, cfg, lde, publde, log_n, pv, lookup, alpha):
+        """lde [WIDTH + 16][M] (main then aux columns), publde [4][M], natural order -> quotient values [4][M]"""
         M = lde.shape[1]
         out = np.empty((4, M), dtype=np.uint32)
         pr = self.params(cfg)
         pv = np.ascontiguousarray(pv, dtype=np.uint32)
         al = np.ascontiguousarray(alpha, dtype=np.uint32)
-        self.l.oracle_quotient(self._p(pr), log_n, self._p(np.ascontiguousarray(lde)), self._p(pv), self._p(al), self._p(out))
+        lk = np.ascontiguousarray(lookup, dtype=np.uint32)
+        self.l.oracle_quotient(self._p(pr), log_n, self._p(np.ascontiguousarray(lde)), self._p(np.ascontiguousarray(publde)), self._p(pv), self._p(lk), self._p(al), self._p(out))
         return out
+
+    def public_columns(self, log_n, program):
+        code = self._code(program)
+        pub = np.empty((self.PUB_WIDTH, 1 << log_n), dtype=np.uint32)
+        self.l.oracle_public_columns(log_n, self._p(code), C.c_uint64(len(code)), self._p(pub))
+        return pub
+
+    def aux_columns(self, cols, program, lookup=None):
+        """-> (aux [16][N], balanced?) for the lookup challenges z, theta"""
+        cols = np.ascontiguousarray(cols)
+        code = self._code(program)
+        lk = np.ascontiguousarray(self.LOOKUP_TEST if lookup is None else lookup, dtype=np.uint32)
+        aux = np.empty((self.AUX_WIDTH, cols.shape[1]), dtype=np.uint32)
+        ok = self.l.oracle_aux_columns(int(cols.shape[1]).bit_length() - 1, self._p(cols), self._p(code), C.c_uint64(len(code)), self._p(lk), self._p(aux))
+        return aux, bool(ok)
+
+    def program_digest(self, program):
+        code = self._code(program)
+        d = np.empty(8, dtype=np.uint32)
+        self.l.oracle_program_digest(self._p(code), C.c_uint64(len(code)), self._p(d))
+        return d
 
     def fri_fold(self, layer, shift, beta):
         a = np.ascontiguousarray(layer, dtype=np.uint32)
@@ -82,18 +112,24 @@ class Oracle:
         self.l.oracle_fri_fold(self._p(a), self._p(out), int(n).bit_length() - 1, C.c_uint32(shift), self._p(b))
         return out
 
-    def check_trace(self, cols, pv):
+    def check_trace(self, cols, pv, program, lookup=None):
+        """every AIR constraint (LogUp included, aux columns built for `lookup`) on the unextended rows:
+        (-1, _) all hold; (-2, _) lookups unbalanced; (k, row) first failing constraint"""
         bad = C.c_uint64()
         cols = np.ascontiguousarray(cols)
-        k = self.l.oracle_check_trace(self._p(cols), int(cols.shape[1]).bit_length() - 1, self._p(np.ascontiguousarray(pv, dtype=np.uint32)), C.byref(bad))
+        code = self._code(program)
+        lk = np.ascontiguousarray(self.LOOKUP_TEST if lookup is None else lookup, dtype=np.uint32)
+        k = self.l.oracle_check_trace(self._p(cols), int(cols.shape[1]).bit_length() - 1, self._p(np.ascontiguousarray(pv, dtype=np.uint32)),
+                                      self._p(code), C.c_uint64(len(code)), self._p(lk), C.byref(bad))
         return k, bad.value
 
-    def prove(self, cfg, cols, pv):
+    def prove(self, cfg, cols, pv, program):
         pr = self.params(cfg)
         cols = np.ascontiguousarray(cols)
+        code = self._code(program)
         log_n = int(cols.shape[1]).bit_length() - 1
         nw = self.l.oracle_proof_words(self._p(pr), log_n)
         proof = np.zeros(nw, dtype=np.uint32)
-        rc = self.l.oracle_prove(self._p(pr), self._p(cols), log_n, self._p(np.ascontiguousarray(pv, dtype=np.uint32)), self._p(proof))
+        rc = self.l.oracle_prove(self._p(pr), self._p(cols), log_n, self._p(np.ascontiguousarray(pv, dtype=np.uint32)), self._p(code), C.c_uint64(len(code)), self._p(proof))
         assert rc == 0, f"oracle_prove failed rc={rc}"
         return proof.tobytes()

@@ -202,36 +202,133 @@ struct Chal {
   u32 sample_bits(int b) { u32 v = sample(); return b >= 32 ? v : (v & ((1u << b) - 1)); }
 };
 
-// ------------------------------------------------------------------ AIR evaluation contexts
-struct AirRowCtx {  // base-field row check / quotient numerator at one point
-  typedef Fp F;
-  const u32* data; size_t stride, row, nxt; const u32* pv;
+// ------------------------------------------------------------------ AIR evaluation contexts (air_generated.h, AIR v2)
+struct Xp { E4 v; };  // ext4 with operators, for the generated code
+static inline Xp operator+(Xp a, Xp b) { Xp r; r.v = e4_add(a.v, b.v); return r; }
+static inline Xp operator-(Xp a, Xp b) { Xp r; r.v = e4_sub(a.v, b.v); return r; }
+static inline Xp operator*(Xp a, Xp b) { Xp r; r.v = e4_mul(a.v, b.v); return r; }
+static inline Xp operator*(Xp a, Fp b) { Xp r; r.v = e4_mulb(a.v, b.v); return r; }
+
+struct LookupChallenges { E4 z, th[4]; };  // th[k] = theta^k
+static LookupChallenges make_challenges(E4 z, E4 theta) {
+  LookupChallenges c; c.z = z; c.th[0] = e4_from(1); c.th[1] = theta; c.th[2] = e4_mul(theta, theta); c.th[3] = e4_mul(c.th[2], theta); return c;
+}
+
+struct AirRowCtx {  // all constraints at one point: main/aux/public columns are column-major with the same stride
+  typedef Fp F; typedef Xp X;
+  const u32 *data, *aux, *pub; size_t stride, row, nxt; const u32* pv; const LookupChallenges* lc;
   Fp is_first, is_last, is_trans;
-  u32 vals[ZKIR_AIR_NUM_CONSTRAINTS];
+  E4 vals[ZKIR_AIR_NUM_CONSTRAINTS];
   Fp L(int i) const { return Fp(data[i * stride + row]); }
   Fp N(int i) const { return Fp(data[i * stride + nxt]); }
+  Fp A(int i) const { return Fp(aux[i * stride + row]); }
+  Fp AN(int i) const { return Fp(aux[i * stride + nxt]); }
+  Fp P(int i) const { return Fp(pub[i * stride + row]); }
   Fp PV(int i) const { return Fp(pv[i]); }
   Fp K(u32 k) const { return Fp(k); }
-  void emit(int idx, Fp v) { vals[idx] = v.v; }
+  Xp z() const { Xp r; r.v = lc->z; return r; }
+  Xp th(int k) const { Xp r; r.v = lc->th[k]; return r; }
+  Xp xf(Fp a) const { Xp r; r.v = e4_from(a.v); return r; }
+  Xp x4(Fp a, Fp b, Fp c, Fp d) const { Xp r; r.v.c[0] = a.v; r.v.c[1] = b.v; r.v.c[2] = c.v; r.v.c[3] = d.v; return r; }
+  void emit(int idx, Fp v) { vals[idx] = e4_from(v.v); }
+  void emit_x(int idx, Xp v) { vals[idx] = v.v; }
+};
+struct FracCtx {  // the LogUp fractions of one row (zkir_air_fractions): numerators and denominators
+  typedef Fp F; typedef Xp X;
+  const u32 *data, *pub; size_t stride, row; const LookupChallenges* lc;
+  u32 num[ZKIR_AIR_NUM_FRACTIONS]; E4 den[ZKIR_AIR_NUM_FRACTIONS];
+  Fp L(int i) const { return Fp(data[i * stride + row]); }
+  Fp P(int i) const { return Fp(pub[i * stride + row]); }
+  Fp K(u32 k) const { return Fp(k); }
+  Xp z() const { Xp r; r.v = lc->z; return r; }
+  Xp th(int k) const { Xp r; r.v = lc->th[k]; return r; }
+  Xp xf(Fp a) const { Xp r; r.v = e4_from(a.v); return r; }
+  void frac(int j, Fp n, Xp d) { num[j] = n.v; den[j] = d.v; }
 };
 
+// ---- public columns (docs/PROVER_SPEC.md section 3.3): range table and decoded program ROM, [4][N] column-major
+static const u32 CODE_BASE = 0x1000;
+static inline int32_t sext32(u32 v, int bits) { int sh = 32 - bits; return ((int32_t)(v << sh)) >> sh; }
+// decoded word of the ROM: opcode | rd << 7 | rs1 << 11 | rs2 << 15 with the fields of the word's FORMAT (encoder.rs:98-151):
+// R: rd rs1 rs2; I: rd rs1 imm17; shift-immediate: rd rs1 shamt; S/B: rs1 (bits 10:7) rs2 (bits 14:11) imm17; J: rd imm21; ECALL/EBREAK: none
+static void rom_decode(u32 w, u32* dec, u32* imm) {
+  const u32 op = w & 0x7F, f7 = (w >> 7) & 15, f11 = (w >> 11) & 15, f15 = (w >> 15) & 15;
+  int64_t im = 0; u32 rd = 0, rs1 = 0, rs2 = 0;
+  const bool itype = op == 0x08 || (op >= 0x13 && op <= 0x15) || (op >= 0x30 && op <= 0x35) || op == 0x49;
+  if (itype) { rd = f7; rs1 = f11; im = sext32((w >> 15) & 0x1FFFF, 17); }
+  else if (op >= 0x1B && op <= 0x1D) { rd = f7; rs1 = f11; im = (w >> 15) & 0xFF; }
+  else if ((op >= 0x38 && op <= 0x3B) || (op >= 0x40 && op <= 0x45)) { rs1 = f7; rs2 = f11; im = sext32((w >> 15) & 0x1FFFF, 17); }
+  else if (op == 0x48) { rd = f7; im = sext32((w >> 11) & 0x1FFFFF, 21); }
+  else if (op == 0x50 || op == 0x51) {}
+  else { rd = f7; rs1 = f11; rs2 = f15; }   // R-type (and anything undefined: it can never match a trace row)
+  *dec = op | rd << 7 | rs1 << 11 | rs2 << 15;
+  *imm = im < 0 ? (u32)(P + im) : (u32)im;
+}
+static void build_public_columns(u32 log_n, const u32* code, size_t n_code, u32* pub) {
+  const size_t N = (size_t)1 << log_n;
+  memset(pub, 0, 4 * N * sizeof(u32));
+  for (size_t i = 0; i < N && i < ((size_t)1 << ZKIR_AIR_RANGE_BITS); i++) pub[0 * N + i] = (u32)i;
+  for (size_t i = 0; i < N; i++) {
+    if (i < n_code) { pub[1 * N + i] = CODE_BASE + 4 * (u32)i; rom_decode(code[i], &pub[2 * N + i], &pub[3 * N + i]); }
+    else pub[2 * N + i] = 127;   // no instruction has opcode 127: an unused ROM row matches no trace row
+  }
+}
+// aux columns [16][N] from the main trace, the public columns and the lookup challenges: helper k = sum of its two fractions,
+// phi = running sum of all fractions of the earlier rows.  Returns false if the lookups do not balance (invalid witness).
+static bool build_aux(u32 log_n, const u32* trace, const u32* pub, const LookupChallenges& lc, u32* aux) {
+  const size_t N = (size_t)1 << log_n;
+  const int NF = ZKIR_AIR_NUM_FRACTIONS;
+  static const int helper_of[NF] = ZKIR_AIR_FRAC_HELPER_INIT;
+  std::vector<E4> den(N * NF), tot(N);
+  std::vector<u32> num(N * NF);
+#pragma omp parallel for
+  for (size_t i = 0; i < N; i++) {
+    FracCtx c; c.data = trace; c.pub = pub; c.stride = N; c.row = i; c.lc = &lc;
+    zkir_air_fractions(c);
+    for (int j = 0; j < NF; j++) { num[i * NF + j] = c.num[j]; den[i * NF + j] = c.den[j]; }
+  }
+  const size_t CH = 4096 * NF;
+#pragma omp parallel for
+  for (size_t c0 = 0; c0 < N * NF; c0 += CH) e4_batch_inv(&den[c0], std::min(CH, N * NF - c0));
+#pragma omp parallel for
+  for (size_t i = 0; i < N; i++) {
+    E4 h[4] = {e4_zero(), e4_zero(), e4_zero(), e4_zero()};
+    for (int j = 0; j < NF; j++) h[helper_of[j]] = e4_add(h[helper_of[j]], e4_mulb(den[i * NF + j], num[i * NF + j]));
+    for (int k = 0; k < 3; k++) for (int q = 0; q < 4; q++) aux[(4 * k + q) * N + i] = h[k].c[q];
+    tot[i] = e4_add(e4_add(h[0], h[1]), e4_add(h[2], h[3]));
+  }
+  E4 phi = e4_zero();
+  for (size_t i = 0; i < N; i++) { for (int q = 0; q < 4; q++) aux[(12 + q) * N + i] = phi.c[q]; phi = e4_add(phi, tot[i]); }
+  return e4_eq(phi, e4_zero());
+}
+// digest of the program the transcript absorbs: hash_tree over the 16-bit halves of the code words (each < p)
+static void program_digest(const u32* code, size_t n_code, u32* digest) {
+  std::vector<u32> halves(2 * n_code + 1);
+  halves[0] = (u32)n_code;
+  for (size_t i = 0; i < n_code; i++) { halves[1 + 2 * i] = code[i] & 0xFFFF; halves[2 + 2 * i] = code[i] >> 16; }
+  hash_tree(halves.data(), halves.size(), digest);
+}
+
 struct Params { u32 log_blowup, num_queries, pow_bits, width, num_public; };
-static const u32 PROOF_MAGIC = 0x5A4B5052u, PROOF_VERSION = 3u;
+static const u32 PROOF_MAGIC = 0x5A4B5052u, PROOF_VERSION = 4u;
+static const size_t AW = ZKIR_AIR_AUX_WIDTH, PW = ZKIR_AIR_PUB_WIDTH;
 
 // FRI rounds (docs/PROVER_SPEC.md section 4.6): log_n / 3 rounds that fold by 8, then one that folds by 2^(log_n mod 3) if that is > 1
 static size_t fri_rounds(u32 log_n) { return log_n / 3 + (log_n % 3 ? 1 : 0); }
 static u32 fri_log_arity(u32 log_n, size_t t) { return t < log_n / 3 ? 3 : log_n % 3; }
 static size_t proof_words(const Params& p, u32 log_n) {
-  size_t lg = log_n + p.log_blowup, W = p.width, R = fri_rounds(log_n);
-  size_t n = 8 + p.num_public + 16 + (2 * W + 8) * 4 + R * 8 + 4 + 1;
-  size_t perq = W + lg * 8 + 8 + lg * 8;
+  size_t lg = log_n + p.log_blowup, W = p.width, WA = W + AW, R = fri_rounds(log_n);
+  size_t n = 8 + p.num_public + 24 + (2 * WA + 8) * 4 + R * 8 + 4 + 1;
+  size_t perq = W + lg * 8 + AW + lg * 8 + 8 + lg * 8;
   size_t ll = lg;  // log2 of the layer length
   for (size_t t = 0; t < R; t++) { const u32 la = fri_log_arity(log_n, t); perq += (4u << la) + (ll - la) * 8; ll -= la; }
   return n + perq * p.num_queries;
 }
 
-// Quotient values on the LDE coset, natural order: out[4][M] (ext4 coefficient planes)
-static void quotient_evals(const Params& p, u32 log_n, const u32* lde, const u32* pv, E4 alpha, u32* out) {
+// Quotient values on the LDE coset, natural order: out[4][M] (ext4 coefficient planes).  lde / aux / pub: the LDEs of the main,
+// aux and public columns, column-major with stride M.
+static void quotient_evals(const Params& p, u32 log_n, const u32* lde, const u32* aux, const u32* pub, const u32* pv,
+                           const LookupChallenges& lc, E4 alpha, u32* out) {
   const int K = ZKIR_AIR_NUM_CONSTRAINTS;
   size_t N = (size_t)1 << log_n, B = (size_t)1 << p.log_blowup, M = N * B;
   u32 w = root_of_unity(log_n + p.log_blowup), g_inv = finv(root_of_unity(log_n));
@@ -247,46 +344,54 @@ static void quotient_evals(const Params& p, u32 log_n, const u32* lde, const u32
     u32 zh = fsub(fpow(xi, N), 1);                 // Z_H(x) = x^N - 1
     u32 zh_inv = finv(zh);
     AirRowCtx c;
-    c.data = lde; c.stride = M; c.row = i; c.nxt = (i + B) % M; c.pv = pv;
+    c.data = lde; c.aux = aux; c.pub = pub; c.stride = M; c.row = i; c.nxt = (i + B) % M; c.pv = pv; c.lc = &lc;
     c.is_first = Fp(fmul(zh, finv(fsub(xi, 1))));  // Z_H(x)/(x-1)
     c.is_last = Fp(fmul(zh, finv(fsub(xi, g_inv))));
     c.is_trans = Fp(fsub(xi, g_inv));
     zkir_air_eval(c);
     E4 acc = e4_zero();
-    for (int k = 0; k < K; k++) acc = e4_add(acc, e4_mulb(apow[k], c.vals[k]));
+    for (int k = 0; k < K; k++) acc = e4_add(acc, e4_mul(apow[k], c.vals[k]));
     acc = e4_mulb(acc, zh_inv);
     for (int k = 0; k < 4; k++) out[k * M + i] = acc.c[k];
   }
-  (void)p;
 }
 
 struct Dump {  // optional intermediates for stage-by-stage parity tests
-  u32 alpha[4], zeta[4], alpha_fri[4];
+  u32 alpha[4], zeta[4], alpha_fri[4], lookup_z[4], lookup_theta[4];
+  u32* aux;          // [16][N] or null
   u32* quotient;     // [4][M] or null
   u32* fri_input;    // [M][4] or null
   u32* lde;          // [W][M] or null
   u32* betas;        // [R][4] or null
 };
 
-static int prove(const Params& p, const u32* trace, u32 log_n, const u32* pv, u32* proof, Dump* dump) {
-  const size_t W = p.width, N = (size_t)1 << log_n, B = (size_t)1 << p.log_blowup, M = N * B;
+static int prove(const Params& p, const u32* trace, u32 log_n, const u32* pv, const u32* code, size_t n_code, u32* proof, Dump* dump) {
+  const size_t W = p.width, WA = W + AW, N = (size_t)1 << log_n, B = (size_t)1 << p.log_blowup, M = N * B;
   const int lg = log_n + p.log_blowup;
   const u32 shift = ZKIR_BB_GEN;
   if (W != ZKIR_AIR_WIDTH || p.num_public != ZKIR_AIR_NUM_PUBLIC) return -1;
+  if (log_n < ZKIR_AIR_RANGE_BITS || n_code > N) return -6;   // the range table and the ROM must fit the trace
   u32* out = proof;
   *out++ = PROOF_MAGIC; *out++ = PROOF_VERSION; *out++ = log_n; *out++ = p.width; *out++ = p.log_blowup;
   *out++ = p.num_queries; *out++ = p.pow_bits; *out++ = p.num_public;
   for (u32 i = 0; i < p.num_public; i++) *out++ = pv[i];
 
-  // ---- 1. trace LDE + commit
-  std::vector<u32> coef(W * N), lde(W * M);
+  // ---- 1. LDE of the main trace (committed) and of the public columns (known to the verifier, not committed)
+  // coef / lde hold main columns [0, W) then aux columns [W, W + AW)
+  std::vector<u32> coef(WA * N), lde(WA * M), pub(PW * N), publde(PW * M);
+  build_public_columns(log_n, code, n_code, pub.data());
 #pragma omp parallel for
-  for (size_t k = 0; k < W; k++) {
-    memcpy(&coef[k * N], trace + k * N, N * 4);
-    ntt_inplace(&coef[k * N], log_n, true);
-    coset_eval(&coef[k * N], N, &lde[k * M], lg, shift);
+  for (size_t k = 0; k < W + PW; k++) {
+    if (k < W) {
+      memcpy(&coef[k * N], trace + k * N, N * 4);
+      ntt_inplace(&coef[k * N], log_n, true);
+      coset_eval(&coef[k * N], N, &lde[k * M], lg, shift);
+    } else {
+      std::vector<u32> c(pub.begin() + (k - W) * N, pub.begin() + (k - W + 1) * N);
+      ntt_inplace(c.data(), log_n, true);
+      coset_eval(c.data(), N, &publde[(k - W) * M], lg, shift);
+    }
   }
-  if (dump && dump->lde) memcpy(dump->lde, lde.data(), W * M * 4);
   std::vector<u32> ttree((2 * M - 1) * 8);
 #pragma omp parallel for
   for (size_t i = 0; i < M; i++) {
@@ -296,17 +401,48 @@ static int prove(const Params& p, const u32* trace, u32 log_n, const u32* pv, u3
   }
   merkle_build(ttree.data(), M);
   Chal ch;
-  ch.observe(log_n); ch.observe(p.width); ch.observe(p.log_blowup); ch.observe(p.num_queries); ch.observe(p.pow_bits);
+  ch.observe(log_n); ch.observe(p.width); ch.observe((u32)AW); ch.observe(p.log_blowup); ch.observe(p.num_queries); ch.observe(p.pow_bits);
   ch.observe(p.num_public);
   ch.observe_n(pv, p.num_public);
+  {
+    u32 pd[8];
+    program_digest(code, n_code, pd);
+    ch.observe_n(pd, 8);
+  }
   ch.observe_n(merkle_root(ttree.data(), M), 8);
   memcpy(out, merkle_root(ttree.data(), M), 32); out += 8;
+
+  // ---- 1b. lookup challenges, aux columns (LogUp helpers and running sum), their LDE and commitment
+  E4 lz = ch.sample_ext(), ltheta = ch.sample_ext();
+  const LookupChallenges lc = make_challenges(lz, ltheta);
+  {
+    std::vector<u32> aux(AW * N);
+    if (!build_aux(log_n, trace, pub.data(), lc, aux.data())) return -7;   // lookups do not balance: invalid witness
+    if (dump) { memcpy(dump->lookup_z, lz.c, 16); memcpy(dump->lookup_theta, ltheta.c, 16); if (dump->aux) memcpy(dump->aux, aux.data(), AW * N * 4); }
+#pragma omp parallel for
+    for (size_t k = 0; k < AW; k++) {
+      memcpy(&coef[(W + k) * N], &aux[k * N], N * 4);
+      ntt_inplace(&coef[(W + k) * N], log_n, true);
+      coset_eval(&coef[(W + k) * N], N, &lde[(W + k) * M], lg, shift);
+    }
+  }
+  if (dump && dump->lde) memcpy(dump->lde, lde.data(), WA * M * 4);
+  std::vector<u32> atree((2 * M - 1) * 8);
+#pragma omp parallel for
+  for (size_t i = 0; i < M; i++) {
+    u32 row[ZKIR_AIR_AUX_WIDTH];
+    for (size_t k = 0; k < AW; k++) row[k] = lde[(W + k) * M + i];
+    hash_elems(row, AW, &atree[i * 8]);
+  }
+  merkle_build(atree.data(), M);
+  ch.observe_n(merkle_root(atree.data(), M), 8);
+  memcpy(out, merkle_root(atree.data(), M), 32); out += 8;
   u32* quot_root_slot = out; out += 8;
 
   // ---- 2. quotient
   E4 alpha = ch.sample_ext();
   std::vector<u32> q(4 * M);
-  quotient_evals(p, log_n, lde.data(), pv, alpha, q.data());
+  quotient_evals(p, log_n, lde.data(), lde.data() + W * M, publde.data(), pv, lc, alpha, q.data());
   if (dump) { memcpy(dump->alpha, alpha.c, 16); if (dump->quotient) memcpy(dump->quotient, q.data(), 4 * M * 4); }
   // coefficients of Q: inverse NTT on the coset, then undo the shift
   std::vector<u32> qcoef(8 * N), qlde(8 * M);
@@ -336,41 +472,41 @@ static int prove(const Params& p, const u32* trace, u32 log_n, const u32* pv, u3
   E4 zeta = ch.sample_ext();
   E4 gzeta = e4_mulb(zeta, root_of_unity(log_n));
   if (dump) memcpy(dump->zeta, zeta.c, 16);
-  std::vector<E4> ot(W), otg(W), oq(8);
+  std::vector<E4> ot(WA), otg(WA), oq(8);   // main columns then aux columns
   {
     std::vector<E4> zp(N), gzp(N);  // powers of zeta and g*zeta
     zp[0] = gzp[0] = e4_from(1);
     for (size_t j = 1; j < N; j++) { zp[j] = e4_mul(zp[j - 1], zeta); gzp[j] = e4_mul(gzp[j - 1], gzeta); }
     auto eval = [&](const u32* c, const std::vector<E4>& pw) { E4 acc = e4_zero(); for (size_t j = 0; j < N; j++) acc = e4_add(acc, e4_mulb(pw[j], c[j])); return acc; };
 #pragma omp parallel for
-    for (size_t k = 0; k < W; k++) { ot[k] = eval(&coef[k * N], zp); otg[k] = eval(&coef[k * N], gzp); }
+    for (size_t k = 0; k < WA; k++) { ot[k] = eval(&coef[k * N], zp); otg[k] = eval(&coef[k * N], gzp); }
     for (int k = 0; k < 8; k++) oq[k] = eval(&qcoef[k * N], zp);
   }
-  for (size_t k = 0; k < W; k++) { memcpy(out, ot[k].c, 16); out += 4; }
-  for (size_t k = 0; k < W; k++) { memcpy(out, otg[k].c, 16); out += 4; }
+  for (size_t k = 0; k < WA; k++) { memcpy(out, ot[k].c, 16); out += 4; }
+  for (size_t k = 0; k < WA; k++) { memcpy(out, otg[k].c, 16); out += 4; }
   for (int k = 0; k < 8; k++) { memcpy(out, oq[k].c, 16); out += 4; }
   {
     u32 od[8];
-    hash_tree(out - (2 * W + 8) * 4, (2 * W + 8) * 4, od);   // the transcript absorbs the tree hash of the opened values
+    hash_tree(out - (2 * WA + 8) * 4, (2 * WA + 8) * 4, od);   // the transcript absorbs the tree hash of the opened values
     ch.observe_n(od, 8);
   }
 
   // ---- 4. FRI input: batched DEEP quotients on the coset
   E4 af = ch.sample_ext();
   if (dump) memcpy(dump->alpha_fri, af.c, 16);
-  std::vector<E4> afp(2 * W + 8);
+  std::vector<E4> afp(2 * WA + 8);
   afp[0] = e4_from(1);
-  for (size_t k = 1; k < 2 * W + 8; k++) afp[k] = e4_mul(afp[k - 1], af);
+  for (size_t k = 1; k < 2 * WA + 8; k++) afp[k] = e4_mul(afp[k - 1], af);
   std::vector<E4> f(M);
   {
     u32 w = root_of_unity(lg);
     std::vector<u32> xs(M);
     u32 x = shift;
     for (size_t i = 0; i < M; i++) { xs[i] = x; x = fmul(x, w); }
-    // F(x) = (Rt(x)-A1)/(x-zeta) + alpha^W (Rt(x)-A2)/(x-g zeta) + alpha^2W (Rq(x)-A3)/(x-zeta),
+    // F(x) = (Rt(x)-A1)/(x-zeta) + alpha^W' (Rt(x)-A2)/(x-g zeta) + alpha^2W' (Rq(x)-A3)/(x-zeta), W' = main + aux columns,
     // Rt(x) = sum_k alpha^k t_k(x), A1 = sum_k alpha^k t_k(zeta), ... (same sum as the per-column DEEP quotients)
     E4 A1 = e4_zero(), A2 = e4_zero(), A3 = e4_zero();
-    for (size_t k = 0; k < W; k++) { A1 = e4_add(A1, e4_mul(afp[k], ot[k])); A2 = e4_add(A2, e4_mul(afp[k], otg[k])); }
+    for (size_t k = 0; k < WA; k++) { A1 = e4_add(A1, e4_mul(afp[k], ot[k])); A2 = e4_add(A2, e4_mul(afp[k], otg[k])); }
     for (int k = 0; k < 8; k++) A3 = e4_add(A3, e4_mul(afp[k], oq[k]));
     std::vector<E4> iz(M), igz(M);
     for (size_t i = 0; i < M; i++) { iz[i] = e4_sub(e4_from(xs[i]), zeta); igz[i] = e4_sub(e4_from(xs[i]), gzeta); }
@@ -380,11 +516,11 @@ static int prove(const Params& p, const u32* trace, u32 log_n, const u32* pv, u3
 #pragma omp parallel for
     for (size_t i = 0; i < M; i++) {
       E4 rt = e4_zero(), rq = e4_zero();
-      for (size_t k = 0; k < W; k++) rt = e4_add(rt, e4_mulb(afp[k], lde[k * M + i]));
+      for (size_t k = 0; k < WA; k++) rt = e4_add(rt, e4_mulb(afp[k], lde[k * M + i]));
       for (int k = 0; k < 8; k++) rq = e4_add(rq, e4_mulb(afp[k], qlde[k * M + i]));
       E4 acc = e4_mul(e4_sub(rt, A1), iz[i]);
-      acc = e4_add(acc, e4_mul(afp[W], e4_mul(e4_sub(rt, A2), igz[i])));
-      acc = e4_add(acc, e4_mul(afp[2 * W], e4_mul(e4_sub(rq, A3), iz[i])));
+      acc = e4_add(acc, e4_mul(afp[WA], e4_mul(e4_sub(rt, A2), igz[i])));
+      acc = e4_add(acc, e4_mul(afp[2 * WA], e4_mul(e4_sub(rq, A3), iz[i])));
       f[i] = acc;
     }
   }
@@ -454,6 +590,8 @@ static int prove(const Params& p, const u32* trace, u32 log_n, const u32* pv, u3
     size_t idx = ch.sample_bits(lg);
     for (size_t k = 0; k < W; k++) *out++ = lde[k * M + idx];
     merkle_path(ttree.data(), M, idx, out); out += lg * 8;
+    for (size_t k = 0; k < AW; k++) *out++ = lde[(W + k) * M + idx];
+    merkle_path(atree.data(), M, idx, out); out += lg * 8;
     for (int k = 0; k < 8; k++) *out++ = qlde[k * M + idx];
     merkle_path(qtree.data(), M, idx, out); out += lg * 8;
     size_t i = idx;
@@ -514,11 +652,23 @@ void oracle_merkle_commit(const u32* mat, int ncols, int log_rows, u32* tree, u3
   merkle_build(tree, n);
   memcpy(root, merkle_root(tree, n), 32);
 }
-void oracle_quotient(const u32* params5, u32 log_n, const u32* lde, const u32* pv, const u32* alpha, u32* out) {
+// lde: [W + 16 aux][M] (main then aux columns), pub: [4][M]; lookup = {z[4], theta[4]}
+void oracle_quotient(const u32* params5, u32 log_n, const u32* lde, const u32* publde, const u32* pv, const u32* lookup8, const u32* alpha, u32* out) {
   Params p = {params5[0], params5[1], params5[2], params5[3], params5[4]};
-  E4 a; memcpy(a.c, alpha, 16);
-  quotient_evals(p, log_n, lde, pv, a, out);
+  E4 a, z, th; memcpy(a.c, alpha, 16); memcpy(z.c, lookup8, 16); memcpy(th.c, lookup8 + 4, 16);
+  const size_t M = (size_t)1 << (log_n + p.log_blowup);
+  quotient_evals(p, log_n, lde, lde + (size_t)p.width * M, publde, pv, make_challenges(z, th), a, out);
 }
+void oracle_public_columns(u32 log_n, const u32* code, u64 n_code, u32* pub) { build_public_columns(log_n, code, (size_t)n_code, pub); }
+// aux columns [16][N] for given lookup challenges; returns 1 if the lookups balance
+int oracle_aux_columns(u32 log_n, const u32* trace, const u32* code, u64 n_code, const u32* lookup8, u32* aux) {
+  const size_t N = (size_t)1 << log_n;
+  std::vector<u32> pub(PW * N);
+  build_public_columns(log_n, code, (size_t)n_code, pub.data());
+  E4 z, th; memcpy(z.c, lookup8, 16); memcpy(th.c, lookup8 + 4, 16);
+  return build_aux(log_n, trace, pub.data(), make_challenges(z, th), aux) ? 1 : 0;
+}
+void oracle_program_digest(const u32* code, u64 n_code, u32* digest8) { program_digest(code, (size_t)n_code, digest8); }
 // one FRI fold: in[n][4] on coset shift*H_n -> out[n/2][4]
 void oracle_fri_fold(const u32* in, u32* out, int logn, u32 shift, const u32* beta4) {
   size_t n = (size_t)1 << logn, h = n / 2;
@@ -533,18 +683,24 @@ void oracle_fri_fold(const u32* in, u32* out, int logn, u32 shift, const u32* be
     x = fmul(x, w);
   }
 }
-// checks every AIR constraint on the (unextended) trace rows; returns -1 if all hold, else the index of the
-// first failing constraint (row in *bad_row)
-int oracle_check_trace(const u32* trace, u32 log_n, const u32* pv, u64* bad_row) {
+// checks every AIR constraint on the (unextended) trace rows, with the aux columns built for the given lookup challenges;
+// returns -1 if all hold, -2 if the lookups do not balance, else the index of the first failing constraint (row in *bad_row)
+int oracle_check_trace(const u32* trace, u32 log_n, const u32* pv, const u32* code, u64 n_code, const u32* lookup8, u64* bad_row) {
   size_t N = (size_t)1 << log_n;
+  if (log_n < ZKIR_AIR_RANGE_BITS || n_code > N) return -3;
+  std::vector<u32> pub(PW * N), aux(AW * N);
+  build_public_columns(log_n, code, (size_t)n_code, pub.data());
+  E4 z, th; memcpy(z.c, lookup8, 16); memcpy(th.c, lookup8 + 4, 16);
+  const LookupChallenges lc = make_challenges(z, th);
+  const bool balanced = build_aux(log_n, trace, pub.data(), lc, aux.data());
   for (size_t i = 0; i < N; i++) {
     AirRowCtx c;
-    c.data = trace; c.stride = N; c.row = i; c.nxt = (i + 1) % N; c.pv = pv;
+    c.data = trace; c.aux = aux.data(); c.pub = pub.data(); c.stride = N; c.row = i; c.nxt = (i + 1) % N; c.pv = pv; c.lc = &lc;
     c.is_first = Fp(i == 0); c.is_last = Fp(i == N - 1); c.is_trans = Fp(i != N - 1);
     zkir_air_eval(c);
-    for (int k = 0; k < ZKIR_AIR_NUM_CONSTRAINTS; k++) if (c.vals[k]) { if (bad_row) *bad_row = i; return k; }
+    for (int k = 0; k < ZKIR_AIR_NUM_CONSTRAINTS; k++) if (!e4_eq(c.vals[k], e4_zero())) { if (bad_row) *bad_row = i; return k; }
   }
-  return -1;
+  return balanced ? -1 : -2;
 }
 void oracle_hash_tree(const u32* words, u64 n, u32* digest8) { hash_tree(words, (size_t)n, digest8); }
 u64 oracle_proof_words(const u32* params5, u32 log_n) {
@@ -552,17 +708,19 @@ u64 oracle_proof_words(const u32* params5, u32 log_n) {
   return proof_words(p, log_n);
 }
 // params5 = {log_blowup, num_queries, pow_bits, width, num_public}; trace column-major [width][1<<log_n]
-int oracle_prove(const u32* params5, const u32* trace, u32 log_n, const u32* pv, u32* proof) {
+int oracle_prove(const u32* params5, const u32* trace, u32 log_n, const u32* pv, const u32* code, u64 n_code, u32* proof) {
   Params p = {params5[0], params5[1], params5[2], params5[3], params5[4]};
-  return prove(p, trace, log_n, pv, proof, nullptr);
+  return prove(p, trace, log_n, pv, code, (size_t)n_code, proof, nullptr);
 }
-int oracle_prove_dump(const u32* params5, const u32* trace, u32 log_n, const u32* pv, u32* proof, u32* challenges12,
-                      u32* lde, u32* quotient, u32* fri_input, u32* betas) {
+// challenges20 = alpha, zeta, gamma, lookup z, lookup theta
+int oracle_prove_dump(const u32* params5, const u32* trace, u32 log_n, const u32* pv, const u32* code, u64 n_code, u32* proof, u32* challenges20,
+                      u32* lde, u32* aux, u32* quotient, u32* fri_input, u32* betas) {
   Params p = {params5[0], params5[1], params5[2], params5[3], params5[4]};
   Dump d; memset(&d, 0, sizeof(d));
-  d.lde = lde; d.quotient = quotient; d.fri_input = fri_input; d.betas = betas;
-  int rc = prove(p, trace, log_n, pv, proof, &d);
-  if (challenges12) { memcpy(challenges12, d.alpha, 16); memcpy(challenges12 + 4, d.zeta, 16); memcpy(challenges12 + 8, d.alpha_fri, 16); }
+  d.lde = lde; d.aux = aux; d.quotient = quotient; d.fri_input = fri_input; d.betas = betas;
+  int rc = prove(p, trace, log_n, pv, code, (size_t)n_code, proof, &d);
+  if (challenges20) { memcpy(challenges20, d.alpha, 16); memcpy(challenges20 + 4, d.zeta, 16); memcpy(challenges20 + 8, d.alpha_fri, 16);
+                      memcpy(challenges20 + 12, d.lookup_z, 16); memcpy(challenges20 + 16, d.lookup_theta, 16); }
   return rc;
 }
 void oracle_ext_mul(const u32* a, const u32* b, u32* out) { E4 x, y; memcpy(x.c, a, 16); memcpy(y.c, b, 16); E4 r = e4_mul(x, y); memcpy(out, r.c, 16); }

@@ -20,9 +20,9 @@ g27 = pow(31, 15, P)
 gold = {"roots": [pow(g27, 1 << (27 - k), P) for k in range(28)]}
 gold["poseidon2_of_0_to_15"] = o.poseidon2(np.arange(16, dtype=np.uint32).reshape(1, 16))[0].tolist()
 gold["poseidon2_of_zeros"] = o.poseidon2(np.zeros((1, 16), dtype=np.uint32))[0].tolist()
-_, cols, pv = fib_trace(30)
+res, cols, pv = fib_trace(30)
 cfg = zkir_b200.ProverConfig(num_queries=20, pow_bits=8)
-pb = o.prove(cfg, cols, pv)
+pb = o.prove(cfg, cols, pv, res.program)
 gold["fib30_trace_sha256"] = hashlib.sha256(cols.tobytes()).hexdigest()
 gold["fib30_proof_sha256"] = hashlib.sha256(pb).hexdigest()
 gold["fib30_proof_len"] = len(pb)

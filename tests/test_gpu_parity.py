@@ -107,35 +107,73 @@ def test_fri_fold_matches_oracle(gpu_ctx, oracle, log_n):
     assert np.array_equal(got, oracle.fri_fold(layer, shift, beta))
 
 
-@pytest.mark.parametrize("n,log_b", [(10, 1), (30, 1), (30, 2)])
+@pytest.mark.parametrize("n,log_b", [(10, 1), (300, 1), (30, 2)])
 def test_quotient_matches_oracle(gpu_ctx, oracle, n, log_b):
-    _, cols, pv = fib_trace(n)
+    """all 169 constraints of the AIR v2 (main + LogUp aux + public columns) on the LDE coset, folded with alpha, divided by Z_H"""
+    res, cols, pv = fib_trace(n)
     cfg = zkir_b200.ProverConfig(log_blowup=log_b, num_queries=4, pow_bits=1)
     log_n = int(cols.shape[1]).bit_length() - 1
-    lde = oracle.lde(cols, log_b)
+    lookup = np.array([11, 12, 13, 14, 21, 22, 23, 24], dtype=np.uint32)
+    aux, balanced = oracle.aux_columns(cols, res.program, lookup)
+    assert balanced
+    lde = oracle.lde(np.concatenate([cols, aux]), log_b)
+    publde = oracle.lde(oracle.public_columns(log_n, res.program), log_b)
     alpha = np.array([5, 6, 7, 8], dtype=np.uint32)
-    d_lde = gpu_ctx.to_device(lde)
+    d_lde, d_pub = gpu_ctx.to_device(lde), gpu_ctx.to_device(publde)
     d_q = gpu_ctx.alloc(16 << (log_n + log_b))
-    gpu_ctx.quotient(cfg, d_lde, log_n, pv, alpha, d_q)
+    gpu_ctx.quotient(cfg, d_lde, d_pub, log_n, pv, lookup, alpha, d_q)
     got = gpu_ctx.to_host(d_q, (4, 1 << (log_n + log_b)))
-    gpu_ctx.free(d_lde); gpu_ctx.free(d_q)
-    assert np.array_equal(got, oracle.quotient(cfg, lde, log_n, pv, alpha))
+    gpu_ctx.free(d_lde); gpu_ctx.free(d_pub); gpu_ctx.free(d_q)
+    assert np.array_equal(got, oracle.quotient(cfg, lde, publde, log_n, pv, lookup, alpha))
 
 
-@pytest.mark.parametrize("n,log_b,nq,pow_bits", [(3, 1, 3, 0), (10, 1, 10, 8), (30, 1, 100, 16), (30, 2, 20, 4), (205, 1, 100, 16), (1000, 1, 30, 10),
+@pytest.mark.parametrize("case", ["fib30", "fib300", "family"])
+def test_aux_columns_match_oracle(gpu_ctx, oracle, case):
+    """LogUp aux columns (three helper sums + running sum, ext4 as 4 base columns each) for fixed lookup challenges"""
+    if case == "family":
+        from test_oracle_cpu import FAMILY_SRC
+        prog = zkir_b200.assemble(FAMILY_SRC.format(jalr_imm=4 * 29 + 1))
+        res = zkir_b200.VM(prog, [(5 << 20) + 3, 9], zkir_b200.VMConfig(enable_execution_trace=True)).run()
+        cols, pv = res.pack(12)
+    else:
+        res, cols, pv = fib_trace(int(case[3:]))
+    log_n = int(cols.shape[1]).bit_length() - 1
+    lookup = np.array([101, 2, 3, 4, 5, 6, 7, 8], dtype=np.uint32)
+    want, balanced = oracle.aux_columns(cols, res.program, lookup)
+    assert balanced
+    gpu_ctx.set_program(res.program)
+    d_t = gpu_ctx.to_device(cols)
+    d_a = gpu_ctx.alloc(want.nbytes)
+    gpu_ctx.aux_columns(d_t, log_n, lookup, d_a)
+    got = gpu_ctx.to_host(d_a, want.shape)
+    gpu_ctx.free(d_t); gpu_ctx.free(d_a)
+    bad = np.argwhere(got != want)
+    assert bad.size == 0, f"first mismatch aux column {bad[0][0]} row {bad[0][1]}"
+    # a trace whose lookups cannot balance (a chunk outside the table) is reported, not proven
+    L = zkir_b200.air_layout.INDEX
+    t2 = cols.copy(); t2[L["ch0"], 4] += 1024
+    d_t = gpu_ctx.to_device(t2)
+    d_a = gpu_ctx.alloc(want.nbytes)
+    with pytest.raises(zkir_b200.RuntimeError) as ei:
+        gpu_ctx.aux_columns(d_t, log_n, lookup, d_a)
+    gpu_ctx.free(d_t); gpu_ctx.free(d_a)
+    assert ei.value.code == -6 and "lookup" in str(ei.value)
+
+
+@pytest.mark.parametrize("n,log_b,nq,pow_bits", [(3, 1, 3, 0), (30, 1, 100, 16), (30, 2, 20, 4), (205, 1, 100, 16), (300, 1, 30, 10), (1000, 1, 30, 10),
                                                     (205, 2, 12, 5), (205, 3, 8, 3), (1000, 2, 10, 6), (3000, 4, 6, 2)])
 def test_proof_bytes_match_oracle_and_verify(gpu_ctx, oracle, n, log_b, nq, pow_bits):
     """BASELINE config 1 (fib n=30 / n=205): whole proof bytes GPU == oracle, and the verifier accepts."""
-    _, cols, pv = fib_trace(n)
+    res, cols, pv = fib_trace(n)
     cfg = zkir_b200.ProverConfig(log_blowup=log_b, num_queries=nq, pow_bits=pow_bits)
-    got = gpu_ctx.prove_columns(cols, pv, cfg)
-    want = oracle.prove(cfg, cols, pv)
+    got = gpu_ctx.prove_columns(cols, pv, cfg, program=res.program)
+    want = oracle.prove(cfg, cols, pv, res.program)
     assert len(got) == len(want)
     if got != want:
         g, w = np.frombuffer(got, dtype=np.uint32), np.frombuffer(want, dtype=np.uint32)
         first = int(np.nonzero(g != w)[0][0])
         pytest.fail(f"proof words differ first at word {first}: gpu={g[first]} oracle={w[first]}")
-    ok, why = zkir_b200.verify(got, cfg, pv)
+    ok, why = zkir_b200.verify(got, cfg, pv, res.program)
     assert ok, why
 
 
@@ -166,6 +204,10 @@ ecall
 }
 
 
+from test_oracle_cpu import FAMILY_SRC  # noqa: E402
+ROW_PROGRAMS["family_lt"] = ("src", FAMILY_SRC.format(jalr_imm=4 * 29 + 1), [3, (5 << 20) + 3])
+ROW_PROGRAMS["family_eq"] = ("src", FAMILY_SRC.format(jalr_imm=4 * 29), [(1 << 40) - 1, (1 << 40) - 1])
+ROW_PROGRAMS["ebreak"] = ("src", "addi r1, r0, 5\nebreak\n", [])
 ROW_PROGRAMS["read_one"] = ("src", "addi r10, r0, 1\necall\nadd r3, r10, r10\naddi r10, r0, 1\necall\nadd r10, r0, r0\necall\n", [1, 1])
 
 
@@ -194,7 +236,7 @@ def test_expand_rows_matches_host_packer(gpu_ctx, name):
 def test_expand_writelog_matches_host_packer(gpu_ctx, name):
     """register write log (16 B/row) -> last-writer scan -> converter == host converter on the full rows"""
     res = _rows_case(name)
-    for log_n in (res.min_log_n(), res.min_log_n() + 1, 11):
+    for log_n in (res.min_log_n(), res.min_log_n() + 1, 12):
         cols, pv = res.pack(log_n)
         d = gpu_ctx.alloc(cols.nbytes)
         gpu_ctx.expand_writelog(res.writelog(), log_n, d)
@@ -219,9 +261,9 @@ def test_expand_writelog_long_trace(gpu_ctx):
 def test_expand_rows_rejects_unconstrained_opcode(gpu_ctx):
     prog = zkir_b200.assemble("addi r1, r0, 3\nmul r2, r1, r1\nadd r10, r0, r0\necall\n")
     res = zkir_b200.VM(prog, [], zkir_b200.VMConfig(enable_execution_trace=True)).run()
-    d = gpu_ctx.alloc(zkir_b200.air_layout.WIDTH * 4 * 4)
+    d = gpu_ctx.alloc(zkir_b200.air_layout.WIDTH * 4 << 10)
     with pytest.raises(zkir_b200.RuntimeError) as ei:
-        gpu_ctx.expand_rows(res.rows(), 2, d)
+        gpu_ctx.expand_rows(res.rows(), 10, d)
     gpu_ctx.free(d)
     assert ei.value.code == -6 and "row 1" in str(ei.value)
 
@@ -231,18 +273,20 @@ def test_prove_rows_equals_prove_columns(gpu_ctx, oracle, name):
     res = _rows_case(name)
     cfg = zkir_b200.ProverConfig(num_queries=12, pow_bits=6)
     cols, pv = res.pack()
-    from_cols = gpu_ctx.prove_columns(cols, pv, cfg)
+    from_cols = gpu_ctx.prove_columns(cols, pv, cfg, program=res.program)
     from_rows, pv2 = gpu_ctx.prove_rows(res.rows(), cfg)
     from_wl, pv3 = gpu_ctx.prove_writelog(res.writelog(), cfg)
     assert np.array_equal(pv, pv2) and np.array_equal(pv, pv3)
-    assert from_rows == from_cols == from_wl == oracle.prove(cfg, cols, pv)
+    assert from_rows == from_cols == from_wl == oracle.prove(cfg, cols, pv, res.program)
+    ok, why = zkir_b200.verify(from_wl, cfg, pv, res.program)
+    assert ok, why
 
 
 def test_prove_api_end_to_end(gpu_ctx):
     from conftest import fib_program
     cfg = zkir_b200.ProverConfig(num_queries=20, pow_bits=8)
     proof = zkir_b200.prove(fib_program(30), [], cfg)
-    assert proof.cycles == 146 and proof.log_n == 8
+    assert proof.cycles == 146 and proof.log_n == 10
     ok, why = zkir_b200.verify(proof, cfg)
     assert ok, why
     bad = bytearray(proof.bytes_)
@@ -259,8 +303,8 @@ def test_full_size_proof_bytes_match_oracle(gpu_ctx, oracle, n_input, log_n):
     res, cols, pv = fib_trace(n_input=n_input)
     assert cols.shape[1] == 1 << log_n and res.cycles == 5 * n_input - 2
     cfg = zkir_b200.ProverConfig()
-    want = oracle.prove(cfg, cols, pv)
-    got = gpu_ctx.prove_columns(cols, pv, cfg)
+    want = oracle.prove(cfg, cols, pv, res.program)
+    got = gpu_ctx.prove_columns(cols, pv, cfg, program=res.program)
     assert len(got) == len(want)
     if got != want:
         g, w = np.frombuffer(got, dtype=np.uint32), np.frombuffer(want, dtype=np.uint32)
@@ -268,8 +312,13 @@ def test_full_size_proof_bytes_match_oracle(gpu_ctx, oracle, n_input, log_n):
         pytest.fail(f"2^{log_n}-row proof differs from the oracle first at word {first}: gpu={g[first]} oracle={w[first]}")
     from_wl, pv_wl = gpu_ctx.prove_writelog(res.writelog(), cfg, log_n)
     assert from_wl == want and list(pv_wl) == list(pv)
-    ok, why = zkir_b200.verify(got, cfg, pv)
+    ok, why = zkir_b200.verify(got, cfg, pv, res.program)
     assert ok, why
+    if log_n == 20:   # Program -> Proof in one call (interpreter + overlapped upload + proof): the same bytes again
+        from conftest import fib_program_input
+        cfg2 = zkir_b200.ProverConfig(max_cycles=1 << 20)
+        pb, pv2, cycles, ln = gpu_ctx.prove_program(fib_program_input(), [n_input], cfg2)
+        assert (cycles, ln) == (res.cycles, 20) and pb == want and list(pv2) == list(pv)
 
 
 def test_writelog_rejects_values_above_40_bits(gpu_ctx):
@@ -298,10 +347,10 @@ def test_writelog_rejects_values_above_40_bits(gpu_ctx):
 def test_large_trace_proves_and_verifies(gpu_ctx):
     """2^16-row trace: too slow for a byte comparison with the scalar oracle in CI time, so use the size-independent
     property: the independent CPU verifier accepts and rejects a flipped bit."""
-    _, cols, pv = fib_trace(n_input=13000, log_n=16)
+    res, cols, pv = fib_trace(n_input=13000, log_n=16)
     cfg = zkir_b200.ProverConfig()
-    pb = gpu_ctx.prove_columns(cols, pv, cfg)
-    ok, why = zkir_b200.verify(pb, cfg, pv)
+    pb = gpu_ctx.prove_columns(cols, pv, cfg, program=res.program)
+    ok, why = zkir_b200.verify(pb, cfg, pv, res.program)
     assert ok, why
 
 
@@ -315,19 +364,19 @@ def test_2p22_row_trace_proves_and_verifies(gpu_ctx):
     cfg = zkir_b200.ProverConfig(num_queries=40, pow_bits=12)
     pb, pv = gpu_ctx.prove_rows(res.rows(), cfg, 22)
     assert list(pv[:2]) == [0x1000, (5 * n - 2) % P]
-    ok, why = zkir_b200.verify(pb, cfg, pv)
+    ok, why = zkir_b200.verify(pb, cfg, pv, res.program)
     assert ok, why
     bad = bytearray(pb)
     bad[len(bad) // 2] ^= 4
-    ok, _ = zkir_b200.verify(bytes(bad), cfg, pv)
+    ok, _ = zkir_b200.verify(bytes(bad), cfg, pv, res.program)
     assert not ok
 
 
-ADD_SRC = "addi r10, r0, 1\necall\nadd r1, r10, r0\naddi r10, r0, 1\necall\nadd r11, r1, r10\naddi r10, r0, 2\necall\naddi r10, r0, 0\naddi r11, r0, 0\necall\n"
+from conftest import ADD_SRC  # noqa: E402
 
 
 def test_prove_batch_matches_single_proofs(gpu_ctx, oracle):
-    """BASELINE config 4 (a+b, 11 cycles -> 2^4 rows, many independent proofs): the concurrent batch path returns, for
+    """BASELINE config 4 (a+b, 11 cycles -> 2^10 rows: the range table sets the minimum; many independent proofs): the concurrent batch path returns, for
     every i, exactly the bytes a single zkir_b200_prove gives, which equal the oracle's."""
     prog = zkir_b200.assemble(ADD_SRC)
     cfg = zkir_b200.ProverConfig(num_queries=16, pow_bits=4)
@@ -336,14 +385,14 @@ def test_prove_batch_matches_single_proofs(gpu_ctx, oracle):
         res = zkir_b200.VM(prog, [i, 2 * i + 1], zkir_b200.VMConfig(enable_execution_trace=True)).run()
         assert res.outputs == [3 * i + 1] and res.cycles == 11
         traces.append(res.pack())
-    batch = gpu_ctx.prove_batch([c for c, _ in traces], [p for _, p in traces], cfg)
+    batch = gpu_ctx.prove_batch([c for c, _ in traces], [p for _, p in traces], cfg, program=prog)
     assert len(batch) == 24
     for i, (cols, pv) in enumerate(traces):
-        assert batch[i] == gpu_ctx.prove_columns(cols, pv, cfg)
-        ok, why = zkir_b200.verify(batch[i], cfg, pv)
+        assert batch[i] == gpu_ctx.prove_columns(cols, pv, cfg, program=prog)
+        ok, why = zkir_b200.verify(batch[i], cfg, pv, prog)
         assert ok, why
     for i in (0, 7, 23):
-        assert batch[i] == oracle.prove(cfg, *traces[i])
+        assert batch[i] == oracle.prove(cfg, *traces[i], prog)
 
 
 def test_error_paths_return_codes(gpu_ctx):
@@ -351,24 +400,39 @@ def test_error_paths_return_codes(gpu_ctx):
     the context stays usable afterwards"""
     import ctypes as C
     from zkir_b200 import _ffi
-    _, cols, pv = fib_trace(30)
+    fres, cols, pv = fib_trace(30)
     cfg = zkir_b200.ProverConfig(num_queries=4, pow_bits=2)
     bad_pv = pv.copy(); bad_pv[1] = P                     # not canonical
     with pytest.raises(zkir_b200.RuntimeError) as ei:
-        gpu_ctx.prove_columns(cols, bad_pv, cfg)
+        gpu_ctx.prove_columns(cols, bad_pv, cfg, program=fres.program)
+    assert ei.value.code == -1
+    lie = pv.copy(); lie[4] = 0; lie[2] = 5               # "did not halt" but claims an exit code
+    with pytest.raises(zkir_b200.RuntimeError) as ei:
+        gpu_ctx.prove_columns(cols, lie, cfg)
     assert ei.value.code == -1
     l = _ffi.lib()
-    params = _ffi.Params(1, 4, 2, 84, 4)                 # wrong width
+    params = _ffi.Params(1, 4, 2, 72, 4)                 # the v1 shape
     proof, plen = C.c_void_p(), C.c_size_t()
-    rc = l.zkir_b200_prove(gpu_ctx._h, C.byref(params), cols.ctypes.data, 8, pv.ctypes.data_as(_ffi.u32p), C.byref(proof), C.byref(plen))
+    rc = l.zkir_b200_prove(gpu_ctx._h, C.byref(params), cols.ctypes.data, 10, pv.ctypes.data_as(_ffi.u32p), C.byref(proof), C.byref(plen))
     assert rc == -1 and b"width" in l.zkir_b200_last_error(gpu_ctx._h)
+    fresh = zkir_b200.Context(0)                          # no program set: refused, not proven against an empty ROM
+    try:
+        with pytest.raises(zkir_b200.RuntimeError) as ei:
+            fresh.prove_columns(cols, pv, cfg)
+        assert ei.value.code == -1 and "program" in str(ei.value)
+    finally:
+        fresh.close()
+    other = list(fres.program.code); other[2] = zkir_b200.encode("addi", 3, 0, imm=31)
+    with pytest.raises(zkir_b200.RuntimeError) as ei:     # a trace of ANOTHER program: the ROM lookups cannot balance
+        gpu_ctx.prove_columns(cols, pv, cfg, program=other)
+    assert ei.value.code == -6 and "lookup" in str(ei.value)
     prog = zkir_b200.assemble("addi r1, r0, 3\nmul r2, r1, r1\nadd r10, r0, r0\necall\n")
     res = zkir_b200.VM(prog, [], zkir_b200.VMConfig(enable_execution_trace=True)).run()
     for call in (lambda: gpu_ctx.prove_rows(res.rows(), cfg), lambda: gpu_ctx.prove_writelog(res.writelog(), cfg)):
         with pytest.raises(zkir_b200.RuntimeError) as ei:
             call()
         assert ei.value.code == -6 and "row 1" in str(ei.value)
-    ok, why = zkir_b200.verify(gpu_ctx.prove_columns(cols, pv, cfg), cfg, pv)   # still healthy
+    ok, why = zkir_b200.verify(gpu_ctx.prove_columns(cols, pv, cfg, program=fres.program), cfg, pv, fres.program)   # still healthy
     assert ok, why
 
 
@@ -398,23 +462,23 @@ def test_full_size_lde_linearity_and_interpolation(gpu_ctx):
 
 
 def test_minimal_programs(gpu_ctx, oracle):
-    """smallest traces: a lone ECALL (r10 = 0 -> EXIT 0 at cycle 0: one live row padded to 4) and a 2-cycle exit with a code"""
+    """smallest traces: a lone ECALL (r10 = 0 -> EXIT 0 at cycle 0: one live row padded to 2^10) and a 2-cycle exit with a code"""
     cfg = zkir_b200.ProverConfig(num_queries=5, pow_bits=3)
     for src, code, cycles in (("ecall\n", 0, 1), ("addi r11, r0, 9\necall\n", 9, 2)):
         res = zkir_b200.VM(zkir_b200.assemble(src), [], zkir_b200.VMConfig(enable_execution_trace=True)).run()
         assert res.cycles == cycles and res.halt_reason == zkir_b200.HaltReason.Exit(code)
         cols, pv = res.pack()
-        assert cols.shape[1] == 4 and oracle.check_trace(cols, pv)[0] == -1
-        want = oracle.prove(cfg, cols, pv)
-        assert gpu_ctx.prove_columns(cols, pv, cfg) == want
+        assert cols.shape[1] == 1024 and oracle.check_trace(cols, pv, res.program)[0] == -1
+        want = oracle.prove(cfg, cols, pv, res.program)
+        assert gpu_ctx.prove_columns(cols, pv, cfg, program=res.program) == want
         assert gpu_ctx.prove_rows(res.rows(), cfg)[0] == want
         assert gpu_ctx.prove_writelog(res.writelog(), cfg)[0] == want
-        ok, why = zkir_b200.verify(want, cfg, pv)
+        ok, why = zkir_b200.verify(want, cfg, pv, res.program)
         assert ok, why
 
 
 def test_small_proofs_replay_a_captured_graph(gpu_ctx, oracle):
-    """Proofs of up to 2^12 rows run as ONE captured CUDA graph from the third proof of a shape on (first: ordinary launches
+    """Proofs of up to 2^12 rows (every small program: 2^10 rows is the minimum) run as ONE captured CUDA graph from the third proof of a shape on (first: ordinary launches
     that fill the table caches, second: capture + replay).  Every replay must pick up the new trace / public values / PoW
     parameter and give the oracle's bytes."""
     cfg = zkir_b200.ProverConfig(num_queries=12, pow_bits=5)
@@ -426,12 +490,12 @@ def test_small_proofs_replay_a_captured_graph(gpu_ctx, oracle):
             cols, pv = res.pack()
             if i == 4:
                 cfg = zkir_b200.ProverConfig(num_queries=12, pow_bits=9)   # same workspace shape, different PoW: re-capture
-            got = ctx.prove_columns(cols, pv, cfg)
-            assert got == oracle.prove(cfg, cols, pv), f"proof {i} differs from the oracle"
-        _, cols, pv = fib_trace(205)                                       # 2^10 rows, fast NTT path
+            got = ctx.prove_columns(cols, pv, cfg, program=prog)
+            assert got == oracle.prove(cfg, cols, pv, prog), f"proof {i} differs from the oracle"
+        fres, cols, pv = fib_trace(205)                                    # another program on the same context and shape
         cfg = zkir_b200.ProverConfig(num_queries=20, pow_bits=6)
-        want = oracle.prove(cfg, cols, pv)
+        want = oracle.prove(cfg, cols, pv, fres.program)
         for i in range(4):
-            assert ctx.prove_columns(cols, pv, cfg) == want
+            assert ctx.prove_columns(cols, pv, cfg, program=fres.program) == want
     finally:
         ctx.close()

@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libzkir_b200.so")
 
 OK, ERR_ARG, ERR_CUDA, ERR_NCCL, ERR_OOM, ERR_VM, ERR_AIR, ERR_VERIFY = 0, -1, -2, -3, -4, -5, -6, -7
-STAGES = ["h2d", "lde", "trace_commit", "quotient", "quotient_commit", "openings", "fri", "queries_d2h"]
+STAGES = ["h2d", "lde", "trace_commit", "aux", "quotient", "quotient_commit", "openings", "fri", "queries_d2h"]
 
 
 class Params(C.Structure):
@@ -30,11 +30,14 @@ SYMBOLS = {
     "zkir_b200_free_pinned": (None, [vp]),
     "zkir_b200_prove": (C.c_int, [vp, C.POINTER(Params), vp, C.c_uint32, u32p, C.POINTER(vp), C.POINTER(C.c_size_t)]),
     "zkir_b200_prove_device": (C.c_int, [vp, C.POINTER(Params), vp, C.c_uint32, u32p, C.POINTER(vp), C.POINTER(C.c_size_t)]),
-    "zkir_b200_prove_rows": (C.c_int, [vp, C.POINTER(Params), vp, vp, vp, C.c_uint64, u64p, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint32, u32p,
+    "zkir_b200_set_program": (C.c_int, [vp, vp, C.c_size_t]),
+    "zkir_b200_prove_rows": (C.c_int, [vp, C.POINTER(Params), vp, vp, vp, C.c_uint64, u64p, C.c_uint64, C.c_uint32, C.c_uint64, C.c_int, C.c_uint32, u32p,
                                       C.POINTER(vp), C.POINTER(C.c_size_t)]),
     "zkir_b200_expand_rows": (C.c_int, [vp, vp, vp, vp, C.c_uint64, u64p, C.c_uint64, C.c_uint32, vp]),
-    "zkir_b200_prove_writelog": (C.c_int, [vp, C.POINTER(Params), vp, vp, vp, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint32, u32p,
+    "zkir_b200_prove_writelog": (C.c_int, [vp, C.POINTER(Params), vp, vp, vp, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint64, C.c_int, C.c_uint32, u32p,
                                           C.POINTER(vp), C.POINTER(C.c_size_t)]),
+    "zkir_b200_prove_program": (C.c_int, [vp, C.POINTER(Params), vp, C.c_size_t, vp, C.c_size_t, C.c_uint32, vp, C.c_size_t, C.c_uint64, u32p,
+                                         C.POINTER(C.c_uint64), u32p, C.POINTER(vp), C.POINTER(C.c_size_t)]),
     "zkir_b200_expand_writelog": (C.c_int, [vp, vp, vp, vp, C.c_uint64, C.c_uint64, C.c_uint32, vp]),
     "zkir_b200_prove_batch": (C.c_int, [vp, C.POINTER(Params), C.POINTER(vp), u32p, C.POINTER(vp), C.c_uint32, C.POINTER(vp), C.POINTER(C.c_size_t)]),
     "zkir_b200_comm_unique_id": (C.c_int, [vp]),
@@ -44,12 +47,16 @@ SYMBOLS = {
     "zkir_b200_shard_plan": (C.c_int, [C.c_uint32, C.c_uint32, C.POINTER(Params), C.c_uint32, C.c_uint64, u64p]),
     "zkir_b200_free_proof": (None, [vp]),
     "zkir_b200_proof_size": (C.c_size_t, [C.POINTER(Params), C.c_uint32]),
-    "zkir_b200_verify": (C.c_int, [C.POINTER(Params), vp, C.c_size_t, u32p]),
+    "zkir_b200_verify": (C.c_int, [C.POINTER(Params), vp, C.c_size_t, u32p, vp, C.c_size_t]),
+    "zkir_host_poseidon2_permute": (None, [vp]),
+    "zkir_rom_entry": (None, [C.c_uint32, u32p, u32p]),
+    "zkir_program_digest": (None, [vp, C.c_size_t, vp]),
     "zkir_b200_ntt": (C.c_int, [vp, vp, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32]),
     "zkir_b200_lde": (C.c_int, [vp, vp, vp, C.c_uint32, C.c_uint32, C.c_uint32]),
     "zkir_b200_poseidon2_permute": (C.c_int, [vp, vp, C.c_uint64]),
     "zkir_b200_merkle_commit": (C.c_int, [vp, vp, C.c_uint32, C.c_uint32, vp, u32p]),
-    "zkir_b200_quotient": (C.c_int, [vp, C.POINTER(Params), vp, C.c_uint32, u32p, u32p, vp]),
+    "zkir_b200_quotient": (C.c_int, [vp, C.POINTER(Params), vp, vp, C.c_uint32, u32p, u32p, u32p, vp]),
+    "zkir_b200_aux_columns": (C.c_int, [vp, vp, C.c_uint32, u32p, vp]),
     "zkir_b200_fri_fold": (C.c_int, [vp, vp, vp, C.c_uint32, C.c_uint32, u32p]),
     "zkir_b200_dev_alloc": (C.c_int, [vp, C.POINTER(vp), C.c_size_t]),
     "zkir_b200_dev_free": (C.c_int, [vp, vp]),
@@ -64,6 +71,7 @@ SYMBOLS = {
     "zkir_decode": (C.c_int, [C.c_uint32, u32p]),
     "zkir_vm_run": (C.c_int, [u32p, C.c_size_t, u8p, C.c_size_t, C.c_uint32, u64p, C.c_size_t, C.c_uint64, C.c_int, C.POINTER(vp)]),
     "zkir_vm_free": (None, [vp]),
+    "zkir_vm_enable_poseidon2": (None, [C.c_int]),
     "zkir_vm_last_error": (C.c_char_p, []),
     "zkir_vm_cycles": (C.c_uint64, [vp]),
     "zkir_vm_halt_kind": (C.c_int, [vp]),
@@ -78,6 +86,11 @@ SYMBOLS = {
     "zkir_vm_trace_memop_begin": (u64p, [vp]),
     "zkir_vm_trace_memops": (C.POINTER(MemOp), [vp]),
     "zkir_vm_trace_writelog": (C.c_int, [vp, vp, vp]),
+    "zkir_vm_run_writelog": (C.c_int, [u32p, C.c_size_t, u8p, C.c_size_t, C.c_uint32, u64p, C.c_size_t, C.c_uint64, vp, vp, vp, C.c_uint64, C.POINTER(vp)]),
+    "zkir_vm_run_writelog_cb": (C.c_int, [u32p, C.c_size_t, u8p, C.c_size_t, C.c_uint32, u64p, C.c_size_t, C.c_uint64, vp, vp, vp, C.c_uint64, vp, vp, C.c_uint64, C.POINTER(vp)]),
+    "zkir_vm_logged_rows": (C.c_uint64, [vp]),
+    "zkir_vm_code_len": (C.c_size_t, [vp]),
+    "zkir_vm_code": (u32p, [vp]),
     "zkir_vm_final_pc": (C.c_uint64, [vp]),
     "zkir_vm_final_regs": (u64p, [vp]),
     "zkir_pack_min_log_n": (C.c_uint32, [vp]),

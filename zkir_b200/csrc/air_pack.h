@@ -1,0 +1,190 @@
+// Row converter of the AIR v2: one interpreter row (pc, instruction word, PRE-state registers) -> the 86 per-row main columns
+// (the two LogUp multiplicity columns are histograms over all rows and are filled by the callers).
+//
+// The reference names this step but does not contain it (zkir-spec/src/trace.rs:41 "converter", zkir-runtime/src/vm.rs:243-244).
+// ONE definition shared by the host packer (host/pack.cc) and the device converter (trace_expand.cu): `__host__ __device__`,
+// no dynamic indexing of the register array, output through a writer functor.  Column meaning: tools/gen_air.py.
+// Semantics restated from zkir-runtime/src/execute.rs (ADD :43-63, SUB :65-78, ADDI :185-197, SLTU/SGEU/SEQ/SNE :330-420,
+// CMOV* :422-470, BEQ/BNE/BLTU/BGEU :578-637, JAL/JALR :639-659, ECALL/EBREAK :661-673) and syscall.rs:94-149.
+#pragma once
+#include <stdint.h>
+#include "bb.cuh"
+#include "air_columns.h"
+
+namespace zkir {
+
+enum PackErr : u32 {
+  PACK_OK = 0, PACK_ERR_PC = 1, PACK_ERR_REG40 = 2, PACK_ERR_TAPE40 = 3, PACK_ERR_SYSCALL = 4, PACK_ERR_OPCODE = 5, PACK_ERR_JALR = 6, PACK_ERR_ROM = 7,
+};
+BB_HD const char* pack_err_text(u32 code) {
+  switch (code) {
+    case PACK_ERR_PC: return "pc does not fit 30 bits";
+    case PACK_ERR_REG40: return "register value exceeds 40 bits";
+    case PACK_ERR_TAPE40: return "input tape value exceeds 40 bits";
+    case PACK_ERR_SYSCALL: return "syscall other than EXIT/READ/WRITE/POSEIDON2";
+    case PACK_ERR_OPCODE: return "opcode is not constrained";
+    case PACK_ERR_JALR: return "jalr base register does not fit 30 bits";
+    case PACK_ERR_ROM: return "pc is outside the program";
+    default: return "?";
+  }
+}
+
+BB_HD int pack_sext(u32 v, int bits) { const int sh = 32 - bits; return ((int)(v << sh)) >> sh; }
+BB_HD u32 pack_inv(u32 canon) { return canon ? bb_from_mont(bb_inv(bb_to_mont(canon))) : 0u; }
+
+// rg = PRE-state registers (rg[0] ignored), w = instruction word, read_val = post-state r10 (only used by READ rows).
+// Wr: void operator()(int column, u32 canonical_value).  Returns a PackErr.
+template <class Wr>
+BB_HD u32 expand_row_v2(u64 i, u64 T, const u64 (&rg)[16], u64 pc, u32 w, u64 read_val, Wr& W) {
+  const u64 LIMB = (1u << 20) - 1, M40 = (1ull << 40) - 1;
+  const bool live = i < T;
+  u32 err = PACK_OK;
+  if (pc + 4 >= (1u << 30)) err = PACK_ERR_PC;
+#pragma unroll
+  for (int k = 1; k < 16; k++) if (rg[k] >> 40) err = PACK_ERR_REG40;
+
+  W(ZKIR_COL_CLK, (u32)((live ? i : T) % BB_P));
+  W(ZKIR_COL_PC, (u32)pc);
+#pragma unroll
+  for (int k = 1; k < 16; k++) { W(ZKIR_COL_R1_LO + 2 * (k - 1), (u32)(rg[k] & LIMB)); W(ZKIR_COL_R1_LO + 2 * (k - 1) + 1, (u32)((rg[k] >> 20) & LIMB)); }
+
+  u32 rd = 0, rs1 = 0, rs2 = 0, writes = 0;
+  u32 sel = 0xffffffffu;  // column of the opcode selector, if any
+  u32 neg = 0, is_exit = 0, is_read = 0, is_write = 0, is_pos2 = 0;
+  u64 av = 0, bv = 0, vv = 0, rc = 0;   // operands, written value, range-checked 40-bit quantity (-> chunks)
+  long long imm = 0;
+  bool has_imm = false;
+  u32 carry0 = 0, carry1 = 0, taken = 0;
+  u32 ch[4] = {0, 0, 0, 0};
+  bool chunks_from_rc = false;
+  if (live) {
+    const u32 op = w & 0x7F;
+    const u32 fa = (w >> 7) & 0xF, fb = (w >> 11) & 0xF, fc = (w >> 15) & 0xF;
+    auto R = [&](u32 k) -> u64 {  // register read without dynamic indexing of the local array
+      u64 v = 0;
+#pragma unroll
+      for (int j = 1; j < 16; j++) if (k == (u32)j) v = rg[j];
+      return v;
+    };
+    const int imm17 = pack_sext((w >> 15) & 0x1FFFF, 17);
+    if (op == 0x00 || op == 0x01) {                     // ADD / SUB
+      rd = fa; rs1 = fb; rs2 = fc; writes = 1;
+      av = R(rs1); bv = R(rs2);
+      sel = op == 0 ? ZKIR_COL_S_ADD : ZKIR_COL_S_SUB;
+    } else if (op == 0x08) {                            // ADDI
+      rd = fa; rs1 = fb; imm = imm17; has_imm = true; writes = 1;
+      av = R(rs1); bv = (u64)imm & M40;
+      sel = ZKIR_COL_S_ADDI;
+    } else if (op == 0x20 || op == 0x21) {              // SLTU / SGEU
+      rd = fa; rs1 = fb; rs2 = fc; writes = 1; neg = op & 1;
+      av = R(rs1); bv = R(rs2);
+      sel = ZKIR_COL_S_SLTU;
+    } else if (op == 0x24 || op == 0x25) {              // SEQ / SNE
+      rd = fa; rs1 = fb; rs2 = fc; writes = 1; neg = op & 1;
+      av = R(rs1); bv = R(rs2);
+      sel = ZKIR_COL_S_SEQ;
+    } else if (op == 0x26 || op == 0x27 || op == 0x28) { // CMOV / CMOVZ / CMOVNZ
+      rd = fa; rs1 = fb; rs2 = fc; neg = op == 0x27;
+      av = R(rs1); bv = R(rs2);
+      sel = op == 0x28 ? ZKIR_COL_S_CMOVNZ : ZKIR_COL_S_CMOV;
+    } else if (op == 0x40 || op == 0x41) {              // BEQ / BNE, B-type: rs1 bits 10:7, rs2 bits 14:11 (encoder.rs:132-140)
+      rs1 = fa; rs2 = fb; imm = imm17; has_imm = true; neg = op & 1;
+      av = R(rs1); bv = R(rs2);
+      sel = ZKIR_COL_S_BEQ;
+    } else if (op == 0x44 || op == 0x45) {              // BLTU / BGEU
+      rs1 = fa; rs2 = fb; imm = imm17; has_imm = true; neg = op & 1;
+      av = R(rs1); bv = R(rs2);
+      sel = ZKIR_COL_S_BLTU;
+    } else if (op == 0x48) {                            // JAL
+      rd = fa; imm = pack_sext((w >> 11) & 0x1FFFFF, 21); has_imm = true; writes = 1;
+      vv = pc + 4; rc = vv; chunks_from_rc = true;
+      sel = ZKIR_COL_S_JAL;
+    } else if (op == 0x49) {                            // JALR: target = (rs1 + imm) & ~1, link = pc + 4
+      rd = fa; rs1 = fb; imm = imm17; has_imm = true; writes = 1;
+      av = R(rs1);
+      vv = pc + 4;
+      if (av >> 30) err = PACK_ERR_JALR;
+      ch[0] = (u32)(vv & 1023); ch[1] = (u32)((vv >> 10) & 1023); ch[2] = (u32)((vv >> 20) & 1023); ch[3] = (u32)((av >> 20) & 1023);
+      taken = (u32)((av + (u64)(long long)imm) & 1);
+      sel = ZKIR_COL_S_JALR;
+    } else if (op == 0x50) {                            // ECALL: number in r10 (syscall.rs:94-149)
+      const u64 num = rg[10];
+      if (num == 0) is_exit = 1;
+      else if (num == 1) {                              // READ: the value is the post-state r10
+        is_read = 1; rd = 10; writes = 1;
+        vv = read_val; rc = vv; chunks_from_rc = true;
+        if (vv >> 40) err = PACK_ERR_TAPE40;
+      } else if (num == 2) is_write = 1;
+      else if (num == 4) { is_pos2 = 1; rd = 10; writes = 1; vv = 0; }
+      else err = PACK_ERR_SYSCALL;
+    } else if (op == 0x51) {                            // EBREAK
+      sel = ZKIR_COL_S_EBREAK;
+    } else {
+      err = PACK_ERR_OPCODE;
+    }
+    const u64 a_lo = av & LIMB, a_hi = (av >> 20) & LIMB, b_lo = bv & LIMB, b_hi = (bv >> 20) & LIMB;
+    if (op == 0x00 || op == 0x08) {
+      vv = (av + bv) & M40; rc = vv; chunks_from_rc = true;
+      const u64 k0 = (a_lo + b_lo) >> 20;
+      carry0 = (u32)k0; carry1 = (u32)((a_hi + b_hi + k0) >> 20);
+    } else if (op == 0x01 || op == 0x20 || op == 0x21 || op == 0x44 || op == 0x45) {
+      rc = (av - bv) & M40; chunks_from_rc = true;    // SUB: the result; compares: a - b mod 2^40, final borrow = (a < b)
+      const u64 k0 = a_lo < b_lo;
+      carry0 = (u32)k0; carry1 = (u32)(a_hi < b_hi + k0);
+      if (op == 0x01) vv = rc;
+      else if (op < 0x40) vv = carry1 ^ neg;
+      else taken = carry1 ^ neg;
+    } else if (op == 0x24 || op == 0x25 || op == 0x40 || op == 0x41 || op == 0x26 || op == 0x27 || op == 0x28) {
+      // is-zero gadget: EQ family on the limbs of a - b, CMOV family on the limbs of b
+      const bool cm = op >= 0x26 && op <= 0x28;
+      const u32 x_lo = cm ? (u32)b_lo : bb_sub((u32)a_lo, (u32)b_lo), x_hi = cm ? (u32)b_hi : bb_sub((u32)a_hi, (u32)b_hi);
+      carry0 = x_lo != 0; carry1 = x_hi != 0;
+      ch[0] = pack_inv(x_lo); ch[1] = pack_inv(x_hi);
+      const u32 nz = carry0 | carry1;
+      if (cm) {
+        const u32 mv = neg ? !nz : nz;
+        ch[3] = nz; ch[2] = mv; writes = mv; vv = av;
+      } else {
+        ch[2] = nz;
+        const u32 eqx = neg ? nz : !nz;
+        if (op < 0x40) vv = eqx; else taken = eqx;
+      }
+    }
+  }
+  if (chunks_from_rc) { ch[0] = (u32)(rc & 1023); ch[1] = (u32)((rc >> 10) & 1023); ch[2] = (u32)((rc >> 20) & 1023); ch[3] = (u32)((rc >> 30) & 1023); }
+  u32 imm_lo = 0, imm_sign = 0;  // the high limb is the sign extension (0 or 2^20-1): not a column
+  if (has_imm) {
+    imm_lo = (u32)(((u64)imm & M40) & LIMB);
+    imm_sign = imm < 0;
+  }
+  W(ZKIR_COL_IMM_LO, imm_lo); W(ZKIR_COL_IMM_SIGN, imm_sign);
+#pragma unroll
+  for (int c = ZKIR_COL_S_ADD; c <= ZKIR_COL_S_EBREAK; c++) W(c, sel == (u32)c);
+  W(ZKIR_COL_NEG, neg);
+  W(ZKIR_COL_IS_EXIT, is_exit); W(ZKIR_COL_IS_READ, is_read); W(ZKIR_COL_IS_WRITE, is_write); W(ZKIR_COL_IS_POS2, is_pos2);
+#pragma unroll
+  for (int k = 0; k < 3; k++) {  // register index = 4*h + l, two 4-way one-hots each (entry 3 implied)
+    W(ZKIR_COL_RD_H0 + k, (rd >> 2) == (u32)k); W(ZKIR_COL_RD_L0 + k, (rd & 3u) == (u32)k);
+    W(ZKIR_COL_RS1_H0 + k, (rs1 >> 2) == (u32)k); W(ZKIR_COL_RS1_L0 + k, (rs1 & 3u) == (u32)k);
+    W(ZKIR_COL_RS2_H0 + k, (rs2 >> 2) == (u32)k); W(ZKIR_COL_RS2_L0 + k, (rs2 & 3u) == (u32)k);
+  }
+#pragma unroll
+  for (int k = 0; k < 4; k++) W(ZKIR_COL_RDW0 + k, ((rd >> 2) == (u32)k) ? writes : 0u);   // rdw[h] = rd_h[h] * write enable
+  W(ZKIR_COL_A_LO, (u32)(av & LIMB)); W(ZKIR_COL_A_HI, (u32)((av >> 20) & LIMB));
+  W(ZKIR_COL_B_LO, (u32)(bv & LIMB)); W(ZKIR_COL_B_HI, (u32)((bv >> 20) & LIMB));
+  W(ZKIR_COL_V_LO, (u32)(vv & LIMB)); W(ZKIR_COL_V_HI, (u32)((vv >> 20) & LIMB));
+#pragma unroll
+  for (int k = 0; k < 4; k++) W(ZKIR_COL_CH0 + k, ch[k]);
+  W(ZKIR_COL_CARRY0, carry0); W(ZKIR_COL_CARRY1, carry1);
+  W(ZKIR_COL_TAKEN, taken);
+  return err;
+}
+
+// does this row's chunk quadruple go to the range table?  (tools/gen_air.py: rc_on)
+BB_HD bool row_range_checked(u32 w, u64 r10) {
+  const u32 op = w & 0x7F;
+  return op == 0x00 || op == 0x01 || op == 0x08 || op == 0x20 || op == 0x21 || op == 0x44 || op == 0x45 || op == 0x48 || op == 0x49 ||
+         (op == 0x50 && r10 == 1);
+}
+
+}  // namespace zkir

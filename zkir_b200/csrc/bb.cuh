@@ -15,8 +15,10 @@ typedef uint64_t u64;
 
 #ifdef __CUDACC__
 #define BB_HD __host__ __device__ __forceinline__
+#define BB_ALIGN16 __align__(16)
 #else
 #define BB_HD inline
+#define BB_ALIGN16 alignas(16)
 #endif
 
 // canonical -> Montgomery at compile time / on the host
@@ -88,7 +90,7 @@ BB_HD Fm operator-(Fm a, Fm b) { return Fm(bb_sub(a.v, b.v)); }
 BB_HD Fm operator*(Fm a, Fm b) { return Fm(bb_mul(a.v, b.v)); }
 
 // ---- F_p[X]/(X^4 - 11), coefficients in Montgomery form
-struct __align__(16) E4 {
+struct BB_ALIGN16 E4 {
   u32 c[4];
 };
 #define BB_W11 bb_to_mont_c(11u)
@@ -128,6 +130,13 @@ BB_HD E4 e4_inv(E4 a) {
   r.c[3] = bb_neg(bb_add(bb_mul(B0, i1), bb_mul(B1, i0)));
   return r;
 }
+
+// ext4 wrapper with operators, used to instantiate the generated AIR (X type of air_generated.h)
+struct Xm { E4 v; };
+BB_HD Xm operator+(Xm a, Xm b) { Xm r; r.v = e4_add(a.v, b.v); return r; }
+BB_HD Xm operator-(Xm a, Xm b) { Xm r; r.v = e4_sub(a.v, b.v); return r; }
+BB_HD Xm operator*(Xm a, Xm b) { Xm r; r.v = e4_mul(a.v, b.v); return r; }
+BB_HD Xm operator*(Xm a, Fm b) { Xm r; r.v = e4_mulb(a.v, b.v); return r; }
 
 // ---- lazy ext4 accumulator for inner products  sum_j x_j * v_j  (x_j in E4, v_j in F_p, all < p, any representation).
 // Each coordinate is a 64-bit integer kept below p*2^32: a product (< p^2) is added with one mad.wide, and after at

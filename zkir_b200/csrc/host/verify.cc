@@ -11,6 +11,8 @@
 #include "zkir_b200.h"
 #include "../constants_generated.h"
 #include "../air_generated.h"
+#include "../air_columns.h"
+#include <algorithm>
 
 std::string& zkir_host_error();
 #define g_verify_error zkir_host_error()
@@ -136,41 +138,87 @@ struct Challenger {
   u32 bits(u32 b) { u32 v = sample(); return b >= 32 ? v : v & ((1u << b) - 1); }
 };
 
-struct AirAtZeta {  // air_generated.h context over ext4
-  typedef X4 F;
-  const X4 *loc, *nxt; const u32* pv;
+struct AirAtZeta {  // air_generated.h context over ext4: base and ext values are both X4 here
+  typedef X4 F; typedef X4 X;
+  const X4 *loc, *nxt;        // opened main columns [0, W) then aux columns [W, W + A) at zeta / g*zeta
+  const X4* pub;              // public columns at zeta, computed by the verifier
+  const u32* pv;
+  X4 zc, thp[4];              // lookup challenges z, theta^k
   X4 is_first, is_last, is_trans, alpha, acc;
   X4 L(int i) const { return loc[i]; }
   X4 N(int i) const { return nxt[i]; }
+  X4 A(int i) const { return loc[ZKIR_AIR_WIDTH + i]; }
+  X4 AN(int i) const { return nxt[ZKIR_AIR_WIDTH + i]; }
+  X4 P(int i) const { return pub[i]; }
   X4 PV(int i) const { return X4(pv[i]); }
   X4 K(u32 k) const { return X4(k); }
+  X4 z() const { return zc; }
+  X4 th(int k) const { return thp[k]; }
+  X4 xf(const X4& a) const { return a; }
+  X4 x4(const X4& a, const X4& b, const X4& c, const X4& d) const {   // a + X b + X^2 c + X^3 d: the ext value of four base polynomials
+    X4 e1, e2, e3; e1.c[1] = 1; e2.c[2] = 1; e3.c[3] = 1;
+    return a + e1 * b + e2 * c + e3 * d;
+  }
   void emit(int, const X4& v) { acc = acc * alpha + v; }  // Horner: sum_i alpha^(K-1-i) c_i
+  void emit_x(int, const X4& v) { acc = acc * alpha + v; }
 };
+
+// ROM decode of one instruction word, as the AIR's ROM lookup sees it (docs/PROVER_SPEC.md section 3.3): the fields of the word's
+// format (zkir-assembler/src/encoder.rs:98-151) packed as opcode | rd << 7 | rs1 << 11 | rs2 << 15, and the signed immediate mod p
+inline int32_t sx(u32 v, int bits) { int sh = 32 - bits; return ((int32_t)(v << sh)) >> sh; }
+void rom_entry(u32 w, u32* dec, u32* imm) {
+  u32 f[5];
+  int64_t im = 0; u32 rd = 0, rs1 = 0, rs2 = 0;
+  const u32 op = w & 0x7F;
+  if (zkir_decode(w, f) != 0) { *dec = op | ((w >> 7) & 15) << 7 | ((w >> 11) & 15) << 11 | ((w >> 15) & 15) << 15; *imm = 0; return; }  // undefined opcode: matches no row
+  const bool stype = (op >= 0x38 && op <= 0x3B) || (op >= 0x40 && op <= 0x45);
+  const bool rtype = !stype && op != 0x48 && op != 0x50 && op != 0x51 && !(op == 0x08 || (op >= 0x13 && op <= 0x15) || (op >= 0x30 && op <= 0x35) || op == 0x49) &&
+                     !(op >= 0x1B && op <= 0x1D);
+  if (stype) { rs1 = f[1]; rs2 = f[2]; im = (int32_t)f[4]; }
+  else if (rtype) { rd = f[1]; rs1 = f[2]; rs2 = f[3]; }
+  else if (op == 0x48) { rd = f[1]; im = (int32_t)f[4]; }
+  else if (op == 0x50 || op == 0x51) {}
+  else { rd = f[1]; rs1 = f[2]; im = (int32_t)f[4]; }     // I-type and shift-immediate
+  *dec = op | rd << 7 | rs1 << 11 | rs2 << 15;
+  *imm = im < 0 ? (u32)((int64_t)P + im) : (u32)im;
+}
+// transcript digest of the program: hash_tree over {n_code, lo16(word_0), hi16(word_0), ...}
+void program_digest(const u32* code, size_t n_code, u32* digest) {
+  std::vector<u32> h(2 * n_code + 1);
+  h[0] = (u32)n_code;
+  for (size_t i = 0; i < n_code; i++) { h[1 + 2 * i] = code[i] & 0xFFFF; h[2 + 2 * i] = code[i] >> 16; }
+  hash_tree(h.data(), h.size(), digest);
+}
 
 bool fail(const char* m) { g_verify_error = m; return false; }
 
-bool verify(const zkir_params* p, const u32* w, size_t nwords, const u32* pv_in) {
+bool verify(const zkir_params* p, const u32* w, size_t nwords, const u32* pv_in, const u32* code, size_t n_code) {
   if (!p || !w) return fail("null argument");
   if (p->width != ZKIR_AIR_WIDTH || p->num_public != ZKIR_AIR_NUM_PUBLIC || p->log_blowup < 1) return fail("unsupported params");
   if (nwords < 8) return fail("proof too short");
-  if (w[0] != 0x5A4B5052u || w[1] != 3) return fail("bad magic/version");
+  if (w[0] != 0x5A4B5052u || w[1] != 4) return fail("bad magic/version");
+  if (!code && n_code) return fail("null program");
   const u32 log_n = w[2];
   if (w[3] != p->width || w[4] != p->log_blowup || w[5] != p->num_queries || w[6] != p->pow_bits || w[7] != p->num_public)
     return fail("proof header does not match params");
-  if (log_n < 2 || log_n + p->log_blowup > 27) return fail("bad log_n");
+  if (log_n < ZKIR_AIR_RANGE_BITS || log_n + p->log_blowup > 27) return fail("bad log_n");
+  if (n_code > (1ull << log_n)) return fail("program does not fit the trace");
   if (nwords * 4 != zkir_b200_proof_size(p, log_n)) return fail("proof length mismatch");
-  const u32 W = p->width, np = p->num_public, lg = log_n + p->log_blowup, R = log_n / 3 + (log_n % 3 ? 1 : 0), QW = 8;  // R FRI rounds: fold by 8, the last by 2^(log_n mod 3)
+  const u32 W = p->width, AW = ZKIR_AIR_AUX_WIDTH, WA = W + AW, np = p->num_public, lg = log_n + p->log_blowup, R = log_n / 3 + (log_n % 3 ? 1 : 0), QW = 8;  // R FRI rounds: fold by 8, the last by 2^(log_n mod 3)
   const u64 N = 1ull << log_n, M = 1ull << lg;
   for (size_t i = 8; i < nwords; i++) if (w[i] >= P) return fail("non-canonical field element");
   const u32* q = w + 8;
   const u32* pv = q; q += np;
   if (pv_in) for (u32 i = 0; i < np; i++) if (pv[i] != pv_in[i]) return fail("public values differ");
+  // public values that are not bound by constraints alone: halted is a flag, and a run that did not halt has no exit code
+  if (pv[4] > 1 || (pv[4] == 0 && (pv[2] || pv[3]))) return fail("inconsistent halt flag / exit code");
   const u32* troot = q; q += 8;
+  const u32* aroot = q; q += 8;
   const u32* qroot = q; q += 8;
   const u32* open = q;
-  std::vector<X4> ot(W), otg(W), oq(QW);
-  for (u32 k = 0; k < W; k++) { memcpy(ot[k].c, q, 16); q += 4; }
-  for (u32 k = 0; k < W; k++) { memcpy(otg[k].c, q, 16); q += 4; }
+  std::vector<X4> ot(WA), otg(WA), oq(QW);   // main columns then aux columns
+  for (u32 k = 0; k < WA; k++) { memcpy(ot[k].c, q, 16); q += 4; }
+  for (u32 k = 0; k < WA; k++) { memcpy(otg[k].c, q, 16); q += 4; }
   for (u32 k = 0; k < QW; k++) { memcpy(oq[k].c, q, 16); q += 4; }
   const u32* fri_roots = q; q += 8 * R;
   X4 final_v; memcpy(final_v.c, q, 16); const u32* final_w = q; q += 4;
@@ -178,13 +226,17 @@ bool verify(const zkir_params* p, const u32* w, size_t nwords, const u32* pv_in)
 
   // ---- transcript
   Challenger ch;
-  const u32 hdr[6] = {log_n, W, p->log_blowup, p->num_queries, p->pow_bits, np};
-  ch.observe(hdr, 6); ch.observe(pv, np); ch.observe(troot, 8);
+  const u32 hdr[7] = {log_n, W, AW, p->log_blowup, p->num_queries, p->pow_bits, np};
+  u32 pdig[8];
+  program_digest(code, n_code, pdig);
+  ch.observe(hdr, 7); ch.observe(pv, np); ch.observe(pdig, 8); ch.observe(troot, 8);
+  const X4 lz = ch.sample_ext(), ltheta = ch.sample_ext();   // lookup challenges, drawn before the aux columns are committed
+  ch.observe(aroot, 8);
   const X4 alpha = ch.sample_ext();
   ch.observe(qroot, 8);
   const X4 zeta = ch.sample_ext();
   u32 open_digest[8];
-  hash_tree(open, (2 * W + QW) * 4, open_digest);
+  hash_tree(open, (2 * WA + QW) * 4, open_digest);
   ch.observe(open_digest, 8);
   const X4 afri = ch.sample_ext();
   std::vector<X4> betas(R);
@@ -198,8 +250,34 @@ bool verify(const zkir_params* p, const u32* w, size_t nwords, const u32* pv_in)
   const X4 zN = xpow(zeta, N), zh = zN - X4(1);
   X4 i1, i2;
   if (!xinv(zeta - X4(1), &i1) || !xinv(zeta - X4(g_inv), &i2)) return fail("zeta hits the trace domain");
+  // public columns at zeta by the barycentric formula over H_N:  P(zeta) = (zeta^N - 1)/N * sum_i v_i w^i / (zeta - w^i);
+  // only the first max(1024, n_code) rows are non-zero, except the ROM's decoded-word column which is 127 on every unused row:
+  // it is evaluated as the constant 127 plus the interpolant of (dec_i - 127) over the program rows
+  X4 pubz[ZKIR_AIR_PUB_WIDTH];
+  {
+    const size_t rows = std::max<size_t>((size_t)1 << ZKIR_AIR_RANGE_BITS, n_code);
+    const X4 scale_all = scale(zh, inv((u32)(N % P)));
+    u32 wi = 1;
+    for (size_t i = 0; i < rows; i++) {
+      X4 d;
+      if (!xinv(zeta - X4(wi), &d)) return fail("zeta hits the trace domain");
+      const X4 li = scale(d, wi);    // w^i / (zeta - w^i)
+      if (i < ((size_t)1 << ZKIR_AIR_RANGE_BITS)) pubz[ZKIR_PUB_P_T] = pubz[ZKIR_PUB_P_T] + scale(li, (u32)i);
+      if (i < n_code) {
+        u32 dec, im;
+        rom_entry(code[i], &dec, &im);
+        pubz[ZKIR_PUB_P_PC] = pubz[ZKIR_PUB_P_PC] + scale(li, (u32)(0x1000 + 4 * i));
+        pubz[ZKIR_PUB_P_DEC] = pubz[ZKIR_PUB_P_DEC] + scale(li, sub(dec, 127));   // relative to the 127 every row carries
+        pubz[ZKIR_PUB_P_IMM] = pubz[ZKIR_PUB_P_IMM] + scale(li, im);
+      }
+      wi = mul(wi, g);
+    }
+    for (int k = 0; k < ZKIR_AIR_PUB_WIDTH; k++) pubz[k] = pubz[k] * scale_all;
+    pubz[ZKIR_PUB_P_DEC] = pubz[ZKIR_PUB_P_DEC] + X4(127);   // the constant polynomial 127
+  }
   AirAtZeta c;
-  c.loc = ot.data(); c.nxt = otg.data(); c.pv = pv; c.alpha = alpha;
+  c.loc = ot.data(); c.nxt = otg.data(); c.pub = pubz; c.pv = pv; c.alpha = alpha;
+  c.zc = lz; c.thp[0] = X4(1); c.thp[1] = ltheta; c.thp[2] = ltheta * ltheta; c.thp[3] = c.thp[2] * ltheta;
   c.is_first = zh * i1; c.is_last = zh * i2; c.is_trans = zeta - X4(g_inv);
   zkir_air_eval(c);
   X4 xp[4]; for (int k = 0; k < 4; k++) { xp[k] = X4(); xp[k].c[k] = 1; }  // basis 1, X, X^2, X^3
@@ -212,11 +290,11 @@ bool verify(const zkir_params* p, const u32* w, size_t nwords, const u32* pv_in)
   if (!eq(c.acc, zh * qz)) return fail("constraint identity fails at zeta");
 
   // ---- queries
-  std::vector<X4> afp(2 * W + 1);
+  std::vector<X4> afp(2 * WA + 1);
   afp[0] = X4(1);
-  for (u32 k = 1; k <= 2 * W; k++) afp[k] = afp[k - 1] * afri;
+  for (u32 k = 1; k <= 2 * WA; k++) afp[k] = afp[k - 1] * afri;
   X4 A1, A2, A3;
-  for (u32 k = 0; k < W; k++) { A1 = A1 + afp[k] * ot[k]; A2 = A2 + afp[k] * otg[k]; }
+  for (u32 k = 0; k < WA; k++) { A1 = A1 + afp[k] * ot[k]; A2 = A2 + afp[k] * otg[k]; }
   for (u32 k = 0; k < QW; k++) A3 = A3 + afp[k] * oq[k];
   const X4 gzeta = scale(zeta, g);
   const u32 wM = ZKIR_BB_ROOTS[lg], half = inv(2);
@@ -224,19 +302,24 @@ bool verify(const zkir_params* p, const u32* w, size_t nwords, const u32* pv_in)
     const u64 idx = ch.bits(lg);
     const u32* trow = q; q += W;
     const u32* tpath = q; q += 8 * lg;
+    const u32* arow = q; q += AW;
+    const u32* apath = q; q += 8 * lg;
     const u32* qrow = q; q += QW;
     const u32* qpath = q; q += 8 * lg;
     u32 d[8];
     hash_n(trow, W, d);
     if (!check_path(d, idx, tpath, lg, troot)) return fail("trace Merkle path");
+    hash_n(arow, AW, d);
+    if (!check_path(d, idx, apath, lg, aroot)) return fail("aux Merkle path");
     hash_n(qrow, QW, d);
     if (!check_path(d, idx, qpath, lg, qroot)) return fail("quotient Merkle path");
     const u32 x = mul(ZKIR_BB_GEN, pw(wM, idx));
     X4 rt, rq, iz, igz;
     for (u32 k = 0; k < W; k++) rt = rt + scale(afp[k], trow[k]);
+    for (u32 k = 0; k < AW; k++) rt = rt + scale(afp[W + k], arow[k]);
     for (u32 k = 0; k < QW; k++) rq = rq + scale(afp[k], qrow[k]);
     if (!xinv(X4(x) - zeta, &iz) || !xinv(X4(x) - gzeta, &igz)) return fail("zeta on the LDE coset");
-    X4 v = (rt - A1) * iz + afp[W] * ((rt - A2) * igz) + afp[2 * W] * ((rq - A3) * iz);
+    X4 v = (rt - A1) * iz + afp[WA] * ((rt - A2) * igz) + afp[2 * WA] * ((rq - A3) * iz);
     u64 i = idx;
     u32 lshift = ZKIR_BB_GEN;
     u32 ll = lg;  // log2 of the layer length
@@ -277,11 +360,16 @@ bool verify(const zkir_params* p, const u32* w, size_t nwords, const u32* pv_in)
 }  // namespace
 
 extern "C" {
-int zkir_b200_verify(const zkir_params* p, const uint8_t* proof, size_t len, const uint32_t* public_values) {
+int zkir_b200_verify(const zkir_params* p, const uint8_t* proof, size_t len, const uint32_t* public_values, const uint32_t* code, size_t n_code) {
   g_verify_error.clear();
   if (!proof || len % 4) { g_verify_error = "bad proof buffer"; return ZKIR_ERR_VERIFY; }
   std::vector<u32> w(len / 4);
   memcpy(w.data(), proof, len);
-  return verify(p, w.data(), w.size(), public_values) ? 0 : ZKIR_ERR_VERIFY;
+  return verify(p, w.data(), w.size(), public_values, code, n_code) ? 0 : ZKIR_ERR_VERIFY;
 }
+void zkir_program_digest(const uint32_t* code, size_t n_code, uint32_t digest8[8]) { program_digest(code, n_code, digest8); }
+// the width-16 Poseidon2 permutation (canonical values in and out): SYS_POSEIDON2 of the interpreter (vm.cc) uses it
+void zkir_host_poseidon2_permute(uint32_t* state16) { permute(state16); }
+// ROM entry of one code word as the AIR's ROM lookup sees it (used by the prover to build the public ROM columns)
+void zkir_rom_entry(uint32_t word, uint32_t* dec, uint32_t* imm) { rom_entry(word, dec, imm); }
 }

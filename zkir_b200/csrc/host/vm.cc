@@ -69,6 +69,9 @@ struct Memory {  // sparse 4 KiB pages, little endian, uninitialised reads 0 (me
   bool trace_enabled = false;
   u64 timestamp = 0;
   std::vector<zkir_mem_op> trace;
+  // decoded-fetch mirror of the code segment [CODE_BASE, code_end): the interpreter fetches from here instead of four hash-map
+  // byte reads per cycle (memory.rs:297-309); a store into the segment refreshes the word, so self-modifying code still works
+  std::vector<u32> mirror; u64 code_end = 0;
   uint8_t* page(u64 pn, bool create) {
     if (pn == last_page && last_ptr) return last_ptr;
     auto it = pages.find(pn);
@@ -96,6 +99,13 @@ struct Memory {  // sparse 4 KiB pages, little endian, uninitialised reads 0 (me
   void write(u64 a, u64 v, int width) {
     for (int i = 0; i < width; i++) wr8(a + i, (uint8_t)(v >> (8 * i)));
     rec(a, v, true, (uint8_t)width);
+    if (a < code_end && a + width > CODE_BASE) {
+      for (u64 wa = (a > CODE_BASE ? a : CODE_BASE) & ~3ull; wa < a + width && wa < code_end; wa += 4) {
+        u32 x = 0;
+        for (int i = 0; i < 4; i++) x |= (u32)rd8(wa + i) << (8 * i);
+        mirror[(wa - CODE_BASE) / 4] = x;
+      }
+    }
   }
 };
 
@@ -115,6 +125,8 @@ struct zkir_vm_result {
   std::vector<u64> aux;        // READ: value read; WRITE: value written; else 0
   std::vector<u64> memop_begin;  // CSR offsets into memops, size cycles+1
   std::vector<zkir_mem_op> memops;  // data memory ops per row (fetch excluded)
+  std::vector<u32> code;            // the program's code words (the ROM the proof is bound to)
+  u64 logged = 0;                   // write-log mode: rows written to the caller's arrays
   std::string error;
 };
 
@@ -155,25 +167,46 @@ const char* zkir_vm_last_error(void) { return g_vm_error.c_str(); }
 
 void zkir_vm_free(zkir_vm_result* r) { delete r; }
 
-int zkir_vm_run(const uint32_t* code, size_t n_code, const uint8_t* data, size_t n_data, uint32_t entry_point,
-                const uint64_t* inputs, size_t n_inputs, uint64_t max_cycles, int record_trace, zkir_vm_result** out) {
+static thread_local int g_enable_poseidon2 = 0;
+// SYS_POSEIDON2 is a stub that errors upstream (crypto.rs:299-315, pinned by syscall_integration.rs:400-422), and that is the default
+// here too; BASELINE config 3 needs the syscall, so it is an opt-in of the calling thread (VMConfig.enable_poseidon2_syscall)
+void zkir_vm_enable_poseidon2(int on) { g_enable_poseidon2 = on; }
+void zkir_host_poseidon2_permute(uint32_t* state16);   // verify.cc: the Poseidon2 permutation of docs/PROVER_SPEC.md section 2
+
+// One interpreter for the three recording modes: none, full rows (ExecutionResult.execution_trace, trace.rs:24-50) and the
+// register write log written STRAIGHT into caller-provided arrays while the program runs (pinned memory: north_star "the CPU
+// interpreter records the execution trace into pinned memory"): wl_pcs/wl_ins/wl_log[capacity], 16 B per cycle.
+static int vm_run_impl(const uint32_t* code, size_t n_code, const uint8_t* data, size_t n_data, uint32_t entry_point,
+                       const uint64_t* inputs, size_t n_inputs, uint64_t max_cycles, int record_trace,
+                       uint32_t* wl_pcs, uint32_t* wl_ins, uint64_t* wl_log, uint64_t wl_capacity, zkir_vm_result** out,
+                       void (*on_chunk)(void*, uint64_t) = nullptr, void* cb_user = nullptr, uint64_t chunk_rows = 0) {
   *out = nullptr;
   if (entry_point < 0x1000) {  // vm.rs:141-147 (the reference panics)
     g_vm_error = "Program appears to be in debug format (entry_point < 0x1000)";
     return ZKIR_ERR_ARG;
   }
   std::unique_ptr<zkir_vm_result> res(new zkir_vm_result());
+  res->code.assign(code, code + n_code);
   Memory mem;
   for (size_t i = 0; i < n_code; i++) mem.write(CODE_BASE + 4 * i, code[i], 4);
   for (size_t i = 0; i < n_data; i++) mem.wr8(CODE_BASE + 4 * n_code + i, data[i]);
+  mem.mirror.assign(code, code + n_code);
+  mem.code_end = CODE_BASE + 4 * n_code;
   mem.trace.clear();
   mem.trace_enabled = record_trace != 0;
+  const bool wl = wl_log != nullptr;
   u64 regs[16] = {0};
   u64 pc = entry_point, cycles = 0;
   size_t input_pos = 0;
   bool halted = false;
+  u64 cur_log = 0;          // write-log word of the current cycle
+  u64 wide_row = ~0ull;     // first cycle that wrote a value above 40 bits (the log format cannot hold it)
   auto R = [&](u32 i) -> u64 { return i == 0 ? 0 : regs[i]; };
-  auto W = [&](u32 i, u64 v) { if (i) regs[i] = v; };
+  auto W = [&](u32 i, u64 v) {
+    if (!i) return;
+    regs[i] = v;
+    if (wl) { if ((v >> 40) && wide_row == ~0ull) wide_row = cycles; cur_log = ((u64)i << 56) | (v & MASK40); }
+  };
   auto fail = [&](const std::string& m) { g_vm_error = m; return ZKIR_ERR_VM; };
   auto slt40 = [](u64 a, u64 b) { u64 s = 1ull << 39; return ((a & MASK40) ^ s) < ((b & MASK40) ^ s); };
   auto sra40 = [](u64 v, u32 sh) -> u64 {
@@ -191,13 +224,22 @@ int zkir_vm_run(const uint32_t* code, size_t n_code, const uint8_t* data, size_t
     const u64 fetch_pc = pc;
     if (pc % 4 != 0) { char b[64]; snprintf(b, sizeof b, "Misaligned PC: %#llx", (unsigned long long)pc); return fail(b); }
     const size_t ops_before = mem.trace.size();
-    u32 word = (u32)mem.read(pc, 4);
+    // fetch (vm.rs:362-379): from the mirror of the code segment; anywhere else through memory (reads 0 when unmapped).  The fetch
+    // is a memory op of the cycle upstream, but the row filter drops it (address == fetch pc), so it is not recorded here.
+    u32 word;
+    if (pc >= CODE_BASE && pc < mem.code_end) word = mem.mirror[(pc - CODE_BASE) >> 2];
+    else { const bool te = mem.trace_enabled; mem.trace_enabled = false; word = (u32)mem.read(pc, 4); mem.trace_enabled = te; }
     u32 op = word & 0x7F;
     if (!valid_opcode(op)) { char b[64]; snprintf(b, sizeof b, "Decode error: unknown opcode %#x", op); return fail(b); }
     if (record_trace) {
       res->pc.push_back(fetch_pc); res->instr.push_back(word);
       res->regs.insert(res->regs.end(), regs, regs + 16);
       res->aux.push_back(0);
+    }
+    if (wl) {
+      if (cycles >= wl_capacity) return fail("write log is full: raise the capacity (max_cycles) of the pinned arrays");
+      if (pc >> 32) return fail("write log: pc above 32 bits");
+      wl_pcs[cycles] = (u32)pc; wl_ins[cycles] = word; cur_log = 0;
     }
     const u32 fa = (word >> 7) & 0xF, fb = (word >> 11) & 0xF, fc = (word >> 15) & 0xF;
     const i64 imm17 = sext((word >> 15) & 0x1FFFF, 17);
@@ -271,12 +313,29 @@ int zkir_vm_run(const uint32_t* code, size_t n_code, const uint8_t* data, size_t
       u64 num = regs[10];
       switch (num) {
         case 0: halted = true; res->halt_kind = ZKIR_HALT_EXIT; res->exit_code = regs[11]; break;
-        case 1: { u64 v = input_pos < n_inputs ? inputs[input_pos++] : 0; regs[10] = v; if (record_trace) res->aux.back() = v; break; }
+        case 1: { u64 v = input_pos < n_inputs ? inputs[input_pos++] : 0; W(10, v); if (record_trace) res->aux.back() = v; break; }
         case 2: res->outputs.push_back(regs[11]); if (record_trace) res->aux.back() = regs[11]; break;
-        case 4: return fail("Poseidon2 not yet implemented");  // crypto.rs:306-315 (the reference errors too)
+        case 4: {
+          // SYS_POSEIDON2 (syscall.rs:22,140-149).  The reference's implementation is a stub that errors (crypto.rs:299-315), so the
+          // semantics are this build's: read 16 little-endian u32 words at R11 (reduced mod p),
+          // apply the width-16 Poseidon2 permutation of docs/PROVER_SPEC.md section 2, write the 16 words at R13, R10 <- 0.
+          if (!g_enable_poseidon2) return fail("Poseidon2 not yet implemented");  // crypto.rs:306-315 (the reference errors)
+          const u64 src = regs[11], dst = regs[13];
+          if ((src | dst) % 4) { char b[96]; snprintf(b, sizeof b, "Misaligned access at %#llx (alignment 4)", (unsigned long long)((src % 4) ? src : dst)); return fail(b); }
+          uint32_t st[16];
+          for (int k = 0; k < 16; k++) st[k] = (uint32_t)(mem.read(src + 4 * k, 4) % ZKIR_BABYBEAR_P);
+          zkir_host_poseidon2_permute(st);
+          for (int k = 0; k < 16; k++) mem.write(dst + 4 * k, st[k], 4);
+          W(10, 0);
+          break;
+        }
         case 3: case 5: case 6: return fail("hash syscalls (SHA-256/Keccak-256/Blake3) are outside the proving path and not restated here");
         default: { char m[64]; snprintf(m, sizeof m, "Invalid syscall: %llu", (unsigned long long)num); return fail(m); }
       }
+    }
+    if (wl) {
+      wl_log[cycles] = cur_log;
+      if (on_chunk && ((cycles + 1) % chunk_rows) == 0) on_chunk(cb_user, cycles + 1);   // rows [0, cycles + 1) are final: upload may start
     }
     if (record_trace) {
       // data memory ops of this cycle: timestamp == cycle && address != fetch pc (vm.rs:291-298)
@@ -290,9 +349,38 @@ int zkir_vm_run(const uint32_t* code, size_t n_code, const uint8_t* data, size_t
   res->cycles = cycles;
   res->final_pc = pc;
   memcpy(res->final_regs, regs, sizeof regs);
+  if (wl) {
+    res->logged = cycles;
+    if (wide_row != ~0ull) { g_vm_error = "write log: value above 40 bits at row " + std::to_string(wide_row); return ZKIR_ERR_AIR; }
+  }
   *out = res.release();
   return 0;
 }
+
+int zkir_vm_run(const uint32_t* code, size_t n_code, const uint8_t* data, size_t n_data, uint32_t entry_point,
+                const uint64_t* inputs, size_t n_inputs, uint64_t max_cycles, int record_trace, zkir_vm_result** out) {
+  return vm_run_impl(code, n_code, data, n_data, entry_point, inputs, n_inputs, max_cycles, record_trace, nullptr, nullptr, nullptr, 0, out);
+}
+
+int zkir_vm_run_writelog(const uint32_t* code, size_t n_code, const uint8_t* data, size_t n_data, uint32_t entry_point,
+                         const uint64_t* inputs, size_t n_inputs, uint64_t max_cycles, uint32_t* pcs32, uint32_t* instrs, uint64_t* wlog,
+                         uint64_t capacity, zkir_vm_result** out) {
+  if (!pcs32 || !instrs || !wlog) { g_vm_error = "null write-log arrays"; return ZKIR_ERR_ARG; }
+  return vm_run_impl(code, n_code, data, n_data, entry_point, inputs, n_inputs, max_cycles, 0, pcs32, instrs, wlog, capacity, out);
+}
+
+// same, reporting progress: on_chunk(user, rows_done) is called every chunk_rows cycles from the interpreter's thread; the rows
+// before rows_done are final (the prover starts their host->device copy while the interpreter keeps running)
+int zkir_vm_run_writelog_cb(const uint32_t* code, size_t n_code, const uint8_t* data, size_t n_data, uint32_t entry_point,
+                            const uint64_t* inputs, size_t n_inputs, uint64_t max_cycles, uint32_t* pcs32, uint32_t* instrs, uint64_t* wlog,
+                            uint64_t capacity, void (*on_chunk)(void*, uint64_t), void* user, uint64_t chunk_rows, zkir_vm_result** out) {
+  if (!pcs32 || !instrs || !wlog || (on_chunk && !chunk_rows)) { g_vm_error = "null write-log arrays"; return ZKIR_ERR_ARG; }
+  return vm_run_impl(code, n_code, data, n_data, entry_point, inputs, n_inputs, max_cycles, 0, pcs32, instrs, wlog, capacity, out, on_chunk, user, chunk_rows);
+}
+
+size_t zkir_vm_code_len(const zkir_vm_result* r) { return r->code.size(); }
+const uint32_t* zkir_vm_code(const zkir_vm_result* r) { return r->code.data(); }
+uint64_t zkir_vm_logged_rows(const zkir_vm_result* r) { return r->logged; }
 
 uint64_t zkir_vm_cycles(const zkir_vm_result* r) { return r->cycles; }
 int zkir_vm_halt_kind(const zkir_vm_result* r) { return r->halt_kind; }

@@ -65,11 +65,13 @@ int launch_pow_grind(const ChalState* st_dev, u32 bits, u32* result, cudaStream_
 
 // ---- quotient.cu
 struct QuotientArgs {
-  const u32* lde;      // [width][B][N] Montgomery, coset-major: row z*N+i is the point of natural index i*B+z
+  const u32* lde;      // [width + aux][B][N] Montgomery, coset-major: row z*N+i is the point of natural index i*B+z; main columns then aux columns
+  const u32* publde;   // [pub][B][N] Montgomery, same order: the public columns (range table, program ROM)
   u32* q;              // [4][M], natural order
   u32 log_n, log_blowup;
   const u32* pv;       // device, num_public Montgomery values
   const u32* alpha;    // device, ext4 Montgomery
+  const u32* lookup;   // device, lookup challenges z[4], theta[4], Montgomery
   const u32* xs;       // [M] coset-major: x = shift*w^(i*B+z) at z*N+i
   const u32* dinv;     // [M] 1/(x - 1), same order
   u32* apow_scratch;   // [K][4] device scratch for alpha powers
@@ -91,9 +93,10 @@ struct ExpandArgs {
   u64 T, N;              // live rows, padded rows (power of two)
   u64 final_regs[16];    // state after the last instruction (padding rows, last READ value)
   u64 final_pc;
-  u32* cols;             // out [72][N], canonical
+  u32* cols;             // out [88][N], canonical
   u64* err;              // out: min over offending rows of (row << 8 | reason); ~0 = none
-  u32 col_lo = 0, col_hi = 0xffffffffu;   // only columns [col_lo, col_hi) are written (sharded proofs: the rank's own share)
+  u32 col_lo = 0, col_hi = 0xffffffffu;   // only columns [col_lo, col_hi) are written (the multiplicity columns always are)
+  u32 n_code = 0;        // program length: rows whose pc is outside [0x1000, 0x1000 + 4 n_code) are errors
 };
 int launch_trace_expand(const ExpandArgs& a, cudaStream_t st, u64* launches);
 struct WlArgs {          // register write log instead of full rows (trace_expand.cu)
@@ -106,8 +109,23 @@ struct WlArgs {          // register write log instead of full rows (trace_expan
   u32* cols;
   u64* err;
   u32 col_lo = 0, col_hi = 0xffffffffu;
+  u32 n_code = 0;
 };
 u64 trace_expand_wl_scratch_ints(u64 N);
+
+// ---- aux_gen.cu: the LogUp aux columns (three helper sums + running sum, ext4 as 4 base columns each) of a trace
+struct AuxArgs {
+  const u32* trace;      // [88][N] canonical main columns
+  const u32* pub;        // [4][N] canonical public columns
+  const u32* lookup;     // device: z[4], theta[4], Montgomery
+  u32* aux;              // out [16][N] canonical
+  u32 log_n;
+  E4* row_tot;           // scratch [N]: sum of the fractions of each row
+  E4* blk_tot;           // scratch [aux_gen_blocks(N)]
+  u64* err;              // out (may be null): (N-1) << 8 | 8 if the lookups do not balance
+};
+u64 aux_gen_blocks(u64 N);
+int launch_aux_gen(const AuxArgs& a, cudaStream_t st, u64* launches);
 int launch_trace_expand_wl(const WlArgs& a, cudaStream_t st, u64* launches);
 
 // ---- peer.cu: rows of the column-sharded LDE stored straight into the peers' matrices (NVLink peer memory)
@@ -140,6 +158,7 @@ int launch_fri_fold(const E4* in, E4* out, u64 h, const u32* beta_dev, const u32
 struct QueryArgs {
   const u32* indices;   // device [num_queries], canonical
   u32 num_queries, log_m, width, log_n;   // lde / qlde rows are coset-major, trees and layers natural
+  u32 aux_width = 0; const u32* atree = nullptr; u32 atree_sl = 0;   // aux columns = columns [width, width + aux_width) of lde, own tree
   const u32* lde; const u32* ttree;
   const u32* qlde; const u32* qtree;
   const E4* const* layers;        // device array of layer pointers, indexed by fold LEVEL (layer length M >> level)

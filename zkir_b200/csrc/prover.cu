@@ -26,6 +26,8 @@
 #include "comm.h"
 #include "constants_generated.h"
 #include "air_generated.h"
+#include "air_pack.h"
+#include "proof_layout.h"
 
 using namespace zkir;
 namespace zkir { u64 open_scratch_elems(u32 n_cols, u64 n); }
@@ -56,34 +58,8 @@ static u32 hpow(u32 a, u64 e) { u64 r = 1, b = a; while (e) { if (e & 1) r = r *
 static u32 hinv(u32 a) { return hpow(a, BB_P - 2); }
 static u32 hmul(u32 a, u32 b) { return (u32)((u64)a * b % BB_P); }
 
-static const u32 PROOF_MAGIC = 0x5A4B5052u, PROOF_VERSION = 3u;
-static const u32 QW = 8;  // quotient columns: 4 ext planes x 2 chunks, column = 2*plane + chunk
-
-struct Layout {  // proof word offsets
-  u32 log_n, log_m, width, np, nq, R;
-  size_t pv, troot, qroot, open_t, open_tg, open_q, fri_roots, final_, pow_, queries, per_query, total;
-};
-static Layout make_layout(const zkir_params* p, u32 log_n) {
-  Layout L;
-  L.log_n = log_n; L.log_m = log_n + p->log_blowup; L.width = p->width; L.np = p->num_public; L.nq = p->num_queries;
-  L.R = log_n / 3 + (log_n % 3 ? 1 : 0);   // FRI rounds: log_n / 3 that fold by 8, one more by 2^(log_n mod 3) (docs/PROVER_SPEC.md 4.6)
-  size_t o = 8;
-  L.pv = o; o += L.np;
-  L.troot = o; o += 8;
-  L.qroot = o; o += 8;
-  L.open_t = o; o += 4 * (size_t)L.width;
-  L.open_tg = o; o += 4 * (size_t)L.width;
-  L.open_q = o; o += 4 * QW;
-  L.fri_roots = o; o += 8 * (size_t)L.R;
-  L.final_ = o; o += 4;
-  L.pow_ = o; o += 1;
-  L.queries = o;
-  size_t pq = L.width + 8 * (size_t)L.log_m + QW + 8 * (size_t)L.log_m;
-  for (u32 t = 0, ll = L.log_m; t < L.R; t++) { const u32 la = t < log_n / 3 ? 3 : log_n % 3; pq += (4u << la) + 8 * (size_t)(ll - la); ll -= la; }
-  L.per_query = pq;
-  L.total = o + pq * L.nq;
-  return L;
-}
+extern "C" void zkir_program_digest(const uint32_t* code, size_t n_code, uint32_t digest8[8]);   // host/verify.cc
+static const u32 HDR_WORDS = 7;   // transcript header: log_n, W, aux width, log_blowup, num_queries, pow_bits, num_public
 
 enum { PEER_LDE = 0, PEER_Q = 1, PEER_QLDE = 2, PEER_BUFS = 3 };
 #define PEER_REC_WORDS 60
@@ -91,9 +67,13 @@ struct Workspace {
   u32 log_n = 0, log_blowup = 0, width = 0, nq = 0;
   bool valid = false;
   std::vector<void*> allocs;
-  u32 *trace = nullptr, *coef = nullptr, *lde = nullptr, *ttree = nullptr;
+  u32 *trace = nullptr, *coef = nullptr, *lde = nullptr, *ttree = nullptr;   // coef / lde: main columns [0, W) then aux columns [W, W + AW)
+  u32 *aux = nullptr, *atree = nullptr;            // aux columns [AW][N] (canonical), their Merkle tree
+  u32 *pub = nullptr, *publde = nullptr;           // public columns [PW][N] canonical and their LDE [PW][M] (never committed)
+  u64 pub_version = 0;                             // program version publde was built for (0 = none)
+  E4 *aux_row_tot = nullptr, *aux_blk_tot = nullptr;
   u32 *q = nullptr, *qcoef = nullptr, *qlde = nullptr, *qtree = nullptr;
-  u32 *xs = nullptr, *dinv = nullptr, *qscale = nullptr, *lde_nat = nullptr;
+  u32 *xs = nullptr, *dinv = nullptr;
   E4 *U1 = nullptr, *U2 = nullptr, *U1q = nullptr, *open_scratch = nullptr, *dummy_open = nullptr;
   bool fast = false;            // register-tile NTT path (log_n >= 8): digit-reversed coefficients
   FastPlan plan_n, plan_m, plan_chunk;
@@ -102,7 +82,7 @@ struct Workspace {
   std::vector<E4*> h_layers; std::vector<u32*> h_ltrees;
   E4** d_layers = nullptr; u32** d_ltrees = nullptr;
   ChalState* chal = nullptr;
-  u32* chal_buf = nullptr;   // alpha[4] zeta[4] alpha_fri[4] betas[R][4] pow_raw[1] pow_sample[1] hdr_mont[6+np]
+  u32* chal_buf = nullptr;   // alpha[4] zeta[4] alpha_fri[4] betas[R][4] pow_raw[1] pow_sample[1] lookup z[4] theta[4] hdr_mont[7+np+8]
   u32* indices = nullptr;
   u32* apow = nullptr; E4* afp = nullptr;
   u32* otree = nullptr;      // scratch of the tree hash of the opened values
@@ -132,8 +112,14 @@ struct zkir_ctx {
   u32* ntt_tmp = nullptr; u64 ntt_tmp_words = 0;
   u32* scratch[2] = {nullptr, nullptr}; size_t scratch_bytes[2] = {0, 0};
   void* rows_dev = nullptr; size_t rows_bytes = 0;   // staging for raw interpreter rows (prove_rows)
-  u64* d_err = nullptr; u64* h_err = nullptr;
+  // zkir_b200_prove_program: pinned write log the interpreter records into, and the stream its chunks are uploaded on
+  void* log_pinned = nullptr; u64 log_capacity = 0;
+  cudaStream_t copy_stream = nullptr; cudaEvent_t copy_done = nullptr;
+  u64* d_err = nullptr; u64* h_err = nullptr;   // [2]: converter error, aux (lookup balance) error; ~0 = none
   std::vector<zkir_ctx*> workers;                    // extra contexts of the same device for prove_batch
+  std::vector<u32> code;                             // the program (zkir_b200_set_program): ROM of the lookup argument
+  u32 code_digest[8] = {0};                          // its transcript digest
+  u64 program_version = 0;                           // bumped by every set_program; workspaces rebuild their ROM columns lazily
   // one proof sharded over `shards` GPUs (zkir_b200_comm_init): this context computes the Merkle leaf segments
   // [shard_lo, shard_hi) -- its own rank with a communicator, all of them when the shards are emulated on one GPU (tests)
   Comm* comm = nullptr;
@@ -222,28 +208,27 @@ static int ws_prepare(zkir_ctx* ctx, const zkir_params* p, u32 log_n) {
 #define A(ptr, cnt) if ((rc = ws_alloc(ctx, &w.ptr, (cnt))) != 0) return rc;
   // NTT path: the fast kernels need every digit of the three plans to span >= 16 lanes
   w.fast = fast_path_ok(log_n, p->log_blowup, &w.plan_n, &w.plan_m);
-  if (w.fast) {
-    w.plan_chunk = w.plan_m;
-    w.plan_chunk.log_n = (int)log_n;
-    w.plan_chunk.d[w.plan_m.nd - 1] -= (int)p->log_blowup;
-  } else {
-    w.plan_n.log_n = (int)log_n; w.plan_n.nd = 1; w.plan_n.d[0] = (int)log_n; w.plan_n.d[1] = w.plan_n.d[2] = w.plan_n.d[3] = 0;
-    w.plan_chunk = w.plan_n;
-  }
-  A(trace, W * N) A(coef, W * N) A(lde, W * M) A(ttree, (2 * M - 1) * 8)
+  if (!w.fast) { ctx->err = "the register-tile NTT plan does not cover this shape (ZKIR_FORCE_GENERIC_NTT only applies to the per-kernel entry points)"; return ZKIR_ERR_ARG; }
+  w.plan_chunk = w.plan_m;
+  w.plan_chunk.log_n = (int)log_n;
+  w.plan_chunk.d[w.plan_m.nd - 1] -= (int)p->log_blowup;
+  const u64 WA = W + AW;
+  A(trace, W * N) A(coef, WA * N) A(lde, WA * M) A(ttree, (2 * M - 1) * 8)
+  A(aux, (u64)AW * N) A(atree, (2 * M - 1) * 8) A(pub, (u64)PW * N) A(publde, (u64)PW * M)
+  A(aux_row_tot, N) A(aux_blk_tot, aux_gen_blocks(N))
   A(q, 4 * M) A(qlde, QW * M) A(qtree, (2 * M - 1) * 8)
   A(qcoef, QW * N)
   A(xs, M) A(dinv, M)
-  if (!w.fast) { A(qscale, M) A(lde_nat, W * M) }
-  A(U1, N) A(U2, N) A(U1q, N) A(open_scratch, open_scratch_elems((u32)W, N)) A(dummy_open, W)
+  A(U1, N) A(U2, N) A(U1q, N) A(open_scratch, open_scratch_elems((u32)WA, N)) A(dummy_open, WA)
   A(layers, 2 * M) A(ltrees, 2 * M * 8)
   A(d_layers, R + 1) A(d_ltrees, R + 1)
-  A(chal, 1) A(chal_buf, 12 + 4 * R + 2 + 6 + p->num_public) A(indices, p->num_queries + 1)
-  A(apow, 4 * ZKIR_AIR_NUM_CONSTRAINTS) A(afp, W + 5)
-  A(proof, L.total) A(xchg, ZKIR_MAX_SHARDS * PEER_REC_WORDS) A(otree, hash_tree_scratch_words((u32)(2 * W + QW) * 4))
+  A(chal, 1) A(chal_buf, 12 + 4 * R + 2 + 8 + HDR_WORDS + p->num_public + 8) A(indices, p->num_queries + 1)
+  A(apow, 4 * ZKIR_AIR_NUM_CONSTRAINTS) A(afp, WA + 5)
+  A(proof, L.total + 4) A(xchg, ZKIR_MAX_SHARDS * PEER_REC_WORDS) A(otree, hash_tree_scratch_words((u32)(2 * WA + QW) * 4))
 #undef A
+  w.proof += (4 - (L.open_t & 3)) & 3;   // the opened values are read and written as 16-byte ext4 elements: align that section
   CU(cudaMallocHost(&w.h_proof, L.total * 4));
-  CU(cudaMallocHost(&w.h_stage, (8 + 6 + 2 * p->num_public) * 4));
+  CU(cudaMallocHost(&w.h_stage, (8 + HDR_WORDS + 2 * p->num_public + 8) * 4));
   // layer pointers
   w.h_layers.resize(R + 1); w.h_ltrees.resize(R + 1);
   E4* lp = w.layers; u32* tp = w.ltrees;
@@ -255,13 +240,6 @@ static int ws_prepare(zkir_ctx* ctx, const zkir_params* p, u32 log_n) {
   CU(cudaMemcpyAsync(w.d_layers, w.h_layers.data(), (R + 1) * sizeof(E4*), cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemcpyAsync(w.d_ltrees, w.h_ltrees.data(), (R + 1) * sizeof(u32*), cudaMemcpyHostToDevice, ctx->stream));
   RC(launch_domain_tables(w.xs, w.dinv, log_n, p->log_blowup, ZKIR_BB_GEN, ctx->stream, &ctx->launches));
-  if (!w.fast) {  // quotient inverse-NTT output scale: qscale[j] = (1/M) * shift^(-N * floor(j/N))   (Montgomery)
-    std::vector<u32> h(M);
-    const u32 minv = hinv((u32)(M % BB_P)), step = hinv(hpow(ZKIR_BB_GEN, N));
-    u32 c = minv;
-    for (u64 b = 0; b < (M >> log_n); b++) { u32 cm = bb_to_mont_c(c); for (u64 j = 0; j < N; j++) h[b * N + j] = cm; c = hmul(c, step); }
-    CU(cudaMemcpy(w.qscale, h.data(), M * 4, cudaMemcpyHostToDevice));
-  }
   CU(cudaStreamSynchronize(ctx->stream));
   w.log_n = log_n; w.log_blowup = p->log_blowup; w.width = p->width; w.nq = p->num_queries; w.valid = true;
   return 0;
@@ -269,10 +247,12 @@ static int ws_prepare(zkir_ctx* ctx, const zkir_params* p, u32 log_n) {
 
 static int check_params(zkir_ctx* ctx, const zkir_params* p, u32 log_n) {
   if (!p || p->width != ZKIR_AIR_WIDTH || p->num_public != ZKIR_AIR_NUM_PUBLIC || p->log_blowup < 1 || p->log_blowup > 4 ||
-      log_n < 2 || log_n + p->log_blowup > 27 || p->pow_bits > 30 || p->num_queries > 4096) {
-    ctx->err = "bad params: need width=72, num_public=4, 1<=log_blowup<=4, 2<=log_n, log_n+log_blowup<=27, pow_bits<=30";
+      log_n < ZKIR_AIR_RANGE_BITS || log_n + p->log_blowup > 27 || p->pow_bits > 30 || p->num_queries > 4096) {
+    ctx->err = "bad params: need width=88, num_public=5, 1<=log_blowup<=4, 10<=log_n (the range table occupies 1024 trace rows), log_n+log_blowup<=27, pow_bits<=30";
     return ZKIR_ERR_ARG;
   }
+  if (ctx->program_version == 0) { ctx->err = "no program: call zkir_b200_set_program first (the proof binds the executed instructions to it)"; return ZKIR_ERR_ARG; }
+  if (ctx->code.size() > (1ull << log_n)) { ctx->err = "the program has more instructions than the trace has rows: raise log_n"; return ZKIR_ERR_ARG; }
   return 0;
 }
 
@@ -284,6 +264,9 @@ struct ShardPlan {
   u32 G = 1, lo = 0, hi = 1, log_nj = 0;
   u64 nj = 0;          // points per coset and shard
   u32 cols_per = 0, W = 0;
+  u32 acols_per = 0;   // aux columns per rank (column indices W .. W + AW of the coefficient / LDE matrices)
+  u32 a_lo(u32 g) const { const u32 c = g * acols_per; return W + (c < AW ? c : AW); }
+  u32 a_hi(u32 g) const { const u32 c = (g + 1) * acols_per; return W + (c < AW ? c : AW); }
   u32 planes_per = 1;  // quotient planes (of 4) per rank; ranks beyond 4 / planes_per own none
   u32 p_lo(u32 g) const { const u32 c = g * planes_per; return c < 4 ? c : 4; }
   u32 p_hi(u32 g) const { const u32 c = (g + 1) * planes_per; return c < 4 ? c : 4; }
@@ -301,6 +284,7 @@ static ShardPlan shard_plan_for(u32 G, u32 W, u32 log_n, u32 log_blowup, bool fa
     sp.nj = N / G;
     while ((1ull << sp.log_nj) < sp.nj) sp.log_nj++;
     sp.cols_per = (W + G - 1) / G;
+    sp.acols_per = (AW + G - 1) / G;
     sp.planes_per = (4 + G - 1) / G;
   }
   return sp;
@@ -313,9 +297,10 @@ static ShardPlan make_shard_plan(const zkir_ctx* ctx, const zkir_params* p, u32 
 }
 // columns of the trace this context has to materialise: all of them, or -- sharded proof with a communicator -- its own share
 static void trace_col_range(const zkir_ctx* ctx, const zkir_params* p, u32 log_n, u32* lo, u32* hi) {
+  // AIR v2: the aux (LogUp) columns of a row depend on the whole row, so every rank materialises all main columns (the converter
+  // is HBM-write bound, 0.5 ms at 2^20 rows); only the transforms are column-sharded
   *lo = 0; *hi = p->width;
-  const ShardPlan sp = make_shard_plan(ctx, p, log_n);
-  if (sp.on && ctx->comm) { const u32 me = (u32)comm_rank(ctx->comm); *lo = sp.c_lo(me); *hi = sp.c_hi(me); }
+  (void)ctx; (void)log_n;
 }
 
 // After the column-sharded LDE every rank holds whole columns [c_lo, c_hi) of the coset-major matrix [W][B][N]; this moves, for
@@ -346,6 +331,7 @@ static int exchange_lde_rows(zkir_ctx* ctx, const ShardPlan& sp, u32* lde, u64 N
 
 // Map every rank's LDE matrix into this process.  Collective (one all-gather of 96-byte records); runs once per workspace shape.
 struct PeerRec { u64 pid; u32 dev, pad; u64 ptr[PEER_BUFS]; cudaIpcMemHandle_t handle[PEER_BUFS]; u64 pad2; };
+static_assert(ZKIR_AIR_NUM_PUBLIC <= 8, "zkir_b200_quotient scratch layout");
 static_assert(sizeof(PeerRec) == 4 * PEER_REC_WORDS, "PeerRec layout");
 static int peers_open(zkir_ctx* ctx) {
   Workspace& w = ctx->ws;
@@ -435,9 +421,46 @@ static int fill_header_stage(zkir_ctx* ctx, const zkir_params* p, u32 log_n, con
   hs[0] = PROOF_MAGIC; hs[1] = PROOF_VERSION; hs[2] = log_n; hs[3] = p->width; hs[4] = p->log_blowup; hs[5] = p->num_queries;
   hs[6] = p->pow_bits; hs[7] = np;
   for (u32 i = 0; i < np; i++) { if (pv[i] >= BB_P) { ctx->err = "public value not canonical"; return ZKIR_ERR_ARG; } hs[8 + i] = pv[i]; }
-  u32* hm = hs + 8 + np;  // Montgomery copy for the transcript
-  for (u32 i = 0; i < 6; i++) hm[i] = bb_to_mont_c(hs[2 + i]);
-  for (u32 i = 0; i < np; i++) hm[6 + i] = bb_to_mont_c(pv[i]);
+  if (pv[4] > 1 || (pv[4] == 0 && (pv[2] || pv[3]))) { ctx->err = "public values: halted must be 0/1, and a run that did not halt has no exit code"; return ZKIR_ERR_ARG; }
+  u32* hm = hs + 8 + np;  // Montgomery copy for the transcript: header, public values, program digest
+  const u32 hdr[HDR_WORDS] = {log_n, p->width, AW, p->log_blowup, p->num_queries, p->pow_bits, np};
+  for (u32 i = 0; i < HDR_WORDS; i++) hm[i] = bb_to_mont_c(hdr[i]);
+  for (u32 i = 0; i < np; i++) hm[HDR_WORDS + i] = bb_to_mont_c(pv[i]);
+  for (u32 i = 0; i < 8; i++) hm[HDR_WORDS + np + i] = bb_to_mont_c(ctx->code_digest[i]);
+  return 0;
+}
+
+// Public columns of the current program for this workspace shape (docs/PROVER_SPEC.md section 3.3): range table 0..1023, ROM pc,
+// decoded word, immediate; built on the host (program-sized), uploaded, extended to the LDE coset once per (program, shape).
+static int ensure_public_columns(zkir_ctx* ctx, const zkir_params* p, u32 log_n) {
+  Workspace& w = ctx->ws;
+  if (w.pub_version == ctx->program_version) return 0;
+  const u64 N = 1ull << log_n, M = N << p->log_blowup;
+  std::vector<u32> h((size_t)PW * N, 0u);
+  for (u64 i = 0; i < N && i < (1ull << ZKIR_AIR_RANGE_BITS); i++) h[ZKIR_PUB_P_T * N + i] = (u32)i;
+  for (u64 i = 0; i < N; i++) {
+    if (i < ctx->code.size()) {
+      h[ZKIR_PUB_P_PC * N + i] = 0x1000u + 4 * (u32)i;
+      zkir_rom_entry(ctx->code[i], &h[ZKIR_PUB_P_DEC * N + i], &h[ZKIR_PUB_P_IMM * N + i]);
+    } else {
+      h[ZKIR_PUB_P_DEC * N + i] = 127;   // no instruction has opcode 127: an unused ROM row matches no trace row
+    }
+  }
+  cudaStream_t st = ctx->stream;
+  CU(cudaMemcpyAsync(w.pub, h.data(), h.size() * 4, cudaMemcpyHostToDevice, st));
+  CU(cudaStreamSynchronize(st));   // h is pageable and goes out of scope
+  const u32 c0 = hmul(hinv((u32)(N % BB_P)), (u32)((1ull << 32) % BB_P));
+  if (w.fast) {
+    u32* coef = w.lde;   // scratch: the main LDE region is rewritten by every proof
+    RC(fast_intt(ctx->fast, w.plan_n, w.pub, N, coef, N, PW, c0, nullptr, 32, 0, 0, nullptr, 0, st));
+    RC(fast_coset_ntt(ctx->fast, w.plan_n, coef, N, w.publde, M, PW, 1u << p->log_blowup, ZKIR_BB_GEN, ZKIR_BB_ROOTS[log_n + p->log_blowup], 1u, st));
+  } else {
+    ctx->err = "internal: generic NTT path is not available for traces of 2^10 rows and more";
+    return ZKIR_ERR_ARG;
+  }
+  CU(cudaStreamSynchronize(st));
+  w.pub_version = ctx->program_version;
+  if (w.gexec) { cudaGraphExecDestroy(w.gexec); w.gexec = nullptr; }   // a captured proof sequence embeds nothing of the program, but be safe
   return 0;
 }
 
@@ -446,27 +469,29 @@ static int prove_resident(zkir_ctx* ctx, const zkir_params* p, u32 log_n, const 
   Workspace& w = ctx->ws;
   cudaStream_t st = ctx->stream;
   u64* LC = &ctx->launches;
-  const u64 N = 1ull << log_n, M = N << p->log_blowup, W = p->width;
+  const u64 N = 1ull << log_n, M = N << p->log_blowup, W = p->width, WA = W + AW;
   const u32 log_m = log_n + p->log_blowup, R = log_n, np = p->num_public;
   const Layout L = make_layout(p, log_n);
   const u32 shift = ZKIR_BB_GEN;
   const u32 B = 1u << p->log_blowup;
-  if (!w.fast) RC(ensure_ntt_tmp(ctx, M));
+  if (!w.fast) { ctx->err = "internal: the register-tile NTT plan does not cover this shape"; return ZKIR_ERR_ARG; }
+  if (w.pub_version != ctx->program_version) { ctx->err = "internal: public columns are stale"; return ZKIR_ERR_ARG; }
   const ShardPlan sp = make_shard_plan(ctx, p, log_n);
   const bool p2p = sp.on && ctx->comm != nullptr;
   static const int lde_mode = !getenv("ZKIR_LDE_EXCHANGE") ? 0 : (!strcmp(getenv("ZKIR_LDE_EXCHANGE"), "nccl") ? 2 : (!strcmp(getenv("ZKIR_LDE_EXCHANGE"), "scatter") ? 1 : 0));
   if (p2p && !w.peers_valid) { int xrc = peers_open(ctx); if (xrc) return xrc; }
   const u32 me = p2p ? (u32)comm_rank(ctx->comm) : 0;
   u32* c_alpha = w.chal_buf, *c_zeta = w.chal_buf + 4, *c_afri = w.chal_buf + 8, *c_betas = w.chal_buf + 12;
-  u32* c_pow_raw = w.chal_buf + 12 + 4 * R, *c_pow_sample = c_pow_raw + 1, *c_hdr = c_pow_raw + 2;
+  u32* c_pow_raw = w.chal_buf + 12 + 4 * R, *c_pow_sample = c_pow_raw + 1, *c_lookup = c_pow_raw + 2, *c_hdr = c_lookup + 8;
 
   // ---- header + public values (host staging filled by fill_header_stage: also the per-proof step of a graph replay)
   { int frc = fill_header_stage(ctx, p, log_n, pv); if (frc) return frc; }
   u32* hs = w.h_stage;
   u32* hm = hs + 8 + np;  // Montgomery copy for the transcript
   CU(cudaMemcpyAsync(w.proof, hs, (8 + np) * 4, cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(c_hdr, hm, (6 + np) * 4, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(c_hdr, hm, (HDR_WORDS + np + 8) * 4, cudaMemcpyHostToDevice, st));
   CU(cudaMemsetAsync(w.chal, 0, sizeof(ChalState), st));
+  CU(cudaMemsetAsync(ctx->d_err + 1, 0xff, 8, st));
 
   // ---- 1. LDE: iNTT (scale by shift^j/N and lift to Montgomery), zero-pad, forward NTT on the coset
   CU(cudaEventRecord(ctx->ev[ZKIR_STAGE_LDE], st));
@@ -493,7 +518,7 @@ static int prove_resident(zkir_ctx* ctx, const zkir_params* p, u32 log_n, const 
         int brc = peers_barrier(ctx); if (brc) return brc;
       }
     }
-  } else if (w.fast) {
+  } else {
     // column batches (ZKIR_LDE_BATCH) are possible, one batch = all columns by default
     u32 cb = (u32)W;  // measured: the passes are integer-pipe bound, larger launches win over L2 residency
     const char* env = getenv("ZKIR_LDE_BATCH");
@@ -503,24 +528,46 @@ static int prove_resident(zkir_ctx* ctx, const zkir_params* p, u32 log_n, const 
       RC(fast_intt(ctx->fast, w.plan_n, trace + (u64)k0 * N, N, w.coef + (u64)k0 * N, N, nc, c0, nullptr, 32, 0, 0, nullptr, 0, st));
       RC(fast_coset_ntt(ctx->fast, w.plan_n, w.coef + (u64)k0 * N, N, w.lde + (u64)k0 * M, M, nc, B, shift, ZKIR_BB_ROOTS[log_m], 1u, st));
     }
-  } else {
-    const u32* sc = ntt_powers_table(ctx->tables, shift, c0, N);
-    if (!sc) { ctx->err = "table alloc"; return ZKIR_ERR_OOM; }
-    RC(ntt_run(ctx->tables, trace, N, w.coef, N, ctx->ntt_tmp, ctx->ntt_tmp_words, (u32)W, log_n, true, 0, nullptr, sc, BB_ONE, false, st));
-    RC(ntt_run(ctx->tables, w.coef, N, w.lde_nat, M, ctx->ntt_tmp, ctx->ntt_tmp_words, (u32)W, log_m, false, p->log_blowup, nullptr, nullptr, BB_ONE, false, st));
-    RC(launch_coset_reorder(w.lde_nat, w.lde, (u32)W, log_n, p->log_blowup, 0, st, LC));
   }
   // ---- 2. trace commitment
   CU(cudaEventRecord(ctx->ev[ZKIR_STAGE_TRACE_COMMIT], st));
-  u32 t_sl = 0, q_sl = 0;
+  u32 t_sl = 0, a_sl = 0, q_sl = 0;
   int crc;
-  RC(launch_challenger(w.chal, c_hdr, 6 + np, nullptr, 0, 0, st, LC));
-  if ((crc = commit_tree(ctx, w.lde, (u32)W, p->log_blowup, nullptr, w.ttree, M, w.proof + L.troot, c_alpha, 4, &t_sl, sp.on ? 1 : 0)) != 0) return crc;  // root -> proof, observe, sample alpha
+  RC(launch_challenger(w.chal, c_hdr, HDR_WORDS + np + 8, nullptr, 0, 0, st, LC));   // header, public values, program digest
+  if ((crc = commit_tree(ctx, w.lde, (u32)W, p->log_blowup, nullptr, w.ttree, M, w.proof + L.troot, c_lookup, 8, &t_sl, sp.on ? 1 : 0)) != 0) return crc;  // root -> proof, observe, sample z and theta
+  // ---- 2b. LogUp aux columns for the challenges just drawn (aux_gen.cu), their LDE and their own commitment
+  CU(cudaEventRecord(ctx->ev[ZKIR_STAGE_AUX], st));
+  {
+    AuxArgs aa;
+    aa.trace = trace; aa.pub = w.pub; aa.lookup = c_lookup; aa.aux = w.aux; aa.log_n = log_n; aa.row_tot = w.aux_row_tot; aa.blk_tot = w.aux_blk_tot;
+    aa.err = ctx->d_err + 1;
+    RC(launch_aux_gen(aa, st, LC));   // replicated on every rank of a sharded proof (needs whole rows; 16 columns out)
+    const u32 c0a = hmul(hinv((u32)(N % BB_P)), (u32)((1ull << 32) % BB_P));
+    if (sp.on) {
+      const bool fuse_a = p2p && lde_mode == 0 && fast_coset_ntt_can_fuse(w.plan_n, sp.G);
+      for (u32 g = sp.lo; g < sp.hi; g++) {
+        const u32 k0 = sp.a_lo(g), nc = sp.a_hi(g) - k0;
+        if (!nc) continue;
+        RC(fast_intt(ctx->fast, w.plan_n, w.aux + (u64)(k0 - W) * N, N, w.coef + (u64)k0 * N, N, nc, c0a, nullptr, 32, 0, 0, nullptr, 0, st));
+        RC(fast_coset_ntt(ctx->fast, w.plan_n, w.coef + (u64)k0 * N, N, w.lde + (u64)k0 * M, M, nc, B, shift, ZKIR_BB_ROOTS[log_m], 1u, st,
+                          fuse_a ? &w.peers[PEER_LDE] : nullptr, me, sp.G));
+      }
+      if (p2p) {
+        if (lde_mode == 2) { ctx->err = "ZKIR_LDE_EXCHANGE=nccl is not supported with the aux phase"; return ZKIR_ERR_ARG; }
+        if (!fuse_a) RC(launch_lde_scatter(w.lde, w.peers[PEER_LDE], me, sp.G, sp.a_lo(me), sp.a_hi(me) - sp.a_lo(me), N, B, sp.nj, st, LC));
+        int brc = peers_barrier(ctx); if (brc) return brc;
+      }
+    } else {
+      RC(fast_intt(ctx->fast, w.plan_n, w.aux, N, w.coef + W * N, N, AW, c0a, nullptr, 32, 0, 0, nullptr, 0, st));
+      RC(fast_coset_ntt(ctx->fast, w.plan_n, w.coef + W * N, N, w.lde + W * M, M, AW, B, shift, ZKIR_BB_ROOTS[log_m], 1u, st));
+    }
+    if ((crc = commit_tree(ctx, w.lde + W * M, AW, p->log_blowup, nullptr, w.atree, M, w.proof + L.aroot, c_alpha, 4, &a_sl, sp.on ? 1 : 0)) != 0) return crc;  // root -> proof, observe, sample alpha
+  }
   // ---- 3. quotient
   CU(cudaEventRecord(ctx->ev[ZKIR_STAGE_QUOTIENT], st));
   {
     QuotientArgs qa;
-    qa.lde = w.lde; qa.q = w.q; qa.log_n = log_n; qa.log_blowup = p->log_blowup; qa.pv = c_hdr + 6; qa.alpha = c_alpha;
+    qa.lde = w.lde; qa.publde = w.publde; qa.q = w.q; qa.log_n = log_n; qa.log_blowup = p->log_blowup; qa.pv = c_hdr + HDR_WORDS; qa.alpha = c_alpha; qa.lookup = c_lookup;
     qa.xs = w.xs; qa.dinv = w.dinv; qa.apow_scratch = w.apow;
     if (sp.on) {
       // row-sharded: every rank evaluates its natural-order range of Q and stores plane k straight into the matrix of the rank
@@ -537,7 +584,7 @@ static int prove_resident(zkir_ctx* ctx, const zkir_params* p, u32 log_n, const 
   }
   CU(cudaEventRecord(ctx->ev[ZKIR_STAGE_QUOTIENT_COMMIT], st));
   const u32* qcoef = w.qcoef;
-  if (w.fast) {
+  {
     // inverse transform over the whole coset (digits of plan_m, in place on q), unshift by shift^-k, and let the last pass
     // split the lowest digit into the two degree-<N chunks: column 2*plane + chunk of qcoef, digit-reversed under plan_chunk
     const uint2* unshift = fast_scale_table(ctx->fast, w.plan_m, hinv(shift), 1u);
@@ -562,23 +609,13 @@ static int prove_resident(zkir_ctx* ctx, const zkir_params* p, u32 log_n, const 
       RC(fast_intt(ctx->fast, w.plan_m, w.q, M, w.q, M, 4, hinv((u32)(M % BB_P)), unshift, split_log, 2, (u32)N, w.qcoef, 2 * N, st));
       RC(fast_coset_ntt(ctx->fast, w.plan_chunk, w.qcoef, N, w.qlde, M, QW, B, shift, ZKIR_BB_ROOTS[log_m], 1u, st));
     }
-  } else {
-    // coefficients on the coset (in place), chunk c of plane k = words [k*M + c*N, +N)
-    RC(ntt_run(ctx->tables, w.q, M, w.q, M, ctx->ntt_tmp, ctx->ntt_tmp_words, 4, log_m, true, 0, nullptr, w.qscale, BB_ONE, false, st));
-    if (p->log_blowup > 1) {  // compact the two chunks of every plane: column 2k+c <- q[k*M + c*N ..]
-      CU(cudaMemcpy2DAsync(w.qcoef, 2 * N * 4, w.q, M * 4, 2 * N * 4, 4, cudaMemcpyDeviceToDevice, st));
-    } else {
-      qcoef = w.q;
-    }
-    RC(ntt_run(ctx->tables, qcoef, N, w.lde_nat, M, ctx->ntt_tmp, ctx->ntt_tmp_words, QW, log_m, false, p->log_blowup, nullptr, nullptr, BB_ONE, false, st));
-    RC(launch_coset_reorder(w.lde_nat, w.qlde, QW, log_n, p->log_blowup, 0, st, LC));
   }
   if ((crc = commit_tree(ctx, w.qlde, QW, p->log_blowup, nullptr, w.qtree, M, w.proof + L.qroot, c_zeta, 4, &q_sl, sp.on ? 1 : -1)) != 0) return crc;  // root -> proof, observe, sample zeta
   // ---- 4. openings at zeta and g*zeta, evaluated on the shifted coefficients at zeta/shift
   CU(cudaEventRecord(ctx->ev[ZKIR_STAGE_OPENINGS], st));
   {
     // fast path: plain coefficients, digit-reversed; generic path: coefficients pre-multiplied by shift^k, natural order
-    const u32 g = ZKIR_BB_ROOTS[log_n], um = w.fast ? 1u : hinv(shift);
+    const u32 g = ZKIR_BB_ROOTS[log_n], um = 1u;   // plain coefficients, digit-reversed (register-tile NTT path)
     RC(launch_ext_powers(c_zeta, bb_to_mont_c(um), w.plan_n, w.U1, st, LC));
     RC(launch_ext_powers(c_zeta, bb_to_mont_c(hmul(um, g)), w.plan_n, w.U2, st, LC));
     RC(launch_ext_powers(c_zeta, bb_to_mont_c(um), w.plan_chunk, w.U1q, st, LC));
@@ -587,21 +624,23 @@ static int prove_resident(zkir_ctx* ctx, const zkir_params* p, u32 log_n, const 
     E4* oq = reinterpret_cast<E4*>(w.proof + L.open_q);
     if (sp.on) {
       // column-sharded like the LDE (a rank holds the coefficients of its own columns only); disjoint pieces merged by all-reduce
-      if (ctx->comm) CU(cudaMemsetAsync(w.proof + L.open_t, 0, (2 * W + QW) * 16, st));
+      if (ctx->comm) CU(cudaMemsetAsync(w.proof + L.open_t, 0, (2 * WA + QW) * 16, st));
       for (u32 g = sp.lo; g < sp.hi; g++) {
         const u32 k0 = sp.c_lo(g), nc = sp.c_hi(g) - k0;
         if (nc) RC(launch_open(w.coef + (u64)k0 * N, N, nc, N, w.U1, w.U2, ot + k0, otg + k0, w.open_scratch, st, LC));
+        const u32 a0 = sp.a_lo(g), na = sp.a_hi(g) - a0;
+        if (na) RC(launch_open(w.coef + (u64)a0 * N, N, na, N, w.U1, w.U2, ot + a0, otg + a0, w.open_scratch, st, LC));
         const u32 q0 = 2 * sp.p_lo(g), nqc = 2 * sp.p_hi(g) - q0;
         if (nqc) RC(launch_open(qcoef + (u64)q0 * N, N, nqc, N, w.U1q, w.U1q, oq + q0, w.dummy_open, w.open_scratch, st, LC));
       }
-      if (ctx->comm && comm_all_reduce_sum_u32(ctx->comm, w.proof + L.open_t, (2 * W + QW) * 4, st, &ctx->err) != 0) return ZKIR_ERR_NCCL;
+      if (ctx->comm && comm_all_reduce_sum_u32(ctx->comm, w.proof + L.open_t, (2 * WA + QW) * 4, st, &ctx->err) != 0) return ZKIR_ERR_NCCL;
     } else {
-      RC(launch_open(w.coef, N, (u32)W, N, w.U1, w.U2, ot, otg, w.open_scratch, st, LC));
+      RC(launch_open(w.coef, N, (u32)WA, N, w.U1, w.U2, ot, otg, w.open_scratch, st, LC));
       RC(launch_open(qcoef, N, QW, N, w.U1q, w.U1q, oq, w.dummy_open, w.open_scratch, st, LC));
     }
-    RC(launch_observe_hash_tree(w.proof + L.open_t, (u32)(2 * W + QW) * 4, w.otree, w.chal, c_afri, 4, st, LC));   // observe the tree hash, sample gamma
+    RC(launch_observe_hash_tree(w.proof + L.open_t, (u32)(2 * WA + QW) * 4, w.otree, w.chal, c_afri, 4, st, LC));   // observe the tree hash, sample gamma
     DeepArgs da;
-    da.lde = w.lde; da.M = M; da.width = (u32)W; da.qlde = w.qlde; da.qwidth = QW; da.log_n = log_n; da.log_b = p->log_blowup; da.xs = w.xs; da.zeta = c_zeta;
+    da.lde = w.lde; da.M = M; da.width = (u32)WA; da.qlde = w.qlde; da.qwidth = QW; da.log_n = log_n; da.log_b = p->log_blowup; da.xs = w.xs; da.zeta = c_zeta;
     da.g_mont = bb_to_mont_c(g); da.alpha_fri = c_afri; da.open_t = ot; da.open_tg = otg; da.open_q = oq; da.afp_scratch = w.afp;
     da.out = w.h_layers[0];
     if (sp.on) {
@@ -650,6 +689,7 @@ static int prove_resident(zkir_ctx* ctx, const zkir_params* p, u32 log_n, const 
     QueryArgs qa;
     qa.indices = w.indices; qa.num_queries = p->num_queries; qa.log_m = log_m; qa.width = (u32)W; qa.log_n = log_n;
     qa.lde = w.lde; qa.ttree = w.ttree; qa.qlde = w.qlde; qa.qtree = w.qtree;
+    qa.aux_width = AW; qa.atree = w.atree; qa.atree_sl = a_sl;
     qa.layers = w.d_layers; qa.ltrees = w.d_ltrees; qa.fold8_rounds = log_n / 3; qa.last_log_arity = log_n % 3; qa.fri_rounds = (u32)L.R; qa.out = w.proof + L.queries; qa.words_per_query = (u32)L.per_query;
     // sharded trees: the bottom path levels of a leaf exist only on its owner; every rank writes the pieces it owns (zeros
     // elsewhere, rank 0 also everything that is replicated) and one all-reduce assembles the query section ("query gather")
@@ -659,8 +699,21 @@ static int prove_resident(zkir_ctx* ctx, const zkir_params* p, u32 log_n, const 
     if (ctx->comm && L.nq && comm_all_reduce_sum_u32(ctx->comm, w.proof + L.queries, L.per_query * L.nq, st, &ctx->err) != 0) return ZKIR_ERR_NCCL;
     RC(launch_map(w.proof + 8 + np, w.proof + 8 + np, L.total - 8 - np, 0, st, LC));
     CU(cudaMemcpyAsync(w.h_proof, w.proof, L.total * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(ctx->h_err, ctx->d_err, 16, cudaMemcpyDeviceToHost, st));
   }
   CU(cudaEventRecord(ctx->ev[ZKIR_STAGE_COUNT], st));
+  return 0;
+}
+
+static int expand_error(zkir_ctx* ctx) {  // after the stream is drained: converter error first, then the lookup balance
+  for (int k = 0; k < 2; k++) {
+    const u64 e = ctx->h_err[k];
+    if (e == ~0ull) continue;
+    const u32 code = (u32)(e & 0xff);
+    ctx->err = "AIR v2 cannot constrain row " + std::to_string((unsigned long long)(e >> 8)) + ": " +
+               (code == 8 ? "the lookup fractions do not cancel (a chunk outside the range table or an instruction outside the program)" : pack_err_text(code));
+    return ZKIR_ERR_AIR;
+  }
   return 0;
 }
 
@@ -669,6 +722,7 @@ static int finish_proof(zkir_ctx* ctx, const zkir_params* p, u32 log_n, uint8_t*
   const Layout L = make_layout(p, log_n);
   uint8_t* out = (uint8_t*)malloc(L.total * 4);
   if (!out) { ctx->err = "malloc"; return ZKIR_ERR_OOM; }
+  { int erc = expand_error(ctx); if (erc) { free(out); *proof = nullptr; *proof_len = 0; return erc; } }
   memcpy(out, ctx->ws.h_proof, L.total * 4);
   *proof = out; *proof_len = L.total * 4;
   if (ctx->ws.graph_run) {   // the stage events of a replayed graph are not re-recorded
@@ -700,6 +754,8 @@ int zkir_b200_create(zkir_ctx** out, int device_id) {
   for (int i = 0; i <= ZKIR_STAGE_COUNT; i++) cudaEventCreate(&ctx->ev[i]);
   cudaEventCreate(&ctx->tev[0]); cudaEventCreate(&ctx->tev[1]);
   if (poseidon2_init_constants() != 0) { g_last_error = "constant upload failed"; delete ctx; return ZKIR_ERR_CUDA; }
+  if (cudaMalloc(&ctx->d_err, 16) != cudaSuccess || cudaMallocHost(&ctx->h_err, 16) != cudaSuccess) { g_last_error = "error words"; delete ctx; return ZKIR_ERR_OOM; }
+  ctx->h_err[0] = ctx->h_err[1] = ~0ull;
   ctx->tables = ntt_tables_create(ctx->stream, &ctx->launches);
   ctx->fast = fast_ntt_create(ctx->stream, &ctx->launches);
   *out = ctx;
@@ -718,6 +774,9 @@ void zkir_b200_destroy(zkir_ctx* ctx) {
   if (ctx->ntt_tmp) cudaFree(ctx->ntt_tmp);
   for (int i = 0; i < 2; i++) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
   if (ctx->rows_dev) cudaFree(ctx->rows_dev);
+  if (ctx->log_pinned) cudaFreeHost(ctx->log_pinned);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->copy_done) cudaEventDestroy(ctx->copy_done);
   if (ctx->d_err) cudaFree(ctx->d_err);
   if (ctx->h_err) cudaFreeHost(ctx->h_err);
   ntt_tables_destroy(ctx->tables);
@@ -728,6 +787,19 @@ void zkir_b200_destroy(zkir_ctx* ctx) {
   delete ctx;
 }
 
+int zkir_b200_set_program(zkir_ctx* ctx, const uint32_t* code, size_t n_code) {
+  if (!ctx || (!code && n_code) || n_code > (1ull << 26)) return ZKIR_ERR_ARG;
+  ctx->err.clear();
+  cudaSetDevice(ctx->device);
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (ctx->program_version && ctx->code.size() == n_code && (n_code == 0 || !memcmp(ctx->code.data(), code, n_code * 4))) return 0;   // unchanged
+  ctx->code.assign(code, code + n_code);
+  zkir_program_digest(ctx->code.data(), n_code, ctx->code_digest);
+  ctx->program_version++;
+  for (zkir_ctx* w : ctx->workers) { int rc = zkir_b200_set_program(w, code, n_code); if (rc) return rc; }
+  return 0;
+}
+
 const char* zkir_b200_last_error(const zkir_ctx* ctx) {
   return ctx ? ctx->err.c_str() : g_last_error.c_str();
 }
@@ -735,7 +807,6 @@ const char* zkir_b200_last_error(const zkir_ctx* ctx) {
 void* zkir_b200_alloc_pinned(size_t bytes) { void* p = nullptr; return cudaMallocHost(&p, bytes) == cudaSuccess ? p : nullptr; }
 void zkir_b200_free_pinned(void* p) { if (p) cudaFreeHost(p); }
 void zkir_b200_free_proof(uint8_t* p) { free(p); }
-size_t zkir_b200_proof_size(const zkir_params* p, uint32_t log_n) { return make_layout(p, log_n).total * 4; }
 
 int zkir_b200_prove(zkir_ctx* ctx, const zkir_params* p, const uint32_t* trace_cols, uint32_t log_n, const uint32_t* pv,
                     uint8_t** proof, size_t* proof_len) {
@@ -746,9 +817,11 @@ int zkir_b200_prove(zkir_ctx* ctx, const zkir_params* p, const uint32_t* trace_c
   if (rc) return rc;
   if (!trace_cols || !pv || !proof || !proof_len) { ctx->err = "null argument"; return ZKIR_ERR_ARG; }
   if ((rc = ws_prepare(ctx, p, log_n)) != 0) return rc;
+  if ((rc = ensure_public_columns(ctx, p, log_n)) != 0) return rc;
   Workspace& w = ctx->ws;
   const size_t trace_bytes = ((size_t)p->width << log_n) * 4;
   w.graph_run = false;
+  CU(cudaMemsetAsync(ctx->d_err, 0xff, 16, ctx->stream));
   static const int graph_max_log_n = getenv("ZKIR_GRAPH_MAX_LOG_N") ? atoi(getenv("ZKIR_GRAPH_MAX_LOG_N")) : 12;   // 0 disables
   if ((int)log_n <= graph_max_log_n && !ctx->comm && ctx->shards == 1 && !w.graph_failed && w.proofs_done >= 1) {
     if (!w.h_trace_stage) CU(cudaMallocHost(&w.h_trace_stage, trace_bytes));
@@ -801,10 +874,20 @@ int zkir_b200_prove_device(zkir_ctx* ctx, const zkir_params* p, const uint32_t* 
   if (rc) return rc;
   if (!d_trace || !pv || !proof || !proof_len) { ctx->err = "null argument"; return ZKIR_ERR_ARG; }
   if ((rc = ws_prepare(ctx, p, log_n)) != 0) return rc;
+  if ((rc = ensure_public_columns(ctx, p, log_n)) != 0) return rc;
   ctx->ws.graph_run = false;   // only zkir_b200_prove replays graphs; a stale flag would hide this proof's stage timings
+  CU(cudaMemsetAsync(ctx->d_err, 0xff, 16, ctx->stream));
   CU(cudaEventRecord(ctx->ev[ZKIR_STAGE_H2D], ctx->stream));
   if ((rc = prove_resident(ctx, p, log_n, pv, d_trace)) != 0) return rc;  // read in place: no pass writes the caller's matrix
   return finish_proof(ctx, p, log_n, proof, proof_len);
+}
+
+// {entry_pc, num_cycles, exit_lo, exit_hi, halted}: halted = the run ended in EXIT / EBREAK (not cut by the cycle limit)
+static void fill_public_values(u32* pv, u32 entry_point, u64 n_rows, u64 exit_code, int halt_kind) {
+  const u64 LIMB = (1u << 20) - 1;
+  const u64 code = halt_kind == ZKIR_HALT_EXIT ? exit_code : 0;
+  pv[0] = entry_point; pv[1] = (u32)(n_rows % BB_P); pv[2] = (u32)(code & LIMB); pv[3] = (u32)((code >> 20) & LIMB);
+  pv[4] = halt_kind == ZKIR_HALT_CYCLE_LIMIT ? 0u : 1u;
 }
 
 // H2D of the raw rows + the device converter; columns land in d_cols
@@ -819,7 +902,6 @@ static int expand_rows(zkir_ctx* ctx, const uint64_t* pcs, const uint32_t* instr
     CU(cudaMalloc(&ctx->rows_dev, need));
     ctx->rows_bytes = need;
   }
-  if (!ctx->d_err) { CU(cudaMalloc(&ctx->d_err, 8)); CU(cudaMallocHost(&ctx->h_err, 8)); }
   char* base = (char*)ctx->rows_dev;
   u64* d_regs = (u64*)base;
   u64* d_pcs = (u64*)(base + T * 128);
@@ -828,28 +910,17 @@ static int expand_rows(zkir_ctx* ctx, const uint64_t* pcs, const uint32_t* instr
   CU(cudaMemcpyAsync(d_regs, regs, T * 128, cudaMemcpyHostToDevice, st));
   CU(cudaMemcpyAsync(d_pcs, pcs, T * 8, cudaMemcpyHostToDevice, st));
   CU(cudaMemcpyAsync(d_ins, instrs, T * 4, cudaMemcpyHostToDevice, st));
-  CU(cudaMemsetAsync(ctx->d_err, 0xff, 8, st));
+  CU(cudaMemsetAsync(ctx->d_err, 0xff, 16, st));
   ExpandArgs ea;
   ea.pcs = d_pcs; ea.ins = d_ins; ea.regs = d_regs; ea.T = T; ea.N = N;
   for (int k = 0; k < 16; k++) ea.final_regs[k] = final_regs[k];
-  ea.final_pc = final_pc; ea.cols = d_cols; ea.err = ctx->d_err; ea.col_lo = col_lo; ea.col_hi = col_hi;
+  ea.final_pc = final_pc; ea.cols = d_cols; ea.err = ctx->d_err; ea.col_lo = col_lo; ea.col_hi = col_hi; ea.n_code = (u32)ctx->code.size();
   RC(launch_trace_expand(ea, st, &ctx->launches));
-  CU(cudaMemcpyAsync(ctx->h_err, ctx->d_err, 8, cudaMemcpyDeviceToHost, st));
   return 0;
 }
-static int expand_error(zkir_ctx* ctx) {  // after the stream is drained
-  const u64 e = *ctx->h_err;
-  if (e == ~0ull) return 0;
-  static const char* why[] = {"", "pc does not fit 30 bits", "register value exceeds 40 bits", "input tape value exceeds 40 bits",
-                              "syscall other than EXIT/READ/WRITE", "opcode is not constrained"};
-  const u32 code = (u32)(e & 0xff);
-  ctx->err = "core AIR v1 cannot constrain row " + std::to_string((unsigned long long)(e >> 8)) + ": " + (code < 6 ? why[code] : "?");
-  return ZKIR_ERR_AIR;
-}
-
 int zkir_b200_prove_rows(zkir_ctx* ctx, const zkir_params* p, const uint64_t* pcs, const uint32_t* instrs, const uint64_t* regs,
                          uint64_t n_rows, const uint64_t* final_regs, uint64_t final_pc, uint32_t entry_point, uint64_t exit_code,
-                         uint32_t log_n, uint32_t* pv_out, uint8_t** proof, size_t* proof_len) {
+                         int halt_kind, uint32_t log_n, uint32_t* pv_out, uint8_t** proof, size_t* proof_len) {
   if (!ctx) return ZKIR_ERR_ARG;
   ctx->err.clear();
   cudaSetDevice(ctx->device);
@@ -857,20 +928,44 @@ int zkir_b200_prove_rows(zkir_ctx* ctx, const zkir_params* p, const uint64_t* pc
   if (rc) return rc;
   if (!pv_out || !proof || !proof_len) { ctx->err = "null argument"; return ZKIR_ERR_ARG; }
   if ((rc = ws_prepare(ctx, p, log_n)) != 0) return rc;
+  if ((rc = ensure_public_columns(ctx, p, log_n)) != 0) return rc;
   ctx->ws.graph_run = false;   // only zkir_b200_prove replays graphs; a stale flag would hide this proof's stage timings
   CU(cudaEventRecord(ctx->ev[ZKIR_STAGE_H2D], ctx->stream));
   u32 c_lo, c_hi;
   trace_col_range(ctx, p, log_n, &c_lo, &c_hi);   // a sharded proof only materialises the columns this rank transforms
   if ((rc = expand_rows(ctx, pcs, instrs, regs, n_rows, final_regs, final_pc, log_n, ctx->ws.trace, c_lo, c_hi)) != 0) return rc;
-  const u64 LIMB = (1u << 20) - 1;
-  pv_out[0] = entry_point; pv_out[1] = (u32)(n_rows % BB_P); pv_out[2] = (u32)(exit_code & LIMB); pv_out[3] = (u32)((exit_code >> 20) & LIMB);
+  fill_public_values(pv_out, entry_point, n_rows, exit_code, halt_kind);
   if ((rc = prove_resident(ctx, p, log_n, pv_out, ctx->ws.trace)) != 0) return rc;
-  if ((rc = finish_proof(ctx, p, log_n, proof, proof_len)) != 0) return rc;
-  if ((rc = expand_error(ctx)) != 0) { free(*proof); *proof = nullptr; *proof_len = 0; return rc; }
-  return 0;
+  return finish_proof(ctx, p, log_n, proof, proof_len);
 }
 
-// write-log flavour: H2D of (pc32, word, wlog) + last-writer scan + converter
+// write-log flavour: H2D of (pc32, word, wlog) + last-writer scan + converter.  Device staging: wlog[Tc] | pcs[Tc] | ins[Tc] | scan scratch
+struct WlStage { u64* d_wlog; u32* d_pcs; u32* d_ins; int* d_scr; };
+static int wl_stage(zkir_ctx* ctx, u64 Tc, u64 n_scan_rows, WlStage* o) {
+  const size_t scratch = trace_expand_wl_scratch_ints(n_scan_rows) * 4;
+  const size_t need = Tc * 16 + scratch + 64;
+  if (ctx->rows_bytes < need) {
+    if (ctx->rows_dev) cudaFree(ctx->rows_dev);
+    ctx->rows_dev = nullptr; ctx->rows_bytes = 0;
+    CU(cudaMalloc(&ctx->rows_dev, need));
+    ctx->rows_bytes = need;
+  }
+  char* base = (char*)ctx->rows_dev;
+  o->d_wlog = (u64*)base;
+  o->d_pcs = (u32*)(base + Tc * 8);
+  o->d_ins = (u32*)(base + Tc * 12);
+  o->d_scr = (int*)(base + ((Tc * 16 + 15) & ~(size_t)15));
+  return 0;
+}
+static int wl_convert(zkir_ctx* ctx, const WlStage& sg, uint64_t T, uint64_t final_pc, uint32_t log_n, u32* d_cols, u32 col_lo, u32 col_hi) {
+  cudaStream_t st = ctx->stream;
+  CU(cudaMemsetAsync(ctx->d_err, 0xff, 16, st));
+  WlArgs wa;
+  wa.pcs = sg.d_pcs; wa.ins = sg.d_ins; wa.wlog = sg.d_wlog; wa.T = T; wa.N = 1ull << log_n; wa.final_pc = final_pc; wa.chunk_prev = sg.d_scr; wa.cols = d_cols;
+  wa.err = ctx->d_err; wa.col_lo = col_lo; wa.col_hi = col_hi; wa.n_code = (u32)ctx->code.size();
+  RC(launch_trace_expand_wl(wa, st, &ctx->launches));
+  return 0;
+}
 static int expand_writelog(zkir_ctx* ctx, const uint32_t* pcs, const uint32_t* instrs, const uint64_t* wlog, uint64_t T, uint64_t final_pc,
                            uint32_t log_n, u32* d_cols, u32 col_lo = 0, u32 col_hi = 0xffffffffu) {
   const u64 N = 1ull << log_n;
@@ -881,46 +976,29 @@ static int expand_writelog(zkir_ctx* ctx, const uint32_t* pcs, const uint32_t* i
   const bool split = G > 1 && T >= 65536;
   const u64 chunk = split ? (((T + G - 1) / G + 3) & ~3ull) : T;   // rows per rank
   const u64 Tc = split ? chunk * G : T;                             // capacity of the device arrays
-  const size_t scratch = trace_expand_wl_scratch_ints(N) * 4;
-  const size_t need = Tc * 16 + scratch + 64;
-  if (ctx->rows_bytes < need) {
-    if (ctx->rows_dev) cudaFree(ctx->rows_dev);
-    ctx->rows_dev = nullptr; ctx->rows_bytes = 0;
-    CU(cudaMalloc(&ctx->rows_dev, need));
-    ctx->rows_bytes = need;
-  }
-  if (!ctx->d_err) { CU(cudaMalloc(&ctx->d_err, 8)); CU(cudaMallocHost(&ctx->h_err, 8)); }
-  char* base = (char*)ctx->rows_dev;
-  u64* d_wlog = (u64*)base;
-  u32* d_pcs = (u32*)(base + Tc * 8);
-  u32* d_ins = (u32*)(base + Tc * 12);
-  int* d_scr = (int*)(base + ((Tc * 16 + 15) & ~(size_t)15));
+  WlStage sg;
+  { int rc = wl_stage(ctx, Tc, N, &sg); if (rc) return rc; }
   cudaStream_t st = ctx->stream;
   if (split) {
     const u64 r0 = (u64)comm_rank(ctx->comm) * chunk, r1 = r0 + chunk < T ? r0 + chunk : T;
     if (r1 > r0) {
-      CU(cudaMemcpyAsync(d_wlog + r0, wlog + r0, (r1 - r0) * 8, cudaMemcpyHostToDevice, st));
-      CU(cudaMemcpyAsync(d_pcs + r0, pcs + r0, (r1 - r0) * 4, cudaMemcpyHostToDevice, st));
-      CU(cudaMemcpyAsync(d_ins + r0, instrs + r0, (r1 - r0) * 4, cudaMemcpyHostToDevice, st));
+      CU(cudaMemcpyAsync(sg.d_wlog + r0, wlog + r0, (r1 - r0) * 8, cudaMemcpyHostToDevice, st));
+      CU(cudaMemcpyAsync(sg.d_pcs + r0, pcs + r0, (r1 - r0) * 4, cudaMemcpyHostToDevice, st));
+      CU(cudaMemcpyAsync(sg.d_ins + r0, instrs + r0, (r1 - r0) * 4, cudaMemcpyHostToDevice, st));
     }
-    unsigned* bufs[3] = {reinterpret_cast<unsigned*>(d_wlog), d_pcs, d_ins};
+    unsigned* bufs[3] = {reinterpret_cast<unsigned*>(sg.d_wlog), sg.d_pcs, sg.d_ins};
     const size_t per[3] = {(size_t)chunk * 2, (size_t)chunk, (size_t)chunk};
     if (comm_all_gather_group_u32(ctx->comm, bufs, per, 3, st, &ctx->err) != 0) return ZKIR_ERR_NCCL;
   } else {
-    CU(cudaMemcpyAsync(d_wlog, wlog, T * 8, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(d_pcs, pcs, T * 4, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(d_ins, instrs, T * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(sg.d_wlog, wlog, T * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(sg.d_pcs, pcs, T * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(sg.d_ins, instrs, T * 4, cudaMemcpyHostToDevice, st));
   }
-  CU(cudaMemsetAsync(ctx->d_err, 0xff, 8, st));
-  WlArgs wa;
-  wa.pcs = d_pcs; wa.ins = d_ins; wa.wlog = d_wlog; wa.T = T; wa.N = N; wa.final_pc = final_pc; wa.chunk_prev = d_scr; wa.cols = d_cols; wa.err = ctx->d_err; wa.col_lo = col_lo; wa.col_hi = col_hi;
-  RC(launch_trace_expand_wl(wa, st, &ctx->launches));
-  CU(cudaMemcpyAsync(ctx->h_err, ctx->d_err, 8, cudaMemcpyDeviceToHost, st));
-  return 0;
+  return wl_convert(ctx, sg, T, final_pc, log_n, d_cols, col_lo, col_hi);
 }
 
 int zkir_b200_prove_writelog(zkir_ctx* ctx, const zkir_params* p, const uint32_t* pcs, const uint32_t* instrs, const uint64_t* wlog,
-                             uint64_t n_rows, uint64_t final_pc, uint32_t entry_point, uint64_t exit_code, uint32_t log_n,
+                             uint64_t n_rows, uint64_t final_pc, uint32_t entry_point, uint64_t exit_code, int halt_kind, uint32_t log_n,
                              uint32_t* pv_out, uint8_t** proof, size_t* proof_len) {
   if (!ctx) return ZKIR_ERR_ARG;
   ctx->err.clear();
@@ -929,37 +1007,109 @@ int zkir_b200_prove_writelog(zkir_ctx* ctx, const zkir_params* p, const uint32_t
   if (rc) return rc;
   if (!pv_out || !proof || !proof_len) { ctx->err = "null argument"; return ZKIR_ERR_ARG; }
   if ((rc = ws_prepare(ctx, p, log_n)) != 0) return rc;
+  if ((rc = ensure_public_columns(ctx, p, log_n)) != 0) return rc;
   ctx->ws.graph_run = false;   // only zkir_b200_prove replays graphs; a stale flag would hide this proof's stage timings
   CU(cudaEventRecord(ctx->ev[ZKIR_STAGE_H2D], ctx->stream));
   u32 c_lo, c_hi;
   trace_col_range(ctx, p, log_n, &c_lo, &c_hi);   // a sharded proof only materialises the columns this rank transforms
   if ((rc = expand_writelog(ctx, pcs, instrs, wlog, n_rows, final_pc, log_n, ctx->ws.trace, c_lo, c_hi)) != 0) return rc;
-  const u64 LIMB = (1u << 20) - 1;
-  pv_out[0] = entry_point; pv_out[1] = (u32)(n_rows % BB_P); pv_out[2] = (u32)(exit_code & LIMB); pv_out[3] = (u32)((exit_code >> 20) & LIMB);
+  fill_public_values(pv_out, entry_point, n_rows, exit_code, halt_kind);
   if ((rc = prove_resident(ctx, p, log_n, pv_out, ctx->ws.trace)) != 0) return rc;
-  if ((rc = finish_proof(ctx, p, log_n, proof, proof_len)) != 0) return rc;
-  if ((rc = expand_error(ctx)) != 0) { free(*proof); *proof = nullptr; *proof_len = 0; return rc; }
-  return 0;
+  return finish_proof(ctx, p, log_n, proof, proof_len);
+}
+
+// Program -> Proof.  The interpreter (host/vm.cc) runs in the calling thread and appends the write log to pinned memory; every
+// PROG_CHUNK cycles the finished rows start their host->device copy on a second stream, so at the end of the run only the last
+// chunk is left to move.  Then: last-writer scan + converter + proof, as in zkir_b200_prove_writelog.
+#define PROG_CHUNK (1u << 16)
+extern "C" int zkir_vm_run_writelog_cb(const uint32_t*, size_t, const uint8_t*, size_t, uint32_t, const uint64_t*, size_t, uint64_t, uint32_t*, uint32_t*,
+                                       uint64_t*, uint64_t, void (*)(void*, uint64_t), void*, uint64_t, zkir_vm_result**);
+struct ProgUpload { zkir_ctx* ctx; const u32 *h_pcs, *h_ins; const u64* h_wlog; WlStage sg; u64 done; cudaError_t e; };
+static void prog_upload_to(ProgUpload* u, u64 rows_done) {
+  if (rows_done <= u->done || u->e != cudaSuccess) return;
+  const u64 r0 = u->done, n = rows_done - r0;
+  cudaStream_t cs = u->ctx->copy_stream;
+  cudaError_t e = cudaMemcpyAsync(u->sg.d_wlog + r0, u->h_wlog + r0, n * 8, cudaMemcpyHostToDevice, cs);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(u->sg.d_pcs + r0, u->h_pcs + r0, n * 4, cudaMemcpyHostToDevice, cs);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(u->sg.d_ins + r0, u->h_ins + r0, n * 4, cudaMemcpyHostToDevice, cs);
+  u->e = e; u->done = rows_done;
+}
+static void prog_on_chunk(void* user, uint64_t rows_done) { prog_upload_to(static_cast<ProgUpload*>(user), rows_done); }
+
+int zkir_b200_prove_program(zkir_ctx* ctx, const zkir_params* p, const uint32_t* code, size_t n_code, const uint8_t* data, size_t n_data,
+                            uint32_t entry_point, const uint64_t* inputs, size_t n_inputs, uint64_t max_cycles,
+                            uint32_t* pv_out, uint64_t* out_cycles, uint32_t* out_log_n, uint8_t** proof, size_t* proof_len) {
+  if (!ctx || !p || !code || !pv_out || !proof || !proof_len || max_cycles == 0 || max_cycles > (1ull << 26)) return ZKIR_ERR_ARG;
+  ctx->err.clear();
+  cudaSetDevice(ctx->device);
+  int rc = zkir_b200_set_program(ctx, code, n_code);
+  if (rc) return rc;
+  if (ctx->log_capacity < max_cycles) {
+    if (ctx->log_pinned) cudaFreeHost(ctx->log_pinned);
+    ctx->log_pinned = nullptr; ctx->log_capacity = 0;
+    CU(cudaMallocHost(&ctx->log_pinned, max_cycles * 16));
+    ctx->log_capacity = max_cycles;
+  }
+  if (!ctx->copy_stream) { CU(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)); CU(cudaEventCreateWithFlags(&ctx->copy_done, cudaEventDisableTiming)); }
+  u64* h_wlog = (u64*)ctx->log_pinned;
+  u32* h_pcs = (u32*)((char*)ctx->log_pinned + ctx->log_capacity * 8);
+  u32* h_ins = (u32*)((char*)ctx->log_pinned + ctx->log_capacity * 12);
+  CU(cudaStreamSynchronize(ctx->stream));   // the previous proof may still read the device staging
+  ProgUpload up;
+  up.ctx = ctx; up.h_pcs = h_pcs; up.h_ins = h_ins; up.h_wlog = h_wlog; up.done = 0; up.e = cudaSuccess;
+  const bool overlap = ctx->comm == nullptr;   // a sharded proof uploads by row segment inside prove_writelog instead
+  // the scan scratch depends on the (still unknown) padded trace length: size it for the largest trace the log can hold
+  u64 n_scan = 1ull << ZKIR_AIR_RANGE_BITS;
+  while (n_scan < max_cycles || n_scan < n_code) n_scan <<= 1;
+  if (overlap && (rc = wl_stage(ctx, max_cycles, n_scan, &up.sg)) != 0) return rc;
+  zkir_vm_result* res = nullptr;
+  rc = zkir_vm_run_writelog_cb(code, n_code, data, n_data, entry_point, inputs, n_inputs, max_cycles, h_pcs, h_ins, h_wlog, ctx->log_capacity,
+                               overlap ? prog_on_chunk : nullptr, &up, PROG_CHUNK, &res);
+  if (rc) { ctx->err = std::string("interpreter: ") + zkir_vm_last_error(); return rc; }
+  const u64 T = zkir_vm_cycles(res), final_pc = zkir_vm_final_pc(res);
+  const int halt_kind = zkir_vm_halt_kind(res);
+  const u64 exit_code = zkir_vm_exit_code(res);
+  zkir_vm_free(res);
+  u32 log_n = ZKIR_AIR_RANGE_BITS;
+  while ((1ull << log_n) < T || (1ull << log_n) < n_code) log_n++;
+  if (out_cycles) *out_cycles = T;
+  if (out_log_n) *out_log_n = log_n;
+  if (!overlap) return zkir_b200_prove_writelog(ctx, p, h_pcs, h_ins, h_wlog, T, final_pc, entry_point, exit_code, halt_kind, log_n, pv_out, proof, proof_len);
+  if ((rc = check_params(ctx, p, log_n)) != 0) return rc;
+  if ((rc = ws_prepare(ctx, p, log_n)) != 0) return rc;
+  if ((rc = ensure_public_columns(ctx, p, log_n)) != 0) return rc;
+  ctx->ws.graph_run = false;
+  CU(cudaEventRecord(ctx->ev[ZKIR_STAGE_H2D], ctx->stream));
+  prog_upload_to(&up, T);                                   // the tail that no chunk boundary covered
+  if (up.e != cudaSuccess) { ctx->err = std::string("write-log upload: ") + cudaGetErrorString(up.e); return ZKIR_ERR_CUDA; }
+  CU(cudaEventRecord(ctx->copy_done, ctx->copy_stream));
+  CU(cudaStreamWaitEvent(ctx->stream, ctx->copy_done, 0));
+  if ((rc = wl_convert(ctx, up.sg, T, final_pc, log_n, ctx->ws.trace, 0, 0xffffffffu)) != 0) return rc;
+  fill_public_values(pv_out, entry_point, T, exit_code, halt_kind);
+  if ((rc = prove_resident(ctx, p, log_n, pv_out, ctx->ws.trace)) != 0) return rc;
+  return finish_proof(ctx, p, log_n, proof, proof_len);
 }
 
 int zkir_b200_expand_writelog(zkir_ctx* ctx, const uint32_t* pcs, const uint32_t* instrs, const uint64_t* wlog, uint64_t n_rows,
                               uint64_t final_pc, uint32_t log_n, uint32_t* d_cols) {
-  if (!ctx || !d_cols || log_n < 2 || log_n > 26) return ZKIR_ERR_ARG;
+  if (!ctx || !d_cols || log_n < ZKIR_AIR_RANGE_BITS || log_n > 26) return ZKIR_ERR_ARG;
   ctx->err.clear();
   cudaSetDevice(ctx->device);
   int rc = expand_writelog(ctx, pcs, instrs, wlog, n_rows, final_pc, log_n, d_cols);
   if (rc) return rc;
+  CU(cudaMemcpyAsync(ctx->h_err, ctx->d_err, 16, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   return expand_error(ctx);
 }
 
 int zkir_b200_expand_rows(zkir_ctx* ctx, const uint64_t* pcs, const uint32_t* instrs, const uint64_t* regs, uint64_t n_rows,
                           const uint64_t* final_regs, uint64_t final_pc, uint32_t log_n, uint32_t* d_cols) {
-  if (!ctx || !d_cols || log_n < 2 || log_n > 26) return ZKIR_ERR_ARG;
+  if (!ctx || !d_cols || log_n < ZKIR_AIR_RANGE_BITS || log_n > 26) return ZKIR_ERR_ARG;
   ctx->err.clear();
   cudaSetDevice(ctx->device);
   int rc = expand_rows(ctx, pcs, instrs, regs, n_rows, final_regs, final_pc, log_n, d_cols);
   if (rc) return rc;
+  CU(cudaMemcpyAsync(ctx->h_err, ctx->d_err, 16, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   return expand_error(ctx);
 }
@@ -986,6 +1136,7 @@ int zkir_b200_prove_batch(zkir_ctx* ctx, const zkir_params* p, const uint32_t* c
     zkir_ctx* w = nullptr;
     int rc = zkir_b200_create(&w, ctx->device);
     if (rc) { ctx->err = "worker context: " + g_last_error; return rc; }
+    if ((rc = zkir_b200_set_program(w, ctx->code.data(), ctx->code.size())) != 0) { ctx->err = "worker context: program"; zkir_b200_destroy(w); return rc; }
     ctx->workers.push_back(w);
   }
   std::vector<int> rcs(nw, 0);
@@ -1169,37 +1320,73 @@ int zkir_b200_merkle_commit(zkir_ctx* ctx, const uint32_t* d_matrix, uint32_t n_
   return 0;
 }
 
-int zkir_b200_quotient(zkir_ctx* ctx, const zkir_params* p, const uint32_t* d_lde, uint32_t log_n, const uint32_t* pv,
-                       const uint32_t alpha[4], uint32_t* d_q) {
-  if (!ctx) return ZKIR_ERR_ARG;
+int zkir_b200_quotient(zkir_ctx* ctx, const zkir_params* p, const uint32_t* d_lde, const uint32_t* d_publde, uint32_t log_n, const uint32_t* pv,
+                       const uint32_t lookup[8], const uint32_t alpha[4], uint32_t* d_q) {
+  if (!ctx || !p || !d_lde || !d_publde || !pv || !lookup || !alpha || !d_q) return ZKIR_ERR_ARG;
   ctx->err.clear();
   cudaSetDevice(ctx->device);
-  int rc = check_params(ctx, p, log_n);
-  if (rc) return rc;
-  const u32 log_m = log_n + p->log_blowup;
+  if (p->width != ZKIR_AIR_WIDTH || p->num_public != ZKIR_AIR_NUM_PUBLIC || log_n < 2 || p->log_blowup < 1 || log_n + p->log_blowup > 27) { ctx->err = "bad params"; return ZKIR_ERR_ARG; }
+  const u32 log_m = log_n + p->log_blowup, WA = p->width + AW, NP = ZKIR_AIR_NUM_PUBLIC;
   const u64 M = 1ull << log_m;
-  u32 *lde_m = nullptr, *lde_cm = nullptr, *xs = nullptr, *dinv = nullptr, *small = nullptr;
-  CU(cudaMallocAsync(&lde_m, (size_t)p->width * M * 4, ctx->stream));
-  CU(cudaMallocAsync(&lde_cm, (size_t)p->width * M * 4, ctx->stream));
+  u32 *lde_m = nullptr, *lde_cm = nullptr, *pub_m = nullptr, *pub_cm = nullptr, *xs = nullptr, *dinv = nullptr, *small = nullptr;
+  CU(cudaMallocAsync(&lde_m, (size_t)WA * M * 4, ctx->stream));
+  CU(cudaMallocAsync(&lde_cm, (size_t)WA * M * 4, ctx->stream));
+  CU(cudaMallocAsync(&pub_m, (size_t)PW * M * 4, ctx->stream));
+  CU(cudaMallocAsync(&pub_cm, (size_t)PW * M * 4, ctx->stream));
   CU(cudaMallocAsync(&xs, M * 4, ctx->stream));
   CU(cudaMallocAsync(&dinv, M * 4, ctx->stream));
-  CU(cudaMallocAsync(&small, (8 + 4 * ZKIR_AIR_NUM_CONSTRAINTS) * 4, ctx->stream));
-  u32 h[8];
-  for (int i = 0; i < 4; i++) h[i] = bb_to_mont_c(pv[i] % BB_P);
-  for (int i = 0; i < 4; i++) h[4 + i] = bb_to_mont_c(alpha[i] % BB_P);
-  CU(cudaMemcpyAsync(small, h, 32, cudaMemcpyHostToDevice, ctx->stream));
-  rc = launch_map(lde_m, d_lde, (u64)p->width * M, 1, ctx->stream, &ctx->launches);
-  if (!rc) rc = launch_coset_reorder(lde_m, lde_cm, p->width, log_n, p->log_blowup, 0, ctx->stream, &ctx->launches);  // the kernel sweeps coset-major rows
+  // small: pv[8 (NP padded)] alpha[4] lookup[8] apow[K][4] -- the ext4 arrays must stay 16-byte aligned
+  CU(cudaMallocAsync(&small, (20 + 4 * ZKIR_AIR_NUM_CONSTRAINTS) * 4, ctx->stream));
+  u32 h[20] = {0};
+  for (u32 i = 0; i < NP; i++) h[i] = bb_to_mont_c(pv[i] % BB_P);
+  for (int i = 0; i < 4; i++) h[8 + i] = bb_to_mont_c(alpha[i] % BB_P);
+  for (int i = 0; i < 8; i++) h[12 + i] = bb_to_mont_c(lookup[i] % BB_P);
+  CU(cudaMemcpyAsync(small, h, sizeof(h), cudaMemcpyHostToDevice, ctx->stream));
+  int rc = launch_map(lde_m, d_lde, (u64)WA * M, 1, ctx->stream, &ctx->launches);
+  if (!rc) rc = launch_coset_reorder(lde_m, lde_cm, WA, log_n, p->log_blowup, 0, ctx->stream, &ctx->launches);  // the kernel sweeps coset-major rows
+  if (!rc) rc = launch_map(pub_m, d_publde, (u64)PW * M, 1, ctx->stream, &ctx->launches);
+  if (!rc) rc = launch_coset_reorder(pub_m, pub_cm, PW, log_n, p->log_blowup, 0, ctx->stream, &ctx->launches);
   if (!rc) rc = launch_domain_tables(xs, dinv, log_n, p->log_blowup, ZKIR_BB_GEN, ctx->stream, &ctx->launches);
   QuotientArgs qa;
-  qa.lde = lde_cm; qa.q = d_q; qa.log_n = log_n; qa.log_blowup = p->log_blowup; qa.pv = small; qa.alpha = small + 4;
-  qa.xs = xs; qa.dinv = dinv; qa.apow_scratch = small + 8;
+  qa.lde = lde_cm; qa.publde = pub_cm; qa.q = d_q; qa.log_n = log_n; qa.log_blowup = p->log_blowup; qa.pv = small; qa.alpha = small + 8; qa.lookup = small + 12;
+  qa.xs = xs; qa.dinv = dinv; qa.apow_scratch = small + 20;
   if (!rc) rc = launch_quotient(qa, ctx->stream, &ctx->launches);
   if (!rc) rc = launch_map(d_q, d_q, 4 * M, 0, ctx->stream, &ctx->launches);
   CU(cudaStreamSynchronize(ctx->stream));
-  cudaFreeAsync(lde_m, ctx->stream); cudaFreeAsync(lde_cm, ctx->stream); cudaFreeAsync(xs, ctx->stream); cudaFreeAsync(dinv, ctx->stream); cudaFreeAsync(small, ctx->stream);
+  cudaFreeAsync(lde_m, ctx->stream); cudaFreeAsync(lde_cm, ctx->stream); cudaFreeAsync(pub_m, ctx->stream); cudaFreeAsync(pub_cm, ctx->stream);
+  cudaFreeAsync(xs, ctx->stream); cudaFreeAsync(dinv, ctx->stream); cudaFreeAsync(small, ctx->stream);
   RC(rc);
   return 0;
+}
+
+// the LogUp aux columns of a canonical device trace for GIVEN lookup challenges (the prover draws them from the transcript)
+int zkir_b200_aux_columns(zkir_ctx* ctx, const uint32_t* d_trace, uint32_t log_n, const uint32_t lookup[8], uint32_t* d_aux) {
+  if (!ctx || !d_trace || !lookup || !d_aux || log_n < ZKIR_AIR_RANGE_BITS || log_n > 26) return ZKIR_ERR_ARG;
+  ctx->err.clear();
+  cudaSetDevice(ctx->device);
+  if (ctx->program_version == 0 || ctx->code.size() > (1ull << log_n)) { ctx->err = "no program set, or it does not fit the trace"; return ZKIR_ERR_ARG; }
+  const u64 N = 1ull << log_n;
+  std::vector<u32> hp((size_t)PW * N, 0u);
+  for (u64 i = 0; i < N && i < (1ull << ZKIR_AIR_RANGE_BITS); i++) hp[ZKIR_PUB_P_T * N + i] = (u32)i;
+  for (u64 i = 0; i < N; i++) {
+    if (i < ctx->code.size()) { hp[ZKIR_PUB_P_PC * N + i] = 0x1000u + 4 * (u32)i; zkir_rom_entry(ctx->code[i], &hp[ZKIR_PUB_P_DEC * N + i], &hp[ZKIR_PUB_P_IMM * N + i]); }
+    else hp[ZKIR_PUB_P_DEC * N + i] = 127;
+  }
+  u32 *pub = nullptr, *lk = nullptr; E4 *rt = nullptr, *bt = nullptr;
+  CU(cudaMalloc(&pub, hp.size() * 4)); CU(cudaMalloc(&lk, 32)); CU(cudaMalloc(&rt, N * sizeof(E4))); CU(cudaMalloc(&bt, aux_gen_blocks(N) * sizeof(E4)));
+  u32 hl[8];
+  for (int i = 0; i < 8; i++) hl[i] = bb_to_mont_c(lookup[i] % BB_P);
+  CU(cudaMemcpy(pub, hp.data(), hp.size() * 4, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(lk, hl, 32, cudaMemcpyHostToDevice));
+  CU(cudaMemsetAsync(ctx->d_err, 0xff, 16, ctx->stream));
+  AuxArgs aa;
+  aa.trace = d_trace; aa.pub = pub; aa.lookup = lk; aa.aux = d_aux; aa.log_n = log_n; aa.row_tot = rt; aa.blk_tot = bt; aa.err = ctx->d_err + 1;
+  int rc = launch_aux_gen(aa, ctx->stream, &ctx->launches);
+  CU(cudaMemcpyAsync(ctx->h_err, ctx->d_err, 16, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  cudaFree(pub); cudaFree(lk); cudaFree(rt); cudaFree(bt);
+  RC(rc);
+  return expand_error(ctx);
 }
 
 int zkir_b200_fri_fold(zkir_ctx* ctx, const uint32_t* d_in, uint32_t* d_out, uint32_t log_n, uint32_t shift, const uint32_t beta[4]) {

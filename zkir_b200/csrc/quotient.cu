@@ -1,4 +1,4 @@
-// AIR quotient sweep: one thread per row of the LDE coset evaluates every constraint of the core AIR v1
+// AIR quotient sweep: one thread per row of the LDE coset evaluates every constraint of the AIR v2 (main, aux and public columns)
 // (air_generated.h, emitted by tools/gen_air.py -- the same list the CPU oracle and the verifier instantiate),
 // folds them with powers of alpha in ext4 and divides by the vanishing polynomial.  Column-major LDE so adjacent
 // threads read adjacent addresses; the LDE is coset-major, so "next row" (g*x) is simply the next memory row of the same coset.
@@ -16,20 +16,30 @@
 namespace zkir {
 
 struct QCtx {
-  typedef Fm F;
-  const u32* lde; u64 M, row, nxt;
+  typedef Fm F; typedef Xm X;
+  const u32 *lde, *aux, *pub; u64 M, row, nxt;
   const u32* pv;       // shared
   const E4* apow;      // shared, apow[i] = alpha^(K-1-i)
+  const E4* lc;        // shared: lookup challenges z, theta, theta^2, theta^3
   Fm is_first, is_last, is_trans;
-  Acc4 acc;  // lazy 64-bit accumulator of sum_i alpha^(K-1-i) * C_i (bb.cuh)
+  Acc4 acc;  // lazy 64-bit accumulator of sum_i alpha^(K-1-i) * C_i over the base-field constraints (bb.cuh)
+  E4 accx;   // the ext4-valued constraints (LogUp) are few: plain ext4 products
   __device__ __forceinline__ Fm L(int i) const { return Fm(__ldg(lde + (u64)i * M + row)); }
   __device__ __forceinline__ Fm N(int i) const { return Fm(__ldg(lde + (u64)i * M + nxt)); }
+  __device__ __forceinline__ Fm A(int i) const { return Fm(__ldg(aux + (u64)i * M + row)); }
+  __device__ __forceinline__ Fm AN(int i) const { return Fm(__ldg(aux + (u64)i * M + nxt)); }
+  __device__ __forceinline__ Fm P(int i) const { return Fm(__ldg(pub + (u64)i * M + row)); }
   __device__ __forceinline__ Fm PV(int i) const { return Fm(pv[i]); }
   __device__ __forceinline__ Fm K(u32 k) const { return Fm(bb_to_mont_c(k)); }
+  __device__ __forceinline__ Xm z() const { Xm r; r.v = lc[0]; return r; }
+  __device__ __forceinline__ Xm th(int k) const { Xm r; r.v = lc[k]; return r; }
+  __device__ __forceinline__ Xm xf(Fm a) const { Xm r; r.v = e4_from_base(a.v); return r; }
+  __device__ __forceinline__ Xm x4(Fm a, Fm b, Fm c, Fm d) const { Xm r; r.v.c[0] = a.v; r.v.c[1] = b.v; r.v.c[2] = c.v; r.v.c[3] = d.v; return r; }
   __device__ __forceinline__ void emit(int idx, Fm v) {
     acc4_mac(acc, apow[idx], v.v);
-    if (idx & 1) acc4_fix(acc);  // idx is a literal in the generated code: every second emit
+    if (idx & 1) acc4_fix(acc);  // idx is a literal in the generated code: at most two products between fixes
   }
+  __device__ __forceinline__ void emit_x(int idx, Xm v) { accx = e4_add(accx, e4_mul(apow[idx], v.v)); }
 };
 
 __global__ void alpha_powers_kernel(const u32* alpha, E4* apow) {  // apow[i] = alpha^(K-1-i); thread per power
@@ -44,9 +54,22 @@ __global__ void alpha_powers_kernel(const u32* alpha, E4* apow) {  // apow[i] = 
 template <int MINB>
 __global__ void __launch_bounds__(128, MINB) quotient_kernel(QuotientArgs a, const E4* apow_g, u32 g_inv, u32 g, u32 snn /* shift^N */, u32 wb /* w_B */) {
   __shared__ E4 apow[ZKIR_AIR_NUM_CONSTRAINTS];
+  __shared__ E4 lc[4];
   __shared__ u32 pv[ZKIR_AIR_NUM_PUBLIC];
   for (int i = threadIdx.x; i < ZKIR_AIR_NUM_CONSTRAINTS; i += blockDim.x) apow[i] = apow_g[i];
   if (threadIdx.x < ZKIR_AIR_NUM_PUBLIC) pv[threadIdx.x] = a.pv[threadIdx.x];
+  // Z_H(x) = x^N - 1 = shift^N * w_B^z - 1 takes only B = 2^log_blowup (<= 16) values on the coset: one inversion per block and coset
+  __shared__ u32 zh_s[16], zhi_s[16];
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + (1u << a.log_blowup)) {
+    const u32 zz = threadIdx.x - 64;
+    const u32 v = bb_sub(bb_mul(snn, bb_pow(wb, zz)), BB_ONE);
+    zh_s[zz] = v; zhi_s[zz] = bb_inv(v);
+  }
+  if (threadIdx.x == 32) {
+    E4 z, th;
+    for (int k = 0; k < 4; k++) { z.c[k] = a.lookup[k]; th.c[k] = a.lookup[4 + k]; }
+    lc[0] = z; lc[1] = th; lc[2] = e4_mul(th, th); lc[3] = e4_mul(lc[2], th);
+  }
   __syncthreads();
   const u64 M = 1ull << (a.log_n + a.log_blowup), N = 1ull << a.log_n;
   const u64 t = blockIdx.x * (u64)blockDim.x + threadIdx.x;  // memory row: coset z = i / N, point j = i % N, natural index j*B + z
@@ -55,18 +78,18 @@ __global__ void __launch_bounds__(128, MINB) quotient_kernel(QuotientArgs a, con
   const u64 z = t >> log_nj, j = a.seg_j0 + (t & ((1ull << log_nj) - 1));
   const u64 i = (z << a.log_n) | j;
   QCtx c;
-  c.lde = a.lde; c.M = M; c.row = i; c.nxt = (z << a.log_n) | ((j + 1) & (N - 1)); c.pv = pv; c.apow = apow;
+  c.lde = a.lde; c.aux = a.lde + (u64)ZKIR_AIR_WIDTH * M; c.pub = a.publde; c.M = M; c.row = i; c.nxt = (z << a.log_n) | ((j + 1) & (N - 1));
+  c.pv = pv; c.apow = apow; c.lc = lc;
   const u32 x = a.xs[i];
-  // Z_H(x) = x^N - 1 = shift^N * w_B^z - 1
-  const u32 zh = bb_sub(bb_mul(snn, bb_pow(wb, z)), BB_ONE);
+  const u32 zh = zh_s[z];
   c.is_first = Fm(bb_mul(zh, a.dinv[i]));                         // Z_H/(x-1)
   c.is_last = Fm(bb_mul(zh, bb_mul(g, a.dinv[c.nxt])));  // Z_H/(x-g^-1) = Z_H*g/(g x-1), g*x_i = x_{i+B}
   c.is_trans = Fm(bb_sub(x, g_inv));
-  c.acc = acc4_zero();
+  c.acc = acc4_zero(); c.accx = e4_zero();
   zkir_air_eval(c);
-  const u32 zi = bb_inv(zh);
+  const u32 zi = zhi_s[z];
   const u64 nat = (j << a.log_blowup) | z;
-  const E4 accv = acc4_finish(c.acc);
+  const E4 accv = e4_add(acc4_finish(c.acc), c.accx);
 #pragma unroll
   for (int k = 0; k < 4; k++) (a.q_plane[k] ? a.q_plane[k] : a.q)[(u64)k * M + nat] = bb_mul(accv.c[k], zi);
 }

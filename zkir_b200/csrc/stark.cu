@@ -253,6 +253,10 @@ __global__ void __launch_bounds__(128) query_kernel(QueryArgs a) {
   for (u32 k = threadIdx.x; k < a.width; k += blockDim.x) out[k] = row_mine ? a.lde[(u64)k * M + qrow] : 0u;
   out += a.width;
   copy_path(a.ttree, M, a.log_m, q, out, a.ttree_sl, owns(q, a.ttree_sl), top); out += a.log_m * 8;
+  // aux columns (LogUp helpers and running sum): columns [width, width + aux_width) of the same matrix, committed in their own tree
+  for (u32 k = threadIdx.x; k < a.aux_width; k += blockDim.x) out[k] = row_mine ? a.lde[(u64)(a.width + k) * M + qrow] : 0u;
+  out += a.aux_width;
+  if (a.aux_width) { copy_path(a.atree, M, a.log_m, q, out, a.atree_sl, owns(q, a.atree_sl), top); out += a.log_m * 8; }
   const bool qrow_mine = a.qlde_sl ? owns(q, a.qlde_sl) : top;
   for (u32 k = threadIdx.x; k < 8; k += blockDim.x) out[k] = qrow_mine ? a.qlde[(u64)k * M + qrow] : 0u;
   out += 8;

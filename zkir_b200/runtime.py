@@ -10,7 +10,7 @@ import ctypes as C
 from dataclasses import dataclass, field
 import numpy as np
 from . import _ffi
-from .air_layout import WIDTH, NUM_PUBLIC
+from .air_layout import WIDTH, NUM_PUBLIC, AUX_WIDTH, PUB_WIDTH, MIN_LOG_N
 
 P = 2013265921
 
@@ -30,6 +30,7 @@ class VMConfig:  # vm.rs:15-50
     enable_range_checking: bool = False
     enable_execution_trace: bool = False
     enable_deferred_model: bool = False
+    enable_poseidon2_syscall: bool = False   # not upstream: syscall 4 is a stub that errors there (crypto.rs:299-315)
 
 
 @dataclass
@@ -68,10 +69,15 @@ class TraceRow:  # zkir-spec/src/trace.rs:24-50 (bounds / register_states are ho
     memory_ops: list
 
 
+_HALT_KIND = {"Exit": 0, "Ebreak": 1, "CycleLimit": 2}
+
+
 class ExecutionResult:  # vm.rs:54-78
-    def __init__(self, handle, entry_point):
+    def __init__(self, handle, entry_point, program=None, wl_arrays=None):
         self._h = handle
         self._entry = entry_point
+        self.program = program
+        self._wl_arrays = wl_arrays   # write-log mode: the (pinned) arrays the interpreter recorded into
         l = _ffi.lib()
         self.cycles = l.zkir_vm_cycles(handle)
         n = l.zkir_vm_num_outputs(handle)
@@ -125,13 +131,21 @@ class ExecutionResult:  # vm.rs:54-78
             "final_regs": np.ctypeslib.as_array(l.zkir_vm_final_regs(self._h), shape=(16,)).copy(),
             "final_pc": l.zkir_vm_final_pc(self._h),
             "exit_code": self.halt_reason.code if self.halt_reason.kind == "Exit" else 0,
+            "halt_kind": _HALT_KIND[self.halt_reason.kind],
             "entry_point": self._entry,
+            "program": self.program,
         }
 
     def writelog(self, out=None):
         """Register write log of the recorded rows (zkir_vm_trace_writelog): dict(pcs u32[T], instrs u32[T], wlog u64[T], ...).
         `out` = optional dict of preallocated (pinned) arrays 'pcs', 'wlog'."""
         l = _ffi.lib()
+        if self._wl_arrays is not None:   # recorded directly by the interpreter (zkir_vm_run_writelog): nothing to convert
+            n = int(l.zkir_vm_logged_rows(self._h))
+            a = self._wl_arrays
+            return {"pcs": a["pcs"][:n], "instrs": a["instrs"][:n], "wlog": a["wlog"][:n], "final_pc": l.zkir_vm_final_pc(self._h),
+                    "exit_code": self.halt_reason.code if self.halt_reason.kind == "Exit" else 0,
+                    "halt_kind": _HALT_KIND[self.halt_reason.kind], "entry_point": self._entry, "program": self.program}
         n = l.zkir_vm_trace_len(self._h)
         pcs = out["pcs"] if out else np.empty(n, dtype=np.uint32)
         wlog = out["wlog"] if out else np.empty(n, dtype=np.uint64)
@@ -140,14 +154,15 @@ class ExecutionResult:  # vm.rs:54-78
         if rc != 0:
             raise RuntimeError_(rc, l.zkir_vm_last_error().decode())
         r = self.rows()
-        return {"pcs": pcs, "instrs": r["instrs"], "wlog": wlog, "final_pc": r["final_pc"], "exit_code": r["exit_code"], "entry_point": r["entry_point"]}
+        return {"pcs": pcs, "instrs": r["instrs"], "wlog": wlog, "final_pc": r["final_pc"], "exit_code": r["exit_code"],
+                "halt_kind": r["halt_kind"], "entry_point": r["entry_point"], "program": self.program}
 
     # ---- trace -> columns ("converter", trace.rs:41)
     def min_log_n(self):
         return _ffi.lib().zkir_pack_min_log_n(self._h)
 
     def pack(self, log_n=None, out=None):
-        """-> (cols[WIDTH][1<<log_n] uint32, public_values[4] uint32).  `out` may be a pinned buffer view."""
+        """-> (cols[WIDTH][1<<log_n] uint32, public_values[5] uint32).  `out` may be a pinned buffer view."""
         l = _ffi.lib()
         if log_n is None:
             log_n = self.min_log_n()
@@ -172,11 +187,33 @@ class VM:  # vm.rs:104-205
         data = (C.c_uint8 * max(1, len(self.program.data)))(*self.program.data)
         inp = (C.c_uint64 * max(1, len(self.inputs)))(*[v & (2**64 - 1) for v in self.inputs])
         h = C.c_void_p()
+        l.zkir_vm_enable_poseidon2(int(self.config.enable_poseidon2_syscall))
         rc = l.zkir_vm_run(code, len(self.program.code), data, len(self.program.data), self.program.entry_point,
                            inp, len(self.inputs), self.config.max_cycles, int(self.config.enable_execution_trace), C.byref(h))
         if rc != 0:
             raise RuntimeError_(rc, l.zkir_vm_last_error().decode())
-        return ExecutionResult(h, self.program.entry_point)
+        return ExecutionResult(h, self.program.entry_point, self.program)
+
+    def run_writelog(self, out=None):
+        """Run with the register write log recorded STRAIGHT into `out` = dict(pcs u32[cap], instrs u32[cap], wlog u64[cap])
+        (pinned arrays, e.g. PinnedBuffer.array) while the program executes: zkir_vm_run_writelog.  No per-cycle register
+        snapshot exists afterwards: `.writelog()` of the result returns views of the arrays."""
+        l = _ffi.lib()
+        cap = int(self.config.max_cycles) if out is None else int(out["pcs"].shape[0])
+        if out is None:
+            out = {"pcs": np.empty(cap, dtype=np.uint32), "instrs": np.empty(cap, dtype=np.uint32), "wlog": np.empty(cap, dtype=np.uint64)}
+        assert out["pcs"].dtype == np.uint32 and out["instrs"].dtype == np.uint32 and out["wlog"].dtype == np.uint64
+        code = (C.c_uint32 * max(1, len(self.program.code)))(*self.program.code)
+        data = (C.c_uint8 * max(1, len(self.program.data)))(*self.program.data)
+        inp = (C.c_uint64 * max(1, len(self.inputs)))(*[v & (2**64 - 1) for v in self.inputs])
+        h = C.c_void_p()
+        l.zkir_vm_enable_poseidon2(int(self.config.enable_poseidon2_syscall))
+        rc = l.zkir_vm_run_writelog(code, len(self.program.code), data, len(self.program.data), self.program.entry_point,
+                                    inp, len(self.inputs), self.config.max_cycles, out["pcs"].ctypes.data, out["instrs"].ctypes.data,
+                                    out["wlog"].ctypes.data, cap, C.byref(h))
+        if rc != 0:
+            raise RuntimeError_(rc, l.zkir_vm_last_error().decode())
+        return ExecutionResult(h, self.program.entry_point, self.program, wl_arrays=out)
 
 
 def run(program, inputs=()):  # zkir-runtime/src/lib.rs:59-62
@@ -191,6 +228,7 @@ class ProverConfig:
     pow_bits: int = 16
     max_cycles: int = (1 << 24) + 16
     device: int = 0
+    enable_poseidon2_syscall: bool = False
 
     def params(self):
         return _ffi.Params(self.log_blowup, self.num_queries, self.pow_bits, WIDTH, NUM_PUBLIC)
@@ -204,6 +242,7 @@ class Proof:
     cycles: int
     outputs: list = field(default_factory=list)
     stage_ms: dict = field(default_factory=dict)
+    program: object = None
 
 
 class Context:
@@ -226,6 +265,11 @@ class Context:
     def _check(self, rc):
         if rc != 0:
             raise RuntimeError_(rc, self._l.zkir_b200_last_error(self._h).decode())
+
+    def set_program(self, program):
+        """The program whose executions this context proves (zkir_b200_set_program): `Program` or a sequence of code words."""
+        code = np.ascontiguousarray(getattr(program, "code", program), dtype=np.uint32)
+        self._check(self._l.zkir_b200_set_program(self._h, code.ctypes.data, int(code.shape[0])))
 
     # -- device memory helpers
     def alloc(self, nbytes):
@@ -289,8 +333,11 @@ class Context:
         self._check(self._l.zkir_b200_emulate_shards(self._h, shards, min_segment_leaves))
 
     # -- hot path
-    def prove_columns(self, cols, public_values, cfg, device_resident=None):
-        """cols: host uint32 [WIDTH][2^log_n] (or `device_resident`: a device pointer with the same layout)."""
+    def prove_columns(self, cols, public_values, cfg, device_resident=None, program=None):
+        """cols: host uint32 [WIDTH][2^log_n] (or `device_resident`: a device pointer with the same layout).  `program`: sets the
+        context's program first (zkir_b200_set_program; a no-op when it is unchanged)."""
+        if program is not None:
+            self.set_program(program)
         params = cfg.params()
         pv = np.ascontiguousarray(public_values, dtype=np.uint32)
         proof, plen = C.c_void_p(), C.c_size_t()
@@ -307,8 +354,10 @@ class Context:
         self._l.zkir_b200_free_proof(proof)
         return out
 
-    def prove_batch(self, cols_list, pv_list, cfg):
-        """Independent proofs of many (small) traces: zkir_b200_prove_batch.  Returns the list of proof bytes."""
+    def prove_batch(self, cols_list, pv_list, cfg, program=None):
+        """Independent proofs of many (small) traces of ONE program: zkir_b200_prove_batch.  Returns the list of proof bytes."""
+        if program is not None:
+            self.set_program(program)
         n = len(cols_list)
         params = cfg.params()
         keep = [np.ascontiguousarray(c, dtype=np.uint32) for c in cols_list]
@@ -328,10 +377,12 @@ class Context:
     def prove_rows(self, rows, cfg, log_n=None):
         """rows: dict as returned by ExecutionResult.rows() (arrays may live in PinnedBuffers).  The device runs the
         converter; returns (proof bytes, public values)."""
+        if rows.get("program") is not None:
+            self.set_program(rows["program"])
         params = cfg.params()
         n = int(rows["pcs"].shape[0])
         if log_n is None:
-            log_n = max(2, (n - 1).bit_length())
+            log_n = max(MIN_LOG_N, (n - 1).bit_length())
         pcs, ins, regs = (np.ascontiguousarray(rows[k]) for k in ("pcs", "instrs", "regs"))
         assert pcs.dtype == np.uint64 and ins.dtype == np.uint32 and regs.dtype == np.uint64 and regs.shape == (n, 16)
         fr = np.ascontiguousarray(rows["final_regs"], dtype=np.uint64)
@@ -339,7 +390,7 @@ class Context:
         proof, plen = C.c_void_p(), C.c_size_t()
         rc = self._l.zkir_b200_prove_rows(self._h, C.byref(params), pcs.ctypes.data, ins.ctypes.data, regs.ctypes.data, n,
                                           fr.ctypes.data_as(_ffi.u64p), int(rows["final_pc"]), int(rows["entry_point"]), int(rows["exit_code"]),
-                                          log_n, pv.ctypes.data_as(_ffi.u32p), C.byref(proof), C.byref(plen))
+                                          int(rows["halt_kind"]), log_n, pv.ctypes.data_as(_ffi.u32p), C.byref(proof), C.byref(plen))
         self._check(rc)
         out = C.string_at(proof, plen.value)
         self._l.zkir_b200_free_proof(proof)
@@ -347,27 +398,53 @@ class Context:
 
     def prove_writelog(self, wl, cfg, log_n=None):
         """wl: dict as returned by ExecutionResult.writelog().  Returns (proof bytes, public values)."""
+        if wl.get("program") is not None:
+            self.set_program(wl["program"])
         params = cfg.params()
         n = int(wl["pcs"].shape[0])
         if log_n is None:
-            log_n = max(2, (n - 1).bit_length())
+            log_n = max(MIN_LOG_N, (n - 1).bit_length())
         pcs, ins, wlog = (np.ascontiguousarray(wl[k]) for k in ("pcs", "instrs", "wlog"))
         assert pcs.dtype == np.uint32 and ins.dtype == np.uint32 and wlog.dtype == np.uint64
         pv = np.zeros(NUM_PUBLIC, dtype=np.uint32)
         proof, plen = C.c_void_p(), C.c_size_t()
         rc = self._l.zkir_b200_prove_writelog(self._h, C.byref(params), pcs.ctypes.data, ins.ctypes.data, wlog.ctypes.data, n, int(wl["final_pc"]),
-                                              int(wl["entry_point"]), int(wl["exit_code"]), log_n, pv.ctypes.data_as(_ffi.u32p), C.byref(proof), C.byref(plen))
+                                              int(wl["entry_point"]), int(wl["exit_code"]), int(wl["halt_kind"]), log_n, pv.ctypes.data_as(_ffi.u32p),
+                                              C.byref(proof), C.byref(plen))
         self._check(rc)
         out = C.string_at(proof, plen.value)
         self._l.zkir_b200_free_proof(proof)
         return out, pv
 
+    def prove_program(self, program, inputs, cfg):
+        """Program -> Proof in one call (zkir_b200_prove_program): the interpreter records the write log into pinned memory and the
+        log is uploaded chunk by chunk while it runs.  Returns (proof bytes, public values, cycles, log_n)."""
+        params = cfg.params()
+        code = np.ascontiguousarray(program.code, dtype=np.uint32)
+        data = np.ascontiguousarray(list(program.data) or [0], dtype=np.uint8)
+        inp = np.ascontiguousarray([v & (2**64 - 1) for v in inputs] or [0], dtype=np.uint64)
+        pv = np.zeros(NUM_PUBLIC, dtype=np.uint32)
+        cycles, log_n = C.c_uint64(), C.c_uint32()
+        proof, plen = C.c_void_p(), C.c_size_t()
+        self._l.zkir_vm_enable_poseidon2(int(getattr(cfg, "enable_poseidon2_syscall", False)))
+        rc = self._l.zkir_b200_prove_program(self._h, C.byref(params), code.ctypes.data, int(code.shape[0]), data.ctypes.data, len(program.data),
+                                             program.entry_point, inp.ctypes.data, len(inputs), cfg.max_cycles, pv.ctypes.data_as(_ffi.u32p),
+                                             C.byref(cycles), C.byref(log_n), C.byref(proof), C.byref(plen))
+        self._check(rc)
+        out = C.string_at(proof, plen.value)
+        self._l.zkir_b200_free_proof(proof)
+        return out, pv, int(cycles.value), int(log_n.value)
+
     def expand_writelog(self, wl, log_n, d_cols):
+        if wl.get("program") is not None:
+            self.set_program(wl["program"])
         n = int(wl["pcs"].shape[0])
         pcs, ins, wlog = (np.ascontiguousarray(wl[k]) for k in ("pcs", "instrs", "wlog"))
         self._check(self._l.zkir_b200_expand_writelog(self._h, pcs.ctypes.data, ins.ctypes.data, wlog.ctypes.data, n, int(wl["final_pc"]), log_n, d_cols))
 
     def expand_rows(self, rows, log_n, d_cols):
+        if rows.get("program") is not None:
+            self.set_program(rows["program"])
         n = int(rows["pcs"].shape[0])
         pcs, ins, regs = (np.ascontiguousarray(rows[k]) for k in ("pcs", "instrs", "regs"))
         fr = np.ascontiguousarray(rows["final_regs"], dtype=np.uint64)
@@ -389,11 +466,17 @@ class Context:
         self._check(self._l.zkir_b200_merkle_commit(self._h, d_matrix, n_cols, log_rows, d_tree, root.ctypes.data_as(_ffi.u32p)))
         return root
 
-    def quotient(self, cfg, d_lde, log_n, public_values, alpha, d_q):
+    def quotient(self, cfg, d_lde, d_publde, log_n, public_values, lookup, alpha, d_q):
         params = cfg.params()
         pv = np.ascontiguousarray(public_values, dtype=np.uint32)
         al = np.ascontiguousarray(alpha, dtype=np.uint32)
-        self._check(self._l.zkir_b200_quotient(self._h, C.byref(params), d_lde, log_n, pv.ctypes.data_as(_ffi.u32p), al.ctypes.data_as(_ffi.u32p), d_q))
+        lk = np.ascontiguousarray(lookup, dtype=np.uint32)
+        self._check(self._l.zkir_b200_quotient(self._h, C.byref(params), d_lde, d_publde, log_n, pv.ctypes.data_as(_ffi.u32p), lk.ctypes.data_as(_ffi.u32p),
+                                               al.ctypes.data_as(_ffi.u32p), d_q))
+
+    def aux_columns(self, d_trace, log_n, lookup, d_aux):
+        lk = np.ascontiguousarray(lookup, dtype=np.uint32)
+        self._check(self._l.zkir_b200_aux_columns(self._h, d_trace, log_n, lk.ctypes.data_as(_ffi.u32p), d_aux))
 
     def fri_fold(self, d_in, d_out, log_n, shift, beta):
         b = np.ascontiguousarray(beta, dtype=np.uint32)
@@ -432,24 +515,28 @@ def _ctx(device):
 
 
 def prove(program, inputs=(), cfg=None):
-    """Program -> Proof: run the interpreter with trace recording, pack the rows into columns, prove on the GPU.
-    The drop-in the north star describes for `zkir_runtime::prove()` (absent upstream: lib.rs:29-62)."""
+    """Program -> Proof: run the interpreter with the register write log recorded as it executes, rebuild + convert the rows on
+    the GPU, prove.  The drop-in the north star describes for `zkir_runtime::prove()` (absent upstream: lib.rs:29-62)."""
     cfg = cfg or ProverConfig()
-    res = VM(program, inputs, VMConfig(max_cycles=cfg.max_cycles, enable_execution_trace=True)).run()
     ctx = _ctx(cfg.device)
-    log_n = res.min_log_n()
-    pb, pv = ctx.prove_writelog(res.writelog(), cfg, log_n)   # 16 B/row over PCIe, registers rebuilt + converter on the device
-    return Proof(pb, pv, log_n, res.cycles, res.outputs, ctx.stage_ms())
+    pb, pv, cycles, log_n = ctx.prove_program(program, list(inputs), cfg)
+    return Proof(pb, pv, log_n, cycles, [], ctx.stage_ms(), program)
 
 
-def verify(proof, cfg=None, public_values=None):
-    """CPU verification through the C ABI; returns (ok, reason)."""
+def verify(proof, cfg=None, public_values=None, program=None):
+    """CPU verification through the C ABI; returns (ok, reason).  `program` (Program or code words) is the statement's program;
+    a `Proof` returned by prove() carries it."""
     cfg = cfg or ProverConfig()
     l = _ffi.lib()
     pb = proof.bytes_ if isinstance(proof, Proof) else bytes(proof)
     pv = public_values if public_values is not None else (proof.public_values if isinstance(proof, Proof) else None)
+    if program is None and isinstance(proof, Proof):
+        program = proof.program
+    if program is None:
+        return False, "verify() needs the program the proof is about"
+    code = np.ascontiguousarray(getattr(program, "code", program), dtype=np.uint32)
     params = cfg.params()
     buf = C.create_string_buffer(pb, len(pb))
     pvp = np.ascontiguousarray(pv, dtype=np.uint32).ctypes.data_as(_ffi.u32p) if pv is not None else None
-    rc = l.zkir_b200_verify(C.byref(params), C.cast(buf, C.c_void_p), len(pb), pvp)
+    rc = l.zkir_b200_verify(C.byref(params), C.cast(buf, C.c_void_p), len(pb), pvp, code.ctypes.data, int(code.shape[0]))
     return rc == 0, ("" if rc == 0 else l.zkir_b200_last_error(None).decode())
