@@ -152,6 +152,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--fib-n", type=int, default=FIB_N_FULL)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--only-headline", action="store_true", help="skip the sections for BASELINE configs 3, 4 and 5")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -311,11 +312,79 @@ def main():
         ctx.ntt(d_ntt, ntt_cols, ntt_log)
     ntt_ms = ctx.timer_stop() / reps
     ctx.free(d_ntt)
+    ctx.free(d_trace)
+
+    # ---------------- Program -> Proof in ONE call (zkir_b200_prove_program): the interpreter records the register write log into
+    # pinned memory while it runs, chunks are uploaded during the run, then rebuild + convert + prove.  Same proof bytes required.
+    from zkir_b200.workloads import fib_program_input
+    cfg_prog = zkir_b200.ProverConfig(max_cycles=cycles + 16)
+    for _ in range(2):
+        pb_prog, pv_prog, cyc_prog, ln_prog = ctx.prove_program(fib_program_input(), [args.fib_n], cfg_prog)
+    if pb_prog != pb or cyc_prog != cycles or list(pv_prog) != list(pv):
+        raise SystemExit("zkir_b200_prove_program and the step-by-step path disagree")
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ctx.prove_program(fib_program_input(), [args.fib_n], cfg_prog)
+    barrier()
+    prog_ms = (time.perf_counter() - t0) * 1e3
+    prog_stage = ctx.stage_ms()
+
+    # ---------------- the other BASELINE configs, a few repetitions each (skipped with --only-headline)
+    extra = {}
+    if not args.only_headline:
+        from zkir_b200.workloads import pos2_program, pos2_cycles, POS2_ITERS_FULL, add_program
+        # config 3: SYS_POSEIDON2 loop, 2^18 - 1 permutations, 16 cycles each -> 2^22 rows.  The interpreter executes the permutations
+        # (host); the AIR constrains the syscall row as a register write only (no memory argument / hash chip yet: docs/PROVER_SPEC.md 3.5)
+        cfg3 = zkir_b200.ProverConfig(max_cycles=pos2_cycles(POS2_ITERS_FULL) + 16, enable_poseidon2_syscall=True)
+        p3 = pos2_program()
+        pb3, pv3, cyc3, ln3 = ctx.prove_program(p3, [POS2_ITERS_FULL], cfg3)
+        ok3, why3 = zkir_b200.verify(pb3, cfg3, pv3, p3)
+        if not ok3 or cyc3 != pos2_cycles(POS2_ITERS_FULL):
+            raise SystemExit(f"config 3 proof rejected: {why3}")
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(2):
+            ctx.prove_program(p3, [POS2_ITERS_FULL], cfg3)
+        barrier()
+        c3_ms = (time.perf_counter() - t0) * 1e3 / 2
+        c3_stage = ctx.stage_ms()
+        vm = zkir_b200.VM(p3, [POS2_ITERS_FULL], zkir_b200.VMConfig(max_cycles=cfg3.max_cycles, enable_poseidon2_syscall=True))
+        t0 = time.perf_counter(); vm.run(); c3_vm_s = time.perf_counter() - t0
+        extra["config3_poseidon2_loop"] = {
+            "workload": f"SYS_POSEIDON2 loop, {POS2_ITERS_FULL} permutations x 16 cycles = {cyc3} cycles -> 2^{ln3}-row trace, per GPU",
+            "program_to_proof_ms": c3_ms, "value": world * cyc3 / (c3_ms * 1e-3), "unit": UNIT, "interpreter_only_s": c3_vm_s,
+            "proof_stage_ms": {k: v for k, v in c3_stage.items() if k != "h2d"}, "proof_ms": sum(v for k, v in c3_stage.items() if k != "h2d"),
+            "note": "Program -> Proof wall time; the interpreter (host, one thread) executes the permutations and dominates; the syscall is constrained as a register write only"}
+        # config 4: a + b, 11 cycles -> 2^10 rows, 4096 independent proofs over all GPUs (zkir_b200_prove_batch: 8 worker contexts per GPU)
+        n4 = 4096 // world
+        pa = add_program()
+        ctx.set_program(pa)
+        traces = []
+        for i in range(n4):
+            g = rank * n4 + i
+            r4 = zkir_b200.VM(pa, [g, 2 * g + 1], zkir_b200.VMConfig(enable_execution_trace=True)).run()
+            traces.append(r4.pack())
+        cfg4 = zkir_b200.ProverConfig()
+        ctx.prove_batch([c for c, _ in traces[:64]], [q for _, q in traces[:64]], cfg4)     # warm: worker contexts, tables, graphs
+        barrier()
+        t0 = time.perf_counter()
+        out4 = ctx.prove_batch([c for c, _ in traces], [q for _, q in traces], cfg4)
+        barrier()
+        c4_ms = (time.perf_counter() - t0) * 1e3
+        for i in (0, n4 // 2, n4 - 1):
+            ok4, why4 = zkir_b200.verify(out4[i], cfg4, traces[i][1], pa)
+            if not ok4:
+                raise SystemExit(f"config 4 proof {i} rejected: {why4}")
+        extra["config4_add_batch"] = {"workload": f"a + b (11 cycles -> 2^10 rows), 4096 independent proofs over {world} GPU(s), {n4} per GPU", "batch_ms": c4_ms,
+                                      "proofs_per_s": 4096 / (c4_ms * 1e-3), "proof_bytes": len(out4[0])}
+        ctx.set_program(res.program)
+        del traces, out4
 
     # ---------------- N > 1 only: ONE proof sharded over the N GPUs (BASELINE config 5 mode; the headline `value` stays N
     # independent proofs).  Collective zkir_b200_prove_writelog from pinned host memory: column-sharded LDE with NVLink row
     # scatter, row-sharded hashing / quotient / DEEP, NCCL for segment roots and query pieces.  Same proof bytes required.
-    shard_ms, shard_stage, shard_sha = 0.0, {}, None
+    shard_ms, shard_stage, shard_sha, shard24, shard24_ms = 0.0, {}, None, None, 0.0
     if dist is not None:
         import hashlib
         ctx.comm_init()
@@ -338,13 +407,44 @@ def main():
         barrier()
         shard_ms = (time.perf_counter() - t0) * 1e3
         shard_stage = ctx.stage_ms()
+        if world == 8 and not args.only_headline:
+            # config 5: ONE 2^24-row trace sharded over the 8 GPUs (fibonacci n = 3355443: 16_777_213 cycles), Program -> log on the
+            # host once (outside the timed region), then collective zkir_b200_prove_writelog from pinned memory
+            n24 = 3355443
+            vm24 = zkir_b200.VM(fib_program_input(), [n24], zkir_b200.VMConfig(max_cycles=1 << 24))
+            T24 = 5 * n24 - 2
+            pins = {"pcs": zkir_b200.PinnedBuffer((1 << 24,), np.uint32), "instrs": zkir_b200.PinnedBuffer((1 << 24,), np.uint32), "wlog": zkir_b200.PinnedBuffer((1 << 24,), np.uint64)}
+            r24 = vm24.run_writelog({k: v.array for k, v in pins.items()})
+            wl24 = r24.writelog()
+            pb24, pv24 = ctx.prove_writelog(wl24, cfg, 24)
+            ok24, why24 = zkir_b200.verify(pb24, cfg, pv24, res.program) if rank == 0 else (True, "")
+            sha24 = hashlib.sha256(pb24).hexdigest()
+            shas = [None] * world
+            dist.all_gather_object(shas, sha24)
+            if not ok24 or len(set(shas)) != 1 or r24.cycles != T24:
+                raise SystemExit(f"[rank {rank}] config 5: sharded 2^24 proof rejected or ranks disagree: {why24} {shas}")
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(2):
+                ctx.prove_writelog(wl24, cfg, 24)
+            barrier()
+            shard24_ms = (time.perf_counter() - t0) * 1e3 / 2
+            shard24 = {"workload": f"fibonacci n={n24}: {T24} cycles -> ONE 2^24-row trace row/column-sharded over 8 GPUs", "cycles": T24, "unit": UNIT,
+                       "stage_ms_rank0": ctx.stage_ms(), "proof_sha256_all_ranks": sha24, "verifier": "accepted (rank 0)", "proof_bytes": len(pb24)}
+            del pins, wl24
         ctx.comm_shutdown()
 
     # max over ranks
-    vals = torch.tensor([dev_ms, wall_ms, e2e_ms, e2e_rows_ms, pipe_ms, shard_ms, pipe_e2e_ms, vm_s], dtype=torch.float64, device="cuda")
+    c3v = extra.get("config3_poseidon2_loop", {}).get("program_to_proof_ms", 0.0)
+    c4v = extra.get("config4_add_batch", {}).get("batch_ms", 0.0)
+    vals = torch.tensor([dev_ms, wall_ms, e2e_ms, e2e_rows_ms, pipe_ms, shard_ms, pipe_e2e_ms, vm_s, prog_ms, c3v, c4v, shard24_ms], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(vals, op=dist.ReduceOp.MAX)
-    dev_ms, wall_ms, e2e_ms, e2e_rows_ms, pipe_ms, shard_ms, pipe_e2e_ms, vm_s = [float(x) for x in vals.tolist()]
+    dev_ms, wall_ms, e2e_ms, e2e_rows_ms, pipe_ms, shard_ms, pipe_e2e_ms, vm_s, prog_ms, c3v, c4v, shard24_ms = [float(x) for x in vals.tolist()]
+    if "config3_poseidon2_loop" in extra:
+        extra["config3_poseidon2_loop"].update(program_to_proof_ms=c3v, value=world * pos2_cycles(POS2_ITERS_FULL) / (c3v * 1e-3))
+    if "config4_add_batch" in extra:
+        extra["config4_add_batch"].update(batch_ms=c4v, proofs_per_s=4096 / (c4v * 1e-3))
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -372,8 +472,10 @@ def main():
         "e2e": {"value": world * cycles / (e2e_ms / K * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms / K,
                 "h2d_bytes_per_step": wl_bytes, "d2h_bytes_per_step": proof_bytes, "h2d_and_convert_ms": e2e_stage["h2d"],
                 "api": "zkir_b200_prove_writelog: the interpreter's register write log (pc, word, reg<<56|value) in pinned host memory -> proof bytes in host memory",
-                "including_vm": {"value": world * cycles / (vm_s + e2e_ms / K * 1e-3), "unit": UNIT, "vm_seconds": vm_s,
-                                 "note": "Program -> Proof: interpreter run with trace recording (host, one thread) + the end-to-end proof, back to back, no overlap"},
+                "program_to_proof": {"value": world * cycles / (prog_ms / K * 1e-3), "unit": UNIT, "ms_per_step": prog_ms / K, "h2d_and_convert_ms": prog_stage.get("h2d"),
+                                     "api": "zkir_b200_prove_program: Program + inputs -> proof bytes; the interpreter (host, one thread) records the write log into pinned memory, chunks are uploaded while it runs",
+                                     "note": "cycles/s INCLUDING the interpreter run (SURVEY.md 8d: 'also report including VM')"},
+                "interpreter": {"full_rows_seconds": vm_s, "note": "VM::run with the reference's full TraceRow recording (pc, word, 16 registers per cycle), for comparison"},
                 "full_rows": {"value": world * cycles / (e2e_rows_ms / K * 1e-3), "ms_per_step": e2e_rows_ms / K, "h2d_bytes_per_step": rows_bytes,
                               "api": "zkir_b200_prove_rows: TraceRow data as recorded upstream (pc, word, regs[16])"}},
         "pipelined": {"in_flight_per_gpu": 2, "value": world * 2 * K * cycles / (pipe_ms * 1e-3), "unit": UNIT, "ms_per_proof": pipe_ms / (2 * K),
@@ -398,6 +500,9 @@ def main():
             "proof_bytes_identical_to_single_gpu": True, "identity_check": "enforced on every rank before timing (bytes == single-GPU proof, verifier accepts; a mismatch exits non-zero)",
             "proof_sha256": shard_sha, "stage_ms_rank0": shard_stage, "h2d_bytes_per_step_per_gpu": wl_bytes // world,
             "api": "zkir_b200_comm_init + collective zkir_b200_prove_writelog (end to end from pinned host memory, max over ranks)"}
+    out.update(extra)
+    if shard24 is not None:
+        out["config5_sharded_2p24"] = dict(shard24, ms_per_proof=shard24_ms, value=shard24["cycles"] / (shard24_ms * 1e-3))
     if not args.no_cpu_baseline:
         r = cpu_oracle_run(args.fib_n, 1, 0)    # the same workload, proved once (about 10 s on 16 host threads)
         out["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",

@@ -67,3 +67,25 @@ def timed_fib_trace(n_input):
     t1 = time.perf_counter()
     cols, pv = res.pack(None)
     return res, cols, pv, t1 - t0, time.perf_counter() - t1
+
+
+# BASELINE config 3: a loop of SYS_POSEIDON2 over a 16-word state in guest memory, 16 cycles per iteration
+# (syscall 4 in R10, state address in R11, output address in R13: syscall.rs:18-24,140-149)
+POS2_ITER_CYCLES = 16
+POS2_SRC = ("addi r10, r0, 1\necall\nadd r3, r10, r0\n"            # iterations from the input tape
+            "addi r11, r0, 0x2000\naddi r13, r0, 0x2000\naddi r4, r0, 0\n"
+            "addi r10, r0, 4\necall\naddi r4, r4, 1\n"               # loop body: permute the state in place, count
+            + "add r5, r5, r4\n" * 12 +
+            "bne r4, r3, -60\n"
+            "add r10, r0, r0\nadd r11, r5, r0\necall\n")
+POS2_SETUP_CYCLES = 6 + 3
+POS2_ITERS_FULL = (1 << 18) - 1     # 16 * (2^18 - 1) + 9 = 4_194_297 cycles -> 2^22 rows
+
+
+def pos2_program():
+    from . import assemble
+    return assemble(POS2_SRC)
+
+
+def pos2_cycles(iters):
+    return POS2_ITER_CYCLES * iters + POS2_SETUP_CYCLES
