@@ -1,10 +1,19 @@
 #!/bin/bash
-# GPU-box script: ncu --set full of the hot kernels of ONE proof (the second one, caches and tables warm) + launch list.
+# GPU-box script: launch list of one proof and of the bench command, and ncu --set full of the hot kernels of ONE proof (the second
+# one, caches and tables warm).  The .ncu-rep files are summarised ON THE BOX (markdown table + the raw metric csv) and then deleted:
+# gpurun only brings back 64 MiB.
 # usage: bash tools/gpu_profile_round.sh <tag>
 TAG=${1:-prof}
 mkdir -p gpurun_out
 set -x
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_$TAG.csv python tools/prove_once.py 2 > gpurun_out/prove_once_$TAG.log 2>&1
-ncu --set full --clock-control none --import-source on -k "regex:leaf_hash_kernel|dft_tile_kernel|quotient_kernel|open_partial_kernel|deep_kernel|trace_expand" -s 16 -c 18 -o gpurun_out/${TAG}_hot python tools/prove_once.py 2 > gpurun_out/ncu_hot_$TAG.log 2>&1
-ncu --set full --clock-control none --import-source on -k "regex:compress_kernel|leaf_hash_pairs_kernel|merkle_coop_kernel" -s 58 -c 12 -o gpurun_out/${TAG}_tree python tools/prove_once.py 2 > gpurun_out/ncu_tree_$TAG.log 2>&1
+ncu --set full --clock-control none --import-source on -k "regex:leaf_hash_kernel|dft_tile_kernel|quotient_kernel|open_partial_kernel|deep_kernel|aux_rows_kernel|scan_write_kernel" -s 22 -c 22 -o gpurun_out/${TAG}_hot python tools/prove_once.py 2 > gpurun_out/ncu_hot_$TAG.log 2>&1
+ncu --set full --clock-control none --import-source on -k "regex:compress_kernel|leaf_hash_pairs_kernel|merkle_coop_kernel|fri_fold_kernel" -s 80 -c 14 -o gpurun_out/${TAG}_tree python tools/prove_once.py 2 > gpurun_out/ncu_tree_$TAG.log 2>&1
+for r in hot tree; do
+  python tools/ncu_summary.py gpurun_out/${TAG}_$r.ncu-rep > gpurun_out/ncu_${r}_$TAG.md
+  ncu -i gpurun_out/${TAG}_$r.ncu-rep --page raw --csv > gpurun_out/ncu_${r}_${TAG}_raw.csv
+  rm -f gpurun_out/${TAG}_$r.ncu-rep
+done
 tail -2 gpurun_out/prove_once_$TAG.log
+ncu --metrics gpu__time_duration.sum --clock-control none -c 500 --csv --log-file gpurun_out/bench_launches_$TAG.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline --only-headline > gpurun_out/bench_under_ncu_$TAG.log 2>&1
+du -sh gpurun_out

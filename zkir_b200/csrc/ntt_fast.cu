@@ -20,6 +20,7 @@
 // Algorithmic bytes: 8*N*C per transform, 4*N*C*(1+B) per LDE.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <map>
 #include <utility>
 #include <vector>
@@ -106,7 +107,10 @@ struct TileShape {
 
 // PEER: the fused row redistribution of a sharded LDE (TileParams::peer); a separate instantiation so that the ordinary kernels
 // keep their code and register allocation.
-template <int LOG_R, int MODE, bool INV, int LOG_S, bool PEER = false>
+// PROBE (tools/ntt_probe.py, ZKIR_NTT_PROBE): measurement-only instantiations of the 2^10 tiles that split the pass into its two
+// floors -- 1 = memory only (same loads, tables and stores, no arithmetic, no exchange), 2 = arithmetic only (no global loads or
+// table reads; the store is predicated on a value that never occurs).  Their results are garbage by construction.
+template <int LOG_R, int MODE, bool INV, int LOG_S, bool PEER = false, int PROBE = 0>
 __global__ void __launch_bounds__(TileShape<LOG_R, MODE>::NT, (LOG_R >= 10 ? 2 : (LOG_R >= 8 ? 4 : 8)))
 dft_tile_kernel(const TileParams p) {
   typedef TileShape<LOG_R, MODE> SH;
@@ -132,18 +136,24 @@ dft_tile_kernel(const TileParams p) {
   u32 x[EA];
   {
     const u32* pin = in + in_thr;
+    if constexpr (PROBE == 2) {
 #pragma unroll
-    for (int i = 0; i < EA; i++) x[i] = pin[i * in_step];
+      for (int i = 0; i < EA; i++) x[i] = tid * 2654435761u + i * 40503u + p.tiles_b;
+    } else {
+#pragma unroll
+      for (int i = 0; i < EA; i++) x[i] = pin[i * in_step];
+    }
     if (p.in_tab) {
       const uint2* __restrict__ pt = p.in_tab + (u64)z * p.in_tab_z + (in_thr & p.in_tab_mask);
 #pragma unroll
       for (int i = 0; i < EA; i++) {
+        if constexpr (PROBE == 2) { x[i] = shoup_mul(x[i], 0x12345u + i, c_shoup(0x12345u) + tid); continue; }
         const uint2 tw = __ldg(pt + i * in_step);
-        x[i] = shoup_mul(x[i], tw.x, tw.y);
+        if constexpr (PROBE == 1) x[i] ^= tw.x + tw.y; else x[i] = shoup_mul(x[i], tw.x, tw.y);
       }
     }
   }
-  dft_regs<A, INV>(x);
+  if constexpr (PROBE != 1) dft_regs<A, INV>(x);
 
   // ---- store of output index k = ks + EA * kq (kq compile-time), lanes per mode
   const u32 out_k = MODE == 1 ? 1u : (MODE == 0 ? in_r : p.out_k);
@@ -168,6 +178,13 @@ dft_tile_kernel(const TileParams p) {
     }
     u32* po = out + (out_off0 + thr);
     const size_t kstep = (size_t)KSTEP * out_k;
+    if constexpr (PROBE == 2) {   // arithmetic only: keep the values alive, never store
+      u32 acc = 0;
+#pragma unroll
+      for (int j = 0; j < CNT; j++) acc ^= p.out_tab ? shoup_mul(y[j], 0x54321u + j, c_shoup(0x54321u) + lane) : y[j];
+      if (acc == 0xdeadbeefu && p.tiles_per_col == 0xffffffffu) po[0] = acc;
+      return;
+    }
     if constexpr (PEER) {
       // fused redistribution: digit index k = ks + KSTEP*brev(j) decides the owner of the row; (out_off0 + thr) < stride never carries
       const size_t moff = (size_t)(po - p.out);
@@ -192,7 +209,7 @@ dft_tile_kernel(const TileParams p) {
 #pragma unroll
       for (int j = 0; j < CNT; j++) {
         const uint2 tw = __ldg(pt + brev<LC>(j) * kstep);
-        po[brev<LC>(j) * kstep] = shoup_mul(y[j], tw.x, tw.y);
+        if constexpr (PROBE == 1) po[brev<LC>(j) * kstep] = y[j] ^ (tw.x + tw.y); else po[brev<LC>(j) * kstep] = shoup_mul(y[j], tw.x, tw.y);
       }
     } else {
 #pragma unroll
@@ -202,6 +219,17 @@ dft_tile_kernel(const TileParams p) {
 
   if constexpr (B_ == 0) {
     store_group(0u, l, x, std::integral_constant<int, A>{});
+  } else if constexpr (PROBE == 1) {
+    // memory only: every thread stores XB-sized groups of the values it loaded at the addresses the real kernel writes
+    u32 u, l2;
+    if constexpr (MODE == 1) { u = tid & (XB - 1); l2 = tid >> B_; } else { l2 = tid & 15u; u = tid >> 4; }
+#pragma unroll
+    for (int g = 0; g < EA / XB; g++) {
+      u32 y[XB];
+#pragma unroll
+      for (int j = 0; j < XB; j++) y[j] = x[(g * XB + j) % EA];
+      store_group(u + g * XB, l2, y, std::integral_constant<int, B_>{});
+    }
   } else {
     // ---- inter-round twiddle + exchange.  Shared-memory word of (ks, q, lane):
     //  MODE 0: line (q*EA/2 + ks/2) of 32 words, half ((ks^q)&1), lane           -> two thread bases + immediates
@@ -223,8 +251,8 @@ dft_tile_kernel(const TileParams p) {
       const u32 ks = brev<A>(i);
       u32 v = x[i];
       if (ks != 0) {
-        const uint2 tw = __ldg(twq + ks * XB);
-        v = shoup_mul(v, tw.x, tw.y);
+        if constexpr (PROBE == 2) v = shoup_mul(v, 0x777u + ks, c_shoup(0x777u) + q);
+        else { const uint2 tw = __ldg(twq + ks * XB); v = shoup_mul(v, tw.x, tw.y); }
       }
       if constexpr (MODE == 0) sm[((ks & 1u) ? w1 : w0) + (ks >> 1) * 32] = v;
       else if constexpr (MODE == 1) sm[w0 + ks * (XB + 1)] = v;
@@ -255,11 +283,11 @@ dft_tile_kernel(const TileParams p) {
   }
 }
 
-template <int LOG_R, int MODE, bool INV, int LOG_S = -1, bool PEER = false>
+template <int LOG_R, int MODE, bool INV, int LOG_S = -1, bool PEER = false, int PROBE = 0>
 static cudaError_t launch_tile_t(const TileParams& p, u32 blocks, u32 z, cudaStream_t st) {
   typedef TileShape<LOG_R, MODE> SH;
   const size_t smem = (size_t)SH::SMEM_WORDS * sizeof(u32);
-  auto kern = dft_tile_kernel<LOG_R, MODE, INV, LOG_S, PEER>;
+  auto kern = dft_tile_kernel<LOG_R, MODE, INV, LOG_S, PEER, PROBE>;
   if (smem > 48 * 1024) {  // per device and cheap: set it on every launch rather than caching a process-wide flag
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -287,6 +315,12 @@ static cudaError_t launch_tile_m(int log_r, const TileParams& p, u32 blocks, u32
     }
   }
   // hot shape of a 2^20-row trace (digits 10+10): strided digit with a compile-time stride of 2^10
+  static const int probe = getenv("ZKIR_NTT_PROBE") ? atoi(getenv("ZKIR_NTT_PROBE")) : 0;   // measurement only, see dft_tile_kernel
+  if (probe && log_r == 10 && MODE != 2) {
+    if (MODE == 0 && p.in_r == 1024u)
+      return probe == 1 ? launch_tile_t<10, MODE, INV, (MODE == 0 ? 10 : -1), false, 1>(p, blocks, z, st) : launch_tile_t<10, MODE, INV, (MODE == 0 ? 10 : -1), false, 2>(p, blocks, z, st);
+    if (MODE == 1) return probe == 1 ? launch_tile_t<10, MODE, INV, -1, false, 1>(p, blocks, z, st) : launch_tile_t<10, MODE, INV, -1, false, 2>(p, blocks, z, st);
+  }
   if (MODE == 0 && log_r == 10 && p.in_r == 1024u) return launch_tile_t<10, MODE, INV, (MODE == 0 ? 10 : -1)>(p, blocks, z, st);
   switch (log_r) {
     case 1: return launch_tile_t<1, MODE, INV>(p, blocks, z, st);

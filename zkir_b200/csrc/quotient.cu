@@ -121,12 +121,14 @@ int launch_quotient(const QuotientArgs& a, cudaStream_t st, u64* launches) {
   const u32 snn = hpow(ZKIR_BB_GEN, 1ull << a.log_n);
   const u32 wb = ZKIR_BB_ROOTS[a.log_blowup];
   static int variant = -1;
-  if (variant < 0) { const char* e = getenv("ZKIR_QUOTIENT_VARIANT"); variant = e ? atoi(e) : 0; }  // 72-column AIR: 128 registers (4 CTAs/SM) measured fastest: 0.49 / 0.50 / 0.53 ms for variants 0 / 1 / 2
+  // AIR v2 (169 constraints, ext4 LogUp terms): 168 registers / 3 CTAs per SM measured fastest: 1.05 / 1.09 / 1.14 ms for variants 3 / 0 / 1 at 2^20 rows
+  if (variant < 0) { const char* e = getenv("ZKIR_QUOTIENT_VARIANT"); variant = e ? atoi(e) : 3; }
   const u64 n_threads = a.seg_log_nj == 0xffffffffu ? M : (1ull << (a.seg_log_nj + a.log_blowup));
   const unsigned grid = (unsigned)((n_threads + 127) / 128);
   const E4* ap = reinterpret_cast<const E4*>(a.apow_scratch);
   const u32 m_ginv = bb_to_mont_c(g_inv), m_g = bb_to_mont_c(g), m_snn = bb_to_mont_c(snn), m_wb = bb_to_mont_c(wb);
-  if (variant == 1) quotient_kernel<6><<<grid, 128, 0, st>>>(a, ap, m_ginv, m_g, m_snn, m_wb);
+  if (variant == 3) quotient_kernel<3><<<grid, 128, 0, st>>>(a, ap, m_ginv, m_g, m_snn, m_wb);
+  else if (variant == 1) quotient_kernel<6><<<grid, 128, 0, st>>>(a, ap, m_ginv, m_g, m_snn, m_wb);
   else if (variant == 2) quotient_kernel<8><<<grid, 128, 0, st>>>(a, ap, m_ginv, m_g, m_snn, m_wb);
   else quotient_kernel<4><<<grid, 128, 0, st>>>(a, ap, m_ginv, m_g, m_snn, m_wb);
   (*launches) += 2;
