@@ -310,7 +310,7 @@ static void program_digest(const u32* code, size_t n_code, u32* digest) {
 }
 
 struct Params { u32 log_blowup, num_queries, pow_bits, width, num_public; };
-static const u32 PROOF_MAGIC = 0x5A4B5052u, PROOF_VERSION = 4u;
+static const u32 PROOF_MAGIC = 0x5A4B5052u, PROOF_VERSION = 5u;
 static const size_t AW = ZKIR_AIR_AUX_WIDTH, PW = ZKIR_AIR_PUB_WIDTH;
 
 // FRI rounds (docs/PROVER_SPEC.md section 4.6): log_n / 3 rounds that fold by 8, then one that folds by 2^(log_n mod 3) if that is > 1
@@ -319,7 +319,8 @@ static u32 fri_log_arity(u32 log_n, size_t t) { return t < log_n / 3 ? 3 : log_n
 static size_t proof_words(const Params& p, u32 log_n) {
   size_t lg = log_n + p.log_blowup, W = p.width, WA = W + AW, R = fri_rounds(log_n);
   size_t n = 8 + p.num_public + 24 + (2 * WA + 8) * 4 + R * 8 + 4 + 1;
-  size_t perq = W + lg * 8 + AW + lg * 8 + 8 + lg * 8;
+  const size_t lr = (size_t)2 << p.log_blowup, depth = lg - (p.log_blowup + 1);   // rows per Merkle leaf of the LDE matrices, tree depth
+  size_t perq = lr * (W + AW + 8) + 3 * depth * 8;
   size_t ll = lg;  // log2 of the layer length
   for (size_t t = 0; t < R; t++) { const u32 la = fri_log_arity(log_n, t); perq += (4u << la) + (ll - la) * 8; ll -= la; }
   return n + perq * p.num_queries;
@@ -354,6 +355,21 @@ static void quotient_evals(const Params& p, u32 log_n, const u32* lde, const u32
     acc = e4_mulb(acc, zh_inv);
     for (int k = 0; k < 4; k++) out[k * M + i] = acc.c[k];
   }
+}
+
+// Merkle commitment of an LDE matrix (columns [c0, c0 + nc) of `mat`, column stride M): leaf m = hash of the 2*B consecutive
+// natural-order rows m*2B .. m*2B + 2B - 1 concatenated (docs/PROVER_SPEC.md section 4.1); returns the tree ((2*M/2B - 1) * 8 words)
+static std::vector<u32> commit_matrix(const u32* mat, size_t M, size_t nc, u32 log_blowup) {
+  const size_t lr = (size_t)2 << log_blowup, leaves = M / lr;
+  std::vector<u32> tree((2 * leaves - 1) * 8);
+#pragma omp parallel for
+  for (size_t m = 0; m < leaves; m++) {
+    std::vector<u32> buf(lr * nc);
+    for (size_t r = 0; r < lr; r++) for (size_t k = 0; k < nc; k++) buf[r * nc + k] = mat[k * M + m * lr + r];
+    hash_elems(buf.data(), buf.size(), &tree[m * 8]);
+  }
+  merkle_build(tree.data(), leaves);
+  return tree;
 }
 
 struct Dump {  // optional intermediates for stage-by-stage parity tests
@@ -392,14 +408,8 @@ static int prove(const Params& p, const u32* trace, u32 log_n, const u32* pv, co
       coset_eval(c.data(), N, &publde[(k - W) * M], lg, shift);
     }
   }
-  std::vector<u32> ttree((2 * M - 1) * 8);
-#pragma omp parallel for
-  for (size_t i = 0; i < M; i++) {
-    u32 row[ZKIR_AIR_WIDTH];
-    for (size_t k = 0; k < W; k++) row[k] = lde[k * M + i];
-    hash_elems(row, W, &ttree[i * 8]);
-  }
-  merkle_build(ttree.data(), M);
+  const size_t LR = (size_t)2 << p.log_blowup, LEAVES = M / LR;
+  std::vector<u32> ttree = commit_matrix(lde.data(), M, W, p.log_blowup);
   Chal ch;
   ch.observe(log_n); ch.observe(p.width); ch.observe((u32)AW); ch.observe(p.log_blowup); ch.observe(p.num_queries); ch.observe(p.pow_bits);
   ch.observe(p.num_public);
@@ -409,8 +419,8 @@ static int prove(const Params& p, const u32* trace, u32 log_n, const u32* pv, co
     program_digest(code, n_code, pd);
     ch.observe_n(pd, 8);
   }
-  ch.observe_n(merkle_root(ttree.data(), M), 8);
-  memcpy(out, merkle_root(ttree.data(), M), 32); out += 8;
+  ch.observe_n(merkle_root(ttree.data(), LEAVES), 8);
+  memcpy(out, merkle_root(ttree.data(), LEAVES), 32); out += 8;
 
   // ---- 1b. lookup challenges, aux columns (LogUp helpers and running sum), their LDE and commitment
   E4 lz = ch.sample_ext(), ltheta = ch.sample_ext();
@@ -427,16 +437,9 @@ static int prove(const Params& p, const u32* trace, u32 log_n, const u32* pv, co
     }
   }
   if (dump && dump->lde) memcpy(dump->lde, lde.data(), WA * M * 4);
-  std::vector<u32> atree((2 * M - 1) * 8);
-#pragma omp parallel for
-  for (size_t i = 0; i < M; i++) {
-    u32 row[ZKIR_AIR_AUX_WIDTH];
-    for (size_t k = 0; k < AW; k++) row[k] = lde[(W + k) * M + i];
-    hash_elems(row, AW, &atree[i * 8]);
-  }
-  merkle_build(atree.data(), M);
-  ch.observe_n(merkle_root(atree.data(), M), 8);
-  memcpy(out, merkle_root(atree.data(), M), 32); out += 8;
+  std::vector<u32> atree = commit_matrix(lde.data() + W * M, M, AW, p.log_blowup);
+  ch.observe_n(merkle_root(atree.data(), LEAVES), 8);
+  memcpy(out, merkle_root(atree.data(), LEAVES), 32); out += 8;
   u32* quot_root_slot = out; out += 8;
 
   // ---- 2. quotient
@@ -457,16 +460,9 @@ static int prove(const Params& p, const u32* trace, u32 log_n, const u32* pv, co
   }
 #pragma omp parallel for
   for (int k = 0; k < 8; k++) coset_eval(&qcoef[k * N], N, &qlde[k * M], lg, shift);
-  std::vector<u32> qtree((2 * M - 1) * 8);
-#pragma omp parallel for
-  for (size_t i = 0; i < M; i++) {
-    u32 row[8];
-    for (int k = 0; k < 8; k++) row[k] = qlde[k * M + i];
-    hash_elems(row, 8, &qtree[i * 8]);
-  }
-  merkle_build(qtree.data(), M);
-  ch.observe_n(merkle_root(qtree.data(), M), 8);
-  memcpy(quot_root_slot, merkle_root(qtree.data(), M), 32);
+  std::vector<u32> qtree = commit_matrix(qlde.data(), M, 8, p.log_blowup);
+  ch.observe_n(merkle_root(qtree.data(), LEAVES), 8);
+  memcpy(quot_root_slot, merkle_root(qtree.data(), LEAVES), 32);
 
   // ---- 3. out-of-domain openings (Horner on coefficients)
   E4 zeta = ch.sample_ext();
@@ -588,12 +584,13 @@ static int prove(const Params& p, const u32* trace, u32 log_n, const u32* pv, co
   // ---- 7. queries
   for (u32 qi = 0; qi < p.num_queries; qi++) {
     size_t idx = ch.sample_bits(lg);
-    for (size_t k = 0; k < W; k++) *out++ = lde[k * M + idx];
-    merkle_path(ttree.data(), M, idx, out); out += lg * 8;
-    for (size_t k = 0; k < AW; k++) *out++ = lde[(W + k) * M + idx];
-    merkle_path(atree.data(), M, idx, out); out += lg * 8;
-    for (int k = 0; k < 8; k++) *out++ = qlde[k * M + idx];
-    merkle_path(qtree.data(), M, idx, out); out += lg * 8;
+    const size_t leaf = idx / LR, depth = lg - (p.log_blowup + 1);   // the whole leaf is opened: its 2*B rows, natural order
+    for (size_t r = 0; r < LR; r++) for (size_t k = 0; k < W; k++) *out++ = lde[k * M + leaf * LR + r];
+    merkle_path(ttree.data(), LEAVES, leaf, out); out += depth * 8;
+    for (size_t r = 0; r < LR; r++) for (size_t k = 0; k < AW; k++) *out++ = lde[(W + k) * M + leaf * LR + r];
+    merkle_path(atree.data(), LEAVES, leaf, out); out += depth * 8;
+    for (size_t r = 0; r < LR; r++) for (int k = 0; k < 8; k++) *out++ = qlde[k * M + leaf * LR + r];
+    merkle_path(qtree.data(), LEAVES, leaf, out); out += depth * 8;
     size_t i = idx;
     int ql = lg;
     for (size_t t = 0; t < R; t++) {

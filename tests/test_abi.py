@@ -33,7 +33,7 @@ def test_proof_size_is_shape_only():
     p = cfg.params()
     s8, s20 = _ffi.lib().zkir_b200_proof_size(C.byref(p), 10), _ffi.lib().zkir_b200_proof_size(C.byref(p), 20)
     assert s8 % 4 == 0 and s20 > s8
-    assert s20 == 538248   # 2^20 rows, 100 queries, 88 main + 16 aux columns, 6 fold-by-8 + 1 fold-by-4 FRI rounds: the size bench.py reports as d2h_bytes_per_step
+    assert s20 == 653448   # 2^20 rows, 100 queries, 88 main + 16 aux columns, 4-row leaves, 6 fold-by-8 + 1 fold-by-4 FRI rounds: the size bench.py reports as d2h_bytes_per_step
 
 
 def test_no_cpu_fallback_without_gpu():

@@ -196,7 +196,7 @@ bool verify(const zkir_params* p, const u32* w, size_t nwords, const u32* pv_in,
   if (!p || !w) return fail("null argument");
   if (p->width != ZKIR_AIR_WIDTH || p->num_public != ZKIR_AIR_NUM_PUBLIC || p->log_blowup < 1) return fail("unsupported params");
   if (nwords < 8) return fail("proof too short");
-  if (w[0] != 0x5A4B5052u || w[1] != 4) return fail("bad magic/version");
+  if (w[0] != 0x5A4B5052u || w[1] != 5) return fail("bad magic/version");
   if (!code && n_code) return fail("null program");
   const u32 log_n = w[2];
   if (w[3] != p->width || w[4] != p->log_blowup || w[5] != p->num_queries || w[6] != p->pow_bits || w[7] != p->num_public)
@@ -300,19 +300,24 @@ bool verify(const zkir_params* p, const u32* w, size_t nwords, const u32* pv_in,
   const u32 wM = ZKIR_BB_ROOTS[lg], half = inv(2);
   for (u32 qi = 0; qi < p->num_queries; qi++) {
     const u64 idx = ch.bits(lg);
-    const u32* trow = q; q += W;
-    const u32* tpath = q; q += 8 * lg;
-    const u32* arow = q; q += AW;
-    const u32* apath = q; q += 8 * lg;
-    const u32* qrow = q; q += QW;
-    const u32* qpath = q; q += 8 * lg;
+    // a matrix leaf holds LR = 2*B consecutive natural-order rows: all of them are opened, row idx mod LR is the queried one
+    const u32 LR = 2u << p->log_blowup, depth = lg - (p->log_blowup + 1);
+    const u64 leaf = idx / LR;
+    const u32 sub = (u32)(idx % LR);
+    const u32* trows = q; q += LR * W;
+    const u32* tpath = q; q += 8 * depth;
+    const u32* arows = q; q += LR * AW;
+    const u32* apath = q; q += 8 * depth;
+    const u32* qrows = q; q += LR * QW;
+    const u32* qpath = q; q += 8 * depth;
+    const u32 *trow = trows + sub * W, *arow = arows + sub * AW, *qrow = qrows + sub * QW;
     u32 d[8];
-    hash_n(trow, W, d);
-    if (!check_path(d, idx, tpath, lg, troot)) return fail("trace Merkle path");
-    hash_n(arow, AW, d);
-    if (!check_path(d, idx, apath, lg, aroot)) return fail("aux Merkle path");
-    hash_n(qrow, QW, d);
-    if (!check_path(d, idx, qpath, lg, qroot)) return fail("quotient Merkle path");
+    hash_n(trows, LR * W, d);
+    if (!check_path(d, leaf, tpath, depth, troot)) return fail("trace Merkle path");
+    hash_n(arows, LR * AW, d);
+    if (!check_path(d, leaf, apath, depth, aroot)) return fail("aux Merkle path");
+    hash_n(qrows, LR * QW, d);
+    if (!check_path(d, leaf, qpath, depth, qroot)) return fail("quotient Merkle path");
     const u32 x = mul(ZKIR_BB_GEN, pw(wM, idx));
     X4 rt, rq, iz, igz;
     for (u32 k = 0; k < W; k++) rt = rt + scale(afp[k], trow[k]);

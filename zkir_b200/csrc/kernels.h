@@ -52,6 +52,9 @@ int launch_permute(u32* d_states, u64 n, bool canonical_io, cudaStream_t st, u64
 // first_leaf / seg_leaves != 0: only that range of (natural-order) leaves, for a proof sharded over several GPUs
 int launch_leaf_hash(const u32* mat, u64 col_stride, u32 n_cols, u64 n_rows, u32 log_b, u32* digests, cudaStream_t st, u64* launches,
                      u64 first_leaf = 0, u64 seg_leaves = 0);
+// the prover's leaves: 2*B consecutive natural-order rows per leaf (two adjacent trace points on all cosets); leaves [first, first + n)
+int launch_leaf_hash_rows(const u32* mat, u64 col_stride, u32 n_cols, u32 log_n, u32 log_b, u32* digests, cudaStream_t st, u64* launches,
+                          u64 first_leaf, u64 n_leaves);
 // optional fused Fiat-Shamir step on the root: copy to root_dst, observe, sample n_sample elements into sample_out
 // pair_layer != nullptr: the leaves are FRI leaves hash(f[i] || f[i + n_leaves]) of that ext4 layer and are computed here too
 int launch_merkle_levels(u32* tree, u64 n_leaves, cudaStream_t st, u64* launches, ChalState* chal = nullptr, u32* root_dst = nullptr,
@@ -158,6 +161,7 @@ int launch_fri_fold(const E4* in, E4* out, u64 h, const u32* beta_dev, const u32
 struct QueryArgs {
   const u32* indices;   // device [num_queries], canonical
   u32 num_queries, log_m, width, log_n;   // lde / qlde rows are coset-major, trees and layers natural
+  u32 log_lr = 0;                          // a matrix leaf holds 2^log_lr consecutive natural rows; all of them are opened
   u32 aux_width = 0; const u32* atree = nullptr; u32 atree_sl = 0;   // aux columns = columns [width, width + aux_width) of lde, own tree
   const u32* lde; const u32* ttree;
   const u32* qlde; const u32* qtree;

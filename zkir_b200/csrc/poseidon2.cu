@@ -157,6 +157,32 @@ __global__ void __launch_bounds__(128) leaf_hash_kernel(const u32* __restrict__ 
   d[1] = make_uint4(s[4], s[5], s[6], s[7]);
 }
 
+// Prover leaves (docs/PROVER_SPEC.md section 4.1): leaf m = hash of the 2*B consecutive natural-order rows m*2B .. m*2B + 2B - 1 of a
+// coset-major matrix, i.e. the points j = 2m, 2m + 1 of the trace domain on all B cosets, concatenated (n_cols is a multiple of 8, so a
+// sponge block never straddles two rows).  One thread per leaf: 2*B*n_cols/8 dependent permutations, a quarter of the tree above it.
+__global__ void __launch_bounds__(128) leaf_hash_rows_kernel(const u32* __restrict__ mat, u64 col_stride, u32 n_cols, u32 log_n, u32 log_b,
+                                                             u64 first, u64 count, u32* __restrict__ digests) {
+  const u64 t = blockIdx.x * (u64)blockDim.x + threadIdx.x;
+  if (t >= count) return;
+  const u64 m = first + t;
+  u32 s[16];
+#pragma unroll
+  for (int k = 0; k < 16; k++) s[k] = 0;
+  const u32 rows = 2u << log_b;
+  for (u32 r = 0; r < rows; r++) {
+    const u64 j = 2 * m + (r >> log_b), z = r & ((1u << log_b) - 1);
+    const u32* p = mat + (z << log_n) + j;
+    for (u32 c = 0; c < n_cols; c += 8) {
+#pragma unroll
+      for (int k = 0; k < 8; k++) s[k] = __ldg(p + (u64)(c + k) * col_stride);
+      poseidon2_permute(s);
+    }
+  }
+  uint4* d = reinterpret_cast<uint4*>(digests + 8 * m);
+  d[0] = make_uint4(s[0], s[1], s[2], s[3]);
+  d[1] = make_uint4(s[4], s[5], s[6], s[7]);
+}
+
 // FRI layer leaves: leaf i = hash(F[i] || F[i+q] || ... || F[i+(arity-1)q]) over the q leaves of a layer of arity*q ext4 values:
 // arity/2 absorptions of the overwrite-mode sponge (8 words each)
 __global__ void __launch_bounds__(128) leaf_hash_pairs_kernel(const uint4* __restrict__ layer, u64 q, u64 first, u64 count, u32 arity,
@@ -228,6 +254,13 @@ int launch_leaf_hash(const u32* mat, u64 col_stride, u32 n_cols, u64 n_rows, u32
     while ((1ull << log_ni) < (seg_leaves >> log_b)) log_ni++;
   }
   leaf_hash_kernel<<<nblk(n_threads, 128), 128, 0, st>>>(mat, col_stride, n_cols, n_threads, log_nc, log_b, log_ni, i0, digests);
+  (*launches)++;
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+int launch_leaf_hash_rows(const u32* mat, u64 col_stride, u32 n_cols, u32 log_n, u32 log_b, u32* digests, cudaStream_t st, u64* launches,
+                          u64 first_leaf, u64 n_leaves) {
+  if (n_cols % 8 || log_n < 1) return -1;
+  leaf_hash_rows_kernel<<<nblk(n_leaves, 128), 128, 0, st>>>(mat, col_stride, n_cols, log_n, log_b, first_leaf, n_leaves, digests);
   (*launches)++;
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }

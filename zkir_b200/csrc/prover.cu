@@ -387,18 +387,21 @@ static int commit_tree(zkir_ctx* ctx, const u32* mat, u32 n_cols, u32 log_b, con
   cudaStream_t st = ctx->stream;
   u64* LC = &ctx->launches;
   Workspace& w = ctx->ws;
+  // `mat`: n_leaves = M / 2B leaves of 2*B natural rows each (launch_leaf_hash_rows); log_n_mat = log2 of the points per coset
   const u64 G = ctx->shards, seg = n_leaves / (G ? G : 1);
   u64 min_seg = ctx->shard_min_seg;
-  if (mat && min_seg < (1ull << log_b)) min_seg = 1ull << log_b;
   if (min_seg < 2) min_seg = 2;
+  u32 log_n_mat = 1;   // N = 2 * n_leaves points per coset
+  if (mat) while ((1ull << log_n_mat) < 2 * n_leaves) log_n_mat++;
+  const u64 col_stride = mat ? ((1ull << log_n_mat) << log_b) : 0;
   *shard_levels = 0;
-  if (G <= 1 || mode == 0 || (mode < 0 && seg < min_seg)) {
-    if (mat) RC(launch_leaf_hash(mat, n_leaves, n_cols, n_leaves, log_b, tree, st, LC));
+  if (G <= 1 || mode == 0 || (mode < 0 && seg < min_seg) || seg < 1) {
+    if (mat) RC(launch_leaf_hash_rows(mat, col_stride, n_cols, log_n_mat, log_b, tree, st, LC, 0, n_leaves));
     RC(launch_merkle_levels(tree, n_leaves, st, LC, w.chal, root_dst, sample_out, n_sample, pair_layer, 0, 0, leaf_arity));
     return 0;
   }
   for (u32 g = ctx->shard_lo; g < ctx->shard_hi; g++) {
-    if (mat) RC(launch_leaf_hash(mat, n_leaves, n_cols, n_leaves, log_b, tree, st, LC, g * seg, seg));
+    if (mat) RC(launch_leaf_hash_rows(mat, col_stride, n_cols, log_n_mat, log_b, tree, st, LC, g * seg, seg));
     RC(launch_merkle_levels(tree, n_leaves, st, LC, nullptr, nullptr, nullptr, 0, pair_layer, g * seg, seg, leaf_arity));
   }
   u32 ls = 0;
@@ -534,7 +537,7 @@ static int prove_resident(zkir_ctx* ctx, const zkir_params* p, u32 log_n, const 
   u32 t_sl = 0, a_sl = 0, q_sl = 0;
   int crc;
   RC(launch_challenger(w.chal, c_hdr, HDR_WORDS + np + 8, nullptr, 0, 0, st, LC));   // header, public values, program digest
-  if ((crc = commit_tree(ctx, w.lde, (u32)W, p->log_blowup, nullptr, w.ttree, M, w.proof + L.troot, c_lookup, 8, &t_sl, sp.on ? 1 : 0)) != 0) return crc;  // root -> proof, observe, sample z and theta
+  if ((crc = commit_tree(ctx, w.lde, (u32)W, p->log_blowup, nullptr, w.ttree, M >> L.log_lr, w.proof + L.troot, c_lookup, 8, &t_sl, sp.on ? 1 : 0)) != 0) return crc;  // root -> proof, observe, sample z and theta
   // ---- 2b. LogUp aux columns for the challenges just drawn (aux_gen.cu), their LDE and their own commitment
   CU(cudaEventRecord(ctx->ev[ZKIR_STAGE_AUX], st));
   {
@@ -561,7 +564,7 @@ static int prove_resident(zkir_ctx* ctx, const zkir_params* p, u32 log_n, const 
       RC(fast_intt(ctx->fast, w.plan_n, w.aux, N, w.coef + W * N, N, AW, c0a, nullptr, 32, 0, 0, nullptr, 0, st));
       RC(fast_coset_ntt(ctx->fast, w.plan_n, w.coef + W * N, N, w.lde + W * M, M, AW, B, shift, ZKIR_BB_ROOTS[log_m], 1u, st));
     }
-    if ((crc = commit_tree(ctx, w.lde + W * M, AW, p->log_blowup, nullptr, w.atree, M, w.proof + L.aroot, c_alpha, 4, &a_sl, sp.on ? 1 : 0)) != 0) return crc;  // root -> proof, observe, sample alpha
+    if ((crc = commit_tree(ctx, w.lde + W * M, AW, p->log_blowup, nullptr, w.atree, M >> L.log_lr, w.proof + L.aroot, c_alpha, 4, &a_sl, sp.on ? 1 : 0)) != 0) return crc;  // root -> proof, observe, sample alpha
   }
   // ---- 3. quotient
   CU(cudaEventRecord(ctx->ev[ZKIR_STAGE_QUOTIENT], st));
@@ -610,7 +613,7 @@ static int prove_resident(zkir_ctx* ctx, const zkir_params* p, u32 log_n, const 
       RC(fast_coset_ntt(ctx->fast, w.plan_chunk, w.qcoef, N, w.qlde, M, QW, B, shift, ZKIR_BB_ROOTS[log_m], 1u, st));
     }
   }
-  if ((crc = commit_tree(ctx, w.qlde, QW, p->log_blowup, nullptr, w.qtree, M, w.proof + L.qroot, c_zeta, 4, &q_sl, sp.on ? 1 : -1)) != 0) return crc;  // root -> proof, observe, sample zeta
+  if ((crc = commit_tree(ctx, w.qlde, QW, p->log_blowup, nullptr, w.qtree, M >> L.log_lr, w.proof + L.qroot, c_zeta, 4, &q_sl, sp.on ? 1 : -1)) != 0) return crc;  // root -> proof, observe, sample zeta
   // ---- 4. openings at zeta and g*zeta, evaluated on the shifted coefficients at zeta/shift
   CU(cudaEventRecord(ctx->ev[ZKIR_STAGE_OPENINGS], st));
   {
@@ -689,7 +692,7 @@ static int prove_resident(zkir_ctx* ctx, const zkir_params* p, u32 log_n, const 
     QueryArgs qa;
     qa.indices = w.indices; qa.num_queries = p->num_queries; qa.log_m = log_m; qa.width = (u32)W; qa.log_n = log_n;
     qa.lde = w.lde; qa.ttree = w.ttree; qa.qlde = w.qlde; qa.qtree = w.qtree;
-    qa.aux_width = AW; qa.atree = w.atree; qa.atree_sl = a_sl;
+    qa.aux_width = AW; qa.atree = w.atree; qa.atree_sl = a_sl; qa.log_lr = L.log_lr;
     qa.layers = w.d_layers; qa.ltrees = w.d_ltrees; qa.fold8_rounds = log_n / 3; qa.last_log_arity = log_n % 3; qa.fri_rounds = (u32)L.R; qa.out = w.proof + L.queries; qa.words_per_query = (u32)L.per_query;
     // sharded trees: the bottom path levels of a leaf exist only on its owner; every rank writes the pieces it owns (zeros
     // elsewhere, rank 0 also everything that is replicated) and one all-reduce assembles the query section ("query gather")

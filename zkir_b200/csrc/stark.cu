@@ -245,22 +245,25 @@ __global__ void __launch_bounds__(128) query_kernel(QueryArgs a) {
   const u64 M = 1ull << a.log_m;
   const u64 q = a.indices[qi];
   const u32 log_b = a.log_m - a.log_n;
-  const u64 qrow = ((q & ((1ull << log_b) - 1)) << a.log_n) | (q >> log_b);  // memory row of natural index q
   const bool top = a.shard_lo == 0;  // replicated data is contributed by the context that owns segment 0
   auto owns = [&](u64 leaf, u32 sl) { const u64 o = leaf >> sl; return sl == 0 ? top : (o >= a.shard_lo && o < a.shard_hi); };
   u32* out = a.out + (u64)qi * a.words_per_query;
-  const bool row_mine = a.lde_sl ? owns(q, a.lde_sl) : top;
-  for (u32 k = threadIdx.x; k < a.width; k += blockDim.x) out[k] = row_mine ? a.lde[(u64)k * M + qrow] : 0u;
-  out += a.width;
-  copy_path(a.ttree, M, a.log_m, q, out, a.ttree_sl, owns(q, a.ttree_sl), top); out += a.log_m * 8;
+  // matrix trees: leaf m = q >> log_lr holds 2^log_lr consecutive natural rows, all opened in natural order
+  const u64 m = q >> a.log_lr, leaves = M >> a.log_lr;
+  const u32 lr = 1u << a.log_lr, depth = a.log_m - a.log_lr;
+  auto mrow = [&](u32 r) { const u64 nat = (m << a.log_lr) + r; return ((nat & ((1ull << log_b) - 1)) << a.log_n) | (nat >> log_b); };
+  const bool row_mine = a.lde_sl ? owns(m, a.lde_sl) : top;
+  for (u32 k = threadIdx.x; k < lr * a.width; k += blockDim.x) out[k] = row_mine ? a.lde[(u64)(k % a.width) * M + mrow(k / a.width)] : 0u;
+  out += lr * a.width;
+  copy_path(a.ttree, leaves, depth, m, out, a.ttree_sl, owns(m, a.ttree_sl), top); out += depth * 8;
   // aux columns (LogUp helpers and running sum): columns [width, width + aux_width) of the same matrix, committed in their own tree
-  for (u32 k = threadIdx.x; k < a.aux_width; k += blockDim.x) out[k] = row_mine ? a.lde[(u64)(a.width + k) * M + qrow] : 0u;
-  out += a.aux_width;
-  if (a.aux_width) { copy_path(a.atree, M, a.log_m, q, out, a.atree_sl, owns(q, a.atree_sl), top); out += a.log_m * 8; }
-  const bool qrow_mine = a.qlde_sl ? owns(q, a.qlde_sl) : top;
-  for (u32 k = threadIdx.x; k < 8; k += blockDim.x) out[k] = qrow_mine ? a.qlde[(u64)k * M + qrow] : 0u;
-  out += 8;
-  copy_path(a.qtree, M, a.log_m, q, out, a.qtree_sl, owns(q, a.qtree_sl), top); out += a.log_m * 8;
+  for (u32 k = threadIdx.x; k < lr * a.aux_width; k += blockDim.x) out[k] = row_mine ? a.lde[(u64)(a.width + k % a.aux_width) * M + mrow(k / a.aux_width)] : 0u;
+  out += lr * a.aux_width;
+  if (a.aux_width) { copy_path(a.atree, leaves, depth, m, out, a.atree_sl, owns(m, a.atree_sl), top); out += depth * 8; }
+  const bool qrow_mine = a.qlde_sl ? owns(m, a.qlde_sl) : top;
+  for (u32 k = threadIdx.x; k < lr * 8; k += blockDim.x) out[k] = qrow_mine ? a.qlde[(u64)(k & 7) * M + mrow(k >> 3)] : 0u;
+  out += lr * 8;
+  copy_path(a.qtree, leaves, depth, m, out, a.qtree_sl, owns(m, a.qtree_sl), top); out += depth * 8;
   u32 level = 0;
   for (u32 t = 0; t < a.fri_rounds; t++) {
     const u32 la = t < a.fold8_rounds ? 3 : a.last_log_arity;  // log2 of the fold arity of this round
