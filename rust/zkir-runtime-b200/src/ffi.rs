@@ -18,8 +18,12 @@ pub struct zkir_params {
 }
 
 pub const ZKIR_OK: c_int = 0;
-pub const ZKIR_AIR_V1_WIDTH: u32 = 72;
-pub const ZKIR_AIR_V1_NUM_PUBLIC: u32 = 4;
+pub const ZKIR_AIR_V2_WIDTH: u32 = 88;
+pub const ZKIR_AIR_V2_NUM_PUBLIC: u32 = 5; // entry_pc, num_cycles, exit_lo, exit_hi, halted
+pub const ZKIR_MIN_LOG_N: u32 = 10;
+pub const ZKIR_HALT_EXIT: c_int = 0;
+pub const ZKIR_HALT_EBREAK: c_int = 1;
+pub const ZKIR_HALT_CYCLE_LIMIT: c_int = 2;
 
 extern "C" {
     pub fn zkir_b200_create(out: *mut *mut zkir_ctx, device_id: c_int) -> c_int;
@@ -27,6 +31,26 @@ extern "C" {
     pub fn zkir_b200_last_error(ctx: *const zkir_ctx) -> *const c_char;
     pub fn zkir_b200_alloc_pinned(bytes: usize) -> *mut c_void;
     pub fn zkir_b200_free_pinned(p: *mut c_void);
+    /// the program whose executions the context proves: `Program.code` (zkir-spec/src/program.rs:241-250); ROM of the lookup argument
+    pub fn zkir_b200_set_program(ctx: *mut zkir_ctx, code: *const u32, n_code: usize) -> c_int;
+    /// Program + inputs -> proof in one call (the library's own interpreter restatement records the write log into pinned memory)
+    pub fn zkir_b200_prove_program(
+        ctx: *mut zkir_ctx,
+        params: *const zkir_params,
+        code: *const u32,
+        n_code: usize,
+        data: *const u8,
+        n_data: usize,
+        entry_point: u32,
+        inputs: *const u64,
+        n_inputs: usize,
+        max_cycles: u64,
+        public_values_out: *mut u32, // [5]
+        out_cycles: *mut u64,
+        out_log_n: *mut u32,
+        proof: *mut *mut u8,
+        proof_len: *mut usize,
+    ) -> c_int;
     pub fn zkir_b200_prove(
         ctx: *mut zkir_ctx,
         params: *const zkir_params,
@@ -48,8 +72,9 @@ extern "C" {
         final_pc: u64,
         entry_point: u32,
         exit_code: u64,
+        halt_kind: c_int, // ZKIR_HALT_*
         log_n: u32,
-        public_values_out: *mut u32, // [4]
+        public_values_out: *mut u32, // [5]
         proof: *mut *mut u8,
         proof_len: *mut usize,
     ) -> c_int;
@@ -65,8 +90,9 @@ extern "C" {
         final_pc: u64,
         entry_point: u32,
         exit_code: u64,
+        halt_kind: c_int, // ZKIR_HALT_*
         log_n: u32,
-        public_values_out: *mut u32, // [4]
+        public_values_out: *mut u32, // [5]
         proof: *mut *mut u8,
         proof_len: *mut usize,
     ) -> c_int;
@@ -76,5 +102,5 @@ extern "C" {
     pub fn zkir_b200_comm_init(ctx: *mut zkir_ctx, id: *const u8 /* [128] */, rank: c_int, world: c_int) -> c_int;
     pub fn zkir_b200_comm_shutdown(ctx: *mut zkir_ctx) -> c_int;
     pub fn zkir_b200_free_proof(p: *mut u8);
-    pub fn zkir_b200_verify(params: *const zkir_params, proof: *const u8, len: usize, public_values: *const u32) -> c_int;
+    pub fn zkir_b200_verify(params: *const zkir_params, proof: *const u8, len: usize, public_values: *const u32, code: *const u32, n_code: usize) -> c_int;
 }

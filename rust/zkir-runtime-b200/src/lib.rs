@@ -1,9 +1,10 @@
 //! `prove()` / `verify()` next to `zkir_runtime::run()` (zkir-runtime/src/lib.rs:59-62), backed by libzkir_b200.so.
 //!
 //! SOURCE ONLY: the build image has no Rust toolchain, so this file has never been compiled; it is the
-//! binding a zkir-runtime maintainer would add.  The interpreter stays the upstream Rust one: the
-//! only thing this crate does with an execution is copy `TraceRow.pc / instruction / registers` (zkir-spec/src/trace.rs:24-50)
-//! into page-locked arrays and hand them to the C ABI of include/zkir_b200.h.  Nothing here computes a proof on the CPU.
+//! binding a zkir-runtime maintainer would add.  The interpreter stays the upstream Rust one: it
+//! appends a register write log (pc, instruction word, (reg << 56) | value per cycle) to page-locked arrays through a two-line
+//! hook in `VMState::write_reg` (zkir-runtime/src/state.rs:87-91), and this crate hands the arrays and the program to the C ABI
+//! of include/zkir_b200.h.  Nothing here computes a proof on the CPU.
 pub mod ffi;
 
 use std::ffi::CStr;
@@ -36,17 +37,18 @@ impl ProverConfig {
             log_blowup: self.log_blowup,
             num_queries: self.num_queries,
             pow_bits: self.pow_bits,
-            width: ffi::ZKIR_AIR_V1_WIDTH,
-            num_public: ffi::ZKIR_AIR_V1_NUM_PUBLIC,
+            width: ffi::ZKIR_AIR_V2_WIDTH,
+            num_public: ffi::ZKIR_AIR_V2_NUM_PUBLIC,
         }
     }
 }
 
-/// Proof bytes (docs/PROVER_SPEC.md section 5) with the public values they bind: `[entry_pc, num_cycles, exit_lo, exit_hi]`.
+/// Proof bytes (docs/PROVER_SPEC.md section 5) with the public values they bind: `[entry_pc, num_cycles, exit_lo, exit_hi, halted]`.
+/// The program is part of the statement but not of the bytes: `verify` takes it.
 #[derive(Clone, Debug)]
 pub struct Proof {
     pub bytes: Vec<u8>,
-    pub public_values: [u32; 4],
+    pub public_values: [u32; 5],
     pub log_n: u32,
     pub cycles: u64,
     pub outputs: Vec<u64>,
@@ -122,42 +124,31 @@ impl Prover {
         if rc != ffi::ZKIR_OK { Err(error_of(ptr::null(), rc)) } else { Ok(id) }
     }
 
-    /// Packed columns in (`[72][1 << log_n]`, column-major canonical values, host memory): `zkir_b200_prove`.
-    pub fn prove_columns(&mut self, cfg: &ProverConfig, cols: &[u32], log_n: u32, pv: &[u32; 4]) -> Result<Vec<u8>, RuntimeError> {
-        assert_eq!(cols.len(), (ffi::ZKIR_AIR_V1_WIDTH as usize) << log_n);
-        let params = cfg.params();
-        let (mut proof, mut len) = (ptr::null_mut::<u8>(), 0usize);
-        let rc = unsafe { ffi::zkir_b200_prove(self.ctx, &params, cols.as_ptr(), log_n, pv.as_ptr(), &mut proof, &mut len) };
-        if rc != ffi::ZKIR_OK {
-            return Err(error_of(self.ctx, rc));
-        }
-        let bytes = unsafe { std::slice::from_raw_parts(proof, len) }.to_vec();
-        unsafe { ffi::zkir_b200_free_proof(proof) };
-        Ok(bytes)
+    /// The program whose executions this context proves (`zkir_b200_set_program`): every executed (pc, instruction) is bound to it.
+    pub fn set_program(&mut self, code: &[u32]) -> Result<(), RuntimeError> {
+        let rc = unsafe { ffi::zkir_b200_set_program(self.ctx, code.as_ptr(), code.len()) };
+        if rc != ffi::ZKIR_OK { Err(error_of(self.ctx, rc)) } else { Ok(()) }
     }
 
-    /// Raw rows in, proof bytes out: the converter (zkir-spec/src/trace.rs:41, absent upstream) runs on the device.
+    /// Register write log in (16 B per cycle, pinned), proof bytes out: the device rebuilds the pre-state registers of every row
+    /// with a last-writer scan and runs the converter (zkir-spec/src/trace.rs:41, absent upstream).
     #[allow(clippy::too_many_arguments)]
-    pub fn prove_rows(
+    pub fn prove_writelog(
         &mut self,
         cfg: &ProverConfig,
-        pcs: &Pinned<u64>,
-        instrs: &Pinned<u32>,
-        regs: &Pinned<u64>, // [n_rows][16], PRE-state (zkir-runtime/src/vm.rs:245-253)
-        n_rows: u64,
-        final_regs: &[u64; 16],
-        final_pc: u64,
+        log: &WriteLog,
         entry_point: u32,
         exit_code: u64,
+        halt_kind: c_int,
         log_n: u32,
-    ) -> Result<(Vec<u8>, [u32; 4]), RuntimeError> {
+    ) -> Result<(Vec<u8>, [u32; 5]), RuntimeError> {
         let params = cfg.params();
-        let mut pv = [0u32; 4];
+        let mut pv = [0u32; 5];
         let (mut proof, mut len) = (ptr::null_mut::<u8>(), 0usize);
         let rc = unsafe {
-            ffi::zkir_b200_prove_rows(
-                self.ctx, &params, pcs.as_ptr(), instrs.as_ptr(), regs.as_ptr(), n_rows, final_regs.as_ptr(), final_pc,
-                entry_point, exit_code, log_n, pv.as_mut_ptr(), &mut proof, &mut len,
+            ffi::zkir_b200_prove_writelog(
+                self.ctx, &params, log.pcs.as_ptr(), log.instrs.as_ptr(), log.wlog.as_ptr(), log.len as u64, log.final_pc,
+                entry_point, exit_code, halt_kind, log_n, pv.as_mut_ptr(), &mut proof, &mut len,
             )
         };
         if rc != ffi::ZKIR_OK {
@@ -169,47 +160,69 @@ impl Prover {
     }
 }
 
+/// The recorder the interpreter writes into while it executes: three page-locked arrays, one entry per cycle.
+/// Upstream hook: `VMState::write_reg` stores `cur = (reg << 56) | value`; the cycle loop of `VM::run` (vm.rs:234-312) calls
+/// `begin(pc, word)` before and `commit()` after executing an instruction, and sets `final_pc` where the VM halts.
+pub struct WriteLog {
+    pub pcs: Pinned<u32>,
+    pub instrs: Pinned<u32>,
+    pub wlog: Pinned<u64>,
+    pub len: usize,
+    pub cur: u64,
+    pub final_pc: u64,
+}
+
+impl WriteLog {
+    pub fn pinned(capacity: usize) -> Result<Self, RuntimeError> {
+        Ok(Self { pcs: Pinned::new(capacity)?, instrs: Pinned::new(capacity)?, wlog: Pinned::new(capacity)?, len: 0, cur: 0, final_pc: 0 })
+    }
+    #[inline]
+    pub fn begin(&mut self, pc: u32, word: u32) {
+        let k = self.len;
+        self.pcs.as_mut_slice()[k] = pc;
+        self.instrs.as_mut_slice()[k] = word;
+        self.cur = 0;
+    }
+    #[inline]
+    pub fn commit(&mut self) {
+        let k = self.len;
+        self.wlog.as_mut_slice()[k] = self.cur;
+        self.len = k + 1;
+    }
+}
+
 impl Drop for Prover {
     fn drop(&mut self) {
         unsafe { ffi::zkir_b200_destroy(self.ctx) }
     }
 }
 
-/// The new public function, next to `run()`: interpret with the upstream VM (execution trace on), prove on the GPU.
-///
-/// Needs one upstream addition: `ExecutionResult` must carry the machine state after the last instruction
-/// (`final_regs`, `final_pc`); padding rows and the value of a trailing READ are taken from it.
+/// The new public function, next to `run()`: interpret with the upstream VM (write-log hook on), prove on the GPU.
 pub fn prove(program: &Program, inputs: &[u64], cfg: &ProverConfig) -> Result<Proof, RuntimeError> {
-    let vm_cfg = VMConfig { max_cycles: cfg.max_cycles, enable_execution_trace: true, ..VMConfig::default() };
+    let vm_cfg = VMConfig { max_cycles: cfg.max_cycles, ..VMConfig::default() }; // no execution trace needed: the log replaces it
     let entry_point = program.header.entry_point;
-    let result = VM::new(program.clone(), inputs.to_vec(), vm_cfg).run()?; // interpreter untouched
-    let rows = &result.execution_trace; // Vec<TraceRow>, one per cycle, PRE-state registers
-    let n = rows.len();
-    let log_n = (n.max(4).next_power_of_two().trailing_zeros()).max(2);
-
-    let (mut pcs, mut ins, mut regs) = (Pinned::<u64>::new(n)?, Pinned::<u32>::new(n)?, Pinned::<u64>::new(16 * n)?);
-    {
-        let (p, i, r) = (pcs.as_mut_slice(), ins.as_mut_slice(), regs.as_mut_slice());
-        for (k, row) in rows.iter().enumerate() {
-            p[k] = row.pc;
-            i[k] = row.instruction;
-            r[16 * k..16 * k + 16].copy_from_slice(&row.registers);
-        }
-    }
-    let exit_code = match result.halt_reason {
-        HaltReason::Exit(code) => code,
-        _ => 0,
+    let mut log = WriteLog::pinned(cfg.max_cycles as usize)?;
+    let mut vm = VM::new(program.clone(), inputs.to_vec(), vm_cfg);
+    vm.set_write_log(&mut log); // the upstream hook described on `WriteLog`
+    let result = vm.run()?; // interpreter otherwise untouched
+    let (exit_code, halt_kind) = match result.halt_reason {
+        HaltReason::Exit(code) => (code, ffi::ZKIR_HALT_EXIT),
+        HaltReason::Ebreak => (0, ffi::ZKIR_HALT_EBREAK),
+        _ => (0, ffi::ZKIR_HALT_CYCLE_LIMIT),
     };
+    let rows = log.len.max(program.code.len()).max(1 << ffi::ZKIR_MIN_LOG_N); // the range table and the ROM occupy trace rows
+    let log_n = rows.next_power_of_two().trailing_zeros();
     let mut prover = Prover::new(cfg.device)?;
-    let (bytes, public_values) = prover.prove_rows(
-        cfg, &pcs, &ins, &regs, n as u64, &result.final_regs, result.final_pc, entry_point, exit_code, log_n,
-    )?;
+    prover.set_program(&program.code)?;
+    let (bytes, public_values) = prover.prove_writelog(cfg, &log, entry_point, exit_code, halt_kind, log_n)?;
     Ok(Proof { bytes, public_values, log_n, cycles: result.cycles, outputs: result.outputs.clone() })
 }
 
-/// CPU verifier (no GPU needed): accepts or rejects `proof` for these parameters and public values.
-pub fn verify(proof: &Proof, cfg: &ProverConfig) -> bool {
+/// CPU verifier (no GPU needed): accepts or rejects `proof` as a statement about `program` for these parameters and public values.
+pub fn verify(proof: &Proof, program: &Program, cfg: &ProverConfig) -> bool {
     let params = cfg.params();
-    let rc = unsafe { ffi::zkir_b200_verify(&params, proof.bytes.as_ptr(), proof.bytes.len(), proof.public_values.as_ptr()) };
+    let rc = unsafe {
+        ffi::zkir_b200_verify(&params, proof.bytes.as_ptr(), proof.bytes.len(), proof.public_values.as_ptr(), program.code.as_ptr(), program.code.len())
+    };
     rc == ffi::ZKIR_OK
 }
