@@ -458,7 +458,9 @@ def main():
     lde_gbs = lde_bytes / (lde_ms * 1e-3) / 1e9
     ntt_gbs = 8 * (1 << ntt_log) * ntt_cols / (ntt_ms * 1e-3) / 1e9
     commit_ms = stage_acc["trace_commit"] / K
-    hash_gps = (B * N * ((W + 7) // 8) + B * N - 1) / (commit_ms * 1e-3) / 1e9
+    leaf_rows = 2 * B                                   # rows per Merkle leaf (docs/PROVER_SPEC.md 4.1)
+    hash_perms = B * N * ((W + 7) // 8) + (B * N // leaf_rows - 1)   # leaf sponge absorptions + tree compressions of the trace commitment
+    hash_gps = hash_perms / (commit_ms * 1e-3) / 1e9
     prof = ncu_metrics(build)   # profiler-only numbers, quoted only if they were captured on THIS build
     lde_traffic = prof.get("lde_dram_bytes_per_proof") if prof else None
     out = {
@@ -483,14 +485,15 @@ def main():
                       "note": "throughput mode: two contexts (stream + host thread each) per GPU, trace resident (`value`) and end to end from the pinned write log (`e2e_value`); the headline `value` / `e2e` above are the one-proof-at-a-time numbers"},
         "gpu_launches": int(launches),
         "stage_ms": {k: v / K for k, v in stage_acc.items()},
-        "roofline": {"kernel": "dft_tile_kernel: LDE stage = 2 inverse + 2x2 forward digit passes (radix-32 register tiles) over 72 columns, 2^20 -> 2^21 points",
+        "roofline": {"kernel": f"dft_tile_kernel: trace LDE stage = 2 inverse + 2 forward (x{B} cosets) digit passes (radix-32 register tiles) over {W} columns, 2^{log_n} -> 2^{log_n + cfg.log_blowup} points",
                      "bound": "hbm", "achieved": lde_gbs, "peak": peak, "unit": "GB/s", "frac": lde_gbs / peak, "traffic": lde_traffic,
                      "traffic_source": (prof or {}).get("file"), "algorithmic_bytes": lde_bytes, "ms": lde_ms, "peak_source": peak_src},
         "ntt_roofline": {"kernel": f"dft_tile_kernel x2: forward NTT 2^{ntt_log} x {ntt_cols} columns via zkir_b200_ntt, natural order in/out (8*n*C bytes)", "bound": "hbm",
                          "achieved": ntt_gbs, "peak": peak, "unit": "GB/s", "frac": ntt_gbs / peak, "ms": ntt_ms, "timing": "CUDA events on the library stream, 10 launches"},
-        "hash_roofline": {"kernel": "leaf_hash_kernel (Poseidon2 sponge over the 2^21 LDE rows, 9 permutations each) + Merkle levels", "bound": "integer-multiply pipe",
+        "hash_roofline": {"kernel": f"leaf_hash_rows_kernel (Poseidon2 sponge over the {B * N} LDE rows of the {W}-column trace, {(W + 7) // 8} permutations per row, {leaf_rows} rows per leaf) + Merkle levels",
+                          "bound": "integer-multiply pipe", "permutations": hash_perms,
                           "achieved": hash_gps, "unit": "G permutations/s", "ms": commit_ms,
-                          "ncu_fmaheavy_active_frac": (prof or {}).get("leaf_hash_fmaheavy_active_frac"), "ncu_source": (prof or {}).get("file"),
+                          "ncu_fmaheavy_active_frac": (prof or {}).get("leaf_hash_fmaheavy_active_frac"), "ncu_source": (prof or {}).get("file") if (prof or {}).get("leaf_hash_fmaheavy_active_frac") is not None else None,
                           "share_of_step": commit_ms / (dev_ms / K)},
     }
     if world > 1:
