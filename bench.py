@@ -107,19 +107,19 @@ def cpu_oracle_run(fib_n, steps, warmup, budget_s=CPU_BUDGET_S):
     cores = int(o.l.oracle_set_threads(len(os.sched_getaffinity(0))))
     cfg = zkir_b200.ProverConfig()
     t0 = time.time()
-    pb = o.prove(cfg, cols, pv, res.program)           # probe (and the one warm-up proof when warmup >= 1)
+    pb = o.prove(cfg, cols, pv, res)           # probe (and the one warm-up proof when warmup >= 1)
     probe = time.time() - t0
-    ok, why = zkir_b200.verify(pb, cfg, pv, res.program)
+    ok, why = zkir_b200.verify(pb, cfg, pv, res)
     if not ok:
         raise SystemExit(f"CPU oracle proof rejected by the verifier: {why}")
     warm_done = 1
     for _ in range(max(0, min(warmup, 1) - warm_done)):
-        o.prove(cfg, cols, pv, res.program)
+        o.prove(cfg, cols, pv, res)
     if warmup >= 1:
         steps = max(1, min(steps, int(budget_s / max(probe, 1e-3))))
         t0 = time.time()
         for _ in range(steps):
-            o.prove(cfg, cols, pv, res.program)
+            o.prove(cfg, cols, pv, res)
         dt = (time.time() - t0) / steps
     else:                                  # no warm-up asked: the probe IS the single timed proof
         steps, dt = 1, probe
@@ -196,7 +196,7 @@ def main():
     cycles = res.cycles
     log_n = int(cols.shape[1]).bit_length() - 1
     ctx = zkir_b200.Context(local_rank)
-    ctx.set_program(res.program)
+    ctx.set_program(res)
     cfg = zkir_b200.ProverConfig()
     workload = workload_name(args.fib_n, log_n, int(cols.shape[0]), cfg)
     # the interpreter's raw rows (TraceRow: pc, word, 16 registers) in pinned host memory: what crosses PCIe per step
@@ -221,7 +221,7 @@ def main():
     for _ in range(args.warmup):
         pb = ctx.prove_columns(None, pv, cfg, device_resident=(d_trace, log_n))
     proof_bytes = len(pb)
-    ok, why = zkir_b200.verify(pb, cfg, pv, res.program)
+    ok, why = zkir_b200.verify(pb, cfg, pv, res)
     if not ok:
         raise SystemExit(f"proof rejected by the verifier: {why}")
     barrier()
@@ -261,7 +261,7 @@ def main():
     # ---------------- throughput mode: two proofs in flight on this GPU (second context = own stream + host thread); the
     # latency-bound phases of one proof (FRI, Merkle tops, Fiat-Shamir steps) overlap the hashing of the other
     ctx2 = zkir_b200.Context(local_rank)
-    ctx2.set_program(res.program)
+    ctx2.set_program(res)
     d_trace2 = ctx2.to_device(cols)
     for _ in range(2):
         ctx2.prove_columns(None, pv, cfg, device_resident=(d_trace2, log_n))
@@ -338,8 +338,10 @@ def main():
         # (host); the AIR constrains the syscall row as a register write only (no memory argument / hash chip yet: docs/PROVER_SPEC.md 3.5)
         cfg3 = zkir_b200.ProverConfig(max_cycles=pos2_cycles(POS2_ITERS_FULL) + 16, enable_poseidon2_syscall=True)
         p3 = pos2_program()
+        vm = zkir_b200.VM(p3, [POS2_ITERS_FULL], zkir_b200.VMConfig(max_cycles=cfg3.max_cycles, enable_poseidon2_syscall=True))
+        t0 = time.perf_counter(); r3 = vm.run(); c3_vm_s = time.perf_counter() - t0       # interpreter alone (no recording): also yields the public I/O transcript
         pb3, pv3, cyc3, ln3 = ctx.prove_program(p3, [POS2_ITERS_FULL], cfg3)
-        ok3, why3 = zkir_b200.verify(pb3, cfg3, pv3, p3)
+        ok3, why3 = zkir_b200.verify(pb3, cfg3, pv3, p3, io=r3.io)
         if not ok3 or cyc3 != pos2_cycles(POS2_ITERS_FULL):
             raise SystemExit(f"config 3 proof rejected: {why3}")
         barrier()
@@ -349,8 +351,6 @@ def main():
         barrier()
         c3_ms = (time.perf_counter() - t0) * 1e3 / 2
         c3_stage = ctx.stage_ms()
-        vm = zkir_b200.VM(p3, [POS2_ITERS_FULL], zkir_b200.VMConfig(max_cycles=cfg3.max_cycles, enable_poseidon2_syscall=True))
-        t0 = time.perf_counter(); vm.run(); c3_vm_s = time.perf_counter() - t0
         extra["config3_poseidon2_loop"] = {
             "workload": f"SYS_POSEIDON2 loop, {POS2_ITERS_FULL} permutations x 16 cycles = {cyc3} cycles -> 2^{ln3}-row trace, per GPU",
             "program_to_proof_ms": c3_ms, "value": world * cyc3 / (c3_ms * 1e-3), "unit": UNIT, "interpreter_only_s": c3_vm_s,
@@ -364,21 +364,21 @@ def main():
         for i in range(n4):
             g = rank * n4 + i
             r4 = zkir_b200.VM(pa, [g, 2 * g + 1], zkir_b200.VMConfig(enable_execution_trace=True)).run()
-            traces.append(r4.pack())
+            traces.append(r4.pack() + (r4.io,))
         cfg4 = zkir_b200.ProverConfig()
-        ctx.prove_batch([c for c, _ in traces[:64]], [q for _, q in traces[:64]], cfg4)     # warm: worker contexts, tables, graphs
+        ctx.prove_batch([c for c, _, _ in traces[:64]], [q for _, q, _ in traces[:64]], cfg4, io_list=[e for _, _, e in traces[:64]])     # warm: worker contexts, tables, graphs
         barrier()
         t0 = time.perf_counter()
-        out4 = ctx.prove_batch([c for c, _ in traces], [q for _, q in traces], cfg4)
+        out4 = ctx.prove_batch([c for c, _, _ in traces], [q for _, q, _ in traces], cfg4, io_list=[e for _, _, e in traces])
         barrier()
         c4_ms = (time.perf_counter() - t0) * 1e3
         for i in (0, n4 // 2, n4 - 1):
-            ok4, why4 = zkir_b200.verify(out4[i], cfg4, traces[i][1], pa)
+            ok4, why4 = zkir_b200.verify(out4[i], cfg4, traces[i][1], pa, io=traces[i][2])
             if not ok4:
                 raise SystemExit(f"config 4 proof {i} rejected: {why4}")
         extra["config4_add_batch"] = {"workload": f"a + b (11 cycles -> 2^10 rows), 4096 independent proofs over {world} GPU(s), {n4} per GPU", "batch_ms": c4_ms,
                                       "proofs_per_s": 4096 / (c4_ms * 1e-3), "proof_bytes": len(out4[0])}
-        ctx.set_program(res.program)
+        ctx.set_program(res)
         del traces, out4
 
     # ---------------- N > 1 only: ONE proof sharded over the N GPUs (BASELINE config 5 mode; the headline `value` stays N
@@ -393,7 +393,7 @@ def main():
         # ENFORCED on every rank: the sharded proof must be the single-GPU proof, byte for byte, and the verifier must accept it.
         # A mismatch ends the benchmark with a non-zero exit code (no JSON line), it is not a reported flag.
         shard_sha = hashlib.sha256(pb_sh).hexdigest()
-        ok_sh, why_sh = zkir_b200.verify(pb_sh, cfg, pv, res.program)
+        ok_sh, why_sh = zkir_b200.verify(pb_sh, cfg, pv, res)
         same = torch.tensor([1 if (pb_sh == pb and ok_sh) else 0], dtype=torch.int32, device="cuda")
         dist.all_reduce(same, op=dist.ReduceOp.MIN)
         print(f"[rank {rank}] one_proof_sharded sha256={shard_sha} single_gpu sha256={hashlib.sha256(pb).hexdigest()} verifier={'ok' if ok_sh else why_sh}",
@@ -417,7 +417,7 @@ def main():
             r24 = vm24.run_writelog({k: v.array for k, v in pins.items()})
             wl24 = r24.writelog()
             pb24, pv24 = ctx.prove_writelog(wl24, cfg, 24)
-            ok24, why24 = zkir_b200.verify(pb24, cfg, pv24, res.program) if rank == 0 else (True, "")
+            ok24, why24 = zkir_b200.verify(pb24, cfg, pv24, r24) if rank == 0 else (True, "")
             sha24 = hashlib.sha256(pb24).hexdigest()
             shas = [None] * world
             dist.all_gather_object(shas, sha24)

@@ -59,6 +59,12 @@ void zkir_b200_free_pinned(void*);
  * whenever the program changes (the decoded ROM columns and their LDE are cached per trace size).  Copies the words. */
 int zkir_b200_set_program(zkir_ctx*, const uint32_t* code, size_t n_code);
 
+/* ---- the public I/O transcript of the execution about to be proven: n_events x {cycle, kind (0 READ / 1 WRITE), value lo20, value hi20}
+ * (zkir_vm_io).  The AIR sends every READ / WRITE row to a lookup bus whose other side is this list, and the transcript absorbs its
+ * digest: a proof says "this program consumed these inputs and produced these outputs at these cycles".  Defaults to the empty
+ * transcript; zkir_b200_prove_program sets it itself.  A list that does not match the trace gives ZKIR_ERR_AIR. */
+int zkir_b200_set_io(zkir_ctx*, const uint32_t* events, size_t n_events);
+
 /* ---- the hot path: trace columns -> proof.  Sits where `zkir_runtime::prove()` would call into Plonky3
  * (the call does not exist in the reference: zkir-runtime/src/lib.rs:29-62).  `trace_cols` is HOST memory
  * (pinned recommended), `[width][1 << log_n]`; `public_values[num_public]`.  The proof buffer is owned by the
@@ -96,9 +102,11 @@ int zkir_b200_expand_writelog(zkir_ctx*, const uint32_t* pcs, const uint32_t* in
 /* the device converter alone (parity tests): rows -> d_cols [width][1 << log_n] canonical, device memory */
 int zkir_b200_expand_rows(zkir_ctx*, const uint64_t* pcs, const uint32_t* instrs, const uint64_t* regs, uint64_t n_rows,
                           const uint64_t* final_regs, uint64_t final_pc, uint32_t log_n, uint32_t* d_cols);
-/* many independent small proofs (BASELINE config 4); traces[i] is host memory [width][1<<log_ns[i]] */
+/* many independent small proofs of the context's program (BASELINE config 4); traces[i] is host memory [width][1<<log_ns[i]],
+ * ios[i] / n_ios[i] the public I/O transcript of execution i */
 int zkir_b200_prove_batch(zkir_ctx*, const zkir_params*, const uint32_t* const* traces, const uint32_t* log_ns,
-                          const uint32_t* const* public_values, uint32_t n_proofs, uint8_t** proofs, size_t* proof_lens);
+                          const uint32_t* const* public_values, const uint32_t* const* ios, const size_t* n_ios, uint32_t n_proofs,
+                          uint8_t** proofs, size_t* proof_lens);
 void zkir_b200_free_proof(uint8_t*);
 size_t zkir_b200_proof_size(const zkir_params*, uint32_t log_n); /* bytes; depends only on the shape */
 /* ---- ONE proof sharded over several GPUs of a box (BASELINE config 5), one context per GPU, normally one
@@ -124,11 +132,12 @@ int zkir_b200_shard_plan(uint32_t world, uint32_t rank, const zkir_params*, uint
 /* CPU verifier (host code, no GPU needed).  0 = accept, ZKIR_ERR_VERIFY = reject (reason via last_error(NULL)).  `code` = the
  * program the proof is about (the verifier evaluates the ROM polynomials itself and absorbs the program digest). */
 int zkir_b200_verify(const zkir_params*, const uint8_t* proof, size_t len, const uint32_t* public_values, const uint32_t* code,
-                     size_t n_code);
+                     size_t n_code, const uint32_t* io_events, size_t n_io);
 /* host helpers shared by the interpreter, the prover's ROM builder and guest-side tooling */
 void zkir_host_poseidon2_permute(uint32_t state16[16]);          /* width-16 Poseidon2 of docs/PROVER_SPEC.md section 2, canonical */
 void zkir_rom_entry(uint32_t word, uint32_t* dec, uint32_t* imm); /* decoded ROM row of one instruction word (spec section 3.3) */
 void zkir_program_digest(const uint32_t* code, size_t n_code, uint32_t digest8[8]); /* what the transcript absorbs for the program */
+void zkir_io_digest(const uint32_t* io_events, size_t n_io, uint32_t digest8[8]);   /* ... and for the public I/O transcript */
 
 /* ---- per-kernel entry points (parity tests, ncu captures, roofline harness).  Device pointers, canonical values. */
 /* batched NTT over `n_cols` contiguous columns of length 1<<log_n, in place, natural order in and out.
@@ -143,7 +152,7 @@ int zkir_b200_merkle_commit(zkir_ctx*, const uint32_t* d_matrix, uint32_t n_cols
 /* quotient values of the AIR on the LDE coset: d_lde [width + 16][M] (main then aux columns), d_publde [4][M] (public columns),
  * lookup = {z[4], theta[4]}, out d_q [4][M], M = 1<<(log_n+log_blowup); all natural order */
 int zkir_b200_quotient(zkir_ctx*, const zkir_params*, const uint32_t* d_lde, const uint32_t* d_publde, uint32_t log_n,
-                       const uint32_t* public_values, const uint32_t lookup[8], const uint32_t alpha[4], uint32_t* d_q);
+                       const uint32_t* public_values, const uint32_t lookup[8], const uint32_t alpha[4], uint32_t* d_q); /* uses the context's I/O transcript */
 /* the LogUp aux columns of a trace for given lookup challenges: d_trace [width][N] canonical -> d_aux [16][N] canonical; uses the
  * context's program for the ROM columns.  (The prover draws the challenges from the transcript; this entry point is for parity tests.) */
 int zkir_b200_aux_columns(zkir_ctx*, const uint32_t* d_trace, uint32_t log_n, const uint32_t lookup[8], uint32_t* d_aux);
@@ -220,6 +229,10 @@ int zkir_vm_run_writelog_cb(const uint32_t* code, size_t n_code, const uint8_t* 
                             uint64_t* wlog, uint64_t capacity, void (*on_chunk)(void* user, uint64_t rows_done), void* user,
                             uint64_t chunk_rows, zkir_vm_result** out);
 uint64_t zkir_vm_logged_rows(const zkir_vm_result*);
+/* public I/O transcript of the run: zkir_vm_io_len events of 4 words {cycle, kind (0 READ, 1 WRITE), value lo20, value hi20}, one per
+ * READ / WRITE ecall in execution order (syscall.rs:104-119); part of the statement a proof makes (zkir_b200_set_io, zkir_b200_verify) */
+size_t zkir_vm_io_len(const zkir_vm_result*);
+const uint32_t* zkir_vm_io(const zkir_vm_result*);
 size_t zkir_vm_code_len(const zkir_vm_result*);
 const uint32_t* zkir_vm_code(const zkir_vm_result*);
 uint64_t zkir_vm_final_pc(const zkir_vm_result*);

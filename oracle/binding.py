@@ -38,7 +38,16 @@ class Oracle:
 
     @staticmethod
     def _code(program):
+        """`program`: Program, code words, or an ExecutionResult (anything with .program)"""
+        program = getattr(program, "program", program)
         return np.ascontiguousarray(getattr(program, "code", program), dtype=np.uint32)
+
+    @staticmethod
+    def _io(program, io):
+        """public I/O transcript uint32 [n, 4]: explicit, or the ExecutionResult's own, or empty"""
+        if io is None:
+            io = getattr(program, "io", None) if hasattr(program, "program") else None
+        return np.ascontiguousarray(io if io is not None else np.zeros((0, 4)), dtype=np.uint32).reshape(-1, 4)
 
     def ntt(self, cols, inverse=False):
         a = np.ascontiguousarray(cols, dtype=np.uint32).copy()
@@ -72,7 +81,7 @@ class Oracle:
         self.l.oracle_merkle_commit(self._p(a), n_cols, int(rows).bit_length() - 1, self._p(tree), self._p(root))
         return tree, root
 
-    def quotient(self, cfg, lde, publde, log_n, pv, lookup, alpha):
+    def quotient(self, cfg, lde, publde, log_n, pv, lookup, alpha, io=None):
         """lde [WIDTH + 16][M] (main then aux columns), publde [4][M], natural order -> quotient values [4][M]"""
         M = lde.shape[1]
         out = np.empty((4, M), dtype=np.uint32)
@@ -80,7 +89,9 @@ class Oracle:
         pv = np.ascontiguousarray(pv, dtype=np.uint32)
         al = np.ascontiguousarray(alpha, dtype=np.uint32)
         lk = np.ascontiguousarray(lookup, dtype=np.uint32)
-        self.l.oracle_quotient(self._p(pr), log_n, self._p(np.ascontiguousarray(lde)), self._p(np.ascontiguousarray(publde)), self._p(pv), self._p(lk), self._p(al), self._p(out))
+        ev = self._io(None, io)
+        self.l.oracle_quotient(self._p(pr), log_n, self._p(np.ascontiguousarray(lde)), self._p(np.ascontiguousarray(publde)), self._p(pv), self._p(lk),
+                               self._p(ev), C.c_uint64(ev.shape[0]), self._p(al), self._p(out))
         return out
 
     def public_columns(self, log_n, program):
@@ -89,13 +100,15 @@ class Oracle:
         self.l.oracle_public_columns(log_n, self._p(code), C.c_uint64(len(code)), self._p(pub))
         return pub
 
-    def aux_columns(self, cols, program, lookup=None):
+    def aux_columns(self, cols, program, lookup=None, io=None):
         """-> (aux [16][N], balanced?) for the lookup challenges z, theta"""
         cols = np.ascontiguousarray(cols)
         code = self._code(program)
+        ev = self._io(program, io)
         lk = np.ascontiguousarray(self.LOOKUP_TEST if lookup is None else lookup, dtype=np.uint32)
         aux = np.empty((self.AUX_WIDTH, cols.shape[1]), dtype=np.uint32)
-        ok = self.l.oracle_aux_columns(int(cols.shape[1]).bit_length() - 1, self._p(cols), self._p(code), C.c_uint64(len(code)), self._p(lk), self._p(aux))
+        ok = self.l.oracle_aux_columns(int(cols.shape[1]).bit_length() - 1, self._p(cols), self._p(code), C.c_uint64(len(code)), self._p(ev), C.c_uint64(ev.shape[0]),
+                                       self._p(lk), self._p(aux))
         return aux, bool(ok)
 
     def program_digest(self, program):
@@ -112,24 +125,27 @@ class Oracle:
         self.l.oracle_fri_fold(self._p(a), self._p(out), int(n).bit_length() - 1, C.c_uint32(shift), self._p(b))
         return out
 
-    def check_trace(self, cols, pv, program, lookup=None):
+    def check_trace(self, cols, pv, program, lookup=None, io=None):
         """every AIR constraint (LogUp included, aux columns built for `lookup`) on the unextended rows:
         (-1, _) all hold; (-2, _) lookups unbalanced; (k, row) first failing constraint"""
         bad = C.c_uint64()
         cols = np.ascontiguousarray(cols)
         code = self._code(program)
+        ev = self._io(program, io)
         lk = np.ascontiguousarray(self.LOOKUP_TEST if lookup is None else lookup, dtype=np.uint32)
         k = self.l.oracle_check_trace(self._p(cols), int(cols.shape[1]).bit_length() - 1, self._p(np.ascontiguousarray(pv, dtype=np.uint32)),
-                                      self._p(code), C.c_uint64(len(code)), self._p(lk), C.byref(bad))
+                                      self._p(code), C.c_uint64(len(code)), self._p(ev), C.c_uint64(ev.shape[0]), self._p(lk), C.byref(bad))
         return k, bad.value
 
-    def prove(self, cfg, cols, pv, program):
+    def prove(self, cfg, cols, pv, program, io=None):
         pr = self.params(cfg)
         cols = np.ascontiguousarray(cols)
         code = self._code(program)
+        ev = self._io(program, io)
         log_n = int(cols.shape[1]).bit_length() - 1
         nw = self.l.oracle_proof_words(self._p(pr), log_n)
         proof = np.zeros(nw, dtype=np.uint32)
-        rc = self.l.oracle_prove(self._p(pr), self._p(cols), log_n, self._p(np.ascontiguousarray(pv, dtype=np.uint32)), self._p(code), C.c_uint64(len(code)), self._p(proof))
+        rc = self.l.oracle_prove(self._p(pr), self._p(cols), log_n, self._p(np.ascontiguousarray(pv, dtype=np.uint32)), self._p(code), C.c_uint64(len(code)),
+                                 self._p(ev), C.c_uint64(ev.shape[0]), self._p(proof))
         assert rc == 0, f"oracle_prove failed rc={rc}"
         return proof.tobytes()

@@ -209,9 +209,24 @@ static inline Xp operator-(Xp a, Xp b) { Xp r; r.v = e4_sub(a.v, b.v); return r;
 static inline Xp operator*(Xp a, Xp b) { Xp r; r.v = e4_mul(a.v, b.v); return r; }
 static inline Xp operator*(Xp a, Fp b) { Xp r; r.v = e4_mulb(a.v, b.v); return r; }
 
-struct LookupChallenges { E4 z, th[4]; };  // th[k] = theta^k
+struct LookupChallenges { E4 z, th[5], sio; };  // th[k] = theta^k; sio = sum of the public I/O transcript's fractions
 static LookupChallenges make_challenges(E4 z, E4 theta) {
-  LookupChallenges c; c.z = z; c.th[0] = e4_from(1); c.th[1] = theta; c.th[2] = e4_mul(theta, theta); c.th[3] = e4_mul(c.th[2], theta); return c;
+  LookupChallenges c; c.z = z; c.th[0] = e4_from(1); c.th[1] = theta;
+  for (int k = 2; k < 5; k++) c.th[k] = e4_mul(c.th[k - 1], theta);
+  c.sio = e4_zero();
+  return c;
+}
+// public I/O transcript: n events of 4 words (clk, kind: 0 READ / 1 WRITE, value lo, value hi); its LogUp sum
+//   S_io = sum_e 1 / (z - (3 + theta*clk + theta^2*kind + theta^3*lo + theta^4*hi))
+static E4 e4_inv(E4 a);
+static E4 io_sum(const LookupChallenges& c, const u32* io, size_t n_io) {
+  E4 s = e4_zero();
+  for (size_t e = 0; e < n_io; e++) {
+    E4 fp = e4_from(3);
+    for (int k = 0; k < 4; k++) fp = e4_add(fp, e4_mulb(c.th[k + 1], io[4 * e + k] % P));
+    s = e4_add(s, e4_inv(e4_sub(c.z, fp)));
+  }
+  return s;
 }
 
 struct AirRowCtx {  // all constraints at one point: main/aux/public columns are column-major with the same stride
@@ -230,6 +245,7 @@ struct AirRowCtx {  // all constraints at one point: main/aux/public columns are
   Xp th(int k) const { Xp r; r.v = lc->th[k]; return r; }
   Xp xf(Fp a) const { Xp r; r.v = e4_from(a.v); return r; }
   Xp x4(Fp a, Fp b, Fp c, Fp d) const { Xp r; r.v.c[0] = a.v; r.v.c[1] = b.v; r.v.c[2] = c.v; r.v.c[3] = d.v; return r; }
+  Xp sio() const { Xp r; r.v = lc->sio; return r; }
   void emit(int idx, Fp v) { vals[idx] = e4_from(v.v); }
   void emit_x(int idx, Xp v) { vals[idx] = v.v; }
 };
@@ -299,7 +315,15 @@ static bool build_aux(u32 log_n, const u32* trace, const u32* pub, const LookupC
   }
   E4 phi = e4_zero();
   for (size_t i = 0; i < N; i++) { for (int q = 0; q < 4; q++) aux[(12 + q) * N + i] = phi.c[q]; phi = e4_add(phi, tot[i]); }
-  return e4_eq(phi, e4_zero());
+  return e4_eq(phi, lc.sio);   // range and ROM fractions cancel, the I/O rows must add up to the public transcript's sum
+}
+// digest of the public I/O transcript the transcript absorbs: hash_tree over {n_io, clk_0, kind_0, lo_0, hi_0, ...}
+static void hash_tree(const u32* words, size_t n, u32* digest);
+static void io_digest(const u32* io, size_t n_io, u32* digest) {
+  std::vector<u32> w(4 * n_io + 1);
+  w[0] = (u32)n_io;
+  for (size_t i = 0; i < 4 * n_io; i++) w[1 + i] = io[i] % P;
+  hash_tree(w.data(), w.size(), digest);
 }
 // digest of the program the transcript absorbs: hash_tree over the 16-bit halves of the code words (each < p)
 static void program_digest(const u32* code, size_t n_code, u32* digest) {
@@ -310,7 +334,7 @@ static void program_digest(const u32* code, size_t n_code, u32* digest) {
 }
 
 struct Params { u32 log_blowup, num_queries, pow_bits, width, num_public; };
-static const u32 PROOF_MAGIC = 0x5A4B5052u, PROOF_VERSION = 5u;
+static const u32 PROOF_MAGIC = 0x5A4B5052u, PROOF_VERSION = 6u;
 static const size_t AW = ZKIR_AIR_AUX_WIDTH, PW = ZKIR_AIR_PUB_WIDTH;
 
 // FRI rounds (docs/PROVER_SPEC.md section 4.6): log_n / 3 rounds that fold by 8, then one that folds by 2^(log_n mod 3) if that is > 1
@@ -381,7 +405,7 @@ struct Dump {  // optional intermediates for stage-by-stage parity tests
   u32* betas;        // [R][4] or null
 };
 
-static int prove(const Params& p, const u32* trace, u32 log_n, const u32* pv, const u32* code, size_t n_code, u32* proof, Dump* dump) {
+static int prove(const Params& p, const u32* trace, u32 log_n, const u32* pv, const u32* code, size_t n_code, const u32* io, size_t n_io, u32* proof, Dump* dump) {
   const size_t W = p.width, WA = W + AW, N = (size_t)1 << log_n, B = (size_t)1 << p.log_blowup, M = N * B;
   const int lg = log_n + p.log_blowup;
   const u32 shift = ZKIR_BB_GEN;
@@ -418,13 +442,16 @@ static int prove(const Params& p, const u32* trace, u32 log_n, const u32* pv, co
     u32 pd[8];
     program_digest(code, n_code, pd);
     ch.observe_n(pd, 8);
+    io_digest(io, n_io, pd);
+    ch.observe_n(pd, 8);
   }
   ch.observe_n(merkle_root(ttree.data(), LEAVES), 8);
   memcpy(out, merkle_root(ttree.data(), LEAVES), 32); out += 8;
 
   // ---- 1b. lookup challenges, aux columns (LogUp helpers and running sum), their LDE and commitment
   E4 lz = ch.sample_ext(), ltheta = ch.sample_ext();
-  const LookupChallenges lc = make_challenges(lz, ltheta);
+  LookupChallenges lc = make_challenges(lz, ltheta);
+  lc.sio = io_sum(lc, io, n_io);
   {
     std::vector<u32> aux(AW * N);
     if (!build_aux(log_n, trace, pub.data(), lc, aux.data())) return -7;   // lookups do not balance: invalid witness
@@ -650,20 +677,25 @@ void oracle_merkle_commit(const u32* mat, int ncols, int log_rows, u32* tree, u3
   memcpy(root, merkle_root(tree, n), 32);
 }
 // lde: [W + 16 aux][M] (main then aux columns), pub: [4][M]; lookup = {z[4], theta[4]}
-void oracle_quotient(const u32* params5, u32 log_n, const u32* lde, const u32* publde, const u32* pv, const u32* lookup8, const u32* alpha, u32* out) {
+void oracle_quotient(const u32* params5, u32 log_n, const u32* lde, const u32* publde, const u32* pv, const u32* lookup8, const u32* io, u64 n_io,
+                     const u32* alpha, u32* out) {
   Params p = {params5[0], params5[1], params5[2], params5[3], params5[4]};
   E4 a, z, th; memcpy(a.c, alpha, 16); memcpy(z.c, lookup8, 16); memcpy(th.c, lookup8 + 4, 16);
   const size_t M = (size_t)1 << (log_n + p.log_blowup);
-  quotient_evals(p, log_n, lde, lde + (size_t)p.width * M, publde, pv, make_challenges(z, th), a, out);
+  LookupChallenges lc = make_challenges(z, th);
+  lc.sio = io_sum(lc, io, (size_t)n_io);
+  quotient_evals(p, log_n, lde, lde + (size_t)p.width * M, publde, pv, lc, a, out);
 }
 void oracle_public_columns(u32 log_n, const u32* code, u64 n_code, u32* pub) { build_public_columns(log_n, code, (size_t)n_code, pub); }
 // aux columns [16][N] for given lookup challenges; returns 1 if the lookups balance
-int oracle_aux_columns(u32 log_n, const u32* trace, const u32* code, u64 n_code, const u32* lookup8, u32* aux) {
+int oracle_aux_columns(u32 log_n, const u32* trace, const u32* code, u64 n_code, const u32* io, u64 n_io, const u32* lookup8, u32* aux) {
   const size_t N = (size_t)1 << log_n;
   std::vector<u32> pub(PW * N);
   build_public_columns(log_n, code, (size_t)n_code, pub.data());
   E4 z, th; memcpy(z.c, lookup8, 16); memcpy(th.c, lookup8 + 4, 16);
-  return build_aux(log_n, trace, pub.data(), make_challenges(z, th), aux) ? 1 : 0;
+  LookupChallenges lc = make_challenges(z, th);
+  lc.sio = io_sum(lc, io, (size_t)n_io);
+  return build_aux(log_n, trace, pub.data(), lc, aux) ? 1 : 0;
 }
 void oracle_program_digest(const u32* code, u64 n_code, u32* digest8) { program_digest(code, (size_t)n_code, digest8); }
 // one FRI fold: in[n][4] on coset shift*H_n -> out[n/2][4]
@@ -682,13 +714,14 @@ void oracle_fri_fold(const u32* in, u32* out, int logn, u32 shift, const u32* be
 }
 // checks every AIR constraint on the (unextended) trace rows, with the aux columns built for the given lookup challenges;
 // returns -1 if all hold, -2 if the lookups do not balance, else the index of the first failing constraint (row in *bad_row)
-int oracle_check_trace(const u32* trace, u32 log_n, const u32* pv, const u32* code, u64 n_code, const u32* lookup8, u64* bad_row) {
+int oracle_check_trace(const u32* trace, u32 log_n, const u32* pv, const u32* code, u64 n_code, const u32* io, u64 n_io, const u32* lookup8, u64* bad_row) {
   size_t N = (size_t)1 << log_n;
   if (log_n < ZKIR_AIR_RANGE_BITS || n_code > N) return -3;
   std::vector<u32> pub(PW * N), aux(AW * N);
   build_public_columns(log_n, code, (size_t)n_code, pub.data());
   E4 z, th; memcpy(z.c, lookup8, 16); memcpy(th.c, lookup8 + 4, 16);
-  const LookupChallenges lc = make_challenges(z, th);
+  LookupChallenges lc = make_challenges(z, th);
+  lc.sio = io_sum(lc, io, (size_t)n_io);
   const bool balanced = build_aux(log_n, trace, pub.data(), lc, aux.data());
   for (size_t i = 0; i < N; i++) {
     AirRowCtx c;
@@ -705,17 +738,17 @@ u64 oracle_proof_words(const u32* params5, u32 log_n) {
   return proof_words(p, log_n);
 }
 // params5 = {log_blowup, num_queries, pow_bits, width, num_public}; trace column-major [width][1<<log_n]
-int oracle_prove(const u32* params5, const u32* trace, u32 log_n, const u32* pv, const u32* code, u64 n_code, u32* proof) {
+int oracle_prove(const u32* params5, const u32* trace, u32 log_n, const u32* pv, const u32* code, u64 n_code, const u32* io, u64 n_io, u32* proof) {
   Params p = {params5[0], params5[1], params5[2], params5[3], params5[4]};
-  return prove(p, trace, log_n, pv, code, (size_t)n_code, proof, nullptr);
+  return prove(p, trace, log_n, pv, code, (size_t)n_code, io, (size_t)n_io, proof, nullptr);
 }
 // challenges20 = alpha, zeta, gamma, lookup z, lookup theta
-int oracle_prove_dump(const u32* params5, const u32* trace, u32 log_n, const u32* pv, const u32* code, u64 n_code, u32* proof, u32* challenges20,
+int oracle_prove_dump(const u32* params5, const u32* trace, u32 log_n, const u32* pv, const u32* code, u64 n_code, const u32* io, u64 n_io, u32* proof, u32* challenges20,
                       u32* lde, u32* aux, u32* quotient, u32* fri_input, u32* betas) {
   Params p = {params5[0], params5[1], params5[2], params5[3], params5[4]};
   Dump d; memset(&d, 0, sizeof(d));
   d.lde = lde; d.aux = aux; d.quotient = quotient; d.fri_input = fri_input; d.betas = betas;
-  int rc = prove(p, trace, log_n, pv, code, (size_t)n_code, proof, &d);
+  int rc = prove(p, trace, log_n, pv, code, (size_t)n_code, io, (size_t)n_io, proof, &d);
   if (challenges20) { memcpy(challenges20, d.alpha, 16); memcpy(challenges20 + 4, d.zeta, 16); memcpy(challenges20 + 8, d.alpha_fri, 16);
                       memcpy(challenges20 + 12, d.lookup_z, 16); memcpy(challenges20 + 16, d.lookup_theta, 16); }
   return rc;

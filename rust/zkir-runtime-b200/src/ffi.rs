@@ -33,6 +33,8 @@ extern "C" {
     pub fn zkir_b200_free_pinned(p: *mut c_void);
     /// the program whose executions the context proves: `Program.code` (zkir-spec/src/program.rs:241-250); ROM of the lookup argument
     pub fn zkir_b200_set_program(ctx: *mut zkir_ctx, code: *const u32, n_code: usize) -> c_int;
+    /// the public I/O transcript of the execution about to be proven: n events of {cycle, kind (0 READ, 1 WRITE), value lo20, value hi20}
+    pub fn zkir_b200_set_io(ctx: *mut zkir_ctx, events: *const u32, n_events: usize) -> c_int;
     /// Program + inputs -> proof in one call (the library's own interpreter restatement records the write log into pinned memory)
     pub fn zkir_b200_prove_program(
         ctx: *mut zkir_ctx,
@@ -102,5 +104,8 @@ extern "C" {
     pub fn zkir_b200_comm_init(ctx: *mut zkir_ctx, id: *const u8 /* [128] */, rank: c_int, world: c_int) -> c_int;
     pub fn zkir_b200_comm_shutdown(ctx: *mut zkir_ctx) -> c_int;
     pub fn zkir_b200_free_proof(p: *mut u8);
-    pub fn zkir_b200_verify(params: *const zkir_params, proof: *const u8, len: usize, public_values: *const u32, code: *const u32, n_code: usize) -> c_int;
+    pub fn zkir_b200_verify(
+        params: *const zkir_params, proof: *const u8, len: usize, public_values: *const u32, code: *const u32, n_code: usize,
+        io_events: *const u32, n_io: usize,
+    ) -> c_int;
 }

@@ -52,6 +52,8 @@ pub struct Proof {
     pub log_n: u32,
     pub cycles: u64,
     pub outputs: Vec<u64>,
+    /// public I/O transcript: (cycle, kind 0 READ / 1 WRITE, value lo20, value hi20) per READ / WRITE ecall; part of the statement
+    pub io_events: Vec<[u32; 4]>,
 }
 
 fn error_of(ctx: *const ffi::zkir_ctx, code: c_int) -> RuntimeError {
@@ -130,6 +132,12 @@ impl Prover {
         if rc != ffi::ZKIR_OK { Err(error_of(self.ctx, rc)) } else { Ok(()) }
     }
 
+    /// The public I/O transcript of the execution about to be proven (`zkir_b200_set_io`).
+    pub fn set_io(&mut self, events: &[[u32; 4]]) -> Result<(), RuntimeError> {
+        let rc = unsafe { ffi::zkir_b200_set_io(self.ctx, events.as_ptr() as *const u32, events.len()) };
+        if rc != ffi::ZKIR_OK { Err(error_of(self.ctx, rc)) } else { Ok(()) }
+    }
+
     /// Register write log in (16 B per cycle, pinned), proof bytes out: the device rebuilds the pre-state registers of every row
     /// with a last-writer scan and runs the converter (zkir-spec/src/trace.rs:41, absent upstream).
     #[allow(clippy::too_many_arguments)]
@@ -170,11 +178,13 @@ pub struct WriteLog {
     pub len: usize,
     pub cur: u64,
     pub final_pc: u64,
+    /// appended by the READ / WRITE arms of `handle_syscall` (zkir-runtime/src/syscall.rs:104-119): (cycle, kind, value lo20, value hi20)
+    pub io_events: Vec<[u32; 4]>,
 }
 
 impl WriteLog {
     pub fn pinned(capacity: usize) -> Result<Self, RuntimeError> {
-        Ok(Self { pcs: Pinned::new(capacity)?, instrs: Pinned::new(capacity)?, wlog: Pinned::new(capacity)?, len: 0, cur: 0, final_pc: 0 })
+        Ok(Self { pcs: Pinned::new(capacity)?, instrs: Pinned::new(capacity)?, wlog: Pinned::new(capacity)?, len: 0, cur: 0, final_pc: 0, io_events: Vec::new() })
     }
     #[inline]
     pub fn begin(&mut self, pc: u32, word: u32) {
@@ -210,19 +220,23 @@ pub fn prove(program: &Program, inputs: &[u64], cfg: &ProverConfig) -> Result<Pr
         HaltReason::Ebreak => (0, ffi::ZKIR_HALT_EBREAK),
         _ => (0, ffi::ZKIR_HALT_CYCLE_LIMIT),
     };
-    let rows = log.len.max(program.code.len()).max(1 << ffi::ZKIR_MIN_LOG_N); // the range table and the ROM occupy trace rows
+    let rows = (log.len + 1).max(program.code.len()).max(1 << ffi::ZKIR_MIN_LOG_N); // range table, ROM and one padding row fit the trace
     let log_n = rows.next_power_of_two().trailing_zeros();
     let mut prover = Prover::new(cfg.device)?;
     prover.set_program(&program.code)?;
+    prover.set_io(&log.io_events)?;
     let (bytes, public_values) = prover.prove_writelog(cfg, &log, entry_point, exit_code, halt_kind, log_n)?;
-    Ok(Proof { bytes, public_values, log_n, cycles: result.cycles, outputs: result.outputs.clone() })
+    Ok(Proof { bytes, public_values, log_n, cycles: result.cycles, outputs: result.outputs.clone(), io_events: log.io_events.clone() })
 }
 
 /// CPU verifier (no GPU needed): accepts or rejects `proof` as a statement about `program` for these parameters and public values.
 pub fn verify(proof: &Proof, program: &Program, cfg: &ProverConfig) -> bool {
     let params = cfg.params();
     let rc = unsafe {
-        ffi::zkir_b200_verify(&params, proof.bytes.as_ptr(), proof.bytes.len(), proof.public_values.as_ptr(), program.code.as_ptr(), program.code.len())
+        ffi::zkir_b200_verify(
+            &params, proof.bytes.as_ptr(), proof.bytes.len(), proof.public_values.as_ptr(), program.code.as_ptr(), program.code.len(),
+            proof.io_events.as_ptr() as *const u32, proof.io_events.len(),
+        )
     };
     rc == ffi::ZKIR_OK
 }

@@ -22,7 +22,7 @@ gold["poseidon2_of_0_to_15"] = o.poseidon2(np.arange(16, dtype=np.uint32).reshap
 gold["poseidon2_of_zeros"] = o.poseidon2(np.zeros((1, 16), dtype=np.uint32))[0].tolist()
 res, cols, pv = fib_trace(30)
 cfg = zkir_b200.ProverConfig(num_queries=20, pow_bits=8)
-pb = o.prove(cfg, cols, pv, res.program)
+pb = o.prove(cfg, cols, pv, res)
 gold["fib30_trace_sha256"] = hashlib.sha256(cols.tobytes()).hexdigest()
 gold["fib30_proof_sha256"] = hashlib.sha256(pb).hexdigest()
 gold["fib30_proof_len"] = len(pb)

@@ -114,17 +114,18 @@ def test_quotient_matches_oracle(gpu_ctx, oracle, n, log_b):
     cfg = zkir_b200.ProverConfig(log_blowup=log_b, num_queries=4, pow_bits=1)
     log_n = int(cols.shape[1]).bit_length() - 1
     lookup = np.array([11, 12, 13, 14, 21, 22, 23, 24], dtype=np.uint32)
-    aux, balanced = oracle.aux_columns(cols, res.program, lookup)
+    aux, balanced = oracle.aux_columns(cols, res, lookup)
     assert balanced
     lde = oracle.lde(np.concatenate([cols, aux]), log_b)
-    publde = oracle.lde(oracle.public_columns(log_n, res.program), log_b)
+    publde = oracle.lde(oracle.public_columns(log_n, res), log_b)
     alpha = np.array([5, 6, 7, 8], dtype=np.uint32)
     d_lde, d_pub = gpu_ctx.to_device(lde), gpu_ctx.to_device(publde)
     d_q = gpu_ctx.alloc(16 << (log_n + log_b))
+    gpu_ctx.set_io(res.io)
     gpu_ctx.quotient(cfg, d_lde, d_pub, log_n, pv, lookup, alpha, d_q)
     got = gpu_ctx.to_host(d_q, (4, 1 << (log_n + log_b)))
     gpu_ctx.free(d_lde); gpu_ctx.free(d_pub); gpu_ctx.free(d_q)
-    assert np.array_equal(got, oracle.quotient(cfg, lde, publde, log_n, pv, lookup, alpha))
+    assert np.array_equal(got, oracle.quotient(cfg, lde, publde, log_n, pv, lookup, alpha, io=res.io))
 
 
 @pytest.mark.parametrize("case", ["fib30", "fib300", "family"])
@@ -139,9 +140,9 @@ def test_aux_columns_match_oracle(gpu_ctx, oracle, case):
         res, cols, pv = fib_trace(int(case[3:]))
     log_n = int(cols.shape[1]).bit_length() - 1
     lookup = np.array([101, 2, 3, 4, 5, 6, 7, 8], dtype=np.uint32)
-    want, balanced = oracle.aux_columns(cols, res.program, lookup)
+    want, balanced = oracle.aux_columns(cols, res, lookup)
     assert balanced
-    gpu_ctx.set_program(res.program)
+    gpu_ctx.set_program(res)
     d_t = gpu_ctx.to_device(cols)
     d_a = gpu_ctx.alloc(want.nbytes)
     gpu_ctx.aux_columns(d_t, log_n, lookup, d_a)
@@ -166,14 +167,14 @@ def test_proof_bytes_match_oracle_and_verify(gpu_ctx, oracle, n, log_b, nq, pow_
     """BASELINE config 1 (fib n=30 / n=205): whole proof bytes GPU == oracle, and the verifier accepts."""
     res, cols, pv = fib_trace(n)
     cfg = zkir_b200.ProverConfig(log_blowup=log_b, num_queries=nq, pow_bits=pow_bits)
-    got = gpu_ctx.prove_columns(cols, pv, cfg, program=res.program)
-    want = oracle.prove(cfg, cols, pv, res.program)
+    got = gpu_ctx.prove_columns(cols, pv, cfg, program=res)
+    want = oracle.prove(cfg, cols, pv, res)
     assert len(got) == len(want)
     if got != want:
         g, w = np.frombuffer(got, dtype=np.uint32), np.frombuffer(want, dtype=np.uint32)
         first = int(np.nonzero(g != w)[0][0])
         pytest.fail(f"proof words differ first at word {first}: gpu={g[first]} oracle={w[first]}")
-    ok, why = zkir_b200.verify(got, cfg, pv, res.program)
+    ok, why = zkir_b200.verify(got, cfg, pv, res)
     assert ok, why
 
 
@@ -273,12 +274,12 @@ def test_prove_rows_equals_prove_columns(gpu_ctx, oracle, name):
     res = _rows_case(name)
     cfg = zkir_b200.ProverConfig(num_queries=12, pow_bits=6)
     cols, pv = res.pack()
-    from_cols = gpu_ctx.prove_columns(cols, pv, cfg, program=res.program)
+    from_cols = gpu_ctx.prove_columns(cols, pv, cfg, program=res)
     from_rows, pv2 = gpu_ctx.prove_rows(res.rows(), cfg)
     from_wl, pv3 = gpu_ctx.prove_writelog(res.writelog(), cfg)
     assert np.array_equal(pv, pv2) and np.array_equal(pv, pv3)
-    assert from_rows == from_cols == from_wl == oracle.prove(cfg, cols, pv, res.program)
-    ok, why = zkir_b200.verify(from_wl, cfg, pv, res.program)
+    assert from_rows == from_cols == from_wl == oracle.prove(cfg, cols, pv, res)
+    ok, why = zkir_b200.verify(from_wl, cfg, pv, res)
     assert ok, why
 
 
@@ -303,8 +304,8 @@ def test_full_size_proof_bytes_match_oracle(gpu_ctx, oracle, n_input, log_n):
     res, cols, pv = fib_trace(n_input=n_input)
     assert cols.shape[1] == 1 << log_n and res.cycles == 5 * n_input - 2
     cfg = zkir_b200.ProverConfig()
-    want = oracle.prove(cfg, cols, pv, res.program)
-    got = gpu_ctx.prove_columns(cols, pv, cfg, program=res.program)
+    want = oracle.prove(cfg, cols, pv, res)
+    got = gpu_ctx.prove_columns(cols, pv, cfg, program=res)
     assert len(got) == len(want)
     if got != want:
         g, w = np.frombuffer(got, dtype=np.uint32), np.frombuffer(want, dtype=np.uint32)
@@ -312,7 +313,7 @@ def test_full_size_proof_bytes_match_oracle(gpu_ctx, oracle, n_input, log_n):
         pytest.fail(f"2^{log_n}-row proof differs from the oracle first at word {first}: gpu={g[first]} oracle={w[first]}")
     from_wl, pv_wl = gpu_ctx.prove_writelog(res.writelog(), cfg, log_n)
     assert from_wl == want and list(pv_wl) == list(pv)
-    ok, why = zkir_b200.verify(got, cfg, pv, res.program)
+    ok, why = zkir_b200.verify(got, cfg, pv, res)
     assert ok, why
     if log_n == 20:   # Program -> Proof in one call (interpreter + overlapped upload + proof): the same bytes again
         from conftest import fib_program_input
@@ -349,8 +350,8 @@ def test_large_trace_proves_and_verifies(gpu_ctx):
     property: the independent CPU verifier accepts and rejects a flipped bit."""
     res, cols, pv = fib_trace(n_input=13000, log_n=16)
     cfg = zkir_b200.ProverConfig()
-    pb = gpu_ctx.prove_columns(cols, pv, cfg, program=res.program)
-    ok, why = zkir_b200.verify(pb, cfg, pv, res.program)
+    pb = gpu_ctx.prove_columns(cols, pv, cfg, program=res)
+    ok, why = zkir_b200.verify(pb, cfg, pv, res)
     assert ok, why
 
 
@@ -364,11 +365,11 @@ def test_2p22_row_trace_proves_and_verifies(gpu_ctx):
     cfg = zkir_b200.ProverConfig(num_queries=40, pow_bits=12)
     pb, pv = gpu_ctx.prove_rows(res.rows(), cfg, 22)
     assert list(pv[:2]) == [0x1000, (5 * n - 2) % P]
-    ok, why = zkir_b200.verify(pb, cfg, pv, res.program)
+    ok, why = zkir_b200.verify(pb, cfg, pv, res)
     assert ok, why
     bad = bytearray(pb)
     bad[len(bad) // 2] ^= 4
-    ok, _ = zkir_b200.verify(bytes(bad), cfg, pv, res.program)
+    ok, _ = zkir_b200.verify(bytes(bad), cfg, pv, res)
     assert not ok
 
 
@@ -384,15 +385,18 @@ def test_prove_batch_matches_single_proofs(gpu_ctx, oracle):
     for i in range(24):
         res = zkir_b200.VM(prog, [i, 2 * i + 1], zkir_b200.VMConfig(enable_execution_trace=True)).run()
         assert res.outputs == [3 * i + 1] and res.cycles == 11
-        traces.append(res.pack())
-    batch = gpu_ctx.prove_batch([c for c, _ in traces], [p for _, p in traces], cfg, program=prog)
+        assert res.io.tolist() == [[1, 0, i, 0], [4, 0, 2 * i + 1, 0], [7, 1, 3 * i + 1, 0]]     # (cycle, kind, lo, hi) of the two READs and the WRITE
+        traces.append(res.pack() + (res,))
+    batch = gpu_ctx.prove_batch([c for c, _, _ in traces], [p for _, p, _ in traces], cfg, program=prog, io_list=[r.io for _, _, r in traces])
     assert len(batch) == 24
-    for i, (cols, pv) in enumerate(traces):
-        assert batch[i] == gpu_ctx.prove_columns(cols, pv, cfg, program=prog)
-        ok, why = zkir_b200.verify(batch[i], cfg, pv, prog)
+    for i, (cols, pv, res) in enumerate(traces):
+        assert batch[i] == gpu_ctx.prove_columns(cols, pv, cfg, program=res)
+        ok, why = zkir_b200.verify(batch[i], cfg, pv, res)
         assert ok, why
+        ok, _ = zkir_b200.verify(batch[i], cfg, pv, prog, io=traces[(i + 1) % 24][2].io)    # another execution's I/O transcript
+        assert not ok
     for i in (0, 7, 23):
-        assert batch[i] == oracle.prove(cfg, *traces[i], prog)
+        assert batch[i] == oracle.prove(cfg, *traces[i])
 
 
 def test_error_paths_return_codes(gpu_ctx):
@@ -404,7 +408,7 @@ def test_error_paths_return_codes(gpu_ctx):
     cfg = zkir_b200.ProverConfig(num_queries=4, pow_bits=2)
     bad_pv = pv.copy(); bad_pv[1] = P                     # not canonical
     with pytest.raises(zkir_b200.RuntimeError) as ei:
-        gpu_ctx.prove_columns(cols, bad_pv, cfg, program=fres.program)
+        gpu_ctx.prove_columns(cols, bad_pv, cfg, program=fres)
     assert ei.value.code == -1
     lie = pv.copy(); lie[4] = 0; lie[2] = 5               # "did not halt" but claims an exit code
     with pytest.raises(zkir_b200.RuntimeError) as ei:
@@ -432,7 +436,7 @@ def test_error_paths_return_codes(gpu_ctx):
         with pytest.raises(zkir_b200.RuntimeError) as ei:
             call()
         assert ei.value.code == -6 and "row 1" in str(ei.value)
-    ok, why = zkir_b200.verify(gpu_ctx.prove_columns(cols, pv, cfg, program=fres.program), cfg, pv, fres.program)   # still healthy
+    ok, why = zkir_b200.verify(gpu_ctx.prove_columns(cols, pv, cfg, program=fres), cfg, pv, fres)   # still healthy
     assert ok, why
 
 
@@ -468,12 +472,12 @@ def test_minimal_programs(gpu_ctx, oracle):
         res = zkir_b200.VM(zkir_b200.assemble(src), [], zkir_b200.VMConfig(enable_execution_trace=True)).run()
         assert res.cycles == cycles and res.halt_reason == zkir_b200.HaltReason.Exit(code)
         cols, pv = res.pack()
-        assert cols.shape[1] == 1024 and oracle.check_trace(cols, pv, res.program)[0] == -1
-        want = oracle.prove(cfg, cols, pv, res.program)
-        assert gpu_ctx.prove_columns(cols, pv, cfg, program=res.program) == want
+        assert cols.shape[1] == 1024 and oracle.check_trace(cols, pv, res)[0] == -1
+        want = oracle.prove(cfg, cols, pv, res)
+        assert gpu_ctx.prove_columns(cols, pv, cfg, program=res) == want
         assert gpu_ctx.prove_rows(res.rows(), cfg)[0] == want
         assert gpu_ctx.prove_writelog(res.writelog(), cfg)[0] == want
-        ok, why = zkir_b200.verify(want, cfg, pv, res.program)
+        ok, why = zkir_b200.verify(want, cfg, pv, res)
         assert ok, why
 
 
@@ -490,12 +494,12 @@ def test_small_proofs_replay_a_captured_graph(gpu_ctx, oracle):
             cols, pv = res.pack()
             if i == 4:
                 cfg = zkir_b200.ProverConfig(num_queries=12, pow_bits=9)   # same workspace shape, different PoW: re-capture
-            got = ctx.prove_columns(cols, pv, cfg, program=prog)
-            assert got == oracle.prove(cfg, cols, pv, prog), f"proof {i} differs from the oracle"
+            got = ctx.prove_columns(cols, pv, cfg, program=res)
+            assert got == oracle.prove(cfg, cols, pv, res), f"proof {i} differs from the oracle"
         fres, cols, pv = fib_trace(205)                                    # another program on the same context and shape
         cfg = zkir_b200.ProverConfig(num_queries=20, pow_bits=6)
-        want = oracle.prove(cfg, cols, pv, fres.program)
+        want = oracle.prove(cfg, cols, pv, fres)
         for i in range(4):
-            assert ctx.prove_columns(cols, pv, cfg, program=fres.program) == want
+            assert ctx.prove_columns(cols, pv, cfg, program=fres) == want
     finally:
         ctx.close()

@@ -30,17 +30,17 @@ def _first_diff(got, want):
 def test_emulated_shards_give_single_gpu_proof_bytes(gpu_ctx, n, log_n, log_b, nq, shards, min_seg):
     res, cols, pv = fib_trace(n, log_n=log_n)
     cfg = zkir_b200.ProverConfig(log_blowup=log_b, num_queries=nq, pow_bits=6)
-    want = gpu_ctx.prove_columns(cols, pv, cfg, program=res.program)
+    want = gpu_ctx.prove_columns(cols, pv, cfg, program=res)
     ctx = zkir_b200.Context(0)
     try:
         ctx.emulate_shards(shards, min_seg)
-        got = ctx.prove_columns(cols, pv, cfg, program=res.program)
+        got = ctx.prove_columns(cols, pv, cfg, program=res)
     finally:
         ctx.close()
     assert len(got) == len(want)
     if got != want:
         pytest.fail(f"sharded proof differs from the single-GPU proof first at word {_first_diff(got, want)}")
-    ok, why = zkir_b200.verify(got, cfg, pv, res.program)
+    ok, why = zkir_b200.verify(got, cfg, pv, res)
     assert ok, why
 
 
@@ -48,7 +48,7 @@ def test_emulated_shards_full_size(gpu_ctx):
     """BASELINE config 2 size (2^20 rows), 8 segments, default thresholds: same bytes as the unsharded proof."""
     res, cols, pv = fib_trace(n_input=209715)
     cfg = zkir_b200.ProverConfig()
-    gpu_ctx.set_program(res.program)
+    gpu_ctx.set_program(res)
     d = gpu_ctx.to_device(cols)
     want = gpu_ctx.prove_columns(None, pv, cfg, device_resident=(d, 20))
     gpu_ctx.emulate_shards(8)
@@ -73,7 +73,7 @@ def test_nccl_sharded_proof_equals_single_gpu_proof(gpu_ctx, monkeypatch, n, log
         pytest.skip(f"needs {world} GPUs")
     res, cols, pv = fib_trace(n, log_n=log_n)
     cfg = zkir_b200.ProverConfig(num_queries=50, pow_bits=8)
-    want = gpu_ctx.prove_columns(cols, pv, cfg, program=res.program)
+    want = gpu_ctx.prove_columns(cols, pv, cfg, program=res)
     lib = zkir_b200._ffi.lib()
     ident = (C.c_uint8 * 128)()
     assert lib.zkir_b200_comm_unique_id(ident) == 0, lib.zkir_b200_last_error(None)
@@ -84,7 +84,7 @@ def test_nccl_sharded_proof_equals_single_gpu_proof(gpu_ctx, monkeypatch, n, log
             ctx = zkir_b200.Context(r)
             try:
                 ctx._check(lib.zkir_b200_comm_init(ctx._h, ident, r, world))
-                out[r] = [ctx.prove_columns(cols, pv, cfg, program=res.program) for _ in range(2)]
+                out[r] = [ctx.prove_columns(cols, pv, cfg, program=res) for _ in range(2)]
                 ctx.comm_shutdown()
             finally:
                 ctx.close()

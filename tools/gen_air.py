@@ -222,25 +222,29 @@ def shared(g):
 
 
 def fractions(g, sh):
-    """The 7 LogUp fractions of a row as (numerator F, denominator X).  Bus 1 = 10-bit range table, bus 2 = program ROM.
-    Fingerprints: range `1 + theta*value`; ROM `2 + theta*pc + theta^2*dec + theta^3*imm`."""
+    """The 8 LogUp fractions of a row as (numerator F, denominator X).  Bus 1 = 10-bit range table, bus 2 = program ROM, bus 3 = public I/O.
+    Fingerprints: range `1 + theta*value`; ROM `2 + theta*pc + theta^2*dec + theta^3*imm`; I/O `3 + theta*clk + theta^2*kind + theta^3*lo + theta^4*hi`."""
     s, s_ecall, s_pad, live, rc_on, dec, imm_f = sh
     L = g.L
     z = E("c.z()", atom=True, t="X")
-    th = [None] + [E(f"c.th({k})", atom=True, t="X") for k in (1, 2, 3)]
+    th = [None] + [E(f"c.th({k})", atom=True, t="X") for k in (1, 2, 3, 4)]
     out = []
     for j in range(4):
         out.append((rc_on, g.tmp(z - (th[1] * L(CH[j]) + 1), f"range lookup of ch{j}")))
     out.append((g.tmp(0 - L(M_RNG)), g.tmp(z - (th[1] * g.Pc(P_T) + 1), "range table row")))
     out.append((live, g.tmp(z - (th[1] * L(PC) + th[2] * dec + th[3] * imm_f + 2), "ROM lookup of (pc, decoded word, imm)")))
     out.append((g.tmp(0 - L(M_ROM)), g.tmp(z - (th[1] * g.Pc(P_PC) + th[2] * g.Pc(P_DEC) + th[3] * g.Pc(P_IMM) + 2), "ROM table row")))
+    # bus 3 = the public I/O transcript: every READ / WRITE row sends (clk, kind, value); the table side is the public list of events,
+    # summed by the verifier itself (c.sio() in the closing constraint).  On a WRITE row v holds the written word (r11), on a READ row the tape value.
+    out.append((g.tmp(L(IS_READ) + L(IS_WRITE), "I/O row"),
+                g.tmp(z - (th[1] * L(CLK) + th[2] * L(IS_WRITE) + th[3] * L(V_LO) + th[4] * L(V_HI) + 3), "I/O event (clk, kind, value)")))
     return out
 
 
-# helper k sums the fractions FRAC_PAIRS[k]; fraction FRAC_PHI is added by the running-sum transition itself
+# helper k sums the fractions FRAC_PAIRS[k]; the two fractions FRAC_PHI are added by the running-sum transition itself
 FRAC_PAIRS = [(0, 1), (2, 3), (4, 6)]
-FRAC_PHI = 5
-NUM_FRACTIONS = 7
+FRAC_PHI = (5, 7)
+NUM_FRACTIONS = 8
 
 
 def build():
@@ -337,6 +341,8 @@ def build():
     g.emit(s["s_jalr"] * (v_lo + TWO20 * v_hi - L(PC) - 4), "jalr link = pc + 4")
     # --- syscalls (syscall.rs:94-149)
     g.emit((L(IS_READ) + L(IS_POS2)) * (rd_h[2] * rd_l[2] - 1), "read / poseidon2 write r10 (syscall.rs:104-109,140-149)")
+    g.emit(L(IS_WRITE) * (v_lo - L(REG_LO[11])), "write: v = the written word r11 (lo), sent to the I/O bus (syscall.rs:110-119)")
+    g.emit(L(IS_WRITE) * (v_hi - L(REG_HI[11])), "write: v = r11 (hi)")
     g.emit(L(IS_POS2) * v_lo, "poseidon2 returns 0 (lo)")
     g.emit(L(IS_POS2) * v_hi, "poseidon2 returns 0 (hi)")
     # --- register write-back, pre-state rows: next.r[i] = (rd == i && w) ? v : r[i]
@@ -359,13 +365,14 @@ def build():
     g.emit(trans * (N(PC) - L(PC) - 4 * (live - s["s_ebreak"]) - (br * taken + s["s_jal"]) * (imm_f - 4)
                     - s["s_jalr"] * (a_lo + TWO20 * a_hi + imm_f - taken - L(PC) - 4)), "next pc (jalr: (rs1 + imm) & ~1)")
     g.emit(trans * (N(CLK) - L(CLK) - live), "clk counts live rows")
-    g.emit(last * (L(CLK) + live - g.PV(1)), "last row: clk (+1 if live) = num_cycles")
+    # the last row is always a padding row (the packer keeps at least one): the closing constraints below may then ignore its own fractions
+    g.emit(last * live, "the last row is a padding row")
+    g.emit(last * (L(CLK) - g.PV(1)), "last row: clk = num_cycles")
     n_live = g.tmp(sum_e(N(S[n]) for n in SEL_NAMES) + N(IS_EXIT) + N(IS_READ) + N(IS_WRITE) + N(IS_POS2), "1 - next.s_pad")
     hlt = g.tmp(L(IS_EXIT) + s["s_ebreak"], "halting row (syscall.rs:98-103, execute.rs:667-673)")
     g.emit(trans * (s_pad * n_live), "padding is sticky")
     g.emit(trans * (hlt * n_live), "a halting row is followed by padding")
     g.emit(trans * (g.PV(4) * (live * (1 - n_live) * (1 - hlt))), "halted = 1: padding starts only after a halting row")
-    g.emit(last * (g.PV(4) * (live * (1 - hlt))), "halted = 1: a live last row is the halting row")
     # --- ecall decode (syscall.rs:18-24,94-149): number in r10
     g.emit(L(IS_EXIT) * L(REG_LO[10]), "exit: r10 = 0")
     g.emit(L(IS_READ) * (L(REG_LO[10]) - 1), "read: r10 = 1")
@@ -394,11 +401,13 @@ def build():
     for k, (i, j) in enumerate(FRAC_PAIRS):
         (ni, di), (nj, dj) = fr[i], fr[j]
         g.emit(h[k] * di * dj - di * nj - dj * ni, f"helper {k} = fraction {i} + fraction {j}")
-    n5, d5 = fr[FRAC_PHI]
+    (n5, d5), (n7, d7) = fr[FRAC_PHI[0]], fr[FRAC_PHI[1]]
     hs = g.tmp(h[0] + h[1] + h[2], "h0 + h1 + h2")
-    g.emit(((phi_n - phi - hs) * d5 - n5) * trans, "running sum transition (adds the ROM lookup itself)")
+    sio = E("c.sio()", atom=True, t="X")
+    g.emit(((phi_n - phi - hs) * d5 * d7 - d7 * n5 - d5 * n7) * trans, "running sum transition (adds the ROM lookup and the I/O event itself)")
     g.emit(phi * first, "running sum starts at 0")
-    g.emit(((0 - phi - hs) * d5 - n5) * last, "all lookups balance: the sum closes to 0")
+    # last row = padding row: its ROM-lookup and I/O numerators are 0 (live = 0), only the table-side helpers count
+    g.emit((sio - phi - hs) * last, "range and ROM lookups cancel; what remains is the public I/O transcript's sum")
     return g
 
 
@@ -425,14 +434,15 @@ def main():
     hdr.append(f"#define ZKIR_AIR_RANGE_BITS {RANGE_BITS}")
     hdr.append("#define ZKIR_AIR_MAX_DEGREE 3")
     hdr.append("// fraction j is summed by helper ZKIR_AIR_FRAC_HELPER[j] (3 = added by the running-sum transition itself)")
-    helper_of = [3] * NUM_FRACTIONS
+    helper_of = [3] * NUM_FRACTIONS   # 3 = the running sum itself
     for k, (i, j) in enumerate(FRAC_PAIRS):
         helper_of[i] = helper_of[j] = k
     hdr.append("#define ZKIR_AIR_FRAC_HELPER_INIT {" + ", ".join(str(x) for x in helper_of) + "}")
     hdr.append("#ifndef ZKIR_HD\n#ifdef __CUDACC__\n#define ZKIR_HD __host__ __device__ __forceinline__\n#else\n#define ZKIR_HD inline\n#endif\n#endif")
     hdr.append("// Context contract: C::F (base) and C::X (ext4) with + - *, X * F scaling; c.L(i)/c.N(i) main local/next row, c.A(i)/c.AN(i) aux,")
     hdr.append("// c.P(i) public column, c.PV(i) public value, c.K(u32 canonical constant), c.z()/c.th(k) lookup challenges z, theta^k,")
-    hdr.append("// c.xf(F) -> X, c.x4(F,F,F,F) -> X, c.is_first / c.is_last / c.is_trans selectors, c.emit(index, F), c.emit_x(index, X).")
+    hdr.append("// c.xf(F) -> X, c.x4(F,F,F,F) -> X, c.sio() -> X (sum of the public I/O transcript's fractions), c.is_first / c.is_last / c.is_trans selectors,")
+    hdr.append("// c.emit(index, F), c.emit_x(index, X).")
     hdr.append("template <class C> ZKIR_HD void zkir_air_eval(C& c) {")
     hdr.append("  typedef typename C::F F;")
     hdr.append("  typedef typename C::X X;")

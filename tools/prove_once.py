@@ -24,12 +24,12 @@ if use_writelog:
 else:
     res, cols, pv = fib_trace(n_input=n)
     log_n = int(cols.shape[1]).bit_length() - 1
-    ctx.set_program(res.program)
+    ctx.set_program(res)
     d = ctx.to_device(cols)
     for i in range(reps):
         t0 = time.perf_counter()
         pb = ctx.prove_columns(None, pv, cfg, device_resident=(d, log_n))
         dt = (time.perf_counter() - t0) * 1e3
         print(f"proof {i}: {dt:.2f} ms wall, stages {ctx.stage_ms()}")
-ok, why = zkir_b200.verify(pb, cfg, pv, res.program)
+ok, why = zkir_b200.verify(pb, cfg, pv, res)
 print("verify", ok, why)

@@ -31,6 +31,7 @@ SYMBOLS = {
     "zkir_b200_prove": (C.c_int, [vp, C.POINTER(Params), vp, C.c_uint32, u32p, C.POINTER(vp), C.POINTER(C.c_size_t)]),
     "zkir_b200_prove_device": (C.c_int, [vp, C.POINTER(Params), vp, C.c_uint32, u32p, C.POINTER(vp), C.POINTER(C.c_size_t)]),
     "zkir_b200_set_program": (C.c_int, [vp, vp, C.c_size_t]),
+    "zkir_b200_set_io": (C.c_int, [vp, vp, C.c_size_t]),
     "zkir_b200_prove_rows": (C.c_int, [vp, C.POINTER(Params), vp, vp, vp, C.c_uint64, u64p, C.c_uint64, C.c_uint32, C.c_uint64, C.c_int, C.c_uint32, u32p,
                                       C.POINTER(vp), C.POINTER(C.c_size_t)]),
     "zkir_b200_expand_rows": (C.c_int, [vp, vp, vp, vp, C.c_uint64, u64p, C.c_uint64, C.c_uint32, vp]),
@@ -39,7 +40,8 @@ SYMBOLS = {
     "zkir_b200_prove_program": (C.c_int, [vp, C.POINTER(Params), vp, C.c_size_t, vp, C.c_size_t, C.c_uint32, vp, C.c_size_t, C.c_uint64, u32p,
                                          C.POINTER(C.c_uint64), u32p, C.POINTER(vp), C.POINTER(C.c_size_t)]),
     "zkir_b200_expand_writelog": (C.c_int, [vp, vp, vp, vp, C.c_uint64, C.c_uint64, C.c_uint32, vp]),
-    "zkir_b200_prove_batch": (C.c_int, [vp, C.POINTER(Params), C.POINTER(vp), u32p, C.POINTER(vp), C.c_uint32, C.POINTER(vp), C.POINTER(C.c_size_t)]),
+    "zkir_b200_prove_batch": (C.c_int, [vp, C.POINTER(Params), C.POINTER(vp), u32p, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_size_t), C.c_uint32,
+                                       C.POINTER(vp), C.POINTER(C.c_size_t)]),
     "zkir_b200_comm_unique_id": (C.c_int, [vp]),
     "zkir_b200_comm_init": (C.c_int, [vp, vp, C.c_int, C.c_int]),
     "zkir_b200_comm_shutdown": (C.c_int, [vp]),
@@ -47,7 +49,8 @@ SYMBOLS = {
     "zkir_b200_shard_plan": (C.c_int, [C.c_uint32, C.c_uint32, C.POINTER(Params), C.c_uint32, C.c_uint64, u64p]),
     "zkir_b200_free_proof": (None, [vp]),
     "zkir_b200_proof_size": (C.c_size_t, [C.POINTER(Params), C.c_uint32]),
-    "zkir_b200_verify": (C.c_int, [C.POINTER(Params), vp, C.c_size_t, u32p, vp, C.c_size_t]),
+    "zkir_b200_verify": (C.c_int, [C.POINTER(Params), vp, C.c_size_t, u32p, vp, C.c_size_t, vp, C.c_size_t]),
+    "zkir_io_digest": (None, [vp, C.c_size_t, vp]),
     "zkir_host_poseidon2_permute": (None, [vp]),
     "zkir_rom_entry": (None, [C.c_uint32, u32p, u32p]),
     "zkir_program_digest": (None, [vp, C.c_size_t, vp]),
@@ -89,6 +92,8 @@ SYMBOLS = {
     "zkir_vm_run_writelog": (C.c_int, [u32p, C.c_size_t, u8p, C.c_size_t, C.c_uint32, u64p, C.c_size_t, C.c_uint64, vp, vp, vp, C.c_uint64, C.POINTER(vp)]),
     "zkir_vm_run_writelog_cb": (C.c_int, [u32p, C.c_size_t, u8p, C.c_size_t, C.c_uint32, u64p, C.c_size_t, C.c_uint64, vp, vp, vp, C.c_uint64, vp, vp, C.c_uint64, C.POINTER(vp)]),
     "zkir_vm_logged_rows": (C.c_uint64, [vp]),
+    "zkir_vm_io_len": (C.c_size_t, [vp]),
+    "zkir_vm_io": (u32p, [vp]),
     "zkir_vm_code_len": (C.c_size_t, [vp]),
     "zkir_vm_code": (u32p, [vp]),
     "zkir_vm_final_pc": (C.c_uint64, [vp]),

@@ -114,7 +114,7 @@ BB_HD u32 expand_row_v2(u64 i, u64 T, const u64 (&rg)[16], u64 pc, u32 w, u64 re
         is_read = 1; rd = 10; writes = 1;
         vv = read_val; rc = vv; chunks_from_rc = true;
         if (vv >> 40) err = PACK_ERR_TAPE40;
-      } else if (num == 2) is_write = 1;
+      } else if (num == 2) { is_write = 1; vv = rg[11]; }   // the written word goes to the I/O bus through v (no register is written: rd = r0)
       else if (num == 4) { is_pos2 = 1; rd = 10; writes = 1; vv = 0; }
       else err = PACK_ERR_SYSCALL;
     } else if (op == 0x51) {                            // EBREAK

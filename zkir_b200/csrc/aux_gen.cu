@@ -18,7 +18,7 @@ namespace zkir {
 struct FracCtxDev {
   typedef Fm F; typedef Xm X;
   const u32 *trace, *pub; u64 N, row;
-  const E4* lc;   // shared: z, theta, theta^2, theta^3
+  const E4* lc;   // shared: z, theta, theta^2, theta^3, theta^4
   u32 num[ZKIR_AIR_NUM_FRACTIONS]; E4 den[ZKIR_AIR_NUM_FRACTIONS];
   __device__ __forceinline__ Fm L(int i) const { return Fm(bb_to_mont(__ldg(trace + (u64)i * N + row))); }
   __device__ __forceinline__ Fm P(int i) const { return Fm(bb_to_mont(__ldg(pub + (u64)i * N + row))); }
@@ -31,11 +31,11 @@ struct FracCtxDev {
 
 #define AUX_ROWS_THREADS 128
 __global__ void __launch_bounds__(AUX_ROWS_THREADS) aux_rows_kernel(AuxArgs a) {
-  __shared__ E4 lc[4];
+  __shared__ E4 lc[5];
   if (threadIdx.x == 0) {
     E4 z, th;
     for (int k = 0; k < 4; k++) { z.c[k] = a.lookup[k]; th.c[k] = a.lookup[4 + k]; }
-    lc[0] = z; lc[1] = th; lc[2] = e4_mul(th, th); lc[3] = e4_mul(lc[2], th);
+    lc[0] = z; lc[1] = th; lc[2] = e4_mul(th, th); lc[3] = e4_mul(lc[2], th); lc[4] = e4_mul(lc[3], th);
   }
   __syncthreads();
   const u64 N = 1ull << a.log_n;
@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_totals_kernel(const E4* __r
   if (threadIdx.x == 0) blk_tot[blockIdx.x] = s;
 }
 // one block: blk_tot[b] becomes the sum of the totals of the blocks before b; flags an unbalanced grand total
-__global__ void __launch_bounds__(1024) scan_blocks_kernel(E4* blk_tot, u64 n_blocks, u64 N, u64* err) {
+__global__ void __launch_bounds__(1024) scan_blocks_kernel(E4* blk_tot, u64 n_blocks, u64 N, const u32* sio, u64* err) {
   __shared__ E4 part[1024];
   const u32 t = threadIdx.x;
   const u64 per = (n_blocks + 1023) / 1024, b0 = t * per, b1 = b0 + per < n_blocks ? b0 + per : n_blocks;
@@ -95,7 +95,9 @@ __global__ void __launch_bounds__(1024) scan_blocks_kernel(E4* blk_tot, u64 n_bl
   if (t == 0) {
     E4 run = e4_zero();
     for (u32 u = 0; u < 1024; u++) { const E4 v = part[u]; part[u] = run; run = e4_add(run, v); }
-    if (err && (run.c[0] | run.c[1] | run.c[2] | run.c[3]))   // the fractions of all rows must cancel: otherwise the witness is not a valid lookup
+    // the range and ROM fractions of all rows must cancel and the I/O rows must add up to the public transcript's sum: otherwise the
+    // witness is not a valid lookup (a chunk outside the table, an instruction outside the program, another I/O transcript)
+    if (err && ((run.c[0] ^ sio[0]) | (run.c[1] ^ sio[1]) | (run.c[2] ^ sio[2]) | (run.c[3] ^ sio[3])))
       atomicMin(reinterpret_cast<unsigned long long*>(err), (unsigned long long)(((N - 1) << 8) | 8u));
   }
   __syncthreads();
@@ -131,11 +133,33 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_write_kernel(const E4* __re
   }
 }
 
+// S_io of the public I/O transcript: one block, a thread per event (strided), ext4 inversion each, block reduction
+__global__ void __launch_bounds__(256) io_sum_kernel(const u32* __restrict__ ev, u32 n, u32* lookup) {
+  __shared__ E4 sh[8];
+  E4 z, th[5];
+  for (int k = 0; k < 4; k++) { z.c[k] = lookup[k]; th[1].c[k] = lookup[4 + k]; }
+  for (int k = 2; k < 5; k++) th[k] = e4_mul(th[k - 1], th[1]);
+  E4 s = e4_zero();
+  for (u32 e = threadIdx.x; e < n; e += blockDim.x) {
+    E4 fp = e4_from_base(bb_to_mont_c(3u));
+#pragma unroll
+    for (int k = 0; k < 4; k++) fp = e4_add(fp, e4_mulb(th[k + 1], bb_to_mont(ev[4 * e + k] % BB_P)));
+    s = e4_add(s, e4_inv(e4_sub(z, fp)));
+  }
+  s = block_reduce(s, sh);
+  if (threadIdx.x == 0) for (int k = 0; k < 4; k++) lookup[8 + k] = s.c[k];
+}
+int launch_io_sum(const u32* events, u32 n_events, u32* lookup, cudaStream_t st, u64* launches) {
+  io_sum_kernel<<<1, 256, 0, st>>>(events, n_events, lookup);
+  (*launches)++;
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
 int launch_aux_gen(const AuxArgs& a, cudaStream_t st, u64* launches) {
   const u64 N = 1ull << a.log_n, nb = aux_gen_blocks(N);
   aux_rows_kernel<<<(unsigned)((N + AUX_ROWS_THREADS - 1) / AUX_ROWS_THREADS), AUX_ROWS_THREADS, 0, st>>>(a);
   scan_totals_kernel<<<(unsigned)nb, SCAN_THREADS, 0, st>>>(a.row_tot, a.blk_tot, N);
-  scan_blocks_kernel<<<1, 1024, 0, st>>>(a.blk_tot, nb, N, a.err);
+  scan_blocks_kernel<<<1, 1024, 0, st>>>(a.blk_tot, nb, N, a.lookup + 8, a.err);
   scan_write_kernel<<<(unsigned)nb, SCAN_THREADS, 0, st>>>(a.row_tot, a.blk_tot, a.aux, N);
   (*launches) += 4;
   return cudaGetLastError() == cudaSuccess ? 0 : -2;

@@ -143,7 +143,7 @@ struct AirAtZeta {  // air_generated.h context over ext4: base and ext values ar
   const X4 *loc, *nxt;        // opened main columns [0, W) then aux columns [W, W + A) at zeta / g*zeta
   const X4* pub;              // public columns at zeta, computed by the verifier
   const u32* pv;
-  X4 zc, thp[4];              // lookup challenges z, theta^k
+  X4 zc, thp[5], sio_v;       // lookup challenges z, theta^k; the public I/O transcript's sum
   X4 is_first, is_last, is_trans, alpha, acc;
   X4 L(int i) const { return loc[i]; }
   X4 N(int i) const { return nxt[i]; }
@@ -155,6 +155,7 @@ struct AirAtZeta {  // air_generated.h context over ext4: base and ext values ar
   X4 z() const { return zc; }
   X4 th(int k) const { return thp[k]; }
   X4 xf(const X4& a) const { return a; }
+  X4 sio() const { return sio_v; }
   X4 x4(const X4& a, const X4& b, const X4& c, const X4& d) const {   // a + X b + X^2 c + X^3 d: the ext value of four base polynomials
     X4 e1, e2, e3; e1.c[1] = 1; e2.c[2] = 1; e3.c[3] = 1;
     return a + e1 * b + e2 * c + e3 * d;
@@ -192,12 +193,20 @@ void program_digest(const u32* code, size_t n_code, u32* digest) {
 
 bool fail(const char* m) { g_verify_error = m; return false; }
 
-bool verify(const zkir_params* p, const u32* w, size_t nwords, const u32* pv_in, const u32* code, size_t n_code) {
+// transcript digest of the public I/O transcript: hash_tree over {n_io, clk_0, kind_0, lo_0, hi_0, ...}
+void io_digest(const u32* io, size_t n_io, u32* digest) {
+  std::vector<u32> h(4 * n_io + 1);
+  h[0] = (u32)n_io;
+  for (size_t i = 0; i < 4 * n_io; i++) h[1 + i] = io[i] % P;
+  hash_tree(h.data(), h.size(), digest);
+}
+
+bool verify(const zkir_params* p, const u32* w, size_t nwords, const u32* pv_in, const u32* code, size_t n_code, const u32* io, size_t n_io) {
   if (!p || !w) return fail("null argument");
   if (p->width != ZKIR_AIR_WIDTH || p->num_public != ZKIR_AIR_NUM_PUBLIC || p->log_blowup < 1) return fail("unsupported params");
   if (nwords < 8) return fail("proof too short");
-  if (w[0] != 0x5A4B5052u || w[1] != 5) return fail("bad magic/version");
-  if (!code && n_code) return fail("null program");
+  if (w[0] != 0x5A4B5052u || w[1] != 6) return fail("bad magic/version");
+  if ((!code && n_code) || (!io && n_io)) return fail("null program / I/O transcript");
   const u32 log_n = w[2];
   if (w[3] != p->width || w[4] != p->log_blowup || w[5] != p->num_queries || w[6] != p->pow_bits || w[7] != p->num_public)
     return fail("proof header does not match params");
@@ -229,7 +238,9 @@ bool verify(const zkir_params* p, const u32* w, size_t nwords, const u32* pv_in,
   const u32 hdr[7] = {log_n, W, AW, p->log_blowup, p->num_queries, p->pow_bits, np};
   u32 pdig[8];
   program_digest(code, n_code, pdig);
-  ch.observe(hdr, 7); ch.observe(pv, np); ch.observe(pdig, 8); ch.observe(troot, 8);
+  ch.observe(hdr, 7); ch.observe(pv, np); ch.observe(pdig, 8);
+  io_digest(io, n_io, pdig);
+  ch.observe(pdig, 8); ch.observe(troot, 8);
   const X4 lz = ch.sample_ext(), ltheta = ch.sample_ext();   // lookup challenges, drawn before the aux columns are committed
   ch.observe(aroot, 8);
   const X4 alpha = ch.sample_ext();
@@ -277,7 +288,15 @@ bool verify(const zkir_params* p, const u32* w, size_t nwords, const u32* pv_in,
   }
   AirAtZeta c;
   c.loc = ot.data(); c.nxt = otg.data(); c.pub = pubz; c.pv = pv; c.alpha = alpha;
-  c.zc = lz; c.thp[0] = X4(1); c.thp[1] = ltheta; c.thp[2] = ltheta * ltheta; c.thp[3] = c.thp[2] * ltheta;
+  c.zc = lz; c.thp[0] = X4(1); c.thp[1] = ltheta;
+  for (int k = 2; k < 5; k++) c.thp[k] = c.thp[k - 1] * ltheta;
+  // the table side of the I/O bus is public: S_io = sum_e 1 / (z - (3 + theta clk + theta^2 kind + theta^3 lo + theta^4 hi))
+  for (size_t e = 0; e < n_io; e++) {
+    X4 fp(3), d;
+    for (int k = 0; k < 4; k++) fp = fp + scale(c.thp[k + 1], io[4 * e + k] % P);
+    if (!xinv(lz - fp, &d)) return fail("lookup challenge hits an I/O event");
+    c.sio_v = c.sio_v + d;
+  }
   c.is_first = zh * i1; c.is_last = zh * i2; c.is_trans = zeta - X4(g_inv);
   zkir_air_eval(c);
   X4 xp[4]; for (int k = 0; k < 4; k++) { xp[k] = X4(); xp[k].c[k] = 1; }  // basis 1, X, X^2, X^3
@@ -365,14 +384,16 @@ bool verify(const zkir_params* p, const u32* w, size_t nwords, const u32* pv_in,
 }  // namespace
 
 extern "C" {
-int zkir_b200_verify(const zkir_params* p, const uint8_t* proof, size_t len, const uint32_t* public_values, const uint32_t* code, size_t n_code) {
+int zkir_b200_verify(const zkir_params* p, const uint8_t* proof, size_t len, const uint32_t* public_values, const uint32_t* code, size_t n_code,
+                     const uint32_t* io_events, size_t n_io) {
   g_verify_error.clear();
   if (!proof || len % 4) { g_verify_error = "bad proof buffer"; return ZKIR_ERR_VERIFY; }
   std::vector<u32> w(len / 4);
   memcpy(w.data(), proof, len);
-  return verify(p, w.data(), w.size(), public_values, code, n_code) ? 0 : ZKIR_ERR_VERIFY;
+  return verify(p, w.data(), w.size(), public_values, code, n_code, io_events, n_io) ? 0 : ZKIR_ERR_VERIFY;
 }
 void zkir_program_digest(const uint32_t* code, size_t n_code, uint32_t digest8[8]) { program_digest(code, n_code, digest8); }
+void zkir_io_digest(const uint32_t* io_events, size_t n_io, uint32_t digest8[8]) { io_digest(io_events, n_io, digest8); }
 // the width-16 Poseidon2 permutation (canonical values in and out): SYS_POSEIDON2 of the interpreter (vm.cc) uses it
 void zkir_host_poseidon2_permute(uint32_t* state16) { permute(state16); }
 // ROM entry of one code word as the AIR's ROM lookup sees it (used by the prover to build the public ROM columns)

@@ -126,6 +126,7 @@ struct zkir_vm_result {
   std::vector<u64> memop_begin;  // CSR offsets into memops, size cycles+1
   std::vector<zkir_mem_op> memops;  // data memory ops per row (fetch excluded)
   std::vector<u32> code;            // the program's code words (the ROM the proof is bound to)
+  std::vector<u32> io;              // public I/O transcript: 4 words per READ / WRITE ecall (cycle, kind 0/1, value lo20, value hi20)
   u64 logged = 0;                   // write-log mode: rows written to the caller's arrays
   std::string error;
 };
@@ -313,8 +314,21 @@ static int vm_run_impl(const uint32_t* code, size_t n_code, const uint8_t* data,
       u64 num = regs[10];
       switch (num) {
         case 0: halted = true; res->halt_kind = ZKIR_HALT_EXIT; res->exit_code = regs[11]; break;
-        case 1: { u64 v = input_pos < n_inputs ? inputs[input_pos++] : 0; W(10, v); if (record_trace) res->aux.back() = v; break; }
-        case 2: res->outputs.push_back(regs[11]); if (record_trace) res->aux.back() = regs[11]; break;
+        case 1: {
+          u64 v = input_pos < n_inputs ? inputs[input_pos++] : 0;
+          W(10, v);
+          if (record_trace) res->aux.back() = v;
+          const u32 ev[4] = {(u32)cycles, 0u, (u32)(v & 0xFFFFF), (u32)((v >> 20) & 0xFFFFF)};
+          res->io.insert(res->io.end(), ev, ev + 4);
+          break;
+        }
+        case 2: {
+          res->outputs.push_back(regs[11]);
+          if (record_trace) res->aux.back() = regs[11];
+          const u32 ev[4] = {(u32)cycles, 1u, (u32)(regs[11] & 0xFFFFF), (u32)((regs[11] >> 20) & 0xFFFFF)};
+          res->io.insert(res->io.end(), ev, ev + 4);
+          break;
+        }
         case 4: {
           // SYS_POSEIDON2 (syscall.rs:22,140-149).  The reference's implementation is a stub that errors (crypto.rs:299-315), so the
           // semantics are this build's: read 16 little-endian u32 words at R11 (reduced mod p),
@@ -378,6 +392,8 @@ int zkir_vm_run_writelog_cb(const uint32_t* code, size_t n_code, const uint8_t* 
   return vm_run_impl(code, n_code, data, n_data, entry_point, inputs, n_inputs, max_cycles, 0, pcs32, instrs, wlog, capacity, out, on_chunk, user, chunk_rows);
 }
 
+size_t zkir_vm_io_len(const zkir_vm_result* r) { return r->io.size() / 4; }
+const uint32_t* zkir_vm_io(const zkir_vm_result* r) { return r->io.data(); }
 size_t zkir_vm_code_len(const zkir_vm_result* r) { return r->code.size(); }
 const uint32_t* zkir_vm_code(const zkir_vm_result* r) { return r->code.data(); }
 uint64_t zkir_vm_logged_rows(const zkir_vm_result* r) { return r->logged; }

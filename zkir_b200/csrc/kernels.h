@@ -74,7 +74,7 @@ struct QuotientArgs {
   u32 log_n, log_blowup;
   const u32* pv;       // device, num_public Montgomery values
   const u32* alpha;    // device, ext4 Montgomery
-  const u32* lookup;   // device, lookup challenges z[4], theta[4], Montgomery
+  const u32* lookup;   // device, lookup challenges z[4], theta[4], then the public I/O transcript's sum sio[4] (launch_io_sum), Montgomery
   const u32* xs;       // [M] coset-major: x = shift*w^(i*B+z) at z*N+i
   const u32* dinv;     // [M] 1/(x - 1), same order
   u32* apow_scratch;   // [K][4] device scratch for alpha powers
@@ -120,7 +120,7 @@ u64 trace_expand_wl_scratch_ints(u64 N);
 struct AuxArgs {
   const u32* trace;      // [88][N] canonical main columns
   const u32* pub;        // [4][N] canonical public columns
-  const u32* lookup;     // device: z[4], theta[4], Montgomery
+  const u32* lookup;     // device: z[4], theta[4], sio[4] (the sum the fractions of all rows must add up to), Montgomery
   u32* aux;              // out [16][N] canonical
   u32 log_n;
   E4* row_tot;           // scratch [N]: sum of the fractions of each row
@@ -128,6 +128,8 @@ struct AuxArgs {
   u64* err;              // out (may be null): (N-1) << 8 | 8 if the lookups do not balance
 };
 u64 aux_gen_blocks(u64 N);
+// lookup[8..12) <- S_io = sum over the public I/O events (4 words each: clk, kind, lo, hi; canonical, device) of 1 / (z - fingerprint)
+int launch_io_sum(const u32* events, u32 n_events, u32* lookup, cudaStream_t st, u64* launches);
 int launch_aux_gen(const AuxArgs& a, cudaStream_t st, u64* launches);
 int launch_trace_expand_wl(const WlArgs& a, cudaStream_t st, u64* launches);
 

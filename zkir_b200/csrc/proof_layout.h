@@ -1,4 +1,4 @@
-// Word offsets of a protocol v5 proof (docs/PROVER_SPEC.md section 5); shared by the CUDA prover and the host verifier.
+// Word offsets of a protocol v6 proof (docs/PROVER_SPEC.md section 5); shared by the CUDA prover and the host verifier.
 #pragma once
 #include <stddef.h>
 #include <stdint.h>
@@ -7,7 +7,7 @@
 
 namespace zkir {
 
-static const uint32_t PROOF_MAGIC = 0x5A4B5052u, PROOF_VERSION = 5u;
+static const uint32_t PROOF_MAGIC = 0x5A4B5052u, PROOF_VERSION = 6u;
 static const uint32_t QW = 8;                      // quotient columns: 4 ext planes x 2 chunks, column = 2*plane + chunk
 static const uint32_t AW = ZKIR_AIR_AUX_WIDTH;     // aux (LogUp) columns, committed after the lookup challenges
 static const uint32_t PW = ZKIR_AIR_PUB_WIDTH;     // public columns (never committed)

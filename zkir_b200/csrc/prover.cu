@@ -59,6 +59,7 @@ static u32 hinv(u32 a) { return hpow(a, BB_P - 2); }
 static u32 hmul(u32 a, u32 b) { return (u32)((u64)a * b % BB_P); }
 
 extern "C" void zkir_program_digest(const uint32_t* code, size_t n_code, uint32_t digest8[8]);   // host/verify.cc
+extern "C" void zkir_io_digest(const uint32_t* io_events, size_t n_io, uint32_t digest8[8]);
 static const u32 HDR_WORDS = 7;   // transcript header: log_n, W, aux width, log_blowup, num_queries, pow_bits, num_public
 
 enum { PEER_LDE = 0, PEER_Q = 1, PEER_QLDE = 2, PEER_BUFS = 3 };
@@ -82,7 +83,7 @@ struct Workspace {
   std::vector<E4*> h_layers; std::vector<u32*> h_ltrees;
   E4** d_layers = nullptr; u32** d_ltrees = nullptr;
   ChalState* chal = nullptr;
-  u32* chal_buf = nullptr;   // alpha[4] zeta[4] alpha_fri[4] betas[R][4] pow_raw[1] pow_sample[1] lookup z[4] theta[4] hdr_mont[7+np+8]
+  u32* chal_buf = nullptr;   // alpha[4] zeta[4] alpha_fri[4] betas[R][4] pow_raw[1] pow_sample[1] lookup z[4] theta[4] sio[4] hdr_mont[7+np+16]
   u32* indices = nullptr;
   u32* apow = nullptr; E4* afp = nullptr;
   u32* otree = nullptr;      // scratch of the tree hash of the opened values
@@ -97,6 +98,7 @@ struct Workspace {
   cudaGraphExec_t gexec = nullptr;
   u32 proofs_done = 0; bool graph_failed = false, graph_run = false;
   u32 graph_pow_bits = 0;         // the one proving parameter that is not part of the workspace shape
+  size_t graph_n_io = 0; const u32* graph_d_io = nullptr;   // the I/O transcript's length and device buffer are baked into the captured launches
   u64 graph_launches = 0;         // kernels in one proof of this shape (the launch counter advances by this per replay)
   u32* h_trace_stage = nullptr;   // pinned, [W][N]: the fixed source address of the graph's H2D node
   u32* xchg = nullptr;       // [ZKIR_MAX_SHARDS][PEER_REC_WORDS] words: handle exchange; word 0 doubles as the barrier token
@@ -120,6 +122,10 @@ struct zkir_ctx {
   std::vector<u32> code;                             // the program (zkir_b200_set_program): ROM of the lookup argument
   u32 code_digest[8] = {0};                          // its transcript digest
   u64 program_version = 0;                           // bumped by every set_program; workspaces rebuild their ROM columns lazily
+  std::vector<u32> io;                               // public I/O transcript of the next proof (zkir_b200_set_io), 4 words per event
+  u32 io_digest[8] = {0};                            // its transcript digest (of the empty list until set)
+  bool io_digest_valid = false;
+  u32* d_io = nullptr; size_t d_io_cap = 0;          // device copy
   // one proof sharded over `shards` GPUs (zkir_b200_comm_init): this context computes the Merkle leaf segments
   // [shard_lo, shard_hi) -- its own rank with a communicator, all of them when the shards are emulated on one GPU (tests)
   Comm* comm = nullptr;
@@ -222,13 +228,13 @@ static int ws_prepare(zkir_ctx* ctx, const zkir_params* p, u32 log_n) {
   A(U1, N) A(U2, N) A(U1q, N) A(open_scratch, open_scratch_elems((u32)WA, N)) A(dummy_open, WA)
   A(layers, 2 * M) A(ltrees, 2 * M * 8)
   A(d_layers, R + 1) A(d_ltrees, R + 1)
-  A(chal, 1) A(chal_buf, 12 + 4 * R + 2 + 8 + HDR_WORDS + p->num_public + 8) A(indices, p->num_queries + 1)
+  A(chal, 1) A(chal_buf, 12 + 4 * R + 2 + 12 + HDR_WORDS + p->num_public + 16) A(indices, p->num_queries + 1)
   A(apow, 4 * ZKIR_AIR_NUM_CONSTRAINTS) A(afp, WA + 5)
   A(proof, L.total + 4) A(xchg, ZKIR_MAX_SHARDS * PEER_REC_WORDS) A(otree, hash_tree_scratch_words((u32)(2 * WA + QW) * 4))
 #undef A
   w.proof += (4 - (L.open_t & 3)) & 3;   // the opened values are read and written as 16-byte ext4 elements: align that section
   CU(cudaMallocHost(&w.h_proof, L.total * 4));
-  CU(cudaMallocHost(&w.h_stage, (8 + HDR_WORDS + 2 * p->num_public + 8) * 4));
+  CU(cudaMallocHost(&w.h_stage, (8 + HDR_WORDS + 2 * p->num_public + 16) * 4));
   // layer pointers
   w.h_layers.resize(R + 1); w.h_ltrees.resize(R + 1);
   E4* lp = w.layers; u32* tp = w.ltrees;
@@ -430,6 +436,8 @@ static int fill_header_stage(zkir_ctx* ctx, const zkir_params* p, u32 log_n, con
   for (u32 i = 0; i < HDR_WORDS; i++) hm[i] = bb_to_mont_c(hdr[i]);
   for (u32 i = 0; i < np; i++) hm[HDR_WORDS + i] = bb_to_mont_c(pv[i]);
   for (u32 i = 0; i < 8; i++) hm[HDR_WORDS + np + i] = bb_to_mont_c(ctx->code_digest[i]);
+  if (!ctx->io_digest_valid) { zkir_io_digest(ctx->io.data(), ctx->io.size() / 4, ctx->io_digest); ctx->io_digest_valid = true; }
+  for (u32 i = 0; i < 8; i++) hm[HDR_WORDS + np + 8 + i] = bb_to_mont_c(ctx->io_digest[i]);
   return 0;
 }
 
@@ -485,14 +493,14 @@ static int prove_resident(zkir_ctx* ctx, const zkir_params* p, u32 log_n, const 
   if (p2p && !w.peers_valid) { int xrc = peers_open(ctx); if (xrc) return xrc; }
   const u32 me = p2p ? (u32)comm_rank(ctx->comm) : 0;
   u32* c_alpha = w.chal_buf, *c_zeta = w.chal_buf + 4, *c_afri = w.chal_buf + 8, *c_betas = w.chal_buf + 12;
-  u32* c_pow_raw = w.chal_buf + 12 + 4 * R, *c_pow_sample = c_pow_raw + 1, *c_lookup = c_pow_raw + 2, *c_hdr = c_lookup + 8;
+  u32* c_pow_raw = w.chal_buf + 12 + 4 * R, *c_pow_sample = c_pow_raw + 1, *c_lookup = c_pow_raw + 2, *c_hdr = c_lookup + 12;
 
   // ---- header + public values (host staging filled by fill_header_stage: also the per-proof step of a graph replay)
   { int frc = fill_header_stage(ctx, p, log_n, pv); if (frc) return frc; }
   u32* hs = w.h_stage;
   u32* hm = hs + 8 + np;  // Montgomery copy for the transcript
   CU(cudaMemcpyAsync(w.proof, hs, (8 + np) * 4, cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(c_hdr, hm, (HDR_WORDS + np + 8) * 4, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(c_hdr, hm, (HDR_WORDS + np + 16) * 4, cudaMemcpyHostToDevice, st));
   CU(cudaMemsetAsync(w.chal, 0, sizeof(ChalState), st));
   CU(cudaMemsetAsync(ctx->d_err + 1, 0xff, 8, st));
 
@@ -536,11 +544,12 @@ static int prove_resident(zkir_ctx* ctx, const zkir_params* p, u32 log_n, const 
   CU(cudaEventRecord(ctx->ev[ZKIR_STAGE_TRACE_COMMIT], st));
   u32 t_sl = 0, a_sl = 0, q_sl = 0;
   int crc;
-  RC(launch_challenger(w.chal, c_hdr, HDR_WORDS + np + 8, nullptr, 0, 0, st, LC));   // header, public values, program digest
+  RC(launch_challenger(w.chal, c_hdr, HDR_WORDS + np + 16, nullptr, 0, 0, st, LC));   // header, public values, program digest, I/O transcript digest
   if ((crc = commit_tree(ctx, w.lde, (u32)W, p->log_blowup, nullptr, w.ttree, M >> L.log_lr, w.proof + L.troot, c_lookup, 8, &t_sl, sp.on ? 1 : 0)) != 0) return crc;  // root -> proof, observe, sample z and theta
   // ---- 2b. LogUp aux columns for the challenges just drawn (aux_gen.cu), their LDE and their own commitment
   CU(cudaEventRecord(ctx->ev[ZKIR_STAGE_AUX], st));
   {
+    RC(launch_io_sum(ctx->d_io, (u32)(ctx->io.size() / 4), c_lookup, st, LC));   // S_io of the public I/O transcript for the challenges just drawn
     AuxArgs aa;
     aa.trace = trace; aa.pub = w.pub; aa.lookup = c_lookup; aa.aux = w.aux; aa.log_n = log_n; aa.row_tot = w.aux_row_tot; aa.blk_tot = w.aux_blk_tot;
     aa.err = ctx->d_err + 1;
@@ -714,7 +723,7 @@ static int expand_error(zkir_ctx* ctx) {  // after the stream is drained: conver
     if (e == ~0ull) continue;
     const u32 code = (u32)(e & 0xff);
     ctx->err = "AIR v2 cannot constrain row " + std::to_string((unsigned long long)(e >> 8)) + ": " +
-               (code == 8 ? "the lookup fractions do not cancel (a chunk outside the range table or an instruction outside the program)" : pack_err_text(code));
+               (code == 8 ? "the lookup fractions do not balance (a chunk outside the range table, an instruction outside the program, or an I/O transcript that is not the trace's)" : pack_err_text(code));
     return ZKIR_ERR_AIR;
   }
   return 0;
@@ -759,6 +768,8 @@ int zkir_b200_create(zkir_ctx** out, int device_id) {
   if (poseidon2_init_constants() != 0) { g_last_error = "constant upload failed"; delete ctx; return ZKIR_ERR_CUDA; }
   if (cudaMalloc(&ctx->d_err, 16) != cudaSuccess || cudaMallocHost(&ctx->h_err, 16) != cudaSuccess) { g_last_error = "error words"; delete ctx; return ZKIR_ERR_OOM; }
   ctx->h_err[0] = ctx->h_err[1] = ~0ull;
+  if (cudaMalloc(&ctx->d_io, 64) != cudaSuccess) { g_last_error = "io buffer"; delete ctx; return ZKIR_ERR_OOM; }
+  ctx->d_io_cap = 16;
   ctx->tables = ntt_tables_create(ctx->stream, &ctx->launches);
   ctx->fast = fast_ntt_create(ctx->stream, &ctx->launches);
   *out = ctx;
@@ -777,6 +788,7 @@ void zkir_b200_destroy(zkir_ctx* ctx) {
   if (ctx->ntt_tmp) cudaFree(ctx->ntt_tmp);
   for (int i = 0; i < 2; i++) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
   if (ctx->rows_dev) cudaFree(ctx->rows_dev);
+  if (ctx->d_io) cudaFree(ctx->d_io);
   if (ctx->log_pinned) cudaFreeHost(ctx->log_pinned);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->copy_done) cudaEventDestroy(ctx->copy_done);
@@ -800,6 +812,23 @@ int zkir_b200_set_program(zkir_ctx* ctx, const uint32_t* code, size_t n_code) {
   zkir_program_digest(ctx->code.data(), n_code, ctx->code_digest);
   ctx->program_version++;
   for (zkir_ctx* w : ctx->workers) { int rc = zkir_b200_set_program(w, code, n_code); if (rc) return rc; }
+  return 0;
+}
+
+int zkir_b200_set_io(zkir_ctx* ctx, const uint32_t* events, size_t n_events) {
+  if (!ctx || (!events && n_events) || n_events > (1ull << 26)) return ZKIR_ERR_ARG;
+  ctx->err.clear();
+  cudaSetDevice(ctx->device);
+  CU(cudaStreamSynchronize(ctx->stream));
+  ctx->io.assign(events, events + 4 * n_events);
+  ctx->io_digest_valid = false;
+  if (ctx->d_io_cap < 4 * n_events + 4) {
+    if (ctx->d_io) cudaFree(ctx->d_io);
+    ctx->d_io = nullptr; ctx->d_io_cap = 0;
+    CU(cudaMalloc(&ctx->d_io, (4 * n_events + 4) * 4));
+    ctx->d_io_cap = 4 * n_events + 4;
+  }
+  if (n_events) CU(cudaMemcpy(ctx->d_io, ctx->io.data(), 4 * n_events * 4, cudaMemcpyHostToDevice));
   return 0;
 }
 
@@ -829,7 +858,7 @@ int zkir_b200_prove(zkir_ctx* ctx, const zkir_params* p, const uint32_t* trace_c
   if ((int)log_n <= graph_max_log_n && !ctx->comm && ctx->shards == 1 && !w.graph_failed && w.proofs_done >= 1) {
     if (!w.h_trace_stage) CU(cudaMallocHost(&w.h_trace_stage, trace_bytes));
     memcpy(w.h_trace_stage, trace_cols, trace_bytes);
-    if (w.gexec && w.graph_pow_bits != p->pow_bits) { cudaGraphExecDestroy(w.gexec); w.gexec = nullptr; }
+    if (w.gexec && (w.graph_pow_bits != p->pow_bits || w.graph_n_io != ctx->io.size() || w.graph_d_io != ctx->d_io)) { cudaGraphExecDestroy(w.gexec); w.gexec = nullptr; }
     if (!w.gexec) {
       // capture once; thread-local mode: other contexts (prove_batch workers) keep allocating and launching meanwhile
       cudaGraph_t graph = nullptr;
@@ -840,7 +869,7 @@ int zkir_b200_prove(zkir_ctx* ctx, const zkir_params* p, const uint32_t* trace_c
       cudaError_t ee = cudaStreamEndCapture(ctx->stream, &graph);
       w.graph_launches = ctx->launches - launches_before;
       ctx->launches = launches_before;   // nothing ran yet: the replay below counts
-      w.graph_pow_bits = p->pow_bits;
+      w.graph_pow_bits = p->pow_bits; w.graph_n_io = ctx->io.size(); w.graph_d_io = ctx->d_io;
       if (rc == 0 && ee == cudaSuccess && graph && cudaGraphInstantiate(&w.gexec, graph, 0) == cudaSuccess) {
         cudaGraphDestroy(graph);
       } else {                     // fall back to ordinary launches for this shape (still the CUDA path, never a CPU path)
@@ -897,7 +926,7 @@ static void fill_public_values(u32* pv, u32 entry_point, u64 n_rows, u64 exit_co
 static int expand_rows(zkir_ctx* ctx, const uint64_t* pcs, const uint32_t* instrs, const uint64_t* regs, uint64_t T, const uint64_t* final_regs,
                        uint64_t final_pc, uint32_t log_n, u32* d_cols, u32 col_lo = 0, u32 col_hi = 0xffffffffu) {
   const u64 N = 1ull << log_n;
-  if (T > N || !pcs || !instrs || !regs || !final_regs) { ctx->err = "bad rows: need n_rows <= 2^log_n and non-null arrays"; return ZKIR_ERR_ARG; }
+  if (T >= N || !pcs || !instrs || !regs || !final_regs) { ctx->err = "bad rows: need n_rows < 2^log_n (the last row is a padding row) and non-null arrays"; return ZKIR_ERR_ARG; }
   const size_t need = T * (8 + 4 + 128) + 64;
   if (ctx->rows_bytes < need) {
     if (ctx->rows_dev) cudaFree(ctx->rows_dev);
@@ -972,7 +1001,7 @@ static int wl_convert(zkir_ctx* ctx, const WlStage& sg, uint64_t T, uint64_t fin
 static int expand_writelog(zkir_ctx* ctx, const uint32_t* pcs, const uint32_t* instrs, const uint64_t* wlog, uint64_t T, uint64_t final_pc,
                            uint32_t log_n, u32* d_cols, u32 col_lo = 0, u32 col_hi = 0xffffffffu) {
   const u64 N = 1ull << log_n;
-  if (T > N || !pcs || !instrs || !wlog) { ctx->err = "bad write log: need n_rows <= 2^log_n and non-null arrays"; return ZKIR_ERR_ARG; }
+  if (T >= N || !pcs || !instrs || !wlog) { ctx->err = "bad write log: need n_rows < 2^log_n (the last row is a padding row) and non-null arrays"; return ZKIR_ERR_ARG; }
   // Sharded proof (collective call, every rank holds the same log in host memory): each rank uploads only ITS row segment over
   // PCIe and the segments are exchanged over NVLink with one grouped all-gather, so the host link carries T/G rows per GPU.
   const u32 G = ctx->comm ? ctx->shards : 1;
@@ -1072,9 +1101,11 @@ int zkir_b200_prove_program(zkir_ctx* ctx, const zkir_params* p, const uint32_t*
   const u64 T = zkir_vm_cycles(res), final_pc = zkir_vm_final_pc(res);
   const int halt_kind = zkir_vm_halt_kind(res);
   const u64 exit_code = zkir_vm_exit_code(res);
+  rc = zkir_b200_set_io(ctx, zkir_vm_io(res), zkir_vm_io_len(res));   // the run's public I/O transcript is part of the statement
   zkir_vm_free(res);
+  if (rc) return rc;
   u32 log_n = ZKIR_AIR_RANGE_BITS;
-  while ((1ull << log_n) < T || (1ull << log_n) < n_code) log_n++;
+  while ((1ull << log_n) <= T || (1ull << log_n) < n_code) log_n++;   // at least one padding row after the last cycle
   if (out_cycles) *out_cycles = T;
   if (out_log_n) *out_log_n = log_n;
   if (!overlap) return zkir_b200_prove_writelog(ctx, p, h_pcs, h_ins, h_wlog, T, final_pc, entry_point, exit_code, halt_kind, log_n, pv_out, proof, proof_len);
@@ -1121,8 +1152,9 @@ int zkir_b200_expand_rows(zkir_ctx* ctx, const uint64_t* pcs, const uint32_t* in
 // so the batch is spread over up to 8 worker contexts of the same device, each with its own stream and host thread:
 // the GPU overlaps their kernels.  Proof i is bit-identical to zkir_b200_prove(traces[i]) on a single context.
 int zkir_b200_prove_batch(zkir_ctx* ctx, const zkir_params* p, const uint32_t* const* traces, const uint32_t* log_ns,
-                          const uint32_t* const* pvs, uint32_t n_proofs, uint8_t** proofs, size_t* proof_lens) {
-  if (!ctx || !traces || !log_ns || !pvs || !proofs || !proof_lens) return ZKIR_ERR_ARG;
+                          const uint32_t* const* pvs, const uint32_t* const* ios, const size_t* n_ios, uint32_t n_proofs, uint8_t** proofs,
+                          size_t* proof_lens) {
+  if (!ctx || !traces || !log_ns || !pvs || !ios || !n_ios || !proofs || !proof_lens) return ZKIR_ERR_ARG;
   ctx->err.clear();
   for (uint32_t i = 0; i < n_proofs; i++) { proofs[i] = nullptr; proof_lens[i] = 0; }
   uint32_t nw = n_proofs < 8 ? n_proofs : 8;
@@ -1130,7 +1162,8 @@ int zkir_b200_prove_batch(zkir_ctx* ctx, const zkir_params* p, const uint32_t* c
   if (env && atoi(env) > 0) nw = (uint32_t)atoi(env) < n_proofs ? (uint32_t)atoi(env) : n_proofs;
   if (nw <= 1) {
     for (uint32_t i = 0; i < n_proofs; i++) {
-      int rc = zkir_b200_prove(ctx, p, traces[i], log_ns[i], pvs[i], &proofs[i], &proof_lens[i]);
+      int rc = zkir_b200_set_io(ctx, ios[i], n_ios[i]);
+      if (!rc) rc = zkir_b200_prove(ctx, p, traces[i], log_ns[i], pvs[i], &proofs[i], &proof_lens[i]);
       if (rc) { for (uint32_t j = 0; j < i; j++) { free(proofs[j]); proofs[j] = nullptr; } return rc; }
     }
     return 0;
@@ -1148,7 +1181,8 @@ int zkir_b200_prove_batch(zkir_ctx* ctx, const zkir_params* p, const uint32_t* c
     th.emplace_back([&, w]() {
       zkir_ctx* wc = ctx->workers[w];
       for (uint32_t i = w; i < n_proofs; i += nw) {
-        int rc = zkir_b200_prove(wc, p, traces[i], log_ns[i], pvs[i], &proofs[i], &proof_lens[i]);
+        int rc = zkir_b200_set_io(wc, ios[i], n_ios[i]);
+        if (!rc) rc = zkir_b200_prove(wc, p, traces[i], log_ns[i], pvs[i], &proofs[i], &proof_lens[i]);
         if (rc) { rcs[w] = rc; return; }
       }
     });
@@ -1338,13 +1372,14 @@ int zkir_b200_quotient(zkir_ctx* ctx, const zkir_params* p, const uint32_t* d_ld
   CU(cudaMallocAsync(&pub_cm, (size_t)PW * M * 4, ctx->stream));
   CU(cudaMallocAsync(&xs, M * 4, ctx->stream));
   CU(cudaMallocAsync(&dinv, M * 4, ctx->stream));
-  // small: pv[8 (NP padded)] alpha[4] lookup[8] apow[K][4] -- the ext4 arrays must stay 16-byte aligned
-  CU(cudaMallocAsync(&small, (20 + 4 * ZKIR_AIR_NUM_CONSTRAINTS) * 4, ctx->stream));
-  u32 h[20] = {0};
+  // small: pv[8 (NP padded)] alpha[4] lookup[12: z, theta, sio] apow[K][4] -- the ext4 arrays must stay 16-byte aligned
+  CU(cudaMallocAsync(&small, (24 + 4 * ZKIR_AIR_NUM_CONSTRAINTS) * 4, ctx->stream));
+  u32 h[24] = {0};
   for (u32 i = 0; i < NP; i++) h[i] = bb_to_mont_c(pv[i] % BB_P);
   for (int i = 0; i < 4; i++) h[8 + i] = bb_to_mont_c(alpha[i] % BB_P);
   for (int i = 0; i < 8; i++) h[12 + i] = bb_to_mont_c(lookup[i] % BB_P);
   CU(cudaMemcpyAsync(small, h, sizeof(h), cudaMemcpyHostToDevice, ctx->stream));
+  RC(launch_io_sum(ctx->d_io, (u32)(ctx->io.size() / 4), small + 12, ctx->stream, &ctx->launches));
   int rc = launch_map(lde_m, d_lde, (u64)WA * M, 1, ctx->stream, &ctx->launches);
   if (!rc) rc = launch_coset_reorder(lde_m, lde_cm, WA, log_n, p->log_blowup, 0, ctx->stream, &ctx->launches);  // the kernel sweeps coset-major rows
   if (!rc) rc = launch_map(pub_m, d_publde, (u64)PW * M, 1, ctx->stream, &ctx->launches);
@@ -1352,7 +1387,7 @@ int zkir_b200_quotient(zkir_ctx* ctx, const zkir_params* p, const uint32_t* d_ld
   if (!rc) rc = launch_domain_tables(xs, dinv, log_n, p->log_blowup, ZKIR_BB_GEN, ctx->stream, &ctx->launches);
   QuotientArgs qa;
   qa.lde = lde_cm; qa.publde = pub_cm; qa.q = d_q; qa.log_n = log_n; qa.log_blowup = p->log_blowup; qa.pv = small; qa.alpha = small + 8; qa.lookup = small + 12;
-  qa.xs = xs; qa.dinv = dinv; qa.apow_scratch = small + 20;
+  qa.xs = xs; qa.dinv = dinv; qa.apow_scratch = small + 24;
   if (!rc) rc = launch_quotient(qa, ctx->stream, &ctx->launches);
   if (!rc) rc = launch_map(d_q, d_q, 4 * M, 0, ctx->stream, &ctx->launches);
   CU(cudaStreamSynchronize(ctx->stream));
@@ -1376,12 +1411,13 @@ int zkir_b200_aux_columns(zkir_ctx* ctx, const uint32_t* d_trace, uint32_t log_n
     else hp[ZKIR_PUB_P_DEC * N + i] = 127;
   }
   u32 *pub = nullptr, *lk = nullptr; E4 *rt = nullptr, *bt = nullptr;
-  CU(cudaMalloc(&pub, hp.size() * 4)); CU(cudaMalloc(&lk, 32)); CU(cudaMalloc(&rt, N * sizeof(E4))); CU(cudaMalloc(&bt, aux_gen_blocks(N) * sizeof(E4)));
+  CU(cudaMalloc(&pub, hp.size() * 4)); CU(cudaMalloc(&lk, 48)); CU(cudaMalloc(&rt, N * sizeof(E4))); CU(cudaMalloc(&bt, aux_gen_blocks(N) * sizeof(E4)));
   u32 hl[8];
   for (int i = 0; i < 8; i++) hl[i] = bb_to_mont_c(lookup[i] % BB_P);
   CU(cudaMemcpy(pub, hp.data(), hp.size() * 4, cudaMemcpyHostToDevice));
   CU(cudaMemcpy(lk, hl, 32, cudaMemcpyHostToDevice));
   CU(cudaMemsetAsync(ctx->d_err, 0xff, 16, ctx->stream));
+  RC(launch_io_sum(ctx->d_io, (u32)(ctx->io.size() / 4), lk, ctx->stream, &ctx->launches));
   AuxArgs aa;
   aa.trace = d_trace; aa.pub = pub; aa.lookup = lk; aa.aux = d_aux; aa.log_n = log_n; aa.row_tot = rt; aa.blk_tot = bt; aa.err = ctx->d_err + 1;
   int rc = launch_aux_gen(aa, ctx->stream, &ctx->launches);

@@ -20,7 +20,7 @@ struct QCtx {
   const u32 *lde, *aux, *pub; u64 M, row, nxt;
   const u32* pv;       // shared
   const E4* apow;      // shared, apow[i] = alpha^(K-1-i)
-  const E4* lc;        // shared: lookup challenges z, theta, theta^2, theta^3
+  const E4* lc;        // shared: lookup challenges z, theta .. theta^4, then the public I/O transcript's sum
   Fm is_first, is_last, is_trans;
   Acc4 acc;  // lazy 64-bit accumulator of sum_i alpha^(K-1-i) * C_i over the base-field constraints (bb.cuh)
   E4 accx;   // the ext4-valued constraints (LogUp) are few: plain ext4 products
@@ -34,6 +34,7 @@ struct QCtx {
   __device__ __forceinline__ Xm z() const { Xm r; r.v = lc[0]; return r; }
   __device__ __forceinline__ Xm th(int k) const { Xm r; r.v = lc[k]; return r; }
   __device__ __forceinline__ Xm xf(Fm a) const { Xm r; r.v = e4_from_base(a.v); return r; }
+  __device__ __forceinline__ Xm sio() const { Xm r; r.v = lc[5]; return r; }
   __device__ __forceinline__ Xm x4(Fm a, Fm b, Fm c, Fm d) const { Xm r; r.v.c[0] = a.v; r.v.c[1] = b.v; r.v.c[2] = c.v; r.v.c[3] = d.v; return r; }
   __device__ __forceinline__ void emit(int idx, Fm v) {
     acc4_mac(acc, apow[idx], v.v);
@@ -54,7 +55,7 @@ __global__ void alpha_powers_kernel(const u32* alpha, E4* apow) {  // apow[i] = 
 template <int MINB>
 __global__ void __launch_bounds__(128, MINB) quotient_kernel(QuotientArgs a, const E4* apow_g, u32 g_inv, u32 g, u32 snn /* shift^N */, u32 wb /* w_B */) {
   __shared__ E4 apow[ZKIR_AIR_NUM_CONSTRAINTS];
-  __shared__ E4 lc[4];
+  __shared__ E4 lc[6];
   __shared__ u32 pv[ZKIR_AIR_NUM_PUBLIC];
   for (int i = threadIdx.x; i < ZKIR_AIR_NUM_CONSTRAINTS; i += blockDim.x) apow[i] = apow_g[i];
   if (threadIdx.x < ZKIR_AIR_NUM_PUBLIC) pv[threadIdx.x] = a.pv[threadIdx.x];
@@ -66,9 +67,9 @@ __global__ void __launch_bounds__(128, MINB) quotient_kernel(QuotientArgs a, con
     zh_s[zz] = v; zhi_s[zz] = bb_inv(v);
   }
   if (threadIdx.x == 32) {
-    E4 z, th;
-    for (int k = 0; k < 4; k++) { z.c[k] = a.lookup[k]; th.c[k] = a.lookup[4 + k]; }
-    lc[0] = z; lc[1] = th; lc[2] = e4_mul(th, th); lc[3] = e4_mul(lc[2], th);
+    E4 z, th, so;
+    for (int k = 0; k < 4; k++) { z.c[k] = a.lookup[k]; th.c[k] = a.lookup[4 + k]; so.c[k] = a.lookup[8 + k]; }
+    lc[0] = z; lc[1] = th; lc[2] = e4_mul(th, th); lc[3] = e4_mul(lc[2], th); lc[4] = e4_mul(lc[3], th); lc[5] = so;
   }
   __syncthreads();
   const u64 M = 1ull << (a.log_n + a.log_blowup), N = 1ull << a.log_n;

@@ -93,6 +93,13 @@ class ExecutionResult:  # vm.rs:54-78
             self._h = None
 
     @property
+    def io(self):
+        """public I/O transcript of the run: uint32 [n_events, 4] = (cycle, kind 0 READ / 1 WRITE, value lo20, value hi20)"""
+        l = _ffi.lib()
+        n = l.zkir_vm_io_len(self._h)
+        return np.ctypeslib.as_array(l.zkir_vm_io(self._h), shape=(n, 4)).copy() if n else np.zeros((0, 4), dtype=np.uint32)
+
+    @property
     def trace_len(self):
         return _ffi.lib().zkir_vm_trace_len(self._h)
 
@@ -133,7 +140,7 @@ class ExecutionResult:  # vm.rs:54-78
             "exit_code": self.halt_reason.code if self.halt_reason.kind == "Exit" else 0,
             "halt_kind": _HALT_KIND[self.halt_reason.kind],
             "entry_point": self._entry,
-            "program": self.program,
+            "program": self.program, "io": self.io,
         }
 
     def writelog(self, out=None):
@@ -145,7 +152,7 @@ class ExecutionResult:  # vm.rs:54-78
             a = self._wl_arrays
             return {"pcs": a["pcs"][:n], "instrs": a["instrs"][:n], "wlog": a["wlog"][:n], "final_pc": l.zkir_vm_final_pc(self._h),
                     "exit_code": self.halt_reason.code if self.halt_reason.kind == "Exit" else 0,
-                    "halt_kind": _HALT_KIND[self.halt_reason.kind], "entry_point": self._entry, "program": self.program}
+                    "halt_kind": _HALT_KIND[self.halt_reason.kind], "entry_point": self._entry, "program": self.program, "io": self.io}
         n = l.zkir_vm_trace_len(self._h)
         pcs = out["pcs"] if out else np.empty(n, dtype=np.uint32)
         wlog = out["wlog"] if out else np.empty(n, dtype=np.uint64)
@@ -155,7 +162,7 @@ class ExecutionResult:  # vm.rs:54-78
             raise RuntimeError_(rc, l.zkir_vm_last_error().decode())
         r = self.rows()
         return {"pcs": pcs, "instrs": r["instrs"], "wlog": wlog, "final_pc": r["final_pc"], "exit_code": r["exit_code"],
-                "halt_kind": r["halt_kind"], "entry_point": r["entry_point"], "program": self.program}
+                "halt_kind": r["halt_kind"], "entry_point": r["entry_point"], "program": self.program, "io": self.io}
 
     # ---- trace -> columns ("converter", trace.rs:41)
     def min_log_n(self):
@@ -243,6 +250,7 @@ class Proof:
     outputs: list = field(default_factory=list)
     stage_ms: dict = field(default_factory=dict)
     program: object = None
+    io: object = None
 
 
 class Context:
@@ -267,9 +275,18 @@ class Context:
             raise RuntimeError_(rc, self._l.zkir_b200_last_error(self._h).decode())
 
     def set_program(self, program):
-        """The program whose executions this context proves (zkir_b200_set_program): `Program` or a sequence of code words."""
+        """The program whose executions this context proves (zkir_b200_set_program): `Program`, a sequence of code words, or an
+        `ExecutionResult` (then its public I/O transcript is set too: the two halves of the statement besides the public values)."""
+        if isinstance(program, ExecutionResult):
+            self.set_io(program.io)
+            program = program.program
         code = np.ascontiguousarray(getattr(program, "code", program), dtype=np.uint32)
         self._check(self._l.zkir_b200_set_program(self._h, code.ctypes.data, int(code.shape[0])))
+
+    def set_io(self, io):
+        """The public I/O transcript of the execution about to be proven (zkir_b200_set_io): uint32 [n, 4] as `ExecutionResult.io`."""
+        ev = np.ascontiguousarray(io if io is not None else np.zeros((0, 4)), dtype=np.uint32).reshape(-1, 4)
+        self._check(self._l.zkir_b200_set_io(self._h, ev.ctypes.data, int(ev.shape[0])))
 
     # -- device memory helpers
     def alloc(self, nbytes):
@@ -354,11 +371,15 @@ class Context:
         self._l.zkir_b200_free_proof(proof)
         return out
 
-    def prove_batch(self, cols_list, pv_list, cfg, program=None):
-        """Independent proofs of many (small) traces of ONE program: zkir_b200_prove_batch.  Returns the list of proof bytes."""
+    def prove_batch(self, cols_list, pv_list, cfg, program=None, io_list=None):
+        """Independent proofs of many (small) traces of ONE program: zkir_b200_prove_batch.  `io_list[i]` = the public I/O transcript of
+        execution i.  Returns the list of proof bytes."""
         if program is not None:
             self.set_program(program)
         n = len(cols_list)
+        ios = [np.ascontiguousarray(e if e is not None else np.zeros((0, 4)), dtype=np.uint32).reshape(-1, 4) for e in (io_list or [None] * n)]
+        iop = (C.c_void_p * n)(*[e.ctypes.data for e in ios])
+        ion = (C.c_size_t * n)(*[int(e.shape[0]) for e in ios])
         params = cfg.params()
         keep = [np.ascontiguousarray(c, dtype=np.uint32) for c in cols_list]
         pvs = [np.ascontiguousarray(p, dtype=np.uint32) for p in pv_list]
@@ -367,7 +388,7 @@ class Context:
         lg = (C.c_uint32 * n)(*[int(c.shape[1]).bit_length() - 1 for c in keep])
         out = (C.c_void_p * n)()
         lens = (C.c_size_t * n)()
-        self._check(self._l.zkir_b200_prove_batch(self._h, C.byref(params), tr, lg, pp, n, out, lens))
+        self._check(self._l.zkir_b200_prove_batch(self._h, C.byref(params), tr, lg, pp, iop, ion, n, out, lens))
         res = []
         for i in range(n):
             res.append(C.string_at(out[i], lens[i]))
@@ -379,6 +400,8 @@ class Context:
         converter; returns (proof bytes, public values)."""
         if rows.get("program") is not None:
             self.set_program(rows["program"])
+        if rows.get("io") is not None:
+            self.set_io(rows["io"])
         params = cfg.params()
         n = int(rows["pcs"].shape[0])
         if log_n is None:
@@ -400,6 +423,8 @@ class Context:
         """wl: dict as returned by ExecutionResult.writelog().  Returns (proof bytes, public values)."""
         if wl.get("program") is not None:
             self.set_program(wl["program"])
+        if wl.get("io") is not None:
+            self.set_io(wl["io"])
         params = cfg.params()
         n = int(wl["pcs"].shape[0])
         if log_n is None:
@@ -520,23 +545,29 @@ def prove(program, inputs=(), cfg=None):
     cfg = cfg or ProverConfig()
     ctx = _ctx(cfg.device)
     pb, pv, cycles, log_n = ctx.prove_program(program, list(inputs), cfg)
-    return Proof(pb, pv, log_n, cycles, [], ctx.stage_ms(), program)
+    # the statement's public I/O transcript and outputs: one plain interpreter run without any recording (323 M cycles/s)
+    res = VM(program, list(inputs), VMConfig(max_cycles=cfg.max_cycles, enable_poseidon2_syscall=cfg.enable_poseidon2_syscall)).run()
+    return Proof(pb, pv, log_n, cycles, res.outputs, ctx.stage_ms(), program, res.io)
 
 
-def verify(proof, cfg=None, public_values=None, program=None):
-    """CPU verification through the C ABI; returns (ok, reason).  `program` (Program or code words) is the statement's program;
-    a `Proof` returned by prove() carries it."""
+def verify(proof, cfg=None, public_values=None, program=None, io=None):
+    """CPU verification through the C ABI; returns (ok, reason).  The statement is (program, public values, public I/O transcript):
+    `program` = Program / code words, `io` = uint32 [n, 4] as `ExecutionResult.io`; passing an `ExecutionResult` as `program`
+    supplies both, and a `Proof` returned by prove() carries them."""
     cfg = cfg or ProverConfig()
     l = _ffi.lib()
     pb = proof.bytes_ if isinstance(proof, Proof) else bytes(proof)
     pv = public_values if public_values is not None else (proof.public_values if isinstance(proof, Proof) else None)
     if program is None and isinstance(proof, Proof):
-        program = proof.program
+        program, io = proof.program, (proof.io if io is None else io)
+    if isinstance(program, ExecutionResult):
+        program, io = program.program, (program.io if io is None else io)
     if program is None:
         return False, "verify() needs the program the proof is about"
     code = np.ascontiguousarray(getattr(program, "code", program), dtype=np.uint32)
+    ev = np.ascontiguousarray(io if io is not None else np.zeros((0, 4)), dtype=np.uint32).reshape(-1, 4)
     params = cfg.params()
     buf = C.create_string_buffer(pb, len(pb))
     pvp = np.ascontiguousarray(pv, dtype=np.uint32).ctypes.data_as(_ffi.u32p) if pv is not None else None
-    rc = l.zkir_b200_verify(C.byref(params), C.cast(buf, C.c_void_p), len(pb), pvp, code.ctypes.data, int(code.shape[0]))
+    rc = l.zkir_b200_verify(C.byref(params), C.cast(buf, C.c_void_p), len(pb), pvp, code.ctypes.data, int(code.shape[0]), ev.ctypes.data, int(ev.shape[0]))
     return rc == 0, ("" if rc == 0 else l.zkir_b200_last_error(None).decode())
