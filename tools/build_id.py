@@ -1,5 +1,6 @@
 #!/usr/bin/env python3
-"""Identity of the CUDA build: sha256 over the library's sources (zkir_b200/csrc/**, include/*.h), first 12 hex digits.
+"""Identity of the CUDA build: sha256 over the device-side sources of the library (zkir_b200/csrc/*.cu, *.cuh, *.h and include/*.h; the
+host-only files under csrc/host/ -- interpreter, packer, verifier -- do not change any kernel), first 12 hex digits.
 bench.py prints it, the profile tools store it, so a number read from profiles/ can be matched to the build that produced it."""
 import hashlib
 import os
@@ -10,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def build_id():
     h = hashlib.sha256()
     files = []
-    for d in ("zkir_b200/csrc", "zkir_b200/csrc/host", "include"):
+    for d in ("zkir_b200/csrc", "include"):
         for f in sorted(os.listdir(os.path.join(ROOT, d))):
             if f.endswith((".cu", ".cc", ".h", ".cuh")):
                 files.append(os.path.join(d, f))

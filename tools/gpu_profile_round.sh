@@ -7,7 +7,7 @@ TAG=${1:-prof}
 mkdir -p gpurun_out
 set -x
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_$TAG.csv python tools/prove_once.py 2 > gpurun_out/prove_once_$TAG.log 2>&1
-ncu --set full --clock-control none --import-source on -k "regex:leaf_hash_kernel|dft_tile_kernel|quotient_kernel|open_partial_kernel|deep_kernel|aux_rows_kernel|scan_write_kernel" -s 22 -c 22 -o gpurun_out/${TAG}_hot python tools/prove_once.py 2 > gpurun_out/ncu_hot_$TAG.log 2>&1
+ncu --set full --clock-control none --import-source on -k "regex:leaf_hash_rows_kernel|dft_tile_kernel|quotient_kernel|open_partial_kernel|deep_kernel|aux_rows_kernel|scan_write_kernel|io_sum_kernel" -s 26 -c 30 -o gpurun_out/${TAG}_hot python tools/prove_once.py 2 > gpurun_out/ncu_hot_$TAG.log 2>&1
 ncu --set full --clock-control none --import-source on -k "regex:compress_kernel|leaf_hash_pairs_kernel|merkle_coop_kernel|fri_fold_kernel" -s 80 -c 14 -o gpurun_out/${TAG}_tree python tools/prove_once.py 2 > gpurun_out/ncu_tree_$TAG.log 2>&1
 for r in hot tree; do
   python tools/ncu_summary.py gpurun_out/${TAG}_$r.ncu-rep > gpurun_out/ncu_${r}_$TAG.md

@@ -201,6 +201,7 @@ static int vm_run_impl(const uint32_t* code, size_t n_code, const uint8_t* data,
   size_t input_pos = 0;
   bool halted = false;
   u64 cur_log = 0;          // write-log word of the current cycle
+  u64 next_chunk = on_chunk ? chunk_rows : ~0ull;   // cycle count at which the next progress callback is due (no per-cycle division)
   u64 wide_row = ~0ull;     // first cycle that wrote a value above 40 bits (the log format cannot hold it)
   auto R = [&](u32 i) -> u64 { return i == 0 ? 0 : regs[i]; };
   auto W = [&](u32 i, u64 v) {
@@ -349,7 +350,7 @@ static int vm_run_impl(const uint32_t* code, size_t n_code, const uint8_t* data,
     }
     if (wl) {
       wl_log[cycles] = cur_log;
-      if (on_chunk && ((cycles + 1) % chunk_rows) == 0) on_chunk(cb_user, cycles + 1);   // rows [0, cycles + 1) are final: upload may start
+      if (cycles + 1 == next_chunk) { on_chunk(cb_user, next_chunk); next_chunk += chunk_rows; }   // rows [0, next_chunk) are final: upload may start
     }
     if (record_trace) {
       // data memory ops of this cycle: timestamp == cycle && address != fetch pc (vm.rs:291-298)

@@ -828,7 +828,9 @@ int zkir_b200_set_io(zkir_ctx* ctx, const uint32_t* events, size_t n_events) {
     CU(cudaMalloc(&ctx->d_io, (4 * n_events + 4) * 4));
     ctx->d_io_cap = 4 * n_events + 4;
   }
-  if (n_events) CU(cudaMemcpy(ctx->d_io, ctx->io.data(), 4 * n_events * 4, cudaMemcpyHostToDevice));
+  // ON THE CONTEXT'S STREAM: a plain cudaMemcpy from pageable memory returns once the data is staged, and its DMA is ordered in the legacy
+  // default stream, which a non-blocking stream does not wait for -- the next proof could read the previous transcript
+  if (n_events) CU(cudaMemcpyAsync(ctx->d_io, ctx->io.data(), 4 * n_events * 4, cudaMemcpyHostToDevice, ctx->stream));
   return 0;
 }
 
@@ -1414,8 +1416,8 @@ int zkir_b200_aux_columns(zkir_ctx* ctx, const uint32_t* d_trace, uint32_t log_n
   CU(cudaMalloc(&pub, hp.size() * 4)); CU(cudaMalloc(&lk, 48)); CU(cudaMalloc(&rt, N * sizeof(E4))); CU(cudaMalloc(&bt, aux_gen_blocks(N) * sizeof(E4)));
   u32 hl[8];
   for (int i = 0; i < 8; i++) hl[i] = bb_to_mont_c(lookup[i] % BB_P);
-  CU(cudaMemcpy(pub, hp.data(), hp.size() * 4, cudaMemcpyHostToDevice));
-  CU(cudaMemcpy(lk, hl, 32, cudaMemcpyHostToDevice));
+  CU(cudaMemcpyAsync(pub, hp.data(), hp.size() * 4, cudaMemcpyHostToDevice, ctx->stream));   // on the stream the kernels run on (see zkir_b200_set_io)
+  CU(cudaMemcpyAsync(lk, hl, 32, cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemsetAsync(ctx->d_err, 0xff, 16, ctx->stream));
   RC(launch_io_sum(ctx->d_io, (u32)(ctx->io.size() / 4), lk, ctx->stream, &ctx->launches));
   AuxArgs aa;
