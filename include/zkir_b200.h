@@ -30,7 +30,8 @@ extern "C" {
 #define ZKIR_ERR_VERIFY (-7)
 
 #define ZKIR_BABYBEAR_P 2013265921u
-#define ZKIR_AIR_V2_WIDTH 88u      /* main trace columns (docs/PROVER_SPEC.md section 3); 16 aux + 4 public columns are internal */
+#define ZKIR_AIR_V2_WIDTH 88u      /* main trace columns of the CORE profile (docs/PROVER_SPEC.md section 3); 16 aux + 4 public columns are internal */
+#define ZKIR_AIR_FULL_WIDTH 170u   /* main trace columns of the FULL profile (section 3.7: MUL/DIV family, bitwise, shifts, signed compares) */
 #define ZKIR_AIR_V2_NUM_PUBLIC 5u  /* entry_pc, num_cycles, exit_lo, exit_hi, halted */
 #define ZKIR_MIN_LOG_N 10u         /* the 1024-entry range table (zkir-spec/src/config.rs:76-80) occupies trace rows */
 
@@ -39,7 +40,7 @@ typedef struct {
   uint32_t log_blowup;  /* >= 1 */
   uint32_t num_queries;
   uint32_t pow_bits;
-  uint32_t width;       /* must equal ZKIR_AIR_V2_WIDTH */
+  uint32_t width;       /* ZKIR_AIR_V2_WIDTH or ZKIR_AIR_FULL_WIDTH: selects the AIR profile of the proof (zkir_program_profile) */
   uint32_t num_public;  /* must equal ZKIR_AIR_V2_NUM_PUBLIC */
 } zkir_params;
 
@@ -136,6 +137,11 @@ int zkir_b200_verify(const zkir_params*, const uint8_t* proof, size_t len, const
 /* host helpers shared by the interpreter, the prover's ROM builder and guest-side tooling */
 void zkir_host_poseidon2_permute(uint32_t state16[16]);          /* width-16 Poseidon2 of docs/PROVER_SPEC.md section 2, canonical */
 void zkir_rom_entry(uint32_t word, uint32_t* dec, uint32_t* imm); /* decoded ROM row of one instruction word (spec section 3.3) */
+/* public columns of the AIR profile `width` (spec sections 3.3, 3.7): one row / the number of rows that can differ from the default
+ * row (i = ~0) / all columns, column-major [pub width][2^log_n] */
+void zkir_public_row(uint32_t width, uint64_t i, const uint32_t* code, size_t n_code, uint32_t* out);
+uint64_t zkir_public_rows(uint32_t width, size_t n_code);
+void zkir_public_columns(uint32_t width, uint32_t log_n, const uint32_t* code, size_t n_code, uint32_t* cols);
 void zkir_program_digest(const uint32_t* code, size_t n_code, uint32_t digest8[8]); /* what the transcript absorbs for the program */
 void zkir_io_digest(const uint32_t* io_events, size_t n_io, uint32_t digest8[8]);   /* ... and for the public I/O transcript */
 
@@ -243,7 +249,11 @@ const uint64_t* zkir_vm_final_regs(const zkir_vm_result*);
  * public_values[5] = {entry_pc, num_cycles, exit_lo, exit_hi, halted}.  min log_n via zkir_pack_min_log_n (>= 10: the range
  * table and the program ROM occupy trace rows). */
 uint32_t zkir_pack_min_log_n(const zkir_vm_result*);
-int zkir_pack_trace(const zkir_vm_result*, uint32_t entry_point, uint32_t log_n, uint32_t* cols, uint32_t* public_values);
+int zkir_pack_trace(const zkir_vm_result*, uint32_t entry_point, uint32_t log_n, uint32_t* cols, uint32_t* public_values);      /* core: 88 columns */
+int zkir_pack_trace_full(const zkir_vm_result*, uint32_t entry_point, uint32_t log_n, uint32_t* cols, uint32_t* public_values); /* full: 170 columns */
+/* which AIR profile a program needs (execute.rs:35-673 by opcode, zkir-spec/src/opcode.rs:24-144): 1 = core, 0 = full,
+ * -1 = it contains an opcode no profile constrains (the loads and stores).  The ROM is public: prover and verifier agree. */
+int zkir_program_profile(const uint32_t* code, size_t n_code);
 
 #ifdef __cplusplus
 }

@@ -10,9 +10,9 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _build_oracle():
+def _build_oracle(full=False):
     import subprocess
-    so = os.path.join(ROOT, "oracle", "_build", "liboracle.so")
+    so = os.path.join(ROOT, "oracle", "_build", "liboracle_full.so" if full else "liboracle.so")
     src = os.path.join(ROOT, "oracle", "oracle.cc")
     if not os.path.exists(so) or (os.path.exists(src) and os.path.getmtime(src) > os.path.getmtime(so)):
         subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")], check=True, capture_output=True)
@@ -22,15 +22,25 @@ def _build_oracle():
 class Oracle:
     """ctypes view of oracle/_build/liboracle.so -- the checker, never the thing under test."""
 
-    def __init__(self):
-        self.l = C.CDLL(_build_oracle())
+    def __init__(self, width=88):
+        """`width` selects the AIR profile (docs/PROVER_SPEC.md section 3.7): 88 = core (liboracle.so), FULL_WIDTH = full (liboracle_full.so)"""
+        full = width == self.FULL_WIDTH
+        assert full or width == 88
+        self.l = C.CDLL(_build_oracle(full))
         self.l.oracle_proof_words.restype = C.c_uint64
+        if full:
+            self.WIDTH, self.AUX_WIDTH, self.PUB_WIDTH = self.FULL_WIDTH, self.FULL_AUX_WIDTH, self.FULL_PUB_WIDTH
+
+    @classmethod
+    def for_columns(cls, cols):
+        return cls(width=int(cols.shape[0]))
 
     @staticmethod
     def _p(a):
         return a.ctypes.data_as(C.c_void_p)
 
-    WIDTH, AUX_WIDTH, PUB_WIDTH, NUM_PUBLIC = 88, 16, 4, 5   # AIR v2 (oracle/air_generated.h)
+    WIDTH, AUX_WIDTH, PUB_WIDTH, NUM_PUBLIC = 88, 16, 4, 5   # AIR v2, core profile (oracle/air_generated.h)
+    FULL_WIDTH, FULL_AUX_WIDTH, FULL_PUB_WIDTH = 170, 108, 13   # full profile (oracle/air_generated_full.h)
     LOOKUP_TEST = np.array([3, 1, 4, 1, 5, 9, 2, 6], dtype=np.uint32)   # fixed lookup challenges z, theta for row-domain checks
 
     def params(self, cfg):

@@ -22,7 +22,12 @@
 #endif
 #include <algorithm>
 #include "constants_generated.h"
+// compiled once per AIR profile (docs/PROVER_SPEC.md section 3.7): liboracle.so = core, liboracle_full.so = full (-DZKIR_PROFILE_FULL)
+#ifdef ZKIR_PROFILE_FULL
+#include "air_generated_full.h"
+#else
 #include "air_generated.h"
+#endif
 
 typedef uint32_t u32;
 typedef uint64_t u64;
@@ -209,10 +214,10 @@ static inline Xp operator-(Xp a, Xp b) { Xp r; r.v = e4_sub(a.v, b.v); return r;
 static inline Xp operator*(Xp a, Xp b) { Xp r; r.v = e4_mul(a.v, b.v); return r; }
 static inline Xp operator*(Xp a, Fp b) { Xp r; r.v = e4_mulb(a.v, b.v); return r; }
 
-struct LookupChallenges { E4 z, th[5], sio; };  // th[k] = theta^k; sio = sum of the public I/O transcript's fractions
+struct LookupChallenges { E4 z, th[ZKIR_AIR_NUM_THETA + 1], sio; };  // th[k] = theta^k; sio = sum of the public I/O transcript's fractions
 static LookupChallenges make_challenges(E4 z, E4 theta) {
   LookupChallenges c; c.z = z; c.th[0] = e4_from(1); c.th[1] = theta;
-  for (int k = 2; k < 5; k++) c.th[k] = e4_mul(c.th[k - 1], theta);
+  for (int k = 2; k <= ZKIR_AIR_NUM_THETA; k++) c.th[k] = e4_mul(c.th[k - 1], theta);
   c.sio = e4_zero();
   return c;
 }
@@ -282,18 +287,36 @@ static void rom_decode(u32 w, u32* dec, u32* imm) {
 }
 static void build_public_columns(u32 log_n, const u32* code, size_t n_code, u32* pub) {
   const size_t N = (size_t)1 << log_n;
-  memset(pub, 0, 4 * N * sizeof(u32));
+  memset(pub, 0, ZKIR_AIR_PUB_WIDTH * N * sizeof(u32));
   for (size_t i = 0; i < N && i < ((size_t)1 << ZKIR_AIR_RANGE_BITS); i++) pub[0 * N + i] = (u32)i;
   for (size_t i = 0; i < N; i++) {
     if (i < n_code) { pub[1 * N + i] = CODE_BASE + 4 * (u32)i; rom_decode(code[i], &pub[2 * N + i], &pub[3 * N + i]); }
     else pub[2 * N + i] = 127;   // no instruction has opcode 127: an unused ROM row matches no trace row
   }
+#ifdef ZKIR_PROFILE_FULL
+  // docs/PROVER_SPEC.md section 3.7.  Columns 4..6: AND table, row t = x + 32 y (t < 1024) holds (x, y, x & y).  Columns 7..12: power
+  // table (key, multiplier lo/hi limb, zero flag, fill lo/hi limb): rows 0..63 = left shift by s (key s, 2^s or 0 from 40 on),
+  // rows 64..127 = right shift by s (key 1024 + s, 2^(40-s) for 1 <= s <= 40 else 0, flag s == 0, fill = top min(s, 40) bits of a
+  // 40-bit word); every other row repeats row 0.
+  for (size_t i = 0; i < N; i++) {
+    if (i < 1024) { const u32 x = i & 31, y = (u32)i >> 5; pub[4 * N + i] = x; pub[5 * N + i] = y; pub[6 * N + i] = x & y; }
+    u64 key = 0, mul = 1, fill = 0; u32 zf = 0;
+    if (i >= 1 && i < 64) { key = i; mul = i < 40 ? (u64)1 << i : 0; }
+    if (i >= 64 && i < 128) {
+      const u64 sh = i - 64;
+      key = 1024 + sh; zf = sh == 0; mul = (sh >= 1 && sh <= 40) ? (u64)1 << (40 - sh) : 0;
+      for (u64 b = 0; b < sh && b < 40; b++) fill |= (u64)1 << (39 - b);
+    }
+    pub[7 * N + i] = (u32)key; pub[8 * N + i] = (u32)(mul & 0xFFFFF); pub[9 * N + i] = (u32)(mul >> 20); pub[10 * N + i] = zf;
+    pub[11 * N + i] = (u32)(fill & 0xFFFFF); pub[12 * N + i] = (u32)(fill >> 20);
+  }
+#endif
 }
 // aux columns [16][N] from the main trace, the public columns and the lookup challenges: helper k = sum of its two fractions,
 // phi = running sum of all fractions of the earlier rows.  Returns false if the lookups do not balance (invalid witness).
 static bool build_aux(u32 log_n, const u32* trace, const u32* pub, const LookupChallenges& lc, u32* aux) {
   const size_t N = (size_t)1 << log_n;
-  const int NF = ZKIR_AIR_NUM_FRACTIONS;
+  const int NF = ZKIR_AIR_NUM_FRACTIONS, NH = ZKIR_AIR_NUM_HELPERS;
   static const int helper_of[NF] = ZKIR_AIR_FRAC_HELPER_INIT;
   std::vector<E4> den(N * NF), tot(N);
   std::vector<u32> num(N * NF);
@@ -308,13 +331,15 @@ static bool build_aux(u32 log_n, const u32* trace, const u32* pub, const LookupC
   for (size_t c0 = 0; c0 < N * NF; c0 += CH) e4_batch_inv(&den[c0], std::min(CH, N * NF - c0));
 #pragma omp parallel for
   for (size_t i = 0; i < N; i++) {
-    E4 h[4] = {e4_zero(), e4_zero(), e4_zero(), e4_zero()};
+    E4 h[NH + 1];   // helper sums; h[NH] = the fractions the running sum adds itself
+    for (int k = 0; k <= NH; k++) h[k] = e4_zero();
     for (int j = 0; j < NF; j++) h[helper_of[j]] = e4_add(h[helper_of[j]], e4_mulb(den[i * NF + j], num[i * NF + j]));
-    for (int k = 0; k < 3; k++) for (int q = 0; q < 4; q++) aux[(4 * k + q) * N + i] = h[k].c[q];
-    tot[i] = e4_add(e4_add(h[0], h[1]), e4_add(h[2], h[3]));
+    E4 t = h[NH];
+    for (int k = 0; k < NH; k++) { for (int q = 0; q < 4; q++) aux[(4 * k + q) * N + i] = h[k].c[q]; t = e4_add(t, h[k]); }
+    tot[i] = t;
   }
   E4 phi = e4_zero();
-  for (size_t i = 0; i < N; i++) { for (int q = 0; q < 4; q++) aux[(12 + q) * N + i] = phi.c[q]; phi = e4_add(phi, tot[i]); }
+  for (size_t i = 0; i < N; i++) { for (int q = 0; q < 4; q++) aux[(4 * NH + q) * N + i] = phi.c[q]; phi = e4_add(phi, tot[i]); }
   return e4_eq(phi, lc.sio);   // range and ROM fractions cancel, the I/O rows must add up to the public transcript's sum
 }
 // digest of the public I/O transcript the transcript absorbs: hash_tree over {n_io, clk_0, kind_0, lo_0, hi_0, ...}

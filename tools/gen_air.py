@@ -26,6 +26,14 @@ import os
 
 P = 2013265921
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+# Two AIR profiles are generated from this one description (docs/PROVER_SPEC.md section 3.7):
+#   core  the 18 opcodes of the headline workloads, 88 + 16 + 4 columns (this file's round-2 layout, unchanged);
+#   full  every opcode of zkir-spec/src/opcode.rs:24-144 except the loads and stores: the core columns plus a 40x40-bit
+#         multiplier block (MUL MULH DIVU REMU DIV REM and all six shifts), sign extraction (SLT SGE BLT BGE SRA SRAI) and a
+#         5-bit x 5-bit AND table (AND OR XOR ANDI ORI XORI).
+# The profile of a proof is its trace width (zkir_params.width): a program that stays inside the core opcodes is proven with the
+# narrow table; the verifier needs no flag because an opcode outside a profile has no selector there and matches no ROM row.
+FULL = os.environ.get("ZKIR_AIR_PROFILE", "core") == "full"
 
 # ----------------------------------------------------------------------------- column layout
 COLS = []
@@ -75,17 +83,53 @@ CH = [col(f"ch{i}") for i in range(4)]
 CARRY0, CARRY1 = col("carry0"), col("carry1")  # carry / borrow chain; "limb differs" flags of the is-zero gadget
 TAKEN = col("taken")                           # branch taken; JALR: bit 0 of rs1 + imm (execute.rs:655 clears it)
 M_RNG, M_ROM = col("m_rng"), col("m_rom")      # LogUp multiplicities of the range table row / the ROM row at this trace row
+# ----- full profile: appended after the core columns, so every ZKIR_COL_* index of the core layout is valid in both
+FULL_SEL_OPCODE = [("s_mul", 0x02), ("s_divu", 0x04), ("s_div", 0x06),                       # + neg: MULH, REMU, REM
+                   ("s_and", 0x10), ("s_or", 0x11), ("s_xor", 0x12), ("s_andi", 0x13), ("s_ori", 0x14), ("s_xori", 0x15),
+                   ("s_sll", 0x18), ("s_srl", 0x19), ("s_sra", 0x1A), ("s_slli", 0x1B), ("s_srli", 0x1C), ("s_srai", 0x1D),
+                   ("s_slt", 0x22), ("s_blt", 0x42)]                                          # + neg: SGE, BGE
+if FULL:
+    SEL_OPCODE = SEL_OPCODE + FULL_SEL_OPCODE
+    SEL_NAMES = [n for n, _ in SEL_OPCODE]
+    for n, _ in FULL_SEL_OPCODE:
+        S[n] = col(n)
+    # multiplier block: X * Y + R = P over the integers, 10-bit chunks (x, y, r: 4 each, p: 8), carries of the five low columns
+    # as two chunks each.  X = rs1 (MUL, shifts, compares, bitwise) or the quotient (DIV family); Y = rs2 or 2^s / 2^(40-s) from
+    # the power table (shifts); R = the remainder (DIV family) or rs2 (shifts: its low chunk holds the shift amount)
+    XC = [col(f"x{i}") for i in range(4)]
+    YC = [col(f"y{i}") for i in range(4)]
+    RC = [col(f"r{i}") for i in range(4)]
+    PC8 = [col(f"p{i}") for i in range(8)]
+    KLO = [col(f"k{i}_lo") for i in range(5)]
+    KHI = [col(f"k{i}_hi") for i in range(5)]
+    SA, SB = col("sign_a"), col("sign_b")          # bit 39 of X / Y
+    SXOR, LTS = col("sign_xor"), col("lt_signed")  # sign_a xor sign_b; (a <u b) xor sign_xor = (a <s b)
+    SHAMT, SHW = col("shamt"), col("sh_w")         # r0 = shamt + 64 * sh_w (execute.rs:287: shift = rs2 & 0x3F)
+    ZFLAG = col("sh_zero")                         # right shift by 0 (the power table says so)
+    G_LO, G_HI = col("fill_lo"), col("fill_hi")    # SRA: the ones shifted in for a negative value (value.rs:672-691)
+    # bitwise: 5-bit pieces of the chunks of X and Y and of X & Y, looked up as triples in the AND table
+    XL = [col(f"xl{i}") for i in range(4)]
+    XH = [col(f"xh{i}") for i in range(4)]
+    YL = [col(f"yl{i}") for i in range(4)]
+    YH = [col(f"yh{i}") for i in range(4)]
+    ZL = [col(f"zl{i}") for i in range(4)]
+    ZH = [col(f"zh{i}") for i in range(4)]
+    M_AND, M_POW = col("m_and"), col("m_pow")      # multiplicities of the AND-table row / power-table row at this trace row
 WIDTH = len(COLS)
-assert WIDTH == 88   # 11 sponge absorptions per Merkle leaf (rate 8)
+assert FULL or WIDTH == 88   # 11 sponge absorptions per Merkle leaf (rate 8)
 
-# aux columns: ext4 values h0, h1, h2 (helper sums of two fractions each) and phi (running sum), 4 base columns each
-AUX_NAMES = ["h0", "h1", "h2", "phi"]
-AUX_WIDTH = 4 * len(AUX_NAMES)
 # public columns (evaluated by the verifier): range table, ROM pc, ROM decoded word, ROM immediate
 PUB_NAMES = ["p_t", "p_pc", "p_dec", "p_imm"]
 P_T, P_PC, P_DEC, P_IMM = range(4)
+if FULL:
+    # AND table on the 1024 range rows: t = x + 32 y -> (x, y, x & y).  Power table on rows 0..127: key = s + 1024 * right (left: rows 0..63, right: rows 64..127) ->
+    # (key, multiplier limbs, [right and s == 0], fill limbs): left 2^s (0 for s >= 40), right 2^(40-s) (0 for s = 0 or s > 40),
+    # fill = the top min(s, 40) bits of a 40-bit word set; rows 128.. repeat row 0
+    PUB_NAMES += ["p_ax", "p_ay", "p_az", "p_key", "p_mlo", "p_mhi", "p_zf", "p_glo", "p_ghi"]
+    P_AX, P_AY, P_AZ, P_KEY, P_MLO, P_MHI, P_ZF, P_GLO, P_GHI = range(4, 13)
 PUB_WIDTH = len(PUB_NAMES)
 RANGE_BITS = 10
+NUM_THETA = 6 if FULL else 4
 
 PV_NAMES = ["entry_pc", "num_cycles", "exit_lo", "exit_hi", "halted"]
 NUM_PUBLIC = len(PV_NAMES)
@@ -213,21 +257,37 @@ def shared(g):
         hv = 3 - 3 * h[0] - 2 * h[1] - h[2]   # 0*h0 + 1*h1 + 2*h2 + 3*(1 - h0 - h1 - h2)
         lv = 3 - 3 * l[0] - 2 * l[1] - l[2]
         return 4 * hv + lv
-    rc_on = g.tmp(s["s_add"] + s["s_addi"] + s["s_sub"] + L(IS_READ) + s["s_jal"] + s["s_jalr"] + s["s_sltu"] + s["s_bltu"], "rows whose chunks are range-checked")
+    rc_terms = s["s_add"] + s["s_addi"] + s["s_sub"] + L(IS_READ) + s["s_jal"] + s["s_jalr"] + s["s_sltu"] + s["s_bltu"]
+    if FULL:   # signed compares (chunks = a - b mod 2^40) and the DIV family (chunks = remainder - divisor mod 2^40)
+        rc_terms = rc_terms + s["s_slt"] + s["s_blt"] + s["s_divu"] + s["s_div"]
+    rc_on = g.tmp(rc_terms, "rows whose chunks are range-checked")
     opcode = g.tmp(sum_e(op * s[n] for n, op in SEL_OPCODE if op) + ECALL_OPCODE * s_ecall + L(NEG), "opcode number (opcode.rs:24-144)")
     rd_eff = g.tmp(idx(RD_H, RD_L) - 10 * (L(IS_READ) + L(IS_POS2)), "rd field of the word (READ / POSEIDON2 write r10 without an rd field)")
     dec = g.tmp(opcode + 128 * rd_eff + 2048 * idx(RS1_H, RS1_L) + 32768 * idx(RS2_H, RS2_L), "decoded word: opcode | rd << 7 | rs1 << 11 | rs2 << 15")
     imm_f = g.tmp(L(IMM_LO) - TWO20 * L(IMM_SIGN), "signed immediate as a field element (execute.rs:187)")
-    return s, s_ecall, s_pad, live, rc_on, dec, imm_f
+    fam = None
+    if FULL:
+        fam = dict(
+            mulf=s["s_mul"], divf=g.tmp(s["s_divu"] + s["s_div"], "DIV family (DIV / REM act as DIVU / REMU: a provable register value is below 2^40, execute.rs:117-183)"),
+            shl=g.tmp(s["s_sll"] + s["s_slli"], "left shift"), shr=g.tmp(s["s_srl"] + s["s_srli"] + s["s_sra"] + s["s_srai"], "right shift"),
+            sraf=g.tmp(s["s_sra"] + s["s_srai"], "arithmetic right shift"), shi=g.tmp(s["s_slli"] + s["s_srli"] + s["s_srai"], "shift by immediate"),
+            cmps=g.tmp(s["s_slt"] + s["s_blt"], "signed compare"),
+            bitf=g.tmp(s["s_and"] + s["s_or"] + s["s_xor"] + s["s_andi"] + s["s_ori"] + s["s_xori"], "bitwise row"))
+        fam["shf"] = g.tmp(fam["shl"] + fam["shr"], "shift row")
+        fam["mul_on"] = g.tmp(fam["mulf"] + fam["divf"] + fam["shf"], "multiplier block active")
+        fam["dec_on"] = g.tmp(fam["mul_on"] + fam["cmps"] + fam["bitf"], "x / y chunks are range-checked")
+        fam["r_on"] = g.tmp(fam["divf"] + fam["shf"], "r chunks are range-checked")
+        fam["sa_on"] = g.tmp(fam["cmps"] + fam["sraf"], "sign of x is extracted")
+    return s, s_ecall, s_pad, live, rc_on, dec, imm_f, fam
 
 
 def fractions(g, sh):
     """The 8 LogUp fractions of a row as (numerator F, denominator X).  Bus 1 = 10-bit range table, bus 2 = program ROM, bus 3 = public I/O.
     Fingerprints: range `1 + theta*value`; ROM `2 + theta*pc + theta^2*dec + theta^3*imm`; I/O `3 + theta*clk + theta^2*kind + theta^3*lo + theta^4*hi`."""
-    s, s_ecall, s_pad, live, rc_on, dec, imm_f = sh
+    s, s_ecall, s_pad, live, rc_on, dec, imm_f, fam = sh
     L = g.L
     z = E("c.z()", atom=True, t="X")
-    th = [None] + [E(f"c.th({k})", atom=True, t="X") for k in (1, 2, 3, 4)]
+    th = [None] + [E(f"c.th({k})", atom=True, t="X") for k in range(1, NUM_THETA + 1)]
     out = []
     for j in range(4):
         out.append((rc_on, g.tmp(z - (th[1] * L(CH[j]) + 1), f"range lookup of ch{j}")))
@@ -238,13 +298,134 @@ def fractions(g, sh):
     # summed by the verifier itself (c.sio() in the closing constraint).  On a WRITE row v holds the written word (r11), on a READ row the tape value.
     out.append((g.tmp(L(IS_READ) + L(IS_WRITE), "I/O row"),
                 g.tmp(z - (th[1] * L(CLK) + th[2] * L(IS_WRITE) + th[3] * L(V_LO) + th[4] * L(V_HI) + 3), "I/O event (clk, kind, value)")))
+    if FULL:
+        def rng(n, e, note):
+            out.append((n, g.tmp(z - (th[1] * e + 1), note)))
+        for i in range(4):
+            rng(fam["dec_on"], L(XC[i]), f"range lookup of x{i}")
+        for i in range(4):
+            rng(fam["dec_on"], L(YC[i]), f"range lookup of y{i}")
+        for i in range(4):
+            rng(fam["r_on"], L(RC[i]), f"range lookup of r{i}")
+        for i in range(8):
+            rng(fam["mul_on"], L(PC8[i]), f"range lookup of p{i}")
+        for i in range(5):
+            rng(fam["mul_on"], L(KLO[i]), f"range lookup of carry {i} (low chunk)")
+            rng(fam["mul_on"], L(KHI[i]), f"range lookup of carry {i} (high chunk)")
+        # bit 39: x3 = 512 * sign + rest with rest < 512  <=>  2 * rest is a 10-bit value too (x3 itself is range-checked above)
+        rng(fam["sa_on"], 2 * L(XC[3]) - 1024 * L(SA), "sign of x: 2 * (x3 - 512 sign_a) in range")
+        rng(fam["cmps"], 2 * L(YC[3]) - 1024 * L(SB), "sign of y: 2 * (y3 - 512 sign_b) in range")
+        # shift amount: r0 = shamt + 64 w, w < 16 (shamt < 64 comes with the power-table lookup)
+        rng(fam["shf"], L(SHW), "shift: w in range")
+        rng(fam["shf"], 64 * L(SHW), "shift: 64 w in range (w < 16)")
+        y_lo = L(YC[0]) + TWO10 * L(YC[1])
+        y_hi = L(YC[2]) + TWO10 * L(YC[3])
+        out.append((fam["shf"], g.tmp(z - (th[1] * (L(SHAMT) + 1024 * fam["shr"]) + th[2] * y_lo + th[3] * y_hi + th[4] * L(ZFLAG) + th[5] * L(G_LO) + th[6] * L(G_HI) + 5),
+                                      "power-table lookup (shamt + 1024 right, multiplier, zero flag, fill)")))
+        out.append((g.tmp(0 - L(M_POW)), g.tmp(z - (th[1] * g.Pc(P_KEY) + th[2] * g.Pc(P_MLO) + th[3] * g.Pc(P_MHI) + th[4] * g.Pc(P_ZF) + th[5] * g.Pc(P_GLO) + th[6] * g.Pc(P_GHI) + 5),
+                                               "power-table row")))
+        for i in range(4):
+            out.append((fam["bitf"], g.tmp(z - (th[1] * L(XL[i]) + th[2] * L(YL[i]) + th[3] * L(ZL[i]) + 4), f"AND lookup, low pieces of chunk {i}")))
+            out.append((fam["bitf"], g.tmp(z - (th[1] * L(XH[i]) + th[2] * L(YH[i]) + th[3] * L(ZH[i]) + 4), f"AND lookup, high pieces of chunk {i}")))
+        out.append((g.tmp(0 - L(M_AND)), g.tmp(z - (th[1] * g.Pc(P_AX) + th[2] * g.Pc(P_AY) + th[3] * g.Pc(P_AZ) + 4), "AND-table row")))
     return out
 
 
-# helper k sums the fractions FRAC_PAIRS[k]; the two fractions FRAC_PHI are added by the running-sum transition itself
-FRAC_PAIRS = [(0, 1), (2, 3), (4, 6)]
+# The two fractions FRAC_PHI (ROM lookup, I/O event) are added by the running-sum transition itself; the others are summed in pairs
+# by the helper columns: helper k = fractions FRAC_PAIRS[k] (the last helper of an odd count holds one fraction)
 FRAC_PHI = (5, 7)
-NUM_FRACTIONS = 8
+
+
+def _count_fractions():
+    g = Gen(pre="n_")
+    return len(fractions(g, shared(g)))
+
+
+def _pairs(n):
+    rest = [j for j in range(n) if j not in FRAC_PHI]   # core: (0, 1), (2, 3), (4, 6)
+    return [tuple(rest[i:i + 2]) for i in range(0, len(rest), 2)]
+
+
+NUM_FRACTIONS = _count_fractions()
+FRAC_PAIRS = _pairs(NUM_FRACTIONS)
+# aux columns: ext4 helper sums h0.. and phi (running sum), 4 base columns each
+AUX_NAMES = [f"h{k}" for k in range(len(FRAC_PAIRS))] + ["phi"]
+AUX_WIDTH = 4 * len(AUX_NAMES)
+
+
+def full_constraints(g, s, fam, neg, a_lo, a_hi, b_lo, b_hi, v_lo, v_hi, rc_lo, rc_hi, k0, k1):
+    """Full profile: multiplier block, signed compares, shifts, bitwise operations (docs/PROVER_SPEC.md section 3.7)."""
+    L = g.L
+    x = [L(c) for c in XC]
+    y = [L(c) for c in YC]
+    r = [L(c) for c in RC]
+    p = [L(c) for c in PC8]
+    kk = [g.tmp(L(KLO[i]) + TWO10 * L(KHI[i]), f"carry {i}") for i in range(5)]
+    mulf, divf, shl, shr, sraf, shi, cmps, bitf, shf, mul_on = (fam[k] for k in ("mulf", "divf", "shl", "shr", "sraf", "shi", "cmps", "bitf", "shf", "mul_on"))
+    x_lo, x_hi = g.tmp(x[0] + TWO10 * x[1], "x.lo"), g.tmp(x[2] + TWO10 * x[3], "x.hi")
+    y_lo, y_hi = g.tmp(y[0] + TWO10 * y[1], "y.lo"), g.tmp(y[2] + TWO10 * y[3], "y.hi")
+    r_lo, r_hi = g.tmp(r[0] + TWO10 * r[1], "r.lo"), g.tmp(r[2] + TWO10 * r[3], "r.hi")
+    pl_lo, pl_hi = g.tmp(p[0] + TWO10 * p[1], "low product word, lo limb"), g.tmp(p[2] + TWO10 * p[3], "low product word, hi limb")
+    ph_lo, ph_hi = g.tmp(p[4] + TWO10 * p[5], "high product word, lo limb"), g.tmp(p[6] + TWO10 * p[7], "high product word, hi limb")
+    # --- operand binding
+    x_is_a = g.tmp(mulf + shf + cmps + bitf, "x = rs1")
+    g.emit(x_is_a * (a_lo - x_lo), "x.lo = a.lo")
+    g.emit(x_is_a * (a_hi - x_hi), "x.hi = a.hi")
+    y_is_b = g.tmp(mulf + divf + cmps + bitf, "y = rs2 (or the immediate)")
+    g.emit(y_is_b * (b_lo - y_lo), "y.lo = b.lo")
+    g.emit(y_is_b * (b_hi - y_hi), "y.hi = b.hi")
+    g.emit(shf * (b_lo - r_lo), "shift: r.lo = b.lo")
+    g.emit(shf * (b_hi - r_hi), "shift: r.hi = b.hi")
+    # --- X * Y + R = P: the five low base-2^10 columns with carries (the identity mod 2^50) and the identity in the field; both
+    # sides are below 2^80 < p * 2^50, so the two congruences give equality over the integers.  Every column equation stays below p:
+    # four products < 2^22, carry < 2^20, 1024 * carry < 2^30
+    for k in range(5):
+        sk = sum_e(x[i] * y[k - i] for i in range(4) if 0 <= k - i < 4)
+        prev = kk[k - 1] if k else 0
+        radd = divf * r[k] if k < 4 else 0
+        g.emit(mul_on * (sk + prev - p[k] - TWO10 * kk[k]) + radd, f"multiplier column {k}")
+    xf = g.tmp(x_lo + TWO20 * x_hi, "x as a field element")
+    yf = g.tmp(y_lo + TWO20 * y_hi, "y as a field element")
+    pf = g.tmp(sum_e(pow(2, 10 * k, P) * p[k] for k in range(8)), "the 80-bit product as a field element")
+    g.emit(mul_on * (xf * yf - pf) + divf * (r_lo + TWO20 * r_hi), "multiplier identity mod p")
+    # --- MUL / MULH (execute.rs:80-106): low / high 40 bits of the product
+    g.emit(mulf * (v_lo - pl_lo - neg * (ph_lo - pl_lo)), "mul / mulh result lo")
+    g.emit(mulf * (v_hi - pl_hi - neg * (ph_hi - pl_hi)), "mul / mulh result hi")
+    # --- DIVU / REMU / DIV / REM (execute.rs:117-183): a = q * b + rem with rem < b (so b != 0: a zero divisor is a VM error, no row)
+    g.emit(divf * (a_lo - pl_lo), "div: q * b + rem = a (lo)")
+    g.emit(divf * (a_hi - pl_hi), "div: q * b + rem = a (hi)")
+    g.emit(divf * ph_lo, "div: no overflow (lo)")
+    g.emit(divf * ph_hi, "div: no overflow (hi)")
+    g.emit(divf * (v_lo - x_lo - neg * (r_lo - x_lo)), "quotient / remainder result lo")
+    g.emit(divf * (v_hi - x_hi - neg * (r_hi - x_hi)), "quotient / remainder result hi")
+    g.emit(divf * (r_lo - b_lo - rc_lo + TWO20 * k0), "rem - b, lo limb (the chunks hold rem - b mod 2^40)")
+    g.emit(divf * (r_hi - b_hi - k0 - rc_hi + TWO20 * k1), "rem - b, hi limb")
+    g.emit(divf * (k1 - 1), "rem < b")
+    # --- signed compares at bit 39 (execute.rs:361-391, 594-609): (a <s b) = (a <u b) xor sign_a xor sign_b
+    sa, sb, sx, lts = L(SA), L(SB), L(SXOR), L(LTS)
+    g.emit(sx - (sa + sb - 2 * sa * sb), "sign_xor = sign_a xor sign_b")
+    g.emit(cmps * (lts - (k1 + sx - 2 * k1 * sx)), "lt_signed = borrow xor sign_xor")
+    g.emit(s["s_slt"] * (v_lo - (lts + neg - 2 * lts * neg)), "slt / sge result")
+    g.emit(s["s_slt"] * v_hi, "slt / sge result is 0 / 1")
+    # --- shifts (execute.rs:282-358, value.rs:658-691): x * 2^s -> low word, x * 2^(40-s) -> high word = x >> s; the multiplier,
+    # the "shift by zero" flag and the arithmetic fill come from the power table, keyed by shamt (+ 64 for right shifts)
+    g.emit(shf * (r[0] - L(SHAMT) - 64 * L(SHW)), "shift amount = low 6 bits of b")
+    g.emit(shi * L(SHW), "immediate shifts: shamt < 64")
+    g.emit(shl * (v_lo - pl_lo), "left shift result lo")
+    g.emit(shl * (v_hi - pl_hi), "left shift result hi")
+    zf = L(ZFLAG)
+    g.emit(shr * (v_lo - ph_lo - zf * a_lo) - sraf * sa * L(G_LO), "right shift result lo (+ sign fill)")
+    g.emit(shr * (v_hi - ph_hi - zf * a_hi) - sraf * sa * L(G_HI), "right shift result hi (+ sign fill)")
+    # --- bitwise (execute.rs:200-279): chunks split into 5-bit pieces, z = x & y piecewise from the AND table; or = x + y - z, xor = x + y - 2 z
+    zc = []
+    for i in range(4):
+        g.emit(bitf * (x[i] - L(XL[i]) - 32 * L(XH[i])), f"x{i} = low + 32 high piece")
+        g.emit(bitf * (y[i] - L(YL[i]) - 32 * L(YH[i])), f"y{i} = low + 32 high piece")
+        zc.append(L(ZL[i]) + 32 * L(ZH[i]))
+    z_lo, z_hi = g.tmp(zc[0] + TWO10 * zc[1], "(x & y).lo"), g.tmp(zc[2] + TWO10 * zc[3], "(x & y).hi")
+    andf, orf, xorf = s["s_and"] + s["s_andi"], s["s_or"] + s["s_ori"], s["s_xor"] + s["s_xori"]
+    g.emit(bitf * (v_lo - a_lo - b_lo) + andf * (a_lo + b_lo - z_lo) + orf * z_lo + xorf * 2 * z_lo, "bitwise result lo")
+    g.emit(bitf * (v_hi - a_hi - b_hi) + andf * (a_hi + b_hi - z_hi) + orf * z_hi + xorf * 2 * z_hi, "bitwise result hi")
 
 
 def build():
@@ -252,7 +433,7 @@ def build():
     L, N = g.L, g.N
     first, last, trans = E("c.is_first", True), E("c.is_last", True), E("c.is_trans", True)
     sh = shared(g)
-    s, s_ecall, s_pad, live, rc_on, dec, imm_f = sh
+    s, s_ecall, s_pad, live, rc_on, dec, imm_f, fam = sh
     neg = L(NEG)
 
     def onehot(grp, note):
@@ -271,7 +452,12 @@ def build():
     for name, grp in (("rd.h", rd_h), ("rd.l", rd_l), ("rs1.h", rs1_h), ("rs1.l", rs1_l), ("rs2.h", rs2_h), ("rs2.l", rs2_l)):
         for k, x in enumerate(grp):
             g.emit(x * (x - 1), f"bool {name}[{k}]")
-    g.emit(neg * (1 - s["s_beq"] - s["s_sltu"] - s["s_seq"] - s["s_bltu"] - s["s_cmov"]), "polarity only on the paired families")
+    paired = s["s_beq"] + s["s_sltu"] + s["s_seq"] + s["s_bltu"] + s["s_cmov"]
+    if FULL:
+        paired = paired + s["s_mul"] + s["s_divu"] + s["s_div"] + s["s_slt"] + s["s_blt"]
+        for b in (SA, SB):
+            g.emit(L(b) * (L(b) - 1), f"bool {COLS[b]}")
+    g.emit(neg * (1 - paired), "polarity only on the paired families")
 
     # --- operand fetch: reg[4h+l] selected by H[h]*L[l]; r0 contributes nothing (state.rs:76-91)
     def fetch(H, Lo, limb, note):
@@ -289,9 +475,12 @@ def build():
     g.emit(a_lo - rs1_lo, "a.lo = reg[rs1].lo")
     g.emit(a_hi - rs1_hi, "a.hi = reg[rs1].hi")
     # ADDI has no rs2 field: the ROM lookup binds its rs2 index to 0 = r0, so b = reg[rs2] + addi * imm stays degree 3
-    g.emit(b_lo - rs2_lo - s["s_addi"] * L(IMM_LO), "b.lo = reg[rs2].lo + addi * imm.lo")
+    immb = s["s_addi"]
+    if FULL:   # ANDI / ORI / XORI use the sign-extended immediate (execute.rs:241-279), the immediate shifts their shamt (:316-358)
+        immb = g.tmp(s["s_addi"] + s["s_andi"] + s["s_ori"] + s["s_xori"] + fam["shi"], "b is the immediate")
+    g.emit(b_lo - rs2_lo - immb * L(IMM_LO), "b.lo = reg[rs2].lo + [immediate form] * imm.lo")
     imm_hi = g.tmp((TWO20 - 1) * L(IMM_SIGN), "imm.hi = sign-extension limb")
-    g.emit(b_hi - rs2_hi - s["s_addi"] * imm_hi, "b.hi = reg[rs2].hi + addi * imm.hi")
+    g.emit(b_hi - rs2_hi - immb * imm_hi, "b.hi = reg[rs2].hi + [immediate form] * imm.hi")
     # --- range-checked pair: rows in rc_on look ch0..ch3 up in the 10-bit table (range_check.rs:175-192)
     rc_lo = g.tmp(ch[0] + TWO10 * ch[1], "range-checked low limb")
     rc_hi = g.tmp(ch[2] + TWO10 * ch[3], "range-checked high limb")
@@ -306,7 +495,10 @@ def build():
     g.emit(vrc * (v_lo - rc_lo), "v.lo is range-checked")
     g.emit(vrc * (v_hi - rc_hi), "v.hi is range-checked")
     # --- unsigned compare: the chunks hold a - b mod 2^40, carry1 = final borrow = (a < b)   (execute.rs:330-360, 610-637)
-    cmpu = g.tmp(s["s_sltu"] + s["s_bltu"], "unsigned compare row")
+    cmpu = s["s_sltu"] + s["s_bltu"]
+    if FULL:
+        cmpu = cmpu + fam["cmps"]
+    cmpu = g.tmp(cmpu, "compare row: the chunks hold a - b mod 2^40")
     g.emit(cmpu * (a_lo - b_lo - rc_lo + TWO20 * k0), "cmp lo limb")
     g.emit(cmpu * (a_hi - b_hi - k0 - rc_hi + TWO20 * k1), "cmp hi limb")
     lt_x = g.tmp(k1 + neg - 2 * k1 * neg, "(a < b) xor polarity")
@@ -339,6 +531,8 @@ def build():
     g.emit(s["s_jalr"] * (v_hi - ch[2]), "jalr link hi < 2^10")
     g.emit(s["s_jalr"] * (a_hi - ch[3]), "jalr: target base < 2^30")
     g.emit(s["s_jalr"] * (v_lo + TWO20 * v_hi - L(PC) - 4), "jalr link = pc + 4")
+    if FULL:
+        full_constraints(g, s, fam, neg, a_lo, a_hi, b_lo, b_hi, v_lo, v_hi, rc_lo, rc_hi, k0, k1)
     # --- syscalls (syscall.rs:94-149)
     g.emit((L(IS_READ) + L(IS_POS2)) * (rd_h[2] * rd_l[2] - 1), "read / poseidon2 write r10 (syscall.rs:104-109,140-149)")
     g.emit(L(IS_WRITE) * (v_lo - L(REG_LO[11])), "write: v = the written word r11 (lo), sent to the I/O bus (syscall.rs:110-119)")
@@ -346,7 +540,10 @@ def build():
     g.emit(L(IS_POS2) * v_lo, "poseidon2 returns 0 (lo)")
     g.emit(L(IS_POS2) * v_hi, "poseidon2 returns 0 (hi)")
     # --- register write-back, pre-state rows: next.r[i] = (rd == i && w) ? v : r[i]
-    w = g.tmp(addlike + s["s_sub"] + s["s_jal"] + s["s_jalr"] + s["s_sltu"] + s["s_seq"] + L(IS_READ) + L(IS_POS2) + cm * mv, "write enable")
+    w = addlike + s["s_sub"] + s["s_jal"] + s["s_jalr"] + s["s_sltu"] + s["s_seq"] + L(IS_READ) + L(IS_POS2) + cm * mv
+    if FULL:
+        w = w + fam["mul_on"] + fam["bitf"] + s["s_slt"]
+    w = g.tmp(w, "write enable")
     rdw = [L(RDW[h]) for h in range(4)]
     for h in range(4):
         g.emit(rdw[h] - rd_h[h] * w, f"rdw{h} = rd.h{h} * write enable")
@@ -358,7 +555,12 @@ def build():
     taken = L(TAKEN)
     g.emit(s["s_beq"] * (taken - eq_x), "beq / bne taken")
     g.emit(s["s_bltu"] * (taken - lt_x), "bltu / bgeu taken")
-    br = g.tmp(s["s_beq"] + s["s_bltu"], "branch row")
+    br = s["s_beq"] + s["s_bltu"]
+    if FULL:
+        lts = L(LTS)
+        g.emit(s["s_blt"] * (taken - (lts + neg - 2 * lts * neg)), "blt / bge taken (execute.rs:594-609)")
+        br = br + s["s_blt"]
+    br = g.tmp(br, "branch row")
     g.emit((1 - br - s["s_jalr"]) * taken, "taken only on branch rows (jalr: bit 0 of the target)")
     # --- pc / clk / padding / halting
     # EBREAK leaves the pc where it is (execute.rs:667-673: next_pc = pc), every other live row advances by 4 unless it jumps
@@ -396,13 +598,19 @@ def build():
         ld = g.AN if nxt else g.A
         cs = [ld(4 * k + j) for j in range(4)]
         return g.tmp(E(f"c.x4({cs[0].code}, {cs[1].code}, {cs[2].code}, {cs[3].code})", atom=True, t="X"), ("next " if nxt else "") + AUX_NAMES[k])
-    h = [xaux(k) for k in range(3)]
-    phi, phi_n = xaux(3), xaux(3, True)
-    for k, (i, j) in enumerate(FRAC_PAIRS):
+    NH = len(FRAC_PAIRS)
+    h = [xaux(k) for k in range(NH)]
+    phi, phi_n = xaux(NH), xaux(NH, True)
+    for k, pair in enumerate(FRAC_PAIRS):
+        if len(pair) == 1:
+            (ni, di), = (fr[pair[0]],)
+            g.emit(h[k] * di - ni, f"helper {k} = fraction {pair[0]}")
+            continue
+        i, j = pair
         (ni, di), (nj, dj) = fr[i], fr[j]
         g.emit(h[k] * di * dj - di * nj - dj * ni, f"helper {k} = fraction {i} + fraction {j}")
     (n5, d5), (n7, d7) = fr[FRAC_PHI[0]], fr[FRAC_PHI[1]]
-    hs = g.tmp(h[0] + h[1] + h[2], "h0 + h1 + h2")
+    hs = g.tmp(sum_e(h), "h0 + h1 + h2" if NH == 3 else "sum of the helpers")
     sio = E("c.sio()", atom=True, t="X")
     g.emit(((phi_n - phi - hs) * d5 * d7 - d7 * n5 - d5 * n7) * trans, "running sum transition (adds the ROM lookup and the I/O event itself)")
     g.emit(phi * first, "running sum starts at 0")
@@ -432,11 +640,14 @@ def main():
     hdr.append(f"#define ZKIR_AIR_NUM_PUBLIC {NUM_PUBLIC}")
     hdr.append(f"#define ZKIR_AIR_NUM_FRACTIONS {NUM_FRACTIONS}")
     hdr.append(f"#define ZKIR_AIR_RANGE_BITS {RANGE_BITS}")
+    hdr.append(f"#define ZKIR_AIR_NUM_HELPERS {len(FRAC_PAIRS)}")
+    hdr.append(f"#define ZKIR_AIR_NUM_THETA {NUM_THETA}")
     hdr.append("#define ZKIR_AIR_MAX_DEGREE 3")
-    hdr.append("// fraction j is summed by helper ZKIR_AIR_FRAC_HELPER[j] (3 = added by the running-sum transition itself)")
-    helper_of = [3] * NUM_FRACTIONS   # 3 = the running sum itself
-    for k, (i, j) in enumerate(FRAC_PAIRS):
-        helper_of[i] = helper_of[j] = k
+    hdr.append("// fraction j is summed by helper ZKIR_AIR_FRAC_HELPER[j] (ZKIR_AIR_NUM_HELPERS = added by the running-sum transition itself)")
+    helper_of = [len(FRAC_PAIRS)] * NUM_FRACTIONS   # number of helpers = the running sum itself
+    for k, pair in enumerate(FRAC_PAIRS):
+        for i in pair:
+            helper_of[i] = k
     hdr.append("#define ZKIR_AIR_FRAC_HELPER_INIT {" + ", ".join(str(x) for x in helper_of) + "}")
     hdr.append("#ifndef ZKIR_HD\n#ifdef __CUDACC__\n#define ZKIR_HD __host__ __device__ __forceinline__\n#else\n#define ZKIR_HD inline\n#endif\n#endif")
     hdr.append("// Context contract: C::F (base) and C::X (ext4) with + - *, X * F scaling; c.L(i)/c.N(i) main local/next row, c.A(i)/c.AN(i) aux,")
@@ -455,7 +666,8 @@ def main():
     hdr.extend(gf.lines)
     hdr.append("}")
     text = "\n".join(hdr) + "\n"
-    for rel in ("zkir_b200/csrc/air_generated.h", "oracle/air_generated.h"):
+    sfx = "_full" if FULL else ""
+    for rel in (f"zkir_b200/csrc/air_generated{sfx}.h", f"oracle/air_generated{sfx}.h"):
         with open(os.path.join(ROOT, rel), "w") as f:
             f.write(text)
     # column map: C header for the packer + python module for tests
@@ -465,17 +677,45 @@ def main():
     ch.append(f"#define ZKIR_COL_COUNT {WIDTH}")
     for i, n in enumerate(PUB_NAMES):
         ch.append(f"#define ZKIR_PUB_{n.upper()} {i}")
-    with open(os.path.join(ROOT, "zkir_b200/csrc/air_columns.h"), "w") as f:
+    with open(os.path.join(ROOT, f"zkir_b200/csrc/air_columns{sfx}.h"), "w") as f:
         f.write("\n".join(ch) + "\n")
-    with open(os.path.join(ROOT, "zkir_b200/air_layout.py"), "w") as f:
+    with open(os.path.join(ROOT, f"zkir_b200/air_layout{sfx}.py"), "w") as f:
         f.write('"""GENERATED by tools/gen_air.py -- column map of the AIR v2."""\n')
         f.write(f"WIDTH = {WIDTH}\nAUX_WIDTH = {AUX_WIDTH}\nPUB_WIDTH = {PUB_WIDTH}\nNUM_CONSTRAINTS = {g.idx}\nNUM_PUBLIC = {NUM_PUBLIC}\n")
         f.write(f"MIN_LOG_N = {RANGE_BITS}\n")
         f.write(f"PUBLIC_NAMES = {PV_NAMES!r}\n")
         f.write("COLUMNS = " + repr(COLS) + "\n")
         f.write("INDEX = {n: i for i, n in enumerate(COLUMNS)}\n")
-    print(f"AIR: width={WIDTH} aux={AUX_WIDTH} pub={PUB_WIDTH} constraints={g.idx}")
+    print(f"AIR {'full' if FULL else 'core'}: width={WIDTH} aux={AUX_WIDTH} pub={PUB_WIDTH} constraints={g.idx} fractions={NUM_FRACTIONS}")
+    return dict(width=WIDTH, aux=AUX_WIDTH, pub=PUB_WIDTH, constraints=g.idx, fractions=NUM_FRACTIONS, theta=NUM_THETA)
+
+
+def write_profiles(core, full):
+    """Numbers of both profiles for the code that serves either (prover.cu, proof_layout.h): which profile a proof uses is its width."""
+    out = ["// GENERATED by tools/gen_air.py -- the two AIR profiles (docs/PROVER_SPEC.md section 3.7).", "#pragma once"]
+    for name, d in (("CORE", core), ("FULL", full)):
+        for k in ("width", "aux", "pub", "constraints", "theta"):
+            out.append(f"#define ZKIR_PROFILE_{name}_{k.upper()} {d[k]}")
+    out.append(f"#define ZKIR_PROFILE_MAX_CONSTRAINTS {max(core['constraints'], full['constraints'])}")
+    out.append(f"#define ZKIR_PROFILE_MAX_AUX {max(core['aux'], full['aux'])}")
+    out.append(f"#define ZKIR_PROFILE_MAX_PUB {max(core['pub'], full['pub'])}")
+    text = "\n".join(out) + "\n"
+    for rel in ("zkir_b200/csrc/air_profiles_generated.h", "oracle/air_profiles_generated.h"):
+        with open(os.path.join(ROOT, rel), "w") as f:
+            f.write(text)
 
 
 if __name__ == "__main__":
-    main()
+    import json
+    import subprocess
+    import sys
+    if "--one" in sys.argv:      # one profile (ZKIR_AIR_PROFILE), summary as the last stdout line
+        print(json.dumps(main()))
+    else:
+        res = {}
+        for prof in ("core", "full"):
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--one"], env=dict(os.environ, ZKIR_AIR_PROFILE=prof), capture_output=True, text=True, check=True)
+            lines = r.stdout.strip().splitlines()
+            print(lines[0])
+            res[prof] = json.loads(lines[-1])
+        write_profiles(res["core"], res["full"])

@@ -39,11 +39,16 @@ def _headers_mtime():
     return m
 
 
-def _compile(src, hdr_m, verbose):
-    obj = os.path.join(OBJ, os.path.basename(src) + ".o")
+# translation units that instantiate the generated AIR: compiled once per profile (csrc/air_profile.h)
+PER_PROFILE = ("quotient.cu", "aux_gen.cu", "pack.cc", "verify.cc")
+
+
+def _compile(job, hdr_m, verbose):
+    src, full = job
+    obj = os.path.join(OBJ, os.path.basename(src) + (".full" if full else "") + ".o")
     if os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(src), hdr_m):
         return obj, ""
-    cmd = [NVCC] + NVCC_FLAGS + (["-x", "cu"] if src.endswith(".cu") else []) + ["-c", src, "-o", obj]
+    cmd = [NVCC] + NVCC_FLAGS + (["-DZKIR_PROFILE_FULL"] if full else []) + (["-x", "cu"] if src.endswith(".cu") else []) + ["-c", src, "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
@@ -56,7 +61,7 @@ def build(verbose=False, force=False):
         for f in os.listdir(OBJ):
             os.remove(os.path.join(OBJ, f))
     hdr_m = _headers_mtime()
-    srcs = sources()
+    srcs = [(f, False) for f in sources()] + [(f, True) for f in sources() if os.path.basename(f) in PER_PROFILE]
     with ThreadPoolExecutor(max_workers=8) as ex:
         res = list(ex.map(lambda s: _compile(s, hdr_m, verbose), srcs))
     objs = [o for o, _ in res]

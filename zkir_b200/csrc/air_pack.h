@@ -1,20 +1,25 @@
-// Row converter of the AIR v2: one interpreter row (pc, instruction word, PRE-state registers) -> the 86 per-row main columns
-// (the two LogUp multiplicity columns are histograms over all rows and are filled by the callers).
+// Row converter of the AIR v2: one interpreter row (pc, instruction word, PRE-state registers) -> the per-row main columns
+// (the LogUp multiplicity columns are histograms over all rows and are filled by the callers).  Core profile: 86 columns; the full
+// profile (ZKIR_PROFILE_FULL, host packer only) adds the multiplier block, the sign / shift cells and the 5-bit pieces of the
+// bitwise operations (tools/gen_air.py, docs/PROVER_SPEC.md section 3.7).
 //
 // The reference names this step but does not contain it (zkir-spec/src/trace.rs:41 "converter", zkir-runtime/src/vm.rs:243-244).
 // ONE definition shared by the host packer (host/pack.cc) and the device converter (trace_expand.cu): `__host__ __device__`,
 // no dynamic indexing of the register array, output through a writer functor.  Column meaning: tools/gen_air.py.
 // Semantics restated from zkir-runtime/src/execute.rs (ADD :43-63, SUB :65-78, ADDI :185-197, SLTU/SGEU/SEQ/SNE :330-420,
-// CMOV* :422-470, BEQ/BNE/BLTU/BGEU :578-637, JAL/JALR :639-659, ECALL/EBREAK :661-673) and syscall.rs:94-149.
+// CMOV* :422-470, BEQ/BNE/BLTU/BGEU :578-637, JAL/JALR :639-659, ECALL/EBREAK :661-673) and syscall.rs:94-149; full profile:
+// MUL/MULH :80-106, DIVU/REMU/DIV/REM :117-183, AND..XORI :200-279, SLL..SRAI :282-358 (zkir-spec/src/value.rs:658-691),
+// SLT/SGE :361-391, BLT/BGE :594-609.
 #pragma once
 #include <stdint.h>
 #include "bb.cuh"
-#include "air_columns.h"
+#include "air_profile.h"
 
 namespace zkir {
 
 enum PackErr : u32 {
   PACK_OK = 0, PACK_ERR_PC = 1, PACK_ERR_REG40 = 2, PACK_ERR_TAPE40 = 3, PACK_ERR_SYSCALL = 4, PACK_ERR_OPCODE = 5, PACK_ERR_JALR = 6, PACK_ERR_ROM = 7,
+  /* 8 = the lookups do not balance (prover.cu) */ PACK_ERR_SHAMT = 9, PACK_ERR_DIV0 = 10,
 };
 BB_HD const char* pack_err_text(u32 code) {
   switch (code) {
@@ -25,6 +30,8 @@ BB_HD const char* pack_err_text(u32 code) {
     case PACK_ERR_OPCODE: return "opcode is not constrained";
     case PACK_ERR_JALR: return "jalr base register does not fit 30 bits";
     case PACK_ERR_ROM: return "pc is outside the program";
+    case PACK_ERR_SHAMT: return "immediate shift amount above 63";
+    case PACK_ERR_DIV0: return "division by zero";
     default: return "?";
   }
 }
@@ -57,6 +64,12 @@ BB_HD u32 expand_row_v2(u64 i, u64 T, const u64 (&rg)[16], u64 pc, u32 w, u64 re
   u32 carry0 = 0, carry1 = 0, taken = 0;
   u32 ch[4] = {0, 0, 0, 0};
   bool chunks_from_rc = false;
+#ifdef ZKIR_PROFILE_FULL
+  u64 fx = 0, fy = 0, fr = 0;            // multiplier block operands: X * Y + R = P
+  bool f_mul = false, f_cmps = false, f_bit = false, f_shift = false, f_right = false, f_sra = false, f_div = false;
+  u32 sa = 0, sb = 0, lts = 0, shamt = 0, shw = 0, zflag = 0;
+  u64 fill = 0;
+#endif
   if (live) {
     const u32 op = w & 0x7F;
     const u32 fa = (w >> 7) & 0xF, fb = (w >> 11) & 0xF, fc = (w >> 15) & 0xF;
@@ -119,6 +132,50 @@ BB_HD u32 expand_row_v2(u64 i, u64 T, const u64 (&rg)[16], u64 pc, u32 w, u64 re
       else err = PACK_ERR_SYSCALL;
     } else if (op == 0x51) {                            // EBREAK
       sel = ZKIR_COL_S_EBREAK;
+#ifdef ZKIR_PROFILE_FULL
+    } else if (op == 0x02 || op == 0x03) {              // MUL / MULH: low / high 40 bits of the 80-bit product
+      rd = fa; rs1 = fb; rs2 = fc; writes = 1; neg = op & 1;
+      av = R(rs1); bv = R(rs2); fx = av; fy = bv; f_mul = true;
+      sel = ZKIR_COL_S_MUL;
+    } else if (op >= 0x04 && op <= 0x07) {              // DIVU / REMU / DIV / REM (a provable value is below 2^40: the signed forms agree)
+      rd = fa; rs1 = fb; rs2 = fc; writes = 1; neg = op & 1;
+      av = R(rs1); bv = R(rs2);
+      if (bv == 0) { err = PACK_ERR_DIV0; bv = 1; }
+      fx = av / bv; fy = bv; fr = av % bv; f_mul = true; f_div = true;
+      vv = neg ? fr : fx;
+      sel = op < 0x06 ? ZKIR_COL_S_DIVU : ZKIR_COL_S_DIV;
+    } else if (op >= 0x10 && op <= 0x15) {              // AND OR XOR / ANDI ORI XORI
+      rd = fa; rs1 = fb; writes = 1;
+      av = R(rs1);
+      if (op >= 0x13) { imm = imm17; has_imm = true; bv = (u64)imm & M40; } else { rs2 = fc; bv = R(rs2); }
+      fx = av; fy = bv; f_bit = true;
+      const u32 k = (op - 0x10) % 3;
+      vv = k == 0 ? (av & bv) : k == 1 ? (av | bv) : (av ^ bv);
+      sel = ZKIR_COL_S_AND + (op - 0x10);
+    } else if (op >= 0x18 && op <= 0x1D) {              // SLL SRL SRA / SLLI SRLI SRAI
+      rd = fa; rs1 = fb; writes = 1;
+      av = R(rs1);
+      if (op >= 0x1B) { imm = (w >> 15) & 0xFF; has_imm = true; bv = (u64)imm; if (imm > 63) err = PACK_ERR_SHAMT; } else { rs2 = fc; bv = R(rs2); }
+      f_mul = true; f_shift = true; f_right = (op - 0x18) % 3 != 0; f_sra = (op - 0x18) % 3 == 2;
+      shamt = (u32)(bv & 63); shw = (u32)((bv & 1023) >> 6);
+      fx = av; fr = bv;
+      if (!f_right) fy = shamt < 40 ? 1ull << shamt : 0;
+      else {
+        fy = (shamt >= 1 && shamt <= 40) ? 1ull << (40 - shamt) : 0;
+        zflag = shamt == 0;
+        fill = shamt < 40 ? (((1ull << shamt) - 1) << (40 - shamt)) & M40 : M40;
+      }
+      if (f_sra) sa = (u32)((av >> 39) & 1);
+      sel = ZKIR_COL_S_SLL + (op - 0x18);
+    } else if (op == 0x22 || op == 0x23) {              // SLT / SGE
+      rd = fa; rs1 = fb; rs2 = fc; writes = 1; neg = op & 1;
+      av = R(rs1); bv = R(rs2); f_cmps = true;
+      sel = ZKIR_COL_S_SLT;
+    } else if (op == 0x42 || op == 0x43) {              // BLT / BGE
+      rs1 = fa; rs2 = fb; imm = imm17; has_imm = true; neg = op & 1;
+      av = R(rs1); bv = R(rs2); f_cmps = true;
+      sel = ZKIR_COL_S_BLT;
+#endif
     } else {
       err = PACK_ERR_OPCODE;
     }
@@ -127,6 +184,21 @@ BB_HD u32 expand_row_v2(u64 i, u64 T, const u64 (&rg)[16], u64 pc, u32 w, u64 re
       vv = (av + bv) & M40; rc = vv; chunks_from_rc = true;
       const u64 k0 = (a_lo + b_lo) >> 20;
       carry0 = (u32)k0; carry1 = (u32)((a_hi + b_hi + k0) >> 20);
+#ifdef ZKIR_PROFILE_FULL
+    } else if (f_cmps) {                                // signed compare at bit 39: (a <s b) = (a <u b) xor sign(a) xor sign(b)
+      rc = (av - bv) & M40; chunks_from_rc = true;
+      const u64 k0 = a_lo < b_lo;
+      carry0 = (u32)k0; carry1 = (u32)(a_hi < b_hi + k0);
+      fx = av; fy = bv;
+      sa = (u32)((av >> 39) & 1); sb = (u32)((bv >> 39) & 1);
+      lts = carry1 ^ sa ^ sb;
+      if (op < 0x40) vv = lts ^ neg; else taken = lts ^ neg;
+    } else if (f_div) {                                 // the chunks hold rem - divisor mod 2^40: the final borrow says rem < divisor
+      rc = (fr - bv) & M40; chunks_from_rc = true;
+      const u64 r_lo = fr & LIMB, r_hi = (fr >> 20) & LIMB;
+      const u64 k0 = r_lo < b_lo;
+      carry0 = (u32)k0; carry1 = (u32)(r_hi < b_hi + k0);
+#endif
     } else if (op == 0x01 || op == 0x20 || op == 0x21 || op == 0x44 || op == 0x45) {
       rc = (av - bv) & M40; chunks_from_rc = true;    // SUB: the result; compares: a - b mod 2^40, final borrow = (a < b)
       const u64 k0 = a_lo < b_lo;
@@ -160,6 +232,10 @@ BB_HD u32 expand_row_v2(u64 i, u64 T, const u64 (&rg)[16], u64 pc, u32 w, u64 re
   W(ZKIR_COL_IMM_LO, imm_lo); W(ZKIR_COL_IMM_SIGN, imm_sign);
 #pragma unroll
   for (int c = ZKIR_COL_S_ADD; c <= ZKIR_COL_S_EBREAK; c++) W(c, sel == (u32)c);
+#ifdef ZKIR_PROFILE_FULL
+#pragma unroll
+  for (int c = ZKIR_COL_S_MUL; c <= ZKIR_COL_S_BLT; c++) W(c, sel == (u32)c);
+#endif
   W(ZKIR_COL_NEG, neg);
   W(ZKIR_COL_IS_EXIT, is_exit); W(ZKIR_COL_IS_READ, is_read); W(ZKIR_COL_IS_WRITE, is_write); W(ZKIR_COL_IS_POS2, is_pos2);
 #pragma unroll
@@ -177,12 +253,56 @@ BB_HD u32 expand_row_v2(u64 i, u64 T, const u64 (&rg)[16], u64 pc, u32 w, u64 re
   for (int k = 0; k < 4; k++) W(ZKIR_COL_CH0 + k, ch[k]);
   W(ZKIR_COL_CARRY0, carry0); W(ZKIR_COL_CARRY1, carry1);
   W(ZKIR_COL_TAKEN, taken);
+#ifdef ZKIR_PROFILE_FULL
+  {
+    const bool dec = f_mul || f_cmps || f_bit;
+    u32 x[4], y[4], r[4], p[8], klo[5], khi[5];
+#pragma unroll
+    for (int k = 0; k < 4; k++) { x[k] = dec ? (u32)((fx >> (10 * k)) & 1023) : 0u; y[k] = dec ? (u32)((fy >> (10 * k)) & 1023) : 0u; r[k] = (f_div || f_shift) ? (u32)((fr >> (10 * k)) & 1023) : 0u; }
+    u64 c = 0;   // X * Y + R column by column in base 2^10 (only the DIV family adds R: the shifts keep rs2 in the r cells)
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      u64 t = c;
+      if (f_mul) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) if (k - i >= 0 && k - i < 4) t += (u64)x[i] * y[k - i];
+        if (f_div && k < 4) t += r[k];
+      }
+      p[k] = (u32)(t & 1023); c = t >> 10;
+      if (k < 5) { klo[k] = (u32)(c & 1023); khi[k] = (u32)(c >> 10); }
+    }
+    if (f_mul && !f_div && !f_shift) { const u64 lo = (u64)p[0] | (u64)p[1] << 10 | (u64)p[2] << 20 | (u64)p[3] << 30, hi = (u64)p[4] | (u64)p[5] << 10 | (u64)p[6] << 20 | (u64)p[7] << 30; vv = neg ? hi : lo; }
+    if (f_shift) {
+      const u64 lo = (u64)p[0] | (u64)p[1] << 10 | (u64)p[2] << 20 | (u64)p[3] << 30, hi = (u64)p[4] | (u64)p[5] << 10 | (u64)p[6] << 20 | (u64)p[7] << 30;
+      vv = !f_right ? lo : hi + (zflag ? av : 0) + ((f_sra && sa) ? fill : 0);
+    }
+    if (f_mul || f_shift) { W(ZKIR_COL_V_LO, (u32)(vv & LIMB)); W(ZKIR_COL_V_HI, (u32)((vv >> 20) & LIMB)); }   // the product is known only now
+#pragma unroll
+    for (int k = 0; k < 4; k++) { W(ZKIR_COL_X0 + k, x[k]); W(ZKIR_COL_Y0 + k, y[k]); W(ZKIR_COL_R0 + k, r[k]); }
+#pragma unroll
+    for (int k = 0; k < 8; k++) W(ZKIR_COL_P0 + k, p[k]);
+#pragma unroll
+    for (int k = 0; k < 5; k++) { W(ZKIR_COL_K0_LO + k, klo[k]); W(ZKIR_COL_K0_HI + k, khi[k]); }
+    W(ZKIR_COL_SIGN_A, sa); W(ZKIR_COL_SIGN_B, sb); W(ZKIR_COL_SIGN_XOR, sa ^ sb); W(ZKIR_COL_LT_SIGNED, lts);
+    W(ZKIR_COL_SHAMT, shamt); W(ZKIR_COL_SH_W, shw); W(ZKIR_COL_SH_ZERO, zflag);
+    W(ZKIR_COL_FILL_LO, (u32)(fill & LIMB)); W(ZKIR_COL_FILL_HI, (u32)((fill >> 20) & LIMB));
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const u32 xl = f_bit ? x[k] & 31 : 0u, xh = f_bit ? x[k] >> 5 : 0u, yl = f_bit ? y[k] & 31 : 0u, yh = f_bit ? y[k] >> 5 : 0u;
+      W(ZKIR_COL_XL0 + k, xl); W(ZKIR_COL_XH0 + k, xh); W(ZKIR_COL_YL0 + k, yl); W(ZKIR_COL_YH0 + k, yh);
+      W(ZKIR_COL_ZL0 + k, xl & yl); W(ZKIR_COL_ZH0 + k, xh & yh);
+    }
+  }
+#endif
   return err;
 }
 
 // does this row's chunk quadruple go to the range table?  (tools/gen_air.py: rc_on)
 BB_HD bool row_range_checked(u32 w, u64 r10) {
   const u32 op = w & 0x7F;
+#ifdef ZKIR_PROFILE_FULL
+  if (op == 0x22 || op == 0x23 || op == 0x42 || op == 0x43 || (op >= 0x04 && op <= 0x07)) return true;   // signed compares, DIV family
+#endif
   return op == 0x00 || op == 0x01 || op == 0x08 || op == 0x20 || op == 0x21 || op == 0x44 || op == 0x45 || op == 0x48 || op == 0x49 ||
          (op == 0x50 && r10 == 1);
 }

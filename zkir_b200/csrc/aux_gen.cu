@@ -11,14 +11,14 @@
 #include <cuda_runtime.h>
 #include "bb.cuh"
 #include "kernels.h"
-#include "air_generated.h"
+#include "air_profile.h"
 
 namespace zkir {
 
 struct FracCtxDev {
   typedef Fm F; typedef Xm X;
   const u32 *trace, *pub; u64 N, row;
-  const E4* lc;   // shared: z, theta, theta^2, theta^3, theta^4
+  const E4* lc;   // shared: z, theta .. theta^NUM_THETA
   u32 num[ZKIR_AIR_NUM_FRACTIONS]; E4 den[ZKIR_AIR_NUM_FRACTIONS];
   __device__ __forceinline__ Fm L(int i) const { return Fm(bb_to_mont(__ldg(trace + (u64)i * N + row))); }
   __device__ __forceinline__ Fm P(int i) const { return Fm(bb_to_mont(__ldg(pub + (u64)i * N + row))); }
@@ -30,12 +30,13 @@ struct FracCtxDev {
 };
 
 #define AUX_ROWS_THREADS 128
-__global__ void __launch_bounds__(AUX_ROWS_THREADS) aux_rows_kernel(AuxArgs a) {
-  __shared__ E4 lc[5];
+__global__ void __launch_bounds__(AUX_ROWS_THREADS) ZKIR_PF(aux_rows_kernel)(AuxArgs a) {
+  __shared__ E4 lc[ZKIR_AIR_NUM_THETA + 1];
   if (threadIdx.x == 0) {
     E4 z, th;
     for (int k = 0; k < 4; k++) { z.c[k] = a.lookup[k]; th.c[k] = a.lookup[4 + k]; }
-    lc[0] = z; lc[1] = th; lc[2] = e4_mul(th, th); lc[3] = e4_mul(lc[2], th); lc[4] = e4_mul(lc[3], th);
+    lc[0] = z; lc[1] = th;
+    for (int k = 2; k <= ZKIR_AIR_NUM_THETA; k++) lc[k] = e4_mul(lc[k - 1], th);
   }
   __syncthreads();
   const u64 N = 1ull << a.log_n;
@@ -45,23 +46,29 @@ __global__ void __launch_bounds__(AUX_ROWS_THREADS) aux_rows_kernel(AuxArgs a) {
   c.trace = a.trace; c.pub = a.pub; c.N = N; c.row = i; c.lc = lc;
   zkir_air_fractions(c);
   const int helper_of[ZKIR_AIR_NUM_FRACTIONS] = ZKIR_AIR_FRAC_HELPER_INIT;
-  E4 h[4] = {e4_zero(), e4_zero(), e4_zero(), e4_zero()};
+  E4 h[ZKIR_AIR_NUM_HELPERS + 1];   // the helpers, then the fractions the running sum adds itself
+#pragma unroll
+  for (int k = 0; k <= ZKIR_AIR_NUM_HELPERS; k++) h[k] = e4_zero();
 #pragma unroll
   for (int j = 0; j < ZKIR_AIR_NUM_FRACTIONS; j++) {
     // a zero numerator (lookup switched off on this row, table row never hit) needs no inversion
     if (c.num[j] != 0) h[helper_of[j]] = e4_add(h[helper_of[j]], e4_mulb(e4_inv(c.den[j]), c.num[j]));
   }
+  E4 tot = h[ZKIR_AIR_NUM_HELPERS];
 #pragma unroll
-  for (int k = 0; k < 3; k++)
+  for (int k = 0; k < ZKIR_AIR_NUM_HELPERS; k++) {
 #pragma unroll
     for (int q = 0; q < 4; q++) a.aux[(u64)(4 * k + q) * N + i] = bb_from_mont(h[k].c[q]);
-  a.row_tot[i] = e4_add(e4_add(h[0], h[1]), e4_add(h[2], h[3]));
+    tot = e4_add(tot, h[k]);
+  }
+  a.row_tot[i] = tot;
 }
 
 // ---- exclusive prefix sum of row_tot (ext4 = 4 independent sums mod p)
 #define SCAN_THREADS 256
 #define SCAN_PER 4
 #define SCAN_BLOCK (SCAN_THREADS * SCAN_PER)
+#ifndef ZKIR_PROFILE_FULL   // the scan and the I/O sum do not depend on the profile: compiled with the core build only
 u64 aux_gen_blocks(u64 N) { return (N + SCAN_BLOCK - 1) / SCAN_BLOCK; }
 
 __device__ __forceinline__ E4 block_reduce(E4 v, E4* sh) {   // sum over the block, result valid in thread 0
@@ -104,6 +111,7 @@ __global__ void __launch_bounds__(1024) scan_blocks_kernel(E4* blk_tot, u64 n_bl
   E4 run = part[t];
   for (u64 b = b0; b < b1; b++) { const E4 v = blk_tot[b]; blk_tot[b] = run; run = e4_add(run, v); }
 }
+// aux = the four base columns of phi (the last aux columns of the profile)
 __global__ void __launch_bounds__(SCAN_THREADS) scan_write_kernel(const E4* __restrict__ row_tot, const E4* __restrict__ blk_tot, u32* __restrict__ aux, u64 N) {
   __shared__ E4 wsum[SCAN_THREADS / 32];
   const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -127,7 +135,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_write_kernel(const E4* __re
   for (int k = 0; k < SCAN_PER; k++) {
     if (base + k < N) {
 #pragma unroll
-      for (int q = 0; q < 4; q++) aux[(u64)(12 + q) * N + base + k] = bb_from_mont(run.c[q]);
+      for (int q = 0; q < 4; q++) aux[(u64)q * N + base + k] = bb_from_mont(run.c[q]);
     }
     run = e4_add(run, v[k]);
   }
@@ -155,14 +163,23 @@ int launch_io_sum(const u32* events, u32 n_events, u32* lookup, cudaStream_t st,
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
-int launch_aux_gen(const AuxArgs& a, cudaStream_t st, u64* launches) {
+// running sum phi of the per-row totals into the four columns at phi_cols
+int launch_aux_scan(const AuxArgs& a, u32* phi_cols, cudaStream_t st, u64* launches) {
   const u64 N = 1ull << a.log_n, nb = aux_gen_blocks(N);
-  aux_rows_kernel<<<(unsigned)((N + AUX_ROWS_THREADS - 1) / AUX_ROWS_THREADS), AUX_ROWS_THREADS, 0, st>>>(a);
   scan_totals_kernel<<<(unsigned)nb, SCAN_THREADS, 0, st>>>(a.row_tot, a.blk_tot, N);
   scan_blocks_kernel<<<1, 1024, 0, st>>>(a.blk_tot, nb, N, a.lookup + 8, a.err);
-  scan_write_kernel<<<(unsigned)nb, SCAN_THREADS, 0, st>>>(a.row_tot, a.blk_tot, a.aux, N);
-  (*launches) += 4;
+  scan_write_kernel<<<(unsigned)nb, SCAN_THREADS, 0, st>>>(a.row_tot, a.blk_tot, phi_cols, N);
+  (*launches) += 3;
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+#endif  // !ZKIR_PROFILE_FULL
+
+int ZKIR_PF(launch_aux_gen)(const AuxArgs& a, cudaStream_t st, u64* launches) {
+  const u64 N = 1ull << a.log_n;
+  ZKIR_PF(aux_rows_kernel)<<<(unsigned)((N + AUX_ROWS_THREADS - 1) / AUX_ROWS_THREADS), AUX_ROWS_THREADS, 0, st>>>(a);
+  (*launches)++;
+  if (cudaGetLastError() != cudaSuccess) return -2;
+  return launch_aux_scan(a, a.aux + (u64)4 * ZKIR_AIR_NUM_HELPERS * N, st, launches);
 }
 
 }  // namespace zkir

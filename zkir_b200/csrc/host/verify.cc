@@ -10,8 +10,8 @@
 #include <vector>
 #include "zkir_b200.h"
 #include "../constants_generated.h"
-#include "../air_generated.h"
-#include "../air_columns.h"
+#include "../air_profile.h"   // this file is compiled once per AIR profile; zkir_b200_verify (core build) dispatches on the width
+#include "../air_profiles_generated.h"
 #include <algorithm>
 
 std::string& zkir_host_error();
@@ -143,7 +143,7 @@ struct AirAtZeta {  // air_generated.h context over ext4: base and ext values ar
   const X4 *loc, *nxt;        // opened main columns [0, W) then aux columns [W, W + A) at zeta / g*zeta
   const X4* pub;              // public columns at zeta, computed by the verifier
   const u32* pv;
-  X4 zc, thp[5], sio_v;       // lookup challenges z, theta^k; the public I/O transcript's sum
+  X4 zc, thp[ZKIR_AIR_NUM_THETA + 1], sio_v;       // lookup challenges z, theta^k; the public I/O transcript's sum
   X4 is_first, is_last, is_trans, alpha, acc;
   X4 L(int i) const { return loc[i]; }
   X4 N(int i) const { return nxt[i]; }
@@ -264,32 +264,29 @@ bool verify(const zkir_params* p, const u32* w, size_t nwords, const u32* pv_in,
   // public columns at zeta by the barycentric formula over H_N:  P(zeta) = (zeta^N - 1)/N * sum_i v_i w^i / (zeta - w^i);
   // only the first max(1024, n_code) rows are non-zero, except the ROM's decoded-word column which is 127 on every unused row:
   // it is evaluated as the constant 127 plus the interpolant of (dec_i - 127) over the program rows
+  // a column is its default value (the rows past the tables and the program: zkir_public_row(~0)) plus the interpolant of the
+  // differences over the first rows
   X4 pubz[ZKIR_AIR_PUB_WIDTH];
   {
-    const size_t rows = std::max<size_t>((size_t)1 << ZKIR_AIR_RANGE_BITS, n_code);
+    const size_t rows = std::min<size_t>((size_t)zkir_public_rows(p->width, n_code), (size_t)N);
     const X4 scale_all = scale(zh, inv((u32)(N % P)));
+    u32 dflt[ZKIR_AIR_PUB_WIDTH], row[ZKIR_AIR_PUB_WIDTH];
+    zkir_public_row(p->width, ~0ull, code, n_code, dflt);
     u32 wi = 1;
     for (size_t i = 0; i < rows; i++) {
       X4 d;
       if (!xinv(zeta - X4(wi), &d)) return fail("zeta hits the trace domain");
       const X4 li = scale(d, wi);    // w^i / (zeta - w^i)
-      if (i < ((size_t)1 << ZKIR_AIR_RANGE_BITS)) pubz[ZKIR_PUB_P_T] = pubz[ZKIR_PUB_P_T] + scale(li, (u32)i);
-      if (i < n_code) {
-        u32 dec, im;
-        rom_entry(code[i], &dec, &im);
-        pubz[ZKIR_PUB_P_PC] = pubz[ZKIR_PUB_P_PC] + scale(li, (u32)(0x1000 + 4 * i));
-        pubz[ZKIR_PUB_P_DEC] = pubz[ZKIR_PUB_P_DEC] + scale(li, sub(dec, 127));   // relative to the 127 every row carries
-        pubz[ZKIR_PUB_P_IMM] = pubz[ZKIR_PUB_P_IMM] + scale(li, im);
-      }
+      zkir_public_row(p->width, i, code, n_code, row);
+      for (int k = 0; k < ZKIR_AIR_PUB_WIDTH; k++) if (row[k] != dflt[k]) pubz[k] = pubz[k] + scale(li, sub(row[k], dflt[k]));
       wi = mul(wi, g);
     }
-    for (int k = 0; k < ZKIR_AIR_PUB_WIDTH; k++) pubz[k] = pubz[k] * scale_all;
-    pubz[ZKIR_PUB_P_DEC] = pubz[ZKIR_PUB_P_DEC] + X4(127);   // the constant polynomial 127
+    for (int k = 0; k < ZKIR_AIR_PUB_WIDTH; k++) pubz[k] = pubz[k] * scale_all + X4(dflt[k]);
   }
   AirAtZeta c;
   c.loc = ot.data(); c.nxt = otg.data(); c.pub = pubz; c.pv = pv; c.alpha = alpha;
   c.zc = lz; c.thp[0] = X4(1); c.thp[1] = ltheta;
-  for (int k = 2; k < 5; k++) c.thp[k] = c.thp[k - 1] * ltheta;
+  for (int k = 2; k <= ZKIR_AIR_NUM_THETA; k++) c.thp[k] = c.thp[k - 1] * ltheta;
   // the table side of the I/O bus is public: S_io = sum_e 1 / (z - (3 + theta clk + theta^2 kind + theta^3 lo + theta^4 hi))
   for (size_t e = 0; e < n_io; e++) {
     X4 fp(3), d;
@@ -384,12 +381,21 @@ bool verify(const zkir_params* p, const u32* w, size_t nwords, const u32* pv_in,
 }  // namespace
 
 extern "C" {
+#ifdef ZKIR_PROFILE_FULL
+// the full-profile build of this file exports only its verifier; zkir_b200_verify (core build) calls it for full-width proofs
+int zkir_verify_words_full(const zkir_params* p, const uint32_t* w, size_t nwords, const uint32_t* public_values, const uint32_t* code, size_t n_code,
+                           const uint32_t* io_events, size_t n_io) {
+  return verify(p, w, nwords, public_values, code, n_code, io_events, n_io) ? 0 : ZKIR_ERR_VERIFY;
+}
+#else
+int zkir_verify_words_full(const zkir_params*, const uint32_t*, size_t, const uint32_t*, const uint32_t*, size_t, const uint32_t*, size_t);
 int zkir_b200_verify(const zkir_params* p, const uint8_t* proof, size_t len, const uint32_t* public_values, const uint32_t* code, size_t n_code,
                      const uint32_t* io_events, size_t n_io) {
   g_verify_error.clear();
-  if (!proof || len % 4) { g_verify_error = "bad proof buffer"; return ZKIR_ERR_VERIFY; }
+  if (!p || !proof || len % 4) { g_verify_error = "bad proof buffer"; return ZKIR_ERR_VERIFY; }
   std::vector<u32> w(len / 4);
   memcpy(w.data(), proof, len);
+  if (p->width == ZKIR_PROFILE_FULL_WIDTH) return zkir_verify_words_full(p, w.data(), w.size(), public_values, code, n_code, io_events, n_io);
   return verify(p, w.data(), w.size(), public_values, code, n_code, io_events, n_io) ? 0 : ZKIR_ERR_VERIFY;
 }
 void zkir_program_digest(const uint32_t* code, size_t n_code, uint32_t digest8[8]) { program_digest(code, n_code, digest8); }
@@ -398,4 +404,5 @@ void zkir_io_digest(const uint32_t* io_events, size_t n_io, uint32_t digest8[8])
 void zkir_host_poseidon2_permute(uint32_t* state16) { permute(state16); }
 // ROM entry of one code word as the AIR's ROM lookup sees it (used by the prover to build the public ROM columns)
 void zkir_rom_entry(uint32_t word, uint32_t* dec, uint32_t* imm) { rom_entry(word, dec, imm); }
+#endif  // !ZKIR_PROFILE_FULL
 }

@@ -85,7 +85,8 @@ struct QuotientArgs {
   // possibly peer memory over NVLink) instead of q; nullptr = q
   u32* q_plane[4] = {nullptr, nullptr, nullptr, nullptr};
 };
-int launch_quotient(const QuotientArgs& a, cudaStream_t st, u64* launches);
+int launch_quotient(const QuotientArgs& a, cudaStream_t st, u64* launches);        // core profile
+int launch_quotient_full(const QuotientArgs& a, cudaStream_t st, u64* launches);   // full profile (quotient.cu compiled with ZKIR_PROFILE_FULL)
 int launch_domain_tables(u32* xs, u32* dinv, u32 log_n, u32 log_b, u32 shift_canon, cudaStream_t st, u64* launches);
 
 // ---- trace_expand.cu: raw interpreter rows -> AIR columns on the device
@@ -130,7 +131,9 @@ struct AuxArgs {
 u64 aux_gen_blocks(u64 N);
 // lookup[8..12) <- S_io = sum over the public I/O events (4 words each: clk, kind, lo, hi; canonical, device) of 1 / (z - fingerprint)
 int launch_io_sum(const u32* events, u32 n_events, u32* lookup, cudaStream_t st, u64* launches);
-int launch_aux_gen(const AuxArgs& a, cudaStream_t st, u64* launches);
+int launch_aux_gen(const AuxArgs& a, cudaStream_t st, u64* launches);        // core profile
+int launch_aux_gen_full(const AuxArgs& a, cudaStream_t st, u64* launches);   // full profile
+int launch_aux_scan(const AuxArgs& a, u32* phi_cols, cudaStream_t st, u64* launches);   // running sum of row_tot into the four phi columns
 int launch_trace_expand_wl(const WlArgs& a, cudaStream_t st, u64* launches);
 
 // ---- peer.cu: rows of the column-sharded LDE stored straight into the peers' matrices (NVLink peer memory)

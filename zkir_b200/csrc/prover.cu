@@ -25,7 +25,8 @@
 #include "kernels.h"
 #include "comm.h"
 #include "constants_generated.h"
-#include "air_generated.h"
+#include "air_profiles_generated.h"
+#include "air_columns.h"   // the device converter and the write-log path serve the core profile
 #include "air_pack.h"
 #include "proof_layout.h"
 
@@ -218,7 +219,7 @@ static int ws_prepare(zkir_ctx* ctx, const zkir_params* p, u32 log_n) {
   w.plan_chunk = w.plan_m;
   w.plan_chunk.log_n = (int)log_n;
   w.plan_chunk.d[w.plan_m.nd - 1] -= (int)p->log_blowup;
-  const u64 WA = W + AW;
+  const u64 AW = profile_aux_width(p->width), PW = profile_pub_width(p->width), WA = W + AW;
   A(trace, W * N) A(coef, WA * N) A(lde, WA * M) A(ttree, (2 * M - 1) * 8)
   A(aux, (u64)AW * N) A(atree, (2 * M - 1) * 8) A(pub, (u64)PW * N) A(publde, (u64)PW * M)
   A(aux_row_tot, N) A(aux_blk_tot, aux_gen_blocks(N))
@@ -229,7 +230,7 @@ static int ws_prepare(zkir_ctx* ctx, const zkir_params* p, u32 log_n) {
   A(layers, 2 * M) A(ltrees, 2 * M * 8)
   A(d_layers, R + 1) A(d_ltrees, R + 1)
   A(chal, 1) A(chal_buf, 12 + 4 * R + 2 + 12 + HDR_WORDS + p->num_public + 16) A(indices, p->num_queries + 1)
-  A(apow, 4 * ZKIR_AIR_NUM_CONSTRAINTS) A(afp, WA + 5)
+  A(apow, 4 * ZKIR_PROFILE_MAX_CONSTRAINTS) A(afp, WA + 5)
   A(proof, L.total + 4) A(xchg, ZKIR_MAX_SHARDS * PEER_REC_WORDS) A(otree, hash_tree_scratch_words((u32)(2 * WA + QW) * 4))
 #undef A
   w.proof += (4 - (L.open_t & 3)) & 3;   // the opened values are read and written as 16-byte ext4 elements: align that section
@@ -252,8 +253,8 @@ static int ws_prepare(zkir_ctx* ctx, const zkir_params* p, u32 log_n) {
 }
 
 static int check_params(zkir_ctx* ctx, const zkir_params* p, u32 log_n) {
-  if (!p || p->width != ZKIR_AIR_WIDTH || p->num_public != ZKIR_AIR_NUM_PUBLIC || p->log_blowup < 1 || p->log_blowup > 4 ||
-      log_n < ZKIR_AIR_RANGE_BITS || log_n + p->log_blowup > 27 || p->pow_bits > 30 || p->num_queries > 4096) {
+  if (!p || !profile_known(p->width) || p->num_public != ZKIR_NUM_PUBLIC_VALUES || p->log_blowup < 1 || p->log_blowup > 4 ||
+      log_n < ZKIR_RANGE_BITS || log_n + p->log_blowup > 27 || p->pow_bits > 30 || p->num_queries > 4096) {
     ctx->err = "bad params: need width=88, num_public=5, 1<=log_blowup<=4, 10<=log_n (the range table occupies 1024 trace rows), log_n+log_blowup<=27, pow_bits<=30";
     return ZKIR_ERR_ARG;
   }
@@ -270,6 +271,7 @@ struct ShardPlan {
   u32 G = 1, lo = 0, hi = 1, log_nj = 0;
   u64 nj = 0;          // points per coset and shard
   u32 cols_per = 0, W = 0;
+  u32 AW = 0;          // aux columns of the profile
   u32 acols_per = 0;   // aux columns per rank (column indices W .. W + AW of the coefficient / LDE matrices)
   u32 a_lo(u32 g) const { const u32 c = g * acols_per; return W + (c < AW ? c : AW); }
   u32 a_hi(u32 g) const { const u32 c = (g + 1) * acols_per; return W + (c < AW ? c : AW); }
@@ -290,7 +292,8 @@ static ShardPlan shard_plan_for(u32 G, u32 W, u32 log_n, u32 log_blowup, bool fa
     sp.nj = N / G;
     while ((1ull << sp.log_nj) < sp.nj) sp.log_nj++;
     sp.cols_per = (W + G - 1) / G;
-    sp.acols_per = (AW + G - 1) / G;
+    sp.AW = profile_aux_width(W);
+    sp.acols_per = (sp.AW + G - 1) / G;
     sp.planes_per = (4 + G - 1) / G;
   }
   return sp;
@@ -337,7 +340,7 @@ static int exchange_lde_rows(zkir_ctx* ctx, const ShardPlan& sp, u32* lde, u64 N
 
 // Map every rank's LDE matrix into this process.  Collective (one all-gather of 96-byte records); runs once per workspace shape.
 struct PeerRec { u64 pid; u32 dev, pad; u64 ptr[PEER_BUFS]; cudaIpcMemHandle_t handle[PEER_BUFS]; u64 pad2; };
-static_assert(ZKIR_AIR_NUM_PUBLIC <= 8, "zkir_b200_quotient scratch layout");
+static_assert(ZKIR_NUM_PUBLIC_VALUES <= 8, "zkir_b200_quotient scratch layout");
 static_assert(sizeof(PeerRec) == 4 * PEER_REC_WORDS, "PeerRec layout");
 static int peers_open(zkir_ctx* ctx) {
   Workspace& w = ctx->ws;
@@ -432,7 +435,7 @@ static int fill_header_stage(zkir_ctx* ctx, const zkir_params* p, u32 log_n, con
   for (u32 i = 0; i < np; i++) { if (pv[i] >= BB_P) { ctx->err = "public value not canonical"; return ZKIR_ERR_ARG; } hs[8 + i] = pv[i]; }
   if (pv[4] > 1 || (pv[4] == 0 && (pv[2] || pv[3]))) { ctx->err = "public values: halted must be 0/1, and a run that did not halt has no exit code"; return ZKIR_ERR_ARG; }
   u32* hm = hs + 8 + np;  // Montgomery copy for the transcript: header, public values, program digest
-  const u32 hdr[HDR_WORDS] = {log_n, p->width, AW, p->log_blowup, p->num_queries, p->pow_bits, np};
+  const u32 hdr[HDR_WORDS] = {log_n, p->width, profile_aux_width(p->width), p->log_blowup, p->num_queries, p->pow_bits, np};
   for (u32 i = 0; i < HDR_WORDS; i++) hm[i] = bb_to_mont_c(hdr[i]);
   for (u32 i = 0; i < np; i++) hm[HDR_WORDS + i] = bb_to_mont_c(pv[i]);
   for (u32 i = 0; i < 8; i++) hm[HDR_WORDS + np + i] = bb_to_mont_c(ctx->code_digest[i]);
@@ -447,16 +450,9 @@ static int ensure_public_columns(zkir_ctx* ctx, const zkir_params* p, u32 log_n)
   Workspace& w = ctx->ws;
   if (w.pub_version == ctx->program_version) return 0;
   const u64 N = 1ull << log_n, M = N << p->log_blowup;
+  const u32 PW = profile_pub_width(p->width);
   std::vector<u32> h((size_t)PW * N, 0u);
-  for (u64 i = 0; i < N && i < (1ull << ZKIR_AIR_RANGE_BITS); i++) h[ZKIR_PUB_P_T * N + i] = (u32)i;
-  for (u64 i = 0; i < N; i++) {
-    if (i < ctx->code.size()) {
-      h[ZKIR_PUB_P_PC * N + i] = 0x1000u + 4 * (u32)i;
-      zkir_rom_entry(ctx->code[i], &h[ZKIR_PUB_P_DEC * N + i], &h[ZKIR_PUB_P_IMM * N + i]);
-    } else {
-      h[ZKIR_PUB_P_DEC * N + i] = 127;   // no instruction has opcode 127: an unused ROM row matches no trace row
-    }
-  }
+  zkir_public_columns(p->width, log_n, ctx->code.data(), ctx->code.size(), h.data());   // host/public_cols.cc
   cudaStream_t st = ctx->stream;
   CU(cudaMemcpyAsync(w.pub, h.data(), h.size() * 4, cudaMemcpyHostToDevice, st));
   CU(cudaStreamSynchronize(st));   // h is pageable and goes out of scope
@@ -480,7 +476,8 @@ static int prove_resident(zkir_ctx* ctx, const zkir_params* p, u32 log_n, const 
   Workspace& w = ctx->ws;
   cudaStream_t st = ctx->stream;
   u64* LC = &ctx->launches;
-  const u64 N = 1ull << log_n, M = N << p->log_blowup, W = p->width, WA = W + AW;
+  const u64 N = 1ull << log_n, M = N << p->log_blowup, W = p->width, AW = profile_aux_width(p->width), WA = W + AW;
+  const bool full = profile_is_full(p->width);
   const u32 log_m = log_n + p->log_blowup, R = log_n, np = p->num_public;
   const Layout L = make_layout(p, log_n);
   const u32 shift = ZKIR_BB_GEN;
@@ -553,7 +550,7 @@ static int prove_resident(zkir_ctx* ctx, const zkir_params* p, u32 log_n, const 
     AuxArgs aa;
     aa.trace = trace; aa.pub = w.pub; aa.lookup = c_lookup; aa.aux = w.aux; aa.log_n = log_n; aa.row_tot = w.aux_row_tot; aa.blk_tot = w.aux_blk_tot;
     aa.err = ctx->d_err + 1;
-    RC(launch_aux_gen(aa, st, LC));   // replicated on every rank of a sharded proof (needs whole rows; 16 columns out)
+    RC(full ? launch_aux_gen_full(aa, st, LC) : launch_aux_gen(aa, st, LC));   // replicated on every rank of a sharded proof (needs whole rows; 16 columns out)
     const u32 c0a = hmul(hinv((u32)(N % BB_P)), (u32)((1ull << 32) % BB_P));
     if (sp.on) {
       const bool fuse_a = p2p && lde_mode == 0 && fast_coset_ntt_can_fuse(w.plan_n, sp.G);
@@ -570,10 +567,10 @@ static int prove_resident(zkir_ctx* ctx, const zkir_params* p, u32 log_n, const 
         int brc = peers_barrier(ctx); if (brc) return brc;
       }
     } else {
-      RC(fast_intt(ctx->fast, w.plan_n, w.aux, N, w.coef + W * N, N, AW, c0a, nullptr, 32, 0, 0, nullptr, 0, st));
-      RC(fast_coset_ntt(ctx->fast, w.plan_n, w.coef + W * N, N, w.lde + W * M, M, AW, B, shift, ZKIR_BB_ROOTS[log_m], 1u, st));
+      RC(fast_intt(ctx->fast, w.plan_n, w.aux, N, w.coef + W * N, N, (u32)AW, c0a, nullptr, 32, 0, 0, nullptr, 0, st));
+      RC(fast_coset_ntt(ctx->fast, w.plan_n, w.coef + W * N, N, w.lde + W * M, M, (u32)AW, B, shift, ZKIR_BB_ROOTS[log_m], 1u, st));
     }
-    if ((crc = commit_tree(ctx, w.lde + W * M, AW, p->log_blowup, nullptr, w.atree, M >> L.log_lr, w.proof + L.aroot, c_alpha, 4, &a_sl, sp.on ? 1 : 0)) != 0) return crc;  // root -> proof, observe, sample alpha
+    if ((crc = commit_tree(ctx, w.lde + W * M, (u32)AW, p->log_blowup, nullptr, w.atree, M >> L.log_lr, w.proof + L.aroot, c_alpha, 4, &a_sl, sp.on ? 1 : 0)) != 0) return crc;  // root -> proof, observe, sample alpha
   }
   // ---- 3. quotient
   CU(cudaEventRecord(ctx->ev[ZKIR_STAGE_QUOTIENT], st));
@@ -587,11 +584,11 @@ static int prove_resident(zkir_ctx* ctx, const zkir_params* p, u32 log_n, const 
       if (p2p) for (u32 k = 0; k < 4; k++) qa.q_plane[k] = w.peers[PEER_Q].p[k / sp.planes_per];
       for (u32 g = sp.lo; g < sp.hi; g++) {
         qa.seg_log_nj = sp.log_nj; qa.seg_j0 = (u64)g * sp.nj;
-        RC(launch_quotient(qa, st, LC));
+        RC(full ? launch_quotient_full(qa, st, LC) : launch_quotient(qa, st, LC));
       }
       if (p2p) { int brc = peers_barrier(ctx); if (brc) return brc; }
     } else {
-      RC(launch_quotient(qa, st, LC));
+      RC(full ? launch_quotient_full(qa, st, LC) : launch_quotient(qa, st, LC));
     }
   }
   CU(cudaEventRecord(ctx->ev[ZKIR_STAGE_QUOTIENT_COMMIT], st));
@@ -701,7 +698,7 @@ static int prove_resident(zkir_ctx* ctx, const zkir_params* p, u32 log_n, const 
     QueryArgs qa;
     qa.indices = w.indices; qa.num_queries = p->num_queries; qa.log_m = log_m; qa.width = (u32)W; qa.log_n = log_n;
     qa.lde = w.lde; qa.ttree = w.ttree; qa.qlde = w.qlde; qa.qtree = w.qtree;
-    qa.aux_width = AW; qa.atree = w.atree; qa.atree_sl = a_sl; qa.log_lr = L.log_lr;
+    qa.aux_width = (u32)AW; qa.atree = w.atree; qa.atree_sl = a_sl; qa.log_lr = L.log_lr;
     qa.layers = w.d_layers; qa.ltrees = w.d_ltrees; qa.fold8_rounds = log_n / 3; qa.last_log_arity = log_n % 3; qa.fri_rounds = (u32)L.R; qa.out = w.proof + L.queries; qa.words_per_query = (u32)L.per_query;
     // sharded trees: the bottom path levels of a leaf exist only on its owner; every rank writes the pieces it owns (zeros
     // elsewhere, rank 0 also everything that is replicated) and one all-reduce assembles the query section ("query gather")
@@ -1093,7 +1090,7 @@ int zkir_b200_prove_program(zkir_ctx* ctx, const zkir_params* p, const uint32_t*
   up.ctx = ctx; up.h_pcs = h_pcs; up.h_ins = h_ins; up.h_wlog = h_wlog; up.done = 0; up.e = cudaSuccess;
   const bool overlap = ctx->comm == nullptr;   // a sharded proof uploads by row segment inside prove_writelog instead
   // the scan scratch depends on the (still unknown) padded trace length: size it for the largest trace the log can hold
-  u64 n_scan = 1ull << ZKIR_AIR_RANGE_BITS;
+  u64 n_scan = 1ull << ZKIR_RANGE_BITS;
   while (n_scan < max_cycles || n_scan < n_code) n_scan <<= 1;
   if (overlap && (rc = wl_stage(ctx, max_cycles, n_scan, &up.sg)) != 0) return rc;
   zkir_vm_result* res = nullptr;
@@ -1106,7 +1103,7 @@ int zkir_b200_prove_program(zkir_ctx* ctx, const zkir_params* p, const uint32_t*
   rc = zkir_b200_set_io(ctx, zkir_vm_io(res), zkir_vm_io_len(res));   // the run's public I/O transcript is part of the statement
   zkir_vm_free(res);
   if (rc) return rc;
-  u32 log_n = ZKIR_AIR_RANGE_BITS;
+  u32 log_n = ZKIR_RANGE_BITS;
   while ((1ull << log_n) <= T || (1ull << log_n) < n_code) log_n++;   // at least one padding row after the last cycle
   if (out_cycles) *out_cycles = T;
   if (out_log_n) *out_log_n = log_n;
@@ -1128,7 +1125,7 @@ int zkir_b200_prove_program(zkir_ctx* ctx, const zkir_params* p, const uint32_t*
 
 int zkir_b200_expand_writelog(zkir_ctx* ctx, const uint32_t* pcs, const uint32_t* instrs, const uint64_t* wlog, uint64_t n_rows,
                               uint64_t final_pc, uint32_t log_n, uint32_t* d_cols) {
-  if (!ctx || !d_cols || log_n < ZKIR_AIR_RANGE_BITS || log_n > 26) return ZKIR_ERR_ARG;
+  if (!ctx || !d_cols || log_n < ZKIR_RANGE_BITS || log_n > 26) return ZKIR_ERR_ARG;
   ctx->err.clear();
   cudaSetDevice(ctx->device);
   int rc = expand_writelog(ctx, pcs, instrs, wlog, n_rows, final_pc, log_n, d_cols);
@@ -1140,7 +1137,7 @@ int zkir_b200_expand_writelog(zkir_ctx* ctx, const uint32_t* pcs, const uint32_t
 
 int zkir_b200_expand_rows(zkir_ctx* ctx, const uint64_t* pcs, const uint32_t* instrs, const uint64_t* regs, uint64_t n_rows,
                           const uint64_t* final_regs, uint64_t final_pc, uint32_t log_n, uint32_t* d_cols) {
-  if (!ctx || !d_cols || log_n < ZKIR_AIR_RANGE_BITS || log_n > 26) return ZKIR_ERR_ARG;
+  if (!ctx || !d_cols || log_n < ZKIR_RANGE_BITS || log_n > 26) return ZKIR_ERR_ARG;
   ctx->err.clear();
   cudaSetDevice(ctx->device);
   int rc = expand_rows(ctx, pcs, instrs, regs, n_rows, final_regs, final_pc, log_n, d_cols);
@@ -1364,8 +1361,8 @@ int zkir_b200_quotient(zkir_ctx* ctx, const zkir_params* p, const uint32_t* d_ld
   if (!ctx || !p || !d_lde || !d_publde || !pv || !lookup || !alpha || !d_q) return ZKIR_ERR_ARG;
   ctx->err.clear();
   cudaSetDevice(ctx->device);
-  if (p->width != ZKIR_AIR_WIDTH || p->num_public != ZKIR_AIR_NUM_PUBLIC || log_n < 2 || p->log_blowup < 1 || log_n + p->log_blowup > 27) { ctx->err = "bad params"; return ZKIR_ERR_ARG; }
-  const u32 log_m = log_n + p->log_blowup, WA = p->width + AW, NP = ZKIR_AIR_NUM_PUBLIC;
+  if (!profile_known(p->width) || p->num_public != ZKIR_NUM_PUBLIC_VALUES || log_n < 2 || p->log_blowup < 1 || log_n + p->log_blowup > 27) { ctx->err = "bad params"; return ZKIR_ERR_ARG; }
+  const u32 log_m = log_n + p->log_blowup, AW = profile_aux_width(p->width), PW = profile_pub_width(p->width), WA = p->width + AW, NP = ZKIR_NUM_PUBLIC_VALUES;
   const u64 M = 1ull << log_m;
   u32 *lde_m = nullptr, *lde_cm = nullptr, *pub_m = nullptr, *pub_cm = nullptr, *xs = nullptr, *dinv = nullptr, *small = nullptr;
   CU(cudaMallocAsync(&lde_m, (size_t)WA * M * 4, ctx->stream));
@@ -1375,7 +1372,7 @@ int zkir_b200_quotient(zkir_ctx* ctx, const zkir_params* p, const uint32_t* d_ld
   CU(cudaMallocAsync(&xs, M * 4, ctx->stream));
   CU(cudaMallocAsync(&dinv, M * 4, ctx->stream));
   // small: pv[8 (NP padded)] alpha[4] lookup[12: z, theta, sio] apow[K][4] -- the ext4 arrays must stay 16-byte aligned
-  CU(cudaMallocAsync(&small, (24 + 4 * ZKIR_AIR_NUM_CONSTRAINTS) * 4, ctx->stream));
+  CU(cudaMallocAsync(&small, (24 + 4 * ZKIR_PROFILE_MAX_CONSTRAINTS) * 4, ctx->stream));
   u32 h[24] = {0};
   for (u32 i = 0; i < NP; i++) h[i] = bb_to_mont_c(pv[i] % BB_P);
   for (int i = 0; i < 4; i++) h[8 + i] = bb_to_mont_c(alpha[i] % BB_P);
@@ -1390,7 +1387,7 @@ int zkir_b200_quotient(zkir_ctx* ctx, const zkir_params* p, const uint32_t* d_ld
   QuotientArgs qa;
   qa.lde = lde_cm; qa.publde = pub_cm; qa.q = d_q; qa.log_n = log_n; qa.log_blowup = p->log_blowup; qa.pv = small; qa.alpha = small + 8; qa.lookup = small + 12;
   qa.xs = xs; qa.dinv = dinv; qa.apow_scratch = small + 24;
-  if (!rc) rc = launch_quotient(qa, ctx->stream, &ctx->launches);
+  if (!rc) rc = profile_is_full(p->width) ? launch_quotient_full(qa, ctx->stream, &ctx->launches) : launch_quotient(qa, ctx->stream, &ctx->launches);
   if (!rc) rc = launch_map(d_q, d_q, 4 * M, 0, ctx->stream, &ctx->launches);
   CU(cudaStreamSynchronize(ctx->stream));
   cudaFreeAsync(lde_m, ctx->stream); cudaFreeAsync(lde_cm, ctx->stream); cudaFreeAsync(pub_m, ctx->stream); cudaFreeAsync(pub_cm, ctx->stream);
@@ -1401,17 +1398,13 @@ int zkir_b200_quotient(zkir_ctx* ctx, const zkir_params* p, const uint32_t* d_ld
 
 // the LogUp aux columns of a canonical device trace for GIVEN lookup challenges (the prover draws them from the transcript)
 int zkir_b200_aux_columns(zkir_ctx* ctx, const uint32_t* d_trace, uint32_t log_n, const uint32_t lookup[8], uint32_t* d_aux) {
-  if (!ctx || !d_trace || !lookup || !d_aux || log_n < ZKIR_AIR_RANGE_BITS || log_n > 26) return ZKIR_ERR_ARG;
+  if (!ctx || !d_trace || !lookup || !d_aux || log_n < ZKIR_RANGE_BITS || log_n > 26) return ZKIR_ERR_ARG;
   ctx->err.clear();
   cudaSetDevice(ctx->device);
   if (ctx->program_version == 0 || ctx->code.size() > (1ull << log_n)) { ctx->err = "no program set, or it does not fit the trace"; return ZKIR_ERR_ARG; }
   const u64 N = 1ull << log_n;
-  std::vector<u32> hp((size_t)PW * N, 0u);
-  for (u64 i = 0; i < N && i < (1ull << ZKIR_AIR_RANGE_BITS); i++) hp[ZKIR_PUB_P_T * N + i] = (u32)i;
-  for (u64 i = 0; i < N; i++) {
-    if (i < ctx->code.size()) { hp[ZKIR_PUB_P_PC * N + i] = 0x1000u + 4 * (u32)i; zkir_rom_entry(ctx->code[i], &hp[ZKIR_PUB_P_DEC * N + i], &hp[ZKIR_PUB_P_IMM * N + i]); }
-    else hp[ZKIR_PUB_P_DEC * N + i] = 127;
-  }
+  std::vector<u32> hp((size_t)ZKIR_PROFILE_CORE_PUB * N, 0u);   // per-kernel entry point: core profile
+  zkir_public_columns(ZKIR_PROFILE_CORE_WIDTH, log_n, ctx->code.data(), ctx->code.size(), hp.data());
   u32 *pub = nullptr, *lk = nullptr; E4 *rt = nullptr, *bt = nullptr;
   CU(cudaMalloc(&pub, hp.size() * 4)); CU(cudaMalloc(&lk, 48)); CU(cudaMalloc(&rt, N * sizeof(E4))); CU(cudaMalloc(&bt, aux_gen_blocks(N) * sizeof(E4)));
   u32 hl[8];

@@ -10,7 +10,7 @@
 #include <stdlib.h>
 #include "bb.cuh"
 #include "kernels.h"
-#include "air_generated.h"
+#include "air_profile.h"
 #include "constants_generated.h"
 
 namespace zkir {
@@ -20,7 +20,7 @@ struct QCtx {
   const u32 *lde, *aux, *pub; u64 M, row, nxt;
   const u32* pv;       // shared
   const E4* apow;      // shared, apow[i] = alpha^(K-1-i)
-  const E4* lc;        // shared: lookup challenges z, theta .. theta^4, then the public I/O transcript's sum
+  const E4* lc;        // shared: lookup challenges z, theta .. theta^NUM_THETA, then the public I/O transcript's sum
   Fm is_first, is_last, is_trans;
   Acc4 acc;  // lazy 64-bit accumulator of sum_i alpha^(K-1-i) * C_i over the base-field constraints (bb.cuh)
   E4 accx;   // the ext4-valued constraints (LogUp) are few: plain ext4 products
@@ -34,7 +34,7 @@ struct QCtx {
   __device__ __forceinline__ Xm z() const { Xm r; r.v = lc[0]; return r; }
   __device__ __forceinline__ Xm th(int k) const { Xm r; r.v = lc[k]; return r; }
   __device__ __forceinline__ Xm xf(Fm a) const { Xm r; r.v = e4_from_base(a.v); return r; }
-  __device__ __forceinline__ Xm sio() const { Xm r; r.v = lc[5]; return r; }
+  __device__ __forceinline__ Xm sio() const { Xm r; r.v = lc[ZKIR_AIR_NUM_THETA + 1]; return r; }
   __device__ __forceinline__ Xm x4(Fm a, Fm b, Fm c, Fm d) const { Xm r; r.v.c[0] = a.v; r.v.c[1] = b.v; r.v.c[2] = c.v; r.v.c[3] = d.v; return r; }
   __device__ __forceinline__ void emit(int idx, Fm v) {
     acc4_mac(acc, apow[idx], v.v);
@@ -43,7 +43,7 @@ struct QCtx {
   __device__ __forceinline__ void emit_x(int idx, Xm v) { accx = e4_add(accx, e4_mul(apow[idx], v.v)); }
 };
 
-__global__ void alpha_powers_kernel(const u32* alpha, E4* apow) {  // apow[i] = alpha^(K-1-i); thread per power
+__global__ void ZKIR_PF(alpha_powers_kernel)(const u32* alpha, E4* apow) {  // apow[i] = alpha^(K-1-i); thread per power
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= ZKIR_AIR_NUM_CONSTRAINTS) return;
   E4 a; for (int k = 0; k < 4; k++) a.c[k] = alpha[k];
@@ -53,9 +53,9 @@ __global__ void alpha_powers_kernel(const u32* alpha, E4* apow) {  // apow[i] = 
 }
 
 template <int MINB>
-__global__ void __launch_bounds__(128, MINB) quotient_kernel(QuotientArgs a, const E4* apow_g, u32 g_inv, u32 g, u32 snn /* shift^N */, u32 wb /* w_B */) {
+__global__ void __launch_bounds__(128, MINB) ZKIR_PF(quotient_kernel)(QuotientArgs a, const E4* apow_g, u32 g_inv, u32 g, u32 snn /* shift^N */, u32 wb /* w_B */) {
   __shared__ E4 apow[ZKIR_AIR_NUM_CONSTRAINTS];
-  __shared__ E4 lc[6];
+  __shared__ E4 lc[ZKIR_AIR_NUM_THETA + 2];
   __shared__ u32 pv[ZKIR_AIR_NUM_PUBLIC];
   for (int i = threadIdx.x; i < ZKIR_AIR_NUM_CONSTRAINTS; i += blockDim.x) apow[i] = apow_g[i];
   if (threadIdx.x < ZKIR_AIR_NUM_PUBLIC) pv[threadIdx.x] = a.pv[threadIdx.x];
@@ -69,7 +69,9 @@ __global__ void __launch_bounds__(128, MINB) quotient_kernel(QuotientArgs a, con
   if (threadIdx.x == 32) {
     E4 z, th, so;
     for (int k = 0; k < 4; k++) { z.c[k] = a.lookup[k]; th.c[k] = a.lookup[4 + k]; so.c[k] = a.lookup[8 + k]; }
-    lc[0] = z; lc[1] = th; lc[2] = e4_mul(th, th); lc[3] = e4_mul(lc[2], th); lc[4] = e4_mul(lc[3], th); lc[5] = so;
+    lc[0] = z; lc[1] = th;
+    for (int k = 2; k <= ZKIR_AIR_NUM_THETA; k++) lc[k] = e4_mul(lc[k - 1], th);
+    lc[ZKIR_AIR_NUM_THETA + 1] = so;
   }
   __syncthreads();
   const u64 M = 1ull << (a.log_n + a.log_blowup), N = 1ull << a.log_n;
@@ -95,6 +97,9 @@ __global__ void __launch_bounds__(128, MINB) quotient_kernel(QuotientArgs a, con
   for (int k = 0; k < 4; k++) (a.q_plane[k] ? a.q_plane[k] : a.q)[(u64)k * M + nat] = bb_mul(accv.c[k], zi);
 }
 
+static u32 hpow(u32 a, u64 e) { u64 r = 1, b = a; while (e) { if (e & 1) r = r * b % BB_P; b = b * b % BB_P; e >>= 1; } return (u32)r; }
+
+#ifndef ZKIR_PROFILE_FULL   // profile-independent: compiled with the core build only
 __global__ void domain_tables_kernel(u32* xs, u32* dinv, u64 M, u32 log_n, u32 log_b, u32 shift, u32 w) {
   u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x;
   if (i >= M) return;
@@ -104,7 +109,6 @@ __global__ void domain_tables_kernel(u32* xs, u32* dinv, u64 M, u32 log_n, u32 l
   dinv[i] = bb_inv(bb_sub(x, BB_ONE));
 }
 
-static u32 hpow(u32 a, u64 e) { u64 r = 1, b = a; while (e) { if (e & 1) r = r * b % BB_P; b = b * b % BB_P; e >>= 1; } return (u32)r; }
 
 int launch_domain_tables(u32* xs, u32* dinv, u32 log_n, u32 log_b, u32 shift_canon, cudaStream_t st, u64* launches) {
   const u32 log_m = log_n + log_b;
@@ -114,9 +118,11 @@ int launch_domain_tables(u32* xs, u32* dinv, u32 log_n, u32 log_b, u32 shift_can
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
-int launch_quotient(const QuotientArgs& a, cudaStream_t st, u64* launches) {
+#endif  // !ZKIR_PROFILE_FULL
+
+int ZKIR_PF(launch_quotient)(const QuotientArgs& a, cudaStream_t st, u64* launches) {
   const u64 M = 1ull << (a.log_n + a.log_blowup);
-  alpha_powers_kernel<<<(ZKIR_AIR_NUM_CONSTRAINTS + 63) / 64, 64, 0, st>>>(a.alpha, reinterpret_cast<E4*>(a.apow_scratch));
+  ZKIR_PF(alpha_powers_kernel)<<<(ZKIR_AIR_NUM_CONSTRAINTS + 63) / 64, 64, 0, st>>>(a.alpha, reinterpret_cast<E4*>(a.apow_scratch));
   const u32 g = ZKIR_BB_ROOTS[a.log_n];
   const u32 g_inv = hpow(g, BB_P - 2);
   const u32 snn = hpow(ZKIR_BB_GEN, 1ull << a.log_n);
@@ -128,10 +134,10 @@ int launch_quotient(const QuotientArgs& a, cudaStream_t st, u64* launches) {
   const unsigned grid = (unsigned)((n_threads + 127) / 128);
   const E4* ap = reinterpret_cast<const E4*>(a.apow_scratch);
   const u32 m_ginv = bb_to_mont_c(g_inv), m_g = bb_to_mont_c(g), m_snn = bb_to_mont_c(snn), m_wb = bb_to_mont_c(wb);
-  if (variant == 3) quotient_kernel<3><<<grid, 128, 0, st>>>(a, ap, m_ginv, m_g, m_snn, m_wb);
-  else if (variant == 1) quotient_kernel<6><<<grid, 128, 0, st>>>(a, ap, m_ginv, m_g, m_snn, m_wb);
-  else if (variant == 2) quotient_kernel<8><<<grid, 128, 0, st>>>(a, ap, m_ginv, m_g, m_snn, m_wb);
-  else quotient_kernel<4><<<grid, 128, 0, st>>>(a, ap, m_ginv, m_g, m_snn, m_wb);
+  if (variant == 3) ZKIR_PF(quotient_kernel)<3><<<grid, 128, 0, st>>>(a, ap, m_ginv, m_g, m_snn, m_wb);
+  else if (variant == 1) ZKIR_PF(quotient_kernel)<6><<<grid, 128, 0, st>>>(a, ap, m_ginv, m_g, m_snn, m_wb);
+  else if (variant == 2) ZKIR_PF(quotient_kernel)<8><<<grid, 128, 0, st>>>(a, ap, m_ginv, m_g, m_snn, m_wb);
+  else ZKIR_PF(quotient_kernel)<4><<<grid, 128, 0, st>>>(a, ap, m_ginv, m_g, m_snn, m_wb);
   (*launches) += 2;
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }

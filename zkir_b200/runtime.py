@@ -11,6 +11,21 @@ from dataclasses import dataclass, field
 import numpy as np
 from . import _ffi
 from .air_layout import WIDTH, NUM_PUBLIC, AUX_WIDTH, PUB_WIDTH, MIN_LOG_N
+from . import air_layout_full as _full_layout
+
+FULL_WIDTH = _full_layout.WIDTH
+
+
+def program_profile(program):
+    """AIR profile of a program (docs/PROVER_SPEC.md section 3.7): "core" if it stays inside the 18 core opcodes, "full" if it uses MUL /
+    DIV / bitwise / shift / signed-compare opcodes, None if it contains an opcode no profile constrains (the loads and stores)."""
+    code = np.ascontiguousarray(getattr(program, "code", program), dtype=np.uint32)
+    return {1: "core", 0: "full", -1: None}[_ffi.lib().zkir_program_profile(code.ctypes.data, int(code.shape[0]))]
+
+
+def profile_width(profile):
+    return FULL_WIDTH if profile == "full" else WIDTH
+
 
 P = 2013265921
 
@@ -168,15 +183,20 @@ class ExecutionResult:  # vm.rs:54-78
     def min_log_n(self):
         return _ffi.lib().zkir_pack_min_log_n(self._h)
 
-    def pack(self, log_n=None, out=None):
-        """-> (cols[WIDTH][1<<log_n] uint32, public_values[5] uint32).  `out` may be a pinned buffer view."""
+    def pack(self, log_n=None, out=None, profile=None):
+        """-> (cols[width][1<<log_n] uint32, public_values[5] uint32).  `out` may be a pinned buffer view.  `profile`: "core" (88 columns),
+        "full" (the full-ISA table) or None = what the program needs (program_profile)."""
         l = _ffi.lib()
         if log_n is None:
             log_n = self.min_log_n()
-        cols = out if out is not None else np.empty((WIDTH, 1 << log_n), dtype=np.uint32)
-        assert cols.dtype == np.uint32 and cols.shape == (WIDTH, 1 << log_n) and cols.flags["C_CONTIGUOUS"]
+        if profile is None:
+            profile = (program_profile(self.program) if self.program is not None else "core") or "core"   # an unconstrained opcode: the core packer names the row
+        width = profile_width(profile)
+        cols = out if out is not None else np.empty((width, 1 << log_n), dtype=np.uint32)
+        assert cols.dtype == np.uint32 and cols.shape == (width, 1 << log_n) and cols.flags["C_CONTIGUOUS"]
         pv = np.zeros(NUM_PUBLIC, dtype=np.uint32)
-        rc = l.zkir_pack_trace(self._h, self._entry, log_n, cols.ctypes.data, pv.ctypes.data_as(_ffi.u32p))
+        fn = l.zkir_pack_trace_full if profile == "full" else l.zkir_pack_trace
+        rc = fn(self._h, self._entry, log_n, cols.ctypes.data, pv.ctypes.data_as(_ffi.u32p))
         if rc != 0:
             raise RuntimeError_(rc, l.zkir_b200_last_error(None).decode())
         return cols, pv
@@ -237,8 +257,8 @@ class ProverConfig:
     device: int = 0
     enable_poseidon2_syscall: bool = False
 
-    def params(self):
-        return _ffi.Params(self.log_blowup, self.num_queries, self.pow_bits, WIDTH, NUM_PUBLIC)
+    def params(self, width=WIDTH):
+        return _ffi.Params(self.log_blowup, self.num_queries, self.pow_bits, width, NUM_PUBLIC)
 
 
 @dataclass
@@ -355,14 +375,14 @@ class Context:
         context's program first (zkir_b200_set_program; a no-op when it is unchanged)."""
         if program is not None:
             self.set_program(program)
-        params = cfg.params()
+        params = cfg.params(WIDTH if device_resident is not None and cols is None else int(cols.shape[0]))
         pv = np.ascontiguousarray(public_values, dtype=np.uint32)
         proof, plen = C.c_void_p(), C.c_size_t()
         if device_resident is not None:
             ptr, log_n = device_resident
             rc = self._l.zkir_b200_prove_device(self._h, C.byref(params), ptr, log_n, pv.ctypes.data_as(_ffi.u32p), C.byref(proof), C.byref(plen))
         else:
-            assert cols.dtype == np.uint32 and cols.flags["C_CONTIGUOUS"] and cols.shape[0] == WIDTH
+            assert cols.dtype == np.uint32 and cols.flags["C_CONTIGUOUS"] and cols.shape[0] in (WIDTH, FULL_WIDTH)
             log_n = int(cols.shape[1]).bit_length() - 1
             assert cols.shape[1] == 1 << log_n
             rc = self._l.zkir_b200_prove(self._h, C.byref(params), cols.ctypes.data, log_n, pv.ctypes.data_as(_ffi.u32p), C.byref(proof), C.byref(plen))
@@ -544,6 +564,14 @@ def prove(program, inputs=(), cfg=None):
     the GPU, prove.  The drop-in the north star describes for `zkir_runtime::prove()` (absent upstream: lib.rs:29-62)."""
     cfg = cfg or ProverConfig()
     ctx = _ctx(cfg.device)
+    if program_profile(program) == "full":
+        # full-ISA programs: the interpreter records full rows, the host packer builds the wide table (the device converter and the
+        # write-log path serve the core profile), the proof itself is the same CUDA path
+        res = VM(program, list(inputs), VMConfig(max_cycles=cfg.max_cycles, enable_execution_trace=True, enable_poseidon2_syscall=cfg.enable_poseidon2_syscall)).run()
+        cols, pv = res.pack(profile="full")
+        ctx.set_io(res.io)
+        pb = ctx.prove_columns(cols, pv, cfg, program=program)
+        return Proof(pb, pv, int(cols.shape[1]).bit_length() - 1, res.cycles, res.outputs, ctx.stage_ms(), program, res.io)
     pb, pv, cycles, log_n = ctx.prove_program(program, list(inputs), cfg)
     # the statement's public I/O transcript and outputs: one plain interpreter run without any recording (323 M cycles/s)
     res = VM(program, list(inputs), VMConfig(max_cycles=cfg.max_cycles, enable_poseidon2_syscall=cfg.enable_poseidon2_syscall)).run()
@@ -566,7 +594,7 @@ def verify(proof, cfg=None, public_values=None, program=None, io=None):
         return False, "verify() needs the program the proof is about"
     code = np.ascontiguousarray(getattr(program, "code", program), dtype=np.uint32)
     ev = np.ascontiguousarray(io if io is not None else np.zeros((0, 4)), dtype=np.uint32).reshape(-1, 4)
-    params = cfg.params()
+    params = cfg.params(int.from_bytes(pb[12:16], "little") if len(pb) >= 16 else WIDTH)   # the profile is the proof header's width
     buf = C.create_string_buffer(pb, len(pb))
     pvp = np.ascontiguousarray(pv, dtype=np.uint32).ctypes.data_as(_ffi.u32p) if pv is not None else None
     rc = l.zkir_b200_verify(C.byref(params), C.cast(buf, C.c_void_p), len(pb), pvp, code.ctypes.data, int(code.shape[0]), ev.ctypes.data, int(ev.shape[0]))

@@ -89,3 +89,54 @@ def pos2_program():
 
 def pos2_cycles(iters):
     return POS2_ITER_CYCLES * iters + POS2_SETUP_CYCLES
+
+
+# Full-ISA workload (docs/PROVER_SPEC.md section 3.7): a xorshift-multiply generator loop that exercises the multiplier block (MUL,
+# MULH, DIVU, REMU), all three shift kinds, the bitwise table and the signed compares; 16 cycles per iteration.
+MIX_ITER_CYCLES = 16
+MIX_SETUP_CYCLES = 8 + 3
+MIX_SRC = ("addi r10, r0, 1\necall\nadd r3, r10, r0\n"            # iterations from the input tape
+           "addi r1, r0, 12345\naddi r2, r0, 25173\naddi r4, r0, 0\naddi r6, r0, 1000\naddi r9, r0, 0\n"
+           "mul r1, r1, r2\n"          # loop body
+           "addi r1, r1, 13849\n"
+           "srli r5, r1, 7\n"
+           "xor r1, r1, r5\n"
+           "slli r5, r1, 9\n"
+           "xor r1, r1, r5\n"
+           "mulh r7, r1, r2\n"
+           "or r7, r7, r1\n"
+           "andi r7, r7, 1023\n"
+           "divu r8, r1, r6\n"
+           "remu r8, r8, r6\n"
+           "srai r5, r1, 3\n"
+           "slt r5, r5, r7\n"
+           "add r9, r9, r5\n"
+           "addi r4, r4, 1\n"
+           "bne r4, r3, -60\n"
+           "add r10, r0, r0\nadd r11, r9, r0\necall\n")
+
+
+def mix_program():
+    from . import assemble
+    return assemble(MIX_SRC)
+
+
+def mix_cycles(iters):
+    return MIX_ITER_CYCLES * iters + MIX_SETUP_CYCLES
+
+
+def mix_reference(iters):
+    """The loop restated in Python (semantics of zkir-runtime/src/execute.rs: everything wraps at 40 bits, SRAI / SLT are signed at bit 39)."""
+    M = (1 << 40) - 1
+    sg = lambda v: v - (1 << 40) if v >> 39 else v
+    r1, r2, r9 = 12345, 25173, 0
+    for _ in range(iters):
+        r1 = (r1 * r2) & M
+        r1 = (r1 + 13849) & M
+        r1 ^= r1 >> 7
+        r1 ^= (r1 << 9) & M
+        r7 = ((r1 * r2) >> 40) & M
+        r7 = (r7 | r1) & 1023
+        r5 = (sg(r1) >> 3) & M
+        r9 += int(sg(r5) < sg(r7))
+    return r9
