@@ -31,7 +31,7 @@ extern "C" {
 
 #define ZKIR_BABYBEAR_P 2013265921u
 #define ZKIR_AIR_V2_WIDTH 88u      /* main trace columns of the CORE profile (docs/PROVER_SPEC.md section 3); 16 aux + 4 public columns are internal */
-#define ZKIR_AIR_FULL_WIDTH 170u   /* main trace columns of the FULL profile (section 3.7: MUL/DIV family, bitwise, shifts, signed compares) */
+#define ZKIR_AIR_FULL_WIDTH 176u   /* main trace columns of the FULL profile (section 3.7: MUL/DIV family, bitwise, shifts, signed compares) */
 #define ZKIR_AIR_V2_NUM_PUBLIC 5u  /* entry_pc, num_cycles, exit_lo, exit_hi, halted */
 #define ZKIR_MIN_LOG_N 10u         /* the 1024-entry range table (zkir-spec/src/config.rs:76-80) occupies trace rows */
 
@@ -250,7 +250,7 @@ const uint64_t* zkir_vm_final_regs(const zkir_vm_result*);
  * table and the program ROM occupy trace rows). */
 uint32_t zkir_pack_min_log_n(const zkir_vm_result*);
 int zkir_pack_trace(const zkir_vm_result*, uint32_t entry_point, uint32_t log_n, uint32_t* cols, uint32_t* public_values);      /* core: 88 columns */
-int zkir_pack_trace_full(const zkir_vm_result*, uint32_t entry_point, uint32_t log_n, uint32_t* cols, uint32_t* public_values); /* full: 170 columns */
+int zkir_pack_trace_full(const zkir_vm_result*, uint32_t entry_point, uint32_t log_n, uint32_t* cols, uint32_t* public_values); /* full: ZKIR_AIR_FULL_WIDTH columns */
 /* which AIR profile a program needs (execute.rs:35-673 by opcode, zkir-spec/src/opcode.rs:24-144): 1 = core, 0 = full,
  * -1 = it contains an opcode no profile constrains (the loads and stores).  The ROM is public: prover and verifier agree. */
 int zkir_program_profile(const uint32_t* code, size_t n_code);

@@ -19,6 +19,16 @@ def _build_oracle(full=False):
     return so
 
 
+def _profile_numbers():
+    """the #defines of oracle/air_profiles_generated.h (tools/gen_air.py)"""
+    out = {}
+    for line in open(os.path.join(ROOT, "oracle", "air_profiles_generated.h")):
+        f = line.split()
+        if len(f) == 3 and f[0] == "#define":
+            out[f[1]] = int(f[2])
+    return out
+
+
 class Oracle:
     """ctypes view of oracle/_build/liboracle.so -- the checker, never the thing under test."""
 
@@ -40,7 +50,7 @@ class Oracle:
         return a.ctypes.data_as(C.c_void_p)
 
     WIDTH, AUX_WIDTH, PUB_WIDTH, NUM_PUBLIC = 88, 16, 4, 5   # AIR v2, core profile (oracle/air_generated.h)
-    FULL_WIDTH, FULL_AUX_WIDTH, FULL_PUB_WIDTH = 170, 108, 13   # full profile (oracle/air_generated_full.h)
+    FULL_WIDTH, FULL_AUX_WIDTH, FULL_PUB_WIDTH = (_profile_numbers()[f"ZKIR_PROFILE_FULL_{k}"] for k in ("WIDTH", "AUX", "PUB"))   # full profile
     LOOKUP_TEST = np.array([3, 1, 4, 1, 5, 9, 2, 6], dtype=np.uint32)   # fixed lookup challenges z, theta for row-domain checks
 
     def params(self, cfg):

@@ -28,6 +28,13 @@ def test_library_exports_every_declared_symbol():
     assert set(names) == set(_ffi.SYMBOLS), "ctypes table and header disagree"
 
 
+def test_header_profile_widths_match_the_generated_air():
+    text = open(os.path.join(ROOT, "include", "zkir_b200.h")).read()
+    assert int(re.search(r"#define ZKIR_AIR_V2_WIDTH (\d+)u", text).group(1)) == zkir_b200.air_layout.WIDTH
+    assert int(re.search(r"#define ZKIR_AIR_FULL_WIDTH (\d+)u", text).group(1)) == zkir_b200.air_layout_full.WIDTH == zkir_b200.runtime.FULL_WIDTH
+    assert zkir_b200.air_layout_full.COLUMNS[:zkir_b200.air_layout.WIDTH] == zkir_b200.air_layout.COLUMNS   # the full table extends the core table
+
+
 def test_proof_size_is_shape_only():
     cfg = zkir_b200.ProverConfig()
     p = cfg.params()

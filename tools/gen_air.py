@@ -115,6 +115,8 @@ if FULL:
     ZL = [col(f"zl{i}") for i in range(4)]
     ZH = [col(f"zh{i}") for i in range(4)]
     M_AND, M_POW = col("m_and"), col("m_pow")      # multiplicities of the AND-table row / power-table row at this trace row
+    while len(COLS) % 8:                           # a Merkle leaf absorbs whole rows in blocks of 8 columns (csrc/poseidon2.cu)
+        col(f"pad{len(COLS) % 8}")                 # unconstrained, zero
 WIDTH = len(COLS)
 assert FULL or WIDTH == 88   # 11 sponge absorptions per Merkle leaf (rate 8)
 
@@ -343,7 +345,10 @@ def _count_fractions():
 
 def _pairs(n):
     rest = [j for j in range(n) if j not in FRAC_PHI]   # core: (0, 1), (2, 3), (4, 6)
-    return [tuple(rest[i:i + 2]) for i in range(0, len(rest), 2)]
+    pairs = [tuple(rest[i:i + 2]) for i in range(0, len(rest), 2)]
+    if len(pairs) % 2 == 0:   # helpers + phi = an even number of ext4 columns: the aux width stays a multiple of 8 (Merkle leaf blocks)
+        pairs.append(())      # a helper that is constrained to zero
+    return pairs
 
 
 NUM_FRACTIONS = _count_fractions()
@@ -602,6 +607,9 @@ def build():
     h = [xaux(k) for k in range(NH)]
     phi, phi_n = xaux(NH), xaux(NH, True)
     for k, pair in enumerate(FRAC_PAIRS):
+        if len(pair) == 0:
+            g.emit(h[k], f"helper {k} pads the aux width: zero")
+            continue
         if len(pair) == 1:
             (ni, di), = (fr[pair[0]],)
             g.emit(h[k] * di - ni, f"helper {k} = fraction {pair[0]}")
