@@ -31,7 +31,7 @@ extern "C" {
 
 #define ZKIR_BABYBEAR_P 2013265921u
 #define ZKIR_AIR_V2_WIDTH 88u      /* main trace columns of the CORE profile (docs/PROVER_SPEC.md section 3); 16 aux + 4 public columns are internal */
-#define ZKIR_AIR_FULL_WIDTH 176u   /* main trace columns of the FULL profile (section 3.7: MUL/DIV family, bitwise, shifts, signed compares) */
+#define ZKIR_AIR_FULL_WIDTH 248u   /* main trace columns of the FULL profile (sections 3.7, 3.8: MUL/DIV family, bitwise, shifts, signed compares, loads / stores) */
 #define ZKIR_AIR_V2_NUM_PUBLIC 5u  /* entry_pc, num_cycles, exit_lo, exit_hi, halted */
 #define ZKIR_MIN_LOG_N 10u         /* the 1024-entry range table (zkir-spec/src/config.rs:76-80) occupies trace rows */
 
@@ -141,6 +141,7 @@ void zkir_rom_entry(uint32_t word, uint32_t* dec, uint32_t* imm); /* decoded ROM
  * row (i = ~0) / all columns, column-major [pub width][2^log_n] */
 void zkir_public_row(uint32_t width, uint64_t i, const uint32_t* code, size_t n_code, uint32_t* out);
 uint64_t zkir_public_rows(uint32_t width, size_t n_code);
+uint64_t zkir_image_words(size_t n_code); /* aligned 8-byte words of the initial memory image [0, 0x1000 + 4 n_code); RAM starts here */
 void zkir_public_columns(uint32_t width, uint32_t log_n, const uint32_t* code, size_t n_code, uint32_t* cols);
 void zkir_program_digest(const uint32_t* code, size_t n_code, uint32_t digest8[8]); /* what the transcript absorbs for the program */
 void zkir_io_digest(const uint32_t* io_events, size_t n_io, uint32_t digest8[8]);   /* ... and for the public I/O transcript */
@@ -252,7 +253,7 @@ uint32_t zkir_pack_min_log_n(const zkir_vm_result*);
 int zkir_pack_trace(const zkir_vm_result*, uint32_t entry_point, uint32_t log_n, uint32_t* cols, uint32_t* public_values);      /* core: 88 columns */
 int zkir_pack_trace_full(const zkir_vm_result*, uint32_t entry_point, uint32_t log_n, uint32_t* cols, uint32_t* public_values); /* full: ZKIR_AIR_FULL_WIDTH columns */
 /* which AIR profile a program needs (execute.rs:35-673 by opcode, zkir-spec/src/opcode.rs:24-144): 1 = core, 0 = full,
- * -1 = it contains an opcode no profile constrains (the loads and stores).  The ROM is public: prover and verifier agree. */
+ * -1 = it contains an undefined opcode.  The ROM is public: prover and verifier agree. */
 int zkir_program_profile(const uint32_t* code, size_t n_code);
 
 #ifdef __cplusplus

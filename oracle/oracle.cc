@@ -310,6 +310,23 @@ static void build_public_columns(u32 log_n, const u32* code, size_t n_code, u32*
     pub[7 * N + i] = (u32)key; pub[8 * N + i] = (u32)(mul & 0xFFFFF); pub[9 * N + i] = (u32)(mul >> 20); pub[10 * N + i] = zf;
     pub[11 * N + i] = (u32)(fill & 0xFFFFF); pub[12 * N + i] = (u32)(fill >> 20);
   }
+  // docs/PROVER_SPEC.md section 3.8.  Columns 13..15: 8 / 4 / 7-bit range tables (row t holds t while t < 2^k, else 0).  Columns 16..25: the
+  // memory image, one aligned 8-byte word per row: flag, word index, the eight bytes (zeros below 0x1000, then the code words, little
+  // endian).  Column 26: the first RAM word index (= number of image words), on row 0 only.
+  const size_t n_img = (CODE_BASE + 4 * n_code + 7) / 8;
+  for (size_t i = 0; i < N; i++) {
+    if (i < 256) pub[13 * N + i] = (u32)i;
+    if (i < 16) pub[14 * N + i] = (u32)i;
+    if (i < 128) pub[15 * N + i] = (u32)i;
+    if (i < n_img) {
+      pub[16 * N + i] = 1; pub[17 * N + i] = (u32)i;
+      for (size_t k = 0; k < 8; k++) {
+        const size_t addr = 8 * i + k;
+        if (addr >= CODE_BASE && (addr - CODE_BASE) / 4 < n_code) pub[(18 + k) * N + i] = (code[(addr - CODE_BASE) / 4] >> (8 * (addr % 4))) & 0xFF;
+      }
+    }
+  }
+  pub[26 * N + 0] = (u32)n_img;
 #endif
 }
 // aux columns [16][N] from the main trace, the public columns and the lookup challenges: helper k = sum of its two fractions,

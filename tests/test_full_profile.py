@@ -1,5 +1,5 @@
-"""The FULL AIR profile (docs/PROVER_SPEC.md section 3.7): MUL MULH DIVU REMU DIV REM, AND OR XOR (+ immediates), the six shifts,
-SLT SGE BLT BGE on top of the core opcodes.  CPU tests: the packer's witness against the oracle's row-by-row AIR check with expected
+"""The FULL AIR profile (docs/PROVER_SPEC.md sections 3.7, 3.8): MUL MULH DIVU REMU DIV REM, AND OR XOR (+ immediates), the six shifts,
+SLT SGE BLT BGE and the loads / stores (offline memory checking) on top of the core opcodes: all 50 opcodes of zkir-spec/src/opcode.rs.  CPU tests: the packer's witness against the oracle's row-by-row AIR check with expected
 register values restated from zkir-runtime/src/execute.rs (:80-183 arithmetic, :200-279 logical, :282-358 shifts, :361-391 / :594-609
 signed compares), tamper tests per family, oracle proof -> product verifier.  GPU tests: proof bytes == oracle, verifier accepts."""
 import numpy as np
@@ -134,13 +134,12 @@ def test_profiles_of_programs_and_what_no_profile_constrains():
             res.pack(profile="core")
         assert e.value.code == -6 and "not constrained" in str(e.value)
         assert res.pack()[0].shape[0] == FULL_WIDTH
-    # loads and stores: no memory argument in either profile
+    # loads and stores need the full profile's memory argument
     res = run("addi r1, r0, 0x2000\nsw r1, 0(r1)\nlw r2, 0(r1)\nebreak")
-    assert program_profile(res.program) is None
-    for prof in ("core", "full"):
-        with pytest.raises(zkir_b200.RuntimeError) as e:
-            res.pack(profile=prof)
-        assert e.value.code == -6
+    assert program_profile(res.program) == "full"
+    with pytest.raises(zkir_b200.RuntimeError) as e:
+        res.pack(profile="core")
+    assert e.value.code == -6
     # an immediate shift amount above 63 behaves like "40 or more" upstream (value.rs:658-691); the power table stops at 63
     res = run("addi r1, r0, 3\nslli r2, r1, 64\nebreak")
     assert int(res.rows()["final_regs"][2]) == 0
@@ -210,9 +209,120 @@ def test_gpu_full_profile_every_opcode(gpu_ctx, oracle_full):
 def test_gpu_full_profile_2p16_rows_and_prove_api(gpu_ctx, oracle_full):
     iters = 4000     # 64 011 cycles -> 2^16 rows
     prog = mix_program()
-    proof = zkir_b200.prove(prog, [iters], zkir_b200.ProverConfig(num_queries=30, pow_bits=8))
+    cfg = zkir_b200.ProverConfig(num_queries=30, pow_bits=8)
+    proof = zkir_b200.prove(prog, [iters], cfg)
     assert proof.log_n == 16 and proof.cycles == mix_cycles(iters) and int.from_bytes(proof.bytes_[12:16], "little") == FULL_WIDTH
-    assert zkir_b200.verify(proof) == (True, "")
+    assert zkir_b200.verify(proof, cfg) == (True, "")
     res = zkir_b200.VM(prog, [iters], zkir_b200.VMConfig(enable_execution_trace=True)).run()
     cols, pv = res.pack()
-    assert proof.bytes_ == oracle_full.prove(zkir_b200.ProverConfig(num_queries=30, pow_bits=8), cols, pv, res)
+    assert proof.bytes_ == oracle_full.prove(cfg, cols, pv, res)
+
+
+# ------------------------------------------------------------------------------------------------ loads and stores (section 3.8)
+MEM_SRC = """
+    addi r1, r0, 0x2000
+    addi r2, r0, 1234
+    sw r2, 0(r1)
+    lw r3, 0(r1)
+    addi r4, r0, -2
+    sd r4, 8(r1)
+    ld r5, 8(r1)
+    sb r2, 3(r1)
+    lbu r6, 3(r1)
+    lb r7, 1(r1)
+    sh r4, 6(r1)
+    lhu r8, 6(r1)
+    lh r9, 0(r1)
+    lw r12, 4(r1)
+    lw r13, 0x1000(r0)
+    ld r14, -8(r1)
+    addi r1, r1, 0x1000
+    sw r2, 16(r1)
+    lw r15, 16(r1)
+    ebreak
+"""
+
+
+def test_loads_and_stores_satisfy_the_air(oracle_full):
+    res = run(MEM_SRC)
+    f = [int(x) for x in res.rows()["final_regs"]]
+    # execute.rs:477-575: little endian, loads zero-extend (LW too: Appendix A), stores truncate to the width
+    word0 = (1234 & 0x00FFFFFF) | ((1234 & 0xFF) << 24)          # sw 1234, then sb 0xD2 at byte 3
+    assert f[3] == 1234 and f[5] == (-2) & M40 and f[6] == 0xD2 and f[7] == 0x04 and f[8] == 0xFFFE and f[9] == 0x04D2
+    assert f[12] == 0xFFFE0000 and f[13] == res.program.code[0] and f[14] == 0 and f[15] == 1234
+    assert word0 == 0xD20004D2
+    cols, pv = res.pack()
+    assert cols.shape[0] == FULL_WIDTH and oracle_full.check_trace(cols, pv, res) == (-1, 0)
+    rows = res.rows()
+    by_op = {}
+    for i in range(res.cycles):
+        by_op.setdefault(int(rows["instrs"][i]) & 0x7F, i)
+    for op, cell in ((0x3A, "nb0"), (0x3A, "ob0"), (0x3A, "gb1"), (0x3A, "off0"), (0x3A, "mw"), (0x3A, "prev_ts"), (0x3A, "td0"), (0x3A, "ch1"), (0x3A, "nb5"),
+                     (0x34, "v_lo"), (0x34, "ob1"), (0x34, "nb2"), (0x34, "gb0"), (0x34, "prev_ts"), (0x34, "nib_lo"), (0x35, "v_hi"), (0x35, "ob6"), (0x35, "gb4"),
+                     (0x3B, "nb7"), (0x3B, "gb3"), (0x38, "nb3"), (0x38, "off3"), (0x31, "v_lo"), (0x30, "gb0"), (0x39, "nb6"), (0x39, "nb7"), (0x33, "gb1"),
+                     (0x32, "v_lo"), (0x3A, "carry0"), (0x35, "carry1"), (0x3A, "m_b8"), (0x34, "m_b4"), (0x34, "m_b7")):
+        bad = cols.copy()
+        bad[LF[cell], by_op[op]] ^= 1
+        assert oracle_full.check_trace(bad, pv, res)[0] != -1, (hex(op), cell)
+    # boundary cells: final values / timestamps of image and RAM words, the RAM list itself
+    n_img = int(zkir_b200._ffi.lib().zkir_image_words(len(res.program.code)))
+    for cell, row in (("img_fin0", n_img - 1), ("img_fin_ts", 0x1000 // 8), ("ram_on", 0), ("ram_on", 3), ("ram_a0", 0), ("ram_a0", 1), ("ram_e0", 1), ("ram_fin0", 0),
+                      ("ram_fin_ts", 1), ("ram_fin3", 2)):
+        bad = cols.copy()
+        bad[LF[cell], row] ^= 1
+        assert oracle_full.check_trace(bad, pv, res)[0] != -1, (cell, row)
+    # a word listed twice would fork memory: duplicate the first RAM entry onto the next free row
+    nram = int(cols[LF["ram_on"]].sum())
+    bad = cols.copy()
+    for name in ["ram_on"] + [f"ram_a{k}" for k in range(3)] + [f"ram_fin{k}" for k in range(8)] + ["ram_fin_ts"]:
+        bad[LF[name], nram] = bad[LF[name], 0]
+    assert oracle_full.check_trace(bad, pv, res)[0] != -1
+
+
+def test_reference_memory_and_arithmetic_programs_are_provable(oracle_full):
+    """Programs of the reference's own tests: tests/stress_tests.rs:192-216 (100 stores over the program's own first words), :218-248
+    (sparse addresses), :304-330 (add sub mul divu remu), tests/cross_module.rs:334-365 (store / load round trip, output [42])."""
+    many = "addi r1, zero, 0x1000\naddi r2, zero, 1\n" + "".join(f"sw r2, {4 * i}(r1)\naddi r2, r2, 1\n" for i in range(100)) + "addi t2, zero, 0\naddi a0, zero, 0\necall\n"
+    sparse = "addi r1, zero, 42\naddi r2, zero, 0x1000\nsw r1, 0(r2)\naddi r2, zero, 0x2000\nsw r1, 0(r2)\naddi r2, zero, 0x3000\nsw r1, 0(r2)\naddi t2, zero, 0\naddi a0, zero, 0\necall\n"
+    arith = "addi r1, zero, 100\naddi r2, zero, 7\nadd r3, r1, r2\nsub r4, r1, r2\nmul r5, r1, r2\ndivu r6, r1, r2\nremu r7, r1, r2\naddi t2, zero, 0\naddi a0, zero, 0\necall\n"
+    round_trip = "addi r1, zero, 42\naddi r2, zero, 0x1000\nsw r1, 0(r2)\nlw r3, 0(r2)\naddi a0, r3, 0\naddi t2, zero, 2\necall\naddi t2, zero, 0\naddi a0, zero, 0\necall\n"
+    cfg = zkir_b200.ProverConfig(num_queries=8, pow_bits=2)
+    for src, outputs in ((many, []), (sparse, []), (arith, []), (round_trip, [42])):
+        res = run(src)
+        assert res.halt_reason == zkir_b200.HaltReason.Exit(0) and res.outputs == outputs
+        cols, pv = res.pack()
+        assert oracle_full.check_trace(cols, pv, res) == (-1, 0)
+        assert zkir_b200.verify(oracle_full.prove(cfg, cols, pv, res), cfg, pv, res) == (True, "")
+    f = [int(x) for x in run(arith).rows()["final_regs"]]
+    assert f[3:8] == [107, 93, 700, 14, 2]
+
+
+def test_memory_rows_outside_the_model_are_rejected():
+    # lb / lh of a negative value sign-extend to 64 bits upstream (execute.rs:477-500): outside the 40-bit register model
+    res = run("addi r1, r0, 0x2000\naddi r2, r0, 200\nsb r2, 0(r1)\nlb r3, 0(r1)\nebreak")
+    assert int(res.rows()["final_regs"][3]) == (200 - 256) & (2**64 - 1)
+    with pytest.raises(zkir_b200.RuntimeError) as e:
+        res.pack()
+    assert e.value.code == -6
+    # the unsigned form of the same load is fine
+    res = run("addi r1, r0, 0x2000\naddi r2, r0, 200\nsb r2, 0(r1)\nlbu r3, 0(r1)\nebreak")
+    assert res.pack()[0].shape[0] == FULL_WIDTH
+    # SYS_POSEIDON2 writes guest memory outside the memory argument: a later load of its output is refused, not mis-proven
+    src = "addi r11, r0, 0x2000\naddi r13, r0, 0x2000\naddi r10, r0, 4\necall\nlw r3, 0(r13)\nebreak"
+    res = zkir_b200.VM(zkir_b200.assemble(src), [], zkir_b200.VMConfig(enable_execution_trace=True, enable_poseidon2_syscall=True)).run()
+    with pytest.raises(zkir_b200.RuntimeError) as e:
+        res.pack()
+    assert "memory the AIR tracks" in str(e.value)
+
+
+@pytest.mark.gpu
+def test_gpu_memory_programs_equal_oracle(gpu_ctx, oracle_full):
+    many = "addi r1, zero, 0x1000\naddi r2, zero, 1\n" + "".join(f"sw r2, {4 * i}(r1)\naddi r2, r2, 1\n" for i in range(100)) + "addi t2, zero, 0\naddi a0, zero, 0\necall\n"
+    cfg = zkir_b200.ProverConfig(num_queries=16, pow_bits=4)
+    for src in (MEM_SRC, many):
+        res = run(src)
+        cols, pv = res.pack()
+        gpu_ctx.set_io(res.io)
+        pb = gpu_ctx.prove_columns(cols, pv, cfg, program=res)
+        assert pb == oracle_full.prove(cfg, cols, pv, res)
+        assert zkir_b200.verify(pb, cfg, pv, res) == (True, "")

@@ -28,9 +28,9 @@ P = 2013265921
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 # Two AIR profiles are generated from this one description (docs/PROVER_SPEC.md section 3.7):
 #   core  the 18 opcodes of the headline workloads, 88 + 16 + 4 columns (this file's round-2 layout, unchanged);
-#   full  every opcode of zkir-spec/src/opcode.rs:24-144 except the loads and stores: the core columns plus a 40x40-bit
-#         multiplier block (MUL MULH DIVU REMU DIV REM and all six shifts), sign extraction (SLT SGE BLT BGE SRA SRAI) and a
-#         5-bit x 5-bit AND table (AND OR XOR ANDI ORI XORI).
+#   full  every opcode of zkir-spec/src/opcode.rs:24-144: the core columns plus a 40x40-bit multiplier block (MUL MULH DIVU REMU
+#         DIV REM and all six shifts), sign extraction (SLT SGE BLT BGE SRA SRAI), a 5-bit x 5-bit AND table (AND OR XOR ANDI ORI
+#         XORI) and an offline memory-checking argument over aligned 8-byte words (LB LBU LH LHU LW LD SB SH SW SD).
 # The profile of a proof is its trace width (zkir_params.width): a program that stays inside the core opcodes is proven with the
 # narrow table; the verifier needs no flag because an opcode outside a profile has no selector there and matches no ROM row.
 FULL = os.environ.get("ZKIR_AIR_PROFILE", "core") == "full"
@@ -87,7 +87,9 @@ M_RNG, M_ROM = col("m_rng"), col("m_rom")      # LogUp multiplicities of the ran
 FULL_SEL_OPCODE = [("s_mul", 0x02), ("s_divu", 0x04), ("s_div", 0x06),                       # + neg: MULH, REMU, REM
                    ("s_and", 0x10), ("s_or", 0x11), ("s_xor", 0x12), ("s_andi", 0x13), ("s_ori", 0x14), ("s_xori", 0x15),
                    ("s_sll", 0x18), ("s_srl", 0x19), ("s_sra", 0x1A), ("s_slli", 0x1B), ("s_srli", 0x1C), ("s_srai", 0x1D),
-                   ("s_slt", 0x22), ("s_blt", 0x42)]                                          # + neg: SGE, BGE
+                   ("s_slt", 0x22), ("s_blt", 0x42),                                          # + neg: SGE, BGE
+                   ("s_lb", 0x30), ("s_lbu", 0x31), ("s_lh", 0x32), ("s_lhu", 0x33), ("s_lw", 0x34), ("s_ld", 0x35),
+                   ("s_sb", 0x38), ("s_sh", 0x39), ("s_sw", 0x3A), ("s_sd", 0x3B)]
 if FULL:
     SEL_OPCODE = SEL_OPCODE + FULL_SEL_OPCODE
     SEL_NAMES = [n for n, _ in SEL_OPCODE]
@@ -115,6 +117,27 @@ if FULL:
     ZL = [col(f"zl{i}") for i in range(4)]
     ZH = [col(f"zh{i}") for i in range(4)]
     M_AND, M_POW = col("m_and"), col("m_pow")      # multiplicities of the AND-table row / power-table row at this trace row
+    # memory (docs/PROVER_SPEC.md section 3.8): one access per row to ONE aligned 8-byte word (natural alignment, memory.rs:329,383,440).
+    # The range-checked chunks ch0..ch3 hold the effective address; ch0 = offset + 8 * mw.
+    OH = [col(f"off{k}") for k in range(8)]        # one-hot byte offset inside the word
+    MW = col("mw")                                 # ch0 >> 3 (7 bits)
+    OB = [col(f"ob{k}") for k in range(8)]         # the word's bytes before the access
+    NB = [col(f"nb{k}") for k in range(8)]         # ... and after it (loads: unchanged)
+    GB = [col(f"gb{k}") for k in range(5)]         # bytes of the register-side value: the loaded value / the stored register
+    NL, NH = col("nib_lo"), col("nib_hi")          # gb2 = nib_lo + 16 nib_hi: limbs are 20 bits, the boundary cuts byte 2
+    PTS = col("prev_ts")                           # timestamp of the previous access to the word (0 = initial value)
+    TD = [col(f"td{k}") for k in range(3)]         # clk - prev_ts in three chunks: the previous access is earlier
+    # boundary of the memory argument.  Image words (below the end of the code segment) get their initial value from public columns;
+    # this row's cells hold the final value / timestamp of image word `row`.  RAM words (above): a prover-chosen strictly increasing
+    # list, initial value zero (memory.rs:297-309), final value / timestamp committed here.
+    IF = [col(f"img_fin{k}") for k in range(8)]
+    IFTS = col("img_fin_ts")
+    RON = col("ram_on")
+    RA = [col(f"ram_a{k}") for k in range(3)]      # word index, 10 + 10 + 7 bits (addresses below 2^30)
+    RE = [col(f"ram_e{k}") for k in range(3)]      # this word index - previous one - 1 (row 0: - first RAM word index)
+    RF = [col(f"ram_fin{k}") for k in range(8)]
+    RFTS = col("ram_fin_ts")
+    M_B8, M_B4, M_B7 = col("m_b8"), col("m_b4"), col("m_b7")   # multiplicities of the 8 / 4 / 7-bit range tables
     while len(COLS) % 8:                           # a Merkle leaf absorbs whole rows in blocks of 8 columns (csrc/poseidon2.cu)
         col(f"pad{len(COLS) % 8}")                 # unconstrained, zero
 WIDTH = len(COLS)
@@ -129,9 +152,18 @@ if FULL:
     # fill = the top min(s, 40) bits of a 40-bit word set; rows 128.. repeat row 0
     PUB_NAMES += ["p_ax", "p_ay", "p_az", "p_key", "p_mlo", "p_mhi", "p_zf", "p_glo", "p_ghi"]
     P_AX, P_AY, P_AZ, P_KEY, P_MLO, P_MHI, P_ZF, P_GLO, P_GHI = range(4, 13)
+    # narrow range tables on the range rows (t below 2^k, else 0: a duplicate of row 0), and the memory image: row i = aligned word i
+    # of [0, end of code): p_img_on = 1, p_img_a = i, its eight bytes; p_ram0 = first RAM word index, on row 0
+    PUB_NAMES += ["p_b8", "p_b4", "p_b7", "p_img_on", "p_img_a"] + [f"p_img{k}" for k in range(8)] + ["p_ram0"]
+    P_B8, P_B4, P_B7, P_IMG_ON, P_IMG_A = range(13, 18)
+    P_IMG = list(range(18, 26))
+    P_RAM0 = 26
 PUB_WIDTH = len(PUB_NAMES)
 RANGE_BITS = 10
-NUM_THETA = 6 if FULL else 4
+NUM_THETA = 10 if FULL else 4
+LOADS = ["s_lb", "s_lbu", "s_lh", "s_lhu", "s_lw", "s_ld"]
+STORES = ["s_sb", "s_sh", "s_sw", "s_sd"]
+ACCESS_WIDTH = {"s_lb": 1, "s_lbu": 1, "s_lh": 2, "s_lhu": 2, "s_lw": 4, "s_ld": 8, "s_sb": 1, "s_sh": 2, "s_sw": 4, "s_sd": 8}
 
 PV_NAMES = ["entry_pc", "num_cycles", "exit_lo", "exit_hi", "halted"]
 NUM_PUBLIC = len(PV_NAMES)
@@ -261,7 +293,7 @@ def shared(g):
         return 4 * hv + lv
     rc_terms = s["s_add"] + s["s_addi"] + s["s_sub"] + L(IS_READ) + s["s_jal"] + s["s_jalr"] + s["s_sltu"] + s["s_bltu"]
     if FULL:   # signed compares (chunks = a - b mod 2^40) and the DIV family (chunks = remainder - divisor mod 2^40)
-        rc_terms = rc_terms + s["s_slt"] + s["s_blt"] + s["s_divu"] + s["s_div"]
+        rc_terms = rc_terms + s["s_slt"] + s["s_blt"] + s["s_divu"] + s["s_div"] + sum_e(s[n] for n in LOADS + STORES)   # memory rows: the effective address
     rc_on = g.tmp(rc_terms, "rows whose chunks are range-checked")
     opcode = g.tmp(sum_e(op * s[n] for n, op in SEL_OPCODE if op) + ECALL_OPCODE * s_ecall + L(NEG), "opcode number (opcode.rs:24-144)")
     rd_eff = g.tmp(idx(RD_H, RD_L) - 10 * (L(IS_READ) + L(IS_POS2)), "rd field of the word (READ / POSEIDON2 write r10 without an rd field)")
@@ -280,6 +312,9 @@ def shared(g):
         fam["dec_on"] = g.tmp(fam["mul_on"] + fam["cmps"] + fam["bitf"], "x / y chunks are range-checked")
         fam["r_on"] = g.tmp(fam["divf"] + fam["shf"], "r chunks are range-checked")
         fam["sa_on"] = g.tmp(fam["cmps"] + fam["sraf"], "sign of x is extracted")
+        fam["ld"] = g.tmp(sum_e(s[n] for n in LOADS), "load row")
+        fam["st"] = g.tmp(sum_e(s[n] for n in STORES), "store row")
+        fam["mem"] = g.tmp(fam["ld"] + fam["st"], "memory row")
     return s, s_ecall, s_pad, live, rc_on, dec, imm_f, fam
 
 
@@ -330,6 +365,44 @@ def fractions(g, sh):
             out.append((fam["bitf"], g.tmp(z - (th[1] * L(XL[i]) + th[2] * L(YL[i]) + th[3] * L(ZL[i]) + 4), f"AND lookup, low pieces of chunk {i}")))
             out.append((fam["bitf"], g.tmp(z - (th[1] * L(XH[i]) + th[2] * L(YH[i]) + th[3] * L(ZH[i]) + 4), f"AND lookup, high pieces of chunk {i}")))
         out.append((g.tmp(0 - L(M_AND)), g.tmp(z - (th[1] * g.Pc(P_AX) + th[2] * g.Pc(P_AY) + th[3] * g.Pc(P_AZ) + 4), "AND-table row")))
+        # --- memory.  Narrow range buses: 8 (byte), 9 (nibble), 10 (7 bits); memory bus 6: (word index, timestamp, the eight bytes) -- bytes as
+        # separate tuple entries, so a consumer cannot re-split a packed value: every byte on the bus is a stored (range-checked) or public byte
+        mem, st = fam["mem"], fam["st"]
+
+        def nar(bus, n, e, note):
+            out.append((n, g.tmp(z - (th[1] * e + bus), note)))
+        for k in range(5):
+            nar(8, st, L(GB[k]), f"stored byte {k} is a byte")     # loaded bytes come from memory: every byte there was checked when it was stored
+        nar(9, mem, L(NL), "nibble split of byte 2 (low)")
+        nar(9, mem, L(NH), "nibble split of byte 2 (high)")
+        nar(10, mem, L(MW), "ch0 >> 3 has 7 bits")
+        # LB / LH sign-extend to 64 bits upstream (execute.rs:477-500): a set sign bit leaves the 40-bit register model, so it must be clear
+        nar(10, s["s_lb"], L(GB[0]), "lb: byte below 128")
+        nar(10, s["s_lh"], L(GB[1]), "lh: high byte below 128")
+        for k in range(3):
+            rng(mem, L(TD[k]), f"range lookup of timestamp distance chunk {k}")
+        widx = L(MW) + 128 * L(CH[1]) + (1 << 17) * L(CH[2])
+
+        def mfp(a, ts, w):
+            e = th[1] * a + sum_e(th[3 + k] * w[k] for k in range(8)) + 6
+            return z - (e if ts is None else e + th[2] * ts)
+        out.append((g.tmp(0 - mem), g.tmp(mfp(widx, L(PTS), [L(c) for c in OB]), "memory: consume the word as the previous access left it")))
+        out.append((mem, g.tmp(mfp(widx, L(CLK) + 1, [L(c) for c in NB]), "memory: produce the word at timestamp clk + 1")))
+        img_on = g.Pc(P_IMG_ON)
+        out.append((img_on, g.tmp(mfp(g.Pc(P_IMG_A), None, [g.Pc(c) for c in P_IMG]), "memory: initial value of image word `row` (timestamp 0)")))
+        out.append((g.tmp(0 - img_on), g.tmp(mfp(g.Pc(P_IMG_A), L(IFTS), [L(c) for c in IF]), "memory: final value of image word `row`")))
+        ram_a = L(RA[0]) + TWO10 * L(RA[1]) + TWO20 * L(RA[2])
+        ron = L(RON)
+        out.append((ron, g.tmp(z - (th[1] * ram_a + 6), "memory: a RAM word starts as zero at timestamp 0")))
+        out.append((g.tmp(0 - ron), g.tmp(mfp(ram_a, L(RFTS), [L(c) for c in RF]), "memory: final value of the RAM word")))
+        rng(ron, L(RA[0]), "RAM word index chunk 0")
+        rng(ron, L(RA[1]), "RAM word index chunk 1")
+        nar(10, ron, L(RA[2]), "RAM word index chunk 2 (7 bits)")
+        for k in range(3):
+            rng(ron, L(RE[k]), f"RAM word index distance chunk {k}")
+        out.append((g.tmp(0 - L(M_B8)), g.tmp(z - (th[1] * g.Pc(P_B8) + 8), "byte-table row")))
+        out.append((g.tmp(0 - L(M_B4)), g.tmp(z - (th[1] * g.Pc(P_B4) + 9), "nibble-table row")))
+        out.append((g.tmp(0 - L(M_B7)), g.tmp(z - (th[1] * g.Pc(P_B7) + 10), "7-bit-table row")))
     return out
 
 
@@ -431,6 +504,70 @@ def full_constraints(g, s, fam, neg, a_lo, a_hi, b_lo, b_hi, v_lo, v_hi, rc_lo, 
     andf, orf, xorf = s["s_and"] + s["s_andi"], s["s_or"] + s["s_ori"], s["s_xor"] + s["s_xori"]
     g.emit(bitf * (v_lo - a_lo - b_lo) + andf * (a_lo + b_lo - z_lo) + orf * z_lo + xorf * 2 * z_lo, "bitwise result lo")
     g.emit(bitf * (v_hi - a_hi - b_hi) + andf * (a_hi + b_hi - z_hi) + orf * z_hi + xorf * 2 * z_hi, "bitwise result hi")
+
+
+def memory_constraints(g, s, fam, a_lo, a_hi, b_lo, b_hi, v_lo, v_hi, rc_lo, rc_hi, k0, k1, trans, first):
+    """Full profile: loads and stores (execute.rs:477-575, memory.rs:297-489) as one access to an aligned 8-byte word, checked offline
+    (docs/PROVER_SPEC.md section 3.8): every access consumes (word, previous timestamp, bytes) and produces (word, clk + 1, bytes)."""
+    L, N = g.L, g.N
+    mem, ld, st = fam["mem"], fam["ld"], fam["st"]
+    oh = [L(c) for c in OH]
+    ob = [L(c) for c in OB]
+    nb = [L(c) for c in NB]
+    gb = [L(c) for c in GB]
+    ch = [L(c) for c in CH]
+    for k in range(8):
+        g.emit(oh[k] * (oh[k] - 1), f"bool off{k}")
+    g.emit(sum_e(oh) - mem, "exactly one byte offset on a memory row, none elsewhere")
+    # effective address = rs1 + imm, no wrap in 40 bits (execute.rs:478 wraps in 64: such an address is not provable), below 2^30
+    imm_hi = (TWO20 - 1) * L(IMM_SIGN)
+    g.emit(mem * (a_lo + L(IMM_LO) - rc_lo - TWO20 * k0), "address lo limb")
+    g.emit(mem * (a_hi + imm_hi + k0 - rc_hi - TWO20 * k1), "address hi limb")
+    g.emit(mem * (k1 - L(IMM_SIGN)), "address: a negative offset borrows exactly once, a positive one never carries out")
+    g.emit(mem * ch[3], "address below 2^30")
+    g.emit(mem * (ch[0] - sum_e(k * oh[k] for k in range(1, 8)) - 8 * L(MW)), "ch0 = byte offset + 8 * mw")
+    # natural alignment (memory.rs:329,383,440: MisalignedAccess is a VM error, no row)
+    for w in (2, 4, 8):
+        sel = sum_e(s[n] for n, ww in ACCESS_WIDTH.items() if ww == w)
+        g.emit(sel * sum_e(oh[k] for k in range(8) if k % w), f"{w}-byte accesses are aligned")
+    # the previous access is earlier: clk + 1 - prev_ts - 1 >= 0
+    g.emit(mem * (L(CLK) - L(PTS) - L(TD[0]) - TWO10 * L(TD[1]) - TWO20 * L(TD[2])), "clk - prev_ts is a 30-bit value")
+    # register-side value g: bytes gb0..gb4 (byte 2 split into nibbles at the limb boundary)
+    g.emit(mem * (gb[2] - L(NL) - 16 * L(NH)), "byte 2 = nibbles")
+    g_lo = g.tmp(gb[0] + 256 * gb[1] + 65536 * L(NL), "register-side value, lo limb")
+    g_hi = g.tmp(L(NH) + 16 * gb[3] + 4096 * gb[4], "register-side value, hi limb")
+    g.emit(ld * (v_lo - g_lo) + st * (b_lo - g_lo), "loaded value / stored register, lo limb")
+    g.emit(ld * (v_hi - g_hi) + st * (b_hi - g_hi), "loaded value / stored register, hi limb")
+    # loads (zero-extended; LB / LH with a clear sign bit; LD needs bytes 5..7 zero to stay inside 40 bits): gb[j] = ob[offset + j] for j < width
+    for j in range(5):
+        terms = []
+        for n in LOADS:
+            w = ACCESS_WIDTH[n]
+            if j < w:
+                terms.append(s[n] * sum_e(oh[k] * ob[k + j] for k in range(0, 8, w)))
+        g.emit(ld * gb[j] - sum_e(terms), f"load: byte {j} of the value")
+    for k in (5, 6, 7):
+        g.emit(s["s_ld"] * ob[k], f"ld: byte {k} is zero (the value fits 40 bits)")
+    # new bytes: stores replace `width` bytes at the offset with the low bytes of rs2 (bytes 5..7 of an SD are zero), loads change nothing
+    for k in range(8):
+        terms = []
+        for n in STORES:
+            w = ACCESS_WIDTH[n]
+            base = k - k % w
+            j = k - base
+            src = gb[j] if j < 5 else 0
+            terms.append(s[n] * oh[base] * (src - ob[k]))
+        g.emit(mem * (nb[k] - ob[k]) - sum_e(terms), f"new byte {k}")
+    # --- boundary: RAM list = strictly increasing word indices from p_ram0 on, packed at the first rows
+    ron = L(RON)
+    g.emit(ron * (ron - 1), "bool ram_on")
+    g.emit(trans * (N(RON) * (1 - ron)), "the RAM list is packed at the first rows")
+    ram_a = g.tmp(L(RA[0]) + TWO10 * L(RA[1]) + TWO20 * L(RA[2]), "RAM word index")
+    ram_an = N(RA[0]) + TWO10 * N(RA[1]) + TWO20 * N(RA[2])
+    dist = L(RE[0]) + TWO10 * L(RE[1]) + TWO20 * L(RE[2])
+    dist_n = N(RE[0]) + TWO10 * N(RE[1]) + TWO20 * N(RE[2])
+    g.emit(trans * (N(RON) * (ram_an - ram_a - 1 - dist_n)), "RAM word indices increase strictly")
+    g.emit(first * (ron * (ram_a - g.Pc(P_RAM0) - dist)), "the first RAM word lies above the program image")
 
 
 def build():
@@ -538,6 +675,7 @@ def build():
     g.emit(s["s_jalr"] * (v_lo + TWO20 * v_hi - L(PC) - 4), "jalr link = pc + 4")
     if FULL:
         full_constraints(g, s, fam, neg, a_lo, a_hi, b_lo, b_hi, v_lo, v_hi, rc_lo, rc_hi, k0, k1)
+        memory_constraints(g, s, fam, a_lo, a_hi, b_lo, b_hi, v_lo, v_hi, rc_lo, rc_hi, k0, k1, trans, first)
     # --- syscalls (syscall.rs:94-149)
     g.emit((L(IS_READ) + L(IS_POS2)) * (rd_h[2] * rd_l[2] - 1), "read / poseidon2 write r10 (syscall.rs:104-109,140-149)")
     g.emit(L(IS_WRITE) * (v_lo - L(REG_LO[11])), "write: v = the written word r11 (lo), sent to the I/O bus (syscall.rs:110-119)")
@@ -547,7 +685,7 @@ def build():
     # --- register write-back, pre-state rows: next.r[i] = (rd == i && w) ? v : r[i]
     w = addlike + s["s_sub"] + s["s_jal"] + s["s_jalr"] + s["s_sltu"] + s["s_seq"] + L(IS_READ) + L(IS_POS2) + cm * mv
     if FULL:
-        w = w + fam["mul_on"] + fam["bitf"] + s["s_slt"]
+        w = w + fam["mul_on"] + fam["bitf"] + s["s_slt"] + fam["ld"]
     w = g.tmp(w, "write enable")
     rdw = [L(RDW[h]) for h in range(4)]
     for h in range(4):

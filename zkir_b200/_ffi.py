@@ -104,6 +104,7 @@ SYMBOLS = {
     "zkir_program_profile": (C.c_int, [vp, C.c_size_t]),
     "zkir_public_row": (None, [C.c_uint32, C.c_uint64, vp, C.c_size_t, u32p]),
     "zkir_public_rows": (C.c_uint64, [C.c_uint32, C.c_size_t]),
+    "zkir_image_words": (C.c_uint64, [C.c_size_t]),
     "zkir_public_columns": (None, [C.c_uint32, C.c_uint32, vp, C.c_size_t, vp]),
 }
 

@@ -19,7 +19,8 @@ namespace zkir {
 
 enum PackErr : u32 {
   PACK_OK = 0, PACK_ERR_PC = 1, PACK_ERR_REG40 = 2, PACK_ERR_TAPE40 = 3, PACK_ERR_SYSCALL = 4, PACK_ERR_OPCODE = 5, PACK_ERR_JALR = 6, PACK_ERR_ROM = 7,
-  /* 8 = the lookups do not balance (prover.cu) */ PACK_ERR_SHAMT = 9, PACK_ERR_DIV0 = 10,
+  /* 8 = the lookups do not balance (prover.cu) */ PACK_ERR_SHAMT = 9, PACK_ERR_DIV0 = 10, PACK_ERR_MEMADDR = 11, PACK_ERR_MEMSIGN = 12,
+  PACK_ERR_MEMVAL = 13, PACK_ERR_RAMROWS = 14,
 };
 BB_HD const char* pack_err_text(u32 code) {
   switch (code) {
@@ -32,6 +33,10 @@ BB_HD const char* pack_err_text(u32 code) {
     case PACK_ERR_ROM: return "pc is outside the program";
     case PACK_ERR_SHAMT: return "immediate shift amount above 63";
     case PACK_ERR_DIV0: return "division by zero";
+    case PACK_ERR_MEMADDR: return "memory address outside [0, 2^30)";
+    case PACK_ERR_MEMSIGN: return "lb / lh of a negative value (sign extension to 64 bits exceeds the 40-bit register model)";
+    case PACK_ERR_MEMVAL: return "loaded value differs from the memory the AIR tracks (written by a syscall, or a data segment)";
+    case PACK_ERR_RAMROWS: return "more RAM words touched than trace rows: use a larger log_n";
     default: return "?";
   }
 }
@@ -39,7 +44,7 @@ BB_HD const char* pack_err_text(u32 code) {
 BB_HD int pack_sext(u32 v, int bits) { const int sh = 32 - bits; return ((int)(v << sh)) >> sh; }
 BB_HD u32 pack_inv(u32 canon) { return canon ? bb_from_mont(bb_inv(bb_to_mont(canon))) : 0u; }
 
-// rg = PRE-state registers (rg[0] ignored), w = instruction word, read_val = post-state r10 (only used by READ rows).
+// rg = PRE-state registers (rg[0] ignored), w = instruction word, read_val = post-state r10 (READ rows) / the loaded value (load rows).
 // Wr: void operator()(int column, u32 canonical_value).  Returns a PackErr.
 template <class Wr>
 BB_HD u32 expand_row_v2(u64 i, u64 T, const u64 (&rg)[16], u64 pc, u32 w, u64 read_val, Wr& W) {
@@ -175,6 +180,17 @@ BB_HD u32 expand_row_v2(u64 i, u64 T, const u64 (&rg)[16], u64 pc, u32 w, u64 re
       rs1 = fa; rs2 = fb; imm = imm17; has_imm = true; neg = op & 1;
       av = R(rs1); bv = R(rs2); f_cmps = true;
       sel = ZKIR_COL_S_BLT;
+    } else if ((op >= 0x30 && op <= 0x35) || (op >= 0x38 && op <= 0x3B)) {   // loads (I-type) / stores (S-type: base in bits 10:7, source in 14:11)
+      imm = imm17; has_imm = true;
+      if (op < 0x38) { rd = fa; rs1 = fb; writes = 1; vv = read_val; if (vv >> 40) err = PACK_ERR_REG40; sel = ZKIR_COL_S_LB + (op - 0x30); }
+      else { rs1 = fa; rs2 = fb; bv = R(rs2); sel = ZKIR_COL_S_SB + (op - 0x38); }
+      av = R(rs1);
+      const u64 ea = av + (u64)imm;                     // execute.rs:478: rs1 + sign-extended offset
+      if (ea >> 30) err = PACK_ERR_MEMADDR;
+      rc = ea & M40; chunks_from_rc = true;
+      const u64 i_lo = (u64)imm & LIMB, i_hi = imm < 0 ? LIMB : 0;
+      const u64 k0 = ((av & LIMB) + i_lo) >> 20;
+      carry0 = (u32)k0; carry1 = (u32)((((av >> 20) & LIMB) + i_hi + k0) >> 20);
 #endif
     } else {
       err = PACK_ERR_OPCODE;
@@ -234,7 +250,7 @@ BB_HD u32 expand_row_v2(u64 i, u64 T, const u64 (&rg)[16], u64 pc, u32 w, u64 re
   for (int c = ZKIR_COL_S_ADD; c <= ZKIR_COL_S_EBREAK; c++) W(c, sel == (u32)c);
 #ifdef ZKIR_PROFILE_FULL
 #pragma unroll
-  for (int c = ZKIR_COL_S_MUL; c <= ZKIR_COL_S_BLT; c++) W(c, sel == (u32)c);
+  for (int c = ZKIR_COL_S_MUL; c <= ZKIR_COL_S_SD; c++) W(c, sel == (u32)c);
 #endif
   W(ZKIR_COL_NEG, neg);
   W(ZKIR_COL_IS_EXIT, is_exit); W(ZKIR_COL_IS_READ, is_read); W(ZKIR_COL_IS_WRITE, is_write); W(ZKIR_COL_IS_POS2, is_pos2);
@@ -302,6 +318,7 @@ BB_HD bool row_range_checked(u32 w, u64 r10) {
   const u32 op = w & 0x7F;
 #ifdef ZKIR_PROFILE_FULL
   if (op == 0x22 || op == 0x23 || op == 0x42 || op == 0x43 || (op >= 0x04 && op <= 0x07)) return true;   // signed compares, DIV family
+  if ((op >= 0x30 && op <= 0x35) || (op >= 0x38 && op <= 0x3B)) return true;                              // loads / stores: the effective address
 #endif
   return op == 0x00 || op == 0x01 || op == 0x08 || op == 0x20 || op == 0x21 || op == 0x44 || op == 0x45 || op == 0x48 || op == 0x49 ||
          (op == 0x50 && r10 == 1);

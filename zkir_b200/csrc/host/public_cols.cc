@@ -3,13 +3,16 @@
 //
 // Both profiles: range table 0..1023 (zkir-spec/src/config.rs:76-80: 10-bit chunks), the program ROM as (pc, decoded word, imm)
 // per instruction (zkir-assembler/src/encoder.rs:98-151).  Full profile only: the 5-bit x 5-bit AND table on the 1024 range rows
-// and the power table of the shifts on rows 0..127 (zkir-spec/src/value.rs:658-691: shifts of 40 and more give 0 / the sign fill).
+// and the power table of the shifts on rows 0..127 (zkir-spec/src/value.rs:658-691: shifts of 40 and more give 0 / the sign fill);
+// the 8 / 4 / 7-bit range tables; the initial memory image as aligned 8-byte words: zeros below the load address 0x1000
+// (zkir-runtime/src/memory.rs:297-309: uninitialised reads give 0), then the code words, little endian (zkir-runtime/src/vm.rs:138-170).
 #include <stdint.h>
 #include <stddef.h>
 #include "zkir_b200.h"
 #include "../air_profiles_generated.h"
 
 extern "C" {
+uint64_t zkir_image_words(size_t n_code);
 
 // One row of the public columns: out[0 .. pub width of the profile).  Rows past the tables and the program hold the default row
 // (i = ~0): zeros, decoded word 127 (no instruction has opcode 127), power-table copy of row 0.
@@ -31,7 +34,21 @@ void zkir_public_row(uint32_t width, uint64_t i, const uint32_t* code, size_t n_
   }
   out[7] = (uint32_t)key; out[8] = (uint32_t)(mul & LIMB); out[9] = (uint32_t)(mul >> 20); out[10] = zf;
   out[11] = (uint32_t)(fill & LIMB); out[12] = (uint32_t)(fill >> 20);   // p_key, p_mlo, p_mhi, p_zf, p_glo, p_ghi
+  out[13] = i < 256 ? (uint32_t)i : 0u; out[14] = i < 16 ? (uint32_t)i : 0u; out[15] = i < 128 ? (uint32_t)i : 0u;   // p_b8, p_b4, p_b7
+  const uint64_t n_img = zkir_image_words(n_code);
+  const bool img = i < n_img;
+  out[16] = img; out[17] = img ? (uint32_t)i : 0u;                         // p_img_on, p_img_a
+  for (uint32_t k = 0; k < 8; k++) {                                       // p_img0..7: byte 8 i + k of the image
+    const uint64_t addr = 8 * i + k;
+    uint32_t b = 0;
+    if (img && addr >= 0x1000 && (addr - 0x1000) / 4 < n_code) b = (code[(addr - 0x1000) / 4] >> (8 * (addr & 3))) & 255u;
+    out[18 + k] = b;
+  }
+  out[26] = i == 0 ? (uint32_t)n_img : 0u;                                 // p_ram0
 }
+
+// aligned 8-byte words of the memory image [0, 0x1000 + 4 n_code): every word index from this on is RAM (starts as zero)
+uint64_t zkir_image_words(size_t n_code) { return (0x1000 + 4 * (uint64_t)n_code + 7) / 8; }
 
 // rows [0, zkir_public_rows) can differ from the default row
 uint64_t zkir_public_rows(uint32_t width, size_t n_code) { (void)width; return n_code > 1024 ? n_code : 1024; }
