@@ -207,7 +207,7 @@ def test_gpu_full_profile_every_opcode(gpu_ctx, oracle_full):
 
 @pytest.mark.gpu
 def test_gpu_full_profile_2p16_rows_and_prove_api(gpu_ctx, oracle_full):
-    iters = 4000     # 64 011 cycles -> 2^16 rows
+    iters = 2900     # 63 811 cycles -> 2^16 rows
     prog = mix_program()
     cfg = zkir_b200.ProverConfig(num_queries=30, pow_bits=8)
     proof = zkir_b200.prove(prog, [iters], cfg)

@@ -375,7 +375,7 @@ class Context:
         context's program first (zkir_b200_set_program; a no-op when it is unchanged)."""
         if program is not None:
             self.set_program(program)
-        params = cfg.params(WIDTH if device_resident is not None and cols is None else int(cols.shape[0]))
+        params = cfg.params(WIDTH if cols is None else int(cols.shape[0]))   # the profile is the table's width (device-resident: pass the host array or None = core)
         pv = np.ascontiguousarray(public_values, dtype=np.uint32)
         proof, plen = C.c_void_p(), C.c_size_t()
         if device_resident is not None:

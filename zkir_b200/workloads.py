@@ -91,9 +91,10 @@ def pos2_cycles(iters):
     return POS2_ITER_CYCLES * iters + POS2_SETUP_CYCLES
 
 
-# Full-ISA workload (docs/PROVER_SPEC.md section 3.7): a xorshift-multiply generator loop that exercises the multiplier block (MUL,
-# MULH, DIVU, REMU), all three shift kinds, the bitwise table and the signed compares; 16 cycles per iteration.
-MIX_ITER_CYCLES = 16
+# Full-ISA workload (docs/PROVER_SPEC.md sections 3.7, 3.8): a xorshift-multiply generator loop that exercises the multiplier block (MUL,
+# MULH, DIVU, REMU), all three shift kinds, the bitwise table, the signed compares and the memory argument (a 1 KiB table of 8-byte
+# slots written and read at data-dependent offsets); 22 cycles per iteration.
+MIX_ITER_CYCLES = 22
 MIX_SETUP_CYCLES = 8 + 3
 MIX_SRC = ("addi r10, r0, 1\necall\nadd r3, r10, r0\n"            # iterations from the input tape
            "addi r1, r0, 12345\naddi r2, r0, 25173\naddi r4, r0, 0\naddi r6, r0, 1000\naddi r9, r0, 0\n"
@@ -111,8 +112,14 @@ MIX_SRC = ("addi r10, r0, 1\necall\nadd r3, r10, r0\n"            # iterations f
            "srai r5, r1, 3\n"
            "slt r5, r5, r7\n"
            "add r9, r9, r5\n"
+           "andi r12, r1, 1016\n"
+           "sd r1, 0x4000(r12)\n"
+           "andi r14, r7, 1016\n"
+           "ld r13, 0x4000(r14)\n"
+           "andi r13, r13, 1\n"
+           "add r9, r9, r13\n"
            "addi r4, r4, 1\n"
-           "bne r4, r3, -60\n"
+           "bne r4, r3, -84\n"
            "add r10, r0, r0\nadd r11, r9, r0\necall\n")
 
 
@@ -129,7 +136,7 @@ def mix_reference(iters):
     """The loop restated in Python (semantics of zkir-runtime/src/execute.rs: everything wraps at 40 bits, SRAI / SLT are signed at bit 39)."""
     M = (1 << 40) - 1
     sg = lambda v: v - (1 << 40) if v >> 39 else v
-    r1, r2, r9 = 12345, 25173, 0
+    r1, r2, r9, table = 12345, 25173, 0, {}
     for _ in range(iters):
         r1 = (r1 * r2) & M
         r1 = (r1 + 13849) & M
@@ -139,4 +146,6 @@ def mix_reference(iters):
         r7 = (r7 | r1) & 1023
         r5 = (sg(r1) >> 3) & M
         r9 += int(sg(r5) < sg(r7))
+        table[r1 & 1016] = r1
+        r9 += table.get(r7 & 1016, 0) & 1
     return r9
