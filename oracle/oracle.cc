@@ -251,6 +251,7 @@ struct AirRowCtx {  // all constraints at one point: main/aux/public columns are
   Xp xf(Fp a) const { Xp r; r.v = e4_from(a.v); return r; }
   Xp x4(Fp a, Fp b, Fp c, Fp d) const { Xp r; r.v.c[0] = a.v; r.v.c[1] = b.v; r.v.c[2] = c.v; r.v.c[3] = d.v; return r; }
   Xp sio() const { Xp r; r.v = lc->sio; return r; }
+  void fence() const {}
   void emit(int idx, Fp v) { vals[idx] = e4_from(v.v); }
   void emit_x(int idx, Xp v) { vals[idx] = v.v; }
 };

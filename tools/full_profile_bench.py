@@ -1,0 +1,26 @@
+#!/usr/bin/env python3
+"""Stage times of one full-profile proof (mix workload, 2^18 rows by default), trace resident.  ZKIR_QUOTIENT_VARIANT selects the quotient kernel shape."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import zkir_b200
+from zkir_b200.workloads import mix_program
+
+log_n = int(sys.argv[1]) if len(sys.argv) > 1 else 18
+iters = ((1 << log_n) - 16) // 22
+res = zkir_b200.VM(mix_program(), [iters], zkir_b200.VMConfig(max_cycles=1 << 26, enable_execution_trace=True)).run()
+cols, pv = res.pack()
+ctx = zkir_b200.Context(0)
+ctx.set_program(res)
+d = ctx.to_device(cols)
+cfg = zkir_b200.ProverConfig()
+ln = int(cols.shape[1]).bit_length() - 1
+for _ in range(2):
+    pb = ctx.prove_columns(cols, pv, cfg, device_resident=(d, ln))
+assert zkir_b200.verify(pb, cfg, pv, res) == (True, "")
+ctx.timer_start()
+for _ in range(5):
+    ctx.prove_columns(cols, pv, cfg, device_resident=(d, ln))
+ms = ctx.timer_stop() / 5
+print(f"variant={os.environ.get('ZKIR_QUOTIENT_VARIANT', 'default')} rows=2^{ln} cycles={res.cycles} ms/proof={ms:.3f} " + " ".join(f"{k}={v:.3f}" for k, v in ctx.stage_ms().items()))

@@ -225,6 +225,7 @@ class Gen:
         self.ntmp = 0
         self.idx = 0
         self.pre = pre
+        self.gen = 0     # bumped by flush(): reloaded columns get fresh names
 
     def L(self, i):
         return self._ld("l", "L", i, COLS[i])
@@ -244,12 +245,21 @@ class Gen:
     def _ld(self, pre, fn, i, note):
         key = (pre, i)
         if key not in self.loaded:
-            self.lines.append(f"  const F {self.pre}{pre}{i} = c.{fn}({i});  // {note}")
-            self.loaded[key] = E(f"{self.pre}{pre}{i}", atom=True)
+            name = f"{self.pre}{pre}{i}" + (f"_{self.gen}" if self.gen else "")
+            self.lines.append(f"  const F {name} = c.{fn}({i});  // {note}")
+            self.loaded[key] = E(name, atom=True)
         return self.loaded[key]
 
     def PV(self, i):
         return E(f"c.PV({i})", atom=True)
+
+    def flush(self):
+        """Forget the cached column loads: later uses load again (an L1 / L2 hit) instead of keeping hundreds of values live across
+        the whole constraint list -- the full profile's straight-line code would otherwise spill kilobytes per thread."""
+        if FULL:
+            self.loaded = {}
+            self.gen += 1
+            self.lines.append("  c.fence();  // the loads below stay below (register pressure of the wide profile)")
 
     def tmp(self, e, note=""):
         e = lift(e)
@@ -265,6 +275,35 @@ class Gen:
         self.idx += 1
 
 
+_DEF = None
+
+
+def slice_lines(lines, roots):
+    """The definitions among `lines` (`const F|X name = expr;`) that the names in `roots` depend on, in their original order."""
+    import re
+    defs = {}
+    for k, ln in enumerate(lines):
+        m = re.match(r"\s*const [FX] (\w+) = (.*?);", ln)
+        if m:
+            defs[m.group(1)] = (k, m.group(2))
+    need, todo = set(), [r for r in roots if r in defs]
+    while todo:
+        n = todo.pop()
+        if n in need:
+            continue
+        need.add(n)
+        todo.extend(t for t in re.findall(r"[A-Za-z_]\w*", defs[n][1]) if t in defs and t not in need)
+    return [lines[defs[n][0]] for n in sorted(need, key=lambda n: defs[n][0])]
+
+
+def names_in(*exprs):
+    import re
+    out = []
+    for e in exprs:
+        out += re.findall(r"[A-Za-z_]\w*", lift(e).code)
+    return out
+
+
 def sum_e(xs):
     xs = list(xs)
     acc = xs[0]
@@ -276,10 +315,37 @@ def sum_e(xs):
 TWO10, TWO20 = 1 << 10, 1 << 20
 
 
+class LazySel:
+    """Full profile: selector columns are loaded where they are used (and again after a Gen.flush()), not all 43 up front."""
+
+    def __init__(self, g):
+        self.g = g
+
+    def __getitem__(self, n):
+        return self.g.L(S[n])
+
+    def values(self):
+        return [self[n] for n in SEL_NAMES]
+
+
+class LazyFam:
+    """Full profile: opcode-family sums, computed on first use and again after a Gen.flush()."""
+
+    def __init__(self, g, defs):
+        self.g, self.defs = g, defs
+
+    def __getitem__(self, k):
+        key = ("fam", k)
+        if key not in self.g.loaded:
+            thunk, note = self.defs[k]
+            self.g.loaded[key] = self.g.tmp(thunk(self), note)
+        return self.g.loaded[key]
+
+
 def shared(g):
     """Row-local expressions used both by the constraints and by the lookup fractions."""
     L = g.L
-    s = {n: L(S[n]) for n in SEL_NAMES}
+    s = LazySel(g) if FULL else {n: L(S[n]) for n in SEL_NAMES}
     s_ecall = g.tmp(L(IS_EXIT) + L(IS_READ) + L(IS_WRITE) + L(IS_POS2), "ecall row (syscall.rs:94-149)")
     s_pad = g.tmp(1 - sum_e(s.values()) - s_ecall, "padding row: no other selector set")
     live = g.tmp(1 - s_pad, "live row")
@@ -301,20 +367,23 @@ def shared(g):
     imm_f = g.tmp(L(IMM_LO) - TWO20 * L(IMM_SIGN), "signed immediate as a field element (execute.rs:187)")
     fam = None
     if FULL:
-        fam = dict(
-            mulf=s["s_mul"], divf=g.tmp(s["s_divu"] + s["s_div"], "DIV family (DIV / REM act as DIVU / REMU: a provable register value is below 2^40, execute.rs:117-183)"),
-            shl=g.tmp(s["s_sll"] + s["s_slli"], "left shift"), shr=g.tmp(s["s_srl"] + s["s_srli"] + s["s_sra"] + s["s_srai"], "right shift"),
-            sraf=g.tmp(s["s_sra"] + s["s_srai"], "arithmetic right shift"), shi=g.tmp(s["s_slli"] + s["s_srli"] + s["s_srai"], "shift by immediate"),
-            cmps=g.tmp(s["s_slt"] + s["s_blt"], "signed compare"),
-            bitf=g.tmp(s["s_and"] + s["s_or"] + s["s_xor"] + s["s_andi"] + s["s_ori"] + s["s_xori"], "bitwise row"))
-        fam["shf"] = g.tmp(fam["shl"] + fam["shr"], "shift row")
-        fam["mul_on"] = g.tmp(fam["mulf"] + fam["divf"] + fam["shf"], "multiplier block active")
-        fam["dec_on"] = g.tmp(fam["mul_on"] + fam["cmps"] + fam["bitf"], "x / y chunks are range-checked")
-        fam["r_on"] = g.tmp(fam["divf"] + fam["shf"], "r chunks are range-checked")
-        fam["sa_on"] = g.tmp(fam["cmps"] + fam["sraf"], "sign of x is extracted")
-        fam["ld"] = g.tmp(sum_e(s[n] for n in LOADS), "load row")
-        fam["st"] = g.tmp(sum_e(s[n] for n in STORES), "store row")
-        fam["mem"] = g.tmp(fam["ld"] + fam["st"], "memory row")
+        fam = LazyFam(g, dict(
+            mulf=(lambda f: s["s_mul"] + 0, "MUL / MULH"),
+            divf=(lambda f: s["s_divu"] + s["s_div"], "DIV family (DIV / REM act as DIVU / REMU: a provable register value is below 2^40, execute.rs:117-183)"),
+            shl=(lambda f: s["s_sll"] + s["s_slli"], "left shift"),
+            shr=(lambda f: s["s_srl"] + s["s_srli"] + s["s_sra"] + s["s_srai"], "right shift"),
+            sraf=(lambda f: s["s_sra"] + s["s_srai"], "arithmetic right shift"),
+            shi=(lambda f: s["s_slli"] + s["s_srli"] + s["s_srai"], "shift by immediate"),
+            cmps=(lambda f: s["s_slt"] + s["s_blt"], "signed compare"),
+            bitf=(lambda f: s["s_and"] + s["s_or"] + s["s_xor"] + s["s_andi"] + s["s_ori"] + s["s_xori"], "bitwise row"),
+            shf=(lambda f: f["shl"] + f["shr"], "shift row"),
+            mul_on=(lambda f: f["mulf"] + f["divf"] + f["shf"], "multiplier block active"),
+            dec_on=(lambda f: f["mul_on"] + f["cmps"] + f["bitf"], "x / y chunks are range-checked"),
+            r_on=(lambda f: f["divf"] + f["shf"], "r chunks are range-checked"),
+            sa_on=(lambda f: f["cmps"] + f["sraf"], "sign of x is extracted"),
+            ld=(lambda f: sum_e(s[n] for n in LOADS), "load row"),
+            st=(lambda f: sum_e(s[n] for n in STORES), "store row"),
+            mem=(lambda f: f["ld"] + f["st"], "memory row")))
     return s, s_ecall, s_pad, live, rc_on, dec, imm_f, fam
 
 
@@ -439,7 +508,7 @@ def full_constraints(g, s, fam, neg, a_lo, a_hi, b_lo, b_hi, v_lo, v_hi, rc_lo, 
     r = [L(c) for c in RC]
     p = [L(c) for c in PC8]
     kk = [g.tmp(L(KLO[i]) + TWO10 * L(KHI[i]), f"carry {i}") for i in range(5)]
-    mulf, divf, shl, shr, sraf, shi, cmps, bitf, shf, mul_on = (fam[k] for k in ("mulf", "divf", "shl", "shr", "sraf", "shi", "cmps", "bitf", "shf", "mul_on"))
+    mulf, divf, shf, cmps, bitf, mul_on = (fam[k] for k in ("mulf", "divf", "shf", "cmps", "bitf", "mul_on"))
     x_lo, x_hi = g.tmp(x[0] + TWO10 * x[1], "x.lo"), g.tmp(x[2] + TWO10 * x[3], "x.hi")
     y_lo, y_hi = g.tmp(y[0] + TWO10 * y[1], "y.lo"), g.tmp(y[2] + TWO10 * y[3], "y.hi")
     r_lo, r_hi = g.tmp(r[0] + TWO10 * r[1], "r.lo"), g.tmp(r[2] + TWO10 * r[3], "r.hi")
@@ -480,6 +549,12 @@ def full_constraints(g, s, fam, neg, a_lo, a_hi, b_lo, b_hi, v_lo, v_hi, rc_lo, 
     g.emit(divf * (r_hi - b_hi - k0 - rc_hi + TWO20 * k1), "rem - b, hi limb")
     g.emit(divf * (k1 - 1), "rem < b")
     # --- signed compares at bit 39 (execute.rs:361-391, 594-609): (a <s b) = (a <u b) xor sign_a xor sign_b
+    g.flush()
+    cmps, shf, shl, shr, sraf, shi = (fam[k] for k in ("cmps", "shf", "shl", "shr", "sraf", "shi"))
+    r = [L(c) for c in RC]
+    p = [L(c) for c in PC8]
+    pl_lo, pl_hi = g.tmp(p[0] + TWO10 * p[1], "low product word, lo limb"), g.tmp(p[2] + TWO10 * p[3], "low product word, hi limb")
+    ph_lo, ph_hi = g.tmp(p[4] + TWO10 * p[5], "high product word, lo limb"), g.tmp(p[6] + TWO10 * p[7], "high product word, hi limb")
     sa, sb, sx, lts = L(SA), L(SB), L(SXOR), L(LTS)
     g.emit(sx - (sa + sb - 2 * sa * sb), "sign_xor = sign_a xor sign_b")
     g.emit(cmps * (lts - (k1 + sx - 2 * k1 * sx)), "lt_signed = borrow xor sign_xor")
@@ -495,6 +570,10 @@ def full_constraints(g, s, fam, neg, a_lo, a_hi, b_lo, b_hi, v_lo, v_hi, rc_lo, 
     g.emit(shr * (v_lo - ph_lo - zf * a_lo) - sraf * sa * L(G_LO), "right shift result lo (+ sign fill)")
     g.emit(shr * (v_hi - ph_hi - zf * a_hi) - sraf * sa * L(G_HI), "right shift result hi (+ sign fill)")
     # --- bitwise (execute.rs:200-279): chunks split into 5-bit pieces, z = x & y piecewise from the AND table; or = x + y - z, xor = x + y - 2 z
+    g.flush()
+    bitf = fam["bitf"]
+    x = [L(c) for c in XC]
+    y = [L(c) for c in YC]
     zc = []
     for i in range(4):
         g.emit(bitf * (x[i] - L(XL[i]) - 32 * L(XH[i])), f"x{i} = low + 32 high piece")
@@ -568,6 +647,49 @@ def memory_constraints(g, s, fam, a_lo, a_hi, b_lo, b_hi, v_lo, v_hi, rc_lo, rc_
     dist_n = N(RE[0]) + TWO10 * N(RE[1]) + TWO20 * N(RE[2])
     g.emit(trans * (N(RON) * (ram_an - ram_a - 1 - dist_n)), "RAM word indices increase strictly")
     g.emit(first * (ron * (ram_a - g.Pc(P_RAM0) - dist)), "the first RAM word lies above the program image")
+
+
+def logup_full(g, sh, first, last, trans, sio):
+    """LogUp constraints of the full profile.  Same constraints as the core tail of build(), but every helper is evaluated inside its
+    own block from freshly loaded cells (the definitions it needs are sliced out of a scratch generator), and the helpers are summed
+    as they go: 81 ext4 denominators never have to be live at once."""
+    gs = Gen(pre="q")
+    fr = fractions(gs, sh)
+    NH = len(FRAC_PAIRS)
+
+    def xaux(k, nxt=False):
+        ld = gs.AN if nxt else gs.A
+        cs = [ld(4 * k + j) for j in range(4)]
+        return gs.tmp(E(f"c.x4({cs[0].code}, {cs[1].code}, {cs[2].code}, {cs[3].code})", atom=True, t="X"), ("next " if nxt else "") + AUX_NAMES[k])
+    h = [xaux(k) for k in range(NH)]
+    phi, phi_n = xaux(NH), xaux(NH, True)
+    g.lines.append("  X hsum = c.xf(c.K(0u));  // sum of the helpers, accumulated block by block")
+    for k, pair in enumerate(FRAC_PAIRS):
+        if len(pair) == 0:
+            expr, note = h[k], f"helper {k} pads the aux width: zero"
+        elif len(pair) == 1:
+            (ni, di), = (fr[pair[0]],)
+            expr, note = h[k] * di - ni, f"helper {k} = fraction {pair[0]}"
+        else:
+            i, j = pair
+            (ni, di), (nj, dj) = fr[i], fr[j]
+            expr, note = h[k] * di * dj - di * nj - dj * ni, f"helper {k} = fraction {i} + fraction {j}"
+        g.lines.append("  {")
+        g.lines.extend(slice_lines(gs.lines, names_in(expr)))
+        g.emit(expr, note)
+        g.lines.append(f"  hsum = hsum + {h[k].code};")
+        g.lines.append("  }")
+        if k % 2:
+            g.lines.append("  c.fence();")
+    (n5, d5), (n7, d7) = fr[FRAC_PHI[0]], fr[FRAC_PHI[1]]
+    hs = E("hsum", atom=True, t="X")
+    tail = [((phi_n - phi - hs) * d5 * d7 - d7 * n5 - d5 * n7) * trans, phi * first, (sio - phi - hs) * last]
+    g.lines.append("  {")
+    g.lines.extend(slice_lines(gs.lines, names_in(*tail)))
+    g.emit(tail[0], "running sum transition (adds the ROM lookup and the I/O event itself)")
+    g.emit(tail[1], "running sum starts at 0")
+    g.emit(tail[2], "range and ROM lookups cancel; what remains is the public I/O transcript's sum")
+    g.lines.append("  }")
 
 
 def build():
@@ -674,8 +796,11 @@ def build():
     g.emit(s["s_jalr"] * (a_hi - ch[3]), "jalr: target base < 2^30")
     g.emit(s["s_jalr"] * (v_lo + TWO20 * v_hi - L(PC) - 4), "jalr link = pc + 4")
     if FULL:
+        g.flush()
         full_constraints(g, s, fam, neg, a_lo, a_hi, b_lo, b_hi, v_lo, v_hi, rc_lo, rc_hi, k0, k1)
+        g.flush()
         memory_constraints(g, s, fam, a_lo, a_hi, b_lo, b_hi, v_lo, v_hi, rc_lo, rc_hi, k0, k1, trans, first)
+    g.flush()
     # --- syscalls (syscall.rs:94-149)
     g.emit((L(IS_READ) + L(IS_POS2)) * (rd_h[2] * rd_l[2] - 1), "read / poseidon2 write r10 (syscall.rs:104-109,140-149)")
     g.emit(L(IS_WRITE) * (v_lo - L(REG_LO[11])), "write: v = the written word r11 (lo), sent to the I/O bus (syscall.rs:110-119)")
@@ -734,7 +859,11 @@ def build():
     for i in range(1, 16):
         g.emit(first * L(REG_LO[i]), f"r{i}.lo starts 0")
         g.emit(first * L(REG_HI[i]), f"r{i}.hi starts 0")
-    # --- LogUp: helper k = n_i/d_i + n_j/d_j; phi' = phi + h0 + h1 + h2 + n_5/d_5; phi_first = 0; the last row closes the sum to 0
+    # --- LogUp: helper k = n_i/d_i + n_j/d_j; phi' = phi + sum of the helpers + n_5/d_5 + n_7/d_7; phi_first = 0; the last row closes the sum
+    sio = E("c.sio()", atom=True, t="X")
+    if FULL:
+        logup_full(g, sh, first, last, trans, sio)
+        return g
     fr = fractions(g, sh)
 
     def xaux(k, nxt=False):
@@ -745,19 +874,11 @@ def build():
     h = [xaux(k) for k in range(NH)]
     phi, phi_n = xaux(NH), xaux(NH, True)
     for k, pair in enumerate(FRAC_PAIRS):
-        if len(pair) == 0:
-            g.emit(h[k], f"helper {k} pads the aux width: zero")
-            continue
-        if len(pair) == 1:
-            (ni, di), = (fr[pair[0]],)
-            g.emit(h[k] * di - ni, f"helper {k} = fraction {pair[0]}")
-            continue
         i, j = pair
         (ni, di), (nj, dj) = fr[i], fr[j]
         g.emit(h[k] * di * dj - di * nj - dj * ni, f"helper {k} = fraction {i} + fraction {j}")
     (n5, d5), (n7, d7) = fr[FRAC_PHI[0]], fr[FRAC_PHI[1]]
-    hs = g.tmp(sum_e(h), "h0 + h1 + h2" if NH == 3 else "sum of the helpers")
-    sio = E("c.sio()", atom=True, t="X")
+    hs = g.tmp(sum_e(h), "h0 + h1 + h2")
     g.emit(((phi_n - phi - hs) * d5 * d7 - d7 * n5 - d5 * n7) * trans, "running sum transition (adds the ROM lookup and the I/O event itself)")
     g.emit(phi * first, "running sum starts at 0")
     # last row = padding row: its ROM-lookup and I/O numerators are 0 (live = 0), only the table-side helpers count
@@ -767,9 +888,19 @@ def build():
 
 def build_fractions():
     g = Gen(pre="f_")
-    fr = fractions(g, shared(g))
+    sh = shared(g)
+    if not FULL:
+        fr = fractions(g, sh)
+        for j, (n, d) in enumerate(fr):
+            g.lines.append(f"  c.frac({j}, {lift(n).code}, {d.code});")
+        return g
+    gs = Gen(pre="fq")   # full profile: one block per fraction (see logup_full); the context consumes fraction j before j + 1 is built
+    fr = fractions(gs, sh)
     for j, (n, d) in enumerate(fr):
+        g.lines.append("  {")
+        g.lines.extend(slice_lines(gs.lines, names_in(n, d)))
         g.lines.append(f"  c.frac({j}, {lift(n).code}, {d.code});")
+        g.lines.append("  }")
     return g
 
 
@@ -799,7 +930,7 @@ def main():
     hdr.append("// Context contract: C::F (base) and C::X (ext4) with + - *, X * F scaling; c.L(i)/c.N(i) main local/next row, c.A(i)/c.AN(i) aux,")
     hdr.append("// c.P(i) public column, c.PV(i) public value, c.K(u32 canonical constant), c.z()/c.th(k) lookup challenges z, theta^k,")
     hdr.append("// c.xf(F) -> X, c.x4(F,F,F,F) -> X, c.sio() -> X (sum of the public I/O transcript's fractions), c.is_first / c.is_last / c.is_trans selectors,")
-    hdr.append("// c.emit(index, F), c.emit_x(index, X).")
+    hdr.append("// c.emit(index, F), c.emit_x(index, X); full profile: c.fence() = a scheduling barrier for loads (a no-op off the GPU).")
     hdr.append("template <class C> ZKIR_HD void zkir_air_eval(C& c) {")
     hdr.append("  typedef typename C::F F;")
     hdr.append("  typedef typename C::X X;")

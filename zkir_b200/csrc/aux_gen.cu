@@ -15,6 +15,42 @@
 
 namespace zkir {
 
+#ifdef ZKIR_PROFILE_FULL
+__device__ __noinline__ E4 e4_inv_call(E4 a) { return e4_inv(a); }   // 81 inlined tower inversions would be most of the kernel's code
+// Full profile (81 fractions, 41 helpers): the generated code builds one fraction at a time inside its own block (tools/gen_air.py:
+// build_fractions), and this context consumes it at once -- invert, add to the helper it belongs to, store a helper as soon as the next
+// one begins (the fractions of a helper are consecutive) -- so neither the fractions nor the helpers are ever all live.
+struct FracCtxDev {
+  typedef Fm F; typedef Xm X;
+  const u32 *trace, *pub; u64 N, row;
+  const E4* lc;   // shared: z, theta .. theta^NUM_THETA
+  u32* aux;       // out: helper columns
+  E4 cur, tot;    // the helper being summed; sum of everything (helpers and the fractions phi adds itself)
+  int cur_k;      // index of that helper (the next one to store)
+  __device__ __forceinline__ Fm L(int i) const { return Fm(bb_to_mont(__ldg(trace + (u64)i * N + row))); }
+  __device__ __forceinline__ Fm P(int i) const { return Fm(bb_to_mont(__ldg(pub + (u64)i * N + row))); }
+  __device__ __forceinline__ Fm K(u32 k) const { return Fm(bb_to_mont_c(k)); }
+  __device__ __forceinline__ Xm z() const { Xm r; r.v = lc[0]; return r; }
+  __device__ __forceinline__ Xm th(int k) const { Xm r; r.v = lc[k]; return r; }
+  __device__ __forceinline__ Xm xf(Fm a) const { Xm r; r.v = e4_from_base(a.v); return r; }
+  __device__ __forceinline__ void store_upto(int k) {   // helpers cur_k .. k-1 are complete: cur, then zeros
+    for (; cur_k < k; cur_k++) {
+#pragma unroll
+      for (int q = 0; q < 4; q++) aux[(u64)(4 * cur_k + q) * N + row] = bb_from_mont(cur.c[q]);
+      tot = e4_add(tot, cur);
+      cur = e4_zero();
+    }
+  }
+  __device__ __forceinline__ void frac(int j, Fm n, Xm d) {
+    const int helper_of[ZKIR_AIR_NUM_FRACTIONS] = ZKIR_AIR_FRAC_HELPER_INIT;
+    const int k = helper_of[j];   // j is a literal in the generated code
+    if (k != ZKIR_AIR_NUM_HELPERS) store_upto(k);
+    if (n.v == 0) return;         // lookup switched off on this row, table row never hit: no inversion
+    const E4 v = e4_mulb(e4_inv_call(d.v), n.v);
+    if (k == ZKIR_AIR_NUM_HELPERS) tot = e4_add(tot, v); else cur = e4_add(cur, v);
+  }
+};
+#else
 struct FracCtxDev {
   typedef Fm F; typedef Xm X;
   const u32 *trace, *pub; u64 N, row;
@@ -28,6 +64,7 @@ struct FracCtxDev {
   __device__ __forceinline__ Xm xf(Fm a) const { Xm r; r.v = e4_from_base(a.v); return r; }
   __device__ __forceinline__ void frac(int j, Fm n, Xm d) { num[j] = n.v; den[j] = d.v; }
 };
+#endif
 
 #define AUX_ROWS_THREADS 128
 __global__ void __launch_bounds__(AUX_ROWS_THREADS) ZKIR_PF(aux_rows_kernel)(AuxArgs a) {
@@ -44,6 +81,12 @@ __global__ void __launch_bounds__(AUX_ROWS_THREADS) ZKIR_PF(aux_rows_kernel)(Aux
   if (i >= N) return;
   FracCtxDev c;
   c.trace = a.trace; c.pub = a.pub; c.N = N; c.row = i; c.lc = lc;
+#ifdef ZKIR_PROFILE_FULL
+  c.aux = a.aux; c.cur = e4_zero(); c.tot = e4_zero(); c.cur_k = 0;
+  zkir_air_fractions(c);
+  c.store_upto(ZKIR_AIR_NUM_HELPERS);
+  a.row_tot[i] = c.tot;
+#else
   zkir_air_fractions(c);
   const int helper_of[ZKIR_AIR_NUM_FRACTIONS] = ZKIR_AIR_FRAC_HELPER_INIT;
   E4 h[ZKIR_AIR_NUM_HELPERS + 1];   // the helpers, then the fractions the running sum adds itself
@@ -62,6 +105,7 @@ __global__ void __launch_bounds__(AUX_ROWS_THREADS) ZKIR_PF(aux_rows_kernel)(Aux
     tot = e4_add(tot, h[k]);
   }
   a.row_tot[i] = tot;
+#endif
 }
 
 // ---- exclusive prefix sum of row_tot (ext4 = 4 independent sums mod p)

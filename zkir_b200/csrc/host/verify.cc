@@ -160,6 +160,7 @@ struct AirAtZeta {  // air_generated.h context over ext4: base and ext values ar
     X4 e1, e2, e3; e1.c[1] = 1; e2.c[2] = 1; e3.c[3] = 1;
     return a + e1 * b + e2 * c + e3 * d;
   }
+  void fence() const {}
   void emit(int, const X4& v) { acc = acc * alpha + v; }  // Horner: sum_i alpha^(K-1-i) c_i
   void emit_x(int, const X4& v) { acc = acc * alpha + v; }
 };

@@ -36,6 +36,9 @@ struct QCtx {
   __device__ __forceinline__ Xm xf(Fm a) const { Xm r; r.v = e4_from_base(a.v); return r; }
   __device__ __forceinline__ Xm sio() const { Xm r; r.v = lc[ZKIR_AIR_NUM_THETA + 1]; return r; }
   __device__ __forceinline__ Xm x4(Fm a, Fm b, Fm c, Fm d) const { Xm r; r.v.c[0] = a.v; r.v.c[1] = b.v; r.v.c[2] = c.v; r.v.c[3] = d.v; return r; }
+  // Full profile only: the constraint list is ~38 000 straight-line instructions (600 KB of code, far beyond the instruction cache).
+  // The block re-converges at every fence, so its warps walk the code together and one instruction fetch serves all of them.
+  __device__ __forceinline__ void fence() const { __syncthreads(); }
   __device__ __forceinline__ void emit(int idx, Fm v) {
     acc4_mac(acc, apow[idx], v.v);
     if (idx & 1) acc4_fix(acc);  // idx is a literal in the generated code: at most two products between fixes
@@ -52,8 +55,13 @@ __global__ void ZKIR_PF(alpha_powers_kernel)(const u32* alpha, E4* apow) {  // a
   apow[i] = r;
 }
 
+#ifdef ZKIR_PROFILE_FULL
+#define QUOTIENT_THREADS 256
+#else
+#define QUOTIENT_THREADS 128
+#endif
 template <int MINB>
-__global__ void __launch_bounds__(128, MINB) ZKIR_PF(quotient_kernel)(QuotientArgs a, const E4* apow_g, u32 g_inv, u32 g, u32 snn /* shift^N */, u32 wb /* w_B */) {
+__global__ void __launch_bounds__(QUOTIENT_THREADS, MINB) ZKIR_PF(quotient_kernel)(QuotientArgs a, const E4* apow_g, u32 g_inv, u32 g, u32 snn /* shift^N */, u32 wb /* w_B */) {
   __shared__ E4 apow[ZKIR_AIR_NUM_CONSTRAINTS];
   __shared__ E4 lc[ZKIR_AIR_NUM_THETA + 2];
   __shared__ u32 pv[ZKIR_AIR_NUM_PUBLIC];
@@ -77,7 +85,7 @@ __global__ void __launch_bounds__(128, MINB) ZKIR_PF(quotient_kernel)(QuotientAr
   const u64 M = 1ull << (a.log_n + a.log_blowup), N = 1ull << a.log_n;
   const u64 t = blockIdx.x * (u64)blockDim.x + threadIdx.x;  // memory row: coset z = i / N, point j = i % N, natural index j*B + z
   const u32 log_nj = a.seg_log_nj == 0xffffffffu ? a.log_n : a.seg_log_nj;
-  if (t >= (1ull << (log_nj + a.log_blowup))) return;
+  if (t >= (1ull << (log_nj + a.log_blowup))) return;   // never inside a block: the row count is a power of two >= 2^11
   const u64 z = t >> log_nj, j = a.seg_j0 + (t & ((1ull << log_nj) - 1));
   const u64 i = (z << a.log_n) | j;
   QCtx c;
@@ -131,13 +139,20 @@ int ZKIR_PF(launch_quotient)(const QuotientArgs& a, cudaStream_t st, u64* launch
   // AIR v2 (169 constraints, ext4 LogUp terms): 168 registers / 3 CTAs per SM measured fastest: 1.05 / 1.09 / 1.14 ms for variants 3 / 0 / 1 at 2^20 rows
   if (variant < 0) { const char* e = getenv("ZKIR_QUOTIENT_VARIANT"); variant = e ? atoi(e) : 3; }
   const u64 n_threads = a.seg_log_nj == 0xffffffffu ? M : (1ull << (a.seg_log_nj + a.log_blowup));
-  const unsigned grid = (unsigned)((n_threads + 127) / 128);
+  const unsigned grid = (unsigned)((n_threads + QUOTIENT_THREADS - 1) / QUOTIENT_THREADS);
   const E4* ap = reinterpret_cast<const E4*>(a.apow_scratch);
   const u32 m_ginv = bb_to_mont_c(g_inv), m_g = bb_to_mont_c(g), m_snn = bb_to_mont_c(snn), m_wb = bb_to_mont_c(wb);
-  if (variant == 3) ZKIR_PF(quotient_kernel)<3><<<grid, 128, 0, st>>>(a, ap, m_ginv, m_g, m_snn, m_wb);
-  else if (variant == 1) ZKIR_PF(quotient_kernel)<6><<<grid, 128, 0, st>>>(a, ap, m_ginv, m_g, m_snn, m_wb);
-  else if (variant == 2) ZKIR_PF(quotient_kernel)<8><<<grid, 128, 0, st>>>(a, ap, m_ginv, m_g, m_snn, m_wb);
-  else ZKIR_PF(quotient_kernel)<4><<<grid, 128, 0, st>>>(a, ap, m_ginv, m_g, m_snn, m_wb);
+#ifdef ZKIR_PROFILE_FULL
+  // full profile: 256-thread blocks (see QCtx::fence); variants = resident blocks per SM (registers per thread 255 / 128 / 80)
+  if (variant == 3) ZKIR_PF(quotient_kernel)<1><<<grid, QUOTIENT_THREADS, 0, st>>>(a, ap, m_ginv, m_g, m_snn, m_wb);
+  else if (variant == 1) ZKIR_PF(quotient_kernel)<3><<<grid, QUOTIENT_THREADS, 0, st>>>(a, ap, m_ginv, m_g, m_snn, m_wb);
+  else ZKIR_PF(quotient_kernel)<2><<<grid, QUOTIENT_THREADS, 0, st>>>(a, ap, m_ginv, m_g, m_snn, m_wb);
+#else
+  if (variant == 3) ZKIR_PF(quotient_kernel)<3><<<grid, QUOTIENT_THREADS, 0, st>>>(a, ap, m_ginv, m_g, m_snn, m_wb);
+  else if (variant == 1) ZKIR_PF(quotient_kernel)<6><<<grid, QUOTIENT_THREADS, 0, st>>>(a, ap, m_ginv, m_g, m_snn, m_wb);
+  else if (variant == 2) ZKIR_PF(quotient_kernel)<8><<<grid, QUOTIENT_THREADS, 0, st>>>(a, ap, m_ginv, m_g, m_snn, m_wb);
+  else ZKIR_PF(quotient_kernel)<4><<<grid, QUOTIENT_THREADS, 0, st>>>(a, ap, m_ginv, m_g, m_snn, m_wb);
+#endif
   (*launches) += 2;
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
