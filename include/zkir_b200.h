@@ -80,7 +80,9 @@ int zkir_b200_prove_device(zkir_ctx*, const zkir_params*, const uint32_t* d_trac
  * recommended).  The converter (trace.rs:41) runs on the device, so 140 B/row cross PCIe instead of 340 B/row.
  * final_regs / final_pc: machine state after the last instruction; exit_code: HaltReason::Exit code (0 otherwise).
  * halt_kind: ZKIR_HALT_* of the run.  Writes the 5 public values {entry_pc, num_cycles, exit_lo, exit_hi, halted} it proves to
- * public_values_out.  Rows the AIR v2 cannot constrain give ZKIR_ERR_AIR (same rules as zkir_pack_trace). */
+ * public_values_out.  Rows the AIR v2 cannot constrain give ZKIR_ERR_AIR (same rules as zkir_pack_trace).
+ * params.width = ZKIR_AIR_FULL_WIDTH (a program that needs the full profile: zkir_program_profile): the wide table is built by the host
+ * packer (zkir_pack_rows_full: the memory argument replays the run's memory in order) and copied to the device; the proof is the same path. */
 int zkir_b200_prove_rows(zkir_ctx*, const zkir_params*, const uint64_t* pcs, const uint32_t* instrs, const uint64_t* regs,
                          uint64_t n_rows, const uint64_t* final_regs, uint64_t final_pc, uint32_t entry_point, uint64_t exit_code,
                          int halt_kind, uint32_t log_n, uint32_t* public_values_out, uint8_t** proof, size_t* proof_len);
@@ -252,6 +254,13 @@ const uint64_t* zkir_vm_final_regs(const zkir_vm_result*);
 uint32_t zkir_pack_min_log_n(const zkir_vm_result*);
 int zkir_pack_trace(const zkir_vm_result*, uint32_t entry_point, uint32_t log_n, uint32_t* cols, uint32_t* public_values);      /* core: 88 columns */
 int zkir_pack_trace_full(const zkir_vm_result*, uint32_t entry_point, uint32_t log_n, uint32_t* cols, uint32_t* public_values); /* full: ZKIR_AIR_FULL_WIDTH columns */
+/* the same from plain arrays (what an upstream `ExecutionResult.execution_trace` holds, vm.rs:54-78; arguments as zkir_b200_prove_rows) */
+int zkir_pack_rows(const uint64_t* pcs, const uint32_t* instrs, const uint64_t* regs, uint64_t n_rows, const uint64_t* final_regs, uint64_t final_pc,
+                   const uint32_t* code, size_t n_code, uint32_t entry_point, uint64_t exit_code, int halt_kind, uint32_t log_n, uint32_t* cols,
+                   uint32_t* public_values);
+int zkir_pack_rows_full(const uint64_t* pcs, const uint32_t* instrs, const uint64_t* regs, uint64_t n_rows, const uint64_t* final_regs,
+                        uint64_t final_pc, const uint32_t* code, size_t n_code, uint32_t entry_point, uint64_t exit_code, int halt_kind,
+                        uint32_t log_n, uint32_t* cols, uint32_t* public_values);
 /* which AIR profile a program needs (execute.rs:35-673 by opcode, zkir-spec/src/opcode.rs:24-144): 1 = core, 0 = full,
  * -1 = it contains an undefined opcode.  The ROM is public: prover and verifier agree. */
 int zkir_program_profile(const uint32_t* code, size_t n_code);

@@ -101,6 +101,8 @@ SYMBOLS = {
     "zkir_pack_min_log_n": (C.c_uint32, [vp]),
     "zkir_pack_trace": (C.c_int, [vp, C.c_uint32, C.c_uint32, vp, u32p]),
     "zkir_pack_trace_full": (C.c_int, [vp, C.c_uint32, C.c_uint32, vp, u32p]),
+    "zkir_pack_rows": (C.c_int, [vp, vp, vp, C.c_uint64, u64p, C.c_uint64, vp, C.c_size_t, C.c_uint32, C.c_uint64, C.c_int, C.c_uint32, vp, u32p]),
+    "zkir_pack_rows_full": (C.c_int, [vp, vp, vp, C.c_uint64, u64p, C.c_uint64, vp, C.c_size_t, C.c_uint32, C.c_uint64, C.c_int, C.c_uint32, vp, u32p]),
     "zkir_program_profile": (C.c_int, [vp, C.c_size_t]),
     "zkir_public_row": (None, [C.c_uint32, C.c_uint64, vp, C.c_size_t, u32p]),
     "zkir_public_rows": (C.c_uint64, [C.c_uint32, C.c_size_t]),

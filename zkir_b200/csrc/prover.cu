@@ -115,6 +115,7 @@ struct zkir_ctx {
   u32* ntt_tmp = nullptr; u64 ntt_tmp_words = 0;
   u32* scratch[2] = {nullptr, nullptr}; size_t scratch_bytes[2] = {0, 0};
   void* rows_dev = nullptr; size_t rows_bytes = 0;   // staging for raw interpreter rows (prove_rows)
+  u32* full_stage = nullptr; size_t full_stage_bytes = 0;   // pinned host staging of a full-profile table packed on the host (prove_rows)
   // zkir_b200_prove_program: pinned write log the interpreter records into, and the stream its chunks are uploaded on
   void* log_pinned = nullptr; u64 log_capacity = 0;
   cudaStream_t copy_stream = nullptr; cudaEvent_t copy_done = nullptr;
@@ -785,6 +786,7 @@ void zkir_b200_destroy(zkir_ctx* ctx) {
   if (ctx->ntt_tmp) cudaFree(ctx->ntt_tmp);
   for (int i = 0; i < 2; i++) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
   if (ctx->rows_dev) cudaFree(ctx->rows_dev);
+  if (ctx->full_stage) cudaFreeHost(ctx->full_stage);
   if (ctx->d_io) cudaFree(ctx->d_io);
   if (ctx->log_pinned) cudaFreeHost(ctx->log_pinned);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
@@ -929,6 +931,7 @@ static int expand_rows(zkir_ctx* ctx, const uint64_t* pcs, const uint32_t* instr
   const size_t need = T * (8 + 4 + 128) + 64;
   if (ctx->rows_bytes < need) {
     if (ctx->rows_dev) cudaFree(ctx->rows_dev);
+  if (ctx->full_stage) cudaFreeHost(ctx->full_stage);
     ctx->rows_dev = nullptr; ctx->rows_bytes = 0;
     CU(cudaMalloc(&ctx->rows_dev, need));
     ctx->rows_bytes = need;
@@ -962,6 +965,24 @@ int zkir_b200_prove_rows(zkir_ctx* ctx, const zkir_params* p, const uint64_t* pc
   if ((rc = ensure_public_columns(ctx, p, log_n)) != 0) return rc;
   ctx->ws.graph_run = false;   // only zkir_b200_prove replays graphs; a stale flag would hide this proof's stage timings
   CU(cudaEventRecord(ctx->ev[ZKIR_STAGE_H2D], ctx->stream));
+  if (profile_is_full(p->width)) {
+    // full profile: the wide table is built on the host (the memory argument replays the run's memory in order: host/pack.cc), staged in
+    // pinned memory and copied to the device; from there on the proof is the same CUDA path
+    const size_t bytes = (size_t)p->width << log_n << 2;
+    if (ctx->full_stage_bytes < bytes) {
+      if (ctx->full_stage) cudaFreeHost(ctx->full_stage);
+      ctx->full_stage = nullptr; ctx->full_stage_bytes = 0;
+      CU(cudaMallocHost(&ctx->full_stage, bytes));
+      ctx->full_stage_bytes = bytes;
+    }
+    rc = zkir_pack_rows_full(pcs, instrs, regs, n_rows, final_regs, final_pc, ctx->code.data(), ctx->code.size(), entry_point, exit_code, halt_kind, log_n,
+                             ctx->full_stage, pv_out);
+    if (rc) { ctx->err = zkir_b200_last_error(nullptr); return rc; }
+    CU(cudaMemcpyAsync(ctx->ws.trace, ctx->full_stage, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_err, 0xff, 16, ctx->stream));
+    if ((rc = prove_resident(ctx, p, log_n, pv_out, ctx->ws.trace)) != 0) return rc;
+    return finish_proof(ctx, p, log_n, proof, proof_len);
+  }
   u32 c_lo, c_hi;
   trace_col_range(ctx, p, log_n, &c_lo, &c_hi);   // a sharded proof only materialises the columns this rank transforms
   if ((rc = expand_rows(ctx, pcs, instrs, regs, n_rows, final_regs, final_pc, log_n, ctx->ws.trace, c_lo, c_hi)) != 0) return rc;
@@ -977,6 +998,7 @@ static int wl_stage(zkir_ctx* ctx, u64 Tc, u64 n_scan_rows, WlStage* o) {
   const size_t need = Tc * 16 + scratch + 64;
   if (ctx->rows_bytes < need) {
     if (ctx->rows_dev) cudaFree(ctx->rows_dev);
+  if (ctx->full_stage) cudaFreeHost(ctx->full_stage);
     ctx->rows_dev = nullptr; ctx->rows_bytes = 0;
     CU(cudaMalloc(&ctx->rows_dev, need));
     ctx->rows_bytes = need;

@@ -60,8 +60,8 @@ __global__ void ZKIR_PF(alpha_powers_kernel)(const u32* alpha, E4* apow) {  // a
 #else
 #define QUOTIENT_THREADS 128
 #endif
-template <int MINB>
-__global__ void __launch_bounds__(QUOTIENT_THREADS, MINB) ZKIR_PF(quotient_kernel)(QuotientArgs a, const E4* apow_g, u32 g_inv, u32 g, u32 snn /* shift^N */, u32 wb /* w_B */) {
+template <int MINB, int THREADS = QUOTIENT_THREADS>
+__global__ void __launch_bounds__(THREADS, MINB) ZKIR_PF(quotient_kernel)(QuotientArgs a, const E4* apow_g, u32 g_inv, u32 g, u32 snn /* shift^N */, u32 wb /* w_B */) {
   __shared__ E4 apow[ZKIR_AIR_NUM_CONSTRAINTS];
   __shared__ E4 lc[ZKIR_AIR_NUM_THETA + 2];
   __shared__ u32 pv[ZKIR_AIR_NUM_PUBLIC];
@@ -143,10 +143,16 @@ int ZKIR_PF(launch_quotient)(const QuotientArgs& a, cudaStream_t st, u64* launch
   const E4* ap = reinterpret_cast<const E4*>(a.apow_scratch);
   const u32 m_ginv = bb_to_mont_c(g_inv), m_g = bb_to_mont_c(g), m_snn = bb_to_mont_c(snn), m_wb = bb_to_mont_c(wb);
 #ifdef ZKIR_PROFILE_FULL
-  // full profile: 256-thread blocks (see QCtx::fence); variants = resident blocks per SM (registers per thread 255 / 128 / 80)
-  if (variant == 3) ZKIR_PF(quotient_kernel)<1><<<grid, QUOTIENT_THREADS, 0, st>>>(a, ap, m_ginv, m_g, m_snn, m_wb);
-  else if (variant == 1) ZKIR_PF(quotient_kernel)<3><<<grid, QUOTIENT_THREADS, 0, st>>>(a, ap, m_ginv, m_g, m_snn, m_wb);
-  else ZKIR_PF(quotient_kernel)<2><<<grid, QUOTIENT_THREADS, 0, st>>>(a, ap, m_ginv, m_g, m_snn, m_wb);
+  // full profile: blocks that re-converge at every fence (see QCtx::fence).  Measured at 2^18 rows (2^19 LDE rows), 256-thread blocks:
+  // 1 / 2 / 3 resident blocks per SM (255 / 128 / 80 registers) = 3.56 / 2.16 / 1.88 ms: occupancy wins over spills
+  auto launch = [&](auto kernel, unsigned threads) { kernel<<<(unsigned)(n_threads / threads), threads, 0, st>>>(a, ap, m_ginv, m_g, m_snn, m_wb); };
+  if (variant == 0) launch(ZKIR_PF(quotient_kernel)<2, 256>, 256);
+  else if (variant == 1) launch(ZKIR_PF(quotient_kernel)<1, 256>, 256);
+  else if (variant == 2) launch(ZKIR_PF(quotient_kernel)<4, 256>, 256);
+  else if (variant == 4) launch(ZKIR_PF(quotient_kernel)<1, 512>, 512);
+  else if (variant == 5) launch(ZKIR_PF(quotient_kernel)<1, 1024>, 1024);
+  else if (variant == 6) launch(ZKIR_PF(quotient_kernel)<2, 512>, 512);
+  else launch(ZKIR_PF(quotient_kernel)<3, 256>, 256);
 #else
   if (variant == 3) ZKIR_PF(quotient_kernel)<3><<<grid, QUOTIENT_THREADS, 0, st>>>(a, ap, m_ginv, m_g, m_snn, m_wb);
   else if (variant == 1) ZKIR_PF(quotient_kernel)<6><<<grid, QUOTIENT_THREADS, 0, st>>>(a, ap, m_ginv, m_g, m_snn, m_wb);

@@ -415,17 +415,20 @@ class Context:
             self._l.zkir_b200_free_proof(out[i])
         return res
 
-    def prove_rows(self, rows, cfg, log_n=None):
-        """rows: dict as returned by ExecutionResult.rows() (arrays may live in PinnedBuffers).  The device runs the
-        converter; returns (proof bytes, public values)."""
+    def prove_rows(self, rows, cfg, log_n=None, profile=None):
+        """rows: dict as returned by ExecutionResult.rows() (arrays may live in PinnedBuffers).  Core profile: the device runs the
+        converter; full profile (`profile="full"`, or None = what the rows' program needs): the library packs the wide table on the host.
+        Returns (proof bytes, public values)."""
         if rows.get("program") is not None:
             self.set_program(rows["program"])
+            if profile is None:
+                profile = program_profile(rows["program"])
         if rows.get("io") is not None:
             self.set_io(rows["io"])
-        params = cfg.params()
+        params = cfg.params(profile_width(profile))
         n = int(rows["pcs"].shape[0])
         if log_n is None:
-            log_n = max(MIN_LOG_N, (n - 1).bit_length())
+            log_n = max(MIN_LOG_N, n.bit_length(), (len(getattr(rows.get("program"), "code", ())) - 1).bit_length())   # one padding row, the ROM
         pcs, ins, regs = (np.ascontiguousarray(rows[k]) for k in ("pcs", "instrs", "regs"))
         assert pcs.dtype == np.uint64 and ins.dtype == np.uint32 and regs.dtype == np.uint64 and regs.shape == (n, 16)
         fr = np.ascontiguousarray(rows["final_regs"], dtype=np.uint64)
@@ -568,10 +571,9 @@ def prove(program, inputs=(), cfg=None):
         # full-ISA programs: the interpreter records full rows, the host packer builds the wide table (the device converter and the
         # write-log path serve the core profile), the proof itself is the same CUDA path
         res = VM(program, list(inputs), VMConfig(max_cycles=cfg.max_cycles, enable_execution_trace=True, enable_poseidon2_syscall=cfg.enable_poseidon2_syscall)).run()
-        cols, pv = res.pack(profile="full")
-        ctx.set_io(res.io)
-        pb = ctx.prove_columns(cols, pv, cfg, program=program)
-        return Proof(pb, pv, int(cols.shape[1]).bit_length() - 1, res.cycles, res.outputs, ctx.stage_ms(), program, res.io)
+        log_n = res.min_log_n()
+        pb, pv = ctx.prove_rows(res.rows(), cfg, log_n, profile="full")   # zkir_b200_prove_rows with the full width
+        return Proof(pb, pv, log_n, res.cycles, res.outputs, ctx.stage_ms(), program, res.io)
     pb, pv, cycles, log_n = ctx.prove_program(program, list(inputs), cfg)
     # the statement's public I/O transcript and outputs: one plain interpreter run without any recording (323 M cycles/s)
     res = VM(program, list(inputs), VMConfig(max_cycles=cfg.max_cycles, enable_poseidon2_syscall=cfg.enable_poseidon2_syscall)).run()
