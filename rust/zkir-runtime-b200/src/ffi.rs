@@ -19,6 +19,8 @@ pub struct zkir_params {
 
 pub const ZKIR_OK: c_int = 0;
 pub const ZKIR_AIR_V2_WIDTH: u32 = 88;
+/// trace width of the full AIR profile (all 50 opcodes: docs/PROVER_SPEC.md sections 3.6-3.8); include/zkir_b200.h ZKIR_AIR_FULL_WIDTH
+pub const ZKIR_AIR_FULL_WIDTH: u32 = 248;
 pub const ZKIR_AIR_V2_NUM_PUBLIC: u32 = 5; // entry_pc, num_cycles, exit_lo, exit_hi, halted
 pub const ZKIR_MIN_LOG_N: u32 = 10;
 pub const ZKIR_HALT_EXIT: c_int = 0;
@@ -103,6 +105,8 @@ extern "C" {
     pub fn zkir_b200_comm_unique_id(id: *mut u8 /* [128] */) -> c_int;
     pub fn zkir_b200_comm_init(ctx: *mut zkir_ctx, id: *const u8 /* [128] */, rank: c_int, world: c_int) -> c_int;
     pub fn zkir_b200_comm_shutdown(ctx: *mut zkir_ctx) -> c_int;
+    /// which AIR profile a program needs: 1 = core (88 columns), 0 = full (ZKIR_AIR_FULL_WIDTH), -1 = undefined opcode
+    pub fn zkir_program_profile(code: *const u32, n_code: usize) -> c_int;
     pub fn zkir_b200_free_proof(p: *mut u8);
     pub fn zkir_b200_verify(
         params: *const zkir_params, proof: *const u8, len: usize, public_values: *const u32, code: *const u32, n_code: usize,

@@ -11,8 +11,8 @@ use std::ffi::CStr;
 use std::os::raw::c_int;
 use std::ptr;
 
-use zkir_runtime::{HaltReason, RuntimeError, VMConfig, VM};
-use zkir_spec::Program;
+use zkir_runtime::{ExecutionResult, HaltReason, RuntimeError, VMConfig, VM};
+use zkir_spec::{Program, TraceRow};
 
 /// Proving parameters (Plonky3's FriConfig fields; docs/PROVER_SPEC.md section 4).
 #[derive(Clone, Copy, Debug)]
@@ -33,11 +33,16 @@ impl Default for ProverConfig {
 
 impl ProverConfig {
     fn params(&self) -> ffi::zkir_params {
+        self.params_for(ffi::ZKIR_AIR_V2_WIDTH)
+    }
+
+    /// `width` selects the AIR profile of the proof: ZKIR_AIR_V2_WIDTH (core, 18 opcodes) or ZKIR_AIR_FULL_WIDTH (all 50)
+    fn params_for(&self, width: u32) -> ffi::zkir_params {
         ffi::zkir_params {
             log_blowup: self.log_blowup,
             num_queries: self.num_queries,
             pow_bits: self.pow_bits,
-            width: ffi::ZKIR_AIR_V2_WIDTH,
+            width,
             num_public: ffi::ZKIR_AIR_V2_NUM_PUBLIC,
         }
     }
@@ -168,6 +173,43 @@ impl Prover {
     }
 }
 
+impl Prover {
+    /// Full-profile programs (MUL / DIV, bitwise, shifts, signed compares, loads / stores): the rows `VM::run` records with
+    /// `enable_execution_trace` (zkir-spec/src/trace.rs:24-50) go in as three flat arrays; the library builds the 248-column table
+    /// (zkir_pack_rows_full: multiplier block, lookup multiplicities, offline memory checking) and proves it on the GPU.
+    #[allow(clippy::too_many_arguments)]
+    pub fn prove_rows_full(
+        &mut self,
+        cfg: &ProverConfig,
+        rows: &[TraceRow],
+        final_regs: &[u64; 16],
+        final_pc: u64,
+        entry_point: u32,
+        exit_code: u64,
+        halt_kind: c_int,
+        log_n: u32,
+    ) -> Result<(Vec<u8>, [u32; 5]), RuntimeError> {
+        let params = cfg.params_for(ffi::ZKIR_AIR_FULL_WIDTH);
+        let pcs: Vec<u64> = rows.iter().map(|r| r.pc).collect();
+        let instrs: Vec<u32> = rows.iter().map(|r| r.instruction).collect();
+        let regs: Vec<u64> = rows.iter().flat_map(|r| r.registers.iter().copied()).collect();
+        let mut pv = [0u32; 5];
+        let (mut proof, mut len) = (ptr::null_mut::<u8>(), 0usize);
+        let rc = unsafe {
+            ffi::zkir_b200_prove_rows(
+                self.ctx, &params, pcs.as_ptr(), instrs.as_ptr(), regs.as_ptr(), rows.len() as u64, final_regs.as_ptr(), final_pc,
+                entry_point, exit_code, halt_kind, log_n, pv.as_mut_ptr(), &mut proof, &mut len,
+            )
+        };
+        if rc != ffi::ZKIR_OK {
+            return Err(error_of(self.ctx, rc));
+        }
+        let bytes = unsafe { std::slice::from_raw_parts(proof, len) }.to_vec();
+        unsafe { ffi::zkir_b200_free_proof(proof) };
+        Ok((bytes, pv))
+    }
+}
+
 /// The recorder the interpreter writes into while it executes: three page-locked arrays, one entry per cycle.
 /// Upstream hook: `VMState::write_reg` stores `cur = (reg << 56) | value`; the cycle loop of `VM::run` (vm.rs:234-312) calls
 /// `begin(pc, word)` before and `commit()` after executing an instruction, and sets `final_pc` where the VM halts.
@@ -220,6 +262,9 @@ pub fn prove(program: &Program, inputs: &[u64], cfg: &ProverConfig) -> Result<Pr
         HaltReason::Ebreak => (0, ffi::ZKIR_HALT_EBREAK),
         _ => (0, ffi::ZKIR_HALT_CYCLE_LIMIT),
     };
+    if unsafe { ffi::zkir_program_profile(program.code.as_ptr(), program.code.len()) } == 0 {
+        return prove_full(program, inputs, cfg); // the program leaves the 18 core opcodes: full AIR profile
+    }
     let rows = (log.len + 1).max(program.code.len()).max(1 << ffi::ZKIR_MIN_LOG_N); // range table, ROM and one padding row fit the trace
     let log_n = rows.next_power_of_two().trailing_zeros();
     let mut prover = Prover::new(cfg.device)?;
@@ -229,9 +274,52 @@ pub fn prove(program: &Program, inputs: &[u64], cfg: &ProverConfig) -> Result<Pr
     Ok(Proof { bytes, public_values, log_n, cycles: result.cycles, outputs: result.outputs.clone(), io_events: log.io_events.clone() })
 }
 
+/// Full-profile flavour of `prove`: the interpreter records `Vec<TraceRow>` (`enable_execution_trace`), the library packs and proves.
+/// Needs the machine state after the last instruction, which `ExecutionResult` does not carry upstream (vm.rs:54-78): two fields
+/// (`final_regs`, `final_pc`) filled where `VM::run` builds the result (vm.rs:349-357).
+fn prove_full(program: &Program, inputs: &[u64], cfg: &ProverConfig) -> Result<Proof, RuntimeError> {
+    let vm_cfg = VMConfig { max_cycles: cfg.max_cycles, enable_execution_trace: true, ..VMConfig::default() };
+    let result = VM::new(program.clone(), inputs.to_vec(), vm_cfg).run()?;
+    let (exit_code, halt_kind) = match result.halt_reason {
+        HaltReason::Exit(code) => (code, ffi::ZKIR_HALT_EXIT),
+        HaltReason::Ebreak => (0, ffi::ZKIR_HALT_EBREAK),
+        _ => (0, ffi::ZKIR_HALT_CYCLE_LIMIT),
+    };
+    let n = result.execution_trace.len();
+    let log_n = (n + 1).max(program.code.len()).max(1 << ffi::ZKIR_MIN_LOG_N).next_power_of_two().trailing_zeros();
+    let io_events = io_events_of(&result); // (cycle, kind, lo20, hi20) per READ / WRITE ecall, from the rows (r10 selects the syscall)
+    let mut prover = Prover::new(cfg.device)?;
+    prover.set_program(&program.code)?;
+    prover.set_io(&io_events)?;
+    let (bytes, public_values) = prover.prove_rows_full(
+        cfg, &result.execution_trace, &result.final_regs, result.final_pc, program.header.entry_point, exit_code, halt_kind, log_n,
+    )?;
+    Ok(Proof { bytes, public_values, log_n, cycles: result.cycles, outputs: result.outputs.clone(), io_events })
+}
+
+/// The public I/O transcript of a recorded run: an ECALL row with r10 = 1 (READ: the value is the next row's r10) or 2 (WRITE: r11).
+fn io_events_of(result: &ExecutionResult) -> Vec<[u32; 4]> {
+    let rows = &result.execution_trace;
+    let mut out = Vec::new();
+    for (i, r) in rows.iter().enumerate() {
+        if r.instruction & 0x7F != 0x50 {
+            continue;
+        }
+        let v = match r.registers[10] {
+            1 => rows.get(i + 1).map(|n| n.registers[10]).unwrap_or(result.final_regs[10]),
+            2 => r.registers[11],
+            _ => continue,
+        };
+        out.push([i as u32, (r.registers[10] == 2) as u32, (v & 0xF_FFFF) as u32, ((v >> 20) & 0xF_FFFF) as u32]);
+    }
+    out
+}
+
 /// CPU verifier (no GPU needed): accepts or rejects `proof` as a statement about `program` for these parameters and public values.
+/// The AIR profile is read from the proof header (word 3 = trace width).
 pub fn verify(proof: &Proof, program: &Program, cfg: &ProverConfig) -> bool {
-    let params = cfg.params();
+    let width = proof.bytes.get(12..16).map(|b| u32::from_le_bytes([b[0], b[1], b[2], b[3]])).unwrap_or(ffi::ZKIR_AIR_V2_WIDTH);
+    let params = cfg.params_for(width);
     let rc = unsafe {
         ffi::zkir_b200_verify(
             &params, proof.bytes.as_ptr(), proof.bytes.len(), proof.public_values.as_ptr(), program.code.as_ptr(), program.code.len(),
