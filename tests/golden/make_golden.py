@@ -26,5 +26,14 @@ pb = o.prove(cfg, cols, pv, res)
 gold["fib30_trace_sha256"] = hashlib.sha256(cols.tobytes()).hexdigest()
 gold["fib30_proof_sha256"] = hashlib.sha256(pb).hexdigest()
 gold["fib30_proof_len"] = len(pb)
+# full AIR profile (docs/PROVER_SPEC.md 3.6-3.8): the mix workload (multiplier, shifts, bitwise, signed compare, 8-byte stores / loads), 40 iterations
+from zkir_b200.workloads import mix_program  # noqa: E402
+from zkir_b200.runtime import FULL_WIDTH  # noqa: E402
+rf = zkir_b200.VM(mix_program(), [40], zkir_b200.VMConfig(enable_execution_trace=True)).run()
+cf, pvf = rf.pack()
+pbf = Oracle(width=FULL_WIDTH).prove(cfg, cf, pvf, rf)
+gold["mix40_full_trace_sha256"] = hashlib.sha256(cf.tobytes()).hexdigest()
+gold["mix40_full_proof_sha256"] = hashlib.sha256(pbf).hexdigest()
+gold["mix40_full_proof_len"] = len(pbf)
 json.dump(gold, open(os.path.join(ROOT, "tests", "golden", "golden.json"), "w"), indent=1)
 print("wrote golden.json", gold["fib30_proof_sha256"])

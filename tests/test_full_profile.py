@@ -326,3 +326,44 @@ def test_gpu_memory_programs_equal_oracle(gpu_ctx, oracle_full):
         pb = gpu_ctx.prove_columns(cols, pv, cfg, program=res)
         assert pb == oracle_full.prove(cfg, cols, pv, res)
         assert zkir_b200.verify(pb, cfg, pv, res) == (True, "")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shards,min_seg", [(2, 2), (8, 2), (4, 0)])
+def test_gpu_full_profile_emulated_shards_give_single_gpu_bytes(gpu_ctx, shards, min_seg):
+    """the sharded code path (segment hashing, column / row / plane partitions: tests/test_gpu_sharded.py) takes the widths at run time"""
+    res = zkir_b200.VM(mix_program(), [180], zkir_b200.VMConfig(enable_execution_trace=True)).run()   # 3971 cycles -> 2^12 rows
+    cols, pv = res.pack()
+    cfg = zkir_b200.ProverConfig(num_queries=24, pow_bits=6)
+    gpu_ctx.set_io(res.io)
+    want = gpu_ctx.prove_columns(cols, pv, cfg, program=res)
+    ctx = zkir_b200.Context(0)
+    try:
+        ctx.emulate_shards(shards, min_seg)
+        ctx.set_io(res.io)
+        got = ctx.prove_columns(cols, pv, cfg, program=res)
+    finally:
+        ctx.close()
+    assert got == want
+
+
+def test_full_profile_golden_proof_digest(oracle_full):
+    """Pins the full-profile generator, packer and oracle against drift (tests/golden/make_golden.py; self-generated: SURVEY.md 8c)."""
+    import hashlib, json, os
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "golden.json")))
+    res = zkir_b200.VM(mix_program(), [40], zkir_b200.VMConfig(enable_execution_trace=True)).run()
+    cols, pv = res.pack()
+    pb = oracle_full.prove(zkir_b200.ProverConfig(num_queries=20, pow_bits=8), cols, pv, res)
+    assert hashlib.sha256(cols.tobytes()).hexdigest() == gold["mix40_full_trace_sha256"]
+    assert hashlib.sha256(pb).hexdigest() == gold["mix40_full_proof_sha256"] and len(pb) == gold["mix40_full_proof_len"]
+
+
+@pytest.mark.gpu
+def test_gpu_full_profile_golden_proof_digest(gpu_ctx):
+    import hashlib, json, os
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "golden.json")))
+    res = zkir_b200.VM(mix_program(), [40], zkir_b200.VMConfig(enable_execution_trace=True)).run()
+    cols, pv = res.pack()
+    gpu_ctx.set_io(res.io)
+    pb = gpu_ctx.prove_columns(cols, pv, zkir_b200.ProverConfig(num_queries=20, pow_bits=8), program=res)
+    assert hashlib.sha256(pb).hexdigest() == gold["mix40_full_proof_sha256"]
