@@ -313,6 +313,96 @@ BB_HD u32 expand_row_v2(u64 i, u64 T, const u64 (&rg)[16], u64 pc, u32 w, u64 re
   return err;
 }
 
+#ifdef ZKIR_PROFILE_FULL
+// ---- full profile: the memory cells of a load / store row and the lookup multiplicities of a row, shared by the host packer and the
+// device converter like the row function above (docs/PROVER_SPEC.md sections 3.7, 3.8)
+struct MemAccess { bool is_ld, is_st; u32 op, width, off; u64 ea; };
+// is `w` a load / store?  its width and effective address rs1 + sign-extended offset (execute.rs:478)
+BB_HD bool mem_decode(u32 w, const u64 (&rg)[16], MemAccess& m) {
+  m.op = w & 0x7F;
+  m.is_ld = m.op >= 0x30 && m.op <= 0x35; m.is_st = m.op >= 0x38 && m.op <= 0x3B;
+  if (!m.is_ld && !m.is_st) return false;
+  const u32 ldw = m.op - 0x30, stw = m.op - 0x38;
+  m.width = m.is_ld ? (ldw < 2 ? 1u : ldw < 4 ? 2u : ldw == 4 ? 4u : 8u) : (1u << stw);
+  const u32 base = m.is_ld ? (w >> 11) & 15 : (w >> 7) & 15;
+  u64 bv = 0;
+#pragma unroll
+  for (int j = 1; j < 16; j++) if (base == (u32)j) bv = rg[j];
+  m.ea = bv + (u64)(long long)pack_sext((w >> 15) & 0x1FFFF, 17);
+  m.off = (u32)(m.ea & 7);
+  return true;
+}
+// cells of the memory row `i`: the word before (old_word, little endian; prev_ts = timestamp of its last access, 0 = initial) and after
+// the access, offset one-hot, register-side bytes, timestamp distance.  *loaded = the value a load returns, *new_word = the word afterwards.
+template <class Wr>
+BB_HD u32 expand_mem_cells(u64 i, u32 w, const u64 (&rg)[16], const MemAccess& m, u64 old_word, u64 prev_ts, Wr& W, u64* loaded, u64* new_word) {
+  u32 err = PACK_OK;
+  if (m.ea >> 30) err = PACK_ERR_MEMADDR;
+#pragma unroll
+  for (int k = 0; k < 8; k++) W(ZKIR_COL_OFF0 + k, m.off == (u32)k);
+  W(ZKIR_COL_MW, (u32)((m.ea & 1023) >> 3));
+  u64 gval = 0, nw = old_word;
+  if (m.is_ld) {
+    const u64 sh = old_word >> (8 * m.off);
+    gval = m.width == 8 ? sh : sh & ((1ull << (8 * m.width)) - 1);
+    if ((m.op == 0x30 && (gval & 0x80)) || (m.op == 0x32 && (gval & 0x8000))) err = PACK_ERR_MEMSIGN;   // lb / lh of a negative value
+    if (gval >> 40) err = PACK_ERR_REG40;
+  } else {
+    const u32 srcr = (w >> 11) & 15;
+#pragma unroll
+    for (int j = 1; j < 16; j++) if (srcr == (u32)j) gval = rg[j];
+    if (gval >> 40) err = PACK_ERR_REG40;
+    const u64 mask = m.width == 8 ? ~0ull : ((1ull << (8 * m.width)) - 1) << (8 * m.off);
+    nw = (old_word & ~mask) | ((gval << (8 * m.off)) & mask);   // the low `width` bytes of rs2 (bytes 5..7 of an SD are zero: gval < 2^40)
+  }
+#pragma unroll
+  for (int k = 0; k < 8; k++) { W(ZKIR_COL_OB0 + k, (u32)((old_word >> (8 * k)) & 255)); W(ZKIR_COL_NB0 + k, (u32)((nw >> (8 * k)) & 255)); }
+#pragma unroll
+  for (int k = 0; k < 5; k++) W(ZKIR_COL_GB0 + k, (u32)((gval >> (8 * k)) & 255));
+  W(ZKIR_COL_NIB_LO, (u32)((gval >> 16) & 15)); W(ZKIR_COL_NIB_HI, (u32)((gval >> 20) & 15));
+  W(ZKIR_COL_PREV_TS, (u32)(prev_ts % BB_P));
+  const u64 dist = i - prev_ts;   // clk - prev_ts (prev_ts = clk' + 1 of the previous access, or 0)
+#pragma unroll
+  for (int k = 0; k < 3; k++) W(ZKIR_COL_TD0 + k, (u32)((dist >> (10 * k)) & 1023));
+  *loaded = gval; *new_word = nw;
+  return err;
+}
+// LogUp multiplicities a live row adds to the tables (tools/gen_air.py: fractions), from its opcode and its own cells:
+// cell(column) -> value, add(table, index).  The range lookups of ch0..3 (row_range_checked) and the ROM row are the callers'.
+enum MultTable : int { MT_RNG = 0, MT_AND, MT_POW, MT_B8, MT_B4, MT_B7 };
+template <class Cell, class Add>
+BB_HD void full_row_multiplicities(u32 w, Cell cell, Add add) {
+  const u32 op = w & 0x7F;
+  const bool mulf = op == 0x02 || op == 0x03, divf = op >= 0x04 && op <= 0x07, shf = op >= 0x18 && op <= 0x1D, cmps = op == 0x22 || op == 0x23 || op == 0x42 || op == 0x43;
+  const bool bitf = op >= 0x10 && op <= 0x15, sraf = op == 0x1A || op == 0x1D, right = shf && (op - 0x18) % 3 != 0;
+  const bool mul_on = mulf || divf || shf, is_ld = op >= 0x30 && op <= 0x35, is_st = op >= 0x38 && op <= 0x3B;
+  if (mul_on || cmps || bitf) for (int k = 0; k < 4; k++) { add(MT_RNG, cell(ZKIR_COL_X0 + k)); add(MT_RNG, cell(ZKIR_COL_Y0 + k)); }
+  if (divf || shf) for (int k = 0; k < 4; k++) add(MT_RNG, cell(ZKIR_COL_R0 + k));
+  if (mul_on) {
+    for (int k = 0; k < 8; k++) add(MT_RNG, cell(ZKIR_COL_P0 + k));
+    for (int k = 0; k < 5; k++) { add(MT_RNG, cell(ZKIR_COL_K0_LO + k)); add(MT_RNG, cell(ZKIR_COL_K0_HI + k)); }
+  }
+  if (cmps || sraf) add(MT_RNG, 2 * (cell(ZKIR_COL_X0 + 3) - 512 * cell(ZKIR_COL_SIGN_A)));
+  if (cmps) add(MT_RNG, 2 * (cell(ZKIR_COL_Y0 + 3) - 512 * cell(ZKIR_COL_SIGN_B)));
+  if (shf) {
+    add(MT_RNG, cell(ZKIR_COL_SH_W)); add(MT_RNG, 64 * cell(ZKIR_COL_SH_W));
+    add(MT_POW, (right ? 64u : 0u) + cell(ZKIR_COL_SHAMT));
+  }
+  if (bitf) for (int k = 0; k < 4; k++) {
+    add(MT_AND, cell(ZKIR_COL_XL0 + k) + 32 * cell(ZKIR_COL_YL0 + k));
+    add(MT_AND, cell(ZKIR_COL_XH0 + k) + 32 * cell(ZKIR_COL_YH0 + k));
+  }
+  if (is_ld || is_st) {
+    if (is_st) for (int k = 0; k < 5; k++) add(MT_B8, cell(ZKIR_COL_GB0 + k));
+    add(MT_B4, cell(ZKIR_COL_NIB_LO)); add(MT_B4, cell(ZKIR_COL_NIB_HI));
+    add(MT_B7, cell(ZKIR_COL_MW));
+    if (op == 0x30) add(MT_B7, cell(ZKIR_COL_GB0));
+    if (op == 0x32) add(MT_B7, cell(ZKIR_COL_GB0 + 1));
+    for (int k = 0; k < 3; k++) add(MT_RNG, cell(ZKIR_COL_TD0 + k));
+  }
+}
+#endif  // ZKIR_PROFILE_FULL
+
 // does this row's chunk quadruple go to the range table?  (tools/gen_air.py: rc_on)
 BB_HD bool row_range_checked(u32 w, u64 r10) {
   const u32 op = w & 0x7F;
