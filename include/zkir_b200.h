@@ -81,8 +81,9 @@ int zkir_b200_prove_device(zkir_ctx*, const zkir_params*, const uint32_t* d_trac
  * final_regs / final_pc: machine state after the last instruction; exit_code: HaltReason::Exit code (0 otherwise).
  * halt_kind: ZKIR_HALT_* of the run.  Writes the 5 public values {entry_pc, num_cycles, exit_lo, exit_hi, halted} it proves to
  * public_values_out.  Rows the AIR v2 cannot constrain give ZKIR_ERR_AIR (same rules as zkir_pack_trace).
- * params.width = ZKIR_AIR_FULL_WIDTH (a program that needs the full profile: zkir_program_profile): the wide table is built by the host
- * packer (zkir_pack_rows_full: the memory argument replays the run's memory in order) and copied to the device; the proof is the same path. */
+ * params.width = ZKIR_AIR_FULL_WIDTH (a program that needs the full profile: zkir_program_profile): the host replays the run's memory in
+ * program order (12 B per row more over PCIe: the word and the previous timestamp each load / store sees), the device expands the
+ * 248-column table; the proof is the same path. */
 int zkir_b200_prove_rows(zkir_ctx*, const zkir_params*, const uint64_t* pcs, const uint32_t* instrs, const uint64_t* regs,
                          uint64_t n_rows, const uint64_t* final_regs, uint64_t final_pc, uint32_t entry_point, uint64_t exit_code,
                          int halt_kind, uint32_t log_n, uint32_t* public_values_out, uint8_t** proof, size_t* proof_len);
@@ -105,6 +106,10 @@ int zkir_b200_expand_writelog(zkir_ctx*, const uint32_t* pcs, const uint32_t* in
 /* the device converter alone (parity tests): rows -> d_cols [width][1 << log_n] canonical, device memory */
 int zkir_b200_expand_rows(zkir_ctx*, const uint64_t* pcs, const uint32_t* instrs, const uint64_t* regs, uint64_t n_rows,
                           const uint64_t* final_regs, uint64_t final_pc, uint32_t log_n, uint32_t* d_cols);
+/* ... and of the full profile: d_cols [ZKIR_AIR_FULL_WIDTH][1 << log_n]; the host replays the run's memory (which word and previous
+ * timestamp every load / store sees), the device expands the rows; bit-identical to zkir_pack_rows_full */
+int zkir_b200_expand_rows_full(zkir_ctx*, const uint64_t* pcs, const uint32_t* instrs, const uint64_t* regs, uint64_t n_rows,
+                               const uint64_t* final_regs, uint64_t final_pc, uint32_t log_n, uint32_t* d_cols);
 /* many independent small proofs of the context's program (BASELINE config 4); traces[i] is host memory [width][1<<log_ns[i]],
  * ios[i] / n_ios[i] the public I/O transcript of execution i */
 int zkir_b200_prove_batch(zkir_ctx*, const zkir_params*, const uint32_t* const* traces, const uint32_t* log_ns,

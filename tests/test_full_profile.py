@@ -367,3 +367,42 @@ def test_gpu_full_profile_golden_proof_digest(gpu_ctx):
     gpu_ctx.set_io(res.io)
     pb = gpu_ctx.prove_columns(cols, pv, zkir_b200.ProverConfig(num_queries=20, pow_bits=8), program=res)
     assert hashlib.sha256(pb).hexdigest() == gold["mix40_full_proof_sha256"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("which", ["mem", "ops", "mix", "many_stores"])
+def test_gpu_full_profile_device_converter_equals_host_packer(gpu_ctx, which):
+    """zkir_b200_expand_rows_full (host memory replay + device row expansion, csrc/trace_expand.cu) == zkir_pack_trace_full, column for column"""
+    if which == "mem":
+        res = run(MEM_SRC)
+    elif which == "ops":
+        res = run(two_operand_program(list(OPS)), [0xABCDE12345, 0x8000000025])
+    elif which == "mix":
+        res = zkir_b200.VM(mix_program(), [700], zkir_b200.VMConfig(enable_execution_trace=True)).run()    # 2^14 rows
+    else:
+        res = run("addi r1, zero, 0x1000\naddi r2, zero, 1\n" + "".join(f"sw r2, {4 * i}(r1)\naddi r2, r2, 1\n" for i in range(100)) + "addi t2, zero, 0\naddi a0, zero, 0\necall\n")
+    want, pv = res.pack()
+    log_n = int(want.shape[1]).bit_length() - 1
+    d = gpu_ctx.alloc(want.nbytes)
+    try:
+        gpu_ctx.expand_rows(res.rows(), log_n, d, profile="full")
+        got = gpu_ctx.to_host(d, want.shape)
+    finally:
+        gpu_ctx.free(d)
+    bad = np.nonzero((got != want).any(axis=1))[0]
+    assert bad.size == 0, [air_layout_full.COLUMNS[c] for c in bad[:10]]
+
+
+@pytest.mark.gpu
+def test_gpu_full_profile_prove_rows_errors(gpu_ctx):
+    cfg = zkir_b200.ProverConfig(num_queries=8, pow_bits=2)
+    # a negative lb leaves the 40-bit register model: refused by the replay, like the host packer
+    res = run("addi r1, r0, 0x2000\naddi r2, r0, 200\nsb r2, 0(r1)\nlb r3, 0(r1)\nebreak")
+    with pytest.raises(zkir_b200.RuntimeError) as e:
+        gpu_ctx.prove_rows(res.rows(), cfg, profile="full")
+    assert e.value.code == -6 and "lb / lh" in str(e.value)
+    # an immediate shift amount above 63: refused by the device converter
+    res = run("addi r1, r0, 3\nslli r2, r1, 64\nebreak")
+    with pytest.raises(zkir_b200.RuntimeError) as e:
+        gpu_ctx.prove_rows(res.rows(), cfg, profile="full")
+    assert e.value.code == -6 and "shift amount" in str(e.value)

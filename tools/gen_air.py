@@ -964,7 +964,9 @@ def main():
         f.write("COLUMNS = " + repr(COLS) + "\n")
         f.write("INDEX = {n: i for i, n in enumerate(COLUMNS)}\n")
     print(f"AIR {'full' if FULL else 'core'}: width={WIDTH} aux={AUX_WIDTH} pub={PUB_WIDTH} constraints={g.idx} fractions={NUM_FRACTIONS}")
-    return dict(width=WIDTH, aux=AUX_WIDTH, pub=PUB_WIDTH, constraints=g.idx, fractions=NUM_FRACTIONS, theta=NUM_THETA)
+    named = {n: i for i, n in enumerate(COLS)}
+    return dict(width=WIDTH, aux=AUX_WIDTH, pub=PUB_WIDTH, constraints=g.idx, fractions=NUM_FRACTIONS, theta=NUM_THETA,
+                cols={k: named[k] for k in ("img_fin0", "ram_fin_ts", "m_b7") if k in named})
 
 
 def write_profiles(core, full):
@@ -973,6 +975,10 @@ def write_profiles(core, full):
     for name, d in (("CORE", core), ("FULL", full)):
         for k in ("width", "aux", "pub", "constraints", "theta"):
             out.append(f"#define ZKIR_PROFILE_{name}_{k.upper()} {d[k]}")
+    # the boundary cells of the memory argument are one contiguous column range (img_fin0 .. ram_fin_ts): the prover uploads them as a block
+    out.append(f"#define ZKIR_PROFILE_FULL_COL_BOUNDARY0 {full['cols']['img_fin0']}")
+    out.append(f"#define ZKIR_PROFILE_FULL_BOUNDARY_COLS {full['cols']['ram_fin_ts'] - full['cols']['img_fin0'] + 1}")
+    out.append(f"#define ZKIR_PROFILE_FULL_COL_M_B7 {full['cols']['m_b7']}")
     out.append(f"#define ZKIR_PROFILE_MAX_CONSTRAINTS {max(core['constraints'], full['constraints'])}")
     out.append(f"#define ZKIR_PROFILE_MAX_AUX {max(core['aux'], full['aux'])}")
     out.append(f"#define ZKIR_PROFILE_MAX_PUB {max(core['pub'], full['pub'])}")

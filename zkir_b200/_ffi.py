@@ -35,6 +35,7 @@ SYMBOLS = {
     "zkir_b200_prove_rows": (C.c_int, [vp, C.POINTER(Params), vp, vp, vp, C.c_uint64, u64p, C.c_uint64, C.c_uint32, C.c_uint64, C.c_int, C.c_uint32, u32p,
                                       C.POINTER(vp), C.POINTER(C.c_size_t)]),
     "zkir_b200_expand_rows": (C.c_int, [vp, vp, vp, vp, C.c_uint64, u64p, C.c_uint64, C.c_uint32, vp]),
+    "zkir_b200_expand_rows_full": (C.c_int, [vp, vp, vp, vp, C.c_uint64, u64p, C.c_uint64, C.c_uint32, vp]),
     "zkir_b200_prove_writelog": (C.c_int, [vp, C.POINTER(Params), vp, vp, vp, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint64, C.c_int, C.c_uint32, u32p,
                                           C.POINTER(vp), C.POINTER(C.c_size_t)]),
     "zkir_b200_prove_program": (C.c_int, [vp, C.POINTER(Params), vp, C.c_size_t, vp, C.c_size_t, C.c_uint32, vp, C.c_size_t, C.c_uint64, u32p,

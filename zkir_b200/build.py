@@ -40,7 +40,7 @@ def _headers_mtime():
 
 
 # translation units that instantiate the generated AIR: compiled once per profile (csrc/air_profile.h)
-PER_PROFILE = ("quotient.cu", "aux_gen.cu", "pack.cc", "verify.cc")
+PER_PROFILE = ("quotient.cu", "aux_gen.cu", "trace_expand.cu", "pack.cc", "verify.cc")
 
 
 def _compile(job, hdr_m, verbose):

@@ -103,6 +103,17 @@ struct ExpandArgs {
   u32 n_code = 0;        // program length: rows whose pc is outside [0x1000, 0x1000 + 4 n_code) are errors
 };
 int launch_trace_expand(const ExpandArgs& a, cudaStream_t st, u64* launches);
+// full profile (trace_expand.cu compiled with ZKIR_PROFILE_FULL): the same rows plus, for every load / store row, the aligned 8-byte word
+// before the access and the timestamp of its previous access (from the host's replay of the run's memory: host/pack.cc zkir_mem_replay_full).
+// Writes every per-row column of the full table and the histogram columns; the boundary cells of the memory argument (final values of
+// image / RAM words: a few rows) are uploaded by the caller afterwards.
+struct ExpandFullArgs {
+  ExpandArgs rows;
+  const u64* old_word;   // [T] little-endian word before the access (memory rows only)
+  const u32* prev_ts;    // [T]
+};
+int launch_trace_expand_full(const ExpandFullArgs& a, cudaStream_t st, u64* launches);
+int launch_add_u32(u32* dst, const u32* src, u64 n, cudaStream_t st, u64* launches);   // dst[i] += src[i]
 struct WlArgs {          // register write log instead of full rows (trace_expand.cu)
   const u32* pcs;        // [T]
   const u32* ins;        // [T]

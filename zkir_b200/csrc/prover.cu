@@ -952,6 +952,83 @@ static int expand_rows(zkir_ctx* ctx, const uint64_t* pcs, const uint32_t* instr
   RC(launch_trace_expand(ea, st, &ctx->launches));
   return 0;
 }
+// full profile: rows + host memory replay -> device converter (trace_expand.cu, full build) + boundary cells of the memory argument
+extern "C" int zkir_mem_replay_full(const uint32_t*, const uint64_t*, uint64_t, const uint64_t*, const uint32_t*, size_t, uint64_t*, uint32_t*, uint64_t*, uint64_t*);
+extern "C" int zkir_mem_boundary_full(uint32_t, uint32_t*, uint64_t, uint32_t*, uint32_t*);
+static const u32 MEM_BOUNDARY_COL0 = ZKIR_PROFILE_FULL_COL_BOUNDARY0, MEM_BOUNDARY_COLS = ZKIR_PROFILE_FULL_BOUNDARY_COLS;   // img_fin0 .. ram_fin_ts of the full table
+static int expand_rows_full(zkir_ctx* ctx, const uint32_t* instrs, const uint64_t* pcs, const uint64_t* regs, uint64_t T, const uint64_t* final_regs,
+                            uint64_t final_pc, uint32_t log_n, u32* d_cols) {
+  const u64 N = 1ull << log_n;
+  if (T >= N || !pcs || !instrs || !regs || !final_regs) { ctx->err = "bad rows: need n_rows < 2^log_n (the last row is a padding row) and non-null arrays"; return ZKIR_ERR_ARG; }
+  // pinned staging: old_word[T] | prev_ts[T] | multiplicity deltas [1024 + 128] | boundary columns [25][bstride]
+  auto stage = [&](size_t bytes) -> int {
+    if (ctx->full_stage_bytes < bytes) {
+      if (ctx->full_stage) cudaFreeHost(ctx->full_stage);
+      ctx->full_stage = nullptr; ctx->full_stage_bytes = 0;
+      CU(cudaMallocHost(&ctx->full_stage, bytes));
+      ctx->full_stage_bytes = bytes;
+    }
+    return 0;
+  };
+  const size_t fixed = T * 12 + 64 + (1024 + 128) * 4;
+  RC(stage(fixed + (size_t)MEM_BOUNDARY_COLS * 4096 * 4));
+  char* hb = (char*)ctx->full_stage;
+  u64* h_old = (u64*)hb;
+  u32* h_pts = (u32*)(hb + T * 8);
+  memset(hb, 0, T * 12);
+  u64 n_img = 0, n_ram = 0;
+  int rc = zkir_mem_replay_full(instrs, regs, T, final_regs, ctx->code.data(), ctx->code.size(), h_old, h_pts, &n_img, &n_ram);
+  if (rc) { ctx->err = zkir_b200_last_error(nullptr); return rc; }
+  const u64 bstride = std::max<u64>(std::max(n_img, n_ram), 1);
+  if (bstride > 4096) {   // grow the staging, keep what the replay wrote
+    std::vector<char> keep(hb, hb + T * 12);
+    RC(stage(fixed + (size_t)MEM_BOUNDARY_COLS * bstride * 4));
+    hb = (char*)ctx->full_stage; h_old = (u64*)hb; h_pts = (u32*)(hb + T * 8);
+    memcpy(hb, keep.data(), keep.size());
+  }
+  u32* h_delta = (u32*)(hb + ((T * 12 + 63) & ~(size_t)63));
+  u32* h_bcols = h_delta + 1024 + 128;
+  memset(h_bcols, 0, (size_t)MEM_BOUNDARY_COLS * bstride * 4);
+  rc = zkir_mem_boundary_full(log_n, h_bcols, bstride, h_delta, h_delta + 1024);
+  if (rc) { ctx->err = zkir_b200_last_error(nullptr); return rc; }
+  // device staging: regs | pcs | ins | old_word | prev_ts | deltas
+  const size_t need = T * (128 + 8 + 4 + 8 + 4) + 64 + (1024 + 128) * 4 + 64;
+  if (ctx->rows_bytes < need) {
+    if (ctx->rows_dev) cudaFree(ctx->rows_dev);
+    ctx->rows_dev = nullptr; ctx->rows_bytes = 0;
+    CU(cudaMalloc(&ctx->rows_dev, need));
+    ctx->rows_bytes = need;
+  }
+  char* base = (char*)ctx->rows_dev;
+  u64* d_regs = (u64*)base;
+  u64* d_pcs = (u64*)(base + T * 128);
+  u64* d_old = (u64*)(base + T * 136);
+  u32* d_ins = (u32*)(base + T * 144);
+  u32* d_pts = (u32*)(base + T * 148);
+  u32* d_delta = (u32*)(base + ((T * 152 + 63) & ~(size_t)63));
+  cudaStream_t st = ctx->stream;
+  CU(cudaMemcpyAsync(d_regs, regs, T * 128, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d_pcs, pcs, T * 8, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d_ins, instrs, T * 4, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d_old, h_old, T * 8, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d_pts, h_pts, T * 4, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d_delta, h_delta, (1024 + 128) * 4, cudaMemcpyHostToDevice, st));
+  CU(cudaMemsetAsync(ctx->d_err, 0xff, 16, st));
+  ExpandFullArgs fa;
+  fa.rows.pcs = d_pcs; fa.rows.ins = d_ins; fa.rows.regs = d_regs; fa.rows.T = T; fa.rows.N = N;
+  for (int k = 0; k < 16; k++) fa.rows.final_regs[k] = final_regs[k];
+  fa.rows.final_pc = final_pc; fa.rows.cols = d_cols; fa.rows.err = ctx->d_err; fa.rows.n_code = (u32)ctx->code.size();
+  fa.old_word = d_old; fa.prev_ts = d_pts;
+  RC(launch_trace_expand_full(fa, st, &ctx->launches));
+  // boundary cells: the first n_img rows of the image columns, the first n_ram rows of the RAM columns (the kernel zeroed them)
+  for (u32 c = 0; c < MEM_BOUNDARY_COLS; c++) {
+    const u64 n = c < 9 ? n_img : n_ram;   // img_fin0..7, img_fin_ts (9 columns) | ram_on, ram_a0..2, ram_e0..2, ram_fin0..7, ram_fin_ts (16)
+    if (n) CU(cudaMemcpyAsync(d_cols + (u64)(MEM_BOUNDARY_COL0 + c) * N, h_bcols + (size_t)c * bstride, n * 4, cudaMemcpyHostToDevice, st));
+  }
+  RC(launch_add_u32(d_cols + (u64)ZKIR_COL_M_RNG * N, d_delta, 1024, st, &ctx->launches));
+  RC(launch_add_u32(d_cols + (u64)ZKIR_PROFILE_FULL_COL_M_B7 * N, d_delta + 1024, 128, st, &ctx->launches));
+  return 0;
+}
 int zkir_b200_prove_rows(zkir_ctx* ctx, const zkir_params* p, const uint64_t* pcs, const uint32_t* instrs, const uint64_t* regs,
                          uint64_t n_rows, const uint64_t* final_regs, uint64_t final_pc, uint32_t entry_point, uint64_t exit_code,
                          int halt_kind, uint32_t log_n, uint32_t* pv_out, uint8_t** proof, size_t* proof_len) {
@@ -966,20 +1043,10 @@ int zkir_b200_prove_rows(zkir_ctx* ctx, const zkir_params* p, const uint64_t* pc
   ctx->ws.graph_run = false;   // only zkir_b200_prove replays graphs; a stale flag would hide this proof's stage timings
   CU(cudaEventRecord(ctx->ev[ZKIR_STAGE_H2D], ctx->stream));
   if (profile_is_full(p->width)) {
-    // full profile: the wide table is built on the host (the memory argument replays the run's memory in order: host/pack.cc), staged in
-    // pinned memory and copied to the device; from there on the proof is the same CUDA path
-    const size_t bytes = (size_t)p->width << log_n << 2;
-    if (ctx->full_stage_bytes < bytes) {
-      if (ctx->full_stage) cudaFreeHost(ctx->full_stage);
-      ctx->full_stage = nullptr; ctx->full_stage_bytes = 0;
-      CU(cudaMallocHost(&ctx->full_stage, bytes));
-      ctx->full_stage_bytes = bytes;
-    }
-    rc = zkir_pack_rows_full(pcs, instrs, regs, n_rows, final_regs, final_pc, ctx->code.data(), ctx->code.size(), entry_point, exit_code, halt_kind, log_n,
-                             ctx->full_stage, pv_out);
-    if (rc) { ctx->err = zkir_b200_last_error(nullptr); return rc; }
-    CU(cudaMemcpyAsync(ctx->ws.trace, ctx->full_stage, bytes, cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaMemsetAsync(ctx->d_err, 0xff, 16, ctx->stream));
+    // full profile: the host only replays the run's memory in program order (the one sequential step: which word and which previous
+    // timestamp every load / store sees); the 248-column table is expanded on the device from the rows, like the core converter
+    if ((rc = expand_rows_full(ctx, instrs, pcs, regs, n_rows, final_regs, final_pc, log_n, ctx->ws.trace)) != 0) return rc;
+    fill_public_values(pv_out, entry_point, n_rows, exit_code, halt_kind);
     if ((rc = prove_resident(ctx, p, log_n, pv_out, ctx->ws.trace)) != 0) return rc;
     return finish_proof(ctx, p, log_n, proof, proof_len);
   }
@@ -1163,6 +1230,18 @@ int zkir_b200_expand_rows(zkir_ctx* ctx, const uint64_t* pcs, const uint32_t* in
   ctx->err.clear();
   cudaSetDevice(ctx->device);
   int rc = expand_rows(ctx, pcs, instrs, regs, n_rows, final_regs, final_pc, log_n, d_cols);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(ctx->h_err, ctx->d_err, 16, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return expand_error(ctx);
+}
+
+int zkir_b200_expand_rows_full(zkir_ctx* ctx, const uint64_t* pcs, const uint32_t* instrs, const uint64_t* regs, uint64_t n_rows,
+                               const uint64_t* final_regs, uint64_t final_pc, uint32_t log_n, uint32_t* d_cols) {
+  if (!ctx || !d_cols || log_n < ZKIR_RANGE_BITS || log_n > 26) return ZKIR_ERR_ARG;
+  ctx->err.clear();
+  cudaSetDevice(ctx->device);
+  int rc = expand_rows_full(ctx, instrs, pcs, regs, n_rows, final_regs, final_pc, log_n, d_cols);
   if (rc) return rc;
   CU(cudaMemcpyAsync(ctx->h_err, ctx->d_err, 16, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));

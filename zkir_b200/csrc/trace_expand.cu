@@ -15,6 +15,93 @@
 
 namespace zkir {
 
+#ifdef ZKIR_PROFILE_FULL
+// ---- full profile (docs/PROVER_SPEC.md 3.6-3.8): one thread per row writes all 248 columns.  The per-row functions are air_pack.h's
+// (shared with the host packer, bit-identical); the six lookup multiplicity columns are per-block shared-memory histograms flushed with
+// atomics.  Bound: HBM writes (992 B/row).
+struct FullWriter {
+  u32* col; u64 N;
+  __device__ __forceinline__ void operator()(int c, u32 v) { col[(u64)c * N] = v; }
+};
+#define FH_RNG 0
+#define FH_AND 1024
+#define FH_POW 2048
+#define FH_B8 2176
+#define FH_B4 2432
+#define FH_B7 2448
+#define FH_SIZE 2576
+__global__ void __launch_bounds__(128) trace_expand_full_kernel(ExpandFullArgs fa) {
+  __shared__ u32 hist[FH_SIZE];
+  const ExpandArgs& a = fa.rows;
+  for (u32 k = threadIdx.x; k < FH_SIZE; k += blockDim.x) hist[k] = 0;
+  __syncthreads();
+  const u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x;
+  if (i < a.N) {
+    const bool live = i < a.T;
+    u64 rg[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) rg[k] = live ? a.regs[16 * i + k] : a.final_regs[k];
+    const u64 pc = live ? a.pcs[i] : a.final_pc;
+    const u32 w = live ? a.ins[i] : 0u;
+    u64 read_val = (i + 1 < a.T) ? a.regs[16 * (i + 1) + 10] : a.final_regs[10];   // READ rows: post-state r10
+    FullWriter W = {a.cols + i, a.N};
+    u32 err = PACK_OK;
+    MemAccess ma;
+    if (live && mem_decode(w, rg, ma)) {
+      u64 loaded, new_word;
+      err = expand_mem_cells(i, w, rg, ma, fa.old_word[i], (u64)fa.prev_ts[i], W, &loaded, &new_word);
+      if (ma.is_ld) read_val = loaded;
+    }
+    const u32 rerr = expand_row_v2(i, a.T, rg, pc, w, read_val, W);
+    if (!err) err = rerr;
+    const u32 slot = (u32)((pc - 0x1000) >> 2);
+    const bool in_rom = live && pc >= 0x1000 && !(pc & 3) && slot < a.n_code;
+    if (live && !in_rom && !err) err = PACK_ERR_ROM;
+    const unsigned active = __activemask();
+    const unsigned peers = __match_any_sync(active, in_rom ? slot : 0xffffffffu);
+    if (in_rom && (u32)(__ffs(peers) - 1) == (threadIdx.x & 31)) atomicAdd(a.cols + (u64)ZKIR_COL_M_ROM * a.N + slot, (u32)__popc(peers));
+    if (live && !err) {
+      const u32* mine = a.cols + i;   // this thread's own stores above: visible to itself
+      auto cell = [&](int c) { return mine[(u64)c * a.N]; };
+      if (row_range_checked(w, rg[10])) for (int k = 0; k < 4; k++) atomicAdd(&hist[FH_RNG + (cell(ZKIR_COL_CH0 + k) & 1023u)], 1u);
+      full_row_multiplicities(w, cell, [&](int t, u32 v) {
+        const u32 base = t == MT_RNG ? FH_RNG : t == MT_AND ? FH_AND : t == MT_POW ? FH_POW : t == MT_B8 ? FH_B8 : t == MT_B4 ? FH_B4 : FH_B7;
+        const u32 mask = t == MT_RNG || t == MT_AND ? 1023u : t == MT_POW || t == MT_B7 ? 127u : t == MT_B8 ? 255u : 15u;
+        atomicAdd(&hist[base + (v & mask)], 1u);   // a value outside its table fails the lookup balance later; the mask only keeps the bin in range
+      });
+    }
+    if (err) atomicMin(reinterpret_cast<unsigned long long*>(a.err), (unsigned long long)((i << 8) | err));
+  }
+  __syncthreads();
+  const int tcol[6] = {ZKIR_COL_M_RNG, ZKIR_COL_M_AND, ZKIR_COL_M_POW, ZKIR_COL_M_B8, ZKIR_COL_M_B4, ZKIR_COL_M_B7};
+  const u32 tbase[7] = {FH_RNG, FH_AND, FH_POW, FH_B8, FH_B4, FH_B7, FH_SIZE};
+  for (u32 k = threadIdx.x; k < FH_SIZE; k += blockDim.x) {
+    const u32 v = hist[k];
+    if (!v) continue;
+    int t = 0;
+    while (k >= tbase[t + 1]) t++;
+    atomicAdd(a.cols + (u64)tcol[t] * a.N + (k - tbase[t]), v);
+  }
+}
+__global__ void add_u32_kernel(u32* dst, const u32* __restrict__ src, u64 n) {
+  const u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x;
+  if (i < n && src[i]) dst[i] += src[i];
+}
+int launch_add_u32(u32* dst, const u32* src, u64 n, cudaStream_t st, u64* launches) {
+  add_u32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dst, src, n);
+  (*launches)++;
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+int launch_trace_expand_full(const ExpandFullArgs& fa, cudaStream_t st, u64* launches) {
+  const ExpandArgs& a = fa.rows;
+  // columns no row writes in full (histograms, memory cells of non-memory rows, boundary cells, padding columns): zero first
+  if (cudaMemsetAsync(a.cols + (u64)ZKIR_COL_M_RNG * a.N, 0, 2 * a.N * sizeof(u32), st) != cudaSuccess) return -2;
+  if (cudaMemsetAsync(a.cols + (u64)ZKIR_COL_M_AND * a.N, 0, (u64)(ZKIR_COL_COUNT - ZKIR_COL_M_AND) * a.N * sizeof(u32), st) != cudaSuccess) return -2;
+  trace_expand_full_kernel<<<(unsigned)((a.N + 127) / 128), 128, 0, st>>>(fa);
+  (*launches)++;
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+#else   // core profile
 struct ColWriter {
   u32* col; u64 N; u32 lo, hi;
   u32 ch[4];   // the four chunk values of the row, kept for the range histogram
@@ -186,5 +273,7 @@ int launch_trace_expand_wl(const WlArgs& a, cudaStream_t st, u64* launches) {
   (*launches) += 3;
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
+
+#endif  // ZKIR_PROFILE_FULL
 
 }  // namespace zkir

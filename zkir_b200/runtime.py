@@ -490,13 +490,14 @@ class Context:
         pcs, ins, wlog = (np.ascontiguousarray(wl[k]) for k in ("pcs", "instrs", "wlog"))
         self._check(self._l.zkir_b200_expand_writelog(self._h, pcs.ctypes.data, ins.ctypes.data, wlog.ctypes.data, n, int(wl["final_pc"]), log_n, d_cols))
 
-    def expand_rows(self, rows, log_n, d_cols):
+    def expand_rows(self, rows, log_n, d_cols, profile="core"):
         if rows.get("program") is not None:
             self.set_program(rows["program"])
         n = int(rows["pcs"].shape[0])
         pcs, ins, regs = (np.ascontiguousarray(rows[k]) for k in ("pcs", "instrs", "regs"))
         fr = np.ascontiguousarray(rows["final_regs"], dtype=np.uint64)
-        self._check(self._l.zkir_b200_expand_rows(self._h, pcs.ctypes.data, ins.ctypes.data, regs.ctypes.data, n, fr.ctypes.data_as(_ffi.u64p),
+        fn = self._l.zkir_b200_expand_rows_full if profile == "full" else self._l.zkir_b200_expand_rows
+        self._check(fn(self._h, pcs.ctypes.data, ins.ctypes.data, regs.ctypes.data, n, fr.ctypes.data_as(_ffi.u64p),
                                                   int(rows["final_pc"]), log_n, d_cols))
 
     # -- per-kernel entry points (device pointers)
