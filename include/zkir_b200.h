@@ -97,7 +97,9 @@ int zkir_b200_prove_writelog(zkir_ctx*, const zkir_params*, const uint32_t* pcs,
                              uint32_t* public_values_out, uint8_t** proof, size_t* proof_len);
 /* Program -> Proof in one call, the drop-in for `zkir_runtime::prove(program, inputs)` (absent upstream: lib.rs:29-62): runs the
  * interpreter (vm.cc) with the register write log recorded straight into pinned memory, uploads the log in chunks WHILE the
- * interpreter is still running, then proves.  Sets the context's program itself.  out_cycles / out_log_n may be NULL. */
+ * interpreter is still running, then proves.  Sets the context's program itself.  out_cycles / out_log_n may be NULL.
+ * params.width selects the profile the program needs (zkir_program_profile); with ZKIR_AIR_FULL_WIDTH the interpreter records full rows
+ * and the call continues as zkir_b200_prove_rows. */
 int zkir_b200_prove_program(zkir_ctx*, const zkir_params*, const uint32_t* code, size_t n_code, const uint8_t* data, size_t n_data,
                             uint32_t entry_point, const uint64_t* inputs, size_t n_inputs, uint64_t max_cycles,
                             uint32_t* public_values_out, uint64_t* out_cycles, uint32_t* out_log_n, uint8_t** proof, size_t* proof_len);

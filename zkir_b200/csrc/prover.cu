@@ -1164,6 +1164,23 @@ int zkir_b200_prove_program(zkir_ctx* ctx, const zkir_params* p, const uint32_t*
   cudaSetDevice(ctx->device);
   int rc = zkir_b200_set_program(ctx, code, n_code);
   if (rc) return rc;
+  if (profile_is_full(p->width)) {
+    // full profile: the interpreter records full rows (zkir_vm_run with the execution trace on); zkir_b200_prove_rows replays the run's
+    // memory on the host and expands the wide table on the device
+    zkir_vm_result* res = nullptr;
+    rc = zkir_vm_run(code, n_code, data, n_data, entry_point, inputs, n_inputs, max_cycles, 1, &res);
+    if (rc) { ctx->err = std::string("interpreter: ") + zkir_vm_last_error(); return rc; }
+    const u64 T = zkir_vm_cycles(res);
+    u32 log_n = ZKIR_RANGE_BITS;
+    while ((1ull << log_n) <= T || (1ull << log_n) < n_code) log_n++;
+    if (out_cycles) *out_cycles = T;
+    if (out_log_n) *out_log_n = log_n;
+    rc = zkir_b200_set_io(ctx, zkir_vm_io(res), zkir_vm_io_len(res));
+    if (!rc) rc = zkir_b200_prove_rows(ctx, p, zkir_vm_trace_pc(res), zkir_vm_trace_instr(res), zkir_vm_trace_regs(res), T, zkir_vm_final_regs(res),
+                                       zkir_vm_final_pc(res), entry_point, zkir_vm_exit_code(res), zkir_vm_halt_kind(res), log_n, pv_out, proof, proof_len);
+    zkir_vm_free(res);
+    return rc;
+  }
   if (ctx->log_capacity < max_cycles) {
     if (ctx->log_pinned) cudaFreeHost(ctx->log_pinned);
     ctx->log_pinned = nullptr; ctx->log_capacity = 0;

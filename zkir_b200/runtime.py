@@ -466,8 +466,9 @@ class Context:
 
     def prove_program(self, program, inputs, cfg):
         """Program -> Proof in one call (zkir_b200_prove_program): the interpreter records the write log into pinned memory and the
-        log is uploaded chunk by chunk while it runs.  Returns (proof bytes, public values, cycles, log_n)."""
-        params = cfg.params()
+        log is uploaded chunk by chunk while it runs (core profile); a program that needs the full profile is interpreted with full rows,
+        its memory replayed on the host and the wide table expanded on the device.  Returns (proof bytes, public values, cycles, log_n)."""
+        params = cfg.params(profile_width(program_profile(program)))
         code = np.ascontiguousarray(program.code, dtype=np.uint32)
         data = np.ascontiguousarray(list(program.data) or [0], dtype=np.uint8)
         inp = np.ascontiguousarray([v & (2**64 - 1) for v in inputs] or [0], dtype=np.uint64)
@@ -568,14 +569,7 @@ def prove(program, inputs=(), cfg=None):
     the GPU, prove.  The drop-in the north star describes for `zkir_runtime::prove()` (absent upstream: lib.rs:29-62)."""
     cfg = cfg or ProverConfig()
     ctx = _ctx(cfg.device)
-    if program_profile(program) == "full":
-        # full-ISA programs: the interpreter records full rows, the host packer builds the wide table (the device converter and the
-        # write-log path serve the core profile), the proof itself is the same CUDA path
-        res = VM(program, list(inputs), VMConfig(max_cycles=cfg.max_cycles, enable_execution_trace=True, enable_poseidon2_syscall=cfg.enable_poseidon2_syscall)).run()
-        log_n = res.min_log_n()
-        pb, pv = ctx.prove_rows(res.rows(), cfg, log_n, profile="full")   # zkir_b200_prove_rows with the full width
-        return Proof(pb, pv, log_n, res.cycles, res.outputs, ctx.stage_ms(), program, res.io)
-    pb, pv, cycles, log_n = ctx.prove_program(program, list(inputs), cfg)
+    pb, pv, cycles, log_n = ctx.prove_program(program, list(inputs), cfg)   # either profile: zkir_b200_prove_program takes the width the program needs
     # the statement's public I/O transcript and outputs: one plain interpreter run without any recording (323 M cycles/s)
     res = VM(program, list(inputs), VMConfig(max_cycles=cfg.max_cycles, enable_poseidon2_syscall=cfg.enable_poseidon2_syscall)).run()
     return Proof(pb, pv, log_n, cycles, res.outputs, ctx.stage_ms(), program, res.io)
