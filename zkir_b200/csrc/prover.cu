@@ -115,7 +115,7 @@ struct zkir_ctx {
   u32* ntt_tmp = nullptr; u64 ntt_tmp_words = 0;
   u32* scratch[2] = {nullptr, nullptr}; size_t scratch_bytes[2] = {0, 0};
   void* rows_dev = nullptr; size_t rows_bytes = 0;   // staging for raw interpreter rows (prove_rows)
-  u32* full_stage = nullptr; size_t full_stage_bytes = 0;   // pinned host staging of a full-profile table packed on the host (prove_rows)
+  u32* full_stage = nullptr; size_t full_stage_bytes = 0;   // pinned host staging of the full profile (prove_rows): memory replay arrays, boundary cells
   // zkir_b200_prove_program: pinned write log the interpreter records into, and the stream its chunks are uploaded on
   void* log_pinned = nullptr; u64 log_capacity = 0;
   cudaStream_t copy_stream = nullptr; cudaEvent_t copy_done = nullptr;
@@ -931,7 +931,6 @@ static int expand_rows(zkir_ctx* ctx, const uint64_t* pcs, const uint32_t* instr
   const size_t need = T * (8 + 4 + 128) + 64;
   if (ctx->rows_bytes < need) {
     if (ctx->rows_dev) cudaFree(ctx->rows_dev);
-  if (ctx->full_stage) cudaFreeHost(ctx->full_stage);
     ctx->rows_dev = nullptr; ctx->rows_bytes = 0;
     CU(cudaMalloc(&ctx->rows_dev, need));
     ctx->rows_bytes = need;
@@ -1065,7 +1064,6 @@ static int wl_stage(zkir_ctx* ctx, u64 Tc, u64 n_scan_rows, WlStage* o) {
   const size_t need = Tc * 16 + scratch + 64;
   if (ctx->rows_bytes < need) {
     if (ctx->rows_dev) cudaFree(ctx->rows_dev);
-  if (ctx->full_stage) cudaFreeHost(ctx->full_stage);
     ctx->rows_dev = nullptr; ctx->rows_bytes = 0;
     CU(cudaMalloc(&ctx->rows_dev, need));
     ctx->rows_bytes = need;

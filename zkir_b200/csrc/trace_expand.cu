@@ -9,6 +9,7 @@
 //
 // Bound: HBM writes (352 B/row) -- every store of a warp is one 128 B segment of one column.
 #include <cuda_runtime.h>
+#include <stdio.h>
 #include "bb.cuh"
 #include "kernels.h"
 #include "air_pack.h"
@@ -261,7 +262,8 @@ int launch_trace_expand(const ExpandArgs& a, cudaStream_t st, u64* launches) {
   if (clear_multiplicities(a.cols, a.N, st)) return -2;
   trace_expand_kernel<<<(unsigned)((a.N + 127) / 128), 128, 0, st>>>(a);
   (*launches)++;
-  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+  { const cudaError_t e = cudaGetLastError(); if (e != cudaSuccess) { fprintf(stderr, "[zkir_b200] row converter launch (N=%llu T=%llu cols=%p): %s\n", (unsigned long long)a.N, (unsigned long long)a.T, (void*)a.cols, cudaGetErrorString(e)); return -2; } }
+  return 0;
 }
 u64 trace_expand_wl_scratch_ints(u64 N) { return ((N + WL_CHUNK - 1) / WL_CHUNK) * 16; }
 int launch_trace_expand_wl(const WlArgs& a, cudaStream_t st, u64* launches) {
@@ -271,7 +273,8 @@ int launch_trace_expand_wl(const WlArgs& a, cudaStream_t st, u64* launches) {
   wl_chunk_scan_kernel<<<1, WL_SCAN_THREADS, 0, st>>>(a.chunk_prev, n_chunks);
   trace_expand_wl_kernel<<<n_chunks, WL_CHUNK, 0, st>>>(a);
   (*launches) += 3;
-  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+  { const cudaError_t e = cudaGetLastError(); if (e != cudaSuccess) { fprintf(stderr, "[zkir_b200] write-log converter launch (N=%llu T=%llu chunks=%u): %s\n", (unsigned long long)a.N, (unsigned long long)a.T, n_chunks, cudaGetErrorString(e)); return -2; } }
+  return 0;
 }
 
 #endif  // ZKIR_PROFILE_FULL
