@@ -432,7 +432,8 @@ def test_error_paths_return_codes(gpu_ctx):
     assert ei.value.code == -6 and "lookup" in str(ei.value)
     prog = zkir_b200.assemble("addi r1, r0, 3\nmul r2, r1, r1\nadd r10, r0, r0\necall\n")
     res = zkir_b200.VM(prog, [], zkir_b200.VMConfig(enable_execution_trace=True)).run()
-    for call in (lambda: gpu_ctx.prove_rows(res.rows(), cfg), lambda: gpu_ctx.prove_writelog(res.writelog(), cfg)):
+    # a MUL has no selector in the core table (the full profile proves it: tests/test_full_profile.py); the write-log path is core only
+    for call in (lambda: gpu_ctx.prove_rows(res.rows(), cfg, profile="core"), lambda: gpu_ctx.prove_writelog(res.writelog(), cfg)):
         with pytest.raises(zkir_b200.RuntimeError) as ei:
             call()
         assert ei.value.code == -6 and "row 1" in str(ei.value)
