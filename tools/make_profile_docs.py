@@ -50,4 +50,14 @@ open(f"{P}/{rnd}_ncu_{label}.md", "w").write(
     f"Captured with `bash tools/gpu_profile_round.sh {tag}` (`ncu --set full --clock-control none --import-source on`); the .ncu-rep files are summarised on the "
     "GPU box (this table + the raw metric csv) because gpurun brings back at most 64 MiB.  time_us under ncu is cold-cache and serialised.\n\n"
     + hot + "\n" + tree + ("\n" + leaf if leaf else ""))
+if os.path.exists(f"{G}/launches_full_{tag}.csv"):
+    fl = run("tools/launch_summary.py", f"{G}/launches_full_{tag}.csv")
+    fn = open(f"{G}/ncu_full_{tag}.md").read() if os.path.exists(f"{G}/ncu_full_{tag}.md") else ""
+    fo = open(f"{G}/full_once_{tag}.log").read() if os.path.exists(f"{G}/full_once_{tag}.log") else ""
+    open(f"{P}/{rnd}_full_profile_{label}.md", "w").write(
+        f"# {rnd} {label} -- full AIR profile (248 + 168 columns, all 50 opcodes), mix workload at 2^18 rows ({head})\n\n"
+        "Command: `ncu --metrics gpu__time_duration.sum --clock-control none --csv python tools/full_profile_bench.py 18 1` -- the LAST proof of the run, "
+        "proven from rows in host memory (host memory replay, device converter `trace_expand_full_kernel`, then the ordinary proof).\n\n" + fl
+        + "\nOutput of the same command without the profiler's per-launch serialisation is in the bench JSON (`full_profile_mix`); under ncu:\n\n```\n" + fo + "```\n\n"
+        "## ncu --set full of the profile-specific kernels\n\n" + fn)
 print("wrote", f"{P}/{rnd}_launches_{label}.md", f"{P}/{rnd}_bench_launches_{label}.md", f"{P}/{rnd}_ncu_{label}.md")

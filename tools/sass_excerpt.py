@@ -21,6 +21,9 @@ KERNELS = {
     "quotient_kernel_3": r"quotient_kernelILi3E",
     "aux_rows_kernel": r"aux_rows_kernel",
     "compress_kernel": r"compress_kernel",
+    "quotient_kernel_full_3x256": r"quotient_kernel_fullILi3ELi256E",
+    "aux_rows_kernel_full": r"aux_rows_kernel_full",
+    "trace_expand_full_kernel": r"trace_expand_full_kernel",
 }
 MUL_PIPE = ("IMAD", "IMUL")          # fmaheavy (integer multiply-add) pipe; IMAD.IADD / IMAD.MOV are adds / moves issued there
 TAG = sys.argv[1] if len(sys.argv) > 1 else "r02"
