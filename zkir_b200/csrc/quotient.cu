@@ -144,7 +144,9 @@ int ZKIR_PF(launch_quotient)(const QuotientArgs& a, cudaStream_t st, u64* launch
   const u32 m_ginv = bb_to_mont_c(g_inv), m_g = bb_to_mont_c(g), m_snn = bb_to_mont_c(snn), m_wb = bb_to_mont_c(wb);
 #ifdef ZKIR_PROFILE_FULL
   // full profile: blocks that re-converge at every fence (see QCtx::fence).  Measured at 2^18 rows (2^19 LDE rows), 256-thread blocks:
-  // 1 / 2 / 3 resident blocks per SM (255 / 128 / 80 registers) = 3.56 / 2.16 / 1.88 ms: occupancy wins over spills
+  // 1 / 2 / 3 resident blocks per SM (255 / 128 / 80 registers) = 3.56 / 2.16 / 1.88 ms: occupancy wins over spills.  Splitting the
+  // constraint list over 2 / 4 / 8 launches of consecutive index ranges (no spills left in most parts) measured 3.67 / 2.81 / 2.39 ms:
+  // every part repeats the operand fetch and selector sums that most constraints share, so one launch stays
   auto launch = [&](auto kernel, unsigned threads) { kernel<<<(unsigned)(n_threads / threads), threads, 0, st>>>(a, ap, m_ginv, m_g, m_snn, m_wb); };
   if (variant == 0) launch(ZKIR_PF(quotient_kernel)<2, 256>, 256);
   else if (variant == 1) launch(ZKIR_PF(quotient_kernel)<1, 256>, 256);
