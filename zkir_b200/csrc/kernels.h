@@ -193,6 +193,10 @@ struct QueryArgs {
   u32 qlde_sl = 0;      // same for the quotient LDE rows
   u32 layer_sl[32] = {0};
 };
+// LA half-folds of one committed FRI round in one launch: in = layer of n values, out = layer of n >> la values (la = 1..3);
+// c_mont[s] = 1 / (2 * shift^(2^s)) in Montgomery form, tw_stride = 1 << (level of `in`)
+int launch_fri_fold_multi(const E4* in, E4* out, u64 n, u32 la, const u32* beta_dev, const u32* inv_w_table, u32 tw_stride, const u32 c_mont[3],
+                          cudaStream_t st, u64* launches);
 int launch_queries(const QueryArgs& a, cudaStream_t st, u64* launches);
 
 }  // namespace zkir

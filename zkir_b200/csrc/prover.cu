@@ -678,13 +678,14 @@ static int prove_resident(zkir_ctx* ctx, const zkir_params* p, u32 log_n, const 
       // leaves hash(f[i] || f[i+qn] || ... || f[i+(2^la-1)qn]) + tree + root -> proof, observe, sample beta_t
       if ((crc = commit_tree(ctx, nullptr, 0, 0, reinterpret_cast<const u32*>(w.h_layers[level]), w.h_ltrees[level], qn, w.proof + L.fri_roots + 8 * t,
                              c_betas + 4 * t, 4, &l_sl[t], -1, 1u << la)) != 0) return crc;
-      for (u32 s = 0; s < la; s++) {   // half-folds with beta, beta^2, beta^4 on the coset, its square, its fourth power
-        const u64 h = (M >> level) / 2;
-        const u32 c = hinv(hmul(2, lshift));
-        RC(launch_fri_fold(w.h_layers[level], w.h_layers[level + 1], h, c_betas + 4 * t, inv_w, 1u << level, bb_to_mont_c(c), st, LC, (int)s));
-        lshift = hmul(lshift, lshift);
-        level++;
-      }
+      // half-folds with beta, beta^2, beta^4 on the coset, its square, its fourth power: one launch per round (stark.cu), the
+      // intermediate layers stay in registers
+      u32 cs[3] = {0, 0, 0};
+      u32 ls = lshift;
+      for (u32 s = 0; s < la; s++) { cs[s] = bb_to_mont_c(hinv(hmul(2, ls))); ls = hmul(ls, ls); }
+      RC(launch_fri_fold_multi(w.h_layers[level], w.h_layers[level + la], M >> level, la, c_betas + 4 * t, inv_w, 1u << level, cs, st, LC));
+      lshift = ls;
+      level += la;
     }
     CU(cudaMemcpyAsync(w.proof + L.final_, w.h_layers[R], 16, cudaMemcpyDeviceToDevice, st));
     RC(launch_challenger(w.chal, w.proof + L.final_, 4, nullptr, 0, 0, st, LC));

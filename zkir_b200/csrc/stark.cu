@@ -231,6 +231,49 @@ int launch_fri_fold(const E4* in, E4* out, u64 h, const u32* beta_dev, const u32
   return CHECK_LAUNCH();
 }
 
+// One committed FRI round = LA half-folds (fold by 2^LA) in ONE launch: thread i of the qn = n >> LA outputs loads the 2^LA values
+// f[i + k*qn] -- exactly the values one Merkle leaf of the round holds -- and applies the half-folds of fri_fold_kernel level by level in
+// registers (same operations in the same order: bit-identical), so the intermediate layers are never written and a round costs one
+// launch instead of LA.  Level s pairs position j with j + (n >> (s+1)), challenge beta^(2^s), twiddle inv_w[j * (tw_stride << s)].
+struct FoldConsts { u32 c_mont[3]; };
+template <int LA>
+__global__ void __launch_bounds__(256) fri_fold_multi_kernel(const E4* __restrict__ in, E4* __restrict__ out, u64 qn, const u32* beta_dev,
+                                                            const u32* __restrict__ inv_w, u32 tw_stride, FoldConsts fc) {
+  const u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x;
+  if (i >= qn) return;
+  E4 beta; for (int k = 0; k < 4; k++) beta.c[k] = beta_dev[k];
+  E4 v[1 << LA];
+#pragma unroll
+  for (int k = 0; k < (1 << LA); k++) v[k] = ld_e4(in + i + (u64)k * qn);
+  const u32 half = bb_to_mont_c((BB_P + 1) / 2);
+#pragma unroll
+  for (int s = 0; s < LA; s++) {
+    const int hk = 1 << (LA - s - 1);   // pairs (k, k + hk) of this thread's values
+#pragma unroll
+    for (int k = 0; k < hk; k++) {
+      const E4 a = v[k], b = v[k + hk];
+      const u64 j = i + (u64)k * qn;
+      const E4 sm = e4_mulb(e4_add(a, b), half);
+      const E4 d = e4_mulb(e4_sub(a, b), bb_mul(fc.c_mont[s], inv_w[j * ((u64)tw_stride << s)]));
+      v[k] = e4_add(sm, e4_mul(beta, d));
+    }
+    beta = e4_mul(beta, beta);
+  }
+  st_e4(out + i, v[0]);
+}
+int launch_fri_fold_multi(const E4* in, E4* out, u64 n, u32 la, const u32* beta_dev, const u32* inv_w_table, u32 tw_stride, const u32 c_mont[3],
+                          cudaStream_t st, u64* launches) {
+  FoldConsts fc;
+  for (int k = 0; k < 3; k++) fc.c_mont[k] = c_mont[k];
+  const u64 qn = n >> la;
+  if (la == 3) fri_fold_multi_kernel<3><<<nblk(qn, 256), 256, 0, st>>>(in, out, qn, beta_dev, inv_w_table, tw_stride, fc);
+  else if (la == 2) fri_fold_multi_kernel<2><<<nblk(qn, 256), 256, 0, st>>>(in, out, qn, beta_dev, inv_w_table, tw_stride, fc);
+  else if (la == 1) fri_fold_multi_kernel<1><<<nblk(qn, 256), 256, 0, st>>>(in, out, qn, beta_dev, inv_w_table, tw_stride, fc);
+  else return -1;
+  (*launches)++;
+  return CHECK_LAUNCH();
+}
+
 // ---- query gather: one block per query, everything copied into the proof at fixed offsets
 __device__ __forceinline__ void copy_path(const u32* tree, u64 n_leaves, u32 log_leaves, u64 idx, u32* out, u32 sl, bool own_leaf, bool own_top) {
   for (u32 t = threadIdx.x; t < log_leaves * 8; t += blockDim.x) {
