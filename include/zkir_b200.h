@@ -249,6 +249,11 @@ uint64_t zkir_vm_logged_rows(const zkir_vm_result*);
  * READ / WRITE ecall in execution order (syscall.rs:104-119); part of the statement a proof makes (zkir_b200_set_io, zkir_b200_verify) */
 size_t zkir_vm_io_len(const zkir_vm_result*);
 const uint32_t* zkir_vm_io(const zkir_vm_result*);
+/* Poseidon2Witness records of a traced run (zkir-spec/src/trace.rs:287-304): one per SYS_POSEIDON2 call, 34 words each = timestamp
+ * (cycle, lo / hi word), input_state[16], output_state[16] (canonical field elements).  The permutation itself is not part of the AIR yet
+ * (docs/PROVER_SPEC.md 3.5); a batch of these is what zkir_b200_poseidon2_permute re-computes on the device. */
+size_t zkir_vm_poseidon2_count(const zkir_vm_result*);
+const uint32_t* zkir_vm_poseidon2_witness(const zkir_vm_result*);
 size_t zkir_vm_code_len(const zkir_vm_result*);
 const uint32_t* zkir_vm_code(const zkir_vm_result*);
 uint64_t zkir_vm_final_pc(const zkir_vm_result*);

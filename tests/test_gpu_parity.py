@@ -504,3 +504,17 @@ def test_small_proofs_replay_a_captured_graph(gpu_ctx, oracle):
             assert ctx.prove_columns(cols, pv, cfg, program=fres) == want
     finally:
         ctx.close()
+
+
+def test_poseidon2_witness_of_a_run_recomputed_on_the_device(gpu_ctx):
+    """BASELINE config 3 in miniature: the Poseidon2Witness records of a SYS_POSEIDON2 loop (zkir-spec/src/trace.rs:287-304) -- every
+    permutation the interpreter executed -- recomputed in one batch by zkir_b200_poseidon2_permute"""
+    from zkir_b200.workloads import pos2_program
+    res = zkir_b200.VM(pos2_program(), [3000], zkir_b200.VMConfig(max_cycles=1 << 20, enable_execution_trace=True, enable_poseidon2_syscall=True)).run()
+    ts, ins, outs = res.poseidon2_witness
+    assert ins.shape == (3000, 16)
+    d = gpu_ctx.to_device(ins)
+    gpu_ctx.poseidon2_permute(d, ins.shape[0])
+    got = gpu_ctx.to_host(d, ins.shape)
+    gpu_ctx.free(d)
+    assert np.array_equal(got, outs)

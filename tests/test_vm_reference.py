@@ -227,3 +227,17 @@ def test_writelog_matches_register_diff():
             assert len(changed) == 1
             k = int(changed[0])
             assert int(wl["wlog"][i]) == (k << 56) | int(regs[i + 1][k])
+
+
+def test_poseidon2_witness_records(oracle):
+    """Poseidon2Witness (zkir-spec/src/trace.rs:287-304: input_state, output_state, timestamp per SYS_POSEIDON2 call) of a traced run; the
+    permutation is the spec's (docs/PROVER_SPEC.md section 2), checked against the oracle's."""
+    from zkir_b200.workloads import pos2_program, pos2_cycles
+    res = z.VM(pos2_program(), [5], z.VMConfig(enable_execution_trace=True, enable_poseidon2_syscall=True)).run()
+    assert res.cycles == pos2_cycles(5)
+    ts, ins, outs = res.poseidon2_witness
+    assert ts.tolist() == [7 + 16 * k for k in range(5)] and ins.shape == outs.shape == (5, 16)   # cycle of each ecall: 6 set-up cycles, 16 per iteration
+    assert np.array_equal(oracle.poseidon2(ins), outs)
+    assert ins[0].tolist() == [0] * 16 and np.array_equal(ins[1:], outs[:-1])     # the loop permutes the state in place
+    # a run without the syscall has no records; an untraced run records none either
+    assert z.run(z.assemble("ebreak")).poseidon2_witness[1].shape == (0, 16)

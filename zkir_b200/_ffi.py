@@ -95,6 +95,8 @@ SYMBOLS = {
     "zkir_vm_logged_rows": (C.c_uint64, [vp]),
     "zkir_vm_io_len": (C.c_size_t, [vp]),
     "zkir_vm_io": (u32p, [vp]),
+    "zkir_vm_poseidon2_count": (C.c_size_t, [vp]),
+    "zkir_vm_poseidon2_witness": (u32p, [vp]),
     "zkir_vm_code_len": (C.c_size_t, [vp]),
     "zkir_vm_code": (u32p, [vp]),
     "zkir_vm_final_pc": (C.c_uint64, [vp]),

@@ -127,6 +127,8 @@ struct zkir_vm_result {
   std::vector<zkir_mem_op> memops;  // data memory ops per row (fetch excluded)
   std::vector<u32> code;            // the program's code words (the ROM the proof is bound to)
   std::vector<u32> io;              // public I/O transcript: 4 words per READ / WRITE ecall (cycle, kind 0/1, value lo20, value hi20)
+  std::vector<u32> pos2;            // Poseidon2Witness records (zkir-spec/src/trace.rs:287-304): 34 words per SYS_POSEIDON2 call --
+                                    // timestamp lo / hi, input_state[16], output_state[16] (traced runs only)
   u64 logged = 0;                   // write-log mode: rows written to the caller's arrays
   std::string error;
 };
@@ -339,7 +341,9 @@ static int vm_run_impl(const uint32_t* code, size_t n_code, const uint8_t* data,
           if ((src | dst) % 4) { char b[96]; snprintf(b, sizeof b, "Misaligned access at %#llx (alignment 4)", (unsigned long long)((src % 4) ? src : dst)); return fail(b); }
           uint32_t st[16];
           for (int k = 0; k < 16; k++) st[k] = (uint32_t)(mem.read(src + 4 * k, 4) % ZKIR_BABYBEAR_P);
+          if (record_trace) { res->pos2.push_back((u32)cycles); res->pos2.push_back((u32)(cycles >> 32)); res->pos2.insert(res->pos2.end(), st, st + 16); }
           zkir_host_poseidon2_permute(st);
+          if (record_trace) res->pos2.insert(res->pos2.end(), st, st + 16);
           for (int k = 0; k < 16; k++) mem.write(dst + 4 * k, st[k], 4);
           W(10, 0);
           break;
@@ -395,6 +399,8 @@ int zkir_vm_run_writelog_cb(const uint32_t* code, size_t n_code, const uint8_t* 
 
 size_t zkir_vm_io_len(const zkir_vm_result* r) { return r->io.size() / 4; }
 const uint32_t* zkir_vm_io(const zkir_vm_result* r) { return r->io.data(); }
+size_t zkir_vm_poseidon2_count(const zkir_vm_result* r) { return r->pos2.size() / 34; }
+const uint32_t* zkir_vm_poseidon2_witness(const zkir_vm_result* r) { return r->pos2.data(); }
 size_t zkir_vm_code_len(const zkir_vm_result* r) { return r->code.size(); }
 const uint32_t* zkir_vm_code(const zkir_vm_result* r) { return r->code.data(); }
 uint64_t zkir_vm_logged_rows(const zkir_vm_result* r) { return r->logged; }

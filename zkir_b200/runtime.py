@@ -115,6 +115,17 @@ class ExecutionResult:  # vm.rs:54-78
         return np.ctypeslib.as_array(l.zkir_vm_io(self._h), shape=(n, 4)).copy() if n else np.zeros((0, 4), dtype=np.uint32)
 
     @property
+    def poseidon2_witness(self):
+        """Poseidon2Witness records of a traced run (zkir-spec/src/trace.rs:287-304): (timestamps uint64 [n], input_state uint32 [n, 16],
+        output_state uint32 [n, 16]), one per SYS_POSEIDON2 call."""
+        l = _ffi.lib()
+        n = l.zkir_vm_poseidon2_count(self._h)
+        if n == 0:
+            return np.zeros(0, dtype=np.uint64), np.zeros((0, 16), dtype=np.uint32), np.zeros((0, 16), dtype=np.uint32)
+        w = np.ctypeslib.as_array(l.zkir_vm_poseidon2_witness(self._h), shape=(n, 34)).copy()
+        return w[:, 0].astype(np.uint64) | (w[:, 1].astype(np.uint64) << np.uint64(32)), w[:, 2:18].copy(), w[:, 18:34].copy()
+
+    @property
     def trace_len(self):
         return _ffi.lib().zkir_vm_trace_len(self._h)
 
