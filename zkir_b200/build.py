@@ -18,7 +18,7 @@ HOST_CXX = "/usr/bin/g++"
 GENCODE = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = GENCODE + ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-ccbin", HOST_CXX,
                         "-I", os.path.join(ROOT, "include"), "-I", CSRC, "--expt-relaxed-constexpr",
-                        "-Xptxas", "-v"]
+                        "-Xptxas", "-v"] + os.environ.get("ZKIR_NVCC_EXTRA", "").split()   # experiments, e.g. ZKIR_NVCC_EXTRA=-DZKIR_P2_PIN=0
 
 
 def sources():

@@ -38,15 +38,40 @@ __device__ __forceinline__ u32 sbox7(u32 x) {
   u32 x2 = bb_sqr(x), x3 = bb_mul(x2, x), x4 = bb_sqr(x2);
   return bb_mul(x4, x3);
 }
+// Pipe placement of the plain adds of the thread-per-permutation kernels (leaves, compressions).  A modular add is `s = a + b` followed by
+// VIADDMNMX(s, -p, s); ptxas issues about half of the `a + b` as IMAD.IADD on the integer-multiply pipe and half as IADD3 on the ALU pipe.
+// Writing an add as __viaddmin_u32(a, b, ~0u) = min(a + b, 2^32 - 1) = a + b pins it to the ALU pipe (VIADDMNMX exists only there) and makes
+// ptxas re-balance the rest.  Measured on the 2^20-row proof (ms per proof / trace commitment; ZKIR_P2_PIN bit 0 = the external linear
+// layer, bit 1 = the internal one, bit 2 = the round-constant adds): 0: 13.89 / 6.69, 1: 14.56 / 7.18, 2: 14.01 / 6.78, 3: 14.40 / 7.06,
+// **4: 13.57 / 6.47**, 5: 14.15 / 6.89, 6: 13.77 / 6.61; unrolling the round loops on top of 4: 14.4 - 15.5 (instruction cache).
+// Only the round-constant adds gain (their second operand comes from constant memory); pinning the layers' adds overloads the ALU pipe.
+#ifndef ZKIR_P2_PIN
+#define ZKIR_P2_PIN 4
+#endif
+template <int ON>
+__device__ __forceinline__ u32 p2_add(u32 a, u32 b) {
+  if (ON) { const u32 t = __viaddmin_u32(a, b, 0xffffffffu); return __viaddmin_u32(t, 0u - BB_P, t); }
+  return bb_add(a, b);
+}
+template <int ON>
+__device__ __forceinline__ u32 p2_sub(u32 a, u32 b) {
+  if (ON) { const u32 d = __viaddmin_u32(a, 0u - b, 0xffffffffu); return __viaddmin_u32(d, BB_P, d); }   // a - b wraps mod 2^32; min(d + p, d)
+  return bb_sub(a, b);
+}
+#define EA p2_add<(ZKIR_P2_PIN & 1)>
+#define IA p2_add<((ZKIR_P2_PIN >> 1) & 1)>
+#define IS p2_sub<((ZKIR_P2_PIN >> 1) & 1)>
+#define RA p2_add<((ZKIR_P2_PIN >> 2) & 1)>
+
 // circ(2,3,1,1) on 4 values
 __device__ __forceinline__ void m4(u32& a, u32& b, u32& c, u32& d) {
-  u32 t01 = bb_add(a, b), t23 = bb_add(c, d);
-  u32 t0123 = bb_add(t01, t23);
-  u32 t01123 = bb_add(t0123, b), t01233 = bb_add(t0123, d);
-  u32 nd = bb_add(t01233, bb_dbl(a));  // 3a + b + c + 2d
-  u32 nb = bb_add(t01123, bb_dbl(c));  // a + 2b + 3c + d
-  u32 na = bb_add(t01123, t01);        // 2a + 3b + c + d
-  u32 nc = bb_add(t01233, t23);        // a + b + 2c + 3d
+  u32 t01 = EA(a, b), t23 = EA(c, d);
+  u32 t0123 = EA(t01, t23);
+  u32 t01123 = EA(t0123, b), t01233 = EA(t0123, d);
+  u32 nd = EA(t01233, EA(a, a));  // 3a + b + c + 2d
+  u32 nb = EA(t01123, EA(c, c));  // a + 2b + 3c + d
+  u32 na = EA(t01123, t01);       // 2a + 3b + c + d
+  u32 nc = EA(t01233, t23);       // a + b + 2c + 3d
   a = na; b = nb; c = nc; d = nd;
 }
 __device__ __forceinline__ void external_linear(u32* s) {
@@ -54,9 +79,9 @@ __device__ __forceinline__ void external_linear(u32* s) {
   for (int c = 0; c < 4; c++) m4(s[4 * c], s[4 * c + 1], s[4 * c + 2], s[4 * c + 3]);
   u32 sums[4];
 #pragma unroll
-  for (int k = 0; k < 4; k++) sums[k] = bb_add(bb_add(s[k], s[4 + k]), bb_add(s[8 + k], s[12 + k]));
+  for (int k = 0; k < 4; k++) sums[k] = EA(EA(s[k], s[4 + k]), EA(s[8 + k], s[12 + k]));
 #pragma unroll
-  for (int i = 0; i < 16; i++) s[i] = bb_add(s[i], sums[i & 3]);
+  for (int i = 0; i < 16; i++) s[i] = EA(s[i], sums[i & 3]);
 }
 // s[i] <- V[i]*s[i] + sum(s) with the frozen diagonal V = [-2, 1, 2, 1/2, 3, 4, -1/2, -3, -4, 2^-8, 1/4, 1/8, 2^-27,
 // -2^-8, -1/16, -2^-27] (docs/PROVER_SPEC.md section 2; poseidon2_init_constants() checks the generated header against it).
@@ -73,41 +98,41 @@ __device__ __forceinline__ u32 diag_tail_mul(u32 x) {
 __device__ __forceinline__ void internal_linear(u32* s) {
   u32 sum = s[0];
 #pragma unroll
-  for (int i = 1; i < 16; i++) sum = bb_add(sum, s[i]);
-  s[0] = bb_sub(sum, bb_dbl(s[0]));
-  s[1] = bb_add(s[1], sum);
-  s[2] = bb_add(bb_dbl(s[2]), sum);
-  s[3] = bb_add(bb_halve(s[3]), sum);
-  s[4] = bb_add(bb_add(bb_dbl(s[4]), s[4]), sum);
-  s[5] = bb_add(bb_dbl(bb_dbl(s[5])), sum);
-  s[6] = bb_sub(sum, bb_halve(s[6]));
-  s[7] = bb_sub(sum, bb_add(bb_dbl(s[7]), s[7]));
-  s[8] = bb_sub(sum, bb_dbl(bb_dbl(s[8])));
-  s[9] = bb_add(diag_tail_mul<0>(s[9]), sum);
-  s[10] = bb_add(diag_tail_mul<1>(s[10]), sum);
-  s[11] = bb_add(diag_tail_mul<2>(s[11]), sum);
-  s[12] = bb_add(diag_tail_mul<3>(s[12]), sum);
-  s[13] = bb_add(diag_tail_mul<4>(s[13]), sum);
-  s[14] = bb_add(diag_tail_mul<5>(s[14]), sum);
-  s[15] = bb_add(diag_tail_mul<6>(s[15]), sum);
+  for (int i = 1; i < 16; i++) sum = IA(sum, s[i]);
+  s[0] = IS(sum, IA(s[0], s[0]));
+  s[1] = IA(s[1], sum);
+  s[2] = IA(IA(s[2], s[2]), sum);
+  s[3] = IA(bb_halve(s[3]), sum);
+  s[4] = IA(IA(IA(s[4], s[4]), s[4]), sum);
+  { const u32 d = IA(s[5], s[5]); s[5] = IA(IA(d, d), sum); }
+  s[6] = IS(sum, bb_halve(s[6]));
+  s[7] = IS(sum, IA(IA(s[7], s[7]), s[7]));
+  { const u32 d = IA(s[8], s[8]); s[8] = IS(sum, IA(d, d)); }
+  s[9] = IA(diag_tail_mul<0>(s[9]), sum);
+  s[10] = IA(diag_tail_mul<1>(s[10]), sum);
+  s[11] = IA(diag_tail_mul<2>(s[11]), sum);
+  s[12] = IA(diag_tail_mul<3>(s[12]), sum);
+  s[13] = IA(diag_tail_mul<4>(s[13]), sum);
+  s[14] = IA(diag_tail_mul<5>(s[14]), sum);
+  s[15] = IA(diag_tail_mul<6>(s[15]), sum);
 }
 __device__ __forceinline__ void poseidon2_permute(u32* s) {
   external_linear(s);
 #pragma unroll 1
   for (int r = 0; r < 4; r++) {
 #pragma unroll
-    for (int i = 0; i < 16; i++) s[i] = sbox7(bb_add(s[i], c_rc_ext[r * 16 + i]));
+    for (int i = 0; i < 16; i++) s[i] = sbox7(RA(s[i], c_rc_ext[r * 16 + i]));
     external_linear(s);
   }
 #pragma unroll 1
   for (int r = 0; r < ZKIR_P2_RP; r++) {
-    s[0] = sbox7(bb_add(s[0], c_rc_int[r]));
+    s[0] = sbox7(RA(s[0], c_rc_int[r]));
     internal_linear(s);
   }
 #pragma unroll 1
   for (int r = 4; r < 8; r++) {
 #pragma unroll
-    for (int i = 0; i < 16; i++) s[i] = sbox7(bb_add(s[i], c_rc_ext[r * 16 + i]));
+    for (int i = 0; i < 16; i++) s[i] = sbox7(RA(s[i], c_rc_ext[r * 16 + i]));
     external_linear(s);
   }
 }
