@@ -451,7 +451,7 @@ def main():
             "stage_ms": {k: v for k, v in f_stage.items() if k != "h2d"}, "interpreter_full_rows_s": f_vm_s, "host_packer_s": f_pack_s,
             "e2e_rows": {"ms_per_proof": f_rows_ms, "value": world * rf.cycles / (f_rows_ms * 1e-3), "h2d_and_convert_ms": f_conv_ms, "h2d_bytes_per_step": int(rf.cycles) * 152,
                          "api": "zkir_b200_prove_rows (full width): TraceRow data in host memory -> host replay of the run's memory -> device converter -> proof bytes"},
-            "program_to_proof": {"ms_per_proof": f_prog_ms, "value": world * rf.cycles / (f_prog_ms * 1e-3), "api": "zkir_b200_prove_program (full width), interpreter included"},
+            "program_to_proof": {"ms_per_proof": f_prog_ms, "value": world * rf.cycles / (f_prog_ms * 1e-3), "api": "zkir_b200_prove_program (full width), interpreter included: register write log + memory log (28 B/cycle) in pinned memory, chunks uploaded while it runs, device converter"},
             "note": "`value`: trace resident in HBM (packed by the host packer outside the timed region, which the e2e paths do not use)"}
         ctx.set_program(res)
         del cols_f

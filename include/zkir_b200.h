@@ -249,6 +249,18 @@ uint64_t zkir_vm_logged_rows(const zkir_vm_result*);
  * READ / WRITE ecall in execution order (syscall.rs:104-119); part of the statement a proof makes (zkir_b200_set_io, zkir_b200_verify) */
 size_t zkir_vm_io_len(const zkir_vm_result*);
 const uint32_t* zkir_vm_io(const zkir_vm_result*);
+/* write log + MEMORY log, for programs that need the full AIR profile (docs/PROVER_SPEC.md 3.8): like zkir_vm_run_writelog_cb, and on
+ * every load / store row mem_old / mem_pts [capacity] receive the aligned 8-byte word before the access and the timestamp (cycle + 1;
+ * 0 = never) of that word's previous access -- what the memory argument needs and only the interpreter has for free (upstream:
+ * Memory::record_op, memory.rs:243-253).  zkir_vm_memlog_*: the touched words in ascending order, their final contents and last timestamps. */
+int zkir_vm_run_writelog_mem_cb(const uint32_t* code, size_t n_code, const uint8_t* data, size_t n_data, uint32_t entry_point,
+                                const uint64_t* inputs, size_t n_inputs, uint64_t max_cycles, uint32_t* pcs32, uint32_t* instrs, uint64_t* wlog,
+                                uint64_t* mem_old, uint32_t* mem_pts, uint64_t capacity, void (*on_chunk)(void*, uint64_t), void* user,
+                                uint64_t chunk_rows, zkir_vm_result** out);
+size_t zkir_vm_memlog_count(const zkir_vm_result*);
+const uint64_t* zkir_vm_memlog_widx(const zkir_vm_result*);
+const uint64_t* zkir_vm_memlog_word(const zkir_vm_result*);
+const uint32_t* zkir_vm_memlog_ts(const zkir_vm_result*);
 /* Poseidon2Witness records of a traced run (zkir-spec/src/trace.rs:287-304): one per SYS_POSEIDON2 call, 34 words each = timestamp
  * (cycle, lo / hi word), input_state[16], output_state[16] (canonical field elements).  The permutation itself is not part of the AIR yet
  * (docs/PROVER_SPEC.md 3.5); a batch of these is what zkir_b200_poseidon2_permute re-computes on the device. */

@@ -326,6 +326,21 @@ def test_gpu_memory_programs_equal_oracle(gpu_ctx, oracle_full):
         pb = gpu_ctx.prove_columns(cols, pv, cfg, program=res)
         assert pb == oracle_full.prove(cfg, cols, pv, res)
         assert zkir_b200.verify(pb, cfg, pv, res) == (True, "")
+        # Program -> Proof (interpreter write log + memory log -> device converter) and rows -> proof give the same bytes
+        assert zkir_b200.prove(res.program, [], cfg).bytes_ == pb
+        assert gpu_ctx.prove_rows(res.rows(), cfg)[0] == pb
+
+
+@pytest.mark.gpu
+def test_gpu_full_profile_program_to_proof_malformed_runs(gpu_ctx):
+    """Rows the full profile cannot constrain must fail with an error through Program -> Proof too (the device converter reports them)."""
+    cfg = zkir_b200.ProverConfig(num_queries=8, pow_bits=2)
+    for src in ("addi r1, zero, 5\ndivu r2, r1, zero\nebreak\n",                    # division by zero
+                "addi r1, zero, 0x1001\nlw r2, 0(r1)\nebreak\n"):                   # misaligned load: the interpreter refuses (memory.rs alignment)
+        with pytest.raises(Exception):
+            zkir_b200.prove(zkir_b200.assemble(src), [], cfg)
+    # and the context stays usable
+    assert zkir_b200.verify(zkir_b200.prove(mix_program(), [10], cfg), cfg) == (True, "")
 
 
 @pytest.mark.gpu
@@ -406,3 +421,104 @@ def test_gpu_full_profile_prove_rows_errors(gpu_ctx):
     with pytest.raises(zkir_b200.RuntimeError) as e:
         gpu_ctx.prove_rows(res.rows(), cfg, profile="full")
     assert e.value.code == -6 and "shift amount" in str(e.value)
+
+
+def _run_memlog(prog, inputs, cap, poseidon2=False):
+    import ctypes as C
+    l = zkir_b200._ffi.lib()
+    code = np.asarray(prog.code, dtype=np.uint32)
+    arr = (np.zeros(cap, dtype=np.uint32), np.zeros(cap, dtype=np.uint32), np.zeros(cap, dtype=np.uint64), np.zeros(cap, dtype=np.uint64), np.zeros(cap, dtype=np.uint32))
+    data = (C.c_uint8 * max(1, len(prog.data)))(*prog.data)
+    inp = (C.c_uint64 * max(1, len(inputs)))(*inputs)
+    h = C.c_void_p()
+    l.zkir_vm_enable_poseidon2(int(poseidon2))
+    rc = l.zkir_vm_run_writelog_mem_cb(code.ctypes.data_as(C.POINTER(C.c_uint32)), len(code), data, len(prog.data), prog.entry_point, inp, len(inputs), cap,
+                                       *[a.ctypes.data for a in arr], cap, None, None, 0, C.byref(h))
+    l.zkir_vm_enable_poseidon2(0)
+    return rc, h, arr
+
+
+def test_interpreter_memory_log_refuses_what_the_replay_refuses():
+    """Same refusals as test_memory_rows_outside_the_model_are_rejected, through the memory-log interpreter (ZKIR_ERR_AIR = -6)."""
+    l = zkir_b200._ffi.lib()
+    asm = zkir_b200.assemble
+    # a sign-extended load leaves the 40-bit register model
+    rc, h, _ = _run_memlog(asm("addi r1, r0, 0x2000\naddi r2, r0, 200\nsb r2, 0(r1)\nlb r3, 0(r1)\nebreak"), [], 64)
+    assert rc == -6 and b"above 40 bits" in l.zkir_vm_last_error()
+    # SYS_POSEIDON2 writes memory the argument does not see: a later load (or store) of those words is refused ...
+    pos = "addi r11, r0, 0x2000\naddi r13, r0, 0x2000\naddi r10, r0, 4\necall\n"
+    for tail in ("lw r3, 0(r13)\nebreak", "sb r3, 60(r13)\nebreak", "lbu r3, 57(r13)\nebreak"):
+        rc, h, _ = _run_memlog(asm(pos + tail), [], 64, poseidon2=True)
+        assert rc == -6 and b"memory the AIR tracks" in l.zkir_vm_last_error(), tail
+    # ... a neighbouring word is fine, and a word the program stored BEFORE the syscall overwrote it keeps the value the argument saw
+    rc, h, arr = _run_memlog(asm("addi r13, r0, 0x2000\naddi r2, r0, 77\nsw r2, 4(r13)\naddi r11, r0, 0x2000\naddi r10, r0, 4\necall\nlw r3, 64(r13)\nebreak"), [], 64, poseidon2=True)
+    assert rc == 0
+    nw = l.zkir_vm_memlog_count(h)
+    widx = np.ctypeslib.as_array(l.zkir_vm_memlog_widx(h), shape=(nw,)); word = np.ctypeslib.as_array(l.zkir_vm_memlog_word(h), shape=(nw,))
+    assert list(widx) == [0x2000 // 8, 0x2040 // 8] and list(word) == [77 << 32, 0]
+    l.zkir_vm_free(h)
+    # a data segment is not part of the public image: its first load is refused
+    prog = asm("addi r1, r0, 0x1000\nlw r2, 0(r1)\nlw r3, 12(r1)\nebreak")
+    rc, h, _ = _run_memlog(prog, [], 64)
+    assert rc == 0
+    l.zkir_vm_free(h)
+    prog.data = bytes([1, 2, 3, 4])
+    rc, h, _ = _run_memlog(prog, [], 64)
+    assert rc == 0   # never loaded
+    l.zkir_vm_free(h)
+    prog2 = asm("addi r1, r0, 0x1000\nlw r2, 16(r1)\nebreak\nebreak")
+    prog2.data = bytes([1, 2, 3, 4])
+    rc, h, _ = _run_memlog(prog2, [], 64)
+    assert rc == -6 and b"data segment" in l.zkir_vm_last_error()
+
+
+def test_interpreter_memory_log_equals_the_host_replay():
+    """Program -> Proof for the full profile feeds the device converter from the interpreter's own memory log (zkir_vm_run_writelog_mem_cb:
+    the word before each load / store, that word's previous timestamp, and the touched words at the end).  It must be the same data the
+    host replay of recorded rows (zkir_mem_replay_full / zkir_mem_boundary_full, the prove_rows path) derives."""
+    import ctypes as C
+    from zkir_b200 import _ffi
+    l = _ffi.lib()
+    raw = C.CDLL(_ffi.LIB_PATH)   # the two-step host replay is internal to the library (not part of include/zkir_b200.h)
+    for prog, inputs in ((mix_program(), [60]), (run(MEM_SRC).program, [])):
+        res = zkir_b200.VM(prog, inputs, zkir_b200.VMConfig(enable_execution_trace=True)).run()
+        rows = res.rows()
+        T = len(rows["instrs"])
+        code = np.asarray(prog.code, dtype=np.uint32)
+        # (1) host replay of the recorded rows
+        old_r = np.zeros(T, dtype=np.uint64); pts_r = np.zeros(T, dtype=np.uint32)
+        n_img = C.c_uint64(); n_ram = C.c_uint64()
+        regs = np.ascontiguousarray(rows["regs"]); fin = np.ascontiguousarray(rows["final_regs"]); ins = np.ascontiguousarray(rows["instrs"])
+        raw.zkir_mem_replay_full.restype = C.c_int
+        rc = raw.zkir_mem_replay_full(C.c_void_p(ins.ctypes.data), C.c_void_p(regs.ctypes.data), C.c_uint64(T), C.c_void_p(fin.ctypes.data),
+                                      C.c_void_p(code.ctypes.data), C.c_size_t(len(code)), C.c_void_p(old_r.ctypes.data), C.c_void_p(pts_r.ctypes.data),
+                                      C.byref(n_img), C.byref(n_ram))
+        assert rc == 0
+        log_n = 10
+        while (1 << log_n) <= T:
+            log_n += 1
+        bs = max(n_img.value, n_ram.value, 1)
+        b_r = np.zeros((25, bs), dtype=np.uint32); rng_r = np.zeros(1024, dtype=np.uint32); b7_r = np.zeros(128, dtype=np.uint32)
+        rc = raw.zkir_mem_boundary_full(C.c_uint32(log_n), C.c_void_p(b_r.ctypes.data), C.c_uint64(bs), C.c_void_p(rng_r.ctypes.data), C.c_void_p(b7_r.ctypes.data))
+        assert rc == 0
+        # (2) the interpreter's memory log
+        rc, h, (pcs, ins2, wlog, old_l, pts_l) = _run_memlog(prog, inputs, T + 8)
+        assert rc == 0 and l.zkir_vm_logged_rows(h) == T
+        assert np.array_equal(ins2[:T], ins)
+        is_mem = (pts_r != 0) | (old_r != 0) | (pts_l[:T] != 0) | (old_l[:T] != 0)
+        assert is_mem.any()
+        assert np.array_equal(old_l[:T], old_r) and np.array_equal(pts_l[:T], pts_r)
+        nw = l.zkir_vm_memlog_count(h)
+        widx = np.ctypeslib.as_array(l.zkir_vm_memlog_widx(h), shape=(nw,)).copy()
+        word = np.ctypeslib.as_array(l.zkir_vm_memlog_word(h), shape=(nw,)).copy()
+        ts = np.ctypeslib.as_array(l.zkir_vm_memlog_ts(h), shape=(nw,)).copy()
+        assert np.all(np.diff(widx.astype(np.int64)) > 0)   # ascending, no duplicates
+        assert int((widx >= l.zkir_image_words(len(code))).sum()) == n_ram.value
+        b_l = np.zeros((25, bs), dtype=np.uint32); rng_l = np.zeros(1024, dtype=np.uint32); b7_l = np.zeros(128, dtype=np.uint32)
+        raw.zkir_mem_boundary_from_words_full.restype = C.c_int
+        rc = raw.zkir_mem_boundary_from_words_full(C.c_void_p(code.ctypes.data), C.c_size_t(len(code)), C.c_void_p(widx.ctypes.data), C.c_void_p(word.ctypes.data),
+                                                   C.c_void_p(ts.ctypes.data), C.c_size_t(nw), C.c_uint32(log_n), C.c_void_p(b_l.ctypes.data), C.c_uint64(bs),
+                                                   C.c_void_p(rng_l.ctypes.data), C.c_void_p(b7_l.ctypes.data))
+        assert rc == 0
+        assert np.array_equal(b_l, b_r) and np.array_equal(rng_l, rng_r) and np.array_equal(b7_l, b7_r)
+        l.zkir_vm_free(h)

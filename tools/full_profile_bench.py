@@ -28,3 +28,11 @@ print(f"variant={os.environ.get('ZKIR_QUOTIENT_VARIANT', 'default')} rows=2^{ln}
 pb_rows, _ = ctx.prove_rows(res.rows(), cfg, ln, profile="full")   # the device converter + the same proof
 assert pb_rows == pb
 print("from rows (host memory replay + device converter): stage_ms", {k: round(v, 3) for k, v in ctx.stage_ms().items()})
+import time
+proof = zkir_b200.prove(res.program, [iters], cfg)    # Program -> Proof: write log + memory log, no host replay
+assert proof.bytes_ == pb
+t0 = time.perf_counter()
+for _ in range(reps):
+    proof = zkir_b200.prove(res.program, [iters], cfg)
+print(f"Program -> Proof (interpreter + write log + memory log + device converter): {(time.perf_counter() - t0) / reps * 1e3:.3f} ms wall, stage_ms",
+      {k: round(v, 3) for k, v in proof.stage_ms.items()})

@@ -93,6 +93,12 @@ SYMBOLS = {
     "zkir_vm_run_writelog": (C.c_int, [u32p, C.c_size_t, u8p, C.c_size_t, C.c_uint32, u64p, C.c_size_t, C.c_uint64, vp, vp, vp, C.c_uint64, C.POINTER(vp)]),
     "zkir_vm_run_writelog_cb": (C.c_int, [u32p, C.c_size_t, u8p, C.c_size_t, C.c_uint32, u64p, C.c_size_t, C.c_uint64, vp, vp, vp, C.c_uint64, vp, vp, C.c_uint64, C.POINTER(vp)]),
     "zkir_vm_logged_rows": (C.c_uint64, [vp]),
+    "zkir_vm_run_writelog_mem_cb": (C.c_int, [u32p, C.c_size_t, u8p, C.c_size_t, C.c_uint32, u64p, C.c_size_t, C.c_uint64, vp, vp, vp, vp, vp, C.c_uint64, vp, vp,
+                                            C.c_uint64, C.POINTER(vp)]),
+    "zkir_vm_memlog_count": (C.c_size_t, [vp]),
+    "zkir_vm_memlog_widx": (u64p, [vp]),
+    "zkir_vm_memlog_word": (u64p, [vp]),
+    "zkir_vm_memlog_ts": (u32p, [vp]),
     "zkir_vm_io_len": (C.c_size_t, [vp]),
     "zkir_vm_io": (u32p, [vp]),
     "zkir_vm_poseidon2_count": (C.c_size_t, [vp]),

@@ -21,7 +21,9 @@
 #include <string>
 #include <vector>
 #include <unordered_map>
+#include <unordered_set>
 #include <memory>
+#include <algorithm>
 #include "../../../include/zkir_b200.h"
 
 namespace {
@@ -127,6 +129,8 @@ struct zkir_vm_result {
   std::vector<zkir_mem_op> memops;  // data memory ops per row (fetch excluded)
   std::vector<u32> code;            // the program's code words (the ROM the proof is bound to)
   std::vector<u32> io;              // public I/O transcript: 4 words per READ / WRITE ecall (cycle, kind 0/1, value lo20, value hi20)
+  std::vector<u64> ml_widx, ml_word;   // memory-log mode: the aligned 8-byte words the run touched (ascending), their final contents
+  std::vector<u32> ml_ts;              // ... and the timestamp (cycle + 1) of their last access
   std::vector<u32> pos2;            // Poseidon2Witness records (zkir-spec/src/trace.rs:287-304): 34 words per SYS_POSEIDON2 call --
                                     // timestamp lo / hi, input_state[16], output_state[16] (traced runs only)
   u64 logged = 0;                   // write-log mode: rows written to the caller's arrays
@@ -182,7 +186,8 @@ void zkir_host_poseidon2_permute(uint32_t* state16);   // verify.cc: the Poseido
 static int vm_run_impl(const uint32_t* code, size_t n_code, const uint8_t* data, size_t n_data, uint32_t entry_point,
                        const uint64_t* inputs, size_t n_inputs, uint64_t max_cycles, int record_trace,
                        uint32_t* wl_pcs, uint32_t* wl_ins, uint64_t* wl_log, uint64_t wl_capacity, zkir_vm_result** out,
-                       void (*on_chunk)(void*, uint64_t) = nullptr, void* cb_user = nullptr, uint64_t chunk_rows = 0) {
+                       void (*on_chunk)(void*, uint64_t) = nullptr, void* cb_user = nullptr, uint64_t chunk_rows = 0,
+                       uint64_t* ml_old = nullptr, uint32_t* ml_pts = nullptr) {
   *out = nullptr;
   if (entry_point < 0x1000) {  // vm.rs:141-147 (the reference panics)
     g_vm_error = "Program appears to be in debug format (entry_point < 0x1000)";
@@ -210,6 +215,32 @@ static int vm_run_impl(const uint32_t* code, size_t n_code, const uint8_t* data,
     if (!i) return;
     regs[i] = v;
     if (wl) { if ((v >> 40) && wide_row == ~0ull) wide_row = cycles; cur_log = ((u64)i << 56) | (v & MASK40); }
+  };
+  // memory log (full AIR profile, docs/PROVER_SPEC.md 3.8): what the memory argument needs to know about a load / store and only the
+  // interpreter has for free -- the aligned 8-byte word before the access and the timestamp of that word's previous access
+  // The argument starts from the PUBLIC image (the code words; zero elsewhere) and sees loads and stores only: a word whose first
+  // access finds anything else (a data segment), or that SYS_POSEIDON2 wrote, is outside it and the run is refused (PACK_ERR_MEMVAL).
+  std::unordered_map<u64, u32> ml_last;
+  std::unordered_set<u64> ml_untracked;   // words written by a syscall
+  std::unordered_map<u64, u64> ml_shadow; // ... and what the argument still holds for those it had seen before
+  u64 ml_bad_row = ~0ull;
+  auto ML = [&](u64 a) {
+    if (!ml_old) return;
+    const u64 w = a >> 3;
+    const u64 cur = mem.read(w << 3, 8);
+    ml_old[cycles] = cur;
+    u32& ts = ml_last[w];
+    if (ts == 0) {
+      u64 init = 0;
+      for (int h = 0; h < 2; h++) {
+        const u64 wa = (w << 3) + 4 * h;
+        if (wa >= CODE_BASE && (wa - CODE_BASE) / 4 < n_code) init |= (u64)code[(wa - CODE_BASE) / 4] << (32 * h);
+      }
+      if (cur != init && ml_bad_row == ~0ull) ml_bad_row = cycles;
+    }
+    if (!ml_untracked.empty() && ml_untracked.count(w) && ml_bad_row == ~0ull) ml_bad_row = cycles;
+    ml_pts[cycles] = ts;
+    ts = (u32)(cycles + 1);
   };
   auto fail = [&](const std::string& m) { g_vm_error = m; return ZKIR_ERR_VM; };
   auto slt40 = [](u64 a, u64 b) { u64 s = 1ull << 39; return ((a & MASK40) ^ s) < ((b & MASK40) ^ s); };
@@ -285,22 +316,23 @@ static int vm_run_impl(const uint32_t* code, size_t n_code, const uint8_t* data,
       case SNE: W(fa, R(fb) != R(fc)); break;
       case CMOV: case CMOVNZ: if (R(fc) != 0) W(fa, R(fb)); break;
       case CMOVZ: if (R(fc) == 0) W(fa, R(fb)); break;
-      case LB: W(fa, (u64)(i64)(int8_t)mem.read(R(fb) + (u64)imm17, 1)); break;
-      case LBU: W(fa, mem.read(R(fb) + (u64)imm17, 1)); break;
+      case LB: ML(R(fb) + (u64)imm17); W(fa, (u64)(i64)(int8_t)mem.read(R(fb) + (u64)imm17, 1)); break;
+      case LBU: ML(R(fb) + (u64)imm17); W(fa, mem.read(R(fb) + (u64)imm17, 1)); break;
       case LH: case LHU: {
         u64 a = R(fb) + (u64)imm17;
         if (a % 2) return misaligned(a, 2);
+        ML(a);
         u64 v = mem.read(a, 2);
         W(fa, op == LH ? (u64)(i64)(int16_t)v : v);
         break;
       }
-      case LW: { u64 a = R(fb) + (u64)imm17; if (a % 4) return misaligned(a, 4); W(fa, mem.read(a, 4)); break; }
-      case LD: { u64 a = R(fb) + (u64)imm17; if (a % 8) return misaligned(a, 8); W(fa, mem.read(a, 8)); break; }
+      case LW: { u64 a = R(fb) + (u64)imm17; if (a % 4) return misaligned(a, 4); ML(a); W(fa, mem.read(a, 4)); break; }
+      case LD: { u64 a = R(fb) + (u64)imm17; if (a % 8) return misaligned(a, 8); ML(a); W(fa, mem.read(a, 8)); break; }
       // stores: S-type has rs1 (base) in bits 10:7 and rs2 (value) in bits 14:11 (encoder.rs:122-130)
-      case SB: mem.write(R(fa) + (u64)imm17, R(fb) & 0xFF, 1); break;
-      case SH: { u64 a = R(fa) + (u64)imm17; if (a % 2) return misaligned(a, 2); mem.write(a, R(fb) & 0xFFFF, 2); break; }
-      case SW: { u64 a = R(fa) + (u64)imm17; if (a % 4) return misaligned(a, 4); mem.write(a, R(fb) & 0xFFFFFFFFull, 4); break; }
-      case SD: { u64 a = R(fa) + (u64)imm17; if (a % 8) return misaligned(a, 8); mem.write(a, R(fb), 8); break; }
+      case SB: ML(R(fa) + (u64)imm17); mem.write(R(fa) + (u64)imm17, R(fb) & 0xFF, 1); break;
+      case SH: { u64 a = R(fa) + (u64)imm17; if (a % 2) return misaligned(a, 2); ML(a); mem.write(a, R(fb) & 0xFFFF, 2); break; }
+      case SW: { u64 a = R(fa) + (u64)imm17; if (a % 4) return misaligned(a, 4); ML(a); mem.write(a, R(fb) & 0xFFFFFFFFull, 4); break; }
+      case SD: { u64 a = R(fa) + (u64)imm17; if (a % 8) return misaligned(a, 8); ML(a); mem.write(a, R(fb), 8); break; }
       case BEQ: if (R(fa) == R(fb)) next_pc = pc + (u64)imm17; break;
       case BNE: if (R(fa) != R(fb)) next_pc = pc + (u64)imm17; break;
       case BLT: if (slt40(R(fa), R(fb))) next_pc = pc + (u64)imm17; break;
@@ -344,6 +376,10 @@ static int vm_run_impl(const uint32_t* code, size_t n_code, const uint8_t* data,
           if (record_trace) { res->pos2.push_back((u32)cycles); res->pos2.push_back((u32)(cycles >> 32)); res->pos2.insert(res->pos2.end(), st, st + 16); }
           zkir_host_poseidon2_permute(st);
           if (record_trace) res->pos2.insert(res->pos2.end(), st, st + 16);
+          if (ml_old) for (int k = 0; k < 16; k++) {   // the argument keeps the value its own loads / stores left in these words
+            const u64 w = (dst + 4 * k) >> 3;
+            if (ml_untracked.insert(w).second && ml_last.count(w)) ml_shadow[w] = mem.read(w << 3, 8);
+          }
           for (int k = 0; k < 16; k++) mem.write(dst + 4 * k, st[k], 4);
           W(10, 0);
           break;
@@ -372,6 +408,17 @@ static int vm_run_impl(const uint32_t* code, size_t n_code, const uint8_t* data,
     res->logged = cycles;
     if (wide_row != ~0ull) { g_vm_error = "write log: value above 40 bits at row " + std::to_string(wide_row); return ZKIR_ERR_AIR; }
   }
+  if (ml_bad_row != ~0ull) {
+    g_vm_error = "AIR v2 cannot constrain row " + std::to_string(ml_bad_row) + ": loaded value differs from the memory the AIR tracks (written by a syscall, or a data segment)";
+    return ZKIR_ERR_AIR;
+  }
+  if (ml_old) {   // the touched words in ascending order with their final contents: the boundary of the memory argument
+    std::vector<u64> ws;
+    ws.reserve(ml_last.size());
+    for (const auto& kv : ml_last) ws.push_back(kv.first);
+    std::sort(ws.begin(), ws.end());
+    for (u64 w : ws) { res->ml_widx.push_back(w); auto sh = ml_shadow.find(w); res->ml_word.push_back(sh != ml_shadow.end() ? sh->second : mem.read(w << 3, 8)); res->ml_ts.push_back(ml_last[w]); }
+  }
   *out = res.release();
   return 0;
 }
@@ -396,6 +443,21 @@ int zkir_vm_run_writelog_cb(const uint32_t* code, size_t n_code, const uint8_t* 
   if (!pcs32 || !instrs || !wlog || (on_chunk && !chunk_rows)) { g_vm_error = "null write-log arrays"; return ZKIR_ERR_ARG; }
   return vm_run_impl(code, n_code, data, n_data, entry_point, inputs, n_inputs, max_cycles, 0, pcs32, instrs, wlog, capacity, out, on_chunk, user, chunk_rows);
 }
+
+// write log + memory log (full AIR profile): additionally mem_old[capacity] / mem_pts[capacity] receive, on every load / store row, the
+// aligned 8-byte word before the access and the timestamp (cycle + 1, 0 = never) of that word's previous access
+int zkir_vm_run_writelog_mem_cb(const uint32_t* code, size_t n_code, const uint8_t* data, size_t n_data, uint32_t entry_point,
+                                const uint64_t* inputs, size_t n_inputs, uint64_t max_cycles, uint32_t* pcs32, uint32_t* instrs, uint64_t* wlog,
+                                uint64_t* mem_old, uint32_t* mem_pts, uint64_t capacity, void (*on_chunk)(void*, uint64_t), void* user,
+                                uint64_t chunk_rows, zkir_vm_result** out) {
+  if (!pcs32 || !instrs || !wlog || !mem_old || !mem_pts || (on_chunk && !chunk_rows)) { g_vm_error = "null write-log arrays"; return ZKIR_ERR_ARG; }
+  return vm_run_impl(code, n_code, data, n_data, entry_point, inputs, n_inputs, max_cycles, 0, pcs32, instrs, wlog, capacity, out, on_chunk, user, chunk_rows,
+                     mem_old, mem_pts);
+}
+size_t zkir_vm_memlog_count(const zkir_vm_result* r) { return r->ml_widx.size(); }
+const uint64_t* zkir_vm_memlog_widx(const zkir_vm_result* r) { return r->ml_widx.data(); }
+const uint64_t* zkir_vm_memlog_word(const zkir_vm_result* r) { return r->ml_word.data(); }
+const uint32_t* zkir_vm_memlog_ts(const zkir_vm_result* r) { return r->ml_ts.data(); }
 
 size_t zkir_vm_io_len(const zkir_vm_result* r) { return r->io.size() / 4; }
 const uint32_t* zkir_vm_io(const zkir_vm_result* r) { return r->io.data(); }

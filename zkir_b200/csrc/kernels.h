@@ -113,6 +113,23 @@ struct ExpandFullArgs {
   const u32* prev_ts;    // [T]
 };
 int launch_trace_expand_full(const ExpandFullArgs& a, cudaStream_t st, u64* launches);
+// ... and from the interpreter's register write log + memory log (16 + 12 B per row; zkir_vm_run_writelog_mem_cb): registers by the
+// last-writer scan (launch_wl_prefix, then pass 3 inside the kernel), memory cells from the logged word / previous timestamp
+struct WlFullArgs {
+  const u32* pcs;        // [T]
+  const u32* ins;        // [T]
+  const u64* wlog;       // [T]
+  const u64* old_word;   // [T] (memory rows only)
+  const u32* prev_ts;    // [T]
+  u64 T, N;
+  u64 final_pc;
+  int* chunk_prev;       // scratch, trace_expand_wl_scratch_ints(N) ints
+  u32* cols;
+  u64* err;
+  u32 n_code = 0;
+};
+int launch_wl_prefix(const u64* wlog, u64 T, u64 N, int* chunk_prev, cudaStream_t st, u64* launches);   // core build of trace_expand.cu
+int launch_trace_expand_wl_full(const WlFullArgs& a, cudaStream_t st, u64* launches);
 int launch_add_u32(u32* dst, const u32* src, u64 n, cudaStream_t st, u64* launches);   // dst[i] += src[i]
 struct WlArgs {          // register write log instead of full rows (trace_expand.cu)
   const u32* pcs;        // [T]

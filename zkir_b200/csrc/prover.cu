@@ -115,6 +115,7 @@ struct zkir_ctx {
   u32* ntt_tmp = nullptr; u64 ntt_tmp_words = 0;
   u32* scratch[2] = {nullptr, nullptr}; size_t scratch_bytes[2] = {0, 0};
   void* rows_dev = nullptr; size_t rows_bytes = 0;   // staging for raw interpreter rows (prove_rows)
+  void* memlog_pinned = nullptr; u64 memlog_capacity = 0;   // pinned write log + memory log of prove_program (full profile), 28 B per cycle
   u32* full_stage = nullptr; size_t full_stage_bytes = 0;   // pinned host staging of the full profile (prove_rows): memory replay arrays, boundary cells
   // zkir_b200_prove_program: pinned write log the interpreter records into, and the stream its chunks are uploaded on
   void* log_pinned = nullptr; u64 log_capacity = 0;
@@ -788,6 +789,7 @@ void zkir_b200_destroy(zkir_ctx* ctx) {
   for (int i = 0; i < 2; i++) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
   if (ctx->rows_dev) cudaFree(ctx->rows_dev);
   if (ctx->full_stage) cudaFreeHost(ctx->full_stage);
+  if (ctx->memlog_pinned) cudaFreeHost(ctx->memlog_pinned);
   if (ctx->d_io) cudaFree(ctx->d_io);
   if (ctx->log_pinned) cudaFreeHost(ctx->log_pinned);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
@@ -956,6 +958,18 @@ static int expand_rows(zkir_ctx* ctx, const uint64_t* pcs, const uint32_t* instr
 extern "C" int zkir_mem_replay_full(const uint32_t*, const uint64_t*, uint64_t, const uint64_t*, const uint32_t*, size_t, uint64_t*, uint32_t*, uint64_t*, uint64_t*);
 extern "C" int zkir_mem_boundary_full(uint32_t, uint32_t*, uint64_t, uint32_t*, uint32_t*);
 static const u32 MEM_BOUNDARY_COL0 = ZKIR_PROFILE_FULL_COL_BOUNDARY0, MEM_BOUNDARY_COLS = ZKIR_PROFILE_FULL_BOUNDARY_COLS;   // img_fin0 .. ram_fin_ts of the full table
+// boundary cells of the memory argument, after the converter kernel (which zeroed those columns): the first n_img rows of the image
+// columns, the first n_ram rows of the RAM columns, and the boundary's own lookup multiplicities (d_delta: [1024] range + [128] 7-bit)
+static int upload_mem_boundary(zkir_ctx* ctx, const u32* h_bcols, u64 bstride, u64 n_img, u64 n_ram, const u32* d_delta, u32* d_cols, u64 N) {
+  cudaStream_t st = ctx->stream;
+  for (u32 c = 0; c < MEM_BOUNDARY_COLS; c++) {
+    const u64 n = c < 9 ? n_img : n_ram;   // img_fin0..7, img_fin_ts (9 columns) | ram_on, ram_a0..2, ram_e0..2, ram_fin0..7, ram_fin_ts (16)
+    if (n) CU(cudaMemcpyAsync(d_cols + (u64)(MEM_BOUNDARY_COL0 + c) * N, h_bcols + (size_t)c * bstride, n * 4, cudaMemcpyHostToDevice, st));
+  }
+  RC(launch_add_u32(d_cols + (u64)ZKIR_COL_M_RNG * N, d_delta, 1024, st, &ctx->launches));
+  RC(launch_add_u32(d_cols + (u64)ZKIR_PROFILE_FULL_COL_M_B7 * N, d_delta + 1024, 128, st, &ctx->launches));
+  return 0;
+}
 static int expand_rows_full(zkir_ctx* ctx, const uint32_t* instrs, const uint64_t* pcs, const uint64_t* regs, uint64_t T, const uint64_t* final_regs,
                             uint64_t final_pc, uint32_t log_n, u32* d_cols) {
   const u64 N = 1ull << log_n;
@@ -1020,14 +1034,7 @@ static int expand_rows_full(zkir_ctx* ctx, const uint32_t* instrs, const uint64_
   fa.rows.final_pc = final_pc; fa.rows.cols = d_cols; fa.rows.err = ctx->d_err; fa.rows.n_code = (u32)ctx->code.size();
   fa.old_word = d_old; fa.prev_ts = d_pts;
   RC(launch_trace_expand_full(fa, st, &ctx->launches));
-  // boundary cells: the first n_img rows of the image columns, the first n_ram rows of the RAM columns (the kernel zeroed them)
-  for (u32 c = 0; c < MEM_BOUNDARY_COLS; c++) {
-    const u64 n = c < 9 ? n_img : n_ram;   // img_fin0..7, img_fin_ts (9 columns) | ram_on, ram_a0..2, ram_e0..2, ram_fin0..7, ram_fin_ts (16)
-    if (n) CU(cudaMemcpyAsync(d_cols + (u64)(MEM_BOUNDARY_COL0 + c) * N, h_bcols + (size_t)c * bstride, n * 4, cudaMemcpyHostToDevice, st));
-  }
-  RC(launch_add_u32(d_cols + (u64)ZKIR_COL_M_RNG * N, d_delta, 1024, st, &ctx->launches));
-  RC(launch_add_u32(d_cols + (u64)ZKIR_PROFILE_FULL_COL_M_B7 * N, d_delta + 1024, 128, st, &ctx->launches));
-  return 0;
+  return upload_mem_boundary(ctx, h_bcols, bstride, n_img, n_ram, d_delta, d_cols, N);
 }
 int zkir_b200_prove_rows(zkir_ctx* ctx, const zkir_params* p, const uint64_t* pcs, const uint32_t* instrs, const uint64_t* regs,
                          uint64_t n_rows, const uint64_t* final_regs, uint64_t final_pc, uint32_t entry_point, uint64_t exit_code,
@@ -1143,7 +1150,10 @@ int zkir_b200_prove_writelog(zkir_ctx* ctx, const zkir_params* p, const uint32_t
 #define PROG_CHUNK (1u << 16)
 extern "C" int zkir_vm_run_writelog_cb(const uint32_t*, size_t, const uint8_t*, size_t, uint32_t, const uint64_t*, size_t, uint64_t, uint32_t*, uint32_t*,
                                        uint64_t*, uint64_t, void (*)(void*, uint64_t), void*, uint64_t, zkir_vm_result**);
-struct ProgUpload { zkir_ctx* ctx; const u32 *h_pcs, *h_ins; const u64* h_wlog; WlStage sg; u64 done; cudaError_t e; };
+struct ProgUpload {
+  zkir_ctx* ctx; const u32 *h_pcs, *h_ins; const u64* h_wlog; WlStage sg; u64 done; cudaError_t e;
+  const u64* h_old = nullptr; const u32* h_pts = nullptr; u64* d_old = nullptr; u32* d_pts = nullptr;   // memory log (full profile)
+};
 static void prog_upload_to(ProgUpload* u, u64 rows_done) {
   if (rows_done <= u->done || u->e != cudaSuccess) return;
   const u64 r0 = u->done, n = rows_done - r0;
@@ -1151,9 +1161,109 @@ static void prog_upload_to(ProgUpload* u, u64 rows_done) {
   cudaError_t e = cudaMemcpyAsync(u->sg.d_wlog + r0, u->h_wlog + r0, n * 8, cudaMemcpyHostToDevice, cs);
   if (e == cudaSuccess) e = cudaMemcpyAsync(u->sg.d_pcs + r0, u->h_pcs + r0, n * 4, cudaMemcpyHostToDevice, cs);
   if (e == cudaSuccess) e = cudaMemcpyAsync(u->sg.d_ins + r0, u->h_ins + r0, n * 4, cudaMemcpyHostToDevice, cs);
+  if (e == cudaSuccess && u->h_old) e = cudaMemcpyAsync(u->d_old + r0, u->h_old + r0, n * 8, cudaMemcpyHostToDevice, cs);
+  if (e == cudaSuccess && u->h_old) e = cudaMemcpyAsync(u->d_pts + r0, u->h_pts + r0, n * 4, cudaMemcpyHostToDevice, cs);
   u->e = e; u->done = rows_done;
 }
 static void prog_on_chunk(void* user, uint64_t rows_done) { prog_upload_to(static_cast<ProgUpload*>(user), rows_done); }
+
+// Full profile, Program -> Proof: the interpreter appends the register write log AND the memory log (the word before each load / store
+// and that word's previous timestamp: 16 + 12 B per cycle) to pinned memory, chunks upload while it runs, the device rebuilds the
+// registers and expands the 248-column table; the boundary cells come from the interpreter's list of touched words.  No host replay.
+extern "C" int zkir_vm_run_writelog_mem_cb(const uint32_t*, size_t, const uint8_t*, size_t, uint32_t, const uint64_t*, size_t, uint64_t, uint32_t*, uint32_t*,
+                                           uint64_t*, uint64_t*, uint32_t*, uint64_t, void (*)(void*, uint64_t), void*, uint64_t, zkir_vm_result**);
+extern "C" int zkir_mem_boundary_from_words_full(const uint32_t*, size_t, const uint64_t*, const uint64_t*, const uint32_t*, size_t, uint32_t, uint32_t*, uint64_t,
+                                                 uint32_t*, uint32_t*);
+static int prove_program_full_wl(zkir_ctx* ctx, const zkir_params* p, const uint32_t* code, size_t n_code, const uint8_t* data, size_t n_data,
+                                 uint32_t entry_point, const uint64_t* inputs, size_t n_inputs, uint64_t max_cycles, uint32_t* pv_out,
+                                 uint64_t* out_cycles, uint32_t* out_log_n, uint8_t** proof, size_t* proof_len) {
+  int rc;
+  if (ctx->memlog_capacity < max_cycles) {   // 28 B per cycle: wlog, old word | pcs, ins, prev_ts
+    if (ctx->memlog_pinned) cudaFreeHost(ctx->memlog_pinned);
+    ctx->memlog_pinned = nullptr; ctx->memlog_capacity = 0;
+    CU(cudaMallocHost(&ctx->memlog_pinned, max_cycles * 28));
+    ctx->memlog_capacity = max_cycles;
+  }
+  if (!ctx->copy_stream) { CU(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)); CU(cudaEventCreateWithFlags(&ctx->copy_done, cudaEventDisableTiming)); }
+  const u64 cap = ctx->memlog_capacity;
+  char* hb = (char*)ctx->memlog_pinned;
+  u64* h_wlog = (u64*)hb; u64* h_old = (u64*)(hb + cap * 8);
+  u32* h_pcs = (u32*)(hb + cap * 16); u32* h_ins = (u32*)(hb + cap * 20); u32* h_pts = (u32*)(hb + cap * 24);
+  CU(cudaStreamSynchronize(ctx->stream));   // the previous proof may still read the device staging
+  u64 n_scan = 1ull << ZKIR_RANGE_BITS;
+  while (n_scan < max_cycles || n_scan < n_code) n_scan <<= 1;
+  // device staging: wlog | old | pcs | ins | pts | scan scratch | multiplicity deltas
+  const size_t scratch = trace_expand_wl_scratch_ints(n_scan) * 4;
+  const size_t need = max_cycles * 28 + scratch + 64 + (1024 + 128) * 4 + 64;
+  if (ctx->rows_bytes < need) {
+    if (ctx->rows_dev) cudaFree(ctx->rows_dev);
+    ctx->rows_dev = nullptr; ctx->rows_bytes = 0;
+    CU(cudaMalloc(&ctx->rows_dev, need));
+    ctx->rows_bytes = need;
+  }
+  char* db = (char*)ctx->rows_dev;
+  ProgUpload up;
+  up.ctx = ctx; up.h_pcs = h_pcs; up.h_ins = h_ins; up.h_wlog = h_wlog; up.done = 0; up.e = cudaSuccess;
+  up.sg.d_wlog = (u64*)db; up.d_old = (u64*)(db + max_cycles * 8);
+  up.sg.d_pcs = (u32*)(db + max_cycles * 16); up.sg.d_ins = (u32*)(db + max_cycles * 20); up.d_pts = (u32*)(db + max_cycles * 24);
+  up.sg.d_scr = (int*)(db + ((max_cycles * 28 + 15) & ~(size_t)15));
+  u32* d_delta = (u32*)(db + ((max_cycles * 28 + scratch + 63) & ~(size_t)63));
+  up.h_old = h_old; up.h_pts = h_pts;
+  zkir_vm_result* res = nullptr;
+  rc = zkir_vm_run_writelog_mem_cb(code, n_code, data, n_data, entry_point, inputs, n_inputs, max_cycles, h_pcs, h_ins, h_wlog, h_old, h_pts, cap,
+                                   prog_on_chunk, &up, PROG_CHUNK, &res);
+  if (rc) { ctx->err = std::string("interpreter: ") + zkir_vm_last_error(); return rc; }
+  const u64 T = zkir_vm_cycles(res), final_pc = zkir_vm_final_pc(res);
+  const int halt_kind = zkir_vm_halt_kind(res);
+  const u64 exit_code = zkir_vm_exit_code(res);
+  u32 log_n = ZKIR_RANGE_BITS;
+  while ((1ull << log_n) <= T || (1ull << log_n) < n_code) log_n++;   // at least one padding row after the last cycle
+  const u64 N = 1ull << log_n;
+  if (out_cycles) *out_cycles = T;
+  if (out_log_n) *out_log_n = log_n;
+  // boundary cells from the interpreter's list of touched words (host, a few rows), staged in pinned memory
+  const size_t n_words = zkir_vm_memlog_count(res);
+  const u64* widx = zkir_vm_memlog_widx(res);
+  const u64 n_img = zkir_image_words(n_code);
+  u64 n_ram = 0;
+  for (size_t k = 0; k < n_words; k++) n_ram += widx[k] >= n_img;
+  const u64 bstride = std::max<u64>(std::max(n_img, n_ram), 1);
+  const size_t bbytes = (1024 + 128) * 4 + (size_t)MEM_BOUNDARY_COLS * bstride * 4;
+  if (ctx->full_stage_bytes < bbytes) {
+    if (ctx->full_stage) cudaFreeHost(ctx->full_stage);
+    ctx->full_stage = nullptr; ctx->full_stage_bytes = 0;
+    cudaError_t me = cudaMallocHost(&ctx->full_stage, bbytes);
+    if (me != cudaSuccess) { zkir_vm_free(res); ctx->err = std::string("cudaMallocHost: ") + cudaGetErrorString(me); return ZKIR_ERR_OOM; }
+    ctx->full_stage_bytes = bbytes;
+  }
+  u32* h_delta = ctx->full_stage;
+  u32* h_bcols = h_delta + 1024 + 128;
+  memset(h_bcols, 0, (size_t)MEM_BOUNDARY_COLS * bstride * 4);
+  rc = zkir_mem_boundary_from_words_full(code, n_code, widx, zkir_vm_memlog_word(res), zkir_vm_memlog_ts(res), n_words, log_n, h_bcols, bstride, h_delta, h_delta + 1024);
+  if (!rc) rc = zkir_b200_set_io(ctx, zkir_vm_io(res), zkir_vm_io_len(res));   // the run's public I/O transcript is part of the statement
+  zkir_vm_free(res);
+  if (rc) { if (ctx->err.empty()) ctx->err = zkir_b200_last_error(nullptr); return rc; }
+  if ((rc = check_params(ctx, p, log_n)) != 0) return rc;
+  if ((rc = ws_prepare(ctx, p, log_n)) != 0) return rc;
+  if ((rc = ensure_public_columns(ctx, p, log_n)) != 0) return rc;
+  ctx->ws.graph_run = false;
+  CU(cudaEventRecord(ctx->ev[ZKIR_STAGE_H2D], ctx->stream));
+  prog_upload_to(&up, T);                                   // the tail that no chunk boundary covered
+  if (up.e != cudaSuccess) { ctx->err = std::string("write-log upload: ") + cudaGetErrorString(up.e); return ZKIR_ERR_CUDA; }
+  CU(cudaEventRecord(ctx->copy_done, ctx->copy_stream));
+  CU(cudaStreamWaitEvent(ctx->stream, ctx->copy_done, 0));
+  cudaStream_t st = ctx->stream;
+  CU(cudaMemcpyAsync(d_delta, h_delta, (1024 + 128) * 4, cudaMemcpyHostToDevice, st));
+  CU(cudaMemsetAsync(ctx->d_err, 0xff, 16, st));
+  WlFullArgs wa;
+  wa.pcs = up.sg.d_pcs; wa.ins = up.sg.d_ins; wa.wlog = up.sg.d_wlog; wa.old_word = up.d_old; wa.prev_ts = up.d_pts; wa.T = T; wa.N = N; wa.final_pc = final_pc;
+  wa.chunk_prev = up.sg.d_scr; wa.cols = ctx->ws.trace; wa.err = ctx->d_err; wa.n_code = (u32)ctx->code.size();
+  RC(launch_trace_expand_wl_full(wa, st, &ctx->launches));
+  if ((rc = upload_mem_boundary(ctx, h_bcols, bstride, n_img, n_ram, d_delta, ctx->ws.trace, N)) != 0) return rc;
+  fill_public_values(pv_out, entry_point, T, exit_code, halt_kind);
+  if ((rc = prove_resident(ctx, p, log_n, pv_out, ctx->ws.trace)) != 0) return rc;
+  return finish_proof(ctx, p, log_n, proof, proof_len);
+}
 
 int zkir_b200_prove_program(zkir_ctx* ctx, const zkir_params* p, const uint32_t* code, size_t n_code, const uint8_t* data, size_t n_data,
                             uint32_t entry_point, const uint64_t* inputs, size_t n_inputs, uint64_t max_cycles,
@@ -1163,9 +1273,11 @@ int zkir_b200_prove_program(zkir_ctx* ctx, const zkir_params* p, const uint32_t*
   cudaSetDevice(ctx->device);
   int rc = zkir_b200_set_program(ctx, code, n_code);
   if (rc) return rc;
+  if (profile_is_full(p->width) && ctx->comm == nullptr) return prove_program_full_wl(ctx, p, code, n_code, data, n_data, entry_point, inputs, n_inputs, max_cycles,
+                                                                                       pv_out, out_cycles, out_log_n, proof, proof_len);
   if (profile_is_full(p->width)) {
-    // full profile: the interpreter records full rows (zkir_vm_run with the execution trace on); zkir_b200_prove_rows replays the run's
-    // memory on the host and expands the wide table on the device
+    // full profile on a sharded context: the interpreter records full rows (zkir_vm_run with the execution trace on); zkir_b200_prove_rows
+    // replays the run's memory on the host and expands the wide table on the device
     zkir_vm_result* res = nullptr;
     rc = zkir_vm_run(code, n_code, data, n_data, entry_point, inputs, n_inputs, max_cycles, 1, &res);
     if (rc) { ctx->err = std::string("interpreter: ") + zkir_vm_last_error(); return rc; }
