@@ -445,12 +445,35 @@ def main():
         for _ in range(3):
             ctx.prove_program(pf, [it_f], cfg_fp)
         f_prog_ms = (time.perf_counter() - t0) * 1e3 / 3
+        # end to end from the write log + memory log in PINNED host memory (zkir_b200_prove_writelog_mem, 28 B/row): the full profile's
+        # counterpart of the headline `e2e`
+        cap_f = int(rf.cycles) + 8
+        pin_f = {k: zkir_b200.PinnedBuffer((cap_f,), dt) for k, dt in (("wlog", np.uint64), ("mem_old", np.uint64), ("pcs", np.uint32), ("instrs", np.uint32), ("mem_pts", np.uint32))}
+        out_f = {k: b.array for k, b in pin_f.items()}
+        out_f["mem_old"][:] = 0
+        out_f["mem_pts"][:] = 0
+        wl_f = zkir_b200.VM(pf, [it_f], zkir_b200.VMConfig(max_cycles=cap_f)).run_writelog(out_f, memory_log=True).writelog()
+        pb_w, _ = ctx.prove_writelog(wl_f, cfg_f, ln_f)
+        if pb_w != pb_f:
+            raise SystemExit("full profile: zkir_b200_prove_writelog_mem and the packed-columns path disagree")
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            ctx.prove_writelog(wl_f, cfg_f, ln_f)
+        f_wl_ms = (time.perf_counter() - t0) * 1e3 / 3
+        f_wl_conv_ms = ctx.stage_ms()["h2d"]
+        del wl_f, out_f
+        for b in pin_f.values():
+            b.close()
         extra["full_profile_mix"] = {
             "workload": f"MUL/MULH/DIVU/REMU + shifts + bitwise + SLT + SD/LD loop, {rf.cycles} cycles -> 2^{ln_f}-row trace, full AIR profile ({cols_f.shape[0]} main columns), per GPU",
             "ms_per_proof": f_ms, "value": world * rf.cycles / (f_ms * 1e-3), "unit": UNIT, "proof_bytes": len(pb_f),
             "stage_ms": {k: v for k, v in f_stage.items() if k != "h2d"}, "interpreter_full_rows_s": f_vm_s, "host_packer_s": f_pack_s,
             "e2e_rows": {"ms_per_proof": f_rows_ms, "value": world * rf.cycles / (f_rows_ms * 1e-3), "h2d_and_convert_ms": f_conv_ms, "h2d_bytes_per_step": int(rf.cycles) * 152,
                          "api": "zkir_b200_prove_rows (full width): TraceRow data in host memory -> host replay of the run's memory -> device converter -> proof bytes"},
+            "e2e": {"ms_per_proof": f_wl_ms, "value": world * rf.cycles / (f_wl_ms * 1e-3), "h2d_and_convert_ms": f_wl_conv_ms, "h2d_bytes_per_step": int(rf.cycles) * 28,
+                    "d2h_bytes_per_step": len(pb_f),
+                    "api": "zkir_b200_prove_writelog_mem: register write log + memory log in pinned host memory -> device register rebuild + 248-column converter -> proof bytes in host memory"},
             "program_to_proof": {"ms_per_proof": f_prog_ms, "value": world * rf.cycles / (f_prog_ms * 1e-3), "api": "zkir_b200_prove_program (full width), interpreter included: register write log + memory log (28 B/cycle) in pinned memory, chunks uploaded while it runs, device converter"},
             "note": "`value`: trace resident in HBM (packed by the host packer outside the timed region, which the e2e paths do not use)"}
         ctx.set_program(res)

@@ -95,11 +95,22 @@ int zkir_b200_prove_rows(zkir_ctx*, const zkir_params*, const uint64_t* pcs, con
 int zkir_b200_prove_writelog(zkir_ctx*, const zkir_params*, const uint32_t* pcs, const uint32_t* instrs, const uint64_t* wlog,
                              uint64_t n_rows, uint64_t final_pc, uint32_t entry_point, uint64_t exit_code, int halt_kind, uint32_t log_n,
                              uint32_t* public_values_out, uint8_t** proof, size_t* proof_len);
+/* FULL profile (params.width = ZKIR_AIR_FULL_WIDTH) from the write log + MEMORY log of zkir_vm_run_writelog_mem_cb (or a Rust recorder hooked
+ * into Memory::record_op, memory.rs:243-253): mem_old / mem_pts [n_rows] = on load / store rows the aligned 8-byte word before the access and
+ * the timestamp (cycle + 1, 0 = never) of its previous access; mem_widx / mem_word / mem_ts [n_words] = the touched words in strictly
+ * ascending order, their final contents and last timestamps.  28 B/row cross PCIe; the device rebuilds the registers and expands the 248
+ * columns (no host replay); rows the AIR cannot constrain return ZKIR_ERR_AIR as in zkir_pack_trace_full.  Needs zkir_b200_set_program (and
+ * zkir_b200_set_io) first.  A log inconsistent with the program's loads and stores gives a proof the verifier rejects, never a wrong one. */
+int zkir_b200_prove_writelog_mem(zkir_ctx*, const zkir_params*, const uint32_t* pcs, const uint32_t* instrs, const uint64_t* wlog,
+                                 const uint64_t* mem_old, const uint32_t* mem_pts, uint64_t n_rows, const uint64_t* mem_widx,
+                                 const uint64_t* mem_word, const uint32_t* mem_ts, size_t n_words, uint64_t final_pc, uint32_t entry_point,
+                                 uint64_t exit_code, int halt_kind, uint32_t log_n, uint32_t* public_values_out, uint8_t** proof, size_t* proof_len);
 /* Program -> Proof in one call, the drop-in for `zkir_runtime::prove(program, inputs)` (absent upstream: lib.rs:29-62): runs the
  * interpreter (vm.cc) with the register write log recorded straight into pinned memory, uploads the log in chunks WHILE the
  * interpreter is still running, then proves.  Sets the context's program itself.  out_cycles / out_log_n may be NULL.
- * params.width selects the profile the program needs (zkir_program_profile); with ZKIR_AIR_FULL_WIDTH the interpreter records full rows
- * and the call continues as zkir_b200_prove_rows. */
+ * params.width selects the profile the program needs (zkir_program_profile); with ZKIR_AIR_FULL_WIDTH the interpreter also records the
+ * memory log (zkir_vm_run_writelog_mem_cb, 28 B/cycle) and the call continues as zkir_b200_prove_writelog_mem (on a sharded context: full
+ * rows and zkir_b200_prove_rows). */
 int zkir_b200_prove_program(zkir_ctx*, const zkir_params*, const uint32_t* code, size_t n_code, const uint8_t* data, size_t n_data,
                             uint32_t entry_point, const uint64_t* inputs, size_t n_inputs, uint64_t max_cycles,
                             uint32_t* public_values_out, uint64_t* out_cycles, uint32_t* out_log_n, uint8_t** proof, size_t* proof_len);

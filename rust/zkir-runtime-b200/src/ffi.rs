@@ -100,6 +100,32 @@ extern "C" {
         proof: *mut *mut u8,
         proof_len: *mut usize,
     ) -> c_int;
+    /// full profile from the write log + memory log (28 B/row): mem_old[n] / mem_pts[n] = on load / store rows the aligned 8-byte word
+    /// before the access and the timestamp (cycle + 1, 0 = never) of its previous access, logged where Memory::record_op runs
+    /// (zkir-runtime/src/memory.rs:243-253); mem_widx / mem_word / mem_ts [n_words] = the touched words (address / 8) in strictly
+    /// ascending order with their final contents and last timestamps
+    pub fn zkir_b200_prove_writelog_mem(
+        ctx: *mut zkir_ctx,
+        params: *const zkir_params,
+        pcs: *const u32,
+        instrs: *const u32,
+        wlog: *const u64,
+        mem_old: *const u64,
+        mem_pts: *const u32,
+        n_rows: u64,
+        mem_widx: *const u64,
+        mem_word: *const u64,
+        mem_ts: *const u32,
+        n_words: usize,
+        final_pc: u64,
+        entry_point: u32,
+        exit_code: u64,
+        halt_kind: c_int,
+        log_n: u32,
+        public_values_out: *mut u32, // [5]
+        proof: *mut *mut u8,
+        proof_len: *mut usize,
+    ) -> c_int;
     /// one proof sharded over several GPUs (one context per GPU): rank 0 draws the id, the host hands it to the other ranks,
     /// every rank calls comm_init; afterwards the prove_* calls are collective and return the single-GPU proof bytes everywhere
     pub fn zkir_b200_comm_unique_id(id: *mut u8 /* [128] */) -> c_int;

@@ -173,7 +173,49 @@ impl Prover {
     }
 }
 
+/// Memory log of a run, beside the register write log: what the full profile's offline memory checking needs from the interpreter.
+/// A recorder hooked into `Memory::record_op` (zkir-runtime/src/memory.rs:243-253) fills it with one HashMap<u64, u32> of last
+/// timestamps; rows without a load / store stay 0.
+pub struct MemoryLog {
+    pub old: Vec<u64>,   // [cycles] aligned 8-byte word before the access
+    pub pts: Vec<u32>,   // [cycles] timestamp (cycle + 1) of the word's previous access, 0 = never
+    pub widx: Vec<u64>,  // touched words (address / 8), strictly ascending
+    pub word: Vec<u64>,  // their final contents
+    pub ts: Vec<u32>,    // their last timestamps
+}
+
 impl Prover {
+    /// Full-profile programs from the write log + memory log (28 B per cycle over PCIe, no host replay): the device rebuilds the
+    /// registers, expands the 248-column table and proves it.
+    #[allow(clippy::too_many_arguments)]
+    pub fn prove_writelog_mem(
+        &mut self,
+        cfg: &ProverConfig,
+        log: &WriteLog,
+        mem: &MemoryLog,
+        entry_point: u32,
+        exit_code: u64,
+        halt_kind: c_int,
+        log_n: u32,
+    ) -> Result<(Vec<u8>, [u32; 5]), RuntimeError> {
+        let params = cfg.params_for(ffi::ZKIR_AIR_FULL_WIDTH);
+        let mut pv = [0u32; 5];
+        let (mut proof, mut len) = (ptr::null_mut::<u8>(), 0usize);
+        let rc = unsafe {
+            ffi::zkir_b200_prove_writelog_mem(
+                self.ctx, &params, log.pcs.as_ptr(), log.instrs.as_ptr(), log.wlog.as_ptr(), mem.old.as_ptr(), mem.pts.as_ptr(),
+                log.len as u64, mem.widx.as_ptr(), mem.word.as_ptr(), mem.ts.as_ptr(), mem.widx.len(), log.final_pc, entry_point,
+                exit_code, halt_kind, log_n, pv.as_mut_ptr(), &mut proof, &mut len,
+            )
+        };
+        if rc != ffi::ZKIR_OK {
+            return Err(error_of(self.ctx, rc));
+        }
+        let bytes = unsafe { std::slice::from_raw_parts(proof, len) }.to_vec();
+        unsafe { ffi::zkir_b200_free_proof(proof) };
+        Ok((bytes, pv))
+    }
+
     /// Full-profile programs (MUL / DIV, bitwise, shifts, signed compares, loads / stores): the rows `VM::run` records with
     /// `enable_execution_trace` (zkir-spec/src/trace.rs:24-50) go in as three flat arrays; the library builds the 248-column table
     /// (zkir_pack_rows_full: multiplier block, lookup multiplicities, offline memory checking) and proves it on the GPU.

@@ -332,6 +332,49 @@ def test_gpu_memory_programs_equal_oracle(gpu_ctx, oracle_full):
 
 
 @pytest.mark.gpu
+def test_gpu_full_profile_from_write_log_and_memory_log(gpu_ctx, oracle_full):
+    """zkir_b200_prove_writelog_mem: 28 B/row of logs -> the same proof bytes as the host packer + oracle; inconsistent logs never give a
+    proof that verifies."""
+    cfg = zkir_b200.ProverConfig(num_queries=16, pow_bits=4)
+    for prog, inputs in ((mix_program(), [700]), (zkir_b200.assemble(MEM_SRC), [])):
+        res = zkir_b200.VM(prog, inputs, zkir_b200.VMConfig(enable_execution_trace=True)).run()
+        cols, pv = res.pack()
+        want = oracle_full.prove(cfg, cols, pv, res)
+        r = zkir_b200.VM(prog, inputs, zkir_b200.VMConfig(max_cycles=res.cycles + 8)).run_writelog()
+        wl = r.writelog()
+        assert "mem_old" in wl and wl["pcs"].shape[0] == res.cycles
+        pb, pv2 = gpu_ctx.prove_writelog(wl, cfg)
+        assert pb == want and np.array_equal(pv2, pv)
+    # the register write log alone cannot describe a full-profile run
+    core_wl = {k: v for k, v in wl.items() if not k.startswith("mem_")}
+    with pytest.raises(zkir_b200.RuntimeError) as e:
+        gpu_ctx.prove_writelog(core_wl, cfg)          # core width: the ROM lookup / opcode check refuses the rows
+    import ctypes as C
+    params = cfg.params(FULL_WIDTH)
+    proof, plen = C.c_void_p(), C.c_size_t()
+    pvb = np.zeros(5, dtype=np.uint32)
+    rc = gpu_ctx._l.zkir_b200_prove_writelog(gpu_ctx._h, C.byref(params), wl["pcs"].ctypes.data, wl["instrs"].ctypes.data, wl["wlog"].ctypes.data, len(wl["pcs"]),
+                                             int(wl["final_pc"]), int(wl["entry_point"]), 0, int(wl["halt_kind"]), 10, pvb.ctypes.data_as(zkir_b200._ffi.u32p),
+                                             C.byref(proof), C.byref(plen))
+    assert rc == -1 and b"memory log" in gpu_ctx._l.zkir_b200_last_error(gpu_ctx._h)
+    # tampered logs: a wrong old word contradicts the loaded value (refused); a wrong previous timestamp or final word breaks the bus (rejected)
+    rows = res.rows()
+    ld = next(i for i in range(res.cycles) if int(rows["instrs"][i]) & 0x7F in (0x30, 0x31, 0x32, 0x33, 0x34, 0x35))
+    bad = dict(wl); bad["mem_old"] = wl["mem_old"].copy(); bad["mem_old"][ld] ^= 0xFF
+    with pytest.raises(zkir_b200.RuntimeError):
+        gpu_ctx.prove_writelog(bad, cfg)
+    for key, idx in (("mem_pts", ld), ("mem_word", 0), ("mem_ts", 0)):
+        bad = dict(wl); bad[key] = wl[key].copy(); bad[key][idx] += 1
+        try:
+            pb_bad, pv_bad = gpu_ctx.prove_writelog(bad, cfg)
+        except zkir_b200.RuntimeError:
+            continue
+        assert zkir_b200.verify(pb_bad, cfg, pv_bad, res)[0] is False, key
+    pb, _ = gpu_ctx.prove_writelog(wl, cfg)           # the context is still good
+    assert pb == want
+
+
+@pytest.mark.gpu
 def test_gpu_full_profile_program_to_proof_malformed_runs(gpu_ctx):
     """Rows the full profile cannot constrain must fail with an error through Program -> Proof too (the device converter reports them)."""
     cfg = zkir_b200.ProverConfig(num_queries=8, pow_bits=2)

@@ -95,6 +95,8 @@ SYMBOLS = {
     "zkir_vm_logged_rows": (C.c_uint64, [vp]),
     "zkir_vm_run_writelog_mem_cb": (C.c_int, [u32p, C.c_size_t, u8p, C.c_size_t, C.c_uint32, u64p, C.c_size_t, C.c_uint64, vp, vp, vp, vp, vp, C.c_uint64, vp, vp,
                                             C.c_uint64, C.POINTER(vp)]),
+    "zkir_b200_prove_writelog_mem": (C.c_int, [vp, C.POINTER(Params), vp, vp, vp, vp, vp, C.c_uint64, vp, vp, vp, C.c_size_t, C.c_uint64, C.c_uint32, C.c_uint64,
+                                              C.c_int, C.c_uint32, u32p, C.POINTER(vp), C.POINTER(C.c_size_t)]),
     "zkir_vm_memlog_count": (C.c_size_t, [vp]),
     "zkir_vm_memlog_widx": (u64p, [vp]),
     "zkir_vm_memlog_word": (u64p, [vp]),

@@ -1132,6 +1132,7 @@ int zkir_b200_prove_writelog(zkir_ctx* ctx, const zkir_params* p, const uint32_t
   int rc = check_params(ctx, p, log_n);
   if (rc) return rc;
   if (!pv_out || !proof || !proof_len) { ctx->err = "null argument"; return ZKIR_ERR_ARG; }
+  if (profile_is_full(p->width)) { ctx->err = "the register write log alone does not describe loads and stores: full-profile runs take zkir_b200_prove_writelog_mem (write log + memory log), zkir_b200_prove_rows or zkir_b200_prove_program"; return ZKIR_ERR_ARG; }
   if ((rc = ws_prepare(ctx, p, log_n)) != 0) return rc;
   if ((rc = ensure_public_columns(ctx, p, log_n)) != 0) return rc;
   ctx->ws.graph_run = false;   // only zkir_b200_prove replays graphs; a stale flag would hide this proof's stage timings
@@ -1174,6 +1175,94 @@ extern "C" int zkir_vm_run_writelog_mem_cb(const uint32_t*, size_t, const uint8_
                                            uint64_t*, uint64_t*, uint32_t*, uint64_t, void (*)(void*, uint64_t), void*, uint64_t, zkir_vm_result**);
 extern "C" int zkir_mem_boundary_from_words_full(const uint32_t*, size_t, const uint64_t*, const uint64_t*, const uint32_t*, size_t, uint32_t, uint32_t*, uint64_t,
                                                  uint32_t*, uint32_t*);
+// device staging of the full profile's logs: wlog | old | pcs | ins | pts [cap each] | scan scratch | multiplicity deltas
+struct FullWlStage { WlStage sg; u64* d_old; u32* d_pts; u32* d_delta; };
+static int full_wl_stage(zkir_ctx* ctx, u64 cap, u64 n_scan_min, FullWlStage* fs) {
+  u64 n_scan = 1ull << ZKIR_RANGE_BITS;
+  while (n_scan < cap || n_scan < n_scan_min) n_scan <<= 1;
+  const size_t scratch = trace_expand_wl_scratch_ints(n_scan) * 4;
+  const size_t need = cap * 28 + scratch + 64 + (1024 + 128) * 4 + 64;
+  if (ctx->rows_bytes < need) {
+    if (ctx->rows_dev) cudaFree(ctx->rows_dev);
+    ctx->rows_dev = nullptr; ctx->rows_bytes = 0;
+    CU(cudaMalloc(&ctx->rows_dev, need));
+    ctx->rows_bytes = need;
+  }
+  char* db = (char*)ctx->rows_dev;
+  fs->sg.d_wlog = (u64*)db; fs->d_old = (u64*)(db + cap * 8);
+  fs->sg.d_pcs = (u32*)(db + cap * 16); fs->sg.d_ins = (u32*)(db + cap * 20); fs->d_pts = (u32*)(db + cap * 24);
+  fs->sg.d_scr = (int*)(db + ((cap * 28 + 15) & ~(size_t)15));
+  fs->d_delta = (u32*)(db + ((cap * 28 + scratch + 63) & ~(size_t)63));
+  return 0;
+}
+// logs on the device (copies ordered before ctx->stream's next work) -> proof: boundary cells from the touched words (host, a few rows),
+// register rebuild + 248-column converter, boundary upload, proof.  ws_prepare / check_params done by the caller.
+static int prove_full_from_logs(zkir_ctx* ctx, const zkir_params* p, const FullWlStage& fs, u64 T, u64 final_pc, const uint64_t* widx, const uint64_t* word,
+                                const uint32_t* ts, size_t n_words, uint32_t log_n, uint32_t entry_point, uint64_t exit_code, int halt_kind, uint32_t* pv_out,
+                                uint8_t** proof, size_t* proof_len) {
+  int rc;
+  const u64 N = 1ull << log_n;
+  const size_t n_code = ctx->code.size();
+  const u64 n_img = zkir_image_words(n_code);
+  u64 n_ram = 0;
+  for (size_t k = 0; k < n_words; k++) n_ram += widx[k] >= n_img;
+  const u64 bstride = std::max<u64>(std::max(n_img, n_ram), 1);
+  const size_t bbytes = (1024 + 128) * 4 + (size_t)MEM_BOUNDARY_COLS * bstride * 4;
+  CU(cudaStreamSynchronize(ctx->stream));   // a previous proof's boundary upload may still read the pinned staging
+  if (ctx->full_stage_bytes < bbytes) {
+    if (ctx->full_stage) cudaFreeHost(ctx->full_stage);
+    ctx->full_stage = nullptr; ctx->full_stage_bytes = 0;
+    cudaError_t me = cudaMallocHost(&ctx->full_stage, bbytes);
+    if (me != cudaSuccess) { ctx->err = std::string("cudaMallocHost: ") + cudaGetErrorString(me); return ZKIR_ERR_OOM; }
+    ctx->full_stage_bytes = bbytes;
+  }
+  u32* h_delta = ctx->full_stage;
+  u32* h_bcols = h_delta + 1024 + 128;
+  memset(h_bcols, 0, (size_t)MEM_BOUNDARY_COLS * bstride * 4);
+  rc = zkir_mem_boundary_from_words_full(ctx->code.data(), n_code, widx, word, ts, n_words, log_n, h_bcols, bstride, h_delta, h_delta + 1024);
+  if (rc) { ctx->err = zkir_b200_last_error(nullptr); return rc; }
+  cudaStream_t st = ctx->stream;
+  CU(cudaMemcpyAsync(fs.d_delta, h_delta, (1024 + 128) * 4, cudaMemcpyHostToDevice, st));
+  CU(cudaMemsetAsync(ctx->d_err, 0xff, 16, st));
+  WlFullArgs wa;
+  wa.pcs = fs.sg.d_pcs; wa.ins = fs.sg.d_ins; wa.wlog = fs.sg.d_wlog; wa.old_word = fs.d_old; wa.prev_ts = fs.d_pts; wa.T = T; wa.N = N; wa.final_pc = final_pc;
+  wa.chunk_prev = fs.sg.d_scr; wa.cols = ctx->ws.trace; wa.err = ctx->d_err; wa.n_code = (u32)n_code;
+  RC(launch_trace_expand_wl_full(wa, st, &ctx->launches));
+  if ((rc = upload_mem_boundary(ctx, h_bcols, bstride, n_img, n_ram, fs.d_delta, ctx->ws.trace, N)) != 0) return rc;
+  fill_public_values(pv_out, entry_point, T, exit_code, halt_kind);
+  if ((rc = prove_resident(ctx, p, log_n, pv_out, ctx->ws.trace)) != 0) return rc;
+  return finish_proof(ctx, p, log_n, proof, proof_len);
+}
+
+int zkir_b200_prove_writelog_mem(zkir_ctx* ctx, const zkir_params* p, const uint32_t* pcs, const uint32_t* instrs, const uint64_t* wlog,
+                                 const uint64_t* mem_old, const uint32_t* mem_pts, uint64_t n_rows, const uint64_t* mem_widx, const uint64_t* mem_word,
+                                 const uint32_t* mem_ts, size_t n_words, uint64_t final_pc, uint32_t entry_point, uint64_t exit_code, int halt_kind,
+                                 uint32_t log_n, uint32_t* pv_out, uint8_t** proof, size_t* proof_len) {
+  if (!ctx) return ZKIR_ERR_ARG;
+  ctx->err.clear();
+  cudaSetDevice(ctx->device);
+  int rc = check_params(ctx, p, log_n);
+  if (rc) return rc;
+  if (!profile_is_full(p->width)) { ctx->err = "zkir_b200_prove_writelog_mem is the full profile's entry (params.width = ZKIR_AIR_FULL_WIDTH); the core profile takes zkir_b200_prove_writelog"; return ZKIR_ERR_ARG; }
+  if (ctx->comm) { ctx->err = "a sharded context proves full-profile runs from rows (zkir_b200_prove_rows)"; return ZKIR_ERR_ARG; }
+  if (!pv_out || !proof || !proof_len || !pcs || !instrs || !wlog || !mem_old || !mem_pts || (n_words && (!mem_widx || !mem_word || !mem_ts))) { ctx->err = "null argument"; return ZKIR_ERR_ARG; }
+  if (n_rows >= (1ull << log_n)) { ctx->err = "bad write log: need n_rows < 2^log_n (the last row is a padding row)"; return ZKIR_ERR_ARG; }
+  for (size_t k = 1; k < n_words; k++) if (mem_widx[k] <= mem_widx[k - 1]) { ctx->err = "memory log: touched words must be strictly ascending"; return ZKIR_ERR_ARG; }
+  if ((rc = ws_prepare(ctx, p, log_n)) != 0) return rc;
+  if ((rc = ensure_public_columns(ctx, p, log_n)) != 0) return rc;
+  ctx->ws.graph_run = false;
+  CU(cudaEventRecord(ctx->ev[ZKIR_STAGE_H2D], ctx->stream));
+  FullWlStage fs;
+  if ((rc = full_wl_stage(ctx, std::max<u64>(n_rows, 1), ctx->code.size(), &fs)) != 0) return rc;
+  cudaStream_t st = ctx->stream;
+  CU(cudaMemcpyAsync(fs.sg.d_wlog, wlog, n_rows * 8, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(fs.d_old, mem_old, n_rows * 8, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(fs.sg.d_pcs, pcs, n_rows * 4, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(fs.sg.d_ins, instrs, n_rows * 4, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(fs.d_pts, mem_pts, n_rows * 4, cudaMemcpyHostToDevice, st));
+  return prove_full_from_logs(ctx, p, fs, n_rows, final_pc, mem_widx, mem_word, mem_ts, n_words, log_n, entry_point, exit_code, halt_kind, pv_out, proof, proof_len);
+}
+
 static int prove_program_full_wl(zkir_ctx* ctx, const zkir_params* p, const uint32_t* code, size_t n_code, const uint8_t* data, size_t n_data,
                                  uint32_t entry_point, const uint64_t* inputs, size_t n_inputs, uint64_t max_cycles, uint32_t* pv_out,
                                  uint64_t* out_cycles, uint32_t* out_log_n, uint8_t** proof, size_t* proof_len) {
@@ -1190,59 +1279,24 @@ static int prove_program_full_wl(zkir_ctx* ctx, const zkir_params* p, const uint
   u64* h_wlog = (u64*)hb; u64* h_old = (u64*)(hb + cap * 8);
   u32* h_pcs = (u32*)(hb + cap * 16); u32* h_ins = (u32*)(hb + cap * 20); u32* h_pts = (u32*)(hb + cap * 24);
   CU(cudaStreamSynchronize(ctx->stream));   // the previous proof may still read the device staging
-  u64 n_scan = 1ull << ZKIR_RANGE_BITS;
-  while (n_scan < max_cycles || n_scan < n_code) n_scan <<= 1;
-  // device staging: wlog | old | pcs | ins | pts | scan scratch | multiplicity deltas
-  const size_t scratch = trace_expand_wl_scratch_ints(n_scan) * 4;
-  const size_t need = max_cycles * 28 + scratch + 64 + (1024 + 128) * 4 + 64;
-  if (ctx->rows_bytes < need) {
-    if (ctx->rows_dev) cudaFree(ctx->rows_dev);
-    ctx->rows_dev = nullptr; ctx->rows_bytes = 0;
-    CU(cudaMalloc(&ctx->rows_dev, need));
-    ctx->rows_bytes = need;
-  }
-  char* db = (char*)ctx->rows_dev;
+  FullWlStage fs;
+  if ((rc = full_wl_stage(ctx, max_cycles, n_code, &fs)) != 0) return rc;
   ProgUpload up;
   up.ctx = ctx; up.h_pcs = h_pcs; up.h_ins = h_ins; up.h_wlog = h_wlog; up.done = 0; up.e = cudaSuccess;
-  up.sg.d_wlog = (u64*)db; up.d_old = (u64*)(db + max_cycles * 8);
-  up.sg.d_pcs = (u32*)(db + max_cycles * 16); up.sg.d_ins = (u32*)(db + max_cycles * 20); up.d_pts = (u32*)(db + max_cycles * 24);
-  up.sg.d_scr = (int*)(db + ((max_cycles * 28 + 15) & ~(size_t)15));
-  u32* d_delta = (u32*)(db + ((max_cycles * 28 + scratch + 63) & ~(size_t)63));
-  up.h_old = h_old; up.h_pts = h_pts;
+  up.sg = fs.sg; up.d_old = fs.d_old; up.d_pts = fs.d_pts; up.h_old = h_old; up.h_pts = h_pts;
   zkir_vm_result* res = nullptr;
   rc = zkir_vm_run_writelog_mem_cb(code, n_code, data, n_data, entry_point, inputs, n_inputs, max_cycles, h_pcs, h_ins, h_wlog, h_old, h_pts, cap,
                                    prog_on_chunk, &up, PROG_CHUNK, &res);
   if (rc) { ctx->err = std::string("interpreter: ") + zkir_vm_last_error(); return rc; }
+  struct Free { zkir_vm_result* r; ~Free() { zkir_vm_free(r); } } free_res{res};   // the touched-word list is read until the converter is launched
   const u64 T = zkir_vm_cycles(res), final_pc = zkir_vm_final_pc(res);
   const int halt_kind = zkir_vm_halt_kind(res);
   const u64 exit_code = zkir_vm_exit_code(res);
   u32 log_n = ZKIR_RANGE_BITS;
   while ((1ull << log_n) <= T || (1ull << log_n) < n_code) log_n++;   // at least one padding row after the last cycle
-  const u64 N = 1ull << log_n;
   if (out_cycles) *out_cycles = T;
   if (out_log_n) *out_log_n = log_n;
-  // boundary cells from the interpreter's list of touched words (host, a few rows), staged in pinned memory
-  const size_t n_words = zkir_vm_memlog_count(res);
-  const u64* widx = zkir_vm_memlog_widx(res);
-  const u64 n_img = zkir_image_words(n_code);
-  u64 n_ram = 0;
-  for (size_t k = 0; k < n_words; k++) n_ram += widx[k] >= n_img;
-  const u64 bstride = std::max<u64>(std::max(n_img, n_ram), 1);
-  const size_t bbytes = (1024 + 128) * 4 + (size_t)MEM_BOUNDARY_COLS * bstride * 4;
-  if (ctx->full_stage_bytes < bbytes) {
-    if (ctx->full_stage) cudaFreeHost(ctx->full_stage);
-    ctx->full_stage = nullptr; ctx->full_stage_bytes = 0;
-    cudaError_t me = cudaMallocHost(&ctx->full_stage, bbytes);
-    if (me != cudaSuccess) { zkir_vm_free(res); ctx->err = std::string("cudaMallocHost: ") + cudaGetErrorString(me); return ZKIR_ERR_OOM; }
-    ctx->full_stage_bytes = bbytes;
-  }
-  u32* h_delta = ctx->full_stage;
-  u32* h_bcols = h_delta + 1024 + 128;
-  memset(h_bcols, 0, (size_t)MEM_BOUNDARY_COLS * bstride * 4);
-  rc = zkir_mem_boundary_from_words_full(code, n_code, widx, zkir_vm_memlog_word(res), zkir_vm_memlog_ts(res), n_words, log_n, h_bcols, bstride, h_delta, h_delta + 1024);
-  if (!rc) rc = zkir_b200_set_io(ctx, zkir_vm_io(res), zkir_vm_io_len(res));   // the run's public I/O transcript is part of the statement
-  zkir_vm_free(res);
-  if (rc) { if (ctx->err.empty()) ctx->err = zkir_b200_last_error(nullptr); return rc; }
+  if ((rc = zkir_b200_set_io(ctx, zkir_vm_io(res), zkir_vm_io_len(res))) != 0) return rc;   // the run's public I/O transcript is part of the statement
   if ((rc = check_params(ctx, p, log_n)) != 0) return rc;
   if ((rc = ws_prepare(ctx, p, log_n)) != 0) return rc;
   if ((rc = ensure_public_columns(ctx, p, log_n)) != 0) return rc;
@@ -1252,17 +1306,8 @@ static int prove_program_full_wl(zkir_ctx* ctx, const zkir_params* p, const uint
   if (up.e != cudaSuccess) { ctx->err = std::string("write-log upload: ") + cudaGetErrorString(up.e); return ZKIR_ERR_CUDA; }
   CU(cudaEventRecord(ctx->copy_done, ctx->copy_stream));
   CU(cudaStreamWaitEvent(ctx->stream, ctx->copy_done, 0));
-  cudaStream_t st = ctx->stream;
-  CU(cudaMemcpyAsync(d_delta, h_delta, (1024 + 128) * 4, cudaMemcpyHostToDevice, st));
-  CU(cudaMemsetAsync(ctx->d_err, 0xff, 16, st));
-  WlFullArgs wa;
-  wa.pcs = up.sg.d_pcs; wa.ins = up.sg.d_ins; wa.wlog = up.sg.d_wlog; wa.old_word = up.d_old; wa.prev_ts = up.d_pts; wa.T = T; wa.N = N; wa.final_pc = final_pc;
-  wa.chunk_prev = up.sg.d_scr; wa.cols = ctx->ws.trace; wa.err = ctx->d_err; wa.n_code = (u32)ctx->code.size();
-  RC(launch_trace_expand_wl_full(wa, st, &ctx->launches));
-  if ((rc = upload_mem_boundary(ctx, h_bcols, bstride, n_img, n_ram, d_delta, ctx->ws.trace, N)) != 0) return rc;
-  fill_public_values(pv_out, entry_point, T, exit_code, halt_kind);
-  if ((rc = prove_resident(ctx, p, log_n, pv_out, ctx->ws.trace)) != 0) return rc;
-  return finish_proof(ctx, p, log_n, proof, proof_len);
+  return prove_full_from_logs(ctx, p, fs, T, final_pc, zkir_vm_memlog_widx(res), zkir_vm_memlog_word(res), zkir_vm_memlog_ts(res), zkir_vm_memlog_count(res), log_n,
+                              entry_point, exit_code, halt_kind, pv_out, proof, proof_len);
 }
 
 int zkir_b200_prove_program(zkir_ctx* ctx, const zkir_params* p, const uint32_t* code, size_t n_code, const uint8_t* data, size_t n_data,

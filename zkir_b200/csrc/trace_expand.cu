@@ -76,7 +76,7 @@ struct FullWriter {
 __global__ void __launch_bounds__(128) trace_expand_full_kernel(ExpandFullArgs fa);
 // one row of the full table + its histogram contributions: shared by the rows converter and the write-log converter
 __device__ __forceinline__ void expand_row_full(u64 i, u64 N, u64 T, const u64 (&rg)[16], u64 pc, u32 w, u64 read_val, u64 old_word, u32 prev_ts,
-                                                u32 pre_err, u32* cols, u64* errp, u32 n_code, u32* hist) {
+                                                u32 pre_err, u32* cols, u64* errp, u32 n_code, u32* hist, bool check_log = false, u64 wl = 0) {
   const bool live = i < T;
   FullWriter W = {cols + i, N};
   u32 err = pre_err;
@@ -85,7 +85,12 @@ __device__ __forceinline__ void expand_row_full(u64 i, u64 N, u64 T, const u64 (
     u64 loaded, new_word;
     const u32 merr = expand_mem_cells(i, w, rg, ma, old_word, (u64)prev_ts, W, &loaded, &new_word);
     if (!err) err = merr;
-    if (ma.is_ld) read_val = loaded;
+    if (ma.is_ld) {
+      read_val = loaded;
+      // write-log path: the register rebuild of the rows below used the LOGGED value of this load; it must be the one the memory log gives
+      const u32 rd = (w >> 7) & 15;
+      if (check_log && !err && rd && wl != (((u64)rd << 56) | loaded)) err = PACK_ERR_MEMVAL;
+    }
   }
   const u32 rerr = expand_row_v2(i, T, rg, pc, w, read_val, W);
   if (!err) err = rerr;
@@ -134,7 +139,7 @@ __global__ void __launch_bounds__(WL_CHUNK) trace_expand_wl_full_kernel(WlFullAr
     if (live && wl_word_malformed(wl, kw)) pre_err = ((a.ins[i] & 0x7F) == 0x50 && rg[10] == 1) ? PACK_ERR_TAPE40 : PACK_ERR_REG40;
     const u64 read_val = kw == 10u ? (wl & M40) : rg[10];   // READ rows: the post-state r10 (loads take theirs from the logged word)
     expand_row_full(i, a.N, a.T, rg, live ? (u64)a.pcs[i] : a.final_pc, live ? a.ins[i] : 0u, read_val, live ? a.old_word[i] : 0ull, live ? a.prev_ts[i] : 0u,
-                    pre_err, a.cols, a.err, a.n_code, hist);
+                    pre_err, a.cols, a.err, a.n_code, hist, true, wl);
   }
   full_hist_flush(hist, a.cols, a.N);
 }

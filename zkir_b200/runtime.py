@@ -176,9 +176,15 @@ class ExecutionResult:  # vm.rs:54-78
         if self._wl_arrays is not None:   # recorded directly by the interpreter (zkir_vm_run_writelog): nothing to convert
             n = int(l.zkir_vm_logged_rows(self._h))
             a = self._wl_arrays
-            return {"pcs": a["pcs"][:n], "instrs": a["instrs"][:n], "wlog": a["wlog"][:n], "final_pc": l.zkir_vm_final_pc(self._h),
-                    "exit_code": self.halt_reason.code if self.halt_reason.kind == "Exit" else 0,
-                    "halt_kind": _HALT_KIND[self.halt_reason.kind], "entry_point": self._entry, "program": self.program, "io": self.io}
+            wl = {"pcs": a["pcs"][:n], "instrs": a["instrs"][:n], "wlog": a["wlog"][:n], "final_pc": l.zkir_vm_final_pc(self._h),
+                  "exit_code": self.halt_reason.code if self.halt_reason.kind == "Exit" else 0,
+                  "halt_kind": _HALT_KIND[self.halt_reason.kind], "entry_point": self._entry, "program": self.program, "io": self.io}
+            if "mem_old" in a:   # memory log (full profile): per-row arrays + the touched words, ascending
+                nw = int(l.zkir_vm_memlog_count(self._h))
+                view = lambda ptr, dt: np.ctypeslib.as_array(ptr, shape=(nw,)).copy() if nw else np.zeros(0, dtype=dt)
+                wl.update(mem_old=a["mem_old"][:n], mem_pts=a["mem_pts"][:n], mem_widx=view(l.zkir_vm_memlog_widx(self._h), np.uint64),
+                          mem_word=view(l.zkir_vm_memlog_word(self._h), np.uint64), mem_ts=view(l.zkir_vm_memlog_ts(self._h), np.uint32))
+            return wl
         n = l.zkir_vm_trace_len(self._h)
         pcs = out["pcs"] if out else np.empty(n, dtype=np.uint32)
         wlog = out["wlog"] if out else np.empty(n, dtype=np.uint64)
@@ -232,23 +238,35 @@ class VM:  # vm.rs:104-205
             raise RuntimeError_(rc, l.zkir_vm_last_error().decode())
         return ExecutionResult(h, self.program.entry_point, self.program)
 
-    def run_writelog(self, out=None):
+    def run_writelog(self, out=None, memory_log=None):
         """Run with the register write log recorded STRAIGHT into `out` = dict(pcs u32[cap], instrs u32[cap], wlog u64[cap])
         (pinned arrays, e.g. PinnedBuffer.array) while the program executes: zkir_vm_run_writelog.  No per-cycle register
-        snapshot exists afterwards: `.writelog()` of the result returns views of the arrays."""
+        snapshot exists afterwards: `.writelog()` of the result returns views of the arrays.
+        `memory_log` (None = when the program needs the full AIR profile): also record mem_old u64[cap] / mem_pts u32[cap], the word before
+        each load / store and its previous timestamp (zkir_vm_run_writelog_mem_cb): what Context.prove_writelog needs for such programs."""
         l = _ffi.lib()
+        if memory_log is None:
+            memory_log = program_profile(self.program) == "full"
         cap = int(self.config.max_cycles) if out is None else int(out["pcs"].shape[0])
         if out is None:
             out = {"pcs": np.empty(cap, dtype=np.uint32), "instrs": np.empty(cap, dtype=np.uint32), "wlog": np.empty(cap, dtype=np.uint64)}
+        if memory_log and "mem_old" not in out:
+            out = dict(out, mem_old=np.zeros(cap, dtype=np.uint64), mem_pts=np.zeros(cap, dtype=np.uint32))
         assert out["pcs"].dtype == np.uint32 and out["instrs"].dtype == np.uint32 and out["wlog"].dtype == np.uint64
         code = (C.c_uint32 * max(1, len(self.program.code)))(*self.program.code)
         data = (C.c_uint8 * max(1, len(self.program.data)))(*self.program.data)
         inp = (C.c_uint64 * max(1, len(self.inputs)))(*[v & (2**64 - 1) for v in self.inputs])
         h = C.c_void_p()
         l.zkir_vm_enable_poseidon2(int(self.config.enable_poseidon2_syscall))
-        rc = l.zkir_vm_run_writelog(code, len(self.program.code), data, len(self.program.data), self.program.entry_point,
-                                    inp, len(self.inputs), self.config.max_cycles, out["pcs"].ctypes.data, out["instrs"].ctypes.data,
-                                    out["wlog"].ctypes.data, cap, C.byref(h))
+        if memory_log:
+            assert out["mem_old"].dtype == np.uint64 and out["mem_pts"].dtype == np.uint32 and out["mem_old"].shape[0] >= cap and out["mem_pts"].shape[0] >= cap
+            rc = l.zkir_vm_run_writelog_mem_cb(code, len(self.program.code), data, len(self.program.data), self.program.entry_point,
+                                               inp, len(self.inputs), self.config.max_cycles, out["pcs"].ctypes.data, out["instrs"].ctypes.data,
+                                               out["wlog"].ctypes.data, out["mem_old"].ctypes.data, out["mem_pts"].ctypes.data, cap, None, None, 0, C.byref(h))
+        else:
+            rc = l.zkir_vm_run_writelog(code, len(self.program.code), data, len(self.program.data), self.program.entry_point,
+                                        inp, len(self.inputs), self.config.max_cycles, out["pcs"].ctypes.data, out["instrs"].ctypes.data,
+                                        out["wlog"].ctypes.data, cap, C.byref(h))
         if rc != 0:
             raise RuntimeError_(rc, l.zkir_vm_last_error().decode())
         return ExecutionResult(h, self.program.entry_point, self.program, wl_arrays=out)
@@ -459,17 +477,27 @@ class Context:
             self.set_program(wl["program"])
         if wl.get("io") is not None:
             self.set_io(wl["io"])
-        params = cfg.params()
+        full = "mem_old" in wl     # write log + memory log: the full profile (zkir_b200_prove_writelog_mem)
+        params = cfg.params(FULL_WIDTH if full else WIDTH)
         n = int(wl["pcs"].shape[0])
         if log_n is None:
-            log_n = max(MIN_LOG_N, (n - 1).bit_length())
+            log_n = max(MIN_LOG_N, n.bit_length(), (len(getattr(wl.get("program"), "code", ())) - 1).bit_length()) if full else max(MIN_LOG_N, (n - 1).bit_length())
         pcs, ins, wlog = (np.ascontiguousarray(wl[k]) for k in ("pcs", "instrs", "wlog"))
         assert pcs.dtype == np.uint32 and ins.dtype == np.uint32 and wlog.dtype == np.uint64
         pv = np.zeros(NUM_PUBLIC, dtype=np.uint32)
         proof, plen = C.c_void_p(), C.c_size_t()
-        rc = self._l.zkir_b200_prove_writelog(self._h, C.byref(params), pcs.ctypes.data, ins.ctypes.data, wlog.ctypes.data, n, int(wl["final_pc"]),
-                                              int(wl["entry_point"]), int(wl["exit_code"]), int(wl["halt_kind"]), log_n, pv.ctypes.data_as(_ffi.u32p),
-                                              C.byref(proof), C.byref(plen))
+        if full:
+            old, pts = np.ascontiguousarray(wl["mem_old"]), np.ascontiguousarray(wl["mem_pts"])
+            widx, word, ts = (np.ascontiguousarray(wl[k]) for k in ("mem_widx", "mem_word", "mem_ts"))
+            assert old.dtype == np.uint64 and pts.dtype == np.uint32 and widx.dtype == np.uint64 and word.dtype == np.uint64 and ts.dtype == np.uint32
+            rc = self._l.zkir_b200_prove_writelog_mem(self._h, C.byref(params), pcs.ctypes.data, ins.ctypes.data, wlog.ctypes.data, old.ctypes.data, pts.ctypes.data, n,
+                                                      widx.ctypes.data, word.ctypes.data, ts.ctypes.data, int(widx.shape[0]), int(wl["final_pc"]),
+                                                      int(wl["entry_point"]), int(wl["exit_code"]), int(wl["halt_kind"]), log_n, pv.ctypes.data_as(_ffi.u32p),
+                                                      C.byref(proof), C.byref(plen))
+        else:
+            rc = self._l.zkir_b200_prove_writelog(self._h, C.byref(params), pcs.ctypes.data, ins.ctypes.data, wlog.ctypes.data, n, int(wl["final_pc"]),
+                                                  int(wl["entry_point"]), int(wl["exit_code"]), int(wl["halt_kind"]), log_n, pv.ctypes.data_as(_ffi.u32p),
+                                                  C.byref(proof), C.byref(plen))
         self._check(rc)
         out = C.string_at(proof, plen.value)
         self._l.zkir_b200_free_proof(proof)
@@ -477,8 +505,8 @@ class Context:
 
     def prove_program(self, program, inputs, cfg):
         """Program -> Proof in one call (zkir_b200_prove_program): the interpreter records the write log into pinned memory and the
-        log is uploaded chunk by chunk while it runs (core profile); a program that needs the full profile is interpreted with full rows,
-        its memory replayed on the host and the wide table expanded on the device.  Returns (proof bytes, public values, cycles, log_n)."""
+        log is uploaded chunk by chunk while it runs; for a program that needs the full profile the interpreter also records the memory
+        log (28 B/cycle in all) and the device expands the wide table.  Returns (proof bytes, public values, cycles, log_n)."""
         params = cfg.params(profile_width(program_profile(program)))
         code = np.ascontiguousarray(program.code, dtype=np.uint32)
         data = np.ascontiguousarray(list(program.data) or [0], dtype=np.uint8)
