@@ -523,7 +523,12 @@ def test_interpreter_memory_log_equals_the_host_replay():
     from zkir_b200 import _ffi
     l = _ffi.lib()
     raw = C.CDLL(_ffi.LIB_PATH)   # the two-step host replay is internal to the library (not part of include/zkir_b200.h)
-    for prog, inputs in ((mix_program(), [60]), (run(MEM_SRC).program, [])):
+    import test_fuzz_full_profile as fz
+    cases = [(mix_program(), [60]), (run(MEM_SRC).program, [])]
+    for seed in (3, 11, 29):
+        lines, body, inputs = fz.random_program(np.random.default_rng(1000 + seed), 200)
+        cases.append((zkir_b200.assemble(fz.run_model_and_emit(lines, body, inputs)[0]), inputs))
+    for prog, inputs in cases:
         res = zkir_b200.VM(prog, inputs, zkir_b200.VMConfig(enable_execution_trace=True)).run()
         rows = res.rows()
         T = len(rows["instrs"])

@@ -202,3 +202,22 @@ def test_the_random_programs_covered_the_instruction_set():
     all_ops = set(range(0x00, 0x09)) | set(range(0x10, 0x16)) | set(range(0x18, 0x1E)) | set(range(0x20, 0x29)) | set(range(0x30, 0x36)) | set(range(0x38, 0x3C)) | \
         set(range(0x40, 0x46)) | {0x50, 0x51}
     assert all_ops - SEEN_OPCODES == set(), sorted(hex(o) for o in all_ops - SEEN_OPCODES)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(0, 48, 6))
+def test_gpu_random_programs_program_to_proof_equals_oracle(oracle_full, seed):
+    """Program -> Proof on the device (interpreter write log + memory log -> register rebuild -> 248-column converter -> prover) gives the
+    bytes the oracle computes from the host packer's table, and the independent verifier accepts them."""
+    rng = np.random.default_rng(1000 + seed)
+    lines, body, inputs = random_program(rng, 200)
+    src, _ = run_model_and_emit(lines, body, inputs)
+    prog = zkir_b200.assemble(src)
+    assert zkir_b200.runtime.program_profile(prog) == "full"
+    res = zkir_b200.VM(prog, inputs, zkir_b200.VMConfig(enable_execution_trace=True)).run()
+    cols, pv = res.pack(profile="full")
+    cfg = zkir_b200.ProverConfig(num_queries=8, pow_bits=2)
+    want = oracle_full.prove(cfg, cols, pv, res)
+    proof = zkir_b200.prove(prog, inputs, cfg)
+    assert proof.bytes_ == want
+    assert zkir_b200.verify(proof, cfg) == (True, "")

@@ -18,7 +18,7 @@ tail -2 gpurun_out/prove_once_$TAG.log
 # the full AIR profile (2^18-row mix workload): launch list of the last two proofs (resident columns, then rows through the device
 # converter) and ncu --set full of its profile-specific kernels
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_full_$TAG.csv python tools/full_profile_bench.py 18 1 > gpurun_out/full_once_$TAG.log 2>&1
-ncu --set full --clock-control none --import-source on -k "regex:quotient_kernel_full|aux_rows_kernel_full|trace_expand_full_kernel" -c 5 -o gpurun_out/${TAG}_full python tools/full_profile_bench.py 18 1 > gpurun_out/ncu_full_$TAG.log 2>&1
+ncu --set full --clock-control none --import-source on -k "regex:quotient_kernel_full|aux_rows_kernel_full|trace_expand_full_kernel|trace_expand_wl_full_kernel" -c 8 -o gpurun_out/${TAG}_full python tools/full_profile_bench.py 18 1 > gpurun_out/ncu_full_$TAG.log 2>&1
 python tools/ncu_summary.py gpurun_out/${TAG}_full.ncu-rep > gpurun_out/ncu_full_$TAG.md
 rm -f gpurun_out/${TAG}_full.ncu-rep
 tail -2 gpurun_out/full_once_$TAG.log

@@ -57,7 +57,7 @@ if os.path.exists(f"{G}/launches_full_{tag}.csv"):
     open(f"{P}/{rnd}_full_profile_{label}.md", "w").write(
         f"# {rnd} {label} -- full AIR profile (248 + 168 columns, all 50 opcodes), mix workload at 2^18 rows ({head})\n\n"
         "Command: `ncu --metrics gpu__time_duration.sum --clock-control none --csv python tools/full_profile_bench.py 18 1` -- the LAST proof of the run, "
-        "proven from rows in host memory (host memory replay, device converter `trace_expand_full_kernel`, then the ordinary proof).\n\n" + fl
+        "Program -> Proof (interpreter write log + memory log, device register rebuild + converter `trace_expand_wl_full_kernel`, then the ordinary proof).\n\n" + fl
         + "\nOutput of the same command without the profiler's per-launch serialisation is in the bench JSON (`full_profile_mix`); under ncu:\n\n```\n" + fo + "```\n\n"
         "## ncu --set full of the profile-specific kernels\n\n" + fn)
 print("wrote", f"{P}/{rnd}_launches_{label}.md", f"{P}/{rnd}_bench_launches_{label}.md", f"{P}/{rnd}_ncu_{label}.md")
