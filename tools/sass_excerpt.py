@@ -24,6 +24,7 @@ KERNELS = {
     "quotient_kernel_full_3x256": r"quotient_kernel_fullILi3ELi256E",
     "aux_rows_kernel_full": r"aux_rows_kernel_full",
     "trace_expand_full_kernel": r"trace_expand_full_kernel",
+    "trace_expand_wl_full_kernel": r"trace_expand_wl_full_kernel",
 }
 MUL_PIPE = ("IMAD", "IMUL")          # fmaheavy (integer multiply-add) pipe; IMAD.IADD / IMAD.MOV are adds / moves issued there
 TAG = sys.argv[1] if len(sys.argv) > 1 else "r02"
