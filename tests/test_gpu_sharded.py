@@ -102,3 +102,49 @@ def test_nccl_sharded_proof_equals_single_gpu_proof(gpu_ctx, monkeypatch, n, log
     assert errs == [None] * world, errs
     for r in range(world):
         assert out[r][0] == want and out[r][1] == want, f"rank {r} differs at word {_first_diff(out[r][0], want)}"
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_nccl_sharded_full_profile_proof_equals_single_gpu_proof(gpu_ctx, world):
+    """The full AIR profile (248 + 168 columns) over real NCCL: packed columns, recorded rows (host memory replay + device converter on
+    every rank) and Program -> Proof (the sharded context takes the rows path) all return the single-GPU proof bytes on every rank."""
+    if _n_gpus() < world:
+        pytest.skip(f"needs {world} GPUs")
+    from zkir_b200.workloads import mix_program
+    prog, inputs = mix_program(), [2900]                     # 63 811 cycles -> 2^16 rows
+    res = zkir_b200.VM(prog, inputs, zkir_b200.VMConfig(enable_execution_trace=True)).run()
+    cols, pv = res.pack()
+    rows = res.rows()
+    cfg = zkir_b200.ProverConfig(num_queries=50, pow_bits=8, max_cycles=1 << 17)
+    want = gpu_ctx.prove_columns(cols, pv, cfg, program=res)
+    assert zkir_b200.verify(want, cfg, pv, res) == (True, "")
+    lib = zkir_b200._ffi.lib()
+    ident = (C.c_uint8 * 128)()
+    assert lib.zkir_b200_comm_unique_id(ident) == 0, lib.zkir_b200_last_error(None)
+    out, errs = [None] * world, [None] * world
+
+    def rank_main(r):
+        try:
+            ctx = zkir_b200.Context(r)
+            try:
+                ctx._check(lib.zkir_b200_comm_init(ctx._h, ident, r, world))
+                a = ctx.prove_columns(cols, pv, cfg, program=res)
+                b = ctx.prove_rows(rows, cfg)[0]
+                c = ctx.prove_program(prog, inputs, cfg)[0]
+                out[r] = [a, b, c]
+                ctx.comm_shutdown()
+            finally:
+                ctx.close()
+        except Exception as e:  # noqa: BLE001
+            errs[r] = e
+
+    th = [threading.Thread(target=rank_main, args=(r,)) for r in range(world)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join(timeout=300)
+    assert not any(t.is_alive() for t in th), "a rank hung"
+    assert errs == [None] * world, errs
+    for r in range(world):
+        for k, name in enumerate(("columns", "rows", "program")):
+            assert out[r][k] == want, f"rank {r} {name} differs at word {_first_diff(out[r][k], want)}"
