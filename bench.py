@@ -144,7 +144,25 @@ def ncu_metrics(build):
     return best
 
 
+_JSON_FD = None
+
+
+def emit_json(obj):
+    """The ONE line of the contract goes to the process's original stdout; everything else any library prints (NCCL's version banner
+    and NCCL_DEBUG output go to fd 1) was redirected to stderr by main()."""
+    line = (json.dumps(obj) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, line)
+
+
 def main():
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -164,14 +182,14 @@ def main():
         v = r["value"]
         sample = (f"the full workload: fibonacci n={args.fib_n}, {r['cycles']} cycles, 2^{r['log_n']} rows, same AIR and parameters as the GPU arm; "
                   f"{r['steps']} timed proofs of {r['s_per_proof']:.2f} s after {r['warmup']} warm-up (asked: --steps {args.steps} --warmup {args.warmup}, cut to a {CPU_BUDGET_S:.0f} s budget)")
-        print(json.dumps({
+        emit_json({
             "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": r["steps"], "warmup": r["warmup"],
             "ms_per_step": r["s_per_proof"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 (BabyBear mod p)",
             "data": "synthetic",
             "config": {"workload": workload_name(args.fib_n, r["log_n"], r["width"], r["cfg"]), "rows": 1 << r["log_n"], "width": r["width"],
                        "reference_note": "seceq/zkir contains no prover; the CPU arm is this repo's oracle (own restatement of docs/PROVER_SPEC.md, OpenMP, not Plonky3)"},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": sample},
-            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0})
         return 0
 
     import torch
@@ -609,7 +627,7 @@ def main():
         r = cpu_oracle_run(args.fib_n, 1, 0)    # the same workload, proved once (about 10 s on 16 host threads)
         out["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
                                "sample": f"CPU oracle (OpenMP, {r['cores']} threads) proving the full workload once: fibonacci n={args.fib_n}, {r['cycles']} cycles, 2^{r['log_n']} rows ({r['s_per_proof']:.2f} s)"}
-    print(json.dumps(out))
+    emit_json(out)
     if dist is not None:
         dist.destroy_process_group()
     return 0
