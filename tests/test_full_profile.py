@@ -382,6 +382,10 @@ def test_gpu_full_profile_program_to_proof_malformed_runs(gpu_ctx):
                 "addi r1, zero, 0x1001\nlw r2, 0(r1)\nebreak\n"):                   # misaligned load: the interpreter refuses (memory.rs alignment)
         with pytest.raises(Exception):
             zkir_b200.prove(zkir_b200.assemble(src), [], cfg)
+    # a store above 2^30 runs fine in the interpreter; the DEVICE converter reports the row (PACK_ERR_MEMADDR), as the host packer does
+    with pytest.raises(zkir_b200.RuntimeError) as e:
+        zkir_b200.prove(zkir_b200.assemble("addi r1, r0, 1\nslli r1, r1, 30\nsd r1, 0(r1)\nebreak"), [], cfg)
+    assert e.value.code == -6 and "row 2" in str(e.value) and "memory address" in str(e.value)
     # and the context stays usable
     assert zkir_b200.verify(zkir_b200.prove(mix_program(), [10], cfg), cfg) == (True, "")
 
