@@ -574,3 +574,30 @@ def test_interpreter_memory_log_equals_the_host_replay():
         assert rc == 0
         assert np.array_equal(b_l, b_r) and np.array_equal(rng_l, rng_r) and np.array_equal(b7_l, b7_r)
         l.zkir_vm_free(h)
+
+
+def test_full_profile_verifier_survives_malformed_proofs(oracle_full):
+    """Untrusted bytes against the full profile's verifier: extreme header fields (incl. the width word that selects the profile), a core
+    proof offered for a full-profile program and the reverse are all rejected without a crash."""
+    from zkir_b200.workloads import fib_trace
+    res = zkir_b200.VM(mix_program(), [20], zkir_b200.VMConfig(enable_execution_trace=True)).run()
+    cols, pv = res.pack()
+    cfg = zkir_b200.ProverConfig(num_queries=6, pow_bits=2)
+    pb = oracle_full.prove(cfg, cols, pv, res)
+    assert zkir_b200.verify(pb, cfg, pv, res) == (True, "")
+    w = np.frombuffer(pb, dtype=np.uint32)
+    for pos in range(24):
+        for v in (0, 1, 7, 31, 32, 64, 88, 248, 255, 1 << 16, 1 << 20, 0x7FFFFFFF, 0xFFFFFFFF):
+            if int(w[pos]) == v:
+                continue
+            bad = w.copy()
+            bad[pos] = v
+            assert not zkir_b200.verify(bad.tobytes(), cfg, pv, res)[0], (pos, v)
+    r2, c2, p2 = fib_trace(30)
+    core = Oracle().prove(cfg, c2, p2, r2.program)
+    assert zkir_b200.verify(core, cfg, p2, r2.program) == (True, "")
+    assert not zkir_b200.verify(core, cfg, p2, res)[0]            # a core proof is no statement about a program that needs the full profile
+    assert not zkir_b200.verify(pb, cfg, pv, r2.program)[0]
+    relabel = np.frombuffer(core, dtype=np.uint32).copy()
+    relabel[3] = FULL_WIDTH
+    assert not zkir_b200.verify(relabel.tobytes(), cfg, p2, r2.program)[0]
