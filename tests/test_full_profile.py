@@ -370,6 +370,13 @@ def test_gpu_full_profile_from_write_log_and_memory_log(gpu_ctx, oracle_full):
         except zkir_b200.RuntimeError:
             continue
         assert zkir_b200.verify(pb_bad, cfg, pv_bad, res)[0] is False, key
+    bad = dict(wl); bad["mem_widx"] = wl["mem_widx"].copy(); bad["mem_widx"][-1] = 1 << 45     # a word index no address reaches
+    try:
+        pb_bad, pv_bad = gpu_ctx.prove_writelog(bad, cfg)
+    except zkir_b200.RuntimeError:
+        pass
+    else:
+        assert zkir_b200.verify(pb_bad, cfg, pv_bad, res)[0] is False
     pb, _ = gpu_ctx.prove_writelog(wl, cfg)           # the context is still good
     assert pb == want
 
@@ -385,6 +392,10 @@ def test_gpu_full_profile_program_to_proof_malformed_runs(gpu_ctx):
     # a store above 2^30 runs fine in the interpreter; the DEVICE converter reports the row (PACK_ERR_MEMADDR), as the host packer does
     with pytest.raises(zkir_b200.RuntimeError) as e:
         zkir_b200.prove(zkir_b200.assemble("addi r1, r0, 1\nslli r1, r1, 30\nsd r1, 0(r1)\nebreak"), [], cfg)
+    assert e.value.code == -6 and "row 2" in str(e.value) and "memory address" in str(e.value)
+    # far outside: the touched word has no place in the boundary's chunk tables either (it is left out there; the row is still reported)
+    with pytest.raises(zkir_b200.RuntimeError) as e:
+        zkir_b200.prove(zkir_b200.assemble("addi r1, r0, 1\nslli r1, r1, 39\nsd r1, 0(r1)\nebreak"), [], cfg)
     assert e.value.code == -6 and "row 2" in str(e.value) and "memory address" in str(e.value)
     # and the context stays usable
     assert zkir_b200.verify(zkir_b200.prove(mix_program(), [10], cfg), cfg) == (True, "")
