@@ -64,6 +64,20 @@ extern "C" {
         proof: *mut *mut u8,
         proof_len: *mut usize,
     ) -> c_int;
+    /// many independent small proofs of the context's program (BASELINE config 4): traces[i] = packed columns [width][1 << log_ns[i]],
+    /// ios[i] / n_ios[i] = the public I/O transcript of execution i; up to 8 worker contexts overlap the launch-bound tiny proofs
+    pub fn zkir_b200_prove_batch(
+        ctx: *mut zkir_ctx,
+        params: *const zkir_params,
+        traces: *const *const u32,
+        log_ns: *const u32,
+        public_values: *const *const u32,
+        ios: *const *const u32,
+        n_ios: *const usize,
+        n_proofs: u32,
+        proofs: *mut *mut u8,   // [n_proofs], each freed with zkir_b200_free_proof
+        proof_lens: *mut usize, // [n_proofs]
+    ) -> c_int;
     /// raw TraceRow data (zkir-spec/src/trace.rs:24-50): pcs[n], instrs[n], regs[n][16] pre-state; converter on the device
     pub fn zkir_b200_prove_rows(
         ctx: *mut zkir_ctx,

@@ -216,6 +216,50 @@ impl Prover {
         Ok((bytes, pv))
     }
 
+    /// Many independent small proofs of ONE program (BASELINE config 4: add.zkasm x 4096): `traces[i]` = packed columns
+    /// `[width][1 << log_ns[i]]` (zkir_pack_trace), `public_values[i]` its five public values, `ios[i]` its I/O transcript.
+    /// The library overlaps the launch-latency-bound proofs on up to eight worker contexts of the same GPU.
+    pub fn prove_batch(
+        &mut self,
+        cfg: &ProverConfig,
+        traces: &[&[u32]],
+        log_ns: &[u32],
+        public_values: &[[u32; 5]],
+        ios: &[Vec<[u32; 4]>],
+    ) -> Result<Vec<Vec<u8>>, RuntimeError> {
+        let n = traces.len();
+        assert!(log_ns.len() == n && public_values.len() == n && ios.len() == n);
+        let params = cfg.params();
+        let t_ptrs: Vec<*const u32> = traces.iter().map(|t| t.as_ptr()).collect();
+        let pv_ptrs: Vec<*const u32> = public_values.iter().map(|p| p.as_ptr()).collect();
+        let io_ptrs: Vec<*const u32> = ios.iter().map(|e| e.as_ptr() as *const u32).collect();
+        let io_lens: Vec<usize> = ios.iter().map(|e| e.len()).collect();
+        let mut proofs = vec![ptr::null_mut::<u8>(); n];
+        let mut lens = vec![0usize; n];
+        let rc = unsafe {
+            ffi::zkir_b200_prove_batch(
+                self.ctx, &params, t_ptrs.as_ptr(), log_ns.as_ptr(), pv_ptrs.as_ptr(), io_ptrs.as_ptr(), io_lens.as_ptr(), n as u32,
+                proofs.as_mut_ptr(), lens.as_mut_ptr(),
+            )
+        };
+        let out = proofs
+            .iter()
+            .zip(&lens)
+            .map(|(&p, &l)| {
+                if p.is_null() {
+                    return Vec::new();
+                }
+                let v = unsafe { std::slice::from_raw_parts(p, l) }.to_vec();
+                unsafe { ffi::zkir_b200_free_proof(p) };
+                v
+            })
+            .collect();
+        if rc != ffi::ZKIR_OK {
+            return Err(error_of(self.ctx, rc));
+        }
+        Ok(out)
+    }
+
     /// Full-profile programs (MUL / DIV, bitwise, shifts, signed compares, loads / stores): the rows `VM::run` records with
     /// `enable_execution_trace` (zkir-spec/src/trace.rs:24-50) go in as three flat arrays; the library builds the 248-column table
     /// (zkir_pack_rows_full: multiplier block, lookup multiplicities, offline memory checking) and proves it on the GPU.
