@@ -7,8 +7,9 @@
 //                    cp.async.bulk into shared memory, completion on an mbarrier, double-buffered: the copy of tile t+1 flies while tile t
 //                    is transformed; both cosets are computed from the one staged tile (no second read at all)
 //
-// build: nvcc -O3 -std=c++17 --expt-relaxed-constexpr -gencode arch=compute_100a,code=sm_100a -lineinfo -o tools/bin/ntt_tma_probe tools/ntt_tma_probe.cu
+// build: nvcc -O3 -std=c++17 --expt-relaxed-constexpr -gencode arch=compute_100a,code=sm_100a -lineinfo -o tools/bin/ntt_tma_probe tools/ntt_tma_probe.cu -lcuda
 // run  : tools/bin/ntt_tma_probe [n_cols=88] [reps=20]
+#include <cuda.h>
 #include "../zkir_b200/csrc/ntt_fast.cu"
 
 namespace zkir {
@@ -170,6 +171,63 @@ __global__ void __launch_bounds__(512, 2) dft_row_tma1_kernel(const TileParams p
   }
 }
 
+// Variant 3: the STRIDED digit (dft_tile_kernel<10, 0, fwd, stride 2^10>: tile = 1024 rows x 16 contiguous lanes, 64-byte global segments,
+// in place, no tables but the inter-round twiddles) with the tile fetched by cp.async.bulk.tensor from a 3-D tensor map
+// {1024 inner, 1024 rows, planes}: four 16 x 256 boxes land in the exchange buffer, the threads pick their 32 points with LDS.
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+               ::"r"(smem_u32(dst)), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)) : "memory");
+}
+template <bool INV>
+__global__ void __launch_bounds__(512, 2) dft_strided_tma_kernel(const TileParams p, const __grid_constant__ CUtensorMap tm) {
+  typedef TileShape<10, 0> SH;
+  constexpr int A = SH::A, B_ = SH::B_, EA = SH::EA, XB = SH::XB, R = SH::R;
+  extern __shared__ __align__(128) u32 sm[];
+  __shared__ __align__(8) uint64_t bar;
+  const u32 tid = threadIdx.x;
+  const u32 l = tid & 15u, q = tid >> 4;
+  const u32 z = blockIdx.x % p.nz, bid = blockIdx.x / p.nz;
+  const u32 tile = bid % p.tiles_per_col, col = bid / p.tiles_per_col;   // one block of 2^20 per column: tile = lane group tb
+  const u32 out_off0 = tile * p.out_b;
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_expect_tx(&bar, 16 * R * 4);
+    for (int k = 0; k < 4; k++) tma_load_3d(sm + k * 256 * 16, &tm, (int)(tile * 16), k * 256, (int)(col * p.nz + z), &bar);
+  }
+  __syncthreads();
+  mbar_wait(&bar, 0);
+  u32 x[EA];
+#pragma unroll
+  for (int i = 0; i < EA; i++) x[i] = sm[(q + i * XB) * 16 + l];
+  __syncthreads();   // the staged tile has been read: the buffer becomes the exchange buffer
+  dft_regs<A, INV>(x);
+  u32* out = p.out + (u64)col * p.out_col + (u64)z * p.out_z;
+  const uint2* __restrict__ twq = p.tw_mid + q;
+  const u32 w0 = q * (EA / 2) * 32 + l + ((q & 1u) << 4), w1 = q * (EA / 2) * 32 + l + (((q & 1u) ^ 1u) << 4);
+#pragma unroll
+  for (int i = 0; i < EA; i++) {
+    const u32 ks = brev<A>(i);
+    u32 v = x[i];
+    if (ks != 0) { const uint2 tw = __ldg(twq + ks * XB); v = shoup_mul(v, tw.x, tw.y); }
+    sm[((ks & 1u) ? w1 : w0) + (ks >> 1) * 32] = v;
+  }
+  __syncthreads();
+  const u32 l2 = tid & 15u, u = tid >> 4;
+#pragma unroll
+  for (int g = 0; g < EA / XB; g++) {
+    const u32 ks = u + g * XB;
+    u32 y[XB];
+    const u32 r0 = (ks >> 1) * 32 + l2 + ((ks & 1u) << 4), r1 = (ks >> 1) * 32 + l2 + (((ks & 1u) ^ 1u) << 4);
+#pragma unroll
+    for (int j = 0; j < XB; j++) y[j] = sm[((j & 1) ? r1 : r0) + j * (EA / 2) * 32];
+    dft_regs<B_, INV>(y);
+    u32* po = out + (out_off0 + ks * 1024u + l2);
+#pragma unroll
+    for (int j = 0; j < XB; j++) po[(size_t)brev<B_>(j) * EA * 1024u] = y[j];
+  }
+}
+
 }  // namespace zkir
 
 using namespace zkir;
@@ -258,6 +316,49 @@ int main(int argc, char** argv) {
     printf("load-only variant: outputs %s (%llu words differ)\n", d2 ? "DIFFER" : "identical", (unsigned long long)d2);
     cudaFree(out_c);
     if (d2) return 2;
+  }
+  // ---- the strided (top) digit of the forward transform, in place on a copy of the row pass's output
+  {
+    u32 *buf_a, *buf_b;
+    CK(cudaMalloc(&buf_a, n_cols * M * 4)); CK(cudaMalloc(&buf_b, n_cols * M * 4));
+    TileParams ps = {};
+    ps.in_col = ps.out_col = M; ps.in_z = ps.out_z = N;
+    ps.tiles_b = (1u << pl.d[1]) / 16; ps.tiles_per_col = ps.tiles_b;                 // one block of 2^20 per (column, coset)
+    ps.in_a = ps.out_a = 1u << log_n; ps.in_b = ps.out_b = 16; ps.in_r = ps.out_k = 1u << pl.d[1]; ps.in_t = ps.out_t = 1;
+    ps.split_log = 32; ps.peer_shift = 0xffffffffu; ps.nz = nz;
+    ps.tw_mid = f->tw_mid(pl.d[0], false);
+    if (!ps.tw_mid) return 1;
+    const u32 nt = n_cols * ps.tiles_per_col;
+    TileParams pa2 = ps, pb2 = ps;
+    pa2.in = buf_a; pa2.out = buf_a; pb2.in = buf_b; pb2.out = buf_b;
+    CUtensorMap tm;
+    const cuuint64_t gdim[3] = {1024, 1024, (cuuint64_t)n_cols * nz};
+    const cuuint64_t gstr[2] = {4096, (cuuint64_t)N * 4};
+    const cuuint32_t box[3] = {16, 256, 1}, estr[3] = {1, 1, 1};
+    CUresult cr = cuTensorMapEncodeTiled(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, buf_b, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) { fprintf(stderr, "cuTensorMapEncodeTiled failed: %d\n", (int)cr); return 1; }
+    const size_t smem0 = (size_t)16 * 1024 * 4;
+    CK(cudaFuncSetAttribute(dft_strided_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0));
+    // correctness first: one pass each from the same input
+    CK(cudaMemcpy(buf_a, out_a, n_cols * M * 4, cudaMemcpyDeviceToDevice));
+    CK(cudaMemcpy(buf_b, out_a, n_cols * M * 4, cudaMemcpyDeviceToDevice));
+    CK((launch_tile_t<10, 0, false, 10>(pa2, nt, nz, st)));
+    dft_strided_tma_kernel<false><<<nt * nz, 512, smem0, st>>>(pb2, tm);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(st));
+    std::vector<u32> h1(n_cols * M), h2(n_cols * M);
+    CK(cudaMemcpy(h1.data(), buf_a, h1.size() * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(h2.data(), buf_b, h2.size() * 4, cudaMemcpyDeviceToHost));
+    u64 d3 = 0;
+    for (size_t i = 0; i < h1.size(); i++) d3 += h1[i] != h2[i];
+    printf("strided digit: outputs %s (%llu words differ)\n", d3 ? "DIFFER" : "identical", (unsigned long long)d3);
+    // timing (the passes run in place on whatever the buffers hold: the arithmetic is data-independent)
+    if (time_it([&] { launch_tile_t<10, 0, false, 10>(pa2, nt, nz, st); }, "shipped dft_tile_kernel<10,0,fwd,2^10> strided digit")) return 1;
+    if (time_it([&] { dft_strided_tma_kernel<false><<<nt * nz, 512, smem0, st>>>(pb2, tm); }, "strided digit, cp.async.bulk.tensor as the load")) return 1;
+    CK(cudaGetLastError());
+    cudaFree(buf_a); cudaFree(buf_b);
+    if (d3) return 2;
   }
   // same bytes?
   std::vector<u32> ha(n_cols * M), hb(n_cols * M);
